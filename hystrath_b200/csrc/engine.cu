@@ -1,0 +1,1159 @@
+// engine.cu -- the C ABI of libdsmcb200 (include/dsmcb200.h): context, device memory, stage
+// sequencing of dsmcCloud::evolve() (DSMC/clouds/dsmcCloud.C:819-926) and NCCL migration
+// (the MPI block of Cloud<T>::move, BASIC/Cloud/Cloud.C:258-455).
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+
+using namespace dsmc;
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, bound at run time so single-GPU use does not need the library at all
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct NcclUniqueId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load(std::string& err) {
+        if (h) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+        if (!h) { err = "cannot dlopen libnccl.so.2"; return false; }
+#define LD(f, s) f = reinterpret_cast<decltype(f)>(dlsym(h, s)); if (!f) { err = std::string("nccl symbol missing: ") + s; return false; }
+        LD(GetUniqueId, "ncclGetUniqueId") LD(CommInitRank, "ncclCommInitRank") LD(CommDestroy, "ncclCommDestroy")
+        LD(AllGather, "ncclAllGather") LD(Send, "ncclSend") LD(Recv, "ncclRecv") LD(GroupStart, "ncclGroupStart")
+        LD(GroupEnd, "ncclGroupEnd") LD(GetErrorString, "ncclGetErrorString")
+#undef LD
+        return true;
+    }
+};
+NcclApi g_nccl;
+constexpr int NCCL_CHAR = 0, NCCL_INT32 = 2;
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// small conversion kernels (host AoS layouts <-> device SoA)
+// ------------------------------------------------------------------------------------------------
+__global__ void deinterleave3(const double* __restrict__ in, double* x, double* y, double* z, int32_t n) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { x[i] = in[3 * i]; y[i] = in[3 * i + 1]; z[i] = in[3 * i + 2]; }
+}
+__global__ void interleave3(const double* x, const double* y, const double* z, double* __restrict__ out, int32_t n) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { out[3 * i] = x[i]; out[3 * i + 1] = y[i]; out[3 * i + 2] = z[i]; }
+}
+__global__ void toTetId(const int32_t* cell, const int32_t* tetFace, const int32_t* tetPt, const int32_t* faceTetPair0,
+                        const int32_t* owner, int32_t* tet, int32_t n, int32_t nFaces, int* bad) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t f = tetFace[i];
+    if (f < 0 || f >= nFaces || cell[i] < 0) { *bad = 1; tet[i] = 0; return; }
+    const int32_t nT = faceTetPair0[f + 1] - faceTetPair0[f];
+    const int32_t tp = tetPt[i];
+    if (tp < 1 || tp > nT) { *bad = 1; tet[i] = 0; return; }
+    tet[i] = 2 * (faceTetPair0[f] + tp - 1) + (owner[f] != cell[i] ? 1 : 0);
+}
+__global__ void fromTetId(const int32_t* tet, const int32_t* faceTetPair0, int32_t nFaces, int32_t* tetFace, int32_t* tetPt, int32_t n) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t pair = tet[i] >> 1;
+    int32_t lo = 0, hi = nFaces;  // last f with faceTetPair0[f] <= pair
+    while (hi - lo > 1) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (faceTetPair0[mid] <= pair) lo = mid; else hi = mid;
+    }
+    tetFace[i] = lo;
+    tetPt[i] = pair - faceTetPair0[lo] + 1;
+}
+__global__ void i32ToU8(const int32_t* in, uint8_t* out, int32_t n) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = uint8_t(in[i]);
+}
+__global__ void u8ToI32(const uint8_t* in, int32_t* out, int32_t n) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+__global__ void stridedToMode(const int32_t* in, int32_t* out, int32_t n, int32_t stride, int32_t m) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[size_t(i) * stride + m];
+}
+__global__ void modeToStrided(const int32_t* in, int32_t* out, int32_t n, int32_t stride, int32_t m) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[size_t(i) * stride + m] = in[i];
+}
+__global__ void iotaKernel(int32_t* out, int32_t n, int32_t base) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = base + i;
+}
+__global__ void fillRemainder(double* rem, int32_t nCells, uint64_t seed) {
+    int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    Rng r;
+    r.init(seed, uint32_t(c), 0u, 0u, STREAM_REMAINDER);
+    rem[c] = r.sample01();  // dsmcCloud::buildCollisionSelectionRemainderFromScratch
+}
+__global__ void fillDouble(double* p, int64_t n, double v) {
+    int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void fillCellIds(const int32_t* cellOffset, int32_t nCells, int32_t* cellOut) {
+    const int lane = threadIdx.x & 31;
+    const int32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int32_t nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (int32_t c = warp; c < nCells; c += nWarps)
+        for (int32_t k = cellOffset[c] + lane; k < cellOffset[c + 1]; k += 32) cellOut[k] = c;
+}
+
+#define GRID(n) (int(((n) + 255) / 256)), 256
+
+// ------------------------------------------------------------------------------------------------
+struct ParcelBuffer {
+    double* dslab = nullptr;
+    int32_t* islab = nullptr;
+    uint8_t* bslab = nullptr;
+    ParcelArrays a{};
+};
+
+struct StageEvents { cudaEvent_t ev[8]; };
+
+struct dsmcb200_ctx {
+    int device = 0, rank = 0, nRanks = 1;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    HostMesh mesh;
+    bool haveMesh = false, haveSpecies = false, haveModels = false, ready = false;
+    std::vector<dsmcb200_species> species;
+    dsmcb200_models models{};
+    std::vector<dsmcb200_patch_model> patchModels;
+    std::vector<dsmcb200_inflow> inflows;
+    DevParams hP{};
+    DevParams* dP = nullptr;
+    // device mesh
+    TetRec* dTets = nullptr;
+    BFaceRec* dBFaces = nullptr;
+    double *dBFaceArea = nullptr, *dPoints = nullptr, *dCellCentres = nullptr, *dCellVolumes = nullptr, *dFaceCentres = nullptr,
+           *dFaceAreas = nullptr;
+    int32_t *dFaceOffsets = nullptr, *dFacePoints = nullptr, *dOwner = nullptr, *dTetBasePtIs = nullptr, *dFaceTetPair0 = nullptr,
+            *dCellFaceOffsets = nullptr, *dCellFaces = nullptr;
+    // cloud
+    ParcelBuffer buf[2];
+    int cur = 0;
+    int64_t capacity = 0, N = 0;
+    int nModes = 0;
+    bool internal = false, useCls = false;
+    int32_t *dCellCount = nullptr, *dCellOffset = nullptr, *dCursor = nullptr, *dPerm = nullptr, *dScanScratch = nullptr;
+    double *dSigma = nullptr, *dRem = nullptr, *dNColls = nullptr, *dCollSep = nullptr, *dAcc = nullptr, *dCollCum = nullptr,
+           *dWallAcc = nullptr, *dSfTail = nullptr, *dInfo = nullptr, *dInfoScratch = nullptr;
+    int64_t sfCap = 0;
+    DevCounters* dCounters = nullptr;
+    DevCounters hCounters{};
+    int* dBad = nullptr;
+    MigRec *dMigSend = nullptr, *dMigRecv = nullptr;
+    int32_t migCapacity = 0;
+    std::vector<double*> dInflowAcc;
+    std::vector<int32_t*> dInflowCounts;
+    int32_t* dInflowScan = nullptr;
+    int nQ = 0, nWallQ = 0, nMeasFaces = 0;
+    double nTimeSteps = 0;
+    uint32_t step = 0;
+    int32_t nextOrigId = 0;
+    bool occupancyValid = false;
+    // counters of the last evolve
+    dsmcb200_counters last{};
+    // neighbours
+    std::vector<int> nbrProcs;                       // slot -> proc
+    std::vector<std::vector<int32_t>> ordinalToPatch;  // slot -> ordinal -> patch
+    int32_t* dOrdinalToPatch = nullptr;              // [MAX_NEIGHBOURS][MAX_PATCHES]
+    int32_t* dCountsMatrix = nullptr;                // [nRanks*nRanks]
+    NcclComm comm = nullptr;
+    // timing
+    std::map<std::string, std::pair<double, int64_t>> ktimes;
+    std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+    std::vector<cudaEvent_t> evPool;
+    size_t evUsed = 0;
+    bool timeKernels = true;
+};
+
+namespace {
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            c->err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"; \
+            return DSMCB200_ERR_CUDA;                                                                     \
+        }                                                                                                 \
+    } while (0)
+
+int fail(dsmcb200_ctx* c, int code, const std::string& msg) { c->err = msg; return code; }
+
+template <class T>
+cudaError_t devAlloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)); }
+template <class T>
+void devFree(T*& p) { if (p) cudaFree(p); p = nullptr; }
+
+template <class T>
+cudaError_t upload(T** d, const std::vector<T>& h) {
+    cudaError_t e = devAlloc(d, h.size());
+    if (e != cudaSuccess) return e;
+    if (!h.empty()) e = cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+cudaEvent_t getEvent(dsmcb200_ctx* c) {
+    if (c->evUsed == c->evPool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->evPool.push_back(e);
+    }
+    return c->evPool[c->evUsed++];
+}
+struct KT {  // scoped kernel timer: events on the launching stream
+    dsmcb200_ctx* c; const char* name; cudaEvent_t a, b;
+    KT(dsmcb200_ctx* c_, const char* n) : c(c_), name(n) {
+        if (c->timeKernels) { a = getEvent(c); b = getEvent(c); cudaEventRecord(a, c->stream); }
+    }
+    ~KT() {
+        if (c->timeKernels) { cudaEventRecord(b, c->stream); c->pending.push_back({name, {a, b}}); }
+    }
+};
+void resolveTimers(dsmcb200_ctx* c) {
+    for (auto& p : c->pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.second.first, p.second.second) == cudaSuccess) {
+            auto& e = c->ktimes[p.first];
+            e.first += ms; e.second += 1;
+        }
+    }
+    c->pending.clear();
+    c->evUsed = 0;
+}
+
+void setArrays(ParcelBuffer& b, int64_t cap, int nModes, bool internal, bool useCls) {
+    ParcelArrays& a = b.a;
+    a.px = b.dslab; a.py = a.px + cap; a.pz = a.py + cap; a.ux = a.pz + cap; a.uy = a.ux + cap; a.uz = a.uy + cap;
+    a.erot = internal ? a.uz + cap : nullptr;
+    a.cell = b.islab; a.tet = a.cell + cap; a.origId = a.tet + cap;
+    for (int m = 0; m < MAX_MODES; ++m) a.vib[m] = (internal && m < nModes) ? a.origId + cap * (1 + m) : nullptr;
+    a.typeId = b.bslab; a.elevel = internal ? b.bslab + cap : nullptr; a.cls = useCls ? b.bslab + 2 * cap : nullptr;
+}
+
+int allocBuffer(dsmcb200_ctx* c, ParcelBuffer& b, int64_t cap) {
+    // one extra double row and one extra int row so that every buffer can stage host AoS arrays
+    CK(devAlloc(&b.dslab, size_t(cap) * 7));
+    CK(devAlloc(&b.islab, size_t(cap) * (3 + MAX_MODES)));
+    CK(devAlloc(&b.bslab, size_t(cap) * 3));
+    setArrays(b, cap, c->nModes, c->internal, c->useCls);
+    return 0;
+}
+
+int ensureCapacity(dsmcb200_ctx* c, int64_t n) {
+    if (n <= c->capacity) return 0;
+    if (n >= (int64_t(1) << 31) - 1024) return fail(c, DSMCB200_ERR_CAPACITY, "more than 2^31 parcels on one GPU");
+    int64_t cap = std::max<int64_t>(n, c->capacity + c->capacity / 4 + 4096);
+    ParcelBuffer nb[2];
+    for (int k = 0; k < 2; ++k) { int r = allocBuffer(c, nb[k], cap); if (r) return r; }
+    if (c->N > 0) {
+        const ParcelArrays& o = c->buf[c->cur].a;
+        const ParcelArrays& d = nb[c->cur].a;
+        const size_t nb8 = size_t(c->N) * 8, nb4 = size_t(c->N) * 4, nb1 = size_t(c->N);
+        double* const od[7] = {o.px, o.py, o.pz, o.ux, o.uy, o.uz, o.erot};
+        double* const dd[7] = {d.px, d.py, d.pz, d.ux, d.uy, d.uz, d.erot};
+        for (int k = 0; k < 7; ++k) if (od[k]) CK(cudaMemcpyAsync(dd[k], od[k], nb8, cudaMemcpyDeviceToDevice, c->stream));
+        int32_t* const oi[3] = {o.cell, o.tet, o.origId};
+        int32_t* const di[3] = {d.cell, d.tet, d.origId};
+        for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(di[k], oi[k], nb4, cudaMemcpyDeviceToDevice, c->stream));
+        for (int m = 0; m < MAX_MODES; ++m) if (o.vib[m]) CK(cudaMemcpyAsync(d.vib[m], o.vib[m], nb4, cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(d.typeId, o.typeId, nb1, cudaMemcpyDeviceToDevice, c->stream));
+        if (o.elevel) CK(cudaMemcpyAsync(d.elevel, o.elevel, nb1, cudaMemcpyDeviceToDevice, c->stream));
+        if (o.cls) CK(cudaMemcpyAsync(d.cls, o.cls, nb1, cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    for (int k = 0; k < 2; ++k) {
+        devFree(c->buf[k].dslab); devFree(c->buf[k].islab); devFree(c->buf[k].bslab);
+        c->buf[k] = nb[k];
+    }
+    devFree(c->dPerm);
+    CK(devAlloc(&c->dPerm, size_t(cap)));
+    c->capacity = cap;
+    return 0;
+}
+
+int ensureSfTail(dsmcb200_ctx* c, int64_t n) {
+    if (n <= c->sfCap) return 0;
+    int64_t cap = std::max<int64_t>(n, c->sfCap * 2 + 4096);
+    double* nd = nullptr;
+    CK(devAlloc(&nd, size_t(cap)));
+    if (c->dSfTail && c->sfCap) CK(cudaMemcpy(nd, c->dSfTail, size_t(c->sfCap) * 8, cudaMemcpyDeviceToDevice));
+    devFree(c->dSfTail);
+    c->dSfTail = nd;
+    c->sfCap = cap;
+    return 0;
+}
+
+// Everything that depends on mesh + species + models: device parameter block, tet table, accumulators.
+int finalize(dsmcb200_ctx* c) {
+    if (c->ready) return 0;
+    if (!c->haveMesh || !c->haveSpecies || !c->haveModels) return fail(c, DSMCB200_ERR_STATE, "set_mesh, set_species and set_models must all be called first");
+    HostMesh& M = c->mesh;
+    DevParams& P = c->hP;
+    std::memset(&P, 0, sizeof(P));
+    const dsmcb200_models& md = c->models;
+    P.nSpecies = int(c->species.size());
+    P.nPatches = int(M.patches.size());
+    if (P.nPatches > MAX_PATCHES) return fail(c, DSMCB200_ERR_CAPACITY, "more than 64 patches");
+    P.collisionModel = md.collisionModel;
+    P.invZvFormulation = md.invZvFormulation;
+    P.kB = md.kB > 0 ? md.kB : 1.38065e-23;  // OpenFOAM v1706 physicoChemical::k (pinned by shipped couette fields)
+    P.Tref = md.Tref > 0 ? md.Tref : 273.0;
+    P.nParticles = md.nEquivalentParticles;
+    P.deltaT = md.deltaT;
+    P.seed = md.seed;
+    P.invZrot = 1.0 / (md.rotationalRelaxationCollisionNumber > 0 ? md.rotationalRelaxationCollisionNumber : 5.0);
+    P.Zvib = md.vibrationalRelaxationCollisionNumber;
+    P.invZelec = 1.0 / (md.electronicRelaxationCollisionNumber > 0 ? md.electronicRelaxationCollisionNumber : 500.0);
+    P.measureFlux = md.measureHeatFluxShearStress ? 1 : 0;
+    P.measureClass = md.measureClassifications ? 1 : 0;
+    P.nInternalFaces = M.nInternalFaces;
+    for (int d = 0; d < 3; ++d) {
+        P.solutionD[d] = M.solutionD[d];
+        P.centre[d] = 0.5 * (comp(M.boundsMin, d) + comp(M.boundsMax, d));  // meshTools::constrainToMeshCentre
+    }
+    int nModes = 0;
+    bool internal = md.collisionModel == DSMCB200_COLL_LB_VHS;
+    for (int s = 0; s < P.nSpecies; ++s) {
+        const dsmcb200_species& h = c->species[s];
+        DevSpecies& d = P.sp[s];
+        d.mass = h.mass; d.d = h.diameter; d.omega = h.omega; d.alpha = h.alpha; d.rotDof = h.rotationalDegreesOfFreedom;
+        d.thetaD = h.thetaD; d.nVib = h.nVibrationalModes; d.charge = h.charge; d.nElec = std::max(1, h.nElectronicLevels);
+        for (int m = 0; m < MAX_MODES; ++m) { d.thetaV[m] = h.thetaV[m]; d.Zref[m] = h.Zref[m]; d.TrefZv[m] = h.TrefZv[m]; }
+        for (int l = 0; l < MAX_ELEC; ++l) { d.eElec[l] = l < d.nElec ? h.electronicEnergyList[l] : 0.0; d.gElec[l] = l < d.nElec ? h.electronicDegeneracyList[l] : 0; }
+        if (h.nElectronicLevels <= 1) { d.eElec[0] = h.nElectronicLevels == 1 ? h.electronicEnergyList[0] : 0.0; d.gElec[0] = h.nElectronicLevels == 1 ? h.electronicDegeneracyList[0] : 1; }
+        // dsmcParcel::constantProperties type_ (dsmcParcelI.H:158-199)
+        if (d.charge == -1) d.type = 0;
+        else d.type = (d.nVib == 0 ? 10 : (d.nVib == 1 ? 20 : 30)) + (d.charge == 1 ? 1 : 0);
+        nModes = std::max(nModes, d.nVib);
+        if (d.rotDof > 0 || d.nVib > 0 || d.nElec > 1) internal = true;
+    }
+    for (int p = 0; p < P.nSpecies; ++p)
+        for (int q = 0; q < P.nSpecies; ++q) {
+            const double dPQ = 0.5 * (P.sp[p].d + P.sp[q].d);
+            const double omegaPQ = 0.5 * (P.sp[p].omega + P.sp[q].omega);
+            const double mP = P.sp[p].mass, mQ = P.sp[q].mass;
+            P.vhsA[p][q] = PI * (dPQ * dPQ);
+            P.vhsG[p][q] = std::exp(std::lgamma(2.5 - omegaPQ));
+            P.omegaPQ[p][q] = omegaPQ;
+            P.mR[p][q] = mP * mQ / (mP + mQ);
+        }
+    P.nModes = nModes;
+    P.hasInternalEnergy = internal ? 1 : 0;
+    c->nModes = nModes; c->internal = internal; c->useCls = md.measureClassifications != 0;
+
+    // patches, neighbours
+    c->nbrProcs.clear(); c->ordinalToPatch.clear();
+    for (int p = 0; p < P.nPatches; ++p) {
+        const PatchInfo& pi = M.patches[p];
+        DevPatch& d = P.patch[p];
+        d.type = pi.type; d.model = DSMCB200_BND_NONE; d.start = pi.start; d.size = pi.size; d.nbrPatch = pi.neighbPatch;
+        d.nbrSlot = -1; d.nbrOrdinal = -1; d.T = 0;
+        d.sep[0] = pi.separation.x; d.sep[1] = pi.separation.y; d.sep[2] = pi.separation.z;
+        if (pi.type == DSMCB200_PATCH_PROCESSOR || pi.type == DSMCB200_PATCH_PROCESSORCYCLIC) {
+            int slot = -1;
+            for (size_t k = 0; k < c->nbrProcs.size(); ++k) if (c->nbrProcs[k] == pi.neighbProcNo) slot = int(k);
+            if (slot < 0) { slot = int(c->nbrProcs.size()); c->nbrProcs.push_back(pi.neighbProcNo); c->ordinalToPatch.emplace_back(); }
+            if (slot >= MAX_NEIGHBOURS) return fail(c, DSMCB200_ERR_CAPACITY, "more than 16 neighbour processors");
+            d.nbrSlot = slot;
+            d.nbrOrdinal = int(c->ordinalToPatch[slot].size());
+            c->ordinalToPatch[slot].push_back(p);
+        }
+    }
+    std::vector<int32_t> measIndex(M.nFaces - M.nInternalFaces, -1);
+    c->nMeasFaces = 0;
+    for (const dsmcb200_patch_model& pm : c->patchModels) {
+        if (pm.patch < 0 || pm.patch >= P.nPatches) return fail(c, DSMCB200_ERR_INVALID, "patch model refers to an unknown patch");
+        DevPatch& d = P.patch[pm.patch];
+        if (d.type != DSMCB200_PATCH_WALL && d.type != DSMCB200_PATCH_PATCH)
+            return fail(c, DSMCB200_ERR_INVALID, "Patch: " + M.patches[pm.patch].name + " must be of type wall or patch to carry a dsmcPatchBoundary model");
+        if (pm.model < DSMCB200_BND_DIFFUSE_WALL || pm.model > DSMCB200_BND_DELETION) return fail(c, DSMCB200_ERR_UNSUPPORTED, "unknown dsmcPatchBoundary type");
+        d.model = pm.model; d.T = pm.temperature;
+        d.vel[0] = pm.velocity[0]; d.vel[1] = pm.velocity[1]; d.vel[2] = pm.velocity[2];
+        if (pm.model != DSMCB200_BND_DELETION)
+            for (int i = 0; i < d.size; ++i) measIndex[d.start - M.nInternalFaces + i] = c->nMeasFaces++;
+    }
+    // dsmcBoundaries::checkPatchBoundaryModels (dsmcBoundaries.C:455-520): every wall/patch needs a model
+    for (int p = 0; p < P.nPatches; ++p) {
+        const DevPatch& d = P.patch[p];
+        if ((d.type == DSMCB200_PATCH_WALL || d.type == DSMCB200_PATCH_PATCH) && d.size > 0 && d.model == DSMCB200_BND_NONE)
+            return fail(c, DSMCB200_ERR_INVALID, "patch '" + M.patches[p].name + "' has no dsmcPatchBoundary model (one model per non-coupled patch is mandatory)");
+    }
+    for (const dsmcb200_inflow& in : c->inflows) {
+        if (in.patch < 0 || in.patch >= P.nPatches) return fail(c, DSMCB200_ERR_INVALID, "inflow refers to an unknown patch");
+        if (in.nTypes <= 0 || in.nTypes > MAX_SPECIES) return fail(c, DSMCB200_ERR_INVALID, "Cannot have zero typeIds being inserted.");
+        for (int i = 0; i < in.nTypes; ++i)
+            if (in.typeIds[i] < 0 || in.typeIds[i] >= P.nSpecies) return fail(c, DSMCB200_ERR_INVALID, "inflow typeId out of range");
+    }
+
+    CK(devAlloc(&c->dP, 1));
+    CK(cudaMemcpy(c->dP, &P, sizeof(P), cudaMemcpyHostToDevice));
+
+    // ---- bake and upload the tracking tables in chunks
+    const int64_t nT = M.nTets();
+    CK(devAlloc(&c->dTets, size_t(nT)));
+    {
+        const int64_t chunk = 1 << 20;
+        std::vector<TetRec> h(size_t(std::min<int64_t>(chunk, nT)));
+        for (int64_t t0 = 0; t0 < nT; t0 += chunk) {
+            const int64_t n = std::min<int64_t>(chunk, nT - t0);
+            M.bakeTets(t0, n, h.data());
+            CK(cudaMemcpy(c->dTets + t0, h.data(), size_t(n) * sizeof(TetRec), cudaMemcpyHostToDevice));
+        }
+    }
+    {
+        std::vector<BFaceRec> bf;
+        M.bakeBFaces(bf);
+        for (size_t i = 0; i < bf.size(); ++i) bf[i].measIndex = measIndex[i];
+        CK(upload(&c->dBFaces, bf));
+        std::vector<double> ar(bf.size() * 3);
+        for (size_t i = 0; i < bf.size(); ++i) {
+            const V3& s = M.faceAreas[M.nInternalFaces + i];
+            ar[3 * i] = s.x; ar[3 * i + 1] = s.y; ar[3 * i + 2] = s.z;
+        }
+        CK(upload(&c->dBFaceArea, ar));
+    }
+    {
+        auto flat = [](const std::vector<V3>& v) { std::vector<double> o(v.size() * 3); for (size_t i = 0; i < v.size(); ++i) { o[3 * i] = v[i].x; o[3 * i + 1] = v[i].y; o[3 * i + 2] = v[i].z; } return o; };
+        CK(upload(&c->dPoints, flat(M.points)));
+        CK(upload(&c->dCellCentres, flat(M.cellCentres)));
+        CK(upload(&c->dFaceCentres, flat(M.faceCentres)));
+        CK(upload(&c->dFaceAreas, flat(M.faceAreas)));
+        CK(upload(&c->dCellVolumes, M.cellVolumes));
+        CK(upload(&c->dFaceOffsets, M.faceOffsets));
+        CK(upload(&c->dFacePoints, M.facePoints));
+        CK(upload(&c->dOwner, M.owner));
+        CK(upload(&c->dTetBasePtIs, M.tetBasePtIs));
+        CK(upload(&c->dFaceTetPair0, M.faceTetPair0));
+        CK(upload(&c->dCellFaceOffsets, M.cellFaceOffsets));
+        CK(upload(&c->dCellFaces, M.cellFaces));
+    }
+    // ---- per-cell state and accumulators
+    const size_t nC = size_t(M.nCells);
+    CK(devAlloc(&c->dCellCount, nC + 1)); CK(devAlloc(&c->dCellOffset, nC + 1)); CK(devAlloc(&c->dCursor, nC + 1));
+    CK(devAlloc(&c->dScanScratch, size_t(scanScratchInts(int32_t(nC + 1))) + 8));
+    CK(devAlloc(&c->dSigma, nC)); CK(devAlloc(&c->dRem, nC)); CK(devAlloc(&c->dNColls, nC)); CK(devAlloc(&c->dCollSep, nC));
+    CK(cudaMemset(c->dSigma, 0, nC * 8)); CK(cudaMemset(c->dNColls, 0, nC * 8)); CK(cudaMemset(c->dCollSep, 0, nC * 8));
+    CK(cudaMemset(c->dCellOffset, 0, (nC + 1) * 4));
+    fillRemainder<<<GRID(nC), 0, c->stream>>>(c->dRem, int32_t(nC), P.seed);
+    c->nQ = 5 + (internal ? 2 + nModes : 0) + (P.measureFlux ? 12 : 0) + (P.measureClass ? 3 : 0);
+    CK(devAlloc(&c->dAcc, nC * P.nSpecies * c->nQ)); CK(devAlloc(&c->dCollCum, nC * 2));
+    CK(cudaMemset(c->dAcc, 0, nC * P.nSpecies * c->nQ * 8)); CK(cudaMemset(c->dCollCum, 0, nC * 16));
+    c->nWallQ = WQ_EVIBMOD0 + nModes;
+    CK(devAlloc(&c->dWallAcc, size_t(c->nMeasFaces) * P.nSpecies * c->nWallQ));
+    CK(cudaMemset(c->dWallAcc, 0, std::max<size_t>(1, size_t(c->nMeasFaces) * P.nSpecies * c->nWallQ) * 8));
+    CK(devAlloc(&c->dCounters, 1)); CK(cudaMemset(c->dCounters, 0, sizeof(DevCounters)));
+    CK(devAlloc(&c->dBad, 1));
+    CK(devAlloc(&c->dInfo, 8)); CK(devAlloc(&c->dInfoScratch, size_t(infoScratchDoubles())));
+    // inflow state
+    size_t maxInflow = 1;
+    for (const dsmcb200_inflow& in : c->inflows) {
+        const size_t n = size_t(in.nTypes) * M.patches[in.patch].size;
+        double* acc = nullptr; int32_t* cnt = nullptr;
+        CK(devAlloc(&acc, n)); CK(cudaMemset(acc, 0, std::max<size_t>(n, 1) * 8));
+        CK(devAlloc(&cnt, n + 1));
+        c->dInflowAcc.push_back(acc); c->dInflowCounts.push_back(cnt);
+        maxInflow = std::max(maxInflow, n + 1);
+    }
+    CK(devAlloc(&c->dInflowScan, maxInflow + 1));
+    // migration buffers
+    if (!c->nbrProcs.empty()) {
+        std::vector<int32_t> o2p(size_t(MAX_NEIGHBOURS) * MAX_PATCHES, -1);
+        for (size_t s = 0; s < c->ordinalToPatch.size(); ++s)
+            for (size_t k = 0; k < c->ordinalToPatch[s].size(); ++k) o2p[s * MAX_PATCHES + k] = c->ordinalToPatch[s][k];
+        CK(upload(&c->dOrdinalToPatch, o2p));
+        CK(devAlloc(&c->dCountsMatrix, size_t(c->nRanks) * c->nRanks + c->nRanks));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    c->ready = true;
+    return 0;
+}
+
+int ensureMigBuffers(dsmcb200_ctx* c) {
+    if (c->nbrProcs.empty()) return 0;
+    const int32_t want = int32_t(std::max<int64_t>(1 << 16, c->capacity / 8));
+    if (want <= c->migCapacity) return 0;
+    devFree(c->dMigSend); devFree(c->dMigRecv);
+    CK(devAlloc(&c->dMigSend, size_t(want) * MAX_NEIGHBOURS));
+    CK(devAlloc(&c->dMigRecv, size_t(want) * MAX_NEIGHBOURS));
+    c->migCapacity = want;
+    return 0;
+}
+
+// ---- stage 2: dsmcCloud::buildCellOccupancy ----
+int stageSort(dsmcb200_ctx* c, bool histogramDone) {
+    const int32_t nCells = c->mesh.nCells;
+    const int32_t nIn = int32_t(c->N);
+    ParcelArrays& src = c->buf[c->cur].a;
+    if (!histogramDone) {
+        KT t(c, "histogram");
+        CK(cudaMemsetAsync(c->dCellCount, 0, size_t(nCells + 1) * 4, c->stream));
+        CK(launchHistogram(src.cell, nIn, c->dCellCount, c->stream));
+    }
+    { KT t(c, "scan"); CK(launchExclusiveScan(c->dCellCount, c->dCellOffset, c->dCursor, nCells, c->dScanScratch, c->stream)); }
+    int32_t nOut = 0;
+    CK(cudaMemcpyAsync(&nOut, c->dCellOffset + nCells, 4, cudaMemcpyDeviceToHost, c->stream));
+    { KT t(c, "scatterIndex"); CK(launchScatterIndex(src.cell, nIn, c->dCursor, c->dPerm, c->stream)); }
+    { KT t(c, "segmentSort"); CK(launchSegmentSort(c->dCellOffset, nCells, c->dPerm, c->dCounters, c->stream)); }
+    CK(cudaStreamSynchronize(c->stream));  // nOut
+    ParcelArrays& dst = c->buf[1 - c->cur].a;
+    { KT t(c, "gather"); CK(launchGather(src, dst, c->dPerm, c->dCellOffset, nCells, nOut, c->nModes, c->internal, c->stream)); }
+    c->cur = 1 - c->cur;
+    c->N = nOut;
+    c->occupancyValid = true;
+    return 0;
+}
+
+int stageInflow(dsmcb200_ctx* c, int64_t tailStart) {
+    HostMesh& M = c->mesh;
+    for (size_t k = 0; k < c->inflows.size(); ++k) {
+        const dsmcb200_inflow& in = c->inflows[k];
+        const PatchInfo& pi = M.patches[in.patch];
+        if (pi.size == 0) continue;
+        InflowArgs a{};
+        a.nFaces = pi.size; a.patch = in.patch; a.patchStart = pi.start;
+        a.faceOffsets = c->dFaceOffsets; a.facePoints = c->dFacePoints; a.owner = c->dOwner; a.tetBasePtIs = c->dTetBasePtIs;
+        a.faceTetPair0 = c->dFaceTetPair0; a.points = c->dPoints; a.faceCentres = c->dFaceCentres; a.faceAreas = c->dFaceAreas;
+        a.P = c->dP; a.nTypes = in.nTypes;
+        for (int i = 0; i < in.nTypes; ++i) { a.typeIds[i] = in.typeIds[i]; a.numberDensities[i] = in.numberDensities[i]; }
+        for (int d = 0; d < 3; ++d) a.velocity[d] = in.velocity[d];
+        a.Ttra = in.translationalTemperature; a.Trot = in.rotationalTemperature; a.Tvib = in.vibrationalTemperature; a.Telec = in.electronicTemperature;
+        a.accumulator = c->dInflowAcc[k]; a.counts = c->dInflowCounts[k];
+        a.counters = c->dCounters; a.step = c->step;
+        const int32_t n = in.nTypes * pi.size;
+        { KT t(c, "inflowCount"); CK(launchInflow(a, 0, c->stream)); }
+        CK(launchExclusiveScan(a.counts, c->dInflowScan, nullptr, n, c->dScanScratch, c->stream));
+        int32_t total = 0;
+        CK(cudaMemcpyAsync(&total, c->dInflowScan + n, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (total <= 0) continue;
+        { int r = ensureCapacity(c, c->N + total); if (r) return r; }
+        { int r = ensureSfTail(c, c->N + total - tailStart); if (r) return r; }
+        a.p = c->buf[c->cur].a;
+        a.counts = c->dInflowScan; a.base = int32_t(c->N); a.capacity = int32_t(c->capacity);
+        a.sfTail = c->dSfTail; a.tailStart = int32_t(tailStart); a.origIdBase = c->nextOrigId;
+        { KT t(c, "inflowInsert"); CK(launchInflow(a, 1, c->stream)); }
+        c->N += total;
+        c->nextOrigId += total;
+        c->last.inserted += total;
+    }
+    return 0;
+}
+
+MoveArgs moveArgs(dsmcb200_ctx* c, int32_t first, int32_t count, int32_t tailStart) {
+    MoveArgs a{};
+    a.p = c->buf[c->cur].a; a.first = first; a.count = count; a.tailStart = tailStart; a.sfTail = c->dSfTail;
+    a.tets = c->dTets; a.bfaces = c->dBFaces; a.bfaceArea = c->dBFaceArea; a.P = c->dP; a.wallAcc = c->dWallAcc; a.nWallQ = c->nWallQ;
+    a.migBuf = c->dMigSend; a.migCapacity = c->migCapacity; a.cellCount = c->dCellCount; a.counters = c->dCounters; a.step = c->step;
+    return a;
+}
+
+int ncclFail(dsmcb200_ctx* c, int r, const char* what) {
+    c->err = std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error");
+    return DSMCB200_ERR_NCCL;
+}
+
+// ---- stage 1 incl. processor-patch migration rounds ----
+int stageMove(dsmcb200_ctx* c, int64_t tailStart) {
+    const int32_t nCells = c->mesh.nCells;
+    { int r = ensureMigBuffers(c); if (r) return r; }
+    CK(cudaMemsetAsync(c->dCellCount, 0, size_t(nCells + 1) * 4, c->stream));
+    CK(cudaMemsetAsync(c->dCounters->nMig, 0, sizeof(int32_t) * MAX_NEIGHBOURS, c->stream));
+    if (tailStart >= c->N) { int r = ensureSfTail(c, 1); if (r) return r; }
+    { KT t(c, "move"); CK(launchMove(moveArgs(c, 0, int32_t(c->N), int32_t(tailStart)), c->stream)); }
+    if (c->nRanks <= 1 || c->nbrProcs.empty()) return 0;
+    if (!c->comm) return fail(c, DSMCB200_ERR_STATE, "mesh has processor patches but dsmcb200_init_comm was not called");
+
+    const int R = c->nRanks;
+    std::vector<int32_t> sendTo(R), matrix(size_t(R) * R);
+    for (int round = 0; round < 1000; ++round) {
+        KT t(c, "migrate");
+        int32_t nMig[MAX_NEIGHBOURS];
+        CK(cudaMemcpyAsync(nMig, c->dCounters->nMig, sizeof(nMig), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        std::fill(sendTo.begin(), sendTo.end(), 0);
+        for (size_t s = 0; s < c->nbrProcs.size(); ++s) {
+            if (nMig[s] > c->migCapacity) return fail(c, DSMCB200_ERR_CAPACITY, "migration buffer overflow");
+            sendTo[c->nbrProcs[s]] = nMig[s];
+        }
+        // pBufs.finishedSends(allNTrans) + reduce(transfered, orOp) -> one all-gather of the send-count rows
+        int32_t* dRow = c->dCountsMatrix + size_t(R) * R;
+        CK(cudaMemcpyAsync(dRow, sendTo.data(), size_t(R) * 4, cudaMemcpyHostToDevice, c->stream));
+        int r = g_nccl.AllGather(dRow, c->dCountsMatrix, size_t(R), NCCL_INT32, c->comm, c->stream);
+        if (r) return ncclFail(c, r, "ncclAllGather");
+        CK(cudaMemcpyAsync(matrix.data(), c->dCountsMatrix, size_t(R) * R * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        bool any = false;
+        for (int32_t v : matrix) if (v) { any = true; break; }
+        if (!any) break;
+        int64_t nRecvTotal = 0;
+        std::vector<int32_t> recvFrom(c->nbrProcs.size());
+        for (size_t s = 0; s < c->nbrProcs.size(); ++s) {
+            recvFrom[s] = matrix[size_t(c->nbrProcs[s]) * R + c->rank];
+            if (recvFrom[s] > c->migCapacity) return fail(c, DSMCB200_ERR_CAPACITY, "migration receive buffer overflow");
+            nRecvTotal += recvFrom[s];
+        }
+        { int rr = ensureCapacity(c, c->N + nRecvTotal); if (rr) return rr; }
+        { int rr = ensureSfTail(c, c->N + nRecvTotal - tailStart + 1); if (rr) return rr; }
+        r = g_nccl.GroupStart();
+        if (r) return ncclFail(c, r, "ncclGroupStart");
+        for (size_t s = 0; s < c->nbrProcs.size(); ++s) {
+            if (nMig[s]) { r = g_nccl.Send(c->dMigSend + s * c->migCapacity, size_t(nMig[s]) * sizeof(MigRec), NCCL_CHAR, c->nbrProcs[s], c->comm, c->stream); if (r) return ncclFail(c, r, "ncclSend"); }
+            if (recvFrom[s]) { r = g_nccl.Recv(c->dMigRecv + s * c->migCapacity, size_t(recvFrom[s]) * sizeof(MigRec), NCCL_CHAR, c->nbrProcs[s], c->comm, c->stream); if (r) return ncclFail(c, r, "ncclRecv"); }
+        }
+        r = g_nccl.GroupEnd();
+        if (r) return ncclFail(c, r, "ncclGroupEnd");
+        const int64_t firstNew = c->N;
+        for (size_t s = 0; s < c->nbrProcs.size(); ++s) {
+            if (!recvFrom[s]) continue;
+            UnpackArgs u{};
+            u.p = c->buf[c->cur].a; u.recv = c->dMigRecv + s * c->migCapacity; u.nRecv = recvFrom[s]; u.base = int32_t(c->N);
+            u.sfTail = c->dSfTail; u.tailStart = int32_t(tailStart); u.ordinalToPatch = c->dOrdinalToPatch + s * MAX_PATCHES;
+            u.bfaces = c->dBFaces; u.P = c->dP;
+            CK(launchUnpack(u, c->stream));
+            c->N += recvFrom[s];
+            c->last.migratedIn += recvFrom[s];
+        }
+        CK(cudaMemsetAsync(c->dCounters->nMig, 0, sizeof(int32_t) * MAX_NEIGHBOURS, c->stream));
+        if (nRecvTotal) CK(launchMove(moveArgs(c, int32_t(firstNew), int32_t(nRecvTotal), int32_t(tailStart)), c->stream));
+    }
+    return 0;
+}
+
+int stageCollide(dsmcb200_ctx* c) {
+    if (!c->occupancyValid) return fail(c, DSMCB200_ERR_STATE, "cell occupancy is stale: run the sort stage first");
+    CollideArgs a{};
+    a.p = c->buf[c->cur].a; a.cellOffset = c->dCellOffset; a.nCells = c->mesh.nCells; a.cellCentres = c->dCellCentres;
+    a.cellVolumes = c->dCellVolumes; a.sigmaTcRMax = c->dSigma; a.remainder = c->dRem; a.nCollsStep = c->dNColls; a.collSepStep = c->dCollSep;
+    a.bigScratch = c->dPerm; a.P = c->dP; a.counters = c->dCounters; a.step = c->step;
+    KT t(c, "collide");
+    CK(launchCollide(a, c->stream));
+    return 0;
+}
+
+int stageSample(dsmcb200_ctx* c) {
+    if (!c->occupancyValid) return fail(c, DSMCB200_ERR_STATE, "cell occupancy is stale: run the sort stage first");
+    SampleArgs a{};
+    a.p = c->buf[c->cur].a; a.cellOffset = c->dCellOffset; a.nCells = c->mesh.nCells; a.acc = c->dAcc; a.nQ = c->nQ;
+    a.collCum = c->dCollCum; a.nCollsStep = c->dNColls; a.collSepStep = c->dCollSep; a.P = c->dP;
+    KT t(c, "sample");
+    CK(launchSample(a, c->stream));
+    c->nTimeSteps += 1.0;
+    // cellMeas_.clean() (dsmcCloud.C:925): the per-step arrays are rewritten by the next collide stage
+    return 0;
+}
+
+int fetchCounters(dsmcb200_ctx* c) {
+    CK(cudaMemcpyAsync(&c->hCounters, c->dCounters, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int dsmcb200_abi_version(void) { return DSMCB200_ABI_VERSION; }
+
+int dsmcb200_create(dsmcb200_ctx** out, int device, int rank, int nRanks) {
+    if (!out) return DSMCB200_ERR_INVALID;
+    *out = nullptr;
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) return DSMCB200_ERR_CUDA;  // no CPU fallback
+    if (device < 0 || device >= nDev) return DSMCB200_ERR_INVALID;
+    dsmcb200_ctx* c = new dsmcb200_ctx();
+    c->device = device; c->rank = rank; c->nRanks = nRanks < 1 ? 1 : nRanks;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return DSMCB200_ERR_CUDA;
+    }
+    *out = c;
+    return 0;
+}
+
+void dsmcb200_destroy(dsmcb200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (int k = 0; k < 2; ++k) { devFree(c->buf[k].dslab); devFree(c->buf[k].islab); devFree(c->buf[k].bslab); }
+    devFree(c->dP); devFree(c->dTets); devFree(c->dBFaces); devFree(c->dBFaceArea); devFree(c->dPoints); devFree(c->dCellCentres);
+    devFree(c->dCellVolumes); devFree(c->dFaceCentres); devFree(c->dFaceAreas); devFree(c->dFaceOffsets); devFree(c->dFacePoints);
+    devFree(c->dOwner); devFree(c->dTetBasePtIs); devFree(c->dFaceTetPair0); devFree(c->dCellFaceOffsets); devFree(c->dCellFaces);
+    devFree(c->dCellCount); devFree(c->dCellOffset); devFree(c->dCursor); devFree(c->dPerm); devFree(c->dScanScratch);
+    devFree(c->dSigma); devFree(c->dRem); devFree(c->dNColls); devFree(c->dCollSep); devFree(c->dAcc); devFree(c->dCollCum);
+    devFree(c->dWallAcc); devFree(c->dSfTail); devFree(c->dInfo); devFree(c->dInfoScratch); devFree(c->dCounters); devFree(c->dBad);
+    devFree(c->dMigSend); devFree(c->dMigRecv); devFree(c->dInflowScan); devFree(c->dOrdinalToPatch); devFree(c->dCountsMatrix);
+    for (auto& p : c->dInflowAcc) devFree(p);
+    for (auto& p : c->dInflowCounts) devFree(p);
+    for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* dsmcb200_last_error(const dsmcb200_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int dsmcb200_nccl_unique_id(void* id128) {
+    std::string err;
+    if (!id128 || !g_nccl.load(err)) return DSMCB200_ERR_NCCL;
+    NcclUniqueId id;
+    if (g_nccl.GetUniqueId(&id)) return DSMCB200_ERR_NCCL;
+    std::memcpy(id128, &id, sizeof(id));
+    return 0;
+}
+
+int dsmcb200_init_comm(dsmcb200_ctx* c, const void* id128) {
+    if (!c || !id128) return DSMCB200_ERR_INVALID;
+    if (!g_nccl.load(c->err)) return DSMCB200_ERR_NCCL;
+    cudaSetDevice(c->device);
+    NcclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    int r = g_nccl.CommInitRank(&c->comm, c->nRanks, id, c->rank);
+    if (r) return ncclFail(c, r, "ncclCommInitRank");
+    return 0;
+}
+
+int dsmcb200_set_mesh(dsmcb200_ctx* c, const dsmcb200_mesh* m) {
+    if (!c || !m) return DSMCB200_ERR_INVALID;
+    if (c->ready) return fail(c, DSMCB200_ERR_STATE, "mesh cannot change after the engine has been finalised");
+    std::string e = c->mesh.build(*m);
+    if (!e.empty()) return fail(c, DSMCB200_ERR_INVALID, e);
+    c->haveMesh = true;
+    return 0;
+}
+
+int dsmcb200_set_species(dsmcb200_ctx* c, int nSpecies, const dsmcb200_species* sp) {
+    if (!c || !sp) return DSMCB200_ERR_INVALID;
+    if (c->ready) return fail(c, DSMCB200_ERR_STATE, "species cannot change after the engine has been finalised");
+    if (nSpecies < 1 || nSpecies > MAX_SPECIES) return fail(c, DSMCB200_ERR_CAPACITY, "between 1 and 8 species are supported");
+    for (int s = 0; s < nSpecies; ++s) {
+        const dsmcb200_species& h = sp[s];
+        if (!(h.mass > 0) || !(h.diameter > 0)) return fail(c, DSMCB200_ERR_INVALID, "species mass and diameter must be positive");
+        if (h.nVibrationalModes < 0 || h.nVibrationalModes > MAX_MODES) return fail(c, DSMCB200_ERR_CAPACITY, "at most 3 vibrational modes per species");
+        if (h.nElectronicLevels > MAX_ELEC) return fail(c, DSMCB200_ERR_CAPACITY, "at most 16 electronic levels per species");
+        if (h.charge < -1 || h.charge > 1) return fail(c, DSMCB200_ERR_INVALID, "Charge value should be 0 for neutrals, 1 for ions, or -1 for electrons");
+    }
+    c->species.assign(sp, sp + nSpecies);
+    c->haveSpecies = true;
+    return 0;
+}
+
+int dsmcb200_set_models(dsmcb200_ctx* c, const dsmcb200_models* m) {
+    if (!c || !m) return DSMCB200_ERR_INVALID;
+    if (c->ready) return fail(c, DSMCB200_ERR_STATE, "models cannot change after the engine has been finalised");
+    if (m->collisionModel < DSMCB200_COLL_NONE || m->collisionModel > DSMCB200_COLL_LB_VHS)
+        return fail(c, DSMCB200_ERR_UNSUPPORTED, "unknown BinaryCollisionModel type; valid types are: NoBinaryCollision VariableHardSphere LarsenBorgnakkeVariableHardSphere");
+    if (!(m->nEquivalentParticles > 0) || !(m->deltaT > 0)) return fail(c, DSMCB200_ERR_INVALID, "nEquivalentParticles and deltaT must be positive");
+    c->models = *m;
+    c->patchModels.assign(m->patchModels, m->patchModels + (m->patchModels ? m->nPatchModels : 0));
+    c->inflows.assign(m->inflows, m->inflows + (m->inflows ? m->nInflows : 0));
+    c->models.patchModels = nullptr; c->models.inflows = nullptr;
+    c->haveModels = true;
+    return 0;
+}
+
+int dsmcb200_reserve(dsmcb200_ctx* c, int64_t maxParcels) {
+    if (!c) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    return ensureCapacity(c, maxParcels);
+}
+
+int dsmcb200_upload_parcels(dsmcb200_ctx* c, int64_t n, const dsmcb200_parcels_soa* h) {
+    if (!c || !h || n < 0) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    if (n && (!h->position || !h->U || !h->cell || !h->typeId)) return fail(c, DSMCB200_ERR_INVALID, "position, U, cell and typeId are required");
+    { int r = ensureCapacity(c, std::max<int64_t>(n, 1)); if (r) return r; }
+    c->N = 0;
+    const int32_t n32 = int32_t(n);
+    ParcelArrays& a = c->buf[c->cur].a;
+    ParcelBuffer& st = c->buf[1 - c->cur];  // staging: the double slab holds 7*cap doubles, the int slab 6*cap ints
+    cudaStream_t s = c->stream;
+    if (n == 0) { c->occupancyValid = false; return stageSort(c, false); }
+    // locate tets on the host when the caller has none (particle::initCellFacePtOrDeleteLostParticle)
+    std::vector<int32_t> locFace, locPt;
+    const int32_t *tetFace = h->tetFace, *tetPt = h->tetPt;
+    std::vector<int32_t> cellFix;
+    const int32_t* cellPtr = h->cell;
+    if (!tetFace || !tetPt) {
+        locFace.resize(n); locPt.resize(n); cellFix.assign(h->cell, h->cell + n);
+        const HostMesh& M = c->mesh;
+        int64_t lost = 0;
+#pragma omp parallel for schedule(static) reduction(+ : lost)
+        for (int64_t i = 0; i < n; ++i) {
+            V3 p = mk(h->position[3 * i], h->position[3 * i + 1], h->position[3 * i + 2]);
+            int32_t cell = cellFix[i], f = -1, tp = -1;
+            if (cell < 0 || cell >= M.nCells || !M.findTetFacePt(cell, p, f, tp)) {
+                // walk towards the cell centre in trackingCorrectionTol steps (particleI.H:927-976)
+                bool ok = false;
+                if (cell >= 0 && cell < M.nCells && M.pointInCellBB(p, cell, 0.1)) {
+                    const V3 cc = M.cellCentres[cell];
+                    V3 q = p;
+                    for (int it = 0; it < 200 && !ok; ++it) {
+                        q += 1.0e-5 * (cc - q);
+                        ok = M.findTetFacePt(cell, q, f, tp);
+                    }
+                }
+                if (!ok) { cellFix[i] = -1; f = 0; tp = 1; ++lost; }
+            }
+            locFace[i] = f; locPt[i] = tp;
+        }
+        tetFace = locFace.data(); tetPt = locPt.data(); cellPtr = cellFix.data();
+        c->last.deleted += lost;
+    }
+    CK(cudaMemcpyAsync(st.dslab, h->position, size_t(n) * 24, cudaMemcpyHostToDevice, s));
+    deinterleave3<<<GRID(n), 0, s>>>(st.dslab, a.px, a.py, a.pz, n32);
+    CK(cudaMemcpyAsync(st.dslab, h->U, size_t(n) * 24, cudaMemcpyHostToDevice, s));
+    deinterleave3<<<GRID(n), 0, s>>>(st.dslab, a.ux, a.uy, a.uz, n32);
+    CK(cudaMemcpyAsync(a.cell, cellPtr, size_t(n) * 4, cudaMemcpyHostToDevice, s));
+    int32_t* sf = st.islab;                 // staging rows
+    int32_t* sp2 = st.islab + c->capacity;
+    CK(cudaMemcpyAsync(sf, tetFace, size_t(n) * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(sp2, tetPt, size_t(n) * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(c->dBad, 0, 4, s));
+    toTetId<<<GRID(n), 0, s>>>(a.cell, sf, sp2, c->dFaceTetPair0, c->dOwner, a.tet, n32, c->mesh.nFaces, c->dBad);
+    CK(cudaMemcpyAsync(sf, h->typeId, size_t(n) * 4, cudaMemcpyHostToDevice, s));
+    i32ToU8<<<GRID(n), 0, s>>>(sf, a.typeId, n32);
+    if (h->origId) CK(cudaMemcpyAsync(a.origId, h->origId, size_t(n) * 4, cudaMemcpyHostToDevice, s));
+    else iotaKernel<<<GRID(n), 0, s>>>(a.origId, n32, 0);
+    if (c->internal) {
+        if (h->ERot) CK(cudaMemcpyAsync(a.erot, h->ERot, size_t(n) * 8, cudaMemcpyHostToDevice, s));
+        else CK(cudaMemsetAsync(a.erot, 0, size_t(n) * 8, s));
+        for (int m = 0; m < c->nModes; ++m) {
+            if (h->vibLevel && m < h->maxModes) {
+                if (h->maxModes == 1) CK(cudaMemcpyAsync(a.vib[m], h->vibLevel, size_t(n) * 4, cudaMemcpyHostToDevice, s));
+                else {
+                    // parcel-major [n][maxModes] staged through the double slab of the other buffer
+                    int32_t* stv = reinterpret_cast<int32_t*>(st.dslab);
+                    CK(cudaMemcpyAsync(stv, h->vibLevel, size_t(n) * 4 * h->maxModes, cudaMemcpyHostToDevice, s));
+                    stridedToMode<<<GRID(n), 0, s>>>(stv, a.vib[m], n32, h->maxModes, m);
+                }
+            } else CK(cudaMemsetAsync(a.vib[m], 0, size_t(n) * 4, s));
+        }
+        if (h->ELevel) { CK(cudaMemcpyAsync(sf, h->ELevel, size_t(n) * 4, cudaMemcpyHostToDevice, s)); i32ToU8<<<GRID(n), 0, s>>>(sf, a.elevel, n32); }
+        else CK(cudaMemsetAsync(a.elevel, 0, size_t(n), s));
+    }
+    if (a.cls) {
+        if (h->classification) { CK(cudaMemcpyAsync(sf, h->classification, size_t(n) * 4, cudaMemcpyHostToDevice, s)); i32ToU8<<<GRID(n), 0, s>>>(sf, a.cls, n32); }
+        else CK(cudaMemsetAsync(a.cls, 0, size_t(n), s));
+    }
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, c->dBad, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (bad) return fail(c, DSMCB200_ERR_INVALID, "upload_parcels: cell / tetFace / tetPt out of range");
+    c->N = n;
+    int32_t maxId = -1;
+    if (h->origId) { for (int64_t i = 0; i < n; ++i) maxId = std::max(maxId, h->origId[i]); } else maxId = n32 - 1;
+    c->nextOrigId = maxId + 1;
+    c->occupancyValid = false;
+    return stageSort(c, false);  // buildCellOccupancyFromScratch (dsmcCloud.C:677)
+}
+
+int dsmcb200_download_parcels(dsmcb200_ctx* c, int64_t capacity, int64_t* nOut, dsmcb200_parcels_soa* h) {
+    if (!c || !nOut) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    *nOut = c->N;
+    if (!h) return 0;
+    if (capacity < c->N) return fail(c, DSMCB200_ERR_CAPACITY, "download_parcels: caller buffer too small");
+    const int64_t n = c->N;
+    if (n == 0) return 0;
+    const int32_t n32 = int32_t(n);
+    ParcelArrays& a = c->buf[c->cur].a;
+    ParcelBuffer& st = c->buf[1 - c->cur];
+    cudaStream_t s = c->stream;
+    if (h->position) { interleave3<<<GRID(n), 0, s>>>(a.px, a.py, a.pz, st.dslab, n32); CK(cudaMemcpyAsync(h->position, st.dslab, size_t(n) * 24, cudaMemcpyDeviceToHost, s)); }
+    if (h->U) { interleave3<<<GRID(n), 0, s>>>(a.ux, a.uy, a.uz, st.dslab + 3 * c->capacity, n32); CK(cudaMemcpyAsync(h->U, st.dslab + 3 * c->capacity, size_t(n) * 24, cudaMemcpyDeviceToHost, s)); }
+    if (h->cell) CK(cudaMemcpyAsync(h->cell, a.cell, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+    int32_t* r0 = st.islab; int32_t* r1 = st.islab + c->capacity; int32_t* r2 = r1 + c->capacity; int32_t* r3 = r2 + c->capacity; int32_t* r4 = r3 + c->capacity;
+    if (h->tetFace || h->tetPt) {
+        fromTetId<<<GRID(n), 0, s>>>(a.tet, c->dFaceTetPair0, c->mesh.nFaces, r0, r1, n32);
+        if (h->tetFace) CK(cudaMemcpyAsync(h->tetFace, r0, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+        if (h->tetPt) CK(cudaMemcpyAsync(h->tetPt, r1, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+    }
+    if (h->typeId) { u8ToI32<<<GRID(n), 0, s>>>(a.typeId, r2, n32); CK(cudaMemcpyAsync(h->typeId, r2, size_t(n) * 4, cudaMemcpyDeviceToHost, s)); }
+    if (h->origId) CK(cudaMemcpyAsync(h->origId, a.origId, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+    if (h->ERot) { if (c->internal) CK(cudaMemcpyAsync(h->ERot, a.erot, size_t(n) * 8, cudaMemcpyDeviceToHost, s)); else std::memset(h->ERot, 0, size_t(n) * 8); }
+    if (h->ELevel) { if (c->internal) { u8ToI32<<<GRID(n), 0, s>>>(a.elevel, r3, n32); CK(cudaMemcpyAsync(h->ELevel, r3, size_t(n) * 4, cudaMemcpyDeviceToHost, s)); } else std::memset(h->ELevel, 0, size_t(n) * 4); }
+    if (h->classification) { if (a.cls) { u8ToI32<<<GRID(n), 0, s>>>(a.cls, r4, n32); CK(cudaMemcpyAsync(h->classification, r4, size_t(n) * 4, cudaMemcpyDeviceToHost, s)); } else std::memset(h->classification, 0, size_t(n) * 4); }
+    if (h->newParcel) for (int64_t i = 0; i < n; ++i) h->newParcel[i] = -1;
+    if (h->vibLevel && h->maxModes > 0) {
+        CK(cudaStreamSynchronize(s));
+        int32_t* stv = reinterpret_cast<int32_t*>(st.dslab);  // [n][maxModes]
+        CK(cudaMemsetAsync(stv, 0, size_t(n) * 4 * h->maxModes, s));
+        for (int m = 0; m < std::min(c->nModes, h->maxModes); ++m) modeToStrided<<<GRID(n), 0, s>>>(a.vib[m], stv, n32, h->maxModes, m);
+        CK(cudaMemcpyAsync(h->vibLevel, stv, size_t(n) * 4 * h->maxModes, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int dsmcb200_upload_cellstate(dsmcb200_ctx* c, const double* sigma, const double* rem) {
+    if (!c) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    const size_t nC = size_t(c->mesh.nCells);
+    if (sigma) CK(cudaMemcpy(c->dSigma, sigma, nC * 8, cudaMemcpyHostToDevice));
+    if (rem) CK(cudaMemcpy(c->dRem, rem, nC * 8, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int dsmcb200_download_cellstate(dsmcb200_ctx* c, double* sigma, double* rem) {
+    if (!c) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    const size_t nC = size_t(c->mesh.nCells);
+    CK(cudaStreamSynchronize(c->stream));
+    if (sigma) CK(cudaMemcpy(sigma, c->dSigma, nC * 8, cudaMemcpyDeviceToHost));
+    if (rem) CK(cudaMemcpy(rem, c->dRem, nC * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dsmcb200_mesh_fill(dsmcb200_ctx* c, int nTypes, const int32_t* typeIds, const double* numberDensities, double Ttra, double Trot,
+                       double Tvib, double Telec, const double velocity[3]) {
+    if (!c || !typeIds || !numberDensities || nTypes < 1 || nTypes > MAX_SPECIES) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    for (int i = 0; i < nTypes; ++i)
+        if (typeIds[i] < 0 || typeIds[i] >= c->hP.nSpecies) return fail(c, DSMCB200_ERR_INVALID, "mesh_fill: typeId not defined");
+    const HostMesh& M = c->mesh;
+    FillArgs a{};
+    a.nCells = M.nCells; a.cellFaceOffsets = c->dCellFaceOffsets; a.cellFaces = c->dCellFaces; a.faceOffsets = c->dFaceOffsets;
+    a.facePoints = c->dFacePoints; a.owner = c->dOwner; a.tetBasePtIs = c->dTetBasePtIs; a.faceTetPair0 = c->dFaceTetPair0;
+    a.points = c->dPoints; a.cellCentres = c->dCellCentres; a.P = c->dP; a.nTypes = nTypes;
+    for (int i = 0; i < nTypes; ++i) { a.typeIds[i] = typeIds[i]; a.numberDensities[i] = numberDensities[i]; }
+    a.Ttra = Ttra; a.Trot = Trot; a.Tvib = Tvib; a.Telec = Telec;
+    for (int d = 0; d < 3; ++d) a.velocity[d] = velocity ? velocity[d] : 0.0;
+    a.cellCount = c->dCellCount; a.origIdBase = 0;
+    a.p = c->buf[c->cur].a;
+    CK(launchFill(a, 0, c->stream));
+    CK(launchExclusiveScan(c->dCellCount, c->dCellOffset, nullptr, M.nCells, c->dScanScratch, c->stream));
+    int32_t total = 0;
+    CK(cudaMemcpyAsync(&total, c->dCellOffset + M.nCells, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->N = 0;
+    { int r = ensureCapacity(c, std::max<int64_t>(total, 1)); if (r) return r; }
+    a.p = c->buf[c->cur].a;
+    a.cellCount = c->dCellOffset;
+    CK(launchFill(a, 1, c->stream));
+    c->N = total;
+    c->nextOrigId = total;
+    c->occupancyValid = true;
+    // sigmaTcRMax = sigmaT(most abundant) * most probable speed (dsmcMeshFill.C:224-235)
+    int most = 0;
+    for (int i = 1; i < nTypes; ++i) if (numberDensities[i] > numberDensities[most]) most = i;
+    // the reference indexes constProps by dictionary position (SURVEY 8a quirk list); the typeId is used here
+    const DevSpecies& S = c->hP.sp[typeIds[most]];
+    const double sig = PI * S.d * S.d * std::sqrt(2.0 * c->hP.kB * Ttra / S.mass);
+    fillDouble<<<GRID(M.nCells), 0, c->stream>>>(c->dSigma, M.nCells, sig);
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int dsmcb200_set_step(dsmcb200_ctx* c, uint32_t step) { if (!c) return DSMCB200_ERR_INVALID; c->step = step; return 0; }
+
+int dsmcb200_stage(dsmcb200_ctx* c, int stage) {
+    if (!c) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    int r = 0;
+    switch (stage) {
+        case DSMCB200_STAGE_INFLOW: r = stageInflow(c, c->N); break;  // note: step fractions are only kept until the next stage call
+        case DSMCB200_STAGE_MOVE: r = stageMove(c, c->N); c->occupancyValid = false; break;
+        case DSMCB200_STAGE_SORT: r = stageSort(c, false); break;
+        case DSMCB200_STAGE_COLLIDE: r = stageCollide(c); break;
+        case DSMCB200_STAGE_SAMPLE: r = stageSample(c); break;
+        default: return fail(c, DSMCB200_ERR_INVALID, "unknown stage");
+    }
+    if (r) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    resolveTimers(c);
+    return fetchCounters(c);
+}
+
+int dsmcb200_evolve(dsmcb200_ctx* c, int nSteps) {
+    if (!c || nSteps < 0) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    for (int it = 0; it < nSteps; ++it) {
+        cudaEvent_t e0 = getEvent(c), e1 = getEvent(c), e2 = getEvent(c), e3 = getEvent(c), e4 = getEvent(c), e5 = getEvent(c);
+        c->last.inserted = 0; c->last.migratedIn = 0;
+        CK(cudaMemsetAsync(c->dCounters, 0, sizeof(DevCounters), c->stream));
+        const int64_t tailStart = c->N;
+        cudaEventRecord(e0, c->stream);
+        { int r = stageInflow(c, tailStart); if (r) return r; }    // boundaries_.controlBeforeMove()
+        cudaEventRecord(e1, c->stream);
+        { int r = stageMove(c, tailStart); if (r) return r; }      // Cloud<dsmcParcel>::move
+        cudaEventRecord(e2, c->stream);
+        { int r = stageSort(c, true); if (r) return r; }           // buildCellOccupancy()
+        cudaEventRecord(e3, c->stream);
+        { int r = stageCollide(c); if (r) return r; }              // collisions()
+        cudaEventRecord(e4, c->stream);
+        { int r = stageSample(c); if (r) return r; }               // fields_.calculateFields()
+        cudaEventRecord(e5, c->stream);
+        c->step++;
+        { int r = fetchCounters(c); if (r) return r; }
+        float ms[5] = {0, 0, 0, 0, 0};
+        cudaEventElapsedTime(&ms[0], e0, e1); cudaEventElapsedTime(&ms[1], e1, e2); cudaEventElapsedTime(&ms[2], e2, e3);
+        cudaEventElapsedTime(&ms[3], e3, e4); cudaEventElapsedTime(&ms[4], e4, e5);
+        c->last.stageMs[0] = ms[0]; c->last.stageMs[1] = ms[1]; c->last.stageMs[2] = 0; c->last.stageMs[3] = ms[2];
+        c->last.stageMs[4] = ms[3]; c->last.stageMs[5] = ms[4]; c->last.stageMs[6] = 0;
+        c->last.stageMs[7] = ms[0] + ms[1] + ms[2] + ms[3] + ms[4];
+        resolveTimers(c);
+        if (c->hCounters.overflow) return fail(c, DSMCB200_ERR_CAPACITY, "a fixed-capacity device buffer overflowed during the step");
+    }
+    return 0;
+}
+
+int dsmcb200_download_occupancy(dsmcb200_ctx* c, int32_t* cellOffsets) {
+    if (!c || !cellOffsets) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    if (!c->occupancyValid) return fail(c, DSMCB200_ERR_STATE, "cell occupancy is stale: run the sort stage first");
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(cellOffsets, c->dCellOffset, size_t(c->mesh.nCells + 1) * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dsmcb200_accum_info_get(dsmcb200_ctx* c, dsmcb200_accum_info* o) {
+    if (!c || !o) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    o->nCells = c->mesh.nCells; o->nSpecies = c->hP.nSpecies; o->nQuantities = c->nQ; o->nModes = c->internal ? c->nModes : -1;
+    o->nTimeSteps = c->nTimeSteps;
+    return 0;
+}
+
+int dsmcb200_download_accumulators(dsmcb200_ctx* c, double* acc, double* coll) {
+    if (!c) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    CK(cudaStreamSynchronize(c->stream));
+    const size_t nC = size_t(c->mesh.nCells);
+    if (acc) CK(cudaMemcpy(acc, c->dAcc, nC * c->hP.nSpecies * c->nQ * 8, cudaMemcpyDeviceToHost));
+    if (coll) CK(cudaMemcpy(coll, c->dCollCum, nC * 16, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dsmcb200_upload_accumulators(dsmcb200_ctx* c, const double* acc, const double* coll, double nTimeSteps) {
+    if (!c) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    const size_t nC = size_t(c->mesh.nCells);
+    if (acc) CK(cudaMemcpy(c->dAcc, acc, nC * c->hP.nSpecies * c->nQ * 8, cudaMemcpyHostToDevice));
+    if (coll) CK(cudaMemcpy(c->dCollCum, coll, nC * 16, cudaMemcpyHostToDevice));
+    c->nTimeSteps = nTimeSteps;
+    return 0;
+}
+
+int dsmcb200_reset_accumulators(dsmcb200_ctx* c) {
+    if (!c) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    const size_t nC = size_t(c->mesh.nCells);
+    CK(cudaMemsetAsync(c->dAcc, 0, nC * c->hP.nSpecies * c->nQ * 8, c->stream));
+    CK(cudaMemsetAsync(c->dCollCum, 0, nC * 16, c->stream));
+    if (c->nMeasFaces) CK(cudaMemsetAsync(c->dWallAcc, 0, size_t(c->nMeasFaces) * c->hP.nSpecies * c->nWallQ * 8, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->nTimeSteps = 0;
+    return 0;
+}
+
+int dsmcb200_wall_info(dsmcb200_ctx* c, int32_t* nFaces, int32_t* nWallQ) {
+    if (!c) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    if (nFaces) *nFaces = c->nMeasFaces;
+    if (nWallQ) *nWallQ = c->nWallQ;
+    return 0;
+}
+
+int dsmcb200_download_wall_accumulators(dsmcb200_ctx* c, double* wall) {
+    if (!c || !wall) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->nMeasFaces) CK(cudaMemcpy(wall, c->dWallAcc, size_t(c->nMeasFaces) * c->hP.nSpecies * c->nWallQ * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dsmcb200_get_counters(dsmcb200_ctx* c, dsmcb200_counters* o) {
+    if (!c || !o) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    // dsmcCloud::info(): one pass over the cloud for the energy sums
+    double e5[5] = {0, 0, 0, 0, 0};
+    if (c->N > 0) {
+        CK(launchInfo(c->buf[c->cur].a, int32_t(c->N), c->dP, c->dInfo, c->dInfoScratch, c->stream));
+        CK(cudaMemcpyAsync(e5, c->dInfo, sizeof(e5), cudaMemcpyDeviceToHost, c->stream));
+    }
+    { int r = fetchCounters(c); if (r) return r; }
+    dsmcb200_counters& L = c->last;
+    L.nParcels = c->N; L.collisions = int64_t(c->hCounters.collisions); L.collisionCandidates = int64_t(c->hCounters.candidates);
+    L.trackingRescues = int64_t(c->hCounters.rescues); L.deleted = int64_t(c->hCounters.deleted);
+    L.migratedOut = int64_t(c->hCounters.migratedOut); L.unsortedLargeCells = int64_t(c->hCounters.unsortedLargeCells);
+    L.mass = e5[0]; L.linearKineticEnergy = e5[1]; L.rotationalEnergy = e5[2]; L.vibrationalEnergy = e5[3]; L.electronicEnergy = e5[4];
+    *o = L;
+    return 0;
+}
+
+int dsmcb200_kernel_times(dsmcb200_ctx* c, int capacity, int* n, char* names, float* ms, int64_t* launches) {
+    if (!c || !n) return DSMCB200_ERR_INVALID;
+    int k = 0;
+    for (auto& e : c->ktimes) {
+        if (k >= capacity) break;
+        if (names) { std::memset(names + size_t(k) * DSMCB200_NAME_LEN, 0, DSMCB200_NAME_LEN); std::strncpy(names + size_t(k) * DSMCB200_NAME_LEN, e.first.c_str(), DSMCB200_NAME_LEN - 1); }
+        if (ms) ms[k] = float(e.second.first);
+        if (launches) launches[k] = e.second.second;
+        ++k;
+    }
+    *n = k;
+    if (capacity == 0) c->ktimes.clear();  // capacity 0 resets the table
+    return 0;
+}
+
+int dsmcb200_download_geometry(dsmcb200_ctx* c, double* cellCentres, double* cellVolumes, double* faceCentres, double* faceAreas,
+                               int32_t* tetBasePtIs) {
+    if (!c || !c->haveMesh) return DSMCB200_ERR_STATE;
+    const HostMesh& M = c->mesh;
+    for (int i = 0; i < M.nCells; ++i) {
+        if (cellCentres) { cellCentres[3 * i] = M.cellCentres[i].x; cellCentres[3 * i + 1] = M.cellCentres[i].y; cellCentres[3 * i + 2] = M.cellCentres[i].z; }
+        if (cellVolumes) cellVolumes[i] = M.cellVolumes[i];
+    }
+    for (int f = 0; f < M.nFaces; ++f) {
+        if (faceCentres) { faceCentres[3 * f] = M.faceCentres[f].x; faceCentres[3 * f + 1] = M.faceCentres[f].y; faceCentres[3 * f + 2] = M.faceCentres[f].z; }
+        if (faceAreas) { faceAreas[3 * f] = M.faceAreas[f].x; faceAreas[3 * f + 1] = M.faceAreas[f].y; faceAreas[3 * f + 2] = M.faceAreas[f].z; }
+        if (tetBasePtIs) tetBasePtIs[f] = M.tetBasePtIs[f];
+    }
+    return 0;
+}
+
+}  // extern "C"

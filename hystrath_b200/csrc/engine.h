@@ -1,0 +1,201 @@
+// engine.h -- device-side data layout of libdsmcb200 and the launchers of its kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "host_mesh.h"
+#include "philox.h"
+#include "vec3.h"
+
+namespace dsmc {
+
+constexpr int MAX_SPECIES = DSMCB200_MAX_SPECIES;
+constexpr int MAX_MODES = DSMCB200_MAX_VIB_MODES;
+constexpr int MAX_ELEC = DSMCB200_MAX_ELEC_LEVELS;
+constexpr int MAX_PATCHES = 64;
+constexpr int MAX_NEIGHBOURS = 16;
+constexpr int MAX_INFLOWS = 8;
+
+struct DevSpecies {
+    double mass, d, omega, alpha, rotDof, thetaD;
+    double thetaV[MAX_MODES], Zref[MAX_MODES], TrefZv[MAX_MODES];
+    double eElec[MAX_ELEC];
+    int32_t gElec[MAX_ELEC];
+    int32_t nVib, charge, nElec, type;
+};
+
+struct DevPatch {
+    int32_t type;        // dsmcb200_patch_type
+    int32_t model;       // dsmcb200_patch_model_kind (wall / patch types)
+    int32_t start, size;
+    int32_t nbrPatch;    // cyclic: neighbourPatch
+    int32_t pad_;
+    int32_t nbrSlot;     // processor patches: slot in the neighbour list
+    int32_t nbrOrdinal;  // processor patches: ordinal of this patch among those facing that neighbour
+    double T;            // wall temperature
+    double vel[3];       // wall velocity
+    double sep[3];       // cyclic separation (receiving side subtracts)
+};
+
+struct DevParams {
+    int32_t nSpecies, nPatches, collisionModel, invZvFormulation;
+    int32_t nModes;  // max vibrational modes over species (stride of vib arrays)
+    int32_t hasInternalEnergy, measureFlux, measureClass;
+    int32_t solutionD[3];
+    int32_t nInternalFaces;
+    double centre[3];  // bounds mid-point for constrainToMeshCentre
+    double nParticles, deltaT, kB, Tref;
+    double invZrot, Zvib, invZelec;
+    uint64_t seed;
+    DevSpecies sp[MAX_SPECIES];
+    DevPatch patch[MAX_PATCHES];
+    // per species pair: pi*dPQ^2, exp(lgamma(2.5-omegaPQ)), omegaPQ, reduced mass
+    double vhsA[MAX_SPECIES][MAX_SPECIES], vhsG[MAX_SPECIES][MAX_SPECIES];
+    double omegaPQ[MAX_SPECIES][MAX_SPECIES], mR[MAX_SPECIES][MAX_SPECIES];
+};
+
+// Structure-of-arrays cloud: one array per component so every stage streams coalesced.
+struct ParcelArrays {
+    double *px, *py, *pz, *ux, *uy, *uz, *erot;
+    int32_t *cell, *tet, *origId;
+    int32_t* vib[MAX_MODES];
+    uint8_t *typeId, *elevel, *cls;
+};
+
+// Packed record shipped across a processor patch (BASIC/particle/particleIO.C:121-132 +
+// DSMC/parcels/dsmcParcelIO.C:491-501 carry the same information).
+struct alignas(16) MigRec {
+    double pos[3], U[3], erot, stepFraction;
+    int32_t patchOrdinal, patchFace, tetLocal, origId;
+    int32_t vib[MAX_MODES];
+    uint8_t typeId, elevel, cls, pad_;
+};
+static_assert(sizeof(MigRec) == 96, "MigRec must be 96 bytes");
+
+struct DevCounters {
+    unsigned long long collisions, candidates, rescues, deleted, migratedOut, unsortedLargeCells, overflow;
+    int32_t nMig[MAX_NEIGHBOURS];
+    int32_t nInserted;
+    int32_t pad_;
+};
+
+// wall accumulator quantities per (measured face, species)
+enum WallQ { WQ_RHON = 0, WQ_RHON_INT, WQ_RHON_ELEC, WQ_RHOM, WQ_LINKE, WQ_MCC, WQ_MOMX, WQ_MOMY, WQ_MOMZ,
+             WQ_EROT, WQ_ZETAROT, WQ_EVIB, WQ_EELEC, WQ_Q, WQ_FDX, WQ_FDY, WQ_FDZ, WQ_EVIBMOD0, WQ_BASE = WQ_EVIBMOD0 };
+
+struct MoveArgs {
+    ParcelArrays p;
+    int32_t first, count;         // parcel range [first, first+count)
+    int32_t tailStart;            // parcels >= tailStart carry a step fraction in sfTail[i - tailStart]
+    const double* sfTail;
+    const TetRec* tets;
+    const BFaceRec* bfaces;
+    const double* bfaceArea;      // [nBFaces*3] face area vectors
+    const DevParams* P;
+    double* wallAcc;              // [nMeasFaces][nSpecies][nWallQ]
+    int32_t nWallQ;
+    MigRec* migBuf;               // [MAX_NEIGHBOURS][migCapacity]
+    int32_t migCapacity;
+    int32_t* cellCount;           // histogram for the sort (stage 2), fused here
+    DevCounters* counters;
+    uint32_t step;
+};
+
+struct CollideArgs {
+    ParcelArrays p;
+    const int32_t* cellOffset;    // [nCells+1]
+    int32_t nCells;
+    const double* cellCentres;    // [nCells*3]
+    const double* cellVolumes;
+    double* sigmaTcRMax;
+    double* remainder;
+    double* nCollsStep;           // cellMeasurements: nColls_ of this step
+    double* collSepStep;          // cellMeasurements: collisionSeparation_ of this step
+    int32_t* bigScratch;          // [nParcels] sub-cell index lists of cells too large for shared memory
+    const DevParams* P;
+    DevCounters* counters;
+    uint32_t step;
+};
+
+struct SampleArgs {
+    ParcelArrays p;
+    const int32_t* cellOffset;
+    int32_t nCells;
+    double* acc;                  // [nCells][nSpecies][nQ]
+    int32_t nQ;
+    double* collCum;              // [nCells][2]
+    const double* nCollsStep;
+    const double* collSepStep;
+    const DevParams* P;
+};
+
+struct KernelTimer;  // engine.cu
+
+// ---- launchers (each returns cudaGetLastError()) ----
+cudaError_t launchMove(const MoveArgs& a, cudaStream_t s);
+cudaError_t launchExclusiveScan(const int32_t* in, int32_t* out, int32_t* out2, int32_t n, int32_t* blockSums, cudaStream_t s);
+int32_t scanScratchInts(int32_t n);
+cudaError_t launchScatterIndex(const int32_t* cell, int32_t n, int32_t* cursor, int32_t* perm, cudaStream_t s);
+cudaError_t launchSegmentSort(const int32_t* cellOffset, int32_t nCells, int32_t* perm, DevCounters* c, cudaStream_t s);
+cudaError_t launchGather(const ParcelArrays& src, const ParcelArrays& dst, const int32_t* perm, const int32_t* cellOffset,
+                         int32_t nCells, int32_t nOut, int32_t nModes, bool hasInternal, cudaStream_t s);
+cudaError_t launchHistogram(const int32_t* cell, int32_t n, int32_t* cellCount, cudaStream_t s);
+cudaError_t launchCollide(const CollideArgs& a, cudaStream_t s);
+cudaError_t launchSample(const SampleArgs& a, cudaStream_t s);
+cudaError_t launchInfo(const ParcelArrays& p, int32_t n, const DevParams* P, double* out5, double* scratch, cudaStream_t s);
+int32_t infoScratchDoubles();
+
+struct FillArgs {
+    ParcelArrays p;
+    int32_t nCells;
+    const int32_t *cellFaceOffsets, *cellFaces, *faceOffsets, *facePoints, *owner, *tetBasePtIs, *faceTetPair0;
+    const double *points, *cellCentres;
+    const DevParams* P;
+    int32_t nTypes;
+    int32_t typeIds[MAX_SPECIES];
+    double numberDensities[MAX_SPECIES];
+    double Ttra, Trot, Tvib, Telec;
+    double velocity[3];
+    int32_t* cellCount;   // pass 0 output / pass 1 input: offsets
+    int32_t origIdBase;
+};
+cudaError_t launchFill(const FillArgs& a, int pass, cudaStream_t s);
+
+struct InflowArgs {
+    ParcelArrays p;
+    int32_t nFaces;               // faces of the inflow patch
+    int32_t patch, patchStart;
+    const int32_t *faceOffsets, *facePoints, *owner, *tetBasePtIs, *faceTetPair0;
+    const double *points, *faceCentres, *faceAreas;
+    const DevParams* P;
+    int32_t nTypes;
+    int32_t typeIds[MAX_SPECIES];
+    double numberDensities[MAX_SPECIES];
+    double velocity[3];
+    double Ttra, Trot, Tvib, Telec;
+    double* accumulator;          // [nTypes][nFaces] accumulatedParcelsToInsert_
+    int32_t* counts;              // [nTypes*nFaces] -> offsets after scan
+    int32_t base;                 // first free parcel slot
+    int32_t capacity;
+    double* sfTail;               // step fractions of the new parcels, indexed slot - tailStart
+    int32_t tailStart;
+    int32_t origIdBase;
+    DevCounters* counters;
+    uint32_t step;
+};
+cudaError_t launchInflow(const InflowArgs& a, int pass, cudaStream_t s);
+
+struct UnpackArgs {
+    ParcelArrays p;
+    const MigRec* recv;
+    int32_t nRecv, base;
+    double* sfTail;
+    int32_t tailStart;
+    const int32_t* ordinalToPatch;  // [MAX_PATCHES] for the sending neighbour
+    const BFaceRec* bfaces;
+    const DevParams* P;
+};
+cudaError_t launchUnpack(const UnpackArgs& a, cudaStream_t s);
+
+}  // namespace dsmc

@@ -1,0 +1,562 @@
+// kernels_collide.cu -- stages 3+4 (noTimeCounter candidate selection, VHS / Larsen-Borgnakke
+// binary collisions) and stage 5 (per-cell sampling), one warp per cell.
+//
+// Stage 3 follows noTimeCounter::collide (DSMC/collisionPartnerSelection/derived/noTimeCounter/
+// noTimeCounter.C:81-339); stage 4 VariableHardSphere (DSMC/collisions/derived/VariableHardSphere/
+// VariableHardSphere.C:80-228) and LarsenBorgnakkeVariableHardSphere (.../LarsenBorgnakkeVariableHardSphere.C:
+// 110-279) with the cloud helpers postCollision{Rotational,Vibrational,Electronic}* (DSMC/clouds/
+// dsmcCloud.C:1327-1656).  The reference processes the candidates of a cell serially; a later candidate
+// sees the velocities written by an earlier accepted one.  Every candidate owns a Philox stream keyed by
+// (cell, candidate index, step), so its partners (P,Q) are known independently of the others; the 32
+// candidates of a batch are then resolved in dependency order (a candidate waits for every earlier
+// candidate that shares a parcel with it), which yields exactly the serial result.
+//
+// Stage 5 follows the per-parcel accumulation of dsmcVolFields::calculateField (DSMC/macroscopicProperties/
+// derived/combined/dsmcVolFields/dsmcVolFields.C:1115-1237): parcels are cell-sorted, so each warp reduces
+// the parcels of its cell and adds one row of per-species moment sums -- no atomics.
+#include "device_models.cuh"
+#include "engine.h"
+
+namespace dsmc {
+
+namespace {
+
+constexpr int COL_WARPS = 4;
+constexpr int COL_CAP = 128;  // parcels of a cell staged in shared memory per warp
+
+struct CellView {  // the parcels of one cell, in shared memory (small cells) or in place (large cells)
+    double *ux, *uy, *uz, *erot;
+    int32_t* vib[MAX_MODES];
+    uint8_t *typ, *elev;
+    uint8_t* dirty;  // null when operating in place
+};
+
+struct WarpSmem {
+    double ux[COL_CAP], uy[COL_CAP], uz[COL_CAP], erot[COL_CAP];
+    int32_t vib[MAX_MODES][COL_CAP];
+    uint16_t subList[COL_CAP];
+    uint8_t typ[COL_CAP], elev[COL_CAP], oct[COL_CAP], dirty[COL_CAP];
+    int32_t subStart[9];
+};
+
+__device__ __forceinline__ int octantOf(double x, double y, double z, const double* cc) {
+    // pos(relPos.x()) + 2*pos(relPos.y()) + 4*pos(relPos.z()), pos(s) = (s >= 0) ? 1 : 0
+    const double rx = x - cc[0], ry = y - cc[1], rz = z - cc[2];
+    return (rx >= 0 ? 1 : 0) + 2 * (ry >= 0 ? 1 : 0) + 4 * (rz >= 0 ? 1 : 0);
+}
+
+// VariableHardSphere::sigmaTcR
+__device__ __forceinline__ double sigmaTcR(const DevParams& P, int tP, int tQ, double cR) {
+    if (cR < VSMALL) return 0.0;
+    const double sigmaTPQ = P.vhsA[tP][tQ] * pow(2.0 * P.kB * P.Tref / (P.mR[tP][tQ] * (cR * cR)), P.omegaPQ[tP][tQ] - 0.5) / P.vhsG[tP][tQ];
+    return sigmaTPQ * cR;
+}
+
+// VariableHardSphere::postCollisionVelocities
+__device__ __forceinline__ void postCollisionVelocities(const DevParams& P, Rng& rng, int tP, int tQ, V3& UP, V3& UQ, double cR) {
+    if (cR == -1) cR = mag(UP - UQ);
+    const double mP = P.sp[tP].mass, mQ = P.sp[tQ].mass;
+    const V3 Ucm = (mP * UP + mQ * UQ) / (mP + mQ);
+    const double cosTheta = 2.0 * rng.sample01() - 1.0;
+    const double sinTheta = sqrt(1.0 - cosTheta * cosTheta);
+    const double phi = TWO_PI * rng.sample01();
+    const V3 postCollisionRelativeU = cR * mk(cosTheta, sinTheta * cos(phi), sinTheta * sin(phi));
+    UP = Ucm + postCollisionRelativeU * mQ / (mP + mQ);
+    UQ = Ucm - postCollisionRelativeU * mP / (mP + mQ);
+}
+
+// dsmcCloud::postCollisionRotationalEnergy
+__device__ double postCollisionRotationalEnergy(Rng& rng, double rotationalDof, double ChiB) {
+    double energyRatio = 0.0;
+    if (rotationalDof == 2.0) {
+        energyRatio = 1.0 - pow(rng.sample01(), 1.0 / ChiB);
+    } else {
+        const double ChiA = 0.5 * rotationalDof;
+        const double ChiAMinusOne = ChiA - 1., ChiBMinusOne = ChiB - 1.;
+        if (ChiAMinusOne < SMALL && ChiBMinusOne < SMALL) return rng.sample01();
+        double Pp = 0.0;
+        do {
+            energyRatio = rng.sample01();
+            if (ChiAMinusOne < SMALL) Pp = pow(1.0 - energyRatio, ChiBMinusOne);
+            else if (ChiBMinusOne < SMALL) Pp = pow(1.0 - energyRatio, ChiAMinusOne);
+            else
+                Pp = pow((ChiAMinusOne + ChiBMinusOne) * energyRatio / ChiAMinusOne, ChiAMinusOne) *
+                     pow((ChiAMinusOne + ChiBMinusOne) * (1 - energyRatio) / ChiBMinusOne, ChiBMinusOne);
+        } while (Pp < rng.sample01());
+    }
+    return energyRatio;
+}
+
+// dsmcCloud::postCollisionVibrationalEnergyLevel (postReaction = false)
+__device__ int32_t postCollisionVibrationalEnergyLevel(const DevParams& P, Rng& rng, int32_t vibLevel, int32_t iMax, double thetaV,
+                                                       double thetaD, double refTempZv, double omega, double Zref, double Ec) {
+    int32_t iDash = vibLevel;
+    double inverseVibrationalCollisionNumber = 1.0;
+    const double fixedZv = P.Zvib;
+    if (fixedZv == 0) {
+        // invZvFormulation 0 and 2 use the quantised collision temperature; formulation 1 (macroscopic Tov)
+        // falls back to it exactly as the reference does when Tov is not yet available (dsmcCloud.C:1445-1454)
+        const double T = iMax * thetaV / (3.5 - omega);
+        const double pow1 = pow(thetaD / T, 1. / 3.) - 1.0;
+        const double pow2 = pow(thetaD / refTempZv, 1. / 3.) - 1.0;
+        const double ZvP1 = pow(thetaD / T, omega);
+        const double ZvP2 = pow(Zref * pow(thetaD / refTempZv, -omega), pow1 / pow2);
+        const double Zv = ZvP1 * ZvP2;
+        if (P.invZvFormulation == 2) inverseVibrationalCollisionNumber = 1.0 / (5.0 * Zv);
+        else inverseVibrationalCollisionNumber = 1.0 / Zv;
+    } else {
+        inverseVibrationalCollisionNumber = 1.0 / fixedZv;
+    }
+    if (inverseVibrationalCollisionNumber > rng.sample01()) {
+        double func, EVib;
+        do {
+            iDash = rng.randomLabel(0, iMax);
+            EVib = iDash * P.kB * thetaV;
+            func = pow(1.0 - EVib / Ec, 1.5 - omega);
+        } while (func < rng.sample01());
+    }
+    return iDash;
+}
+
+// dsmcCloud::postCollisionElectronicEnergyLevel
+__device__ int32_t postCollisionElectronicEnergyLevel(Rng& rng, double Ec, double omega, const DevSpecies& S) {
+    int jSelectA = 0, jSelectB = 0;
+    double gMax = 0.0;
+    for (int i = 0; i < S.nElec; ++i) {
+        if (S.eElec[i] > Ec) break;
+        jSelectA = i;
+        const double g = S.gElec[i] * pow(Ec - S.eElec[i], 1.5 - omega);
+        if (gMax < g) { gMax = g; jSelectB = i; }
+    }
+    const int jSelect = jSelectA < jSelectB ? jSelectA : jSelectB;
+    const double denomMax = S.gElec[jSelect] * pow(Ec - S.eElec[jSelect], 1.5 - omega);
+    int jDash = 0;
+    double prob;
+    do {
+        jDash = rng.randomLabel(0, jSelectA);
+        prob = S.gElec[jDash] * pow(Ec - S.eElec[jDash], 1.5 - omega) / denomMax;
+    } while (prob < rng.sample01());
+    return jDash;
+}
+
+// LarsenBorgnakkeVariableHardSphere::redistribute (postReaction = false)
+__device__ void redistribute(const DevParams& P, Rng& rng, const CellView& v, int j, double& translationalEnergy, double omegaPQ) {
+    const DevSpecies& S = P.sp[v.typ[j]];
+    if (S.type == 0) return;  // electron
+    // electronic mode
+    if (P.invZelec > rng.sample01()) {
+        const double EcP = translationalEnergy + S.eElec[v.elev[j]];
+        const int lvl = postCollisionElectronicEnergyLevel(rng, EcP, omegaPQ, S);
+        v.elev[j] = uint8_t(lvl);
+        translationalEnergy = EcP - S.eElec[lvl];
+    }
+    // vibrational modes
+    if (S.nVib > 0) {
+        double preEVib[MAX_MODES];
+        for (int m = 0; m < S.nVib; ++m) preEVib[m] = v.vib[m][j] * P.kB * S.thetaV[m];
+        for (int m = 0; m < S.nVib; ++m) {
+            const double EcP = translationalEnergy + preEVib[m];
+            const int32_t iMaxP = int32_t(EcP / (P.kB * S.thetaV[m]));
+            if (iMaxP > 0) {
+                const int32_t lvl = postCollisionVibrationalEnergyLevel(P, rng, v.vib[m][j], iMaxP, S.thetaV[m], S.thetaD, S.TrefZv[m],
+                                                                        omegaPQ, S.Zref[m], EcP);
+                v.vib[m][j] = lvl;
+                translationalEnergy = EcP - lvl * P.kB * S.thetaV[m];
+            }
+        }
+    }
+    // rotational mode
+    if (S.rotDof > 0) {
+        const double preCollisionERotP = v.erot[j];
+        if (P.invZrot > rng.sample01()) {
+            const double EcP = translationalEnergy + preCollisionERotP;
+            const double ChiB = 2.5 - omegaPQ;
+            const double energyRatio = postCollisionRotationalEnergy(rng, S.rotDof, ChiB);
+            v.erot[j] = energyRatio * EcP;
+            translationalEnergy = EcP - v.erot[j];
+        }
+    }
+}
+
+__device__ __forceinline__ double warpSumOrdered(double v) {
+    // fixed-shape tree: the same order on every run
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(COL_WARPS * 32) collideKernel(CollideArgs a) {
+    int32_t* const bigScratch = a.bigScratch;
+    __shared__ WarpSmem smAll[COL_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    WarpSmem& sm = smAll[w];
+    const DevParams& P = *a.P;
+    const bool LB = P.collisionModel == DSMCB200_COLL_LB_VHS;
+    const bool internal = P.hasInternalEnergy != 0;
+    const int32_t nWarps = gridDim.x * COL_WARPS;
+    unsigned long long totColl = 0, totCand = 0;
+
+    for (int32_t c = blockIdx.x * COL_WARPS + w; c < a.nCells; c += nWarps) {
+        const int32_t b = a.cellOffset[c];
+        const int32_t nC = a.cellOffset[c + 1] - b;
+        if (nC <= 1 || P.collisionModel == DSMCB200_COLL_NONE) {
+            if (lane == 0) { a.nCollsStep[c] = 0.0; a.collSepStep[c] = 0.0; }
+            continue;
+        }
+        const bool small = nC <= COL_CAP;
+        const double cc[3] = {a.cellCentres[3 * c], a.cellCentres[3 * c + 1], a.cellCentres[3 * c + 2]};
+        CellView v;
+        if (small) {
+            v.ux = sm.ux; v.uy = sm.uy; v.uz = sm.uz; v.erot = sm.erot;
+            for (int m = 0; m < MAX_MODES; ++m) v.vib[m] = sm.vib[m];
+            v.typ = sm.typ; v.elev = sm.elev; v.dirty = sm.dirty;
+            for (int j = lane; j < nC; j += 32) {
+                const int32_t g = b + j;
+                sm.ux[j] = a.p.ux[g]; sm.uy[j] = a.p.uy[g]; sm.uz[j] = a.p.uz[g];
+                sm.typ[j] = a.p.typeId[g];
+                sm.dirty[j] = 0;
+                sm.oct[j] = uint8_t(octantOf(a.p.px[g], a.p.py[g], a.p.pz[g], cc));
+                if (internal) {
+                    sm.erot[j] = a.p.erot[g];
+                    for (int m = 0; m < P.nModes; ++m) sm.vib[m][j] = a.p.vib[m][g];
+                    sm.elev[j] = a.p.elevel[g];
+                } else {
+                    sm.erot[j] = 0.0; sm.elev[j] = 0;
+                }
+            }
+        } else {
+            v.ux = a.p.ux + b; v.uy = a.p.uy + b; v.uz = a.p.uz + b; v.erot = a.p.erot ? a.p.erot + b : nullptr;
+            for (int m = 0; m < MAX_MODES; ++m) v.vib[m] = a.p.vib[m] ? a.p.vib[m] + b : nullptr;
+            v.typ = a.p.typeId + b; v.elev = a.p.elevel ? a.p.elevel + b : nullptr; v.dirty = nullptr;
+        }
+        __syncwarp();
+
+        // ---- the 8 Cartesian sub-cells (noTimeCounter.C:112-138): stable counting sort of parcel indices by octant
+        int32_t cnt[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) cnt[s] = 0;
+        for (int j0 = 0; j0 < nC; j0 += 32) {
+            const int j = j0 + lane;
+            int o = -1;
+            if (j < nC) o = small ? sm.oct[j] : octantOf(a.p.px[b + j], a.p.py[b + j], a.p.pz[b + j], cc);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) cnt[s] += __popc(__ballot_sync(0xffffffffu, o == s));
+        }
+        int32_t start[9];
+        start[0] = 0;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) start[s + 1] = start[s] + cnt[s];
+        if (lane < 9) {
+            int32_t val = 0;
+#pragma unroll
+            for (int s = 0; s < 9; ++s) if (lane == s) val = start[s];
+            sm.subStart[lane] = val;
+        }
+        {
+            int32_t run[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) run[s] = start[s];
+            for (int j0 = 0; j0 < nC; j0 += 32) {
+                const int j = j0 + lane;
+                int o = -1;
+                if (j < nC) o = small ? sm.oct[j] : octantOf(a.p.px[b + j], a.p.py[b + j], a.p.pz[b + j], cc);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const unsigned m = __ballot_sync(0xffffffffu, o == s);
+                    if (o == s) {
+                        const int32_t posn = run[s] + __popc(m & ((1u << lane) - 1u));
+                        if (small) sm.subList[posn] = uint16_t(j);
+                        else bigScratch[b + posn] = j;
+                    }
+                    run[s] += __popc(m);
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- number of candidate pairs (noTimeCounter.C:142-155)
+        const double sigmaTcRMaxLatched = a.sigmaTcRMax[c];
+        const double selectedPairs =
+            a.remainder[c] + 0.5 * nC * (nC - 1) * P.nParticles * sigmaTcRMaxLatched * P.deltaT / a.cellVolumes[c];
+        const int32_t nCandidates = int32_t(selectedPairs);
+        if (lane == 0) a.remainder[c] = selectedPairs - nCandidates;
+        totCand += (lane == 0) ? (unsigned long long)(nCandidates > 0 ? nCandidates : 0) : 0ULL;
+
+        double newMax = sigmaTcRMaxLatched;
+        double nColl = 0.0, sepSum = 0.0;
+
+        for (int32_t c0 = 0; c0 < nCandidates; c0 += 32) {
+            const int32_t cand = c0 + lane;
+            const bool active = cand < nCandidates;
+            int32_t cp = -1, cq = -2;
+            Rng rng;
+            if (active) {
+                rng.init(P.seed, uint32_t(c), uint32_t(cand), a.step, STREAM_COLLIDE);
+                cp = rng.randomLabel(0, nC - 1);
+                const int sub = small ? sm.oct[cp] : octantOf(a.p.px[b + cp], a.p.py[b + cp], a.p.pz[b + cp], cc);
+                const int32_t s0 = sm.subStart[sub];
+                const int32_t nSC = sm.subStart[sub + 1] - s0;
+                if (nSC > 1) {
+                    do {
+                        const int32_t k = s0 + rng.randomLabel(0, nSC - 1);
+                        cq = small ? int32_t(sm.subList[k]) : bigScratch[b + k];
+                    } while (cp == cq);
+                } else {
+                    do { cq = rng.randomLabel(0, nC - 1); } while (cp == cq);
+                }
+            }
+            const unsigned activeMask = __ballot_sync(0xffffffffu, active);
+            // earlier candidates of the batch that touch one of my parcels
+            unsigned confl = 0;
+#pragma unroll 4
+            for (int j = 0; j < 32; ++j) {
+                const int32_t pj = __shfl_sync(0xffffffffu, cp, j);
+                const int32_t qj = __shfl_sync(0xffffffffu, cq, j);
+                if (j < lane && (pj == cp || pj == cq || qj == cp || qj == cq)) confl |= 1u << j;
+            }
+            confl &= activeMask;
+            unsigned done = ~activeMask;
+            while (done != 0xffffffffu) {
+                const bool ready = active && !((done >> lane) & 1u) && ((confl & ~done) == 0u);
+                if (ready) {
+                    const int tP = v.typ[cp], tQ = v.typ[cq];
+                    if (!(P.sp[tP].charge == -1 && P.sp[tQ].charge == -1)) {
+                        V3 UP = mk(v.ux[cp], v.uy[cp], v.uz[cp]);
+                        V3 UQ = mk(v.ux[cq], v.uy[cq], v.uz[cq]);
+                        const double cR0 = mag(UP - UQ);
+                        const double sTcR = sigmaTcR(P, tP, tQ, cR0);
+                        if (sTcR > newMax) newMax = sTcR;
+                        if ((sTcR / sigmaTcRMaxLatched) > rng.sample01()) {
+                            double cR = -1;
+                            if (LB) {
+                                // LarsenBorgnakkeVariableHardSphere::collide
+                                const double mR = P.mR[tP][tQ];
+                                const double cRsqr = magSqr(UP - UQ);
+                                double translationalEnergy = 0.5 * mR * cRsqr;
+                                const double omegaPQ = P.omegaPQ[tP][tQ];
+                                redistribute(P, rng, v, cp, translationalEnergy, omegaPQ);
+                                redistribute(P, rng, v, cq, translationalEnergy, omegaPQ);
+                                cR = sqrt(2.0 * translationalEnergy / mR);
+                            }
+                            postCollisionVelocities(P, rng, tP, tQ, UP, UQ, cR);
+                            v.ux[cp] = UP.x; v.uy[cp] = UP.y; v.uz[cp] = UP.z;
+                            v.ux[cq] = UQ.x; v.uy[cq] = UQ.y; v.uz[cq] = UQ.z;
+                            if (v.dirty) { v.dirty[cp] = 1; v.dirty[cq] = 1; }
+                            // cellMeasurements (VariableHardSphere.C:154-162)
+                            const int32_t gp = b + cp, gq = b + cq;
+                            const double dx = a.p.px[gp] - a.p.px[gq], dy = a.p.py[gp] - a.p.py[gq], dz = a.p.pz[gp] - a.p.pz[gq];
+                            sepSum += sqrt(dx * dx + dy * dy + dz * dz);
+                            nColl += 1.0;
+                            // classification promotion (VariableHardSphere.C:164-187)
+                            if (a.p.cls) {
+                                const int clP = a.p.cls[gp], clQ = a.p.cls[gq];
+                                if (clP == 0 && (clQ == 1 || clQ == 2)) a.p.cls[gp] = 2;
+                                if (clQ == 0 && (clP == 1 || clP == 2)) a.p.cls[gq] = 2;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                done |= __ballot_sync(0xffffffffu, ready);
+            }
+        }
+
+        // ---- per-cell results
+        double mx = newMax;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const double nCollTot = warpSumOrdered(nColl);
+        const double sepTot = warpSumOrdered(sepSum);
+        if (lane == 0) {
+            a.sigmaTcRMax[c] = mx;
+            a.nCollsStep[c] = nCollTot;
+            a.collSepStep[c] = sepTot;
+            totColl += (unsigned long long)nCollTot;
+        }
+        if (small) {
+            __syncwarp();
+            for (int j = lane; j < nC; j += 32) {
+                if (sm.dirty[j]) {
+                    const int32_t g = b + j;
+                    a.p.ux[g] = sm.ux[j]; a.p.uy[g] = sm.uy[j]; a.p.uz[g] = sm.uz[j];
+                    if (LB) {
+                        a.p.erot[g] = sm.erot[j];
+                        for (int m = 0; m < P.nModes; ++m) a.p.vib[m][g] = sm.vib[m][j];
+                        a.p.elevel[g] = sm.elev[j];
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && (totColl | totCand)) {
+        atomicAdd(&a.counters->collisions, totColl);
+        atomicAdd(&a.counters->candidates, totCand);
+    }
+}
+
+cudaError_t launchCollide(const CollideArgs& a, cudaStream_t s) {
+    int grid = (a.nCells + COL_WARPS - 1) / COL_WARPS;
+    const int maxGrid = 148 * 12;
+    if (grid > maxGrid) grid = maxGrid;
+    if (grid < 1) grid = 1;
+    collideKernel<<<grid, COL_WARPS * 32, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 5
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int SMP_WARPS = 4;
+constexpr int SMP_MAXQ = 32;
+}
+
+__global__ void __launch_bounds__(SMP_WARPS * 32) sampleKernel(SampleArgs a) {
+    __shared__ double stage[SMP_WARPS][32][SMP_MAXQ + 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const DevParams& P = *a.P;
+    const int nQ = a.nQ, S = P.nSpecies;
+    const bool internal = P.hasInternalEnergy != 0;
+    const int qFlux = 5 + (internal ? 2 + P.nModes : 0);
+    const int qClass = qFlux + (P.measureFlux ? 12 : 0);
+    const int32_t nWarps = gridDim.x * SMP_WARPS;
+
+    for (int32_t c = blockIdx.x * SMP_WARPS + w; c < a.nCells; c += nWarps) {
+        const int32_t b = a.cellOffset[c];
+        const int32_t nC = a.cellOffset[c + 1] - b;
+        if (lane < 2) {
+            // fold this step's cellMeasurements into the cumulative pair (dsmcVolFields.C:1244-1248)
+            const double add = lane == 0 ? a.nCollsStep[c] : a.collSepStep[c];
+            if (add != 0.0) a.collCum[2 * size_t(c) + lane] += add;
+        }
+        if (nC == 0) continue;
+        double sum[MAX_SPECIES];
+#pragma unroll
+        for (int s = 0; s < MAX_SPECIES; ++s) sum[s] = 0.0;
+
+        for (int32_t j0 = 0; j0 < nC; j0 += 32) {
+            const int32_t g = b + j0 + lane;
+            const bool valid = j0 + lane < nC;
+            int mySp = -1;
+            if (valid) {
+                mySp = a.p.typeId[g];
+                const double ux = a.p.ux[g], uy = a.p.uy[g], uz = a.p.uz[g];
+                double* row = stage[w][lane];
+                const double cc = ux * ux + uy * uy + uz * uz;
+                row[0] = 1.0; row[1] = ux; row[2] = uy; row[3] = uz; row[4] = cc;
+                double Eint = 0.0;
+                if (internal) {
+                    const DevSpecies& Sp = P.sp[mySp];
+                    const double er = a.p.erot[g];
+                    row[5] = er;
+                    row[6] = Sp.eElec[a.p.elevel[g]];
+                    Eint = er;
+                    for (int m = 0; m < P.nModes; ++m) {
+                        const double ev = (m < Sp.nVib) ? a.p.vib[m][g] * P.kB * Sp.thetaV[m] : 0.0;
+                        row[7 + m] = ev;
+                        Eint += ev;
+                    }
+                }
+                if (P.measureFlux) {
+                    double* f = row + qFlux;
+                    f[0] = ux * ux; f[1] = ux * uy; f[2] = ux * uz; f[3] = uy * uy; f[4] = uy * uz; f[5] = uz * uz;
+                    f[6] = cc * ux; f[7] = cc * uy; f[8] = cc * uz;
+                    f[9] = Eint * ux; f[10] = Eint * uy; f[11] = Eint * uz;
+                }
+                if (P.measureClass) {
+                    const int cl = a.p.cls ? a.p.cls[g] : 0;
+                    row[qClass] = cl == 0 ? 1.0 : 0.0; row[qClass + 1] = cl == 1 ? 1.0 : 0.0; row[qClass + 2] = cl == 2 ? 1.0 : 0.0;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < MAX_SPECIES; ++s) {
+                if (s < S) {
+                    unsigned m = __ballot_sync(0xffffffffu, mySp == s);
+                    if (lane < nQ) {
+                        while (m) {
+                            const int j = __ffs(m) - 1;
+                            m &= m - 1;
+                            sum[s] += stage[w][j][lane];
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (lane < nQ) {
+            double* row = a.acc + size_t(c) * S * nQ;
+#pragma unroll
+            for (int s = 0; s < MAX_SPECIES; ++s)
+                if (s < S && sum[s] != 0.0) row[s * nQ + lane] += sum[s];
+        }
+    }
+}
+
+cudaError_t launchSample(const SampleArgs& a, cudaStream_t s) {
+    int grid = (a.nCells + SMP_WARPS - 1) / SMP_WARPS;
+    const int maxGrid = 148 * 8;
+    if (grid > maxGrid) grid = maxGrid;
+    if (grid < 1) grid = 1;
+    sampleKernel<<<grid, SMP_WARPS * 32, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// dsmcCloud::info / infoMeasurements (DSMC/clouds/dsmcCloud.C:935-985, dsmcCloudI.H:268-297):
+// mass, linear KE, rotational, vibrational, electronic energy of the whole cloud (real molecules).
+// ------------------------------------------------------------------------------------------------
+namespace { constexpr int INFO_BLOCKS = 296; constexpr int INFO_THREADS = 256; }
+
+__global__ void __launch_bounds__(INFO_THREADS) infoKernel(ParcelArrays p, int32_t n, const DevParams* Pp, double* scratch) {
+    __shared__ double red[5][INFO_THREADS / 32];
+    const DevParams& P = *Pp;
+    double v[5] = {0, 0, 0, 0, 0};
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (p.cell[i] < 0) continue;
+        const DevSpecies& S = P.sp[p.typeId[i]];
+        const double ux = p.ux[i], uy = p.uy[i], uz = p.uz[i];
+        v[0] += S.mass;
+        v[1] += 0.5 * S.mass * (ux * ux + uy * uy + uz * uz);
+        if (P.hasInternalEnergy) {
+            v[2] += p.erot[i];
+            for (int m = 0; m < S.nVib; ++m) v[3] += p.vib[m][i] * P.kB * S.thetaV[m];
+            v[4] += S.eElec[p.elevel[i]];
+        }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) red[k][w] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double x = 0;
+        for (int k = 0; k < INFO_THREADS / 32; ++k) x += red[threadIdx.x][k];
+        scratch[blockIdx.x * 5 + threadIdx.x] = x;
+    }
+}
+
+__global__ void infoFinalKernel(const double* scratch, const DevParams* Pp, double* out5) {
+    if (threadIdx.x < 5) {
+        double x = 0;
+        for (int b = 0; b < INFO_BLOCKS; ++b) x += scratch[b * 5 + threadIdx.x];
+        out5[threadIdx.x] = x * Pp->nParticles;
+    }
+}
+
+int32_t infoScratchDoubles() { return INFO_BLOCKS * 5; }
+
+cudaError_t launchInfo(const ParcelArrays& p, int32_t n, const DevParams* P, double* out5, double* scratch, cudaStream_t s) {
+    infoKernel<<<INFO_BLOCKS, INFO_THREADS, 0, s>>>(p, n, P, scratch);
+    infoFinalKernel<<<1, 32, 0, s>>>(scratch, P, out5);
+    return cudaGetLastError();
+}
+
+}  // namespace dsmc

@@ -1,0 +1,197 @@
+// kernels_init.cu -- parcel generation on the device: the dsmcMeshFill initialiser
+// (DSMC/initialiseDsmcParcels/derived/dsmcMeshFill/dsmcMeshFill.C:70-240) used for synthetic loads,
+// and dsmcFreeStreamInflowPatch::controlParcelsBeforeMove
+// (DSMC/boundaries/derived/generalBoundaries/dsmcFreeStreamInflowPatch/dsmcFreeStreamInflowPatch.C:86-375).
+// Both run in two passes around an exclusive scan: pass 0 decides how many parcels each
+// (cell | face, species) inserts, pass 1 generates them into the slots the scan assigned.
+#include "device_models.cuh"
+#include "engine.h"
+
+namespace dsmc {
+
+namespace {
+
+struct FaceView {
+    const int32_t* pts;
+    int n, base;
+};
+
+// tetIndices::tet for (cell, face, tetPt): Cc, basePt, pA, pB
+__device__ __forceinline__ void tetPointsDev(const double* points, const FaceView& f, bool own, int tetPt, V3& b, V3& c, V3& d) {
+    const int facePtI = (tetPt + f.base) % f.n;
+    const int otherFacePtI = (facePtI + 1) % f.n;
+    const int fPtAI = own ? facePtI : otherFacePtI;
+    const int fPtBI = own ? otherFacePtI : facePtI;
+    const int32_t lb = f.pts[f.base], la = f.pts[fPtAI], lbb = f.pts[fPtBI];
+    b = mk(points[3 * lb], points[3 * lb + 1], points[3 * lb + 2]);
+    c = mk(points[3 * la], points[3 * la + 1], points[3 * la + 2]);
+    d = mk(points[3 * lbb], points[3 * lbb + 1], points[3 * lbb + 2]);
+}
+
+__device__ __forceinline__ void storeParcel(const ParcelArrays& p, const DevParams& P, int32_t slot, const V3& pos, const V3& U, double ERot,
+                                            const int32_t* vib, int elevel, int32_t cell, int32_t tet, int typeId, int32_t origId) {
+    p.px[slot] = pos.x; p.py[slot] = pos.y; p.pz[slot] = pos.z;
+    p.ux[slot] = U.x; p.uy[slot] = U.y; p.uz[slot] = U.z;
+    p.cell[slot] = cell; p.tet[slot] = tet; p.origId[slot] = origId;
+    p.typeId[slot] = uint8_t(typeId);
+    if (P.hasInternalEnergy) {
+        p.erot[slot] = ERot;
+        for (int m = 0; m < P.nModes; ++m) p.vib[m][slot] = vib[m];
+        p.elevel[slot] = uint8_t(elevel);
+    }
+    if (p.cls) p.cls[slot] = 0;
+}
+
+}  // namespace
+
+// pass 0: cellCount[cell] = parcels to insert; pass 1: cellCount holds exclusive offsets
+__global__ void __launch_bounds__(128) fillKernel(FillArgs a, int pass) {
+    const int32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= a.nCells) return;
+    const DevParams& P = *a.P;
+    const V3 Cc = mk(a.cellCentres[3 * cell], a.cellCentres[3 * cell + 1], a.cellCentres[3 * cell + 2]);
+    int32_t count = 0;
+    int32_t slot = pass == 1 ? a.cellCount[cell] : 0;
+    int tetLocal = 0;
+    for (int k = a.cellFaceOffsets[cell]; k < a.cellFaceOffsets[cell + 1]; ++k) {
+        const int32_t face = a.cellFaces[k];
+        FaceView f{a.facePoints + a.faceOffsets[face], a.faceOffsets[face + 1] - a.faceOffsets[face], a.tetBasePtIs[face]};
+        const bool own = a.owner[face] == cell;
+        for (int tetPt = 1; tetPt < f.n - 1; ++tetPt, ++tetLocal) {
+            V3 b, c, d;
+            tetPointsDev(a.points, f, own, tetPt, b, c, d);
+            const double tetVolume = (1.0 / 6.0) * dot(cross(b - Cc, c - Cc), d - Cc);  // tetrahedron::mag
+            for (int i = 0; i < a.nTypes; ++i) {
+                const int typeId = a.typeIds[i];
+                const DevSpecies& S = P.sp[typeId];
+                Rng rng;
+                rng.init(P.seed, uint32_t(cell), uint32_t(tetLocal * MAX_SPECIES + i), 0u, STREAM_FILL);
+                const double particlesRequired = a.numberDensities[i] * tetVolume / P.nParticles;
+                int32_t nParticlesToInsert = int32_t(particlesRequired);
+                if ((particlesRequired - nParticlesToInsert) > rng.sample01()) nParticlesToInsert++;
+                if (pass == 0) { count += nParticlesToInsert; continue; }
+                const int32_t tet = 2 * (a.faceTetPair0[face] + tetPt - 1) + (own ? 0 : 1);
+                for (int32_t pI = 0; pI < nParticlesToInsert; ++pI) {
+                    const V3 pos = tetRandomPoint(rng, Cc, b, c, d);
+                    V3 U = equipartitionLinearVelocity(rng, P.kB, a.Ttra, S.mass);
+                    const double ERot = equipartitionRotationalEnergy(rng, P.kB, a.Trot, S.rotDof);
+                    int32_t vib[MAX_MODES] = {0, 0, 0};
+                    for (int m = 0; m < S.nVib; ++m) vib[m] = equipartitionVibrationalEnergyLevel(rng, a.Tvib, S.thetaV[m]);
+                    const int elevel = equipartitionElectronicLevel(rng, P.kB, a.Telec, S);
+                    U += mk(a.velocity[0], a.velocity[1], a.velocity[2]);
+                    storeParcel(a.p, P, slot, pos, U, ERot, vib, elevel, cell, tet, typeId, a.origIdBase + slot);
+                    ++slot;
+                }
+            }
+        }
+    }
+    if (pass == 0) a.cellCount[cell] = count;
+}
+
+cudaError_t launchFill(const FillArgs& a, int pass, cudaStream_t s) {
+    fillKernel<<<(a.nCells + 127) / 128, 128, 0, s>>>(a, pass);
+    return cudaGetLastError();
+}
+
+// pass 0: accumulator update (Bird eq. 4.22) and the integer number to insert per (species, face)
+// pass 1: counts holds exclusive offsets; generate
+__global__ void __launch_bounds__(128) inflowKernel(InflowArgs a, int pass) {
+    const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nFaces * a.nTypes) return;
+    const int32_t m = t / a.nFaces, fl = t % a.nFaces;  // counts layout [species][face]
+    const DevParams& P = *a.P;
+    const int typeId = a.typeIds[m];
+    const DevSpecies& S = P.sp[typeId];
+    const int32_t faceI = a.patchStart + fl;
+    const V3 sF = mk(a.faceAreas[3 * faceI], a.faceAreas[3 * faceI + 1], a.faceAreas[3 * faceI + 2]);
+    const double fA = mag(sF);
+    const double mass = S.mass;
+    const V3 velocity = mk(a.velocity[0], a.velocity[1], a.velocity[2]);
+    const double mostProbableSpeed = sqrt(2.0 * P.kB * a.Ttra / mass);  // maxwellianMostProbableSpeed
+    const double sqrtPi = sqrt(PI);
+    Rng rng;
+    rng.init(P.seed, uint32_t(faceI), uint32_t(a.patch * MAX_SPECIES + m), a.step, STREAM_INFLOW);
+
+    if (pass == 0) {
+        const double sCosTheta = dot(velocity, -sF / fA) / mostProbableSpeed;
+        double acc = a.accumulator[t];
+        acc += (fA * a.numberDensities[m] * P.deltaT * mostProbableSpeed *
+                (exp(-(sCosTheta * sCosTheta)) + sqrtPi * sCosTheta * (1 + erf(sCosTheta)))) /
+               (2.0 * sqrtPi * P.nParticles);
+        int32_t nI = int32_t(acc) > 0 ? int32_t(acc) : 0;
+        if ((acc - nI) > rng.sample01()) nI++;
+        acc -= nI;
+        a.accumulator[t] = acc;
+        a.counts[t] = nI;
+        return;
+    }
+
+    const int32_t nI = a.counts[t + 1] - a.counts[t];
+    if (nI <= 0) return;
+    rng.idx = 1;  // draw 0 was the insertion decision of pass 0
+    int32_t slot = a.base + a.counts[t];
+    if (slot + nI > a.capacity) { atomicAdd(&a.counters->overflow, 1ULL); return; }
+
+    const int32_t cellI = a.owner[faceI];
+    FaceView f{a.facePoints + a.faceOffsets[faceI], a.faceOffsets[faceI + 1] - a.faceOffsets[faceI], a.tetBasePtIs[faceI]};
+    const V3 fC = mk(a.faceCentres[3 * faceI], a.faceCentres[3 * faceI + 1], a.faceCentres[3 * faceI + 2]);
+    V3 n = sF;
+    n /= -mag(n);
+    const int32_t l0 = f.pts[0];
+    V3 t1 = fC - mk(a.points[3 * l0], a.points[3 * l0 + 1], a.points[3 * l0 + 2]);
+    t1 /= mag(t1);
+    V3 t2 = cross(n, t1);
+    t2 /= mag(t2);
+
+    for (int32_t i = 0; i < nI; ++i, ++slot) {
+        // triangle chosen by cumulative area fraction
+        const double triSelection = rng.sample01();
+        int selectedTriI = -1;
+        double cum = 0.0;
+        V3 b, c, d;
+        for (int tetPt = 1; tetPt < f.n - 1; ++tetPt) {
+            selectedTriI = tetPt;
+            tetPointsDev(a.points, f, true, tetPt, b, c, d);
+            cum = mag(0.5 * cross(c - b, d - b)) / fA + cum;
+            const double frac = (tetPt == f.n - 2) ? 1.0 : cum;
+            if (frac >= triSelection) break;
+        }
+        const V3 pos = triRandomPoint(rng, b, c, d);
+        const double sCosTheta = dot(velocity, n) / mostProbableSpeed;
+        const double uNormProbCoeffA = sCosTheta + sqrt(sCosTheta * sCosTheta + 2.0);
+        const double uNormProbCoeffB = 0.5 * (1.0 + sCosTheta * (sCosTheta - sqrt(sCosTheta * sCosTheta + 2.0)));
+        double randomScaling = 3.0;
+        if (sCosTheta < -3) randomScaling = fabs(sCosTheta) + 1;
+        double Pp = -1, uNormal, uNormalThermal;
+        if (fabs(dot(velocity, n)) > VSMALL) {
+            do {
+                uNormalThermal = randomScaling * (2.0 * rng.sample01() - 1);
+                uNormal = uNormalThermal + sCosTheta;
+                if (uNormal < 0.0) Pp = -1;
+                else Pp = 2.0 * uNormal / uNormProbCoeffA * exp(uNormProbCoeffB - uNormalThermal * uNormalThermal);
+            } while (Pp < rng.sample01());
+        } else {
+            uNormal = sqrt(-log(rng.sample01()));
+        }
+        const double g1 = rng.gaussNormal(), g2 = rng.gaussNormal();
+        const V3 U = sqrt(P.kB * a.Ttra / mass) * (g1 * t1 + g2 * t2) + dot(t1, velocity) * t1 + dot(t2, velocity) * t2 +
+                     mostProbableSpeed * uNormal * n;
+        const double ERot = equipartitionRotationalEnergy(rng, P.kB, a.Trot, S.rotDof);
+        int32_t vib[MAX_MODES] = {0, 0, 0};
+        for (int mo = 0; mo < S.nVib; ++mo) vib[mo] = equipartitionVibrationalEnergyLevel(rng, a.Tvib, S.thetaV[mo]);
+        const int elevel = equipartitionElectronicLevel(rng, P.kB, a.Telec, S);
+        const int32_t tet = 2 * (a.faceTetPair0[faceI] + selectedTriI - 1);
+        storeParcel(a.p, P, slot, pos, U, ERot, vib, elevel, cellI, tet, typeId, a.origIdBase + (slot - a.base));
+        // dsmcParcel::move: a freshly inserted parcel moves a random fraction of the step (dsmcParcel.C:52-59)
+        a.sfTail[slot - a.tailStart] = rng.sample01();
+    }
+}
+
+cudaError_t launchInflow(const InflowArgs& a, int pass, cudaStream_t s) {
+    const int n = a.nFaces * a.nTypes;
+    if (n <= 0) return cudaSuccess;
+    inflowKernel<<<(n + 127) / 128, 128, 0, s>>>(a, pass);
+    return cudaGetLastError();
+}
+
+}  // namespace dsmc

@@ -1,0 +1,223 @@
+// kernels_sort.cu -- stage 2: rebuild cellOccupancy by a per-cell counting sort.
+//
+// Reference: dsmcCloud::buildCellOccupancy (DSMC/clouds/dsmcCloud.C:63-74) clears one
+// DynamicList<dsmcParcel*> per cell and appends every parcel pointer in cloud-list order.
+// Here occupancy is a CSR offset array over a physically reordered SoA cloud:
+//   histogram (fused into the move kernel) -> exclusive scan -> index scatter (atomic cursor)
+//   -> per-cell ordering of the scattered indices (restores list order => deterministic,
+//      stable result) -> payload gather into the second buffer.
+// All integer work: results are bit-exact by construction.
+#include "engine.h"
+
+namespace dsmc {
+
+namespace {
+constexpr int SCAN_BLOCK = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+__device__ __forceinline__ int warpInclusiveScan(int v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) >= o) v += n;
+    }
+    return v;
+}
+
+// exclusive scan of `v` over the block; returns exclusive prefix, total via *total
+__device__ int blockExclusiveScan(int v, int* total) {
+    __shared__ int warpSums[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = warpInclusiveScan(v);
+    if (lane == 31) warpSums[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < (blockDim.x >> 5) ? warpSums[lane] : 0;
+        int si = warpInclusiveScan(s);
+        warpSums[lane] = si - s;
+        if (lane == 31) *total = si;
+    }
+    __syncthreads();
+    int r = warpSums[w] + inc - v;
+    __syncthreads();
+    return r;
+}
+}  // namespace
+
+__global__ void __launch_bounds__(SCAN_BLOCK) scanTileSums(const int32_t* __restrict__ in, int32_t n, int32_t* __restrict__ tileSums) {
+    __shared__ int total;
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) s += in[base + k];
+    blockExclusiveScan(s, &total);
+    if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) scanTileOffsets(int32_t* tileSums, int32_t nTiles) {
+    __shared__ int total;
+    int carry = 0;
+    for (int base = 0; base < nTiles; base += SCAN_BLOCK) {
+        int idx = base + threadIdx.x;
+        int v = idx < nTiles ? tileSums[idx] : 0;
+        int ex = blockExclusiveScan(v, &total);
+        if (idx < nTiles) tileSums[idx] = carry + ex;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tileSums[nTiles] = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) scanFinal(const int32_t* __restrict__ in, int32_t n, const int32_t* __restrict__ tileSums,
+                                                        int32_t nTiles, int32_t* __restrict__ out, int32_t* __restrict__ out2) {
+    __shared__ int total;
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    int ex = blockExclusiveScan(s, &total) + tileSums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) {
+            out[base + k] = ex;
+            if (out2) out2[base + k] = ex;
+        }
+        ex += v[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = tileSums[nTiles];
+}
+
+int32_t scanScratchInts(int32_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE + 2; }
+
+// out[0..n] = exclusive scan of in[0..n) (out[n] = total); out2 (optional) receives a copy of out[0..n)
+cudaError_t launchExclusiveScan(const int32_t* in, int32_t* out, int32_t* out2, int32_t n, int32_t* tileSums, cudaStream_t s) {
+    const int nTiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    scanTileSums<<<nTiles, SCAN_BLOCK, 0, s>>>(in, n, tileSums);
+    scanTileOffsets<<<1, SCAN_BLOCK, 0, s>>>(tileSums, nTiles);
+    scanFinal<<<nTiles, SCAN_BLOCK, 0, s>>>(in, n, tileSums, nTiles, out, out2);
+    return cudaGetLastError();
+}
+
+__global__ void histogramKernel(const int32_t* __restrict__ cell, int32_t n, int32_t* __restrict__ cellCount) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t c = cell[i];
+    if (c >= 0) atomicAdd(&cellCount[c], 1);
+}
+
+cudaError_t launchHistogram(const int32_t* cell, int32_t n, int32_t* cellCount, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    histogramKernel<<<(n + 255) / 256, 256, 0, s>>>(cell, n, cellCount);
+    return cudaGetLastError();
+}
+
+__global__ void scatterIndexKernel(const int32_t* __restrict__ cell, int32_t n, int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t c = cell[i];
+    if (c < 0) return;
+    const int32_t slot = atomicAdd(&cursor[c], 1);
+    perm[slot] = i;
+}
+
+cudaError_t launchScatterIndex(const int32_t* cell, int32_t n, int32_t* cursor, int32_t* perm, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    scatterIndexKernel<<<(n + 255) / 256, 256, 0, s>>>(cell, n, cursor, perm);
+    return cudaGetLastError();
+}
+
+// Order the indices of every cell ascending (= cloud-list order).  One warp per cell:
+// cells of <= 32 parcels rank by shuffles, up to SEG_SMEM by a shared-memory rank sort.
+namespace {
+constexpr int SEG_WARPS = 8;
+constexpr int SEG_SMEM = 1024;  // per warp
+}
+
+__global__ void __launch_bounds__(SEG_WARPS * 32) segmentSortKernel(const int32_t* __restrict__ cellOffset, int32_t nCells,
+                                                                    int32_t* __restrict__ perm, DevCounters* counters) {
+    __shared__ int32_t sm[SEG_WARPS][SEG_SMEM];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int32_t nWarps = gridDim.x * SEG_WARPS;
+    for (int32_t c = blockIdx.x * SEG_WARPS + w; c < nCells; c += nWarps) {
+        const int32_t b = cellOffset[c], n = cellOffset[c + 1] - b;
+        if (n <= 1) continue;
+        if (n <= 32) {
+            const int32_t v = lane < n ? perm[b + lane] : 0x7fffffff;
+            int rank = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int32_t o = __shfl_sync(0xffffffffu, v, j);
+                rank += (o < v) ? 1 : 0;
+            }
+            if (lane < n) perm[b + rank] = v;
+        } else if (n <= SEG_SMEM) {
+            for (int k = lane; k < n; k += 32) sm[w][k] = perm[b + k];
+            __syncwarp();
+            for (int k = lane; k < n; k += 32) {
+                const int32_t v = sm[w][k];
+                int rank = 0;
+                for (int j = 0; j < n; ++j) rank += (sm[w][j] < v) ? 1 : 0;
+                perm[b + rank] = v;
+            }
+            __syncwarp();
+        } else {
+            // very large cells: global-memory rank sort in chunks is O(n^2); leave the atomic order and report it
+            if (lane == 0) atomicAdd(&counters->unsortedLargeCells, 1ULL);
+        }
+    }
+}
+
+cudaError_t launchSegmentSort(const int32_t* cellOffset, int32_t nCells, int32_t* perm, DevCounters* c, cudaStream_t s) {
+    int grid = (nCells + SEG_WARPS - 1) / SEG_WARPS;
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid < 1) grid = 1;
+    segmentSortKernel<<<grid, SEG_WARPS * 32, 0, s>>>(cellOffset, nCells, perm, c);
+    return cudaGetLastError();
+}
+
+// cell id of output slot k: binary search in the CSR offsets is avoided by writing the cell
+// array from a per-cell fill kernel instead.
+__global__ void fillCellKernel(const int32_t* __restrict__ cellOffset, int32_t nCells, int32_t* __restrict__ cellOut) {
+    const int lane = threadIdx.x & 31;
+    const int32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int32_t nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (int32_t c = warp; c < nCells; c += nWarps) {
+        const int32_t b = cellOffset[c], e = cellOffset[c + 1];
+        for (int32_t k = b + lane; k < e; k += 32) cellOut[k] = c;
+    }
+}
+
+__global__ void __launch_bounds__(256) gatherKernel(ParcelArrays src, ParcelArrays dst, const int32_t* __restrict__ perm, int32_t nOut,
+                                                    int32_t nModes, int hasInternal) {
+    const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nOut) return;
+    const int32_t i = perm[k];
+    dst.px[k] = src.px[i]; dst.py[k] = src.py[i]; dst.pz[k] = src.pz[i];
+    dst.ux[k] = src.ux[i]; dst.uy[k] = src.uy[i]; dst.uz[k] = src.uz[i];
+    dst.cell[k] = src.cell[i];
+    dst.tet[k] = src.tet[i];
+    dst.origId[k] = src.origId[i];
+    dst.typeId[k] = src.typeId[i];
+    if (hasInternal) {
+        dst.erot[k] = src.erot[i];
+        for (int m = 0; m < nModes; ++m) dst.vib[m][k] = src.vib[m][i];
+        dst.elevel[k] = src.elevel[i];
+    }
+    if (src.cls) dst.cls[k] = src.cls[i];
+}
+
+cudaError_t launchGather(const ParcelArrays& src, const ParcelArrays& dst, const int32_t* perm, const int32_t* cellOffset,
+                         int32_t nCells, int32_t nOut, int32_t nModes, bool hasInternal, cudaStream_t s) {
+    (void)cellOffset; (void)nCells;
+    if (nOut <= 0) return cudaSuccess;
+    gatherKernel<<<(nOut + 255) / 256, 256, 0, s>>>(src, dst, perm, nOut, nModes, hasInternal ? 1 : 0);
+    return cudaGetLastError();
+}
+
+}  // namespace dsmc

@@ -1,0 +1,174 @@
+"""Structured hex polyMesh generator (a blockMesh equivalent for box-shaped blocks) and the
+brick decomposition used by the weak-scaling cases.
+
+The reference meshes its cases with OpenFOAM's blockMesh and partitions them with decomposePar
+(run/hyStrath/dsmcFoam+/*/Allrun); neither tool exists outside an OpenFOAM install, so synthetic
+loads are meshed here with the same conventions: points x-fastest, cells x-fastest, internal faces
+in upper-triangular order (owner ascending, then neighbour ascending), face normals pointing from
+owner to neighbour / out of the domain, boundary faces grouped per patch, processor patches after
+all other patches with plain `processor` before `processorCyclic`.  Coupled faces (cyclic halves,
+processor pairs) have matched first vertices and opposite circulation, which is what
+particle::hitCyclicPatch / correctAfterParallelTransfer rely on (tetPtI -> nPts - 1 - tetPtI,
+BASIC/particle/particleTemplates.C:90-111,1539).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .capi import MeshData
+
+SIDES = ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")
+
+
+def _pid(i, j, k, nx, ny):
+    return i + (nx + 1) * (j + (ny + 1) * k)
+
+
+def _side_faces(side, nx, ny, nz):
+    """(faces[n,4] point labels, owner[n]) of one side, outward normals, coupled-compatible ordering."""
+    if side in ("xmin", "xmax"):
+        k, j = np.meshgrid(np.arange(nz), np.arange(ny), indexing="ij")
+        j, k = j.ravel(), k.ravel()
+        i = np.zeros_like(j) if side == "xmin" else np.full_like(j, nx)
+        a, b, c, d = _pid(i, j, k, nx, ny), _pid(i, j + 1, k, nx, ny), _pid(i, j + 1, k + 1, nx, ny), _pid(i, j, k + 1, nx, ny)
+        faces = np.stack([a, d, c, b], 1) if side == "xmin" else np.stack([a, b, c, d], 1)
+        own = (0 if side == "xmin" else nx - 1) + nx * (j + ny * k)
+    elif side in ("ymin", "ymax"):
+        k, i = np.meshgrid(np.arange(nz), np.arange(nx), indexing="ij")
+        i, k = i.ravel(), k.ravel()
+        j = np.zeros_like(i) if side == "ymin" else np.full_like(i, ny)
+        a, b, c, d = _pid(i, j, k, nx, ny), _pid(i, j, k + 1, nx, ny), _pid(i + 1, j, k + 1, nx, ny), _pid(i + 1, j, k, nx, ny)
+        faces = np.stack([a, d, c, b], 1) if side == "ymin" else np.stack([a, b, c, d], 1)
+        own = i + nx * ((0 if side == "ymin" else ny - 1) + ny * k)
+    else:
+        j, i = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+        i, j = i.ravel(), j.ravel()
+        k = np.zeros_like(i) if side == "zmin" else np.full_like(i, nz)
+        a, b, c, d = _pid(i, j, k, nx, ny), _pid(i + 1, j, k, nx, ny), _pid(i + 1, j + 1, k, nx, ny), _pid(i, j + 1, k, nx, ny)
+        faces = np.stack([a, d, c, b], 1) if side == "zmin" else np.stack([a, b, c, d], 1)
+        own = i + nx * (j + ny * (0 if side == "zmin" else nz - 1))
+    return faces.astype(np.int32), own.astype(np.int32)
+
+
+def box_mesh(n, lengths, origin=(0.0, 0.0, 0.0), sides=None, my_proc=-1):
+    """Hex mesh of a box.
+
+    sides: dict side -> spec, spec one of
+      ("cyclic",)                        paired with the opposite side
+      ("wall", name) / ("patch", name) / ("empty", name) / ("symmetryPlane", name) / ("symmetry", name)
+      ("processor", neighbProcNo)
+      ("processorCyclic", neighbProcNo, separation_xyz)
+    Sides sharing (type, name) are merged into one patch (e.g. frontAndBack).
+    """
+    nx, ny, nz = (int(v) for v in n)
+    lx, ly, lz = (float(v) for v in lengths)
+    sides = dict(sides or {s: ("cyclic",) for s in SIDES})
+    xs = origin[0] + lx * np.arange(nx + 1) / nx
+    ys = origin[1] + ly * np.arange(ny + 1) / ny
+    zs = origin[2] + lz * np.arange(nz + 1) / nz
+    Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+    points = np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1)
+
+    # internal faces: per cell (+x, +y, +z), upper-triangular order
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    i, j, k = i.ravel(), j.ravel(), k.ravel()
+    cell = (i + nx * (j + ny * k)).astype(np.int32)
+    fx = np.stack([_pid(i + 1, j, k, nx, ny), _pid(i + 1, j + 1, k, nx, ny), _pid(i + 1, j + 1, k + 1, nx, ny), _pid(i + 1, j, k + 1, nx, ny)], 1)
+    fy = np.stack([_pid(i, j + 1, k, nx, ny), _pid(i, j + 1, k + 1, nx, ny), _pid(i + 1, j + 1, k + 1, nx, ny), _pid(i + 1, j + 1, k, nx, ny)], 1)
+    fz = np.stack([_pid(i, j, k + 1, nx, ny), _pid(i + 1, j, k + 1, nx, ny), _pid(i + 1, j + 1, k + 1, nx, ny), _pid(i, j + 1, k + 1, nx, ny)], 1)
+    allf = np.stack([fx, fy, fz], 1)  # [nCells, 3, 4]
+    mask = np.stack([i < nx - 1, j < ny - 1, k < nz - 1], 1)
+    nbr = np.stack([cell + 1, cell + nx, cell + nx * ny], 1)
+    own_int = np.repeat(cell[:, None], 3, 1)[mask]
+    nbr_int = nbr[mask].astype(np.int32)
+    faces_int = allf[mask].astype(np.int32)
+
+    # group sides into patches
+    groups = []  # (type, name, [sides], extra)
+    for s in SIDES:
+        spec = sides[s]
+        t = spec[0]
+        if t == "cyclic":
+            groups.append((t, {"xmin": "cyclicX_half0", "xmax": "cyclicX_half1", "ymin": "cyclicY_half0", "ymax": "cyclicY_half1",
+                               "zmin": "cyclicZ_half0", "zmax": "cyclicZ_half1"}[s], [s], None))
+        elif t in ("processor", "processorCyclic"):
+            groups.append((t, f"proc{t[9:]}{my_proc}to{spec[1]}_{s}", [s], spec))
+        else:
+            name = spec[1] if len(spec) > 1 else s
+            for g in groups:
+                if g[0] == t and g[1] == name:
+                    g[2].append(s)
+                    break
+            else:
+                groups.append((t, name, [s], None))
+    order = [g for g in groups if g[0] not in ("processor", "processorCyclic")]
+    order += [g for g in groups if g[0] == "processor"] + [g for g in groups if g[0] == "processorCyclic"]
+
+    bfaces, bown, patches = [], [], []
+    start = len(own_int)
+    for t, name, ss, spec in order:
+        size = 0
+        for s in ss:
+            f, o = _side_faces(s, nx, ny, nz)
+            bfaces.append(f)
+            bown.append(o)
+            size += len(o)
+        p = {"name": name, "type": t, "start": start, "size": size, "sides": ss}
+        if t in ("processor", "processorCyclic"):
+            p["myProcNo"] = my_proc
+            p["neighbProcNo"] = spec[1]
+            p["separation"] = tuple(spec[2]) if t == "processorCyclic" else (0.0, 0.0, 0.0)
+        patches.append(p)
+        start += size
+    opposite = {"xmin": "xmax", "xmax": "xmin", "ymin": "ymax", "ymax": "ymin", "zmin": "zmax", "zmax": "zmin"}
+    for idx, p in enumerate(patches):
+        if p["type"] == "cyclic":
+            opp = opposite[p["sides"][0]]
+            if sides[opp][0] != "cyclic":
+                raise ValueError(f"cyclic side {p['sides'][0]} needs a cyclic opposite side")
+            p["neighbPatch"] = next(q for q, pp in enumerate(patches) if pp["type"] == "cyclic" and pp["sides"][0] == opp)
+
+    faces = np.concatenate([faces_int] + bfaces) if bfaces else faces_int
+    owner = np.concatenate([own_int] + bown).astype(np.int32) if bown else own_int
+    face_offsets = (4 * np.arange(len(owner) + 1)).astype(np.int32)
+    mesh = MeshData(points, face_offsets, faces.ravel(), owner, nbr_int, patches)
+    mesh.shape = (nx, ny, nz)
+    mesh.lengths = (lx, ly, lz)
+    mesh.origin = tuple(float(v) for v in origin)
+    return mesh
+
+
+def decomposed_box(n_local, lengths_local, procs, rank, outer=("cyclic", "cyclic", "cyclic")):
+    """Brick `rank` of a procs=(px,py,pz) tiling of identical bricks (weak-scaling layout).
+
+    outer[d] is the treatment of the global domain boundary in direction d: "cyclic" (periodic:
+    a same-rank cyclic pair when p==1, processorCyclic otherwise) or a (type, name) spec.
+    """
+    px, py, pz = procs
+    rx, ry, rz = rank % px, (rank // px) % py, rank // (px * py)
+    coords, P = (rx, ry, rz), (px, py, pz)
+    origin = tuple(coords[d] * lengths_local[d] for d in range(3))
+    total = tuple(P[d] * lengths_local[d] for d in range(3))
+
+    def rank_of(c):
+        return c[0] + px * (c[1] + py * c[2])
+
+    sides = {}
+    for d, (lo, hi) in enumerate((("xmin", "xmax"), ("ymin", "ymax"), ("zmin", "zmax"))):
+        for side, step in ((lo, -1), (hi, +1)):
+            c = list(coords)
+            c[d] += step
+            if 0 <= c[d] < P[d]:
+                sides[side] = ("processor", rank_of(c))
+            elif outer[d] == "cyclic":
+                if P[d] == 1:
+                    sides[side] = ("cyclic",)
+                else:
+                    c[d] %= P[d]
+                    sep = [0.0, 0.0, 0.0]
+                    # separation of the receiving patch = C_send - C_recv
+                    sep[d] = -total[d] if step > 0 else total[d]
+                    sides[side] = ("processorCyclic", rank_of(c), tuple(sep))
+            else:
+                sides[side] = tuple(outer[d])
+    return box_mesh(n_local, lengths_local, origin, sides, my_proc=rank)

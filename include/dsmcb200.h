@@ -1,0 +1,319 @@
+/*
+ * dsmcb200.h -- C ABI of libdsmcb200.so, the B200-native engine behind
+ * dsmcFoam+'s per-timestep particle loop (dsmcCloud::evolve()).
+ *
+ * The reference (hyStrath, OpenFOAM v1706 add-on) has no FFI of its own: its
+ * plugin surface is OpenFOAM run-time selection.  Each
+ * entry point below therefore cites the reference member function whose work
+ * it takes over; the OpenFOAM-side shim in INTEGRATION.md is the binding a
+ * maintainer adds to call them.  Paths are relative to the reference root;
+ * DSMC/ = src/lagrangian/dsmc/, BASIC/ = src/lagrangian/basic/.
+ *
+ * Conventions
+ *  - plain C, POD structs, raw pointers + sizes; no C++/torch types.
+ *  - caller owns every host buffer, the library copies; the library owns all
+ *    device memory; download buffers are caller-allocated with capacity
+ *    passed in.
+ *  - every call returns 0 on success or a negative dsmcb200_status; the text
+ *    is available through dsmcb200_last_error().  Nothing throws or exits
+ *    across this boundary (the shim turns errors into FatalErrorIn, cf.
+ *    DSMC/clouds/dsmcCloudI.H:141-147).
+ *  - one ctx per GPU / rank; a ctx is not re-entrant; calls are synchronous
+ *    on return unless stated otherwise.
+ *  - label -> int32_t (reference build is Int32), scalar -> double, SI units.
+ *  - there is NO CPU fallback: dsmcb200_create fails if no CUDA device.
+ */
+#ifndef DSMCB200_H
+#define DSMCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSMCB200_ABI_VERSION 1
+#define DSMCB200_MAX_SPECIES 8
+#define DSMCB200_MAX_VIB_MODES 3
+#define DSMCB200_MAX_ELEC_LEVELS 16
+#define DSMCB200_NAME_LEN 64
+
+typedef struct dsmcb200_ctx dsmcb200_ctx;
+
+typedef enum {
+    DSMCB200_OK = 0,
+    DSMCB200_ERR_INVALID = -1,   /* bad argument / inconsistent input      */
+    DSMCB200_ERR_CUDA = -2,      /* CUDA runtime failure                   */
+    DSMCB200_ERR_STATE = -3,     /* call order violated (e.g. no mesh yet) */
+    DSMCB200_ERR_CAPACITY = -4,  /* a fixed-capacity buffer overflowed     */
+    DSMCB200_ERR_UNSUPPORTED = -5, /* model name outside the scoped path   */
+    DSMCB200_ERR_NCCL = -6
+} dsmcb200_status;
+
+/* polyPatch types dispatched by particle::trackToFace
+ * (BASIC/particle/particleTemplates.C:1110-1164). */
+typedef enum {
+    DSMCB200_PATCH_WALL = 0,
+    DSMCB200_PATCH_PATCH = 1,
+    DSMCB200_PATCH_CYCLIC = 2,
+    DSMCB200_PATCH_PROCESSOR = 3,
+    DSMCB200_PATCH_EMPTY = 4,
+    DSMCB200_PATCH_SYMMETRYPLANE = 5,
+    DSMCB200_PATCH_SYMMETRY = 6,
+    DSMCB200_PATCH_WEDGE = 7,
+    DSMCB200_PATCH_PROCESSORCYCLIC = 8
+} dsmcb200_patch_type;
+
+typedef struct {
+    char name[DSMCB200_NAME_LEN];
+    int32_t type;        /* dsmcb200_patch_type                                  */
+    int32_t start;       /* first face (global face index)                       */
+    int32_t size;        /* nFaces                                               */
+    int32_t neighbPatch; /* cyclic: index of neighbourPatch; else -1             */
+    int32_t myProcNo;    /* processor patches; else -1                           */
+    int32_t neighbProcNo;
+    int32_t referPatch;  /* processorCyclic: the cyclic patch it derives from    */
+    int32_t hasSeparation; /* 1: separation[] below is authoritative; 0: cyclic
+                              patches get (nf & (Cr - Cf))*nf from the geometry   */
+    double separation[3];  /* coupledPolyPatch::separation() of THIS patch: a
+                              parcel arriving on it has position -= separation    */
+} dsmcb200_patch;
+
+/* polyMesh as read from constant/polyMesh/{points,faces,owner,neighbour,boundary}. */
+typedef struct {
+    int32_t nPoints, nFaces, nInternalFaces, nCells, nPatches;
+    const double* points;        /* [nPoints*3]                    */
+    const int32_t* faceOffsets;  /* [nFaces+1] CSR into facePoints */
+    const int32_t* facePoints;
+    const int32_t* owner;        /* [nFaces]                       */
+    const int32_t* neighbour;    /* [nInternalFaces]               */
+    const dsmcb200_patch* patches;
+    /* Optional precomputed geometry (NULL -> computed by the library with the
+     * primitiveMesh algorithms).  The OpenFOAM shim passes
+     * OpenFOAM's own arrays so geometry is identical by construction. */
+    const double* cellCentres;   /* [nCells*3] */
+    const double* cellVolumes;   /* [nCells]   */
+    const double* faceCentres;   /* [nFaces*3] */
+    const double* faceAreas;     /* [nFaces*3] */
+    const int32_t* tetBasePtIs;  /* [nFaces]   */
+} dsmcb200_mesh;
+
+/* dsmcParcel::constantProperties (DSMC/parcels/dsmcParcel.H:72-236,
+ * parsed at DSMC/parcels/dsmcParcelI.H:37-200). */
+typedef struct {
+    char name[DSMCB200_NAME_LEN];
+    double mass, diameter, omega, alpha;
+    double rotationalDegreesOfFreedom;
+    int32_t nVibrationalModes;
+    int32_t charge;
+    double thetaV[DSMCB200_MAX_VIB_MODES];   /* characteristicVibrationalTemperature */
+    double Zref[DSMCB200_MAX_VIB_MODES];
+    double TrefZv[DSMCB200_MAX_VIB_MODES];   /* referenceTempForZref                 */
+    double thetaD;                            /* dissociationTemperature              */
+    int32_t nElectronicLevels;
+    int32_t pad_;
+    double electronicEnergyList[DSMCB200_MAX_ELEC_LEVELS];
+    int32_t electronicDegeneracyList[DSMCB200_MAX_ELEC_LEVELS];
+} dsmcb200_species;
+
+typedef enum {
+    DSMCB200_COLL_NONE = 0,                /* NoBinaryCollision                  */
+    DSMCB200_COLL_VHS = 1,                 /* VariableHardSphere                 */
+    DSMCB200_COLL_LB_VHS = 2               /* LarsenBorgnakkeVariableHardSphere  */
+} dsmcb200_collision_model;
+
+typedef enum {
+    DSMCB200_BND_NONE = 0,
+    DSMCB200_BND_DIFFUSE_WALL = 1,   /* dsmcDiffuseWallPatch  */
+    DSMCB200_BND_SPECULAR_WALL = 2,  /* dsmcSpecularWallPatch */
+    DSMCB200_BND_DELETION = 3        /* dsmcDeletionPatch     */
+} dsmcb200_patch_model_kind;
+
+/* One entry of system/boundariesDict dsmcPatchBoundaries
+ * (DSMC/boundaries/basic/dsmcPatchBoundary/dsmcPatchBoundary.C:56-125). */
+typedef struct {
+    int32_t patch;          /* index into mesh patches */
+    int32_t model;          /* dsmcb200_patch_model_kind */
+    double temperature;     /* dsmcDiffuseWallPatchProperties.temperature */
+    double velocity[3];
+} dsmcb200_patch_model;
+
+/* One dsmcFreeStreamInflowPatch of dsmcGeneralBoundaries
+ * (DSMC/boundaries/derived/generalBoundaries/dsmcFreeStreamInflowPatch/
+ *  dsmcFreeStreamInflowPatch.C:393-470). */
+typedef struct {
+    int32_t patch;
+    int32_t nTypes;
+    int32_t typeIds[DSMCB200_MAX_SPECIES];
+    double numberDensities[DSMCB200_MAX_SPECIES];
+    double velocity[3];
+    double translationalTemperature, rotationalTemperature;
+    double vibrationalTemperature, electronicTemperature;
+} dsmcb200_inflow;
+
+/* constant/dsmcProperties + system/controlDict + system/boundariesDict,
+ * reduced to POD (DSMC/clouds/dsmcCloud.C:586-691). */
+typedef struct {
+    int32_t collisionModel;        /* dsmcb200_collision_model                    */
+    int32_t invZvFormulation;      /* "pre-2008"->0, "2008"->1, default 2         */
+    double Tref;                   /* VariableHardSphereCoeffs.Tref (273)         */
+    double rotationalRelaxationCollisionNumber;   /* 5   */
+    double vibrationalRelaxationCollisionNumber;  /* 0 -> variable Zv */
+    double electronicRelaxationCollisionNumber;   /* 500 */
+    double nEquivalentParticles;
+    double deltaT;
+    uint64_t seed;                 /* Philox key (dsmcProperties seedNumber)      */
+    double kB;                     /* physicoChemical::k; 0 -> 1.38065e-23 (v1706)*/
+    int32_t nPatchModels;
+    int32_t nInflows;
+    const dsmcb200_patch_model* patchModels;
+    const dsmcb200_inflow* inflows;
+    int32_t measureHeatFluxShearStress; /* sample the optional 2nd-moment set     */
+    int32_t measureClassifications;
+    int32_t trackFaceFluxes;       /* dsmcFaceTracker counters (off by default)   */
+    int32_t fusedCollideSample;    /* 1: stages 3-5 in one kernel                 */
+} dsmcb200_models;
+
+/* Host-side SoA view of the cloud.  Layout of vectors is OpenFOAM's
+ * (x y z) interleaved.  Optional arrays may be NULL on upload (defaults:
+ * ERot 0, vibLevel 0, ELevel 0, newParcel -1, classification 0, origId = i,
+ * stepFraction 0). */
+typedef struct {
+    double* position;      /* [3n] */
+    double* U;             /* [3n] */
+    double* ERot;          /* [n]  */
+    int32_t* cell;         /* [n]  */
+    int32_t* tetFace;      /* [n]  */
+    int32_t* tetPt;        /* [n]  */
+    int32_t* typeId;       /* [n]  */
+    int32_t* vibLevel;     /* [n*maxModes], parcel-major */
+    int32_t* ELevel;       /* [n]  */
+    int32_t* newParcel;    /* [n]  */
+    int32_t* classification; /* [n] */
+    int32_t* origId;       /* [n]  */
+    int32_t maxModes;      /* stride of vibLevel */
+    int32_t pad_;
+} dsmcb200_parcels_soa;
+
+/* Counters of one evolve() (noTimeCounter.C:312-337, dsmcCloud.C:935-985,
+ * Cloud.H:193-204). */
+typedef struct {
+    int64_t nParcels;
+    int64_t collisions;
+    int64_t collisionCandidates;
+    int64_t trackingRescues;
+    int64_t deleted;
+    int64_t inserted;
+    int64_t migratedOut;
+    int64_t migratedIn;
+    int64_t unsortedLargeCells;  /* cells too large for the in-cell ordering pass */
+    double mass, linearKineticEnergy, rotationalEnergy, vibrationalEnergy, electronicEnergy;
+    double stageMs[8];  /* last step: inflow, move, migrate, sort, collide, sample, info, total */
+} dsmcb200_counters;
+
+/* Sampled per-cell accumulators of stage 5: the per-species moment sums from
+ * which every dsmcVolFields instance (any typeIds subset) is derived
+ * (DSMC/macroscopicProperties/derived/combined/dsmcVolFields/dsmcVolFields.C:1115-1237). */
+typedef struct {
+    int32_t nCells, nSpecies, nQuantities, nModes;
+    double nTimeSteps;
+} dsmcb200_accum_info;
+
+/* Index of quantity q inside one species block of an accumulator row. */
+enum {
+    DSMCB200_Q_N = 0,   /* dsmcNSpeciesCum             */
+    DSMCB200_Q_PX = 1,  /* sum U (momentum / mass)     */
+    DSMCB200_Q_PY = 2,
+    DSMCB200_Q_PZ = 3,
+    DSMCB200_Q_CC = 4,  /* sum U.U                     */
+    DSMCB200_Q_EROT = 5,
+    DSMCB200_Q_EELEC = 6,
+    DSMCB200_Q_EVIB0 = 7 /* + mode                      */
+};
+
+/* ---- life cycle ------------------------------------------------------- */
+/* replaces: dsmcCloud ctor, DSMC/clouds/dsmcCloud.C:586-691 (device side) */
+int dsmcb200_create(dsmcb200_ctx** out, int device, int rank, int nRanks);
+void dsmcb200_destroy(dsmcb200_ctx*);
+const char* dsmcb200_last_error(const dsmcb200_ctx*);
+int dsmcb200_abi_version(void);
+
+/* NCCL plumbing for processor-patch migration (replaces PstreamBuffers,
+ * BASIC/Cloud/Cloud.C:255,324-454).  id is ncclUniqueId (128 bytes). */
+int dsmcb200_nccl_unique_id(void* id128);
+int dsmcb200_init_comm(dsmcb200_ctx*, const void* id128);
+
+/* ---- configuration ---------------------------------------------------- */
+/* replaces: polyMesh addressing + tetBasePtIs used by particle::trackToFace,
+ * BASIC/particle/particleTemplates.C:741-743,830-861 */
+int dsmcb200_set_mesh(dsmcb200_ctx*, const dsmcb200_mesh*);
+/* replaces: dsmcCloud::buildConstProps, DSMC/clouds/dsmcCloud.C:40-59 */
+int dsmcb200_set_species(dsmcb200_ctx*, int nSpecies, const dsmcb200_species*);
+/* replaces: BinaryCollisionModel::New / collisionPartnerSelection::New /
+ * dsmcBoundaries ctor, DSMC/clouds/dsmcCloud.C:653-683 */
+int dsmcb200_set_models(dsmcb200_ctx*, const dsmcb200_models*);
+/* Reserve device storage for up to maxParcels (0 -> grow on demand). */
+int dsmcb200_reserve(dsmcb200_ctx*, int64_t maxParcels);
+
+/* ---- cloud state ------------------------------------------------------ */
+/* replaces: Cloud<T>::initCloud + dsmcParcel::readFields,
+ * BASIC/Cloud/CloudIO.C:111-165, DSMC/parcels/dsmcParcelIO.C:133-335.
+ * If tetFace/tetPt are NULL they are located like
+ * particle::initCellFacePtOrDeleteLostParticle (BASIC/particle/particleI.H:851-996). */
+int dsmcb200_upload_parcels(dsmcb200_ctx*, int64_t n, const dsmcb200_parcels_soa*);
+int dsmcb200_download_parcels(dsmcb200_ctx*, int64_t capacity, int64_t* n, dsmcb200_parcels_soa*);
+/* replaces: read of <time>/dsmcSigmaTcRMax and
+ * buildCollisionSelectionRemainderFromScratch, DSMC/clouds/dsmcCloud.C:105-116,625-636.
+ * remainder NULL -> uniform Philox randoms. */
+int dsmcb200_upload_cellstate(dsmcb200_ctx*, const double* sigmaTcRMax, const double* remainderOrNull);
+int dsmcb200_download_cellstate(dsmcb200_ctx*, double* sigmaTcRMax, double* remainder);
+/* replaces: dsmcMeshFill::setInitialConfiguration,
+ * DSMC/initialiseDsmcParcels/derived/dsmcMeshFill/dsmcMeshFill.C:70-240
+ * (synthetic loads are generated on the device). */
+int dsmcb200_mesh_fill(dsmcb200_ctx*, int nTypes, const int32_t* typeIds, const double* numberDensities,
+                       double translationalT, double rotationalT, double vibrationalT, double electronicT,
+                       const double velocity[3]);
+
+/* ---- the hot path ----------------------------------------------------- */
+/* replaces: dsmcCloud::evolve(), DSMC/clouds/dsmcCloud.C:819-926 */
+int dsmcb200_evolve(dsmcb200_ctx*, int nSteps);
+
+typedef enum {
+    DSMCB200_STAGE_INFLOW = 0,  /* dsmcFreeStreamInflowPatch::controlParcelsBeforeMove */
+    DSMCB200_STAGE_MOVE = 1,    /* Cloud<dsmcParcel>::move, BASIC/Cloud/Cloud.C:204     */
+    DSMCB200_STAGE_SORT = 2,    /* dsmcCloud::buildCellOccupancy, dsmcCloud.C:63-74     */
+    DSMCB200_STAGE_COLLIDE = 3, /* noTimeCounter::collide, noTimeCounter.C:81           */
+    DSMCB200_STAGE_SAMPLE = 4   /* dsmcVolFields::calculateField, dsmcVolFields.C:1071  */
+} dsmcb200_stage_id;
+/* Single-stage entry points for parity tests and ncu. */
+int dsmcb200_stage(dsmcb200_ctx*, int stage);
+/* Time-step index used as the Philox step word (evolve increments it). */
+int dsmcb200_set_step(dsmcb200_ctx*, uint32_t step);
+
+/* ---- results ---------------------------------------------------------- */
+/* cellOccupancy as CSR offsets [nCells+1] (valid after STAGE_SORT). */
+int dsmcb200_download_occupancy(dsmcb200_ctx*, int32_t* cellOffsets);
+/* replaces: the accumulators of dsmcVolFields (calculateField, :1115-1237) and
+ * resumeSampling_<name> (writeOut/readIn, :647-835).
+ * acc layout: [nCells][nSpecies][nQuantities]; coll: [nCells][2] = (nCollsCum, collisionSeparationCum). */
+int dsmcb200_accum_info_get(dsmcb200_ctx*, dsmcb200_accum_info*);
+int dsmcb200_download_accumulators(dsmcb200_ctx*, double* acc, double* coll);
+int dsmcb200_upload_accumulators(dsmcb200_ctx*, const double* acc, const double* coll, double nTimeSteps);
+int dsmcb200_reset_accumulators(dsmcb200_ctx*);      /* dsmcVolFields resetField / resetAtOutput */
+/* Wall-patch accumulators of boundaryMeasurements
+ * (DSMC/boundaryMeasurements/boundaryMeasurements.C:364-401):
+ * layout [nBoundaryFaces][nSpecies][nWallQuantities]. */
+int dsmcb200_wall_info(dsmcb200_ctx*, int32_t* nBoundaryFaces, int32_t* nWallQuantities);
+int dsmcb200_download_wall_accumulators(dsmcb200_ctx*, double* wall);
+int dsmcb200_get_counters(dsmcb200_ctx*, dsmcb200_counters*);
+/* Per-kernel device time of the last step, for bench.py: names[i] is filled with up to
+ * DSMCB200_NAME_LEN chars; returns the count through *n (capacity in). */
+int dsmcb200_kernel_times(dsmcb200_ctx*, int capacity, int* n, char* names, float* ms, int64_t* launches);
+/* Derived geometry back to the caller (tests / writers). */
+int dsmcb200_download_geometry(dsmcb200_ctx*, double* cellCentres, double* cellVolumes,
+                               double* faceCentres, double* faceAreas, int32_t* tetBasePtIs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSMCB200_H */
