@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the dsmcCloud::evolve() hot path (move + sort + NTC collide + sample).
+
+Workload (BASELINE.json configs[4], the one its metric "at 1/2/4/8 B200" is quoted on): a
+weak-scaling periodic box, one brick of cells per GPU tiled 1x1x1 -> 2x1x1 -> 2x2x1 -> 2x2x2
+(processor / processorCyclic patches between bricks, NCCL parcel migration), ~31 parcels per
+cell, argon VHS or 5-species air Larsen-Borgnakke, equilibrium at rest.  A "step" is one full
+evolve() of every parcel of every brick.
+
+  python bench.py --gpus N --steps K --warmup W            (torchrun launches one rank per GPU for N>1)
+  python bench.py --impl reference ...                     CPU oracle arm on the host cores
+
+One JSON line is printed by rank 0 (see README / DESIGN.md for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KB = 1.38065e-23
+# algorithmic bytes per parcel-step and stage (BASELINE.md section 3 / SURVEY.md 8d), FP64 state
+STAGE_BYTES_AIR = {"move": 96.0, "sort": 168.0, "collide": 71.0, "sample": 40.0}
+STAGE_BYTES_AR = {"move": 96.0, "sort": 136.0, "collide": 63.0, "sample": 28.0}   # no ERot / vibLevel / ELevel
+SORT_KERNELS = ("scan", "scatterIndex", "segmentSort", "gather", "histogram")
+KERNELS_PER_STEP = 9  # move, scan x3, scatterIndex, segmentSort, gather, collide, sample
+
+
+def species_table(gas):
+    from hystrath_b200 import capi
+
+    if gas == "argon":
+        return [capi.make_species("Ar", 66.3e-27, 4.17e-10, 0.81)], [0], [1.0]
+    sp = [
+        capi.make_species("N2", 46.5e-27, 4.17e-10, 0.74, 1.36, 2, (3371,), (52560,), (3371,), 113500),
+        capi.make_species("O2", 53.12e-27, 4.07e-10, 0.77, 1.4, 2, (2256,), (17900,), (2256,), 59500),
+        capi.make_species("NO", 49.81e-27, 4.2e-10, 0.79, 1.0, 2, (2719,), (1400,), (2719,), 75500),
+        capi.make_species("N", 23.25e-27, 3.0e-10, 0.8, 1.0),
+        capi.make_species("O", 26.56e-27, 3.0e-10, 0.8, 1.0),
+    ]
+    return sp, [0, 1, 2, 3, 4], [0.76, 0.2, 0.02, 0.01, 0.01]
+
+
+def case_parameters(gas, cells, ppc):
+    """Equilibrium box: cell size ~ lambda/3, dt ~ tau_c/5."""
+    n = 1e20
+    T = 300.0 if gas == "argon" else 1000.0
+    dx = 4e-3
+    L = cells * dx
+    fnum = n * dx ** 3 / ppc
+    dt = 5e-6 if gas == "argon" else 2.5e-6
+    return dict(n=n, T=T, dx=dx, L=L, fnum=fnum, dt=dt)
+
+
+def procs_for(n):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n]
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for s in self.samples for k in range(4) if len(s) > 2 + k and s[2 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores.  dsmcFoam+ itself cannot be built here
+    (needs OpenFOAM v1706 + MPI, neither vendored nor installed), so this is the oracle port, OpenMP over all cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from hystrath_b200 import capi, meshgen
+    from oracle.pyoracle import Oracle
+
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cells = args.ref_cells
+    cp = case_parameters(args.gas, cells, args.ppc)
+    sp, tids, frac = species_table(args.gas)
+    mesh = meshgen.box_mesh((cells,) * 3, (cp["L"],) * 3)
+    model = "VariableHardSphere" if args.gas == "argon" else "LarsenBorgnakkeVariableHardSphere"
+    md = capi.build_models(model, nEquivalentParticles=cp["fnum"], deltaT=cp["dt"], seed=0xD5C00005)
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
+    o.mesh_fill(tids, [cp["n"] * f for f in frac], cp["T"], cp["T"], cp["T"])
+    n = o.num_parcels()
+    o.evolve(args.warmup)
+    t0 = time.perf_counter()
+    o.evolve(args.steps)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = f"{cells}^3-cell periodic {args.gas} box, {n} parcels, {args.steps} steps after {args.warmup} warm-up (same cell size, density, dt and models as the GPU arm)"
+    line = {
+        "impl": "reference", "metric": "particle-steps/s (move+sort+NTC collide+sample)", "value": value, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, cells_per_gpu=cells ** 3, parcels_per_gpu=n),
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cells_per_gpu, parcels_per_gpu):
+    return {"workload": "weak-scaling periodic box (BASELINE configs[4]), %s, %d cells and ~%d parcels per GPU" % (
+        "argon VHS" if args.gas == "argon" else "5-species air (N2,O2,NO,N,O) Larsen-Borgnakke VHS", cells_per_gpu, parcels_per_gpu),
+        "cells_per_gpu": cells_per_gpu, "parcels_per_gpu": parcels_per_gpu, "parcels_per_cell": args.ppc, "gas": args.gas,
+        "collision_model": "VariableHardSphere" if args.gas == "argon" else "LarsenBorgnakkeVariableHardSphere",
+        "partition": "x".join(str(v) for v in procs_for(args.gpus)) + " bricks",
+        "l2_policy": "inputs larger than L2 (parcel state >> 126 MB per GPU), no flush needed"}
+
+
+def cpu_baseline_leg(args):
+    """Oracle (port of the reference algorithm) on a bounded sample of the same workload, rank 0 / N=1 only."""
+    from hystrath_b200 import capi, meshgen
+    from oracle.pyoracle import Oracle
+
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cells = args.cpu_cells
+    cp = case_parameters(args.gas, cells, args.ppc)
+    sp, tids, frac = species_table(args.gas)
+    mesh = meshgen.box_mesh((cells,) * 3, (cp["L"],) * 3)
+    model = "VariableHardSphere" if args.gas == "argon" else "LarsenBorgnakkeVariableHardSphere"
+    md = capi.build_models(model, nEquivalentParticles=cp["fnum"], deltaT=cp["dt"], seed=0xD5C00005)
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
+    o.mesh_fill(tids, [cp["n"] * f for f in frac], cp["T"], cp["T"], cp["T"])
+    n = o.num_parcels()
+    o.evolve(1)
+    steps = args.cpu_steps
+    t0 = time.perf_counter()
+    o.evolve(steps)
+    dt = time.perf_counter() - t0
+    return {"value": n * steps / dt, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{cells}^3-cell periodic {args.gas} box, {n} parcels, {steps} steps (oracle, OpenMP over {cores} threads)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dsmcb200", choices=["dsmcb200", "reference"])
+    ap.add_argument("--gas", default=os.environ.get("DSMCB200_BENCH_GAS", "air5"), choices=["argon", "air5"])
+    ap.add_argument("--cells", type=int, default=int(os.environ.get("DSMCB200_BENCH_CELLS", "200")), help="cells per direction per GPU")
+    ap.add_argument("--ppc", type=int, default=31)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-cells", type=int, default=32)
+    ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--ref-cells", type=int, default=48)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "dsmcb200":
+        args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+
+    from hystrath_b200 import capi, meshgen
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    cp = case_parameters(args.gas, args.cells, args.ppc)
+    sp, tids, frac = species_table(args.gas)
+    procs = procs_for(world)
+    t_setup = time.perf_counter()
+    mesh = meshgen.decomposed_box((args.cells,) * 3, (cp["L"],) * 3, procs, rank)
+    model = "VariableHardSphere" if args.gas == "argon" else "LarsenBorgnakkeVariableHardSphere"
+    md = capi.build_models(model, nEquivalentParticles=cp["fnum"], deltaT=cp["dt"], seed=0xD5C00005 + rank)
+    eng = capi.Engine(local, rank, world)
+    eng.set_mesh(mesh); eng.set_species(sp); eng.set_models(md)
+    if world > 1:
+        ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            ident = torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(ident, 0)
+        eng.init_comm(bytes(ident.cpu().numpy().tobytes()))
+    expected = int(args.cells ** 3 * args.ppc * 1.02) + 4096
+    eng.reserve(expected)
+    eng.mesh_fill(tids, [cp["n"] * f for f in frac], cp["T"], cp["T"], cp["T"])
+    n_local = eng.num_parcels()
+    setup_s = time.perf_counter() - t_setup
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        eng.evolve(1)
+    eng.kernel_times(reset=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    eng.timer_start()
+    t0 = time.perf_counter()
+    n_processed = 0
+    for _ in range(args.steps):
+        eng.evolve(1)
+        n_processed += eng.num_parcels()
+    ms = eng.timer_stop()
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    kt = eng.kernel_times()
+    stage_ms = np.array(eng.counters().stageMs[:8])
+
+    tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    ntot = torch.tensor([float(n_processed)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ntot, op=dist.ReduceOp.SUM)
+    ms_total = float(tmax.item())
+    value = float(ntot.item()) / (ms_total * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers: upload cloud, evolve, download cloud + fields, every step
+    e2e = None
+    if not args.no_e2e:
+        host = eng.download_parcels()
+        pinned = {}
+        for name, _, _ in capi.ParcelData.FIELDS:
+            a = getattr(host, name)
+            if a is None:
+                continue
+            t = torch.from_numpy(a).pin_memory()
+            pinned[name] = t
+            setattr(host, name, t.numpy())
+        h2d = sum(getattr(host, k).nbytes for k in ("position", "U", "cell", "tetFace", "tetPt", "typeId", "origId") if getattr(host, k) is not None)
+        if args.gas != "argon":
+            h2d += host.ERot.nbytes + host.vibLevel.nbytes + host.ELevel.nbytes
+        acc_bytes = 0
+        barrier()
+        t1 = time.perf_counter()
+        n_e2e = 0
+        for _ in range(args.e2e_steps):
+            eng.upload_parcels(host)
+            eng.evolve(1)
+            host = eng.download_parcels(host) if False else _download_into(eng, host)
+            acc, coll, _ = eng.accumulators()
+            acc_bytes = acc.nbytes + coll.nbytes
+            n_e2e += host.n
+        barrier()
+        t_e2e = time.perf_counter() - t1
+        te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+        ne = torch.tensor([float(n_e2e)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ne, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(ne.item()) / float(te.item()), "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(h2d + acc_bytes), "steps": args.e2e_steps,
+               "note": "per step: upload the whole cloud from pinned host memory, evolve(), download cloud and field accumulators"}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        sb = STAGE_BYTES_AR if args.gas == "argon" else STAGE_BYTES_AIR
+        per_step = {k: v[0] / max(1, args.steps) for k, v in kt.items()}
+        stage_t = {"move": per_step.get("move", 0.0), "sort": sum(per_step.get(k, 0.0) for k in SORT_KERNELS),
+                   "collide": per_step.get("collide", 0.0), "sample": per_step.get("sample", 0.0)}
+        stages = {}
+        for k, t in stage_t.items():
+            if t > 0:
+                gbs = n_local * sb[k] / (t * 1e-3) / 1e9
+                stages[k] = {"ms": t, "bytes_per_parcel": sb[k], "achieved_gbs": gbs, "frac": gbs / peak}
+        dom = max(stage_t, key=stage_t.get)
+        roofline = {"bound": "hbm", "kernel": {"move": "moveKernel", "sort": "gatherKernel+scan+scatterIndex+segmentSort",
+                                               "collide": "collideKernel", "sample": "sampleKernel"}[dom],
+                    "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_parcel": sb[dom], "parcels_per_launch": n_local,
+                    "share_of_step": stage_t[dom] / max(1e-9, sum(stage_t.values()))}
+        line = {
+            "metric": "particle-steps/s (move+sort+NTC collide+sample)", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, args.cells ** 3, n_local),
+            "roofline": roofline, "stages": stages,
+            "kernel_ms_per_step": per_step, "wall_ms_per_step": 1e3 * wall / args.steps, "setup_s": setup_s,
+            "clocks": sampler.summary(), "gpu_launches": KERNELS_PER_STEP * args.steps,
+            "hbm_frac_of_step": sum(n_local * sb[k] for k in sb) / (ms_total / args.steps * 1e-3) / 1e9 / peak,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg(args)
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _download_into(eng, host):
+    """dsmcb200_download_parcels into the caller's (pinned) buffers."""
+    import ctypes as C
+
+    st = host.as_struct()
+    nn = C.c_int64()
+    eng._ck(eng.lib.dsmcb200_download_parcels(eng.h, len(host.position), C.byref(nn), C.byref(st)))
+    host.n = nn.value
+    return host
+
+
+if __name__ == "__main__":
+    main()

@@ -270,6 +270,8 @@ def load_library():
         "dsmcb200_get_counters": ([P, C.POINTER(Counters)], C.c_int),
         "dsmcb200_kernel_times": ([P, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
         "dsmcb200_download_geometry": ([P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+        "dsmcb200_timer_start": ([P], C.c_int),
+        "dsmcb200_timer_stop": ([P, C.POINTER(C.c_float)], C.c_int),
     }
     for name, (args, res) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
@@ -286,7 +288,7 @@ EXPORTED_SYMBOLS = [
     "dsmcb200_mesh_fill", "dsmcb200_evolve", "dsmcb200_stage", "dsmcb200_set_step", "dsmcb200_download_occupancy",
     "dsmcb200_accum_info_get", "dsmcb200_download_accumulators", "dsmcb200_upload_accumulators",
     "dsmcb200_reset_accumulators", "dsmcb200_wall_info", "dsmcb200_download_wall_accumulators", "dsmcb200_get_counters",
-    "dsmcb200_kernel_times", "dsmcb200_download_geometry",
+    "dsmcb200_kernel_times", "dsmcb200_download_geometry", "dsmcb200_timer_start", "dsmcb200_timer_stop",
 ]
 
 
@@ -495,6 +497,14 @@ class Engine:
         if reset:
             self._ck(self.lib.dsmcb200_kernel_times(self.h, 0, C.byref(n), None, None, None))
         return out
+
+    def timer_start(self):
+        self._ck(self.lib.dsmcb200_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self.lib.dsmcb200_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     def geometry(self):
         m = self._mesh

@@ -190,6 +190,7 @@ struct dsmcb200_ctx {
     std::vector<cudaEvent_t> evPool;
     size_t evUsed = 0;
     bool timeKernels = true;
+    cudaEvent_t tmr0 = nullptr, tmr1 = nullptr;
 };
 
 namespace {
@@ -1137,6 +1138,23 @@ int dsmcb200_kernel_times(dsmcb200_ctx* c, int capacity, int* n, char* names, fl
     }
     *n = k;
     if (capacity == 0) c->ktimes.clear();  // capacity 0 resets the table
+    return 0;
+}
+
+int dsmcb200_timer_start(dsmcb200_ctx* c) {
+    if (!c) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (!c->tmr0) { CK(cudaEventCreate(&c->tmr0)); CK(cudaEventCreate(&c->tmr1)); }
+    CK(cudaEventRecord(c->tmr0, c->stream));
+    return 0;
+}
+
+int dsmcb200_timer_stop(dsmcb200_ctx* c, float* ms) {
+    if (!c || !ms || !c->tmr0) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    CK(cudaEventRecord(c->tmr1, c->stream));
+    CK(cudaEventSynchronize(c->tmr1));
+    CK(cudaEventElapsedTime(ms, c->tmr0, c->tmr1));
     return 0;
 }
 
