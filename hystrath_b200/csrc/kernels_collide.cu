@@ -153,8 +153,11 @@ __device__ void redistribute(const DevParams& P, Rng& rng, const CellView& v, in
     // vibrational modes
     if (S.nVib > 0) {
         double preEVib[MAX_MODES];
-        for (int m = 0; m < S.nVib; ++m) preEVib[m] = v.vib[m][j] * P.kB * S.thetaV[m];
-        for (int m = 0; m < S.nVib; ++m) {
+#pragma unroll
+        for (int m = 0; m < MAX_MODES; ++m) preEVib[m] = m < S.nVib ? v.vib[m][j] * P.kB * S.thetaV[m] : 0.0;
+#pragma unroll
+        for (int m = 0; m < MAX_MODES; ++m) {
+            if (m >= S.nVib) break;
             const double EcP = translationalEnergy + preEVib[m];
             const int32_t iMaxP = int32_t(EcP / (P.kB * S.thetaV[m]));
             if (iMaxP > 0) {
@@ -187,7 +190,7 @@ __device__ __forceinline__ double warpSumOrdered(double v) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(COL_WARPS * 32) collideKernel(CollideArgs a) {
+__global__ void __launch_bounds__(COL_WARPS * 32) collideKernel(const __grid_constant__ CollideArgs a) {
     int32_t* const bigScratch = a.bigScratch;
     __shared__ WarpSmem smAll[COL_WARPS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -220,7 +223,8 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideKernel(CollideArgs a) {
                 sm.oct[j] = uint8_t(octantOf(a.p.px[g], a.p.py[g], a.p.pz[g], cc));
                 if (internal) {
                     sm.erot[j] = a.p.erot[g];
-                    for (int m = 0; m < P.nModes; ++m) sm.vib[m][j] = a.p.vib[m][g];
+#pragma unroll
+                    for (int m = 0; m < MAX_MODES; ++m) if (m < P.nModes) sm.vib[m][j] = a.p.vib[m][g];
                     sm.elev[j] = a.p.elevel[g];
                 } else {
                     sm.erot[j] = 0.0; sm.elev[j] = 0;
@@ -383,7 +387,8 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideKernel(CollideArgs a) {
                     a.p.ux[g] = sm.ux[j]; a.p.uy[g] = sm.uy[j]; a.p.uz[g] = sm.uz[j];
                     if (LB) {
                         a.p.erot[g] = sm.erot[j];
-                        for (int m = 0; m < P.nModes; ++m) a.p.vib[m][g] = sm.vib[m][j];
+#pragma unroll
+                        for (int m = 0; m < MAX_MODES; ++m) if (m < P.nModes) a.p.vib[m][g] = sm.vib[m][j];
                         a.p.elevel[g] = sm.elev[j];
                     }
                 }
@@ -414,7 +419,7 @@ constexpr int SMP_WARPS = 4;
 constexpr int SMP_MAXQ = 32;
 }
 
-__global__ void __launch_bounds__(SMP_WARPS * 32) sampleKernel(SampleArgs a) {
+__global__ void __launch_bounds__(SMP_WARPS * 32) sampleKernel(const __grid_constant__ SampleArgs a) {
     __shared__ double stage[SMP_WARPS][32][SMP_MAXQ + 1];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const DevParams& P = *a.P;
@@ -454,10 +459,13 @@ __global__ void __launch_bounds__(SMP_WARPS * 32) sampleKernel(SampleArgs a) {
                     row[5] = er;
                     row[6] = Sp.eElec[a.p.elevel[g]];
                     Eint = er;
-                    for (int m = 0; m < P.nModes; ++m) {
-                        const double ev = (m < Sp.nVib) ? a.p.vib[m][g] * P.kB * Sp.thetaV[m] : 0.0;
-                        row[7 + m] = ev;
-                        Eint += ev;
+#pragma unroll
+                    for (int m = 0; m < MAX_MODES; ++m) {
+                        if (m < P.nModes) {
+                            const double ev = (m < Sp.nVib) ? a.p.vib[m][g] * P.kB * Sp.thetaV[m] : 0.0;
+                            row[7 + m] = ev;
+                            Eint += ev;
+                        }
                     }
                 }
                 if (P.measureFlux) {
@@ -511,7 +519,7 @@ cudaError_t launchSample(const SampleArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 namespace { constexpr int INFO_BLOCKS = 296; constexpr int INFO_THREADS = 256; }
 
-__global__ void __launch_bounds__(INFO_THREADS) infoKernel(ParcelArrays p, int32_t n, const DevParams* Pp, double* scratch) {
+__global__ void __launch_bounds__(INFO_THREADS) infoKernel(const __grid_constant__ ParcelArrays p, int32_t n, const DevParams* Pp, double* scratch) {
     __shared__ double red[5][INFO_THREADS / 32];
     const DevParams& P = *Pp;
     double v[5] = {0, 0, 0, 0, 0};
@@ -523,7 +531,8 @@ __global__ void __launch_bounds__(INFO_THREADS) infoKernel(ParcelArrays p, int32
         v[1] += 0.5 * S.mass * (ux * ux + uy * uy + uz * uz);
         if (P.hasInternalEnergy) {
             v[2] += p.erot[i];
-            for (int m = 0; m < S.nVib; ++m) v[3] += p.vib[m][i] * P.kB * S.thetaV[m];
+#pragma unroll
+            for (int m = 0; m < MAX_MODES; ++m) if (m < S.nVib) v[3] += p.vib[m][i] * P.kB * S.thetaV[m];
             v[4] += S.eElec[p.elevel[i]];
         }
     }

@@ -45,7 +45,7 @@ __device__ __forceinline__ void storeParcel(const ParcelArrays& p, const DevPara
 }  // namespace
 
 // pass 0: cellCount[cell] = parcels to insert; pass 1: cellCount holds exclusive offsets
-__global__ void __launch_bounds__(128) fillKernel(FillArgs a, int pass) {
+__global__ void __launch_bounds__(128) fillKernel(const __grid_constant__ FillArgs a, int pass) {
     const int32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= a.nCells) return;
     const DevParams& P = *a.P;
@@ -95,7 +95,7 @@ cudaError_t launchFill(const FillArgs& a, int pass, cudaStream_t s) {
 
 // pass 0: accumulator update (Bird eq. 4.22) and the integer number to insert per (species, face)
 // pass 1: counts holds exclusive offsets; generate
-__global__ void __launch_bounds__(128) inflowKernel(InflowArgs a, int pass) {
+__global__ void __launch_bounds__(128) inflowKernel(const __grid_constant__ InflowArgs a, int pass) {
     const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.nFaces * a.nTypes) return;
     const int32_t m = t / a.nFaces, fl = t % a.nFaces;  // counts layout [species][face]

@@ -75,7 +75,7 @@ __device__ void wallMeasure(const WallCtx& w, int32_t measIndex, int32_t bfi, in
     const V3 Ut = U - U_dot_nw * nw;
     const double rwf = 1.0 / fmax(fabs(U_dot_nw) * fA * P.deltaT, SMALL);
     double EVib = 0.0;
-    for (int mo = 0; mo < S.nVib; ++mo) EVib += vib[mo] * P.kB * S.thetaV[mo];
+    EVib = (S.nVib > 0 ? vib[0] * P.kB * S.thetaV[0] : 0.0) + (S.nVib > 1 ? vib[1] * P.kB * S.thetaV[1] : 0.0) + (S.nVib > 2 ? vib[2] * P.kB * S.thetaV[2] : 0.0);
     const double EEle = S.eElec[elevel];
     const double UU = dot(U, U);
     if (measIndex >= 0) {
@@ -115,9 +115,95 @@ __device__ void wallMeasureDelta(const WallCtx& w, int32_t measIndex, int32_t bf
     atomicAdd(a + WQ_FDZ, deltaFD.z);
 }
 
+// findTris without the division: (lambda > 0 && lambda < 1) for lambda = num/den is decided from the signs and
+// magnitudes of num and den.  For IEEE doubles RN(num/den) < 1 <=> |num| < |den| and RN(num/den) > 0 <=> same
+// sign and num != 0 (quotients of the magnitudes met here cannot underflow), so the result is identical to
+// particle::findTris + tetLambda (BASIC/particle/particleI.H:31-140) while the FP64 divider is left to the
+// one or two lambdas that are actually needed.
+__device__ __forceinline__ bool planeCrossed(const V3& Ct, const V3& to, const V3& n, const V3& base, double tol) {
+    const double num = dot(base - Ct, n);
+    double den = dot(to - Ct, n);
+    if (fabs(den) < tol) {
+        if (fabs(num) < tol) return false;                 // lambda = 0
+        if (mag(to - Ct) < tol / mag(n)) return false;     // lambda = GREAT
+        den = (den >= 0 ? 1.0 : -1.0) * SMALL;
+    }
+    return den > 0 ? (num > 0 && num < den) : (num < 0 && num > den);
+}
+
+struct Internal {  // internal energy state, loaded lazily (only wall models and migration touch it)
+    double ERot;
+    int32_t vib[MAX_MODES];
+    int elevel;
+    bool loaded, dirty;
+};
+
+__device__ __forceinline__ void loadInternal(const MoveArgs& a, const DevParams& P, int32_t i, Internal& in) {
+    if (in.loaded) return;
+    in.loaded = true;
+    if (!P.hasInternalEnergy) return;
+    in.ERot = a.p.erot[i];
+    if (P.nModes > 0) in.vib[0] = a.p.vib[0][i];
+    if (P.nModes > 1) in.vib[1] = a.p.vib[1][i];
+    if (P.nModes > 2) in.vib[2] = a.p.vib[2][i];
+    in.elevel = a.p.elevel[i];
+}
+
+// dsmcParcel::hitWallPatch / hitPatch -> dsmc{Diffuse,Specular}WallPatch::controlParticle
+__device__ __forceinline__ void wallInteraction(const MoveArgs& a, const DevParams& P, int32_t i, int sp, const DevPatch& pt, int32_t measIndex,
+                                             int32_t bfi, const V3& nw, V3& U, Internal& in, Rng& wallRng, bool& wallRngInit) {
+    WallCtx wctx{a.P, a.wallAcc, a.nWallQ, a.bfaceArea};
+    loadInternal(a, P, i, in);
+    double preIE, postIE;
+    V3 preIMom, postIMom;
+    wallMeasure(wctx, measIndex, bfi, sp, U, in.ERot, in.vib, in.elevel, preIE, preIMom);
+    if (pt.model == DSMCB200_BND_SPECULAR_WALL) {
+        // dsmcSpecularWallPatch::performSpecularReflection
+        const double U_dot_nw = dot(U, nw);
+        if (U_dot_nw > 0.0) U -= 2.0 * U_dot_nw * nw;
+    } else {
+        // dsmcDiffuseWallPatch::performDiffuseReflection
+        if (!wallRngInit) {
+            wallRng.init(P.seed, uint32_t(a.p.origId[i]), 0u, a.step, STREAM_WALL);
+            wallRngInit = true;
+        }
+        const DevSpecies& S = P.sp[sp];
+        // dsmcPatchBoundary::calculateWallUnitVectors
+        double U_dot_nw = dot(U, nw);
+        V3 Ut = U - U_dot_nw * nw;
+        while (mag(Ut) < SMALL) {
+            double r0 = wallRng.sample01(), r1 = wallRng.sample01(), r2 = wallRng.sample01();
+            U = mk(U.x * (0.8 + 0.2 * r0), U.y * (0.8 + 0.2 * r1), U.z * (0.8 + 0.2 * r2));
+            U_dot_nw = dot(U, nw);
+            Ut = U - U_dot_nw * nw;
+            if (magSqr(U) == 0.0) { Ut = mk(nw.y, -nw.x, 0.0); if (mag(Ut) < SMALL) Ut = mk(0.0, nw.z, -nw.y); break; }
+        }
+        const V3 tw1 = Ut / mag(Ut);
+        const V3 tw2 = cross(nw, tw1);
+        const double Tw = pt.T;
+        const double g1 = wallRng.gaussNormal();
+        const double g2 = wallRng.gaussNormal();
+        const double r = wallRng.sample01();
+        U = sqrt(P.kB * Tw / S.mass) * (g1 * tw1 + g2 * tw2 - sqrt(-2.0 * log(fmax(1 - r, VSMALL))) * nw);
+        in.ERot = equipartitionRotationalEnergy(wallRng, P.kB, Tw, S.rotDof);
+        if (S.nVib > 0) in.vib[0] = equipartitionVibrationalEnergyLevel(wallRng, Tw, S.thetaV[0]);
+        if (S.nVib > 1) in.vib[1] = equipartitionVibrationalEnergyLevel(wallRng, Tw, S.thetaV[1]);
+        if (S.nVib > 2) in.vib[2] = equipartitionVibrationalEnergyLevel(wallRng, Tw, S.thetaV[2]);
+        in.elevel = equipartitionElectronicLevel(wallRng, P.kB, Tw, S);
+        U += mk(pt.vel[0], pt.vel[1], pt.vel[2]);
+        in.dirty = true;
+    }
+    wallMeasure(wctx, measIndex, bfi, sp, U, in.ERot, in.vib, in.elevel, postIE, postIMom);
+    wallMeasureDelta(wctx, measIndex, bfi, sp, preIE, preIMom, postIE, postIMom);
+}
+
 }  // namespace
 
-__global__ void __launch_bounds__(256) moveKernel(MoveArgs a) {
+// One loop iteration = one tetrahedron: every active lane loads a TetRec and either crosses one of its triangles or
+// stops inside it.  The nesting of the reference (dsmcParcel::move loop around the trackToFace do-while) is flattened
+// into this single loop so that the lanes of a warp stay converged while they make different numbers of hops and
+// face crossings; the sequence of floating-point operations per parcel is unchanged.
+__global__ void __launch_bounds__(256, 2) moveKernel(const __grid_constant__ MoveArgs a) {
     const int32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= a.count) return;
     const int32_t i = a.first + li;
@@ -130,225 +216,167 @@ __global__ void __launch_bounds__(256) moveKernel(MoveArgs a) {
     V3 U = mk(a.p.ux[i], a.p.uy[i], a.p.uz[i]);
     double stepFraction = (a.sfTail != nullptr && i >= a.tailStart) ? a.sfTail[i - a.tailStart] : 0.0;
     const double deltaT = P.deltaT;
-
-    // internal state is only touched by wall models
     const int sp = a.p.typeId[i];
-    bool internalDirty = false, Udirty = false;
-    double ERot = 0.0;
-    int32_t vib[MAX_MODES] = {0, 0, 0};
-    int elevel = 0;
-    bool internalLoaded = false;
+
+    Internal in;
+    in.ERot = 0.0; in.vib[0] = in.vib[1] = in.vib[2] = 0; in.elevel = 0; in.loaded = false; in.dirty = false;
+    bool Udirty = false;
     Rng wallRng;
     bool wallRngInit = false;
-    WallCtx wctx{a.P, a.wallAcc, a.nWallQ, a.bfaceArea};
 
     bool keepParticle = true, switchProcessor = false;
     int32_t procBfi = -1;
     unsigned rescues = 0;
-
     double tEnd = (1.0 - stepFraction) * deltaT;
-    Tet T;
+
+    // state of the trackToFace call in flight
+    bool inCall = false, rescuePending = false, faceSet = false;
+    int32_t faceBfi = -1;
+    V3 endPosition = pos;
+    double dt = 0.0, trackFraction = 0.0;
+    const bool constrained = P.solutionD[0] == -1 || P.solutionD[1] == -1 || P.solutionD[2] == -1;
+
+    bool active = tEnd > ROOTVSMALL;
     int guard = 0;
-
-    while (keepParticle && !switchProcessor && tEnd > ROOTVSMALL) {
-        if (++guard > 100000) break;  // cannot happen on a valid mesh; keeps a corrupt one from hanging the GPU
-        V3 Utracking = U;
-        // meshTools::constrainToMeshCentre / constrainDirection (DSMC/parcels/dsmcParcel.C:76-85)
+    while (active) {
+        if (++guard > 200000) { keepParticle = false; break; }  // corrupt tet table: drop the parcel rather than hang
+        if (!inCall) {
+            // dsmcParcel::move loop body up to the trackToFace call (DSMC/parcels/dsmcParcel.C:74-92)
+            V3 Utracking = U;
+            if (constrained) {
 #pragma unroll
-        for (int d = 0; d < 3; ++d)
-            if (P.solutionD[d] == -1) { setComp(pos, d, P.centre[d]); setComp(Utracking, d, 0.0); }
-
-        double dt = tEnd;
-        const V3 endPosition = pos + dt * Utracking;
-
-        // ---------------- particle::trackToFace ----------------
-        double trackFraction = 0.0;
-        int triI = -1;
-        double lambdaMin = VGREAT;
-        bool faceSet = false;       // faceI_ >= 0
-        int32_t faceBfi = -1;       // boundary-face index of faceI_ when it is a boundary face
-        bool returned = false;
-        double retVal = 0.0;
-        Tet cur;                    // tet on which the face was hit
-        do {
-            if (++guard > 100000) {  // lost in a corrupt tet table: drop the parcel rather than hang
-                keepParticle = false; returned = true; retVal = 1.0;
-                break;
+                for (int d = 0; d < 3; ++d)
+                    if (P.solutionD[d] == -1) { setComp(pos, d, P.centre[d]); setComp(Utracking, d, 0.0); }
             }
-            if (triI != -1) tet = T.nbr(triI);  // particle::tetNeighbour (triI in 1..3 here)
-            loadTet(a.tets, tet, T);
-            if (lambdaMin < SMALL) {
-                // tracking correction towards the tet centre
-                pos += kTrackingCorrectionTol * (T.ct() - pos);
-                ++rescues;
-                returned = true; retVal = trackFraction;
-                break;
-            }
+            dt = tEnd;
+            endPosition = pos + dt * Utracking;
+            trackFraction = 0.0;
+            inCall = true; rescuePending = false; faceSet = false; faceBfi = -1;
+        }
+        Tet T;
+        loadTet(a.tets, tet, T);
+        double retVal;
+        bool finished = false;
+        if (rescuePending) {
+            // lambdaMin < SMALL: tracking correction towards the centre of the tet now occupied
+            pos += kTrackingCorrectionTol * (T.ct() - pos);
+            ++rescues;
+            retVal = trackFraction;
+            finished = true;
+        } else {
             const double tol = T.tol();
-            // findTris: which planes does the ray tetCentre -> end cross
             const V3 Ct = T.ct();
-            unsigned tris = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const V3 base = (k == 1) ? T.pA() : T.base();
-                const double lambda = tetLambda(Ct, endPosition, T.n(k), base, tol);
-                if (lambda > 0.0 && lambda < 1.0) tris |= 1u << k;
-            }
-            triI = -1;
-            lambdaMin = VGREAT;
-            if (tris == 0) {  // (faceI_ < 0 always holds here: hitWallFaces is inactive for DSMC)
+            const V3 base = T.base(), pA = T.pA();
+            const bool c0 = planeCrossed(Ct, endPosition, T.n(0), base, tol);
+            const bool c1 = planeCrossed(Ct, endPosition, T.n(1), pA, tol);
+            const bool c2 = planeCrossed(Ct, endPosition, T.n(2), base, tol);
+            const bool c3 = planeCrossed(Ct, endPosition, T.n(3), base, tol);
+            if (!(c0 | c1 | c2 | c3)) {
                 pos = endPosition;
                 faceSet = false; faceBfi = -1;
-                returned = true; retVal = 1.0;
-                break;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (tris & (1u << k)) {
-                    const V3 base = (k == 1) ? T.pA() : T.base();
-                    const double lam = tetLambda(pos, endPosition, T.n(k), base, tol);
-                    if (lam < lambdaMin) { lambdaMin = lam; triI = k; }
-                }
-            }
-            if (triI == 0) {
-                faceSet = true;
-                faceBfi = T.nbr(0) < 0 ? (-1 - T.nbr(0)) : -1;
-            } else if (triI > 0) {
-                faceSet = false; faceBfi = -1;
-            }
-            if (lambdaMin > SMALL) {
-                if (lambdaMin <= 1.0) {
-                    trackFraction += lambdaMin * (1 - trackFraction);
-                    pos += lambdaMin * (endPosition - pos);
+                retVal = 1.0;
+                finished = true;
+            } else {
+                int triI = -1;
+                double lambdaMin = VGREAT;
+                if (c0) { const double lam = tetLambda(pos, endPosition, T.n(0), base, tol); if (lam < lambdaMin) { lambdaMin = lam; triI = 0; } }
+                if (c1) { const double lam = tetLambda(pos, endPosition, T.n(1), pA, tol); if (lam < lambdaMin) { lambdaMin = lam; triI = 1; } }
+                if (c2) { const double lam = tetLambda(pos, endPosition, T.n(2), base, tol); if (lam < lambdaMin) { lambdaMin = lam; triI = 2; } }
+                if (c3) { const double lam = tetLambda(pos, endPosition, T.n(3), base, tol); if (lam < lambdaMin) { lambdaMin = lam; triI = 3; } }
+                const int32_t nb0 = T.nbr(0);
+                if (triI == 0) { faceSet = true; faceBfi = nb0 < 0 ? (-1 - nb0) : -1; }
+                else if (triI > 0) { faceSet = false; faceBfi = -1; }
+                bool needRescue = false;
+                if (lambdaMin > SMALL) {
+                    if (lambdaMin <= 1.0) {
+                        trackFraction += lambdaMin * (1 - trackFraction);
+                        pos += lambdaMin * (endPosition - pos);
+                    } else {
+                        pos = endPosition;
+                        retVal = 1.0;
+                        finished = true;
+                    }
                 } else {
-                    pos = endPosition;
-                    returned = true; retVal = 1.0;
-                    break;
+                    needRescue = true;  // lambdaMin = 0.0
                 }
-            } else {
-                lambdaMin = 0.0;
-            }
-        } while (!faceSet);
-
-        if (!returned) {
-            // a cell face has been hit on tri 0 of tet T
-            const int32_t nb0 = T.nbr(0);
-            if (nb0 >= 0) {
-                cell = nb0;   // internal face: the same face-triangle seen from the other cell
-                tet ^= 1;
-            } else {
-                const int32_t bfi = -1 - nb0;
-                const BFaceRec bf = a.bfaces[bfi];
-                const DevPatch& pt = P.patch[bf.patch];
-                switch (pt.type) {
-                    case DSMCB200_PATCH_PROCESSOR:
-                    case DSMCB200_PATCH_PROCESSORCYCLIC:
-                        switchProcessor = true;  // dsmcParcel::hitProcessorPatch
-                        break;
-                    case DSMCB200_PATCH_SYMMETRYPLANE:
-                    case DSMCB200_PATCH_SYMMETRY:
-                    case DSMCB200_PATCH_WEDGE: {
-                        // transformProperties(I - 2.0*nf*nf), particleTemplates.C:1474-1522
-                        const V3 nf = T.n(0);
-                        const V3 t2 = 2.0 * nf;
-                        const double xx = 1.0 - t2.x * nf.x, xy = 0.0 - t2.x * nf.y, xz = 0.0 - t2.x * nf.z;
-                        const double yx = 0.0 - t2.y * nf.x, yy = 1.0 - t2.y * nf.y, yz = 0.0 - t2.y * nf.z;
-                        const double zx = 0.0 - t2.z * nf.x, zy = 0.0 - t2.z * nf.y, zz = 1.0 - t2.z * nf.z;
-                        U = mk(xx * U.x + xy * U.y + xz * U.z, yx * U.x + yy * U.y + yz * U.z, zx * U.x + zy * U.y + zz * U.z);
-                        Udirty = true;
-                        break;
-                    }
-                    case DSMCB200_PATCH_CYCLIC: {
-                        // particle::hitCyclicPatch, particleTemplates.C:1525-1570
-                        const int32_t k = (tet >> 1) - bf.tetPair0;
-                        tet = 2 * (bf.coupledTetPair0 + (bf.nPts - 3) - k);
-                        cell = bf.coupledCell;
-                        const DevPatch& rp = P.patch[pt.nbrPatch];
-                        pos -= mk(rp.sep[0], rp.sep[1], rp.sep[2]);
-                        faceBfi = bfi - (pt.start - P.nInternalFaces) + (rp.start - P.nInternalFaces);
-                        break;
-                    }
-                    case DSMCB200_PATCH_WALL:
-                    case DSMCB200_PATCH_PATCH: {
-                        // dsmcParcel::hitWallPatch / hitPatch -> patch model controlParticle
-                        if (pt.model == DSMCB200_BND_DELETION) {
-                            keepParticle = false;  // dsmcDeletionPatch::controlParticle
-                        } else if (pt.model == DSMCB200_BND_SPECULAR_WALL || pt.model == DSMCB200_BND_DIFFUSE_WALL) {
-                            if (!internalLoaded) {
-                                if (P.hasInternalEnergy) {
-                                    ERot = a.p.erot[i];
-                                    for (int mo = 0; mo < P.nModes; ++mo) vib[mo] = a.p.vib[mo][i];
-                                    elevel = a.p.elevel[i];
+                if (!finished) {
+                    if (triI > 0) {
+                        // particle::tetNeighbour: enter the adjacent tet of the same cell
+                        tet = triI == 1 ? T.nbr(1) : (triI == 2 ? T.nbr(2) : T.nbr(3));
+                        rescuePending = needRescue;
+                    } else if (triI == 0) {
+                        if (nb0 >= 0) {
+                            cell = nb0;  // internal face: the same face triangle seen from the other cell
+                            tet ^= 1;
+                        } else {
+                            const int32_t bfi = -1 - nb0;
+                            const BFaceRec bf = a.bfaces[bfi];
+                            const DevPatch& pt = P.patch[bf.patch];
+                            switch (pt.type) {
+                                case DSMCB200_PATCH_PROCESSOR:
+                                case DSMCB200_PATCH_PROCESSORCYCLIC:
+                                    switchProcessor = true;  // dsmcParcel::hitProcessorPatch
+                                    break;
+                                case DSMCB200_PATCH_SYMMETRYPLANE:
+                                case DSMCB200_PATCH_SYMMETRY:
+                                case DSMCB200_PATCH_WEDGE: {
+                                    // transformProperties(I - 2.0*nf*nf), particleTemplates.C:1474-1522
+                                    const V3 nf = T.n(0);
+                                    const V3 t2 = 2.0 * nf;
+                                    const double xx = 1.0 - t2.x * nf.x, xy = 0.0 - t2.x * nf.y, xz = 0.0 - t2.x * nf.z;
+                                    const double yx = 0.0 - t2.y * nf.x, yy = 1.0 - t2.y * nf.y, yz = 0.0 - t2.y * nf.z;
+                                    const double zx = 0.0 - t2.z * nf.x, zy = 0.0 - t2.z * nf.y, zz = 1.0 - t2.z * nf.z;
+                                    U = mk(xx * U.x + xy * U.y + xz * U.z, yx * U.x + yy * U.y + yz * U.z, zx * U.x + zy * U.y + zz * U.z);
+                                    Udirty = true;
+                                    break;
                                 }
-                                internalLoaded = true;
+                                case DSMCB200_PATCH_CYCLIC: {
+                                    // particle::hitCyclicPatch, particleTemplates.C:1525-1570
+                                    const int32_t k = (tet >> 1) - bf.tetPair0;
+                                    tet = 2 * (bf.coupledTetPair0 + (bf.nPts - 3) - k);
+                                    cell = bf.coupledCell;
+                                    const DevPatch& rp = P.patch[pt.nbrPatch];
+                                    pos -= mk(rp.sep[0], rp.sep[1], rp.sep[2]);
+                                    faceBfi = bfi - (pt.start - P.nInternalFaces) + (rp.start - P.nInternalFaces);
+                                    break;
+                                }
+                                case DSMCB200_PATCH_WALL:
+                                case DSMCB200_PATCH_PATCH:
+                                    if (pt.model == DSMCB200_BND_DELETION) {
+                                        keepParticle = false;  // dsmcDeletionPatch::controlParticle
+                                    } else if (pt.model != DSMCB200_BND_NONE) {
+                                        wallInteraction(a, P, i, sp, pt, bf.measIndex, bfi, T.n(0), U, in, wallRng, wallRngInit);
+                                        Udirty = true;
+                                    }
+                                    break;
+                                default:  // empty patches cannot be hit by constrained tracks
+                                    break;
                             }
-                            double preIE, postIE;
-                            V3 preIMom, postIMom;
-                            wallMeasure(wctx, bf.measIndex, bfi, sp, U, ERot, vib, elevel, preIE, preIMom);
-                            const V3 nw = T.n(0);
-                            if (pt.model == DSMCB200_BND_SPECULAR_WALL) {
-                                // dsmcSpecularWallPatch::performSpecularReflection
-                                const double U_dot_nw = dot(U, nw);
-                                if (U_dot_nw > 0.0) U -= 2.0 * U_dot_nw * nw;
-                            } else {
-                                // dsmcDiffuseWallPatch::performDiffuseReflection
-                                if (!wallRngInit) {
-                                    wallRng.init(P.seed, uint32_t(a.p.origId[i]), 0u, a.step, STREAM_WALL);
-                                    wallRngInit = true;
-                                }
-                                const DevSpecies& S = P.sp[sp];
-                                // dsmcPatchBoundary::calculateWallUnitVectors
-                                double U_dot_nw = dot(U, nw);
-                                V3 Ut = U - U_dot_nw * nw;
-                                while (mag(Ut) < SMALL) {
-                                    double r0 = wallRng.sample01(), r1 = wallRng.sample01(), r2 = wallRng.sample01();
-                                    U = mk(U.x * (0.8 + 0.2 * r0), U.y * (0.8 + 0.2 * r1), U.z * (0.8 + 0.2 * r2));
-                                    U_dot_nw = dot(U, nw);
-                                    Ut = U - U_dot_nw * nw;
-                                    if (magSqr(U) == 0.0) { Ut = mk(nw.y, -nw.x, 0.0); if (mag(Ut) < SMALL) Ut = mk(0.0, nw.z, -nw.y); break; }
-                                }
-                                const V3 tw1 = Ut / mag(Ut);
-                                const V3 tw2 = cross(nw, tw1);
-                                const double Tw = pt.T;
-                                const double g1 = wallRng.gaussNormal();
-                                const double g2 = wallRng.gaussNormal();
-                                const double r = wallRng.sample01();
-                                U = sqrt(P.kB * Tw / S.mass) * (g1 * tw1 + g2 * tw2 - sqrt(-2.0 * log(fmax(1 - r, VSMALL))) * nw);
-                                ERot = equipartitionRotationalEnergy(wallRng, P.kB, Tw, S.rotDof);
-                                for (int mo = 0; mo < S.nVib; ++mo) vib[mo] = equipartitionVibrationalEnergyLevel(wallRng, Tw, S.thetaV[mo]);
-                                elevel = equipartitionElectronicLevel(wallRng, P.kB, Tw, S);
-                                U += mk(pt.vel[0], pt.vel[1], pt.vel[2]);
-                                internalDirty = true;
-                            }
-                            Udirty = true;
-                            wallMeasure(wctx, bf.measIndex, bfi, sp, U, ERot, vib, elevel, postIE, postIMom);
-                            wallMeasureDelta(wctx, bf.measIndex, bfi, sp, preIE, preIMom, postIE, postIMom);
                         }
-                        break;
+                        if (needRescue) {
+                            rescuePending = true;  // correction towards the new tet's centre, then return trackFraction
+                        } else {
+                            retVal = trackFraction;
+                            finished = true;
+                        }
                     }
-                    default:  // empty patches cannot be hit by constrained tracks
-                        break;
                 }
             }
-            if (lambdaMin < SMALL) {
-                // tracking correction towards the centre of the tet now occupied
-                Tet C;
-                loadTet(a.tets, tet, C);
-                pos += kTrackingCorrectionTol * (C.ct() - pos);
-                ++rescues;
-            }
-            retVal = trackFraction;
         }
-        // ---------------- back in dsmcParcel::move ----------------
-        dt *= retVal;
-        tEnd -= dt;
-        stepFraction = 1.0 - tEnd / deltaT;
-        if (faceSet && faceBfi >= 0 && keepParticle) {
-            const int ptype = P.patch[a.bfaces[faceBfi].patch].type;
-            if (ptype == DSMCB200_PATCH_PROCESSOR || ptype == DSMCB200_PATCH_PROCESSORCYCLIC) {
-                switchProcessor = true;
-                procBfi = faceBfi;
+        if (finished) {
+            // back in dsmcParcel::move (DSMC/parcels/dsmcParcel.C:92-118)
+            dt *= retVal;
+            tEnd -= dt;
+            stepFraction = 1.0 - tEnd / deltaT;
+            if (faceSet && faceBfi >= 0 && keepParticle) {
+                const int ptype = P.patch[a.bfaces[faceBfi].patch].type;
+                if (ptype == DSMCB200_PATCH_PROCESSOR || ptype == DSMCB200_PATCH_PROCESSORCYCLIC) {
+                    switchProcessor = true;
+                    procBfi = faceBfi;
+                }
             }
+            inCall = false;
+            active = keepParticle && !switchProcessor && tEnd > ROOTVSMALL;
         }
     }
 
@@ -366,21 +394,17 @@ __global__ void __launch_bounds__(256) moveKernel(MoveArgs a) {
         const int slot = pt.nbrSlot;
         const int32_t k = atomicAdd(&a.counters->nMig[slot], 1);
         if (k < a.migCapacity) {
+            loadInternal(a, P, i, in);
             MigRec r;
             r.pos[0] = pos.x; r.pos[1] = pos.y; r.pos[2] = pos.z;
             r.U[0] = U.x; r.U[1] = U.y; r.U[2] = U.z;
-            if (!internalLoaded && P.hasInternalEnergy) {
-                ERot = a.p.erot[i];
-                for (int mo = 0; mo < P.nModes; ++mo) vib[mo] = a.p.vib[mo][i];
-                elevel = a.p.elevel[i];
-            }
-            r.erot = ERot; r.stepFraction = stepFraction;
+            r.erot = in.ERot; r.stepFraction = stepFraction;
             r.patchOrdinal = pt.nbrOrdinal;
             r.patchFace = procBfi - (pt.start - P.nInternalFaces);
             r.tetLocal = (tet >> 1) - bf.tetPair0;
             r.origId = a.p.origId[i];
-            for (int mo = 0; mo < MAX_MODES; ++mo) r.vib[mo] = vib[mo];
-            r.typeId = uint8_t(sp); r.elevel = uint8_t(elevel); r.cls = a.p.cls ? a.p.cls[i] : 0; r.pad_ = 0;
+            r.vib[0] = in.vib[0]; r.vib[1] = in.vib[1]; r.vib[2] = in.vib[2];
+            r.typeId = uint8_t(sp); r.elevel = uint8_t(in.elevel); r.cls = a.p.cls ? a.p.cls[i] : 0; r.pad_ = 0;
             a.migBuf[size_t(slot) * a.migCapacity + k] = r;
         } else {
             atomicAdd(&a.counters->overflow, 1ULL);
@@ -394,13 +418,16 @@ __global__ void __launch_bounds__(256) moveKernel(MoveArgs a) {
     a.p.cell[i] = cell;
     a.p.tet[i] = tet;
     if (Udirty) { a.p.ux[i] = U.x; a.p.uy[i] = U.y; a.p.uz[i] = U.z; }
-    if (internalDirty && P.hasInternalEnergy) {
-        a.p.erot[i] = ERot;
-        for (int mo = 0; mo < P.nModes; ++mo) a.p.vib[mo][i] = vib[mo];
-        a.p.elevel[i] = uint8_t(elevel);
+    if (in.dirty && P.hasInternalEnergy) {
+        a.p.erot[i] = in.ERot;
+        if (P.nModes > 0) a.p.vib[0][i] = in.vib[0];
+        if (P.nModes > 1) a.p.vib[1][i] = in.vib[1];
+        if (P.nModes > 2) a.p.vib[2][i] = in.vib[2];
+        a.p.elevel[i] = uint8_t(in.elevel);
     }
     if (a.cellCount) atomicAdd(&a.cellCount[cell], 1);
 }
+
 
 cudaError_t launchMove(const MoveArgs& a, cudaStream_t s) {
     if (a.count <= 0) return cudaSuccess;
@@ -412,7 +439,7 @@ cudaError_t launchMove(const MoveArgs& a, cudaStream_t s) {
 
 // ---- arrivals over a processor patch: particle::correctAfterParallelTransfer,
 // BASIC/particle/particleTemplates.C:52-123
-__global__ void unpackKernel(UnpackArgs a) {
+__global__ void unpackKernel(const __grid_constant__ UnpackArgs a) {
     const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.nRecv) return;
     const MigRec r = a.recv[k];

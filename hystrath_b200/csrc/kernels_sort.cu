@@ -193,7 +193,7 @@ __global__ void fillCellKernel(const int32_t* __restrict__ cellOffset, int32_t n
     }
 }
 
-__global__ void __launch_bounds__(256) gatherKernel(ParcelArrays src, ParcelArrays dst, const int32_t* __restrict__ perm, int32_t nOut,
+__global__ void __launch_bounds__(256) gatherKernel(const __grid_constant__ ParcelArrays src, const __grid_constant__ ParcelArrays dst, const int32_t* __restrict__ perm, int32_t nOut,
                                                     int32_t nModes, int hasInternal) {
     const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nOut) return;
@@ -206,7 +206,9 @@ __global__ void __launch_bounds__(256) gatherKernel(ParcelArrays src, ParcelArra
     dst.typeId[k] = src.typeId[i];
     if (hasInternal) {
         dst.erot[k] = src.erot[i];
-        for (int m = 0; m < nModes; ++m) dst.vib[m][k] = src.vib[m][i];
+        if (nModes > 0) dst.vib[0][k] = src.vib[0][i];
+        if (nModes > 1) dst.vib[1][k] = src.vib[1][i];
+        if (nModes > 2) dst.vib[2][k] = src.vib[2][i];
         dst.elevel[k] = src.elevel[i];
     }
     if (src.cls) dst.cls[k] = src.cls[i];
