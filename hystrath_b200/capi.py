@@ -227,7 +227,8 @@ _LIB = None
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdsmcb200.so")
+    # DSMCB200_LIB selects an alternative build of the same library (kernel tuning experiments)
+    return os.environ.get("DSMCB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdsmcb200.so")
 
 
 def load_library():

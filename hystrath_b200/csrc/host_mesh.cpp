@@ -366,7 +366,7 @@ void HostMesh::bakeTets(int64_t first, int64_t count, TetRec* out) const {
         int32_t tetPt = pair - faceTetPair0[face] + 1;
         if (side == 1 && face >= nInternalFaces) {  // unused slot: boundary faces have no neighbour side
             std::memset(&r, 0, sizeof(TetRec));
-            r.nbr[0] = r.nbr[1] = r.nbr[2] = r.nbr[3] = int32_t(t);
+            r.nbr01[0] = r.nbr01[1] = r.nbr23[0] = r.nbr23[1] = int32_t(t);
             continue;
         }
         int32_t cell = side == 0 ? owner[face] : neighbour[face];
@@ -377,22 +377,26 @@ void HostMesh::bakeTets(int64_t first, int64_t count, TetRec* out) const {
         S[1] = triNormal(a, d, c);  // Sb
         S[2] = triNormal(a, b, d);  // Sc
         S[3] = triNormal(a, c, b);  // Sd
+        const V3 ct = 0.25 * (a + b + c + d);
         for (int i = 0; i < 4; ++i) {
             S[i] /= (mag(S[i]) + VSMALL);  // BASIC/particle/particleTemplates.C:901-904
-            r.n[i][0] = S[i].x; r.n[i][1] = S[i].y; r.n[i][2] = S[i].z;
+            r.plane[i][0] = S[i].x; r.plane[i][1] = S[i].y; r.plane[i][2] = S[i].z;
+            const V3& planeBase = (i == 1) ? c : b;  // tetPlaneBasePtIs, particleTemplates.C:907-912
+            r.plane[i][3] = dot(planeBase - ct, S[i]);  // lambdaNumerator of findTris (from = tet centre)
         }
         r.base[0] = b.x; r.base[1] = b.y; r.base[2] = b.z;
         r.pA[0] = c.x; r.pA[1] = c.y; r.pA[2] = c.z;
-        V3 ct = 0.25 * (a + b + c + d);
         r.ct[0] = ct.x; r.ct[1] = ct.y; r.ct[2] = ct.z;
         r.tol = kLambdaDistanceToleranceCoeff * cellVolumes[cell];
-        if (face < nInternalFaces) r.nbr[0] = side == 0 ? neighbour[face] : owner[face];
-        else r.nbr[0] = -1 - (face - nInternalFaces);
+        if (face < nInternalFaces) r.nbr01[0] = side == 0 ? neighbour[face] : owner[face];
+        else r.nbr01[0] = -1 - (face - nInternalFaces);
+        int32_t nb[4] = {0, 0, 0, 0};
         for (int tri = 1; tri <= 3; ++tri) {
             int32_t nf, np;
             tetNeighbour(cell, face, tetPt, tri, nf, np);
-            r.nbr[tri] = tetId(cell, nf, np);
+            nb[tri] = tetId(cell, nf, np);
         }
+        r.nbr01[1] = nb[1]; r.nbr23[0] = nb[2]; r.nbr23[1] = nb[3];
     }
 }
 

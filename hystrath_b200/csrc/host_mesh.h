@@ -17,17 +17,19 @@
 namespace dsmc {
 
 // One tetrahedron (Cc, basePt, pA, pB) of the cell decomposition, with everything the
-// tracker needs to cross it: 192 bytes, 16-byte aligned, one record per (face-tri, side).
-struct alignas(16) TetRec {
-    double n[4][3];   // unit normals of tris 0..3: Sa,Sb,Sc,Sd / (|S| + VSMALL)
-    double base[3];   // basePt  (plane base point of tris 0,2,3)
-    double pA[3];     // pA      (plane base point of tri 1)
-    double ct[3];     // tet centre
-    double tol;       // lambdaDistanceToleranceCoeff * cellVolume
-    int32_t nbr[4];   // [0]: >=0 neighbour cell over an internal face, <0: -1-boundaryFace
-                      // [1..3]: tet id entered through tri i (same cell)
+// tracker needs to cross it: 224 bytes (seven 32-byte sectors), one record per (face-tri, side).
+// Each plane k = 0..3 is one aligned sector {unit normal, (base_k - Ct) . n_k}: the numerator of
+// findTris' lambda from the tet centre is a constant of the tet and is baked with it.
+struct alignas(32) TetRec {
+    double plane[4][4];  // [k] = {Sk/(|Sk| + VSMALL) xyz, (planeBase_k - ct) & n_k}, S = Sa,Sb,Sc,Sd
+    double base[3];      // basePt  (plane base point of tris 0,2,3)
+    double tol;          // lambdaDistanceToleranceCoeff * cellVolume
+    double pA[3];        // pA      (plane base point of tri 1)
+    int32_t nbr01[2];    // [0]: >=0 neighbour cell over an internal face, <0: -1-boundaryFace; [1]: tet entered through tri 1
+    double ct[3];        // tet centre
+    int32_t nbr23[2];    // tets entered through tris 2 and 3 (same cell)
 };
-static_assert(sizeof(TetRec) == 192, "TetRec must be 192 bytes");
+static_assert(sizeof(TetRec) == 224, "TetRec must be 224 bytes");
 
 // Per boundary face (index = face - nInternalFaces).
 struct alignas(16) BFaceRec {

@@ -726,18 +726,27 @@ cudaError_t launchCollide(const CollideArgs& a, cudaStream_t s) {
 // Stage 5
 // ------------------------------------------------------------------------------------------------
 namespace {
-constexpr int SMP_WARPS = 4;
-constexpr int SMP_MAXQ = 32;
+constexpr int SMP_WARPS = 8;
 }
 
+// One warp per cell.  Each lane turns one parcel into its row of moment contributions in shared memory
+// (stride nQ|1 doubles, conflict free); then lane (sub, q) adds up the rows j = sub (mod G) of quantity q,
+// G = 32 / Qpad sub-groups working in parallel, and a shuffle tree folds the sub-groups.  Every lane of
+// quantity q finally owns sum[s] for all species and lane (0, q) adds it to the cell's accumulator row.
 __global__ void __launch_bounds__(SMP_WARPS * 32) sampleKernel(const __grid_constant__ SampleArgs a) {
-    __shared__ double stage[SMP_WARPS][32][SMP_MAXQ + 1];
+    extern __shared__ double stageAll[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const DevParams& P = *a.P;
     const int nQ = a.nQ, S = P.nSpecies;
+    const int stride = nQ | 1;
+    double* stage = stageAll + size_t(w) * 32 * stride;
+    uint8_t* stageSp = reinterpret_cast<uint8_t*>(stageAll + size_t(SMP_WARPS) * 32 * stride) + w * 32;
     const bool internal = P.hasInternalEnergy != 0;
     const int qFlux = 5 + (internal ? 2 + P.nModes : 0);
     const int qClass = qFlux + (P.measureFlux ? 12 : 0);
+    const int Qpad = nQ <= 8 ? 8 : (nQ <= 16 ? 16 : 32);
+    const int G = 32 / Qpad;
+    const int q = lane % Qpad, sub = lane / Qpad;
     const int32_t nWarps = gridDim.x * SMP_WARPS;
 
     for (int32_t c = blockIdx.x * SMP_WARPS + w; c < a.nCells; c += nWarps) {
@@ -755,14 +764,14 @@ __global__ void __launch_bounds__(SMP_WARPS * 32) sampleKernel(const __grid_cons
 
         for (int32_t j0 = 0; j0 < nC; j0 += 32) {
             const int32_t g = b + j0 + lane;
-            const bool valid = j0 + lane < nC;
-            int mySp = -1;
-            if (valid) {
-                mySp = a.p.typeId[g];
+            const int nHere = nC - j0 < 32 ? nC - j0 : 32;
+            if (lane < nHere) {
+                const int mySp = a.p.typeId[g];
                 const double ux = a.p.ux[g], uy = a.p.uy[g], uz = a.p.uz[g];
-                double* row = stage[w][lane];
+                double* row = stage + lane * stride;
                 const double cc = ux * ux + uy * uy + uz * uz;
                 row[0] = 1.0; row[1] = ux; row[2] = uy; row[3] = uz; row[4] = cc;
+                stageSp[lane] = uint8_t(mySp);
                 double Eint = 0.0;
                 if (internal) {
                     const DevSpecies& Sp = P.sp[mySp];
@@ -791,26 +800,31 @@ __global__ void __launch_bounds__(SMP_WARPS * 32) sampleKernel(const __grid_cons
                 }
             }
             __syncwarp();
+            if (q < nQ) {
+                for (int j = sub; j < nHere; j += G) {
+                    const double v = stage[j * stride + q];
+                    const int sp = stageSp[j];
 #pragma unroll
-            for (int s = 0; s < MAX_SPECIES; ++s) {
-                if (s < S) {
-                    unsigned m = __ballot_sync(0xffffffffu, mySp == s);
-                    if (lane < nQ) {
-                        while (m) {
-                            const int j = __ffs(m) - 1;
-                            m &= m - 1;
-                            sum[s] += stage[w][j][lane];
-                        }
-                    }
+                    for (int s = 0; s < MAX_SPECIES; ++s)
+                        if (s < S) sum[s] += (sp == s) ? v : 0.0;
                 }
             }
             __syncwarp();
         }
-        if (lane < nQ) {
+        // fold the G sub-groups (lanes q, q+Qpad, ...) and add the row
+#pragma unroll
+        for (int s = 0; s < MAX_SPECIES; ++s) {
+            if (s < S) {
+                double v = sum[s];
+                for (int o = 16; o >= Qpad; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                sum[s] = v;
+            }
+        }
+        if (sub == 0 && q < nQ) {
             double* row = a.acc + size_t(c) * S * nQ;
 #pragma unroll
             for (int s = 0; s < MAX_SPECIES; ++s)
-                if (s < S && sum[s] != 0.0) row[s * nQ + lane] += sum[s];
+                if (s < S && sum[s] != 0.0) row[s * nQ + q] += sum[s];
         }
     }
 }
@@ -820,7 +834,8 @@ cudaError_t launchSample(const SampleArgs& a, cudaStream_t s) {
     const int maxGrid = 148 * 8;
     if (grid > maxGrid) grid = maxGrid;
     if (grid < 1) grid = 1;
-    sampleKernel<<<grid, SMP_WARPS * 32, 0, s>>>(a);
+    const size_t smem = size_t(SMP_WARPS) * 32 * (a.nQ | 1) * sizeof(double) + SMP_WARPS * 32;
+    sampleKernel<<<grid, SMP_WARPS * 32, smem, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -6,9 +6,16 @@
 // (BASIC/particle/particleTemplates.C:727-1241) with findTris/tetLambda
 // (BASIC/particle/particleI.H:31-140).  The reference walks mesh topology on every tet hop
 // (tetNeighbour / crossEdgeConnectedFace, particleI.H:339-601) and recomputes the four
-// normalised face-area vectors; here both are table look-ups in a 192-byte TetRec baked by
+// normalised face-area vectors; here both are look-ups in a 224-byte TetRec baked by
 // host_mesh.cpp with the same arithmetic, so the FP64 comparisons see identical operands.
 // Compiled with --fmad=false: x86 gcc -O3 without -march does not contract to FMA either.
+//
+// Execution shape.  The nesting of the reference (dsmcParcel::move loop around the trackToFace
+// do-while) is flattened into one loop whose iteration is "one tetrahedron": load its record, decide
+// which plane (if any) the remaining track crosses, advance.  Parcels need different numbers of
+// iterations, so each warp owns a chunk of MOVE_CHUNK*32 consecutive parcels and a lane that finishes
+// its parcel immediately takes the next unprocessed one of the chunk (warp-private work queue); the
+// lanes of a warp therefore stay busy and memory accesses stay inside the chunk's cache lines.
 #include "device_models.cuh"
 #include "engine.h"
 
@@ -17,37 +24,42 @@ namespace dsmc {
 namespace {
 
 constexpr double kTrackingCorrectionTol = 1.0e-5;  // BASIC/particle/particle.C:33
+constexpr int MOVE_CHUNK = 4;                      // parcels per lane in a warp's work queue
+constexpr int MOVE_BLOCK = 256;
+#ifndef MOVE_MIN_BLOCKS
+#define MOVE_MIN_BLOCKS 2
+#endif
 
-struct Tet {
-    double d[24];
-    __device__ __forceinline__ V3 n(int i) const { return mk(d[3 * i], d[3 * i + 1], d[3 * i + 2]); }
-    __device__ __forceinline__ V3 base() const { return mk(d[12], d[13], d[14]); }
-    __device__ __forceinline__ V3 pA() const { return mk(d[15], d[16], d[17]); }
-    __device__ __forceinline__ V3 ct() const { return mk(d[18], d[19], d[20]); }
-    __device__ __forceinline__ double tol() const { return d[21]; }
-    __device__ __forceinline__ int32_t nbr(int i) const {
-        long long w = __double_as_longlong(d[22 + (i >> 1)]);
-        return (i & 1) ? int32_t(w >> 32) : int32_t(w & 0xffffffffLL);
-    }
-};
+__device__ __forceinline__ void ld4(const double* __restrict__ p, double& a, double& b, double& c, double& d) {
+    const double2 u = __ldg(reinterpret_cast<const double2*>(p));
+    const double2 v = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    a = u.x; b = u.y; c = v.x; d = v.y;
+}
+__device__ __forceinline__ int32_t loInt(double w) { return int32_t(__double_as_longlong(w) & 0xffffffffLL); }
+__device__ __forceinline__ int32_t hiInt(double w) { return int32_t(__double_as_longlong(w) >> 32); }
 
-__device__ __forceinline__ void loadTet(const TetRec* __restrict__ tets, int32_t id, Tet& t) {
-    const double2* s = reinterpret_cast<const double2*>(tets + id);
-#pragma unroll
-    for (int i = 0; i < 12; ++i) {
-        double2 v = __ldg(s + i);
-        t.d[2 * i] = v.x;
-        t.d[2 * i + 1] = v.y;
+// findTris without the division: (lambda > 0 && lambda < 1) for lambda = num/den is decided from the signs and
+// magnitudes of num and den.  For IEEE doubles RN(num/den) < 1 <=> |num| < |den| and RN(num/den) > 0 <=> same
+// sign and num != 0 (quotients of the magnitudes met here cannot underflow), so the result is identical to
+// particle::findTris + tetLambda (BASIC/particle/particleI.H:31-140) while the FP64 divider is left to the
+// one or two lambdas that are actually needed.  num = (planeBase - tetCentre) & n is baked into the record.
+__device__ __forceinline__ bool planeCrossed(double num, const V3& toMinusCt, const V3& n, double tol) {
+    double den = dot(toMinusCt, n);
+    if (fabs(den) < tol) {
+        if (fabs(num) < tol) return false;                   // lambda = 0
+        if (mag(toMinusCt) < tol / mag(n)) return false;     // lambda = GREAT
+        den = (den >= 0 ? 1.0 : -1.0) * SMALL;
     }
+    return den > 0 ? (num > 0 && num < den) : (num < 0 && num > den);
 }
 
 // particle::tetLambda, BASIC/particle/particleI.H:68-140 (static mesh branch)
-__device__ __forceinline__ double tetLambda(const V3& from, const V3& to, const V3& n, const V3& base, double tol) {
-    double lambdaNumerator = dot(base - from, n);
-    double lambdaDenominator = dot(to - from, n);
+__device__ __forceinline__ double tetLambda(const V3& from, const V3& toMinusFrom, const V3& n, const V3& base, double tol) {
+    const double lambdaNumerator = dot(base - from, n);
+    double lambdaDenominator = dot(toMinusFrom, n);
     if (fabs(lambdaDenominator) < tol) {
         if (fabs(lambdaNumerator) < tol) return 0.0;
-        if (mag(to - from) < tol / mag(n)) return GREAT;
+        if (mag(toMinusFrom) < tol / mag(n)) return GREAT;
         lambdaDenominator = (lambdaDenominator >= 0 ? 1.0 : -1.0) * SMALL;
     }
     return lambdaNumerator / lambdaDenominator;
@@ -60,10 +72,16 @@ struct WallCtx {
     const double* bfaceArea;
 };
 
+struct Internal {  // internal energy state, loaded lazily (only wall models and migration touch it)
+    double ERot;
+    int32_t vib0, vib1, vib2;
+    int elevel;
+    bool loaded, dirty;
+};
+
 // dsmcPatchBoundary::measurePropertiesBeforeControl / AfterControl accumulation,
 // DSMC/boundaries/basic/dsmcPatchBoundary/dsmcPatchBoundary.C:263-356,358-482
-__device__ void wallMeasure(const WallCtx& w, int32_t measIndex, int32_t bfi, int sp, const V3& U, double ERot,
-                            const int32_t* vib, int elevel, double& IE, V3& IMom) {
+__device__ void wallMeasure(const WallCtx& w, int32_t measIndex, int32_t bfi, int sp, const V3& U, const Internal& in, double& IE, V3& IMom) {
     const DevParams& P = *w.P;
     const DevSpecies& S = P.sp[sp];
     V3 Sf = mk(w.bfaceArea[3 * bfi], w.bfaceArea[3 * bfi + 1], w.bfaceArea[3 * bfi + 2]);
@@ -74,9 +92,11 @@ __device__ void wallMeasure(const WallCtx& w, int32_t measIndex, int32_t bfi, in
     const double U_dot_nw = dot(U, nw);
     const V3 Ut = U - U_dot_nw * nw;
     const double rwf = 1.0 / fmax(fabs(U_dot_nw) * fA * P.deltaT, SMALL);
-    double EVib = 0.0;
-    EVib = (S.nVib > 0 ? vib[0] * P.kB * S.thetaV[0] : 0.0) + (S.nVib > 1 ? vib[1] * P.kB * S.thetaV[1] : 0.0) + (S.nVib > 2 ? vib[2] * P.kB * S.thetaV[2] : 0.0);
-    const double EEle = S.eElec[elevel];
+    const double ev0 = S.nVib > 0 ? in.vib0 * P.kB * S.thetaV[0] : 0.0;
+    const double ev1 = S.nVib > 1 ? in.vib1 * P.kB * S.thetaV[1] : 0.0;
+    const double ev2 = S.nVib > 2 ? in.vib2 * P.kB * S.thetaV[2] : 0.0;
+    const double EVib = ev0 + ev1 + ev2;
+    const double EEle = S.eElec[in.elevel];
     const double UU = dot(U, U);
     if (measIndex >= 0) {
         double* a = w.wallAcc + (size_t(measIndex) * P.nSpecies + sp) * w.nWallQ;
@@ -89,13 +109,15 @@ __device__ void wallMeasure(const WallCtx& w, int32_t measIndex, int32_t bfi, in
         atomicAdd(a + WQ_MOMX, m * Ut.x * rwf);
         atomicAdd(a + WQ_MOMY, m * Ut.y * rwf);
         atomicAdd(a + WQ_MOMZ, m * Ut.z * rwf);
-        atomicAdd(a + WQ_EROT, ERot * rwf);
+        atomicAdd(a + WQ_EROT, in.ERot * rwf);
         atomicAdd(a + WQ_ZETAROT, S.rotDof * rwf);
         atomicAdd(a + WQ_EVIB, EVib * rwf);
-        for (int mo = 0; mo < S.nVib; ++mo) atomicAdd(a + WQ_EVIBMOD0 + mo, vib[mo] * P.kB * S.thetaV[mo] * rwf);
+        if (S.nVib > 0) atomicAdd(a + WQ_EVIBMOD0 + 0, ev0 * rwf);
+        if (S.nVib > 1) atomicAdd(a + WQ_EVIBMOD0 + 1, ev1 * rwf);
+        if (S.nVib > 2) atomicAdd(a + WQ_EVIBMOD0 + 2, ev2 * rwf);
         atomicAdd(a + WQ_EELEC, EEle * rwf);
     }
-    IE = 0.5 * m * UU + ERot + EVib + EEle;
+    IE = 0.5 * m * UU + in.ERot + EVib + EEle;
     IMom = m * U;
 }
 
@@ -115,58 +137,38 @@ __device__ void wallMeasureDelta(const WallCtx& w, int32_t measIndex, int32_t bf
     atomicAdd(a + WQ_FDZ, deltaFD.z);
 }
 
-// findTris without the division: (lambda > 0 && lambda < 1) for lambda = num/den is decided from the signs and
-// magnitudes of num and den.  For IEEE doubles RN(num/den) < 1 <=> |num| < |den| and RN(num/den) > 0 <=> same
-// sign and num != 0 (quotients of the magnitudes met here cannot underflow), so the result is identical to
-// particle::findTris + tetLambda (BASIC/particle/particleI.H:31-140) while the FP64 divider is left to the
-// one or two lambdas that are actually needed.
-__device__ __forceinline__ bool planeCrossed(const V3& Ct, const V3& to, const V3& n, const V3& base, double tol) {
-    const double num = dot(base - Ct, n);
-    double den = dot(to - Ct, n);
-    if (fabs(den) < tol) {
-        if (fabs(num) < tol) return false;                 // lambda = 0
-        if (mag(to - Ct) < tol / mag(n)) return false;     // lambda = GREAT
-        den = (den >= 0 ? 1.0 : -1.0) * SMALL;
-    }
-    return den > 0 ? (num > 0 && num < den) : (num < 0 && num > den);
-}
-
-struct Internal {  // internal energy state, loaded lazily (only wall models and migration touch it)
-    double ERot;
-    int32_t vib[MAX_MODES];
-    int elevel;
-    bool loaded, dirty;
-};
-
 __device__ __forceinline__ void loadInternal(const MoveArgs& a, const DevParams& P, int32_t i, Internal& in) {
     if (in.loaded) return;
     in.loaded = true;
     if (!P.hasInternalEnergy) return;
     in.ERot = a.p.erot[i];
-    if (P.nModes > 0) in.vib[0] = a.p.vib[0][i];
-    if (P.nModes > 1) in.vib[1] = a.p.vib[1][i];
-    if (P.nModes > 2) in.vib[2] = a.p.vib[2][i];
+    if (P.nModes > 0) in.vib0 = a.p.vib[0][i];
+    if (P.nModes > 1) in.vib1 = a.p.vib[1][i];
+    if (P.nModes > 2) in.vib2 = a.p.vib[2][i];
     in.elevel = a.p.elevel[i];
 }
 
 // dsmcParcel::hitWallPatch / hitPatch -> dsmc{Diffuse,Specular}WallPatch::controlParticle
-__device__ __forceinline__ void wallInteraction(const MoveArgs& a, const DevParams& P, int32_t i, int sp, const DevPatch& pt, int32_t measIndex,
-                                             int32_t bfi, const V3& nw, V3& U, Internal& in, Rng& wallRng, bool& wallRngInit) {
+__device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int sp, int patch, int32_t measIndex, int32_t bfi, V3 nw, V3 U,
+                                           Internal* inOut, int* wallHits) {
+    const DevParams& P = *a.P;
+    const DevPatch& pt = P.patch[patch];
     WallCtx wctx{a.P, a.wallAcc, a.nWallQ, a.bfaceArea};
+    Internal in = *inOut;
     loadInternal(a, P, i, in);
     double preIE, postIE;
     V3 preIMom, postIMom;
-    wallMeasure(wctx, measIndex, bfi, sp, U, in.ERot, in.vib, in.elevel, preIE, preIMom);
+    wallMeasure(wctx, measIndex, bfi, sp, U, in, preIE, preIMom);
     if (pt.model == DSMCB200_BND_SPECULAR_WALL) {
         // dsmcSpecularWallPatch::performSpecularReflection
         const double U_dot_nw = dot(U, nw);
         if (U_dot_nw > 0.0) U -= 2.0 * U_dot_nw * nw;
     } else {
-        // dsmcDiffuseWallPatch::performDiffuseReflection
-        if (!wallRngInit) {
-            wallRng.init(P.seed, uint32_t(a.p.origId[i]), 0u, a.step, STREAM_WALL);
-            wallRngInit = true;
-        }
+        // dsmcDiffuseWallPatch::performDiffuseReflection; the k-th diffuse hit of a parcel within a step owns
+        // the Philox stream (origId, k, step)
+        Rng wallRng;
+        wallRng.init(P.seed, uint32_t(a.p.origId[i]), uint32_t(*wallHits), a.step, STREAM_WALL);
+        *wallHits += 1;
         const DevSpecies& S = P.sp[sp];
         // dsmcPatchBoundary::calculateWallUnitVectors
         double U_dot_nw = dot(U, nw);
@@ -186,254 +188,298 @@ __device__ __forceinline__ void wallInteraction(const MoveArgs& a, const DevPara
         const double r = wallRng.sample01();
         U = sqrt(P.kB * Tw / S.mass) * (g1 * tw1 + g2 * tw2 - sqrt(-2.0 * log(fmax(1 - r, VSMALL))) * nw);
         in.ERot = equipartitionRotationalEnergy(wallRng, P.kB, Tw, S.rotDof);
-        if (S.nVib > 0) in.vib[0] = equipartitionVibrationalEnergyLevel(wallRng, Tw, S.thetaV[0]);
-        if (S.nVib > 1) in.vib[1] = equipartitionVibrationalEnergyLevel(wallRng, Tw, S.thetaV[1]);
-        if (S.nVib > 2) in.vib[2] = equipartitionVibrationalEnergyLevel(wallRng, Tw, S.thetaV[2]);
+        if (S.nVib > 0) in.vib0 = equipartitionVibrationalEnergyLevel(wallRng, Tw, S.thetaV[0]);
+        if (S.nVib > 1) in.vib1 = equipartitionVibrationalEnergyLevel(wallRng, Tw, S.thetaV[1]);
+        if (S.nVib > 2) in.vib2 = equipartitionVibrationalEnergyLevel(wallRng, Tw, S.thetaV[2]);
         in.elevel = equipartitionElectronicLevel(wallRng, P.kB, Tw, S);
         U += mk(pt.vel[0], pt.vel[1], pt.vel[2]);
         in.dirty = true;
     }
-    wallMeasure(wctx, measIndex, bfi, sp, U, in.ERot, in.vib, in.elevel, postIE, postIMom);
+    wallMeasure(wctx, measIndex, bfi, sp, U, in, postIE, postIMom);
     wallMeasureDelta(wctx, measIndex, bfi, sp, preIE, preIMom, postIE, postIMom);
+    *inOut = in;
+    return U;
 }
 
 }  // namespace
 
-// One loop iteration = one tetrahedron: every active lane loads a TetRec and either crosses one of its triangles or
-// stops inside it.  The nesting of the reference (dsmcParcel::move loop around the trackToFace do-while) is flattened
-// into this single loop so that the lanes of a warp stay converged while they make different numbers of hops and
-// face crossings; the sequence of floating-point operations per parcel is unchanged.
-__global__ void __launch_bounds__(256, 2) moveKernel(const __grid_constant__ MoveArgs a) {
-    const int32_t li = blockIdx.x * blockDim.x + threadIdx.x;
-    if (li >= a.count) return;
-    const int32_t i = a.first + li;
+__global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const __grid_constant__ MoveArgs a) {
     const DevParams& P = *a.P;
+    const int lane = threadIdx.x & 31;
+    const int32_t warpGlobal = (blockIdx.x * MOVE_BLOCK + threadIdx.x) >> 5;
+    const int32_t chunkBeg = a.first + warpGlobal * (32 * MOVE_CHUNK);
+    int32_t chunkEnd = chunkBeg + 32 * MOVE_CHUNK;
+    if (chunkEnd > a.first + a.count) chunkEnd = a.first + a.count;
+    if (chunkBeg >= chunkEnd) return;
+    int32_t warpNext = chunkBeg;  // warp-uniform: next unassigned parcel of the chunk
 
-    int32_t cell = a.p.cell[i];
-    if (cell < 0) return;
-    int32_t tet = a.p.tet[i];
-    V3 pos = mk(a.p.px[i], a.p.py[i], a.p.pz[i]);
-    V3 U = mk(a.p.ux[i], a.p.uy[i], a.p.uz[i]);
-    double stepFraction = (a.sfTail != nullptr && i >= a.tailStart) ? a.sfTail[i - a.tailStart] : 0.0;
     const double deltaT = P.deltaT;
-    const int sp = a.p.typeId[i];
-
-    Internal in;
-    in.ERot = 0.0; in.vib[0] = in.vib[1] = in.vib[2] = 0; in.elevel = 0; in.loaded = false; in.dirty = false;
-    bool Udirty = false;
-    Rng wallRng;
-    bool wallRngInit = false;
-
-    bool keepParticle = true, switchProcessor = false;
-    int32_t procBfi = -1;
-    unsigned rescues = 0;
-    double tEnd = (1.0 - stepFraction) * deltaT;
-
-    // state of the trackToFace call in flight
-    bool inCall = false, rescuePending = false, faceSet = false;
-    int32_t faceBfi = -1;
-    V3 endPosition = pos;
-    double dt = 0.0, trackFraction = 0.0;
     const bool constrained = P.solutionD[0] == -1 || P.solutionD[1] == -1 || P.solutionD[2] == -1;
+    const double* __restrict__ tetBase = reinterpret_cast<const double*>(a.tets);
 
-    bool active = tEnd > ROOTVSMALL;
+    // per-lane parcel state
+    bool active = false;
+    int32_t i = -1, cell = -1, tet = 0, sp = 0;
+    V3 pos = mk(0, 0, 0), U = mk(0, 0, 0), endPosition = mk(0, 0, 0);
+    double tEnd = 0.0, stepFraction = 0.0, dt = 0.0, trackFraction = 0.0;
+    bool inCall = false, rescuePending = false, faceSet = false, Udirty = false;
+    bool keepParticle = true, switchProcessor = false;
+    int32_t faceBfi = -1, procBfi = -1;
+    Internal in;
+    in.ERot = 0.0; in.vib0 = in.vib1 = in.vib2 = 0; in.elevel = 0; in.loaded = false; in.dirty = false;
+    int wallHits = 0;
+    unsigned rescues = 0, nDeleted = 0;
     int guard = 0;
-    while (active) {
-        if (++guard > 200000) { keepParticle = false; break; }  // corrupt tet table: drop the parcel rather than hang
-        if (!inCall) {
-            // dsmcParcel::move loop body up to the trackToFace call (DSMC/parcels/dsmcParcel.C:74-92)
-            V3 Utracking = U;
-            if (constrained) {
-#pragma unroll
-                for (int d = 0; d < 3; ++d)
-                    if (P.solutionD[d] == -1) { setComp(pos, d, P.centre[d]); setComp(Utracking, d, 0.0); }
+
+    while (true) {
+        // ---- refill idle lanes from the warp's queue ----
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle) {
+            const int32_t avail = chunkEnd - warpNext;
+            if (avail <= 0) {
+                if (idle == 0xffffffffu) break;
+            } else {
+                const int r = __popc(idle & ((1u << lane) - 1u));
+                if (!active && r < avail) {
+                    i = warpNext + r;
+                    cell = a.p.cell[i];
+                    if (cell >= 0) {
+                        tet = a.p.tet[i];
+                        pos = mk(a.p.px[i], a.p.py[i], a.p.pz[i]);
+                        U = mk(a.p.ux[i], a.p.uy[i], a.p.uz[i]);
+                        sp = a.p.typeId[i];
+                        stepFraction = (a.sfTail != nullptr && i >= a.tailStart) ? a.sfTail[i - a.tailStart] : 0.0;
+                        tEnd = (1.0 - stepFraction) * deltaT;
+                        inCall = false; rescuePending = false; faceSet = false; Udirty = false;
+                        keepParticle = true; switchProcessor = false; faceBfi = -1; procBfi = -1;
+                        in.loaded = false; in.dirty = false; in.ERot = 0.0; in.vib0 = in.vib1 = in.vib2 = 0; in.elevel = 0;
+                        wallHits = 0;
+                        guard = 0;
+                        if (tEnd > ROOTVSMALL) active = true;
+                        else if (a.cellCount) atomicAdd(&a.cellCount[cell], 1);  // nothing left to move (stepFraction == 1)
+                    }
+                }
+                const int nIdle = __popc(idle);
+                warpNext += nIdle < avail ? nIdle : avail;
             }
-            dt = tEnd;
-            endPosition = pos + dt * Utracking;
-            trackFraction = 0.0;
-            inCall = true; rescuePending = false; faceSet = false; faceBfi = -1;
         }
-        Tet T;
-        loadTet(a.tets, tet, T);
-        double retVal;
-        bool finished = false;
-        if (rescuePending) {
-            // lambdaMin < SMALL: tracking correction towards the centre of the tet now occupied
-            pos += kTrackingCorrectionTol * (T.ct() - pos);
-            ++rescues;
-            retVal = trackFraction;
-            finished = true;
-        } else {
-            const double tol = T.tol();
-            const V3 Ct = T.ct();
-            const V3 base = T.base(), pA = T.pA();
-            const bool c0 = planeCrossed(Ct, endPosition, T.n(0), base, tol);
-            const bool c1 = planeCrossed(Ct, endPosition, T.n(1), pA, tol);
-            const bool c2 = planeCrossed(Ct, endPosition, T.n(2), base, tol);
-            const bool c3 = planeCrossed(Ct, endPosition, T.n(3), base, tol);
-            if (!(c0 | c1 | c2 | c3)) {
-                pos = endPosition;
-                faceSet = false; faceBfi = -1;
-                retVal = 1.0;
+        if (!active) continue;
+
+        // ---- one tetrahedron ----
+        if (++guard > 200000) keepParticle = false;  // corrupt tet table: drop the parcel rather than hang
+        bool finished = !keepParticle;
+        double retVal = 1.0;
+        if (!finished) {
+            if (!inCall) {
+                // dsmcParcel::move loop body up to the trackToFace call (DSMC/parcels/dsmcParcel.C:74-92)
+                V3 Utracking = U;
+                if (constrained) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+                        if (P.solutionD[d] == -1) { setComp(pos, d, P.centre[d]); setComp(Utracking, d, 0.0); }
+                }
+                dt = tEnd;
+                endPosition = pos + dt * Utracking;
+                trackFraction = 0.0;
+                inCall = true; rescuePending = false; faceSet = false; faceBfi = -1;
+            }
+            // the whole record up front: seven independent 32-byte sectors in flight before any branch
+            const double* __restrict__ R = tetBase + size_t(tet) * 28;
+            double n0x, n0y, n0z, numC0, n1x, n1y, n1z, numC1, n2x, n2y, n2z, numC2, n3x, n3y, n3z, numC3;
+            double bx, by, bz, tol, ax, ay, az, nb01, ctx, cty, ctz, nb23;
+            ld4(R + 24, ctx, cty, ctz, nb23);
+            ld4(R + 16, bx, by, bz, tol);
+            ld4(R + 0, n0x, n0y, n0z, numC0);
+            ld4(R + 4, n1x, n1y, n1z, numC1);
+            ld4(R + 8, n2x, n2y, n2z, numC2);
+            ld4(R + 12, n3x, n3y, n3z, numC3);
+            ld4(R + 20, ax, ay, az, nb01);
+            const V3 Ct = mk(ctx, cty, ctz);
+            if (rescuePending) {
+                // lambdaMin < SMALL: tracking correction towards the centre of the tet now occupied
+                pos += kTrackingCorrectionTol * (Ct - pos);
+                ++rescues;
+                retVal = trackFraction;
                 finished = true;
             } else {
-                int triI = -1;
-                double lambdaMin = VGREAT;
-                if (c0) { const double lam = tetLambda(pos, endPosition, T.n(0), base, tol); if (lam < lambdaMin) { lambdaMin = lam; triI = 0; } }
-                if (c1) { const double lam = tetLambda(pos, endPosition, T.n(1), pA, tol); if (lam < lambdaMin) { lambdaMin = lam; triI = 1; } }
-                if (c2) { const double lam = tetLambda(pos, endPosition, T.n(2), base, tol); if (lam < lambdaMin) { lambdaMin = lam; triI = 2; } }
-                if (c3) { const double lam = tetLambda(pos, endPosition, T.n(3), base, tol); if (lam < lambdaMin) { lambdaMin = lam; triI = 3; } }
-                const int32_t nb0 = T.nbr(0);
-                if (triI == 0) { faceSet = true; faceBfi = nb0 < 0 ? (-1 - nb0) : -1; }
-                else if (triI > 0) { faceSet = false; faceBfi = -1; }
-                bool needRescue = false;
-                if (lambdaMin > SMALL) {
-                    if (lambdaMin <= 1.0) {
-                        trackFraction += lambdaMin * (1 - trackFraction);
-                        pos += lambdaMin * (endPosition - pos);
-                    } else {
-                        pos = endPosition;
-                        retVal = 1.0;
-                        finished = true;
-                    }
+                const V3 N0 = mk(n0x, n0y, n0z), N1 = mk(n1x, n1y, n1z), N2 = mk(n2x, n2y, n2z), N3 = mk(n3x, n3y, n3z);
+                const V3 base = mk(bx, by, bz), pA = mk(ax, ay, az);
+                const V3 toMinusCt = endPosition - Ct;
+                const bool c0 = planeCrossed(numC0, toMinusCt, N0, tol);
+                const bool c1 = planeCrossed(numC1, toMinusCt, N1, tol);
+                const bool c2 = planeCrossed(numC2, toMinusCt, N2, tol);
+                const bool c3 = planeCrossed(numC3, toMinusCt, N3, tol);
+                if (!(c0 | c1 | c2 | c3)) {
+                    pos = endPosition;
+                    faceSet = false; faceBfi = -1;
+                    retVal = 1.0;
+                    finished = true;
                 } else {
-                    needRescue = true;  // lambdaMin = 0.0
-                }
-                if (!finished) {
-                    if (triI > 0) {
-                        // particle::tetNeighbour: enter the adjacent tet of the same cell
-                        tet = triI == 1 ? T.nbr(1) : (triI == 2 ? T.nbr(2) : T.nbr(3));
-                        rescuePending = needRescue;
-                    } else if (triI == 0) {
-                        if (nb0 >= 0) {
-                            cell = nb0;  // internal face: the same face triangle seen from the other cell
-                            tet ^= 1;
+                    // all four lambdas from the current position as independent chains (the ones of planes that are
+                    // not crossed are discarded); order and strict '<' as in the reference's loop over tris
+                    const V3 toMinusFrom = endPosition - pos;
+                    const double l0 = tetLambda(pos, toMinusFrom, N0, base, tol);
+                    const double l1 = tetLambda(pos, toMinusFrom, N1, pA, tol);
+                    const double l2 = tetLambda(pos, toMinusFrom, N2, base, tol);
+                    const double l3 = tetLambda(pos, toMinusFrom, N3, base, tol);
+                    int triI = -1;
+                    double lambdaMin = VGREAT;
+                    if (c0 && l0 < lambdaMin) { lambdaMin = l0; triI = 0; }
+                    if (c1 && l1 < lambdaMin) { lambdaMin = l1; triI = 1; }
+                    if (c2 && l2 < lambdaMin) { lambdaMin = l2; triI = 2; }
+                    if (c3 && l3 < lambdaMin) { lambdaMin = l3; triI = 3; }
+                    const int32_t nb0 = loInt(nb01);
+                    if (triI == 0) { faceSet = true; faceBfi = nb0 < 0 ? (-1 - nb0) : -1; }
+                    else if (triI > 0) { faceSet = false; faceBfi = -1; }
+                    bool needRescue = false;
+                    if (lambdaMin > SMALL) {
+                        if (lambdaMin <= 1.0) {
+                            trackFraction += lambdaMin * (1 - trackFraction);
+                            pos += lambdaMin * (endPosition - pos);
                         } else {
-                            const int32_t bfi = -1 - nb0;
-                            const BFaceRec bf = a.bfaces[bfi];
-                            const DevPatch& pt = P.patch[bf.patch];
-                            switch (pt.type) {
-                                case DSMCB200_PATCH_PROCESSOR:
-                                case DSMCB200_PATCH_PROCESSORCYCLIC:
-                                    switchProcessor = true;  // dsmcParcel::hitProcessorPatch
-                                    break;
-                                case DSMCB200_PATCH_SYMMETRYPLANE:
-                                case DSMCB200_PATCH_SYMMETRY:
-                                case DSMCB200_PATCH_WEDGE: {
-                                    // transformProperties(I - 2.0*nf*nf), particleTemplates.C:1474-1522
-                                    const V3 nf = T.n(0);
-                                    const V3 t2 = 2.0 * nf;
-                                    const double xx = 1.0 - t2.x * nf.x, xy = 0.0 - t2.x * nf.y, xz = 0.0 - t2.x * nf.z;
-                                    const double yx = 0.0 - t2.y * nf.x, yy = 1.0 - t2.y * nf.y, yz = 0.0 - t2.y * nf.z;
-                                    const double zx = 0.0 - t2.z * nf.x, zy = 0.0 - t2.z * nf.y, zz = 1.0 - t2.z * nf.z;
-                                    U = mk(xx * U.x + xy * U.y + xz * U.z, yx * U.x + yy * U.y + yz * U.z, zx * U.x + zy * U.y + zz * U.z);
-                                    Udirty = true;
-                                    break;
-                                }
-                                case DSMCB200_PATCH_CYCLIC: {
-                                    // particle::hitCyclicPatch, particleTemplates.C:1525-1570
-                                    const int32_t k = (tet >> 1) - bf.tetPair0;
-                                    tet = 2 * (bf.coupledTetPair0 + (bf.nPts - 3) - k);
-                                    cell = bf.coupledCell;
-                                    const DevPatch& rp = P.patch[pt.nbrPatch];
-                                    pos -= mk(rp.sep[0], rp.sep[1], rp.sep[2]);
-                                    faceBfi = bfi - (pt.start - P.nInternalFaces) + (rp.start - P.nInternalFaces);
-                                    break;
-                                }
-                                case DSMCB200_PATCH_WALL:
-                                case DSMCB200_PATCH_PATCH:
-                                    if (pt.model == DSMCB200_BND_DELETION) {
-                                        keepParticle = false;  // dsmcDeletionPatch::controlParticle
-                                    } else if (pt.model != DSMCB200_BND_NONE) {
-                                        wallInteraction(a, P, i, sp, pt, bf.measIndex, bfi, T.n(0), U, in, wallRng, wallRngInit);
-                                        Udirty = true;
-                                    }
-                                    break;
-                                default:  // empty patches cannot be hit by constrained tracks
-                                    break;
-                            }
-                        }
-                        if (needRescue) {
-                            rescuePending = true;  // correction towards the new tet's centre, then return trackFraction
-                        } else {
-                            retVal = trackFraction;
+                            pos = endPosition;
+                            retVal = 1.0;
                             finished = true;
+                        }
+                    } else {
+                        needRescue = true;  // lambdaMin = 0.0
+                    }
+                    if (!finished) {
+                        if (triI > 0) {
+                            // particle::tetNeighbour: enter the adjacent tet of the same cell
+                            tet = triI == 1 ? hiInt(nb01) : (triI == 2 ? loInt(nb23) : hiInt(nb23));
+                            rescuePending = needRescue;
+                        } else {
+                            if (nb0 >= 0) {
+                                cell = nb0;  // internal face: the same face triangle seen from the other cell
+                                tet ^= 1;
+                            } else {
+                                const int32_t bfi = -1 - nb0;
+                                const BFaceRec bf = a.bfaces[bfi];
+                                const DevPatch& pt = P.patch[bf.patch];
+                                switch (pt.type) {
+                                    case DSMCB200_PATCH_PROCESSOR:
+                                    case DSMCB200_PATCH_PROCESSORCYCLIC:
+                                        switchProcessor = true;  // dsmcParcel::hitProcessorPatch
+                                        break;
+                                    case DSMCB200_PATCH_SYMMETRYPLANE:
+                                    case DSMCB200_PATCH_SYMMETRY:
+                                    case DSMCB200_PATCH_WEDGE: {
+                                        // transformProperties(I - 2.0*nf*nf), particleTemplates.C:1474-1522
+                                        const V3 nf = N0;
+                                        const V3 t2 = 2.0 * nf;
+                                        const double xx = 1.0 - t2.x * nf.x, xy = 0.0 - t2.x * nf.y, xz = 0.0 - t2.x * nf.z;
+                                        const double yx = 0.0 - t2.y * nf.x, yy = 1.0 - t2.y * nf.y, yz = 0.0 - t2.y * nf.z;
+                                        const double zx = 0.0 - t2.z * nf.x, zy = 0.0 - t2.z * nf.y, zz = 1.0 - t2.z * nf.z;
+                                        U = mk(xx * U.x + xy * U.y + xz * U.z, yx * U.x + yy * U.y + yz * U.z, zx * U.x + zy * U.y + zz * U.z);
+                                        Udirty = true;
+                                        break;
+                                    }
+                                    case DSMCB200_PATCH_CYCLIC: {
+                                        // particle::hitCyclicPatch, particleTemplates.C:1525-1570
+                                        const int32_t k = (tet >> 1) - bf.tetPair0;
+                                        tet = 2 * (bf.coupledTetPair0 + (bf.nPts - 3) - k);
+                                        cell = bf.coupledCell;
+                                        const DevPatch& rp = P.patch[pt.nbrPatch];
+                                        pos -= mk(rp.sep[0], rp.sep[1], rp.sep[2]);
+                                        faceBfi = bfi - (pt.start - P.nInternalFaces) + (rp.start - P.nInternalFaces);
+                                        break;
+                                    }
+                                    case DSMCB200_PATCH_WALL:
+                                    case DSMCB200_PATCH_PATCH:
+                                        if (pt.model == DSMCB200_BND_DELETION) {
+                                            keepParticle = false;  // dsmcDeletionPatch::controlParticle
+                                        } else if (pt.model != DSMCB200_BND_NONE) {
+                                            U = wallInteraction(a, i, sp, bf.patch, bf.measIndex, bfi, N0, U, &in, &wallHits);
+                                            Udirty = true;
+                                        }
+                                        break;
+                                    default:  // empty patches cannot be hit by constrained tracks
+                                        break;
+                                }
+                            }
+                            if (needRescue) {
+                                rescuePending = true;  // correction towards the new tet's centre, then return trackFraction
+                            } else {
+                                retVal = trackFraction;
+                                finished = true;
+                            }
                         }
                     }
                 }
             }
         }
         if (finished) {
-            // back in dsmcParcel::move (DSMC/parcels/dsmcParcel.C:92-118)
-            dt *= retVal;
-            tEnd -= dt;
-            stepFraction = 1.0 - tEnd / deltaT;
-            if (faceSet && faceBfi >= 0 && keepParticle) {
-                const int ptype = P.patch[a.bfaces[faceBfi].patch].type;
-                if (ptype == DSMCB200_PATCH_PROCESSOR || ptype == DSMCB200_PATCH_PROCESSORCYCLIC) {
-                    switchProcessor = true;
-                    procBfi = faceBfi;
+            if (keepParticle) {
+                // back in dsmcParcel::move (DSMC/parcels/dsmcParcel.C:92-118)
+                dt *= retVal;
+                tEnd -= dt;  // stepFraction = 1 - tEnd/deltaT is only consumed by a processor transfer: evaluated there
+                if (faceSet && faceBfi >= 0) {
+                    const int ptype = P.patch[a.bfaces[faceBfi].patch].type;
+                    if (ptype == DSMCB200_PATCH_PROCESSOR || ptype == DSMCB200_PATCH_PROCESSORCYCLIC) {
+                        switchProcessor = true;
+                        procBfi = faceBfi;
+                    }
                 }
             }
             inCall = false;
-            active = keepParticle && !switchProcessor && tEnd > ROOTVSMALL;
+            if (!(keepParticle && !switchProcessor && tEnd > ROOTVSMALL)) {
+                // ---- this parcel is done: write it back ----
+                active = false;
+                if (!keepParticle) {
+                    a.p.cell[i] = -1;
+                    ++nDeleted;
+                } else if (switchProcessor) {
+                    // Cloud<T>::move transfer list + particle::prepareForParallelTransfer, fused with the packing
+                    const BFaceRec bf = a.bfaces[procBfi];
+                    const DevPatch& pt = P.patch[bf.patch];
+                    const int slot = pt.nbrSlot;
+                    stepFraction = 1.0 - tEnd / deltaT;
+                    const int32_t k = atomicAdd(&a.counters->nMig[slot], 1);
+                    if (k < a.migCapacity) {
+                        loadInternal(a, P, i, in);
+                        MigRec r;
+                        r.pos[0] = pos.x; r.pos[1] = pos.y; r.pos[2] = pos.z;
+                        r.U[0] = U.x; r.U[1] = U.y; r.U[2] = U.z;
+                        r.erot = in.ERot; r.stepFraction = stepFraction;
+                        r.patchOrdinal = pt.nbrOrdinal;
+                        r.patchFace = procBfi - (pt.start - P.nInternalFaces);
+                        r.tetLocal = (tet >> 1) - bf.tetPair0;
+                        r.origId = a.p.origId[i];
+                        r.vib[0] = in.vib0; r.vib[1] = in.vib1; r.vib[2] = in.vib2;
+                        r.typeId = uint8_t(sp); r.elevel = uint8_t(in.elevel); r.cls = a.p.cls ? a.p.cls[i] : 0; r.pad_ = 0;
+                        a.migBuf[size_t(slot) * a.migCapacity + k] = r;
+                    } else {
+                        atomicAdd(&a.counters->overflow, 1ULL);
+                    }
+                    a.p.cell[i] = -1;
+                    atomicAdd(&a.counters->migratedOut, 1ULL);
+                } else {
+                    a.p.px[i] = pos.x; a.p.py[i] = pos.y; a.p.pz[i] = pos.z;
+                    a.p.cell[i] = cell;
+                    a.p.tet[i] = tet;
+                    if (Udirty) { a.p.ux[i] = U.x; a.p.uy[i] = U.y; a.p.uz[i] = U.z; }
+                    if (in.dirty && P.hasInternalEnergy) {
+                        a.p.erot[i] = in.ERot;
+                        if (P.nModes > 0) a.p.vib[0][i] = in.vib0;
+                        if (P.nModes > 1) a.p.vib[1][i] = in.vib1;
+                        if (P.nModes > 2) a.p.vib[2][i] = in.vib2;
+                        a.p.elevel[i] = uint8_t(in.elevel);
+                    }
+                    if (a.cellCount) atomicAdd(&a.cellCount[cell], 1);
+                }
+            }
         }
     }
-
     if (rescues) atomicAdd(&a.counters->rescues, (unsigned long long)rescues);
-
-    if (!keepParticle) {
-        a.p.cell[i] = -1;
-        atomicAdd(&a.counters->deleted, 1ULL);
-        return;
-    }
-    if (switchProcessor) {
-        // Cloud<T>::move transfer list + particle::prepareForParallelTransfer, fused with the packing
-        const BFaceRec bf = a.bfaces[procBfi];
-        const DevPatch& pt = P.patch[bf.patch];
-        const int slot = pt.nbrSlot;
-        const int32_t k = atomicAdd(&a.counters->nMig[slot], 1);
-        if (k < a.migCapacity) {
-            loadInternal(a, P, i, in);
-            MigRec r;
-            r.pos[0] = pos.x; r.pos[1] = pos.y; r.pos[2] = pos.z;
-            r.U[0] = U.x; r.U[1] = U.y; r.U[2] = U.z;
-            r.erot = in.ERot; r.stepFraction = stepFraction;
-            r.patchOrdinal = pt.nbrOrdinal;
-            r.patchFace = procBfi - (pt.start - P.nInternalFaces);
-            r.tetLocal = (tet >> 1) - bf.tetPair0;
-            r.origId = a.p.origId[i];
-            r.vib[0] = in.vib[0]; r.vib[1] = in.vib[1]; r.vib[2] = in.vib[2];
-            r.typeId = uint8_t(sp); r.elevel = uint8_t(in.elevel); r.cls = a.p.cls ? a.p.cls[i] : 0; r.pad_ = 0;
-            a.migBuf[size_t(slot) * a.migCapacity + k] = r;
-        } else {
-            atomicAdd(&a.counters->overflow, 1ULL);
-        }
-        a.p.cell[i] = -1;
-        atomicAdd(&a.counters->migratedOut, 1ULL);
-        return;
-    }
-
-    a.p.px[i] = pos.x; a.p.py[i] = pos.y; a.p.pz[i] = pos.z;
-    a.p.cell[i] = cell;
-    a.p.tet[i] = tet;
-    if (Udirty) { a.p.ux[i] = U.x; a.p.uy[i] = U.y; a.p.uz[i] = U.z; }
-    if (in.dirty && P.hasInternalEnergy) {
-        a.p.erot[i] = in.ERot;
-        if (P.nModes > 0) a.p.vib[0][i] = in.vib[0];
-        if (P.nModes > 1) a.p.vib[1][i] = in.vib[1];
-        if (P.nModes > 2) a.p.vib[2][i] = in.vib[2];
-        a.p.elevel[i] = uint8_t(in.elevel);
-    }
-    if (a.cellCount) atomicAdd(&a.cellCount[cell], 1);
+    if (nDeleted) atomicAdd(&a.counters->deleted, (unsigned long long)nDeleted);
 }
-
 
 cudaError_t launchMove(const MoveArgs& a, cudaStream_t s) {
     if (a.count <= 0) return cudaSuccess;
-    const int block = 256;
-    const int grid = (a.count + block - 1) / block;
-    moveKernel<<<grid, block, 0, s>>>(a);
+    const int perBlock = MOVE_BLOCK * MOVE_CHUNK;
+    const int grid = (a.count + perBlock - 1) / perBlock;
+    moveKernel<<<grid, MOVE_BLOCK, 0, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -460,7 +506,9 @@ __global__ void unpackKernel(const __grid_constant__ UnpackArgs a) {
     a.p.typeId[i] = r.typeId;
     if (P.hasInternalEnergy) {
         a.p.erot[i] = r.erot;
-        for (int mo = 0; mo < P.nModes; ++mo) a.p.vib[mo][i] = r.vib[mo];
+        if (P.nModes > 0) a.p.vib[0][i] = r.vib[0];
+        if (P.nModes > 1) a.p.vib[1][i] = r.vib[1];
+        if (P.nModes > 2) a.p.vib[2][i] = r.vib[2];
         a.p.elevel[i] = r.elevel;
     }
     if (a.p.cls) a.p.cls[i] = r.cls;
