@@ -1,0 +1,102 @@
+"""numpy restatement of the per-cell field reduction of dsmcVolFields::calculateField
+(DSMC/macroscopicProperties/derived/combined/dsmcVolFields/dsmcVolFields.C:1242-1290 every step,
+:1401-1508 and :1663-1790 at output time), fed with the per-species moment sums of the sampling
+stage (layout of include/dsmcb200.h: N, sum U (3), sum U.U, ERot, Eelec, Evib per mode).
+
+TEST INFRASTRUCTURE (oracle side).  Pinned against the fields the reference ships for
+couette_N2-O2/backup-5 (tests/test_oracle_golden.py): rhoN = dsmcNMean*FN/V, p = rhoN k Ttra with
+k = 1.38065e-23, and the mean-free-path / mean-collision-time formulas (Bird 4.74/4.76/4.77/1.38).
+"""
+import numpy as np
+
+SMALL, VSMALL, GREAT = 1e-15, 1e-300, 1e15
+
+
+def derive(acc, coll, n_time_steps, species, type_ids, fnum, cell_volumes, kB=1.38065e-23, deltaT=1.0,
+           mfp_tref=273.0, has_internal=True, n_modes=1):
+    """acc: [nCells, nSpecies, nQ]; species: list of dicts(mass, diameter, omega, rotDof, thetaV[list]);
+    type_ids: the `typeIds` of the dsmcVolFields instance (subset of species indices)."""
+    acc = np.asarray(acc, float)
+    V = np.asarray(cell_volumes, float)
+    nT = float(n_time_steps)
+    ids = list(type_ids)
+    m = np.array([species[s]["mass"] for s in ids])
+    zeta = np.array([species[s].get("rotDof", 0.0) for s in ids])
+    Ns = acc[:, ids, 0]                                  # dsmcNSpeciesCum
+    dsmcNCum = Ns.sum(1)
+    nCum = fnum * dsmcNCum
+    mCum = fnum * (Ns * m).sum(1)
+    momentumCum = fnum * (acc[:, ids, 1:4] * m[None, :, None]).sum(1)
+    linearKECum = fnum * (acc[:, ids, 4] * m).sum(1)
+    out = {}
+    ok = dsmcNCum > 1e-3
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out["dsmcNMean"] = np.where(ok, dsmcNCum / nT, 0.001)
+        rhoN = np.where(ok, nCum / (nT * V), 0.0)
+        rhoM = np.where(ok, mCum / (nT * V), 0.0)
+        UMean = np.where(ok[:, None], momentumCum / mCum[:, None], 0.0)
+        linearKEMean = 0.5 * linearKECum / (V * nT)
+        Ttra = np.where(ok, 2.0 / (3.0 * kB * rhoN) * (linearKEMean - 0.5 * rhoM * (UMean * UMean).sum(1)), 0.0)
+        out.update(rhoN=rhoN, rhoM=rhoM, UMean=UMean, Ttra=Ttra, p=rhoN * kB * Ttra)
+        if has_internal:
+            ErotCum = acc[:, ids, 5].sum(1)
+            ZetaRotCum = (Ns * zeta).sum(1)
+            zetaRotTot = np.where(dsmcNCum > SMALL, ZetaRotCum / dsmcNCum, 0.0)
+            Trot = np.where(ZetaRotCum > SMALL, 2.0 * ErotCum / (kB * ZetaRotCum), 0.0)
+            Tvib = np.zeros_like(Trot)
+            zetaVib = np.zeros_like(Trot)
+            moleculesRhoN = np.zeros_like(Trot)
+            for k, s in enumerate(ids):
+                thv = species[s].get("thetaV", [])
+                spZeta = np.zeros_like(Trot)
+                zetaByT = np.zeros_like(Trot)
+                for mode, th in enumerate(thv):
+                    E = acc[:, s, 7 + mode]
+                    good = (E > VSMALL) & (Ns[:, k] > SMALL)
+                    iMean = np.where(good, E / (kB * th * Ns[:, k]), 0.0)
+                    good &= iMean > SMALL
+                    logF = np.where(good, np.log(1.0 + 1.0 / np.where(good, iMean, 1.0)), 1.0)
+                    TvibMod = np.where(good, th / logF, 0.0)
+                    zMod = np.where(good, 2.0 * iMean * logF, 0.0)
+                    spZeta = spZeta + zMod
+                    zetaByT = np.where(good, zMod * TvibMod, zetaByT)   # assigned, not accumulated (:1469)
+                has = spZeta > SMALL
+                nS = fnum * Ns[:, k]
+                moleculesRhoN += np.where(has, nS, 0.0)
+                Tvib += np.where(has, nS * zetaByT / np.where(has, spZeta, 1.0), 0.0)
+                zetaVib += np.where(has, nS * spZeta, 0.0)
+            Tvib = np.where(moleculesRhoN > SMALL, Tvib / moleculesRhoN, Tvib)
+            zetaVib = np.where(moleculesRhoN > SMALL, zetaVib / moleculesRhoN, zetaVib)
+            Tov = (3.0 * Ttra + zetaRotTot * Trot + zetaVib * Tvib) / (3.0 + zetaRotTot + zetaVib)
+            out.update(Trot=Trot, Tvib=Tvib, Tov=Tov, zetaVib=zetaVib)
+        # mean free path, mean collision rate (dsmcVolFields.C:1663-1790)
+        mfp = np.zeros_like(rhoN)
+        mcr = np.zeros_like(rhoN)
+        valid = Ttra > 1.0
+        T = np.where(valid, Ttra, 1.0)
+        for k, sp in enumerate(ids):
+            spMfp = np.zeros_like(rhoN)
+            spMcr = np.zeros_like(rhoN)
+            for r, sq in enumerate(ids):
+                dPQ = 0.5 * (species[sp]["diameter"] + species[sq]["diameter"])
+                omegaPQ = 0.5 * (species[sp]["omega"] + species[sq]["omega"])
+                massRatio = species[sp]["mass"] / species[sq]["mass"]
+                reduced = species[sp]["mass"] * species[sq]["mass"] / (species[sp]["mass"] + species[sq]["mass"])
+                has = Ns[:, r] > SMALL
+                nDensQ = fnum * Ns[:, r] / (V * nT)
+                spMfp += np.where(has, np.pi * dPQ ** 2 * nDensQ * (mfp_tref / T) ** (omegaPQ - 0.5) * np.sqrt(1.0 + massRatio), 0.0)
+                spMcr += np.where(has, 2.0 * np.sqrt(np.pi) * dPQ ** 2 * nDensQ * (T / mfp_tref) ** (1.0 - omegaPQ)
+                                  * np.sqrt(2.0 * kB * mfp_tref / reduced), 0.0)
+            spMfp = np.where(spMfp > SMALL, 1.0 / np.where(spMfp > SMALL, spMfp, 1.0), spMfp)
+            w = np.where(nCum > 0, fnum * Ns[:, k] / np.where(nCum > 0, nCum, 1.0), 0.0)
+            mfp += spMfp * w
+            mcr += spMcr * w
+        mfp = np.where(valid & (mfp >= SMALL), mfp, GREAT)
+        out["mfp"] = mfp
+        out["meanCollisionRate"] = np.where(valid, mcr, 0.0)
+        out["mct"] = np.where(valid & (mcr > SMALL), 1.0 / np.where(mcr > SMALL, mcr, 1.0), GREAT)
+        if coll is not None:
+            coll = np.asarray(coll, float)
+            out["measuredCollisionRate"] = np.where(nCum > SMALL, coll[:, 0] * fnum / (np.where(nCum > SMALL, nCum, 1.0) * deltaT), 0.0)
+            out["meanCollisionSeparation"] = np.where(coll[:, 0] > SMALL, coll[:, 1] / np.where(coll[:, 0] > SMALL, coll[:, 0], 1.0), GREAT)
+    return out

@@ -1,0 +1,169 @@
+"""CPU tests of the oracle's physics: the identities SURVEY.md 8c lists as the parity anchors where no
+reference-side vector exists (conservation per collision, NTC candidate counts, equilibrium collision rate,
+wall / inflow fluxes)."""
+import numpy as np
+import pytest
+
+from hystrath_b200 import capi, meshgen
+from oracle.pyoracle import Oracle
+from tests import helpers as H
+
+
+def box(n, L, species, model="VariableHardSphere", ppc=30, dens=1e20, dt=5e-6, sides=None, **kw):
+    mesh = meshgen.box_mesh(n, L, sides=sides)
+    vol = np.prod(L)
+    fnum = dens * vol / (np.prod(n) * ppc)
+    md = capi.build_models(model, nEquivalentParticles=fnum, deltaT=dt, seed=42, **kw)
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species(species); o.set_models(md)
+    return mesh, md, o
+
+
+def test_vhs_collisions_conserve_momentum_and_energy_per_cell():
+    sp = [H.argon()]
+    mesh, md, o = box((4, 4, 4), (0.016,) * 3, sp, ppc=50)
+    o.mesh_fill([0], [1e20], 300.0)
+    a = o.download_parcels()
+    o.stage(capi.STAGE_COLLIDE)
+    b = o.download_parcels()
+    assert o.counters()["collisions"] > 50
+    off = o.occupancy()
+    m = sp[0].mass
+    p0, p1 = np.add.reduceat(a.U, off[:-1], axis=0) * m, np.add.reduceat(b.U, off[:-1], axis=0) * m
+    e0, e1 = np.add.reduceat((a.U ** 2).sum(1), off[:-1]), np.add.reduceat((b.U ** 2).sum(1), off[:-1])
+    assert np.abs(p1 - p0).max() / (m * 400 * 50) < 1e-12
+    assert np.abs(e1 / e0 - 1).max() < 1e-12
+    assert np.array_equal(a.position, b.position)
+
+
+def test_larsen_borgnakke_conserves_total_energy():
+    sp = H.air5()
+    mesh, md, o = box((3, 3, 3), (0.012,) * 3, sp, "LarsenBorgnakkeVariableHardSphere", ppc=80, dens=1e21, dt=2e-6,
+                      rotationalRelaxationCollisionNumber=1.0, vibrationalRelaxationCollisionNumber=1.0)
+    o.mesh_fill([0, 1, 2, 3, 4], [0.5e21, 0.2e21, 0.1e21, 0.1e21, 0.1e21], 8000.0, 2000.0, 1000.0)
+    mass = np.array([s.mass for s in sp]); thv = np.array([s.thetaV[0] for s in sp])
+
+    def energy(p):
+        return 0.5 * mass[p.typeId] * (p.U ** 2).sum(1) + p.ERot + p.vibLevel[:, 0] * H.KB * thv[p.typeId]
+
+    a = o.download_parcels()
+    o.stage(capi.STAGE_COLLIDE)
+    b = o.download_parcels()
+    off = o.occupancy()
+    e0, e1 = np.add.reduceat(energy(a), off[:-1]), np.add.reduceat(energy(b), off[:-1])
+    assert np.abs(e1 / e0 - 1).max() < 1e-12
+    assert (a.vibLevel != b.vibLevel).sum() > 0 and (a.ERot != b.ERot).sum() > 0
+    # atoms carry no internal energy
+    assert np.all(b.ERot[b.typeId >= 3] == 0) and np.all(b.vibLevel[b.typeId >= 3] == 0)
+
+
+def test_ntc_candidate_count_and_remainder():
+    sp = [H.argon()]
+    mesh, md, o = box((4, 4, 4), (0.016,) * 3, sp, ppc=40)
+    o.mesh_fill([0], [1e20], 300.0)
+    sig, rem = o.download_cellstate()
+    nC = np.diff(o.occupancy()).astype(float)
+    o.stage(capi.STAGE_COLLIDE)
+    sig1, rem1 = o.download_cellstate()
+    V = (0.004) ** 3
+    selected = rem + 0.5 * nC * (nC - 1) * md.nEquivalentParticles * sig * md.deltaT / V
+    assert o.counters()["collisionCandidates"] == int(np.floor(selected).sum())
+    assert np.allclose(rem1, selected - np.floor(selected), atol=1e-12)
+    assert np.all(sig1 >= sig)
+
+
+def test_equilibrium_collision_rate_within_one_percent_cpu():
+    sp = [H.argon()]
+    mesh, md, o = box((10, 10, 10), (0.04,) * 3, sp, ppc=40)
+    o.mesh_fill([0], [1e20], 300.0)
+    o.evolve(15)
+    c0 = o.counters()["collisions"]
+    steps = 40
+    o.evolve(steps)
+    total = o.counters()["collisions"] - c0
+    expected = H.vhs_equilibrium_collision_rate(1e20, 300.0, sp[0]) * 0.04 ** 3 * md.deltaT * steps / md.nEquivalentParticles
+    assert abs(total / expected - 1) < 0.01, (total, expected)
+
+
+def test_heat_bath_relaxes_towards_equipartition():
+    sp = H.air5()[:1]
+    mesh, md, o = box((2, 2, 2), (0.008,) * 3, sp, "LarsenBorgnakkeVariableHardSphere", ppc=2000, dens=1e21, dt=2e-6,
+                      rotationalRelaxationCollisionNumber=1.0)
+    o.mesh_fill([0], [1e21], 3000.0, 300.0, 0.0)
+    a = o.download_parcels()
+    o.evolve(40)
+    b = o.download_parcels()
+    m = sp[0].mass
+    Ttr = lambda p: m * (p.U ** 2).sum(1).mean() / (3 * H.KB)
+    Trot = lambda p: p.ERot.mean() / H.KB
+    assert Trot(a) < 350 and Ttr(a) > 2900
+    assert abs(Ttr(b) - Trot(b)) < 0.08 * Ttr(b)          # rotation equilibrated with translation
+    assert Ttr(b) < Ttr(a)
+
+
+def test_diffuse_wall_reemits_at_wall_temperature_and_measures_fluxes():
+    sides = {"xmin": ("cyclic",), "xmax": ("cyclic",), "ymin": ("wall", "cold"), "ymax": ("wall", "hot"), "zmin": ("cyclic",), "zmax": ("cyclic",)}
+    mesh = meshgen.box_mesh((2, 6, 2), (0.01, 0.03, 0.01), sides=sides)
+    sp = [H.argon()]
+    pm = [dict(patch=mesh.patch_index("cold"), boundaryModel="dsmcDiffuseWallPatch", temperature=300.0),
+          dict(patch=mesh.patch_index("hot"), boundaryModel="dsmcDiffuseWallPatch", temperature=300.0)]
+    md = capi.build_models("NoBinaryCollision", nEquivalentParticles=1e20 * 3e-6 / (24 * 400), deltaT=5e-6, seed=3, patch_models=pm)
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
+    o.mesh_fill([0], [1e20], 300.0)
+    n0 = o.num_parcels()
+    o.evolve(30)
+    assert o.num_parcels() == n0                 # walls never delete
+    w = o.wall_accumulators()
+    assert w.shape == (8, 1, 17)
+    # equilibrium gas against an isothermal wall at the same temperature: no net heat flux within scatter, pressure = n k T
+    q = w[:, 0, 13].sum() / 30 / 8
+    fD = w[:, 0, 14:17] / 30
+    p_wall = np.abs(fD[:, 1]).mean()
+    assert abs(p_wall / (1e20 * H.KB * 300.0) - 1) < 0.05
+    incident_energy_flux = 1e20 * np.sqrt(8 * H.KB * 300 / (np.pi * sp[0].mass)) / 4 * 2 * H.KB * 300
+    assert abs(q) < 0.05 * incident_energy_flux
+    b = o.download_parcels()
+    assert b.position[:, 1].min() >= 0 and b.position[:, 1].max() <= 0.03
+
+
+def test_free_stream_inflow_flux_matches_bird_4_22():
+    sides = {"xmin": ("patch", "inlet"), "xmax": ("patch", "outlet"), "ymin": ("cyclic",), "ymax": ("cyclic",), "zmin": ("cyclic",), "zmax": ("cyclic",)}
+    mesh = meshgen.box_mesh((8, 3, 3), (0.08, 0.03, 0.03), sides=sides)
+    sp = [H.argon()]
+    pm = [dict(patch=mesh.patch_index("inlet"), boundaryModel="dsmcDeletionPatch"), dict(patch=mesh.patch_index("outlet"), boundaryModel="dsmcDeletionPatch")]
+    U = 500.0
+    inflow = [dict(patch=mesh.patch_index("inlet"), typeIds=[0], numberDensities=[1e20], velocity=(U, 0, 0), translationalTemperature=300.0)]
+    fnum = 1e20 * 0.08 * 0.03 * 0.03 / (72 * 200)
+    md = capi.build_models("NoBinaryCollision", nEquivalentParticles=fnum, deltaT=2e-6, seed=9, patch_models=pm, inflows=inflow)
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
+    p = capi.ParcelData(0, 1)
+    o.upload_parcels(p)
+    steps = 200
+    o.evolve(steps)
+    from math import erf, exp, pi, sqrt
+    cmp_ = sqrt(2 * H.KB * 300 / sp[0].mass)
+    s = U / cmp_
+    flux = 1e20 * cmp_ * (exp(-s * s) + sqrt(pi) * s * (1 + erf(s))) / (2 * sqrt(pi))      # Bird eq. 4.22
+    expected = flux * 0.03 * 0.03 * md.deltaT * steps / fnum
+    ins = o.counters()["inserted"]
+    assert abs(ins / expected - 1) < 3.5 / np.sqrt(expected) + 1e-3
+    q = o.download_parcels()
+    assert q.n > 0 and abs(q.U[:, 0].mean() / U - 1) < 0.1
+
+
+def test_cyclic_box_keeps_parcels_and_cells_consistent():
+    sp = [H.argon()]
+    mesh, md, o = box((5, 4, 3), (0.02, 0.016, 0.012), sp, "NoBinaryCollision", ppc=60)
+    o.mesh_fill([0], [1e20], 300.0, velocity=(300.0, -200.0, 100.0))
+    a = H.by_id(o.download_parcels())
+    o.evolve(6)
+    b = H.by_id(o.download_parcels())
+    assert len(b["origId"]) == len(a["origId"])
+    L = np.array([0.02, 0.016, 0.012])
+    free = a["position"] + 6 * md.deltaT * a["U"]
+    assert np.allclose(b["position"], np.mod(free, L), atol=1e-12)      # ballistic flight with periodic wrap
+    ijk = np.floor(b["position"] / 0.004).astype(int)
+    assert np.array_equal(ijk[:, 0] + 5 * (ijk[:, 1] + 4 * ijk[:, 2]), b["cell"])
+    assert np.array_equal(a["U"], b["U"])
