@@ -1,0 +1,728 @@
+// dsmc_cloud.cpp -- see dsmc_cloud.h
+#include "dsmc_cloud.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <sstream>
+
+namespace dsmcb200 {
+
+using foam::Dict;
+using foam::FoamError;
+
+namespace {
+const double SMALL = 1e-15, VSMALL = 1e-300, GREAT = 1e15;
+
+std::string joinNames(const std::vector<std::string>& v) {
+    std::ostringstream s;
+    s << v.size() << "(";
+    for (size_t i = 0; i < v.size(); ++i) s << (i ? " " : "") << v[i];
+    s << ")";
+    return s.str();
+}
+
+// the message shape of OpenFOAM's run-time selection failure (BinaryCollisionModel.C:70-85)
+[[noreturn]] void unknownType(const std::string& where, const std::string& family, const std::string& name, const std::vector<std::string>& valid) {
+    throw FoamError(where + " : \n    unknown " + family + " type " + name + ", constructor not in hash table\n\n    Valid " + family +
+                    " types are :\n" + joinNames(valid));
+}
+
+void copyName(char* dst, const std::string& s) {
+    std::memset(dst, 0, DSMCB200_NAME_LEN);
+    std::strncpy(dst, s.c_str(), DSMCB200_NAME_LEN - 1);
+}
+}  // namespace
+
+int selectBinaryCollisionModel(const std::string& name) {
+    if (name == "NoBinaryCollision") return DSMCB200_COLL_NONE;
+    if (name == "VariableHardSphere") return DSMCB200_COLL_VHS;
+    if (name == "LarsenBorgnakkeVariableHardSphere") return DSMCB200_COLL_LB_VHS;
+    unknownType("BinaryCollisionModel::New(const dictionary&, CloudType&)", "BinaryCollisionModel", name,
+                {"LarsenBorgnakkeVariableHardSphere", "NoBinaryCollision", "VariableHardSphere"});
+}
+int selectCollisionPartnerSelection(const std::string& name) {
+    if (name == "noTimeCounter") return 1;
+    unknownType("collisionPartnerSelection::New(const dictionary&)", "collisionPartnerSelection", name, {"noTimeCounter"});
+}
+int selectPatchBoundaryModel(const std::string& name) {
+    if (name == "dsmcDiffuseWallPatch") return DSMCB200_BND_DIFFUSE_WALL;
+    if (name == "dsmcSpecularWallPatch") return DSMCB200_BND_SPECULAR_WALL;
+    if (name == "dsmcDeletionPatch") return DSMCB200_BND_DELETION;
+    unknownType("dsmcPatchBoundary::New(const dictionary&)", "patch boundary", name,
+                {"dsmcDeletionPatch", "dsmcDiffuseWallPatch", "dsmcSpecularWallPatch"});
+}
+void selectGeneralBoundaryModel(const std::string& name) {
+    if (name != "dsmcFreeStreamInflowPatch")
+        unknownType("dsmcGeneralBoundary::New(const dictionary&)", "general boundary", name, {"dsmcFreeStreamInflowPatch"});
+}
+void selectFieldModel(const std::string& name) {
+    if (name != "dsmcVolFields") unknownType("dsmcField::New(const dictionary&)", "dsmcField", name, {"dsmcVolFields"});
+}
+void selectCoordinateSystem(const std::string& name) {
+    if (name != "dsmcCartesian") unknownType("dsmcCoordinateSystem::New", "dsmcCoordinateSystem", name, {"dsmcCartesian"});
+}
+void selectTimeStepModel(const std::string& name) {
+    if (name != "constant" && name != "dsmcConstantTimeStepModel")
+        unknownType("dsmcTimeStepModel::New", "dsmcTimeStepModel", name, {"constant"});
+}
+int patchTypeFromWord(const std::string& t) {
+    if (t == "wall") return DSMCB200_PATCH_WALL;
+    if (t == "patch") return DSMCB200_PATCH_PATCH;
+    if (t == "cyclic") return DSMCB200_PATCH_CYCLIC;
+    if (t == "processor") return DSMCB200_PATCH_PROCESSOR;
+    if (t == "empty") return DSMCB200_PATCH_EMPTY;
+    if (t == "symmetryPlane") return DSMCB200_PATCH_SYMMETRYPLANE;
+    if (t == "symmetry") return DSMCB200_PATCH_SYMMETRY;
+    if (t == "wedge") return DSMCB200_PATCH_WEDGE;
+    if (t == "processorCyclic") return DSMCB200_PATCH_PROCESSORCYCLIC;
+    throw FoamError("polyPatch type " + t + " is not supported by the dsmcb200 tracker");
+}
+
+void dsmcCloud::check(int rc, const char* what) {
+    if (rc != 0) throw FoamError(std::string(what) + ": " + (ctx_ ? dsmcb200_last_error(ctx_) : "no context") + " (" + std::to_string(rc) + ")");
+}
+
+dsmcCloud::dsmcCloud(const std::string& caseDir, const std::string& cloudName, int rank, int nRanks, int device, const void* ncclId128, bool dryRun)
+    : caseDir_(caseDir), cloudName_(cloudName), rank_(rank), nRanks_(nRanks), dryRun_(dryRun) {
+    root_ = nRanks > 1 ? caseDir + "/processor" + std::to_string(rank) : caseDir;
+    readControl();
+    readMesh();
+    readProperties();
+    readBoundaries();
+    readFieldProperties();
+    if (dryRun_) { readCloud(); return; }
+    int rc = dsmcb200_create(&ctx_, device, rank, nRanks);
+    if (rc != 0) throw FoamError("dsmcb200_create failed: a CUDA device is required, there is no CPU fallback");
+    if (nRanks > 1) {
+        if (!ncclId128) throw FoamError("parallel run needs an ncclUniqueId");
+        check(dsmcb200_init_comm(ctx_, ncclId128), "dsmcb200_init_comm");
+    }
+    dsmcb200_mesh m{};
+    m.nPoints = int32_t(points_.size() / 3); m.nFaces = nFaces_; m.nInternalFaces = nInternal_; m.nCells = nCells_;
+    m.nPatches = int32_t(patches_.size());
+    m.points = points_.data(); m.faceOffsets = faceOffsets_.data(); m.facePoints = facePoints_.data();
+    m.owner = owner_.data(); m.neighbour = neighbour_.data(); m.patches = patches_.data();
+    check(dsmcb200_set_mesh(ctx_, &m), "dsmcb200_set_mesh");
+    check(dsmcb200_set_species(ctx_, int(species_.size()), species_.data()), "dsmcb200_set_species");
+    models_.nPatchModels = int32_t(patchModels_.size()); models_.patchModels = patchModels_.data();
+    models_.nInflows = int32_t(inflows_.size()); models_.inflows = inflows_.data();
+    check(dsmcb200_set_models(ctx_, &models_), "dsmcb200_set_models");
+    cellVolumes_.resize(nCells_); cellCentres_.resize(size_t(nCells_) * 3); faceAreas_.resize(size_t(nFaces_) * 3); faceCentres_.resize(size_t(nFaces_) * 3);
+    check(dsmcb200_download_geometry(ctx_, cellCentres_.data(), cellVolumes_.data(), faceCentres_.data(), faceAreas_.data(), nullptr), "dsmcb200_download_geometry");
+    readCloud();
+}
+
+dsmcCloud::~dsmcCloud() {
+    if (ctx_) dsmcb200_destroy(ctx_);
+}
+
+void dsmcCloud::readControl() {
+    Dict c = foam::readDict(caseDir_ + "/system/controlDict");
+    deltaT_ = c.scalar("deltaT");
+    endTime_ = c.scalar("endTime");
+    writeControl_ = c.wordOr("writeControl", "timeStep");
+    writeInterval_ = c.scalarOr("writeInterval", 1.0);
+    timePrecision_ = int(c.labelOr("timePrecision", 6));
+    nTerminalOutputs_ = int(c.labelOr("nTerminalOutputs", 1));  // dsmcCloud.C:612-615
+    std::string startFrom = c.wordOr("startFrom", "latestTime");
+    std::vector<std::pair<double, std::string>> times;
+    for (auto& n : foam::listDir(root_)) {
+        char* e = nullptr;
+        double v = std::strtod(n.c_str(), &e);
+        if (e && *e == '\0' && !n.empty() && foam::exists(root_ + "/" + n + "/lagrangian")) times.push_back({v, n});
+    }
+    if (times.empty()) throw FoamError("no time directory with a lagrangian cloud under " + root_);
+    std::sort(times.begin(), times.end());
+    if (startFrom == "latestTime") { startTime_ = times.back().first; timeName_ = times.back().second; }
+    else if (startFrom == "firstTime") { startTime_ = times.front().first; timeName_ = times.front().second; }
+    else {
+        startTime_ = c.scalarOr("startTime", 0.0);
+        timeName_.clear();
+        for (auto& t : times) if (std::fabs(t.first - startTime_) <= 1e-12 * std::max(1.0, std::fabs(startTime_))) timeName_ = t.second;
+        if (timeName_.empty()) throw FoamError("start time directory not found under " + root_);
+    }
+    time_ = startTime_;
+}
+
+void dsmcCloud::readMesh() {
+    const std::string pm = root_ + "/constant/polyMesh/";
+    points_ = foam::readVectorField(pm + "points");
+    foam::readFaces(pm + "faces", faceOffsets_, facePoints_);
+    owner_ = foam::readLabelField(pm + "owner");
+    neighbour_ = foam::readLabelField(pm + "neighbour");
+    boundary_ = foam::readBoundary(pm + "boundary");
+    nFaces_ = int(owner_.size());
+    nInternal_ = int(neighbour_.size());
+    nCells_ = 0;
+    for (int32_t c : owner_) nCells_ = std::max(nCells_, c + 1);
+    for (int32_t c : neighbour_) nCells_ = std::max(nCells_, c + 1);
+    patches_.clear();
+    for (auto& b : boundary_) {
+        dsmcb200_patch p{};
+        copyName(p.name, b.name);
+        p.type = patchTypeFromWord(b.type);
+        p.start = b.startFace; p.size = b.nFaces; p.neighbPatch = -1; p.referPatch = -1;
+        p.myProcNo = b.myProcNo; p.neighbProcNo = b.neighbProcNo;
+        p.hasSeparation = b.hasSeparation ? 1 : 0;
+        for (int k = 0; k < 3; ++k) p.separation[k] = b.separation[k];
+        patches_.push_back(p);
+    }
+    for (size_t i = 0; i < boundary_.size(); ++i) {
+        auto find = [&](const std::string& n) { for (size_t k = 0; k < boundary_.size(); ++k) if (boundary_[k].name == n) return int(k); return -1; };
+        if (!boundary_[i].neighbourPatch.empty()) patches_[i].neighbPatch = find(boundary_[i].neighbourPatch);
+        if (!boundary_[i].referPatch.empty()) patches_[i].referPatch = find(boundary_[i].referPatch);
+        if (patches_[i].type == DSMCB200_PATCH_CYCLIC && patches_[i].neighbPatch < 0)
+            throw FoamError("cyclic patch " + boundary_[i].name + " has no neighbourPatch entry");
+    }
+}
+
+void dsmcCloud::readProperties() {
+    Dict d = foam::readDict(caseDir_ + "/constant/dsmcProperties");
+    std::memset(&models_, 0, sizeof(models_));
+    models_.nEquivalentParticles = d.scalar("nEquivalentParticles");
+    models_.deltaT = deltaT_;
+    const std::string bcm = d.word("BinaryCollisionModel");
+    models_.collisionModel = selectBinaryCollisionModel(bcm);
+    selectCollisionPartnerSelection(d.word("collisionPartnerSelectionModel"));
+    selectCoordinateSystem(d.wordOr("coordinateSystem", "dsmcCartesian"));
+    selectTimeStepModel(d.wordOr("timeStepModel", "constant"));
+    // VariableHardSphere reads Tref from VariableHardSphereCoeffs even under the LB model (VariableHardSphere.C:56-62)
+    models_.Tref = d.isDict("VariableHardSphereCoeffs") ? d.subDict("VariableHardSphereCoeffs").scalarOr("Tref", 273.0) : 273.0;
+    models_.rotationalRelaxationCollisionNumber = 5.0;
+    models_.vibrationalRelaxationCollisionNumber = 0.0;
+    models_.electronicRelaxationCollisionNumber = 500.0;
+    models_.invZvFormulation = 2;
+    if (d.isDict("LarsenBorgnakkeVariableHardSphereCoeffs")) {
+        const Dict& lb = d.subDict("LarsenBorgnakkeVariableHardSphereCoeffs");
+        models_.rotationalRelaxationCollisionNumber = lb.scalarOr("rotationalRelaxationCollisionNumber", 5.0);
+        models_.vibrationalRelaxationCollisionNumber = lb.scalarOr("vibrationalRelaxationCollisionNumber", 0.0);
+        models_.electronicRelaxationCollisionNumber = lb.scalarOr("electronicRelaxationCollisionNumber", 500.0);
+        const std::string v = lb.wordOr("inverseZvFormulation", "");
+        models_.invZvFormulation = v == "pre-2008" ? 0 : (v == "2008" ? 1 : 2);
+    }
+    // dsmcCloud.C:639-646: seedNumber or clock + 7183*rank
+    models_.seed = d.found("seedNumber") ? uint64_t(d.label("seedNumber")) + 7183ull * uint64_t(rank_)
+                                         : uint64_t(std::time(nullptr)) + 7183ull * uint64_t(rank_);
+    typeIdList_ = d.wordList("typeIdList");
+    if (typeIdList_.empty()) throw FoamError("typeIdList is empty in " + d.name);
+    const Dict& mp = d.subDict("moleculeProperties");
+    species_.clear();
+    maxModes_ = 1;
+    for (auto& id : typeIdList_) {
+        const Dict& s = mp.subDict(id);
+        dsmcb200_species sp{};
+        copyName(sp.name, id);
+        sp.mass = s.scalar("mass"); sp.diameter = s.scalar("diameter"); sp.omega = s.scalar("omega"); sp.alpha = s.scalarOr("alpha", 1.0);
+        sp.rotationalDegreesOfFreedom = s.scalarOr("rotationalDegreesOfFreedom", 0.0);
+        sp.nVibrationalModes = int32_t(s.labelOr("nVibrationalModes", 0));
+        auto thetaV = s.scalarListOr("characteristicVibrationalTemperature", {});
+        auto Zref = s.scalarListOr("Zref", {});
+        auto TrefZv = s.scalarListOr("referenceTempForZref", {});
+        if (int(thetaV.size()) != sp.nVibrationalModes)
+            throw FoamError("Number of characteristic vibrational temperatures is " + std::to_string(thetaV.size()) + ", instead of " + std::to_string(sp.nVibrationalModes));
+        if (int(Zref.size()) != sp.nVibrationalModes)
+            throw FoamError("Number of reference vibrational relaxation numbers is" + std::to_string(Zref.size()) + ", instead of " + std::to_string(sp.nVibrationalModes));
+        if (int(TrefZv.size()) != sp.nVibrationalModes)
+            throw FoamError("Number of reference temperature for vibrational relaxation is" + std::to_string(TrefZv.size()) + ", instead of " + std::to_string(sp.nVibrationalModes));
+        if (sp.nVibrationalModes > DSMCB200_MAX_VIB_MODES) throw FoamError("species " + id + ": more than 3 vibrational modes are not supported");
+        for (int m = 0; m < sp.nVibrationalModes; ++m) { sp.thetaV[m] = thetaV[m]; sp.Zref[m] = Zref[m]; sp.TrefZv[m] = TrefZv[m]; }
+        sp.thetaD = s.scalarOr("dissociationTemperature", 0.0);
+        sp.charge = int32_t(s.labelOr("charge", 0));
+        if (sp.charge < -1 || sp.charge > 1) throw FoamError("Charge value should be 0 for neutrals, 1 for ions, or -1 for electrons, instead of " + std::to_string(sp.charge));
+        sp.nElectronicLevels = int32_t(s.labelOr("nElectronicLevels", 1));
+        auto ee = s.scalarListOr("electronicEnergyList", {0.0});
+        auto eg = s.labelListOr("electronicDegeneracyList", {1});
+        if (int(eg.size()) != sp.nElectronicLevels) throw FoamError("Number of degeneracy levels should be " + std::to_string(sp.nElectronicLevels) + ", instead of " + std::to_string(eg.size()));
+        if (int(ee.size()) != sp.nElectronicLevels) throw FoamError("Number of electronic energy levels should be " + std::to_string(sp.nElectronicLevels) + ", instead of " + std::to_string(ee.size()));
+        if (sp.nElectronicLevels > DSMCB200_MAX_ELEC_LEVELS) throw FoamError("species " + id + ": more than 16 electronic levels are not supported");
+        for (int l = 0; l < sp.nElectronicLevels; ++l) { sp.electronicEnergyList[l] = ee[l]; sp.electronicDegeneracyList[l] = int32_t(eg[l]); }
+        maxModes_ = std::max(maxModes_, int(sp.nVibrationalModes));
+        species_.push_back(sp);
+    }
+    if (foam::exists(caseDir_ + "/system/chemReactDict")) {
+        Dict cr = foam::readDict(caseDir_ + "/system/chemReactDict");
+        if (!cr.dictList("reactions").empty())
+            throw FoamError("chemReactDict lists reactions: QK chemistry is outside the scoped path (SURVEY 8f-2); use `reactions ();`");
+    }
+}
+
+void dsmcCloud::readBoundaries() {
+    patchModels_.clear(); inflows_.clear();
+    const std::string path = caseDir_ + "/system/boundariesDict";
+    if (!foam::exists(path)) return;
+    Dict d = foam::readDict(path);
+    auto patchId = [&](const std::string& n) {
+        for (size_t k = 0; k < boundary_.size(); ++k) if (boundary_[k].name == n) return int(k);
+        return -1;
+    };
+    auto typeId = [&](const std::string& n) {
+        for (size_t k = 0; k < typeIdList_.size(); ++k) if (typeIdList_[k] == n) return int(k);
+        return -1;
+    };
+    for (auto& e : d.dictList("dsmcPatchBoundaries")) {
+        const Dict& b = *e.second;
+        const std::string patchName = b.subDict("patchBoundaryProperties").word("patchName");
+        const std::string model = b.word("boundaryModel");
+        const int kind = selectPatchBoundaryModel(model);
+        const int pid = patchId(patchName);
+        if (pid < 0) {
+            if (nRanks_ > 1) continue;  // the patch has no faces on this processor
+            throw FoamError("Cannot find patch: " + patchName + "\nin: " + path);
+        }
+        dsmcb200_patch_model pm{};
+        pm.patch = pid; pm.model = kind;
+        if (kind == DSMCB200_BND_DIFFUSE_WALL) {
+            const Dict& pr = b.subDict(model + "Properties");
+            pm.temperature = pr.found("groundLevelTemperature") ? pr.scalar("groundLevelTemperature") : pr.scalar("temperature");
+            auto v = pr.vector3("velocity");
+            for (int k = 0; k < 3; ++k) pm.velocity[k] = v[k];
+        }
+        patchModels_.push_back(pm);
+    }
+    if (!d.dictList("dsmcCyclicBoundaries").empty())
+        throw FoamError("dsmcCyclicBoundaries models are outside the scoped path (only an empty list is supported)");
+    for (auto& e : d.dictList("dsmcGeneralBoundaries")) {
+        const Dict& b = *e.second;
+        const std::string patchName = b.subDict("generalBoundaryProperties").word("patchName");
+        const std::string model = b.word("boundaryModel");
+        selectGeneralBoundaryModel(model);
+        const int pid = patchId(patchName);
+        if (pid < 0) {
+            if (nRanks_ > 1) continue;
+            throw FoamError("Cannot find patch: " + patchName + "\nin: " + path);
+        }
+        const Dict& pr = b.subDict(model + "Properties");
+        dsmcb200_inflow in{};
+        in.patch = pid;
+        std::vector<std::string> mols;
+        for (auto& w : pr.wordList("typeIds")) if (std::find(mols.begin(), mols.end(), w) == mols.end()) mols.push_back(w);
+        if (mols.empty()) throw FoamError("Cannot have zero typeIds being inserted.\nin: " + path);
+        const Dict& nd = pr.subDict("numberDensities");
+        in.nTypes = int32_t(mols.size());
+        for (size_t k = 0; k < mols.size(); ++k) {
+            const int t = typeId(mols[k]);
+            if (t < 0) throw FoamError("Cannot find typeId: " + mols[k] + "\nin: " + path);
+            in.typeIds[k] = t;
+            in.numberDensities[k] = nd.scalar(mols[k]);
+        }
+        auto v = pr.vector3("velocity");
+        for (int k = 0; k < 3; ++k) in.velocity[k] = v[k];
+        in.translationalTemperature = pr.scalar("translationalTemperature");
+        in.rotationalTemperature = pr.scalarOr("rotationalTemperature", 0.0);
+        in.vibrationalTemperature = pr.scalarOr("vibrationalTemperature", 0.0);
+        in.electronicTemperature = pr.scalarOr("electronicTemperature", 0.0);
+        inflows_.push_back(in);
+    }
+}
+
+void dsmcCloud::readFieldProperties() {
+    fields_.clear();
+    const std::string path = caseDir_ + "/system/fieldPropertiesDict";
+    if (!foam::exists(path)) return;
+    Dict d = foam::readDict(path);
+    for (auto& e : d.dictList("dsmcFields")) {
+        const Dict& f = *e.second;
+        const std::string model = f.word("fieldModel");
+        selectFieldModel(model);
+        const Dict& pr = f.subDict(model + "Properties");
+        FieldSpec s;
+        s.fieldName = pr.word("fieldName");
+        for (auto& w : pr.wordList("typeIds")) {
+            int t = -1;
+            for (size_t k = 0; k < typeIdList_.size(); ++k) if (typeIdList_[k] == w) t = int(k);
+            if (t < 0) throw FoamError("Cannot find typeId: " + w + "\nin: " + path);
+            if (std::find(s.typeIds.begin(), s.typeIds.end(), t) == s.typeIds.end()) s.typeIds.push_back(t);
+        }
+        s.measureMeanFreePath = pr.boolOr("measureMeanFreePath", false);
+        s.densityOnly = pr.boolOr("densityOnly", false);
+        s.measureHeatFluxShearStress = pr.boolOr("measureHeatFluxShearStress", false);
+        s.measureClassifications = pr.boolOr("measureClassifications", false);
+        s.mfpReferenceTemperature = pr.scalarOr("mfpReferenceTemperature", 273.0);
+        s.sampleInterval = int(pr.labelOr("sampleInterval", 1));
+        if (f.isDict("timeProperties")) {
+            const Dict& tp = f.subDict("timeProperties");
+            s.resetAtOutput = tp.boolOr("resetAtOutput", true);
+            s.resetAtOutputUntilTime = tp.scalarOr("resetAtOutputUntilTime", 1e300);
+        }
+        if (s.measureHeatFluxShearStress) models_.measureHeatFluxShearStress = 1;
+        if (s.measureClassifications) models_.measureClassifications = 1;
+        fields_.push_back(s);
+    }
+}
+
+void dsmcCloud::readCloud() {
+    const std::string dir = root_ + "/" + timeName_ + "/lagrangian/" + cloudName_ + "/";
+    std::vector<double> xyz, U, ERot;
+    std::vector<int32_t> cell, typeId, vib, elevel, cls, origId;
+    foam::readPositions(dir + "positions", xyz, cell);
+    const int64_t n = int64_t(cell.size());
+    U = foam::readVectorField(dir + "U");
+    typeId = foam::readLabelField(dir + "typeId");
+    if (int64_t(U.size()) != 3 * n || int64_t(typeId.size()) != n) throw FoamError("cloud files under " + dir + " have inconsistent sizes");
+    dsmcb200_parcels_soa s{};
+    s.position = xyz.data(); s.U = U.data(); s.cell = cell.data(); s.typeId = typeId.data();
+    s.maxModes = maxModes_;
+    if (foam::exists(dir + "ERot")) { ERot = foam::readScalarField(dir + "ERot"); if (int64_t(ERot.size()) == n) s.ERot = ERot.data(); }
+    if (foam::exists(dir + "vibLevel")) {
+        int w = 0;
+        vib = foam::readLabelListList(dir + "vibLevel", w);
+        if (w > 0) { s.vibLevel = vib.data(); s.maxModes = w; }
+    }
+    if (foam::exists(dir + "ELevel")) { elevel = foam::readLabelField(dir + "ELevel"); if (int64_t(elevel.size()) == n) s.ELevel = elevel.data(); }
+    if (foam::exists(dir + "classification")) { cls = foam::readLabelField(dir + "classification"); if (int64_t(cls.size()) == n) s.classification = cls.data(); }
+    if (foam::exists(dir + "origId")) { origId = foam::readLabelField(dir + "origId"); if (int64_t(origId.size()) == n) s.origId = origId.data(); }
+    nRead_ = n;
+    // <time>/dsmcSigmaTcRMax is MUST_READ (dsmcCloud.C:625-636)
+    auto sig = foam::readInternalField(root_ + "/" + timeName_ + "/dsmcSigmaTcRMax", nCells_, 1);
+    if (dryRun_) return;
+    check(dsmcb200_upload_parcels(ctx_, n, &s), "dsmcb200_upload_parcels");
+    check(dsmcb200_upload_cellstate(ctx_, sig.data(), nullptr), "dsmcb200_upload_cellstate");
+}
+
+std::string dsmcCloud::summary() const {
+    std::ostringstream o;
+    o << "case " << caseDir_ << "\n  startTime " << timeName_ << " deltaT " << deltaT_ << " endTime " << endTime_ << " writeControl " << writeControl_
+      << " writeInterval " << writeInterval_ << " nTerminalOutputs " << nTerminalOutputs_ << "\n  mesh: " << points_.size() / 3 << " points "
+      << nFaces_ << " faces " << nInternal_ << " internal " << nCells_ << " cells " << boundary_.size() << " patches\n";
+    for (auto& b : boundary_) o << "    patch " << b.name << " " << b.type << " " << b.nFaces << " @" << b.startFace << "\n";
+    o << "  species:";
+    for (auto& t : typeIdList_) o << " " << t;
+    o << "\n  collisionModel " << models_.collisionModel << " invZv " << models_.invZvFormulation << " nEquivalentParticles " << models_.nEquivalentParticles
+      << " seed " << models_.seed << "\n  patchModels " << patchModels_.size() << " inflows " << inflows_.size() << " fields " << fields_.size() << "\n";
+    for (auto& f : fields_) {
+        o << "    field " << f.fieldName << " typeIds";
+        for (int t : f.typeIds) o << " " << t;
+        o << " mfp " << f.measureMeanFreePath << " reset " << f.resetAtOutput << "\n";
+    }
+    o << "  parcels " << nRead_ << "\n";
+    return o.str();
+}
+
+bool dsmcCloud::loop() {
+    if (!(time_ < endTime_ - 0.5 * deltaT_)) return false;
+    ++timeIndex_;
+    time_ = startTime_ + double(timeIndex_) * deltaT_;
+    timeName_ = foam::timeName(time_, timePrecision_);
+    return true;
+}
+
+bool dsmcCloud::outputTime() const {
+    if (writeControl_ == "timeStep") return timeIndex_ % std::max<int64_t>(1, int64_t(std::llround(writeInterval_))) == 0;
+    // runTime / adjustableRunTime: Time::adjustDeltaT-free form of Time::operator++
+    const int64_t now = int64_t(((time_ - startTime_) + 0.5 * deltaT_) / writeInterval_);
+    const int64_t before = int64_t(((time_ - deltaT_ - startTime_) + 0.5 * deltaT_) / writeInterval_);
+    return now > before;
+}
+
+int64_t dsmcCloud::nParcels() {
+    int64_t n = 0;
+    check(dsmcb200_download_parcels(ctx_, 0, &n, nullptr), "dsmcb200_download_parcels");
+    return n;
+}
+
+void dsmcCloud::evolve() {
+    check(dsmcb200_evolve(ctx_, 1), "dsmcb200_evolve");
+    ++infoCounter_;
+    if (infoCounter_ >= nTerminalOutputs_) {
+        dsmcb200_counters c{};
+        check(dsmcb200_get_counters(ctx_, &c), "dsmcb200_get_counters");
+        double v[2] = {double(c.collisions), double(c.collisionCandidates)};
+        if (nRanks_ > 1) check(dsmcb200_allreduce_sum(ctx_, v, 2), "dsmcb200_allreduce_sum");
+        if (rank_ == 0) {
+            // noTimeCounter.C:320-337
+            if (v[1] > 0) std::printf("    Collisions                      = %lld\n\n", (long long)v[0]);
+            else std::printf("    No collisions\n");
+        }
+        infoCounter_ = 0;
+    }
+}
+
+void dsmcCloud::info() {
+    dsmcb200_counters c{};
+    check(dsmcb200_get_counters(ctx_, &c), "dsmcb200_get_counters");
+    double v[6] = {double(c.nParcels), c.mass, c.linearKineticEnergy, c.rotationalEnergy, c.vibrationalEnergy, c.electronicEnergy};
+    if (nRanks_ > 1) check(dsmcb200_allreduce_sum(ctx_, v, 6), "dsmcb200_allreduce_sum");
+    if (rank_ != 0) return;
+    const double nP = models_.nEquivalentParticles;
+    const double nMol = v[0] * nP;
+    // dsmcCloud.C:960-981
+    std::printf("    Number of DSMC particles        = %lld\n", (long long)v[0]);
+    if (v[0] > 0) {
+        std::printf("    Number of stuck particles       = %g\n", 0.0);
+        std::printf("    Number of free particles        = %g\n", nMol / nP);
+        std::printf("    Average linear kinetic energy   = %g\n", v[2] / nMol);
+        std::printf("    Average rotational energy       = %g\n", v[3] / nMol);
+        std::printf("    Average vibrational energy      = %g\n", v[4] / nMol);
+        std::printf("    Average electronic energy       = %g\n", v[5] / nMol);
+        std::printf("    Total energy                    = %g\n", v[2] + v[3] + v[4] + v[5]);
+    }
+    std::fflush(stdout);
+}
+
+// dsmcVolFields::calculateField reductions (dsmcVolFields.C:1242-1290, 1401-1508, 1663-1790) from the per-species
+// moment sums accumulated on the device.
+DerivedFields dsmcCloud::calculateField(const FieldSpec& f) {
+    dsmcb200_accum_info ai{};
+    check(dsmcb200_accum_info_get(ctx_, &ai), "dsmcb200_accum_info_get");
+    const int S = ai.nSpecies, nQ = ai.nQuantities, nC = ai.nCells;
+    std::vector<double> acc(size_t(nC) * S * nQ), coll(size_t(nC) * 2);
+    check(dsmcb200_download_accumulators(ctx_, acc.data(), coll.data()), "dsmcb200_download_accumulators");
+    const bool internal = ai.nModes >= 0;
+    const double nT = ai.nTimeSteps > 0 ? ai.nTimeSteps : 1.0;
+    const double kB = models_.kB > 0 ? models_.kB : 1.38065e-23;
+    const double FN = models_.nEquivalentParticles;
+    DerivedFields o;
+    auto z = [&](std::vector<double>& v, int w = 1) { v.assign(size_t(nC) * w, 0.0); };
+    z(o.dsmcNMean); z(o.rhoN); z(o.rhoM); z(o.p); z(o.Ttra); z(o.Trot); z(o.Tvib); z(o.Tov); z(o.Ma); z(o.mfp); z(o.mct); z(o.mctToDt);
+    z(o.mfpToDx); z(o.measuredCollisionRate); z(o.UMean, 3);
+    const double NAvo = 6.02214e26;  // OpenFOAM SI physicoChemical::NA is per kmol
+    (void)NAvo;
+    for (int c = 0; c < nC; ++c) {
+        const double V = cellVolumes_[c];
+        double dsmcNCum = 0, mCumP = 0, ErotCum = 0, ZetaRotCum = 0, keP = 0;
+        double mom[3] = {0, 0, 0};
+        for (int s : f.typeIds) {
+            const double* r = &acc[(size_t(c) * S + s) * nQ];
+            const double m = species_[s].mass;
+            dsmcNCum += r[0]; mCumP += m * r[0];
+            for (int k = 0; k < 3; ++k) mom[k] += m * r[1 + k];
+            keP += m * r[4];
+            if (internal) { ErotCum += r[5]; ZetaRotCum += species_[s].rotationalDegreesOfFreedom * r[0]; }
+        }
+        const double nCum = FN * dsmcNCum, mCum = FN * mCumP, linearKECum = FN * keP;
+        if (dsmcNCum > 1e-3) {
+            o.dsmcNMean[c] = dsmcNCum / nT;
+            const double rhoNMean = nCum / (nT * V), rhoMMean = mCum / (nT * V);
+            o.rhoN[c] = rhoNMean; o.rhoM[c] = rhoMMean;
+            double uu = 0;
+            for (int k = 0; k < 3; ++k) { o.UMean[3 * c + k] = FN * mom[k] / mCum; uu += o.UMean[3 * c + k] * o.UMean[3 * c + k]; }
+            const double linearKEMean = 0.5 * linearKECum / (V * nT);
+            o.Ttra[c] = 2.0 / (3.0 * kB * rhoNMean) * (linearKEMean - 0.5 * rhoMMean * uu);
+            o.p[c] = rhoNMean * kB * o.Ttra[c];
+        } else {
+            o.dsmcNMean[c] = 0.001;
+        }
+        if (f.densityOnly) continue;
+        const double zetaRotTot = dsmcNCum > SMALL ? ZetaRotCum / dsmcNCum : 0.0;
+        o.Trot[c] = ZetaRotCum > SMALL ? 2.0 * ErotCum / (kB * ZetaRotCum) : 0.0;
+        double moleculesRhoN = 0, Tvib = 0, zetaVib = 0;
+        if (internal) {
+            for (int s : f.typeIds) {
+                const double* r = &acc[(size_t(c) * S + s) * nQ];
+                double speciesZetaVib = 0, zetaByTvibMod = 0;
+                for (int m = 0; m < species_[s].nVibrationalModes; ++m) {
+                    const double E = r[7 + m];
+                    if (E > VSMALL && r[0] > SMALL) {
+                        const double thetaV = species_[s].thetaV[m];
+                        const double iMean = E / (kB * thetaV * r[0]);
+                        if (iMean > SMALL) {
+                            const double logFactor = std::log(1.0 + 1.0 / iMean);
+                            const double TvibMod = thetaV / logFactor, zMod = 2.0 * iMean * logFactor;
+                            speciesZetaVib += zMod;
+                            zetaByTvibMod = zMod * TvibMod;  // assigned, not accumulated (dsmcVolFields.C:1469)
+                        }
+                    }
+                }
+                if (speciesZetaVib > SMALL) {
+                    const double nS = FN * r[0];
+                    moleculesRhoN += nS;
+                    Tvib += nS * zetaByTvibMod / speciesZetaVib;
+                    zetaVib += nS * speciesZetaVib;
+                }
+            }
+            if (moleculesRhoN > SMALL) { Tvib /= moleculesRhoN; zetaVib /= moleculesRhoN; }
+        }
+        o.Tvib[c] = Tvib;
+        o.Tov[c] = (3.0 * o.Ttra[c] + zetaRotTot * o.Trot[c] + zetaVib * Tvib) / (3.0 + zetaRotTot + zetaVib);
+        // Mach number (dsmcVolFields.C:1624-1661)
+        if (dsmcNCum > SMALL && o.Ttra[c] > SMALL) {
+            double molecularMass = 0, cv = 0, cp = 0;
+            for (int s : f.typeIds) {
+                const double Xs = acc[(size_t(c) * S + s) * nQ] / dsmcNCum;
+                molecularMass += Xs * species_[s].mass;
+                cv += Xs * (3.0 + species_[s].rotationalDegreesOfFreedom);
+                cp += Xs * (5.0 + species_[s].rotationalDegreesOfFreedom);
+            }
+            const double gamma = cp / cv;
+            const double a = std::sqrt(gamma * kB / molecularMass * o.Ttra[c]);
+            const double* u = &o.UMean[3 * c];
+            o.Ma[c] = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]) / a;
+        }
+        if (f.measureMeanFreePath && o.Ttra[c] > 1.0) {
+            double mfp = 0, mcr = 0;
+            for (int sp : f.typeIds) {
+                double spMfp = 0, spMcr = 0;
+                for (int sq : f.typeIds) {
+                    const double Nq = acc[(size_t(c) * S + sq) * nQ];
+                    if (!(Nq > SMALL)) continue;
+                    const double dPQ = 0.5 * (species_[sp].diameter + species_[sq].diameter);
+                    const double omegaPQ = 0.5 * (species_[sp].omega + species_[sq].omega);
+                    const double massRatio = species_[sp].mass / species_[sq].mass;
+                    const double reducedMass = species_[sp].mass * species_[sq].mass / (species_[sp].mass + species_[sq].mass);
+                    const double nDensQ = FN * Nq / (V * nT);
+                    spMfp += M_PI * dPQ * dPQ * nDensQ * std::pow(f.mfpReferenceTemperature / o.Ttra[c], omegaPQ - 0.5) * std::sqrt(1.0 + massRatio);
+                    spMcr += 2.0 * std::sqrt(M_PI) * dPQ * dPQ * nDensQ * std::pow(o.Ttra[c] / f.mfpReferenceTemperature, 1.0 - omegaPQ) *
+                             std::sqrt(2.0 * kB * f.mfpReferenceTemperature / reducedMass);
+                }
+                if (spMfp > SMALL) spMfp = 1.0 / spMfp;
+                if (o.rhoN[c] > SMALL) {
+                    const double w = acc[(size_t(c) * S + sp) * nQ] / dsmcNCum;
+                    mfp += spMfp * w; mcr += spMcr * w;
+                }
+            }
+            if (mfp < SMALL) mfp = GREAT;
+            o.mfp[c] = mfp;
+            if (mcr > SMALL) { o.mct[c] = 1.0 / mcr; o.mctToDt[c] = o.mct[c] / deltaT_; } else { o.mct[c] = GREAT; o.mctToDt[c] = GREAT; }
+            if (nCum > SMALL) o.measuredCollisionRate[c] = coll[2 * size_t(c)] * FN / (nCum * deltaT_);
+        }
+    }
+    return o;
+}
+
+void dsmcCloud::writeFields(const std::string& timeDir) {
+    // boundary values: wall patches get rhoN/rhoM/fD/p/q from the wall accumulators (dsmcVolFields.C:1879-2141),
+    // everything else the adjacent cell value (the zeroGradient branch :2142-2204)
+    int32_t nMeas = 0, nWallQ = 0;
+    check(dsmcb200_wall_info(ctx_, &nMeas, &nWallQ), "dsmcb200_wall_info");
+    const int S = int(species_.size());
+    std::vector<double> wall(size_t(std::max(nMeas, 1)) * S * std::max(nWallQ, 1));
+    if (nMeas) check(dsmcb200_download_wall_accumulators(ctx_, wall.data()), "dsmcb200_download_wall_accumulators");
+    dsmcb200_accum_info ai{};
+    check(dsmcb200_accum_info_get(ctx_, &ai), "dsmcb200_accum_info_get");
+    const double nT = ai.nTimeSteps > 0 ? ai.nTimeSteps : 1.0;
+    // measured-face index of a boundary face follows the order of the patch models with a wall model
+    std::vector<int> measStart(boundary_.size(), -1);
+    {
+        int k = 0;
+        for (auto& pm : patchModels_)
+            if (pm.model != DSMCB200_BND_DELETION) { measStart[pm.patch] = k; k += boundary_[pm.patch].nFaces; }
+    }
+    for (auto& f : fields_) {
+        DerivedFields d = calculateField(f);
+        auto scalarPatches = [&](const std::vector<double>& cellField, int wq, double scale) {
+            std::vector<foam::PatchValues> pv;
+            for (size_t j = 0; j < boundary_.size(); ++j) {
+                foam::PatchValues p;
+                p.name = boundary_[j].name; p.type = boundary_[j].type;
+                if (p.type == "wall" || p.type == "patch") {
+                    p.values.resize(boundary_[j].nFaces);
+                    for (int k = 0; k < boundary_[j].nFaces; ++k) {
+                        if (wq >= 0 && measStart[j] >= 0) {
+                            double v = 0;
+                            for (int s : f.typeIds) v += wall[(size_t(measStart[j] + k) * S + s) * nWallQ + wq];
+                            p.values[k] = v * scale;
+                        } else {
+                            p.values[k] = cellField.empty() ? 0.0 : cellField[owner_[boundary_[j].startFace + k]];
+                        }
+                    }
+                }
+                pv.push_back(p);
+            }
+            return pv;
+        };
+        const double FN = models_.nEquivalentParticles;
+        auto wr = [&](const std::string& name, const std::string& dims, const std::vector<double>& v, int wq = -1, double scale = 1.0) {
+            foam::writeVolField(timeDir + "/" + name + "_" + f.fieldName, timeName_, name + "_" + f.fieldName, dims, v.data(), nCells_, 1,
+                                scalarPatches(v, wq, scale));
+        };
+        wr("dsmcNMean", "[0 0 0 0 0 0 0]", d.dsmcNMean);
+        wr("rhoN", "[0 -3 0 0 0 0 0]", d.rhoN, 0 /*WQ_RHON*/, FN / nT);
+        wr("rhoM", "[1 -3 0 0 0 0 0]", d.rhoM, 3 /*WQ_RHOM*/, FN / nT);
+        if (f.densityOnly) continue;
+        wr("p", "[1 -1 -2 0 0 0 0]", d.p);
+        wr("Ttra", "[0 0 0 1 0 0 0]", d.Ttra);
+        wr("Trot", "[0 0 0 1 0 0 0]", d.Trot);
+        wr("Tvib", "[0 0 0 1 0 0 0]", d.Tvib);
+        wr("Tov", "[0 0 0 1 0 0 0]", d.Tov);
+        wr("Ma", "[0 0 0 0 0 0 0]", d.Ma);
+        std::vector<double> zero(size_t(nCells_), 0.0);
+        wr("wallHeatFlux", "[1 0 -3 0 0 0 0]", zero, 13 /*WQ_Q*/, 1.0 / nT);
+        if (f.measureMeanFreePath) {
+            wr("mfp", "[0 1 0 0 0 0 0]", d.mfp);
+            wr("mct", "[0 0 1 0 0 0 0]", d.mct);
+            wr("mctToDt", "[0 0 0 0 0 0 0]", d.mctToDt);
+        }
+        // vectors: U and the wall force density fD
+        {
+            std::vector<foam::PatchValues> pu, pf;
+            std::vector<double> zero3(size_t(nCells_) * 3, 0.0);
+            for (size_t j = 0; j < boundary_.size(); ++j) {
+                foam::PatchValues a, b;
+                a.name = b.name = boundary_[j].name; a.type = b.type = boundary_[j].type;
+                if (a.type == "wall" || a.type == "patch") {
+                    a.values.resize(size_t(boundary_[j].nFaces) * 3); b.values.assign(size_t(boundary_[j].nFaces) * 3, 0.0);
+                    for (int k = 0; k < boundary_[j].nFaces; ++k) {
+                        const int c = owner_[boundary_[j].startFace + k];
+                        for (int q = 0; q < 3; ++q) a.values[3 * k + q] = d.UMean[3 * size_t(c) + q];
+                        if (measStart[j] >= 0)
+                            for (int s : f.typeIds)
+                                for (int q = 0; q < 3; ++q) b.values[3 * k + q] += wall[(size_t(measStart[j] + k) * S + s) * nWallQ + 14 + q] / nT;
+                    }
+                }
+                pu.push_back(a); pf.push_back(b);
+            }
+            foam::writeVolField(timeDir + "/U_" + f.fieldName, timeName_, "U_" + f.fieldName, "[0 1 -1 0 0 0 0]", d.UMean.data(), nCells_, 3, pu);
+            foam::writeVolField(timeDir + "/fD_" + f.fieldName, timeName_, "fD_" + f.fieldName, "[1 -1 -2 0 0 0 0]", zero3.data(), nCells_, 3, pf);
+        }
+    }
+}
+
+void dsmcCloud::write() {
+    const std::string timeDir = root_ + "/" + timeName_;
+    const std::string cdir = timeDir + "/lagrangian/" + cloudName_;
+    foam::makeDirs(cdir);
+    const int64_t n = nParcels();
+    std::vector<double> xyz(size_t(n) * 3), U(size_t(n) * 3), ERot(static_cast<size_t>(n));
+    std::vector<int32_t> cell(n), typeId(n), vib(size_t(n) * maxModes_), elevel(n), cls(n), origId(n), newParcel(size_t(n), -1);
+    dsmcb200_parcels_soa s{};
+    s.position = xyz.data(); s.U = U.data(); s.ERot = ERot.data(); s.cell = cell.data(); s.typeId = typeId.data(); s.vibLevel = vib.data();
+    s.ELevel = elevel.data(); s.classification = cls.data(); s.origId = origId.data(); s.maxModes = maxModes_;
+    int64_t got = 0;
+    check(dsmcb200_download_parcels(ctx_, n, &got, &s), "dsmcb200_download_parcels");
+    const std::string loc = timeName_ + "/lagrangian/" + cloudName_;
+    // the file set of dsmcParcel::writeFields (DSMC/parcels/dsmcParcelIO.C:338-450): optional files only if non-trivial
+    foam::writePositions(cdir + "/positions", loc, xyz.data(), cell.data(), got);
+    foam::writeVectorField(cdir + "/U", "vectorField", loc, "U", U.data(), got);
+    foam::writeLabelField(cdir + "/typeId", "labelField", loc, "typeId", typeId.data(), got);
+    foam::writeLabelField(cdir + "/newParcel", "labelField", loc, "newParcel", newParcel.data(), got);
+    foam::writeLabelField(cdir + "/classification", "labelField", loc, "classification", cls.data(), got);
+    foam::writeLabelField(cdir + "/origId", "labelField", loc, "origId", origId.data(), got);
+    std::vector<int32_t> origProc(size_t(got), rank_);
+    foam::writeLabelField(cdir + "/origProcId", "labelField", loc, "origProcId", origProc.data(), got);
+    bool anyRot = false, anyEl = false;
+    for (int64_t i = 0; i < got; ++i) { anyRot |= ERot[i] > 0; anyEl |= elevel[i] > 0; }
+    if (anyRot) foam::writeScalarField(cdir + "/ERot", "scalarField", loc, "ERot", ERot.data(), got);
+    if (anyEl) foam::writeLabelField(cdir + "/ELevel", "labelField", loc, "ELevel", elevel.data(), got);
+    foam::writeLabelListList(cdir + "/vibLevel", "labelFieldField", loc, "vibLevel", vib.data(), got, maxModes_);
+    {
+        const std::string ud = timeDir + "/uniform/lagrangian/" + cloudName_;
+        foam::makeDirs(ud);
+        FILE* f = std::fopen((ud + "/cloudProperties").c_str(), "w");
+        if (f) {
+            std::fputs(foam::header("dictionary", timeName_ + "/uniform/lagrangian/" + cloudName_, "cloudProperties").c_str(), f);
+            std::fprintf(f, "processor%d\n{\n    particleCount   %lld;\n}\n", rank_, (long long)got);
+            std::fclose(f);
+        }
+    }
+    std::vector<double> sig(nCells_), rem(nCells_);
+    check(dsmcb200_download_cellstate(ctx_, sig.data(), rem.data()), "dsmcb200_download_cellstate");
+    std::vector<foam::PatchValues> pv;
+    for (auto& b : boundary_) {
+        foam::PatchValues p;
+        p.name = b.name; p.type = b.type;
+        if (b.type == "wall" || b.type == "patch") { p.values.resize(b.nFaces); for (int k = 0; k < b.nFaces; ++k) p.values[k] = sig[owner_[b.startFace + k]]; }
+        pv.push_back(p);
+    }
+    foam::writeVolField(timeDir + "/dsmcSigmaTcRMax", timeName_, "dsmcSigmaTcRMax", "[0 3 -1 0 0 0 0]", sig.data(), nCells_, 1, pv);
+    writeFields(timeDir);
+    // resetAtOutput (dsmcField.C:113-152): the accumulators are shared by all instances, so they reset together
+    bool reset = !fields_.empty();
+    for (auto& f : fields_) reset = reset && f.resetAtOutput && !(time_ + deltaT_ > f.resetAtOutputUntilTime);
+    if (reset) check(dsmcb200_reset_accumulators(ctx_), "dsmcb200_reset_accumulators");
+}
+
+}  // namespace dsmcb200

@@ -1,0 +1,112 @@
+// dsmc_cloud.h -- host-side mirror of the reference's dsmcCloud and of the run-time-selection surface
+// it exposes (level 1), for callers that are not OpenFOAM: the standalone driver
+// dsmcb200_run reads an unchanged dsmcFoam+ case directory with it.
+//
+// Mirrors  Foam::dsmcCloud            DSMC/clouds/dsmcCloud.H:76,257-263,574-681  (ctor, evolve, info, nTerminalOutputs)
+//          BinaryCollisionModel::New  DSMC/collisions/basic/BinaryCollisionModel/BinaryCollisionModel.C:59-98
+//          collisionPartnerSelection::New  DSMC/collisionPartnerSelection/basic/collisionPartnerSelection.C:60-95
+//          dsmcBoundaries / dsmcPatchBoundary::New / dsmcGeneralBoundary::New
+//                                     DSMC/boundaries/basic/dsmcBoundaries/dsmcBoundaries.C:82-520
+//          dsmcFieldProperties / dsmcVolFields  DSMC/macroscopicProperties/...  (createField, calculateField, writeField)
+// All compute goes through the C ABI (include/dsmcb200.h); nothing here touches CUDA directly.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dsmcb200.h"
+#include "foam_io.h"
+
+namespace dsmcb200 {
+
+// name -> enum tables with the reference's "unknown ... type / Valid ... types are" failure
+int selectBinaryCollisionModel(const std::string& name);
+int selectCollisionPartnerSelection(const std::string& name);
+int selectPatchBoundaryModel(const std::string& name);
+void selectGeneralBoundaryModel(const std::string& name);
+void selectFieldModel(const std::string& name);
+void selectCoordinateSystem(const std::string& name);
+void selectTimeStepModel(const std::string& name);
+int patchTypeFromWord(const std::string& type);
+
+struct FieldSpec {  // one dsmcVolFields entry of system/fieldPropertiesDict
+    std::string fieldName;
+    std::vector<int> typeIds;
+    bool measureMeanFreePath = false, densityOnly = false, measureHeatFluxShearStress = false, measureClassifications = false;
+    double mfpReferenceTemperature = 273.0;
+    bool resetAtOutput = true;
+    double resetAtOutputUntilTime = 1e300;
+    int sampleInterval = 1;
+};
+
+struct DerivedFields {  // per-cell results of dsmcVolFields::calculateField for one instance
+    std::vector<double> dsmcNMean, rhoN, rhoM, p, Ttra, Trot, Tvib, Tov, Ma, mfp, mct, mctToDt, mfpToDx, measuredCollisionRate;
+    std::vector<double> UMean;  // [3n]
+};
+
+class dsmcCloud {
+   public:
+    dsmcCloud(const std::string& caseDir, const std::string& cloudName = "dsmc", int rank = 0, int nRanks = 1, int device = 0,
+              const void* ncclId128 = nullptr, bool dryRun = false);
+    ~dsmcCloud();
+    dsmcCloud(const dsmcCloud&) = delete;
+
+    void evolve();                 // dsmcCloud::evolve(): one time step
+    void info();                   // dsmcCloud::info(): the 8-line summary (same strings as the reference)
+    int nTerminalOutputs() const { return nTerminalOutputs_; }
+    bool loop();                   // runTime.loop()
+    bool outputTime() const;       // runTime.outputTime()
+    void write();                  // runTime.write(): cloud, dsmcSigmaTcRMax, fields
+    const std::string& timeName() const { return timeName_; }
+    double time() const { return time_; }
+    int64_t nParcels();
+    int nCells() const { return nCells_; }
+    const std::vector<FieldSpec>& fields() const { return fields_; }
+    DerivedFields calculateField(const FieldSpec& f);   // from the current accumulators
+    dsmcb200_ctx* ctx() { return ctx_; }
+    const std::vector<std::string>& typeIdList() const { return typeIdList_; }
+
+   private:
+    void readControl();
+    void readMesh();
+    void readProperties();
+    void readBoundaries();
+    void readFieldProperties();
+    void readCloud();
+    void writeFields(const std::string& timeDir);
+    void check(int rc, const char* what);
+
+    std::string caseDir_, root_, cloudName_, timeName_;
+    int rank_, nRanks_;
+    dsmcb200_ctx* ctx_ = nullptr;
+    // time
+    double time_ = 0, startTime_ = 0, endTime_ = 0, deltaT_ = 0, writeInterval_ = 1;
+    std::string writeControl_ = "timeStep";
+    int timePrecision_ = 6, nTerminalOutputs_ = 1, infoCounter_ = 0;
+    int64_t timeIndex_ = 0, startIndex_ = 0;
+    // mesh
+    int nCells_ = 0, nFaces_ = 0, nInternal_ = 0;
+    std::vector<double> points_;
+    std::vector<int32_t> faceOffsets_, facePoints_, owner_, neighbour_;
+    std::vector<foam::BoundaryPatch> boundary_;
+    std::vector<dsmcb200_patch> patches_;
+    std::vector<double> cellVolumes_, cellCentres_, faceAreas_, faceCentres_;
+    // models
+    std::vector<std::string> typeIdList_;
+    std::vector<dsmcb200_species> species_;
+    dsmcb200_models models_{};
+    std::vector<dsmcb200_patch_model> patchModels_;
+    std::vector<dsmcb200_inflow> inflows_;
+    std::vector<FieldSpec> fields_;
+    int maxModes_ = 1;
+    int64_t lastCollisions_ = 0;
+    bool dryRun_ = false;
+    int64_t nRead_ = 0;
+
+   public:
+    // -dryRun: what was parsed from the case directory (no GPU context is created)
+    std::string summary() const;
+};
+
+}  // namespace dsmcb200

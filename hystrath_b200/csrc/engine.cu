@@ -27,6 +27,7 @@ struct NcclApi {
     int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
     int (*CommDestroy)(NcclComm) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
     int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -39,7 +40,7 @@ struct NcclApi {
         if (!h) { err = "cannot dlopen libnccl.so.2"; return false; }
 #define LD(f, s) f = reinterpret_cast<decltype(f)>(dlsym(h, s)); if (!f) { err = std::string("nccl symbol missing: ") + s; return false; }
         LD(GetUniqueId, "ncclGetUniqueId") LD(CommInitRank, "ncclCommInitRank") LD(CommDestroy, "ncclCommDestroy")
-        LD(AllGather, "ncclAllGather") LD(Send, "ncclSend") LD(Recv, "ncclRecv") LD(GroupStart, "ncclGroupStart")
+        LD(AllGather, "ncclAllGather") LD(AllReduce, "ncclAllReduce") LD(Send, "ncclSend") LD(Recv, "ncclRecv") LD(GroupStart, "ncclGroupStart")
         LD(GroupEnd, "ncclGroupEnd") LD(GetErrorString, "ncclGetErrorString")
 #undef LD
         return true;
@@ -1138,6 +1139,20 @@ int dsmcb200_kernel_times(dsmcb200_ctx* c, int capacity, int* n, char* names, fl
     }
     *n = k;
     if (capacity == 0) c->ktimes.clear();  // capacity 0 resets the table
+    return 0;
+}
+
+int dsmcb200_allreduce_sum(dsmcb200_ctx* c, double* vals, int n) {
+    if (!c || !vals || n < 0 || n > 8) return DSMCB200_ERR_INVALID;
+    if (c->nRanks <= 1 || !c->comm || n == 0) return 0;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    CK(cudaMemcpyAsync(c->dInfo, vals, size_t(n) * 8, cudaMemcpyHostToDevice, c->stream));
+    const int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+    int r = g_nccl.AllReduce(c->dInfo, c->dInfo, size_t(n), NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
+    if (r) return ncclFail(c, r, "ncclAllReduce");
+    CK(cudaMemcpyAsync(vals, c->dInfo, size_t(n) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

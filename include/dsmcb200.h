@@ -309,6 +309,9 @@ int dsmcb200_get_counters(dsmcb200_ctx*, dsmcb200_counters*);
 /* Per-kernel device time of the last step, for bench.py: names[i] is filled with up to
  * DSMCB200_NAME_LEN chars; returns the count through *n (capacity in). */
 int dsmcb200_kernel_times(dsmcb200_ctx*, int capacity, int* n, char* names, float* ms, int64_t* launches);
+/* Sum of vals[0..n) over all ranks (replaces the reduce(..., sumOp) calls of dsmcCloud::info and
+ * noTimeCounter::collide, DSMC/clouds/dsmcCloud.C:938-958); a no-op on one rank. */
+int dsmcb200_allreduce_sum(dsmcb200_ctx*, double* vals, int n);
 /* CUDA-event stopwatch on the context's launching stream (bench.py times the K steps with it). */
 int dsmcb200_timer_start(dsmcb200_ctx*);
 int dsmcb200_timer_stop(dsmcb200_ctx*, float* ms);

@@ -1,0 +1,62 @@
+"""CPU tests of the standalone driver's case reader (C++: foam_io + dsmcCloud) via `dsmcb200_run -dryRun`, and of
+the Python foamfile reader/writer round trip, on a case directory in the reference's layout."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from hystrath_b200 import foamfile as ff
+from tests import casegen
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RUN = os.path.join(ROOT, "hystrath_b200", "dsmcb200_run")
+
+
+def test_driver_parses_couette_case(tmp_path):
+    g, mesh, p = casegen.couette_case(str(tmp_path))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout
+    assert "1212 points 2105 faces 895 internal 500 cells 5 patches" in out
+    assert "patch periodicX_half0 cyclic 100 @905" in out and "patch frontAndBack empty 1000 @1105" in out
+    assert "species: N2 O2" in out
+    assert "collisionModel 2 invZv 0" in out and "seed 5" in out
+    assert "patchModels 2 inflows 0 fields 3" in out
+    assert "field mixture typeIds 0 1 mfp 1" in out
+    assert "parcels 47583" in out
+    assert "startTime 5 " in out
+
+
+def test_driver_rejects_unknown_models_like_the_reference(tmp_path):
+    casegen.couette_case(str(tmp_path))
+    path = os.path.join(str(tmp_path), "constant", "dsmcProperties")
+    text = open(path).read().replace("BinaryCollisionModel            LarsenBorgnakkeVariableHardSphere;", "BinaryCollisionModel            VariableSoftSphere;")
+    open(path, "w").write(text)
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1
+    assert "FOAM FATAL ERROR" in r.stderr and "unknown BinaryCollisionModel type VariableSoftSphere" in r.stderr
+    assert "Valid BinaryCollisionModel types are" in r.stderr
+    # a missing keyword fails with OpenFOAM's message shape
+    open(path, "w").write(text.replace("VariableSoftSphere", "VariableHardSphere").replace("nEquivalentParticles", "nEquivParticles"))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "keyword nEquivalentParticles is undefined in dictionary" in r.stderr
+
+
+def test_python_reader_round_trip(tmp_path):
+    g, mesh, p = casegen.couette_case(str(tmp_path))
+    d = os.path.join(str(tmp_path), "5", "lagrangian", "dsmc")
+    xyz, cell = ff.read_positions(os.path.join(d, "positions"))
+    assert np.array_equal(xyz, g["positions"]) and np.array_equal(cell, g["cell"])       # %.17g round-trips doubles
+    assert np.array_equal(ff.read_vector_list(os.path.join(d, "U")), g["U"])
+    assert np.array_equal(ff.read_label_list_list(os.path.join(d, "vibLevel")), g["vibLevel"])
+    assert np.array_equal(ff.read_scalar_list(os.path.join(d, "classification"), np.int32), np.zeros(47583, np.int32))  # N{0} form
+    bnd = ff.read_boundary(os.path.join(str(tmp_path), "constant", "polyMesh", "boundary"))
+    assert [b["name"] for b in bnd] == ["upperWall", "lowerWall", "periodicX_half0", "periodicX_half1", "frontAndBack"]
+    props = ff.read_dict(os.path.join(str(tmp_path), "constant", "dsmcProperties"))
+    assert props["typeIdList"] == ["N2", "O2"]
+    assert props["moleculeProperties"]["O2"]["Zref"] == [17900]
+    assert props["LarsenBorgnakkeVariableHardSphereCoeffs"]["inverseZvFormulation"] == "pre-2008"
+    bd = ff.read_dict(os.path.join(str(tmp_path), "system", "boundariesDict"))
+    assert len(bd["dsmcPatchBoundaries"]) == 2 and bd["dsmcPatchBoundaries"][0][1]["boundaryModel"] == "dsmcDiffuseWallPatch"
+    assert bd["dsmcGeneralBoundaries"] == []

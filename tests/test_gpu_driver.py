@@ -1,0 +1,71 @@
+"""GPU: the standalone driver (dsmcb200_run) on the couette_N2-O2 case directory -- dictionaries, polyMesh and
+cloud files in the reference's layout -- against the oracle fed with the same state and seed."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from hystrath_b200 import capi, foamfile as ff
+from oracle import fields_ref
+from oracle.pyoracle import Oracle
+from tests import casegen, helpers as H
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RUN = os.path.join(ROOT, "hystrath_b200", "dsmcb200_run")
+
+
+def test_driver_runs_couette_case_and_matches_oracle(tmp_path):
+    n_steps = 4
+    g, mesh, p = casegen.couette_case(str(tmp_path), n_steps=n_steps, seed=5, nto=2)
+    r = subprocess.run([RUN, "-case", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    log = r.stdout
+    # log strings the reference's monitor scripts grep for (dsmcCloud.C:960-981, noTimeCounter.C:320-337)
+    assert "Number of DSMC particles        = 47583" in log
+    assert "Collisions                      = " in log and "Average linear kinetic energy   = " in log
+    assert "Time = 5.00002" in log and "End stage 0" in log
+
+    # the same run on the oracle
+    sp = H.air5()[:2]
+    pm = [dict(patch=mesh.patch_index("upperWall"), boundaryModel="dsmcDiffuseWallPatch", temperature=3000.0, velocity=(300.0, 0, 0)),
+          dict(patch=mesh.patch_index("lowerWall"), boundaryModel="dsmcDiffuseWallPatch", temperature=2000.0, velocity=(0, 0, 0))]
+    md = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=float(g["nEquivalentParticles"]), deltaT=1e-5,
+                           seed=5, patch_models=pm, inverseZvFormulation="pre-2008", rotationalRelaxationCollisionNumber=5.0)
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
+    o.upload_parcels(p)
+    o.upload_cellstate(g["dsmcSigmaTcRMax"], None)
+    o.evolve(n_steps)
+    ref = o.download_parcels()
+
+    tdir = os.path.join(str(tmp_path), "5.00004")
+    assert os.path.isdir(tdir), os.listdir(str(tmp_path))
+    cdir = os.path.join(tdir, "lagrangian", "dsmc")
+    for name in ("positions", "U", "ERot", "typeId", "vibLevel", "newParcel", "classification", "origId", "origProcId"):
+        assert os.path.exists(os.path.join(cdir, name)), name
+    xyz, cell = ff.read_positions(os.path.join(cdir, "positions"))
+    ids = ff.read_scalar_list(os.path.join(cdir, "origId"), np.int32)
+    assert len(cell) == ref.n
+    assert np.array_equal(ids, ref.origId)            # same physical order as the oracle
+    assert np.array_equal(cell, ref.cell)             # cell indexing identical after 4 steps with walls + LB collisions
+    assert np.allclose(xyz, ref.position, rtol=0, atol=5e-10)      # files carry 10 significant digits
+    U = ff.read_vector_list(os.path.join(cdir, "U"))
+    assert np.allclose(U, ref.U, rtol=1e-9, atol=1e-6)
+
+    # sampled fields written by the driver == reduction of the oracle's accumulators
+    acc, coll, nt = o.accumulators()
+    _, cv, *_ = o.geometry()
+    spd = [dict(mass=s.mass, diameter=s.diameter, omega=s.omega, rotDof=2.0, thetaV=[s.thetaV[0]]) for s in sp]
+    for inst, idl in (("mixture", [0, 1]), ("N2", [0]), ("O2", [1])):
+        f = fields_ref.derive(acc, coll, nt, spd, idl, float(g["nEquivalentParticles"]), cv, deltaT=1e-5)
+        for name, key in (("rhoN", "rhoN"), ("rhoM", "rhoM"), ("Ttra", "Ttra"), ("p", "p"), ("Trot", "Trot"), ("Tvib", "Tvib"), ("Tov", "Tov"),
+                          ("mfp", "mfp"), ("mct", "mct")):
+            got = ff.read_internal_field(os.path.join(tdir, f"{name}_{inst}"))
+            assert np.allclose(got, f[key], rtol=2e-9, atol=1e-300), (name, inst)
+    # wall fields exist with per-face values on the two wall patches
+    text = open(os.path.join(tdir, "wallHeatFlux_mixture")).read()
+    assert "upperWall" in text and "nonuniform List<scalar>" in text.split("boundaryField")[1]
+    assert os.path.exists(os.path.join(tdir, "dsmcSigmaTcRMax"))
+    assert os.path.exists(os.path.join(tdir, "uniform", "lagrangian", "dsmc", "cloudProperties"))
