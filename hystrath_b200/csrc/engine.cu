@@ -167,6 +167,7 @@ struct dsmcb200_ctx {
     DevCounters* dCounters = nullptr;
     DevCounters hCounters{};
     int* dBad = nullptr;
+    double* dZvTab = nullptr;
     MigRec *dMigSend = nullptr, *dMigRecv = nullptr;
     int32_t migCapacity = 0;
     std::vector<double*> dInflowAcc;
@@ -413,6 +414,29 @@ int finalize(dsmcb200_ctx* c) {
             if (in.typeIds[i] < 0 || in.typeIds[i] >= P.nSpecies) return fail(c, DSMCB200_ERR_INVALID, "inflow typeId out of range");
     }
 
+    {
+        // 1/Zv of dsmcCloud::postCollisionVibrationalEnergyLevel (dsmcCloud.C:1429-1504) depends on the species, the
+        // partner (through omegaPQ) and the integer iMax only: tabulated on the host with the reference's expression
+        std::vector<double> tab(size_t(P.nSpecies) * P.nSpecies * MAX_MODES * ZV_TABLE, 1.0);
+        for (int s1 = 0; s1 < P.nSpecies; ++s1)
+            for (int s2 = 0; s2 < P.nSpecies; ++s2)
+                for (int m = 0; m < P.sp[s1].nVib; ++m)
+                    for (int iMax = 1; iMax < ZV_TABLE; ++iMax) {
+                        const DevSpecies& S = P.sp[s1];
+                        const double omega = P.omegaPQ[s1][s2];
+                        const double T = iMax * S.thetaV[m] / (3.5 - omega);
+                        const double pow1 = std::pow(S.thetaD / T, 1. / 3.) - 1.0;
+                        const double pow2 = std::pow(S.thetaD / S.TrefZv[m], 1. / 3.) - 1.0;
+                        const double ZvP1 = std::pow(S.thetaD / T, omega);
+                        const double ZvP2 = std::pow(S.Zref[m] * std::pow(S.thetaD / S.TrefZv[m], -omega), pow1 / pow2);
+                        const double Zv = ZvP1 * ZvP2;
+                        tab[((size_t(s1) * P.nSpecies + s2) * MAX_MODES + m) * ZV_TABLE + iMax] = P.invZvFormulation == 2 ? 1.0 / (5.0 * Zv) : 1.0 / Zv;
+                    }
+        double* dTab = nullptr;
+        CK(upload(&dTab, tab));
+        c->dZvTab = dTab;
+        P.invZvTab = dTab;
+    }
     CK(devAlloc(&c->dP, 1));
     CK(cudaMemcpy(c->dP, &P, sizeof(P), cudaMemcpyHostToDevice));
 
@@ -500,7 +524,7 @@ int ensureMigBuffers(dsmcb200_ctx* c) {
     if (c->nbrProcs.empty()) return 0;
     const int32_t want = int32_t(std::max<int64_t>(1 << 16, c->capacity / 8));
     if (want <= c->migCapacity) return 0;
-    devFree(c->dMigSend); devFree(c->dMigRecv);
+    devFree(c->dZvTab); devFree(c->dMigSend); devFree(c->dMigRecv);
     CK(devAlloc(&c->dMigSend, size_t(want) * MAX_NEIGHBOURS));
     CK(devAlloc(&c->dMigRecv, size_t(want) * MAX_NEIGHBOURS));
     c->migCapacity = want;

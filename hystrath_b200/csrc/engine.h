@@ -16,6 +16,7 @@ constexpr int MAX_ELEC = DSMCB200_MAX_ELEC_LEVELS;
 constexpr int MAX_PATCHES = 64;
 constexpr int MAX_NEIGHBOURS = 16;
 constexpr int MAX_INFLOWS = 8;
+constexpr int ZV_TABLE = 128;  // tabulated iMax range of the variable vibrational collision number
 
 struct DevSpecies {
     double mass, d, omega, alpha, rotDof, thetaD;
@@ -47,6 +48,8 @@ struct DevParams {
     double centre[3];  // bounds mid-point for constrainToMeshCentre
     double nParticles, deltaT, kB, Tref;
     double invZrot, Zvib, invZelec;
+    const double* invZvTab;  // [species][partner][mode][ZV_TABLE]: 1/Zv (or 1/(5 Zv)) of the quantised collision temperature
+
     uint64_t seed;
     DevSpecies sp[MAX_SPECIES];
     DevPatch patch[MAX_PATCHES];

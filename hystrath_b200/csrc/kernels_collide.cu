@@ -46,15 +46,17 @@ __device__ __forceinline__ int octantOf(double x, double y, double z, const doub
     return (rx >= 0 ? 1 : 0) + 2 * (ry >= 0 ? 1 : 0) + 4 * (rz >= 0 ? 1 : 0);
 }
 
+__device__ __noinline__ double powNI(double a, double b) { return pow(a, b); }
+
 // VariableHardSphere::sigmaTcR
 __device__ __forceinline__ double sigmaTcR(const DevParams& P, int tP, int tQ, double cR) {
     if (cR < VSMALL) return 0.0;
-    const double sigmaTPQ = P.vhsA[tP][tQ] * pow(2.0 * P.kB * P.Tref / (P.mR[tP][tQ] * (cR * cR)), P.omegaPQ[tP][tQ] - 0.5) / P.vhsG[tP][tQ];
+    const double sigmaTPQ = P.vhsA[tP][tQ] * powNI(2.0 * P.kB * P.Tref / (P.mR[tP][tQ] * (cR * cR)), P.omegaPQ[tP][tQ] - 0.5) / P.vhsG[tP][tQ];
     return sigmaTPQ * cR;
 }
 
 // VariableHardSphere::postCollisionVelocities
-__device__ __forceinline__ void postCollisionVelocities(const DevParams& P, Rng& rng, int tP, int tQ, V3& UP, V3& UQ, double cR) {
+__device__ __noinline__ void postCollisionVelocities(const DevParams& P, Rng& rng, int tP, int tQ, V3& UP, V3& UQ, double cR) {
     if (cR == -1) cR = mag(UP - UQ);
     const double mP = P.sp[tP].mass, mQ = P.sp[tQ].mass;
     const V3 Ucm = (mP * UP + mQ * UQ) / (mP + mQ);
@@ -70,7 +72,7 @@ __device__ __forceinline__ void postCollisionVelocities(const DevParams& P, Rng&
 __device__ double postCollisionRotationalEnergy(Rng& rng, double rotationalDof, double ChiB) {
     double energyRatio = 0.0;
     if (rotationalDof == 2.0) {
-        energyRatio = 1.0 - pow(rng.sample01(), 1.0 / ChiB);
+        energyRatio = 1.0 - powNI(rng.sample01(), 1.0 / ChiB);
     } else {
         const double ChiA = 0.5 * rotationalDof;
         const double ChiAMinusOne = ChiA - 1., ChiBMinusOne = ChiB - 1.;
@@ -78,11 +80,11 @@ __device__ double postCollisionRotationalEnergy(Rng& rng, double rotationalDof, 
         double Pp = 0.0;
         do {
             energyRatio = rng.sample01();
-            if (ChiAMinusOne < SMALL) Pp = pow(1.0 - energyRatio, ChiBMinusOne);
-            else if (ChiBMinusOne < SMALL) Pp = pow(1.0 - energyRatio, ChiAMinusOne);
+            if (ChiAMinusOne < SMALL) Pp = powNI(1.0 - energyRatio, ChiBMinusOne);
+            else if (ChiBMinusOne < SMALL) Pp = powNI(1.0 - energyRatio, ChiAMinusOne);
             else
-                Pp = pow((ChiAMinusOne + ChiBMinusOne) * energyRatio / ChiAMinusOne, ChiAMinusOne) *
-                     pow((ChiAMinusOne + ChiBMinusOne) * (1 - energyRatio) / ChiBMinusOne, ChiBMinusOne);
+                Pp = powNI((ChiAMinusOne + ChiBMinusOne) * energyRatio / ChiAMinusOne, ChiAMinusOne) *
+                     powNI((ChiAMinusOne + ChiBMinusOne) * (1 - energyRatio) / ChiBMinusOne, ChiBMinusOne);
         } while (Pp < rng.sample01());
     }
     return energyRatio;
@@ -90,18 +92,21 @@ __device__ double postCollisionRotationalEnergy(Rng& rng, double rotationalDof, 
 
 // dsmcCloud::postCollisionVibrationalEnergyLevel (postReaction = false)
 __device__ int32_t postCollisionVibrationalEnergyLevel(const DevParams& P, Rng& rng, int32_t vibLevel, int32_t iMax, double thetaV,
-                                                       double thetaD, double refTempZv, double omega, double Zref, double Ec) {
+                                                       double thetaD, double refTempZv, double omega, double Zref, double Ec,
+                                                       const double* zvRow) {
     int32_t iDash = vibLevel;
     double inverseVibrationalCollisionNumber = 1.0;
     const double fixedZv = P.Zvib;
-    if (fixedZv == 0) {
+    if (fixedZv == 0 && iMax < ZV_TABLE) {
+        inverseVibrationalCollisionNumber = zvRow[iMax];  // host-tabulated value of the expression below
+    } else if (fixedZv == 0) {
         // invZvFormulation 0 and 2 use the quantised collision temperature; formulation 1 (macroscopic Tov)
         // falls back to it exactly as the reference does when Tov is not yet available (dsmcCloud.C:1445-1454)
         const double T = iMax * thetaV / (3.5 - omega);
-        const double pow1 = pow(thetaD / T, 1. / 3.) - 1.0;
-        const double pow2 = pow(thetaD / refTempZv, 1. / 3.) - 1.0;
-        const double ZvP1 = pow(thetaD / T, omega);
-        const double ZvP2 = pow(Zref * pow(thetaD / refTempZv, -omega), pow1 / pow2);
+        const double pow1 = powNI(thetaD / T, 1. / 3.) - 1.0;
+        const double pow2 = powNI(thetaD / refTempZv, 1. / 3.) - 1.0;
+        const double ZvP1 = powNI(thetaD / T, omega);
+        const double ZvP2 = powNI(Zref * powNI(thetaD / refTempZv, -omega), pow1 / pow2);
         const double Zv = ZvP1 * ZvP2;
         if (P.invZvFormulation == 2) inverseVibrationalCollisionNumber = 1.0 / (5.0 * Zv);
         else inverseVibrationalCollisionNumber = 1.0 / Zv;
@@ -113,7 +118,7 @@ __device__ int32_t postCollisionVibrationalEnergyLevel(const DevParams& P, Rng& 
         do {
             iDash = rng.randomLabel(0, iMax);
             EVib = iDash * P.kB * thetaV;
-            func = pow(1.0 - EVib / Ec, 1.5 - omega);
+            func = powNI(1.0 - EVib / Ec, 1.5 - omega);
         } while (func < rng.sample01());
     }
     return iDash;
@@ -126,22 +131,22 @@ __device__ int32_t postCollisionElectronicEnergyLevel(Rng& rng, double Ec, doubl
     for (int i = 0; i < S.nElec; ++i) {
         if (S.eElec[i] > Ec) break;
         jSelectA = i;
-        const double g = S.gElec[i] * pow(Ec - S.eElec[i], 1.5 - omega);
+        const double g = S.gElec[i] * powNI(Ec - S.eElec[i], 1.5 - omega);
         if (gMax < g) { gMax = g; jSelectB = i; }
     }
     const int jSelect = jSelectA < jSelectB ? jSelectA : jSelectB;
-    const double denomMax = S.gElec[jSelect] * pow(Ec - S.eElec[jSelect], 1.5 - omega);
+    const double denomMax = S.gElec[jSelect] * powNI(Ec - S.eElec[jSelect], 1.5 - omega);
     int jDash = 0;
     double prob;
     do {
         jDash = rng.randomLabel(0, jSelectA);
-        prob = S.gElec[jDash] * pow(Ec - S.eElec[jDash], 1.5 - omega) / denomMax;
+        prob = S.gElec[jDash] * powNI(Ec - S.eElec[jDash], 1.5 - omega) / denomMax;
     } while (prob < rng.sample01());
     return jDash;
 }
 
 // LarsenBorgnakkeVariableHardSphere::redistribute (postReaction = false)
-__device__ void redistribute(const DevParams& P, Rng& rng, const CellView& v, int j, double& translationalEnergy, double omegaPQ) {
+__device__ __noinline__ void redistribute(const DevParams& P, Rng& rng, const CellView& v, int j, int tOther, double& translationalEnergy, double omegaPQ) {
     const DevSpecies& S = P.sp[v.typ[j]];
     if (S.type == 0) return;  // electron
     // electronic mode
@@ -163,7 +168,8 @@ __device__ void redistribute(const DevParams& P, Rng& rng, const CellView& v, in
             const int32_t iMaxP = int32_t(EcP / (P.kB * S.thetaV[m]));
             if (iMaxP > 0) {
                 const int32_t lvl = postCollisionVibrationalEnergyLevel(P, rng, v.vib[m][j], iMaxP, S.thetaV[m], S.thetaD, S.TrefZv[m],
-                                                                        omegaPQ, S.Zref[m], EcP);
+                                                                        omegaPQ, S.Zref[m], EcP,
+                                                                        P.invZvTab + ((size_t(v.typ[j]) * P.nSpecies + tOther) * MAX_MODES + m) * ZV_TABLE);
                 v.vib[m][j] = lvl;
                 translationalEnergy = EcP - lvl * P.kB * S.thetaV[m];
             }
@@ -338,8 +344,8 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
                                 const double cRsqr = magSqr(UP - UQ);
                                 double translationalEnergy = 0.5 * mR * cRsqr;
                                 const double omegaPQ = P.omegaPQ[tP][tQ];
-                                redistribute(P, rng, v, cp, translationalEnergy, omegaPQ);
-                                redistribute(P, rng, v, cq, translationalEnergy, omegaPQ);
+                                redistribute(P, rng, v, cp, tQ, translationalEnergy, omegaPQ);
+                                redistribute(P, rng, v, cq, tP, translationalEnergy, omegaPQ);
                                 cR = sqrt(2.0 * translationalEnergy / mR);
                             }
                             postCollisionVelocities(P, rng, tP, tQ, UP, UQ, cR);
@@ -421,6 +427,7 @@ struct GroupSmem {
     uint8_t typ[GRP_CAP], elev[GRP_CAP], key[GRP_CAP], dirty[GRP_CAP];
     int32_t binStart[33];
     int32_t binRun[32];
+    double resSigma[32], resSep[32];
 };
 
 __device__ __forceinline__ int warpExclusiveScanInt(int v, int lane, int* total) {
@@ -435,7 +442,7 @@ __device__ __forceinline__ int warpExclusiveScanInt(int v, int lane, int* total)
 }
 
 // LarsenBorgnakkeVariableHardSphere::redistribute on the staged parcel j
-__device__ void redistributeStaged(const DevParams& P, Rng& rng, GroupSmem& sm, int j, double& translationalEnergy, double omegaPQ) {
+__device__ __noinline__ void redistributeStaged(const DevParams& P, Rng& rng, GroupSmem& sm, int j, int tOther, double& translationalEnergy, double omegaPQ) {
     const DevSpecies& S = P.sp[sm.typ[j]];
     if (S.type == 0) return;  // electron
     if (P.invZelec > rng.sample01()) {
@@ -455,7 +462,8 @@ __device__ void redistributeStaged(const DevParams& P, Rng& rng, GroupSmem& sm, 
             const int32_t iMaxP = int32_t(EcP / (P.kB * S.thetaV[m]));
             if (iMaxP > 0) {
                 const int32_t lvl = postCollisionVibrationalEnergyLevel(P, rng, sm.vib[m][j], iMaxP, S.thetaV[m], S.thetaD, S.TrefZv[m], omegaPQ,
-                                                                        S.Zref[m], EcP);
+                                                                        S.Zref[m], EcP,
+                                                                        P.invZvTab + ((size_t(sm.typ[j]) * P.nSpecies + tOther) * MAX_MODES + m) * ZV_TABLE);
                 sm.vib[m][j] = lvl;
                 translationalEnergy = EcP - lvl * P.kB * S.thetaV[m];
             }
@@ -634,8 +642,8 @@ __global__ void __launch_bounds__(GRP_WARPS * 32) collideGroupKernel(const __gri
                                     const double cRsqr = magSqr(UP - UQ);
                                     double translationalEnergy = 0.5 * mR * cRsqr;
                                     const double omegaPQ = P.omegaPQ[tP][tQ];
-                                    redistributeStaged(P, rng, sm, cp, translationalEnergy, omegaPQ);
-                                    redistributeStaged(P, rng, sm, cq, translationalEnergy, omegaPQ);
+                                    redistributeStaged(P, rng, sm, cp, tQ, translationalEnergy, omegaPQ);
+                                    redistributeStaged(P, rng, sm, cq, tP, translationalEnergy, omegaPQ);
                                     cR = sqrt(2.0 * translationalEnergy / mR);
                                 }
                                 postCollisionVelocities(P, rng, tP, tQ, UP, UQ, cR);
@@ -659,19 +667,24 @@ __global__ void __launch_bounds__(GRP_WARPS * 32) collideGroupKernel(const __gri
                     }
                     __syncwarp();
                 }
-                // fold the batch into the per-cell results (lane l holds cell l of the pass)
-#pragma unroll
-                for (int l = 0; l < GRP_CELLS; ++l) {
-                    if (l < (g1 - g0)) {
-                        const bool mine = active && g == l;
-                        double mx = mine ? mySigma : -1.0;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                        const int nAcc = __popc(__ballot_sync(0xffffffffu, mine && accepted));
-                        const double sep = warpSumOrdered(mine ? mySep : 0.0);
-                        if (lane == l) { cellMax = fmax(cellMax, mx); cellColl += double(nAcc); cellSep += sep; }
+                // fold the batch into the per-cell results: every candidate leaves (sigma, accepted, separation) in shared
+                // memory and the lane that owns the cell adds its candidates up in candidate order (= the reference's order)
+                __syncwarp();
+                sm.resSigma[lane] = mySigma;
+                sm.resSep[lane] = accepted ? mySep : -1.0;
+                __syncwarp();
+                if (isCellLane && nCand > 0) {
+                    int kb = candStart - k0, ke = candStart + nCand - k0;
+                    if (kb < 0) kb = 0;
+                    if (ke > 32) ke = 32;
+                    for (int k2 = kb; k2 < ke; ++k2) {
+                        const double sg = sm.resSigma[k2];
+                        if (sg > cellMax) cellMax = sg;
+                        const double sp2 = sm.resSep[k2];
+                        if (sp2 >= 0.0) { cellColl += 1.0; cellSep += sp2; }
                     }
                 }
+                __syncwarp();
             }
             if (isCellLane) {
                 const int32_t c = c0 + g0 + gl;

@@ -23,7 +23,15 @@ enum PhiloxStream : uint32_t {
     STREAM_NEWPARCEL = 6   // random step fraction of freshly inserted parcels
 };
 
-DSMC_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+#if defined(__CUDACC__)
+#define DSMC_HD_NOINLINE static __host__ __device__ __noinline__
+#else
+#define DSMC_HD_NOINLINE inline
+#endif
+
+// out of line on the device: ~40 call sites otherwise inline 10 rounds each and the collision kernel no longer
+// fits the instruction cache
+DSMC_HD_NOINLINE void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                            uint32_t out[4]) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
