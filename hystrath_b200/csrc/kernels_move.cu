@@ -24,10 +24,16 @@ namespace dsmc {
 namespace {
 
 constexpr double kTrackingCorrectionTol = 1.0e-5;  // BASIC/particle/particle.C:33
-constexpr int MOVE_CHUNK = 4;                      // parcels per lane in a warp's work queue
-constexpr int MOVE_BLOCK = 256;
+#ifndef MOVE_CHUNK_SZ
+#define MOVE_CHUNK_SZ 16
+#endif
+constexpr int MOVE_CHUNK = MOVE_CHUNK_SZ;  // parcels per lane in a warp work queue
+#ifndef MOVE_BLOCK_SZ
+#define MOVE_BLOCK_SZ 128
+#endif
+constexpr int MOVE_BLOCK = MOVE_BLOCK_SZ;
 #ifndef MOVE_MIN_BLOCKS
-#define MOVE_MIN_BLOCKS 2
+#define MOVE_MIN_BLOCKS 4
 #endif
 
 __device__ __forceinline__ void ld4(const double* __restrict__ p, double& a, double& b, double& c, double& d) {
@@ -54,9 +60,12 @@ __device__ __forceinline__ bool planeCrossed(double num, const V3& toMinusCt, co
 }
 
 // particle::tetLambda, BASIC/particle/particleI.H:68-140 (static mesh branch)
-__device__ __forceinline__ double tetLambda(const V3& from, const V3& toMinusFrom, const V3& n, const V3& base, double tol) {
-    const double lambdaNumerator = dot(base - from, n);
+__device__ __forceinline__ double tetLambda(const V3& from, const V3& toMinusFrom, const V3& n, const V3& base, double tol, bool crossed) {
+    double lambdaNumerator = dot(base - from, n);
     double lambdaDenominator = dot(toMinusFrom, n);
+    // The quotient of a plane that is not crossed is discarded.  A parcel that has just entered through a face sits on
+    // that plane (numerator == 0 after cancellation) and 0/x sends the FP64 divide to its slow path: feed it 1/1 instead.
+    if (!crossed) { lambdaNumerator = 1.0; lambdaDenominator = 1.0; }
     if (fabs(lambdaDenominator) < tol) {
         if (fabs(lambdaNumerator) < tol) return 0.0;
         if (mag(toMinusFrom) < tol / mag(n)) return GREAT;
@@ -318,10 +327,10 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                     // all four lambdas from the current position as independent chains (the ones of planes that are
                     // not crossed are discarded); order and strict '<' as in the reference's loop over tris
                     const V3 toMinusFrom = endPosition - pos;
-                    const double l0 = tetLambda(pos, toMinusFrom, N0, base, tol);
-                    const double l1 = tetLambda(pos, toMinusFrom, N1, pA, tol);
-                    const double l2 = tetLambda(pos, toMinusFrom, N2, base, tol);
-                    const double l3 = tetLambda(pos, toMinusFrom, N3, base, tol);
+                    const double l0 = tetLambda(pos, toMinusFrom, N0, base, tol, c0);
+                    const double l1 = tetLambda(pos, toMinusFrom, N1, pA, tol, c1);
+                    const double l2 = tetLambda(pos, toMinusFrom, N2, base, tol, c2);
+                    const double l3 = tetLambda(pos, toMinusFrom, N3, base, tol, c3);
                     int triI = -1;
                     double lambdaMin = VGREAT;
                     if (c0 && l0 < lambdaMin) { lambdaMin = l0; triI = 0; }
