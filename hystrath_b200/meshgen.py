@@ -172,3 +172,75 @@ def decomposed_box(n_local, lengths_local, procs, rank, outer=("cyclic", "cyclic
             else:
                 sides[side] = tuple(outer[d])
     return box_mesh(n_local, lengths_local, origin, sides, my_proc=rank)
+
+
+def cylinder_ogrid(nr, ntheta, r_in, r_out, thickness=None, grading=1.0):
+    """2-D body-fitted O-grid around a circular cylinder (one cell thick in z, `empty` front and back): the mesh
+    topology of BASELINE configs[1] (Mach-10 argon flow over a cylinder, Lofthouse).  Cells are hexahedra with
+    non-axis-aligned faces; the grid closes on itself in theta (no cyclic patch needed).
+
+    Patches: `cylinder` (wall), `outer` (patch: free-stream inflow + deletion), `frontAndBack` (empty).
+    grading = (last radial cell size) / (first radial cell size), geometric.
+    """
+    nr, nt = int(nr), int(ntheta)
+    if grading == 1.0:
+        r = r_in + (r_out - r_in) * np.arange(nr + 1) / nr
+    else:
+        q = grading ** (1.0 / max(nr - 1, 1))
+        w = np.concatenate([[0.0], np.cumsum(q ** np.arange(nr))])
+        r = r_in + (r_out - r_in) * w / w[-1]
+    th = 2.0 * np.pi * np.arange(nt) / nt
+    t = thickness if thickness is not None else (r[1] - r[0])
+    # points p(i, j, k) = i + (nr+1) * (j + nt * k)
+    R, TH = np.meshgrid(r, th, indexing="xy")           # [nt, nr+1]
+    xy = np.stack([(R * np.cos(TH)).ravel(), (R * np.sin(TH)).ravel()], 1)
+    points = np.concatenate([np.column_stack([xy, np.zeros(len(xy))]), np.column_stack([xy, np.full(len(xy), t)])])
+
+    def pid(i, j, k):
+        return i + (nr + 1) * ((j % nt) + nt * k)
+
+    def cid(i, j):
+        return i + nr * (j % nt)
+
+    J, I = np.meshgrid(np.arange(nt), np.arange(nr), indexing="ij")
+    I, J = I.ravel(), J.ravel()
+    faces, own, nei = [], [], []
+    # radial internal faces at radius index i = 1..nr-1 between (i-1, j) and (i, j): normal +r
+    m = I >= 1
+    i, j = I[m], J[m]
+    faces.append(np.stack([pid(i, j, 0), pid(i, j + 1, 0), pid(i, j + 1, 1), pid(i, j, 1)], 1))
+    own.append(cid(i - 1, j)); nei.append(cid(i, j))
+    # angular internal faces between (i, j) and (i, j+1), j+1 < nt: normal +theta
+    m = J < nt - 1
+    i, j = I[m], J[m]
+    faces.append(np.stack([pid(i, j + 1, 0), pid(i, j + 1, 1), pid(i + 1, j + 1, 1), pid(i + 1, j + 1, 0)], 1))
+    own.append(cid(i, j)); nei.append(cid(i, j + 1))
+    # the closing faces at theta index 0: owner (i, 0) (lower label), neighbour (i, nt-1): normal -theta
+    i = np.arange(nr)
+    z = np.zeros_like(i)
+    faces.append(np.stack([pid(i, z, 0), pid(i + 1, z, 0), pid(i + 1, z, 1), pid(i, z, 1)], 1))
+    own.append(cid(i, z)); nei.append(cid(i, z + nt - 1))
+    n_int = sum(len(o) for o in own)
+    j = np.arange(nt)
+    z = np.zeros_like(j)
+    # cylinder wall (i = 0), outward = -r
+    f_wall = np.stack([pid(z, j, 0), pid(z, j, 1), pid(z, j + 1, 1), pid(z, j + 1, 0)], 1)
+    o_wall = cid(z, j)
+    # outer boundary (i = nr), outward = +r
+    f_out = np.stack([pid(z + nr, j, 0), pid(z + nr, j + 1, 0), pid(z + nr, j + 1, 1), pid(z + nr, j, 1)], 1)
+    o_out = cid(z + nr - 1, j)
+    # back (k = 0, -z) and front (k = 1, +z)
+    f_back = np.stack([pid(I, J, 0), pid(I, J + 1, 0), pid(I + 1, J + 1, 0), pid(I + 1, J, 0)], 1)
+    f_front = np.stack([pid(I, J, 1), pid(I + 1, J, 1), pid(I + 1, J + 1, 1), pid(I, J + 1, 1)], 1)
+    o_fb = cid(I, J)
+    patches = [dict(name="cylinder", type="wall", start=n_int, size=nt),
+               dict(name="outer", type="patch", start=n_int + nt, size=nt),
+               dict(name="frontAndBack", type="empty", start=n_int + 2 * nt, size=2 * nr * nt)]
+    allf = np.concatenate(faces + [f_wall, f_out, f_back, f_front]).astype(np.int32)
+    owner = np.concatenate(own + [o_wall, o_out, o_fb, o_fb]).astype(np.int32)
+    neighbour = np.concatenate(nei).astype(np.int32)
+    mesh = MeshData(points, (4 * np.arange(len(owner) + 1)).astype(np.int32), allf.ravel(), owner, neighbour, patches)
+    mesh.shape = (nr, nt, 1)
+    mesh.r = r
+    mesh.thickness = t
+    return mesh

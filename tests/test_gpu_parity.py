@@ -244,3 +244,34 @@ def test_mesh_fill_on_device_matches_oracle():
     assert np.allclose(g.U, o.U, rtol=1e-12, atol=1e-9)
     assert np.array_equal(g.vibLevel, o.vibLevel)
     eng.close()
+
+
+def test_cylinder_ogrid_inflow_wall_matches_oracle():
+    """BASELINE configs[1] topology at test size: body-fitted O-grid (non-axis-aligned hexahedra, 2-D with empty
+    patches), hypersonic free stream, diffuse cylinder wall, inflow + deletion on the outer boundary."""
+    from hystrath_b200 import cases
+
+    mesh, sp, md, fill = cases.lofthouse_cylinder(nr=24, ntheta=64, ppc=20, r_out=0.4)
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    H.same_start(eng, ora, fill["type_ids"], fill["number_densities"], fill["Ttra"], velocity=fill["velocity"])
+    n0 = ora.num_parcels()
+    eng.evolve(6)
+    ora.evolve(6)
+    g, o = eng.download_parcels(), ora.download_parcels()
+    oc = ora.counters()
+    assert oc["inserted"] > 0 and oc["deleted"] > 0
+    assert g.n == o.n
+    assert np.array_equal(g.origId, o.origId)
+    assert np.array_equal(g.cell, o.cell)
+    assert np.array_equal(eng.occupancy(), ora.occupancy())
+    assert np.array_equal(g.tetFace, o.tetFace) and np.array_equal(g.tetPt, o.tetPt)
+    assert np.allclose(g.position, o.position, rtol=0, atol=1e-12)
+    assert np.allclose(g.U, o.U, rtol=1e-12, atol=1e-8)
+    gw, ow = eng.wall_accumulators(), ora.wall_accumulators()
+    assert np.abs(ow).sum() > 0
+    scale = np.abs(ow).max(axis=(0, 1), keepdims=True) + 1e-300
+    assert (np.abs(gw - ow) / scale).max() < 1e-9
+    # every parcel stays between the cylinder and the outer boundary
+    r = np.hypot(g.position[:, 0], g.position[:, 1])
+    assert r.min() >= 0.1524 * np.cos(np.pi / 64) - 1e-12 and r.max() <= 0.4 + 1e-12
+    eng.close()
