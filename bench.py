@@ -32,7 +32,6 @@ KB = 1.38065e-23
 STAGE_BYTES_AIR = {"move": 96.0, "sort": 168.0, "collide": 71.0, "sample": 40.0}
 STAGE_BYTES_AR = {"move": 96.0, "sort": 136.0, "collide": 63.0, "sample": 28.0}   # no ERot / vibLevel / ELevel
 SORT_KERNELS = ("scan", "scatterIndex", "segmentSort", "gather", "histogram")
-KERNELS_PER_STEP = 9  # move, scan x3, scatterIndex, segmentSort, gather, collide, sample
 
 
 def species_table(gas):
@@ -136,6 +135,12 @@ def run_reference(args):
 
 
 def workload_config(args, cells_per_gpu, parcels_per_gpu):
+    if getattr(args, "workload", "box") == "cylinder":
+        return {"workload": "2-D Mach-10 argon flow over a cylinder (BASELINE configs[1], Lofthouse): O-grid %s cells, ~%d parcels, VHS, "
+                            "diffuse 500 K wall, free-stream inflow + deletion" % (args.cyl, parcels_per_gpu),
+                "cells_per_gpu": cells_per_gpu, "parcels_per_gpu": parcels_per_gpu, "parcels_per_cell": args.ppc, "gas": "argon",
+                "collision_model": "VariableHardSphere", "partition": "1 GPU",
+                "l2_policy": "inputs larger than L2 (parcel state >> 126 MB), no flush needed"}
     return {"workload": "weak-scaling periodic box (BASELINE configs[4]), %s, %d cells and ~%d parcels per GPU" % (
         "argon VHS" if args.gas == "argon" else "5-species air (N2,O2,NO,N,O) Larsen-Borgnakke VHS", cells_per_gpu, parcels_per_gpu),
         "cells_per_gpu": cells_per_gpu, "parcels_per_gpu": parcels_per_gpu, "parcels_per_cell": args.ppc, "gas": args.gas,
@@ -151,6 +156,20 @@ def cpu_baseline_leg(args):
 
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    if getattr(args, "workload", "box") == "cylinder":
+        from hystrath_b200 import cases
+
+        mesh, sp, md, fill = cases.lofthouse_cylinder(160, 312, 25)
+        o = Oracle()
+        o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
+        o.mesh_fill(fill["type_ids"], fill["number_densities"], fill["Ttra"], 0.0, 0.0, 0.0, fill["velocity"])
+        n = o.num_parcels()
+        o.evolve(1)
+        t0 = time.perf_counter()
+        o.evolve(args.cpu_steps)
+        dt = time.perf_counter() - t0
+        return {"value": n * args.cpu_steps / dt, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+                "sample": f"160x312-cell cylinder O-grid, {n} parcels, {args.cpu_steps} steps (oracle, OpenMP over {cores} threads)"}
     cells = args.cpu_cells
     cp = case_parameters(args.gas, cells, args.ppc)
     sp, tids, frac = species_table(args.gas)
@@ -176,6 +195,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dsmcb200", choices=["dsmcb200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("DSMCB200_BENCH_WORKLOAD", "box"), choices=["box", "cylinder"],
+                    help="box: BASELINE configs[4] weak-scaling periodic box (default, any N); cylinder: configs[1] Mach-10 argon cylinder (N=1)")
+    ap.add_argument("--cyl", default="640x1250", help="cylinder O-grid cells nr x ntheta")
     ap.add_argument("--gas", default=os.environ.get("DSMCB200_BENCH_GAS", "air5"), choices=["argon", "air5"])
     ap.add_argument("--cells", type=int, default=int(os.environ.get("DSMCB200_BENCH_CELLS", "200")), help="cells per direction per GPU")
     ap.add_argument("--ppc", type=int, default=31)
@@ -209,13 +231,27 @@ def main():
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    cp = case_parameters(args.gas, args.cells, args.ppc)
-    sp, tids, frac = species_table(args.gas)
-    procs = procs_for(world)
     t_setup = time.perf_counter()
-    mesh = meshgen.decomposed_box((args.cells,) * 3, (cp["L"],) * 3, procs, rank)
-    model = "VariableHardSphere" if args.gas == "argon" else "LarsenBorgnakkeVariableHardSphere"
-    md = capi.build_models(model, nEquivalentParticles=cp["fnum"], deltaT=cp["dt"], seed=0xD5C00005 + rank)
+    if args.workload == "cylinder":
+        if world != 1:
+            raise SystemExit("--workload cylinder is a single-GPU configuration (BASELINE configs[1])")
+        from hystrath_b200 import cases
+
+        nr, nt = (int(v) for v in args.cyl.split("x"))
+        args.gas = "argon"
+        args.ppc = 25
+        mesh, sp, md, fill = cases.lofthouse_cylinder(nr, nt, args.ppc)
+        tids, dens, Tfill, vfill = fill["type_ids"], fill["number_densities"], fill["Ttra"], fill["velocity"]
+        n_cells_gpu = mesh.n_cells
+    else:
+        cp = case_parameters(args.gas, args.cells, args.ppc)
+        sp, tids, frac = species_table(args.gas)
+        procs = procs_for(world)
+        mesh = meshgen.decomposed_box((args.cells,) * 3, (cp["L"],) * 3, procs, rank)
+        model = "VariableHardSphere" if args.gas == "argon" else "LarsenBorgnakkeVariableHardSphere"
+        md = capi.build_models(model, nEquivalentParticles=cp["fnum"], deltaT=cp["dt"], seed=0xD5C00005 + rank)
+        dens, Tfill, vfill = [cp["n"] * f for f in frac], cp["T"], (0.0, 0.0, 0.0)
+        n_cells_gpu = args.cells ** 3
     eng = capi.Engine(local, rank, world)
     eng.set_mesh(mesh); eng.set_species(sp); eng.set_models(md)
     if world > 1:
@@ -224,9 +260,9 @@ def main():
             ident = torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8).cuda()
         dist.broadcast(ident, 0)
         eng.init_comm(bytes(ident.cpu().numpy().tobytes()))
-    expected = int(args.cells ** 3 * args.ppc * 1.02) + 4096
+    expected = int(n_cells_gpu * args.ppc * 1.05) + 4096
     eng.reserve(expected)
-    eng.mesh_fill(tids, [cp["n"] * f for f in frac], cp["T"], cp["T"], cp["T"])
+    eng.mesh_fill(tids, dens, Tfill, Tfill, Tfill, 0.0, vfill)
     n_local = eng.num_parcels()
     setup_s = time.perf_counter() - t_setup
 
@@ -266,7 +302,8 @@ def main():
     # ---- end to end through the C ABI with host buffers: upload cloud, evolve, download cloud + fields, every step
     e2e = None
     if not args.no_e2e:
-        host = eng.download_parcels()
+        host = capi.ParcelData(int(eng.num_parcels() * 1.02) + 4096, eng.max_modes)   # headroom: inflow changes the count
+        host = _download_into(eng, host)
         pinned = {}
         for name, _, _ in capi.ParcelData.FIELDS:
             a = getattr(host, name)
@@ -275,9 +312,10 @@ def main():
             t = torch.from_numpy(a).pin_memory()
             pinned[name] = t
             setattr(host, name, t.numpy())
-        h2d = sum(getattr(host, k).nbytes for k in ("position", "U", "cell", "tetFace", "tetPt", "typeId", "origId") if getattr(host, k) is not None)
+        row = sum(getattr(host, k)[:1].nbytes for k in ("position", "U", "cell", "tetFace", "tetPt", "typeId", "origId"))
         if args.gas != "argon":
-            h2d += host.ERot.nbytes + host.vibLevel.nbytes + host.ELevel.nbytes
+            row += host.ERot[:1].nbytes + host.vibLevel[:1].nbytes + host.ELevel[:1].nbytes
+        h2d = row * host.n
         acc_bytes = 0
         barrier()
         t1 = time.perf_counter()
@@ -327,10 +365,10 @@ def main():
             "metric": "particle-steps/s (move+sort+NTC collide+sample)", "value": value, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, args.cells ** 3, n_local),
+            "config": workload_config(args, n_cells_gpu, n_local),
             "roofline": roofline, "stages": stages,
             "kernel_ms_per_step": per_step, "wall_ms_per_step": 1e3 * wall / args.steps, "setup_s": setup_s,
-            "clocks": sampler.summary(), "gpu_launches": KERNELS_PER_STEP * args.steps,
+            "clocks": sampler.summary(), "gpu_launches": int(sum(v[1] for v in kt.values())),
             "hbm_frac_of_step": sum(n_local * sb[k] for k in sb) / (ms_total / args.steps * 1e-3) / 1e9 / peak,
         }
         if e2e is not None:
