@@ -23,7 +23,11 @@ namespace {
 
 constexpr int COL_WARPS = 4;
 constexpr int COL_CAP = 128;  // parcels of a cell staged in shared memory per warp
-constexpr int BIG_CELL_THRESHOLD = 160;  // = GRP_CAP: larger cells are processed in place by collideBigCellsKernel
+#ifndef COLLIDE_LANE
+#define COLLIDE_LANE 1
+#endif
+// larger cells are processed in place by collideBigCellsKernel (= LANE_CELL_MAX, or GRP_CAP of the cell-group kernel)
+constexpr int BIG_CELL_THRESHOLD = COLLIDE_LANE ? 255 : 160;
 
 struct CellView {  // the parcels of one cell, in shared memory (small cells) or in place (large cells)
     double *ux, *uy, *uz, *erot;
@@ -721,13 +725,275 @@ __global__ void __launch_bounds__(GRP_WARPS * 32) collideGroupKernel(const __gri
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Lane-per-cell kernel: a warp takes 32 consecutive cells and every lane walks the candidates of ITS cell
+// in the reference's serial order.  Candidates of one cell are then ordered by construction (no owner table,
+// no atomics) and every lane of the warp executes the expensive parts -- Philox, pow() of sigmaTcR, the
+// Larsen-Borgnakke exchange -- at the same time.  Only the per-parcel octant keys, species and the sub-cell
+// index lists live in shared memory (3 bytes per parcel); velocities and internal energies of the ~2 parcels a
+// candidate touches are read and written in place.  Cells with more than LANE_CELL_MAX parcels are left to
+// collideBigCellsKernel.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int LANE_WARPS = 4;
+constexpr int LANE_CAP = 2048;       // parcels of one pass (<= 32 cells) per warp
+constexpr int LANE_CELL_MAX = 255;   // indices within a cell are stored in a byte
+
+struct LaneSmem {
+    uint8_t key[LANE_CAP], typ[LANE_CAP], sub[LANE_CAP];
+    uint8_t cnt[8][32];    // [octant][lane]: running fill position of the lane's cell
+    uint8_t start[9][32];  // [octant][lane]: first slot of the octant in the cell's sub-list
+};
+
+struct InPlace {  // accessor of the parcels of one cell where they lie in the sorted cloud
+    const ParcelArrays& p;
+    int32_t b;
+    __device__ __forceinline__ int elev(int j) const { return p.elevel[b + j]; }
+    __device__ __forceinline__ void setElev(int j, int v) const { p.elevel[b + j] = uint8_t(v); }
+    __device__ __forceinline__ int32_t vib(int m, int j) const { return p.vib[m][b + j]; }
+    __device__ __forceinline__ void setVib(int m, int j, int32_t v) const { p.vib[m][b + j] = v; }
+    __device__ __forceinline__ double erot(int j) const { return p.erot[b + j]; }
+    __device__ __forceinline__ void setErot(int j, double v) const { p.erot[b + j] = v; }
+};
+
+// LarsenBorgnakkeVariableHardSphere::redistribute (postReaction = false) on parcel j of the view
+__device__ __noinline__ void redistributeInPlace(const DevParams& P, Rng& rng, const InPlace v, int j, int tSelf, int tOther,
+                                                 double& translationalEnergy, double omegaPQ) {
+    const DevSpecies& S = P.sp[tSelf];
+    if (S.type == 0) return;  // electron
+    if (P.invZelec > rng.sample01()) {
+        const double EcP = translationalEnergy + S.eElec[v.elev(j)];
+        const int lvl = postCollisionElectronicEnergyLevel(rng, EcP, omegaPQ, S);
+        v.setElev(j, lvl);
+        translationalEnergy = EcP - S.eElec[lvl];
+    }
+    if (S.nVib > 0) {
+        double preEVib[MAX_MODES];
+        int32_t lvl0[MAX_MODES];
+#pragma unroll
+        for (int m = 0; m < MAX_MODES; ++m) {
+            lvl0[m] = m < S.nVib ? v.vib(m, j) : 0;
+            preEVib[m] = m < S.nVib ? lvl0[m] * P.kB * S.thetaV[m] : 0.0;
+        }
+#pragma unroll
+        for (int m = 0; m < MAX_MODES; ++m) {
+            if (m >= S.nVib) break;
+            const double EcP = translationalEnergy + preEVib[m];
+            const int32_t iMaxP = int32_t(EcP / (P.kB * S.thetaV[m]));
+            if (iMaxP > 0) {
+                const int32_t lvl = postCollisionVibrationalEnergyLevel(P, rng, lvl0[m], iMaxP, S.thetaV[m], S.thetaD, S.TrefZv[m], omegaPQ,
+                                                                        S.Zref[m], EcP,
+                                                                        P.invZvTab + ((size_t(tSelf) * P.nSpecies + tOther) * MAX_MODES + m) * ZV_TABLE);
+                if (lvl != lvl0[m]) v.setVib(m, j, lvl);
+                translationalEnergy = EcP - lvl * P.kB * S.thetaV[m];
+            }
+        }
+    }
+    if (S.rotDof > 0) {
+        const double preCollisionERotP = v.erot(j);
+        if (P.invZrot > rng.sample01()) {
+            const double EcP = translationalEnergy + preCollisionERotP;
+            const double ChiB = 2.5 - omegaPQ;
+            const double energyRatio = postCollisionRotationalEnergy(rng, S.rotDof, ChiB);
+            const double e = energyRatio * EcP;
+            v.setErot(j, e);
+            translationalEnergy = EcP - e;
+        }
+    }
+}
+
+__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+}  // namespace
+
+__global__ void __launch_bounds__(LANE_WARPS * 32) collideLaneKernel(const __grid_constant__ CollideArgs a) {
+    __shared__ LaneSmem smAll[LANE_WARPS];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    LaneSmem& sm = smAll[w];
+    const DevParams& P = *a.P;
+    const bool LB = P.collisionModel == DSMCB200_COLL_LB_VHS;
+    const bool internal = P.hasInternalEnergy != 0;
+    const bool none = P.collisionModel == DSMCB200_COLL_NONE;
+    const int32_t nWarps = gridDim.x * LANE_WARPS;
+    const int32_t nGroups = (a.nCells + 31) / 32;
+    unsigned long long totColl = 0, totCand = 0;
+
+    for (int32_t grp = blockIdx.x * LANE_WARPS + w; grp < nGroups; grp += nWarps) {
+        const int32_t c = grp * 32 + lane;  // this lane's cell
+        const bool haveCell = c < a.nCells;
+        const int32_t off = haveCell ? a.cellOffset[c] : a.cellOffset[a.nCells];
+        const int32_t n = haveCell ? a.cellOffset[c + 1] - off : 0;
+        const int nG = a.nCells - grp * 32 < 32 ? a.nCells - grp * 32 : 32;
+        if (none) {
+            if (haveCell) { a.nCollsStep[c] = 0.0; a.collSepStep[c] = 0.0; }
+            continue;
+        }
+        double ccx = 0, ccy = 0, ccz = 0;
+        if (haveCell) { ccx = a.cellCentres[3 * size_t(c)]; ccy = a.cellCentres[3 * size_t(c) + 1]; ccz = a.cellCentres[3 * size_t(c) + 2]; }
+
+        for (int g0 = 0; g0 < nG;) {
+            // ---- the pass: the longest run of cells [g0, g1) whose parcels fit the shared-memory lists ----
+            const int32_t passBeg = __shfl_sync(FULL, off, g0);
+            const unsigned fitMask = __ballot_sync(FULL, lane >= g0 && lane < nG && off + n - passBeg <= LANE_CAP);
+            const unsigned notFit = ~(fitMask >> g0);  // bit r: cell g0 + r does not fit any more
+            const int g1 = g0 + (notFit ? __ffs(notFit) - 1 : 32);
+            if (g1 == g0) {  // a single cell larger than the lists: collideBigCellsKernel
+                ++g0;
+                continue;
+            }
+            const bool inPass = lane >= g0 && lane < g1;
+            const bool mine = inPass && n <= LANE_CELL_MAX;  // larger cells: collideBigCellsKernel
+            const int32_t rel = off - passBeg;
+            __syncwarp();
+            // ---- octant key and species of every parcel of the pass (coalesced), velocities towards L2 ----
+            for (int l = g0; l < g1; ++l) {
+                const int32_t nl = __shfl_sync(FULL, n, l);
+                const int32_t ol = __shfl_sync(FULL, off, l);
+                const double cx = __shfl_sync(FULL, ccx, l), cy = __shfl_sync(FULL, ccy, l), cz = __shfl_sync(FULL, ccz, l);
+                if (nl > LANE_CELL_MAX || nl < 2) continue;
+                const double cc[3] = {cx, cy, cz};
+                for (int j = lane; j < nl; j += 32) {
+                    const int32_t g = ol + j;
+                    sm.key[ol - passBeg + j] = uint8_t(octantOf(a.p.px[g], a.p.py[g], a.p.pz[g], cc));
+                    sm.typ[ol - passBeg + j] = a.p.typeId[g];
+                    if ((j & 3) == 0) {
+                        prefetchL2(a.p.ux + g); prefetchL2(a.p.uy + g); prefetchL2(a.p.uz + g);
+                        if (internal) prefetchL2(a.p.erot + g);
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 8; ++s) sm.cnt[s][lane] = 0;
+            __syncwarp();
+            // ---- sub-cell lists: every lane does the stable counting sort of its own cell ----
+            const int nMine = (mine && n > 1) ? n : 0;
+            int nMax = nMine;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nMax = max(nMax, __shfl_xor_sync(FULL, nMax, o));
+            for (int j = 0; j < nMax; ++j)
+                if (j < nMine) sm.cnt[sm.key[rel + j]][lane] += 1;
+            {
+                int acc = 0;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const int cs = sm.cnt[s][lane];
+                    sm.start[s][lane] = uint8_t(acc);
+                    sm.cnt[s][lane] = uint8_t(acc);
+                    acc += cs;
+                }
+                sm.start[8][lane] = uint8_t(acc);
+            }
+            for (int j = 0; j < nMax; ++j) {
+                if (j < nMine) {
+                    const int k = sm.key[rel + j];
+                    const int posn = sm.cnt[k][lane];
+                    sm.cnt[k][lane] = uint8_t(posn + 1);
+                    sm.sub[rel + posn] = uint8_t(j);
+                }
+            }
+            // ---- candidate count (noTimeCounter.C:142-155) ----
+            double sigmaL = 0.0;
+            int32_t nCand = 0;
+            if (nMine) {
+                sigmaL = a.sigmaTcRMax[c];
+                const double selectedPairs = a.remainder[c] + 0.5 * n * (n - 1) * P.nParticles * sigmaL * P.deltaT / a.cellVolumes[c];
+                nCand = int32_t(selectedPairs);
+                a.remainder[c] = selectedPairs - nCand;
+                if (nCand < 0) nCand = 0;
+            }
+            double cellMax = sigmaL, cellColl = 0.0, cellSep = 0.0;
+            const InPlace v{a.p, off};
+            // ---- the candidates of the lane's cell, in order ----
+            for (int32_t k = 0; __any_sync(FULL, k < nCand); ++k) {
+                if (k < nCand) {
+                    Rng rng;
+                    rng.init(P.seed, uint32_t(c), uint32_t(k), a.step, STREAM_COLLIDE);
+                    const int32_t cp = rng.randomLabel(0, n - 1);
+                    int32_t cq;
+                    const int sub = sm.key[rel + cp];
+                    const int32_t s0 = sm.start[sub][lane];
+                    const int32_t nSC = int32_t(sm.start[sub + 1][lane]) - s0;
+                    if (nSC > 1) {
+                        do { cq = sm.sub[rel + s0 + rng.randomLabel(0, nSC - 1)]; } while (cp == cq);
+                    } else {
+                        do { cq = rng.randomLabel(0, n - 1); } while (cp == cq);
+                    }
+                    const int tP = sm.typ[rel + cp], tQ = sm.typ[rel + cq];
+                    if (!(P.sp[tP].charge == -1 && P.sp[tQ].charge == -1)) {
+                        const int32_t gp = off + cp, gq = off + cq;
+                        V3 UP = mk(a.p.ux[gp], a.p.uy[gp], a.p.uz[gp]);
+                        V3 UQ = mk(a.p.ux[gq], a.p.uy[gq], a.p.uz[gq]);
+                        const double sTcR = sigmaTcR(P, tP, tQ, mag(UP - UQ));
+                        if (sTcR > cellMax) cellMax = sTcR;
+                        if ((sTcR / sigmaL) > rng.sample01()) {
+                            double cR = -1;
+                            if (LB) {
+                                const double mR = P.mR[tP][tQ];
+                                const double cRsqr = magSqr(UP - UQ);
+                                double translationalEnergy = 0.5 * mR * cRsqr;
+                                const double omegaPQ = P.omegaPQ[tP][tQ];
+                                redistributeInPlace(P, rng, v, cp, tP, tQ, translationalEnergy, omegaPQ);
+                                redistributeInPlace(P, rng, v, cq, tQ, tP, translationalEnergy, omegaPQ);
+                                cR = sqrt(2.0 * translationalEnergy / mR);
+                            }
+                            postCollisionVelocities(P, rng, tP, tQ, UP, UQ, cR);
+                            a.p.ux[gp] = UP.x; a.p.uy[gp] = UP.y; a.p.uz[gp] = UP.z;
+                            a.p.ux[gq] = UQ.x; a.p.uy[gq] = UQ.y; a.p.uz[gq] = UQ.z;
+                            // cellMeasurements (VariableHardSphere.C:154-162)
+                            const double dx = a.p.px[gp] - a.p.px[gq], dy = a.p.py[gp] - a.p.py[gq], dz = a.p.pz[gp] - a.p.pz[gq];
+                            cellSep += sqrt(dx * dx + dy * dy + dz * dz);
+                            cellColl += 1.0;
+                            // classification promotion (VariableHardSphere.C:164-187)
+                            if (a.p.cls) {
+                                const int clP = a.p.cls[gp], clQ = a.p.cls[gq];
+                                if (clP == 0 && (clQ == 1 || clQ == 2)) a.p.cls[gp] = 2;
+                                if (clQ == 0 && (clP == 1 || clP == 2)) a.p.cls[gq] = 2;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            if (inPass && n <= LANE_CELL_MAX) {
+                if (n > 1) a.sigmaTcRMax[c] = cellMax;
+                a.nCollsStep[c] = cellColl;
+                a.collSepStep[c] = cellSep;
+                totColl += (unsigned long long)cellColl;
+                totCand += (unsigned long long)nCand;
+            }
+            __syncwarp();
+            g0 = g1;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        totColl += __shfl_xor_sync(FULL, totColl, o);
+        totCand += __shfl_xor_sync(FULL, totCand, o);
+    }
+    if (lane == 0 && (totColl | totCand)) {
+        atomicAdd(&a.counters->collisions, totColl);
+        atomicAdd(&a.counters->candidates, totCand);
+    }
+}
+
 cudaError_t launchCollide(const CollideArgs& a, cudaStream_t s) {
+#if COLLIDE_LANE
+    {
+        const int nGroups = (a.nCells + 31) / 32;
+        int grid = (nGroups + LANE_WARPS - 1) / LANE_WARPS;
+        if (grid > 148 * 16) grid = 148 * 16;
+        if (grid < 1) grid = 1;
+        collideLaneKernel<<<grid, LANE_WARPS * 32, 0, s>>>(a);
+    }
+#else
     const int nGroups = (a.nCells + GRP_CELLS - 1) / GRP_CELLS;
     int grid = (nGroups + GRP_WARPS - 1) / GRP_WARPS;
     const int maxGrid = 148 * 16;
     if (grid > maxGrid) grid = maxGrid;
     if (grid < 1) grid = 1;
     collideGroupKernel<<<grid, GRP_WARPS * 32, 0, s>>>(a);
+#endif
     int gridBig = (a.nCells + COL_WARPS - 1) / COL_WARPS;
     if (gridBig > 148 * 4) gridBig = 148 * 4;
     if (gridBig < 1) gridBig = 1;

@@ -36,10 +36,9 @@ constexpr int MOVE_BLOCK = MOVE_BLOCK_SZ;
 #define MOVE_MIN_BLOCKS 4
 #endif
 
+// one 32-byte sector per instruction (sm_100 LDG.256): halves the L1 tag look-ups of the scattered record reads
 __device__ __forceinline__ void ld4(const double* __restrict__ p, double& a, double& b, double& c, double& d) {
-    const double2 u = __ldg(reinterpret_cast<const double2*>(p));
-    const double2 v = __ldg(reinterpret_cast<const double2*>(p) + 1);
-    a = u.x; b = u.y; c = v.x; d = v.y;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 __device__ __forceinline__ int32_t loInt(double w) { return int32_t(__double_as_longlong(w) & 0xffffffffLL); }
 __device__ __forceinline__ int32_t hiInt(double w) { return int32_t(__double_as_longlong(w) >> 32); }
@@ -81,11 +80,10 @@ struct WallCtx {
     const double* bfaceArea;
 };
 
-struct Internal {  // internal energy state, loaded lazily (only wall models and migration touch it)
+struct Internal {  // internal energy state: read and written in place by the rare consumers (wall models, migration)
     double ERot;
     int32_t vib0, vib1, vib2;
     int elevel;
-    bool loaded, dirty;
 };
 
 // dsmcPatchBoundary::measurePropertiesBeforeControl / AfterControl accumulation,
@@ -147,8 +145,7 @@ __device__ void wallMeasureDelta(const WallCtx& w, int32_t measIndex, int32_t bf
 }
 
 __device__ __forceinline__ void loadInternal(const MoveArgs& a, const DevParams& P, int32_t i, Internal& in) {
-    if (in.loaded) return;
-    in.loaded = true;
+    in.ERot = 0.0; in.vib0 = in.vib1 = in.vib2 = 0; in.elevel = 0;
     if (!P.hasInternalEnergy) return;
     in.ERot = a.p.erot[i];
     if (P.nModes > 0) in.vib0 = a.p.vib[0][i];
@@ -159,11 +156,11 @@ __device__ __forceinline__ void loadInternal(const MoveArgs& a, const DevParams&
 
 // dsmcParcel::hitWallPatch / hitPatch -> dsmc{Diffuse,Specular}WallPatch::controlParticle
 __device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int sp, int patch, int32_t measIndex, int32_t bfi, V3 nw, V3 U,
-                                           Internal* inOut, int* wallHits) {
+                                           int* wallHits) {
     const DevParams& P = *a.P;
     const DevPatch& pt = P.patch[patch];
     WallCtx wctx{a.P, a.wallAcc, a.nWallQ, a.bfaceArea};
-    Internal in = *inOut;
+    Internal in;
     loadInternal(a, P, i, in);
     double preIE, postIE;
     V3 preIMom, postIMom;
@@ -202,11 +199,16 @@ __device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int sp,
         if (S.nVib > 2) in.vib2 = equipartitionVibrationalEnergyLevel(wallRng, Tw, S.thetaV[2]);
         in.elevel = equipartitionElectronicLevel(wallRng, P.kB, Tw, S);
         U += mk(pt.vel[0], pt.vel[1], pt.vel[2]);
-        in.dirty = true;
+        if (P.hasInternalEnergy) {
+            a.p.erot[i] = in.ERot;
+            if (P.nModes > 0) a.p.vib[0][i] = in.vib0;
+            if (P.nModes > 1) a.p.vib[1][i] = in.vib1;
+            if (P.nModes > 2) a.p.vib[2][i] = in.vib2;
+            a.p.elevel[i] = uint8_t(in.elevel);
+        }
     }
     wallMeasure(wctx, measIndex, bfi, sp, U, in, postIE, postIMom);
     wallMeasureDelta(wctx, measIndex, bfi, sp, preIE, preIMom, postIE, postIMom);
-    *inOut = in;
     return U;
 }
 
@@ -214,6 +216,7 @@ __device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int sp,
 
 __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const __grid_constant__ MoveArgs a) {
     const DevParams& P = *a.P;
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int32_t warpGlobal = (blockIdx.x * MOVE_BLOCK + threadIdx.x) >> 5;
     const int32_t chunkBeg = a.first + warpGlobal * (32 * MOVE_CHUNK);
@@ -228,25 +231,25 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
 
     // per-lane parcel state
     bool active = false;
-    int32_t i = -1, cell = -1, tet = 0, sp = 0;
+    int32_t i = -1, cell = -1, tet = 0;
     V3 pos = mk(0, 0, 0), U = mk(0, 0, 0), endPosition = mk(0, 0, 0);
-    double tEnd = 0.0, stepFraction = 0.0, dt = 0.0, trackFraction = 0.0;
+    double tEnd = 0.0, trackFraction = 0.0;
     bool inCall = false, rescuePending = false, faceSet = false, Udirty = false;
     bool keepParticle = true, switchProcessor = false;
-    int32_t faceBfi = -1, procBfi = -1;
-    Internal in;
-    in.ERot = 0.0; in.vib0 = in.vib1 = in.vib2 = 0; in.elevel = 0; in.loaded = false; in.dirty = false;
+    int32_t faceBfi = -1;
     int wallHits = 0;
     unsigned rescues = 0, nDeleted = 0;
     int guard = 0;
 
+    // Every lane runs through every section of the loop body and the sections are separated by __syncwarp(), so
+    // the warp is converged again at each section head whatever happened in the (divergent) section before it.
     while (true) {
-        // ---- refill idle lanes from the warp's queue ----
-        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        // ---- section 0: refill idle lanes from the warp's queue ----
+        const unsigned idle = __ballot_sync(FULL, !active);
         if (idle) {
             const int32_t avail = chunkEnd - warpNext;
             if (avail <= 0) {
-                if (idle == 0xffffffffu) break;
+                if (idle == FULL) break;
             } else {
                 const int r = __popc(idle & ((1u << lane) - 1u));
                 if (!active && r < avail) {
@@ -256,12 +259,10 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                         tet = a.p.tet[i];
                         pos = mk(a.p.px[i], a.p.py[i], a.p.pz[i]);
                         U = mk(a.p.ux[i], a.p.uy[i], a.p.uz[i]);
-                        sp = a.p.typeId[i];
-                        stepFraction = (a.sfTail != nullptr && i >= a.tailStart) ? a.sfTail[i - a.tailStart] : 0.0;
+                        const double stepFraction = (a.sfTail != nullptr && i >= a.tailStart) ? a.sfTail[i - a.tailStart] : 0.0;
                         tEnd = (1.0 - stepFraction) * deltaT;
                         inCall = false; rescuePending = false; faceSet = false; Udirty = false;
-                        keepParticle = true; switchProcessor = false; faceBfi = -1; procBfi = -1;
-                        in.loaded = false; in.dirty = false; in.ERot = 0.0; in.vib0 = in.vib1 = in.vib2 = 0; in.elevel = 0;
+                        keepParticle = true; switchProcessor = false; faceBfi = -1;
                         wallHits = 0;
                         guard = 0;
                         if (tEnd > ROOTVSMALL) active = true;
@@ -272,13 +273,13 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                 warpNext += nIdle < avail ? nIdle : avail;
             }
         }
-        if (!active) continue;
+        __syncwarp();
 
-        // ---- one tetrahedron ----
-        if (++guard > 200000) keepParticle = false;  // corrupt tet table: drop the parcel rather than hang
-        bool finished = !keepParticle;
+        // ---- section 1: one tetrahedron -- its record and the planes crossed by (tet centre -> end position) ----
+        bool finished = false;
         double retVal = 1.0;
-        if (!finished) {
+        if (active) {
+            if (++guard > 200000) keepParticle = false;  // corrupt tet table: drop the parcel rather than hang
             if (!inCall) {
                 // dsmcParcel::move loop body up to the trackToFace call (DSMC/parcels/dsmcParcel.C:74-92)
                 V3 Utracking = U;
@@ -287,15 +288,14 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                     for (int d = 0; d < 3; ++d)
                         if (P.solutionD[d] == -1) { setComp(pos, d, P.centre[d]); setComp(Utracking, d, 0.0); }
                 }
-                dt = tEnd;
-                endPosition = pos + dt * Utracking;
+                endPosition = pos + tEnd * Utracking;  // dt = tEnd
                 trackFraction = 0.0;
                 inCall = true; rescuePending = false; faceSet = false; faceBfi = -1;
             }
-            // the whole record up front: seven independent 32-byte sectors in flight before any branch
+            // the whole record up front: seven independent 32-byte sectors in flight
             const double* __restrict__ R = tetBase + size_t(tet) * 28;
             double n0x, n0y, n0z, numC0, n1x, n1y, n1z, numC1, n2x, n2y, n2z, numC2, n3x, n3y, n3z, numC3;
-            double bx, by, bz, tol, ax, ay, az, nb01, ctx, cty, ctz, nb23;
+            double bx, by, bz, ax, ay, az, ctx, cty, ctz, tol, nb01, nb23;
             ld4(R + 24, ctx, cty, ctz, nb23);
             ld4(R + 16, bx, by, bz, tol);
             ld4(R + 0, n0x, n0y, n0z, numC0);
@@ -304,130 +304,132 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
             ld4(R + 12, n3x, n3y, n3z, numC3);
             ld4(R + 20, ax, ay, az, nb01);
             const V3 Ct = mk(ctx, cty, ctz);
-            if (rescuePending) {
+            const V3 N0 = mk(n0x, n0y, n0z), N1 = mk(n1x, n1y, n1z), N2 = mk(n2x, n2y, n2z), N3 = mk(n3x, n3y, n3z);
+            const V3 base = mk(bx, by, bz), pA = mk(ax, ay, az);
+            const V3 toMinusCt = endPosition - Ct;
+            const bool c0 = planeCrossed(numC0, toMinusCt, N0, tol);
+            const bool c1 = planeCrossed(numC1, toMinusCt, N1, tol);
+            const bool c2 = planeCrossed(numC2, toMinusCt, N2, tol);
+            const bool c3 = planeCrossed(numC3, toMinusCt, N3, tol);
+            if (!keepParticle) {
+                finished = true;
+            } else if (rescuePending) {
                 // lambdaMin < SMALL: tracking correction towards the centre of the tet now occupied
                 pos += kTrackingCorrectionTol * (Ct - pos);
                 ++rescues;
                 retVal = trackFraction;
                 finished = true;
+            } else if (!(c0 | c1 | c2 | c3)) {
+                pos = endPosition;
+                faceSet = false; faceBfi = -1;
+                retVal = 1.0;
+                finished = true;
             } else {
-                const V3 N0 = mk(n0x, n0y, n0z), N1 = mk(n1x, n1y, n1z), N2 = mk(n2x, n2y, n2z), N3 = mk(n3x, n3y, n3z);
-                const V3 base = mk(bx, by, bz), pA = mk(ax, ay, az);
-                const V3 toMinusCt = endPosition - Ct;
-                const bool c0 = planeCrossed(numC0, toMinusCt, N0, tol);
-                const bool c1 = planeCrossed(numC1, toMinusCt, N1, tol);
-                const bool c2 = planeCrossed(numC2, toMinusCt, N2, tol);
-                const bool c3 = planeCrossed(numC3, toMinusCt, N3, tol);
-                if (!(c0 | c1 | c2 | c3)) {
+                // ---- advance to the nearest crossed plane and step through it ----
+            // all four lambdas from the current position as independent chains (the ones of planes that are
+            // not crossed are discarded); order and strict '<' as in the reference's loop over tris
+            const V3 toMinusFrom = endPosition - pos;
+            const double l0 = tetLambda(pos, toMinusFrom, N0, base, tol, c0);
+            const double l1 = tetLambda(pos, toMinusFrom, N1, pA, tol, c1);
+            const double l2 = tetLambda(pos, toMinusFrom, N2, base, tol, c2);
+            const double l3 = tetLambda(pos, toMinusFrom, N3, base, tol, c3);
+            int triI = -1;
+            double lambdaMin = VGREAT;
+            if (c0 && l0 < lambdaMin) { lambdaMin = l0; triI = 0; }
+            if (c1 && l1 < lambdaMin) { lambdaMin = l1; triI = 1; }
+            if (c2 && l2 < lambdaMin) { lambdaMin = l2; triI = 2; }
+            if (c3 && l3 < lambdaMin) { lambdaMin = l3; triI = 3; }
+            const int32_t nb0 = loInt(nb01);
+            if (triI == 0) { faceSet = true; faceBfi = nb0 < 0 ? (-1 - nb0) : -1; }
+            else if (triI > 0) { faceSet = false; faceBfi = -1; }
+            bool needRescue = false;
+            if (lambdaMin > SMALL) {
+                if (lambdaMin <= 1.0) {
+                    trackFraction += lambdaMin * (1 - trackFraction);
+                    pos += lambdaMin * (endPosition - pos);
+                } else {
                     pos = endPosition;
-                    faceSet = false; faceBfi = -1;
                     retVal = 1.0;
                     finished = true;
+                }
+            } else {
+                needRescue = true;  // lambdaMin = 0.0
+            }
+            if (!finished) {
+                if (triI > 0) {
+                    // particle::tetNeighbour: enter the adjacent tet of the same cell
+                    tet = triI == 1 ? hiInt(nb01) : (triI == 2 ? loInt(nb23) : hiInt(nb23));
+                    rescuePending = needRescue;
                 } else {
-                    // all four lambdas from the current position as independent chains (the ones of planes that are
-                    // not crossed are discarded); order and strict '<' as in the reference's loop over tris
-                    const V3 toMinusFrom = endPosition - pos;
-                    const double l0 = tetLambda(pos, toMinusFrom, N0, base, tol, c0);
-                    const double l1 = tetLambda(pos, toMinusFrom, N1, pA, tol, c1);
-                    const double l2 = tetLambda(pos, toMinusFrom, N2, base, tol, c2);
-                    const double l3 = tetLambda(pos, toMinusFrom, N3, base, tol, c3);
-                    int triI = -1;
-                    double lambdaMin = VGREAT;
-                    if (c0 && l0 < lambdaMin) { lambdaMin = l0; triI = 0; }
-                    if (c1 && l1 < lambdaMin) { lambdaMin = l1; triI = 1; }
-                    if (c2 && l2 < lambdaMin) { lambdaMin = l2; triI = 2; }
-                    if (c3 && l3 < lambdaMin) { lambdaMin = l3; triI = 3; }
-                    const int32_t nb0 = loInt(nb01);
-                    if (triI == 0) { faceSet = true; faceBfi = nb0 < 0 ? (-1 - nb0) : -1; }
-                    else if (triI > 0) { faceSet = false; faceBfi = -1; }
-                    bool needRescue = false;
-                    if (lambdaMin > SMALL) {
-                        if (lambdaMin <= 1.0) {
-                            trackFraction += lambdaMin * (1 - trackFraction);
-                            pos += lambdaMin * (endPosition - pos);
-                        } else {
-                            pos = endPosition;
-                            retVal = 1.0;
-                            finished = true;
-                        }
+                    if (nb0 >= 0) {
+                        cell = nb0;  // internal face: the same face triangle seen from the other cell
+                        tet ^= 1;
                     } else {
-                        needRescue = true;  // lambdaMin = 0.0
-                    }
-                    if (!finished) {
-                        if (triI > 0) {
-                            // particle::tetNeighbour: enter the adjacent tet of the same cell
-                            tet = triI == 1 ? hiInt(nb01) : (triI == 2 ? loInt(nb23) : hiInt(nb23));
-                            rescuePending = needRescue;
-                        } else {
-                            if (nb0 >= 0) {
-                                cell = nb0;  // internal face: the same face triangle seen from the other cell
-                                tet ^= 1;
-                            } else {
-                                const int32_t bfi = -1 - nb0;
-                                const BFaceRec bf = a.bfaces[bfi];
-                                const DevPatch& pt = P.patch[bf.patch];
-                                switch (pt.type) {
-                                    case DSMCB200_PATCH_PROCESSOR:
-                                    case DSMCB200_PATCH_PROCESSORCYCLIC:
-                                        switchProcessor = true;  // dsmcParcel::hitProcessorPatch
-                                        break;
-                                    case DSMCB200_PATCH_SYMMETRYPLANE:
-                                    case DSMCB200_PATCH_SYMMETRY:
-                                    case DSMCB200_PATCH_WEDGE: {
-                                        // transformProperties(I - 2.0*nf*nf), particleTemplates.C:1474-1522
-                                        const V3 nf = N0;
-                                        const V3 t2 = 2.0 * nf;
-                                        const double xx = 1.0 - t2.x * nf.x, xy = 0.0 - t2.x * nf.y, xz = 0.0 - t2.x * nf.z;
-                                        const double yx = 0.0 - t2.y * nf.x, yy = 1.0 - t2.y * nf.y, yz = 0.0 - t2.y * nf.z;
-                                        const double zx = 0.0 - t2.z * nf.x, zy = 0.0 - t2.z * nf.y, zz = 1.0 - t2.z * nf.z;
-                                        U = mk(xx * U.x + xy * U.y + xz * U.z, yx * U.x + yy * U.y + yz * U.z, zx * U.x + zy * U.y + zz * U.z);
-                                        Udirty = true;
-                                        break;
-                                    }
-                                    case DSMCB200_PATCH_CYCLIC: {
-                                        // particle::hitCyclicPatch, particleTemplates.C:1525-1570
-                                        const int32_t k = (tet >> 1) - bf.tetPair0;
-                                        tet = 2 * (bf.coupledTetPair0 + (bf.nPts - 3) - k);
-                                        cell = bf.coupledCell;
-                                        const DevPatch& rp = P.patch[pt.nbrPatch];
-                                        pos -= mk(rp.sep[0], rp.sep[1], rp.sep[2]);
-                                        faceBfi = bfi - (pt.start - P.nInternalFaces) + (rp.start - P.nInternalFaces);
-                                        break;
-                                    }
-                                    case DSMCB200_PATCH_WALL:
-                                    case DSMCB200_PATCH_PATCH:
-                                        if (pt.model == DSMCB200_BND_DELETION) {
-                                            keepParticle = false;  // dsmcDeletionPatch::controlParticle
-                                        } else if (pt.model != DSMCB200_BND_NONE) {
-                                            U = wallInteraction(a, i, sp, bf.patch, bf.measIndex, bfi, N0, U, &in, &wallHits);
-                                            Udirty = true;
-                                        }
-                                        break;
-                                    default:  // empty patches cannot be hit by constrained tracks
-                                        break;
+                        const int32_t bfi = -1 - nb0;
+                        const BFaceRec bf = a.bfaces[bfi];
+                        const DevPatch& pt = P.patch[bf.patch];
+                        switch (pt.type) {
+                            case DSMCB200_PATCH_PROCESSOR:
+                            case DSMCB200_PATCH_PROCESSORCYCLIC:
+                                switchProcessor = true;  // dsmcParcel::hitProcessorPatch
+                                break;
+                            case DSMCB200_PATCH_SYMMETRYPLANE:
+                            case DSMCB200_PATCH_SYMMETRY:
+                            case DSMCB200_PATCH_WEDGE: {
+                                // transformProperties(I - 2.0*nf*nf), particleTemplates.C:1474-1522
+                                const V3 nf = N0;
+                                const V3 t2 = 2.0 * nf;
+                                const double xx = 1.0 - t2.x * nf.x, xy = 0.0 - t2.x * nf.y, xz = 0.0 - t2.x * nf.z;
+                                const double yx = 0.0 - t2.y * nf.x, yy = 1.0 - t2.y * nf.y, yz = 0.0 - t2.y * nf.z;
+                                const double zx = 0.0 - t2.z * nf.x, zy = 0.0 - t2.z * nf.y, zz = 1.0 - t2.z * nf.z;
+                                U = mk(xx * U.x + xy * U.y + xz * U.z, yx * U.x + yy * U.y + yz * U.z, zx * U.x + zy * U.y + zz * U.z);
+                                Udirty = true;
+                                break;
+                            }
+                            case DSMCB200_PATCH_CYCLIC: {
+                                // particle::hitCyclicPatch, particleTemplates.C:1525-1570
+                                const int32_t k = (tet >> 1) - bf.tetPair0;
+                                tet = 2 * (bf.coupledTetPair0 + (bf.nPts - 3) - k);
+                                cell = bf.coupledCell;
+                                const DevPatch& rp = P.patch[pt.nbrPatch];
+                                pos -= mk(rp.sep[0], rp.sep[1], rp.sep[2]);
+                                faceBfi = bfi - (pt.start - P.nInternalFaces) + (rp.start - P.nInternalFaces);
+                                break;
+                            }
+                            case DSMCB200_PATCH_WALL:
+                            case DSMCB200_PATCH_PATCH:
+                                if (pt.model == DSMCB200_BND_DELETION) {
+                                    keepParticle = false;  // dsmcDeletionPatch::controlParticle
+                                } else if (pt.model != DSMCB200_BND_NONE) {
+                                    U = wallInteraction(a, i, a.p.typeId[i], bf.patch, bf.measIndex, bfi, N0, U, &wallHits);
+                                    Udirty = true;
                                 }
-                            }
-                            if (needRescue) {
-                                rescuePending = true;  // correction towards the new tet's centre, then return trackFraction
-                            } else {
-                                retVal = trackFraction;
-                                finished = true;
-                            }
+                                break;
+                            default:  // empty patches cannot be hit by constrained tracks
+                                break;
                         }
+                    }
+                    if (needRescue) {
+                        rescuePending = true;  // correction towards the new tet's centre, then return trackFraction
+                    } else {
+                        retVal = trackFraction;
+                        finished = true;
                     }
                 }
             }
         }
+        }
+        __syncwarp();
+
+        // ---- section 3: trackToFace returned -- back in dsmcParcel::move (DSMC/parcels/dsmcParcel.C:92-118) ----
         if (finished) {
             if (keepParticle) {
-                // back in dsmcParcel::move (DSMC/parcels/dsmcParcel.C:92-118)
-                dt *= retVal;
+                const double dt = tEnd * retVal;
                 tEnd -= dt;  // stepFraction = 1 - tEnd/deltaT is only consumed by a processor transfer: evaluated there
                 if (faceSet && faceBfi >= 0) {
                     const int ptype = P.patch[a.bfaces[faceBfi].patch].type;
                     if (ptype == DSMCB200_PATCH_PROCESSOR || ptype == DSMCB200_PATCH_PROCESSORCYCLIC) {
-                        switchProcessor = true;
-                        procBfi = faceBfi;
+                        switchProcessor = true;  // the patch face of the transfer is faceBfi
                     }
                 }
             }
@@ -440,23 +442,24 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                     ++nDeleted;
                 } else if (switchProcessor) {
                     // Cloud<T>::move transfer list + particle::prepareForParallelTransfer, fused with the packing
-                    const BFaceRec bf = a.bfaces[procBfi];
+                    const BFaceRec bf = a.bfaces[faceBfi];
                     const DevPatch& pt = P.patch[bf.patch];
                     const int slot = pt.nbrSlot;
-                    stepFraction = 1.0 - tEnd / deltaT;
+                    const double stepFraction = 1.0 - tEnd / deltaT;
                     const int32_t k = atomicAdd(&a.counters->nMig[slot], 1);
                     if (k < a.migCapacity) {
+                        Internal in;
                         loadInternal(a, P, i, in);
                         MigRec r;
                         r.pos[0] = pos.x; r.pos[1] = pos.y; r.pos[2] = pos.z;
                         r.U[0] = U.x; r.U[1] = U.y; r.U[2] = U.z;
                         r.erot = in.ERot; r.stepFraction = stepFraction;
                         r.patchOrdinal = pt.nbrOrdinal;
-                        r.patchFace = procBfi - (pt.start - P.nInternalFaces);
+                        r.patchFace = faceBfi - (pt.start - P.nInternalFaces);
                         r.tetLocal = (tet >> 1) - bf.tetPair0;
                         r.origId = a.p.origId[i];
                         r.vib[0] = in.vib0; r.vib[1] = in.vib1; r.vib[2] = in.vib2;
-                        r.typeId = uint8_t(sp); r.elevel = uint8_t(in.elevel); r.cls = a.p.cls ? a.p.cls[i] : 0; r.pad_ = 0;
+                        r.typeId = a.p.typeId[i]; r.elevel = uint8_t(in.elevel); r.cls = a.p.cls ? a.p.cls[i] : 0; r.pad_ = 0;
                         a.migBuf[size_t(slot) * a.migCapacity + k] = r;
                     } else {
                         atomicAdd(&a.counters->overflow, 1ULL);
@@ -468,13 +471,6 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                     a.p.cell[i] = cell;
                     a.p.tet[i] = tet;
                     if (Udirty) { a.p.ux[i] = U.x; a.p.uy[i] = U.y; a.p.uz[i] = U.z; }
-                    if (in.dirty && P.hasInternalEnergy) {
-                        a.p.erot[i] = in.ERot;
-                        if (P.nModes > 0) a.p.vib[0][i] = in.vib0;
-                        if (P.nModes > 1) a.p.vib[1][i] = in.vib1;
-                        if (P.nModes > 2) a.p.vib[2][i] = in.vib2;
-                        a.p.elevel[i] = uint8_t(in.elevel);
-                    }
                     if (a.cellCount) atomicAdd(&a.cellCount[cell], 1);
                 }
             }
