@@ -161,6 +161,7 @@ struct dsmcb200_ctx {
     int nModes = 0;
     bool internal = false, useCls = false;
     int32_t *dCellCount = nullptr, *dCellOffset = nullptr, *dCursor = nullptr, *dPerm = nullptr, *dScanScratch = nullptr;
+    uint8_t* dOctKey = nullptr;  // sub-cell of every sorted parcel (sort -> collide)
     double *dSigma = nullptr, *dRem = nullptr, *dNColls = nullptr, *dCollSep = nullptr, *dAcc = nullptr, *dCollCum = nullptr,
            *dWallAcc = nullptr, *dSfTail = nullptr, *dInfo = nullptr, *dInfoScratch = nullptr;
     int64_t sfCap = 0;
@@ -296,6 +297,8 @@ int ensureCapacity(dsmcb200_ctx* c, int64_t n) {
     }
     devFree(c->dPerm);
     CK(devAlloc(&c->dPerm, size_t(cap)));
+    devFree(c->dOctKey);
+    CK(devAlloc(&c->dOctKey, size_t(cap)));
     c->capacity = cap;
     return 0;
 }
@@ -548,7 +551,7 @@ int stageSort(dsmcb200_ctx* c, bool histogramDone) {
     { KT t(c, "segmentSort"); CK(launchSegmentSort(c->dCellOffset, nCells, c->dPerm, c->dCounters, c->stream)); }
     CK(cudaStreamSynchronize(c->stream));  // nOut
     ParcelArrays& dst = c->buf[1 - c->cur].a;
-    { KT t(c, "gather"); CK(launchGather(src, dst, c->dPerm, c->dCellOffset, nCells, nOut, c->nModes, c->internal, c->stream)); }
+    { KT t(c, "gather"); CK(launchGather(src, dst, c->dPerm, c->dCellCentres, c->dOctKey, nOut, c->nModes, c->internal, c->stream)); }
     c->cur = 1 - c->cur;
     c->N = nOut;
     c->occupancyValid = true;
@@ -676,7 +679,7 @@ int stageCollide(dsmcb200_ctx* c) {
     CollideArgs a{};
     a.p = c->buf[c->cur].a; a.cellOffset = c->dCellOffset; a.nCells = c->mesh.nCells; a.cellCentres = c->dCellCentres;
     a.cellVolumes = c->dCellVolumes; a.sigmaTcRMax = c->dSigma; a.remainder = c->dRem; a.nCollsStep = c->dNColls; a.collSepStep = c->dCollSep;
-    a.bigScratch = c->dPerm; a.P = c->dP; a.counters = c->dCounters; a.step = c->step;
+    a.bigScratch = c->dPerm; a.octKey = c->dOctKey; a.P = c->dP; a.counters = c->dCounters; a.step = c->step;
     KT t(c, "collide");
     CK(launchCollide(a, c->stream));
     return 0;
@@ -734,7 +737,7 @@ void dsmcb200_destroy(dsmcb200_ctx* c) {
     devFree(c->dP); devFree(c->dTets); devFree(c->dBFaces); devFree(c->dBFaceArea); devFree(c->dPoints); devFree(c->dCellCentres);
     devFree(c->dCellVolumes); devFree(c->dFaceCentres); devFree(c->dFaceAreas); devFree(c->dFaceOffsets); devFree(c->dFacePoints);
     devFree(c->dOwner); devFree(c->dTetBasePtIs); devFree(c->dFaceTetPair0); devFree(c->dCellFaceOffsets); devFree(c->dCellFaces);
-    devFree(c->dCellCount); devFree(c->dCellOffset); devFree(c->dCursor); devFree(c->dPerm); devFree(c->dScanScratch);
+    devFree(c->dCellCount); devFree(c->dCellOffset); devFree(c->dCursor); devFree(c->dPerm); devFree(c->dOctKey); devFree(c->dScanScratch);
     devFree(c->dSigma); devFree(c->dRem); devFree(c->dNColls); devFree(c->dCollSep); devFree(c->dAcc); devFree(c->dCollCum);
     devFree(c->dWallAcc); devFree(c->dSfTail); devFree(c->dInfo); devFree(c->dInfoScratch); devFree(c->dCounters); devFree(c->dBad);
     devFree(c->dMigSend); devFree(c->dMigRecv); devFree(c->dInflowScan); devFree(c->dOrdinalToPatch); devFree(c->dCountsMatrix);

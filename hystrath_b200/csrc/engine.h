@@ -116,6 +116,7 @@ struct CollideArgs {
     double* nCollsStep;           // cellMeasurements: nColls_ of this step
     double* collSepStep;          // cellMeasurements: collisionSeparation_ of this step
     int32_t* bigScratch;          // [nParcels] sub-cell index lists of cells too large for shared memory
+    const uint8_t* octKey;        // [nParcels] sub-cell (octant) of every sorted parcel, written by the sort's gather
     const DevParams* P;
     DevCounters* counters;
     uint32_t step;
@@ -141,8 +142,8 @@ cudaError_t launchExclusiveScan(const int32_t* in, int32_t* out, int32_t* out2, 
 int32_t scanScratchInts(int32_t n);
 cudaError_t launchScatterIndex(const int32_t* cell, int32_t n, int32_t* cursor, int32_t* perm, cudaStream_t s);
 cudaError_t launchSegmentSort(const int32_t* cellOffset, int32_t nCells, int32_t* perm, DevCounters* c, cudaStream_t s);
-cudaError_t launchGather(const ParcelArrays& src, const ParcelArrays& dst, const int32_t* perm, const int32_t* cellOffset,
-                         int32_t nCells, int32_t nOut, int32_t nModes, bool hasInternal, cudaStream_t s);
+cudaError_t launchGather(const ParcelArrays& src, const ParcelArrays& dst, const int32_t* perm, const double* cellCentres,
+                         uint8_t* octKey, int32_t nOut, int32_t nModes, bool hasInternal, cudaStream_t s);
 cudaError_t launchHistogram(const int32_t* cell, int32_t n, int32_t* cellCount, cudaStream_t s);
 cudaError_t launchCollide(const CollideArgs& a, cudaStream_t s);
 cudaError_t launchSample(const SampleArgs& a, cudaStream_t s);

@@ -829,8 +829,6 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) collideLaneKernel(const __gri
             if (haveCell) { a.nCollsStep[c] = 0.0; a.collSepStep[c] = 0.0; }
             continue;
         }
-        double ccx = 0, ccy = 0, ccz = 0;
-        if (haveCell) { ccx = a.cellCentres[3 * size_t(c)]; ccy = a.cellCentres[3 * size_t(c) + 1]; ccz = a.cellCentres[3 * size_t(c) + 2]; }
 
         for (int g0 = 0; g0 < nG;) {
             // ---- the pass: the longest run of cells [g0, g1) whose parcels fit the shared-memory lists ----
@@ -846,18 +844,15 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) collideLaneKernel(const __gri
             const bool mine = inPass && n <= LANE_CELL_MAX;  // larger cells: collideBigCellsKernel
             const int32_t rel = off - passBeg;
             __syncwarp();
-            // ---- octant key and species of every parcel of the pass (coalesced), velocities towards L2 ----
-            for (int l = g0; l < g1; ++l) {
-                const int32_t nl = __shfl_sync(FULL, n, l);
-                const int32_t ol = __shfl_sync(FULL, off, l);
-                const double cx = __shfl_sync(FULL, ccx, l), cy = __shfl_sync(FULL, ccy, l), cz = __shfl_sync(FULL, ccz, l);
-                if (nl > LANE_CELL_MAX || nl < 2) continue;
-                const double cc[3] = {cx, cy, cz};
-                for (int j = lane; j < nl; j += 32) {
-                    const int32_t g = ol + j;
-                    sm.key[ol - passBeg + j] = uint8_t(octantOf(a.p.px[g], a.p.py[g], a.p.pz[g], cc));
-                    sm.typ[ol - passBeg + j] = a.p.typeId[g];
-                    if ((j & 3) == 0) {
+            // ---- octant key (from the sort) and species of every parcel of the pass: one coalesced sweep ----
+            {
+                const int32_t passEnd = __shfl_sync(FULL, off + n, g1 - 1);
+                const int32_t nPass = passEnd - passBeg;
+                for (int j = lane; j < nPass; j += 32) {
+                    sm.key[j] = a.octKey[passBeg + j];
+                    sm.typ[j] = a.p.typeId[passBeg + j];
+                    if ((j & 3) == 0) {  // one 32-byte sector of each velocity component towards L2 ahead of the candidate loop
+                        const int32_t g = passBeg + j;
                         prefetchL2(a.p.ux + g); prefetchL2(a.p.uy + g); prefetchL2(a.p.uz + g);
                         if (internal) prefetchL2(a.p.erot + g);
                     }
@@ -982,7 +977,7 @@ cudaError_t launchCollide(const CollideArgs& a, cudaStream_t s) {
     {
         const int nGroups = (a.nCells + 31) / 32;
         int grid = (nGroups + LANE_WARPS - 1) / LANE_WARPS;
-        if (grid > 148 * 16) grid = 148 * 16;
+        if (grid > 148 * 4) grid = 148 * 4;  // persistent: 4 resident blocks per SM, grid-stride over the cell groups
         if (grid < 1) grid = 1;
         collideLaneKernel<<<grid, LANE_WARPS * 32, 0, s>>>(a);
     }

@@ -193,14 +193,24 @@ __global__ void fillCellKernel(const int32_t* __restrict__ cellOffset, int32_t n
     }
 }
 
-__global__ void __launch_bounds__(256) gatherKernel(const __grid_constant__ ParcelArrays src, const __grid_constant__ ParcelArrays dst, const int32_t* __restrict__ perm, int32_t nOut,
+__global__ void __launch_bounds__(256) gatherKernel(const __grid_constant__ ParcelArrays src, const __grid_constant__ ParcelArrays dst, const int32_t* __restrict__ perm,
+                                                    const double* __restrict__ cellCentres, uint8_t* __restrict__ octKey, int32_t nOut,
                                                     int32_t nModes, int hasInternal) {
     const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nOut) return;
     const int32_t i = perm[k];
-    dst.px[k] = src.px[i]; dst.py[k] = src.py[i]; dst.pz[k] = src.pz[i];
+    const double x = src.px[i], y = src.py[i], z = src.pz[i];
+    const int32_t cell = src.cell[i];
+    dst.px[k] = x; dst.py[k] = y; dst.pz[k] = z;
     dst.ux[k] = src.ux[i]; dst.uy[k] = src.uy[i]; dst.uz[k] = src.uz[i];
-    dst.cell[k] = src.cell[i];
+    dst.cell[k] = cell;
+    // the Cartesian sub-cell of noTimeCounter (noTimeCounter.C:124-138) while position and cell are in registers:
+    // pos(relPos.x()) + 2*pos(relPos.y()) + 4*pos(relPos.z())
+    {
+        const double* cc = cellCentres + 3 * size_t(cell);
+        const double rx = x - cc[0], ry = y - cc[1], rz = z - cc[2];
+        octKey[k] = uint8_t((rx >= 0 ? 1 : 0) + 2 * (ry >= 0 ? 1 : 0) + 4 * (rz >= 0 ? 1 : 0));
+    }
     dst.tet[k] = src.tet[i];
     dst.origId[k] = src.origId[i];
     dst.typeId[k] = src.typeId[i];
@@ -214,11 +224,10 @@ __global__ void __launch_bounds__(256) gatherKernel(const __grid_constant__ Parc
     if (src.cls) dst.cls[k] = src.cls[i];
 }
 
-cudaError_t launchGather(const ParcelArrays& src, const ParcelArrays& dst, const int32_t* perm, const int32_t* cellOffset,
-                         int32_t nCells, int32_t nOut, int32_t nModes, bool hasInternal, cudaStream_t s) {
-    (void)cellOffset; (void)nCells;
+cudaError_t launchGather(const ParcelArrays& src, const ParcelArrays& dst, const int32_t* perm, const double* cellCentres,
+                         uint8_t* octKey, int32_t nOut, int32_t nModes, bool hasInternal, cudaStream_t s) {
     if (nOut <= 0) return cudaSuccess;
-    gatherKernel<<<(nOut + 255) / 256, 256, 0, s>>>(src, dst, perm, nOut, nModes, hasInternal ? 1 : 0);
+    gatherKernel<<<(nOut + 255) / 256, 256, 0, s>>>(src, dst, perm, cellCentres, octKey, nOut, nModes, hasInternal ? 1 : 0);
     return cudaGetLastError();
 }
 
