@@ -1023,13 +1023,30 @@ __global__ void __launch_bounds__(SMP_WARPS * 32) sampleKernel(const __grid_cons
     const int q = lane % Qpad, sub = lane / Qpad;
     const int32_t nWarps = gridDim.x * SMP_WARPS;
 
-    for (int32_t c = blockIdx.x * SMP_WARPS + w; c < a.nCells; c += nWarps) {
-        const int32_t b = a.cellOffset[c];
-        const int32_t nC = a.cellOffset[c + 1] - b;
+    // the offsets of the warp's next cell are read one cell ahead and its parcel rows are requested towards L2 while the
+    // current cell is reduced
+    int32_t c = blockIdx.x * SMP_WARPS + w;
+    int32_t bNext = 0, nCNext = 0;
+    if (c < a.nCells) { bNext = a.cellOffset[c]; nCNext = a.cellOffset[c + 1] - bNext; }
+    for (; c < a.nCells; c += nWarps) {
+        const int32_t b = bNext;
+        const int32_t nC = nCNext;
+        {
+            const int32_t cn = c + nWarps;
+            if (cn < a.nCells) {
+                bNext = a.cellOffset[cn];
+                nCNext = a.cellOffset[cn + 1] - bNext;
+                if (lane < nCNext && (lane & 3) == 0) {
+                    const int32_t g = bNext + lane;
+                    prefetchL2(a.p.ux + g); prefetchL2(a.p.uy + g); prefetchL2(a.p.uz + g);
+                    if (internal) prefetchL2(a.p.erot + g);
+                }
+            }
+        }
         if (lane < 2) {
             // fold this step's cellMeasurements into the cumulative pair (dsmcVolFields.C:1244-1248)
             const double add = lane == 0 ? a.nCollsStep[c] : a.collSepStep[c];
-            if (add != 0.0) a.collCum[2 * size_t(c) + lane] += add;
+            if (add != 0.0) atomicAdd(&a.collCum[2 * size_t(c) + lane], add);
         }
         if (nC == 0) continue;
         double sum[MAX_SPECIES];
@@ -1098,7 +1115,7 @@ __global__ void __launch_bounds__(SMP_WARPS * 32) sampleKernel(const __grid_cons
             double* row = a.acc + size_t(c) * S * nQ;
 #pragma unroll
             for (int s = 0; s < MAX_SPECIES; ++s)
-                if (s < S && sum[s] != 0.0) row[s * nQ + q] += sum[s];
+                if (s < S && sum[s] != 0.0) atomicAdd(&row[s * nQ + q], sum[s]);  // one writer per element: a fire-and-forget RED
         }
     }
 }
