@@ -1,5 +1,5 @@
 // kernels_collide.cu -- stages 3+4 (noTimeCounter candidate selection, VHS / Larsen-Borgnakke
-// binary collisions) and stage 5 (per-cell sampling), one warp per cell.
+// binary collisions) and stage 5 (per-cell sampling).
 //
 // Stage 3 follows noTimeCounter::collide (DSMC/collisionPartnerSelection/derived/noTimeCounter/
 // noTimeCounter.C:81-339); stage 4 VariableHardSphere (DSMC/collisions/derived/VariableHardSphere/
@@ -7,13 +7,15 @@
 // 110-279) with the cloud helpers postCollision{Rotational,Vibrational,Electronic}* (DSMC/clouds/
 // dsmcCloud.C:1327-1656).  The reference processes the candidates of a cell serially; a later candidate
 // sees the velocities written by an earlier accepted one.  Every candidate owns a Philox stream keyed by
-// (cell, candidate index, step), so its partners (P,Q) are known independently of the others; the 32
-// candidates of a batch are then resolved in dependency order (a candidate waits for every earlier
-// candidate that shares a parcel with it), which yields exactly the serial result.
+// (cell, candidate index, step), so its partners (P,Q) are known independently of the others.
+//   collideLaneKernel      one LANE per cell: the lane walks its cell's candidates in order (cells <= 255 parcels)
+//   collideBigCellsKernel  one WARP per cell: batches of 32 candidates resolved in dependency order (a candidate
+//                          waits for every earlier candidate that shares a parcel with it)
+// Both yield exactly the serial result.
 //
 // Stage 5 follows the per-parcel accumulation of dsmcVolFields::calculateField (DSMC/macroscopicProperties/
 // derived/combined/dsmcVolFields/dsmcVolFields.C:1115-1237): parcels are cell-sorted, so each warp reduces
-// the parcels of its cell and adds one row of per-species moment sums -- no atomics.
+// the parcels of its cell and adds one row of per-species moment sums (single writer per accumulator element).
 #include "device_models.cuh"
 #include "engine.h"
 
@@ -23,11 +25,7 @@ namespace {
 
 constexpr int COL_WARPS = 4;
 constexpr int COL_CAP = 128;  // parcels of a cell staged in shared memory per warp
-#ifndef COLLIDE_LANE
-#define COLLIDE_LANE 1
-#endif
-// larger cells are processed in place by collideBigCellsKernel (= LANE_CELL_MAX, or GRP_CAP of the cell-group kernel)
-constexpr int BIG_CELL_THRESHOLD = COLLIDE_LANE ? 255 : 160;
+constexpr int BIG_CELL_THRESHOLD = 255;  // = LANE_CELL_MAX: larger cells are processed by collideBigCellsKernel
 
 struct CellView {  // the parcels of one cell, in shared memory (small cells) or in place (large cells)
     double *ux, *uy, *uz, *erot;
@@ -215,7 +213,7 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
     for (int32_t c = blockIdx.x * COL_WARPS + w; c < a.nCells; c += nWarps) {
         const int32_t b = a.cellOffset[c];
         const int32_t nC = a.cellOffset[c + 1] - b;
-        if (nC <= BIG_CELL_THRESHOLD || P.collisionModel == DSMCB200_COLL_NONE) continue;  // handled by collideGroupKernel
+        if (nC <= BIG_CELL_THRESHOLD || P.collisionModel == DSMCB200_COLL_NONE) continue;  // handled by collideLaneKernel
         const bool small = false;
         const double cc[3] = {a.cellCentres[3 * c], a.cellCentres[3 * c + 1], a.cellCentres[3 * c + 2]};
         CellView v;
@@ -409,322 +407,6 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
         atomicAdd(&a.counters->candidates, totCand);
     }
 }
-
-// ------------------------------------------------------------------------------------------------
-// Cell-group kernel: one warp stages a run of GRP_CELLS consecutive cells (their parcels are one
-// contiguous, coalesced range of the sorted cloud) in shared memory and resolves the candidates of all
-// of them together, one candidate per lane.  Candidates of different cells never share a parcel, so
-// the dependency rule is unchanged: a candidate runs once every earlier candidate touching one of its
-// two parcels has finished (owner table with atomicMin in shared memory).  Cells larger than GRP_CAP
-// parcels are left to collideBigCellsKernel.
-// ------------------------------------------------------------------------------------------------
-namespace {
-constexpr int GRP_WARPS = 4;
-constexpr int GRP_CELLS = 4;
-constexpr int GRP_CAP = 160;
-
-struct GroupSmem {
-    double ux[GRP_CAP], uy[GRP_CAP], uz[GRP_CAP], erot[GRP_CAP];
-    int32_t vib[MAX_MODES][GRP_CAP];
-    int32_t owner[GRP_CAP];
-    uint16_t subList[GRP_CAP];
-    uint8_t typ[GRP_CAP], elev[GRP_CAP], key[GRP_CAP], dirty[GRP_CAP];
-    int32_t binStart[33];
-    int32_t binRun[32];
-    double resSigma[32], resSep[32];
-};
-
-__device__ __forceinline__ int warpExclusiveScanInt(int v, int lane, int* total) {
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int n = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += n;
-    }
-    *total = __shfl_sync(0xffffffffu, inc, 31);
-    return inc - v;
-}
-
-// LarsenBorgnakkeVariableHardSphere::redistribute on the staged parcel j
-__device__ __noinline__ void redistributeStaged(const DevParams& P, Rng& rng, GroupSmem& sm, int j, int tOther, double& translationalEnergy, double omegaPQ) {
-    const DevSpecies& S = P.sp[sm.typ[j]];
-    if (S.type == 0) return;  // electron
-    if (P.invZelec > rng.sample01()) {
-        const double EcP = translationalEnergy + S.eElec[sm.elev[j]];
-        const int lvl = postCollisionElectronicEnergyLevel(rng, EcP, omegaPQ, S);
-        sm.elev[j] = uint8_t(lvl);
-        translationalEnergy = EcP - S.eElec[lvl];
-    }
-    if (S.nVib > 0) {
-        double preEVib[MAX_MODES];
-#pragma unroll
-        for (int m = 0; m < MAX_MODES; ++m) preEVib[m] = m < S.nVib ? sm.vib[m][j] * P.kB * S.thetaV[m] : 0.0;
-#pragma unroll
-        for (int m = 0; m < MAX_MODES; ++m) {
-            if (m >= S.nVib) break;
-            const double EcP = translationalEnergy + preEVib[m];
-            const int32_t iMaxP = int32_t(EcP / (P.kB * S.thetaV[m]));
-            if (iMaxP > 0) {
-                const int32_t lvl = postCollisionVibrationalEnergyLevel(P, rng, sm.vib[m][j], iMaxP, S.thetaV[m], S.thetaD, S.TrefZv[m], omegaPQ,
-                                                                        S.Zref[m], EcP,
-                                                                        P.invZvTab + ((size_t(sm.typ[j]) * P.nSpecies + tOther) * MAX_MODES + m) * ZV_TABLE);
-                sm.vib[m][j] = lvl;
-                translationalEnergy = EcP - lvl * P.kB * S.thetaV[m];
-            }
-        }
-    }
-    if (S.rotDof > 0) {
-        const double preCollisionERotP = sm.erot[j];
-        if (P.invZrot > rng.sample01()) {
-            const double EcP = translationalEnergy + preCollisionERotP;
-            const double ChiB = 2.5 - omegaPQ;
-            const double energyRatio = postCollisionRotationalEnergy(rng, S.rotDof, ChiB);
-            sm.erot[j] = energyRatio * EcP;
-            translationalEnergy = EcP - sm.erot[j];
-        }
-    }
-}
-}  // namespace
-
-__global__ void __launch_bounds__(GRP_WARPS * 32) collideGroupKernel(const __grid_constant__ CollideArgs a) {
-    __shared__ GroupSmem smAll[GRP_WARPS];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    GroupSmem& sm = smAll[w];
-    const DevParams& P = *a.P;
-    const bool LB = P.collisionModel == DSMCB200_COLL_LB_VHS;
-    const bool internal = P.hasInternalEnergy != 0;
-    const bool none = P.collisionModel == DSMCB200_COLL_NONE;
-    const int32_t nWarps = gridDim.x * GRP_WARPS;
-    const int32_t nGroups = (a.nCells + GRP_CELLS - 1) / GRP_CELLS;
-    unsigned long long totColl = 0, totCand = 0;
-
-    for (int32_t grp = blockIdx.x * GRP_WARPS + w; grp < nGroups; grp += nWarps) {
-        const int32_t c0 = grp * GRP_CELLS;
-        int nG = a.nCells - c0;
-        if (nG > GRP_CELLS) nG = GRP_CELLS;
-        // lane l <= nG holds cellOffset[c0 + l]
-        const int32_t myOff = a.cellOffset[c0 + (lane <= nG ? lane : nG)];
-        const int32_t b0 = __shfl_sync(0xffffffffu, myOff, 0);
-        int32_t relOff[GRP_CELLS + 1];
-#pragma unroll
-        for (int l = 0; l <= GRP_CELLS; ++l) relOff[l] = __shfl_sync(0xffffffffu, myOff, l <= nG ? l : nG) - b0;
-        // sub-range of cells this pass handles together: whole group if it fits, else one cell at a time
-        const bool fits = relOff[GRP_CELLS] <= GRP_CAP;
-        for (int g0 = 0; g0 < nG; g0 += (fits ? GRP_CELLS : 1)) {
-            const int g1 = fits ? nG : g0 + 1;
-            const int32_t base = relOff[g0];                 // group-relative start of this pass
-            const int32_t nTot = relOff[g1] - base;
-            // per-cell bookkeeping lives in lane (g - g0)
-            const int gl = lane;
-            const bool isCellLane = gl < (g1 - g0);
-            int32_t cellBeg = 0, cellN = 0;
-#pragma unroll
-            for (int l = 0; l < GRP_CELLS; ++l)
-                if (g0 + gl == l) { cellBeg = relOff[l] - base; cellN = relOff[l + 1] - relOff[l]; }
-            if (!isCellLane) { cellBeg = 0; cellN = 0; }
-            if (nTot > GRP_CAP || none) {
-                // too large for shared memory (left to collideBigCellsKernel) or collisions switched off
-                if (isCellLane && (none || cellN <= 1)) { a.nCollsStep[c0 + g0 + gl] = 0.0; a.collSepStep[c0 + g0 + gl] = 0.0; }
-                continue;
-            }
-            __syncwarp();
-            // ---- stage the parcels of the pass (coalesced) ----
-            for (int j = lane; j < nTot; j += 32) {
-                const int32_t g = b0 + base + j;
-                int cg = g0;
-#pragma unroll
-                for (int l = 1; l < GRP_CELLS; ++l)
-                    if (l > g0 && l < g1 && j + base >= relOff[l]) cg = l;
-                const double* cc = a.cellCentres + 3 * size_t(c0 + cg);
-                sm.ux[j] = a.p.ux[g]; sm.uy[j] = a.p.uy[g]; sm.uz[j] = a.p.uz[g];
-                sm.typ[j] = a.p.typeId[g];
-                sm.dirty[j] = 0;
-                sm.owner[j] = 0x7fffffff;
-                sm.key[j] = uint8_t((cg - g0) * 8 + octantOf(a.p.px[g], a.p.py[g], a.p.pz[g], cc));
-                if (internal) {
-                    sm.erot[j] = a.p.erot[g];
-#pragma unroll
-                    for (int m = 0; m < MAX_MODES; ++m) if (m < P.nModes) sm.vib[m][j] = a.p.vib[m][g];
-                    sm.elev[j] = a.p.elevel[g];
-                } else {
-                    sm.erot[j] = 0.0; sm.elev[j] = 0;
-                }
-            }
-            sm.binRun[lane] = 0;
-            __syncwarp();
-            // ---- sub-cell lists: stable counting sort of the staged indices by key = (cell in pass)*8 + octant ----
-            for (int j0 = 0; j0 < nTot; j0 += 32) {
-                const int j = j0 + lane;
-                const int key = j < nTot ? sm.key[j] : 255;
-                const unsigned m = __match_any_sync(0xffffffffu, key);
-                if (j < nTot && (m & ((1u << lane) - 1u)) == 0) sm.binRun[key] += __popc(m);
-                __syncwarp();
-            }
-            {
-                int total;
-                const int cnt = sm.binRun[lane];
-                const int ex = warpExclusiveScanInt(cnt, lane, &total);
-                __syncwarp();
-                sm.binStart[lane] = ex;
-                if (lane == 31) sm.binStart[32] = total;
-                sm.binRun[lane] = 0;
-            }
-            __syncwarp();
-            for (int j0 = 0; j0 < nTot; j0 += 32) {
-                const int j = j0 + lane;
-                const int key = j < nTot ? sm.key[j] : 255;
-                const unsigned m = __match_any_sync(0xffffffffu, key);
-                const int rank = __popc(m & ((1u << lane) - 1u));
-                if (j < nTot) sm.subList[sm.binStart[key] + sm.binRun[key] + rank] = uint16_t(j);
-                __syncwarp();
-                if (j < nTot && rank == 0) sm.binRun[key] += __popc(m);
-                __syncwarp();
-            }
-            // ---- candidate counts per cell (noTimeCounter.C:142-155), one cell per lane ----
-            double sigmaL = 0.0;
-            int32_t nCand = 0;
-            if (isCellLane && cellN > 1) {
-                const int32_t c = c0 + g0 + gl;
-                sigmaL = a.sigmaTcRMax[c];
-                const double selectedPairs = a.remainder[c] + 0.5 * cellN * (cellN - 1) * P.nParticles * sigmaL * P.deltaT / a.cellVolumes[c];
-                nCand = int32_t(selectedPairs);
-                a.remainder[c] = selectedPairs - nCand;
-                if (nCand < 0) nCand = 0;
-            }
-            int totalCand;
-            const int candStart = warpExclusiveScanInt(nCand, lane, &totalCand);
-            totCand += (lane == 0) ? (unsigned long long)totalCand : 0ULL;
-            double cellMax = sigmaL, cellColl = 0.0, cellSep = 0.0;  // results of the cell held by this lane
-
-            for (int32_t k0 = 0; k0 < totalCand; k0 += 32) {
-                const int32_t k = k0 + lane;
-                const bool active = k < totalCand;
-                // which cell of the pass does candidate k belong to
-                int g = 0;
-#pragma unroll
-                for (int l = 1; l < GRP_CELLS; ++l) {
-                    const int st = __shfl_sync(0xffffffffu, candStart, l);
-                    if (l < (g1 - g0) && k >= st) g = l;
-                }
-                const int32_t cBeg = __shfl_sync(0xffffffffu, cellBeg, g);
-                const int32_t nC = __shfl_sync(0xffffffffu, cellN, g);
-                const int32_t cSt = __shfl_sync(0xffffffffu, candStart, g);
-                const double sigmaLatched = __shfl_sync(0xffffffffu, sigmaL, g);
-                int32_t cp = 0, cq = 0;
-                Rng rng;
-                if (active) {
-                    rng.init(P.seed, uint32_t(c0 + g0 + g), uint32_t(k - cSt), a.step, STREAM_COLLIDE);
-                    cp = cBeg + rng.randomLabel(0, nC - 1);
-                    const int sub = sm.key[cp];
-                    const int32_t s0 = sm.binStart[sub];
-                    const int32_t nSC = sm.binStart[sub + 1] - s0;
-                    if (nSC > 1) {
-                        do { cq = sm.subList[s0 + rng.randomLabel(0, nSC - 1)]; } while (cp == cq);
-                    } else {
-                        do { cq = cBeg + rng.randomLabel(0, nC - 1); } while (cp == cq);
-                    }
-                }
-                double mySigma = -1.0, mySep = 0.0;
-                bool accepted = false;
-                bool done = !active;
-                while (__ballot_sync(0xffffffffu, !done)) {
-                    if (!done) { atomicMin(&sm.owner[cp], k); atomicMin(&sm.owner[cq], k); }
-                    __syncwarp();
-                    const bool ready = !done && sm.owner[cp] == k && sm.owner[cq] == k;
-                    __syncwarp();
-                    if (ready) {
-                        const int tP = sm.typ[cp], tQ = sm.typ[cq];
-                        if (!(P.sp[tP].charge == -1 && P.sp[tQ].charge == -1)) {
-                            V3 UP = mk(sm.ux[cp], sm.uy[cp], sm.uz[cp]);
-                            V3 UQ = mk(sm.ux[cq], sm.uy[cq], sm.uz[cq]);
-                            const double sTcR = sigmaTcR(P, tP, tQ, mag(UP - UQ));
-                            mySigma = sTcR;
-                            if ((sTcR / sigmaLatched) > rng.sample01()) {
-                                double cR = -1;
-                                if (LB) {
-                                    const double mR = P.mR[tP][tQ];
-                                    const double cRsqr = magSqr(UP - UQ);
-                                    double translationalEnergy = 0.5 * mR * cRsqr;
-                                    const double omegaPQ = P.omegaPQ[tP][tQ];
-                                    redistributeStaged(P, rng, sm, cp, tQ, translationalEnergy, omegaPQ);
-                                    redistributeStaged(P, rng, sm, cq, tP, translationalEnergy, omegaPQ);
-                                    cR = sqrt(2.0 * translationalEnergy / mR);
-                                }
-                                postCollisionVelocities(P, rng, tP, tQ, UP, UQ, cR);
-                                sm.ux[cp] = UP.x; sm.uy[cp] = UP.y; sm.uz[cp] = UP.z;
-                                sm.ux[cq] = UQ.x; sm.uy[cq] = UQ.y; sm.uz[cq] = UQ.z;
-                                sm.dirty[cp] = 1; sm.dirty[cq] = 1;
-                                const int32_t gp = b0 + base + cp, gq = b0 + base + cq;
-                                const double dx = a.p.px[gp] - a.p.px[gq], dy = a.p.py[gp] - a.p.py[gq], dz = a.p.pz[gp] - a.p.pz[gq];
-                                mySep = sqrt(dx * dx + dy * dy + dz * dz);
-                                accepted = true;
-                                if (a.p.cls) {
-                                    const int clP = a.p.cls[gp], clQ = a.p.cls[gq];
-                                    if (clP == 0 && (clQ == 1 || clQ == 2)) a.p.cls[gp] = 2;
-                                    if (clQ == 0 && (clP == 1 || clP == 2)) a.p.cls[gq] = 2;
-                                }
-                            }
-                        }
-                        sm.owner[cp] = 0x7fffffff;
-                        sm.owner[cq] = 0x7fffffff;
-                        done = true;
-                    }
-                    __syncwarp();
-                }
-                // fold the batch into the per-cell results: every candidate leaves (sigma, accepted, separation) in shared
-                // memory and the lane that owns the cell adds its candidates up in candidate order (= the reference's order)
-                __syncwarp();
-                sm.resSigma[lane] = mySigma;
-                sm.resSep[lane] = accepted ? mySep : -1.0;
-                __syncwarp();
-                if (isCellLane && nCand > 0) {
-                    int kb = candStart - k0, ke = candStart + nCand - k0;
-                    if (kb < 0) kb = 0;
-                    if (ke > 32) ke = 32;
-                    for (int k2 = kb; k2 < ke; ++k2) {
-                        const double sg = sm.resSigma[k2];
-                        if (sg > cellMax) cellMax = sg;
-                        const double sp2 = sm.resSep[k2];
-                        if (sp2 >= 0.0) { cellColl += 1.0; cellSep += sp2; }
-                    }
-                }
-                __syncwarp();
-            }
-            if (isCellLane) {
-                const int32_t c = c0 + g0 + gl;
-                if (cellN > 1) a.sigmaTcRMax[c] = cellMax;
-                a.nCollsStep[c] = cellColl;
-                a.collSepStep[c] = cellSep;
-                totColl += (unsigned long long)cellColl;
-            }
-            __syncwarp();
-            for (int j = lane; j < nTot; j += 32) {
-                if (sm.dirty[j]) {
-                    const int32_t g = b0 + base + j;
-                    a.p.ux[g] = sm.ux[j]; a.p.uy[g] = sm.uy[j]; a.p.uz[g] = sm.uz[j];
-                    if (LB) {
-                        a.p.erot[g] = sm.erot[j];
-#pragma unroll
-                        for (int m = 0; m < MAX_MODES; ++m) if (m < P.nModes) a.p.vib[m][g] = sm.vib[m][j];
-                        a.p.elevel[g] = sm.elev[j];
-                    }
-                }
-            }
-            __syncwarp();
-        }
-    }
-    // warp totals -> one atomic per counter
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        totColl += __shfl_xor_sync(0xffffffffu, totColl, o);
-        totCand += __shfl_xor_sync(0xffffffffu, totCand, o);
-    }
-    if (lane == 0 && (totColl | totCand)) {
-        atomicAdd(&a.counters->collisions, totColl);
-        atomicAdd(&a.counters->candidates, totCand);
-    }
-}
-
 
 // ------------------------------------------------------------------------------------------------
 // Lane-per-cell kernel: a warp takes 32 consecutive cells and every lane walks the candidates of ITS cell
@@ -973,7 +655,6 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) collideLaneKernel(const __gri
 }
 
 cudaError_t launchCollide(const CollideArgs& a, cudaStream_t s) {
-#if COLLIDE_LANE
     {
         const int nGroups = (a.nCells + 31) / 32;
         int grid = (nGroups + LANE_WARPS - 1) / LANE_WARPS;
@@ -981,14 +662,6 @@ cudaError_t launchCollide(const CollideArgs& a, cudaStream_t s) {
         if (grid < 1) grid = 1;
         collideLaneKernel<<<grid, LANE_WARPS * 32, 0, s>>>(a);
     }
-#else
-    const int nGroups = (a.nCells + GRP_CELLS - 1) / GRP_CELLS;
-    int grid = (nGroups + GRP_WARPS - 1) / GRP_WARPS;
-    const int maxGrid = 148 * 16;
-    if (grid > maxGrid) grid = maxGrid;
-    if (grid < 1) grid = 1;
-    collideGroupKernel<<<grid, GRP_WARPS * 32, 0, s>>>(a);
-#endif
     int gridBig = (a.nCells + COL_WARPS - 1) / COL_WARPS;
     if (gridBig > 148 * 4) gridBig = 148 * 4;
     if (gridBig < 1) gridBig = 1;
