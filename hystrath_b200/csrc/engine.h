@@ -80,7 +80,7 @@ struct DevCounters {
     unsigned long long collisions, candidates, rescues, deleted, migratedOut, unsortedLargeCells, overflow;
     int32_t nMig[MAX_NEIGHBOURS];
     int32_t nInserted;
-    int32_t pad_;
+    int32_t bigCells;  // cells handed from collideLaneKernel to collideBigCellsKernel this step
 };
 
 // wall accumulator quantities per (measured face, species)
@@ -116,6 +116,7 @@ struct CollideArgs {
     double* nCollsStep;           // cellMeasurements: nColls_ of this step
     double* collSepStep;          // cellMeasurements: collisionSeparation_ of this step
     int32_t* bigScratch;          // [nParcels] sub-cell index lists of cells too large for shared memory
+    int32_t* bigList;             // [nCells] ids of those cells (written by the lane kernel)
     const uint8_t* octKey;        // [nParcels] sub-cell (octant) of every sorted parcel, written by the sort's gather
     const DevParams* P;
     DevCounters* counters;

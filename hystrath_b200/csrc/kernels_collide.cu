@@ -210,7 +210,9 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
     const int32_t nWarps = gridDim.x * COL_WARPS;
     unsigned long long totColl = 0, totCand = 0;
 
-    for (int32_t c = blockIdx.x * COL_WARPS + w; c < a.nCells; c += nWarps) {
+    const int32_t nBig = a.counters->bigCells;  // the cells collideLaneKernel left to this kernel
+    for (int32_t ib = blockIdx.x * COL_WARPS + w; ib < nBig; ib += nWarps) {
+        const int32_t c = a.bigList[ib];
         const int32_t b = a.cellOffset[c];
         const int32_t nC = a.cellOffset[c + 1] - b;
         if (nC <= BIG_CELL_THRESHOLD || P.collisionModel == DSMCB200_COLL_NONE) continue;  // handled by collideLaneKernel
@@ -511,6 +513,7 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) collideLaneKernel(const __gri
             if (haveCell) { a.nCollsStep[c] = 0.0; a.collSepStep[c] = 0.0; }
             continue;
         }
+        if (n > LANE_CELL_MAX) a.bigList[atomicAdd(&a.counters->bigCells, 1)] = c;  // one warp per such cell, afterwards
 
         for (int g0 = 0; g0 < nG;) {
             // ---- the pass: the longest run of cells [g0, g1) whose parcels fit the shared-memory lists ----

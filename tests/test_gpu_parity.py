@@ -111,6 +111,34 @@ def test_collide_larsen_borgnakke_air5_matches_oracle():
     eng.close()
 
 
+def test_collide_cells_above_and_below_the_lane_kernel_limit():
+    """Mean occupancy 250: about half of the cells exceed the 255-parcel limit of collideLaneKernel and are handed to
+    collideBigCellsKernel through the big-cell list; both must reproduce the serial oracle."""
+    sp = H.air5()
+    mesh, _, md = periodic_case((4, 4, 3), ppc=250, species=sp, model="LarsenBorgnakkeVariableHardSphere", dens=1e21, dt=2e-6,
+                                rotationalRelaxationCollisionNumber=5.0)
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    dens = [0.6e21, 0.2e21, 0.05e21, 0.1e21, 0.05e21]
+    H.same_start(eng, ora, [0, 1, 2, 3, 4], dens, 5000.0, 5000.0, 5000.0)
+    occ = np.diff(eng.occupancy())
+    assert (occ > 255).any() and (occ <= 255).any()
+    for x in (eng, ora):
+        x.stage(capi.STAGE_COLLIDE)
+    g, o = eng.download_parcels(), ora.download_parcels()
+    c, oc = eng.counters(), ora.counters()
+    assert c.collisionCandidates == oc["collisionCandidates"]
+    assert c.collisions == oc["collisions"] > 0
+    assert np.array_equal(g.vibLevel, o.vibLevel)
+    assert np.array_equal(g.ELevel, o.ELevel)
+    assert np.allclose(g.U, o.U, rtol=0, atol=1e-8)
+    assert np.allclose(g.ERot, o.ERot, rtol=1e-10, atol=1e-30)
+    gs, gr = eng.download_cellstate()
+    os_, or_ = ora.download_cellstate()
+    assert np.allclose(gs, os_, rtol=1e-13)
+    assert np.array_equal(gr, or_)
+    eng.close()
+
+
 def test_sample_matches_oracle():
     sp = H.air5()
     mesh, _, md = periodic_case((5, 5, 5), ppc=50, species=sp, model="LarsenBorgnakkeVariableHardSphere", dens=1e21, dt=2e-6,
