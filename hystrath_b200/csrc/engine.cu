@@ -689,7 +689,7 @@ int stageCollide(dsmcb200_ctx* c) {
 int stageSample(dsmcb200_ctx* c) {
     if (!c->occupancyValid) return fail(c, DSMCB200_ERR_STATE, "cell occupancy is stale: run the sort stage first");
     SampleArgs a{};
-    a.p = c->buf[c->cur].a; a.cellOffset = c->dCellOffset; a.nCells = c->mesh.nCells; a.acc = c->dAcc; a.nQ = c->nQ;
+    a.p = c->buf[c->cur].a; a.cellOffset = c->dCellOffset; a.nCells = c->mesh.nCells; a.acc = c->dAcc; a.nQ = c->nQ; a.nSpecies = int(c->species.size());
     a.collCum = c->dCollCum; a.nCollsStep = c->dNColls; a.collSepStep = c->dCollSep; a.P = c->dP;
     KT t(c, "sample");
     CK(launchSample(a, c->stream));

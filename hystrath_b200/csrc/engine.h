@@ -128,7 +128,7 @@ struct SampleArgs {
     const int32_t* cellOffset;
     int32_t nCells;
     double* acc;                  // [nCells][nSpecies][nQ]
-    int32_t nQ;
+    int32_t nQ, nSpecies;
     double* collCum;              // [nCells][2]
     const double* nCollsStep;
     const double* collSepStep;

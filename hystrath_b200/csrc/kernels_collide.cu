@@ -689,8 +689,10 @@ __global__ void __launch_bounds__(SMP_WARPS * 32) sampleKernel(const __grid_cons
     const DevParams& P = *a.P;
     const int nQ = a.nQ, S = P.nSpecies;
     const int stride = nQ | 1;
-    double* stage = stageAll + size_t(w) * 32 * stride;
-    uint8_t* stageSp = reinterpret_cast<uint8_t*>(stageAll + size_t(SMP_WARPS) * 32 * stride) + w * 32;
+    // per warp: 32 staged rows, 32*S accumulators [sub-group][species][quantity], 32 species bytes
+    double* stage = stageAll + size_t(w) * (32 * stride + 32 * S);
+    double* accS = stage + 32 * stride;
+    uint8_t* stageSp = reinterpret_cast<uint8_t*>(stageAll + size_t(SMP_WARPS) * (32 * stride + 32 * S)) + w * 32;
     const bool internal = P.hasInternalEnergy != 0;
     const int qFlux = 5 + (internal ? 2 + P.nModes : 0);
     const int qClass = qFlux + (P.measureFlux ? 12 : 0);
@@ -725,9 +727,8 @@ __global__ void __launch_bounds__(SMP_WARPS * 32) sampleKernel(const __grid_cons
             if (add != 0.0) atomicAdd(&a.collCum[2 * size_t(c) + lane], add);
         }
         if (nC == 0) continue;
-        double sum[MAX_SPECIES];
-#pragma unroll
-        for (int s = 0; s < MAX_SPECIES; ++s) sum[s] = 0.0;
+        for (int k = lane; k < 32 * S; k += 32) accS[k] = 0.0;
+        __syncwarp();
 
         for (int32_t j0 = 0; j0 < nC; j0 += 32) {
             const int32_t g = b + j0 + lane;
@@ -768,31 +769,24 @@ __global__ void __launch_bounds__(SMP_WARPS * 32) sampleKernel(const __grid_cons
             }
             __syncwarp();
             if (q < nQ) {
+                // the species of the row selects the accumulator: no per-species select chain
                 for (int j = sub; j < nHere; j += G) {
                     const double v = stage[j * stride + q];
                     const int sp = stageSp[j];
-#pragma unroll
-                    for (int s = 0; s < MAX_SPECIES; ++s)
-                        if (s < S) sum[s] += (sp == s) ? v : 0.0;
+                    accS[(sub * S + sp) * Qpad + q] += v;
                 }
             }
             __syncwarp();
         }
-        // fold the G sub-groups (lanes q, q+Qpad, ...) and add the row
-#pragma unroll
-        for (int s = 0; s < MAX_SPECIES; ++s) {
-            if (s < S) {
-                double v = sum[s];
-                for (int o = 16; o >= Qpad; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-                sum[s] = v;
-            }
+        // fold the G sub-groups in a fixed order and add the cell's row: element k = (species, quantity) has one writer
+        double* row = a.acc + size_t(c) * S * nQ;
+        for (int k = lane; k < S * nQ; k += 32) {
+            const int sI = k / nQ, qI = k - sI * nQ;
+            double t = 0.0;
+            for (int g2 = 0; g2 < G; ++g2) t += accS[(g2 * S + sI) * Qpad + qI];
+            if (t != 0.0) atomicAdd(&row[k], t);  // fire-and-forget RED
         }
-        if (sub == 0 && q < nQ) {
-            double* row = a.acc + size_t(c) * S * nQ;
-#pragma unroll
-            for (int s = 0; s < MAX_SPECIES; ++s)
-                if (s < S && sum[s] != 0.0) atomicAdd(&row[s * nQ + q], sum[s]);  // one writer per element: a fire-and-forget RED
-        }
+        __syncwarp();
     }
 }
 
@@ -801,7 +795,11 @@ cudaError_t launchSample(const SampleArgs& a, cudaStream_t s) {
     const int maxGrid = 148 * 8;
     if (grid > maxGrid) grid = maxGrid;
     if (grid < 1) grid = 1;
-    const size_t smem = size_t(SMP_WARPS) * 32 * (a.nQ | 1) * sizeof(double) + SMP_WARPS * 32;
+    const size_t smem = size_t(SMP_WARPS) * (32 * (a.nQ | 1) + 32 * a.nSpecies) * sizeof(double) + SMP_WARPS * 32;
+    if (smem > 48 * 1024) {  // many quantities x species: beyond the default dynamic shared-memory window
+        const cudaError_t e = cudaFuncSetAttribute(sampleKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+    }
     sampleKernel<<<grid, SMP_WARPS * 32, smem, s>>>(a);
     return cudaGetLastError();
 }
