@@ -58,7 +58,7 @@ __device__ __forceinline__ double sigmaTcR(const DevParams& P, int tP, int tQ, d
 }
 
 // VariableHardSphere::postCollisionVelocities
-__device__ __noinline__ void postCollisionVelocities(const DevParams& P, Rng& rng, int tP, int tQ, V3& UP, V3& UQ, double cR) {
+__device__ __forceinline__ void postCollisionVelocities(const DevParams& P, Rng& rng, int tP, int tQ, V3& UP, V3& UQ, double cR) {
     if (cR == -1) cR = mag(UP - UQ);
     const double mP = P.sp[tP].mass, mQ = P.sp[tQ].mass;
     const V3 Ucm = (mP * UP + mQ * UQ) / (mP + mQ);
@@ -442,7 +442,7 @@ struct InPlace {  // accessor of the parcels of one cell where they lie in the s
 };
 
 // LarsenBorgnakkeVariableHardSphere::redistribute (postReaction = false) on parcel j of the view
-__device__ __noinline__ void redistributeInPlace(const DevParams& P, Rng& rng, const InPlace v, int j, int tSelf, int tOther,
+__device__ __forceinline__ void redistributeInPlace(const DevParams& P, Rng& rng, const InPlace v, int j, int tSelf, int tOther,
                                                  double& translationalEnergy, double omegaPQ) {
     const DevSpecies& S = P.sp[tSelf];
     if (S.type == 0) return;  // electron
