@@ -268,6 +268,7 @@ def load_library():
         "dsmcb200_reset_accumulators": ([P], C.c_int),
         "dsmcb200_wall_info": ([P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)], C.c_int),
         "dsmcb200_download_wall_accumulators": ([P, C.c_void_p], C.c_int),
+        "dsmcb200_upload_wall_accumulators": ([P, C.c_void_p], C.c_int),
         "dsmcb200_get_counters": ([P, C.POINTER(Counters)], C.c_int),
         "dsmcb200_kernel_times": ([P, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
         "dsmcb200_download_geometry": ([P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
@@ -289,7 +290,8 @@ EXPORTED_SYMBOLS = [
     "dsmcb200_upload_parcels", "dsmcb200_download_parcels", "dsmcb200_upload_cellstate", "dsmcb200_download_cellstate",
     "dsmcb200_mesh_fill", "dsmcb200_evolve", "dsmcb200_stage", "dsmcb200_set_step", "dsmcb200_download_occupancy",
     "dsmcb200_accum_info_get", "dsmcb200_download_accumulators", "dsmcb200_upload_accumulators",
-    "dsmcb200_reset_accumulators", "dsmcb200_wall_info", "dsmcb200_download_wall_accumulators", "dsmcb200_get_counters",
+    "dsmcb200_reset_accumulators", "dsmcb200_wall_info", "dsmcb200_download_wall_accumulators",
+    "dsmcb200_upload_wall_accumulators", "dsmcb200_get_counters",
     "dsmcb200_kernel_times", "dsmcb200_download_geometry", "dsmcb200_timer_start", "dsmcb200_timer_stop", "dsmcb200_allreduce_sum",
 ]
 

@@ -114,6 +114,10 @@ dsmcCloud::dsmcCloud(const std::string& caseDir, const std::string& cloudName, i
     cellVolumes_.resize(nCells_); cellCentres_.resize(size_t(nCells_) * 3); faceAreas_.resize(size_t(nFaces_) * 3); faceCentres_.resize(size_t(nFaces_) * 3);
     check(dsmcb200_download_geometry(ctx_, cellCentres_.data(), cellVolumes_.data(), faceCentres_.data(), faceAreas_.data(), nullptr), "dsmcb200_download_geometry");
     readCloud();
+    // counter-based RNG streams are keyed by the global time index, so a restarted run does not replay the streams of the first one
+    startIndex_ = deltaT_ > 0 ? int64_t(std::llround(startTime_ / deltaT_)) : 0;
+    check(dsmcb200_set_step(ctx_, uint32_t(startIndex_)), "dsmcb200_set_step");
+    readResumeSampling();
 }
 
 dsmcCloud::~dsmcCloud() {
@@ -343,6 +347,7 @@ void dsmcCloud::readFieldProperties() {
         s.measureClassifications = pr.boolOr("measureClassifications", false);
         s.mfpReferenceTemperature = pr.scalarOr("mfpReferenceTemperature", 273.0);
         s.sampleInterval = int(pr.labelOr("sampleInterval", 1));
+        s.averagingAcrossManyRuns = pr.boolOr("averagingAcrossManyRuns", false);
         if (f.isDict("timeProperties")) {
             const Dict& tp = f.subDict("timeProperties");
             s.resetAtOutput = tp.boolOr("resetAtOutput", true);
@@ -671,6 +676,284 @@ void dsmcCloud::writeFields(const std::string& timeDir) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Sampling restart files.  dsmcVolFields::writeOut / readIn (DSMC/macroscopicProperties/derived/combined/dsmcVolFields/
+// dsmcVolFields.C:647-835) keep one dictionary `<time>/uniform/resumeSampling_<fieldName>` per field instance.  The engine
+// samples per SPECIES and derives every instance from those rows, so its own restart state is the per-species rows:
+// they go, losslessly, to `<time>/uniform/resumeSampling_dsmcb200` (read back here), and each instance's dictionary is
+// written with the reference's key set computed from them (accumulation rules of dsmcVolFields.C:1115-1237), so that
+// the reference's tools and dsmcFoam+ itself can pick the run up.  Not tracked by the engine and written as zeros:
+// dsmcNGrndElecLvlSpeciesCum / dsmcN1stElecLvlSpeciesCum (only feed Telec, which the reference forces to 0, :1497).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct ListOut {
+    FILE* f;
+    int prec;
+    void num(double v) const { std::fprintf(f, "%.*g", prec, v); }
+    void scalars(const double* a, int64_t n) const {
+        if (n == 0) { std::fputs("0 ( )", f); return; }
+        bool uniform = true;
+        for (int64_t i = 1; i < n && uniform; ++i) uniform = a[i] == a[0];
+        if (uniform) { std::fprintf(f, "%lld { ", (long long)n); num(a[0]); std::fputs(" }", f); return; }
+        std::fprintf(f, "%lld ( ", (long long)n);
+        for (int64_t i = 0; i < n; ++i) { num(a[i]); std::fputc(' ', f); }
+        std::fputc(')', f);
+    }
+    void vectors(const double* a, int64_t n) const {
+        if (n == 0) { std::fputs("0 ( )", f); return; }
+        bool uniform = true;
+        for (int64_t i = 1; i < n && uniform; ++i) uniform = a[3 * i] == a[0] && a[3 * i + 1] == a[1] && a[3 * i + 2] == a[2];
+        auto one = [&](const double* v) { std::fputs("( ", f); num(v[0]); std::fputc(' ', f); num(v[1]); std::fputc(' ', f); num(v[2]); std::fputs(" )", f); };
+        if (uniform) { std::fprintf(f, "%lld { ", (long long)n); one(a); std::fputs(" }", f); return; }
+        std::fprintf(f, "%lld ( ", (long long)n);
+        for (int64_t i = 0; i < n; ++i) { one(a + 3 * i); std::fputc(' ', f); }
+        std::fputc(')', f);
+    }
+    void key(const char* k) const { std::fprintf(f, "%-15s ", k); }
+    void end() const { std::fputs(";\n\n", f); }
+    void entry(const char* k, const std::vector<double>& a) const { key(k); scalars(a.data(), int64_t(a.size())); end(); }
+    void entryV(const char* k, const std::vector<double>& a) const { key(k); vectors(a.data(), int64_t(a.size() / 3)); end(); }
+    // List<scalarField>: one list per species / per patch
+    void entryLL(const char* k, const std::vector<std::vector<double>>& a) const {
+        key(k);
+        std::fprintf(f, "%zu ( ", a.size());
+        for (auto& v : a) { scalars(v.data(), int64_t(v.size())); std::fputc(' ', f); }
+        std::fputc(')', f);
+        end();
+    }
+};
+}  // namespace
+
+void dsmcCloud::writeResumeSampling(const std::string& timeDir) {
+    bool any = false;
+    for (auto& f : fields_) any = any || f.averagingAcrossManyRuns;
+    if (!any) return;
+    dsmcb200_accum_info ai{};
+    check(dsmcb200_accum_info_get(ctx_, &ai), "dsmcb200_accum_info_get");
+    const int S = ai.nSpecies, nQ = ai.nQuantities, nC = ai.nCells;
+    std::vector<double> acc(size_t(nC) * S * nQ), coll(size_t(nC) * 2), sig(nC), rem(nC);
+    check(dsmcb200_download_accumulators(ctx_, acc.data(), coll.data()), "dsmcb200_download_accumulators");
+    check(dsmcb200_download_cellstate(ctx_, sig.data(), rem.data()), "dsmcb200_download_cellstate");
+    int32_t nMeas = 0, nWallQ = 0;
+    check(dsmcb200_wall_info(ctx_, &nMeas, &nWallQ), "dsmcb200_wall_info");
+    std::vector<double> wall(size_t(nMeas) * S * nWallQ);
+    if (nMeas) check(dsmcb200_download_wall_accumulators(ctx_, wall.data()), "dsmcb200_download_wall_accumulators");
+    const std::string ud = timeDir + "/uniform";
+    foam::makeDirs(ud);
+    const bool internal = ai.nModes >= 0;
+    const int nModes = internal ? ai.nModes : 0;
+    const int qFlux = 5 + (internal ? 2 + nModes : 0);
+    const bool hasFlux = models_.measureHeatFluxShearStress != 0;
+    const int qClass = qFlux + (hasFlux ? 12 : 0);
+    const bool hasClass = models_.measureClassifications != 0;
+
+    // ---- the engine's own state: per-species rows, lossless
+    {
+        FILE* f = std::fopen((ud + "/resumeSampling_dsmcb200").c_str(), "w");
+        if (!f) throw FoamError("cannot write " + ud + "/resumeSampling_dsmcb200");
+        std::fputs(foam::header("dictionary", timeName_ + "/uniform", "resumeSampling_dsmcb200").c_str(), f);
+        ListOut o{f, 17};
+        std::fprintf(f, "nTimeSteps      %.17g;\n\nnCells          %d;\n\nnSpecies        %d;\n\nnQuantities     %d;\n\nnMeasuredFaces  %d;\n\nnWallQuantities %d;\n\n",
+                     ai.nTimeSteps, nC, S, nQ, nMeas, nWallQ);
+        o.entry("accumulators", acc);
+        o.entry("collisionCumulative", coll);
+        o.entry("wallAccumulators", wall);
+        o.entry("collisionSelectionRemainder", rem);
+        std::fclose(f);
+    }
+
+    // ---- one dictionary per field instance with the reference's keys
+    std::vector<int> measStart(boundary_.size(), -1);
+    {
+        int k = 0;
+        for (auto& pm : patchModels_)
+            if (pm.model != DSMCB200_BND_DELETION) { measStart[pm.patch] = k; k += boundary_[pm.patch].nFaces; }
+    }
+    const double FN = models_.nEquivalentParticles;
+    for (auto& fs : fields_) {
+        if (!fs.averagingAcrossManyRuns) continue;
+        const int nT = int(fs.typeIds.size());
+        auto cells = [&]() { return std::vector<double>(size_t(nC), 0.0); };
+        std::vector<double> dsmcNCum = cells(), dsmcMCum = cells(), dsmcLinearKECum = cells(), dsmcErotCum = cells(), dsmcZetaRotCum = cells(),
+                            dsmcMom(size_t(nC) * 3, 0.0), dsmcECum = cells(), dsmcNElecLvlCum = cells(), nColls = cells(), collSep = cells();
+        std::vector<double> Muu = cells(), Muv = cells(), Muw = cells(), Mvv = cells(), Mvw = cells(), Mww = cells(), Mccu = cells(), Mccv = cells(),
+                            Mccw = cells(), Eu = cells(), Ev = cells(), Ew = cells(), cI = cells(), cII = cells(), cIII = cells();
+        std::vector<std::vector<double>> spN(nT, cells()), spMcc(nT, cells()), spEelec(nT, cells()), spZero(nT, cells());
+        std::vector<std::vector<std::vector<double>>> spEvibMod(nT);
+        for (int t = 0; t < nT; ++t) spEvibMod[t].assign(species_[fs.typeIds[t]].nVibrationalModes, cells());
+        for (int c = 0; c < nC; ++c) {
+            for (int t = 0; t < nT; ++t) {
+                const int s = fs.typeIds[t];
+                const double* r = &acc[(size_t(c) * S + s) * nQ];
+                const double m = species_[s].mass;
+                dsmcNCum[c] += r[0]; dsmcMCum[c] += m * r[0]; dsmcLinearKECum[c] += m * r[4];
+                for (int k = 0; k < 3; ++k) dsmcMom[3 * size_t(c) + k] += m * r[1 + k];
+                spN[t][c] = r[0]; spMcc[t][c] = m * r[4];
+                if (internal) {
+                    dsmcErotCum[c] += r[5]; dsmcZetaRotCum[c] += species_[s].rotationalDegreesOfFreedom * r[0];
+                    spEelec[t][c] = r[6];
+                    double eint = r[5];
+                    for (int md = 0; md < species_[s].nVibrationalModes; ++md) { spEvibMod[t][md][c] = r[7 + md]; eint += r[7 + md]; }
+                    dsmcECum[c] += eint;
+                    if (species_[s].nElectronicLevels > 1) dsmcNElecLvlCum[c] += r[0];
+                }
+                if (hasFlux) {
+                    const double* q = r + qFlux;
+                    Muu[c] += m * q[0]; Muv[c] += m * q[1]; Muw[c] += m * q[2]; Mvv[c] += m * q[3]; Mvw[c] += m * q[4]; Mww[c] += m * q[5];
+                    Mccu[c] += m * q[6]; Mccv[c] += m * q[7]; Mccw[c] += m * q[8];
+                    Eu[c] += q[9]; Ev[c] += q[10]; Ew[c] += q[11];
+                }
+                if (hasClass) { cI[c] += r[qClass]; cII[c] += r[qClass + 1]; cIII[c] += r[qClass + 2]; }
+            }
+            nColls[c] = coll[2 * size_t(c)]; collSep[c] = coll[2 * size_t(c) + 1];
+        }
+        auto scaled = [&](const std::vector<double>& v) { std::vector<double> o(v); for (auto& x : o) x *= FN; return o; };
+        const std::string name = "resumeSampling_" + fs.fieldName;
+        FILE* f = std::fopen((ud + "/" + name).c_str(), "w");
+        if (!f) throw FoamError("cannot write " + ud + "/" + name);
+        std::fputs(foam::header("dictionary", timeName_ + "/uniform", name).c_str(), f);
+        ListOut o{f, 10};
+        std::fprintf(f, "nTimeSteps      %.10g;\n\n", ai.nTimeSteps);
+        o.entry("dsmcNCum", dsmcNCum); o.entry("dsmcMCum", dsmcMCum); o.entry("dsmcLinearKECum", dsmcLinearKECum);
+        o.entryV("dsmcMomentumCum", dsmcMom); o.entry("dsmcErotCum", dsmcErotCum); o.entry("dsmcZetaRotCum", dsmcZetaRotCum);
+        o.entryLL("dsmcSpeciesEelecCum", spEelec); o.entryLL("dsmcNSpeciesCum", spN); o.entryLL("dsmcMccSpeciesCum", spMcc);
+        o.entry("dsmcMuuCum", Muu); o.entry("dsmcMuvCum", Muv); o.entry("dsmcMuwCum", Muw); o.entry("dsmcMvvCum", Mvv); o.entry("dsmcMvwCum", Mvw);
+        o.entry("dsmcMwwCum", Mww); o.entry("dsmcMccCum", dsmcLinearKECum); o.entry("dsmcMccuCum", Mccu); o.entry("dsmcMccvCum", Mccv);
+        o.entry("dsmcMccwCum", Mccw); o.entry("dsmcEuCum", Eu); o.entry("dsmcEvCum", Ev); o.entry("dsmcEwCum", Ew); o.entry("dsmcECum", dsmcECum);
+        o.entry("dsmcNElecLvlCum", dsmcNElecLvlCum); o.entryLL("dsmcNGrndElecLvlSpeciesCum", spZero); o.entryLL("dsmcN1stElecLvlSpeciesCum", spZero);
+        if (fs.measureClassifications) { o.entry("dsmcNClassICum", cI); o.entry("dsmcNClassIICum", cII); o.entry("dsmcNClassIIICum", cIII); }
+        {   // List<List<scalarField>> [species][mode]
+            o.key("dsmcSpeciesEvibModCum");
+            std::fprintf(f, "%d ( ", nT);
+            for (int t = 0; t < nT; ++t) {
+                std::fprintf(f, "%zu ( ", spEvibMod[t].size());
+                for (auto& v : spEvibMod[t]) { o.scalars(v.data(), int64_t(v.size())); std::fputc(' ', f); }
+                std::fputs(") ", f);
+            }
+            std::fputc(')', f);
+            o.end();
+        }
+        o.entry("dsmcNCollsCum", nColls);
+        o.entry("nCum", scaled(dsmcNCum)); o.entry("mCum", scaled(dsmcMCum));
+        {
+            std::vector<std::vector<double>> nSp;
+            for (auto& v : spN) nSp.push_back(scaled(v));
+            o.entryLL("nSpeciesCum", nSp);
+        }
+        o.entryV("momentumCum", scaled(dsmcMom)); o.entry("linearKECum", scaled(dsmcLinearKECum)); o.entry("collisionSeparation", collSep);
+        // ---- boundary measurements: List<scalarField> over ALL patches (zero where no wall model samples)
+        auto patchSum = [&](int wq, int nCmpt) {
+            std::vector<std::vector<double>> out(boundary_.size());
+            for (size_t j = 0; j < boundary_.size(); ++j) {
+                out[j].assign(size_t(boundary_[j].nFaces) * nCmpt, 0.0);
+                if (measStart[j] < 0) continue;
+                for (int k = 0; k < boundary_[j].nFaces; ++k)
+                    for (int s : fs.typeIds)
+                        for (int q = 0; q < nCmpt; ++q) out[j][size_t(k) * nCmpt + q] += wall[(size_t(measStart[j] + k) * S + s) * nWallQ + wq + q];
+            }
+            return out;
+        };
+        auto patchSpecies = [&](int wq) {
+            std::vector<std::vector<std::vector<double>>> out(nT, std::vector<std::vector<double>>(boundary_.size()));
+            for (int t = 0; t < nT; ++t)
+                for (size_t j = 0; j < boundary_.size(); ++j) {
+                    out[t][j].assign(size_t(boundary_[j].nFaces), 0.0);
+                    if (measStart[j] < 0 || wq < 0) continue;
+                    for (int k = 0; k < boundary_[j].nFaces; ++k) out[t][j][k] = wall[(size_t(measStart[j] + k) * S + fs.typeIds[t]) * nWallQ + wq];
+                }
+            return out;
+        };
+        auto writeVecPatches = [&](const char* k, const std::vector<std::vector<double>>& a) {
+            o.key(k);
+            std::fprintf(f, "%zu ( ", a.size());
+            for (auto& v : a) { o.vectors(v.data(), int64_t(v.size() / 3)); std::fputc(' ', f); }
+            std::fputc(')', f);
+            o.end();
+        };
+        auto writeSpeciesPatches = [&](const char* k, const std::vector<std::vector<std::vector<double>>>& a) {
+            o.key(k);
+            std::fprintf(f, "%zu ( ", a.size());
+            for (auto& sp : a) {
+                std::fprintf(f, "%zu ( ", sp.size());
+                for (auto& v : sp) { o.scalars(v.data(), int64_t(v.size())); std::fputc(' ', f); }
+                std::fputs(") ", f);
+            }
+            std::fputc(')', f);
+            o.end();
+        };
+        // WallQ order of the engine (csrc/engine.h): rhoN 0, rhoNInt 1, rhoNElec 2, rhoM 3, linearKE 4, mcc 5, momentum 6-8, Erot 9,
+        // zetaRot 10, Evib 11, Eelec 12, q 13, fD 14-16, EvibMod 17+
+        if (nWallQ >= 17) {
+            o.entryLL("rhoNBF", patchSum(0, 1)); o.entryLL("rhoMBF", patchSum(3, 1)); o.entryLL("linearKEBF", patchSum(4, 1));
+            writeVecPatches("momentumBF", patchSum(6, 3));
+            o.entryLL("ErotBF", patchSum(9, 1)); o.entryLL("zetaRotBF", patchSum(10, 1)); o.entryLL("rhoNIntBF", patchSum(1, 1));
+            o.entryLL("rhoNElecBF", patchSum(2, 1)); o.entryLL("qBF", patchSum(13, 1));
+            writeVecPatches("fDBF", patchSum(14, 3));
+            writeSpeciesPatches("speciesRhoNBF", patchSpecies(0)); writeSpeciesPatches("speciesEvibBF", patchSpecies(11));
+            writeSpeciesPatches("speciesEelecBF", patchSpecies(12)); writeSpeciesPatches("speciesMccBF", patchSpecies(5));
+            {   // [species][mode][patch]
+                o.key("speciesEvibModBF");
+                std::fprintf(f, "%d ( ", nT);
+                for (int t = 0; t < nT; ++t) {
+                    const int nM = species_[fs.typeIds[t]].nVibrationalModes;
+                    std::fprintf(f, "%d ( ", nM);
+                    for (int md = 0; md < nM; ++md) {
+                        std::fprintf(f, "%zu ( ", boundary_.size());
+                        for (size_t j = 0; j < boundary_.size(); ++j) {
+                            std::vector<double> v(size_t(boundary_[j].nFaces), 0.0);
+                            if (measStart[j] >= 0 && 17 + md < nWallQ)
+                                for (int k = 0; k < boundary_[j].nFaces; ++k) v[k] = wall[(size_t(measStart[j] + k) * S + fs.typeIds[t]) * nWallQ + 17 + md];
+                            o.scalars(v.data(), int64_t(v.size())); std::fputc(' ', f);
+                        }
+                        std::fputs(") ", f);
+                    }
+                    std::fputs(") ", f);
+                }
+                std::fputc(')', f);
+                o.end();
+            }
+        }
+        std::fclose(f);
+    }
+}
+
+void dsmcCloud::readResumeSampling() {
+    // dsmcVolFields.C:1052-1066: read only with averagingAcrossManyRuns and resetAtOutput off
+    bool any = false, reset = !fields_.empty();
+    for (auto& f : fields_) { any = any || f.averagingAcrossManyRuns; reset = reset && f.resetAtOutput && !(time_ + deltaT_ > f.resetAtOutputUntilTime); }
+    if (!any) return;
+    if (reset) {
+        std::printf("Averaging across many runs will be enabled as soon as resetAtOutput is turned off.\n");
+        return;
+    }
+    const std::string path = root_ + "/" + timeName_ + "/uniform/resumeSampling_dsmcb200";
+    if (!foam::exists(path)) return;
+    foam::Dict d = foam::readDict(path);
+    dsmcb200_accum_info ai{};
+    check(dsmcb200_accum_info_get(ctx_, &ai), "dsmcb200_accum_info_get");
+    int32_t nMeas = 0, nWallQ = 0;
+    check(dsmcb200_wall_info(ctx_, &nMeas, &nWallQ), "dsmcb200_wall_info");
+    if (d.labelOr("nCells", -1) != ai.nCells || d.labelOr("nSpecies", -1) != ai.nSpecies || d.labelOr("nQuantities", -1) != ai.nQuantities ||
+        d.labelOr("nMeasuredFaces", -1) != nMeas || d.labelOr("nWallQuantities", -1) != nWallQ) {
+        std::printf("resumeSampling_dsmcb200 does not match the current mesh / species / field set: sampling starts afresh\n");
+        return;
+    }
+    std::vector<double> acc = d.scalarList("accumulators"), coll = d.scalarList("collisionCumulative");
+    if (acc.size() != size_t(ai.nCells) * ai.nSpecies * ai.nQuantities || coll.size() != size_t(ai.nCells) * 2)
+        throw FoamError("resumeSampling_dsmcb200: list sizes do not match the header in " + path);
+    check(dsmcb200_upload_accumulators(ctx_, acc.data(), coll.data(), d.scalar("nTimeSteps")), "dsmcb200_upload_accumulators");
+    if (nMeas) {
+        std::vector<double> wall = d.scalarList("wallAccumulators");
+        if (wall.size() != size_t(nMeas) * ai.nSpecies * nWallQ) throw FoamError("resumeSampling_dsmcb200: wallAccumulators size mismatch in " + path);
+        check(dsmcb200_upload_wall_accumulators(ctx_, wall.data()), "dsmcb200_upload_wall_accumulators");
+    }
+    if (d.found("collisionSelectionRemainder")) {
+        std::vector<double> rem = d.scalarList("collisionSelectionRemainder");
+        if (rem.size() == size_t(ai.nCells)) check(dsmcb200_upload_cellstate(ctx_, nullptr, rem.data()), "dsmcb200_upload_cellstate");
+    }
+    std::printf("Resuming sampling from %s (nTimeSteps = %g)\n", path.c_str(), d.scalar("nTimeSteps"));
+}
+
 void dsmcCloud::write() {
     const std::string timeDir = root_ + "/" + timeName_;
     const std::string cdir = timeDir + "/lagrangian/" + cloudName_;
@@ -723,6 +1006,8 @@ void dsmcCloud::write() {
     bool reset = !fields_.empty();
     for (auto& f : fields_) reset = reset && f.resetAtOutput && !(time_ + deltaT_ > f.resetAtOutputUntilTime);
     if (reset) check(dsmcb200_reset_accumulators(ctx_), "dsmcb200_reset_accumulators");
+    // dsmcVolFields.C:2375-2378: only with averagingAcrossManyRuns and resetAtOutput off
+    if (!reset) writeResumeSampling(timeDir);
 }
 
 }  // namespace dsmcb200

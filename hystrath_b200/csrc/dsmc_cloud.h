@@ -38,6 +38,7 @@ struct FieldSpec {  // one dsmcVolFields entry of system/fieldPropertiesDict
     bool resetAtOutput = true;
     double resetAtOutputUntilTime = 1e300;
     int sampleInterval = 1;
+    bool averagingAcrossManyRuns = false;  // dsmcVolFields.C:1048: keep / restore uniform/resumeSampling_<fieldName>
 };
 
 struct DerivedFields {  // per-cell results of dsmcVolFields::calculateField for one instance
@@ -75,6 +76,8 @@ class dsmcCloud {
     void readFieldProperties();
     void readCloud();
     void writeFields(const std::string& timeDir);
+    void writeResumeSampling(const std::string& timeDir);  // dsmcVolFields::writeOut + the engine's own lossless checkpoint
+    void readResumeSampling();                              // dsmcVolFields::readIn
     void check(int rc, const char* what);
 
     std::string caseDir_, root_, cloudName_, timeName_;

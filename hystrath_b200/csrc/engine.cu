@@ -1104,6 +1104,14 @@ int dsmcb200_upload_accumulators(dsmcb200_ctx* c, const double* acc, const doubl
     return 0;
 }
 
+int dsmcb200_upload_wall_accumulators(dsmcb200_ctx* c, const double* wall) {
+    if (!c || !wall) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    if (c->nMeasFaces) CK(cudaMemcpy(c->dWallAcc, wall, size_t(c->nMeasFaces) * c->hP.nSpecies * c->nWallQ * 8, cudaMemcpyHostToDevice));
+    return 0;
+}
+
 int dsmcb200_reset_accumulators(dsmcb200_ctx* c) {
     if (!c) return DSMCB200_ERR_INVALID;
     cudaSetDevice(c->device);

@@ -305,6 +305,8 @@ int dsmcb200_reset_accumulators(dsmcb200_ctx*);      /* dsmcVolFields resetField
  * layout [nBoundaryFaces][nSpecies][nWallQuantities]. */
 int dsmcb200_wall_info(dsmcb200_ctx*, int32_t* nBoundaryFaces, int32_t* nWallQuantities);
 int dsmcb200_download_wall_accumulators(dsmcb200_ctx*, double* wall);
+/* restart of the wall sampling: the *BF_ arrays dsmcVolFields::readIn restores (dsmcVolFields.C:723-738) */
+int dsmcb200_upload_wall_accumulators(dsmcb200_ctx*, const double* wall);
 int dsmcb200_get_counters(dsmcb200_ctx*, dsmcb200_counters*);
 /* Per-kernel device time of the last step, for bench.py: names[i] is filled with up to
  * DSMCB200_NAME_LEN chars; returns the count through *n (capacity in). */

@@ -37,6 +37,7 @@ def test_driver_runs_couette_case_and_matches_oracle(tmp_path):
     o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
     o.upload_parcels(p)
     o.upload_cellstate(g["dsmcSigmaTcRMax"], None)
+    o.set_step(500000)   # the driver keys its Philox streams by the global time index: startTime 5 / deltaT 1e-5
     o.evolve(n_steps)
     ref = o.download_parcels()
 
@@ -69,3 +70,41 @@ def test_driver_runs_couette_case_and_matches_oracle(tmp_path):
     assert "upperWall" in text and "nonuniform List<scalar>" in text.split("boundaryField")[1]
     assert os.path.exists(os.path.join(tdir, "dsmcSigmaTcRMax"))
     assert os.path.exists(os.path.join(tdir, "uniform", "lagrangian", "dsmc", "cloudProperties"))
+
+
+def test_driver_resume_sampling_round_trip(tmp_path):
+    """averagingAcrossManyRuns: the run writes uniform/resumeSampling_<fieldName> with the reference's key set
+    (dsmcVolFields::writeOut, dsmcVolFields.C:745-835; key list taken from the shipped
+    hypersonicCorner/.../uniform/resumeSampling_Ar) and a restarted run continues the averages (readIn, :647-743)."""
+    import json
+
+    n_steps = 3
+    casegen.couette_case(str(tmp_path), n_steps=n_steps, seed=7, nto=1)
+    fp = os.path.join(str(tmp_path), "system", "fieldPropertiesDict")
+    text = open(fp).read().replace("resetAtOutput       on;", "resetAtOutput       off;")
+    text = text.replace("measureMeanFreePath     true;", "measureMeanFreePath     true;\n            averagingAcrossManyRuns true;")
+    open(fp, "w").write(text)
+    r = subprocess.run([RUN, "-case", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    t1 = os.path.join(str(tmp_path), "5.00003")
+    keys = json.load(open(os.path.join(ROOT, "tests", "golden", "resumeSampling_keys.json")))["keys"]
+    for inst in ("mixture", "N2", "O2"):
+        d = open(os.path.join(t1, "uniform", f"resumeSampling_{inst}")).read()
+        body = d.split("// * * *")[1] if "// * * *" in d else d
+        got = [ln.split()[0] for ln in body.splitlines() if ln and ln[0].isalpha()]
+        assert got == keys, (inst, got)
+        assert "nTimeSteps      3;" in d
+    n1 = ff.read_internal_field(os.path.join(t1, "dsmcNMean_mixture"))
+    # second run: starts from the latest time, reads the accumulators back and keeps averaging
+    cd = os.path.join(str(tmp_path), "system", "controlDict")
+    open(cd, "w").write(open(cd).read().replace("5.00003;", "5.00006;"))
+    r2 = subprocess.run([RUN, "-case", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r2.returncode == 0, r2.stderr + r2.stdout
+    assert "Resuming sampling" in r2.stdout and "nTimeSteps = 3" in r2.stdout
+    t2 = os.path.join(str(tmp_path), "5.00006")
+    d = open(os.path.join(t2, "uniform", "resumeSampling_mixture")).read()
+    assert "nTimeSteps      6;" in d
+    n2 = ff.read_internal_field(os.path.join(t2, "dsmcNMean_mixture"))
+    # 47 583 parcels in a closed box: the six-step mean number per cell still sums to the parcel count
+    assert abs(n1.sum() - 47583) < 1e-3 and abs(n2.sum() - 47583) < 1e-3   # files carry 10 significant digits
+    assert not np.allclose(n1, n2)
