@@ -597,7 +597,8 @@ int stageInflow(dsmcb200_ctx* c, int64_t tailStart) {
 MoveArgs moveArgs(dsmcb200_ctx* c, int32_t first, int32_t count, int32_t tailStart) {
     MoveArgs a{};
     a.p = c->buf[c->cur].a; a.first = first; a.count = count; a.tailStart = tailStart; a.sfTail = c->dSfTail;
-    a.tets = c->dTets; a.bfaces = c->dBFaces; a.bfaceArea = c->dBFaceArea; a.P = c->dP; a.wallAcc = c->dWallAcc; a.nWallQ = c->nWallQ;
+    a.tets = c->dTets; a.cellFaceOffsets = c->dCellFaceOffsets; a.cellFaces = c->dCellFaces; a.faceTetPair0 = c->dFaceTetPair0; a.nCells = c->mesh.nCells;
+    a.bfaces = c->dBFaces; a.bfaceArea = c->dBFaceArea; a.P = c->dP; a.wallAcc = c->dWallAcc; a.nWallQ = c->nWallQ;
     a.migBuf = c->dMigSend; a.migCapacity = c->migCapacity; a.cellCount = c->dCellCount; a.counters = c->dCounters; a.step = c->step;
     return a;
 }
@@ -689,7 +690,7 @@ int stageCollide(dsmcb200_ctx* c) {
 int stageSample(dsmcb200_ctx* c) {
     if (!c->occupancyValid) return fail(c, DSMCB200_ERR_STATE, "cell occupancy is stale: run the sort stage first");
     SampleArgs a{};
-    a.p = c->buf[c->cur].a; a.cellOffset = c->dCellOffset; a.nCells = c->mesh.nCells; a.acc = c->dAcc; a.nQ = c->nQ; a.nSpecies = int(c->species.size());
+    a.p = c->buf[c->cur].a; a.cellOffset = c->dCellOffset; a.nCells = c->mesh.nCells; a.acc = c->dAcc; a.nQ = c->nQ; a.nSpecies = int(c->species.size()); a.nParcels = int32_t(c->N);
     a.collCum = c->dCollCum; a.nCollsStep = c->dNColls; a.collSepStep = c->dCollSep; a.P = c->dP;
     KT t(c, "sample");
     CK(launchSample(a, c->stream));

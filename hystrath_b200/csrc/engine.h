@@ -93,6 +93,8 @@ struct MoveArgs {
     int32_t tailStart;            // parcels >= tailStart carry a step fraction in sfTail[i - tailStart]
     const double* sfTail;
     const TetRec* tets;
+    const int32_t *cellFaceOffsets, *cellFaces, *faceTetPair0;  // for the record prefetch of a chunk's cells
+    int32_t nCells;
     const BFaceRec* bfaces;
     const double* bfaceArea;      // [nBFaces*3] face area vectors
     const DevParams* P;
@@ -129,6 +131,7 @@ struct SampleArgs {
     int32_t nCells;
     double* acc;                  // [nCells][nSpecies][nQ]
     int32_t nQ, nSpecies;
+    int32_t nParcels;             // sorted parcels (= cellOffset[nCells])
     double* collCum;              // [nCells][2]
     const double* nCollsStep;
     const double* collSepStep;

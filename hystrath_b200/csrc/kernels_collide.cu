@@ -676,70 +676,77 @@ cudaError_t launchCollide(const CollideArgs& a, cudaStream_t s) {
 // Stage 5
 // ------------------------------------------------------------------------------------------------
 namespace {
-constexpr int SMP_WARPS = 8;
+constexpr int SMP_THREADS = 256;
+
+// sum[sp] += x with sp a run-time index and sum[] in registers: one predicated add per species
+template <int I, int S>
+__device__ __forceinline__ void addToSpecies(double (&sum)[S], int sp, double x) {
+    if constexpr (I < S) {
+        asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\t@p add.rn.f64 %0, %0, %3;\n\t}" : "+d"(sum[I]) : "r"(sp), "n"(I), "d"(x));
+        addToSpecies<I + 1, S>(sum, sp, x);
+    }
+}
 }
 
-// One warp per cell.  Each lane turns one parcel into its row of moment contributions in shared memory
-// (stride nQ|1 doubles, conflict free); then lane (sub, q) adds up the rows j = sub (mod G) of quantity q,
-// G = 32 / Qpad sub-groups working in parallel, and a shuffle tree folds the sub-groups.  Every lane of
-// quantity q finally owns sum[s] for all species and lane (0, q) adds it to the cell's accumulator row.
-__global__ void __launch_bounds__(SMP_WARPS * 32) sampleKernel(const __grid_constant__ SampleArgs a) {
-    extern __shared__ double stageAll[];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+// A block takes a group of consecutive cells and walks their (contiguous, sorted) parcels in chunks.
+// Phase 1, thread = parcel: coalesced loads, the parcel's row of moment contributions goes to shared memory
+// (row stride nQ|1 doubles: conflict free both ways).  Phase 2, thread = (sub-range, cell, quantity): adds the rows of
+// its cell that lie in the chunk, in parcel order, into its own accumulator selected by the row's species
+// (accS[species][thread], conflict free).  After the last chunk the sub-ranges are folded in a fixed order and thread
+// (cell, quantity) adds sum[s] to the cell's accumulator row with one RED per non-zero element: a single writer per
+// element per step, so the sums are run-to-run deterministic.
+template <int S>
+__global__ void __launch_bounds__(SMP_THREADS) sampleKernel(const __grid_constant__ SampleArgs a, const int cellsPerGroup, const int nSub,
+                                                            const int tile) {
+    extern __shared__ double smemD[];
     const DevParams& P = *a.P;
-    const int nQ = a.nQ, S = P.nSpecies;
+    const int nQ = a.nQ;
     const int stride = nQ | 1;
-    // per warp: 32 staged rows, 32*S accumulators [sub-group][species][quantity], 32 species bytes
-    double* stage = stageAll + size_t(w) * (32 * stride + 32 * S);
-    double* accS = stage + 32 * stride;
-    uint8_t* stageSp = reinterpret_cast<uint8_t*>(stageAll + size_t(SMP_WARPS) * (32 * stride + 32 * S)) + w * 32;
+    double* __restrict__ val = smemD;                                                 // [tile][stride]
+    double* __restrict__ accS = val + size_t(tile) * stride;                          // [S][SMP_THREADS]
+    int32_t* __restrict__ offS = reinterpret_cast<int32_t*>(accS + S * SMP_THREADS);  // [cellsPerGroup + 1]
+    uint8_t* __restrict__ spS = reinterpret_cast<uint8_t*>(offS + cellsPerGroup + 1); // [tile]
     const bool internal = P.hasInternalEnergy != 0;
     const int qFlux = 5 + (internal ? 2 + P.nModes : 0);
     const int qClass = qFlux + (P.measureFlux ? 12 : 0);
-    const int Qpad = nQ <= 8 ? 8 : (nQ <= 16 ? 16 : 32);
-    const int G = 32 / Qpad;
-    const int q = lane % Qpad, sub = lane / Qpad;
-    const int32_t nWarps = gridDim.x * SMP_WARPS;
+    const int tid = threadIdx.x;
+    // phase-2 role
+    const int perSub = cellsPerGroup * nQ;
+    const int sub = tid / perSub;
+    const int rem = tid - sub * perSub;
+    const int cl = rem / nQ, q = rem - cl * nQ;
+    const int32_t nGroups = (a.nCells + cellsPerGroup - 1) / cellsPerGroup;
 
-    // the offsets of the warp's next cell are read one cell ahead and its parcel rows are requested towards L2 while the
-    // current cell is reduced
-    int32_t c = blockIdx.x * SMP_WARPS + w;
-    int32_t bNext = 0, nCNext = 0;
-    if (c < a.nCells) { bNext = a.cellOffset[c]; nCNext = a.cellOffset[c + 1] - bNext; }
-    for (; c < a.nCells; c += nWarps) {
-        const int32_t b = bNext;
-        const int32_t nC = nCNext;
-        {
-            const int32_t cn = c + nWarps;
-            if (cn < a.nCells) {
-                bNext = a.cellOffset[cn];
-                nCNext = a.cellOffset[cn + 1] - bNext;
-                if (lane < nCNext && (lane & 3) == 0) {
-                    const int32_t g = bNext + lane;
-                    prefetchL2(a.p.ux + g); prefetchL2(a.p.uy + g); prefetchL2(a.p.uz + g);
-                    if (internal) prefetchL2(a.p.erot + g);
-                }
-            }
-        }
-        if (lane < 2) {
+    for (int32_t grp = blockIdx.x; grp < nGroups; grp += gridDim.x) {
+        const int32_t c0 = grp * cellsPerGroup;
+        const int nc = a.nCells - c0 < cellsPerGroup ? a.nCells - c0 : cellsPerGroup;
+        __syncthreads();  // the previous group is done with the shared arrays
+        for (int k = tid; k <= nc; k += SMP_THREADS) offS[k] = a.cellOffset[c0 + k];
+        for (int k = tid; k < 2 * nc; k += SMP_THREADS) {
             // fold this step's cellMeasurements into the cumulative pair (dsmcVolFields.C:1244-1248)
-            const double add = lane == 0 ? a.nCollsStep[c] : a.collSepStep[c];
-            if (add != 0.0) atomicAdd(&a.collCum[2 * size_t(c) + lane], add);
+            const int32_t c = c0 + (k >> 1);
+            const double add = (k & 1) ? a.collSepStep[c] : a.nCollsStep[c];
+            if (add != 0.0) a.collCum[2 * size_t(c0) + k] += add;
         }
-        if (nC == 0) continue;
-        for (int k = lane; k < 32 * S; k += 32) accS[k] = 0.0;
-        __syncwarp();
+        __syncthreads();
+        double sum[S];  // my accumulator per species (registers: the species of a row selects by predicate, not by address)
+#pragma unroll
+        for (int s = 0; s < S; ++s) sum[s] = 0.0;
+        const int32_t pBeg = offS[0], pEnd = offS[nc];
+        const bool role = sub < nSub && cl < nc;
+        const int32_t myLo = role ? offS[cl] : 0, myHi = role ? offS[cl + 1] : 0;
 
-        for (int32_t j0 = 0; j0 < nC; j0 += 32) {
-            const int32_t g = b + j0 + lane;
-            const int nHere = nC - j0 < 32 ? nC - j0 : 32;
-            if (lane < nHere) {
+        for (int32_t pos = pBeg; pos < pEnd; pos += tile) {
+            const int n = pEnd - pos < tile ? pEnd - pos : tile;
+            // ---- phase 1: one parcel per thread
+            for (int j = tid; j < n; j += SMP_THREADS) {
+                const int32_t g = pos + j;
                 const int mySp = a.p.typeId[g];
                 const double ux = a.p.ux[g], uy = a.p.uy[g], uz = a.p.uz[g];
-                double* row = stage + lane * stride;
+                double* row = val + j * stride;
                 const double cc = ux * ux + uy * uy + uz * uz;
                 row[0] = 1.0; row[1] = ux; row[2] = uy; row[3] = uz; row[4] = cc;
-                stageSp[lane] = uint8_t(mySp);
+                spS[j] = uint8_t(mySp);
                 double Eint = 0.0;
                 if (internal) {
                     const DevSpecies& Sp = P.sp[mySp];
@@ -763,45 +770,81 @@ __global__ void __launch_bounds__(SMP_WARPS * 32) sampleKernel(const __grid_cons
                     f[9] = Eint * ux; f[10] = Eint * uy; f[11] = Eint * uz;
                 }
                 if (P.measureClass) {
-                    const int cl = a.p.cls ? a.p.cls[g] : 0;
-                    row[qClass] = cl == 0 ? 1.0 : 0.0; row[qClass + 1] = cl == 1 ? 1.0 : 0.0; row[qClass + 2] = cl == 2 ? 1.0 : 0.0;
+                    const int cls = a.p.cls ? a.p.cls[g] : 0;
+                    row[qClass] = cls == 0 ? 1.0 : 0.0; row[qClass + 1] = cls == 1 ? 1.0 : 0.0; row[qClass + 2] = cls == 2 ? 1.0 : 0.0;
                 }
             }
-            __syncwarp();
-            if (q < nQ) {
-                // the species of the row selects the accumulator: no per-species select chain
-                for (int j = sub; j < nHere; j += G) {
-                    const double v = stage[j * stride + q];
-                    const int sp = stageSp[j];
-                    accS[(sub * S + sp) * Qpad + q] += v;
+            __syncthreads();
+            // ---- phase 2: the rows of my cell inside this chunk, every nSub-th one starting at sub
+            if (role) {
+                int lo = (myLo > pos ? myLo : pos), hi = (myHi < pos + n ? myHi : pos + n);
+                if (nSub > 1) lo += ((sub - (lo - myLo)) % nSub + nSub) % nSub;  // first index >= lo with (index - myLo) = sub (mod nSub)
+                const double* v = val + q + (lo - pos) * stride;
+                const uint8_t* ps = spS + (lo - pos);
+                const int vStep = nSub * stride;
+                for (int32_t g = lo; g < hi; g += nSub, v += vStep, ps += nSub) {
+                    const int sp = *ps;
+                    const double x = *v;
+                    // one predicated add per species (a select chain would cost three instructions per species)
+                    addToSpecies<0, S>(sum, sp, x);
                 }
             }
-            __syncwarp();
+            __syncthreads();
         }
-        // fold the G sub-groups in a fixed order and add the cell's row: element k = (species, quantity) has one writer
-        double* row = a.acc + size_t(c) * S * nQ;
-        for (int k = lane; k < S * nQ; k += 32) {
-            const int sI = k / nQ, qI = k - sI * nQ;
-            double t = 0.0;
-            for (int g2 = 0; g2 < G; ++g2) t += accS[(g2 * S + sI) * Qpad + qI];
-            if (t != 0.0) atomicAdd(&row[k], t);  // fire-and-forget RED
+        // ---- fold the sub-ranges in a fixed order; one writer per accumulator element
+        if (nSub > 1) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) accS[s * SMP_THREADS + tid] = sum[s];
+            __syncthreads();
+            if (role && sub == 0) {
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    for (int k = 1; k < nSub; ++k) sum[s] += accS[s * SMP_THREADS + k * perSub + rem];
+            }
         }
-        __syncwarp();
+        if (role && sub == 0) {
+            double* row = a.acc + (size_t(c0 + cl) * S) * nQ + q;
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                if (sum[s] != 0.0) atomicAdd(&row[size_t(s) * nQ], sum[s]);  // fire-and-forget RED
+        }
     }
 }
 
 cudaError_t launchSample(const SampleArgs& a, cudaStream_t s) {
-    int grid = (a.nCells + SMP_WARPS - 1) / SMP_WARPS;
-    const int maxGrid = 148 * 8;
-    if (grid > maxGrid) grid = maxGrid;
+    // group size: about 1000 parcels of consecutive cells, at most SMP_THREADS / nQ cells (one phase-2 thread per (cell, quantity));
+    // spare threads split each cell's parcels into nSub interleaved sub-ranges (few, crowded cells)
+    const int maxCells = SMP_THREADS / a.nQ > 0 ? SMP_THREADS / a.nQ : 1;
+    const double ppc = a.nCells > 0 ? double(a.nParcels) / a.nCells : 1.0;
+    int cpg = int(1024.0 / (ppc > 1.0 ? ppc : 1.0));
+    if (cpg > maxCells) cpg = maxCells;
+    if (cpg < 1) cpg = 1;
+    int nSub = SMP_THREADS / (cpg * a.nQ);
+    if (nSub < 1) nSub = 1;
+    const int stride = a.nQ | 1;
+    int tile = ((40 * 1024) / (stride * 8)) & ~31;
+    if (tile > 512) tile = 512;
+    if (tile < 32) tile = 32;
+    const size_t smem = (size_t(tile) * stride + size_t(a.nSpecies) * SMP_THREADS) * sizeof(double) + size_t(cpg + 1) * 4 + tile;
+    const int nGroups = (a.nCells + cpg - 1) / cpg;
+    int grid = nGroups < 148 * 4 ? nGroups : 148 * 4;
     if (grid < 1) grid = 1;
-    const size_t smem = size_t(SMP_WARPS) * (32 * (a.nQ | 1) + 32 * a.nSpecies) * sizeof(double) + SMP_WARPS * 32;
-    if (smem > 48 * 1024) {  // many quantities x species: beyond the default dynamic shared-memory window
-        const cudaError_t e = cudaFuncSetAttribute(sampleKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    auto go = [&](auto kernel) -> cudaError_t {
+        const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return e;
+        kernel<<<grid, SMP_THREADS, smem, s>>>(a, cpg, nSub, tile);
+        return cudaGetLastError();
+    };
+    switch (a.nSpecies) {
+        case 1: return go(sampleKernel<1>);
+        case 2: return go(sampleKernel<2>);
+        case 3: return go(sampleKernel<3>);
+        case 4: return go(sampleKernel<4>);
+        case 5: return go(sampleKernel<5>);
+        case 6: return go(sampleKernel<6>);
+        case 7: return go(sampleKernel<7>);
+        default: return go(sampleKernel<8>);
     }
-    sampleKernel<<<grid, SMP_WARPS * 32, smem, s>>>(a);
-    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -83,7 +83,8 @@ def test_driver_resume_sampling_round_trip(tmp_path):
     fp = os.path.join(str(tmp_path), "system", "fieldPropertiesDict")
     text = open(fp).read().replace("resetAtOutput       on;", "resetAtOutput       off;")
     text = text.replace("measureMeanFreePath     true;", "measureMeanFreePath     true;\n            averagingAcrossManyRuns true;")
-    open(fp, "w").write(text)
+    with open(fp, "w") as fh:
+        fh.write(text)
     r = subprocess.run([RUN, "-case", str(tmp_path)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr + r.stdout
     t1 = os.path.join(str(tmp_path), "5.00003")
@@ -97,7 +98,10 @@ def test_driver_resume_sampling_round_trip(tmp_path):
     n1 = ff.read_internal_field(os.path.join(t1, "dsmcNMean_mixture"))
     # second run: starts from the latest time, reads the accumulators back and keeps averaging
     cd = os.path.join(str(tmp_path), "system", "controlDict")
-    open(cd, "w").write(open(cd).read().replace("5.00003;", "5.00006;"))
+    control = open(cd).read()
+    assert "5.00003;" in control
+    with open(cd, "w") as fh:
+        fh.write(control.replace("5.00003;", "5.00006;"))
     r2 = subprocess.run([RUN, "-case", str(tmp_path)], capture_output=True, text=True, timeout=600)
     assert r2.returncode == 0, r2.stderr + r2.stdout
     assert "Resuming sampling" in r2.stdout and "nTimeSteps = 3" in r2.stdout
