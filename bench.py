@@ -26,6 +26,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries the one JSON line only
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 KB = 1.38065e-23
 # algorithmic bytes per parcel-step and stage (BASELINE.md section 3 / SURVEY.md 8d), FP64 state
@@ -358,10 +361,21 @@ def main():
                 gbs = n_local * sb[k] / (t * 1e-3) / 1e9
                 stages[k] = {"ms": t, "bytes_per_parcel": sb[k], "achieved_gbs": gbs, "frac": gbs / peak}
         dom = max(stage_t, key=stage_t.get)
+        # DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json: dram__bytes_read.sum +
+        # dram__bytes_write.sum of one launch on this workload), scaled by parcel count when the capture was taken at another size
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            ent = tj.get(f"{args.workload}:{args.gas}", {}).get(dom)
+            if ent:
+                traffic = ent["dram_bytes"] / ent["parcels"] * n_local
+                traffic_src = f"ncu dram__bytes_read.sum+dram__bytes_write.sum of one {dom} launch at {ent['parcels']} parcels ({tj.get('capture', '')}), scaled by parcel count"
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": {"move": "moveKernel", "sort": "gatherKernel+scan+scatterIndex+segmentSort",
                                                "collide": "collideKernel", "sample": "sampleKernel"}[dom],
-                    "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": None,
-                    "peak_source": peak_src, "algorithmic_bytes_per_parcel": sb[dom], "parcels_per_launch": n_local,
+                    "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": traffic,
+                    "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_parcel": sb[dom], "parcels_per_launch": n_local,
                     "share_of_step": stage_t[dom] / max(1e-9, sum(stage_t.values()))}
         line = {
             "metric": "particle-steps/s (move+sort+NTC collide+sample)", "value": value, "unit": "particle-steps/s", "n_gpus": world,

@@ -33,6 +33,8 @@ COLLISION_MODEL_NAMES = {
     "NoBinaryCollision": COLL_NONE,
     "VariableHardSphere": COLL_VHS,
     "LarsenBorgnakkeVariableHardSphere": COLL_LB_VHS,
+    "VariableSoftSphere": 3,
+    "LarsenBorgnakkeVariableSoftSphere": 4,
 }
 PATCH_MODEL_NAMES = {
     "dsmcDiffuseWallPatch": BND_DIFFUSE_WALL,

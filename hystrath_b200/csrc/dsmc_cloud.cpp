@@ -41,8 +41,10 @@ int selectBinaryCollisionModel(const std::string& name) {
     if (name == "NoBinaryCollision") return DSMCB200_COLL_NONE;
     if (name == "VariableHardSphere") return DSMCB200_COLL_VHS;
     if (name == "LarsenBorgnakkeVariableHardSphere") return DSMCB200_COLL_LB_VHS;
+    if (name == "VariableSoftSphere") return DSMCB200_COLL_VSS;
+    if (name == "LarsenBorgnakkeVariableSoftSphere") return DSMCB200_COLL_LB_VSS;
     unknownType("BinaryCollisionModel::New(const dictionary&, CloudType&)", "BinaryCollisionModel", name,
-                {"LarsenBorgnakkeVariableHardSphere", "NoBinaryCollision", "VariableHardSphere"});
+                {"LarsenBorgnakkeVariableHardSphere", "LarsenBorgnakkeVariableSoftSphere", "NoBinaryCollision", "VariableHardSphere", "VariableSoftSphere"});
 }
 int selectCollisionPartnerSelection(const std::string& name) {
     if (name == "noTimeCounter") return 1;
@@ -195,13 +197,17 @@ void dsmcCloud::readProperties() {
     selectCoordinateSystem(d.wordOr("coordinateSystem", "dsmcCartesian"));
     selectTimeStepModel(d.wordOr("timeStepModel", "constant"));
     // VariableHardSphere reads Tref from VariableHardSphereCoeffs even under the LB model (VariableHardSphere.C:56-62)
-    models_.Tref = d.isDict("VariableHardSphereCoeffs") ? d.subDict("VariableHardSphereCoeffs").scalarOr("Tref", 273.0) : 273.0;
+    // (VariableSoftSphere.C:54-60 does the same with VariableSoftSphereCoeffs)
+    const bool soft = models_.collisionModel == DSMCB200_COLL_VSS || models_.collisionModel == DSMCB200_COLL_LB_VSS;
+    const std::string baseCoeffs = soft ? "VariableSoftSphereCoeffs" : "VariableHardSphereCoeffs";
+    const std::string lbCoeffs = soft ? "LarsenBorgnakkeVariableSoftSphereCoeffs" : "LarsenBorgnakkeVariableHardSphereCoeffs";
+    models_.Tref = d.isDict(baseCoeffs) ? d.subDict(baseCoeffs).scalarOr("Tref", 273.0) : 273.0;
     models_.rotationalRelaxationCollisionNumber = 5.0;
     models_.vibrationalRelaxationCollisionNumber = 0.0;
     models_.electronicRelaxationCollisionNumber = 500.0;
     models_.invZvFormulation = 2;
-    if (d.isDict("LarsenBorgnakkeVariableHardSphereCoeffs")) {
-        const Dict& lb = d.subDict("LarsenBorgnakkeVariableHardSphereCoeffs");
+    if (d.isDict(lbCoeffs)) {
+        const Dict& lb = d.subDict(lbCoeffs);
         models_.rotationalRelaxationCollisionNumber = lb.scalarOr("rotationalRelaxationCollisionNumber", 5.0);
         models_.vibrationalRelaxationCollisionNumber = lb.scalarOr("vibrationalRelaxationCollisionNumber", 0.0);
         models_.electronicRelaxationCollisionNumber = lb.scalarOr("electronicRelaxationCollisionNumber", 500.0);

@@ -344,7 +344,7 @@ int finalize(dsmcb200_ctx* c) {
         P.centre[d] = 0.5 * (comp(M.boundsMin, d) + comp(M.boundsMax, d));  // meshTools::constrainToMeshCentre
     }
     int nModes = 0;
-    bool internal = md.collisionModel == DSMCB200_COLL_LB_VHS;
+    bool internal = md.collisionModel == DSMCB200_COLL_LB_VHS || md.collisionModel == DSMCB200_COLL_LB_VSS;
     for (int s = 0; s < P.nSpecies; ++s) {
         const dsmcb200_species& h = c->species[s];
         DevSpecies& d = P.sp[s];
@@ -597,8 +597,7 @@ int stageInflow(dsmcb200_ctx* c, int64_t tailStart) {
 MoveArgs moveArgs(dsmcb200_ctx* c, int32_t first, int32_t count, int32_t tailStart) {
     MoveArgs a{};
     a.p = c->buf[c->cur].a; a.first = first; a.count = count; a.tailStart = tailStart; a.sfTail = c->dSfTail;
-    a.tets = c->dTets; a.cellFaceOffsets = c->dCellFaceOffsets; a.cellFaces = c->dCellFaces; a.faceTetPair0 = c->dFaceTetPair0; a.nCells = c->mesh.nCells;
-    a.bfaces = c->dBFaces; a.bfaceArea = c->dBFaceArea; a.P = c->dP; a.wallAcc = c->dWallAcc; a.nWallQ = c->nWallQ;
+    a.tets = c->dTets; a.bfaces = c->dBFaces; a.bfaceArea = c->dBFaceArea; a.P = c->dP; a.wallAcc = c->dWallAcc; a.nWallQ = c->nWallQ;
     a.migBuf = c->dMigSend; a.migCapacity = c->migCapacity; a.cellCount = c->dCellCount; a.counters = c->dCounters; a.step = c->step;
     return a;
 }
@@ -800,7 +799,7 @@ int dsmcb200_set_species(dsmcb200_ctx* c, int nSpecies, const dsmcb200_species* 
 int dsmcb200_set_models(dsmcb200_ctx* c, const dsmcb200_models* m) {
     if (!c || !m) return DSMCB200_ERR_INVALID;
     if (c->ready) return fail(c, DSMCB200_ERR_STATE, "models cannot change after the engine has been finalised");
-    if (m->collisionModel < DSMCB200_COLL_NONE || m->collisionModel > DSMCB200_COLL_LB_VHS)
+    if (m->collisionModel < DSMCB200_COLL_NONE || m->collisionModel > DSMCB200_COLL_LB_VSS)
         return fail(c, DSMCB200_ERR_UNSUPPORTED, "unknown BinaryCollisionModel type; valid types are: NoBinaryCollision VariableHardSphere LarsenBorgnakkeVariableHardSphere");
     if (!(m->nEquivalentParticles > 0) || !(m->deltaT > 0)) return fail(c, DSMCB200_ERR_INVALID, "nEquivalentParticles and deltaT must be positive");
     c->models = *m;

@@ -93,8 +93,6 @@ struct MoveArgs {
     int32_t tailStart;            // parcels >= tailStart carry a step fraction in sfTail[i - tailStart]
     const double* sfTail;
     const TetRec* tets;
-    const int32_t *cellFaceOffsets, *cellFaces, *faceTetPair0;  // for the record prefetch of a chunk's cells
-    int32_t nCells;
     const BFaceRec* bfaces;
     const double* bfaceArea;      // [nBFaces*3] face area vectors
     const DevParams* P;

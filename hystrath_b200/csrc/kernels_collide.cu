@@ -62,6 +62,22 @@ __device__ __forceinline__ void postCollisionVelocities(const DevParams& P, Rng&
     if (cR == -1) cR = mag(UP - UQ);
     const double mP = P.sp[tP].mass, mQ = P.sp[tQ].mass;
     const V3 Ucm = (mP * UP + mQ * UQ) / (mP + mQ);
+    if (P.collisionModel == DSMCB200_COLL_VSS || P.collisionModel == DSMCB200_COLL_LB_VSS) {
+        // VariableSoftSphere::postCollisionVelocities, VariableSoftSphere.C:195-262 (Bird, equation 2.22)
+        const double alphaPQ = 0.5 * (P.sp[tP].alpha + P.sp[tQ].alpha);
+        const V3 cRComponents = UP - UQ;
+        const double cosTheta = 2.0 * (pow(rng.sample01(), 1.0 / alphaPQ)) - 1.0;
+        const double sinTheta = sqrt(1.0 - cosTheta * cosTheta);
+        const double phi = TWO_PI * rng.sample01();
+        const double D = sqrt(cRComponents.y * cRComponents.y + cRComponents.z * cRComponents.z);
+        const V3 postCollisionRelU =
+            mk(cosTheta * cRComponents.x + sinTheta * sin(phi) * D,
+               cosTheta * cRComponents.y + sinTheta * (cR * cRComponents.z * cos(phi) - cRComponents.x * cRComponents.y * sin(phi)) / D,
+               cosTheta * cRComponents.z - sinTheta * (cR * cRComponents.y * cos(phi) + cRComponents.x * cRComponents.z * sin(phi)) / D);
+        UP = Ucm + postCollisionRelU * mQ / (mP + mQ);
+        UQ = Ucm - postCollisionRelU * mP / (mP + mQ);
+        return;
+    }
     const double cosTheta = 2.0 * rng.sample01() - 1.0;
     const double sinTheta = sqrt(1.0 - cosTheta * cosTheta);
     const double phi = TWO_PI * rng.sample01();
@@ -205,7 +221,7 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     WarpSmem& sm = smAll[w];
     const DevParams& P = *a.P;
-    const bool LB = P.collisionModel == DSMCB200_COLL_LB_VHS;
+    const bool LB = P.collisionModel == DSMCB200_COLL_LB_VHS || P.collisionModel == DSMCB200_COLL_LB_VSS;
     const bool internal = P.hasInternalEnergy != 0;
     const int32_t nWarps = gridDim.x * COL_WARPS;
     unsigned long long totColl = 0, totCand = 0;
@@ -496,7 +512,7 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) collideLaneKernel(const __gri
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     LaneSmem& sm = smAll[w];
     const DevParams& P = *a.P;
-    const bool LB = P.collisionModel == DSMCB200_COLL_LB_VHS;
+    const bool LB = P.collisionModel == DSMCB200_COLL_LB_VHS || P.collisionModel == DSMCB200_COLL_LB_VSS;
     const bool internal = P.hasInternalEnergy != 0;
     const bool none = P.collisionModel == DSMCB200_COLL_NONE;
     const int32_t nWarps = gridDim.x * LANE_WARPS;

@@ -40,7 +40,6 @@ constexpr int MOVE_BLOCK = MOVE_BLOCK_SZ;
 __device__ __forceinline__ void ld4(const double* __restrict__ p, double& a, double& b, double& c, double& d) {
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
-__device__ __forceinline__ void pfL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ int32_t loInt(double w) { return int32_t(__double_as_longlong(w) & 0xffffffffLL); }
 __device__ __forceinline__ int32_t hiInt(double w) { return int32_t(__double_as_longlong(w) >> 32); }
 
@@ -225,30 +224,6 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
     if (chunkEnd > a.first + a.count) chunkEnd = a.first + a.count;
     if (chunkBeg >= chunkEnd) return;
     int32_t warpNext = chunkBeg;  // warp-uniform: next unassigned parcel of the chunk
-#ifdef MOVE_PF_PARCELS
-    {   // the chunk's parcel rows towards L2: one line per lane and array
-        const int32_t nChunk = chunkEnd - chunkBeg;
-        if (lane * 16 < nChunk) {
-            const int32_t g = chunkBeg + lane * 16;
-            pfL2(a.p.px + g); pfL2(a.p.py + g); pfL2(a.p.pz + g); pfL2(a.p.ux + g); pfL2(a.p.uy + g); pfL2(a.p.uz + g);
-        }
-        if (lane * 32 < nChunk) { const int32_t g = chunkBeg + lane * 32; pfL2(a.p.cell + g); pfL2(a.p.tet + g); }
-    }
-#endif
-#ifdef MOVE_PF_TETS
-    {   // the tet records of every face of the chunk's cells towards L2 (the cloud is cell-sorted after the first step)
-        int32_t cFirst = a.p.cell[chunkBeg], cLast = a.p.cell[chunkEnd - 1];
-        if (cFirst >= 0 && cLast >= cFirst && cLast - cFirst < 64 && cLast < a.nCells) {
-            const int32_t k0 = a.cellFaceOffsets[cFirst], k1 = a.cellFaceOffsets[cLast + 1];
-            const char* tb = reinterpret_cast<const char*>(a.tets);
-            for (int32_t k = k0 + lane; k < k1; k += 32) {
-                const int32_t f = a.cellFaces[k];
-                const size_t b0 = size_t(a.faceTetPair0[f]) * 448, b1 = size_t(a.faceTetPair0[f + 1]) * 448;
-                for (size_t b = b0 & ~size_t(127); b < b1; b += 128) pfL2(tb + b);
-            }
-        }
-    }
-#endif
 
     const double deltaT = P.deltaT;
     const bool constrained = P.solutionD[0] == -1 || P.solutionD[1] == -1 || P.solutionD[2] == -1;

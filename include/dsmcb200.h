@@ -119,7 +119,9 @@ typedef struct {
 typedef enum {
     DSMCB200_COLL_NONE = 0,                /* NoBinaryCollision                  */
     DSMCB200_COLL_VHS = 1,                 /* VariableHardSphere                 */
-    DSMCB200_COLL_LB_VHS = 2               /* LarsenBorgnakkeVariableHardSphere  */
+    DSMCB200_COLL_LB_VHS = 2,              /* LarsenBorgnakkeVariableHardSphere  */
+    DSMCB200_COLL_VSS = 3,                 /* VariableSoftSphere (collisions/derived/VariableSoftSphere/VariableSoftSphere.C:78-262) */
+    DSMCB200_COLL_LB_VSS = 4               /* LarsenBorgnakkeVariableSoftSphere  */
 } dsmcb200_collision_model;
 
 typedef enum {

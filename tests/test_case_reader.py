@@ -31,14 +31,14 @@ def test_driver_parses_couette_case(tmp_path):
 def test_driver_rejects_unknown_models_like_the_reference(tmp_path):
     casegen.couette_case(str(tmp_path))
     path = os.path.join(str(tmp_path), "constant", "dsmcProperties")
-    text = open(path).read().replace("BinaryCollisionModel            LarsenBorgnakkeVariableHardSphere;", "BinaryCollisionModel            VariableSoftSphere;")
+    text = open(path).read().replace("BinaryCollisionModel            LarsenBorgnakkeVariableHardSphere;", "BinaryCollisionModel            VariableSofterSphere;")
     open(path, "w").write(text)
     r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 1
-    assert "FOAM FATAL ERROR" in r.stderr and "unknown BinaryCollisionModel type VariableSoftSphere" in r.stderr
+    assert "FOAM FATAL ERROR" in r.stderr and "unknown BinaryCollisionModel type VariableSofterSphere" in r.stderr
     assert "Valid BinaryCollisionModel types are" in r.stderr
     # a missing keyword fails with OpenFOAM's message shape
-    open(path, "w").write(text.replace("VariableSoftSphere", "VariableHardSphere").replace("nEquivalentParticles", "nEquivParticles"))
+    open(path, "w").write(text.replace("VariableSofterSphere", "VariableHardSphere").replace("nEquivalentParticles", "nEquivParticles"))
     r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 1 and "keyword nEquivalentParticles is undefined in dictionary" in r.stderr
 

@@ -111,6 +111,31 @@ def test_collide_larsen_borgnakke_air5_matches_oracle():
     eng.close()
 
 
+def test_collide_soft_sphere_models_match_oracle():
+    """VariableSoftSphere and LarsenBorgnakkeVariableSoftSphere (Bird eq. 2.22 scattering with the species' alpha)."""
+    sp = H.air5()
+    dens = [0.6e21, 0.2e21, 0.05e21, 0.1e21, 0.05e21]
+    for model in ("VariableSoftSphere", "LarsenBorgnakkeVariableSoftSphere"):
+        mesh, _, md = periodic_case((5, 5, 5), ppc=60, species=sp, model=model, dens=1e21, dt=2e-6)
+        eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+        lb = model.startswith("Larsen")
+        start = H.same_start(eng, ora, [0, 1, 2, 3, 4], dens, 5000.0, 5000.0 if lb else 0.0, 5000.0 if lb else 0.0)
+        for x in (eng, ora):
+            x.stage(capi.STAGE_COLLIDE)
+        g, o = eng.download_parcels(), ora.download_parcels()
+        assert eng.counters().collisions == ora.counters()["collisions"] > 0
+        assert np.allclose(g.U, o.U, rtol=0, atol=1e-8)
+        mass = np.array([s.mass for s in sp])
+        off = eng.occupancy()
+        p0 = np.add.reduceat(start.U * mass[start.typeId][:, None], off[:-1], axis=0)
+        p1 = np.add.reduceat(g.U * mass[g.typeId][:, None], off[:-1], axis=0)
+        assert np.abs(p1 - p0).max() / (mass.max() * 3000 * 60) < 1e-12
+        if lb:
+            assert np.array_equal(g.vibLevel, o.vibLevel)
+            assert np.allclose(g.ERot, o.ERot, rtol=1e-10, atol=1e-30)
+        eng.close()
+
+
 def test_collide_cells_above_and_below_the_lane_kernel_limit():
     """Mean occupancy 250: about half of the cells exceed the 255-parcel limit of collideLaneKernel and are handed to
     collideBigCellsKernel through the big-cell list; both must reproduce the serial oracle."""
