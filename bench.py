@@ -321,6 +321,10 @@ def main():
         if args.gas != "argon":
             row += host.ERot[:1].nbytes + host.vibLevel[:1].nbytes + host.ELevel[:1].nbytes
         h2d = row * host.n
+        ai = eng.accum_info()
+        acc_pin = torch.empty((ai.nCells, ai.nSpecies, ai.nQuantities), dtype=torch.float64).pin_memory()
+        coll_pin = torch.empty((ai.nCells, 2), dtype=torch.float64).pin_memory()
+        acc_np, coll_np = acc_pin.numpy(), coll_pin.numpy()
         acc_bytes = 0
         barrier()
         t1 = time.perf_counter()
@@ -329,7 +333,7 @@ def main():
             eng.upload_parcels(host)
             eng.evolve(1)
             host = eng.download_parcels(host) if False else _download_into(eng, host)
-            acc, coll, _ = eng.accumulators()
+            acc, coll, _ = eng.accumulators(acc_np, coll_np)
             acc_bytes = acc.nbytes + coll.nbytes
             n_e2e += host.n
         barrier()

@@ -461,10 +461,15 @@ class Engine:
         self._ck(self.lib.dsmcb200_accum_info_get(self.h, C.byref(i)))
         return i
 
-    def accumulators(self):
+    def accumulators(self, acc=None, coll=None):
+        """dsmcb200_download_accumulators; acc / coll may be caller-owned (e.g. pinned) float64 arrays of the right size."""
         i = self.accum_info()
-        acc = np.zeros((i.nCells, i.nSpecies, i.nQuantities))
-        coll = np.zeros((i.nCells, 2))
+        if acc is None:
+            acc = np.zeros((i.nCells, i.nSpecies, i.nQuantities))
+        if coll is None:
+            coll = np.zeros((i.nCells, 2))
+        assert acc.dtype == np.float64 and acc.size == i.nCells * i.nSpecies * i.nQuantities and acc.flags.c_contiguous
+        assert coll.dtype == np.float64 and coll.size == i.nCells * 2 and coll.flags.c_contiguous
         self._ck(self.lib.dsmcb200_download_accumulators(self.h, _ptr(acc), _ptr(coll)))
         return acc, coll, i.nTimeSteps
 
