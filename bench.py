@@ -151,6 +151,8 @@ def workload_config(args, cells_per_gpu, parcels_per_gpu):
         "cells_per_gpu": cells_per_gpu, "parcels_per_gpu": parcels_per_gpu, "parcels_per_cell": args.ppc, "gas": args.gas,
         "collision_model": "VariableHardSphere" if args.gas == "argon" else "LarsenBorgnakkeVariableHardSphere",
         "partition": "x".join(str(v) for v in procs_for(args.gpus)) + " bricks",
+        "cell_numbering": "blockMesh order (x fastest)" if getattr(args, "numbering", "blockMesh") == "blockMesh"
+                          else "cells relabelled along a z-order curve (renumberMesh equivalent)",
         "l2_policy": "inputs larger than L2 (parcel state >> 126 MB per GPU), no flush needed"}
 
 
@@ -206,6 +208,8 @@ def main():
     ap.add_argument("--gas", default=os.environ.get("DSMCB200_BENCH_GAS", "air5"), choices=["argon", "air5"])
     ap.add_argument("--cells", type=int, default=int(os.environ.get("DSMCB200_BENCH_CELLS", "200")), help="cells per direction per GPU")
     ap.add_argument("--ppc", type=int, default=31)
+    ap.add_argument("--numbering", default=os.environ.get("DSMCB200_BENCH_NUMBERING", "blockMesh"), choices=["blockMesh", "morton"],
+                    help="cell labels of the box: blockMesh's x-fastest order, or relabelled along a z-order curve (meshgen.renumber_cells, a renumberMesh equivalent)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-cells", type=int, default=32)
     ap.add_argument("--cpu-steps", type=int, default=5)
@@ -253,6 +257,8 @@ def main():
         sp, tids, frac = species_table(args.gas)
         procs = procs_for(world)
         mesh = meshgen.decomposed_box((args.cells,) * 3, (cp["L"],) * 3, procs, rank)
+        if args.numbering == "morton":
+            mesh, _ = meshgen.renumber_cells(mesh, meshgen.morton_order(mesh))
         model = "VariableHardSphere" if args.gas == "argon" else "LarsenBorgnakkeVariableHardSphere"
         md = capi.build_models(model, nEquivalentParticles=cp["fnum"], deltaT=cp["dt"], seed=0xD5C00005 + rank)
         dens, Tfill, vfill = [cp["n"] * f for f in frac], cp["T"], (0.0, 0.0, 0.0)

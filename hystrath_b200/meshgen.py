@@ -244,3 +244,68 @@ def cylinder_ogrid(nr, ntheta, r_in, r_out, thickness=None, grading=1.0):
     mesh.r = r
     mesh.thickness = t
     return mesh
+
+
+def _morton3(i, j, k, bits=10):
+    """Interleave the low `bits` bits of three non-negative integer arrays (z-order curve key)."""
+    key = np.zeros(len(i), dtype=np.int64)
+    i, j, k = i.astype(np.int64), j.astype(np.int64), k.astype(np.int64)
+    for b in range(bits):
+        key |= ((i >> b) & 1) << (3 * b)
+        key |= ((j >> b) & 1) << (3 * b + 1)
+        key |= ((k >> b) & 1) << (3 * b + 2)
+    return key
+
+
+def morton_order(mesh, bits=10):
+    """new_of_old cell labels following a z-order curve through the cell centres (approximated by the mean of the
+    cell's face-point coordinates), quantised to 2^bits per direction.  Works for any polyMesh."""
+    nF = mesh.n_faces
+    nPts = np.diff(mesh.face_offsets)
+    fc = np.add.reduceat(mesh.points[mesh.face_points], mesh.face_offsets[:-1], axis=0) / nPts[:, None]
+    cc = np.zeros((mesh.n_cells, 3))
+    cnt = np.zeros(mesh.n_cells)
+    np.add.at(cc, mesh.owner, fc)
+    np.add.at(cnt, mesh.owner, 1.0)
+    np.add.at(cc, mesh.neighbour, fc[: mesh.n_internal])
+    np.add.at(cnt, mesh.neighbour, 1.0)
+    cc /= cnt[:, None]
+    lo, hi = cc.min(0), cc.max(0)
+    span = np.where(hi > lo, hi - lo, 1.0)
+    # one common cell-size scale so that the curve's bricks are cubes, not slabs
+    scale = ((1 << bits) - 1) / span.max()
+    q = np.minimum(((cc - lo) * scale).astype(np.int64), (1 << bits) - 1)
+    key = _morton3(q[:, 0], q[:, 1], q[:, 2], bits)
+    order = np.argsort(key, kind="stable")          # order[new] = old
+    new_of_old = np.empty(mesh.n_cells, dtype=np.int32)
+    new_of_old[order] = np.arange(mesh.n_cells, dtype=np.int32)
+    return new_of_old
+
+
+def renumber_cells(mesh, new_of_old):
+    """The polyMesh with cell `c` relabelled `new_of_old[c]` -- what OpenFOAM's renumberMesh does to the mesh files: owner / neighbour
+    relabelled, an internal face whose owner would exceed its neighbour is flipped (same first vertex, opposite circulation), internal
+    faces re-sorted into upper-triangular order; boundary faces keep their order (patch starts and coupled-face matching unchanged).
+    Returns (mesh, new_of_old)."""
+    new_of_old = np.asarray(new_of_old, dtype=np.int32)
+    nI = mesh.n_internal
+    own = new_of_old[mesh.owner]
+    nei = new_of_old[mesh.neighbour]
+    if not np.all(np.diff(mesh.face_offsets) == np.diff(mesh.face_offsets)[0]):
+        raise NotImplementedError("renumber_cells: faces of mixed size")
+    npf = int(mesh.face_offsets[1] - mesh.face_offsets[0])
+    faces = mesh.face_points.reshape(-1, npf).copy()
+    flip = own[:nI] > nei
+    o_int = np.where(flip, nei, own[:nI])
+    n_int = np.where(flip, own[:nI], nei)
+    fi = faces[:nI]
+    fi[flip] = np.concatenate([fi[flip][:, :1], fi[flip][:, :0:-1]], axis=1)
+    perm = np.lexsort((n_int, o_int))
+    faces[:nI] = fi[perm]
+    owner = np.concatenate([o_int[perm], own[nI:]]).astype(np.int32)
+    out = MeshData(mesh.points, mesh.face_offsets, faces.ravel(), owner, n_int[perm].astype(np.int32), [dict(p) for p in mesh.patches])
+    for a in ("shape", "lengths", "origin", "r", "thickness"):
+        if hasattr(mesh, a):
+            setattr(out, a, getattr(mesh, a))
+    out.cell_numbering = "renumbered"
+    return out, new_of_old

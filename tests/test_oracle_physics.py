@@ -240,3 +240,31 @@ def test_cyclic_box_keeps_parcels_and_cells_consistent():
     ijk = np.floor(b["position"] / 0.004).astype(int)
     assert np.array_equal(ijk[:, 0] + 5 * (ijk[:, 1] + 4 * ijk[:, 2]), b["cell"])
     assert np.array_equal(a["U"], b["U"])
+
+
+def test_renumbered_mesh_tracks_like_the_original():
+    """meshgen.renumber_cells (a renumberMesh equivalent: cells relabelled along a z-order curve, internal faces flipped / re-sorted
+    into upper-triangular order) yields a valid polyMesh: ballistic flight with periodic wrap ends in the relabelled cell of the
+    direct point location."""
+    sp = [H.argon()]
+    base = meshgen.box_mesh((6, 5, 4), (0.024, 0.02, 0.016))
+    new_of_old = meshgen.morton_order(base)
+    mesh, _ = meshgen.renumber_cells(base, new_of_old)
+    assert sorted(new_of_old) == list(range(120)) and not np.array_equal(new_of_old, np.arange(120))
+    assert np.all(mesh.owner[: mesh.n_internal] < mesh.neighbour)
+    key = mesh.owner[: mesh.n_internal].astype(np.int64) * mesh.n_cells + mesh.neighbour
+    assert np.all(np.diff(key) > 0)                                     # upper-triangular face order
+    md = capi.build_models("NoBinaryCollision", nEquivalentParticles=1e20 * 0.024 * 0.02 * 0.016 / (120 * 50), deltaT=5e-6, seed=42)
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
+    o.mesh_fill([0], [1e20], 300.0, velocity=(300.0, -200.0, 100.0))
+    a = H.by_id(o.download_parcels())
+    ijk = np.floor(a["position"] / 0.004).astype(int)
+    assert np.array_equal(new_of_old[ijk[:, 0] + 6 * (ijk[:, 1] + 5 * ijk[:, 2])], a["cell"])
+    o.evolve(6)
+    b = H.by_id(o.download_parcels())
+    assert len(b["origId"]) == len(a["origId"])
+    free = a["position"] + 6 * md.deltaT * a["U"]
+    assert np.allclose(b["position"], np.mod(free, [0.024, 0.02, 0.016]), atol=1e-12)
+    ijk = np.floor(b["position"] / 0.004).astype(int)
+    assert np.array_equal(new_of_old[ijk[:, 0] + 6 * (ijk[:, 1] + 5 * ijk[:, 2])], b["cell"])
