@@ -309,3 +309,116 @@ def renumber_cells(mesh, new_of_old):
             setattr(out, a, getattr(mesh, a))
     out.cell_numbering = "renumbered"
     return out, new_of_old
+
+
+def poly_mesh_from_cells(points, cells, patch_of_face, patch_specs):
+    """A polyMesh from an explicit cell list -- the general (non-hex) path of the tracker's tests.
+
+    cells: list of cells, each a list of faces, each face a tuple of point labels with the normal pointing OUT of that cell.
+    A face shared by two cells becomes an internal face (stored as seen from the lower-labelled cell, starting at its lowest point
+    label); internal faces are put in upper-triangular order.  A face seen once is a boundary face of patch
+    patch_of_face(face_points) -> name; patch_specs: ordered list of (name, type).  Faces may mix sizes (triangles, quads, ...)."""
+    seen = {}
+    for c, faces in enumerate(cells):
+        for f in faces:
+            key = tuple(sorted(f))
+            seen.setdefault(key, []).append((c, tuple(f)))
+
+    def canon(f):
+        k = f.index(min(f))
+        return f[k:] + f[:k]
+
+    internal, boundary = [], {name: [] for name, _ in patch_specs}
+    for key, lst in seen.items():
+        if len(lst) == 2:
+            (c0, f0), (c1, f1) = sorted(lst)
+            internal.append((c0, c1, canon(f0)))
+        elif len(lst) == 1:
+            c0, f0 = lst[0]
+            boundary[patch_of_face(f0)].append((c0, canon(f0)))
+        else:
+            raise ValueError("face shared by more than two cells")
+    internal.sort(key=lambda t: (t[0], t[1]))
+    faces = [f for _, _, f in internal]
+    owner = [o for o, _, _ in internal]
+    neighbour = [n for _, n, _ in internal]
+    patches = []
+    for name, typ in patch_specs:
+        lst = sorted(boundary[name], key=lambda t: t[0])
+        patches.append({"name": name, "type": typ, "start": len(faces), "size": len(lst)})
+        faces += [f for _, f in lst]
+        owner += [o for o, _ in lst]
+    offsets = np.concatenate([[0], np.cumsum([len(f) for f in faces])]).astype(np.int32)
+    flat = np.array([p for f in faces for p in f], dtype=np.int32)
+    return MeshData(points, offsets, flat, np.array(owner, np.int32), np.array(neighbour, np.int32), patches)
+
+
+def split_box_mesh(n, lengths, kind="prism", wall_type="wall"):
+    """A box of n hexahedra cut into triangular prisms (2 per hex, cut along the x-y diagonal) or tetrahedra (6 per hex, Kuhn
+    subdivision, conforming), one `wall`-type patch `walls` all round: meshes with triangular faces and non-hex cells.
+    Returns (mesh, locate) where locate(xyz[n,3]) -> cell labels by direct point location."""
+    nx, ny, nz = (int(v) for v in n)
+    lx, ly, lz = (float(v) for v in lengths)
+    xs, ys, zs = lx * np.arange(nx + 1) / nx, ly * np.arange(ny + 1) / ny, lz * np.arange(nz + 1) / nz
+    Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+    points = np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1)
+
+    def pid(i, j, k):
+        return i + (nx + 1) * (j + (ny + 1) * k)
+
+    def outward(face, centre):
+        p = points[list(face)]
+        nrm = np.cross(p[1] - p[0], p[2] - p[0])
+        return tuple(face) if np.dot(nrm, p.mean(0) - centre) > 0 else tuple(reversed(face))
+
+    cells = []
+    for k in range(nz):
+        for j in range(ny):
+            for i in range(nx):
+                v = {(a, b, c): pid(i + a, j + b, k + c) for a in (0, 1) for b in (0, 1) for c in (0, 1)}
+                if kind == "prism":
+                    # lower-right (y - y0 <= x - x0) and upper-left prisms, triangles in the z planes
+                    tris = [((0, 0), (1, 0), (1, 1)), ((0, 0), (1, 1), (0, 1))]
+                    for t in tris:
+                        bot = tuple(v[(a, b, 0)] for a, b in t)
+                        top = tuple(v[(a, b, 1)] for a, b in t)
+                        fs = [bot, top] + [(bot[e], bot[(e + 1) % 3], top[(e + 1) % 3], top[e]) for e in range(3)]
+                        ctr = points[list(bot + top)].mean(0)
+                        cells.append([outward(f, ctr) for f in fs])
+                elif kind == "tet":
+                    # Kuhn: one tet per permutation of the axes, all sharing the diagonal (0,0,0)-(1,1,1)
+                    import itertools
+
+                    for perm in itertools.permutations(range(3)):
+                        cur = [0, 0, 0]
+                        verts = [tuple(cur)]
+                        for ax in perm:
+                            cur[ax] = 1
+                            verts.append(tuple(cur))
+                        t = [v[x] for x in verts]
+                        fs = [(t[1], t[2], t[3]), (t[0], t[2], t[3]), (t[0], t[1], t[3]), (t[0], t[1], t[2])]
+                        ctr = points[t].mean(0)
+                        cells.append([outward(f, ctr) for f in fs])
+                else:
+                    raise ValueError(kind)
+    mesh = poly_mesh_from_cells(points, cells, lambda f: "walls", [("walls", wall_type)])
+    mesh.shape = (nx, ny, nz)
+    mesh.lengths = (lx, ly, lz)
+
+    def locate(xyz):
+        q = np.asarray(xyz) / np.array([lx / nx, ly / ny, lz / nz])
+        ijk = np.minimum(np.floor(q).astype(int), [nx - 1, ny - 1, nz - 1])
+        r = q - ijk
+        hexid = ijk[:, 0] + nx * (ijk[:, 1] + ny * ijk[:, 2])
+        if kind == "prism":
+            return 2 * hexid + (r[:, 1] > r[:, 0]).astype(int)
+        import itertools
+
+        out = np.zeros(len(q), dtype=int)
+        for t, perm in enumerate(itertools.permutations(range(3))):
+            # the tet of `perm` holds the points with r[perm[0]] >= r[perm[1]] >= r[perm[2]]
+            m = (r[:, perm[0]] >= r[:, perm[1]]) & (r[:, perm[1]] >= r[:, perm[2]])
+            out[m] = t
+        return 6 * hexid + out
+
+    return mesh, locate
