@@ -422,3 +422,68 @@ def split_box_mesh(n, lengths, kind="prism", wall_type="wall"):
         return 6 * hexid + out
 
     return mesh, locate
+
+
+def refined_interface_mesh(nx_coarse=2, h=0.004, wall_type="wall"):
+    """nx_coarse unit hexahedra in a row followed by one hexahedron refined 2 x 2 in y, z (an OpenFOAM 2:1 refinement interface):
+    the coarse cell next to the interface has nine faces -- four small quads towards the fine cells, one quad, and four FIVE-point
+    faces whose extra point is the hanging node in the middle of a straight edge, i.e. polygons with a degenerate fan triangle, the
+    case polyMeshTetDecomposition's base-point search exists for.  One patch `walls`.  Returns (mesh, locate)."""
+    pts, index = [], {}
+
+    def P(x, y, z):
+        key = (round(2 * x), round(2 * y), round(2 * z))
+        if key not in index:
+            index[key] = len(pts)
+            pts.append((x * h, y * h, z * h))
+        return index[key]
+
+    cells = []
+    X = nx_coarse
+    for i in range(X):
+        x0, x1 = float(i), float(i + 1)
+        last = i == X - 1
+        if not last:
+            fs = [
+                (P(x0, 0, 0), P(x0, 0, 1), P(x0, 1, 1), P(x0, 1, 0)),      # x-
+                (P(x1, 0, 0), P(x1, 1, 0), P(x1, 1, 1), P(x1, 0, 1)),      # x+
+                (P(x0, 0, 0), P(x1, 0, 0), P(x1, 0, 1), P(x0, 0, 1)),      # y-
+                (P(x0, 1, 0), P(x0, 1, 1), P(x1, 1, 1), P(x1, 1, 0)),      # y+
+                (P(x0, 0, 0), P(x0, 1, 0), P(x1, 1, 0), P(x1, 0, 0)),      # z-
+                (P(x0, 0, 1), P(x1, 0, 1), P(x1, 1, 1), P(x0, 1, 1)),      # z+
+            ]
+        else:
+            fs = [(P(x0, 0, 0), P(x0, 0, 1), P(x0, 1, 1), P(x0, 1, 0))]
+            for j in (0, 0.5):
+                for k in (0, 0.5):
+                    fs.append((P(x1, j, k), P(x1, j + .5, k), P(x1, j + .5, k + .5), P(x1, j, k + .5)))   # four small x+ faces
+            fs += [
+                (P(x0, 0, 0), P(x1, 0, 0), P(x1, 0, .5), P(x1, 0, 1), P(x0, 0, 1)),     # y-  (hanging node on the x1 edge)
+                (P(x0, 1, 0), P(x0, 1, 1), P(x1, 1, 1), P(x1, 1, .5), P(x1, 1, 0)),     # y+
+                (P(x0, 0, 0), P(x0, 1, 0), P(x1, 1, 0), P(x1, .5, 0), P(x1, 0, 0)),     # z-
+                (P(x0, 0, 1), P(x1, 0, 1), P(x1, .5, 1), P(x1, 1, 1), P(x0, 1, 1)),     # z+
+            ]
+        cells.append(fs)
+    x0, x1 = float(X), float(X + 1)
+    for j in (0, 0.5):
+        for k in (0, 0.5):
+            j1, k1 = j + .5, k + .5
+            cells.append([
+                (P(x0, j, k), P(x0, j, k1), P(x0, j1, k1), P(x0, j1, k)),
+                (P(x1, j, k), P(x1, j1, k), P(x1, j1, k1), P(x1, j, k1)),
+                (P(x0, j, k), P(x1, j, k), P(x1, j, k1), P(x0, j, k1)),
+                (P(x0, j1, k), P(x0, j1, k1), P(x1, j1, k1), P(x1, j1, k)),
+                (P(x0, j, k), P(x0, j1, k), P(x1, j1, k), P(x1, j, k)),
+                (P(x0, j, k1), P(x1, j, k1), P(x1, j1, k1), P(x0, j1, k1)),
+            ])
+    points = np.array(pts, dtype=np.float64)
+    mesh = poly_mesh_from_cells(points, cells, lambda f: "walls", [("walls", wall_type)])
+
+    def locate(xyz):
+        q = np.asarray(xyz) / h
+        i = np.minimum(np.floor(q[:, 0]).astype(int), X)
+        fine = i >= X
+        sub = 2 * (q[:, 1] >= 0.5).astype(int) + (q[:, 2] >= 0.5).astype(int)
+        return np.where(fine, X + sub, i)
+
+    return mesh, locate

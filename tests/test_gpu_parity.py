@@ -91,6 +91,25 @@ def test_move_on_non_hex_cells_bit_exact(kind):
     eng.close()
 
 
+def test_move_across_refinement_interface_bit_exact():
+    """Pentagonal faces with a hanging node (2:1 refinement interface): base points, tet links and tracking against the oracle."""
+    mesh, locate = meshgen.refined_interface_mesh()
+    sp = [H.argon()]
+    md = capi.build_models("NoBinaryCollision", nEquivalentParticles=1e20 * 3 * 0.004 ** 3 / (6 * 400), deltaT=2e-6, seed=3,
+                           patch_models=[dict(patch=0, boundaryModel="dsmcSpecularWallPatch")])
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    H.same_start(eng, ora, [0], [1e20], 300.0)
+    for x in (eng, ora):
+        x.evolve(6)
+    g, o = H.by_id(eng.download_parcels()), H.by_id(ora.download_parcels())
+    assert len(g["cell"]) == len(o["cell"])
+    assert np.array_equal(g["cell"], o["cell"])
+    assert np.array_equal(g["tetFace"], o["tetFace"]) and np.array_equal(g["tetPt"], o["tetPt"])
+    assert np.array_equal(g["position"], o["position"]) and np.array_equal(g["U"], o["U"])   # specular walls: no libm in the loop
+    assert np.array_equal(locate(g["position"]), g["cell"])
+    eng.close()
+
+
 def test_sort_is_stable_and_matches_oracle_order():
     mesh, sp, md = periodic_case((6, 5, 4))
     eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)

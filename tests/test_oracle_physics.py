@@ -290,3 +290,26 @@ def test_tracking_on_non_hex_cells(kind):
     assert np.array_equal(locate(b["position"]), b["cell"])
     assert np.allclose((a["U"] ** 2).sum(1), (b["U"] ** 2).sum(1), rtol=1e-12)
     assert (a["cell"] != b["cell"]).mean() > 0.5
+
+
+def test_tracking_across_a_refinement_interface_with_five_point_faces():
+    """A 2:1 refinement interface: the coarse cell has nine faces, four of them pentagons with a hanging node on a straight edge (one
+    fan triangle of the face is degenerate for most base points: polyMeshTetDecomposition::findBasePoint).  Cell volumes are exact,
+    every parcel stays locatable through 12 steps in a specular box."""
+    mesh, locate = meshgen.refined_interface_mesh()
+    assert sorted(set(np.diff(mesh.face_offsets))) == [4, 5] and mesh.n_cells == 6
+    sp = [H.argon()]
+    md = capi.build_models("NoBinaryCollision", nEquivalentParticles=1e20 * 3 * 0.004 ** 3 / (6 * 400), deltaT=2e-6, seed=3,
+                           patch_models=[dict(patch=0, boundaryModel="dsmcSpecularWallPatch")])
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
+    _, cv, *_ = o.geometry()
+    assert np.allclose(np.asarray(cv) / 0.004 ** 3, [1, 1, 0.25, 0.25, 0.25, 0.25], rtol=1e-12)
+    o.mesh_fill([0], [1e20], 300.0)
+    a = H.by_id(o.download_parcels())
+    assert np.array_equal(locate(a["position"]), a["cell"])
+    o.evolve(12)
+    b = H.by_id(o.download_parcels())
+    assert len(b["cell"]) == len(a["cell"]) > 2000
+    assert np.array_equal(locate(b["position"]), b["cell"])
+    assert (a["cell"] != b["cell"]).mean() > 0.5 and o.counters()["trackingRescues"] == 0
