@@ -62,11 +62,12 @@ __global__ void interleave3(const double* x, const double* y, const double* z, d
     if (i < n) { out[3 * i] = x[i]; out[3 * i + 1] = y[i]; out[3 * i + 2] = z[i]; }
 }
 __global__ void toTetId(const int32_t* cell, const int32_t* tetFace, const int32_t* tetPt, const int32_t* faceTetPair0,
-                        const int32_t* owner, int32_t* tet, int32_t n, int32_t nFaces, int* bad) {
+                        const int32_t* owner, int32_t* tet, int32_t n, int32_t nFaces, int32_t nCells, int* bad) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int32_t f = tetFace[i];
-    if (f < 0 || f >= nFaces || cell[i] < 0) { *bad = 1; tet[i] = 0; return; }
+    if (cell[i] < 0) { tet[i] = 0; return; }   // a lost parcel (deleted by the sort), see upload_parcels
+    if (f < 0 || f >= nFaces || cell[i] >= nCells) { *bad = 1; tet[i] = 0; return; }
     const int32_t nT = faceTetPair0[f + 1] - faceTetPair0[f];
     const int32_t tp = tetPt[i];
     if (tp < 1 || tp > nT) { *bad = 1; tet[i] = 0; return; }
@@ -87,6 +88,14 @@ __global__ void fromTetId(const int32_t* tet, const int32_t* faceTetPair0, int32
 __global__ void i32ToU8(const int32_t* in, uint8_t* out, int32_t n) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = uint8_t(in[i]);
+}
+// the same with a range check: values outside [0, limit) raise *bad (typeId against typeIdList, dsmcParcelI.H constProps lookup)
+__global__ void i32ToU8Checked(const int32_t* in, uint8_t* out, int32_t n, int32_t limit, int* bad) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t v = in[i];
+    if (v < 0 || v >= limit) { *bad = 2; out[i] = 0; return; }
+    out[i] = uint8_t(v);
 }
 __global__ void u8ToI32(const uint8_t* in, int32_t* out, int32_t n) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -870,9 +879,9 @@ int dsmcb200_upload_parcels(dsmcb200_ctx* c, int64_t n, const dsmcb200_parcels_s
     CK(cudaMemcpyAsync(sf, tetFace, size_t(n) * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(sp2, tetPt, size_t(n) * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(c->dBad, 0, 4, s));
-    toTetId<<<GRID(n), 0, s>>>(a.cell, sf, sp2, c->dFaceTetPair0, c->dOwner, a.tet, n32, c->mesh.nFaces, c->dBad);
+    toTetId<<<GRID(n), 0, s>>>(a.cell, sf, sp2, c->dFaceTetPair0, c->dOwner, a.tet, n32, c->mesh.nFaces, c->mesh.nCells, c->dBad);
     CK(cudaMemcpyAsync(sf, h->typeId, size_t(n) * 4, cudaMemcpyHostToDevice, s));
-    i32ToU8<<<GRID(n), 0, s>>>(sf, a.typeId, n32);
+    i32ToU8Checked<<<GRID(n), 0, s>>>(sf, a.typeId, n32, c->hP.nSpecies, c->dBad);
     if (h->origId) CK(cudaMemcpyAsync(a.origId, h->origId, size_t(n) * 4, cudaMemcpyHostToDevice, s));
     else iotaKernel<<<GRID(n), 0, s>>>(a.origId, n32, 0);
     if (c->internal) {
@@ -899,6 +908,7 @@ int dsmcb200_upload_parcels(dsmcb200_ctx* c, int64_t n, const dsmcb200_parcels_s
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, c->dBad, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (bad == 2) return fail(c, DSMCB200_ERR_INVALID, "upload_parcels: typeId not defined in typeIdList");
     if (bad) return fail(c, DSMCB200_ERR_INVALID, "upload_parcels: cell / tetFace / tetPt out of range");
     c->N = n;
     int32_t maxId = -1;

@@ -1,0 +1,88 @@
+"""GPU: degenerate inputs through the C ABI -- empty cloud, a single parcel, a cloud that is deleted completely, invalid uploads.
+The reference loops over an empty IDLList / empty cellOccupancy lists without special cases (Cloud.C:204-312, noTimeCounter.C:96-155:
+nC <= 1 cells select nothing); the engine must do the same and keep its counters and accumulators consistent."""
+import numpy as np
+import pytest
+
+from hystrath_b200 import capi, meshgen
+from oracle.pyoracle import Oracle
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _box(model="VariableHardSphere", sides=None, patch_models=None):
+    mesh = meshgen.box_mesh((4, 4, 4), (0.016,) * 3, sides=sides)
+    md = capi.build_models(model, nEquivalentParticles=1e20 * 0.016 ** 3 / (64 * 30), deltaT=5e-6, seed=9, patch_models=patch_models or [])
+    return mesh, [H.argon()], md
+
+
+def test_empty_cloud_evolves():
+    mesh, sp, md = _box()
+    eng = capi.Engine(0)
+    eng.set_mesh(mesh); eng.set_species(sp); eng.set_models(md)
+    eng.upload_parcels(capi.ParcelData(0, 1))
+    eng.evolve(3)
+    assert eng.num_parcels() == 0
+    assert np.array_equal(eng.occupancy(), np.zeros(65, dtype=np.int32))
+    acc, coll, nt = eng.accumulators()
+    assert nt == 3 and not acc.any() and not coll.any()
+    c = eng.counters()
+    assert c.collisions == 0 and c.collisionCandidates == 0
+    eng.close()
+
+
+def test_single_parcel_flies_and_never_collides():
+    mesh, sp, md = _box()
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    p = capi.ParcelData(1, 1)
+    p.position[:] = [[0.0021, 0.0093, 0.0157]]
+    p.U[:] = [[412.0, -233.0, 157.0]]
+    p.cell[:] = 0 + 4 * (2 + 4 * 3)
+    p.tetFace = p.tetPt = None  # tet not known: located on upload like Cloud<T>::initCloud does after reading `positions`
+    p.origId[:] = 7
+    for x in (eng, ora):
+        x.upload_parcels(p)
+        x.evolve(40)
+    g, o = eng.download_parcels(), ora.download_parcels()
+    assert g.n == o.n == 1
+    assert np.array_equal(g.position, o.position) and np.array_equal(g.cell, o.cell) and np.array_equal(g.U, p.U)
+    free = np.mod(p.position + 40 * 5e-6 * p.U, 0.016)
+    assert np.allclose(g.position, free, atol=1e-12)
+    assert eng.counters().collisions == 0
+    occ = eng.occupancy()
+    assert occ[-1] == 1 and (np.diff(occ) == 1).sum() == 1
+    eng.close()
+
+
+def test_cloud_deleted_completely():
+    sides = {s: ("patch", "outlet") for s in meshgen.SIDES}
+    mesh, sp, md = _box(sides=sides, patch_models=[dict(patch=0, boundaryModel="dsmcDeletionPatch")])
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    H.same_start(eng, ora, [0], [1e20], 300.0, velocity=(3000.0, 0.0, 0.0))
+    n0 = eng.num_parcels()
+    assert n0 > 1000
+    for x in (eng, ora):
+        x.evolve(4)             # 3000 m/s * 20 us = 0.06 m >> 0.016 m: everything has left through the deletion patch
+    assert eng.num_parcels() == ora.num_parcels() == 0
+    eng.evolve(2)               # and an empty cloud keeps stepping
+    assert eng.num_parcels() == 0 and eng.occupancy()[-1] == 0
+    eng.close()
+
+
+def test_invalid_uploads_fail_loudly():
+    mesh, sp, md = _box()
+    eng = capi.Engine(0)
+    eng.set_mesh(mesh); eng.set_species(sp); eng.set_models(md)
+    p = capi.ParcelData(4, 1)
+    p.position[:] = 0.001
+    p.cell[:] = [0, 1, 64, 2]     # cell 64 does not exist
+    p.tetFace[:] = 0
+    p.tetPt[:] = 1
+    with pytest.raises(capi.Dsmcb200Error):
+        eng.upload_parcels(p)
+    p.cell[:] = [0, 0, 0, 0]
+    p.typeId[:] = [0, 0, 3, 0]    # typeId 3 is not in typeIdList
+    with pytest.raises(capi.Dsmcb200Error):
+        eng.upload_parcels(p)
+    eng.close()
