@@ -2,6 +2,7 @@
 #include "dsmc_cloud.h"
 
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -88,15 +89,16 @@ void dsmcCloud::check(int rc, const char* what) {
     if (rc != 0) throw FoamError(std::string(what) + ": " + (ctx_ ? dsmcb200_last_error(ctx_) : "no context") + " (" + std::to_string(rc) + ")");
 }
 
-dsmcCloud::dsmcCloud(const std::string& caseDir, const std::string& cloudName, int rank, int nRanks, int device, const void* ncclId128, bool dryRun)
-    : caseDir_(caseDir), cloudName_(cloudName), rank_(rank), nRanks_(nRanks), dryRun_(dryRun) {
+dsmcCloud::dsmcCloud(const std::string& caseDir, const std::string& cloudName, int rank, int nRanks, int device, const void* ncclId128, bool dryRun,
+                     bool initialise)
+    : caseDir_(caseDir), cloudName_(cloudName), rank_(rank), nRanks_(nRanks), dryRun_(dryRun), initialise_(initialise) {
     root_ = nRanks > 1 ? caseDir + "/processor" + std::to_string(rank) : caseDir;
     readControl();
     readMesh();
     readProperties();
     readBoundaries();
     readFieldProperties();
-    if (dryRun_) { readCloud(); return; }
+    if (dryRun_) { if (initialise_) initialiseFromDict(); else readCloud(); return; }
     int rc = dsmcb200_create(&ctx_, device, rank, nRanks);
     if (rc != 0) throw FoamError("dsmcb200_create failed: a CUDA device is required, there is no CPU fallback");
     if (nRanks > 1) {
@@ -115,6 +117,7 @@ dsmcCloud::dsmcCloud(const std::string& caseDir, const std::string& cloudName, i
     check(dsmcb200_set_models(ctx_, &models_), "dsmcb200_set_models");
     cellVolumes_.resize(nCells_); cellCentres_.resize(size_t(nCells_) * 3); faceAreas_.resize(size_t(nFaces_) * 3); faceCentres_.resize(size_t(nFaces_) * 3);
     check(dsmcb200_download_geometry(ctx_, cellCentres_.data(), cellVolumes_.data(), faceCentres_.data(), faceAreas_.data(), nullptr), "dsmcb200_download_geometry");
+    if (initialise_) { initialiseFromDict(); return; }
     readCloud();
     // counter-based RNG streams are keyed by the global time index, so a restarted run does not replay the streams of the first one
     startIndex_ = deltaT_ > 0 ? int64_t(std::llround(startTime_ / deltaT_)) : 0;
@@ -140,6 +143,22 @@ void dsmcCloud::readControl() {
         char* e = nullptr;
         double v = std::strtod(n.c_str(), &e);
         if (e && *e == '\0' && !n.empty() && foam::exists(root_ + "/" + n + "/lagrangian")) times.push_back({v, n});
+    }
+    // writePrecision (default 6 in OpenFOAM); dsmcInitialise+ forces 15 (dsmcInitialise+.C:73)
+    foam::setWritePrecision(initialise_ ? 15 : int(c.labelOr("writePrecision", 6)));
+    if (initialise_) {
+        // createTime.H: the start time of controlDict; a fresh case has no time directory with a cloud yet
+        startTime_ = startFrom == "startTime" ? c.scalarOr("startTime", 0.0) : 0.0;
+        if (startFrom != "startTime") {
+            for (auto& n : foam::listDir(root_)) {
+                char* e = nullptr;
+                const double v = std::strtod(n.c_str(), &e);
+                if (e && *e == '\0' && !n.empty() && std::isdigit(static_cast<unsigned char>(n[0])) && (startFrom == "latestTime" ? v > startTime_ : false)) startTime_ = v;
+            }
+        }
+        timeName_ = foam::timeName(startTime_, timePrecision_);
+        time_ = startTime_;
+        return;
     }
     if (times.empty()) throw FoamError("no time directory with a lagrangian cloud under " + root_);
     std::sort(times.begin(), times.end());
@@ -363,6 +382,55 @@ void dsmcCloud::readFieldProperties() {
         if (s.measureClassifications) models_.measureClassifications = 1;
         fields_.push_back(s);
     }
+}
+
+// dsmcInitialise+ (applications/utilities/preProcessing/dsmc/dsmcInitialise+/dsmcInitialise+.C:37-90): the cloud constructor that
+// clears the field of parcels and runs every `configuration` of system/dsmcInitialiseDict (dsmcCloud.C:697-809,
+// dsmcAllConfigurations.C:45-77).  dsmcMeshFill (initialiseDsmcParcels/derived/dsmcMeshFill/dsmcMeshFill.C:70-240) is executed by
+// dsmcb200_mesh_fill on the device.
+void dsmcCloud::initialiseFromDict() {
+    const std::string path = caseDir_ + "/system/dsmcInitialiseDict";
+    Dict d = foam::readDict(path);
+    auto confs = d.dictList("configurations");
+    const bool master = rank_ == 0;
+    if (master) std::printf("clearing existing field of parcels \n\nCreating dsmc configurations: \n\n");
+    if (confs.size() > 1)
+        throw FoamError("dsmcInitialiseDict: " + std::to_string(confs.size()) + " configurations; this engine fills the mesh from one configuration\nin: " + path);
+    int64_t added = 0;
+    for (auto& e : confs) {
+        const Dict& cf = *e.second;
+        const std::string type = cf.word("type");
+        if (type != "dsmcMeshFill")
+            throw FoamError("dsmcConfiguration::New(const dictionary&) : \n    unknown dsmcConfiguration type " + type +
+                            ", constructor not in hash table\n\n    Valid  types are :\n(dsmcMeshFill)");
+        if (master) std::printf("\nInitialising particles\n");
+        const double Ttra = cf.scalar("translationalTemperature"), Trot = cf.scalar("rotationalTemperature");
+        const double Tvib = cf.scalar("vibrationalTemperature"), Telec = cf.scalar("electronicTemperature");
+        const std::vector<double> vel = cf.vector3("velocity");
+        const Dict& nd = cf.subDict("numberDensities");
+        std::vector<int32_t> ids;
+        std::vector<double> dens;
+        for (auto& mol : nd.toc()) {
+            int t = -1;
+            for (size_t k = 0; k < typeIdList_.size(); ++k) if (typeIdList_[k] == mol) t = int(k);
+            if (t < 0) throw FoamError("Cannot find typeId: " + mol + "\nin: " + path);   // dsmcMeshFill.C:131-137 shape
+            ids.push_back(t);
+            dens.push_back(nd.scalar(mol));
+        }
+        if (ids.empty()) throw FoamError("numberDensities is empty in " + path);
+        if (dryRun_) {
+            std::printf("configuration dsmcMeshFill: Ttra %g Trot %g Tvib %g Telec %g velocity (%g %g %g)\n", Ttra, Trot, Tvib, Telec, vel[0], vel[1], vel[2]);
+            for (size_t k = 0; k < ids.size(); ++k) std::printf("  numberDensity %s %g\n", typeIdList_[ids[k]].c_str(), dens[k]);
+            continue;
+        }
+        check(dsmcb200_mesh_fill(ctx_, int(ids.size()), ids.data(), dens.data(), Ttra, Trot, Tvib, Telec, vel.data()), "dsmcb200_mesh_fill");
+        added = nParcels();
+    }
+    if (dryRun_) return;
+    double tot[1] = {double(added)};
+    if (nRanks_ > 1) check(dsmcb200_allreduce_sum(ctx_, tot, 1), "dsmcb200_allreduce_sum");
+    if (master)
+        std::printf("\nInitial no. of parcels: 0 added parcels: %lld, total no. of parcels: %lld\n", (long long)tot[0], (long long)tot[0]);
 }
 
 void dsmcCloud::readCloud() {
@@ -1007,6 +1075,7 @@ void dsmcCloud::write() {
         pv.push_back(p);
     }
     foam::writeVolField(timeDir + "/dsmcSigmaTcRMax", timeName_, "dsmcSigmaTcRMax", "[0 3 -1 0 0 0 0]", sig.data(), nCells_, 1, pv);
+    if (initialise_) return;  // dsmcInitialise+ writes the cloud and dsmcSigmaTcRMax only
     writeFields(timeDir);
     // resetAtOutput (dsmcField.C:113-152): the accumulators are shared by all instances, so they reset together
     bool reset = !fields_.empty();

@@ -49,7 +49,7 @@ struct DerivedFields {  // per-cell results of dsmcVolFields::calculateField for
 class dsmcCloud {
    public:
     dsmcCloud(const std::string& caseDir, const std::string& cloudName = "dsmc", int rank = 0, int nRanks = 1, int device = 0,
-              const void* ncclId128 = nullptr, bool dryRun = false);
+              const void* ncclId128 = nullptr, bool dryRun = false, bool initialise = false);
     ~dsmcCloud();
     dsmcCloud(const dsmcCloud&) = delete;
 
@@ -105,6 +105,8 @@ class dsmcCloud {
     int maxModes_ = 1;
     int64_t lastCollisions_ = 0;
     bool dryRun_ = false;
+    bool initialise_ = false;   // dsmcInitialise+: no cloud is read, system/dsmcInitialiseDict fills the mesh
+    void initialiseFromDict();  // dsmcAllConfigurations::setInitialConfig (dsmcCloud.C:795-796)
     int64_t nRead_ = 0;
 
    public:

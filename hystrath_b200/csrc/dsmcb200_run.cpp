@@ -3,6 +3,8 @@
 // with dsmcCloud::evolve() executed by libdsmcb200 on the GPU.
 //
 //   dsmcb200_run -case <caseDir> [-parallel] [-device N]
+//   dsmcb200_run -initialise -case <caseDir> [-parallel]     the dsmcInitialise+ step: fill the mesh from system/dsmcInitialiseDict
+//                                                            and write the start-time cloud (15 significant digits)
 //
 // -parallel: one process per GPU, rank/size from RANK / WORLD_SIZE / LOCAL_RANK (torchrun-style launchers) or
 // OMPI_COMM_WORLD_*; rank k runs processor<k>/ as written by decomposePar.  The ncclUniqueId is handed from
@@ -26,15 +28,16 @@ static int envInt(const char* a, const char* b, int dflt) {
 
 int main(int argc, char** argv) {
     std::string caseDir = ".";
-    bool parallel = false, dryRun = false;
+    bool parallel = false, dryRun = false, initialise = false;
     int device = -1;
     for (int i = 1; i < argc; ++i) {
         if (!std::strcmp(argv[i], "-case") && i + 1 < argc) caseDir = argv[++i];
         else if (!std::strcmp(argv[i], "-parallel")) parallel = true;
         else if (!std::strcmp(argv[i], "-device") && i + 1 < argc) device = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "-dryRun")) dryRun = true;
+        else if (!std::strcmp(argv[i], "-initialise")) initialise = true;
         else if (!std::strcmp(argv[i], "-AMR")) { std::fprintf(stderr, "-AMR (dynamic mesh refinement) is outside the scoped path\n"); return 2; }
-        else { std::fprintf(stderr, "usage: dsmcb200_run -case <dir> [-parallel] [-device N]\n"); return 2; }
+        else { std::fprintf(stderr, "usage: dsmcb200_run [-initialise] -case <dir> [-parallel] [-device N]\n"); return 2; }
     }
     int rank = 0, nRanks = 1;
     if (parallel) {
@@ -43,8 +46,8 @@ int main(int argc, char** argv) {
     }
     if (device < 0) device = parallel ? envInt("LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", rank) : 0;
     try {
-        if (dryRun) {  // parse the whole case (dictionaries, mesh, cloud) and report; needs no GPU
-            dsmcb200::dsmcCloud probe(caseDir, "dsmc", rank, nRanks, 0, nullptr, true);
+        if (dryRun) {  // parse the whole case (dictionaries, mesh, cloud or dsmcInitialiseDict) and report; needs no GPU
+            dsmcb200::dsmcCloud probe(caseDir, "dsmc", rank, nRanks, 0, nullptr, true, initialise);
             std::printf("%s", probe.summary().c_str());
             return 0;
         }
@@ -68,6 +71,15 @@ int main(int argc, char** argv) {
             idPtr = id;
         }
         const bool master = rank == 0;
+        if (initialise) {
+            // dsmcInitialise+.C:57-88
+            dsmcb200::dsmcCloud dsmc(caseDir, "dsmc", rank, nRanks, device, idPtr, false, true);
+            if (nRanks > 1 && master) std::remove((caseDir + "/.dsmcb200_nccl_id").c_str());
+            if (master) std::printf("Initialising dsmc for Time = %s\n\n", dsmc.timeName().c_str());
+            dsmc.write();
+            if (master) std::printf("\nEnd\n\n");
+            return 0;
+        }
         if (master) std::printf("\nConstructing dsmcCloud \n");
         dsmcb200::dsmcCloud dsmc(caseDir, "dsmc", rank, nRanks, device, idPtr);
         if (nRanks > 1 && master) std::remove((caseDir + "/.dsmcb200_nccl_id").c_str());

@@ -126,6 +126,7 @@ Dict parseBody(Tokens& k, const std::string& name) {
     d.name = name;
     while (!k.end() && k.peek() != "}") {
         std::string key = k.next();
+        if (key == ";") continue;  // a stray ';' after a sub-dictionary's '}' (common in the shipped dsmcInitialiseDict files)
         if (k.end()) break;
         if (k.peek() == "{") {
             k.next();
@@ -499,7 +500,12 @@ std::string header(const std::string& cls, const std::string& location, const st
 }
 
 namespace {
-void fmt(FILE* f, double v) { std::fprintf(f, "%.10g", v); }
+int gWritePrecision = 10;
+}
+void setWritePrecision(int p) { gWritePrecision = p < 1 ? 1 : (p > 17 ? 17 : p); }
+int writePrecision() { return gWritePrecision; }
+namespace {
+void fmt(FILE* f, double v) { std::fprintf(f, "%.*g", gWritePrecision, v); }
 FILE* openw(const std::string& path) {
     FILE* f = std::fopen(path.c_str(), "w");
     if (!f) throw FoamError("cannot write " + path);
@@ -556,7 +562,7 @@ void writeVectorField(const std::string& path, const std::string& cls, const std
     FILE* f = openw(path);
     std::fputs(header(cls, location, object).c_str(), f);
     std::fprintf(f, "%lld\n(\n", (long long)n);
-    for (int64_t i = 0; i < n; ++i) std::fprintf(f, "(%.10g %.10g %.10g)\n", a[3 * i], a[3 * i + 1], a[3 * i + 2]);
+    for (int64_t i = 0; i < n; ++i) std::fprintf(f, "(%.*g %.*g %.*g)\n", gWritePrecision, a[3 * i], gWritePrecision, a[3 * i + 1], gWritePrecision, a[3 * i + 2]);
     std::fputs(")\n", f);
     std::fclose(f);
 }
@@ -564,7 +570,7 @@ void writePositions(const std::string& path, const std::string& location, const 
     FILE* f = openw(path);
     std::fputs(header("Cloud<dsmcParcel>", location, "positions").c_str(), f);
     std::fprintf(f, "%lld\n(\n", (long long)n);
-    for (int64_t i = 0; i < n; ++i) std::fprintf(f, "(%.10g %.10g %.10g) %d\n", xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], cell[i]);
+    for (int64_t i = 0; i < n; ++i) std::fprintf(f, "(%.*g %.*g %.*g) %d\n", gWritePrecision, xyz[3 * i], gWritePrecision, xyz[3 * i + 1], gWritePrecision, xyz[3 * i + 2], cell[i]);
     std::fputs(")\n", f);
     std::fclose(f);
 }

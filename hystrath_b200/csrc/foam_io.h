@@ -97,6 +97,9 @@ struct PatchValues {
 void writeVolField(const std::string& path, const std::string& location, const std::string& object, const std::string& dimensions,
                    const double* internal, int64_t nCells, int nCmpt, const std::vector<PatchValues>& patches);
 void makeDirs(const std::string& path);
+// controlDict writePrecision (IOstream::defaultPrecision): significant digits of every ASCII writer above
+void setWritePrecision(int p);
+int writePrecision();
 std::string timeName(double t, int precision);
 
 }  // namespace foam

@@ -60,3 +60,45 @@ def test_python_reader_round_trip(tmp_path):
     bd = ff.read_dict(os.path.join(str(tmp_path), "system", "boundariesDict"))
     assert len(bd["dsmcPatchBoundaries"]) == 2 and bd["dsmcPatchBoundaries"][0][1]["boundaryModel"] == "dsmcDiffuseWallPatch"
     assert bd["dsmcGeneralBoundaries"] == []
+
+
+def test_driver_parses_dsmc_initialise_dict(tmp_path):
+    """`-initialise -dryRun`: system/dsmcInitialiseDict in the shipped layout (a stray ';' after the numberDensities block, as in
+    run/hyStrath/dsmcFoam+/hypersonicCorner/system/dsmcInitialiseDict) and the dsmcConfiguration::New failure for other types."""
+    from hystrath_b200 import case as casew
+
+    casegen.couette_case(str(tmp_path))
+    init = """
+configurations
+(
+    configuration
+    {
+        type			dsmcMeshFill;
+
+		    numberDensities
+		    {
+			      N2         1.0e20;
+			      O2         2.5e19;
+		    };
+
+		    translationalTemperature     	300;
+		    rotationalTemperature			      290;
+		    vibrationalTemperature			    280;
+        electronicTemperature           0;
+
+		    velocity        (1936 0 0);
+	  }
+);
+"""
+    path = os.path.join(str(tmp_path), "system", "dsmcInitialiseDict")
+    casew.write_dict(path, "system", "dsmcInitialiseDict", init)
+    r = subprocess.run([RUN, "-initialise", "-dryRun", "-case", str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "configuration dsmcMeshFill: Ttra 300 Trot 290 Tvib 280 Telec 0 velocity (1936 0 0)" in r.stdout
+    assert "numberDensity N2 1e+20" in r.stdout and "numberDensity O2 2.5e+19" in r.stdout
+    casew.write_dict(path, "system", "dsmcInitialiseDict", init.replace("dsmcMeshFill", "dsmcZoneFill"))
+    r = subprocess.run([RUN, "-initialise", "-dryRun", "-case", str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "unknown dsmcConfiguration type dsmcZoneFill" in r.stderr and "(dsmcMeshFill)" in r.stderr
+    casew.write_dict(path, "system", "dsmcInitialiseDict", init.replace("O2 ", "Xe "))
+    r = subprocess.run([RUN, "-initialise", "-dryRun", "-case", str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "Cannot find typeId: Xe" in r.stderr

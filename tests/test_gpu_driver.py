@@ -112,3 +112,65 @@ def test_driver_resume_sampling_round_trip(tmp_path):
     # 47 583 parcels in a closed box: the six-step mean number per cell still sums to the parcel count
     assert abs(n1.sum() - 47583) < 1e-3 and abs(n2.sum() - 47583) < 1e-3   # files carry 10 significant digits
     assert not np.allclose(n1, n2)
+
+
+def test_driver_initialise_step_then_run(tmp_path):
+    """The dsmcInitialise+ step of every shipped Allrun (blockMesh; dsmcInitialise+; dsmcFoam+): `dsmcb200_run -initialise` fills the
+    mesh from system/dsmcInitialiseDict (dsmcMeshFill) and writes the start-time cloud with 15 significant digits
+    (dsmcInitialise+.C:57-88); the solver then starts from it."""
+    import shutil
+
+    g, mesh, _ = casegen.couette_case(str(tmp_path), n_steps=2, seed=3, nto=1, start_time="0")
+    shutil.rmtree(os.path.join(str(tmp_path), "0"))                      # a fresh case: no cloud yet
+    init = """
+configurations
+(
+    configuration
+    {
+        type            dsmcMeshFill;
+
+            numberDensities
+            {
+                  N2         3.2e22;
+                  O2         0.8e22;
+            };
+
+            translationalTemperature        2500;
+            rotationalTemperature           2500;
+            vibrationalTemperature          2500;
+        electronicTemperature           0;
+
+            velocity        (150 0 0);
+      }
+);
+"""
+    from hystrath_b200 import case as casew
+
+    casew.write_dict(os.path.join(str(tmp_path), "system", "dsmcInitialiseDict"), "system", "dsmcInitialiseDict", init)
+    r = subprocess.run([RUN, "-initialise", "-case", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "Initialising dsmc for Time = 0" in r.stdout and "End" in r.stdout
+    n = int(r.stdout.split("total no. of parcels:")[1].split()[0])
+    expect = 4.0e22 * 500 * 1e-6 / float(g["nEquivalentParticles"])       # n V / F_N, 500 cells of 1e-6 m^3
+    assert abs(n / expect - 1) < 0.02
+    cdir = os.path.join(str(tmp_path), "0", "lagrangian", "dsmc")
+    xyz, cell = ff.read_positions(os.path.join(cdir, "positions"))
+    tid = ff.read_scalar_list(os.path.join(cdir, "typeId"), np.int32)
+    assert len(cell) == n and abs((tid == 0).mean() - 0.8) < 0.02
+    toks = [ln for ln in open(os.path.join(cdir, "positions")).read().splitlines() if ln.startswith("(") and ln[-1].isdigit()][:50]
+    digits = max(len(t.strip("()").split()[0].split("e")[0].replace(".", "").replace("-", "").lstrip("0")) for t in toks)
+    assert digits >= 14                                                   # 15 significant digits (defaultPrecision(15)), not 10
+    ijk = np.floor(xyz / 0.01).astype(int)
+    assert np.array_equal(ijk[:, 0] + 5 * ijk[:, 1], cell)
+    assert os.path.exists(os.path.join(str(tmp_path), "0", "dsmcSigmaTcRMax"))
+    U = ff.read_vector_list(os.path.join(cdir, "U"))
+    assert abs(U[:, 0].mean() - 150.0) < 15.0
+    # unknown configuration types fail like dsmcConfiguration::New
+    bad = init.replace("dsmcMeshFill", "dsmcZoneFill")
+    casew.write_dict(os.path.join(str(tmp_path), "system", "dsmcInitialiseDict"), "system", "dsmcInitialiseDict", bad)
+    rb = subprocess.run([RUN, "-initialise", "-case", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert rb.returncode == 1 and "unknown dsmcConfiguration type dsmcZoneFill" in rb.stderr
+    # and the solver runs from the initialised state
+    r2 = subprocess.run([RUN, "-case", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r2.returncode == 0, r2.stderr + r2.stdout
+    assert f"Number of DSMC particles        = {n}" in r2.stdout and "End stage 0" in r2.stdout
