@@ -146,12 +146,13 @@ def workload_config(args, cells_per_gpu, parcels_per_gpu):
                 "cells_per_gpu": cells_per_gpu, "parcels_per_gpu": parcels_per_gpu, "parcels_per_cell": args.ppc, "gas": "argon",
                 "collision_model": "VariableHardSphere", "partition": "1 GPU",
                 "l2_policy": "inputs larger than L2 (parcel state >> 126 MB), no flush needed"}
-    return {"workload": "weak-scaling periodic box (BASELINE configs[4]), %s, %d cells and ~%d parcels per GPU" % (
-        "argon VHS" if args.gas == "argon" else "5-species air (N2,O2,NO,N,O) Larsen-Borgnakke VHS", cells_per_gpu, parcels_per_gpu),
+    return {"workload": "weak-scaling periodic box (BASELINE configs[4]), %s, %d cells and ~%d parcels per GPU, %s" % (
+        "argon VHS" if args.gas == "argon" else "5-species air (N2,O2,NO,N,O) Larsen-Borgnakke VHS", cells_per_gpu, parcels_per_gpu,
+        "blockMesh cell order" if getattr(args, "numbering", "morton") == "blockMesh" else "cells renumbered along a z-order curve (renumberMesh equivalent)"),
         "cells_per_gpu": cells_per_gpu, "parcels_per_gpu": parcels_per_gpu, "parcels_per_cell": args.ppc, "gas": args.gas,
         "collision_model": "VariableHardSphere" if args.gas == "argon" else "LarsenBorgnakkeVariableHardSphere",
         "partition": "x".join(str(v) for v in procs_for(args.gpus)) + " bricks",
-        "cell_numbering": "blockMesh order (x fastest)" if getattr(args, "numbering", "blockMesh") == "blockMesh"
+        "cell_numbering": "blockMesh order (x fastest)" if getattr(args, "numbering", "morton") == "blockMesh"
                           else "cells relabelled along a z-order curve (renumberMesh equivalent)",
         "l2_policy": "inputs larger than L2 (parcel state >> 126 MB per GPU), no flush needed"}
 
@@ -208,7 +209,7 @@ def main():
     ap.add_argument("--gas", default=os.environ.get("DSMCB200_BENCH_GAS", "air5"), choices=["argon", "air5"])
     ap.add_argument("--cells", type=int, default=int(os.environ.get("DSMCB200_BENCH_CELLS", "200")), help="cells per direction per GPU")
     ap.add_argument("--ppc", type=int, default=31)
-    ap.add_argument("--numbering", default=os.environ.get("DSMCB200_BENCH_NUMBERING", "blockMesh"), choices=["blockMesh", "morton"],
+    ap.add_argument("--numbering", default=os.environ.get("DSMCB200_BENCH_NUMBERING", "morton"), choices=["blockMesh", "morton"],
                     help="cell labels of the box: blockMesh's x-fastest order, or relabelled along a z-order curve (meshgen.renumber_cells, a renumberMesh equivalent)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-cells", type=int, default=32)
