@@ -287,6 +287,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         eng.evolve(1)
     eng.kernel_times(reset=True)
+    c_before = eng.counters()      # dsmcCloud::info sums (mass, energies) before the timed steps: size-independent invariants below
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -301,7 +302,25 @@ def main():
     wall = time.perf_counter() - t0
     sampler.stop_flag = True
     kt = eng.kernel_times()
-    stage_ms = np.array(eng.counters().stageMs[:8])
+    c_after = eng.counters()
+    stage_ms = np.array(c_after.stageMs[:8])
+    # ---- parity by property at the full size (outside the timed region): a closed periodic box keeps its parcels and its mass, collisions
+    # conserve total energy (translational + rotational + vibrational + electronic), the occupancy offsets are a CSR of the cloud
+    def energy(c):
+        return c.linearKineticEnergy + c.rotationalEnergy + c.vibrationalEnergy + c.electronicEnergy
+    occ = eng.occupancy()
+    inv_local = torch.tensor([c_before.mass, c_after.mass, energy(c_before), energy(c_after), float(c_before.nParcels), float(c_after.nParcels),
+                              float(c_after.collisions)], dtype=torch.float64, device="cuda")
+    occ_ok = bool(occ[0] == 0 and occ[-1] == eng.num_parcels() and (np.diff(occ) >= 0).all())
+    occ_t = torch.tensor([1.0 if occ_ok else 0.0], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(inv_local, op=dist.ReduceOp.SUM)
+        dist.all_reduce(occ_t, op=dist.ReduceOp.MIN)
+    iv = inv_local.cpu().numpy()
+    invariants = {"occupancy_is_csr_of_cloud": bool(occ_t.item() == 1.0), "collisions_last_step": int(iv[6])}
+    if args.workload == "box":
+        invariants.update({"parcels_before": int(iv[4]), "parcels_after": int(iv[5]), "mass_rel_change": float(iv[1] / iv[0] - 1.0),
+                           "total_energy_rel_change": float(iv[3] / iv[2] - 1.0), "steps_between": args.steps})
 
     tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
     ntot = torch.tensor([float(n_processed)], dtype=torch.float64, device="cuda")
@@ -397,6 +416,7 @@ def main():
             "kernel_ms_per_step": per_step, "wall_ms_per_step": 1e3 * wall / args.steps, "setup_s": setup_s,
             "clocks": sampler.summary(), "gpu_launches": int(sum(v[1] * KERNELS_PER_TIMER.get(k, 1) for k, v in kt.items())),
             "hbm_frac_of_step": sum(n_local * sb[k] for k in sb) / (ms_total / args.steps * 1e-3) / 1e9 / peak,
+            "invariants": invariants,
         }
         if e2e is not None:
             line["e2e"] = e2e

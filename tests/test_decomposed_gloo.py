@@ -38,7 +38,7 @@ def _global_reference():
     return fnum, start, H.by_id(o.download_parcels())
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, renumber=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -46,13 +46,17 @@ def _worker(rank, world, port, q):
         fnum, start, _ = _global_reference()          # deterministic: both ranks generate the same global cloud
         sp = [H.argon()]
         mesh = meshgen.decomposed_box(N_LOCAL, L_LOCAL, PROCS, rank)
+        new_of_old = np.arange(mesh.n_cells, dtype=np.int32)
+        if renumber:   # every rank relabels its own brick (renumberMesh per processor directory); patch faces keep their order
+            mesh, new_of_old = meshgen.renumber_cells(mesh, meshgen.morton_order(mesh))
+        old_of_new = np.argsort(new_of_old)
         o = Oracle()
         o.set_mesh(mesh); o.set_species(sp); o.set_models(_models(fnum))
         # my share of the global cloud: global cell (i,j,k) -> rank i // 4, local cell (i % 4, j, k)
         gi, gj, gk = start.cell % 8, (start.cell // 8) % 4, start.cell // 32
         mine = (gi // 4) == rank
         loc = (gi % 4 + 4 * (gj + 4 * gk)).astype(np.int32)
-        p = capi.ParcelData(int(mine.sum()), 1, allocate=False, position=start.position[mine], U=start.U[mine], cell=loc[mine],
+        p = capi.ParcelData(int(mine.sum()), 1, allocate=False, position=start.position[mine], U=start.U[mine], cell=new_of_old[loc[mine]],
                             typeId=start.typeId[mine], origId=start.origId[mine])
         o.upload_parcels(p)
         sent_total = np.zeros(world, np.int64)
@@ -72,20 +76,25 @@ def _worker(rank, world, port, q):
                         o.receive_and_move(src, *gathered[src][rank])
             o.evolve_end()
         res = o.download_parcels()
-        li, lj, lk = res.cell % 4, (res.cell // 4) % 4, res.cell // 16
+        lc = old_of_new[res.cell]
+        li, lj, lk = lc % 4, (lc // 4) % 4, lc // 16
         gcell = (li + 4 * rank) + 8 * (lj + 4 * lk)
         q.put((rank, res.origId.copy(), res.position.copy(), gcell.astype(np.int32), sent_total))
     finally:
         dist.destroy_process_group()
 
 
-def test_two_rank_migration_matches_single_domain():
+import pytest
+
+
+@pytest.mark.parametrize("renumber", [False, True])
+def test_two_rank_migration_matches_single_domain(renumber):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, renumber)) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=240) for _ in range(2)]
