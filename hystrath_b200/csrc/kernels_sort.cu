@@ -117,13 +117,20 @@ cudaError_t launchHistogram(const int32_t* cell, int32_t n, int32_t* cellCount, 
     return cudaGetLastError();
 }
 
+// Warp-aggregated: the cloud enters cell-sorted and most parcels stay in their cell, so the 32 lanes of a warp fall into a handful
+// of cells; the lanes of one cell send ONE atomic for the whole group and take consecutive slots in lane order.
 __global__ void scatterIndexKernel(const int32_t* __restrict__ cell, int32_t n, int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
     const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int32_t c = cell[i];
+    const int lane = threadIdx.x & 31;
+    const int32_t c = i < n ? cell[i] : -1;
+    const unsigned live = __ballot_sync(0xffffffffu, c >= 0);
     if (c < 0) return;
-    const int32_t slot = atomicAdd(&cursor[c], 1);
-    perm[slot] = i;
+    const unsigned peers = __match_any_sync(live, c);
+    const int leader = __ffs(peers) - 1;
+    int32_t base = 0;
+    if (lane == leader) base = atomicAdd(&cursor[c], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    perm[base + __popc(peers & ((1u << lane) - 1u))] = i;
 }
 
 cudaError_t launchScatterIndex(const int32_t* cell, int32_t n, int32_t* cursor, int32_t* perm, cudaStream_t s) {
