@@ -311,7 +311,6 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
             const bool c1 = planeCrossed(numC1, toMinusCt, N1, tol);
             const bool c2 = planeCrossed(numC2, toMinusCt, N2, tol);
             const bool c3 = planeCrossed(numC3, toMinusCt, N3, tol);
-#ifdef MOVE_V3
             // ---- outcome of the visit, decided with predicates and selects; only a boundary face is a real branch.
             // (The nested if/else form of the reference merges position, fraction and flags at every join and the compiler
             // pays for each join with register copies.)
@@ -415,116 +414,6 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                 }
             }
         }
-#else
-            if (!keepParticle) {
-                finished = true;
-            } else if (rescuePending) {
-                // lambdaMin < SMALL: tracking correction towards the centre of the tet now occupied
-                pos += kTrackingCorrectionTol * (Ct - pos);
-                ++rescues;
-                retVal = trackFraction;
-                finished = true;
-            } else if (!(c0 | c1 | c2 | c3)) {
-                pos = endPosition;
-                faceSet = false; faceBfi = -1;
-                retVal = 1.0;
-                finished = true;
-            } else {
-                // ---- advance to the nearest crossed plane and step through it ----
-            // all four lambdas from the current position as independent chains (the ones of planes that are
-            // not crossed are discarded); order and strict '<' as in the reference's loop over tris
-            const V3 toMinusFrom = endPosition - pos;
-            const double l0 = tetLambda(pos, toMinusFrom, N0, base, tol, c0);
-            const double l1 = tetLambda(pos, toMinusFrom, N1, pA, tol, c1);
-            const double l2 = tetLambda(pos, toMinusFrom, N2, base, tol, c2);
-            const double l3 = tetLambda(pos, toMinusFrom, N3, base, tol, c3);
-            int triI = -1;
-            double lambdaMin = VGREAT;
-            if (c0 && l0 < lambdaMin) { lambdaMin = l0; triI = 0; }
-            if (c1 && l1 < lambdaMin) { lambdaMin = l1; triI = 1; }
-            if (c2 && l2 < lambdaMin) { lambdaMin = l2; triI = 2; }
-            if (c3 && l3 < lambdaMin) { lambdaMin = l3; triI = 3; }
-            const int32_t nb0 = loInt(nb01);
-            if (triI == 0) { faceSet = true; faceBfi = nb0 < 0 ? (-1 - nb0) : -1; }
-            else if (triI > 0) { faceSet = false; faceBfi = -1; }
-            bool needRescue = false;
-            if (lambdaMin > SMALL) {
-                if (lambdaMin <= 1.0) {
-                    trackFraction += lambdaMin * (1 - trackFraction);
-                    pos += lambdaMin * (endPosition - pos);
-                } else {
-                    pos = endPosition;
-                    retVal = 1.0;
-                    finished = true;
-                }
-            } else {
-                needRescue = true;  // lambdaMin = 0.0
-            }
-            if (!finished) {
-                if (triI > 0) {
-                    // particle::tetNeighbour: enter the adjacent tet of the same cell
-                    tet = triI == 1 ? hiInt(nb01) : (triI == 2 ? loInt(nb23) : hiInt(nb23));
-                    rescuePending = needRescue;
-                } else {
-                    if (nb0 >= 0) {
-                        cell = nb0;  // internal face: the same face triangle seen from the other cell
-                        tet ^= 1;
-                    } else {
-                        const int32_t bfi = -1 - nb0;
-                        const BFaceRec bf = a.bfaces[bfi];
-                        const DevPatch& pt = P.patch[bf.patch];
-                        switch (pt.type) {
-                            case DSMCB200_PATCH_PROCESSOR:
-                            case DSMCB200_PATCH_PROCESSORCYCLIC:
-                                switchProcessor = true;  // dsmcParcel::hitProcessorPatch
-                                break;
-                            case DSMCB200_PATCH_SYMMETRYPLANE:
-                            case DSMCB200_PATCH_SYMMETRY:
-                            case DSMCB200_PATCH_WEDGE: {
-                                // transformProperties(I - 2.0*nf*nf), particleTemplates.C:1474-1522
-                                const V3 nf = N0;
-                                const V3 t2 = 2.0 * nf;
-                                const double xx = 1.0 - t2.x * nf.x, xy = 0.0 - t2.x * nf.y, xz = 0.0 - t2.x * nf.z;
-                                const double yx = 0.0 - t2.y * nf.x, yy = 1.0 - t2.y * nf.y, yz = 0.0 - t2.y * nf.z;
-                                const double zx = 0.0 - t2.z * nf.x, zy = 0.0 - t2.z * nf.y, zz = 1.0 - t2.z * nf.z;
-                                U = mk(xx * U.x + xy * U.y + xz * U.z, yx * U.x + yy * U.y + yz * U.z, zx * U.x + zy * U.y + zz * U.z);
-                                Udirty = true;
-                                break;
-                            }
-                            case DSMCB200_PATCH_CYCLIC: {
-                                // particle::hitCyclicPatch, particleTemplates.C:1525-1570
-                                const int32_t k = (tet >> 1) - bf.tetPair0;
-                                tet = 2 * (bf.coupledTetPair0 + (bf.nPts - 3) - k);
-                                cell = bf.coupledCell;
-                                const DevPatch& rp = P.patch[pt.nbrPatch];
-                                pos -= mk(rp.sep[0], rp.sep[1], rp.sep[2]);
-                                faceBfi = bfi - (pt.start - P.nInternalFaces) + (rp.start - P.nInternalFaces);
-                                break;
-                            }
-                            case DSMCB200_PATCH_WALL:
-                            case DSMCB200_PATCH_PATCH:
-                                if (pt.model == DSMCB200_BND_DELETION) {
-                                    keepParticle = false;  // dsmcDeletionPatch::controlParticle
-                                } else if (pt.model != DSMCB200_BND_NONE) {
-                                    U = wallInteraction(a, i, a.p.typeId[i], bf.patch, bf.measIndex, bfi, N0, U, &wallHits);
-                                    Udirty = true;
-                                }
-                                break;
-                            default:  // empty patches cannot be hit by constrained tracks
-                                break;
-                        }
-                    }
-                    if (needRescue) {
-                        rescuePending = true;  // correction towards the new tet's centre, then return trackFraction
-                    } else {
-                        retVal = trackFraction;
-                        finished = true;
-                    }
-                }
-            }
-        }
-        }
-#endif
         __syncwarp();
 
         // ---- section 3: trackToFace returned -- back in dsmcParcel::move (DSMC/parcels/dsmcParcel.C:92-118) ----

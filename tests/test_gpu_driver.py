@@ -131,8 +131,8 @@ configurations
 
             numberDensities
             {
-                  N2         3.2e22;
-                  O2         0.8e22;
+                  N2         3.2e19;
+                  O2         0.8e19;
             };
 
             translationalTemperature        2500;
@@ -151,7 +151,7 @@ configurations
     assert r.returncode == 0, r.stderr + r.stdout
     assert "Initialising dsmc for Time = 0" in r.stdout and "End" in r.stdout
     n = int(r.stdout.split("total no. of parcels:")[1].split()[0])
-    expect = 4.0e22 * 500 * 1e-6 / float(g["nEquivalentParticles"])       # n V / F_N, 500 cells of 1e-6 m^3
+    expect = 4.0e19 * 500 * 1e-6 / float(g["nEquivalentParticles"])       # n V / F_N, 500 cells of 1e-6 m^3: ~46 500 parcels
     assert abs(n / expect - 1) < 0.02
     cdir = os.path.join(str(tmp_path), "0", "lagrangian", "dsmc")
     xyz, cell = ff.read_positions(os.path.join(cdir, "positions"))
