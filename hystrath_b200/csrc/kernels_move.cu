@@ -29,11 +29,11 @@ constexpr double kTrackingCorrectionTol = 1.0e-5;  // BASIC/particle/particle.C:
 #endif
 constexpr int MOVE_CHUNK = MOVE_CHUNK_SZ;  // parcels per lane in a warp work queue
 #ifndef MOVE_BLOCK_SZ
-#define MOVE_BLOCK_SZ 128
+#define MOVE_BLOCK_SZ 64
 #endif
 constexpr int MOVE_BLOCK = MOVE_BLOCK_SZ;
 #ifndef MOVE_MIN_BLOCKS
-#define MOVE_MIN_BLOCKS 4
+#define MOVE_MIN_BLOCKS 8
 #endif
 
 // one 32-byte sector per instruction (sm_100 LDG.256): halves the L1 tag look-ups of the scattered record reads
