@@ -115,6 +115,8 @@ def run_reference(args):
     cp = case_parameters(args.gas, cells, args.ppc)
     sp, tids, frac = species_table(args.gas)
     mesh = meshgen.box_mesh((cells,) * 3, (cp["L"],) * 3)
+    if getattr(args, "numbering", "morton") == "morton":
+        mesh, _ = meshgen.renumber_cells(mesh, meshgen.morton_order(mesh))
     model = "VariableHardSphere" if args.gas == "argon" else "LarsenBorgnakkeVariableHardSphere"
     md = capi.build_models(model, nEquivalentParticles=cp["fnum"], deltaT=cp["dt"], seed=0xD5C00005)
     o = Oracle()
@@ -182,6 +184,8 @@ def cpu_baseline_leg(args):
     cp = case_parameters(args.gas, cells, args.ppc)
     sp, tids, frac = species_table(args.gas)
     mesh = meshgen.box_mesh((cells,) * 3, (cp["L"],) * 3)
+    if getattr(args, "numbering", "morton") == "morton":
+        mesh, _ = meshgen.renumber_cells(mesh, meshgen.morton_order(mesh))
     model = "VariableHardSphere" if args.gas == "argon" else "LarsenBorgnakkeVariableHardSphere"
     md = capi.build_models(model, nEquivalentParticles=cp["fnum"], deltaT=cp["dt"], seed=0xD5C00005)
     o = Oracle()
