@@ -40,6 +40,7 @@ PATCH_MODEL_NAMES = {
     "dsmcDiffuseWallPatch": BND_DIFFUSE_WALL,
     "dsmcSpecularWallPatch": BND_SPECULAR_WALL,
     "dsmcDeletionPatch": BND_DELETION,
+    "dsmcDiffuseSpecularWallPatch": 4,
 }
 
 
@@ -68,7 +69,8 @@ class Species(C.Structure):
 
 
 class PatchModel(C.Structure):
-    _fields_ = [("patch", C.c_int32), ("model", C.c_int32), ("temperature", C.c_double), ("velocity", C.c_double * 3)]
+    _fields_ = [("patch", C.c_int32), ("model", C.c_int32), ("temperature", C.c_double), ("velocity", C.c_double * 3),
+                ("diffuseFraction", C.c_double)]
 
 
 class Inflow(C.Structure):
@@ -332,6 +334,7 @@ def build_models(collisionModel="VariableHardSphere", nEquivalentParticles=1.0, 
         pm[i].patch = d["patch"]
         pm[i].model = PATCH_MODEL_NAMES[name]
         pm[i].temperature = d.get("temperature", 0.0)
+        pm[i].diffuseFraction = d.get("diffuseFraction", 0.0)
         for k in range(3):
             pm[i].velocity[k] = d.get("velocity", (0.0, 0.0, 0.0))[k]
     inf = (Inflow * max(1, len(inflows)))()

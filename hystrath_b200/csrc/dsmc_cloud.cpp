@@ -55,8 +55,9 @@ int selectPatchBoundaryModel(const std::string& name) {
     if (name == "dsmcDiffuseWallPatch") return DSMCB200_BND_DIFFUSE_WALL;
     if (name == "dsmcSpecularWallPatch") return DSMCB200_BND_SPECULAR_WALL;
     if (name == "dsmcDeletionPatch") return DSMCB200_BND_DELETION;
+    if (name == "dsmcDiffuseSpecularWallPatch") return DSMCB200_BND_DIFFUSE_SPECULAR_WALL;
     unknownType("dsmcPatchBoundary::New(const dictionary&)", "patch boundary", name,
-                {"dsmcDeletionPatch", "dsmcDiffuseWallPatch", "dsmcSpecularWallPatch"});
+                {"dsmcDeletionPatch", "dsmcDiffuseSpecularWallPatch", "dsmcDiffuseWallPatch", "dsmcSpecularWallPatch"});
 }
 void selectGeneralBoundaryModel(const std::string& name) {
     if (name != "dsmcFreeStreamInflowPatch")
@@ -304,8 +305,9 @@ void dsmcCloud::readBoundaries() {
         }
         dsmcb200_patch_model pm{};
         pm.patch = pid; pm.model = kind;
-        if (kind == DSMCB200_BND_DIFFUSE_WALL) {
+        if (kind == DSMCB200_BND_DIFFUSE_WALL || kind == DSMCB200_BND_DIFFUSE_SPECULAR_WALL) {
             const Dict& pr = b.subDict(model + "Properties");
+            if (kind == DSMCB200_BND_DIFFUSE_SPECULAR_WALL) pm.diffuseFraction = pr.scalar("diffuseFraction");
             pm.temperature = pr.found("groundLevelTemperature") ? pr.scalar("groundLevelTemperature") : pr.scalar("temperature");
             auto v = pr.vector3("velocity");
             for (int k = 0; k < 3; ++k) pm.velocity[k] = v[k];

@@ -407,8 +407,8 @@ int finalize(dsmcb200_ctx* c) {
         DevPatch& d = P.patch[pm.patch];
         if (d.type != DSMCB200_PATCH_WALL && d.type != DSMCB200_PATCH_PATCH)
             return fail(c, DSMCB200_ERR_INVALID, "Patch: " + M.patches[pm.patch].name + " must be of type wall or patch to carry a dsmcPatchBoundary model");
-        if (pm.model < DSMCB200_BND_DIFFUSE_WALL || pm.model > DSMCB200_BND_DELETION) return fail(c, DSMCB200_ERR_UNSUPPORTED, "unknown dsmcPatchBoundary type");
-        d.model = pm.model; d.T = pm.temperature;
+        if (pm.model < DSMCB200_BND_DIFFUSE_WALL || pm.model > DSMCB200_BND_DIFFUSE_SPECULAR_WALL) return fail(c, DSMCB200_ERR_UNSUPPORTED, "unknown dsmcPatchBoundary type");
+        d.model = pm.model; d.T = pm.temperature; d.diffuseFraction = pm.diffuseFraction;
         d.vel[0] = pm.velocity[0]; d.vel[1] = pm.velocity[1]; d.vel[2] = pm.velocity[2];
         if (pm.model != DSMCB200_BND_DELETION)
             for (int i = 0; i < d.size; ++i) measIndex[d.start - M.nInternalFaces + i] = c->nMeasFaces++;

@@ -37,6 +37,7 @@ struct DevPatch {
     double T;            // wall temperature
     double vel[3];       // wall velocity
     double sep[3];       // cyclic separation (receiving side subtracts)
+    double diffuseFraction;  // dsmcDiffuseSpecularWallPatch
 };
 
 struct DevParams {

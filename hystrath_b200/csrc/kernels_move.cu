@@ -165,16 +165,21 @@ __device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int sp,
     double preIE, postIE;
     V3 preIMom, postIMom;
     wallMeasure(wctx, measIndex, bfi, sp, U, in, preIE, preIMom);
-    if (pt.model == DSMCB200_BND_SPECULAR_WALL) {
+    // the k-th hit of a parcel on a wall that draws random numbers within a step owns the Philox stream (origId, k, step)
+    Rng wallRng;
+    bool specular = pt.model == DSMCB200_BND_SPECULAR_WALL;
+    if (!specular) {
+        wallRng.init(P.seed, uint32_t(a.p.origId[i]), uint32_t(*wallHits), a.step, STREAM_WALL);
+        *wallHits += 1;
+        // dsmcDiffuseSpecularWallPatch::controlParticle (mixed/dsmcDiffuseSpecularWallPatch.C:97-115): Maxwell's model
+        if (pt.model == DSMCB200_BND_DIFFUSE_SPECULAR_WALL) specular = !(pt.diffuseFraction > wallRng.sample01());
+    }
+    if (specular) {
         // dsmcSpecularWallPatch::performSpecularReflection
         const double U_dot_nw = dot(U, nw);
         if (U_dot_nw > 0.0) U -= 2.0 * U_dot_nw * nw;
     } else {
-        // dsmcDiffuseWallPatch::performDiffuseReflection; the k-th diffuse hit of a parcel within a step owns
-        // the Philox stream (origId, k, step)
-        Rng wallRng;
-        wallRng.init(P.seed, uint32_t(a.p.origId[i]), uint32_t(*wallHits), a.step, STREAM_WALL);
-        *wallHits += 1;
+        // dsmcDiffuseWallPatch::performDiffuseReflection
         const DevSpecies& S = P.sp[sp];
         // dsmcPatchBoundary::calculateWallUnitVectors
         double U_dot_nw = dot(U, nw);

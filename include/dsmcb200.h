@@ -128,7 +128,8 @@ typedef enum {
     DSMCB200_BND_NONE = 0,
     DSMCB200_BND_DIFFUSE_WALL = 1,   /* dsmcDiffuseWallPatch  */
     DSMCB200_BND_SPECULAR_WALL = 2,  /* dsmcSpecularWallPatch */
-    DSMCB200_BND_DELETION = 3        /* dsmcDeletionPatch     */
+    DSMCB200_BND_DELETION = 3,       /* dsmcDeletionPatch     */
+    DSMCB200_BND_DIFFUSE_SPECULAR_WALL = 4  /* mixed/dsmcDiffuseSpecularWallPatch (Maxwell model: diffuse with probability diffuseFraction) */
 } dsmcb200_patch_model_kind;
 
 /* One entry of system/boundariesDict dsmcPatchBoundaries
@@ -138,6 +139,7 @@ typedef struct {
     int32_t model;          /* dsmcb200_patch_model_kind */
     double temperature;     /* dsmcDiffuseWallPatchProperties.temperature */
     double velocity[3];
+    double diffuseFraction; /* dsmcDiffuseSpecularWallPatchProperties.diffuseFraction (dsmcDiffuseSpecularWallPatch.C:67) */
 } dsmcb200_patch_model;
 
 /* One dsmcFreeStreamInflowPatch of dsmcGeneralBoundaries

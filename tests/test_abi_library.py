@@ -32,7 +32,7 @@ def test_struct_layouts_match_the_header():
     # sizes the C compiler gives the PODs (gcc x86-64); a mismatch would corrupt every call
     assert C.sizeof(capi.Patch) == 64 + 8 * 4 + 24
     assert C.sizeof(capi.Species) == 64 + 5 * 8 + 8 + 9 * 8 + 8 + 8 + 16 * 8 + 16 * 4
-    assert C.sizeof(capi.PatchModel) == 8 + 8 + 24
+    assert C.sizeof(capi.PatchModel) == 8 + 8 + 24 + 8   # + diffuseFraction
     assert C.sizeof(capi.ParcelsSoA) == 12 * 8 + 8
     assert C.sizeof(capi.Counters) == 9 * 8 + 5 * 8 + 8 * 8
     assert C.sizeof(capi.AccumInfo) == 24

@@ -310,6 +310,37 @@ def test_move_with_diffuse_walls_and_empty_patches():
     eng.close()
 
 
+def test_diffuse_specular_wall_matches_oracle():
+    """dsmcDiffuseSpecularWallPatch: the diffuse / specular draw comes first in the hit's Philox stream on both sides."""
+    sides = {"xmin": ("cyclic",), "xmax": ("cyclic",), "ymin": ("wall", "lowerWall"), "ymax": ("wall", "upperWall"),
+             "zmin": ("empty", "frontAndBack"), "zmax": ("empty", "frontAndBack")}
+    mesh = meshgen.box_mesh((5, 20, 1), (0.05, 0.2, 0.01), sides=sides)
+    sp = H.air5()[:2]
+    pm = [dict(patch=mesh.patch_index("lowerWall"), boundaryModel="dsmcDiffuseSpecularWallPatch", temperature=2000.0, velocity=(0, 0, 0),
+               diffuseFraction=0.4),
+          dict(patch=mesh.patch_index("upperWall"), boundaryModel="dsmcDiffuseSpecularWallPatch", temperature=3000.0, velocity=(300.0, 0, 0),
+               diffuseFraction=0.85)]
+    md = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=1e20 * 0.05 * 0.2 * 0.01 / (100 * 60), deltaT=4e-6, seed=7,
+                           patch_models=pm, inverseZvFormulation="pre-2008")
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    start = H.by_id(H.same_start(eng, ora, [0, 1], [0.8e20, 0.2e20], 2500.0, 2500.0, 2500.0))
+    for x in (eng, ora):
+        x.stage(capi.STAGE_MOVE)
+        x.stage(capi.STAGE_SORT)
+    g, o = H.by_id(eng.download_parcels()), H.by_id(ora.download_parcels())
+    assert np.array_equal(g["cell"], o["cell"])
+    assert np.allclose(g["U"], o["U"], rtol=1e-12, atol=1e-9) and np.allclose(g["position"], o["position"], rtol=0, atol=1e-13)
+    assert np.array_equal(g["vibLevel"], o["vibLevel"])
+    hit = (o["U"] != start["U"]).any(1)
+    specular = hit & (np.abs((o["U"] ** 2).sum(1) / (start["U"] ** 2).sum(1) - 1) < 1e-12)
+    assert 0 < specular.sum() < hit.sum()                        # both branches taken
+    assert np.array_equal(g["U"][specular], o["U"][specular])    # no libm in a specular reflection: bit-exact
+    gw, ow = eng.wall_accumulators(), ora.wall_accumulators()
+    scale = np.abs(ow).max(axis=(0, 1), keepdims=True) + 1e-300
+    assert (np.abs(gw - ow) / scale).max() < 1e-10
+    eng.close()
+
+
 def test_inflow_deletion_specular_counts_match_oracle():
     sides = {"xmin": ("patch", "inlet"), "xmax": ("patch", "outlet"), "ymin": ("wall", "plate"), "ymax": ("symmetryPlane", "top"),
              "zmin": ("cyclic",), "zmax": ("cyclic",)}

@@ -313,3 +313,27 @@ def test_tracking_across_a_refinement_interface_with_five_point_faces():
     assert len(b["cell"]) == len(a["cell"]) > 2000
     assert np.array_equal(locate(b["position"]), b["cell"])
     assert (a["cell"] != b["cell"]).mean() > 0.5 and o.counters()["trackingRescues"] == 0
+
+
+def test_diffuse_specular_wall_splits_by_diffuse_fraction():
+    """dsmcDiffuseSpecularWallPatch (Maxwell model, patchBoundaries/mixed/dsmcDiffuseSpecularWallPatch/dsmcDiffuseSpecularWallPatch.C:97-115):
+    a wall hit is diffuse with probability diffuseFraction, specular otherwise.  A specular hit keeps |U|; a diffuse one resamples it."""
+    sp = [H.argon()]
+    sides = {s: ("wall", "walls") for s in meshgen.SIDES}
+    frac = 0.3
+    mesh, md, o = box((4, 4, 4), (0.016,) * 3, sp, "NoBinaryCollision", ppc=400, sides=sides, dt=2e-6,
+                      patch_models=[dict(patch=0, boundaryModel="dsmcDiffuseSpecularWallPatch", temperature=900.0, velocity=(0, 0, 0),
+                                         diffuseFraction=frac)])
+    o.mesh_fill([0], [1e20], 300.0)
+    a = H.by_id(o.download_parcels())
+    o.evolve(1)
+    b = H.by_id(o.download_parcels())
+    hit = (a["U"] != b["U"]).any(1)
+    assert hit.sum() > 1500
+    keeps_speed = np.abs((b["U"][hit] ** 2).sum(1) / (a["U"][hit] ** 2).sum(1) - 1) < 1e-12
+    n = hit.sum()
+    # corner double hits are rare at this time step: the specular share is 1 - diffuseFraction within 4 sigma (+1 % slack)
+    assert abs(keeps_speed.mean() - (1 - frac)) < 4 * np.sqrt(frac * (1 - frac) / n) + 0.01
+    # the diffuse ones come off at the wall temperature: mean kinetic energy of a half-range Maxwellian flux = 2 k T_w
+    ek = 0.5 * sp[0].mass * (b["U"][hit][~keeps_speed] ** 2).sum(1)
+    assert abs(ek.mean() / (2 * H.KB * 900.0) - 1) < 0.1
