@@ -26,9 +26,23 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries the one JSON line only
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries the one JSON line only: native libraries (NCCL's version banner, ...) write to file descriptor 1 behind Python's
+# back, so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 KB = 1.38065e-23
 # algorithmic bytes per parcel-step and stage (BASELINE.md section 3 / SURVEY.md 8d), FP64 state
@@ -138,7 +152,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, cells_per_gpu, parcels_per_gpu):
@@ -222,6 +236,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    _capture_stdout()
     if args.warmup < 3 and args.impl == "dsmcb200":
         args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -426,7 +441,7 @@ def main():
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg(args)
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if dist is not None:
         dist.barrier()
