@@ -559,7 +559,7 @@ DerivedFields dsmcCloud::calculateField(const FieldSpec& f) {
     DerivedFields o;
     auto z = [&](std::vector<double>& v, int w = 1) { v.assign(size_t(nC) * w, 0.0); };
     z(o.dsmcNMean); z(o.rhoN); z(o.rhoM); z(o.p); z(o.Ttra); z(o.Trot); z(o.Tvib); z(o.Tov); z(o.Ma); z(o.mfp); z(o.mct); z(o.mctToDt);
-    z(o.mfpToDx); z(o.measuredCollisionRate); z(o.UMean, 3);
+    z(o.mfpToDx); z(o.SOF); z(o.measuredCollisionRate); z(o.UMean, 3);
     const double NAvo = 6.02214e26;  // OpenFOAM SI physicoChemical::NA is per kmol
     (void)NAvo;
     for (int c = 0; c < nC; ++c) {
@@ -659,14 +659,45 @@ DerivedFields dsmcCloud::calculateField(const FieldSpec& f) {
             o.mfp[c] = mfp;
             if (mcr > SMALL) { o.mct[c] = 1.0 / mcr; o.mctToDt[c] = o.mct[c] / deltaT_; } else { o.mct[c] = GREAT; o.mctToDt[c] = GREAT; }
             if (nCum > SMALL) o.measuredCollisionRate[c] = coll[2 * size_t(c)] * FN / (nCum * deltaT_);
+            // mfpToDx and the separation-of-free-paths ratio (dsmcVolFields.C:1788-1836)
+            if (mfp != GREAT) {
+                o.mfpToDx[c] = mfp / cellMaxDx(c);
+                const double nColl = coll[2 * size_t(c)];
+                const double mcs = nColl > SMALL ? coll[2 * size_t(c) + 1] / nColl : GREAT;   // meanCollisionSeparation_ (:1244-1250)
+                o.SOF[c] = mfp > SMALL ? mcs / mfp : 0.0;
+            } else {
+                o.mfpToDx[c] = GREAT; o.SOF[c] = GREAT;
+            }
         }
     }
     return o;
 }
 
+double dsmcCloud::cellMaxDx(int c) const {
+    if (cellMaxDx_.empty()) {
+        std::vector<double> lo(size_t(nCells_) * 3, GREAT), hi(size_t(nCells_) * 3, -GREAT);
+        auto take = [&](int cell, int f) {
+            for (int q = faceOffsets_[f]; q < faceOffsets_[f + 1]; ++q)
+                for (int d = 0; d < 3; ++d) {
+                    const double x = points_[3 * size_t(facePoints_[q]) + d];
+                    lo[3 * size_t(cell) + d] = std::min(lo[3 * size_t(cell) + d], x);
+                    hi[3 * size_t(cell) + d] = std::max(hi[3 * size_t(cell) + d], x);
+                }
+        };
+        for (int f = 0; f < nFaces_; ++f) {
+            take(owner_[f], f);
+            if (f < nInternal_) take(neighbour_[f], f);
+        }
+        cellMaxDx_.resize(nCells_);
+        for (int k = 0; k < nCells_; ++k)
+            cellMaxDx_[k] = std::max(hi[3 * size_t(k)] - lo[3 * size_t(k)], std::max(hi[3 * size_t(k) + 1] - lo[3 * size_t(k) + 1], hi[3 * size_t(k) + 2] - lo[3 * size_t(k) + 2]));
+    }
+    return cellMaxDx_[c];
+}
+
 void dsmcCloud::writeFields(const std::string& timeDir) {
-    // boundary values: wall patches get rhoN/rhoM/fD/p/q from the wall accumulators (dsmcVolFields.C:1879-2141),
-    // everything else the adjacent cell value (the zeroGradient branch :2142-2204)
+    // Boundary values (dsmcVolFields.C:1878-2206): faces of `wall` patches get every field from the wall accumulators
+    // (the *BF_ arrays of boundaryMeasurements), every other non-empty, non-cyclic patch the adjacent cell value.
     int32_t nMeas = 0, nWallQ = 0;
     check(dsmcb200_wall_info(ctx_, &nMeas, &nWallQ), "dsmcb200_wall_info");
     const int S = int(species_.size());
@@ -675,6 +706,8 @@ void dsmcCloud::writeFields(const std::string& timeDir) {
     dsmcb200_accum_info ai{};
     check(dsmcb200_accum_info_get(ctx_, &ai), "dsmcb200_accum_info_get");
     const double nT = ai.nTimeSteps > 0 ? ai.nTimeSteps : 1.0;
+    const double kB = models_.kB > 0 ? models_.kB : 1.38065e-23;
+    const double FN = models_.nEquivalentParticles;
     // measured-face index of a boundary face follows the order of the patch models with a wall model
     std::vector<int> measStart(boundary_.size(), -1);
     {
@@ -682,9 +715,89 @@ void dsmcCloud::writeFields(const std::string& timeDir) {
         for (auto& pm : patchModels_)
             if (pm.model != DSMCB200_BND_DELETION) { measStart[pm.patch] = k; k += boundary_[pm.patch].nFaces; }
     }
+    // WallQ order of the engine (csrc/engine.h): rhoN 0, rhoNInt 1, rhoNElec 2, rhoM 3, linearKE 4, mcc 5, momentum 6-8, Erot 9,
+    // zetaRot 10, Evib 11, Eelec 12, q 13, fD 14-16, EvibMod 17+
+    struct WallFace { double rhoN, rhoM, U[3], Ttra, Trot, Tvib, Tov, Ma, fD[3], p, tau, q; };
     for (auto& f : fields_) {
         DerivedFields d = calculateField(f);
-        auto scalarPatches = [&](const std::vector<double>& cellField, int wq, double scale) {
+        // ---- wall faces of this instance
+        std::vector<std::vector<WallFace>> wf(boundary_.size());
+        for (size_t j = 0; j < boundary_.size(); ++j) {
+            if (boundary_[j].type != "wall" || measStart[j] < 0) continue;
+            wf[j].resize(boundary_[j].nFaces);
+            for (int k = 0; k < boundary_[j].nFaces; ++k) {
+                WallFace& w = wf[j][k];
+                std::memset(&w, 0, sizeof(w));
+                const int face = boundary_[j].startFace + k;
+                auto W = [&](int s, int q) { return wall[(size_t(measStart[j] + k) * S + s) * nWallQ + q]; };
+                double rhoNBF = 0, rhoMBF = 0, linearKEBF = 0, momBF[3] = {0, 0, 0}, ErotBF = 0, zetaRotBF = 0, qBF = 0, fDBF[3] = {0, 0, 0};
+                for (int s : f.typeIds) {
+                    rhoNBF += W(s, 0); rhoMBF += W(s, 3); linearKEBF += W(s, 4); ErotBF += W(s, 9); zetaRotBF += W(s, 10); qBF += W(s, 13);
+                    for (int q = 0; q < 3; ++q) { momBF[q] += W(s, 6 + q); fDBF[q] += W(s, 14 + q); }
+                }
+                const double rhoNMean = rhoNBF * FN / nT, rhoMMean = rhoMBF * FN / nT, linearKEMean = linearKEBF * FN / nT;
+                w.rhoN = rhoNMean; w.rhoM = rhoMMean;
+                if (rhoMMean > VSMALL) {
+                    for (int q = 0; q < 3; ++q) w.U[q] = momBF[q] / rhoMBF;
+                    w.Ttra = 2.0 / (3.0 * kB * rhoNMean) * (linearKEMean - 0.5 * rhoMMean * (w.U[0] * w.U[0] + w.U[1] * w.U[1] + w.U[2] * w.U[2]));
+                }
+                const double zetaRotTot = rhoNBF > SMALL ? zetaRotBF / rhoNBF : 0.0;
+                w.Trot = zetaRotBF > SMALL ? 2.0 * ErotBF / (kB * zetaRotBF) : 0.0;
+                double zetaVibBF = 0.0, moleculesRhoN = 0.0;
+                for (int s : f.typeIds) {
+                    const double spRhoN = W(s, 0);
+                    double spZetaVib = 0.0, zetaByTvibMod = 0.0;
+                    if (spRhoN > SMALL) {
+                        for (int mod = 0; mod < species_[s].nVibrationalModes; ++mod) {
+                            const double thetaV = species_[s].thetaV[mod];
+                            const double iMean = (17 + mod < nWallQ ? W(s, 17 + mod) : 0.0) / (kB * thetaV * spRhoN);
+                            if (iMean > SMALL) {
+                                const double logFactor = std::log(1.0 + 1.0 / iMean);
+                                const double Tmod = thetaV / logFactor, zmod = 2.0 * iMean * logFactor;
+                                spZetaVib += zmod; zetaByTvibMod += zmod * Tmod;
+                            }
+                        }
+                    }
+                    if (spZetaVib > SMALL) {
+                        moleculesRhoN += spRhoN;
+                        w.Tvib += spRhoN * (zetaByTvibMod / spZetaVib);
+                        zetaVibBF += spRhoN * spZetaVib;
+                    }
+                }
+                if (moleculesRhoN > SMALL) { w.Tvib /= moleculesRhoN; zetaVibBF /= moleculesRhoN; }
+                w.Tov = (3.0 * w.Ttra + zetaRotTot * w.Trot + zetaVibBF * w.Tvib) / (3.0 + zetaRotTot + zetaVibBF);
+                if (rhoNBF > SMALL) {
+                    double molecularMassBF = 0, cv = 0, cp = 0;
+                    for (int s : f.typeIds) {
+                        const double Xs = W(s, 0) / rhoNBF;
+                        molecularMassBF += Xs * species_[s].mass;
+                        cv += Xs * (3.0 + species_[s].rotationalDegreesOfFreedom);
+                        cp += Xs * (5.0 + species_[s].rotationalDegreesOfFreedom);
+                    }
+                    const double gasConstant = (w.Ttra > SMALL) ? kB / molecularMassBF : 0.0;
+                    const double speedOfSound = std::sqrt(cp / cv * gasConstant * w.Ttra);
+                    w.Ma = std::sqrt(w.U[0] * w.U[0] + w.U[1] * w.U[1] + w.U[2] * w.U[2]) / speedOfSound;
+                }
+                // unit vectors of the face (dsmcVolFields::calculateWallUnitVectors, :52-80)
+                const double* Sf = &faceAreas_[3 * size_t(face)];
+                const double magSf = std::sqrt(Sf[0] * Sf[0] + Sf[1] * Sf[1] + Sf[2] * Sf[2]);
+                const double n[3] = {Sf[0] / magSf, Sf[1] / magSf, Sf[2] / magSf};
+                const double* p0 = &points_[3 * size_t(facePoints_[faceOffsets_[face]])];
+                double t1[3] = {faceCentres_[3 * size_t(face)] - p0[0], faceCentres_[3 * size_t(face) + 1] - p0[1], faceCentres_[3 * size_t(face) + 2] - p0[2]};
+                const double m1 = std::sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+                for (double& x : t1) x /= m1;
+                double t2[3] = {n[1] * t1[2] - n[2] * t1[1], n[2] * t1[0] - n[0] * t1[2], n[0] * t1[1] - n[1] * t1[0]};
+                const double m2 = std::sqrt(t2[0] * t2[0] + t2[1] * t2[1] + t2[2] * t2[2]);
+                for (double& x : t2) x /= m2;
+                for (int q = 0; q < 3; ++q) w.fD[q] = fDBF[q] / nT;
+                w.p = w.fD[0] * n[0] + w.fD[1] * n[1] + w.fD[2] * n[2];
+                const double a1 = w.fD[0] * t1[0] + w.fD[1] * t1[1] + w.fD[2] * t1[2], a2 = w.fD[0] * t2[0] + w.fD[1] * t2[1] + w.fD[2] * t2[2];
+                w.tau = std::sqrt(a1 * a1 + a2 * a2);
+                w.q = qBF / nT;
+            }
+        }
+        // per-patch values of a scalar field: `pick` selects the wall-face value, other wall / patch faces copy the cell
+        auto scalarPatches = [&](const std::vector<double>& cellField, double WallFace::*pick) {
             std::vector<foam::PatchValues> pv;
             for (size_t j = 0; j < boundary_.size(); ++j) {
                 foam::PatchValues p;
@@ -692,40 +805,46 @@ void dsmcCloud::writeFields(const std::string& timeDir) {
                 if (p.type == "wall" || p.type == "patch") {
                     p.values.resize(boundary_[j].nFaces);
                     for (int k = 0; k < boundary_[j].nFaces; ++k) {
-                        if (wq >= 0 && measStart[j] >= 0) {
-                            double v = 0;
-                            for (int s : f.typeIds) v += wall[(size_t(measStart[j] + k) * S + s) * nWallQ + wq];
-                            p.values[k] = v * scale;
-                        } else {
-                            p.values[k] = cellField.empty() ? 0.0 : cellField[owner_[boundary_[j].startFace + k]];
-                        }
+                        if (pick && !wf[j].empty()) p.values[k] = wf[j][k].*pick;
+                        else p.values[k] = cellField.empty() ? 0.0 : cellField[owner_[boundary_[j].startFace + k]];
                     }
                 }
                 pv.push_back(p);
             }
             return pv;
         };
-        const double FN = models_.nEquivalentParticles;
-        auto wr = [&](const std::string& name, const std::string& dims, const std::vector<double>& v, int wq = -1, double scale = 1.0) {
+        auto wr = [&](const std::string& name, const std::string& dims, const std::vector<double>& v, double WallFace::*pick = nullptr) {
             foam::writeVolField(timeDir + "/" + name + "_" + f.fieldName, timeName_, name + "_" + f.fieldName, dims, v.data(), nCells_, 1,
-                                scalarPatches(v, wq, scale));
+                                scalarPatches(v, pick));
         };
         wr("dsmcNMean", "[0 0 0 0 0 0 0]", d.dsmcNMean);
-        wr("rhoN", "[0 -3 0 0 0 0 0]", d.rhoN, 0 /*WQ_RHON*/, FN / nT);
-        wr("rhoM", "[1 -3 0 0 0 0 0]", d.rhoM, 3 /*WQ_RHOM*/, FN / nT);
+        wr("rhoN", "[0 -3 0 0 0 0 0]", d.rhoN, &WallFace::rhoN);
+        wr("rhoM", "[1 -3 0 0 0 0 0]", d.rhoM, &WallFace::rhoM);
         if (f.densityOnly) continue;
-        wr("p", "[1 -1 -2 0 0 0 0]", d.p);
-        wr("Ttra", "[0 0 0 1 0 0 0]", d.Ttra);
-        wr("Trot", "[0 0 0 1 0 0 0]", d.Trot);
-        wr("Tvib", "[0 0 0 1 0 0 0]", d.Tvib);
-        wr("Tov", "[0 0 0 1 0 0 0]", d.Tov);
-        wr("Ma", "[0 0 0 0 0 0 0]", d.Ma);
+        wr("p", "[1 -1 -2 0 0 0 0]", d.p, &WallFace::p);
+        wr("Ttra", "[0 0 0 1 0 0 0]", d.Ttra, &WallFace::Ttra);
+        wr("Trot", "[0 0 0 1 0 0 0]", d.Trot, &WallFace::Trot);
+        wr("Tvib", "[0 0 0 1 0 0 0]", d.Tvib, &WallFace::Tvib);
+        wr("Tov", "[0 0 0 1 0 0 0]", d.Tov, &WallFace::Tov);
+        wr("Ma", "[0 0 0 0 0 0 0]", d.Ma, &WallFace::Ma);
         std::vector<double> zero(size_t(nCells_), 0.0);
-        wr("wallHeatFlux", "[1 0 -3 0 0 0 0]", zero, 13 /*WQ_Q*/, 1.0 / nT);
+        // q_ and tau_ live on the walls only (internal field zero, dsmcVolFields.C:231-257)
+        {
+            auto wallOnly = [&](double WallFace::*pick) {
+                auto pv = scalarPatches(zero, pick);
+                return pv;
+            };
+            foam::writeVolField(timeDir + "/wallHeatFlux_" + f.fieldName, timeName_, "wallHeatFlux_" + f.fieldName, "[1 0 -3 0 0 0 0]", zero.data(), nCells_, 1,
+                                wallOnly(&WallFace::q));
+            foam::writeVolField(timeDir + "/wallShearStress_" + f.fieldName, timeName_, "wallShearStress_" + f.fieldName, "[1 -1 -2 0 0 0 0]", zero.data(),
+                                nCells_, 1, wallOnly(&WallFace::tau));
+        }
         if (f.measureMeanFreePath) {
             wr("mfp", "[0 1 0 0 0 0 0]", d.mfp);
+            wr("mfpToDx", "[0 0 0 0 0 0 0]", d.mfpToDx);
             wr("mct", "[0 0 1 0 0 0 0]", d.mct);
             wr("mctToDt", "[0 0 0 0 0 0 0]", d.mctToDt);
+            wr("SOFP", "[0 0 0 0 0 0 0]", d.SOF);
         }
         // vectors: U and the wall force density fD
         {
@@ -738,10 +857,10 @@ void dsmcCloud::writeFields(const std::string& timeDir) {
                     a.values.resize(size_t(boundary_[j].nFaces) * 3); b.values.assign(size_t(boundary_[j].nFaces) * 3, 0.0);
                     for (int k = 0; k < boundary_[j].nFaces; ++k) {
                         const int c = owner_[boundary_[j].startFace + k];
-                        for (int q = 0; q < 3; ++q) a.values[3 * k + q] = d.UMean[3 * size_t(c) + q];
-                        if (measStart[j] >= 0)
-                            for (int s : f.typeIds)
-                                for (int q = 0; q < 3; ++q) b.values[3 * k + q] += wall[(size_t(measStart[j] + k) * S + s) * nWallQ + 14 + q] / nT;
+                        for (int q = 0; q < 3; ++q) {
+                            a.values[3 * k + q] = wf[j].empty() ? d.UMean[3 * size_t(c) + q] : wf[j][k].U[q];
+                            if (!wf[j].empty()) b.values[3 * k + q] = wf[j][k].fD[q];
+                        }
                     }
                 }
                 pu.push_back(a); pf.push_back(b);

@@ -42,7 +42,7 @@ struct FieldSpec {  // one dsmcVolFields entry of system/fieldPropertiesDict
 };
 
 struct DerivedFields {  // per-cell results of dsmcVolFields::calculateField for one instance
-    std::vector<double> dsmcNMean, rhoN, rhoM, p, Ttra, Trot, Tvib, Tov, Ma, mfp, mct, mctToDt, mfpToDx, measuredCollisionRate;
+    std::vector<double> dsmcNMean, rhoN, rhoM, p, Ttra, Trot, Tvib, Tov, Ma, mfp, mct, mctToDt, mfpToDx, SOF, measuredCollisionRate;
     std::vector<double> UMean;  // [3n]
 };
 
@@ -76,6 +76,7 @@ class dsmcCloud {
     void readFieldProperties();
     void readCloud();
     void writeFields(const std::string& timeDir);
+    double cellMaxDx(int c) const;  // largest extent of the cell's points along x, y, z (dsmcVolFields.C:1795-1821)
     void writeResumeSampling(const std::string& timeDir);  // dsmcVolFields::writeOut + the engine's own lossless checkpoint
     void readResumeSampling();                              // dsmcVolFields::readIn
     void check(int rc, const char* what);
@@ -95,6 +96,7 @@ class dsmcCloud {
     std::vector<foam::BoundaryPatch> boundary_;
     std::vector<dsmcb200_patch> patches_;
     std::vector<double> cellVolumes_, cellCentres_, faceAreas_, faceCentres_;
+    mutable std::vector<double> cellMaxDx_;
     // models
     std::vector<std::string> typeIdList_;
     std::vector<dsmcb200_species> species_;

@@ -250,6 +250,28 @@ def read_internal_field(path):
     return a if m.group(2) == "scalar" else a.reshape(n, -1)
 
 
+def read_patch_field(path, patch):
+    """boundaryField value of one patch of a volScalarField / volVectorField -> numpy array ([n] or [n, 3]); a `uniform` value
+    comes back 0-d / (3,)."""
+    body = _body(open(path).read())
+    b = body.index("boundaryField")
+    m = re.search(r"\b" + re.escape(patch) + r"\s*\{", body[b:])
+    if not m:
+        raise KeyError(patch)
+    start = b + m.end()
+    end = body.index("}", start)
+    block = body[start:end]
+    v = re.search(r"value\s+(nonuniform\s+List<(\w+)>|uniform)\s*", block)
+    if not v:
+        raise ValueError(f"{path}: patch {patch} has no value")
+    if v.group(1) == "uniform":
+        e = block.index(";", v.end())
+        return np.array(block[v.end():e].replace("(", " ").replace(")", " ").split(), dtype=np.float64).squeeze()
+    n, inner, _, _ = _sized_block(block, v.end())
+    a = np.array(inner.replace("(", " ").replace(")", " ").split(), dtype=np.float64)
+    return a if v.group(2) == "scalar" else a.reshape(n, -1)
+
+
 # ---------------------------------------------------------------------------------------------
 # writers (cloud + field files in the layout of DSMC/parcels/dsmcParcelIO.C:338-450)
 # ---------------------------------------------------------------------------------------------

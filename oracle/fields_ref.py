@@ -100,3 +100,59 @@ def derive(acc, coll, n_time_steps, species, type_ids, fnum, cell_volumes, kB=1.
             out["measuredCollisionRate"] = np.where(nCum > SMALL, coll[:, 0] * fnum / (np.where(nCum > SMALL, nCum, 1.0) * deltaT), 0.0)
             out["meanCollisionSeparation"] = np.where(coll[:, 0] > SMALL, coll[:, 1] / np.where(coll[:, 0] > SMALL, coll[:, 0], 1.0), GREAT)
     return out
+
+
+def wall_fields(wall, n_time_steps, species, type_ids, fnum, face_areas, face_centres, first_points, kB=1.38065e-23):
+    """Wall-face values of one dsmcVolFields instance from the boundary accumulators (dsmcVolFields.C:1878-2141 and the unit vectors
+    of calculateWallUnitVectors :52-80).  wall: [nFaces, nSpecies, nWallQ] in the engine's WallQ order (rhoN 0, rhoNInt 1,
+    rhoNElec 2, rhoM 3, linearKE 4, mcc 5, momentum 6-8, Erot 9, zetaRot 10, Evib 11, Eelec 12, q 13, fD 14-16, EvibMod 17+);
+    face_areas / face_centres / first_points: [nFaces, 3] of the same faces.  Returns a dict of per-face arrays."""
+    w = np.asarray(wall, float)
+    ids = list(type_ids)
+    nT = float(n_time_steps)
+    nF = w.shape[0]
+    rhoNBF = w[:, ids, 0].sum(1); rhoMBF = w[:, ids, 3].sum(1); linearKEBF = w[:, ids, 4].sum(1)
+    momBF = w[:, ids, 6:9].sum(1); ErotBF = w[:, ids, 9].sum(1); zetaRotBF = w[:, ids, 10].sum(1)
+    rhoN, rhoM, lke = rhoNBF * fnum / nT, rhoMBF * fnum / nT, linearKEBF * fnum / nT
+    out = {"rhoN": rhoN, "rhoM": rhoM}
+    with np.errstate(divide="ignore", invalid="ignore"):
+        has = rhoM > VSMALL
+        U = np.where(has[:, None], momBF / np.where(has, rhoMBF, 1.0)[:, None], 0.0)
+        Ttra = np.where(has, 2.0 / (3.0 * kB * np.where(has, rhoN, 1.0)) * (lke - 0.5 * rhoM * (U * U).sum(1)), 0.0)
+        zetaRotTot = np.where(rhoNBF > SMALL, zetaRotBF / np.where(rhoNBF > SMALL, rhoNBF, 1.0), 0.0)
+        Trot = np.where(zetaRotBF > SMALL, 2.0 * ErotBF / (kB * np.where(zetaRotBF > SMALL, zetaRotBF, 1.0)), 0.0)
+        Tvib = np.zeros(nF); zetaVib = np.zeros(nF); molecules = np.zeros(nF)
+        for s in ids:
+            spRhoN = w[:, s, 0]
+            spZeta = np.zeros(nF); zByT = np.zeros(nF)
+            for mod, thetaV in enumerate(species[s].get("thetaV", [])):
+                ev = w[:, s, 17 + mod] if 17 + mod < w.shape[2] else np.zeros(nF)
+                iMean = np.where(spRhoN > SMALL, ev / (kB * thetaV * np.where(spRhoN > SMALL, spRhoN, 1.0)), 0.0)
+                okm = iMean > SMALL
+                logF = np.log(1.0 + 1.0 / np.where(okm, iMean, 1.0))
+                Tm = np.where(okm, thetaV / logF, 0.0); zm = np.where(okm, 2.0 * iMean * logF, 0.0)
+                spZeta += zm; zByT += zm * Tm
+            oks = spZeta > SMALL
+            molecules += np.where(oks, spRhoN, 0.0)
+            Tvib += np.where(oks, spRhoN * zByT / np.where(oks, spZeta, 1.0), 0.0)
+            zetaVib += np.where(oks, spRhoN * spZeta, 0.0)
+        okM = molecules > SMALL
+        Tvib = np.where(okM, Tvib / np.where(okM, molecules, 1.0), Tvib)
+        zetaVib = np.where(okM, zetaVib / np.where(okM, molecules, 1.0), zetaVib)
+        Tov = (3.0 * Ttra + zetaRotTot * Trot + zetaVib * Tvib) / (3.0 + zetaRotTot + zetaVib)
+        X = w[:, ids, 0] / np.where(rhoNBF > SMALL, rhoNBF, 1.0)[:, None]
+        mass = np.array([species[s]["mass"] for s in ids]); zr = np.array([species[s].get("rotDof", 0.0) for s in ids])
+        mm = (X * mass).sum(1); cv = (X * (3.0 + zr)).sum(1); cp = (X * (5.0 + zr)).sum(1)
+        R = np.where(Ttra > SMALL, kB / np.where(mm > 0, mm, 1.0), 0.0)
+        a = np.sqrt(cp / np.where(cv > 0, cv, 1.0) * R * Ttra)
+        Ma = np.where(rhoNBF > SMALL, np.sqrt((U * U).sum(1)) / a, 0.0)
+    Sf = np.asarray(face_areas, float)
+    n = Sf / np.linalg.norm(Sf, axis=1)[:, None]
+    t1 = np.asarray(face_centres, float) - np.asarray(first_points, float)
+    t1 /= np.linalg.norm(t1, axis=1)[:, None]
+    t2 = np.cross(n, t1)
+    t2 /= np.linalg.norm(t2, axis=1)[:, None]
+    fD = w[:, ids, 14:17].sum(1) / nT
+    out.update(U=U, Ttra=Ttra, Trot=Trot, Tvib=Tvib, Tov=Tov, Ma=Ma, fD=fD, p=(fD * n).sum(1),
+               wallShearStress=np.sqrt((fD * t1).sum(1) ** 2 + (fD * t2).sum(1) ** 2), wallHeatFlux=w[:, ids, 13].sum(1) / nT)
+    return out

@@ -65,7 +65,24 @@ def test_driver_runs_couette_case_and_matches_oracle(tmp_path):
                           ("mfp", "mfp"), ("mct", "mct")):
             got = ff.read_internal_field(os.path.join(tdir, f"{name}_{inst}"))
             assert np.allclose(got, f[key], rtol=2e-9, atol=1e-300), (name, inst)
-    # wall fields exist with per-face values on the two wall patches
+    # wall-face fields of the two wall patches == numpy restatement of dsmcVolFields.C:1878-2141 on the oracle's boundary accumulators
+    wacc = o.wall_accumulators()
+    _, _, fc, fa, _ = o.geometry()
+    for inst, idl in (("mixture", [0, 1]), ("N2", [0])):
+        for patch, row0 in (("upperWall", 0), ("lowerWall", 5)):     # patch models in boundariesDict order: 5 faces each
+            start = mesh.patches[mesh.patch_index(patch)]["start"]
+            faces = np.arange(start, start + 5)
+            first = mesh.points[mesh.face_points[mesh.face_offsets[faces]]]
+            wf = fields_ref.wall_fields(wacc[row0:row0 + 5], nt, spd, idl, float(g["nEquivalentParticles"]), fa[faces], fc[faces], first)
+            for name, key in (("rhoN", "rhoN"), ("rhoM", "rhoM"), ("p", "p"), ("Ttra", "Ttra"), ("Trot", "Trot"), ("Tvib", "Tvib"), ("Tov", "Tov"),
+                              ("Ma", "Ma"), ("wallHeatFlux", "wallHeatFlux"), ("wallShearStress", "wallShearStress"), ("U", "U"), ("fD", "fD")):
+                got = ff.read_patch_field(os.path.join(tdir, f"{name}_{inst}"), patch)
+                scale = np.abs(wf[key]).max() + 1e-300
+                assert np.abs(got - wf[key]).max() / scale < 5e-9, (name, inst, patch)
+        assert np.abs(wf["wallHeatFlux"]).max() > 0 and np.abs(wf["wallShearStress"]).max() > 0
+    for name in ("mfpToDx", "SOFP"):
+        v = ff.read_internal_field(os.path.join(tdir, f"{name}_mixture"))
+        assert v.shape == (500,) and np.all(v > 0)
     text = open(os.path.join(tdir, "wallHeatFlux_mixture")).read()
     assert "upperWall" in text and "nonuniform List<scalar>" in text.split("boundaryField")[1]
     assert os.path.exists(os.path.join(tdir, "dsmcSigmaTcRMax"))
