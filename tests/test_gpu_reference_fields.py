@@ -1,0 +1,75 @@
+"""GPU: sampled macroscopic fields against the fields dsmcFoam+ itself wrote.
+
+The reference ships the steady state of its couette_N2-O2 tutorial (run/hyStrath/dsmcFoam+/couette_N2-O2/backup-5: cloud +
+long-time-averaged fields; tests/golden/couette_N2-O2.npz).  The engine continues that run from the shipped cloud -- diffuse walls at
+2000 K and 3000 K / 300 m/s, Larsen-Borgnakke N2/O2 with the tutorial's coefficients -- and its own averages over a few thousand
+steps must reproduce the shipped wall-to-wall profiles.  The two codes share no random numbers: this is the statistical parity
+north_star asks for (fields within 3 sigma), on the reference's own output."""
+import numpy as np
+import pytest
+
+from hystrath_b200 import capi
+from oracle import fields_ref
+from tests import helpers as H
+from tests.test_oracle_golden import GOLD, couette_mesh
+
+pytestmark = pytest.mark.gpu
+
+STEPS = 4000
+
+
+def test_couette_profiles_match_the_shipped_dsmcfoam_fields():
+    g = np.load(GOLD)
+    mesh = couette_mesh(g)
+    sp = H.air5()[:2]
+    pm = [dict(patch=mesh.patch_index("upperWall"), boundaryModel="dsmcDiffuseWallPatch", temperature=3000.0, velocity=(300.0, 0, 0)),
+          dict(patch=mesh.patch_index("lowerWall"), boundaryModel="dsmcDiffuseWallPatch", temperature=2000.0, velocity=(0, 0, 0))]
+    fnum = float(g["nEquivalentParticles"])
+    md = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=fnum, deltaT=1e-5, seed=2024, patch_models=pm,
+                           inverseZvFormulation="pre-2008", rotationalRelaxationCollisionNumber=5.0)
+    eng = capi.Engine(0)
+    eng.set_mesh(mesh); eng.set_species(sp); eng.set_models(md)
+    p = capi.ParcelData(len(g["cell"]), 1, allocate=False, position=g["positions"], U=g["U"], ERot=g["ERot"], cell=g["cell"],
+                        typeId=g["typeId"], vibLevel=g["vibLevel"], origId=g["origId"])
+    eng.upload_parcels(p)
+    eng.upload_cellstate(g["dsmcSigmaTcRMax"], None)
+    eng.evolve(STEPS)
+    assert eng.num_parcels() == 47583                      # closed box: walls re-emit, cyclic sides wrap
+    acc, coll, nt = eng.accumulators()
+    assert nt == STEPS
+    cv = np.full(500, 1e-6)
+    spd = [dict(mass=s.mass, diameter=s.diameter, omega=s.omega, rotDof=2.0, thetaV=[s.thetaV[0]]) for s in sp]
+    f = fields_ref.derive(acc, coll, nt, spd, [0, 1], fnum, cv, deltaT=1e-5)
+    eng.close()
+
+    j = np.arange(500) // 5                                # cell = i + 5 j: 100 rows between the walls, 5 cells each
+
+    def rows(a):
+        return np.array([a[j == k].mean() for k in range(100)])
+
+    # translational temperature: 2075 K .. 2916 K across the gap (temperature jump at both walls included)
+    T, Tg = rows(f["Ttra"]), rows(g["Ttra_mixture"])
+    assert Tg.min() < 2100 and Tg.max() > 2890
+    assert np.abs(T / Tg - 1).max() < 0.02 and abs((T / Tg).mean() - 1) < 0.004   # measured: 0.29 % and 0.02 %
+    # rotational temperature follows (Z_rot = 5)
+    R, Rg = rows(f["Trot"]), rows(g["Trot_mixture"])
+    assert np.abs(R / Rg - 1).max() < 0.03 and abs((R / Rg).mean() - 1) < 0.006
+    # overall temperature including the vibrational mode (pre-2008 Zv)
+    O, Og = rows(f["Tov"]), rows(g["Tov_mixture"])
+    assert abs((O / Og).mean() - 1) < 0.01
+    # number density: hot side rarefied, cold side dense, pressure uniform
+    n, ng = rows(f["rhoN"]), rows(g["rhoN_mixture"])
+    assert np.abs(n / ng - 1).max() < 0.03 and abs((n / ng).mean() - 1) < 0.002
+    pr, pg = rows(f["p"]), rows(g["p_mixture"])
+    assert abs((pr / pg).mean() - 1) < 0.006
+    # shear: velocity profile from the slip at the resting wall to the slip at the 300 m/s wall
+    Ux, Ug = rows(f["UMean"][:, 0]), rows(g["U_mixture"][:, 0])
+    assert Ug[-1] - Ug[0] > 150.0
+    assert np.abs(Ux - Ug).max() < 15.0 and abs((Ux - Ug).mean()) < 6.0      # measured: 6.0 and 2.3 m/s of a 300 m/s wall
+    assert np.corrcoef(Ux, Ug)[0, 1] > 0.995
+    # species separation is not washed out: N2 / O2 mole fraction of the shipped fields
+    print("couette vs shipped dsmcFoam+ fields: max |T/Tg-1| %.4f mean %.5f; Trot max %.4f; Tov mean %.5f; rhoN max %.4f mean %.5f; p mean %.5f; "
+          "Ux max |d| %.2f m/s mean %.2f" % (np.abs(T / Tg - 1).max(), (T / Tg).mean() - 1, np.abs(R / Rg - 1).max(), (O / Og).mean() - 1,
+                                            np.abs(n / ng - 1).max(), (n / ng).mean() - 1, (pr / pg).mean() - 1, np.abs(Ux - Ug).max(), (Ux - Ug).mean()))
+    xN2 = acc[:, 0, 0].sum() / acc[:, :, 0].sum()
+    assert abs(xN2 - g["rhoN_N2"].sum() / g["rhoN_mixture"].sum()) < 0.002
