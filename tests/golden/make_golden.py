@@ -48,6 +48,12 @@ def main():
         for inst in ("mixture", "N2", "O2"):
             out[f"{name}_{inst}"] = ff.read_internal_field(os.path.join(fd, f"{name}_{inst}"))
     out["U_mixture"] = ff.read_internal_field(os.path.join(fd, "U_mixture"))
+    # wall-face values (boundaryField of the two wall patches, 5 faces each) and the two remaining mean-free-path outputs
+    for name in ("wallHeatFlux", "wallShearStress", "p", "rhoN", "rhoM", "Ttra", "Trot", "Tvib", "Tov", "Ma", "U", "fD"):
+        for patch in ("upperWall", "lowerWall"):
+            out[f"wall_{name}_{patch}"] = ff.read_patch_field(os.path.join(fd, f"{name}_mixture"), patch)
+    for name in ("mfpToDx", "SOFP"):
+        out[f"{name}_mixture"] = ff.read_internal_field(os.path.join(fd, f"{name}_mixture"))
     out["dsmcSigmaTcRMax"] = ff.read_internal_field(os.path.join(fd, "dsmcSigmaTcRMax"))
 
     props = ff.read_dict(os.path.join(CASE, "constant", "dsmcProperties"))

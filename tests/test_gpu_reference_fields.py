@@ -35,6 +35,8 @@ def test_couette_profiles_match_the_shipped_dsmcfoam_fields():
     eng.upload_cellstate(g["dsmcSigmaTcRMax"], None)
     eng.evolve(STEPS)
     assert eng.num_parcels() == 47583                      # closed box: walls re-emit, cyclic sides wrap
+    wall = eng.wall_accumulators()                         # [10 wall faces][2 species][nWallQ]: upperWall first (patch-model order)
+    _, _, face_centres, face_areas, _ = eng.geometry()
     acc, coll, nt = eng.accumulators()
     assert nt == STEPS
     cv = np.full(500, 1e-6)
@@ -67,6 +69,25 @@ def test_couette_profiles_match_the_shipped_dsmcfoam_fields():
     assert Ug[-1] - Ug[0] > 150.0
     assert np.abs(Ux - Ug).max() < 15.0 and abs((Ux - Ug).mean()) < 6.0      # measured: 6.0 and 2.3 m/s of a 300 m/s wall
     assert np.corrcoef(Ux, Ug)[0, 1] > 0.995
+    # ---- the wall faces: boundary measurements of every wall hit (dsmcPatchBoundary.C:263-482) reduced as dsmcVolFields.C:1878-2141
+    # does, against the boundaryField values dsmcFoam+ wrote for the two walls (5 faces each, averaged here)
+    worst = {}
+    for patch, row0 in (("upperWall", 0), ("lowerWall", 5)):
+        start = mesh.patches[mesh.patch_index(patch)]["start"]
+        faces = np.arange(start, start + 5)
+        first = mesh.points[mesh.face_points[mesh.face_offsets[faces]]]
+        wf = fields_ref.wall_fields(wall[row0:row0 + 5], nt, spd, [0, 1], fnum, face_areas[faces], face_centres[faces], first)
+        for name, tol in (("wallHeatFlux", 0.04), ("wallShearStress", 0.06), ("p", 0.01), ("rhoN", 0.01), ("rhoM", 0.01), ("Ttra", 0.01),
+                          ("Trot", 0.015), ("Tvib", 0.02), ("Tov", 0.01)):
+            ref = float(np.mean(g[f"wall_{name}_{patch}"]))
+            got = float(np.mean(wf[name]))
+            worst[(name, patch)] = got / ref - 1
+            assert abs(got / ref - 1) < tol, (name, patch, got, ref)
+        # slip velocity at the wall and the force density (pressure + shear) on it
+        assert abs(wf["U"][:, 0].mean() - g[f"wall_U_{patch}"][:, 0].mean()) < 4.0
+        assert np.abs(wf["fD"].mean(0) - g[f"wall_fD_{patch}"].mean(0)).max() < 0.015 * np.abs(g[f"wall_fD_{patch}"]).max()
+    assert abs(np.mean(g["wall_wallHeatFlux_lowerWall"]) + np.mean(g["wall_wallHeatFlux_upperWall"])) < 1.0   # steady state: what enters leaves
+    print("wall faces vs shipped: " + ", ".join(f"{k[0]}@{k[1][:5]} {v:+.4f}" for k, v in worst.items()))
     # species separation is not washed out: N2 / O2 mole fraction of the shipped fields
     print("couette vs shipped dsmcFoam+ fields: max |T/Tg-1| %.4f mean %.5f; Trot max %.4f; Tov mean %.5f; rhoN max %.4f mean %.5f; p mean %.5f; "
           "Ux max |d| %.2f m/s mean %.2f" % (np.abs(T / Tg - 1).max(), (T / Tg).mean() - 1, np.abs(R / Rg - 1).max(), (O / Og).mean() - 1,
