@@ -88,6 +88,14 @@ def test_couette_profiles_match_the_shipped_dsmcfoam_fields():
         assert np.abs(wf["fD"].mean(0) - g[f"wall_fD_{patch}"].mean(0)).max() < 0.015 * np.abs(g[f"wall_fD_{patch}"]).max()
     assert abs(np.mean(g["wall_wallHeatFlux_lowerWall"]) + np.mean(g["wall_wallHeatFlux_upperWall"])) < 1.0   # steady state: what enters leaves
     print("wall faces vs shipped: " + ", ".join(f"{k[0]}@{k[1][:5]} {v:+.4f}" for k, v in worst.items()))
+    # ---- collisions: the measured collision frequency against the analytic VHS value dsmcFoam+ wrote (mct = 1/nu, Bird 4.74/1.38; the
+    # measured rate counts collisions, i.e. nu/2 per molecule: SURVEY quirk list), and the mean collision separation over the mean free
+    # path (SOFP), which is what the octant sub-cell partner selection of noTimeCounter controls
+    rate = rows(f["measuredCollisionRate"]) * 2.0 * rows(g["mct_mixture"])
+    sofp, sofp_g = (f["meanCollisionSeparation"] / f["mfp"]).mean(), g["SOFP_mixture"].mean()
+    print("collision rate x 2 x shipped mct: mean %.4f min %.4f max %.4f; SOFP %.5f vs shipped %.5f" % (rate.mean(), rate.min(), rate.max(), sofp, sofp_g))
+    assert abs(rate.mean() - 1) < 0.02 and np.abs(rate - 1).max() < 0.06
+    assert abs(sofp / sofp_g - 1) < 0.05
     # species separation is not washed out: N2 / O2 mole fraction of the shipped fields
     print("couette vs shipped dsmcFoam+ fields: max |T/Tg-1| %.4f mean %.5f; Trot max %.4f; Tov mean %.5f; rhoN max %.4f mean %.5f; p mean %.5f; "
           "Ux max |d| %.2f m/s mean %.2f" % (np.abs(T / Tg - 1).max(), (T / Tg).mean() - 1, np.abs(R / Rg - 1).max(), (O / Og).mean() - 1,
