@@ -487,3 +487,49 @@ def refined_interface_mesh(nx_coarse=2, h=0.004, wall_type="wall"):
         return np.where(fine, X + sub, i)
 
     return mesh, locate
+
+
+def corner_mesh(h=0.01):
+    """The mesh of the reference's hypersonicCorner tutorial (Bird 1994, 16.2: supersonic corner flow), restated from its
+    blockMeshDict (run/hyStrath/dsmcFoam+/hypersonicCorner/system/blockMeshDict): block 1 = 5 x 18 x 18 cells over x in [0, 0.05],
+    block 2 = 25 x 18 x 18 over x in [0.05, 0.30], y and z in [0, 0.18], uniform 1 cm cells; cells numbered block by block, i fastest.
+    Patches in the dictionary's order: `flow` (patch: inlet, outlet, top y and top z), `entrance` (symmetry: the y = 0 and z = 0 faces
+    of block 1), `walls` (wall: the y = 0 and z = 0 faces of block 2 -- the two plates forming the corner)."""
+    nxs, ny, nz = (5, 25), 18, 18
+    pts, index = [], {}
+
+    def P(i, j, k):
+        key = (i, j, k)
+        if key not in index:
+            index[key] = len(pts)
+            pts.append((i * h, j * h, k * h))
+        return index[key]
+
+    cells = []
+    x0 = 0
+    for nx in nxs:
+        for k in range(nz):
+            for j in range(ny):
+                for ii in range(nx):
+                    i = x0 + ii
+                    cells.append([
+                        (P(i, j, k), P(i, j, k + 1), P(i, j + 1, k + 1), P(i, j + 1, k)),              # x-
+                        (P(i + 1, j, k), P(i + 1, j + 1, k), P(i + 1, j + 1, k + 1), P(i + 1, j, k + 1)),  # x+
+                        (P(i, j, k), P(i + 1, j, k), P(i + 1, j, k + 1), P(i, j, k + 1)),              # y-
+                        (P(i, j + 1, k), P(i, j + 1, k + 1), P(i + 1, j + 1, k + 1), P(i + 1, j + 1, k)),  # y+
+                        (P(i, j, k), P(i, j + 1, k), P(i + 1, j + 1, k), P(i + 1, j, k)),              # z-
+                        (P(i, j, k + 1), P(i + 1, j, k + 1), P(i + 1, j + 1, k + 1), P(i, j + 1, k + 1)),  # z+
+                    ])
+        x0 += nx
+    points = np.array(pts, dtype=np.float64)
+
+    def patch_of(face):
+        c = points[list(face)].mean(0)
+        on_floor = c[1] < 1e-9 or c[2] < 1e-9
+        if on_floor:
+            return "entrance" if c[0] < nxs[0] * h else "walls"
+        return "flow"
+
+    mesh = poly_mesh_from_cells(points, cells, patch_of, [("flow", "patch"), ("entrance", "symmetry"), ("walls", "wall")])
+    mesh.shape = (sum(nxs), ny, nz)
+    return mesh

@@ -102,3 +102,71 @@ def test_couette_profiles_match_the_shipped_dsmcfoam_fields():
                                             np.abs(n / ng - 1).max(), (n / ng).mean() - 1, (pr / pg).mean() - 1, np.abs(Ux - Ug).max(), (Ux - Ug).mean()))
     xN2 = acc[:, 0, 0].sum() / acc[:, :, 0].sum()
     assert abs(xN2 - g["rhoN_N2"].sum() / g["rhoN_mixture"].sum()) < 0.002
+
+
+def test_hypersonic_corner_matches_the_shipped_dsmcfoam_fields():
+    """Bird's supersonic corner flow (the reference's hypersonicCorner tutorial: Mach-6 argon over two plates at 1000 K forming a corner;
+    free-stream inflow + deletion on `flow`, symmetry `entrance`, diffuse `walls`), run exactly as its Allrun does -- dsmcMeshFill from
+    the free stream, 3000 steps of 1 us, sampling restarted at 1.5 ms -- against the fields dsmcFoam+ wrote at t = 3 ms
+    (tests/golden/hypersonicCorner.npz).  1.6 M parcels, ~200 per cell; both sides are 1500-step averages with independent noise."""
+    import os
+
+    from hystrath_b200 import meshgen
+
+    g = np.load(os.path.join(os.path.dirname(GOLD), "hypersonicCorner.npz"))
+    mesh = meshgen.corner_mesh()
+    ar = capi.make_species("Ar", float(g["Ar_mass"]), float(g["Ar_diameter"]), float(g["Ar_omega"]), float(g["Ar_alpha"]))
+    fnum = float(g["nEquivalentParticles"])
+    pm = [dict(patch=mesh.patch_index("walls"), boundaryModel="dsmcDiffuseWallPatch", temperature=1000.0, velocity=(0, 0, 0)),
+          dict(patch=mesh.patch_index("flow"), boundaryModel="dsmcDeletionPatch")]
+    inflow = [dict(patch=mesh.patch_index("flow"), typeIds=[0], numberDensities=[1e20], velocity=(1936.0, 0.0, 0.0), translationalTemperature=300.0)]
+    md = capi.build_models("VariableHardSphere", nEquivalentParticles=fnum, deltaT=1e-6, seed=16, patch_models=pm, inflows=inflow)
+    eng = capi.Engine(0)
+    eng.set_mesh(mesh); eng.set_species([ar]); eng.set_models(md)
+    eng.reserve(4_000_000)
+    eng.mesh_fill([0], [1e20], 300.0, 0.0, 0.0, 0.0, (1936.0, 0.0, 0.0))
+    assert abs(eng.num_parcels() / (1e20 * 0.30 * 0.18 * 0.18 / fnum) - 1) < 0.01
+    eng.evolve(1500)
+    eng.reset_accumulators()                                  # resetAtOutputUntilTime 1.5e-3
+    eng.evolve(1500)
+    acc, coll, nt = eng.accumulators()
+    wall = eng.wall_accumulators()
+    _, cv, face_centres, face_areas, _ = eng.geometry()
+    n_end = eng.num_parcels()
+    eng.close()
+    assert nt == 1500
+    spd = [dict(mass=ar.mass, diameter=ar.diameter, omega=ar.omega, rotDof=0.0, thetaV=[])]
+    f = fields_ref.derive(acc, coll, nt, spd, [0], fnum, cv, deltaT=1e-6, has_internal=False, n_modes=0)
+
+    # ---- cell fields, cell by cell (9720 cells; the noise of one cell is ~0.5 % in density, ~1 % in temperature on either side)
+    assert abs(n_end * fnum / (g["rhoN"].astype(float) * cv).sum() - 1) < 0.01            # total content of the domain
+    for name, key, tol_rms, tol_mean in (("rhoN", "rhoN", 0.02, 0.003), ("Ttra", "Ttra", 0.03, 0.004), ("p", "p", 0.035, 0.005)):
+        r = f[key] / g[name].astype(float) - 1
+        assert np.sqrt((r ** 2).mean()) < tol_rms and abs(r.mean()) < tol_mean, (name, np.sqrt((r ** 2).mean()), r.mean())
+    dU = f["UMean"] - g["U"].astype(float)
+    assert np.sqrt((dU ** 2).sum(1).mean()) < 25.0 and np.abs(dU.mean(0)).max() < 3.0     # of 1936 m/s
+    # the shock layer on the plates: peak density and temperature and where they are
+    assert abs(f["rhoN"].max() / g["rhoN"].max() - 1) < 0.03 and abs(f["Ttra"].max() / g["Ttra"].max() - 1) < 0.03
+    hot, hot_g = f["Ttra"] > 1500.0, g["Ttra"] > 1500.0
+    assert (hot ^ hot_g).mean() < 0.01
+
+    # ---- the plates: wall faces in patch order are not recoverable without the tutorial's polyMesh (blockMesh output is not shipped),
+    # so the comparison is by patch mean and by the sorted distribution over the 900 faces
+    start = mesh.patches[mesh.patch_index("walls")]["start"]
+    faces = np.arange(start, start + 900)
+    first = mesh.points[mesh.face_points[mesh.face_offsets[faces]]]
+    wf = fields_ref.wall_fields(wall[:900], nt, spd, [0], fnum, face_areas[faces], face_centres[faces], first)
+    report = {}
+    for name, tol_mean, tol_sorted in (("wallHeatFlux", 0.01, 0.03), ("wallShearStress", 0.01, 0.03), ("p", 0.01, 0.03), ("rhoN", 0.01, 0.03),
+                                       ("Ttra", 0.01, 0.02)):
+        got, ref = wf[name], g[f"wall_{name}"].astype(float)
+        report[name] = got.mean() / ref.mean() - 1
+        assert abs(got.mean() / ref.mean() - 1) < tol_mean, (name, got.mean(), ref.mean())
+        q = np.linspace(0.02, 0.98, 49)
+        assert np.abs(np.quantile(got, q) / np.quantile(ref, q) - 1).max() < tol_sorted, name
+    # drag and the two lifts on the plates (integrated force density; the corner is symmetric in y and z)
+    fD, fDg = wf["fD"].mean(0), g["wall_fD"].astype(float).mean(0)
+    assert np.abs(fD / fDg - 1).max() < 0.01 and abs(fD[1] / fD[2] - 1) < 0.01
+    print("corner vs shipped: rhoN rms %.4f, Ttra rms %.4f, wall means %s" % (
+        np.sqrt(((f["rhoN"] / g["rhoN"] - 1) ** 2).mean()), np.sqrt(((f["Ttra"] / g["Ttra"] - 1) ** 2).mean()),
+        ", ".join(f"{k} {v:+.4f}" for k, v in report.items())))
