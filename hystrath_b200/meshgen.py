@@ -533,3 +533,61 @@ def corner_mesh(h=0.01):
     mesh = poly_mesh_from_cells(points, cells, patch_of, [("flow", "patch"), ("entrance", "symmetry"), ("walls", "wall")])
     mesh.shape = (sum(nxs), ny, nz)
     return mesh
+
+
+def _graded(x0, x1, n, ratio):
+    """blockMesh simpleGrading: n cells between x0 and x1 whose sizes form a geometric progression with last/first = ratio."""
+    if n == 1 or abs(ratio - 1.0) < 1e-12:
+        return x0 + (x1 - x0) * np.arange(n + 1) / n
+    r = ratio ** (1.0 / (n - 1))
+    w = np.concatenate([[0.0], np.cumsum(r ** np.arange(n))])
+    return x0 + (x1 - x0) * w / w[-1]
+
+
+def flat_plate_mesh():
+    """The mesh of the reference's supersonicFlatPlate tutorial, restated from its blockMeshDict
+    (run/hyStrath/dsmcFoam+/supersonicFlatPlate/system/blockMeshDict): block 1 = 5 x 60 x 1 cells over x in [0, 50 mm] graded (0.5 2 1),
+    block 2 = 95 x 60 x 1 over x in [50 mm, 1 m] graded (2 2 1), y in [0, 0.6 m], one 1-mm cell in z; cells numbered block by block,
+    i fastest.  Patches: `plate` (wall: y = 0 of block 2), `inlet` (patch: everything else in the x-y outline), `defaultFaces`
+    (front and back; the tutorial's Allrun turns it from empty into wall and gives it a specular model)."""
+    xs = np.concatenate([_graded(0.0, 0.05, 5, 0.5), _graded(0.05, 1.0, 95, 2.0)[1:]])
+    ys = _graded(0.0, 0.6, 60, 2.0)
+    zs = np.array([0.0, 0.001])
+    nx, ny = len(xs) - 1, len(ys) - 1
+    pts, index = [], {}
+
+    def P(i, j, k):
+        key = (i, j, k)
+        if key not in index:
+            index[key] = len(pts)
+            pts.append((xs[i], ys[j], zs[k]))
+        return index[key]
+
+    cells = []
+    for i0, i1 in ((0, 5), (5, nx)):
+        for j in range(ny):
+            for i in range(i0, i1):
+                k = 0
+                cells.append([
+                    (P(i, j, k), P(i, j, k + 1), P(i, j + 1, k + 1), P(i, j + 1, k)),
+                    (P(i + 1, j, k), P(i + 1, j + 1, k), P(i + 1, j + 1, k + 1), P(i + 1, j, k + 1)),
+                    (P(i, j, k), P(i + 1, j, k), P(i + 1, j, k + 1), P(i, j, k + 1)),
+                    (P(i, j + 1, k), P(i, j + 1, k + 1), P(i + 1, j + 1, k + 1), P(i + 1, j + 1, k)),
+                    (P(i, j, k), P(i, j + 1, k), P(i + 1, j + 1, k), P(i + 1, j, k)),
+                    (P(i, j, k + 1), P(i + 1, j, k + 1), P(i + 1, j + 1, k + 1), P(i, j + 1, k + 1)),
+                ])
+    points = np.array(pts, dtype=np.float64)
+
+    def patch_of(face):
+        p = points[list(face)]
+        if np.ptp(p[:, 2]) < 1e-12:
+            return "defaultFaces"
+        c = p.mean(0)
+        if c[1] < 1e-12 and c[0] > 0.05:
+            return "plate"
+        return "inlet"
+
+    mesh = poly_mesh_from_cells(points, cells, patch_of, [("plate", "wall"), ("inlet", "patch"), ("defaultFaces", "wall")])
+    mesh.shape = (nx, ny, 1)
+    mesh.xs, mesh.ys = xs, ys
+    return mesh

@@ -34,5 +34,23 @@ def main():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def flat_plate():
+    """tests/golden/supersonicFlatPlate.npz from run/hyStrath/dsmcFoam+/supersonicFlatPlate/backup-0.04 (averages over t = 8..40 ms)."""
+    case = "/root/reference/run/hyStrath/dsmcFoam+/supersonicFlatPlate"
+    d = os.path.join(case, "backup-0.04")
+    out = {}
+    for n in ("rhoN", "rhoM", "Ttra", "Trot", "Tov", "p", "Ma", "mfp", "dsmcNMean"):
+        out[n] = ff.read_internal_field(os.path.join(d, f"{n}_N2cold")).astype(np.float32)
+    out["U"] = ff.read_internal_field(os.path.join(d, "U_N2cold")).astype(np.float32)
+    for n in ("wallHeatFlux", "wallShearStress", "p", "rhoN", "Ttra", "Trot", "fD", "U"):
+        out[f"wall_{n}"] = ff.read_patch_field(os.path.join(d, f"{n}_N2cold"), "plate").astype(np.float32)
+    props = ff.read_dict(os.path.join(case, "constant", "dsmcProperties"))
+    out["nEquivalentParticles"] = np.float64(props["nEquivalentParticles"])
+    path = os.path.join(ROOT, "tests", "golden", "supersonicFlatPlate.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     main()
+    flat_plate()

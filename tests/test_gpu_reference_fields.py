@@ -170,3 +170,69 @@ def test_hypersonic_corner_matches_the_shipped_dsmcfoam_fields():
     print("corner vs shipped: rhoN rms %.4f, Ttra rms %.4f, wall means %s" % (
         np.sqrt(((f["rhoN"] / g["rhoN"] - 1) ** 2).mean()), np.sqrt(((f["Ttra"] / g["Ttra"] - 1) ** 2).mean()),
         ", ".join(f"{k} {v:+.4f}" for k, v in report.items())))
+
+
+def test_supersonic_flat_plate_matches_the_shipped_dsmcfoam_fields():
+    """The reference's supersonicFlatPlate tutorial (Mach-4 nitrogen, rotational relaxation only, over a 500 K diffuse plate; graded
+    two-block mesh one cell thick with specular front and back walls; free-stream inflow + deletion everywhere else), run as its Allrun
+    does -- dsmcMeshFill, 10 000 steps of 4 us, sampling restarted at 8 ms -- against the fields dsmcFoam+ wrote at t = 40 ms
+    (tests/golden/supersonicFlatPlate.npz).  The mesh restatement itself is pinned by the shipped data: dsmcNMean F_N / (rhoN V) = 1
+    in all 6000 cells with the volumes of meshgen.flat_plate_mesh()."""
+    import os
+
+    from hystrath_b200 import meshgen
+
+    g = np.load(os.path.join(os.path.dirname(GOLD), "supersonicFlatPlate.npz"))
+    mesh = meshgen.flat_plate_mesh()
+    n2 = capi.make_species("N2cold", 46.5e-27, 4.17e-10, 0.74, 1.36, 2)
+    fnum = float(g["nEquivalentParticles"])
+    pm = [dict(patch=mesh.patch_index("plate"), boundaryModel="dsmcDiffuseWallPatch", temperature=500.0, velocity=(0, 0, 0)),
+          dict(patch=mesh.patch_index("defaultFaces"), boundaryModel="dsmcSpecularWallPatch"),
+          dict(patch=mesh.patch_index("inlet"), boundaryModel="dsmcDeletionPatch")]
+    inflow = [dict(patch=mesh.patch_index("inlet"), typeIds=[0], numberDensities=[1e20], velocity=(1412.5, 0.0, 0.0), translationalTemperature=300.0,
+                   rotationalTemperature=300.0)]
+    md = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=fnum, deltaT=4e-6, seed=40, patch_models=pm, inflows=inflow,
+                           rotationalRelaxationCollisionNumber=5.0)
+    eng = capi.Engine(0)
+    eng.set_mesh(mesh); eng.set_species([n2]); eng.set_models(md)
+    eng.reserve(1_000_000)
+    eng.mesh_fill([0], [1e20], 300.0, 300.0, 0.0, 0.0, (1412.5, 0.0, 0.0))
+    _, cv, face_centres, face_areas, _ = eng.geometry()
+    r = g["dsmcNMean"].astype(float) * fnum / (g["rhoN"].astype(float) * cv)
+    assert np.abs(r - 1).max() < 2e-6                        # float32 fixture: the mesh restatement has the reference's cell volumes
+    eng.evolve(2000)
+    eng.reset_accumulators()                                 # resetAtOutputUntilTime 8e-3
+    eng.evolve(8000)
+    acc, coll, nt = eng.accumulators()
+    wall = eng.wall_accumulators()
+    eng.close()
+    assert nt == 8000
+    spd = [dict(mass=n2.mass, diameter=n2.diameter, omega=n2.omega, rotDof=2.0, thetaV=[])]
+    f = fields_ref.derive(acc, coll, nt, spd, [0], fnum, cv, deltaT=4e-6, n_modes=0)
+    for name, tol_rms, tol_mean in (("rhoN", 0.02, 0.003), ("Ttra", 0.025, 0.004), ("Trot", 0.035, 0.005), ("p", 0.03, 0.005)):
+        rr = f[name] / g[name].astype(float) - 1
+        assert np.sqrt((rr ** 2).mean()) < tol_rms and abs(rr.mean()) < tol_mean, (name, np.sqrt((rr ** 2).mean()), rr.mean())
+    dU = f["UMean"] - g["U"].astype(float)
+    assert np.sqrt((dU ** 2).sum(1).mean()) < 20.0 and np.abs(dU.mean(0)).max() < 2.5          # of 1412.5 m/s
+    # rotational non-equilibrium in the boundary layer and the shock: Ttra - Trot where dsmcFoam+ has it
+    lag, lag_g = (f["Ttra"] - f["Trot"]), (g["Ttra"] - g["Trot"]).astype(float)
+    big = lag_g > 100.0
+    assert big.sum() > 100 and abs(lag[big].mean() / lag_g[big].mean() - 1) < 0.03
+    # ---- the plate, face by face from the leading edge (95 faces in x order)
+    start = mesh.patches[mesh.patch_index("plate")]["start"]
+    faces = np.arange(start, start + 95)
+    assert np.all(np.diff(face_centres[faces, 0]) > 0)
+    first = mesh.points[mesh.face_points[mesh.face_offsets[faces]]]
+    row0 = 0                                                 # plate is the first patch model with a wall model
+    wf = fields_ref.wall_fields(wall[row0:row0 + 95], nt, spd, [0], fnum, face_areas[faces], face_centres[faces], first)
+    report = {}
+    for name, tol_mean, tol_face in (("wallHeatFlux", 0.015, 0.10), ("wallShearStress", 0.015, 0.08), ("p", 0.01, 0.05), ("Ttra", 0.01, 0.04),
+                                     ("Trot", 0.01, 0.05)):
+        got, ref = wf[name], g[f"wall_{name}"].astype(float)
+        area = np.linalg.norm(face_areas[faces], axis=1)
+        report[name] = (got * area).sum() / (ref * area).sum() - 1
+        assert abs(report[name]) < tol_mean, (name, report[name])
+        assert np.abs(got / ref - 1).max() < tol_face, (name, np.abs(got / ref - 1).max())
+    print("flat plate vs shipped: rhoN rms %.4f, Ttra rms %.4f, Trot rms %.4f; plate integrals %s" % (
+        np.sqrt(((f["rhoN"] / g["rhoN"] - 1) ** 2).mean()), np.sqrt(((f["Ttra"] / g["Ttra"] - 1) ** 2).mean()),
+        np.sqrt(((f["Trot"] / g["Trot"] - 1) ** 2).mean()), ", ".join(f"{k} {v:+.4f}" for k, v in report.items())))
