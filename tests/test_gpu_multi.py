@@ -70,3 +70,86 @@ def test_two_gpu_migration_matches_single_domain_oracle():
     assert np.array_equal(cell[order], ref["cell"])
     assert np.allclose(pos[order], ref["position"], rtol=0, atol=1e-15)
     assert all(r[4] > 0 for r in results)
+
+
+# ---- the same with walls: a channel (diffuse walls at y = 0 and y = Ly) cut in x between the two GPUs --------------------------------
+def _channel_models(fnum, patch):
+    pm = [dict(patch=patch, boundaryModel="dsmcDiffuseWallPatch", temperature=700.0, velocity=(120.0, 0.0, 0.0))]
+    return capi.build_models("NoBinaryCollision", nEquivalentParticles=fnum, deltaT=6e-6, seed=78, patch_models=pm)
+
+
+def _channel_reference():
+    from oracle.pyoracle import Oracle
+
+    sides = {"xmin": ("cyclic",), "xmax": ("cyclic",), "ymin": ("wall", "walls"), "ymax": ("wall", "walls"), "zmin": ("cyclic",), "zmax": ("cyclic",)}
+    mesh = meshgen.box_mesh((8, 4, 3), (0.032, 0.016, 0.012), sides=sides)
+    fnum = 1e20 * 0.032 * 0.016 * 0.012 / (96 * 40)
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species([H.argon()]); o.set_models(_channel_models(fnum, mesh.patch_index("walls")))
+    o.mesh_fill([0], [1e20], 300.0, velocity=(150.0, 0.0, 0.0))
+    start = o.download_parcels()
+    o.evolve(STEPS)
+    return fnum, start, H.by_id(o.download_parcels()), o.wall_accumulators()
+
+
+def _channel_worker(rank, world, q_id, q_out):
+    try:
+        torch.cuda.set_device(rank)
+        fnum, start, _, _ = _channel_reference()
+        mesh = meshgen.decomposed_box(N_LOCAL, L_LOCAL, PROCS, rank, outer=("cyclic", ("wall", "walls"), "cyclic"))
+        eng = capi.Engine(rank, rank, world)
+        eng.set_mesh(mesh); eng.set_species([H.argon()]); eng.set_models(_channel_models(fnum, mesh.patch_index("walls")))
+        if rank == 0:
+            ident = capi.nccl_unique_id()
+            for _ in range(world - 1):
+                q_id.put(ident)
+        else:
+            ident = q_id.get(timeout=120)
+        eng.init_comm(ident)
+        gi, gj, gk = start.cell % 8, (start.cell // 8) % 4, start.cell // 32
+        mine = (gi // 4) == rank
+        loc = (gi % 4 + 4 * (gj + 4 * gk)).astype(np.int32)
+        p = capi.ParcelData(int(mine.sum()), 1, allocate=False, position=start.position[mine], U=start.U[mine], cell=loc[mine],
+                            typeId=start.typeId[mine], origId=start.origId[mine])
+        eng.upload_parcels(p)
+        eng.evolve(STEPS)
+        res = eng.download_parcels()
+        li, lj, lk = res.cell % 4, (res.cell // 4) % 4, res.cell // 16
+        gcell = (li + 4 * rank) + 8 * (lj + 4 * lk)
+        w = eng.wall_accumulators()
+        q_out.put((rank, res.origId.copy(), res.position.copy(), gcell.astype(np.int32), res.U.copy(), w.sum(axis=(0, 1))))
+        eng.close()
+    except Exception as e:
+        q_out.put((rank, repr(e)))
+
+
+def test_two_gpu_channel_with_diffuse_walls_matches_single_domain_oracle():
+    """Walls and migration together: a parcel re-emitted by a wall on one GPU may cross to the other in the same step; wall draws are
+    keyed by (origId, hit, step), so the union of the two clouds equals the single-domain run, wall-sampled sums included."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q_id, q_out = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_channel_worker, args=(r, 2, q_id, q_out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q_out.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for r in results:
+        assert len(r) == 6, r
+    fnum, start, ref, wref = _channel_reference()
+    ids = np.concatenate([r[1] for r in results])
+    pos = np.concatenate([r[2] for r in results])
+    cell = np.concatenate([r[3] for r in results])
+    U = np.concatenate([r[4] for r in results])
+    order = np.argsort(ids)
+    assert np.array_equal(ids[order], ref["origId"])
+    assert np.array_equal(cell[order], ref["cell"])
+    assert np.allclose(U[order], ref["U"], rtol=0, atol=1e-9)
+    assert np.allclose(pos[order], ref["position"], rtol=0, atol=1e-12)
+    hit = (ref["U"] != H.by_id(start)["U"]).any(1)
+    assert hit.sum() > 200
+    wsum = results[0][5] + results[1][5]
+    wr = wref.sum(axis=(0, 1))
+    assert np.abs(wsum - wr).max() / np.abs(wr).max() < 1e-9 and np.abs(wr).max() > 0
