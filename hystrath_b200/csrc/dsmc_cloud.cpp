@@ -695,7 +695,7 @@ double dsmcCloud::cellMaxDx(int c) const {
     return cellMaxDx_[c];
 }
 
-void dsmcCloud::writeFields(const std::string& timeDir) {
+void dsmcCloud::writeFields(const std::string& timeDir, const std::vector<double>& instN) {
     // Boundary values (dsmcVolFields.C:1878-2206): faces of `wall` patches get every field from the wall accumulators
     // (the *BF_ arrays of boundaryMeasurements), every other non-empty, non-cyclic patch the adjacent cell value.
     int32_t nMeas = 0, nWallQ = 0;
@@ -817,6 +817,12 @@ void dsmcCloud::writeFields(const std::string& timeDir) {
             foam::writeVolField(timeDir + "/" + name + "_" + f.fieldName, timeName_, name + "_" + f.fieldName, dims, v.data(), nCells_, 1,
                                 scalarPatches(v, pick));
         };
+        {
+            std::vector<double> dsmcN(size_t(nCells_), 0.0);
+            for (int c = 0; c < nCells_; ++c)
+                for (int s : f.typeIds) dsmcN[c] += instN[size_t(c) * S + s];
+            wr("dsmcN", "[0 0 0 0 0 0 0]", dsmcN);
+        }
         wr("dsmcNMean", "[0 0 0 0 0 0 0]", d.dsmcNMean);
         wr("rhoN", "[0 -3 0 0 0 0 0]", d.rhoN, &WallFace::rhoN);
         wr("rhoM", "[1 -3 0 0 0 0 0]", d.rhoM, &WallFace::rhoM);
@@ -1197,7 +1203,13 @@ void dsmcCloud::write() {
     }
     foam::writeVolField(timeDir + "/dsmcSigmaTcRMax", timeName_, "dsmcSigmaTcRMax", "[0 3 -1 0 0 0 0]", sig.data(), nCells_, 1, pv);
     if (initialise_) return;  // dsmcInitialise+ writes the cloud and dsmcSigmaTcRMax only
-    writeFields(timeDir);
+    {
+        const int S = int(species_.size());
+        std::vector<double> instN(size_t(nCells_) * S, 0.0);
+        for (int64_t i = 0; i < got; ++i)
+            if (cell[i] >= 0 && cell[i] < nCells_ && typeId[i] >= 0 && typeId[i] < S) instN[size_t(cell[i]) * S + typeId[i]] += 1.0;
+        writeFields(timeDir, instN);
+    }
     // resetAtOutput (dsmcField.C:113-152): the accumulators are shared by all instances, so they reset together
     bool reset = !fields_.empty();
     for (auto& f : fields_) reset = reset && f.resetAtOutput && !(time_ + deltaT_ > f.resetAtOutputUntilTime);

@@ -75,7 +75,8 @@ class dsmcCloud {
     void readBoundaries();
     void readFieldProperties();
     void readCloud();
-    void writeFields(const std::string& timeDir);
+    // instN: [nCells][nSpecies] parcels in the cells right now (dsmcN_, the AUTO_WRITE instantaneous count of dsmcVolFields.C:106-117)
+    void writeFields(const std::string& timeDir, const std::vector<double>& instN);
     double cellMaxDx(int c) const;  // largest extent of the cell's points along x, y, z (dsmcVolFields.C:1795-1821)
     void writeResumeSampling(const std::string& timeDir);  // dsmcVolFields::writeOut + the engine's own lossless checkpoint
     void readResumeSampling();                              // dsmcVolFields::readIn

@@ -80,6 +80,10 @@ def test_driver_runs_couette_case_and_matches_oracle(tmp_path):
                 scale = np.abs(wf[key]).max() + 1e-300
                 assert np.abs(got - wf[key]).max() / scale < 5e-9, (name, inst, patch)
         assert np.abs(wf["wallHeatFlux"]).max() > 0 and np.abs(wf["wallShearStress"]).max() > 0
+    # dsmcN_: the instantaneous parcel count per cell of the instance (AUTO_WRITE in the reference)
+    nN2 = ff.read_internal_field(os.path.join(tdir, "dsmcN_N2"))
+    assert np.array_equal(nN2, np.bincount(ref.cell[ref.typeId == 0], minlength=500))
+    assert ff.read_internal_field(os.path.join(tdir, "dsmcN_mixture")).sum() == ref.n
     for name in ("mfpToDx", "SOFP"):
         v = ff.read_internal_field(os.path.join(tdir, f"{name}_mixture"))
         assert v.shape == (500,) and np.all(v > 0)
