@@ -372,6 +372,7 @@ void dsmcCloud::readFieldProperties() {
         s.densityOnly = pr.boolOr("densityOnly", false);
         s.measureHeatFluxShearStress = pr.boolOr("measureHeatFluxShearStress", false);
         s.measureClassifications = pr.boolOr("measureClassifications", false);
+        s.measureErrors = pr.boolOr("measureErrors", false);
         s.mfpReferenceTemperature = pr.scalarOr("mfpReferenceTemperature", 273.0);
         s.sampleInterval = int(pr.labelOr("sampleInterval", 1));
         s.averagingAcrossManyRuns = pr.boolOr("averagingAcrossManyRuns", false);
@@ -560,6 +561,8 @@ DerivedFields dsmcCloud::calculateField(const FieldSpec& f) {
     auto z = [&](std::vector<double>& v, int w = 1) { v.assign(size_t(nC) * w, 0.0); };
     z(o.dsmcNMean); z(o.rhoN); z(o.rhoM); z(o.p); z(o.Ttra); z(o.Trot); z(o.Tvib); z(o.Tov); z(o.Ma); z(o.mfp); z(o.mct); z(o.mctToDt);
     z(o.mfpToDx); z(o.SOF); z(o.measuredCollisionRate); z(o.UMean, 3);
+    if (f.measureHeatFluxShearStress) { z(o.pressureTensor, 9); z(o.shearStressTensor, 9); z(o.heatFluxVector, 3); }
+    if (f.measureErrors) { z(o.rhoMError); z(o.UError); z(o.TError); z(o.pError); }
     const double NAvo = 6.02214e26;  // OpenFOAM SI physicoChemical::NA is per kmol
     (void)NAvo;
     for (int c = 0; c < nC; ++c) {
@@ -619,7 +622,34 @@ DerivedFields dsmcCloud::calculateField(const FieldSpec& f) {
         }
         o.Tvib[c] = Tvib;
         o.Tov[c] = (3.0 * o.Ttra[c] + zetaRotTot * o.Trot[c] + zetaVib * Tvib) / (3.0 + zetaRotTot + zetaVib);
+        // pressure tensor, shear-stress tensor and heat-flux vector (dsmcVolFields.C:1509-1622)
+        if (f.measureHeatFluxShearStress && models_.measureHeatFluxShearStress && dsmcNCum > SMALL) {
+            const int qF = 5 + (internal ? 2 + (ai.nModes > 0 ? ai.nModes : 0) : 0);
+            double M[6] = {0, 0, 0, 0, 0, 0}, Mcc[3] = {0, 0, 0}, E[3] = {0, 0, 0}, MccAll = 0, ECum = 0;
+            for (int s : f.typeIds) {
+                const double* r = &acc[(size_t(c) * S + s) * nQ];
+                const double m = species_[s].mass;
+                for (int k = 0; k < 6; ++k) M[k] += m * r[qF + k];           // Muu Muv Muw Mvv Mvw Mww
+                for (int k = 0; k < 3; ++k) { Mcc[k] += m * r[qF + 6 + k]; E[k] += r[qF + 9 + k]; }
+                MccAll += m * r[4];
+                if (internal) { ECum += r[5]; for (int md = 0; md < species_[s].nVibrationalModes; ++md) ECum += r[7 + md]; }
+            }
+            const double* u = &o.UMean[3 * size_t(c)];
+            const double k0 = o.rhoN[c] / dsmcNCum;
+            double* P = &o.pressureTensor[9 * size_t(c)];
+            const int idx[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) P[3 * a + b] = k0 * (M[idx[a][b]] - mCumP * u[a] * u[b]);
+            const double scalarPressure = (P[0] + P[4] + P[8]) / 3.0;
+            double* T = &o.shearStressTensor[9 * size_t(c)];
+            for (int k = 0; k < 9; ++k) T[k] = -P[k];
+            T[0] += scalarPressure; T[4] += scalarPressure; T[8] += scalarPressure;
+            for (int a = 0; a < 3; ++a)
+                o.heatFluxVector[3 * size_t(c) + a] = k0 * (0.5 * Mcc[a] - 0.5 * MccAll * u[a] + E[a] - ECum * u[a]) - P[3 * a] * u[0] - P[3 * a + 1] * u[1] -
+                                                      P[3 * a + 2] * u[2];
+        }
         // Mach number (dsmcVolFields.C:1624-1661)
+        double gammaCell = 0.0, particleCv = 0.0;
         if (dsmcNCum > SMALL && o.Ttra[c] > SMALL) {
             double molecularMass = 0, cv = 0, cp = 0;
             for (int s : f.typeIds) {
@@ -629,9 +659,18 @@ DerivedFields dsmcCloud::calculateField(const FieldSpec& f) {
                 cp += Xs * (5.0 + species_[s].rotationalDegreesOfFreedom);
             }
             const double gamma = cp / cv;
+            gammaCell = gamma; particleCv = cv / 6.02214e26;   // molarCv_trarot / NAvo, OpenFOAM's NA is per kmol (dsmcVolFields.C:1647)
             const double a = std::sqrt(gamma * kB / molecularMass * o.Ttra[c]);
             const double* u = &o.UMean[3 * c];
             o.Ma[c] = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]) / a;
+        }
+        // statistical error estimates (dsmcVolFields.C:1857-1873)
+        if (f.measureErrors && o.dsmcNMean[c] > SMALL && o.Ma[c] > SMALL && gammaCell > SMALL && particleCv > SMALL) {
+            const double deno = std::sqrt(o.dsmcNMean[c] * nT);
+            o.rhoMError[c] = 1.0 / deno;
+            o.UError[c] = 1.0 / (deno * o.Ma[c] * std::sqrt(gammaCell));
+            o.TError[c] = std::sqrt(kB / particleCv) / deno;
+            o.pError[c] = std::sqrt(gammaCell) / deno;
         }
         if (f.measureMeanFreePath && o.Ttra[c] > 1.0) {
             double mfp = 0, mcr = 0;
@@ -851,6 +890,30 @@ void dsmcCloud::writeFields(const std::string& timeDir, const std::vector<double
             wr("mct", "[0 0 1 0 0 0 0]", d.mct);
             wr("mctToDt", "[0 0 0 0 0 0 0]", d.mctToDt);
             wr("SOFP", "[0 0 0 0 0 0 0]", d.SOF);
+        }
+        if (f.measureErrors) {
+            wr("rhoMError", "[0 0 0 0 0 0 0]", d.rhoMError); wr("UError", "[0 0 0 0 0 0 0]", d.UError);
+            wr("TError", "[0 0 0 0 0 0 0]", d.TError); wr("pError", "[0 0 0 0 0 0 0]", d.pError);
+        }
+        if (f.measureHeatFluxShearStress && !d.heatFluxVector.empty()) {
+            // zero-gradient boundary values (dsmcVolFields.C:2183-2191)
+            auto multi = [&](const std::string& name, const std::string& dims, const std::vector<double>& v, int nc) {
+                std::vector<foam::PatchValues> pv;
+                for (size_t j = 0; j < boundary_.size(); ++j) {
+                    foam::PatchValues p;
+                    p.name = boundary_[j].name; p.type = boundary_[j].type;
+                    if (p.type == "wall" || p.type == "patch") {
+                        p.values.resize(size_t(boundary_[j].nFaces) * nc);
+                        for (int k = 0; k < boundary_[j].nFaces; ++k)
+                            for (int q = 0; q < nc; ++q) p.values[size_t(k) * nc + q] = v[size_t(owner_[boundary_[j].startFace + k]) * nc + q];
+                    }
+                    pv.push_back(p);
+                }
+                foam::writeVolField(timeDir + "/" + name + "_" + f.fieldName, timeName_, name + "_" + f.fieldName, dims, v.data(), nCells_, nc, pv);
+            };
+            multi("heatFluxVector", "[1 0 -3 0 0 0 0]", d.heatFluxVector, 3);
+            multi("pressureTensor", "[1 -1 -2 0 0 0 0]", d.pressureTensor, 9);
+            multi("shearStressTensor", "[1 -1 -2 0 0 0 0]", d.shearStressTensor, 9);
         }
         // vectors: U and the wall force density fD
         {

@@ -33,7 +33,7 @@ int patchTypeFromWord(const std::string& type);
 struct FieldSpec {  // one dsmcVolFields entry of system/fieldPropertiesDict
     std::string fieldName;
     std::vector<int> typeIds;
-    bool measureMeanFreePath = false, densityOnly = false, measureHeatFluxShearStress = false, measureClassifications = false;
+    bool measureMeanFreePath = false, densityOnly = false, measureHeatFluxShearStress = false, measureClassifications = false, measureErrors = false;
     double mfpReferenceTemperature = 273.0;
     bool resetAtOutput = true;
     double resetAtOutputUntilTime = 1e300;
@@ -44,6 +44,9 @@ struct FieldSpec {  // one dsmcVolFields entry of system/fieldPropertiesDict
 struct DerivedFields {  // per-cell results of dsmcVolFields::calculateField for one instance
     std::vector<double> dsmcNMean, rhoN, rhoM, p, Ttra, Trot, Tvib, Tov, Ma, mfp, mct, mctToDt, mfpToDx, SOF, measuredCollisionRate;
     std::vector<double> UMean;  // [3n]
+    std::vector<double> pressureTensor, shearStressTensor;  // [9n] (measureHeatFluxShearStress)
+    std::vector<double> heatFluxVector;                     // [3n]
+    std::vector<double> rhoMError, UError, TError, pError;  // measureErrors
 };
 
 class dsmcCloud {

@@ -591,13 +591,13 @@ void writeLabelListList(const std::string& path, const std::string& cls, const s
 void writeVolField(const std::string& path, const std::string& location, const std::string& object, const std::string& dimensions,
                    const double* internal, int64_t nCells, int nCmpt, const std::vector<PatchValues>& patches) {
     FILE* f = openw(path);
-    std::fputs(header(nCmpt == 1 ? "volScalarField" : "volVectorField", location, object).c_str(), f);
+    std::fputs(header(nCmpt == 1 ? "volScalarField" : (nCmpt == 3 ? "volVectorField" : "volTensorField"), location, object).c_str(), f);
     std::fprintf(f, "dimensions      %s;\n\n", dimensions.c_str());
     auto put = [&](const double* v) {
         if (nCmpt == 1) fmt(f, v[0]);
         else { std::fputc('(', f); for (int d = 0; d < nCmpt; ++d) { if (d) std::fputc(' ', f); fmt(f, v[d]); } std::fputc(')', f); }
     };
-    std::fprintf(f, "internalField   nonuniform List<%s> \n%lld\n(\n", nCmpt == 1 ? "scalar" : "vector", (long long)nCells);
+    std::fprintf(f, "internalField   nonuniform List<%s> \n%lld\n(\n", nCmpt == 1 ? "scalar" : (nCmpt == 3 ? "vector" : "tensor"), (long long)nCells);
     for (int64_t i = 0; i < nCells; ++i) { put(internal + i * nCmpt); std::fputc('\n', f); }
     std::fputs(")\n;\n\nboundaryField\n{\n", f);
     for (auto& p : patches) {
@@ -609,9 +609,9 @@ void writeVolField(const std::string& path, const std::string& location, const s
             std::fputs("        type            calculated;\n", f);
             const int64_t nf = int64_t(p.values.size()) / nCmpt;
             if (nf == 0) {
-                std::fputs(nCmpt == 1 ? "        value           uniform 0;\n" : "        value           uniform (0 0 0);\n", f);
+                std::fputs(nCmpt == 1 ? "        value           uniform 0;\n" : (nCmpt == 3 ? "        value           uniform (0 0 0);\n" : "        value           uniform (0 0 0 0 0 0 0 0 0);\n"), f);
             } else {
-                std::fprintf(f, "        value           nonuniform List<%s> \n%lld\n(\n", nCmpt == 1 ? "scalar" : "vector", (long long)nf);
+                std::fprintf(f, "        value           nonuniform List<%s> \n%lld\n(\n", nCmpt == 1 ? "scalar" : (nCmpt == 3 ? "vector" : "tensor"), (long long)nf);
                 for (int64_t i = 0; i < nf; ++i) { put(p.values.data() + i * nCmpt); std::fputc('\n', f); }
                 std::fputs(")\n;\n", f);
             }

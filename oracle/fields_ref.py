@@ -156,3 +156,45 @@ def wall_fields(wall, n_time_steps, species, type_ids, fnum, face_areas, face_ce
     out.update(U=U, Ttra=Ttra, Trot=Trot, Tvib=Tvib, Tov=Tov, Ma=Ma, fD=fD, p=(fD * n).sum(1),
                wallShearStress=np.sqrt((fD * t1).sum(1) ** 2 + (fD * t2).sum(1) ** 2), wallHeatFlux=w[:, ids, 13].sum(1) / nT)
     return out
+
+
+def flux_fields(acc, n_time_steps, species, type_ids, fnum, cell_volumes, q_flux, n_modes=1, has_internal=True):
+    """pressureTensor, shearStressTensor and heatFluxVector of dsmcVolFields.C:1509-1622 from the twelve extra moments the sampling
+    stage keeps with measureHeatFluxShearStress (uu uv uw vv vw ww, c^2 u c^2 v c^2 w, E_int u E_int v E_int w at index q_flux..)."""
+    acc = np.asarray(acc, float)
+    ids = list(type_ids)
+    V, nT = np.asarray(cell_volumes, float), float(n_time_steps)
+    m = np.array([species[s]["mass"] for s in ids])
+    Ns = acc[:, ids, 0]
+    dsmcNCum = Ns.sum(1)
+    dsmcMCum = (Ns * m).sum(1)
+    ok = dsmcNCum > SMALL
+    safeN = np.where(ok, dsmcNCum, 1.0)
+    rhoN = fnum * dsmcNCum / (nT * V)
+    U = (acc[:, ids, 1:4] * m[None, :, None]).sum(1) / np.where(ok, dsmcMCum, 1.0)[:, None]
+    M = (acc[:, ids, q_flux:q_flux + 6] * m[None, :, None]).sum(1)
+    Mcc = (acc[:, ids, q_flux + 6:q_flux + 9] * m[None, :, None]).sum(1)
+    E = acc[:, ids, q_flux + 9:q_flux + 12].sum(1)
+    MccAll = (acc[:, ids, 4] * m).sum(1)
+    ECum = np.zeros(len(V))
+    if has_internal:
+        ECum = acc[:, ids, 5].sum(1)
+        for k, s in enumerate(ids):
+            for mode in range(len(species[s].get("thetaV", []))):
+                ECum = ECum + acc[:, s, 7 + mode]
+    k0 = rhoN / safeN
+    idx = [[0, 1, 2], [1, 3, 4], [2, 4, 5]]
+    P = np.zeros((len(V), 3, 3))
+    for a in range(3):
+        for b in range(3):
+            P[:, a, b] = k0 * (M[:, idx[a][b]] - dsmcMCum * U[:, a] * U[:, b])
+    sp = (P[:, 0, 0] + P[:, 1, 1] + P[:, 2, 2]) / 3.0
+    T = -P.copy()
+    for a in range(3):
+        T[:, a, a] += sp
+    q = np.zeros((len(V), 3))
+    for a in range(3):
+        q[:, a] = k0 * (0.5 * Mcc[:, a] - 0.5 * MccAll * U[:, a] + E[:, a] - ECum * U[:, a]) - (P[:, a, :] * U).sum(1)
+    z = ~ok
+    P[z] = 0; T[z] = 0; q[z] = 0
+    return dict(pressureTensor=P.reshape(-1, 9), shearStressTensor=T.reshape(-1, 9), heatFluxVector=q)

@@ -164,6 +164,8 @@ dsmcFields
             fieldName               mixture;
             typeIds                 (N2 O2);
             measureMeanFreePath     true;
+            measureHeatFluxShearStress  true;
+            measureErrors           true;
          }
      }
 );

@@ -32,7 +32,8 @@ def test_driver_runs_couette_case_and_matches_oracle(tmp_path):
     pm = [dict(patch=mesh.patch_index("upperWall"), boundaryModel="dsmcDiffuseWallPatch", temperature=3000.0, velocity=(300.0, 0, 0)),
           dict(patch=mesh.patch_index("lowerWall"), boundaryModel="dsmcDiffuseWallPatch", temperature=2000.0, velocity=(0, 0, 0))]
     md = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=float(g["nEquivalentParticles"]), deltaT=1e-5,
-                           seed=5, patch_models=pm, inverseZvFormulation="pre-2008", rotationalRelaxationCollisionNumber=5.0)
+                           seed=5, patch_models=pm, inverseZvFormulation="pre-2008", rotationalRelaxationCollisionNumber=5.0,
+                           measureHeatFluxShearStress=True)       # the mixture field asks for it in fieldPropertiesDict
     o = Oracle()
     o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
     o.upload_parcels(p)
@@ -80,6 +81,16 @@ def test_driver_runs_couette_case_and_matches_oracle(tmp_path):
                 scale = np.abs(wf[key]).max() + 1e-300
                 assert np.abs(got - wf[key]).max() / scale < 5e-9, (name, inst, patch)
         assert np.abs(wf["wallHeatFlux"]).max() > 0 and np.abs(wf["wallShearStress"]).max() > 0
+    # measureHeatFluxShearStress / measureErrors of the mixture instance (dsmcVolFields.C:1509-1622, :1857-1873)
+    fx = fields_ref.flux_fields(acc, nt, spd, [0, 1], float(g["nEquivalentParticles"]), cv, q_flux=8)
+    for name, key in (("heatFluxVector", "heatFluxVector"), ("pressureTensor", "pressureTensor"), ("shearStressTensor", "shearStressTensor")):
+        got = ff.read_internal_field(os.path.join(tdir, f"{name}_mixture"))
+        assert got.shape == fx[key].shape and np.allclose(got, fx[key], rtol=2e-8, atol=1e-9 * np.abs(fx[key]).max()), name
+    # measureErrors: the reference guards the four estimates with particleCv > SMALL where particleCv = molarCv/(0.5 k)/N_A ~ 1e-26
+    # (dsmcVolFields.C:1647,1859-1864), so its error fields are written but always zero; the driver keeps that
+    for name in ("rhoMError", "UError", "TError", "pError"):
+        assert not ff.read_internal_field(os.path.join(tdir, f"{name}_mixture")).any()
+    assert not os.path.exists(os.path.join(tdir, "heatFluxVector_N2"))
     # dsmcN_: the instantaneous parcel count per cell of the instance (AUTO_WRITE in the reference)
     nN2 = ff.read_internal_field(os.path.join(tdir, "dsmcN_N2"))
     assert np.array_equal(nN2, np.bincount(ref.cell[ref.typeId == 0], minlength=500))

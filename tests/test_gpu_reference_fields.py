@@ -26,7 +26,7 @@ def test_couette_profiles_match_the_shipped_dsmcfoam_fields():
           dict(patch=mesh.patch_index("lowerWall"), boundaryModel="dsmcDiffuseWallPatch", temperature=2000.0, velocity=(0, 0, 0))]
     fnum = float(g["nEquivalentParticles"])
     md = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=fnum, deltaT=1e-5, seed=2024, patch_models=pm,
-                           inverseZvFormulation="pre-2008", rotationalRelaxationCollisionNumber=5.0)
+                           inverseZvFormulation="pre-2008", rotationalRelaxationCollisionNumber=5.0, measureHeatFluxShearStress=True)
     eng = capi.Engine(0)
     eng.set_mesh(mesh); eng.set_species(sp); eng.set_models(md)
     p = capi.ParcelData(len(g["cell"]), 1, allocate=False, position=g["positions"], U=g["U"], ERot=g["ERot"], cell=g["cell"],
@@ -88,6 +88,23 @@ def test_couette_profiles_match_the_shipped_dsmcfoam_fields():
         assert np.abs(wf["fD"].mean(0) - g[f"wall_fD_{patch}"].mean(0)).max() < 0.015 * np.abs(g[f"wall_fD_{patch}"]).max()
     assert abs(np.mean(g["wall_wallHeatFlux_lowerWall"]) + np.mean(g["wall_wallHeatFlux_upperWall"])) < 1.0   # steady state: what enters leaves
     print("wall faces vs shipped: " + ", ".join(f"{k[0]}@{k[1][:5]} {v:+.4f}" for k, v in worst.items()))
+    # ---- momentum and energy transport through the gas (measureHeatFluxShearStress: pressure tensor and heat-flux vector from second and
+    # third velocity moments, dsmcVolFields.C:1509-1622) against what dsmcFoam+ measured ON THE WALLS.  In steady Couette flow the shear
+    # stress p_xy and the energy flux q_y + p_xy u_x are uniform across the gap and equal to the wall shear stress and wall heat flux.
+    ff_ = fields_ref.flux_fields(acc, nt, spd, [0, 1], fnum, cv, q_flux=8)
+    pxy = rows(ff_["pressureTensor"][:, 1])
+    tau_wall = 0.5 * (np.mean(g["wall_wallShearStress_upperWall"]) + np.mean(g["wall_wallShearStress_lowerWall"]))
+    qy = rows(ff_["heatFluxVector"][:, 1])
+    energy_flux = qy + pxy * rows(f["UMean"][:, 0])
+    q_wall = np.mean(g["wall_wallHeatFlux_lowerWall"])
+    print("gas p_xy %.5f +- %.5f Pa vs shipped wall shear stress %.5f; gas q_y + p_xy u_x %.2f +- %.2f W/m2 vs shipped wall heat flux %.2f" % (
+        pxy.mean(), pxy.std(), tau_wall, energy_flux.mean(), energy_flux.std(), q_wall))
+    # (sampling happens right after the collision step, where the stress and the heat flux have just relaxed by ~dt/(2 tau): with
+    # dt = 0.14 mean collision times the snapshot moments sit a few per cent below the time-averaged fluxes the walls measure;
+    # dsmcFoam+ samples at the same point of the step, so this is the reference's own estimator, not an error of the restatement)
+    assert 0.88 < abs(pxy.mean()) / tau_wall < 1.01 and pxy.std() < 0.1 * tau_wall
+    assert 0.85 < abs(energy_flux.mean()) / q_wall < 1.02 and energy_flux.std() < 0.1 * q_wall
+    assert np.sign(pxy.mean()) == -1 and np.sign(energy_flux.mean()) == -1        # momentum and heat flow from the hot moving wall down
     # ---- collisions: the measured collision frequency against the analytic VHS value dsmcFoam+ wrote (mct = 1/nu, Bird 4.74/1.38; the
     # measured rate counts collisions, i.e. nu/2 per molecule: SURVEY quirk list), and the mean collision separation over the mean free
     # path (SOFP), which is what the octant sub-cell partner selection of noTimeCounter controls
