@@ -153,3 +153,95 @@ def test_two_gpu_channel_with_diffuse_walls_matches_single_domain_oracle():
     wsum = results[0][5] + results[1][5]
     wr = wref.sum(axis=(0, 1))
     assert np.abs(wsum - wr).max() / np.abs(wr).max() < 1e-9 and np.abs(wr).max() > 0
+
+
+def test_two_gpu_driver_runs_decomposed_case(tmp_path):
+    """dsmcb200_run -parallel on a decomposePar-style case: processor0/ and processor1/ each hold their brick (polyMesh with processor and
+    processorCyclic patches, start-time cloud), the dictionaries sit at the case root; one process per GPU, ncclUniqueId handed over through
+    the case directory.  A closed channel keeps its parcels; both ranks write their time directories; the log carries the global counts."""
+    import subprocess
+
+    from hystrath_b200 import case as casew
+    from oracle.pyoracle import Oracle
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    case = str(tmp_path)
+    run = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hystrath_b200", "dsmcb200_run")
+    fnum = 1e20 * 0.032 * 0.016 * 0.012 / (96 * 60)
+    total = 0
+    for rank in range(2):
+        mesh = meshgen.decomposed_box(N_LOCAL, L_LOCAL, PROCS, rank, outer=("cyclic", ("wall", "walls"), "cyclic"))
+        root = os.path.join(case, f"processor{rank}")
+        casew.write_poly_mesh(root, mesh)
+        pm = [dict(patch=mesh.patch_index("walls"), boundaryModel="dsmcDiffuseWallPatch", temperature=700.0, velocity=(120.0, 0.0, 0.0))]
+        o = Oracle()
+        o.set_mesh(mesh); o.set_species([H.argon()])
+        o.set_models(capi.build_models("VariableHardSphere", nEquivalentParticles=fnum, deltaT=6e-6, seed=90 + rank, patch_models=pm))
+        o.mesh_fill([0], [1e20], 300.0, velocity=(150.0, 0.0, 0.0))
+        p = o.download_parcels()
+        sig, _ = o.download_cellstate()
+        casew.write_cloud(root, "0", p, sig, mesh)
+        total += p.n
+    casew.write_dict(os.path.join(case, "constant", "dsmcProperties"), "constant", "dsmcProperties", """
+nEquivalentParticles            %.10g;
+seedNumber                      11;
+BinaryCollisionModel            VariableHardSphere;
+collisionPartnerSelectionModel  noTimeCounter;
+typeIdList                      (Ar);
+moleculeProperties
+{
+    Ar { mass 66.3e-27; diameter 4.17e-10; omega 0.81; alpha 1.0; }
+}
+""" % fnum)
+    casew.write_dict(os.path.join(case, "system", "controlDict"), "system", "controlDict", """
+application dsmcFoam+; nTerminalOutputs 5; startFrom latestTime; startTime 0; stopAt endTime; endTime 6e-5; deltaT 6e-6;
+writeControl timeStep; writeInterval 10; writeFormat ascii; writePrecision 10; timeFormat general; timePrecision 10;
+""")
+    casew.write_dict(os.path.join(case, "system", "boundariesDict"), "system", "boundariesDict", """
+dsmcPatchBoundaries
+(
+    boundary
+    {
+        patchBoundaryProperties { patchName walls; }
+        boundaryModel   dsmcDiffuseWallPatch;
+        dsmcDiffuseWallPatchProperties { temperature 700; velocity (120 0 0); }
+    }
+);
+dsmcCyclicBoundaries ( );
+dsmcGeneralBoundaries ( );
+""")
+    casew.write_dict(os.path.join(case, "system", "fieldPropertiesDict"), "system", "fieldPropertiesDict", """
+dsmcFields
+(
+    field
+    {
+        fieldModel dsmcVolFields;
+        timeProperties { timeOption write; resetAtOutput on; }
+        dsmcVolFieldsProperties { fieldName Ar; typeIds (Ar); }
+    }
+);
+""")
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank))
+        procs.append(subprocess.Popen([run, "-case", case, "-parallel"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se + so
+    log = outs[0][0]
+    assert f"Number of DSMC particles        = {total}" in log and "End stage 0" in log
+    n_end = 0
+    for rank in range(2):
+        tdir = os.path.join(case, f"processor{rank}", "6e-05")
+        assert os.path.isdir(tdir), os.listdir(os.path.join(case, f"processor{rank}"))
+        _, cell = ff_read_positions(os.path.join(tdir, "lagrangian", "dsmc", "positions"))
+        n_end += len(cell)
+        assert os.path.exists(os.path.join(tdir, "rhoN_Ar")) and os.path.exists(os.path.join(tdir, "dsmcSigmaTcRMax"))
+    assert n_end == total                                      # diffuse walls re-emit, processor / processorCyclic patches hand over
+
+
+def ff_read_positions(path):
+    from hystrath_b200 import foamfile as ff
+
+    return ff.read_positions(path)
