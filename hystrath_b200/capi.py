@@ -87,7 +87,7 @@ class Models(C.Structure):
                 ("deltaT", C.c_double), ("seed", C.c_uint64), ("kB", C.c_double), ("nPatchModels", C.c_int32),
                 ("nInflows", C.c_int32), ("patchModels", C.POINTER(PatchModel)), ("inflows", C.POINTER(Inflow)),
                 ("measureHeatFluxShearStress", C.c_int32), ("measureClassifications", C.c_int32),
-                ("trackFaceFluxes", C.c_int32), ("fusedCollideSample", C.c_int32)]
+                ("trackFaceFluxes", C.c_int32), ("fusedCollideSample", C.c_int32), ("sampleInterval", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class ParcelsSoA(C.Structure):
@@ -307,7 +307,7 @@ class Dsmcb200Error(RuntimeError):
 def build_models(collisionModel="VariableHardSphere", nEquivalentParticles=1.0, deltaT=1e-6, seed=1, Tref=273.0,
                  rotationalRelaxationCollisionNumber=5.0, vibrationalRelaxationCollisionNumber=0.0,
                  electronicRelaxationCollisionNumber=500.0, inverseZvFormulation="", kB=0.0, patch_models=(), inflows=(),
-                 measureHeatFluxShearStress=False, measureClassifications=False):
+                 measureHeatFluxShearStress=False, measureClassifications=False, sampleInterval=1):
     """POD form of constant/dsmcProperties + boundariesDict.  Unknown model names raise with the
     reference's 'Valid ... types are' message shape (BinaryCollisionModel.C:70-85)."""
     if collisionModel not in COLLISION_MODEL_NAMES:
@@ -350,6 +350,7 @@ def build_models(collisionModel="VariableHardSphere", nEquivalentParticles=1.0, 
         inf[i].rotationalTemperature = d.get("rotationalTemperature", 0.0)
         inf[i].vibrationalTemperature = d.get("vibrationalTemperature", 0.0)
         inf[i].electronicTemperature = d.get("electronicTemperature", 0.0)
+    m.sampleInterval = int(sampleInterval)
     m.nPatchModels = len(patch_models)
     m.nInflows = len(inflows)
     m.patchModels = pm

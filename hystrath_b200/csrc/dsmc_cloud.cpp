@@ -383,6 +383,13 @@ void dsmcCloud::readFieldProperties() {
         }
         if (s.measureHeatFluxShearStress) models_.measureHeatFluxShearStress = 1;
         if (s.measureClassifications) models_.measureClassifications = 1;
+        // every field{} shares the engine's one set of per-species accumulators, so they must agree on sampleInterval
+        // (dsmcVolFields.C:1073-1081,1362: calculateField samples when sampleInterval_ <= ++sampleCounter_)
+        if (!fields_.empty() && fields_.front().sampleInterval != s.sampleInterval)
+            throw FoamError("dsmcVolFields " + s.fieldName + ": sampleInterval " + std::to_string(s.sampleInterval) + " differs from field " +
+                            fields_.front().fieldName + " (" + std::to_string(fields_.front().sampleInterval) +
+                            "); this engine samples all fields on the same steps\nin: " + path);
+        models_.sampleInterval = std::max(1, s.sampleInterval);
         fields_.push_back(s);
     }
 }
@@ -478,7 +485,7 @@ std::string dsmcCloud::summary() const {
     for (auto& f : fields_) {
         o << "    field " << f.fieldName << " typeIds";
         for (int t : f.typeIds) o << " " << t;
-        o << " mfp " << f.measureMeanFreePath << " reset " << f.resetAtOutput << "\n";
+        o << " mfp " << f.measureMeanFreePath << " reset " << f.resetAtOutput << " sampleInterval " << f.sampleInterval << "\n";
     }
     o << "  parcels " << nRead_ << "\n";
     return o.str();

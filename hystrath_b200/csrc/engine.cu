@@ -152,6 +152,7 @@ struct dsmcb200_ctx {
     bool haveMesh = false, haveSpecies = false, haveModels = false, ready = false;
     std::vector<dsmcb200_species> species;
     dsmcb200_models models{};
+    int sampleCounter = 0;   // steps since stage 5 last ran (sampleInterval)
     std::vector<dsmcb200_patch_model> patchModels;
     std::vector<dsmcb200_inflow> inflows;
     DevParams hP{};
@@ -607,6 +608,8 @@ MoveArgs moveArgs(dsmcb200_ctx* c, int32_t first, int32_t count, int32_t tailSta
     MoveArgs a{};
     a.p = c->buf[c->cur].a; a.first = first; a.count = count; a.tailStart = tailStart; a.sfTail = c->dSfTail;
     a.tets = c->dTets; a.bfaces = c->dBFaces; a.bfaceArea = c->dBFaceArea; a.P = c->dP; a.wallAcc = c->dWallAcc; a.nWallQ = c->nWallQ;
+    // boundaryMeas_ is cleaned every step (dsmcCloud.C:924) but only folded into the fields on sampled steps (dsmcVolFields.C:1081,1292)
+    a.wallsDue = c->sampleCounter + 1 >= std::max(1, c->models.sampleInterval);
     a.migBuf = c->dMigSend; a.migCapacity = c->migCapacity; a.cellCount = c->dCellCount; a.counters = c->dCounters; a.step = c->step;
     return a;
 }
@@ -1057,7 +1060,11 @@ int dsmcb200_evolve(dsmcb200_ctx* c, int nSteps) {
         cudaEventRecord(e3, c->stream);
         { int r = stageCollide(c); if (r) return r; }              // collisions()
         cudaEventRecord(e4, c->stream);
-        { int r = stageSample(c); if (r) return r; }               // fields_.calculateFields()
+        // dsmcVolFields::calculateField samples when sampleInterval_ <= ++sampleCounter_ (dsmcVolFields.C:1073-1081,1362)
+        if (++c->sampleCounter >= std::max(1, c->models.sampleInterval)) {
+            { int r = stageSample(c); if (r) return r; }           // fields_.calculateFields()
+            c->sampleCounter = 0;
+        }
         cudaEventRecord(e5, c->stream);
         c->step++;
         { int r = fetchCounters(c); if (r) return r; }

@@ -99,6 +99,7 @@ struct MoveArgs {
     const DevParams* P;
     double* wallAcc;              // [nMeasFaces][nSpecies][nWallQ]
     int32_t nWallQ;
+    int32_t wallsDue;             // 0: this step is not sampled (sampleInterval), wall hits leave no measurement
     MigRec* migBuf;               // [MAX_NEIGHBOURS][migCapacity]
     int32_t migCapacity;
     int32_t* cellCount;           // histogram for the sort (stage 2), fused here

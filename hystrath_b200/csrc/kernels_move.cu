@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                                 if (pt.model == DSMCB200_BND_DELETION) {
                                     keepParticle = false;  // dsmcDeletionPatch::controlParticle
                                 } else if (pt.model != DSMCB200_BND_NONE) {
-                                    U = wallInteraction(a, i, a.p.typeId[i], bf.patch, bf.measIndex, bfi, N0, U, &wallHits);
+                                    U = wallInteraction(a, i, a.p.typeId[i], bf.patch, a.wallsDue ? bf.measIndex : -1, bfi, N0, U, &wallHits);
                                     Udirty = true;
                                 }
                                 break;

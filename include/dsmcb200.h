@@ -176,6 +176,9 @@ typedef struct {
     int32_t measureClassifications;
     int32_t trackFaceFluxes;       /* dsmcFaceTracker counters (off by default)   */
     int32_t fusedCollideSample;    /* 1: stages 3-5 in one kernel                 */
+    int32_t sampleInterval;        /* dsmcVolFieldsProperties.sampleInterval: stage 5 runs every n-th step (0, 1: every step;
+                                      dsmcVolFields.C:1073-1081,1362)             */
+    int32_t reserved_;
 } dsmcb200_models;
 
 /* Host-side SoA view of the cloud.  Layout of vectors is OpenFOAM's

@@ -43,6 +43,21 @@ def test_driver_rejects_unknown_models_like_the_reference(tmp_path):
     assert r.returncode == 1 and "keyword nEquivalentParticles is undefined in dictionary" in r.stderr
 
 
+def test_driver_reads_sample_interval(tmp_path):
+    """dsmcVolFieldsProperties.sampleInterval (dsmcVolFields.C:1038) reaches the engine; fields that disagree are refused."""
+    casegen.couette_case(str(tmp_path))
+    path = os.path.join(str(tmp_path), "system", "fieldPropertiesDict")
+    text = open(path).read()
+    assert "sampleInterval" not in text
+    open(path, "w").write(text.replace("fieldName", "sampleInterval 4;\n            fieldName"))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.count(" sampleInterval 4") == 3
+    open(path, "w").write(text.replace("fieldName", "sampleInterval 4;\n            fieldName", 1))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "this engine samples all fields on the same steps" in r.stderr
+
+
 def test_python_reader_round_trip(tmp_path):
     g, mesh, p = casegen.couette_case(str(tmp_path))
     d = os.path.join(str(tmp_path), "5", "lagrangian", "dsmc")

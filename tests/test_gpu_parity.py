@@ -310,6 +310,32 @@ def test_move_with_diffuse_walls_and_empty_patches():
     eng.close()
 
 
+def test_sample_interval_matches_oracle():
+    """sampleInterval 2 over 5 steps: cells and wall faces are measured on steps 2 and 4 only (dsmcVolFields.C:1073-1081,1362;
+    boundaryMeas_ / cellMeas_ cleaned every step, dsmcCloud.C:923-925)."""
+    mesh, sp, _ = wall_case()
+    pm = [dict(patch=mesh.patch_index("lowerWall"), boundaryModel="dsmcDiffuseWallPatch", temperature=2000.0, velocity=(0, 0, 0)),
+          dict(patch=mesh.patch_index("upperWall"), boundaryModel="dsmcDiffuseWallPatch", temperature=3000.0, velocity=(300.0, 0, 0))]
+    md = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=1e20 * 0.05 * 0.2 * 0.01 / (100 * 60), deltaT=4e-6, seed=7,
+                           patch_models=pm, inverseZvFormulation="pre-2008", sampleInterval=2)
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    H.same_start(eng, ora, [0, 1], [0.8e20, 0.2e20], 2500.0, 2500.0, 2500.0)
+    eng.evolve(5)
+    ora.evolve(5)
+    ga, gc, gn = eng.accumulators()
+    oa, oc, on = ora.accumulators()
+    assert gn == on == 2
+    assert np.array_equal(ga[:, :, 0], oa[:, :, 0])
+    scale = np.abs(oa).max(axis=(0, 1), keepdims=True) + 1e-300
+    assert (np.abs(ga - oa) / scale).max() < 1e-10
+    assert np.allclose(gc, oc, rtol=1e-10)
+    gw, ow = eng.wall_accumulators(), ora.wall_accumulators()
+    assert np.abs(ow).sum() > 0
+    scale = np.abs(ow).max(axis=(0, 1), keepdims=True) + 1e-300
+    assert (np.abs(gw - ow) / scale).max() < 1e-9
+    eng.close()
+
+
 def test_diffuse_specular_wall_matches_oracle():
     """dsmcDiffuseSpecularWallPatch: the diffuse / specular draw comes first in the hit's Philox stream on both sides."""
     sides = {"xmin": ("cyclic",), "xmax": ("cyclic",), "ymin": ("wall", "lowerWall"), "ymax": ("wall", "upperWall"),

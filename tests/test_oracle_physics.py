@@ -337,3 +337,41 @@ def test_diffuse_specular_wall_splits_by_diffuse_fraction():
     # the diffuse ones come off at the wall temperature: mean kinetic energy of a half-range Maxwellian flux = 2 k T_w
     ek = 0.5 * sp[0].mass * (b["U"][hit][~keeps_speed] ** 2).sum(1)
     assert abs(ek.mean() / (2 * H.KB * 900.0) - 1) < 0.1
+
+
+def test_sample_interval_skips_cell_and_wall_measurements():
+    """dsmcVolFields::calculateField samples only when sampleInterval_ <= ++sampleCounter_ (dsmcVolFields.C:1073-1081,1362);
+    boundaryMeas_ / cellMeas_ are cleaned every step (dsmcCloud.C:923-925), so un-sampled steps leave no trace.  The same seeded
+    run with sampleInterval 1 sees identical parcels (sampling draws nothing), hence interval 3 == steps 3 and 6 of it."""
+    sides = {"xmin": ("cyclic",), "xmax": ("cyclic",), "ymin": ("wall", "cold"), "ymax": ("wall", "hot"), "zmin": ("cyclic",), "zmax": ("cyclic",)}
+    mesh = meshgen.box_mesh((2, 6, 2), (0.01, 0.03, 0.01), sides=sides)
+    sp = [H.argon()]
+    pm = [dict(patch=mesh.patch_index("cold"), boundaryModel="dsmcDiffuseWallPatch", temperature=300.0),
+          dict(patch=mesh.patch_index("hot"), boundaryModel="dsmcDiffuseWallPatch", temperature=500.0)]
+
+    def run(interval, stops):
+        md = capi.build_models("VariableHardSphere", nEquivalentParticles=1e20 * 3e-6 / (24 * 100), deltaT=5e-6, seed=3, patch_models=pm,
+                               sampleInterval=interval)
+        o = Oracle()
+        o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
+        o.mesh_fill([0], [1e20], 300.0)
+        out, done = [], 0
+        for s in stops:
+            o.evolve(s - done)
+            done = s
+            out.append((o.accumulators(), o.wall_accumulators().copy()))
+        return out
+
+    every = run(1, [2, 3, 5, 6, 7])
+    third = run(3, [7])[0]
+    (a3, c3, n3), w3 = third
+    assert n3 == 2
+    (a_2, c_2, _), w_2 = every[0]
+    (a_3, c_3, _), w_3 = every[1]
+    (a_5, c_5, _), w_5 = every[2]
+    (a_6, c_6, _), w_6 = every[3]
+    assert np.allclose(a3, (a_3 - a_2) + (a_6 - a_5), rtol=1e-12, atol=0)
+    assert np.allclose(c3, (c_3 - c_2) + (c_6 - c_5), rtol=1e-12, atol=0)
+    assert np.abs(w3).sum() > 0
+    scale = np.abs(w3).max(axis=(0, 1), keepdims=True) + 1e-300
+    assert (np.abs(w3 - ((w_3 - w_2) + (w_6 - w_5))) / scale).max() < 1e-9
