@@ -273,6 +273,7 @@ def load_library():
         "dsmcb200_wall_info": ([P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)], C.c_int),
         "dsmcb200_download_wall_accumulators": ([P, C.c_void_p], C.c_int),
         "dsmcb200_upload_wall_accumulators": ([P, C.c_void_p], C.c_int),
+        "dsmcb200_download_face_fluxes": ([P, C.c_void_p, C.c_void_p], C.c_int),
         "dsmcb200_get_counters": ([P, C.POINTER(Counters)], C.c_int),
         "dsmcb200_kernel_times": ([P, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
         "dsmcb200_download_geometry": ([P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
@@ -295,7 +296,7 @@ EXPORTED_SYMBOLS = [
     "dsmcb200_mesh_fill", "dsmcb200_evolve", "dsmcb200_stage", "dsmcb200_set_step", "dsmcb200_download_occupancy",
     "dsmcb200_accum_info_get", "dsmcb200_download_accumulators", "dsmcb200_upload_accumulators",
     "dsmcb200_reset_accumulators", "dsmcb200_wall_info", "dsmcb200_download_wall_accumulators",
-    "dsmcb200_upload_wall_accumulators", "dsmcb200_get_counters",
+    "dsmcb200_upload_wall_accumulators", "dsmcb200_download_face_fluxes", "dsmcb200_get_counters",
     "dsmcb200_kernel_times", "dsmcb200_download_geometry", "dsmcb200_timer_start", "dsmcb200_timer_stop", "dsmcb200_allreduce_sum",
 ]
 
@@ -307,7 +308,7 @@ class Dsmcb200Error(RuntimeError):
 def build_models(collisionModel="VariableHardSphere", nEquivalentParticles=1.0, deltaT=1e-6, seed=1, Tref=273.0,
                  rotationalRelaxationCollisionNumber=5.0, vibrationalRelaxationCollisionNumber=0.0,
                  electronicRelaxationCollisionNumber=500.0, inverseZvFormulation="", kB=0.0, patch_models=(), inflows=(),
-                 measureHeatFluxShearStress=False, measureClassifications=False, sampleInterval=1):
+                 measureHeatFluxShearStress=False, measureClassifications=False, sampleInterval=1, trackFaceFluxes=False):
     """POD form of constant/dsmcProperties + boundariesDict.  Unknown model names raise with the
     reference's 'Valid ... types are' message shape (BinaryCollisionModel.C:70-85)."""
     if collisionModel not in COLLISION_MODEL_NAMES:
@@ -351,6 +352,7 @@ def build_models(collisionModel="VariableHardSphere", nEquivalentParticles=1.0, 
         inf[i].vibrationalTemperature = d.get("vibrationalTemperature", 0.0)
         inf[i].electronicTemperature = d.get("electronicTemperature", 0.0)
     m.sampleInterval = int(sampleInterval)
+    m.trackFaceFluxes = int(bool(trackFaceFluxes))
     m.nPatchModels = len(patch_models)
     m.nInflows = len(inflows)
     m.patchModels = pm
@@ -492,6 +494,12 @@ class Engine:
         if nf.value:
             self._ck(self.lib.dsmcb200_download_wall_accumulators(self.h, _ptr(w)))
         return w
+
+    def face_fluxes(self):
+        """dsmcFaceTracker parcelIdFlux / massIdFlux of the last step, each [nSpecies][nFaces] (models.trackFaceFluxes)."""
+        pf, mf = np.zeros((self.n_species, self._mesh.n_faces)), np.zeros((self.n_species, self._mesh.n_faces))
+        self._ck(self.lib.dsmcb200_download_face_fluxes(self.h, _ptr(pf), _ptr(mf)))
+        return pf, mf
 
     def counters(self):
         c = Counters()

@@ -153,6 +153,7 @@ struct dsmcb200_ctx {
     std::vector<dsmcb200_species> species;
     dsmcb200_models models{};
     int sampleCounter = 0;   // steps since stage 5 last ran (sampleInterval)
+    double* dFaceFlux = nullptr;   // dsmcFaceTracker: [2][nSpecies][nFaces] of the current step (models.trackFaceFluxes)
     std::vector<dsmcb200_patch_model> patchModels;
     std::vector<dsmcb200_inflow> inflows;
     DevParams hP{};
@@ -506,6 +507,10 @@ int finalize(dsmcb200_ctx* c) {
     c->nWallQ = WQ_EVIBMOD0 + nModes;
     CK(devAlloc(&c->dWallAcc, size_t(c->nMeasFaces) * P.nSpecies * c->nWallQ));
     CK(cudaMemset(c->dWallAcc, 0, std::max<size_t>(1, size_t(c->nMeasFaces) * P.nSpecies * c->nWallQ) * 8));
+    if (c->models.trackFaceFluxes) {
+        CK(devAlloc(&c->dFaceFlux, size_t(2) * P.nSpecies * M.nFaces));
+        CK(cudaMemset(c->dFaceFlux, 0, size_t(2) * P.nSpecies * M.nFaces * 8));
+    }
     CK(devAlloc(&c->dCounters, 1)); CK(cudaMemset(c->dCounters, 0, sizeof(DevCounters)));
     CK(devAlloc(&c->dBad, 1));
     CK(devAlloc(&c->dInfo, 8)); CK(devAlloc(&c->dInfoScratch, size_t(infoScratchDoubles())));
@@ -578,7 +583,7 @@ int stageInflow(dsmcb200_ctx* c, int64_t tailStart) {
         a.nFaces = pi.size; a.patch = in.patch; a.patchStart = pi.start;
         a.faceOffsets = c->dFaceOffsets; a.facePoints = c->dFacePoints; a.owner = c->dOwner; a.tetBasePtIs = c->dTetBasePtIs;
         a.faceTetPair0 = c->dFaceTetPair0; a.points = c->dPoints; a.faceCentres = c->dFaceCentres; a.faceAreas = c->dFaceAreas;
-        a.P = c->dP; a.nTypes = in.nTypes;
+        a.P = c->dP; a.nTypes = in.nTypes; a.faceFlux = c->dFaceFlux; a.nFacesAll = M.nFaces;
         for (int i = 0; i < in.nTypes; ++i) { a.typeIds[i] = in.typeIds[i]; a.numberDensities[i] = in.numberDensities[i]; }
         for (int d = 0; d < 3; ++d) a.velocity[d] = in.velocity[d];
         a.Ttra = in.translationalTemperature; a.Trot = in.rotationalTemperature; a.Tvib = in.vibrationalTemperature; a.Telec = in.electronicTemperature;
@@ -610,6 +615,7 @@ MoveArgs moveArgs(dsmcb200_ctx* c, int32_t first, int32_t count, int32_t tailSta
     a.tets = c->dTets; a.bfaces = c->dBFaces; a.bfaceArea = c->dBFaceArea; a.P = c->dP; a.wallAcc = c->dWallAcc; a.nWallQ = c->nWallQ;
     // boundaryMeas_ is cleaned every step (dsmcCloud.C:924) but only folded into the fields on sampled steps (dsmcVolFields.C:1081,1292)
     a.wallsDue = c->sampleCounter + 1 >= std::max(1, c->models.sampleInterval);
+    a.faceFlux = c->dFaceFlux; a.faceAreas = c->dFaceAreas; a.faceTetPair0 = c->dFaceTetPair0; a.nFacesAll = c->mesh.nFaces;
     a.migBuf = c->dMigSend; a.migCapacity = c->migCapacity; a.cellCount = c->dCellCount; a.counters = c->dCounters; a.step = c->step;
     return a;
 }
@@ -752,7 +758,7 @@ void dsmcb200_destroy(dsmcb200_ctx* c) {
     devFree(c->dOwner); devFree(c->dTetBasePtIs); devFree(c->dFaceTetPair0); devFree(c->dCellFaceOffsets); devFree(c->dCellFaces);
     devFree(c->dCellCount); devFree(c->dCellOffset); devFree(c->dCursor); devFree(c->dPerm); devFree(c->dOctKey); devFree(c->dScanScratch);
     devFree(c->dSigma); devFree(c->dRem); devFree(c->dNColls); devFree(c->dCollSep); devFree(c->dAcc); devFree(c->dCollCum);
-    devFree(c->dWallAcc); devFree(c->dSfTail); devFree(c->dInfo); devFree(c->dInfoScratch); devFree(c->dCounters); devFree(c->dBad);
+    devFree(c->dFaceFlux); devFree(c->dWallAcc); devFree(c->dSfTail); devFree(c->dInfo); devFree(c->dInfoScratch); devFree(c->dCounters); devFree(c->dBad);
     devFree(c->dMigSend); devFree(c->dMigRecv); devFree(c->dInflowScan); devFree(c->dOrdinalToPatch); devFree(c->dCountsMatrix);
     for (auto& p : c->dInflowAcc) devFree(p);
     for (auto& p : c->dInflowCounts) devFree(p);
@@ -1051,6 +1057,8 @@ int dsmcb200_evolve(dsmcb200_ctx* c, int nSteps) {
         c->last.inserted = 0; c->last.migratedIn = 0;
         CK(cudaMemsetAsync(c->dCounters, 0, sizeof(DevCounters), c->stream));
         const int64_t tailStart = c->N;
+        // trackingInfo_.clean() (dsmcCloud.C:923): the face tracker holds one step
+        if (c->dFaceFlux) CK(cudaMemsetAsync(c->dFaceFlux, 0, size_t(2) * c->hP.nSpecies * c->mesh.nFaces * 8, c->stream));
         cudaEventRecord(e0, c->stream);
         { int r = stageInflow(c, tailStart); if (r) return r; }    // boundaries_.controlBeforeMove()
         cudaEventRecord(e1, c->stream);
@@ -1148,6 +1156,18 @@ int dsmcb200_wall_info(dsmcb200_ctx* c, int32_t* nFaces, int32_t* nWallQ) {
     { int r = finalize(c); if (r) return r; }
     if (nFaces) *nFaces = c->nMeasFaces;
     if (nWallQ) *nWallQ = c->nWallQ;
+    return 0;
+}
+
+int dsmcb200_download_face_fluxes(dsmcb200_ctx* c, double* parcelIdFlux, double* massIdFlux) {
+    if (!c || !parcelIdFlux || !massIdFlux) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    if (!c->dFaceFlux) return fail(c, DSMCB200_ERR_STATE, "face fluxes are not tracked: set models.trackFaceFluxes");
+    CK(cudaStreamSynchronize(c->stream));
+    const size_t n = size_t(c->hP.nSpecies) * c->mesh.nFaces;
+    CK(cudaMemcpy(parcelIdFlux, c->dFaceFlux, n * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(massIdFlux, c->dFaceFlux + n, n * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -100,6 +100,10 @@ struct MoveArgs {
     double* wallAcc;              // [nMeasFaces][nSpecies][nWallQ]
     int32_t nWallQ;
     int32_t wallsDue;             // 0: this step is not sampled (sampleInterval), wall hits leave no measurement
+    double* faceFlux;             // dsmcFaceTracker: [2][nSpecies][nFacesAll] (parcelIdFlux, massIdFlux) or nullptr
+    const double* faceAreas;      // [nFacesAll*3], read only by the face tracker
+    const int32_t* faceTetPair0;  // [nFacesAll+1] first face-triangle of each face (tet id >> 1 -> face)
+    int32_t nFacesAll;
     MigRec* migBuf;               // [MAX_NEIGHBOURS][migCapacity]
     int32_t migCapacity;
     int32_t* cellCount;           // histogram for the sort (stage 2), fused here
@@ -189,6 +193,8 @@ struct InflowArgs {
     double* sfTail;               // step fractions of the new parcels, indexed slot - tailStart
     int32_t tailStart;
     int32_t origIdBase;
+    double* faceFlux;             // dsmcFaceTracker arrays (see MoveArgs) or nullptr
+    int32_t nFacesAll;
     DevCounters* counters;
     uint32_t step;
 };

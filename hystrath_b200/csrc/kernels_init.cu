@@ -184,6 +184,12 @@ __global__ void __launch_bounds__(128) inflowKernel(const __grid_constant__ Infl
         storeParcel(a.p, P, slot, pos, U, ERot, vib, elevel, cellI, tet, typeId, a.origIdBase + (slot - a.base));
         // dsmcParcel::move: a freshly inserted parcel moves a random fraction of the step (dsmcParcel.C:52-59)
         a.sfTail[slot - a.tailStart] = rng.sample01();
+        if (a.faceFlux) {
+            // dsmcCloud::addNewParcel with newParcel != -1 (dsmcCloud.C:429-437) -> dsmcFaceTracker::trackFaceTransition
+            const double sgn = dot(U, sF) >= 0 ? 1.0 : -1.0;
+            atomicAdd(a.faceFlux + size_t(typeId) * a.nFacesAll + faceI, sgn);
+            atomicAdd(a.faceFlux + (size_t(P.nSpecies) + typeId) * a.nFacesAll + faceI, sgn * mass);
+        }
     }
 }
 

@@ -144,6 +144,33 @@ __device__ void wallMeasureDelta(const WallCtx& w, int32_t measIndex, int32_t bf
     atomicAdd(a + WQ_FDZ, deltaFD.z);
 }
 
+// dsmcFaceTracker::trackFaceTransition (DSMC/faceTracker/dsmcFaceTracker.C:124-198), RWF = 1.  The parcel's face() is the boundary
+// face bfi when that is >= 0, else the internal face that owns the face-triangle pair of its tet.
+__device__ __noinline__ void trackFaceTransition(const MoveArgs& a, const DevParams& P, int typeId, const V3& U, int32_t tet, int32_t bfi) {
+    int32_t face, target;
+    double unsignedCredit = 0.0;
+    if (bfi >= 0) {
+        face = target = P.nInternalFaces + bfi;
+        const DevPatch& pt = P.patch[a.bfaces[bfi].patch];
+        if (pt.type == DSMCB200_PATCH_CYCLIC) {   // credited to the coupled face without the sign (:160-170)
+            target = P.patch[pt.nbrPatch].start + (face - pt.start);
+            unsignedCredit = 1.0;
+        }
+    } else {
+        const int32_t pair = tet >> 1;
+        int32_t lo = 0, hi = a.nFacesAll;   // last f with faceTetPair0[f] <= pair
+        while (hi - lo > 1) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (a.faceTetPair0[mid] <= pair) lo = mid; else hi = mid;
+        }
+        face = target = lo;
+    }
+    const V3 Sf = mk(a.faceAreas[3 * size_t(face)], a.faceAreas[3 * size_t(face) + 1], a.faceAreas[3 * size_t(face) + 2]);
+    const double sgn = unsignedCredit != 0.0 ? 1.0 : (dot(U, Sf) >= 0 ? 1.0 : -1.0);
+    atomicAdd(a.faceFlux + size_t(typeId) * a.nFacesAll + target, sgn);
+    atomicAdd(a.faceFlux + (size_t(P.nSpecies) + typeId) * a.nFacesAll + target, sgn * P.sp[typeId].mass);
+}
+
 __device__ __forceinline__ void loadInternal(const MoveArgs& a, const DevParams& P, int32_t i, Internal& in) {
     in.ERot = 0.0; in.vib0 = in.vib1 = in.vib2 = 0; in.elevel = 0;
     if (!P.hasInternalEnergy) return;
@@ -423,6 +450,7 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
 
         // ---- section 3: trackToFace returned -- back in dsmcParcel::move (DSMC/parcels/dsmcParcel.C:92-118) ----
         if (finished) {
+            if (a.faceFlux && faceSet) trackFaceTransition(a, P, a.p.typeId[i], U, tet, faceBfi);  // dsmcParcel.C:106-111
             if (keepParticle) {
                 const double dt = tEnd * retVal;
                 tEnd -= dt;  // stepFraction = 1 - tEnd/deltaT is only consumed by a processor transfer: evaluated there

@@ -174,7 +174,7 @@ typedef struct {
     const dsmcb200_inflow* inflows;
     int32_t measureHeatFluxShearStress; /* sample the optional 2nd-moment set     */
     int32_t measureClassifications;
-    int32_t trackFaceFluxes;       /* dsmcFaceTracker counters (off by default)   */
+    int32_t trackFaceFluxes;       /* dsmcFaceTracker counters (off by default), see dsmcb200_download_face_fluxes */
     int32_t fusedCollideSample;    /* 1: stages 3-5 in one kernel                 */
     int32_t sampleInterval;        /* dsmcVolFieldsProperties.sampleInterval: stage 5 runs every n-th step (0, 1: every step;
                                       dsmcVolFields.C:1073-1081,1362)             */
@@ -314,6 +314,12 @@ int dsmcb200_wall_info(dsmcb200_ctx*, int32_t* nBoundaryFaces, int32_t* nWallQua
 int dsmcb200_download_wall_accumulators(dsmcb200_ctx*, double* wall);
 /* restart of the wall sampling: the *BF_ arrays dsmcVolFields::readIn restores (dsmcVolFields.C:723-738) */
 int dsmcb200_upload_wall_accumulators(dsmcb200_ctx*, const double* wall);
+/* dsmcFaceTracker (DSMC/faceTracker/dsmcFaceTracker.C:124-198; models.trackFaceFluxes = 1): parcelIdFlux_ and massIdFlux_ of the
+ * last step, each [nSpecies][nFaces] (all faces, internal first).  A face crossing adds sign(U . S_f) (x mass), U after the
+ * boundary interaction; a cyclic hit is credited, unsigned, to the coupled face; a parcel inserted on an inflow face counts as
+ * a crossing of it (dsmcCloud.C:429-437).  The arrays are cleared at the start of every step (trackingInfo_.clean(),
+ * dsmcCloud.C:923).  Replaces cloud.tracker().parcelIdFlux() / massIdFlux() (dsmcFaceTracker.H). */
+int dsmcb200_download_face_fluxes(dsmcb200_ctx*, double* parcelIdFlux, double* massIdFlux);
 int dsmcb200_get_counters(dsmcb200_ctx*, dsmcb200_counters*);
 /* Per-kernel device time of the last step, for bench.py: names[i] is filled with up to
  * DSMCB200_NAME_LEN chars; returns the count through *n (capacity in). */

@@ -57,6 +57,7 @@ def load():
     lib.oracle_download_accumulators.argtypes = [P, C.c_void_p, C.c_void_p]
     lib.oracle_wall_info.argtypes = [P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.oracle_download_wall_accumulators.argtypes = [P, C.c_void_p]
+    lib.oracle_download_face_fluxes.argtypes = [P, C.c_void_p, C.c_void_p]
     lib.oracle_get_counters.argtypes = [P, C.c_void_p]
     lib.oracle_download_geometry.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _LIB = lib
@@ -163,6 +164,12 @@ class Oracle:
         if nf.value:
             self._ck(self.lib.oracle_download_wall_accumulators(self.h, _ptr(w)))
         return w
+
+    def face_fluxes(self):
+        """dsmcFaceTracker parcelIdFlux / massIdFlux of the last step, each [nSpecies][nFaces]."""
+        pf, mf = np.zeros((self.n_species, self._mesh.n_faces)), np.zeros((self.n_species, self._mesh.n_faces))
+        self._ck(self.lib.oracle_download_face_fluxes(self.h, _ptr(pf), _ptr(mf)))
+        return pf, mf
 
     def counters(self):
         c = np.zeros(6, np.int64)

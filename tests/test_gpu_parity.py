@@ -393,6 +393,40 @@ def test_inflow_deletion_specular_counts_match_oracle():
     eng.close()
 
 
+def test_face_tracker_fluxes_match_oracle():
+    """dsmcFaceTracker (DSMC/faceTracker/dsmcFaceTracker.C:124-198) on every face kind of one case: internal faces, cyclic (credited to
+    the coupled face), inflow insertions (dsmcCloud.C:429-437), deletion patches, a specular wall and a symmetry plane.  Parcel counts
+    per (species, face) are integers: exact."""
+    sides = {"xmin": ("patch", "inlet"), "xmax": ("patch", "outlet"), "ymin": ("wall", "plate"), "ymax": ("symmetryPlane", "top"),
+             "zmin": ("cyclic",), "zmax": ("cyclic",)}
+    mesh = meshgen.box_mesh((10, 6, 4), (0.1, 0.06, 0.04), sides=sides)
+    sp = H.air5()[:2]
+    pm = [dict(patch=mesh.patch_index("inlet"), boundaryModel="dsmcDeletionPatch"),
+          dict(patch=mesh.patch_index("outlet"), boundaryModel="dsmcDeletionPatch"),
+          dict(patch=mesh.patch_index("plate"), boundaryModel="dsmcSpecularWallPatch")]
+    inflow = [dict(patch=mesh.patch_index("inlet"), typeIds=[0, 1], numberDensities=[0.8e20, 0.2e20], velocity=(1500.0, 0, 0),
+                   translationalTemperature=300.0, rotationalTemperature=300.0, vibrationalTemperature=300.0)]
+    vol = 0.1 * 0.06 * 0.04
+    md = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=1e20 * vol / (240 * 30), deltaT=2e-6, seed=11,
+                           patch_models=pm, inflows=inflow, trackFaceFluxes=True)
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    H.same_start(eng, ora, [0, 1], [0.8e20, 0.2e20], 300.0, 300.0, 300.0, velocity=(1500.0, 0, 0))
+    nI = mesh.n_internal
+    for _ in range(3):
+        eng.evolve(1)
+        ora.evolve(1)
+        gp, gm = eng.face_fluxes()
+        op, om = ora.face_fluxes()
+        assert np.array_equal(gp, op)
+        for k, p in enumerate(mesh.patches):
+            assert np.abs(op[:, p["start"]:p["start"] + p["size"]]).sum() > 0, p["name"]   # every patch kind saw crossings
+        assert np.abs(op[:, :nI]).sum() > 1000
+        scale = np.abs(om).max() + 1e-300
+        assert np.abs(gm - om).max() / scale < 1e-12
+    assert eng.num_parcels() == ora.num_parcels()
+    eng.close()
+
+
 def test_equilibrium_collision_rate_within_one_percent():
     # SURVEY 8c (iii): VHS equilibrium collision rate, single species, periodic box
     mesh, sp, md = periodic_case((16, 16, 16), L=0.064, ppc=32)

@@ -375,3 +375,34 @@ def test_sample_interval_skips_cell_and_wall_measurements():
     assert np.abs(w3).sum() > 0
     scale = np.abs(w3).max(axis=(0, 1), keepdims=True) + 1e-300
     assert (np.abs(w3 - ((w_3 - w_2) + (w_6 - w_5))) / scale).max() < 1e-9
+
+
+def test_face_tracker_fluxes_balance_the_cell_occupancy():
+    """dsmcFaceTracker::trackFaceTransition (DSMC/faceTracker/dsmcFaceTracker.C:124-198): per step and species, the signed parcel
+    flux through the internal faces of a cell (S_f points owner -> neighbour) is its change of occupancy; a specular wall hit is
+    tracked with the reflected velocity (-1 on the wall face) and massIdFlux = mass x parcelIdFlux."""
+    sides = {k: ("wall", "walls") for k in ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")}
+    mesh = meshgen.box_mesh((4, 3, 5), (0.02, 0.015, 0.025), sides=sides)
+    sp = H.air5()[:2]
+    pm = [dict(patch=mesh.patch_index("walls"), boundaryModel="dsmcSpecularWallPatch")]
+    md = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=1e20 * 0.02 * 0.015 * 0.025 / (60 * 40), deltaT=5e-6, seed=9,
+                           patch_models=pm, trackFaceFluxes=True)
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
+    o.mesh_fill([0, 1], [0.7e20, 0.3e20], 400.0, 400.0, 400.0)
+    nI = mesh.n_internal
+    owner, neigh = np.asarray(mesh.owner), np.asarray(mesh.neighbour)
+    for _ in range(3):
+        before = o.download_parcels()
+        o.evolve(1)
+        after = o.download_parcels()
+        pf, mf = o.face_fluxes()
+        assert np.abs(pf[:, :nI]).sum() > 100
+        for s in range(2):
+            dn = np.bincount(after.cell[after.typeId == s], minlength=mesh.n_cells) - np.bincount(before.cell[before.typeId == s], minlength=mesh.n_cells)
+            net = np.zeros(mesh.n_cells)
+            np.add.at(net, owner[:nI], -pf[s, :nI])
+            np.add.at(net, neigh[:nI], pf[s, :nI])
+            assert np.array_equal(net, dn)
+            assert np.allclose(mf[s], sp[s].mass * pf[s], rtol=1e-12, atol=1e-12 * sp[s].mass)   # +m -m leaves rounding residue
+        assert (pf[:, nI:] <= 0).all() and pf[:, nI:].sum() < -10     # every wall hit leaves with U . S_f < 0
