@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <filesystem>
 #include <ctime>
 #include <sstream>
 
@@ -137,6 +138,8 @@ void dsmcCloud::readControl() {
     writeControl_ = c.wordOr("writeControl", "timeStep");
     writeInterval_ = c.scalarOr("writeInterval", 1.0);
     timePrecision_ = int(c.labelOr("timePrecision", 6));
+    purgeWrite_ = int(c.labelOr("purgeWrite", 0));
+    if (purgeWrite_ < 0) throw FoamError("invalid value for purgeWrite " + std::to_string(purgeWrite_) + ", should be >= 0, setting to 0\nin: " + caseDir_ + "/system/controlDict");
     nTerminalOutputs_ = int(c.labelOr("nTerminalOutputs", 1));  // dsmcCloud.C:612-615
     std::string startFrom = c.wordOr("startFrom", "latestTime");
     std::vector<std::pair<double, std::string>> times;
@@ -475,7 +478,7 @@ void dsmcCloud::readCloud() {
 std::string dsmcCloud::summary() const {
     std::ostringstream o;
     o << "case " << caseDir_ << "\n  startTime " << timeName_ << " deltaT " << deltaT_ << " endTime " << endTime_ << " writeControl " << writeControl_
-      << " writeInterval " << writeInterval_ << " nTerminalOutputs " << nTerminalOutputs_ << "\n  mesh: " << points_.size() / 3 << " points "
+      << " writeInterval " << writeInterval_ << " nTerminalOutputs " << nTerminalOutputs_ << " purgeWrite " << purgeWrite_ << "\n  mesh: " << points_.size() / 3 << " points "
       << nFaces_ << " faces " << nInternal_ << " internal " << nCells_ << " cells " << boundary_.size() << " patches\n";
     for (auto& b : boundary_) o << "    patch " << b.name << " " << b.type << " " << b.nFaces << " @" << b.startFace << "\n";
     o << "  species:";
@@ -1227,6 +1230,16 @@ void dsmcCloud::readResumeSampling() {
 
 void dsmcCloud::write() {
     const std::string timeDir = root_ + "/" + timeName_;
+    // Time::writeObject (OpenFOAM v1706 Time/TimeIO.C): with purgeWrite N only the N most recent time directories written by this run
+    // are kept; each rank purges its own processorN tree
+    if (purgeWrite_ > 0) {
+        previousWriteTimes_.push_back(timeDir);
+        while (int(previousWriteTimes_.size()) > purgeWrite_) {
+            std::error_code ec;
+            std::filesystem::remove_all(previousWriteTimes_.front(), ec);
+            previousWriteTimes_.pop_front();
+        }
+    }
     const std::string cdir = timeDir + "/lagrangian/" + cloudName_;
     foam::makeDirs(cdir);
     const int64_t n = nParcels();

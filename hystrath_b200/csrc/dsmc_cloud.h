@@ -12,6 +12,7 @@
 #pragma once
 #include <cstdint>
 #include <map>
+#include <deque>
 #include <string>
 #include <vector>
 
@@ -92,6 +93,8 @@ class dsmcCloud {
     double time_ = 0, startTime_ = 0, endTime_ = 0, deltaT_ = 0, writeInterval_ = 1;
     std::string writeControl_ = "timeStep";
     int timePrecision_ = 6, nTerminalOutputs_ = 1, infoCounter_ = 0;
+    int purgeWrite_ = 0;                          // controlDict purgeWrite: time directories kept (0 = all)
+    std::deque<std::string> previousWriteTimes_;  // FIFO of the directories this run wrote
     int64_t timeIndex_ = 0, startIndex_ = 0;
     // mesh
     int nCells_ = 0, nFaces_ = 0, nInternal_ = 0;

@@ -117,3 +117,31 @@ configurations
     casew.write_dict(path, "system", "dsmcInitialiseDict", init.replace("O2 ", "Xe "))
     r = subprocess.run([RUN, "-initialise", "-dryRun", "-case", str(tmp_path)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 1 and "Cannot find typeId: Xe" in r.stderr
+
+
+ORION = "/root/reference/run/hyStrath/dsmcFoam+/orion107kmNR"
+
+
+@pytest.mark.skipif(not os.path.isdir(ORION), reason="the shipped case directory only exists next to the reference checkout")
+def test_driver_parses_the_shipped_orion_dictionaries(tmp_path):
+    """The unchanged system/ and constant/ of the shipped 5-species-air capsule case (its snappyHexMesh polyMesh is not shipped, so a
+    box with the same patch names stands in): LB N2/O2, two dsmcFreeStreamInflowPatch + dsmcDeletionPatch boundaries, a diffuse wall,
+    three dsmcVolFields, dsmcMeshFill, empty chemReactDict, runTime write control with purgeWrite."""
+    import shutil
+
+    from hystrath_b200 import case as casew
+    from hystrath_b200 import meshgen
+
+    for sub in ("system", "constant"):
+        shutil.copytree(os.path.join(ORION, sub), os.path.join(str(tmp_path), sub))
+    os.chmod(os.path.join(str(tmp_path), "constant"), 0o755)
+    sides = {"xmin": ("patch", "inlet"), "xmax": ("patch", "spline"), "ymin": ("wall", "orion"), "ymax": ("patch", "spline"),
+             "zmin": ("patch", "spline"), "zmax": ("patch", "spline")}
+    casew.write_poly_mesh(str(tmp_path), meshgen.box_mesh((6, 5, 5), (1.2, 1.0, 1.0), sides=sides))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-initialise", "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout
+    assert "deltaT 7e-06 endTime 4 writeControl runTime writeInterval 0.007 nTerminalOutputs 10 purgeWrite 2" in out
+    assert "species: N2 O2" in out and "collisionModel 2 invZv 2 nEquivalentParticles 2.6708e+15" in out
+    assert "patchModels 3 inflows 2 fields 3" in out
+    assert "numberDensity N2 2.318e+18" in out and "velocity (6053.4 0 0)" in out

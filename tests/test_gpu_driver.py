@@ -146,6 +146,30 @@ def test_driver_resume_sampling_round_trip(tmp_path):
     assert not np.allclose(n1, n2)
 
 
+def test_driver_purge_write_and_sample_interval(tmp_path):
+    """controlDict purgeWrite (Time::writeObject keeps the N most recent time directories of the run) and
+    dsmcVolFieldsProperties.sampleInterval (dsmcVolFields.C:1073-1081,1362) through the case directory."""
+    casegen.couette_case(str(tmp_path), n_steps=6, seed=7, nto=1)
+    cd = os.path.join(str(tmp_path), "system", "controlDict")
+    control = open(cd).read()
+    assert "writeInterval   6;" in control
+    with open(cd, "w") as fh:
+        fh.write(control.replace("writeInterval   6;", "writeInterval   2;\npurgeWrite      2;"))
+    fp = os.path.join(str(tmp_path), "system", "fieldPropertiesDict")
+    text = open(fp).read().replace("resetAtOutput       on;", "resetAtOutput       off;")
+    with open(fp, "w") as fh:
+        fh.write(text.replace("fieldName", "sampleInterval 3;\n            fieldName").replace(
+            "measureMeanFreePath     true;", "measureMeanFreePath     true;\n            averagingAcrossManyRuns true;"))
+    r = subprocess.run([RUN, "-case", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    times = sorted(d for d in os.listdir(str(tmp_path)) if d[0].isdigit())
+    assert times == ["5", "5.00004", "5.00006"], times            # 5.00002 purged; the start time was not written by this run
+    d = open(os.path.join(str(tmp_path), "5.00006", "uniform", "resumeSampling_mixture")).read()
+    assert "nTimeSteps      2;" in d                               # steps 3 and 6 of 6
+    n = ff.read_internal_field(os.path.join(str(tmp_path), "5.00006", "dsmcNMean_mixture"))
+    assert abs(n.sum() - 47583) < 1e-3
+
+
 def test_driver_initialise_step_then_run(tmp_path):
     """The dsmcInitialise+ step of every shipped Allrun (blockMesh; dsmcInitialise+; dsmcFoam+): `dsmcb200_run -initialise` fills the
     mesh from system/dsmcInitialiseDict (dsmcMeshFill) and writes the start-time cloud with 15 significant digits
