@@ -847,48 +847,35 @@ int dsmcb200_upload_parcels(dsmcb200_ctx* c, int64_t n, const dsmcb200_parcels_s
     ParcelBuffer& st = c->buf[1 - c->cur];  // staging: the double slab holds 7*cap doubles, the int slab 6*cap ints
     cudaStream_t s = c->stream;
     if (n == 0) { c->occupancyValid = false; return stageSort(c, false); }
-    // locate tets on the host when the caller has none (particle::initCellFacePtOrDeleteLostParticle)
-    std::vector<int32_t> locFace, locPt;
     const int32_t *tetFace = h->tetFace, *tetPt = h->tetPt;
-    std::vector<int32_t> cellFix;
-    const int32_t* cellPtr = h->cell;
-    if (!tetFace || !tetPt) {
-        locFace.resize(n); locPt.resize(n); cellFix.assign(h->cell, h->cell + n);
-        const HostMesh& M = c->mesh;
-        int64_t lost = 0;
-#pragma omp parallel for schedule(static) reduction(+ : lost)
-        for (int64_t i = 0; i < n; ++i) {
-            V3 p = mk(h->position[3 * i], h->position[3 * i + 1], h->position[3 * i + 2]);
-            int32_t cell = cellFix[i], f = -1, tp = -1;
-            if (cell < 0 || cell >= M.nCells || !M.findTetFacePt(cell, p, f, tp)) {
-                // walk towards the cell centre in trackingCorrectionTol steps (particleI.H:927-976)
-                bool ok = false;
-                if (cell >= 0 && cell < M.nCells && M.pointInCellBB(p, cell, 0.1)) {
-                    const V3 cc = M.cellCentres[cell];
-                    V3 q = p;
-                    for (int it = 0; it < 200 && !ok; ++it) {
-                        q += 1.0e-5 * (cc - q);
-                        ok = M.findTetFacePt(cell, q, f, tp);
-                    }
-                }
-                if (!ok) { cellFix[i] = -1; f = 0; tp = 1; ++lost; }
-            }
-            locFace[i] = f; locPt[i] = tp;
-        }
-        tetFace = locFace.data(); tetPt = locPt.data(); cellPtr = cellFix.data();
-        c->last.deleted += lost;
-    }
+    const bool locate = !tetFace || !tetPt;   // the caller has no tet indices: located on the device below
     CK(cudaMemcpyAsync(st.dslab, h->position, size_t(n) * 24, cudaMemcpyHostToDevice, s));
     deinterleave3<<<GRID(n), 0, s>>>(st.dslab, a.px, a.py, a.pz, n32);
     CK(cudaMemcpyAsync(st.dslab, h->U, size_t(n) * 24, cudaMemcpyHostToDevice, s));
     deinterleave3<<<GRID(n), 0, s>>>(st.dslab, a.ux, a.uy, a.uz, n32);
-    CK(cudaMemcpyAsync(a.cell, cellPtr, size_t(n) * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(a.cell, h->cell, size_t(n) * 4, cudaMemcpyHostToDevice, s));
     int32_t* sf = st.islab;                 // staging rows
     int32_t* sp2 = st.islab + c->capacity;
-    CK(cudaMemcpyAsync(sf, tetFace, size_t(n) * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(sp2, tetPt, size_t(n) * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(c->dBad, 0, 4, s));
-    toTetId<<<GRID(n), 0, s>>>(a.cell, sf, sp2, c->dFaceTetPair0, c->dOwner, a.tet, n32, c->mesh.nFaces, c->mesh.nCells, c->dBad);
+    if (locate) {
+        // particle::initCellFacePtOrDeleteLostParticle (BASIC/particle/particleI.H:851-996): first tet of the given cell that
+        // contains the position; lost parcels get cell -1 and are dropped by the sort below
+        LocateArgs l{};
+        l.px = a.px; l.py = a.py; l.pz = a.pz; l.cell = a.cell; l.tet = a.tet; l.n = n32; l.nCells = c->mesh.nCells;
+        l.cellFaceOffsets = c->dCellFaceOffsets; l.cellFaces = c->dCellFaces; l.faceOffsets = c->dFaceOffsets; l.facePoints = c->dFacePoints;
+        l.owner = c->dOwner; l.tetBasePtIs = c->dTetBasePtIs; l.faceTetPair0 = c->dFaceTetPair0; l.points = c->dPoints;
+        l.cellCentres = c->dCellCentres; l.lost = &c->dCounters->deleted;
+        CK(cudaMemsetAsync(&c->dCounters->deleted, 0, sizeof(unsigned long long), s));
+        CK(launchLocate(l, s));
+        unsigned long long lost = 0;
+        CK(cudaMemcpyAsync(&lost, &c->dCounters->deleted, sizeof(lost), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        c->last.deleted += int64_t(lost);
+    } else {
+        CK(cudaMemcpyAsync(sf, tetFace, size_t(n) * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(sp2, tetPt, size_t(n) * 4, cudaMemcpyHostToDevice, s));
+        toTetId<<<GRID(n), 0, s>>>(a.cell, sf, sp2, c->dFaceTetPair0, c->dOwner, a.tet, n32, c->mesh.nFaces, c->mesh.nCells, c->dBad);
+    }
     CK(cudaMemcpyAsync(sf, h->typeId, size_t(n) * 4, cudaMemcpyHostToDevice, s));
     i32ToU8Checked<<<GRID(n), 0, s>>>(sf, a.typeId, n32, c->hP.nSpecies, c->dBad);
     if (h->origId) CK(cudaMemcpyAsync(a.origId, h->origId, size_t(n) * 4, cudaMemcpyHostToDevice, s));

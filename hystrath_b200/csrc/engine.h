@@ -174,6 +174,19 @@ struct FillArgs {
 };
 cudaError_t launchFill(const FillArgs& a, int pass, cudaStream_t s);
 
+// particle::initCellFacePtOrDeleteLostParticle for a cloud that arrives without tetFace / tetPt (the `positions` file holds only
+// "(x y z) cell", particleIO.C:51-58)
+struct LocateArgs {
+    const double *px, *py, *pz;
+    int32_t* cell;                // in: host cell label; out: -1 for a lost parcel
+    int32_t* tet;                 // out: tet id 2*(faceTetPair0[tetFace] + tetPt - 1) + side
+    int32_t n, nCells;
+    const int32_t *cellFaceOffsets, *cellFaces, *faceOffsets, *facePoints, *owner, *tetBasePtIs, *faceTetPair0;
+    const double *points, *cellCentres;
+    unsigned long long* lost;     // parcels deleted (outside the inflated cell bounding box or not locatable)
+};
+cudaError_t launchLocate(const LocateArgs& a, cudaStream_t s);
+
 struct InflowArgs {
     ParcelArrays p;
     int32_t nFaces;               // faces of the inflow patch

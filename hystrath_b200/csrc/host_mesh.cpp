@@ -420,46 +420,4 @@ void HostMesh::bakeBFaces(std::vector<BFaceRec>& out) const {
     }
 }
 
-bool HostMesh::findTetFacePt(int32_t cell, const V3& p, int32_t& tetFace, int32_t& tetPt) const {
-    for (int k = cellFaceOffsets[cell]; k < cellFaceOffsets[cell + 1]; ++k) {
-        int f = cellFaces[k];
-        int n = nFacePts(f);
-        for (int tp = 1; tp < n - 1; ++tp) {
-            V3 a, b, c, d;
-            tetPoints(cell, f, tp, a, b, c, d);
-            // tetrahedron::inside
-            V3 nn = triNormal(b, c, d); nn /= (mag(nn) + VSMALL);
-            if (dot(p - b, nn) > SMALL) continue;
-            nn = triNormal(a, d, c); nn /= (mag(nn) + VSMALL);
-            if (dot(p - c, nn) > SMALL) continue;
-            nn = triNormal(a, b, d); nn /= (mag(nn) + VSMALL);
-            if (dot(p - b, nn) > SMALL) continue;
-            nn = triNormal(a, c, b); nn /= (mag(nn) + VSMALL);
-            if (dot(p - b, nn) > SMALL) continue;
-            tetFace = f; tetPt = tp;
-            return true;
-        }
-    }
-    tetFace = -1; tetPt = -1;
-    return false;
-}
-
-bool HostMesh::pointInCellBB(const V3& p, int32_t cell, double inflationFraction) const {
-    V3 mn = mk(VGREAT, VGREAT, VGREAT), mx = mk(-VGREAT, -VGREAT, -VGREAT);
-    for (int k = cellFaceOffsets[cell]; k < cellFaceOffsets[cell + 1]; ++k) {
-        int f = cellFaces[k];
-        for (int i = 0; i < nFacePts(f); ++i) {
-            const V3& q = points[facePts(f)[i]];
-            mn = mk(std::min(mn.x, q.x), std::min(mn.y, q.y), std::min(mn.z, q.z));
-            mx = mk(std::max(mx.x, q.x), std::max(mx.y, q.y), std::max(mx.z, q.z));
-        }
-    }
-    if (inflationFraction > SMALL) {
-        V3 inflationVec = (mx - mn) * inflationFraction;  // polyMesh::pointInCellBB
-        mn = mn - inflationVec;
-        mx = mx + inflationVec;
-    }
-    return p.x >= mn.x && p.x <= mx.x && p.y >= mn.y && p.y <= mx.y && p.z >= mn.z && p.z <= mx.z;
-}
-
 }  // namespace dsmc

@@ -86,9 +86,6 @@ struct HostMesh {
     // Bake records [first, first+count) of the tet table (tet ids) into out.
     void bakeTets(int64_t first, int64_t count, TetRec* out) const;
     void bakeBFaces(std::vector<BFaceRec>& out) const;
-    // polyMesh::findTetFacePt: first tet of the cell containing p; false if none.
-    bool findTetFacePt(int32_t cell, const V3& p, int32_t& tetFace, int32_t& tetPt) const;
-    bool pointInCellBB(const V3& p, int32_t cell, double inflationFraction) const;
 };
 
 }  // namespace dsmc

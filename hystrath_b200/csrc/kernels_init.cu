@@ -93,6 +93,91 @@ cudaError_t launchFill(const FillArgs& a, int pass, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// ---- cloud load without tet indices: particle::initCellFacePtOrDeleteLostParticle (BASIC/particle/particleI.H:851-996) ----
+namespace {
+
+// polyMesh::findTetFacePt: the first tet of the cell (cell faces in cells[] order, tetPt ascending) whose tetrahedron::inside(p)
+// holds -- "inside unless definitively shown otherwise": ((p - pt) & n) > SMALL with n = S/(mag(S) + VSMALL) for the four faces
+__device__ bool findTetFacePtDev(const LocateArgs& a, int32_t cell, const V3& p, int32_t& tet) {
+    const V3 A = mk(a.cellCentres[3 * cell], a.cellCentres[3 * cell + 1], a.cellCentres[3 * cell + 2]);
+    for (int k = a.cellFaceOffsets[cell]; k < a.cellFaceOffsets[cell + 1]; ++k) {
+        const int32_t face = a.cellFaces[k];
+        FaceView f{a.facePoints + a.faceOffsets[face], a.faceOffsets[face + 1] - a.faceOffsets[face], a.tetBasePtIs[face]};
+        const bool own = a.owner[face] == cell;
+        for (int tetPt = 1; tetPt < f.n - 1; ++tetPt) {
+            V3 b, c, d;
+            tetPointsDev(a.points, f, own, tetPt, b, c, d);
+            V3 nn = 0.5 * cross(c - b, d - b); nn /= (mag(nn) + VSMALL);          // Sa = triNormal(b, c, d)
+            if (dot(p - b, nn) > SMALL) continue;
+            nn = 0.5 * cross(d - A, c - A); nn /= (mag(nn) + VSMALL);              // Sb = triNormal(a, d, c)
+            if (dot(p - c, nn) > SMALL) continue;
+            nn = 0.5 * cross(b - A, d - A); nn /= (mag(nn) + VSMALL);              // Sc = triNormal(a, b, d)
+            if (dot(p - b, nn) > SMALL) continue;
+            nn = 0.5 * cross(c - A, b - A); nn /= (mag(nn) + VSMALL);              // Sd = triNormal(a, c, b)
+            if (dot(p - b, nn) > SMALL) continue;
+            tet = 2 * (a.faceTetPair0[face] + tetPt - 1) + (own ? 0 : 1);
+            return true;
+        }
+    }
+    return false;
+}
+
+// polyMesh::pointInCellBB(p, cell, 0.1): bounding box of the cell's points inflated by 10 % of its extent (particleI.H:892-902)
+__device__ bool pointInCellBBDev(const LocateArgs& a, int32_t cell, const V3& p, double inflationFraction) {
+    V3 mn = mk(VGREAT, VGREAT, VGREAT), mx = mk(-VGREAT, -VGREAT, -VGREAT);
+    for (int k = a.cellFaceOffsets[cell]; k < a.cellFaceOffsets[cell + 1]; ++k) {
+        const int32_t face = a.cellFaces[k];
+        for (int j = a.faceOffsets[face]; j < a.faceOffsets[face + 1]; ++j) {
+            const int32_t l = a.facePoints[j];
+            const V3 q = mk(a.points[3 * l], a.points[3 * l + 1], a.points[3 * l + 2]);
+            mn = mk(fmin(mn.x, q.x), fmin(mn.y, q.y), fmin(mn.z, q.z));
+            mx = mk(fmax(mx.x, q.x), fmax(mx.y, q.y), fmax(mx.z, q.z));
+        }
+    }
+    if (inflationFraction > SMALL) {
+        const V3 inflationVec = (mx - mn) * inflationFraction;
+        mn = mn - inflationVec;
+        mx = mx + inflationVec;
+    }
+    return p.x >= mn.x && p.x <= mx.x && p.y >= mn.y && p.y <= mx.y && p.z >= mn.z && p.z <= mx.z;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(128) locateKernel(const __grid_constant__ LocateArgs a) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const int32_t cell = a.cell[i];
+    const V3 p = mk(a.px[i], a.py[i], a.pz[i]);
+    int32_t tet = 0;
+    bool ok = false;
+    if (cell >= 0 && cell < a.nCells) {
+        ok = findTetFacePtDev(a, cell, p, tet);
+        if (!ok && pointInCellBBDev(a, cell, p, 0.1)) {
+            // the parcel sits (within rounding) on the cell surface: walk towards the cell centre in trackingCorrectionTol steps
+            // until a tet claims the point (particleI.H:927-976); the stored position is not changed
+            const V3 cc = mk(a.cellCentres[3 * cell], a.cellCentres[3 * cell + 1], a.cellCentres[3 * cell + 2]);
+            V3 q = p;
+            for (int it = 0; it < 200 && !ok; ++it) {
+                q += 1.0e-5 * (cc - q);
+                ok = findTetFacePtDev(a, cell, q, tet);
+            }
+        }
+    }
+    if (!ok) {   // lost: deleted by the sort (cell -1), hyStrath's change at particleI.H:892-902
+        a.cell[i] = -1;
+        tet = 0;
+        atomicAdd(a.lost, 1ULL);
+    }
+    a.tet[i] = tet;
+}
+
+cudaError_t launchLocate(const LocateArgs& a, cudaStream_t s) {
+    if (a.n <= 0) return cudaSuccess;
+    locateKernel<<<(a.n + 127) / 128, 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
 // pass 0: accumulator update (Bird eq. 4.22) and the integer number to insert per (species, face)
 // pass 1: counts holds exclusive offsets; generate
 __global__ void __launch_bounds__(128) inflowKernel(const __grid_constant__ InflowArgs a, int pass) {
