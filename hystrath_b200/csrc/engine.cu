@@ -181,6 +181,8 @@ struct dsmcb200_ctx {
     int* dBad = nullptr;
     double* dZvTab = nullptr;
     MigRec *dMigSend = nullptr, *dMigRecv = nullptr;
+    int32_t *dMigKey = nullptr, *dMigWork = nullptr;   // cloud index of each packed leaver; 3*migCapacity ints of sort workspace
+    void* dMigTemp = nullptr; size_t migTempBytes = 0;
     int32_t migCapacity = 0;
     std::vector<double*> dInflowAcc;
     std::vector<int32_t*> dInflowCounts;
@@ -542,9 +544,14 @@ int ensureMigBuffers(dsmcb200_ctx* c) {
     if (c->nbrProcs.empty()) return 0;
     const int32_t want = int32_t(std::max<int64_t>(1 << 16, c->capacity / 8));
     if (want <= c->migCapacity) return 0;
-    devFree(c->dZvTab); devFree(c->dMigSend); devFree(c->dMigRecv);
+    devFree(c->dMigSend); devFree(c->dMigRecv); devFree(c->dMigKey); devFree(c->dMigWork);
+    if (c->dMigTemp) { cudaFree(c->dMigTemp); c->dMigTemp = nullptr; }
     CK(devAlloc(&c->dMigSend, size_t(want) * MAX_NEIGHBOURS));
     CK(devAlloc(&c->dMigRecv, size_t(want) * MAX_NEIGHBOURS));
+    CK(devAlloc(&c->dMigKey, size_t(want) * MAX_NEIGHBOURS));
+    CK(devAlloc(&c->dMigWork, size_t(want) * 3));
+    c->migTempBytes = orderMigrantsTempBytes(want);
+    CK(cudaMalloc(&c->dMigTemp, std::max<size_t>(c->migTempBytes, 16)));
     c->migCapacity = want;
     return 0;
 }
@@ -616,7 +623,7 @@ MoveArgs moveArgs(dsmcb200_ctx* c, int32_t first, int32_t count, int32_t tailSta
     // boundaryMeas_ is cleaned every step (dsmcCloud.C:924) but only folded into the fields on sampled steps (dsmcVolFields.C:1081,1292)
     a.wallsDue = c->sampleCounter + 1 >= std::max(1, c->models.sampleInterval);
     a.faceFlux = c->dFaceFlux; a.faceAreas = c->dFaceAreas; a.faceTetPair0 = c->dFaceTetPair0; a.nFacesAll = c->mesh.nFaces;
-    a.migBuf = c->dMigSend; a.migCapacity = c->migCapacity; a.cellCount = c->dCellCount; a.counters = c->dCounters; a.step = c->step;
+    a.migBuf = c->dMigSend; a.migKey = c->dMigKey; a.migCapacity = c->migCapacity; a.cellCount = c->dCellCount; a.counters = c->dCounters; a.step = c->step;
     return a;
 }
 
@@ -647,6 +654,10 @@ int stageMove(dsmcb200_ctx* c, int64_t tailStart) {
         for (size_t s = 0; s < c->nbrProcs.size(); ++s) {
             if (nMig[s] > c->migCapacity) return fail(c, DSMCB200_ERR_CAPACITY, "migration buffer overflow");
             sendTo[c->nbrProcs[s]] = nMig[s];
+            // particleTransferLists[neighbour] in cloud-list order (Cloud.C:283-306); the receive slab of the slot is free until the
+            // exchange below and serves as scratch
+            CK(orderMigrants(c->dMigSend + s * c->migCapacity, c->dMigRecv + s * c->migCapacity, c->dMigKey + s * c->migCapacity, c->dMigWork,
+                             c->dMigTemp, c->migTempBytes, nMig[s], c->stream));
         }
         // pBufs.finishedSends(allNTrans) + reduce(transfered, orOp) -> one all-gather of the send-count rows
         int32_t* dRow = c->dCountsMatrix + size_t(R) * R;
@@ -759,7 +770,8 @@ void dsmcb200_destroy(dsmcb200_ctx* c) {
     devFree(c->dCellCount); devFree(c->dCellOffset); devFree(c->dCursor); devFree(c->dPerm); devFree(c->dOctKey); devFree(c->dScanScratch);
     devFree(c->dSigma); devFree(c->dRem); devFree(c->dNColls); devFree(c->dCollSep); devFree(c->dAcc); devFree(c->dCollCum);
     devFree(c->dFaceFlux); devFree(c->dWallAcc); devFree(c->dSfTail); devFree(c->dInfo); devFree(c->dInfoScratch); devFree(c->dCounters); devFree(c->dBad);
-    devFree(c->dMigSend); devFree(c->dMigRecv); devFree(c->dInflowScan); devFree(c->dOrdinalToPatch); devFree(c->dCountsMatrix);
+    devFree(c->dZvTab); devFree(c->dMigSend); devFree(c->dMigRecv); devFree(c->dMigKey); devFree(c->dMigWork); devFree(c->dInflowScan);
+    if (c->dMigTemp) cudaFree(c->dMigTemp); devFree(c->dOrdinalToPatch); devFree(c->dCountsMatrix);
     for (auto& p : c->dInflowAcc) devFree(p);
     for (auto& p : c->dInflowCounts) devFree(p);
     for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);

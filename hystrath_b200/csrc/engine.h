@@ -105,6 +105,7 @@ struct MoveArgs {
     const int32_t* faceTetPair0;  // [nFacesAll+1] first face-triangle of each face (tet id >> 1 -> face)
     int32_t nFacesAll;
     MigRec* migBuf;               // [MAX_NEIGHBOURS][migCapacity]
+    int32_t* migKey;              // [MAX_NEIGHBOURS][migCapacity] cloud index of the packed parcel: the sender's list order
     int32_t migCapacity;
     int32_t* cellCount;           // histogram for the sort (stage 2), fused here
     DevCounters* counters;
@@ -173,6 +174,13 @@ struct FillArgs {
     int32_t origIdBase;
 };
 cudaError_t launchFill(const FillArgs& a, int pass, cudaStream_t s);
+
+// Cloud<T>::move appends leavers to particleTransferLists[neighbour] in cloud-list order (BASIC/Cloud/Cloud.C:283-306); moveKernel
+// packs them in atomic order, so each neighbour's records are put back into list order (ascending cloud index) before they are sent.
+// scratch: n records; work: 3*n ints; temp: orderMigrantsTempBytes(capacity) bytes.
+size_t orderMigrantsTempBytes(int32_t capacity);
+cudaError_t orderMigrants(MigRec* records, MigRec* scratch, const int32_t* keys, int32_t* work, void* temp, size_t tempBytes, int32_t n,
+                          cudaStream_t s);
 
 // particle::initCellFacePtOrDeleteLostParticle for a cloud that arrives without tetFace / tetPt (the `positions` file holds only
 // "(x y z) cell", particleIO.C:51-58)

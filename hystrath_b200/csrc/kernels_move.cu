@@ -16,6 +16,8 @@
 // iterations, so each warp owns a chunk of MOVE_CHUNK*32 consecutive parcels and a lane that finishes
 // its parcel immediately takes the next unprocessed one of the chunk (warp-private work queue); the
 // lanes of a warp therefore stay busy and memory accesses stay inside the chunk's cache lines.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "device_models.cuh"
 #include "engine.h"
 
@@ -489,6 +491,7 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                         r.vib[0] = in.vib0; r.vib[1] = in.vib1; r.vib[2] = in.vib2;
                         r.typeId = a.p.typeId[i]; r.elevel = uint8_t(in.elevel); r.cls = a.p.cls ? a.p.cls[i] : 0; r.pad_ = 0;
                         a.migBuf[size_t(slot) * a.migCapacity + k] = r;
+                        a.migKey[size_t(slot) * a.migCapacity + k] = i;
                     } else {
                         atomicAdd(&a.counters->overflow, 1ULL);
                     }
@@ -514,6 +517,42 @@ cudaError_t launchMove(const MoveArgs& a, cudaStream_t s) {
     const int grid = (a.count + perBlock - 1) / perBlock;
     moveKernel<<<grid, MOVE_BLOCK, 0, s>>>(a);
     return cudaGetLastError();
+}
+
+// ---- leavers back into cloud-list order (see engine.h) ----
+namespace {
+__global__ void iotaI32(int32_t* v, int32_t n) {
+    const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) v[k] = k;
+}
+__global__ void permuteMigRecs(const MigRec* __restrict__ in, const int32_t* __restrict__ perm, MigRec* __restrict__ out, int32_t n) {
+    // one 16-byte piece of a 96-byte record per thread: coalesced stores, gathers of whole records
+    const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int32_t k = int32_t(t / 6), piece = int32_t(t % 6);
+    if (k >= n) return;
+    static_assert(sizeof(MigRec) == 96, "MigRec is moved in six 16-byte pieces");
+    reinterpret_cast<int4*>(out + k)[piece] = reinterpret_cast<const int4*>(in + perm[k])[piece];
+}
+}  // namespace
+
+size_t orderMigrantsTempBytes(int32_t capacity) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int32_t*)nullptr, (int32_t*)nullptr, (const int32_t*)nullptr, (int32_t*)nullptr,
+                                    capacity);
+    return bytes;
+}
+
+cudaError_t orderMigrants(MigRec* records, MigRec* scratch, const int32_t* keys, int32_t* work, void* temp, size_t tempBytes, int32_t n,
+                          cudaStream_t s) {
+    if (n <= 1) return cudaSuccess;
+    int32_t *keysOut = work, *idxIn = work + n, *idxOut = work + 2 * size_t(n);
+    iotaI32<<<(n + 255) / 256, 256, 0, s>>>(idxIn, n);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, tempBytes, keys, keysOut, idxIn, idxOut, n, 0, 32, s);
+    if (e != cudaSuccess) return e;
+    const int64_t threads = int64_t(n) * 6;
+    permuteMigRecs<<<unsigned((threads + 255) / 256), 256, 0, s>>>(records, idxOut, scratch, n);
+    e = cudaMemcpyAsync(records, scratch, size_t(n) * sizeof(MigRec), cudaMemcpyDeviceToDevice, s);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // ---- arrivals over a processor patch: particle::correctAfterParallelTransfer,

@@ -245,3 +245,117 @@ def ff_read_positions(path):
     from hystrath_b200 import foamfile as ff
 
     return ff.read_positions(path)
+
+
+# ---- collisions on: the decomposed run is reproducible parcel by parcel -----------------------------------------------------------------
+# Cloud<T>::move ships leavers in cloud-list order and appends arrivals neighbour by neighbour (BASIC/Cloud/Cloud.C:283-306,364-397), so
+# the in-cell order that buildCellOccupancy produces -- and with it every NTC pair -- is a function of the decomposition alone.  The
+# engine restores that order (orderMigrants), hence the 2-GPU run equals the 2-rank oracle run: same list order, same collisions.
+LB_STEPS = 4
+
+
+def _lb_models(fnum):
+    return capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=fnum, deltaT=6e-6, seed=79)   # variable Zv table
+
+
+def _lb_start():
+    from oracle.pyoracle import Oracle
+
+    sp = H.air5()[:2]
+    mesh = meshgen.box_mesh((8, 4, 3), (0.032, 0.016, 0.012))
+    fnum = 2e21 * 0.032 * 0.016 * 0.012 / (96 * 40)
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species(sp); o.set_models(_lb_models(fnum))
+    o.mesh_fill([0, 1], [1.5e21, 0.5e21], 4000.0, 4000.0, 4000.0, velocity=(300.0, 0.0, 0.0))
+    return fnum, o.download_parcels(), o.download_cellstate()[0]
+
+
+def _lb_share(start, sigma, rank):
+    gi, gj, gk = start.cell % 8, (start.cell // 8) % 4, start.cell // 32
+    mine = (gi // 4) == rank
+    loc = (gi % 4 + 4 * (gj + 4 * gk)).astype(np.int32)
+    p = capi.ParcelData(int(mine.sum()), 1, allocate=False, position=start.position[mine], U=start.U[mine], ERot=start.ERot[mine],
+                        cell=loc[mine], typeId=start.typeId[mine], vibLevel=start.vibLevel[mine], origId=start.origId[mine])
+    c = np.arange(48)
+    gcell = (c % 4 + 4 * rank) + 8 * ((c // 4) % 4 + 4 * (c // 16))
+    return p, sigma[gcell].copy()
+
+
+def _lb_oracle_two_ranks():
+    """The protocol of tests/test_decomposed_gloo.py with both ranks in this process."""
+    from oracle.pyoracle import Oracle
+
+    fnum, start, sigma = _lb_start()
+    ranks = []
+    for r in range(2):
+        o = Oracle()
+        o.set_mesh(meshgen.decomposed_box(N_LOCAL, L_LOCAL, PROCS, r)); o.set_species(H.air5()[:2]); o.set_models(_lb_models(fnum))
+        p, sig = _lb_share(start, sigma, r)
+        o.upload_parcels(p)
+        o.upload_cellstate(sig, None)
+        ranks.append(o)
+    for _ in range(LB_STEPS):
+        for o in ranks:
+            o.evolve_begin()
+        while True:
+            boxes = [o.outbox() for o in ranks]
+            if not any(len(d) for d, _ in boxes):
+                break
+            for r, o in enumerate(ranks):
+                d, i = boxes[1 - r]
+                sel = i[:, 0] == r
+                if sel.any():
+                    o.receive_and_move(1 - r, d[sel], i[sel])
+        for o in ranks:
+            o.evolve_end()
+    return [(o.download_parcels(), o.counters()) for o in ranks]
+
+
+def _lb_worker(rank, world, q_id, q_out):
+    try:
+        torch.cuda.set_device(rank)
+        fnum, start, sigma = _lb_start()
+        eng = capi.Engine(rank, rank, world)
+        eng.set_mesh(meshgen.decomposed_box(N_LOCAL, L_LOCAL, PROCS, rank)); eng.set_species(H.air5()[:2]); eng.set_models(_lb_models(fnum))
+        if rank == 0:
+            ident = capi.nccl_unique_id()
+            for _ in range(world - 1):
+                q_id.put(ident)
+        else:
+            ident = q_id.get(timeout=120)
+        eng.init_comm(ident)
+        p, sig = _lb_share(start, sigma, rank)
+        eng.upload_parcels(p)
+        eng.upload_cellstate(sig, None)
+        collisions = 0
+        for _ in range(LB_STEPS):
+            eng.evolve(1)
+            collisions += eng.counters().collisions
+        res = eng.download_parcels()
+        q_out.put((rank, res.origId.copy(), res.cell.copy(), res.U.copy(), res.ERot.copy(), res.vibLevel.copy(), int(collisions)))
+        eng.close()
+    except Exception as e:
+        q_out.put((rank, repr(e)))
+
+
+def test_two_gpu_run_with_collisions_equals_the_two_rank_oracle():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q_id, q_out = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_lb_worker, args=(r, 2, q_id, q_out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ref = _lb_oracle_two_ranks()
+    results = sorted([q_out.get(timeout=300) for _ in range(2)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    for r in results:
+        assert len(r) == 7, r
+    for rank, (_, ids, cell, U, erot, vib, ncoll) in enumerate(results):
+        o, oc = ref[rank]
+        assert np.array_equal(ids, o.origId)              # the cloud in the same list order: arrivals included
+        assert np.array_equal(cell, o.cell)
+        assert ncoll == oc["collisions"] and ncoll > 100  # the same NTC pairs were selected and accepted
+        assert np.array_equal(vib, o.vibLevel)            # variable-Zv vibrational exchange (host-tabulated 1/Zv) included
+        assert np.allclose(U, o.U, rtol=0, atol=1e-8) and np.allclose(erot, o.ERot, rtol=1e-9, atol=1e-30)
