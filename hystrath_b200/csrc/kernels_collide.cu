@@ -32,6 +32,7 @@ struct CellView {  // the parcels of one cell, in shared memory (small cells) or
     int32_t* vib[MAX_MODES];
     uint8_t *typ, *elev;
     uint8_t* dirty;  // null when operating in place
+    const double* tMacro;  // &overallT[cell] or null
 };
 
 struct WarpSmem {
@@ -111,16 +112,19 @@ __device__ double postCollisionRotationalEnergy(Rng& rng, double rotationalDof, 
 // dsmcCloud::postCollisionVibrationalEnergyLevel (postReaction = false)
 __device__ int32_t postCollisionVibrationalEnergyLevel(const DevParams& P, Rng& rng, int32_t vibLevel, int32_t iMax, double thetaV,
                                                        double thetaD, double refTempZv, double omega, double Zref, double Ec,
-                                                       const double* zvRow) {
+                                                       const double* zvRow, const double* tMacro) {
     int32_t iDash = vibLevel;
     double inverseVibrationalCollisionNumber = 1.0;
     const double fixedZv = P.Zvib;
-    if (fixedZv == 0 && iMax < ZV_TABLE) {
+    // invZvFormulation 0 and 2 use the quantised collision temperature; formulation 1 ("2008") the macroscopic overall
+    // temperature of the cell, fields().overallT(cellI), and falls back to the former while that is not available
+    // (TMacro <= SMALL, dsmcCloud.C:1441-1456)
+    double TMacro = 0.0;
+    if (fixedZv == 0 && P.invZvFormulation == 1 && tMacro != nullptr) TMacro = *tMacro;
+    if (fixedZv == 0 && iMax < ZV_TABLE && !(TMacro > SMALL)) {
         inverseVibrationalCollisionNumber = zvRow[iMax];  // host-tabulated value of the expression below
     } else if (fixedZv == 0) {
-        // invZvFormulation 0 and 2 use the quantised collision temperature; formulation 1 (macroscopic Tov)
-        // falls back to it exactly as the reference does when Tov is not yet available (dsmcCloud.C:1445-1454)
-        const double T = iMax * thetaV / (3.5 - omega);
+        const double T = TMacro > SMALL ? TMacro : iMax * thetaV / (3.5 - omega);
         const double pow1 = powNI(thetaD / T, 1. / 3.) - 1.0;
         const double pow2 = powNI(thetaD / refTempZv, 1. / 3.) - 1.0;
         const double ZvP1 = powNI(thetaD / T, omega);
@@ -187,7 +191,7 @@ __device__ __noinline__ void redistribute(const DevParams& P, Rng& rng, const Ce
             if (iMaxP > 0) {
                 const int32_t lvl = postCollisionVibrationalEnergyLevel(P, rng, v.vib[m][j], iMaxP, S.thetaV[m], S.thetaD, S.TrefZv[m],
                                                                         omegaPQ, S.Zref[m], EcP,
-                                                                        P.invZvTab + ((size_t(v.typ[j]) * P.nSpecies + tOther) * MAX_MODES + m) * ZV_TABLE);
+                                                                        P.invZvTab + ((size_t(v.typ[j]) * P.nSpecies + tOther) * MAX_MODES + m) * ZV_TABLE, v.tMacro);
                 v.vib[m][j] = lvl;
                 translationalEnergy = EcP - lvl * P.kB * S.thetaV[m];
             }
@@ -459,7 +463,7 @@ struct InPlace {  // accessor of the parcels of one cell where they lie in the s
 
 // LarsenBorgnakkeVariableHardSphere::redistribute (postReaction = false) on parcel j of the view
 __device__ __forceinline__ void redistributeInPlace(const DevParams& P, Rng& rng, const InPlace v, int j, int tSelf, int tOther,
-                                                 double& translationalEnergy, double omegaPQ) {
+                                                 double& translationalEnergy, double omegaPQ, const double* tMacro) {
     const DevSpecies& S = P.sp[tSelf];
     if (S.type == 0) return;  // electron
     if (P.invZelec > rng.sample01()) {
@@ -484,7 +488,7 @@ __device__ __forceinline__ void redistributeInPlace(const DevParams& P, Rng& rng
             if (iMaxP > 0) {
                 const int32_t lvl = postCollisionVibrationalEnergyLevel(P, rng, lvl0[m], iMaxP, S.thetaV[m], S.thetaD, S.TrefZv[m], omegaPQ,
                                                                         S.Zref[m], EcP,
-                                                                        P.invZvTab + ((size_t(tSelf) * P.nSpecies + tOther) * MAX_MODES + m) * ZV_TABLE);
+                                                                        P.invZvTab + ((size_t(tSelf) * P.nSpecies + tOther) * MAX_MODES + m) * ZV_TABLE, tMacro);
                 if (lvl != lvl0[m]) v.setVib(m, j, lvl);
                 translationalEnergy = EcP - lvl * P.kB * S.thetaV[m];
             }
@@ -629,8 +633,9 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) collideLaneKernel(const __gri
                                 const double cRsqr = magSqr(UP - UQ);
                                 double translationalEnergy = 0.5 * mR * cRsqr;
                                 const double omegaPQ = P.omegaPQ[tP][tQ];
-                                redistributeInPlace(P, rng, v, cp, tP, tQ, translationalEnergy, omegaPQ);
-                                redistributeInPlace(P, rng, v, cq, tQ, tP, translationalEnergy, omegaPQ);
+                                const double* tMacro = a.overallT ? a.overallT + c : nullptr;
+                                redistributeInPlace(P, rng, v, cp, tP, tQ, translationalEnergy, omegaPQ, tMacro);
+                                redistributeInPlace(P, rng, v, cq, tQ, tP, translationalEnergy, omegaPQ, tMacro);
                                 cR = sqrt(2.0 * translationalEnergy / mR);
                             }
                             postCollisionVelocities(P, rng, tP, tQ, UP, UQ, cR);
