@@ -274,6 +274,7 @@ def load_library():
         "dsmcb200_download_wall_accumulators": ([P, C.c_void_p], C.c_int),
         "dsmcb200_upload_wall_accumulators": ([P, C.c_void_p], C.c_int),
         "dsmcb200_download_face_fluxes": ([P, C.c_void_p, C.c_void_p], C.c_int),
+        "dsmcb200_upload_overall_temperature": ([P, C.c_void_p], C.c_int),
         "dsmcb200_get_counters": ([P, C.POINTER(Counters)], C.c_int),
         "dsmcb200_kernel_times": ([P, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
         "dsmcb200_download_geometry": ([P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
@@ -296,7 +297,7 @@ EXPORTED_SYMBOLS = [
     "dsmcb200_mesh_fill", "dsmcb200_evolve", "dsmcb200_stage", "dsmcb200_set_step", "dsmcb200_download_occupancy",
     "dsmcb200_accum_info_get", "dsmcb200_download_accumulators", "dsmcb200_upload_accumulators",
     "dsmcb200_reset_accumulators", "dsmcb200_wall_info", "dsmcb200_download_wall_accumulators",
-    "dsmcb200_upload_wall_accumulators", "dsmcb200_download_face_fluxes", "dsmcb200_get_counters",
+    "dsmcb200_upload_wall_accumulators", "dsmcb200_download_face_fluxes", "dsmcb200_upload_overall_temperature", "dsmcb200_get_counters",
     "dsmcb200_kernel_times", "dsmcb200_download_geometry", "dsmcb200_timer_start", "dsmcb200_timer_stop", "dsmcb200_allreduce_sum",
 ]
 
@@ -494,6 +495,12 @@ class Engine:
         if nf.value:
             self._ck(self.lib.dsmcb200_download_wall_accumulators(self.h, _ptr(w)))
         return w
+
+    def upload_overall_temperature(self, Tov):
+        """fields().overallT(cell) for inverseZvFormulation "2008" (dsmcCloud.C:1441-1456)."""
+        t = np.ascontiguousarray(Tov, np.float64)
+        assert t.shape == (self._mesh.n_cells,)
+        self._ck(self.lib.dsmcb200_upload_overall_temperature(self.h, _ptr(t)))
 
     def face_fluxes(self):
         """dsmcFaceTracker parcelIdFlux / massIdFlux of the last step, each [nSpecies][nFaces] (models.trackFaceFluxes)."""

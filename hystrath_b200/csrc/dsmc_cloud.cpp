@@ -767,8 +767,14 @@ void dsmcCloud::writeFields(const std::string& timeDir, const std::vector<double
     // WallQ order of the engine (csrc/engine.h): rhoN 0, rhoNInt 1, rhoNElec 2, rhoM 3, linearKE 4, mcc 5, momentum 6-8, Erot 9,
     // zetaRot 10, Evib 11, Eelec 12, q 13, fD 14-16, EvibMod 17+
     struct WallFace { double rhoN, rhoM, U[3], Ttra, Trot, Tvib, Tov, Ma, fD[3], p, tau, q; };
+    bool firstField = true;
     for (auto& f : fields_) {
         DerivedFields d = calculateField(f);
+        // fields().overallT(cell) is Tov_ of fields_[0] as written here (dsmcFieldProperties.C:235-240): the "2008" Zv formulation
+        // reads it in the collisions of the following steps (dsmcCloud.C:1441-1456)
+        if (firstField && models_.invZvFormulation == 1 && (models_.collisionModel == DSMCB200_COLL_LB_VHS || models_.collisionModel == DSMCB200_COLL_LB_VSS))
+            check(dsmcb200_upload_overall_temperature(ctx_, d.Tov.data()), "dsmcb200_upload_overall_temperature");
+        firstField = false;
         // ---- wall faces of this instance
         std::vector<std::vector<WallFace>> wf(boundary_.size());
         for (size_t j = 0; j < boundary_.size(); ++j) {

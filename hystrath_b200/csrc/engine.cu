@@ -153,6 +153,7 @@ struct dsmcb200_ctx {
     std::vector<dsmcb200_species> species;
     dsmcb200_models models{};
     int sampleCounter = 0;   // steps since stage 5 last ran (sampleInterval)
+    double* dOverallT = nullptr;   // fields().overallT(cell) uploaded by the caller at write times (inverseZvFormulation "2008")
     double* dFaceFlux = nullptr;   // dsmcFaceTracker: [2][nSpecies][nFaces] of the current step (models.trackFaceFluxes)
     std::vector<dsmcb200_patch_model> patchModels;
     std::vector<dsmcb200_inflow> inflows;
@@ -708,6 +709,7 @@ int stageCollide(dsmcb200_ctx* c) {
     CollideArgs a{};
     a.p = c->buf[c->cur].a; a.cellOffset = c->dCellOffset; a.nCells = c->mesh.nCells; a.cellCentres = c->dCellCentres;
     a.cellVolumes = c->dCellVolumes; a.sigmaTcRMax = c->dSigma; a.remainder = c->dRem; a.nCollsStep = c->dNColls; a.collSepStep = c->dCollSep;
+    a.overallT = c->hP.invZvFormulation == 1 ? c->dOverallT : nullptr;
     a.bigScratch = c->dPerm; a.bigList = c->dCursor; a.octKey = c->dOctKey; a.P = c->dP; a.counters = c->dCounters; a.step = c->step;
     CK(cudaMemsetAsync(&c->dCounters->bigCells, 0, sizeof(int32_t), c->stream));
     KT t(c, "collide");
@@ -769,7 +771,7 @@ void dsmcb200_destroy(dsmcb200_ctx* c) {
     devFree(c->dOwner); devFree(c->dTetBasePtIs); devFree(c->dFaceTetPair0); devFree(c->dCellFaceOffsets); devFree(c->dCellFaces);
     devFree(c->dCellCount); devFree(c->dCellOffset); devFree(c->dCursor); devFree(c->dPerm); devFree(c->dOctKey); devFree(c->dScanScratch);
     devFree(c->dSigma); devFree(c->dRem); devFree(c->dNColls); devFree(c->dCollSep); devFree(c->dAcc); devFree(c->dCollCum);
-    devFree(c->dFaceFlux); devFree(c->dWallAcc); devFree(c->dSfTail); devFree(c->dInfo); devFree(c->dInfoScratch); devFree(c->dCounters); devFree(c->dBad);
+    devFree(c->dOverallT); devFree(c->dFaceFlux); devFree(c->dWallAcc); devFree(c->dSfTail); devFree(c->dInfo); devFree(c->dInfoScratch); devFree(c->dCounters); devFree(c->dBad);
     devFree(c->dZvTab); devFree(c->dMigSend); devFree(c->dMigRecv); devFree(c->dMigKey); devFree(c->dMigWork); devFree(c->dInflowScan);
     if (c->dMigTemp) cudaFree(c->dMigTemp); devFree(c->dOrdinalToPatch); devFree(c->dCountsMatrix);
     for (auto& p : c->dInflowAcc) devFree(p);
@@ -1155,6 +1157,17 @@ int dsmcb200_wall_info(dsmcb200_ctx* c, int32_t* nFaces, int32_t* nWallQ) {
     { int r = finalize(c); if (r) return r; }
     if (nFaces) *nFaces = c->nMeasFaces;
     if (nWallQ) *nWallQ = c->nWallQ;
+    return 0;
+}
+
+int dsmcb200_upload_overall_temperature(dsmcb200_ctx* c, const double* Tov) {
+    if (!c || !Tov) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    const size_t nC = size_t(c->mesh.nCells);
+    if (!c->dOverallT) CK(devAlloc(&c->dOverallT, nC));
+    CK(cudaMemcpyAsync(c->dOverallT, Tov, nC * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
         const bool small = false;
         const double cc[3] = {a.cellCentres[3 * c], a.cellCentres[3 * c + 1], a.cellCentres[3 * c + 2]};
         CellView v;
+        v.tMacro = a.overallT ? a.overallT + c : nullptr;
         if (small) {
             v.ux = sm.ux; v.uy = sm.uy; v.uz = sm.uz; v.erot = sm.erot;
             for (int m = 0; m < MAX_MODES; ++m) v.vib[m] = sm.vib[m];

@@ -320,6 +320,12 @@ int dsmcb200_upload_wall_accumulators(dsmcb200_ctx*, const double* wall);
  * a crossing of it (dsmcCloud.C:429-437).  The arrays are cleared at the start of every step (trackingInfo_.clean(),
  * dsmcCloud.C:923).  Replaces cloud.tracker().parcelIdFlux() / massIdFlux() (dsmcFaceTracker.H). */
 int dsmcb200_download_face_fluxes(dsmcb200_ctx*, double* parcelIdFlux, double* massIdFlux);
+/* inverseZvFormulation "2008" (LarsenBorgnakkeVariableHardSphereCoeffs; invZvFormulation = 1): the vibrational collision number is
+ * evaluated at the macroscopic overall temperature of the cell, fields().overallT(cellI) = Tov_ of the first dsmcVolFields entry as of
+ * its last write (dsmcCloud.C:1441-1456, dsmcFieldProperties.C:235-240, dsmcVolFields.H:244-247).  The caller computes Tov when it
+ * writes the fields and hands it over; cells with Tov <= SMALL (and every cell before the first upload) use the quantised
+ * collision temperature, as the reference does.  Tov: [nCells]. */
+int dsmcb200_upload_overall_temperature(dsmcb200_ctx*, const double* Tov);
 int dsmcb200_get_counters(dsmcb200_ctx*, dsmcb200_counters*);
 /* Per-kernel device time of the last step, for bench.py: names[i] is filled with up to
  * DSMCB200_NAME_LEN chars; returns the count through *n (capacity in). */

@@ -58,6 +58,7 @@ def load():
     lib.oracle_wall_info.argtypes = [P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.oracle_download_wall_accumulators.argtypes = [P, C.c_void_p]
     lib.oracle_download_face_fluxes.argtypes = [P, C.c_void_p, C.c_void_p]
+    lib.oracle_upload_overall_temperature.argtypes = [P, C.c_void_p]
     lib.oracle_get_counters.argtypes = [P, C.c_void_p]
     lib.oracle_download_geometry.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _LIB = lib
@@ -164,6 +165,10 @@ class Oracle:
         if nf.value:
             self._ck(self.lib.oracle_download_wall_accumulators(self.h, _ptr(w)))
         return w
+
+    def upload_overall_temperature(self, Tov):
+        t = np.ascontiguousarray(Tov, np.float64)
+        self._ck(self.lib.oracle_upload_overall_temperature(self.h, _ptr(t)))
 
     def face_fluxes(self):
         """dsmcFaceTracker parcelIdFlux / massIdFlux of the last step, each [nSpecies][nFaces]."""

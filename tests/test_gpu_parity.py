@@ -184,6 +184,27 @@ def test_collide_larsen_borgnakke_air5_matches_oracle():
     eng.close()
 
 
+def test_collide_inverse_zv_2008_with_macroscopic_temperature_matches_oracle():
+    """inverseZvFormulation "2008": Zv at fields().overallT(cell) where it exists (> SMALL), the collision temperature elsewhere
+    (dsmcCloud.C:1441-1456); the temperature field comes in through dsmcb200_upload_overall_temperature."""
+    sp = H.air5()
+    mesh, _, md = periodic_case((6, 5, 4), ppc=50, species=sp, model="LarsenBorgnakkeVariableHardSphere", dens=1e21, dt=2e-6,
+                                inverseZvFormulation="2008")
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    start = H.same_start(eng, ora, [0, 1, 2, 3, 4], [0.6e21, 0.2e21, 0.05e21, 0.1e21, 0.05e21], 5000.0, 5000.0, 5000.0)
+    rng = np.random.default_rng(3)
+    Tov = rng.uniform(2000.0, 60000.0, mesh.n_cells)
+    Tov[::7] = 0.0                                   # cells without a macroscopic temperature yet: fallback
+    for x in (eng, ora):
+        x.upload_overall_temperature(Tov)
+        x.stage(capi.STAGE_COLLIDE)
+    g, o = eng.download_parcels(), ora.download_parcels()
+    assert eng.counters().collisions == ora.counters()["collisions"] > 1000
+    assert np.array_equal(g.vibLevel, o.vibLevel) and (o.vibLevel != start.vibLevel).sum() > 50
+    assert np.allclose(g.U, o.U, rtol=0, atol=1e-9) and np.allclose(g.ERot, o.ERot, rtol=1e-10, atol=1e-32)
+    eng.close()
+
+
 def test_collide_soft_sphere_models_match_oracle():
     """VariableSoftSphere and LarsenBorgnakkeVariableSoftSphere (Bird eq. 2.22 scattering with the species' alpha)."""
     sp = H.air5()

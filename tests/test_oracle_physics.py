@@ -406,3 +406,30 @@ def test_face_tracker_fluxes_balance_the_cell_occupancy():
             assert np.array_equal(net, dn)
             assert np.allclose(mf[s], sp[s].mass * pf[s], rtol=1e-12, atol=1e-12 * sp[s].mass)   # +m -m leaves rounding residue
         assert (pf[:, nI:] <= 0).all() and pf[:, nI:].sum() < -10     # every wall hit leaves with U . S_f < 0
+
+
+def test_inverse_zv_formulation_2008_uses_the_macroscopic_temperature():
+    """inverseZvFormulation "2008" (dsmcCloud.C:1441-1456): Zv is evaluated at fields().overallT(cell); while that is <= SMALL the
+    quantised collision temperature is used, i.e. the run equals "pre-2008".  Zv(T = theta_d) = 1 (every eligible collision
+    exchanges vibrational energy), Zv(T -> 0) -> infinity (none does)."""
+    sp = H.air5()[:1]   # N2: theta_v 3371 K, theta_d 113500 K
+
+    def run(formulation, Tov=None):
+        mesh, md, o = box((4, 4, 4), (0.016,) * 3, sp, model="LarsenBorgnakkeVariableHardSphere", ppc=60, dens=1e21, dt=2e-6,
+                          inverseZvFormulation=formulation)
+        o.mesh_fill([0], [1e21], 6000.0, 6000.0, 6000.0)
+        if Tov is not None:
+            o.upload_overall_temperature(np.full(mesh.n_cells, Tov))
+        before = o.download_parcels().vibLevel.copy()
+        o.stage(capi.STAGE_COLLIDE)
+        after = o.download_parcels()
+        return int((after.vibLevel != before).sum()), after, o.counters()["collisions"]
+
+    n_pre, a_pre, c_pre = run("pre-2008")
+    n_fb, a_fb, c_fb = run("2008")                      # no Tov yet: the reference's fallback
+    assert c_pre == c_fb > 500 and n_pre == n_fb > 0
+    assert np.array_equal(a_pre.vibLevel, a_fb.vibLevel) and np.array_equal(a_pre.U, a_fb.U)
+    n_cold, _, c_cold = run("2008", Tov=1.0)
+    assert c_cold > 500 and n_cold == 0                 # 1/Zv(1 K) = 0: no vibrational exchange at all
+    n_hot, _, _ = run("2008", Tov=113500.0)
+    assert n_hot > 5 * n_pre                            # 1/Zv(theta_d) = 1
