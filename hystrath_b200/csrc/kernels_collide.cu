@@ -110,6 +110,8 @@ __device__ double postCollisionRotationalEnergy(Rng& rng, double rotationalDof, 
 }
 
 // dsmcCloud::postCollisionVibrationalEnergyLevel (postReaction = false)
+// ZV2008: inverseZvFormulation "2008" compiled in (the common formulations keep the kernel free of the temperature pointer)
+template <bool ZV2008>
 __device__ int32_t postCollisionVibrationalEnergyLevel(const DevParams& P, Rng& rng, int32_t vibLevel, int32_t iMax, double thetaV,
                                                        double thetaD, double refTempZv, double omega, double Zref, double Ec,
                                                        const double* zvRow, const double* tMacro) {
@@ -120,7 +122,9 @@ __device__ int32_t postCollisionVibrationalEnergyLevel(const DevParams& P, Rng& 
     // temperature of the cell, fields().overallT(cellI), and falls back to the former while that is not available
     // (TMacro <= SMALL, dsmcCloud.C:1441-1456)
     double TMacro = 0.0;
-    if (fixedZv == 0 && P.invZvFormulation == 1 && tMacro != nullptr) TMacro = *tMacro;
+    if constexpr (ZV2008) {
+        if (fixedZv == 0 && P.invZvFormulation == 1 && tMacro != nullptr) TMacro = *tMacro;
+    }
     if (fixedZv == 0 && iMax < ZV_TABLE && !(TMacro > SMALL)) {
         inverseVibrationalCollisionNumber = zvRow[iMax];  // host-tabulated value of the expression below
     } else if (fixedZv == 0) {
@@ -189,7 +193,7 @@ __device__ __noinline__ void redistribute(const DevParams& P, Rng& rng, const Ce
             const double EcP = translationalEnergy + preEVib[m];
             const int32_t iMaxP = int32_t(EcP / (P.kB * S.thetaV[m]));
             if (iMaxP > 0) {
-                const int32_t lvl = postCollisionVibrationalEnergyLevel(P, rng, v.vib[m][j], iMaxP, S.thetaV[m], S.thetaD, S.TrefZv[m],
+                const int32_t lvl = postCollisionVibrationalEnergyLevel<true>(P, rng, v.vib[m][j], iMaxP, S.thetaV[m], S.thetaD, S.TrefZv[m],
                                                                         omegaPQ, S.Zref[m], EcP,
                                                                         P.invZvTab + ((size_t(v.typ[j]) * P.nSpecies + tOther) * MAX_MODES + m) * ZV_TABLE, v.tMacro);
                 v.vib[m][j] = lvl;
@@ -463,6 +467,7 @@ struct InPlace {  // accessor of the parcels of one cell where they lie in the s
 };
 
 // LarsenBorgnakkeVariableHardSphere::redistribute (postReaction = false) on parcel j of the view
+template <bool ZV2008>
 __device__ __forceinline__ void redistributeInPlace(const DevParams& P, Rng& rng, const InPlace v, int j, int tSelf, int tOther,
                                                  double& translationalEnergy, double omegaPQ, const double* tMacro) {
     const DevSpecies& S = P.sp[tSelf];
@@ -487,7 +492,7 @@ __device__ __forceinline__ void redistributeInPlace(const DevParams& P, Rng& rng
             const double EcP = translationalEnergy + preEVib[m];
             const int32_t iMaxP = int32_t(EcP / (P.kB * S.thetaV[m]));
             if (iMaxP > 0) {
-                const int32_t lvl = postCollisionVibrationalEnergyLevel(P, rng, lvl0[m], iMaxP, S.thetaV[m], S.thetaD, S.TrefZv[m], omegaPQ,
+                const int32_t lvl = postCollisionVibrationalEnergyLevel<ZV2008>(P, rng, lvl0[m], iMaxP, S.thetaV[m], S.thetaD, S.TrefZv[m], omegaPQ,
                                                                         S.Zref[m], EcP,
                                                                         P.invZvTab + ((size_t(tSelf) * P.nSpecies + tOther) * MAX_MODES + m) * ZV_TABLE, tMacro);
                 if (lvl != lvl0[m]) v.setVib(m, j, lvl);
@@ -511,6 +516,7 @@ __device__ __forceinline__ void redistributeInPlace(const DevParams& P, Rng& rng
 __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 }  // namespace
 
+template <bool ZV2008>
 __global__ void __launch_bounds__(LANE_WARPS * 32) collideLaneKernel(const __grid_constant__ CollideArgs a) {
     __shared__ LaneSmem smAll[LANE_WARPS];
     const unsigned FULL = 0xffffffffu;
@@ -634,9 +640,10 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) collideLaneKernel(const __gri
                                 const double cRsqr = magSqr(UP - UQ);
                                 double translationalEnergy = 0.5 * mR * cRsqr;
                                 const double omegaPQ = P.omegaPQ[tP][tQ];
-                                const double* tMacro = a.overallT ? a.overallT + c : nullptr;
-                                redistributeInPlace(P, rng, v, cp, tP, tQ, translationalEnergy, omegaPQ, tMacro);
-                                redistributeInPlace(P, rng, v, cq, tQ, tP, translationalEnergy, omegaPQ, tMacro);
+                                const double* tMacro = nullptr;
+                                if constexpr (ZV2008) tMacro = a.overallT ? a.overallT + c : nullptr;
+                                redistributeInPlace<ZV2008>(P, rng, v, cp, tP, tQ, translationalEnergy, omegaPQ, tMacro);
+                                redistributeInPlace<ZV2008>(P, rng, v, cq, tQ, tP, translationalEnergy, omegaPQ, tMacro);
                                 cR = sqrt(2.0 * translationalEnergy / mR);
                             }
                             postCollisionVelocities(P, rng, tP, tQ, UP, UQ, cR);
@@ -685,7 +692,9 @@ cudaError_t launchCollide(const CollideArgs& a, cudaStream_t s) {
         int grid = (nGroups + LANE_WARPS - 1) / LANE_WARPS;
         if (grid > 148 * 4) grid = 148 * 4;  // persistent: 4 resident blocks per SM, grid-stride over the cell groups
         if (grid < 1) grid = 1;
-        collideLaneKernel<<<grid, LANE_WARPS * 32, 0, s>>>(a);
+        // engine.cu passes overallT only for inverseZvFormulation "2008"
+        if (a.overallT) collideLaneKernel<true><<<grid, LANE_WARPS * 32, 0, s>>>(a);
+        else collideLaneKernel<false><<<grid, LANE_WARPS * 32, 0, s>>>(a);
     }
     int gridBig = (a.nCells + COL_WARPS - 1) / COL_WARPS;
     if (gridBig > 148 * 4) gridBig = 148 * 4;
