@@ -710,6 +710,7 @@ int stageCollide(dsmcb200_ctx* c) {
     a.p = c->buf[c->cur].a; a.cellOffset = c->dCellOffset; a.nCells = c->mesh.nCells; a.cellCentres = c->dCellCentres;
     a.cellVolumes = c->dCellVolumes; a.sigmaTcRMax = c->dSigma; a.remainder = c->dRem; a.nCollsStep = c->dNColls; a.collSepStep = c->dCollSep;
     a.overallT = c->hP.invZvFormulation == 1 ? c->dOverallT : nullptr;
+    a.nModes = c->internal ? c->nModes : 0;
     a.bigScratch = c->dPerm; a.bigList = c->dCursor; a.octKey = c->dOctKey; a.P = c->dP; a.counters = c->dCounters; a.step = c->step;
     CK(cudaMemsetAsync(&c->dCounters->bigCells, 0, sizeof(int32_t), c->stream));
     KT t(c, "collide");

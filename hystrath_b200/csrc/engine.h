@@ -123,6 +123,7 @@ struct CollideArgs {
     double* nCollsStep;           // cellMeasurements: nColls_ of this step
     double* collSepStep;          // cellMeasurements: collisionSeparation_ of this step
     const double* overallT;       // [nCells] fields().overallT(cell) for inverseZvFormulation "2008", or nullptr
+    int32_t nModes;               // vibrational modes stored per parcel (selects the kernel instance)
     int32_t* bigScratch;          // [nParcels] sub-cell index lists of cells too large for shared memory
     int32_t* bigList;             // [nCells] ids of those cells (written by the lane kernel)
     const uint8_t* octKey;        // [nParcels] sub-cell (octant) of every sorted parcel, written by the sort's gather

@@ -467,7 +467,8 @@ struct InPlace {  // accessor of the parcels of one cell where they lie in the s
 };
 
 // LarsenBorgnakkeVariableHardSphere::redistribute (postReaction = false) on parcel j of the view
-template <bool ZV2008>
+// NM: vibrational modes stored per parcel (P.nModes), a compile-time bound of the mode loops
+template <bool ZV2008, int NM>
 __device__ __forceinline__ void redistributeInPlace(const DevParams& P, Rng& rng, const InPlace v, int j, int tSelf, int tOther,
                                                  double& translationalEnergy, double omegaPQ, const double* tMacro) {
     const DevSpecies& S = P.sp[tSelf];
@@ -478,16 +479,16 @@ __device__ __forceinline__ void redistributeInPlace(const DevParams& P, Rng& rng
         v.setElev(j, lvl);
         translationalEnergy = EcP - S.eElec[lvl];
     }
-    if (S.nVib > 0) {
-        double preEVib[MAX_MODES];
-        int32_t lvl0[MAX_MODES];
+    if (NM > 0 && S.nVib > 0) {
+        double preEVib[NM > 0 ? NM : 1];
+        int32_t lvl0[NM > 0 ? NM : 1];
 #pragma unroll
-        for (int m = 0; m < MAX_MODES; ++m) {
+        for (int m = 0; m < NM; ++m) {
             lvl0[m] = m < S.nVib ? v.vib(m, j) : 0;
             preEVib[m] = m < S.nVib ? lvl0[m] * P.kB * S.thetaV[m] : 0.0;
         }
 #pragma unroll
-        for (int m = 0; m < MAX_MODES; ++m) {
+        for (int m = 0; m < NM; ++m) {
             if (m >= S.nVib) break;
             const double EcP = translationalEnergy + preEVib[m];
             const int32_t iMaxP = int32_t(EcP / (P.kB * S.thetaV[m]));
@@ -516,7 +517,7 @@ __device__ __forceinline__ void redistributeInPlace(const DevParams& P, Rng& rng
 __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 }  // namespace
 
-template <bool ZV2008>
+template <bool ZV2008, int NM>
 __global__ void __launch_bounds__(LANE_WARPS * 32) collideLaneKernel(const __grid_constant__ CollideArgs a) {
     __shared__ LaneSmem smAll[LANE_WARPS];
     const unsigned FULL = 0xffffffffu;
@@ -642,8 +643,8 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) collideLaneKernel(const __gri
                                 const double omegaPQ = P.omegaPQ[tP][tQ];
                                 const double* tMacro = nullptr;
                                 if constexpr (ZV2008) tMacro = a.overallT ? a.overallT + c : nullptr;
-                                redistributeInPlace<ZV2008>(P, rng, v, cp, tP, tQ, translationalEnergy, omegaPQ, tMacro);
-                                redistributeInPlace<ZV2008>(P, rng, v, cq, tQ, tP, translationalEnergy, omegaPQ, tMacro);
+                                redistributeInPlace<ZV2008, NM>(P, rng, v, cp, tP, tQ, translationalEnergy, omegaPQ, tMacro);
+                                redistributeInPlace<ZV2008, NM>(P, rng, v, cq, tQ, tP, translationalEnergy, omegaPQ, tMacro);
                                 cR = sqrt(2.0 * translationalEnergy / mR);
                             }
                             postCollisionVelocities(P, rng, tP, tQ, UP, UQ, cR);
@@ -693,8 +694,11 @@ cudaError_t launchCollide(const CollideArgs& a, cudaStream_t s) {
         if (grid > 148 * 4) grid = 148 * 4;  // persistent: 4 resident blocks per SM, grid-stride over the cell groups
         if (grid < 1) grid = 1;
         // engine.cu passes overallT only for inverseZvFormulation "2008"
-        if (a.overallT) collideLaneKernel<true><<<grid, LANE_WARPS * 32, 0, s>>>(a);
-        else collideLaneKernel<false><<<grid, LANE_WARPS * 32, 0, s>>>(a);
+        if (a.overallT) collideLaneKernel<true, MAX_MODES><<<grid, LANE_WARPS * 32, 0, s>>>(a);
+        else if (a.nModes <= 0) collideLaneKernel<false, 0><<<grid, LANE_WARPS * 32, 0, s>>>(a);
+        else if (a.nModes == 1) collideLaneKernel<false, 1><<<grid, LANE_WARPS * 32, 0, s>>>(a);
+        else if (a.nModes == 2) collideLaneKernel<false, 2><<<grid, LANE_WARPS * 32, 0, s>>>(a);
+        else collideLaneKernel<false, MAX_MODES><<<grid, LANE_WARPS * 32, 0, s>>>(a);
     }
     int gridBig = (a.nCells + COL_WARPS - 1) / COL_WARPS;
     if (gridBig > 148 * 4) gridBig = 148 * 4;
