@@ -70,7 +70,8 @@ class Species(C.Structure):
 
 class PatchModel(C.Structure):
     _fields_ = [("patch", C.c_int32), ("model", C.c_int32), ("temperature", C.c_double), ("velocity", C.c_double * 3),
-                ("diffuseFraction", C.c_double)]
+                ("diffuseFraction", C.c_double), ("linearTemperature", C.c_int32), ("depthAxis", C.c_int32),
+                ("formationLevelTemperature", C.c_double)]
 
 
 class Inflow(C.Structure):
@@ -337,6 +338,10 @@ def build_models(collisionModel="VariableHardSphere", nEquivalentParticles=1.0, 
         pm[i].model = PATCH_MODEL_NAMES[name]
         pm[i].temperature = d.get("temperature", 0.0)
         pm[i].diffuseFraction = d.get("diffuseFraction", 0.0)
+        if "formationLevelTemperature" in d:   # linear T(depth), dsmcDiffuseWallPatch.C:141-148
+            pm[i].linearTemperature = 1
+            pm[i].formationLevelTemperature = d["formationLevelTemperature"]
+            pm[i].depthAxis = {"x": 0, "y": 1, "z": 2}[d.get("depthAxis", "y")]
         for k in range(3):
             pm[i].velocity[k] = d.get("velocity", (0.0, 0.0, 0.0))[k]
     inf = (Inflow * max(1, len(inflows)))()

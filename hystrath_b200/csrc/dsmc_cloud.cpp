@@ -312,6 +312,12 @@ void dsmcCloud::readBoundaries() {
             const Dict& pr = b.subDict(model + "Properties");
             if (kind == DSMCB200_BND_DIFFUSE_SPECULAR_WALL) pm.diffuseFraction = pr.scalar("diffuseFraction");
             pm.temperature = pr.found("groundLevelTemperature") ? pr.scalar("groundLevelTemperature") : pr.scalar("temperature");
+            if (pr.found("formationLevelTemperature")) {   // linear T(depth), dsmcDiffuseWallPatch.C:62-63,141-148,169-179
+                pm.linearTemperature = 1;
+                pm.formationLevelTemperature = pr.scalar("formationLevelTemperature");
+                const std::string ax = pr.wordOr("depthAxis", "y");
+                pm.depthAxis = ax == "x" ? 0 : (ax == "z" ? 2 : 1);
+            }
             auto v = pr.vector3("velocity");
             for (int k = 0; k < 3; ++k) pm.velocity[k] = v[k];
         }
@@ -485,6 +491,10 @@ std::string dsmcCloud::summary() const {
     for (auto& t : typeIdList_) o << " " << t;
     o << "\n  collisionModel " << models_.collisionModel << " invZv " << models_.invZvFormulation << " nEquivalentParticles " << models_.nEquivalentParticles
       << " seed " << models_.seed << "\n  patchModels " << patchModels_.size() << " inflows " << inflows_.size() << " fields " << fields_.size() << "\n";
+    for (auto& pm : patchModels_)
+        if (pm.linearTemperature)
+            o << "    patchModel " << boundary_[pm.patch].name << " temperature " << pm.temperature << " linearTemperature formationLevel "
+              << pm.formationLevelTemperature << " depthAxis " << pm.depthAxis << "\n";
     for (auto& f : fields_) {
         o << "    field " << f.fieldName << " typeIds";
         for (int t : f.typeIds) o << " " << t;

@@ -414,6 +414,12 @@ int finalize(dsmcb200_ctx* c) {
             return fail(c, DSMCB200_ERR_INVALID, "Patch: " + M.patches[pm.patch].name + " must be of type wall or patch to carry a dsmcPatchBoundary model");
         if (pm.model < DSMCB200_BND_DIFFUSE_WALL || pm.model > DSMCB200_BND_DIFFUSE_SPECULAR_WALL) return fail(c, DSMCB200_ERR_UNSUPPORTED, "unknown dsmcPatchBoundary type");
         d.model = pm.model; d.T = pm.temperature; d.diffuseFraction = pm.diffuseFraction;
+        d.linearT = pm.linearTemperature != 0; d.depthAxis = pm.depthAxis; d.Tformation = pm.formationLevelTemperature;
+        if (d.linearT) {
+            if (pm.depthAxis < 0 || pm.depthAxis > 2) return fail(c, DSMCB200_ERR_INVALID, "dsmcDiffuseWallPatch: depthAxis must be x, y or z");
+            d.maxDepth = comp(M.boundsMax, pm.depthAxis);                       // mesh.bounds() (dsmcDiffuseWallPatch.C:181-184)
+            d.lengthPatch = d.maxDepth - comp(M.boundsMin, pm.depthAxis);
+        }
         d.vel[0] = pm.velocity[0]; d.vel[1] = pm.velocity[1]; d.vel[2] = pm.velocity[2];
         if (pm.model != DSMCB200_BND_DELETION)
             for (int i = 0; i < d.size; ++i) measIndex[d.start - M.nInternalFaces + i] = c->nMeasFaces++;

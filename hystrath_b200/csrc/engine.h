@@ -38,6 +38,9 @@ struct DevPatch {
     double vel[3];       // wall velocity
     double sep[3];       // cyclic separation (receiving side subtracts)
     double diffuseFraction;  // dsmcDiffuseSpecularWallPatch
+    // dsmcDiffuseWallPatch::getLocalTemperature: T + (x[depthAxis] - maxDepth) * (T - Tformation) / lengthPatch
+    int32_t linearT, depthAxis;
+    double Tformation, maxDepth, lengthPatch;
 };
 
 struct DevParams {

@@ -185,7 +185,7 @@ __device__ __forceinline__ void loadInternal(const MoveArgs& a, const DevParams&
 
 // dsmcParcel::hitWallPatch / hitPatch -> dsmc{Diffuse,Specular}WallPatch::controlParticle
 __device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int sp, int patch, int32_t measIndex, int32_t bfi, V3 nw, V3 U,
-                                           int* wallHits) {
+                                           double depthPosition, int* wallHits) {
     const DevParams& P = *a.P;
     const DevPatch& pt = P.patch[patch];
     WallCtx wctx{a.P, a.wallAcc, a.nWallQ, a.bfaceArea};
@@ -222,7 +222,9 @@ __device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int sp,
         }
         const V3 tw1 = Ut / mag(Ut);
         const V3 tw2 = cross(nw, tw1);
-        const double Tw = pt.T;
+        // dsmcDiffuseWallPatch::getLocalTemperature(p.position()[depthAxis_]), dsmcDiffuseWallPatch.C:141-148
+        double Tw = pt.T;
+        if (pt.linearT) Tw = pt.T + (depthPosition - pt.maxDepth) * (pt.T - pt.Tformation) / pt.lengthPatch;
         const double g1 = wallRng.gaussNormal();
         const double g2 = wallRng.gaussNormal();
         const double r = wallRng.sample01();
@@ -248,6 +250,8 @@ __device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int sp,
 
 }  // namespace
 
+// TRACK: the dsmcFaceTracker hook compiled in (its cold call costs the hot loop 1.2 % even when it is never taken: measured A/B)
+template <bool TRACK>
 __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const __grid_constant__ MoveArgs a) {
     const DevParams& P = *a.P;
     const unsigned FULL = 0xffffffffu;
@@ -432,7 +436,8 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                                 if (pt.model == DSMCB200_BND_DELETION) {
                                     keepParticle = false;  // dsmcDeletionPatch::controlParticle
                                 } else if (pt.model != DSMCB200_BND_NONE) {
-                                    U = wallInteraction(a, i, a.p.typeId[i], bf.patch, a.wallsDue ? bf.measIndex : -1, bfi, N0, U, &wallHits);
+                                    U = wallInteraction(a, i, a.p.typeId[i], bf.patch, a.wallsDue ? bf.measIndex : -1, bfi, N0, U,
+                                                            pt.linearT ? comp(pos, pt.depthAxis) : 0.0, &wallHits);
                                     Udirty = true;
                                 }
                                 break;
@@ -452,7 +457,9 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
 
         // ---- section 3: trackToFace returned -- back in dsmcParcel::move (DSMC/parcels/dsmcParcel.C:92-118) ----
         if (finished) {
-            if (a.faceFlux && faceSet) trackFaceTransition(a, P, a.p.typeId[i], U, tet, faceBfi);  // dsmcParcel.C:106-111
+            if constexpr (TRACK) {
+                if (faceSet) trackFaceTransition(a, P, a.p.typeId[i], U, tet, faceBfi);  // dsmcParcel.C:106-111
+            }
             if (keepParticle) {
                 const double dt = tEnd * retVal;
                 tEnd -= dt;  // stepFraction = 1 - tEnd/deltaT is only consumed by a processor transfer: evaluated there
@@ -515,7 +522,8 @@ cudaError_t launchMove(const MoveArgs& a, cudaStream_t s) {
     if (a.count <= 0) return cudaSuccess;
     const int perBlock = MOVE_BLOCK * MOVE_CHUNK;
     const int grid = (a.count + perBlock - 1) / perBlock;
-    moveKernel<<<grid, MOVE_BLOCK, 0, s>>>(a);
+    if (a.faceFlux) moveKernel<true><<<grid, MOVE_BLOCK, 0, s>>>(a);
+    else moveKernel<false><<<grid, MOVE_BLOCK, 0, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -140,6 +140,13 @@ typedef struct {
     double temperature;     /* dsmcDiffuseWallPatchProperties.temperature */
     double velocity[3];
     double diffuseFraction; /* dsmcDiffuseSpecularWallPatchProperties.diffuseFraction (dsmcDiffuseSpecularWallPatch.C:67) */
+    /* dsmcDiffuseWallPatch::getLocalTemperature (dsmcDiffuseWallPatch.C:141-148): T(x) = temperature + (x[depthAxis] - maxDepth) *
+     * (temperature - formationLevelTemperature) / lengthPatch with maxDepth / lengthPatch from the (rank-local) mesh bounds (:181-184).
+     * `temperature` above is groundLevelTemperature when that key is given (:53-60).  linearTemperature = 0: the uniform wall
+     * (formationLevelTemperature defaults to temperature, :62-63). */
+    int32_t linearTemperature;
+    int32_t depthAxis;      /* 0 x, 1 y (default), 2 z (:169-179) */
+    double formationLevelTemperature;
 } dsmcb200_patch_model;
 
 /* One dsmcFreeStreamInflowPatch of dsmcGeneralBoundaries

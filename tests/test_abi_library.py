@@ -32,10 +32,27 @@ def test_struct_layouts_match_the_header():
     # sizes the C compiler gives the PODs (gcc x86-64); a mismatch would corrupt every call
     assert C.sizeof(capi.Patch) == 64 + 8 * 4 + 24
     assert C.sizeof(capi.Species) == 64 + 5 * 8 + 8 + 9 * 8 + 8 + 8 + 16 * 8 + 16 * 4
-    assert C.sizeof(capi.PatchModel) == 8 + 8 + 24 + 8   # + diffuseFraction
+    assert C.sizeof(capi.PatchModel) == 8 + 8 + 24 + 8 + 8 + 8   # + diffuseFraction, linearTemperature / depthAxis, formationLevelTemperature
     assert C.sizeof(capi.ParcelsSoA) == 12 * 8 + 8
     assert C.sizeof(capi.Counters) == 9 * 8 + 5 * 8 + 8 * 8
     assert C.sizeof(capi.AccumInfo) == 24
+
+
+def test_struct_sizes_agree_with_the_c_compiler(tmp_path):
+    """sizeof() of every POD of include/dsmcb200.h as gcc lays it out against the ctypes mirror in capi.py."""
+    import subprocess
+
+    names = {"dsmcb200_patch": capi.Patch, "dsmcb200_species": capi.Species, "dsmcb200_patch_model": capi.PatchModel,
+             "dsmcb200_inflow": capi.Inflow, "dsmcb200_models": capi.Models, "dsmcb200_parcels_soa": capi.ParcelsSoA,
+             "dsmcb200_counters": capi.Counters, "dsmcb200_accum_info": capi.AccumInfo, "dsmcb200_mesh": capi.Mesh}
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "dsmcb200.h"\nint main(void) {\n' +
+                   "".join(f'  printf("{n} %zu\\n", sizeof({n}));\n' for n in names) + "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for n, cls in names.items():
+        assert int(out[n]) == C.sizeof(cls), (n, out[n], C.sizeof(cls))
 
 
 def test_no_cpu_fallback_without_cuda():

@@ -43,6 +43,18 @@ def test_driver_rejects_unknown_models_like_the_reference(tmp_path):
     assert r.returncode == 1 and "keyword nEquivalentParticles is undefined in dictionary" in r.stderr
 
 
+def test_driver_reads_linear_wall_temperature(tmp_path):
+    """groundLevelTemperature / formationLevelTemperature / depthAxis of dsmcDiffuseWallPatchProperties (dsmcDiffuseWallPatch.C:49-64,169-179)."""
+    casegen.couette_case(str(tmp_path))
+    path = os.path.join(str(tmp_path), "system", "boundariesDict")
+    text = open(path).read()
+    assert text.count("temperature") >= 2
+    open(path, "w").write(text.replace("temperature", "formationLevelTemperature 250; depthAxis x; groundLevelTemperature", 1))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "linearTemperature formationLevel 250 depthAxis 0" in r.stdout
+
+
 def test_driver_reads_sample_interval(tmp_path):
     """dsmcVolFieldsProperties.sampleInterval (dsmcVolFields.C:1038) reaches the engine; fields that disagree are refused."""
     casegen.couette_case(str(tmp_path))

@@ -357,6 +357,37 @@ def test_sample_interval_matches_oracle():
     eng.close()
 
 
+def test_diffuse_wall_with_linear_temperature_matches_oracle():
+    """dsmcDiffuseWallPatch::getLocalTemperature (dsmcDiffuseWallPatch.C:141-148): groundLevelTemperature / formationLevelTemperature /
+    depthAxis -- the wall temperature is a linear function of the hit position along the depth axis of the mesh bounds."""
+    sides = {"xmin": ("wall", "walls"), "xmax": ("wall", "walls"), "ymin": ("symmetryPlane", "ends"), "ymax": ("symmetryPlane", "ends"),
+             "zmin": ("cyclic",), "zmax": ("cyclic",)}
+    mesh = meshgen.box_mesh((3, 12, 2), (0.003, 0.06, 0.002), sides=sides)
+    sp = H.air5()[:2]
+    pm = [dict(patch=mesh.patch_index("walls"), boundaryModel="dsmcDiffuseWallPatch", temperature=3000.0, formationLevelTemperature=500.0,
+               depthAxis="y", velocity=(0.0, 50.0, 0.0))]
+    md = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=1e20 * 0.003 * 0.06 * 0.002 / (72 * 80), deltaT=2e-6, seed=13,
+                           patch_models=pm)
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    start = H.by_id(H.same_start(eng, ora, [0, 1], [0.8e20, 0.2e20], 1000.0, 1000.0, 1000.0))
+    for x in (eng, ora):
+        x.stage(capi.STAGE_MOVE)
+        x.stage(capi.STAGE_SORT)
+    g, o = H.by_id(eng.download_parcels()), H.by_id(ora.download_parcels())
+    assert np.array_equal(g["cell"], o["cell"])
+    assert np.allclose(g["U"], o["U"], rtol=1e-12, atol=1e-9) and np.allclose(g["position"], o["position"], rtol=0, atol=1e-13)
+    assert np.array_equal(g["vibLevel"], o["vibLevel"])
+    hit = np.abs((o["U"] ** 2).sum(1) / (start["U"] ** 2).sum(1) - 1) > 1e-9
+    assert hit.sum() > 300
+    # hotter at the ground level (y_max) than at the formation level (y_min)
+    y, e = o["position"][hit, 1], (o["U"][hit] ** 2).sum(1)
+    assert e[y > 0.045].mean() > 2.5 * e[y < 0.015].mean()
+    gw, ow = eng.wall_accumulators(), ora.wall_accumulators()
+    scale = np.abs(ow).max(axis=(0, 1), keepdims=True) + 1e-300
+    assert (np.abs(gw - ow) / scale).max() < 1e-10
+    eng.close()
+
+
 def test_diffuse_specular_wall_matches_oracle():
     """dsmcDiffuseSpecularWallPatch: the diffuse / specular draw comes first in the hit's Philox stream on both sides."""
     sides = {"xmin": ("cyclic",), "xmax": ("cyclic",), "ymin": ("wall", "lowerWall"), "ymax": ("wall", "upperWall"),

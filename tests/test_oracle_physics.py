@@ -433,3 +433,32 @@ def test_inverse_zv_formulation_2008_uses_the_macroscopic_temperature():
     assert c_cold > 500 and n_cold == 0                 # 1/Zv(1 K) = 0: no vibrational exchange at all
     n_hot, _, _ = run("2008", Tov=113500.0)
     assert n_hot > 5 * n_pre                            # 1/Zv(theta_d) = 1
+
+
+def test_diffuse_wall_linear_temperature_along_the_depth_axis():
+    """dsmcDiffuseWallPatch::getLocalTemperature (dsmcDiffuseWallPatch.C:141-148): T(y) = groundLevelTemperature + (y - y_max) *
+    (groundLevelTemperature - formationLevelTemperature) / (y_max - y_min) with the bounds of the mesh; a diffusely re-emitted parcel
+    carries <m U^2 / 2> = 2 k T(y_hit)."""
+    sides = {"xmin": ("wall", "walls"), "xmax": ("wall", "walls"), "ymin": ("symmetryPlane", "ends"), "ymax": ("symmetryPlane", "ends"),
+             "zmin": ("cyclic",), "zmax": ("cyclic",)}
+    mesh = meshgen.box_mesh((2, 10, 1), (0.002, 0.1, 0.002), sides=sides)
+    sp = [H.argon()]
+    Tg, Tf = 1000.0, 200.0
+    pm = [dict(patch=mesh.patch_index("walls"), boundaryModel="dsmcDiffuseWallPatch", temperature=Tg, formationLevelTemperature=Tf, depthAxis="y")]
+    md = capi.build_models("NoBinaryCollision", nEquivalentParticles=1e20 * 0.002 * 0.1 * 0.002 / (20 * 3000), deltaT=2e-6, seed=21, patch_models=pm)
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
+    o.mesh_fill([0], [1e20], 300.0)
+    before = H.by_id(o.download_parcels())
+    o.evolve(1)
+    after = H.by_id(o.download_parcels())
+    e0, e1 = (before["U"] ** 2).sum(1), (after["U"] ** 2).sum(1)
+    hit = np.abs(e1 / e0 - 1) > 1e-9                    # a symmetry-plane reflection keeps |U|, a diffuse wall does not
+    assert hit.sum() > 8000
+    y = after["position"][hit, 1]                       # within |U_y| dt ~ 1 mm of the hit position
+    T_est = sp[0].mass * (after["U"][hit] ** 2).sum(1) / (4 * H.KB)
+    for lo in (0.0, 0.02, 0.04, 0.06, 0.08):
+        sel = (y >= lo) & (y < lo + 0.02)
+        T_expected = Tg + ((lo + 0.01) - 0.1) * (Tg - Tf) / 0.1
+        assert sel.sum() > 1000
+        assert abs(T_est[sel].mean() / T_expected - 1) < 0.06, (lo, T_est[sel].mean(), T_expected)
