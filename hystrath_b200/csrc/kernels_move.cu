@@ -276,7 +276,6 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
     bool keepParticle = true, switchProcessor = false;
     int32_t faceBfi = -1;
     int wallHits = 0;
-    unsigned rescues = 0, nDeleted = 0;
     int guard = 0;
 
     // Every lane runs through every section of the loop body and the sections are separated by __syncwarp(), so
@@ -371,7 +370,7 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
             const bool kAdv = live && !none && gtS && le1;             // advance to the nearest crossed plane
             const bool needRescue = live && !none && !gtS;             // lambdaMin = 0.0
             const bool moving = kAdv || needRescue;
-            if (kResc) ++rescues;
+            if (kResc) atomicAdd(&a.counters->rescues, 1ULL);   // rare: counted where it happens, no per-lane counter register
             {
                 // rescue and advance have the same form: pos += f * (X - pos)
                 const V3 X = kResc ? Ct : endPosition;
@@ -476,7 +475,7 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                 active = false;
                 if (!keepParticle) {
                     a.p.cell[i] = -1;
-                    ++nDeleted;
+                    atomicAdd(&a.counters->deleted, 1ULL);
                 } else if (switchProcessor) {
                     // Cloud<T>::move transfer list + particle::prepareForParallelTransfer, fused with the packing
                     const BFaceRec bf = a.bfaces[faceBfi];
@@ -514,8 +513,6 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
             }
         }
     }
-    if (rescues) atomicAdd(&a.counters->rescues, (unsigned long long)rescues);
-    if (nDeleted) atomicAdd(&a.counters->deleted, (unsigned long long)nDeleted);
 }
 
 cudaError_t launchMove(const MoveArgs& a, cudaStream_t s) {
