@@ -272,8 +272,10 @@ int dsmcb200_reserve(dsmcb200_ctx*, int64_t maxParcels);
 /* ---- cloud state ------------------------------------------------------ */
 /* replaces: Cloud<T>::initCloud + dsmcParcel::readFields,
  * BASIC/Cloud/CloudIO.C:111-165, DSMC/parcels/dsmcParcelIO.C:133-335.
- * If tetFace/tetPt are NULL they are located like
- * particle::initCellFacePtOrDeleteLostParticle (BASIC/particle/particleI.H:851-996). */
+ * If tetFace/tetPt are NULL they are located on the device like
+ * particle::initCellFacePtOrDeleteLostParticle (BASIC/particle/particleI.H:851-996): first tet of the
+ * given cell with tetrahedron::inside, else a walk of 1e-5 steps towards the cell centre; parcels outside
+ * the 10 %-inflated cell bounding box (or not locatable) are deleted and counted in counters.deleted. */
 int dsmcb200_upload_parcels(dsmcb200_ctx*, int64_t n, const dsmcb200_parcels_soa*);
 int dsmcb200_download_parcels(dsmcb200_ctx*, int64_t capacity, int64_t* n, dsmcb200_parcels_soa*);
 /* replaces: read of <time>/dsmcSigmaTcRMax and
