@@ -398,6 +398,12 @@ void dsmcCloud::readFieldProperties() {
             throw FoamError("dsmcVolFields " + s.fieldName + ": sampleInterval " + std::to_string(s.sampleInterval) + " differs from field " +
                             fields_.front().fieldName + " (" + std::to_string(fields_.front().sampleInterval) +
                             "); this engine samples all fields on the same steps\nin: " + path);
+        // ... and on the reset policy of timeProperties (dsmcField.C:113-152): a field that resets at output next to one that keeps
+        // averaging cannot both be served from one accumulator set -- refused rather than silently averaged differently
+        if (!fields_.empty() && (fields_.front().resetAtOutput != s.resetAtOutput ||
+                                 fields_.front().resetAtOutputUntilTime != s.resetAtOutputUntilTime))
+            throw FoamError("dsmcVolFields " + s.fieldName + ": timeProperties (resetAtOutput / resetAtOutputUntilTime) differ from field " +
+                            fields_.front().fieldName + "; this engine resets all fields together\nin: " + path);
         models_.sampleInterval = std::max(1, s.sampleInterval);
         fields_.push_back(s);
     }

@@ -143,6 +143,7 @@ dsmcFields
          {
          	  timeOption      write;
             resetAtOutput       on;
+            resetAtOutputUntilTime       0.5;
          }
          dsmcVolFieldsProperties
          {
@@ -158,6 +159,7 @@ dsmcFields
          {
             timeOption      write;
             resetAtOutput       on;
+            resetAtOutputUntilTime       0.5;
          }
          dsmcVolFieldsProperties
          {

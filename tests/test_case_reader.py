@@ -43,6 +43,20 @@ def test_driver_rejects_unknown_models_like_the_reference(tmp_path):
     assert r.returncode == 1 and "keyword nEquivalentParticles is undefined in dictionary" in r.stderr
 
 
+def test_driver_refuses_fields_with_different_reset_policies(tmp_path):
+    """All field{} entries share one accumulator set: different timeProperties are refused, not silently merged."""
+    casegen.couette_case(str(tmp_path))
+    path = os.path.join(str(tmp_path), "system", "fieldPropertiesDict")
+    text = open(path).read()
+    assert text.count("resetAtOutput       on;") == 3
+    open(path, "w").write(text.replace("resetAtOutput       on;", "resetAtOutput       off;", 1))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "this engine resets all fields together" in r.stderr
+    open(path, "w").write(text.replace("resetAtOutput       on;", "resetAtOutput       off;"))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+
+
 def test_driver_reads_linear_wall_temperature(tmp_path):
     """groundLevelTemperature / formationLevelTemperature / depthAxis of dsmcDiffuseWallPatchProperties (dsmcDiffuseWallPatch.C:49-64,169-179)."""
     casegen.couette_case(str(tmp_path))
