@@ -15,6 +15,7 @@ MAX_SPECIES = 8
 MAX_VIB_MODES = 3
 MAX_ELEC_LEVELS = 16
 NAME_LEN = 64
+MAX_NEIGHBOURS = 16
 
 # dsmcb200_patch_type
 PATCH_WALL, PATCH_PATCH, PATCH_CYCLIC, PATCH_PROCESSOR, PATCH_EMPTY = 0, 1, 2, 3, 4
@@ -88,14 +89,14 @@ class Models(C.Structure):
                 ("deltaT", C.c_double), ("seed", C.c_uint64), ("kB", C.c_double), ("nPatchModels", C.c_int32),
                 ("nInflows", C.c_int32), ("patchModels", C.POINTER(PatchModel)), ("inflows", C.POINTER(Inflow)),
                 ("measureHeatFluxShearStress", C.c_int32), ("measureClassifications", C.c_int32),
-                ("trackFaceFluxes", C.c_int32), ("fusedCollideSample", C.c_int32), ("sampleInterval", C.c_int32), ("reserved_", C.c_int32)]
+                ("trackFaceFluxes", C.c_int32), ("reserved0_", C.c_int32), ("sampleInterval", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class ParcelsSoA(C.Structure):
     _fields_ = [("position", C.c_void_p), ("U", C.c_void_p), ("ERot", C.c_void_p), ("cell", C.c_void_p),
                 ("tetFace", C.c_void_p), ("tetPt", C.c_void_p), ("typeId", C.c_void_p), ("vibLevel", C.c_void_p),
                 ("ELevel", C.c_void_p), ("newParcel", C.c_void_p), ("classification", C.c_void_p), ("origId", C.c_void_p),
-                ("maxModes", C.c_int32), ("pad_", C.c_int32)]
+                ("maxModes", C.c_int32), ("pad_", C.c_int32), ("origProc", C.c_void_p)]
 
 
 class Counters(C.Structure):
@@ -103,7 +104,9 @@ class Counters(C.Structure):
                 ("trackingRescues", C.c_int64), ("deleted", C.c_int64), ("inserted", C.c_int64),
                 ("migratedOut", C.c_int64), ("migratedIn", C.c_int64), ("unsortedLargeCells", C.c_int64),
                 ("mass", C.c_double), ("linearKineticEnergy", C.c_double), ("rotationalEnergy", C.c_double),
-                ("vibrationalEnergy", C.c_double), ("electronicEnergy", C.c_double), ("stageMs", C.c_double * 8)]
+                ("vibrationalEnergy", C.c_double), ("electronicEnergy", C.c_double), ("stageMs", C.c_double * 8),
+                ("nNeighbours", C.c_int32), ("migrationRounds", C.c_int32), ("neighbourProc", C.c_int32 * MAX_NEIGHBOURS),
+                ("migratedTo", C.c_int64 * MAX_NEIGHBOURS), ("migratedFrom", C.c_int64 * MAX_NEIGHBOURS)]
 
 
 class AccumInfo(C.Structure):
@@ -196,7 +199,8 @@ class ParcelData:
 
     FIELDS = [("position", np.float64, 3), ("U", np.float64, 3), ("ERot", np.float64, 1), ("cell", np.int32, 1),
               ("tetFace", np.int32, 1), ("tetPt", np.int32, 1), ("typeId", np.int32, 1), ("vibLevel", np.int32, 0),
-              ("ELevel", np.int32, 1), ("newParcel", np.int32, 1), ("classification", np.int32, 1), ("origId", np.int32, 1)]
+              ("ELevel", np.int32, 1), ("newParcel", np.int32, 1), ("classification", np.int32, 1), ("origId", np.int32, 1),
+              ("origProc", np.int32, 1)]
 
     def __init__(self, n=0, max_modes=1, allocate=True, **arrays):
         self.n = n

@@ -61,29 +61,25 @@ __global__ void interleave3(const double* x, const double* y, const double* z, d
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { out[3 * i] = x[i]; out[3 * i + 1] = y[i]; out[3 * i + 2] = z[i]; }
 }
-__global__ void toTetId(const int32_t* cell, const int32_t* tetFace, const int32_t* tetPt, const int32_t* faceTetPair0,
-                        const int32_t* owner, int32_t* tet, int32_t n, int32_t nFaces, int32_t nCells, int* bad) {
+__global__ void toTetId(const int32_t* cell, const int32_t* tetFace, const int32_t* tetPt, const int32_t* faceTet0, const int32_t* faceOffsets,
+                        const int32_t* owner, const TetRec* tets, int32_t* tet, int32_t n, int32_t nFaces, int32_t nCells, int* bad) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int32_t f = tetFace[i];
     if (cell[i] < 0) { tet[i] = 0; return; }   // a lost parcel (deleted by the sort), see upload_parcels
     if (f < 0 || f >= nFaces || cell[i] >= nCells) { *bad = 1; tet[i] = 0; return; }
-    const int32_t nT = faceTetPair0[f + 1] - faceTetPair0[f];
+    const int32_t nT = faceOffsets[f + 1] - faceOffsets[f] - 2;
     const int32_t tp = tetPt[i];
-    if (tp < 1 || tp > nT) { *bad = 1; tet[i] = 0; return; }
-    tet[i] = 2 * (faceTetPair0[f] + tp - 1) + (owner[f] != cell[i] ? 1 : 0);
+    const int32_t t0 = faceTet0[2 * size_t(f) + (owner[f] != cell[i] ? 1 : 0)];
+    if (tp < 1 || tp > nT || t0 < 0 || tets[t0].cell != cell[i]) { *bad = 1; tet[i] = 0; return; }   // tetFace is not a face of the cell
+    tet[i] = t0 + tp - 1;
 }
-__global__ void fromTetId(const int32_t* tet, const int32_t* faceTetPair0, int32_t nFaces, int32_t* tetFace, int32_t* tetPt, int32_t n) {
+__global__ void fromTetId(const int32_t* tet, const TetRec* tets, int32_t* tetFace, int32_t* tetPt, int32_t n) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int32_t pair = tet[i] >> 1;
-    int32_t lo = 0, hi = nFaces;  // last f with faceTetPair0[f] <= pair
-    while (hi - lo > 1) {
-        const int32_t mid = (lo + hi) >> 1;
-        if (faceTetPair0[mid] <= pair) lo = mid; else hi = mid;
-    }
-    tetFace[i] = lo;
-    tetPt[i] = pair - faceTetPair0[lo] + 1;
+    const TetRec& r = tets[tet[i]];
+    tetFace[i] = r.face;
+    tetPt[i] = r.tetPt;
 }
 __global__ void i32ToU8(const int32_t* in, uint8_t* out, int32_t n) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,8 +160,13 @@ struct dsmcb200_ctx {
     BFaceRec* dBFaces = nullptr;
     double *dBFaceArea = nullptr, *dPoints = nullptr, *dCellCentres = nullptr, *dCellVolumes = nullptr, *dFaceCentres = nullptr,
            *dFaceAreas = nullptr;
-    int32_t *dFaceOffsets = nullptr, *dFacePoints = nullptr, *dOwner = nullptr, *dTetBasePtIs = nullptr, *dFaceTetPair0 = nullptr,
+    int32_t *dFaceOffsets = nullptr, *dFacePoints = nullptr, *dOwner = nullptr, *dTetBasePtIs = nullptr, *dFaceTet0 = nullptr, *dCellTetStart = nullptr, *dGroupCell = nullptr,
             *dCellFaceOffsets = nullptr, *dCellFaces = nullptr;
+    // work list of the move kernel (launchMovePlan)
+    int32_t *dPlanSub = nullptr, *dPlanBase = nullptr;
+    int4* dPlan = nullptr;
+    int64_t planCap = 0;
+    int32_t stageTets = 0, nGroups = 0;
     // cloud
     ParcelBuffer buf[2];
     int cur = 0;
@@ -191,8 +192,10 @@ struct dsmcb200_ctx {
     int nQ = 0, nWallQ = 0, nMeasFaces = 0;
     double nTimeSteps = 0;
     uint32_t step = 0;
-    int32_t nextOrigId = 0;
-    bool occupancyValid = false;
+    int64_t nextOrigId = 0;   // ids handed out by this rank; stored modulo 2^31 (with origProc the parcel's identity)
+    bool occupancyValid = false;   // cellOffset AND the sub-cell keys describe the cloud (collide / sample may run)
+    bool csrValid = false;         // parcels [0, sortedN) are in the cell order of cellOffset (move may use its work list)
+    int64_t sortedN = 0;
     // counters of the last evolve
     dsmcb200_counters last{};
     // neighbours
@@ -265,21 +268,22 @@ void resolveTimers(dsmcb200_ctx* c) {
     c->evUsed = 0;
 }
 
-void setArrays(ParcelBuffer& b, int64_t cap, int nModes, bool internal, bool useCls) {
+void setArrays(ParcelBuffer& b, int64_t cap, int nModes, bool internal, bool useCls, bool useOrigProc) {
     ParcelArrays& a = b.a;
     a.px = b.dslab; a.py = a.px + cap; a.pz = a.py + cap; a.ux = a.pz + cap; a.uy = a.ux + cap; a.uz = a.uy + cap;
     a.erot = internal ? a.uz + cap : nullptr;
     a.cell = b.islab; a.tet = a.cell + cap; a.origId = a.tet + cap;
     for (int m = 0; m < MAX_MODES; ++m) a.vib[m] = (internal && m < nModes) ? a.origId + cap * (1 + m) : nullptr;
     a.typeId = b.bslab; a.elevel = internal ? b.bslab + cap : nullptr; a.cls = useCls ? b.bslab + 2 * cap : nullptr;
+    a.origProc = useOrigProc ? b.bslab + 3 * cap : nullptr;
 }
 
 int allocBuffer(dsmcb200_ctx* c, ParcelBuffer& b, int64_t cap) {
     // one extra double row and one extra int row so that every buffer can stage host AoS arrays
     CK(devAlloc(&b.dslab, size_t(cap) * 7));
     CK(devAlloc(&b.islab, size_t(cap) * (3 + MAX_MODES)));
-    CK(devAlloc(&b.bslab, size_t(cap) * 3));
-    setArrays(b, cap, c->nModes, c->internal, c->useCls);
+    CK(devAlloc(&b.bslab, size_t(cap) * 4));
+    setArrays(b, cap, c->nModes, c->internal, c->useCls, c->nRanks > 1);
     return 0;
 }
 
@@ -303,6 +307,7 @@ int ensureCapacity(dsmcb200_ctx* c, int64_t n) {
         CK(cudaMemcpyAsync(d.typeId, o.typeId, nb1, cudaMemcpyDeviceToDevice, c->stream));
         if (o.elevel) CK(cudaMemcpyAsync(d.elevel, o.elevel, nb1, cudaMemcpyDeviceToDevice, c->stream));
         if (o.cls) CK(cudaMemcpyAsync(d.cls, o.cls, nb1, cudaMemcpyDeviceToDevice, c->stream));
+        if (o.origProc) CK(cudaMemcpyAsync(d.origProc, o.origProc, nb1, cudaMemcpyDeviceToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
     for (int k = 0; k < 2; ++k) {
@@ -313,6 +318,7 @@ int ensureCapacity(dsmcb200_ctx* c, int64_t n) {
     CK(devAlloc(&c->dPerm, size_t(cap)));
     devFree(c->dOctKey);
     CK(devAlloc(&c->dOctKey, size_t(cap)));
+    c->occupancyValid = false;   // the sub-cell keys of the sorted cloud went with the old buffer
     c->capacity = cap;
     return 0;
 }
@@ -464,6 +470,16 @@ int finalize(dsmcb200_ctx* c) {
     CK(cudaMemcpy(c->dP, &P, sizeof(P), cudaMemcpyHostToDevice));
 
     // ---- bake and upload the tracking tables in chunks
+    {
+        // window of the move kernel: two blocks per SM share the 227 KB of shared memory
+        int st = 384;
+        if (const char* e = std::getenv("DSMCB200_STAGE_TETS")) st = std::atoi(e);
+        c->stageTets = std::max(0, std::min(st, 900));
+        M.buildStageGroups(std::max(1, c->stageTets));
+        c->nGroups = int32_t(M.stageGroupCell.size()) - 1;
+        CK(upload(&c->dGroupCell, M.stageGroupCell));
+        CK(devAlloc(&c->dPlanSub, size_t(c->nGroups) + 2)); CK(devAlloc(&c->dPlanBase, size_t(c->nGroups) + 2));
+    }
     const int64_t nT = M.nTets();
     CK(devAlloc(&c->dTets, size_t(nT)));
     {
@@ -498,7 +514,8 @@ int finalize(dsmcb200_ctx* c) {
         CK(upload(&c->dFacePoints, M.facePoints));
         CK(upload(&c->dOwner, M.owner));
         CK(upload(&c->dTetBasePtIs, M.tetBasePtIs));
-        CK(upload(&c->dFaceTetPair0, M.faceTetPair0));
+        CK(upload(&c->dFaceTet0, M.faceTet0));
+        CK(upload(&c->dCellTetStart, M.cellTetStart));
         CK(upload(&c->dCellFaceOffsets, M.cellFaceOffsets));
         CK(upload(&c->dCellFaces, M.cellFaces));
     }
@@ -583,7 +600,9 @@ int stageSort(dsmcb200_ctx* c, bool histogramDone) {
     { KT t(c, "gather"); CK(launchGather(src, dst, c->dPerm, c->dCellCentres, c->dOctKey, nOut, c->nModes, c->internal, c->stream)); }
     c->cur = 1 - c->cur;
     c->N = nOut;
+    c->sortedN = nOut;
     c->occupancyValid = true;
+    c->csrValid = true;
     return 0;
 }
 
@@ -596,7 +615,8 @@ int stageInflow(dsmcb200_ctx* c, int64_t tailStart) {
         InflowArgs a{};
         a.nFaces = pi.size; a.patch = in.patch; a.patchStart = pi.start;
         a.faceOffsets = c->dFaceOffsets; a.facePoints = c->dFacePoints; a.owner = c->dOwner; a.tetBasePtIs = c->dTetBasePtIs;
-        a.faceTetPair0 = c->dFaceTetPair0; a.points = c->dPoints; a.faceCentres = c->dFaceCentres; a.faceAreas = c->dFaceAreas;
+        a.bfaces = c->dBFaces; a.nInternalFaces = M.nInternalFaces; a.points = c->dPoints; a.faceCentres = c->dFaceCentres; a.faceAreas = c->dFaceAreas;
+        a.origProc = c->rank;
         a.P = c->dP; a.nTypes = in.nTypes; a.faceFlux = c->dFaceFlux; a.nFacesAll = M.nFaces;
         for (int i = 0; i < in.nTypes; ++i) { a.typeIds[i] = in.typeIds[i]; a.numberDensities[i] = in.numberDensities[i]; }
         for (int d = 0; d < 3; ++d) a.velocity[d] = in.velocity[d];
@@ -614,7 +634,7 @@ int stageInflow(dsmcb200_ctx* c, int64_t tailStart) {
         { int r = ensureSfTail(c, c->N + total - tailStart); if (r) return r; }
         a.p = c->buf[c->cur].a;
         a.counts = c->dInflowScan; a.base = int32_t(c->N); a.capacity = int32_t(c->capacity);
-        a.sfTail = c->dSfTail; a.tailStart = int32_t(tailStart); a.origIdBase = c->nextOrigId;
+        a.sfTail = c->dSfTail; a.tailStart = int32_t(tailStart); a.origIdBase = int32_t(c->nextOrigId & 0x7fffffff);
         { KT t(c, "inflowInsert"); CK(launchInflow(a, 1, c->stream)); }
         c->N += total;
         c->nextOrigId += total;
@@ -623,15 +643,40 @@ int stageInflow(dsmcb200_ctx* c, int64_t tailStart) {
     return 0;
 }
 
-MoveArgs moveArgs(dsmcb200_ctx* c, int32_t first, int32_t count, int32_t tailStart) {
+// parcels [tailBeg, tailEnd) without a shared-memory window; planBlocks > 0: the cell-sorted prefix through the work list as well
+MoveArgs moveArgs(dsmcb200_ctx* c, int32_t planBlocks, int32_t tailBeg, int32_t tailEnd, int32_t tailStart) {
     MoveArgs a{};
-    a.p = c->buf[c->cur].a; a.first = first; a.count = count; a.tailStart = tailStart; a.sfTail = c->dSfTail;
+    a.p = c->buf[c->cur].a; a.plan = c->dPlan; a.planTotal = c->dPlanBase + c->nGroups; a.nPlanBlocks = planBlocks; a.stageTets = c->stageTets;
+    a.tailBeg = tailBeg; a.tailEnd = tailEnd; a.tailStart = tailStart; a.sfTail = c->dSfTail;
     a.tets = c->dTets; a.bfaces = c->dBFaces; a.bfaceArea = c->dBFaceArea; a.P = c->dP; a.wallAcc = c->dWallAcc; a.nWallQ = c->nWallQ;
     // boundaryMeas_ is cleaned every step (dsmcCloud.C:924) but only folded into the fields on sampled steps (dsmcVolFields.C:1081,1292)
     a.wallsDue = c->sampleCounter + 1 >= std::max(1, c->models.sampleInterval);
-    a.faceFlux = c->dFaceFlux; a.faceAreas = c->dFaceAreas; a.faceTetPair0 = c->dFaceTetPair0; a.nFacesAll = c->mesh.nFaces;
+    a.faceFlux = c->dFaceFlux; a.faceAreas = c->dFaceAreas; a.nFacesAll = c->mesh.nFaces;
     a.migBuf = c->dMigSend; a.migKey = c->dMigKey; a.migCapacity = c->migCapacity; a.cellCount = c->dCellCount; a.counters = c->dCounters; a.step = c->step;
     return a;
+}
+
+// the whole cloud: the prefix that is still in the order of the last sort goes through the per-step work list
+int launchMoveAll(dsmcb200_ctx* c, int64_t tailStart) {
+    const int32_t N = int32_t(c->N);
+    int32_t sorted = (c->csrValid && c->stageTets > 0) ? int32_t(std::min<int64_t>(c->sortedN, c->N)) : 0;
+    int32_t planBlocks = 0;
+    if (sorted > 0) {
+        planBlocks = c->nGroups + sorted / MOVE_PMAX + 1;
+        if (planBlocks > c->planCap) {
+            devFree(c->dPlan);
+            c->planCap = planBlocks + planBlocks / 4 + 64;
+            CK(devAlloc(&c->dPlan, size_t(c->planCap)));
+        }
+        MovePlanArgs m{};
+        m.groupCell = c->dGroupCell; m.nGroups = c->nGroups; m.cellOffset = c->dCellOffset; m.cellTetStart = c->dCellTetStart;
+        m.nSub = c->dPlanSub; m.subBase = c->dPlanBase; m.maxTets = c->stageTets; m.plan = c->dPlan;
+        KT t(c, "movePlan");
+        CK(launchMovePlan(m, c->dScanScratch, c->stream));
+    }
+    KT t(c, "move");
+    CK(launchMove(moveArgs(c, planBlocks, sorted, N, int32_t(tailStart)), c->stream));
+    return 0;
 }
 
 int ncclFail(dsmcb200_ctx* c, int r, const char* what) {
@@ -646,7 +691,8 @@ int stageMove(dsmcb200_ctx* c, int64_t tailStart) {
     CK(cudaMemsetAsync(c->dCellCount, 0, size_t(nCells + 1) * 4, c->stream));
     CK(cudaMemsetAsync(c->dCounters->nMig, 0, sizeof(int32_t) * MAX_NEIGHBOURS, c->stream));
     if (tailStart >= c->N) { int r = ensureSfTail(c, 1); if (r) return r; }
-    { KT t(c, "move"); CK(launchMove(moveArgs(c, 0, int32_t(c->N), int32_t(tailStart)), c->stream)); }
+    { int r = launchMoveAll(c, tailStart); if (r) return r; }
+    c->csrValid = false;
     if (c->nRanks <= 1 || c->nbrProcs.empty()) return 0;
     if (!c->comm) return fail(c, DSMCB200_ERR_STATE, "mesh has processor patches but dsmcb200_init_comm was not called");
 
@@ -661,6 +707,7 @@ int stageMove(dsmcb200_ctx* c, int64_t tailStart) {
         for (size_t s = 0; s < c->nbrProcs.size(); ++s) {
             if (nMig[s] > c->migCapacity) return fail(c, DSMCB200_ERR_CAPACITY, "migration buffer overflow");
             sendTo[c->nbrProcs[s]] = nMig[s];
+            c->last.migratedTo[s] += nMig[s];
             // particleTransferLists[neighbour] in cloud-list order (Cloud.C:283-306); the receive slab of the slot is free until the
             // exchange below and serves as scratch
             CK(orderMigrants(c->dMigSend + s * c->migCapacity, c->dMigRecv + s * c->migCapacity, c->dMigKey + s * c->migCapacity, c->dMigWork,
@@ -676,10 +723,12 @@ int stageMove(dsmcb200_ctx* c, int64_t tailStart) {
         bool any = false;
         for (int32_t v : matrix) if (v) { any = true; break; }
         if (!any) break;
+        c->last.migrationRounds += 1;
         int64_t nRecvTotal = 0;
         std::vector<int32_t> recvFrom(c->nbrProcs.size());
         for (size_t s = 0; s < c->nbrProcs.size(); ++s) {
             recvFrom[s] = matrix[size_t(c->nbrProcs[s]) * R + c->rank];
+            c->last.migratedFrom[s] += recvFrom[s];
             if (recvFrom[s] > c->migCapacity) return fail(c, DSMCB200_ERR_CAPACITY, "migration receive buffer overflow");
             nRecvTotal += recvFrom[s];
         }
@@ -705,7 +754,7 @@ int stageMove(dsmcb200_ctx* c, int64_t tailStart) {
             c->last.migratedIn += recvFrom[s];
         }
         CK(cudaMemsetAsync(c->dCounters->nMig, 0, sizeof(int32_t) * MAX_NEIGHBOURS, c->stream));
-        if (nRecvTotal) CK(launchMove(moveArgs(c, int32_t(firstNew), int32_t(nRecvTotal), int32_t(tailStart)), c->stream));
+        if (nRecvTotal) CK(launchMove(moveArgs(c, 0, int32_t(firstNew), int32_t(firstNew + nRecvTotal), int32_t(tailStart)), c->stream));
     }
     return 0;
 }
@@ -775,7 +824,7 @@ void dsmcb200_destroy(dsmcb200_ctx* c) {
     for (int k = 0; k < 2; ++k) { devFree(c->buf[k].dslab); devFree(c->buf[k].islab); devFree(c->buf[k].bslab); }
     devFree(c->dP); devFree(c->dTets); devFree(c->dBFaces); devFree(c->dBFaceArea); devFree(c->dPoints); devFree(c->dCellCentres);
     devFree(c->dCellVolumes); devFree(c->dFaceCentres); devFree(c->dFaceAreas); devFree(c->dFaceOffsets); devFree(c->dFacePoints);
-    devFree(c->dOwner); devFree(c->dTetBasePtIs); devFree(c->dFaceTetPair0); devFree(c->dCellFaceOffsets); devFree(c->dCellFaces);
+    devFree(c->dOwner); devFree(c->dTetBasePtIs); devFree(c->dFaceTet0); devFree(c->dCellTetStart); devFree(c->dGroupCell); devFree(c->dPlanSub); devFree(c->dPlanBase); devFree(c->dPlan); devFree(c->dCellFaceOffsets); devFree(c->dCellFaces);
     devFree(c->dCellCount); devFree(c->dCellOffset); devFree(c->dCursor); devFree(c->dPerm); devFree(c->dOctKey); devFree(c->dScanScratch);
     devFree(c->dSigma); devFree(c->dRem); devFree(c->dNColls); devFree(c->dCollSep); devFree(c->dAcc); devFree(c->dCollCum);
     devFree(c->dOverallT); devFree(c->dFaceFlux); devFree(c->dWallAcc); devFree(c->dSfTail); devFree(c->dInfo); devFree(c->dInfoScratch); devFree(c->dCounters); devFree(c->dBad);
@@ -884,7 +933,7 @@ int dsmcb200_upload_parcels(dsmcb200_ctx* c, int64_t n, const dsmcb200_parcels_s
         LocateArgs l{};
         l.px = a.px; l.py = a.py; l.pz = a.pz; l.cell = a.cell; l.tet = a.tet; l.n = n32; l.nCells = c->mesh.nCells;
         l.cellFaceOffsets = c->dCellFaceOffsets; l.cellFaces = c->dCellFaces; l.faceOffsets = c->dFaceOffsets; l.facePoints = c->dFacePoints;
-        l.owner = c->dOwner; l.tetBasePtIs = c->dTetBasePtIs; l.faceTetPair0 = c->dFaceTetPair0; l.points = c->dPoints;
+        l.owner = c->dOwner; l.tetBasePtIs = c->dTetBasePtIs; l.cellTetStart = c->dCellTetStart; l.points = c->dPoints;
         l.cellCentres = c->dCellCentres; l.lost = &c->dCounters->deleted;
         CK(cudaMemsetAsync(&c->dCounters->deleted, 0, sizeof(unsigned long long), s));
         CK(launchLocate(l, s));
@@ -895,7 +944,7 @@ int dsmcb200_upload_parcels(dsmcb200_ctx* c, int64_t n, const dsmcb200_parcels_s
     } else {
         CK(cudaMemcpyAsync(sf, tetFace, size_t(n) * 4, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(sp2, tetPt, size_t(n) * 4, cudaMemcpyHostToDevice, s));
-        toTetId<<<GRID(n), 0, s>>>(a.cell, sf, sp2, c->dFaceTetPair0, c->dOwner, a.tet, n32, c->mesh.nFaces, c->mesh.nCells, c->dBad);
+        toTetId<<<GRID(n), 0, s>>>(a.cell, sf, sp2, c->dFaceTet0, c->dFaceOffsets, c->dOwner, c->dTets, a.tet, n32, c->mesh.nFaces, c->mesh.nCells, c->dBad);
     }
     CK(cudaMemcpyAsync(sf, h->typeId, size_t(n) * 4, cudaMemcpyHostToDevice, s));
     i32ToU8Checked<<<GRID(n), 0, s>>>(sf, a.typeId, n32, c->hP.nSpecies, c->dBad);
@@ -918,6 +967,10 @@ int dsmcb200_upload_parcels(dsmcb200_ctx* c, int64_t n, const dsmcb200_parcels_s
         if (h->ELevel) { CK(cudaMemcpyAsync(sf, h->ELevel, size_t(n) * 4, cudaMemcpyHostToDevice, s)); i32ToU8<<<GRID(n), 0, s>>>(sf, a.elevel, n32); }
         else CK(cudaMemsetAsync(a.elevel, 0, size_t(n), s));
     }
+    if (a.origProc) {
+        if (h->origProc) { CK(cudaMemcpyAsync(sf, h->origProc, size_t(n) * 4, cudaMemcpyHostToDevice, s)); i32ToU8<<<GRID(n), 0, s>>>(sf, a.origProc, n32); }
+        else CK(cudaMemsetAsync(a.origProc, c->rank & 0xff, size_t(n), s));
+    }
     if (a.cls) {
         if (h->classification) { CK(cudaMemcpyAsync(sf, h->classification, size_t(n) * 4, cudaMemcpyHostToDevice, s)); i32ToU8<<<GRID(n), 0, s>>>(sf, a.cls, n32); }
         else CK(cudaMemsetAsync(a.cls, 0, size_t(n), s));
@@ -928,8 +981,8 @@ int dsmcb200_upload_parcels(dsmcb200_ctx* c, int64_t n, const dsmcb200_parcels_s
     if (bad == 2) return fail(c, DSMCB200_ERR_INVALID, "upload_parcels: typeId not defined in typeIdList");
     if (bad) return fail(c, DSMCB200_ERR_INVALID, "upload_parcels: cell / tetFace / tetPt out of range");
     c->N = n;
-    int32_t maxId = -1;
-    if (h->origId) { for (int64_t i = 0; i < n; ++i) maxId = std::max(maxId, h->origId[i]); } else maxId = n32 - 1;
+    int64_t maxId = -1;
+    if (h->origId) { for (int64_t i = 0; i < n; ++i) maxId = std::max<int64_t>(maxId, h->origId[i]); } else maxId = n32 - 1;
     c->nextOrigId = maxId + 1;
     c->occupancyValid = false;
     return stageSort(c, false);  // buildCellOccupancyFromScratch (dsmcCloud.C:677)
@@ -952,7 +1005,7 @@ int dsmcb200_download_parcels(dsmcb200_ctx* c, int64_t capacity, int64_t* nOut, 
     if (h->cell) CK(cudaMemcpyAsync(h->cell, a.cell, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
     int32_t* r0 = st.islab; int32_t* r1 = st.islab + c->capacity; int32_t* r2 = r1 + c->capacity; int32_t* r3 = r2 + c->capacity; int32_t* r4 = r3 + c->capacity;
     if (h->tetFace || h->tetPt) {
-        fromTetId<<<GRID(n), 0, s>>>(a.tet, c->dFaceTetPair0, c->mesh.nFaces, r0, r1, n32);
+        fromTetId<<<GRID(n), 0, s>>>(a.tet, c->dTets, r0, r1, n32);
         if (h->tetFace) CK(cudaMemcpyAsync(h->tetFace, r0, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
         if (h->tetPt) CK(cudaMemcpyAsync(h->tetPt, r1, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
     }
@@ -961,6 +1014,10 @@ int dsmcb200_download_parcels(dsmcb200_ctx* c, int64_t capacity, int64_t* nOut, 
     if (h->ERot) { if (c->internal) CK(cudaMemcpyAsync(h->ERot, a.erot, size_t(n) * 8, cudaMemcpyDeviceToHost, s)); else std::memset(h->ERot, 0, size_t(n) * 8); }
     if (h->ELevel) { if (c->internal) { u8ToI32<<<GRID(n), 0, s>>>(a.elevel, r3, n32); CK(cudaMemcpyAsync(h->ELevel, r3, size_t(n) * 4, cudaMemcpyDeviceToHost, s)); } else std::memset(h->ELevel, 0, size_t(n) * 4); }
     if (h->classification) { if (a.cls) { u8ToI32<<<GRID(n), 0, s>>>(a.cls, r4, n32); CK(cudaMemcpyAsync(h->classification, r4, size_t(n) * 4, cudaMemcpyDeviceToHost, s)); } else std::memset(h->classification, 0, size_t(n) * 4); }
+    if (h->origProc) {
+        if (a.origProc) { CK(cudaStreamSynchronize(s)); u8ToI32<<<GRID(n), 0, s>>>(a.origProc, r4, n32); CK(cudaMemcpyAsync(h->origProc, r4, size_t(n) * 4, cudaMemcpyDeviceToHost, s)); }
+        else for (int64_t i = 0; i < n; ++i) h->origProc[i] = c->rank;
+    }
     if (h->newParcel) for (int64_t i = 0; i < n; ++i) h->newParcel[i] = -1;
     if (h->vibLevel && h->maxModes > 0) {
         CK(cudaStreamSynchronize(s));
@@ -1004,12 +1061,12 @@ int dsmcb200_mesh_fill(dsmcb200_ctx* c, int nTypes, const int32_t* typeIds, cons
     const HostMesh& M = c->mesh;
     FillArgs a{};
     a.nCells = M.nCells; a.cellFaceOffsets = c->dCellFaceOffsets; a.cellFaces = c->dCellFaces; a.faceOffsets = c->dFaceOffsets;
-    a.facePoints = c->dFacePoints; a.owner = c->dOwner; a.tetBasePtIs = c->dTetBasePtIs; a.faceTetPair0 = c->dFaceTetPair0;
+    a.facePoints = c->dFacePoints; a.owner = c->dOwner; a.tetBasePtIs = c->dTetBasePtIs; a.cellTetStart = c->dCellTetStart;
     a.points = c->dPoints; a.cellCentres = c->dCellCentres; a.P = c->dP; a.nTypes = nTypes;
     for (int i = 0; i < nTypes; ++i) { a.typeIds[i] = typeIds[i]; a.numberDensities[i] = numberDensities[i]; }
     a.Ttra = Ttra; a.Trot = Trot; a.Tvib = Tvib; a.Telec = Telec;
     for (int d = 0; d < 3; ++d) a.velocity[d] = velocity ? velocity[d] : 0.0;
-    a.cellCount = c->dCellCount; a.origIdBase = 0;
+    a.cellCount = c->dCellCount; a.origIdBase = 0; a.origProc = c->rank;
     a.p = c->buf[c->cur].a;
     CK(launchFill(a, 0, c->stream));
     CK(launchExclusiveScan(c->dCellCount, c->dCellOffset, nullptr, M.nCells, c->dScanScratch, c->stream));
@@ -1023,7 +1080,6 @@ int dsmcb200_mesh_fill(dsmcb200_ctx* c, int nTypes, const int32_t* typeIds, cons
     CK(launchFill(a, 1, c->stream));
     c->N = total;
     c->nextOrigId = total;
-    c->occupancyValid = true;
     // sigmaTcRMax = sigmaT(most abundant) * most probable speed (dsmcMeshFill.C:224-235)
     int most = 0;
     for (int i = 1; i < nTypes; ++i) if (numberDensities[i] > numberDensities[most]) most = i;
@@ -1031,8 +1087,9 @@ int dsmcb200_mesh_fill(dsmcb200_ctx* c, int nTypes, const int32_t* typeIds, cons
     const DevSpecies& S = c->hP.sp[typeIds[most]];
     const double sig = PI * S.d * S.d * std::sqrt(2.0 * c->hP.kB * Ttra / S.mass);
     fillDouble<<<GRID(M.nCells), 0, c->stream>>>(c->dSigma, M.nCells, sig);
-    CK(cudaStreamSynchronize(c->stream));
-    return 0;
+    // the fill writes the cloud in cell order; the sort leaves that order as it is and produces the occupancy arrays and sub-cell keys
+    c->occupancyValid = false; c->csrValid = false;
+    return stageSort(c, false);
 }
 
 int dsmcb200_set_step(dsmcb200_ctx* c, uint32_t step) { if (!c) return DSMCB200_ERR_INVALID; c->step = step; return 0; }
@@ -1043,7 +1100,7 @@ int dsmcb200_stage(dsmcb200_ctx* c, int stage) {
     { int r = finalize(c); if (r) return r; }
     int r = 0;
     switch (stage) {
-        case DSMCB200_STAGE_INFLOW: r = stageInflow(c, c->N); break;  // note: step fractions are only kept until the next stage call
+        case DSMCB200_STAGE_INFLOW: r = stageInflow(c, c->N); c->occupancyValid = false; break;  // new parcels are in no cell list; step fractions are only kept until the next stage call
         case DSMCB200_STAGE_MOVE: r = stageMove(c, c->N); c->occupancyValid = false; break;
         case DSMCB200_STAGE_SORT: r = stageSort(c, false); break;
         case DSMCB200_STAGE_COLLIDE: r = stageCollide(c); break;
@@ -1062,7 +1119,9 @@ int dsmcb200_evolve(dsmcb200_ctx* c, int nSteps) {
     { int r = finalize(c); if (r) return r; }
     for (int it = 0; it < nSteps; ++it) {
         cudaEvent_t e0 = getEvent(c), e1 = getEvent(c), e2 = getEvent(c), e3 = getEvent(c), e4 = getEvent(c), e5 = getEvent(c);
-        c->last.inserted = 0; c->last.migratedIn = 0;
+        c->last.inserted = 0; c->last.migratedIn = 0; c->last.migrationRounds = 0;
+        c->last.nNeighbours = int32_t(c->nbrProcs.size());
+        for (int k = 0; k < MAX_NEIGHBOURS; ++k) { c->last.neighbourProc[k] = k < int(c->nbrProcs.size()) ? c->nbrProcs[k] : -1; c->last.migratedTo[k] = 0; c->last.migratedFrom[k] = 0; }
         CK(cudaMemsetAsync(c->dCounters, 0, sizeof(DevCounters), c->stream));
         const int64_t tailStart = c->N;
         // trackingInfo_.clean() (dsmcCloud.C:923): the face tracker holds one step
@@ -1092,6 +1151,7 @@ int dsmcb200_evolve(dsmcb200_ctx* c, int nSteps) {
         c->last.stageMs[7] = ms[0] + ms[1] + ms[2] + ms[3] + ms[4];
         resolveTimers(c);
         if (c->hCounters.overflow) return fail(c, DSMCB200_ERR_CAPACITY, "a fixed-capacity device buffer overflowed during the step");
+        if (c->hCounters.trackingFailures) return fail(c, DSMCB200_ERR_STATE, "the move stage gave up on " + std::to_string(c->hCounters.trackingFailures) + " parcel(s) after 200000 tet visits: the tet table is inconsistent with the cloud");
     }
     return 0;
 }

@@ -14,7 +14,7 @@ constexpr int MAX_SPECIES = DSMCB200_MAX_SPECIES;
 constexpr int MAX_MODES = DSMCB200_MAX_VIB_MODES;
 constexpr int MAX_ELEC = DSMCB200_MAX_ELEC_LEVELS;
 constexpr int MAX_PATCHES = 64;
-constexpr int MAX_NEIGHBOURS = 16;
+constexpr int MAX_NEIGHBOURS = DSMCB200_MAX_NEIGHBOURS;
 constexpr int MAX_INFLOWS = 8;
 constexpr int ZV_TABLE = 128;  // tabulated iMax range of the variable vibrational collision number
 
@@ -68,6 +68,7 @@ struct ParcelArrays {
     int32_t *cell, *tet, *origId;
     int32_t* vib[MAX_MODES];
     uint8_t *typeId, *elevel, *cls;
+    uint8_t* origProc;   // particle::origProc_: with origId the unique identity of a parcel (keys its wall-model random stream)
 };
 
 // Packed record shipped across a processor patch (BASIC/particle/particleIO.C:121-132 +
@@ -76,12 +77,13 @@ struct alignas(16) MigRec {
     double pos[3], U[3], erot, stepFraction;
     int32_t patchOrdinal, patchFace, tetLocal, origId;
     int32_t vib[MAX_MODES];
-    uint8_t typeId, elevel, cls, pad_;
+    uint8_t typeId, elevel, cls, origProc;
 };
 static_assert(sizeof(MigRec) == 96, "MigRec must be 96 bytes");
 
 struct DevCounters {
     unsigned long long collisions, candidates, rescues, deleted, migratedOut, unsortedLargeCells, overflow;
+    unsigned long long trackingFailures;   // parcels dropped by the move kernel's iteration guard (a corrupt tet table): an error
     int32_t nMig[MAX_NEIGHBOURS];
     int32_t nInserted;
     int32_t bigCells;  // cells handed from collideLaneKernel to collideBigCellsKernel this step
@@ -91,9 +93,17 @@ struct DevCounters {
 enum WallQ { WQ_RHON = 0, WQ_RHON_INT, WQ_RHON_ELEC, WQ_RHOM, WQ_LINKE, WQ_MCC, WQ_MOMX, WQ_MOMY, WQ_MOMZ,
              WQ_EROT, WQ_ZETAROT, WQ_EVIB, WQ_EELEC, WQ_Q, WQ_FDX, WQ_FDY, WQ_FDZ, WQ_EVIBMOD0, WQ_BASE = WQ_EVIBMOD0 };
 
+constexpr int MOVE_PMAX = 2048;   // parcels per block of the move kernel (upper bound)
+
 struct MoveArgs {
     ParcelArrays p;
-    int32_t first, count;         // parcel range [first, first+count)
+    // work list: blocks [0, nPlanBlocks) take plan[] entries (cell-sorted parcels with a shared-memory window of tet records, see
+    // launchMovePlan; entries >= *planTotal are unused), the blocks after them take [tailBeg, tailEnd) in pieces of MOVE_PMAX parcels
+    const int4* plan;
+    const int32_t* planTotal;
+    int32_t nPlanBlocks;
+    int32_t stageTets;            // capacity of the shared-memory window in tet records
+    int32_t tailBeg, tailEnd;
     int32_t tailStart;            // parcels >= tailStart carry a step fraction in sfTail[i - tailStart]
     const double* sfTail;
     const TetRec* tets;
@@ -105,7 +115,6 @@ struct MoveArgs {
     int32_t wallsDue;             // 0: this step is not sampled (sampleInterval), wall hits leave no measurement
     double* faceFlux;             // dsmcFaceTracker: [2][nSpecies][nFacesAll] (parcelIdFlux, massIdFlux) or nullptr
     const double* faceAreas;      // [nFacesAll*3], read only by the face tracker
-    const int32_t* faceTetPair0;  // [nFacesAll+1] first face-triangle of each face (tet id >> 1 -> face)
     int32_t nFacesAll;
     MigRec* migBuf;               // [MAX_NEIGHBOURS][migCapacity]
     int32_t* migKey;              // [MAX_NEIGHBOURS][migCapacity] cloud index of the packed parcel: the sender's list order
@@ -150,8 +159,21 @@ struct SampleArgs {
 
 struct KernelTimer;  // engine.cu
 
+// per-step work list of the move kernel over the cell-sorted part of the cloud
+struct MovePlanArgs {
+    const int32_t* groupCell;     // [nGroups+1] runs of cells whose tet records fit the window (HostMesh::stageGroupCell)
+    int32_t nGroups;
+    const int32_t* cellOffset;    // occupancy CSR of the sorted cloud
+    const int32_t* cellTetStart;  // [nCells+1]
+    int32_t* nSub;                // [nGroups+1] scratch: blocks per run
+    int32_t* subBase;             // [nGroups+1] exclusive scan; subBase[nGroups] = planTotal
+    int32_t maxTets;
+    int4* plan;                   // [nGroups + N/MOVE_PMAX + 1]
+};
+
 // ---- launchers (each returns cudaGetLastError()) ----
 cudaError_t launchMove(const MoveArgs& a, cudaStream_t s);
+cudaError_t launchMovePlan(const MovePlanArgs& m, int32_t* scanScratch, cudaStream_t s);
 cudaError_t launchExclusiveScan(const int32_t* in, int32_t* out, int32_t* out2, int32_t n, int32_t* blockSums, cudaStream_t s);
 int32_t scanScratchInts(int32_t n);
 cudaError_t launchScatterIndex(const int32_t* cell, int32_t n, int32_t* cursor, int32_t* perm, cudaStream_t s);
@@ -167,7 +189,7 @@ int32_t infoScratchDoubles();
 struct FillArgs {
     ParcelArrays p;
     int32_t nCells;
-    const int32_t *cellFaceOffsets, *cellFaces, *faceOffsets, *facePoints, *owner, *tetBasePtIs, *faceTetPair0;
+    const int32_t *cellFaceOffsets, *cellFaces, *faceOffsets, *facePoints, *owner, *tetBasePtIs, *cellTetStart;
     const double *points, *cellCentres;
     const DevParams* P;
     int32_t nTypes;
@@ -177,6 +199,7 @@ struct FillArgs {
     double velocity[3];
     int32_t* cellCount;   // pass 0 output / pass 1 input: offsets
     int32_t origIdBase;
+    int32_t origProc;     // this rank (particle::origProc_ of the parcels it creates)
 };
 cudaError_t launchFill(const FillArgs& a, int pass, cudaStream_t s);
 
@@ -192,9 +215,9 @@ cudaError_t orderMigrants(MigRec* records, MigRec* scratch, const int32_t* keys,
 struct LocateArgs {
     const double *px, *py, *pz;
     int32_t* cell;                // in: host cell label; out: -1 for a lost parcel
-    int32_t* tet;                 // out: tet id 2*(faceTetPair0[tetFace] + tetPt - 1) + side
+    int32_t* tet;                 // out: tet id cellTetStart[cell] + index of (tetFace, tetPt) among the cell's tets
     int32_t n, nCells;
-    const int32_t *cellFaceOffsets, *cellFaces, *faceOffsets, *facePoints, *owner, *tetBasePtIs, *faceTetPair0;
+    const int32_t *cellFaceOffsets, *cellFaces, *faceOffsets, *facePoints, *owner, *tetBasePtIs, *cellTetStart;
     const double *points, *cellCentres;
     unsigned long long* lost;     // parcels deleted (outside the inflated cell bounding box or not locatable)
 };
@@ -204,7 +227,9 @@ struct InflowArgs {
     ParcelArrays p;
     int32_t nFaces;               // faces of the inflow patch
     int32_t patch, patchStart;
-    const int32_t *faceOffsets, *facePoints, *owner, *tetBasePtIs, *faceTetPair0;
+    const int32_t *faceOffsets, *facePoints, *owner, *tetBasePtIs;
+    const BFaceRec* bfaces;       // tet0 of every boundary face
+    int32_t nInternalFaces;
     const double *points, *faceCentres, *faceAreas;
     const DevParams* P;
     int32_t nTypes;
@@ -219,6 +244,7 @@ struct InflowArgs {
     double* sfTail;               // step fractions of the new parcels, indexed slot - tailStart
     int32_t tailStart;
     int32_t origIdBase;
+    int32_t origProc;
     double* faceFlux;             // dsmcFaceTracker arrays (see MoveArgs) or nullptr
     int32_t nFacesAll;
     DevCounters* counters;

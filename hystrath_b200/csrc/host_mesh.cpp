@@ -226,14 +226,23 @@ std::string HostMesh::build(const dsmcb200_mesh& m) {
         (void)bad;  // degenerate faces fall back to base point 0 (the reference would abort in tetNeighbour)
     }
 
-    // ---- tet numbering
-    faceTetPair0.assign(nFaces + 1, 0);
-    for (int f = 0; f < nFaces; ++f) faceTetPair0[f + 1] = faceTetPair0[f] + (nFacePts(f) - 2);
-    nTetPairs = faceTetPair0[nFaces];
-    if (2 * nTetPairs >= (int64_t(1) << 31)) return "mesh: too many tets for int32 tet ids";
-    tetPairFace.resize(nTetPairs);
-    for (int f = 0; f < nFaces; ++f)
-        for (int k = faceTetPair0[f]; k < faceTetPair0[f + 1]; ++k) tetPairFace[k] = f;
+    // ---- tet numbering: cell-major, faces in cells() order, tetPt ascending
+    cellTetStart.assign(nCells + 1, 0);
+    faceTet0.assign(size_t(2) * nFaces, -1);
+    {
+        int64_t t = 0;
+        for (int c = 0; c < nCells; ++c) {
+            cellTetStart[c] = int32_t(t);
+            for (int k = cellFaceOffsets[c]; k < cellFaceOffsets[c + 1]; ++k) {
+                const int f = cellFaces[k];
+                faceTet0[2 * size_t(f) + (owner[f] == c ? 0 : 1)] = int32_t(t);
+                t += nFacePts(f) - 2;
+                if (t >= (int64_t(1) << 31) - 2) return "mesh: too many tets for int32 tet ids";
+            }
+        }
+        cellTetStart[nCells] = int32_t(t);
+        nTetsTotal = t;
+    }
 
     // ---- solution directions (polyMesh::calcDirections)
     {
@@ -356,47 +365,76 @@ void HostMesh::tetNeighbour(int32_t cell, int32_t face, int32_t tetPt, int tri, 
     }
 }
 
+void HostMesh::buildStageGroups(int32_t maxTets) {
+    stageGroupCell.clear();
+    stageGroupCell.push_back(0);
+    int32_t c = 0;
+    while (c < nCells) {
+        const int32_t t0 = cellTetStart[c];
+        int32_t e = c + 1;
+        while (e < nCells && cellTetStart[e + 1] - t0 <= maxTets) ++e;
+        stageGroupCell.push_back(e);
+        c = e;
+    }
+}
+
 void HostMesh::bakeTets(int64_t first, int64_t count, TetRec* out) const {
-#pragma omp parallel for schedule(static)
-    for (int64_t t = first; t < first + count; ++t) {
-        TetRec& r = out[t - first];
-        int32_t pair = int32_t(t >> 1);
-        int side = int(t & 1);
-        int32_t face = tetPairFace[pair];
-        int32_t tetPt = pair - faceTetPair0[face] + 1;
-        if (side == 1 && face >= nInternalFaces) {  // unused slot: boundary faces have no neighbour side
+    // the cell of the first tet, then a running cursor per thread chunk
+#pragma omp parallel
+    {
+        int32_t cell = -1;
+#pragma omp for schedule(static)
+        for (int64_t t = first; t < first + count; ++t) {
+            if (cell < 0 || t < cellTetStart[cell] || t >= cellTetStart[cell + 1])
+                cell = int32_t(std::upper_bound(cellTetStart.begin(), cellTetStart.end(), int32_t(t)) - cellTetStart.begin()) - 1;
+            // (face, tetPt) of the local index
+            int32_t face = -1, tetPt = -1;
+            {
+                int32_t rel = int32_t(t) - cellTetStart[cell];
+                for (int k = cellFaceOffsets[cell]; k < cellFaceOffsets[cell + 1]; ++k) {
+                    const int32_t f = cellFaces[k];
+                    const int32_t nT = nFacePts(f) - 2;
+                    if (rel < nT) { face = f; tetPt = rel + 1; break; }
+                    rel -= nT;
+                }
+            }
+            TetRec& r = out[t - first];
             std::memset(&r, 0, sizeof(TetRec));
-            r.nbr01[0] = r.nbr01[1] = r.nbr23[0] = r.nbr23[1] = int32_t(t);
-            continue;
+            V3 a, b, c, d;
+            tetPoints(cell, face, tetPt, a, b, c, d);
+            V3 S[4];
+            S[0] = triNormal(b, c, d);  // Sa
+            S[1] = triNormal(a, d, c);  // Sb
+            S[2] = triNormal(a, b, d);  // Sc
+            S[3] = triNormal(a, c, b);  // Sd
+            const V3 ct = 0.25 * (a + b + c + d);
+            for (int i = 0; i < 4; ++i) {
+                S[i] /= (mag(S[i]) + VSMALL);  // BASIC/particle/particleTemplates.C:901-904
+                r.plane[i][0] = S[i].x; r.plane[i][1] = S[i].y; r.plane[i][2] = S[i].z;
+                const V3& planeBase = (i == 1) ? c : b;  // tetPlaneBasePtIs, particleTemplates.C:907-912
+                r.plane[i][3] = dot(planeBase - ct, S[i]);  // lambdaNumerator of findTris (from = tet centre)
+            }
+            r.base[0] = b.x; r.base[1] = b.y; r.base[2] = b.z;
+            r.pA[0] = c.x; r.pA[1] = c.y; r.pA[2] = c.z;
+            r.ct[0] = ct.x; r.ct[1] = ct.y; r.ct[2] = ct.z;
+            r.tol = kLambdaDistanceToleranceCoeff * cellVolumes[cell];
+            r.cell = cell; r.face = face; r.tetPt = tetPt;
+            if (face < nInternalFaces) {
+                const bool own = owner[face] == cell;
+                r.nbrCell = own ? neighbour[face] : owner[face];
+                r.across = faceTet0[2 * size_t(face) + (own ? 1 : 0)] + tetPt - 1;  // the same face triangle seen from the other cell
+            } else {
+                r.nbrCell = -1;
+                r.across = -1 - (face - nInternalFaces);
+            }
+            int32_t nb[4] = {0, 0, 0, 0};
+            for (int tri = 1; tri <= 3; ++tri) {
+                int32_t nf, np;
+                tetNeighbour(cell, face, tetPt, tri, nf, np);
+                nb[tri] = tetId(cell, nf, np);
+            }
+            r.nbr1 = nb[1]; r.nbr2 = nb[2]; r.nbr3 = nb[3];
         }
-        int32_t cell = side == 0 ? owner[face] : neighbour[face];
-        V3 a, b, c, d;
-        tetPoints(cell, face, tetPt, a, b, c, d);
-        V3 S[4];
-        S[0] = triNormal(b, c, d);  // Sa
-        S[1] = triNormal(a, d, c);  // Sb
-        S[2] = triNormal(a, b, d);  // Sc
-        S[3] = triNormal(a, c, b);  // Sd
-        const V3 ct = 0.25 * (a + b + c + d);
-        for (int i = 0; i < 4; ++i) {
-            S[i] /= (mag(S[i]) + VSMALL);  // BASIC/particle/particleTemplates.C:901-904
-            r.plane[i][0] = S[i].x; r.plane[i][1] = S[i].y; r.plane[i][2] = S[i].z;
-            const V3& planeBase = (i == 1) ? c : b;  // tetPlaneBasePtIs, particleTemplates.C:907-912
-            r.plane[i][3] = dot(planeBase - ct, S[i]);  // lambdaNumerator of findTris (from = tet centre)
-        }
-        r.base[0] = b.x; r.base[1] = b.y; r.base[2] = b.z;
-        r.pA[0] = c.x; r.pA[1] = c.y; r.pA[2] = c.z;
-        r.ct[0] = ct.x; r.ct[1] = ct.y; r.ct[2] = ct.z;
-        r.tol = kLambdaDistanceToleranceCoeff * cellVolumes[cell];
-        if (face < nInternalFaces) r.nbr01[0] = side == 0 ? neighbour[face] : owner[face];
-        else r.nbr01[0] = -1 - (face - nInternalFaces);
-        int32_t nb[4] = {0, 0, 0, 0};
-        for (int tri = 1; tri <= 3; ++tri) {
-            int32_t nf, np;
-            tetNeighbour(cell, face, tetPt, tri, nf, np);
-            nb[tri] = tetId(cell, nf, np);
-        }
-        r.nbr01[1] = nb[1]; r.nbr23[0] = nb[2]; r.nbr23[1] = nb[3];
     }
 }
 
@@ -408,13 +446,13 @@ void HostMesh::bakeBFaces(std::vector<BFaceRec>& out) const {
         BFaceRec& r = out[i];
         r.patch = facePatch[i];
         r.owner = owner[f];
-        r.tetPair0 = faceTetPair0[f];
+        r.tet0 = faceTet0[2 * size_t(f)];
         r.nPts = nFacePts(f);
-        r.coupledTetPair0 = -1; r.coupledCell = -1; r.measIndex = -1; r.pad_ = 0;
+        r.coupledTet0 = -1; r.coupledCell = -1; r.measIndex = -1; r.pad_ = 0;
         const PatchInfo& p = patches[r.patch];
         if (p.type == DSMCB200_PATCH_CYCLIC) {
             int cf = f - p.start + patches[p.neighbPatch].start;  // cyclicPolyPatch::transformGlobalFace
-            r.coupledTetPair0 = faceTetPair0[cf];
+            r.coupledTet0 = faceTet0[2 * size_t(cf)];
             r.coupledCell = owner[cf];
         }
     }

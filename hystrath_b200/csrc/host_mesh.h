@@ -16,28 +16,36 @@
 
 namespace dsmc {
 
-// One tetrahedron (Cc, basePt, pA, pB) of the cell decomposition, with everything the
-// tracker needs to cross it: 224 bytes (seven 32-byte sectors), one record per (face-tri, side).
-// Each plane k = 0..3 is one aligned sector {unit normal, (base_k - Ct) . n_k}: the numerator of
-// findTris' lambda from the tet centre is a constant of the tet and is baked with it.
-struct alignas(32) TetRec {
+// One tetrahedron (Cc, basePt, pA, pB) of the cell decomposition, with everything the tracker needs to cross it.
+// 240 bytes = fifteen 16-byte units: an odd unit stride, so the lanes of a warp that read the same field of different records
+// from the shared-memory copy of a cell range hit distinct bank groups (LDS.128 conflict free).
+// Tet ids are CELL-MAJOR: the tets of cell c are cellTetStart[c] .. cellTetStart[c+1]-1 in primitiveMesh::cells() face order, tetPt
+// ascending -- the records of a run of cells are one contiguous piece of the table (one bulk copy into shared memory).
+// Each plane k = 0..3 is {unit normal, (base_k - Ct) . n_k}: the numerator of findTris' lambda from the tet centre is a constant of
+// the tet and is baked with it.
+struct alignas(16) TetRec {
     double plane[4][4];  // [k] = {Sk/(|Sk| + VSMALL) xyz, (planeBase_k - ct) & n_k}, S = Sa,Sb,Sc,Sd
     double base[3];      // basePt  (plane base point of tris 0,2,3)
     double tol;          // lambdaDistanceToleranceCoeff * cellVolume
     double pA[3];        // pA      (plane base point of tri 1)
-    int32_t nbr01[2];    // [0]: >=0 neighbour cell over an internal face, <0: -1-boundaryFace; [1]: tet entered through tri 1
+    int32_t across;      // tet on the other side of the cell face (tri 0), or -1-boundaryFace
+    int32_t nbrCell;     // its cell (internal faces), else -1
     double ct[3];        // tet centre
-    int32_t nbr23[2];    // tets entered through tris 2 and 3 (same cell)
+    int32_t nbr1, nbr2;  // tets entered through tris 1 and 2 (same cell)
+    int32_t nbr3;        // tet entered through tri 3 (same cell)
+    int32_t cell;        // the cell this tet belongs to
+    int32_t face;        // tetFace
+    int32_t tetPt;       // tetPt
 };
-static_assert(sizeof(TetRec) == 224, "TetRec must be 224 bytes");
+static_assert(sizeof(TetRec) == 240, "TetRec must be 240 bytes");
 
 // Per boundary face (index = face - nInternalFaces).
 struct alignas(16) BFaceRec {
     int32_t patch;
     int32_t owner;           // faceCells
-    int32_t tetPair0;        // first tet-pair index of this face
+    int32_t tet0;            // tet id of (owner, this face, tetPt = 1); tetPt p is tet0 + p - 1
     int32_t nPts;
-    int32_t coupledTetPair0; // cyclic: first tet-pair index of the coupled face, else -1
+    int32_t coupledTet0;     // cyclic: tet0 of the coupled face, else -1
     int32_t coupledCell;     // cyclic: owner of the coupled face
     int32_t measIndex;       // row in the wall accumulators or -1
     int32_t pad_;
@@ -62,19 +70,22 @@ struct HostMesh {
     std::vector<double> cellVolumes;
     std::vector<int32_t> tetBasePtIs;
     std::vector<int32_t> cellFaceOffsets, cellFaces;  // primitiveMesh::cells()
-    std::vector<int32_t> faceTetPair0;                // prefix sum of (nPts-2) per face
-    std::vector<int32_t> tetPairFace;                 // inverse of faceTetPair0
+    std::vector<int32_t> cellTetStart;                // [nCells+1] first tet id of each cell
+    std::vector<int32_t> faceTet0;                    // [2*nFaces] tet id of (face, tetPt = 1) seen from the owner [2f] / neighbour [2f+1] (-1 on boundary faces)
     std::vector<int32_t> facePatch;                   // per boundary face
-    int64_t nTetPairs = 0;
+    std::vector<int32_t> stageGroupCell;              // [nGroups+1] runs of cells whose tet records fit the move kernel's shared-memory window
+    int64_t nTetsTotal = 0;
     V3 boundsMin, boundsMax;
     int32_t solutionD[3] = {1, 1, 1};
 
     int nFacePts(int f) const { return faceOffsets[f + 1] - faceOffsets[f]; }
     const int32_t* facePts(int f) const { return &facePoints[faceOffsets[f]]; }
-    int64_t nTets() const { return 2 * nTetPairs; }
+    int64_t nTets() const { return nTetsTotal; }
     int32_t tetId(int32_t cell, int32_t tetFace, int32_t tetPt) const {
-        return 2 * (faceTetPair0[tetFace] + tetPt - 1) + (owner[tetFace] != cell ? 1 : 0);
+        return faceTet0[2 * tetFace + (owner[tetFace] != cell ? 1 : 0)] + tetPt - 1;
     }
+    // runs of consecutive cells with at most maxTets tets each (a cell with more gets a run of its own)
+    void buildStageGroups(int32_t maxTets);
 
     // Build from the ABI struct; computes whatever geometry the caller did not supply.
     std::string build(const dsmcb200_mesh& m);

@@ -29,10 +29,11 @@ __device__ __forceinline__ void tetPointsDev(const double* points, const FaceVie
 }
 
 __device__ __forceinline__ void storeParcel(const ParcelArrays& p, const DevParams& P, int32_t slot, const V3& pos, const V3& U, double ERot,
-                                            const int32_t* vib, int elevel, int32_t cell, int32_t tet, int typeId, int32_t origId) {
+                                            const int32_t* vib, int elevel, int32_t cell, int32_t tet, int typeId, int32_t origId, int origProc) {
     p.px[slot] = pos.x; p.py[slot] = pos.y; p.pz[slot] = pos.z;
     p.ux[slot] = U.x; p.uy[slot] = U.y; p.uz[slot] = U.z;
     p.cell[slot] = cell; p.tet[slot] = tet; p.origId[slot] = origId;
+    if (p.origProc) p.origProc[slot] = uint8_t(origProc);
     p.typeId[slot] = uint8_t(typeId);
     if (P.hasInternalEnergy) {
         p.erot[slot] = ERot;
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(128) fillKernel(const __grid_constant__ FillAr
                 int32_t nParticlesToInsert = int32_t(particlesRequired);
                 if ((particlesRequired - nParticlesToInsert) > rng.sample01()) nParticlesToInsert++;
                 if (pass == 0) { count += nParticlesToInsert; continue; }
-                const int32_t tet = 2 * (a.faceTetPair0[face] + tetPt - 1) + (own ? 0 : 1);
+                const int32_t tet = a.cellTetStart[cell] + tetLocal;
                 for (int32_t pI = 0; pI < nParticlesToInsert; ++pI) {
                     const V3 pos = tetRandomPoint(rng, Cc, b, c, d);
                     V3 U = equipartitionLinearVelocity(rng, P.kB, a.Ttra, S.mass);
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(128) fillKernel(const __grid_constant__ FillAr
                     for (int m = 0; m < S.nVib; ++m) vib[m] = equipartitionVibrationalEnergyLevel(rng, a.Tvib, S.thetaV[m]);
                     const int elevel = equipartitionElectronicLevel(rng, P.kB, a.Telec, S);
                     U += mk(a.velocity[0], a.velocity[1], a.velocity[2]);
-                    storeParcel(a.p, P, slot, pos, U, ERot, vib, elevel, cell, tet, typeId, a.origIdBase + slot);
+                    storeParcel(a.p, P, slot, pos, U, ERot, vib, elevel, cell, tet, typeId, a.origIdBase + slot, a.origProc);
                     ++slot;
                 }
             }
@@ -100,11 +101,12 @@ namespace {
 // holds -- "inside unless definitively shown otherwise": ((p - pt) & n) > SMALL with n = S/(mag(S) + VSMALL) for the four faces
 __device__ bool findTetFacePtDev(const LocateArgs& a, int32_t cell, const V3& p, int32_t& tet) {
     const V3 A = mk(a.cellCentres[3 * cell], a.cellCentres[3 * cell + 1], a.cellCentres[3 * cell + 2]);
+    int32_t tetLocal = 0;
     for (int k = a.cellFaceOffsets[cell]; k < a.cellFaceOffsets[cell + 1]; ++k) {
         const int32_t face = a.cellFaces[k];
         FaceView f{a.facePoints + a.faceOffsets[face], a.faceOffsets[face + 1] - a.faceOffsets[face], a.tetBasePtIs[face]};
         const bool own = a.owner[face] == cell;
-        for (int tetPt = 1; tetPt < f.n - 1; ++tetPt) {
+        for (int tetPt = 1; tetPt < f.n - 1; ++tetPt, ++tetLocal) {
             V3 b, c, d;
             tetPointsDev(a.points, f, own, tetPt, b, c, d);
             V3 nn = 0.5 * cross(c - b, d - b); nn /= (mag(nn) + VSMALL);          // Sa = triNormal(b, c, d)
@@ -115,7 +117,7 @@ __device__ bool findTetFacePtDev(const LocateArgs& a, int32_t cell, const V3& p,
             if (dot(p - b, nn) > SMALL) continue;
             nn = 0.5 * cross(c - A, b - A); nn /= (mag(nn) + VSMALL);              // Sd = triNormal(a, c, b)
             if (dot(p - b, nn) > SMALL) continue;
-            tet = 2 * (a.faceTetPair0[face] + tetPt - 1) + (own ? 0 : 1);
+            tet = a.cellTetStart[cell] + tetLocal;
             return true;
         }
     }
@@ -265,8 +267,8 @@ __global__ void __launch_bounds__(128) inflowKernel(const __grid_constant__ Infl
         int32_t vib[MAX_MODES] = {0, 0, 0};
         for (int mo = 0; mo < S.nVib; ++mo) vib[mo] = equipartitionVibrationalEnergyLevel(rng, a.Tvib, S.thetaV[mo]);
         const int elevel = equipartitionElectronicLevel(rng, P.kB, a.Telec, S);
-        const int32_t tet = 2 * (a.faceTetPair0[faceI] + selectedTriI - 1);
-        storeParcel(a.p, P, slot, pos, U, ERot, vib, elevel, cellI, tet, typeId, a.origIdBase + (slot - a.base));
+        const int32_t tet = a.bfaces[faceI - a.nInternalFaces].tet0 + selectedTriI - 1;
+        storeParcel(a.p, P, slot, pos, U, ERot, vib, elevel, cellI, tet, typeId, int32_t((int64_t(a.origIdBase) + (slot - a.base)) & 0x7fffffff), a.origProc);
         // dsmcParcel::move: a freshly inserted parcel moves a random fraction of the step (dsmcParcel.C:52-59)
         a.sfTail[slot - a.tailStart] = rng.sample01();
         if (a.faceFlux) {

@@ -6,73 +6,95 @@
 // (BASIC/particle/particleTemplates.C:727-1241) with findTris/tetLambda
 // (BASIC/particle/particleI.H:31-140).  The reference walks mesh topology on every tet hop
 // (tetNeighbour / crossEdgeConnectedFace, particleI.H:339-601) and recomputes the four
-// normalised face-area vectors; here both are look-ups in a 224-byte TetRec baked by
+// normalised face-area vectors; here both are look-ups in a 240-byte TetRec baked by
 // host_mesh.cpp with the same arithmetic, so the FP64 comparisons see identical operands.
 // Compiled with --fmad=false: x86 gcc -O3 without -march does not contract to FMA either.
 //
 // Execution shape.  The nesting of the reference (dsmcParcel::move loop around the trackToFace
-// do-while) is flattened into one loop whose iteration is "one tetrahedron": load its record, decide
-// which plane (if any) the remaining track crosses, advance.  Parcels need different numbers of
-// iterations, so each warp owns a chunk of MOVE_CHUNK*32 consecutive parcels and a lane that finishes
-// its parcel immediately takes the next unprocessed one of the chunk (warp-private work queue); the
-// lanes of a warp therefore stay busy and memory accesses stay inside the chunk's cache lines.
+// do-while) is flattened into one loop whose iteration is "one tetrahedron" (move_core.h).  The cloud
+// enters the stage sorted by cell, and tet ids are cell-major, so a run of cells is a contiguous
+// piece of both: a block takes one run (<= stageTets records, <= MOVE_PMAX parcels; planned per step
+// by planMoveKernel), brings its tet records into shared memory with one bulk copy (cp.async.bulk,
+// completion on an mbarrier) and walks its parcels from a block-wide queue -- a lane that finishes a
+// parcel takes the next one, so lanes stay busy although parcels need 1-8 visits.  A visit reads its
+// record from shared memory when the tet belongs to the run and the copy has landed, else from the
+// global table (parcels that left the run, the unsorted tail of inflow / migration arrivals).
 #include <cub/device/device_radix_sort.cuh>
 
 #include "device_models.cuh"
 #include "engine.h"
+#include "move_core.h"
 
 namespace dsmc {
 
 namespace {
 
-constexpr double kTrackingCorrectionTol = 1.0e-5;  // BASIC/particle/particle.C:33
-#ifndef MOVE_CHUNK_SZ
-#define MOVE_CHUNK_SZ 16
-#endif
-constexpr int MOVE_CHUNK = MOVE_CHUNK_SZ;  // parcels per lane in a warp work queue
 #ifndef MOVE_BLOCK_SZ
-#define MOVE_BLOCK_SZ 64
+#define MOVE_BLOCK_SZ 256
 #endif
 constexpr int MOVE_BLOCK = MOVE_BLOCK_SZ;
 #ifndef MOVE_MIN_BLOCKS
-#define MOVE_MIN_BLOCKS 8
+#define MOVE_MIN_BLOCKS 2
 #endif
 
-// one 32-byte sector per instruction (sm_100 LDG.256): halves the L1 tag look-ups of the scattered record reads
-__device__ __forceinline__ void ld4(const double* __restrict__ p, double& a, double& b, double& c, double& d) {
-    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+__device__ __forceinline__ void ldg2(const double* __restrict__ p, double& a, double& b) {
+    asm("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+}
+__device__ __forceinline__ void lds2(uint32_t addr, double& a, double& b) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
 }
 __device__ __forceinline__ int32_t loInt(double w) { return int32_t(__double_as_longlong(w) & 0xffffffffLL); }
 __device__ __forceinline__ int32_t hiInt(double w) { return int32_t(__double_as_longlong(w) >> 32); }
 
-// findTris without the division: (lambda > 0 && lambda < 1) for lambda = num/den is decided from the signs and
-// magnitudes of num and den.  For IEEE doubles RN(num/den) < 1 <=> |num| < |den| and RN(num/den) > 0 <=> same
-// sign and num != 0 (quotients of the magnitudes met here cannot underflow), so the result is identical to
-// particle::findTris + tetLambda (BASIC/particle/particleI.H:31-140) while the FP64 divider is left to the
-// one or two lambdas that are actually needed.  num = (planeBase - tetCentre) & n is baked into the record.
-__device__ __forceinline__ bool planeCrossed(double num, const V3& toMinusCt, const V3& n, double tol) {
-    double den = dot(toMinusCt, n);
-    if (fabs(den) < tol) {
-        if (fabs(num) < tol) return false;                   // lambda = 0
-        if (mag(toMinusCt) < tol / mag(n)) return false;     // lambda = GREAT
-        den = (den >= 0 ? 1.0 : -1.0) * SMALL;
-    }
-    return den > 0 ? (num > 0 && num < den) : (num < 0 && num > den);
+// host_mesh.h TetRec -> registers: fifteen 16-byte loads (the trailing {cell, face, tetPt} words are not needed here)
+__device__ __forceinline__ void loadRecGlobal(const TetRec* __restrict__ tets, int32_t tet, TetRegs& r) {
+    const double* __restrict__ R = reinterpret_cast<const double*>(tets + tet);
+    double w0, w1, w2, dummy;
+    ldg2(R + 24, r.Ct.x, r.Ct.y); ldg2(R + 26, r.Ct.z, w1);
+    ldg2(R + 0, r.N0.x, r.N0.y); ldg2(R + 2, r.N0.z, r.numC0);
+    ldg2(R + 4, r.N1.x, r.N1.y); ldg2(R + 6, r.N1.z, r.numC1);
+    ldg2(R + 8, r.N2.x, r.N2.y); ldg2(R + 10, r.N2.z, r.numC2);
+    ldg2(R + 12, r.N3.x, r.N3.y); ldg2(R + 14, r.N3.z, r.numC3);
+    ldg2(R + 16, r.base.x, r.base.y); ldg2(R + 18, r.base.z, r.tol);
+    ldg2(R + 20, r.pA.x, r.pA.y); ldg2(R + 22, r.pA.z, w0);
+    ldg2(R + 28, w2, dummy);
+    r.across = loInt(w0); r.nbrCell = hiInt(w0); r.nbr1 = loInt(w1); r.nbr2 = hiInt(w1); r.nbr3 = loInt(w2);
+}
+__device__ __forceinline__ void loadRecShared(uint32_t addr, TetRegs& r) {
+    double w0, w1, w2, dummy;
+    lds2(addr + 192, r.Ct.x, r.Ct.y); lds2(addr + 208, r.Ct.z, w1);
+    lds2(addr + 0, r.N0.x, r.N0.y); lds2(addr + 16, r.N0.z, r.numC0);
+    lds2(addr + 32, r.N1.x, r.N1.y); lds2(addr + 48, r.N1.z, r.numC1);
+    lds2(addr + 64, r.N2.x, r.N2.y); lds2(addr + 80, r.N2.z, r.numC2);
+    lds2(addr + 96, r.N3.x, r.N3.y); lds2(addr + 112, r.N3.z, r.numC3);
+    lds2(addr + 128, r.base.x, r.base.y); lds2(addr + 144, r.base.z, r.tol);
+    lds2(addr + 160, r.pA.x, r.pA.y); lds2(addr + 176, r.pA.z, w0);
+    lds2(addr + 224, w2, dummy);
+    r.across = loInt(w0); r.nbrCell = hiInt(w0); r.nbr1 = loInt(w1); r.nbr2 = hiInt(w1); r.nbr3 = loInt(w2);
 }
 
-// particle::tetLambda, BASIC/particle/particleI.H:68-140 (static mesh branch)
-__device__ __forceinline__ double tetLambda(const V3& from, const V3& toMinusFrom, const V3& n, const V3& base, double tol, bool crossed) {
-    double lambdaNumerator = dot(base - from, n);
-    double lambdaDenominator = dot(toMinusFrom, n);
-    // The quotient of a plane that is not crossed is discarded.  A parcel that has just entered through a face sits on
-    // that plane (numerator == 0 after cancellation) and 0/x sends the FP64 divide to its slow path: feed it 1/1 instead.
-    if (!crossed) { lambdaNumerator = 1.0; lambdaDenominator = 1.0; }
-    if (fabs(lambdaDenominator) < tol) {
-        if (fabs(lambdaNumerator) < tol) return 0.0;
-        if (mag(toMinusFrom) < tol / mag(n)) return GREAT;
-        lambdaDenominator = (lambdaDenominator >= 0 ? 1.0 : -1.0) * SMALL;
-    }
-    return lambdaNumerator / lambdaDenominator;
+// ---- shared-memory window: mbarrier + bulk copy (cp.async.bulk, sm_90+) ----
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbarInit(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkCopyG2S(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbarTest(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
 
 struct WallCtx {
@@ -147,7 +169,7 @@ __device__ void wallMeasureDelta(const WallCtx& w, int32_t measIndex, int32_t bf
 }
 
 // dsmcFaceTracker::trackFaceTransition (DSMC/faceTracker/dsmcFaceTracker.C:124-198), RWF = 1.  The parcel's face() is the boundary
-// face bfi when that is >= 0, else the internal face that owns the face-triangle pair of its tet.
+// face bfi when that is >= 0, else the internal tetFace of its tet.
 __device__ __noinline__ void trackFaceTransition(const MoveArgs& a, const DevParams& P, int typeId, const V3& U, int32_t tet, int32_t bfi) {
     int32_t face, target;
     double unsignedCredit = 0.0;
@@ -159,13 +181,7 @@ __device__ __noinline__ void trackFaceTransition(const MoveArgs& a, const DevPar
             unsignedCredit = 1.0;
         }
     } else {
-        const int32_t pair = tet >> 1;
-        int32_t lo = 0, hi = a.nFacesAll;   // last f with faceTetPair0[f] <= pair
-        while (hi - lo > 1) {
-            const int32_t mid = (lo + hi) >> 1;
-            if (a.faceTetPair0[mid] <= pair) lo = mid; else hi = mid;
-        }
-        face = target = lo;
+        face = target = a.tets[tet].face;   // the crossed face is the tetFace of either side's tet
     }
     const V3 Sf = mk(a.faceAreas[3 * size_t(face)], a.faceAreas[3 * size_t(face) + 1], a.faceAreas[3 * size_t(face) + 2]);
     const double sgn = unsignedCredit != 0.0 ? 1.0 : (dot(U, Sf) >= 0 ? 1.0 : -1.0);
@@ -194,11 +210,11 @@ __device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int sp,
     double preIE, postIE;
     V3 preIMom, postIMom;
     wallMeasure(wctx, measIndex, bfi, sp, U, in, preIE, preIMom);
-    // the k-th hit of a parcel on a wall that draws random numbers within a step owns the Philox stream (origId, k, step)
+    // the k-th hit of a parcel on a wall that draws random numbers within a step owns the Philox stream ((origProc, origId), k, step)
     Rng wallRng;
     bool specular = pt.model == DSMCB200_BND_SPECULAR_WALL;
     if (!specular) {
-        wallRng.init(P.seed, uint32_t(a.p.origId[i]), uint32_t(*wallHits), a.step, STREAM_WALL);
+        wallRng.init(P.seed, uint32_t(a.p.origId[i]), uint32_t(*wallHits) | (uint32_t(a.p.origProc ? a.p.origProc[i] : 0) << 16), a.step, STREAM_WALL);
         *wallHits += 1;
         // dsmcDiffuseSpecularWallPatch::controlParticle (mixed/dsmcDiffuseSpecularWallPatch.C:97-115): Maxwell's model
         if (pt.model == DSMCB200_BND_DIFFUSE_SPECULAR_WALL) specular = !(pt.diffuseFraction > wallRng.sample01());
@@ -250,22 +266,114 @@ __device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int sp,
 
 }  // namespace
 
+// The visits that visitFast hands back (a denominator inside the tolerance band, the rescue correction): every branch of the
+// reference, out of line so that the hot loop does not carry its registers.
+struct SlowOut { V3 pos; double trackFraction; int32_t packed; };  // packed = code | (triI + 1) << 4 | needRescue << 8
+__device__ __noinline__ SlowOut slowVisit(const TetRec* __restrict__ tets, int32_t tet, V3 pos, V3 end, double trackFraction, bool rescuePending) {
+    TetRegs R;
+    loadRecGlobal(tets, tet, R);
+    const VisitOut v = visitSlow(R, pos, end, trackFraction, rescuePending);
+    SlowOut o;
+    o.pos = pos; o.trackFraction = trackFraction;
+    o.packed = v.code | ((v.triI + 1) << 4) | (v.needRescue ? 256 : 0);
+    return o;
+}
+
+// Cloud<T>::move transfer list + particle::prepareForParallelTransfer, fused with the packing
+__device__ __noinline__ void packMigrant(const MoveArgs& a, const DevParams& P, int32_t i, int32_t faceBfi, int32_t tet, V3 pos, V3 U, double stepFraction) {
+    const BFaceRec bf = a.bfaces[faceBfi];
+    const DevPatch& pt = P.patch[bf.patch];
+    const int slot = pt.nbrSlot;
+    const int32_t k = atomicAdd(&a.counters->nMig[slot], 1);
+    if (k < a.migCapacity) {
+        Internal in;
+        loadInternal(a, P, i, in);
+        MigRec r;
+        r.pos[0] = pos.x; r.pos[1] = pos.y; r.pos[2] = pos.z;
+        r.U[0] = U.x; r.U[1] = U.y; r.U[2] = U.z;
+        r.erot = in.ERot; r.stepFraction = stepFraction;
+        r.patchOrdinal = pt.nbrOrdinal;
+        r.patchFace = faceBfi - (pt.start - P.nInternalFaces);
+        r.tetLocal = tet - bf.tet0;
+        r.origId = a.p.origId[i];
+        r.vib[0] = in.vib0; r.vib[1] = in.vib1; r.vib[2] = in.vib2;
+        r.typeId = a.p.typeId[i]; r.elevel = uint8_t(in.elevel); r.cls = a.p.cls ? a.p.cls[i] : 0; r.origProc = a.p.origProc ? a.p.origProc[i] : 0;
+        a.migBuf[size_t(slot) * a.migCapacity + k] = r;
+        a.migKey[size_t(slot) * a.migCapacity + k] = i;
+    } else {
+        atomicAdd(&a.counters->overflow, 1ULL);
+    }
+    atomicAdd(&a.counters->migratedOut, 1ULL);
+}
+
+// per-step work list of moveKernel: one entry per block {parcelBeg, parcelEnd, tetBeg, nTets}; a run of cells with more than
+// MOVE_PMAX parcels is split over several blocks that stage the same records
+__global__ void planCountKernel(const int32_t* __restrict__ groupCell, int32_t nGroups, const int32_t* __restrict__ cellOffset, int32_t* nSub) {
+    const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > nGroups) return;
+    if (g == nGroups) { nSub[g] = 0; return; }
+    const int32_t cnt = cellOffset[groupCell[g + 1]] - cellOffset[groupCell[g]];
+    nSub[g] = (cnt + MOVE_PMAX - 1) / MOVE_PMAX;
+}
+__global__ void planFillKernel(const int32_t* __restrict__ groupCell, int32_t nGroups, const int32_t* __restrict__ cellOffset,
+                               const int32_t* __restrict__ cellTetStart, const int32_t* __restrict__ subBase, int32_t maxTets, int4* plan) {
+    const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nGroups) return;
+    const int32_t c0 = groupCell[g], c1 = groupCell[g + 1];
+    const int32_t p0 = cellOffset[c0], p1 = cellOffset[c1];
+    const int32_t t0 = cellTetStart[c0];
+    int32_t nT = cellTetStart[c1] - t0;
+    if (nT > maxTets) nT = 0;   // a single cell larger than the window: its parcels read the global table
+    int32_t k = subBase[g];
+    for (int32_t p = p0; p < p1; p += MOVE_PMAX, ++k) plan[k] = make_int4(p, min(p + MOVE_PMAX, p1), t0, nT);
+}
+
+cudaError_t launchMovePlan(const MovePlanArgs& m, int32_t* scanScratch, cudaStream_t s) {
+    const int n = m.nGroups + 1;
+    planCountKernel<<<(n + 255) / 256, 256, 0, s>>>(m.groupCell, m.nGroups, m.cellOffset, m.nSub);
+    cudaError_t e = launchExclusiveScan(m.nSub, m.subBase, nullptr, m.nGroups, scanScratch, s);
+    if (e != cudaSuccess) return e;
+    planFillKernel<<<(m.nGroups + 255) / 256, 256, 0, s>>>(m.groupCell, m.nGroups, m.cellOffset, m.cellTetStart, m.subBase, m.maxTets, m.plan);
+    return cudaGetLastError();
+}
+
 // TRACK: the dsmcFaceTracker hook compiled in (its cold call costs the hot loop 1.2 % even when it is never taken: measured A/B)
 template <bool TRACK>
 __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const __grid_constant__ MoveArgs a) {
+    extern __shared__ __align__(16) unsigned char smRaw[];   // [0,16): mbarrier + queue head, then the window of tet records
+    __shared__ int32_t sQueue;
     const DevParams& P = *a.P;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int32_t warpGlobal = (blockIdx.x * MOVE_BLOCK + threadIdx.x) >> 5;
-    const int32_t chunkBeg = a.first + warpGlobal * (32 * MOVE_CHUNK);
-    int32_t chunkEnd = chunkBeg + 32 * MOVE_CHUNK;
-    if (chunkEnd > a.first + a.count) chunkEnd = a.first + a.count;
-    if (chunkBeg >= chunkEnd) return;
-    int32_t warpNext = chunkBeg;  // warp-uniform: next unassigned parcel of the chunk
+
+    // ---- this block's entry of the work list ----
+    int32_t pBeg, pEnd, tetBeg = 0, nStaged = 0;
+    if (int32_t(blockIdx.x) < a.nPlanBlocks) {
+        if (int32_t(blockIdx.x) >= a.planTotal[0]) return;
+        const int4 e = a.plan[blockIdx.x];
+        pBeg = e.x; pEnd = e.y; tetBeg = e.z; nStaged = e.w;
+    } else {
+        const int32_t k = int32_t(blockIdx.x) - a.nPlanBlocks;
+        pBeg = a.tailBeg + k * MOVE_PMAX;
+        pEnd = min(pBeg + MOVE_PMAX, a.tailEnd);
+    }
+    if (pBeg >= pEnd) return;
+    const uint32_t bar = smemAddr(smRaw);
+    const uint32_t win = bar + 16;
+    if (threadIdx.x == 0) {
+        sQueue = pBeg;
+        if (nStaged > 0) {
+            mbarInit(bar, 1);
+            mbarExpectTx(bar, uint32_t(nStaged) * uint32_t(sizeof(TetRec)));
+            bulkCopyG2S(win, a.tets + tetBeg, uint32_t(nStaged) * uint32_t(sizeof(TetRec)), bar);
+        }
+    }
+    __syncthreads();
+    bool windowReady = false;   // the bulk copy has landed (checked once per iteration until it has)
+    bool drained = false;       // warp-uniform: the block's queue is empty
 
     const double deltaT = P.deltaT;
     const bool constrained = P.solutionD[0] == -1 || P.solutionD[1] == -1 || P.solutionD[2] == -1;
-    const double* __restrict__ tetBase = reinterpret_cast<const double*>(a.tets);
 
     // per-lane parcel state
     bool active = false;
@@ -281,16 +389,19 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
     // Every lane runs through every section of the loop body and the sections are separated by __syncwarp(), so
     // the warp is converged again at each section head whatever happened in the (divergent) section before it.
     while (true) {
-        // ---- section 0: refill idle lanes from the warp's queue ----
+        // ---- section 0: refill idle lanes from the block's queue ----
         const unsigned idle = __ballot_sync(FULL, !active);
         if (idle) {
-            const int32_t avail = chunkEnd - warpNext;
-            if (avail <= 0) {
+            if (drained) {
                 if (idle == FULL) break;
             } else {
-                const int r = __popc(idle & ((1u << lane) - 1u));
-                if (!active && r < avail) {
-                    i = warpNext + r;
+                int32_t base = 0;
+                if (lane == 0) base = atomicAdd(&sQueue, __popc(idle));
+                base = __shfl_sync(FULL, base, 0);
+                if (base + __popc(idle) >= pEnd) drained = true;
+                const int32_t mine = base + __popc(idle & ((1u << lane) - 1u));
+                if (!active && mine < pEnd) {
+                    i = mine;
                     cell = a.p.cell[i];
                     if (cell >= 0) {
                         tet = a.p.tet[i];
@@ -306,17 +417,16 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                         else if (a.cellCount) atomicAdd(&a.cellCount[cell], 1);  // nothing left to move (stepFraction == 1)
                     }
                 }
-                const int nIdle = __popc(idle);
-                warpNext += nIdle < avail ? nIdle : avail;
             }
         }
+        if (nStaged > 0 && !windowReady) windowReady = mbarTest(bar, 0);
         __syncwarp();
 
-        // ---- section 1: one tetrahedron -- its record and the planes crossed by (tet centre -> end position) ----
+        // ---- section 1: one tetrahedron ----
         bool finished = false;
         double retVal = 1.0;
         if (active) {
-            if (++guard > 200000) keepParticle = false;  // corrupt tet table: drop the parcel rather than hang
+            if (++guard > 200000) { keepParticle = false; atomicAdd(&a.counters->trackingFailures, 1ULL); }  // corrupt tet table: reported as an error by the host
             if (!inCall) {
                 // dsmcParcel::move loop body up to the trackToFace call (DSMC/parcels/dsmcParcel.C:74-92)
                 V3 Utracking = U;
@@ -329,77 +439,39 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                 trackFraction = 0.0;
                 inCall = true; rescuePending = false; faceSet = false; faceBfi = -1;
             }
-            // the whole record up front: seven independent 32-byte sectors in flight
-            const double* __restrict__ R = tetBase + size_t(tet) * 28;
-            double n0x, n0y, n0z, numC0, n1x, n1y, n1z, numC1, n2x, n2y, n2z, numC2, n3x, n3y, n3z, numC3;
-            double bx, by, bz, ax, ay, az, ctx, cty, ctz, tol, nb01, nb23;
-            ld4(R + 24, ctx, cty, ctz, nb23);
-            ld4(R + 16, bx, by, bz, tol);
-            ld4(R + 0, n0x, n0y, n0z, numC0);
-            ld4(R + 4, n1x, n1y, n1z, numC1);
-            ld4(R + 8, n2x, n2y, n2z, numC2);
-            ld4(R + 12, n3x, n3y, n3z, numC3);
-            ld4(R + 20, ax, ay, az, nb01);
-            const V3 Ct = mk(ctx, cty, ctz);
-            const V3 N0 = mk(n0x, n0y, n0z), N1 = mk(n1x, n1y, n1z), N2 = mk(n2x, n2y, n2z), N3 = mk(n3x, n3y, n3z);
-            const V3 base = mk(bx, by, bz), pA = mk(ax, ay, az);
-            const V3 toMinusCt = endPosition - Ct;
-            const bool c0 = planeCrossed(numC0, toMinusCt, N0, tol);
-            const bool c1 = planeCrossed(numC1, toMinusCt, N1, tol);
-            const bool c2 = planeCrossed(numC2, toMinusCt, N2, tol);
-            const bool c3 = planeCrossed(numC3, toMinusCt, N3, tol);
-            // ---- outcome of the visit, decided with predicates and selects; only a boundary face is a real branch.
-            // (The nested if/else form of the reference merges position, fraction and flags at every join and the compiler
-            // pays for each join with register copies.)
-            const V3 toMinusFrom = endPosition - pos;
-            const double l0 = tetLambda(pos, toMinusFrom, N0, base, tol, c0);
-            const double l1 = tetLambda(pos, toMinusFrom, N1, pA, tol, c1);
-            const double l2 = tetLambda(pos, toMinusFrom, N2, base, tol, c2);
-            const double l3 = tetLambda(pos, toMinusFrom, N3, base, tol, c3);
-            int triI = -1;
-            double lambdaMin = VGREAT;
-            if (c0 && l0 < lambdaMin) { lambdaMin = l0; triI = 0; }
-            if (c1 && l1 < lambdaMin) { lambdaMin = l1; triI = 1; }
-            if (c2 && l2 < lambdaMin) { lambdaMin = l2; triI = 2; }
-            if (c3 && l3 < lambdaMin) { lambdaMin = l3; triI = 3; }
-            const bool none = !(c0 | c1 | c2 | c3);
-            const bool live = keepParticle && !rescuePending;
-            const bool kResc = keepParticle && rescuePending;         // lambdaMin < SMALL last time: correction towards this tet's centre
-            const bool gtS = lambdaMin > SMALL, le1 = lambdaMin <= 1.0;
-            const bool kEnd = live && (none || (gtS && !le1));         // the end position lies in this tet
-            const bool kAdv = live && !none && gtS && le1;             // advance to the nearest crossed plane
-            const bool needRescue = live && !none && !gtS;             // lambdaMin = 0.0
-            const bool moving = kAdv || needRescue;
-            if (kResc) atomicAdd(&a.counters->rescues, 1ULL);   // rare: counted where it happens, no per-lane counter register
-            {
-                // rescue and advance have the same form: pos += f * (X - pos)
-                const V3 X = kResc ? Ct : endPosition;
-                const double f = kResc ? kTrackingCorrectionTol : lambdaMin;
-                const V3 stepped = pos + f * (X - pos);
-                if (kResc || kAdv) pos = stepped;
-                if (kEnd) pos = endPosition;
-                if (kAdv) trackFraction += lambdaMin * (1 - trackFraction);
+            TetRegs R;
+            const uint32_t rel = uint32_t(tet - tetBeg);
+            if (windowReady && rel < uint32_t(nStaged)) loadRecShared(win + rel * uint32_t(sizeof(TetRec)), R);
+            else loadRecGlobal(a.tets, tet, R);
+            VisitOut v;
+            v.code = VISIT_SLOW; v.triI = -1; v.needRescue = false;
+            if (keepParticle) {
+                if (!rescuePending) v = visitFast(R, pos, endPosition, trackFraction);
+                if (v.code == VISIT_SLOW) {
+                    const SlowOut so = slowVisit(a.tets, tet, pos, endPosition, trackFraction, rescuePending);
+                    pos = so.pos; trackFraction = so.trackFraction;
+                    v.code = so.packed & 15; v.triI = ((so.packed >> 4) & 15) - 1; v.needRescue = (so.packed & 256) != 0;
+                    if (v.code == VISIT_RESCUED) atomicAdd(&a.counters->rescues, 1ULL);   // rare: counted where it happens
+                }
+                if (v.code != VISIT_RESCUED) {
+                    const bool onFace = v.triI == 0;
+                    faceSet = onFace;
+                    faceBfi = (onFace && R.across < 0) ? (-1 - R.across) : -1;
+                }
             }
-            const int32_t nb0 = loInt(nb01);
-            if (live) {
-                const bool onFace = !none && triI == 0;
-                faceSet = onFace;
-                faceBfi = (onFace && nb0 < 0) ? (-1 - nb0) : -1;
-            }
-            finished = !keepParticle || kResc || kEnd;
-            retVal = kResc ? trackFraction : 1.0;
-            const bool hop = moving && triI > 0, face = moving && triI == 0;
-            if (hop) {
-                // particle::tetNeighbour: enter the adjacent tet of the same cell
-                tet = triI == 1 ? hiInt(nb01) : (triI == 2 ? loInt(nb23) : hiInt(nb23));
-                rescuePending = needRescue;
-            }
-            if (face) {
-                if (nb0 >= 0) {
-                    cell = nb0;  // internal face: the same face triangle seen from the other cell
-                    tet ^= 1;
+            finished = !keepParticle || v.code == VISIT_RESCUED || v.code == VISIT_END;
+            retVal = v.code == VISIT_RESCUED ? trackFraction : 1.0;
+            if (keepParticle && v.code == VISIT_MOVE) {
+                if (v.triI > 0) {
+                    // particle::tetNeighbour: enter the adjacent tet of the same cell
+                    tet = v.triI == 1 ? R.nbr1 : (v.triI == 2 ? R.nbr2 : R.nbr3);
+                    rescuePending = v.needRescue;
                 } else {
-                        const int32_t bfi = -1 - nb0;
+                    if (R.across >= 0) {
+                        cell = R.nbrCell;  // internal face: the same face triangle seen from the other cell
+                        tet = R.across;
+                    } else {
+                        const int32_t bfi = -1 - R.across;
                         const BFaceRec bf = a.bfaces[bfi];
                         const DevPatch& pt = P.patch[bf.patch];
                         switch (pt.type) {
@@ -411,7 +483,7 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                             case DSMCB200_PATCH_SYMMETRY:
                             case DSMCB200_PATCH_WEDGE: {
                                 // transformProperties(I - 2.0*nf*nf), particleTemplates.C:1474-1522
-                                const V3 nf = N0;
+                                const V3 nf = R.N0;
                                 const V3 t2 = 2.0 * nf;
                                 const double xx = 1.0 - t2.x * nf.x, xy = 0.0 - t2.x * nf.y, xz = 0.0 - t2.x * nf.z;
                                 const double yx = 0.0 - t2.y * nf.x, yy = 1.0 - t2.y * nf.y, yz = 0.0 - t2.y * nf.z;
@@ -422,8 +494,8 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                             }
                             case DSMCB200_PATCH_CYCLIC: {
                                 // particle::hitCyclicPatch, particleTemplates.C:1525-1570
-                                const int32_t k = (tet >> 1) - bf.tetPair0;
-                                tet = 2 * (bf.coupledTetPair0 + (bf.nPts - 3) - k);
+                                const int32_t k = tet - bf.tet0;
+                                tet = bf.coupledTet0 + (bf.nPts - 3) - k;
                                 cell = bf.coupledCell;
                                 const DevPatch& rp = P.patch[pt.nbrPatch];
                                 pos -= mk(rp.sep[0], rp.sep[1], rp.sep[2]);
@@ -435,7 +507,7 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                                 if (pt.model == DSMCB200_BND_DELETION) {
                                     keepParticle = false;  // dsmcDeletionPatch::controlParticle
                                 } else if (pt.model != DSMCB200_BND_NONE) {
-                                    U = wallInteraction(a, i, a.p.typeId[i], bf.patch, a.wallsDue ? bf.measIndex : -1, bfi, N0, U,
+                                    U = wallInteraction(a, i, a.p.typeId[i], bf.patch, a.wallsDue ? bf.measIndex : -1, bfi, R.N0, U,
                                                             pt.linearT ? comp(pos, pt.depthAxis) : 0.0, &wallHits);
                                     Udirty = true;
                                 }
@@ -443,18 +515,19 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                             default:  // empty patches cannot be hit by constrained tracks
                                 break;
                         }
-                }
-                if (needRescue) {
-                    rescuePending = true;  // correction towards the new tet's centre, then return trackFraction
-                } else {
-                    retVal = trackFraction;
-                    finished = true;
+                    }
+                    if (v.needRescue) {
+                        rescuePending = true;  // correction towards the new tet's centre, then return trackFraction
+                    } else {
+                        retVal = trackFraction;
+                        finished = true;
+                    }
                 }
             }
         }
         __syncwarp();
 
-        // ---- section 3: trackToFace returned -- back in dsmcParcel::move (DSMC/parcels/dsmcParcel.C:92-118) ----
+        // ---- section 2: trackToFace returned -- back in dsmcParcel::move (DSMC/parcels/dsmcParcel.C:92-118) ----
         if (finished) {
             if constexpr (TRACK) {
                 if (faceSet) trackFaceTransition(a, P, a.p.typeId[i], U, tet, faceBfi);  // dsmcParcel.C:106-111
@@ -477,32 +550,8 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                     a.p.cell[i] = -1;
                     atomicAdd(&a.counters->deleted, 1ULL);
                 } else if (switchProcessor) {
-                    // Cloud<T>::move transfer list + particle::prepareForParallelTransfer, fused with the packing
-                    const BFaceRec bf = a.bfaces[faceBfi];
-                    const DevPatch& pt = P.patch[bf.patch];
-                    const int slot = pt.nbrSlot;
-                    const double stepFraction = 1.0 - tEnd / deltaT;
-                    const int32_t k = atomicAdd(&a.counters->nMig[slot], 1);
-                    if (k < a.migCapacity) {
-                        Internal in;
-                        loadInternal(a, P, i, in);
-                        MigRec r;
-                        r.pos[0] = pos.x; r.pos[1] = pos.y; r.pos[2] = pos.z;
-                        r.U[0] = U.x; r.U[1] = U.y; r.U[2] = U.z;
-                        r.erot = in.ERot; r.stepFraction = stepFraction;
-                        r.patchOrdinal = pt.nbrOrdinal;
-                        r.patchFace = faceBfi - (pt.start - P.nInternalFaces);
-                        r.tetLocal = (tet >> 1) - bf.tetPair0;
-                        r.origId = a.p.origId[i];
-                        r.vib[0] = in.vib0; r.vib[1] = in.vib1; r.vib[2] = in.vib2;
-                        r.typeId = a.p.typeId[i]; r.elevel = uint8_t(in.elevel); r.cls = a.p.cls ? a.p.cls[i] : 0; r.pad_ = 0;
-                        a.migBuf[size_t(slot) * a.migCapacity + k] = r;
-                        a.migKey[size_t(slot) * a.migCapacity + k] = i;
-                    } else {
-                        atomicAdd(&a.counters->overflow, 1ULL);
-                    }
+                    packMigrant(a, P, i, faceBfi, tet, pos, U, 1.0 - tEnd / deltaT);
                     a.p.cell[i] = -1;
-                    atomicAdd(&a.counters->migratedOut, 1ULL);
                 } else {
                     a.p.px[i] = pos.x; a.p.py[i] = pos.y; a.p.pz[i] = pos.z;
                     a.p.cell[i] = cell;
@@ -513,14 +562,23 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
             }
         }
     }
+    // the window must have landed before the block's shared memory is released
+    if (threadIdx.x == 0 && nStaged > 0) while (!windowReady) windowReady = mbarTest(bar, 0);
 }
 
 cudaError_t launchMove(const MoveArgs& a, cudaStream_t s) {
-    if (a.count <= 0) return cudaSuccess;
-    const int perBlock = MOVE_BLOCK * MOVE_CHUNK;
-    const int grid = (a.count + perBlock - 1) / perBlock;
-    if (a.faceFlux) moveKernel<true><<<grid, MOVE_BLOCK, 0, s>>>(a);
-    else moveKernel<false><<<grid, MOVE_BLOCK, 0, s>>>(a);
+    const int32_t tailBlocks = a.tailEnd > a.tailBeg ? (a.tailEnd - a.tailBeg + MOVE_PMAX - 1) / MOVE_PMAX : 0;
+    const int32_t grid = a.nPlanBlocks + tailBlocks;
+    if (grid <= 0) return cudaSuccess;
+    const size_t smem = a.nPlanBlocks > 0 ? 16 + size_t(a.stageTets) * sizeof(TetRec) : 16;
+    static bool attrSet = false;
+    if (!attrSet) {
+        cudaFuncSetAttribute(moveKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64);
+        cudaFuncSetAttribute(moveKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64);
+        attrSet = true;
+    }
+    if (a.faceFlux) moveKernel<true><<<grid, MOVE_BLOCK, smem, s>>>(a);
+    else moveKernel<false><<<grid, MOVE_BLOCK, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -578,8 +636,9 @@ __global__ void unpackKernel(const __grid_constant__ UnpackArgs a) {
     a.p.ux[i] = r.U[0]; a.p.uy[i] = r.U[1]; a.p.uz[i] = r.U[2];
     a.p.cell[i] = bf.owner;
     // tetPtI_ = f.size() - 1 - tetPtI_  <=>  local tet index k -> (nPts-3) - k
-    a.p.tet[i] = 2 * (bf.tetPair0 + (bf.nPts - 3) - r.tetLocal);
+    a.p.tet[i] = bf.tet0 + (bf.nPts - 3) - r.tetLocal;
     a.p.origId[i] = r.origId;
+    if (a.p.origProc) a.p.origProc[i] = r.origProc;
     a.p.typeId[i] = r.typeId;
     if (P.hasInternalEnergy) {
         a.p.erot[i] = r.erot;

@@ -32,7 +32,8 @@
 extern "C" {
 #endif
 
-#define DSMCB200_ABI_VERSION 1
+#define DSMCB200_ABI_VERSION 2
+#define DSMCB200_MAX_NEIGHBOURS 16
 #define DSMCB200_MAX_SPECIES 8
 #define DSMCB200_MAX_VIB_MODES 3
 #define DSMCB200_MAX_ELEC_LEVELS 16
@@ -182,7 +183,7 @@ typedef struct {
     int32_t measureHeatFluxShearStress; /* sample the optional 2nd-moment set     */
     int32_t measureClassifications;
     int32_t trackFaceFluxes;       /* dsmcFaceTracker counters (off by default), see dsmcb200_download_face_fluxes */
-    int32_t fusedCollideSample;    /* 1: stages 3-5 in one kernel                 */
+    int32_t reserved0_;
     int32_t sampleInterval;        /* dsmcVolFieldsProperties.sampleInterval: stage 5 runs every n-th step (0, 1: every step;
                                       dsmcVolFields.C:1073-1081,1362)             */
     int32_t reserved_;
@@ -207,6 +208,8 @@ typedef struct {
     int32_t* origId;       /* [n]  */
     int32_t maxModes;      /* stride of vibLevel */
     int32_t pad_;
+    int32_t* origProc;     /* [n] particle::origProc_ (BASIC/particle/particle.H:134): with origId the identity of a parcel; NULL on
+                              upload = this rank.  Kept on the device only when nRanks > 1. */
 } dsmcb200_parcels_soa;
 
 /* Counters of one evolve() (noTimeCounter.C:312-337, dsmcCloud.C:935-985,
@@ -220,9 +223,16 @@ typedef struct {
     int64_t inserted;
     int64_t migratedOut;
     int64_t migratedIn;
-    int64_t unsortedLargeCells;  /* cells too large for the in-cell ordering pass */
+    int64_t unsortedLargeCells;  /* always 0: every cell is put into cloud-list order (kept for ABI stability) */
     double mass, linearKineticEnergy, rotationalEnergy, vibrationalEnergy, electronicEnergy;
     double stageMs[8];  /* last step: inflow, move, migrate, sort, collide, sample, info, total */
+    /* processor-patch transfers of the last step, per neighbour processor, summed over the rounds of Cloud<T>::move
+     * (the sizes of particleTransferLists / the received lists, BASIC/Cloud/Cloud.C:283-306,356-404) */
+    int32_t nNeighbours;
+    int32_t migrationRounds;
+    int32_t neighbourProc[DSMCB200_MAX_NEIGHBOURS];
+    int64_t migratedTo[DSMCB200_MAX_NEIGHBOURS];
+    int64_t migratedFrom[DSMCB200_MAX_NEIGHBOURS];
 } dsmcb200_counters;
 
 /* Sampled per-cell accumulators of stage 5: the per-species moment sums from

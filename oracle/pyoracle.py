@@ -43,6 +43,7 @@ def load():
     lib.oracle_set_models.argtypes = [P, C.POINTER(Models)]
     lib.oracle_set_reorder.argtypes = [P, C.c_int]
     lib.oracle_set_step.argtypes = [P, C.c_uint32]
+    lib.oracle_set_rank.argtypes = [P, C.c_int]
     lib.oracle_upload_parcels.argtypes = [P, C.c_int64, C.POINTER(capi.ParcelsSoA)]
     lib.oracle_download_parcels.argtypes = [P, C.POINTER(capi.ParcelsSoA)]
     lib.oracle_upload_cellstate.argtypes = [P, C.c_void_p, C.c_void_p]
@@ -108,6 +109,10 @@ class Oracle:
 
     def set_step(self, step):
         self.lib.oracle_set_step(self.h, step)
+
+    def set_rank(self, rank):
+        """Pstream::myProcNo() of this instance: origProc of the parcels it creates."""
+        self.lib.oracle_set_rank(self.h, rank)
 
     def upload_parcels(self, p: ParcelData):
         st = p.as_struct()
@@ -196,7 +201,7 @@ class Oracle:
 
     def outbox(self):
         n = self.lib.oracle_outbox_size(self.h)
-        d, i = np.zeros((n, 8)), np.zeros((n, 11), np.int32)
+        d, i = np.zeros((n, 8)), np.zeros((n, 12), np.int32)
         self._ck(self.lib.oracle_outbox_get(self.h, _ptr(d), _ptr(i)))
         return d, i
 
