@@ -79,6 +79,14 @@ def case_parameters(gas, cells, ppc):
     return dict(n=n, T=T, dx=dx, L=L, fnum=fnum, dt=dt)
 
 
+def host_cores():
+    """Cores this process may run on (the cgroup / affinity mask, not the machine's count)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def procs_for(n):
     return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n]
 
@@ -121,10 +129,10 @@ def run_reference(args):
     if rank != 0:
         return
     from hystrath_b200 import capi, meshgen
+    from oracle import pyoracle
     from oracle.pyoracle import Oracle
 
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = pyoracle.set_threads(host_cores())   # the team size actually obtained (torchrun exports OMP_NUM_THREADS=1)
     cells = args.ref_cells
     cp = case_parameters(args.gas, cells, args.ppc)
     sp, tids, frac = species_table(args.gas)
@@ -176,10 +184,10 @@ def workload_config(args, cells_per_gpu, parcels_per_gpu):
 def cpu_baseline_leg(args):
     """Oracle (port of the reference algorithm) on a bounded sample of the same workload, rank 0 / N=1 only."""
     from hystrath_b200 import capi, meshgen
+    from oracle import pyoracle
     from oracle.pyoracle import Oracle
 
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = pyoracle.set_threads(host_cores())
     if getattr(args, "workload", "box") == "cylinder":
         from hystrath_b200 import cases
 

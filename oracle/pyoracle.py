@@ -44,6 +44,8 @@ def load():
     lib.oracle_set_reorder.argtypes = [P, C.c_int]
     lib.oracle_set_step.argtypes = [P, C.c_uint32]
     lib.oracle_set_rank.argtypes = [P, C.c_int]
+    lib.oracle_set_threads.argtypes = [C.c_int]
+    lib.oracle_get_threads.restype = C.c_int
     lib.oracle_upload_parcels.argtypes = [P, C.c_int64, C.POINTER(capi.ParcelsSoA)]
     lib.oracle_download_parcels.argtypes = [P, C.POINTER(capi.ParcelsSoA)]
     lib.oracle_upload_cellstate.argtypes = [P, C.c_void_p, C.c_void_p]
@@ -64,6 +66,13 @@ def load():
     lib.oracle_download_geometry.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _LIB = lib
     return lib
+
+
+def set_threads(n):
+    """OpenMP threads of the oracle in this process (overrides OMP_NUM_THREADS); returns the team size actually obtained."""
+    lib = load()
+    lib.oracle_set_threads(int(n))
+    return int(lib.oracle_get_threads())
 
 
 class Oracle:
