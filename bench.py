@@ -50,7 +50,7 @@ STAGE_BYTES_AIR = {"move": 96.0, "sort": 168.0, "collide": 71.0, "sample": 40.0}
 STAGE_BYTES_AR = {"move": 96.0, "sort": 136.0, "collide": 63.0, "sample": 28.0}   # no ERot / vibLevel / ELevel
 SORT_KERNELS = ("scan", "scatterIndex", "segmentSort", "gather", "histogram")
 # the engine times stages; these timers bracket more than one kernel (3-kernel scan; lane + big-cell collide kernels)
-KERNELS_PER_TIMER = {"scan": 3, "collide": 2}
+KERNELS_PER_TIMER = {"scan": 3, "collide": 2, "movePlan": 5}
 
 
 def species_table(gas):
@@ -410,7 +410,7 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         sb = STAGE_BYTES_AR if args.gas == "argon" else STAGE_BYTES_AIR
         per_step = {k: v[0] / max(1, args.steps) for k, v in kt.items()}
-        stage_t = {"move": per_step.get("move", 0.0), "sort": sum(per_step.get(k, 0.0) for k in SORT_KERNELS),
+        stage_t = {"move": per_step.get("move", 0.0) + per_step.get("movePlan", 0.0), "sort": sum(per_step.get(k, 0.0) for k in SORT_KERNELS),
                    "collide": per_step.get("collide", 0.0), "sample": per_step.get("sample", 0.0)}
         stages = {}
         for k, t in stage_t.items():

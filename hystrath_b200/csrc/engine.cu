@@ -166,7 +166,7 @@ struct dsmcb200_ctx {
     int32_t *dPlanSub = nullptr, *dPlanBase = nullptr;
     int4* dPlan = nullptr;
     int64_t planCap = 0;
-    int32_t stageTets = 0, nGroups = 0;
+    int32_t stageTets = 0, nGroups = 0, moveBlocks = 0;
     // cloud
     ParcelBuffer buf[2];
     int cur = 0;
@@ -472,13 +472,17 @@ int finalize(dsmcb200_ctx* c) {
     // ---- bake and upload the tracking tables in chunks
     {
         // window of the move kernel: two blocks per SM share the 227 KB of shared memory
-        int st = 384;
+        // ring of MOVE_NBUF windows in the 227 KB of one SM (one persistent block per SM)
+        int st = moveMaxStageTets();
         if (const char* e = std::getenv("DSMCB200_STAGE_TETS")) st = std::atoi(e);
-        c->stageTets = std::max(0, std::min(st, 900));
+        c->stageTets = std::max(0, std::min(st, moveMaxStageTets()));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, c->device));
+        c->moveBlocks = prop.multiProcessorCount;
         M.buildStageGroups(std::max(1, c->stageTets));
         c->nGroups = int32_t(M.stageGroupCell.size()) - 1;
         CK(upload(&c->dGroupCell, M.stageGroupCell));
-        CK(devAlloc(&c->dPlanSub, size_t(c->nGroups) + 2)); CK(devAlloc(&c->dPlanBase, size_t(c->nGroups) + 2));
+        CK(devAlloc(&c->dPlanSub, size_t(c->nGroups) + 2)); CK(devAlloc(&c->dPlanBase, size_t(c->nGroups) + 4));
     }
     const int64_t nT = M.nTets();
     CK(devAlloc(&c->dTets, size_t(nT)));
@@ -643,11 +647,10 @@ int stageInflow(dsmcb200_ctx* c, int64_t tailStart) {
     return 0;
 }
 
-// parcels [tailBeg, tailEnd) without a shared-memory window; planBlocks > 0: the cell-sorted prefix through the work list as well
-MoveArgs moveArgs(dsmcb200_ctx* c, int32_t planBlocks, int32_t tailBeg, int32_t tailEnd, int32_t tailStart) {
+MoveArgs moveArgs(dsmcb200_ctx* c, int32_t tailStart) {
     MoveArgs a{};
-    a.p = c->buf[c->cur].a; a.plan = c->dPlan; a.planTotal = c->dPlanBase + c->nGroups; a.nPlanBlocks = planBlocks; a.stageTets = c->stageTets;
-    a.tailBeg = tailBeg; a.tailEnd = tailEnd; a.tailStart = tailStart; a.sfTail = c->dSfTail;
+    a.p = c->buf[c->cur].a; a.plan = c->dPlan; a.planTotal = c->dPlanBase + c->nGroups + 1; a.gridBlocks = c->moveBlocks; a.stageTets = c->stageTets;
+    a.tailStart = tailStart; a.sfTail = c->dSfTail;
     a.tets = c->dTets; a.bfaces = c->dBFaces; a.bfaceArea = c->dBFaceArea; a.P = c->dP; a.wallAcc = c->dWallAcc; a.nWallQ = c->nWallQ;
     // boundaryMeas_ is cleaned every step (dsmcCloud.C:924) but only folded into the fields on sampled steps (dsmcVolFields.C:1081,1292)
     a.wallsDue = c->sampleCounter + 1 >= std::max(1, c->models.sampleInterval);
@@ -656,26 +659,25 @@ MoveArgs moveArgs(dsmcb200_ctx* c, int32_t planBlocks, int32_t tailBeg, int32_t 
     return a;
 }
 
-// the whole cloud: the prefix that is still in the order of the last sort goes through the per-step work list
-int launchMoveAll(dsmcb200_ctx* c, int64_t tailStart) {
-    const int32_t N = int32_t(c->N);
-    int32_t sorted = (c->csrValid && c->stageTets > 0) ? int32_t(std::min<int64_t>(c->sortedN, c->N)) : 0;
-    int32_t planBlocks = 0;
-    if (sorted > 0) {
-        planBlocks = c->nGroups + sorted / MOVE_PMAX + 1;
-        if (planBlocks > c->planCap) {
-            devFree(c->dPlan);
-            c->planCap = planBlocks + planBlocks / 4 + 64;
-            CK(devAlloc(&c->dPlan, size_t(c->planCap)));
-        }
-        MovePlanArgs m{};
-        m.groupCell = c->dGroupCell; m.nGroups = c->nGroups; m.cellOffset = c->dCellOffset; m.cellTetStart = c->dCellTetStart;
-        m.nSub = c->dPlanSub; m.subBase = c->dPlanBase; m.maxTets = c->stageTets; m.plan = c->dPlan;
-        KT t(c, "movePlan");
-        CK(launchMovePlan(m, c->dScanScratch, c->stream));
+// Move parcels [first, last).  useCsr: parcels [0, sortedN) are still in the order of the last sort and take the per-step work list
+// with shared-memory windows (requires first == 0); everything else is walked in plain pieces.
+int launchMoveRange(dsmcb200_ctx* c, int32_t first, int32_t last, bool useCsr, int64_t tailStart) {
+    if (last <= first) return 0;
+    const int32_t sorted = (useCsr && first == 0 && c->csrValid && c->stageTets > 0) ? int32_t(std::min<int64_t>(c->sortedN, last)) : 0;
+    const int32_t nGroups = sorted > 0 ? c->nGroups : 0;
+    const int64_t need = int64_t(nGroups) + sorted / MOVE_PMAX + (last - std::max(first, sorted)) / MOVE_TAIL + 4;
+    if (need > c->planCap) {
+        devFree(c->dPlan);
+        c->planCap = need + need / 4 + 64;
+        CK(devAlloc(&c->dPlan, size_t(c->planCap)));
     }
+    MovePlanArgs m{};
+    m.groupCell = c->dGroupCell; m.nGroups = nGroups; m.cellOffset = c->dCellOffset; m.cellTetStart = c->dCellTetStart;
+    m.nSub = c->dPlanSub; m.subBase = c->dPlanBase; m.maxTets = c->stageTets; m.plan = c->dPlan; m.planTotal = c->dPlanBase + c->nGroups + 1;
+    m.tailBeg = std::max(first, sorted); m.tailEnd = last;
+    { KT t(c, "movePlan"); CK(launchMovePlan(m, c->dScanScratch, c->stream)); }
     KT t(c, "move");
-    CK(launchMove(moveArgs(c, planBlocks, sorted, N, int32_t(tailStart)), c->stream));
+    CK(launchMove(moveArgs(c, int32_t(tailStart)), c->stream));
     return 0;
 }
 
@@ -691,7 +693,7 @@ int stageMove(dsmcb200_ctx* c, int64_t tailStart) {
     CK(cudaMemsetAsync(c->dCellCount, 0, size_t(nCells + 1) * 4, c->stream));
     CK(cudaMemsetAsync(c->dCounters->nMig, 0, sizeof(int32_t) * MAX_NEIGHBOURS, c->stream));
     if (tailStart >= c->N) { int r = ensureSfTail(c, 1); if (r) return r; }
-    { int r = launchMoveAll(c, tailStart); if (r) return r; }
+    { int r = launchMoveRange(c, 0, int32_t(c->N), true, tailStart); if (r) return r; }
     c->csrValid = false;
     if (c->nRanks <= 1 || c->nbrProcs.empty()) return 0;
     if (!c->comm) return fail(c, DSMCB200_ERR_STATE, "mesh has processor patches but dsmcb200_init_comm was not called");
@@ -754,7 +756,7 @@ int stageMove(dsmcb200_ctx* c, int64_t tailStart) {
             c->last.migratedIn += recvFrom[s];
         }
         CK(cudaMemsetAsync(c->dCounters->nMig, 0, sizeof(int32_t) * MAX_NEIGHBOURS, c->stream));
-        if (nRecvTotal) CK(launchMove(moveArgs(c, 0, int32_t(firstNew), int32_t(firstNew + nRecvTotal), int32_t(tailStart)), c->stream));
+        if (nRecvTotal) { int rr = launchMoveRange(c, int32_t(firstNew), int32_t(firstNew + nRecvTotal), false, tailStart); if (rr) return rr; }
     }
     return 0;
 }

@@ -93,17 +93,20 @@ struct DevCounters {
 enum WallQ { WQ_RHON = 0, WQ_RHON_INT, WQ_RHON_ELEC, WQ_RHOM, WQ_LINKE, WQ_MCC, WQ_MOMX, WQ_MOMY, WQ_MOMZ,
              WQ_EROT, WQ_ZETAROT, WQ_EVIB, WQ_EELEC, WQ_Q, WQ_FDX, WQ_FDY, WQ_FDZ, WQ_EVIBMOD0, WQ_BASE = WQ_EVIBMOD0 };
 
-constexpr int MOVE_PMAX = 2048;   // parcels per block of the move kernel (upper bound)
+constexpr int MOVE_PMAX = 1024;   // parcels per work-list entry of the move kernel (upper bound)
+constexpr int MOVE_TAIL = 512;    // parcels per entry of the unsorted tail
+#ifndef MOVE_NBUF_SZ
+#define MOVE_NBUF_SZ 4
+#endif
+constexpr int MOVE_NBUF = MOVE_NBUF_SZ;   // entries in flight per block (ring of shared-memory windows)
 
 struct MoveArgs {
     ParcelArrays p;
-    // work list: blocks [0, nPlanBlocks) take plan[] entries (cell-sorted parcels with a shared-memory window of tet records, see
-    // launchMovePlan; entries >= *planTotal are unused), the blocks after them take [tailBeg, tailEnd) in pieces of MOVE_PMAX parcels
+    // work list (launchMovePlan): plan[0 .. *planTotal) = {parcelBeg, parcelEnd, tetBeg, nTets}
     const int4* plan;
     const int32_t* planTotal;
-    int32_t nPlanBlocks;
-    int32_t stageTets;            // capacity of the shared-memory window in tet records
-    int32_t tailBeg, tailEnd;
+    int32_t gridBlocks;           // persistent blocks (<= SMs)
+    int32_t stageTets;            // capacity of one shared-memory window in tet records
     int32_t tailStart;            // parcels >= tailStart carry a step fraction in sfTail[i - tailStart]
     const double* sfTail;
     const TetRec* tets;
@@ -166,10 +169,14 @@ struct MovePlanArgs {
     const int32_t* cellOffset;    // occupancy CSR of the sorted cloud
     const int32_t* cellTetStart;  // [nCells+1]
     int32_t* nSub;                // [nGroups+1] scratch: blocks per run
-    int32_t* subBase;             // [nGroups+1] exclusive scan; subBase[nGroups] = planTotal
+    int32_t* subBase;             // [nGroups+1] exclusive scan; subBase[nGroups] = entries of the sorted part
     int32_t maxTets;
-    int4* plan;                   // [nGroups + N/MOVE_PMAX + 1]
+    int32_t tailBeg, tailEnd;     // unsorted parcels appended to the list in pieces of MOVE_TAIL
+    int4* plan;                   // [nGroups + N/MOVE_PMAX + tail pieces + 1]
+    int32_t* planTotal;           // out: entries in the list
 };
+size_t moveSharedBytes(int32_t stageTets);
+int32_t moveMaxStageTets();
 
 // ---- launchers (each returns cudaGetLastError()) ----
 cudaError_t launchMove(const MoveArgs& a, cudaStream_t s);

@@ -30,12 +30,14 @@ namespace dsmc {
 namespace {
 
 #ifndef MOVE_BLOCK_SZ
-#define MOVE_BLOCK_SZ 256
+#define MOVE_BLOCK_SZ 512
 #endif
-constexpr int MOVE_BLOCK = MOVE_BLOCK_SZ;
-#ifndef MOVE_MIN_BLOCKS
-#define MOVE_MIN_BLOCKS 2
+constexpr int MOVE_BLOCK = MOVE_BLOCK_SZ;   // one persistent block per SM
+constexpr int MOVE_SCRATCH = 7;             // doubles of per-thread shared scratch
+#ifndef MOVE_SMEM_KB
+#define MOVE_SMEM_KB 227
 #endif
+constexpr size_t MOVE_SMEM_BUDGET = size_t(MOVE_SMEM_KB) * 1024;
 
 __device__ __forceinline__ void ldg2(const double* __restrict__ p, double& a, double& b) {
     asm("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
@@ -86,6 +88,13 @@ __device__ __forceinline__ void bulkCopyG2S(uint32_t dst, const void* src, uint3
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
                  "r"(bar)
                  : "memory");
+}
+// the range [p + first, p + last) of an array towards L2 (16-byte granules): one instruction per array instead of a load per line
+template <class T>
+__device__ __forceinline__ void prefetchRangeL2(const T* p, int32_t first, int32_t last) {
+    const uintptr_t b = reinterpret_cast<uintptr_t>(p + first) & ~uintptr_t(15);
+    const uintptr_t e = (reinterpret_cast<uintptr_t>(p + last) + 15) & ~uintptr_t(15);
+    if (e > b) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b), "r"(uint32_t(e - b)) : "memory");
 }
 __device__ __forceinline__ bool mbarTest(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -306,8 +315,9 @@ __device__ __noinline__ void packMigrant(const MoveArgs& a, const DevParams& P, 
     atomicAdd(&a.counters->migratedOut, 1ULL);
 }
 
-// per-step work list of moveKernel: one entry per block {parcelBeg, parcelEnd, tetBeg, nTets}; a run of cells with more than
-// MOVE_PMAX parcels is split over several blocks that stage the same records
+// per-step work list of moveKernel: one entry per run of cells {parcelBeg, parcelEnd, tetBeg, nTets}; a run with more than MOVE_PMAX
+// parcels is split into several entries that stage the same records; the unsorted tail [tailBeg, tailEnd) (inflow, migration
+// arrivals) follows in pieces of MOVE_TAIL parcels without a window
 __global__ void planCountKernel(const int32_t* __restrict__ groupCell, int32_t nGroups, const int32_t* __restrict__ cellOffset, int32_t* nSub) {
     const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g > nGroups) return;
@@ -316,156 +326,234 @@ __global__ void planCountKernel(const int32_t* __restrict__ groupCell, int32_t n
     nSub[g] = (cnt + MOVE_PMAX - 1) / MOVE_PMAX;
 }
 __global__ void planFillKernel(const int32_t* __restrict__ groupCell, int32_t nGroups, const int32_t* __restrict__ cellOffset,
-                               const int32_t* __restrict__ cellTetStart, const int32_t* __restrict__ subBase, int32_t maxTets, int4* plan) {
+                               const int32_t* __restrict__ cellTetStart, const int32_t* __restrict__ subBase, int32_t maxTets, int32_t tailBeg,
+                               int32_t tailEnd, int4* plan, int32_t* planTotal) {
     const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= nGroups) return;
-    const int32_t c0 = groupCell[g], c1 = groupCell[g + 1];
-    const int32_t p0 = cellOffset[c0], p1 = cellOffset[c1];
-    const int32_t t0 = cellTetStart[c0];
-    int32_t nT = cellTetStart[c1] - t0;
-    if (nT > maxTets) nT = 0;   // a single cell larger than the window: its parcels read the global table
-    int32_t k = subBase[g];
-    for (int32_t p = p0; p < p1; p += MOVE_PMAX, ++k) plan[k] = make_int4(p, min(p + MOVE_PMAX, p1), t0, nT);
+    const int32_t nTail = tailEnd > tailBeg ? (tailEnd - tailBeg + MOVE_TAIL - 1) / MOVE_TAIL : 0;
+    const int32_t nSorted = nGroups > 0 ? subBase[nGroups] : 0;
+    if (g == 0) *planTotal = nSorted + nTail;
+    if (g < nGroups) {
+        const int32_t c0 = groupCell[g], c1 = groupCell[g + 1];
+        const int32_t p0 = cellOffset[c0], p1 = cellOffset[c1];
+        const int32_t t0 = cellTetStart[c0];
+        int32_t nT = cellTetStart[c1] - t0;
+        if (nT > maxTets) nT = 0;   // a single cell larger than the window: its parcels read the global table
+        int32_t k = subBase[g];
+        for (int32_t p = p0; p < p1; p += MOVE_PMAX, ++k) plan[k] = make_int4(p, min(p + MOVE_PMAX, p1), t0, nT);
+    }
+    // the tail entries are written by the threads after the groups
+    const int32_t t = g - nGroups;
+    if (t >= 0 && t < nTail) plan[nSorted + t] = make_int4(tailBeg + t * MOVE_TAIL, min(tailBeg + (t + 1) * MOVE_TAIL, tailEnd), 0, 0);
 }
 
 cudaError_t launchMovePlan(const MovePlanArgs& m, int32_t* scanScratch, cudaStream_t s) {
-    const int n = m.nGroups + 1;
-    planCountKernel<<<(n + 255) / 256, 256, 0, s>>>(m.groupCell, m.nGroups, m.cellOffset, m.nSub);
-    cudaError_t e = launchExclusiveScan(m.nSub, m.subBase, nullptr, m.nGroups, scanScratch, s);
-    if (e != cudaSuccess) return e;
-    planFillKernel<<<(m.nGroups + 255) / 256, 256, 0, s>>>(m.groupCell, m.nGroups, m.cellOffset, m.cellTetStart, m.subBase, m.maxTets, m.plan);
+    if (m.nGroups > 0) {
+        const int n = m.nGroups + 1;
+        planCountKernel<<<(n + 255) / 256, 256, 0, s>>>(m.groupCell, m.nGroups, m.cellOffset, m.nSub);
+        cudaError_t e = launchExclusiveScan(m.nSub, m.subBase, nullptr, m.nGroups, scanScratch, s);
+        if (e != cudaSuccess) return e;
+    }
+    const int32_t nTail = m.tailEnd > m.tailBeg ? (m.tailEnd - m.tailBeg + MOVE_TAIL - 1) / MOVE_TAIL : 0;
+    const int n = m.nGroups + nTail + 1;
+    planFillKernel<<<(n + 255) / 256, 256, 0, s>>>(m.groupCell, m.nGroups, m.cellOffset, m.cellTetStart, m.subBase, m.maxTets, m.tailBeg, m.tailEnd,
+                                                   m.plan, m.planTotal);
     return cudaGetLastError();
 }
 
-// TRACK: the dsmcFaceTracker hook compiled in (its cold call costs the hot loop 1.2 % even when it is never taken: measured A/B)
+// ---- the persistent move kernel ----
+// One block per SM walks the entries b, b + gridDim, b + 2 gridDim, ... of the work list.  A ring of MOVE_NBUF slots holds the entries in
+// flight: arming a slot publishes the entry's parcel range as a queue and starts the bulk copy of its tet records into the slot's
+// window, so the copy of entry q + MOVE_NBUF - 1 runs while the warps drain entry q.  Lanes take parcels from the slot their warp is
+// drawing from and keep the slot of their parcel; an entry is complete when every parcel taken from it has been written back and
+// every warp has moved on, and whoever completes it arms the slot with the next entry.  Nobody waits at entry boundaries.
+struct MoveSlot {
+    int32_t pBeg, pEnd, tetBeg, nStaged;   // nStaged < 0: end of the work list
+    int32_t head;      // queue head (atomically advanced)
+    int32_t pending;   // parcels not yet written back + warps that have not moved on
+    int32_t seq;       // position of the entry in this block's sequence; published last
+    int32_t copies;    // bulk copies issued on this slot so far (phase parity of its mbarrier)
+};
+
+// arm slot S with the entry of sequence number q of this block (one thread; the previous copy into the window has landed)
+__device__ __noinline__ void armSlot(const MoveArgs& a, MoveSlot* S, uint32_t bar, uint32_t win, int32_t q) {
+    const int64_t e = int64_t(blockIdx.x) + int64_t(q) * gridDim.x;
+    if (e < a.planTotal[0]) {
+        const int4 ent = a.plan[e];
+        S->pBeg = ent.x; S->pEnd = ent.y; S->tetBeg = ent.z; S->nStaged = ent.w; S->head = ent.x;
+        S->pending = (ent.y - ent.x) + MOVE_BLOCK / 32;
+        if (ent.w > 0) {
+            const uint32_t bytes = uint32_t(ent.w) * uint32_t(sizeof(TetRec));
+            mbarExpectTx(bar, bytes);
+            bulkCopyG2S(win, a.tets + ent.z, bytes, bar);
+            S->copies += 1;
+        }
+#ifndef MOVE_NO_PREFETCH
+        // the entry's rows of the cloud towards L2 while earlier entries are being walked
+        prefetchRangeL2(a.p.cell, ent.x, ent.y); prefetchRangeL2(a.p.tet, ent.x, ent.y);
+        prefetchRangeL2(a.p.px, ent.x, ent.y); prefetchRangeL2(a.p.py, ent.x, ent.y); prefetchRangeL2(a.p.pz, ent.x, ent.y);
+        prefetchRangeL2(a.p.ux, ent.x, ent.y); prefetchRangeL2(a.p.uy, ent.x, ent.y); prefetchRangeL2(a.p.uz, ent.x, ent.y);
+#endif
+    } else {
+        S->pBeg = 0; S->pEnd = 0; S->tetBeg = 0; S->nStaged = -1; S->head = 0; S->pending = 1 << 30;
+    }
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smemAddr(&S->seq)), "r"(q) : "memory");
+}
+
+// `n` units of slot S are done (parcels written back, or one warp moving on); whoever completes the entry arms the slot with the next one
+__device__ __forceinline__ void releaseSlot(const MoveArgs& a, MoveSlot* S, uint32_t bar, uint32_t win, int32_t n) {
+    if (atomicSub(&S->pending, n) == n) {
+        const int32_t c = S->copies;
+        if (c > 0) while (!mbarTest(bar, uint32_t(c - 1) & 1u)) {}
+        armSlot(a, S, bar, win, S->seq + MOVE_NBUF);
+    }
+}
+
 template <bool TRACK>
-__global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const __grid_constant__ MoveArgs a) {
-    extern __shared__ __align__(16) unsigned char smRaw[];   // [0,16): mbarrier + queue head, then the window of tet records
-    __shared__ int32_t sQueue;
+__global__ void __launch_bounds__(MOVE_BLOCK, 1) moveKernel(const __grid_constant__ MoveArgs a) {
+    extern __shared__ __align__(16) unsigned char smRaw[];
+    // layout: [0, 8 NBUF) mbarriers | slots | per-thread scratch U.xyz, tEnd | windows
+    MoveSlot* sSlot = reinterpret_cast<MoveSlot*>(smRaw + 64);
+    double* sScratch = reinterpret_cast<double*>(smRaw + 64 + MOVE_NBUF * sizeof(MoveSlot));
+    const uint32_t barBase = smemAddr(smRaw);
+    const uint32_t winBase = barBase + 64 + MOVE_NBUF * uint32_t(sizeof(MoveSlot)) + MOVE_SCRATCH * MOVE_BLOCK * 8;
+    const uint32_t winBytes = uint32_t(a.stageTets) * uint32_t(sizeof(TetRec));
     const DevParams& P = *a.P;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    double* const myU = sScratch + threadIdx.x;   // [k * MOVE_BLOCK]: U.x, U.y, U.z, tEnd, endPosition.xyz of this lane's parcel (touched once per visit or less)
 
-    // ---- this block's entry of the work list ----
-    int32_t pBeg, pEnd, tetBeg = 0, nStaged = 0;
-    if (int32_t(blockIdx.x) < a.nPlanBlocks) {
-        if (int32_t(blockIdx.x) >= a.planTotal[0]) return;
-        const int4 e = a.plan[blockIdx.x];
-        pBeg = e.x; pEnd = e.y; tetBeg = e.z; nStaged = e.w;
-    } else {
-        const int32_t k = int32_t(blockIdx.x) - a.nPlanBlocks;
-        pBeg = a.tailBeg + k * MOVE_PMAX;
-        pEnd = min(pBeg + MOVE_PMAX, a.tailEnd);
-    }
-    if (pBeg >= pEnd) return;
-    const uint32_t bar = smemAddr(smRaw);
-    const uint32_t win = bar + 16;
     if (threadIdx.x == 0) {
-        sQueue = pBeg;
-        if (nStaged > 0) {
-            mbarInit(bar, 1);
-            mbarExpectTx(bar, uint32_t(nStaged) * uint32_t(sizeof(TetRec)));
-            bulkCopyG2S(win, a.tets + tetBeg, uint32_t(nStaged) * uint32_t(sizeof(TetRec)), bar);
+        for (int s = 0; s < MOVE_NBUF; ++s) {
+            mbarInit(barBase + 8 * s, 1);
+            sSlot[s].copies = 0; sSlot[s].seq = -1;
         }
+        for (int s = 0; s < MOVE_NBUF; ++s) armSlot(a, &sSlot[s], barBase + 8 * s, winBase + uint32_t(s) * winBytes, s);
     }
     __syncthreads();
-    bool windowReady = false;   // the bulk copy has landed (checked once per iteration until it has)
-    bool drained = false;       // warp-uniform: the block's queue is empty
 
     const double deltaT = P.deltaT;
     const bool constrained = P.solutionD[0] == -1 || P.solutionD[1] == -1 || P.solutionD[2] == -1;
 
-    // per-lane parcel state
-    bool active = false;
+    // warp-uniform: the entry this warp draws parcels from
+    int32_t wq = 0;             // its sequence number
+    bool listDone = false;      // the end of the work list has been reached
+
+    // per-lane parcel state (U and tEnd live in shared memory: they are touched once per trackToFace call)
+    // flags of the lane's parcel in one register (eight bools cost the kernel eight registers and their spills)
+    constexpr uint32_t F_ACTIVE = 1, F_INCALL = 2, F_RESCUE = 4, F_FACESET = 8, F_UDIRTY = 16, F_KEEP = 32, F_SWITCH = 64, F_WINREADY = 128,
+                       F_SLOT_SHIFT = 8;   // bits 8..11: ring slot of the parcel
+    uint32_t st = 0;
     int32_t i = -1, cell = -1, tet = 0;
-    V3 pos = mk(0, 0, 0), U = mk(0, 0, 0), endPosition = mk(0, 0, 0);
-    double tEnd = 0.0, trackFraction = 0.0;
-    bool inCall = false, rescuePending = false, faceSet = false, Udirty = false;
-    bool keepParticle = true, switchProcessor = false;
+    V3 pos = mk(0, 0, 0);
+    double trackFraction = 0.0;
     int32_t faceBfi = -1;
-    int wallHits = 0;
-    int guard = 0;
+    int32_t hitsAndGuard = 0;   // wall hits that drew random numbers (bits 24..31) | tet visits of this parcel (bits 0..23)
 
     // Every lane runs through every section of the loop body and the sections are separated by __syncwarp(), so
     // the warp is converged again at each section head whatever happened in the (divergent) section before it.
     while (true) {
-        // ---- section 0: refill idle lanes from the block's queue ----
-        const unsigned idle = __ballot_sync(FULL, !active);
+        // ---- section 0: refill idle lanes from the entry the warp is drawing from ----
+        bool written = false;   // this lane's parcel left the kernel in this iteration (counted at the end of the body)
+        const unsigned idle = __ballot_sync(FULL, !(st & F_ACTIVE));
         if (idle) {
-            if (drained) {
+            if (listDone) {
                 if (idle == FULL) break;
             } else {
-                int32_t base = 0;
-                if (lane == 0) base = atomicAdd(&sQueue, __popc(idle));
-                base = __shfl_sync(FULL, base, 0);
-                if (base + __popc(idle) >= pEnd) drained = true;
-                const int32_t mine = base + __popc(idle & ((1u << lane) - 1u));
-                if (!active && mine < pEnd) {
-                    i = mine;
-                    cell = a.p.cell[i];
-                    if (cell >= 0) {
-                        tet = a.p.tet[i];
-                        pos = mk(a.p.px[i], a.p.py[i], a.p.pz[i]);
-                        U = mk(a.p.ux[i], a.p.uy[i], a.p.uz[i]);
-                        const double stepFraction = (a.sfTail != nullptr && i >= a.tailStart) ? a.sfTail[i - a.tailStart] : 0.0;
-                        tEnd = (1.0 - stepFraction) * deltaT;
-                        inCall = false; rescuePending = false; faceSet = false; Udirty = false;
-                        keepParticle = true; switchProcessor = false; faceBfi = -1;
-                        wallHits = 0;
-                        guard = 0;
-                        if (tEnd > ROOTVSMALL) active = true;
-                        else if (a.cellCount) atomicAdd(&a.cellCount[cell], 1);  // nothing left to move (stepFraction == 1)
+                const int s = wq % MOVE_NBUF;
+                MoveSlot* const S = &sSlot[s];
+                int32_t sq;
+                asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(sq) : "r"(smemAddr(&S->seq)) : "memory");
+                if (sq == wq) {   // sq < wq: not armed yet (an entry is re-armed only after every warp has moved on, so never sq > wq)
+                    const int32_t end = S->pEnd;
+                    if (S->nStaged < 0) {
+                        listDone = true;
+                    } else {
+                        const int nIdle = __popc(idle);
+                        int32_t base = 0;
+                        if (lane == 0) base = atomicAdd(&S->head, nIdle);
+                        base = __shfl_sync(FULL, base, 0);
+                        const int32_t mine = base + __popc(idle & ((1u << lane) - 1u));
+                        if (!(st & F_ACTIVE) && mine < end) {
+                            i = mine;
+                            st = F_KEEP | (uint32_t(s) << F_SLOT_SHIFT);
+                            cell = a.p.cell[i];
+                            written = true;
+                            if (cell >= 0) {
+                                tet = a.p.tet[i];
+                                pos = mk(a.p.px[i], a.p.py[i], a.p.pz[i]);
+                                myU[0] = a.p.ux[i]; myU[MOVE_BLOCK] = a.p.uy[i]; myU[2 * MOVE_BLOCK] = a.p.uz[i];
+                                const double stepFraction = (a.sfTail != nullptr && i >= a.tailStart) ? a.sfTail[i - a.tailStart] : 0.0;
+                                const double tEnd = (1.0 - stepFraction) * deltaT;
+                                myU[3 * MOVE_BLOCK] = tEnd;
+                                faceBfi = -1;
+                                hitsAndGuard = 0;
+                                if (tEnd > ROOTVSMALL) { st |= F_ACTIVE; written = false; }
+                                else if (a.cellCount) atomicAdd(&a.cellCount[cell], 1);  // nothing left to move (stepFraction == 1)
+                            }
+                        }
+                        if (base + nIdle >= end) {   // the queue is empty: this warp moves on
+                            if (lane == 0) releaseSlot(a, S, barBase + 8 * s, winBase + uint32_t(s) * winBytes, 1);
+                            wq += 1;
+                        }
                     }
                 }
             }
         }
-        if (nStaged > 0 && !windowReady) windowReady = mbarTest(bar, 0);
         __syncwarp();
 
         // ---- section 1: one tetrahedron ----
         bool finished = false;
         double retVal = 1.0;
-        if (active) {
-            if (++guard > 200000) { keepParticle = false; atomicAdd(&a.counters->trackingFailures, 1ULL); }  // corrupt tet table: reported as an error by the host
-            if (!inCall) {
+        if (st & F_ACTIVE) {
+            const int mySlot = int((st >> F_SLOT_SHIFT) & 15u);
+            hitsAndGuard += 1;
+            if ((hitsAndGuard & 0xffffff) > 200000) { st &= ~F_KEEP; atomicAdd(&a.counters->trackingFailures, 1ULL); }  // corrupt tet table: reported as an error by the host
+            if (!(st & F_INCALL)) {
                 // dsmcParcel::move loop body up to the trackToFace call (DSMC/parcels/dsmcParcel.C:74-92)
-                V3 Utracking = U;
+                V3 Utracking = mk(myU[0], myU[MOVE_BLOCK], myU[2 * MOVE_BLOCK]);
                 if (constrained) {
 #pragma unroll
                     for (int d = 0; d < 3; ++d)
                         if (P.solutionD[d] == -1) { setComp(pos, d, P.centre[d]); setComp(Utracking, d, 0.0); }
                 }
-                endPosition = pos + tEnd * Utracking;  // dt = tEnd
+                const V3 endNew = pos + myU[3 * MOVE_BLOCK] * Utracking;  // dt = tEnd
+                myU[4 * MOVE_BLOCK] = endNew.x; myU[5 * MOVE_BLOCK] = endNew.y; myU[6 * MOVE_BLOCK] = endNew.z;
                 trackFraction = 0.0;
-                inCall = true; rescuePending = false; faceSet = false; faceBfi = -1;
+                st = (st | F_INCALL) & ~(F_RESCUE | F_FACESET); faceBfi = -1;
             }
+            const V3 endPosition = mk(myU[4 * MOVE_BLOCK], myU[5 * MOVE_BLOCK], myU[6 * MOVE_BLOCK]);
             TetRegs R;
-            const uint32_t rel = uint32_t(tet - tetBeg);
-            if (windowReady && rel < uint32_t(nStaged)) loadRecShared(win + rel * uint32_t(sizeof(TetRec)), R);
-            else loadRecGlobal(a.tets, tet, R);
+            {
+                const MoveSlot& S = sSlot[mySlot];
+                const uint32_t rel = uint32_t(tet - S.tetBeg);
+                const bool inWin = rel < uint32_t(S.nStaged);   // nStaged = 0: no window
+                if (inWin && !(st & F_WINREADY) && mbarTest(barBase + 8 * mySlot, uint32_t(S.copies - 1) & 1u)) st |= F_WINREADY;
+                if (inWin && (st & F_WINREADY)) loadRecShared(winBase + uint32_t(mySlot) * winBytes + rel * uint32_t(sizeof(TetRec)), R);
+                else loadRecGlobal(a.tets, tet, R);
+            }
             VisitOut v;
             v.code = VISIT_SLOW; v.triI = -1; v.needRescue = false;
-            if (keepParticle) {
-                if (!rescuePending) v = visitFast(R, pos, endPosition, trackFraction);
+            if (st & F_KEEP) {
+                if (!(st & F_RESCUE)) v = visitFast(R, pos, endPosition, trackFraction);
                 if (v.code == VISIT_SLOW) {
-                    const SlowOut so = slowVisit(a.tets, tet, pos, endPosition, trackFraction, rescuePending);
+                    const SlowOut so = slowVisit(a.tets, tet, pos, endPosition, trackFraction, (st & F_RESCUE) != 0);
                     pos = so.pos; trackFraction = so.trackFraction;
                     v.code = so.packed & 15; v.triI = ((so.packed >> 4) & 15) - 1; v.needRescue = (so.packed & 256) != 0;
                     if (v.code == VISIT_RESCUED) atomicAdd(&a.counters->rescues, 1ULL);   // rare: counted where it happens
                 }
                 if (v.code != VISIT_RESCUED) {
                     const bool onFace = v.triI == 0;
-                    faceSet = onFace;
+                    st = onFace ? (st | F_FACESET) : (st & ~F_FACESET);
                     faceBfi = (onFace && R.across < 0) ? (-1 - R.across) : -1;
                 }
             }
-            finished = !keepParticle || v.code == VISIT_RESCUED || v.code == VISIT_END;
+            finished = !(st & F_KEEP) || v.code == VISIT_RESCUED || v.code == VISIT_END;
             retVal = v.code == VISIT_RESCUED ? trackFraction : 1.0;
-            if (keepParticle && v.code == VISIT_MOVE) {
+            if ((st & F_KEEP) && v.code == VISIT_MOVE) {
                 if (v.triI > 0) {
                     // particle::tetNeighbour: enter the adjacent tet of the same cell
                     tet = v.triI == 1 ? R.nbr1 : (v.triI == 2 ? R.nbr2 : R.nbr3);
-                    rescuePending = v.needRescue;
+                    st = v.needRescue ? (st | F_RESCUE) : (st & ~F_RESCUE);
                 } else {
                     if (R.across >= 0) {
                         cell = R.nbrCell;  // internal face: the same face triangle seen from the other cell
@@ -477,19 +565,22 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                         switch (pt.type) {
                             case DSMCB200_PATCH_PROCESSOR:
                             case DSMCB200_PATCH_PROCESSORCYCLIC:
-                                switchProcessor = true;  // dsmcParcel::hitProcessorPatch
+                                st |= F_SWITCH;  // dsmcParcel::hitProcessorPatch
                                 break;
                             case DSMCB200_PATCH_SYMMETRYPLANE:
                             case DSMCB200_PATCH_SYMMETRY:
                             case DSMCB200_PATCH_WEDGE: {
                                 // transformProperties(I - 2.0*nf*nf), particleTemplates.C:1474-1522
+                                const V3 U = mk(myU[0], myU[MOVE_BLOCK], myU[2 * MOVE_BLOCK]);
                                 const V3 nf = R.N0;
                                 const V3 t2 = 2.0 * nf;
                                 const double xx = 1.0 - t2.x * nf.x, xy = 0.0 - t2.x * nf.y, xz = 0.0 - t2.x * nf.z;
                                 const double yx = 0.0 - t2.y * nf.x, yy = 1.0 - t2.y * nf.y, yz = 0.0 - t2.y * nf.z;
                                 const double zx = 0.0 - t2.z * nf.x, zy = 0.0 - t2.z * nf.y, zz = 1.0 - t2.z * nf.z;
-                                U = mk(xx * U.x + xy * U.y + xz * U.z, yx * U.x + yy * U.y + yz * U.z, zx * U.x + zy * U.y + zz * U.z);
-                                Udirty = true;
+                                myU[0] = xx * U.x + xy * U.y + xz * U.z;
+                                myU[MOVE_BLOCK] = yx * U.x + yy * U.y + yz * U.z;
+                                myU[2 * MOVE_BLOCK] = zx * U.x + zy * U.y + zz * U.z;
+                                st |= F_UDIRTY;
                                 break;
                             }
                             case DSMCB200_PATCH_CYCLIC: {
@@ -505,11 +596,15 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                             case DSMCB200_PATCH_WALL:
                             case DSMCB200_PATCH_PATCH:
                                 if (pt.model == DSMCB200_BND_DELETION) {
-                                    keepParticle = false;  // dsmcDeletionPatch::controlParticle
+                                    st &= ~F_KEEP;  // dsmcDeletionPatch::controlParticle
                                 } else if (pt.model != DSMCB200_BND_NONE) {
-                                    U = wallInteraction(a, i, a.p.typeId[i], bf.patch, a.wallsDue ? bf.measIndex : -1, bfi, R.N0, U,
-                                                            pt.linearT ? comp(pos, pt.depthAxis) : 0.0, &wallHits);
-                                    Udirty = true;
+                                    int wallHits = int(uint32_t(hitsAndGuard) >> 24);
+                                    const V3 U = wallInteraction(a, i, a.p.typeId[i], bf.patch, a.wallsDue ? bf.measIndex : -1, bfi, R.N0,
+                                                                 mk(myU[0], myU[MOVE_BLOCK], myU[2 * MOVE_BLOCK]),
+                                                                 pt.linearT ? comp(pos, pt.depthAxis) : 0.0, &wallHits);
+                                    hitsAndGuard = (hitsAndGuard & 0xffffff) | (wallHits << 24);
+                                    myU[0] = U.x; myU[MOVE_BLOCK] = U.y; myU[2 * MOVE_BLOCK] = U.z;
+                                    st |= F_UDIRTY;
                                 }
                                 break;
                             default:  // empty patches cannot be hit by constrained tracks
@@ -517,7 +612,7 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
                         }
                     }
                     if (v.needRescue) {
-                        rescuePending = true;  // correction towards the new tet's centre, then return trackFraction
+                        st |= F_RESCUE;  // correction towards the new tet's centre, then return trackFraction
                     } else {
                         retVal = trackFraction;
                         finished = true;
@@ -530,55 +625,63 @@ __global__ void __launch_bounds__(MOVE_BLOCK, MOVE_MIN_BLOCKS) moveKernel(const 
         // ---- section 2: trackToFace returned -- back in dsmcParcel::move (DSMC/parcels/dsmcParcel.C:92-118) ----
         if (finished) {
             if constexpr (TRACK) {
-                if (faceSet) trackFaceTransition(a, P, a.p.typeId[i], U, tet, faceBfi);  // dsmcParcel.C:106-111
+                if (st & F_FACESET) trackFaceTransition(a, P, a.p.typeId[i], mk(myU[0], myU[MOVE_BLOCK], myU[2 * MOVE_BLOCK]), tet, faceBfi);  // dsmcParcel.C:106-111
             }
-            if (keepParticle) {
+            double tEnd = myU[3 * MOVE_BLOCK];
+            if (st & F_KEEP) {
                 const double dt = tEnd * retVal;
                 tEnd -= dt;  // stepFraction = 1 - tEnd/deltaT is only consumed by a processor transfer: evaluated there
-                if (faceSet && faceBfi >= 0) {
+                myU[3 * MOVE_BLOCK] = tEnd;
+                if ((st & F_FACESET) && faceBfi >= 0) {
                     const int ptype = P.patch[a.bfaces[faceBfi].patch].type;
                     if (ptype == DSMCB200_PATCH_PROCESSOR || ptype == DSMCB200_PATCH_PROCESSORCYCLIC) {
-                        switchProcessor = true;  // the patch face of the transfer is faceBfi
+                        st |= F_SWITCH;  // the patch face of the transfer is faceBfi
                     }
                 }
             }
-            inCall = false;
-            if (!(keepParticle && !switchProcessor && tEnd > ROOTVSMALL)) {
+            st &= ~F_INCALL;
+            if (!((st & F_KEEP) && !(st & F_SWITCH) && tEnd > ROOTVSMALL)) {
                 // ---- this parcel is done: write it back ----
-                active = false;
-                if (!keepParticle) {
+                st &= ~F_ACTIVE;
+                written = true;
+                if (!(st & F_KEEP)) {
                     a.p.cell[i] = -1;
                     atomicAdd(&a.counters->deleted, 1ULL);
-                } else if (switchProcessor) {
-                    packMigrant(a, P, i, faceBfi, tet, pos, U, 1.0 - tEnd / deltaT);
+                } else if (st & F_SWITCH) {
+                    packMigrant(a, P, i, faceBfi, tet, pos, mk(myU[0], myU[MOVE_BLOCK], myU[2 * MOVE_BLOCK]), 1.0 - tEnd / deltaT);
                     a.p.cell[i] = -1;
                 } else {
                     a.p.px[i] = pos.x; a.p.py[i] = pos.y; a.p.pz[i] = pos.z;
                     a.p.cell[i] = cell;
                     a.p.tet[i] = tet;
-                    if (Udirty) { a.p.ux[i] = U.x; a.p.uy[i] = U.y; a.p.uz[i] = U.z; }
+                    if (st & F_UDIRTY) { a.p.ux[i] = myU[0]; a.p.uy[i] = myU[MOVE_BLOCK]; a.p.uz[i] = myU[2 * MOVE_BLOCK]; }
                     if (a.cellCount) atomicAdd(&a.cellCount[cell], 1);
                 }
             }
         }
+        // parcels that left in this iteration are taken off their entries: one atomic per slot
+        if (written) {
+            const int mySlot = int((st >> F_SLOT_SHIFT) & 15u);
+            const unsigned grp = __match_any_sync(__activemask(), mySlot);
+            if (lane == __ffs(grp) - 1) releaseSlot(a, &sSlot[mySlot], barBase + 8 * mySlot, winBase + uint32_t(mySlot) * winBytes, __popc(grp));
+        }
     }
-    // the window must have landed before the block's shared memory is released
-    if (threadIdx.x == 0 && nStaged > 0) while (!windowReady) windowReady = mbarTest(bar, 0);
 }
 
+size_t moveSharedBytes(int32_t stageTets) { return 64 + MOVE_NBUF * sizeof(MoveSlot) + size_t(MOVE_SCRATCH) * MOVE_BLOCK * 8 + size_t(MOVE_NBUF) * stageTets * sizeof(TetRec); }
+int32_t moveMaxStageTets() { return int32_t((MOVE_SMEM_BUDGET - 64 - MOVE_NBUF * sizeof(MoveSlot) - size_t(MOVE_SCRATCH) * MOVE_BLOCK * 8) / (MOVE_NBUF * sizeof(TetRec))); }
+
 cudaError_t launchMove(const MoveArgs& a, cudaStream_t s) {
-    const int32_t tailBlocks = a.tailEnd > a.tailBeg ? (a.tailEnd - a.tailBeg + MOVE_PMAX - 1) / MOVE_PMAX : 0;
-    const int32_t grid = a.nPlanBlocks + tailBlocks;
-    if (grid <= 0) return cudaSuccess;
-    const size_t smem = a.nPlanBlocks > 0 ? 16 + size_t(a.stageTets) * sizeof(TetRec) : 16;
+    if (a.gridBlocks <= 0) return cudaSuccess;
+    const size_t smem = moveSharedBytes(a.stageTets);
     static bool attrSet = false;
     if (!attrSet) {
-        cudaFuncSetAttribute(moveKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64);
-        cudaFuncSetAttribute(moveKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64);
+        cudaFuncSetAttribute(moveKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(moveKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attrSet = true;
     }
-    if (a.faceFlux) moveKernel<true><<<grid, MOVE_BLOCK, smem, s>>>(a);
-    else moveKernel<false><<<grid, MOVE_BLOCK, smem, s>>>(a);
+    if (a.faceFlux) moveKernel<true><<<a.gridBlocks, MOVE_BLOCK, smem, s>>>(a);
+    else moveKernel<false><<<a.gridBlocks, MOVE_BLOCK, smem, s>>>(a);
     return cudaGetLastError();
 }
 
