@@ -33,6 +33,11 @@ namespace {
 #define MOVE_BLOCK_SZ 512
 #endif
 constexpr int MOVE_BLOCK = MOVE_BLOCK_SZ;   // one persistent block per SM
+#ifndef MOVE_BATCH_SZ
+#define MOVE_BATCH_SZ 64
+#endif
+constexpr int MOVE_BATCH = MOVE_BATCH_SZ;   // parcels a warp takes from the block's queue at a time
+constexpr int MOVE_WARPSTATE = 16 * (MOVE_BLOCK / 32);   // bytes: per-warp queue piece
 constexpr int MOVE_SCRATCH = 7;             // doubles of per-thread shared scratch
 #ifndef MOVE_SMEM_KB
 #define MOVE_SMEM_KB 227
@@ -403,7 +408,12 @@ __device__ __noinline__ void armSlot(const MoveArgs& a, MoveSlot* S, uint32_t ba
 __device__ __forceinline__ void releaseSlot(const MoveArgs& a, MoveSlot* S, uint32_t bar, uint32_t win, int32_t n) {
     if (atomicSub(&S->pending, n) == n) {
         const int32_t c = S->copies;
-        if (c > 0) while (!mbarTest(bar, uint32_t(c - 1) & 1u)) {}
+        if (c > 0) {
+            int32_t polls = 0;
+            while (!mbarTest(bar, uint32_t(c - 1) & 1u)) {
+                if (++polls > (1 << 26)) { atomicAdd(&a.counters->trackingFailures, 1ULL << 32); break; }   // watchdog, see the refill section
+            }
+        }
         armSlot(a, S, bar, win, S->seq + MOVE_NBUF);
     }
 }
@@ -413,9 +423,9 @@ __global__ void __launch_bounds__(MOVE_BLOCK, 1) moveKernel(const __grid_constan
     extern __shared__ __align__(16) unsigned char smRaw[];
     // layout: [0, 8 NBUF) mbarriers | slots | per-thread scratch U.xyz, tEnd | windows
     MoveSlot* sSlot = reinterpret_cast<MoveSlot*>(smRaw + 64);
-    double* sScratch = reinterpret_cast<double*>(smRaw + 64 + MOVE_NBUF * sizeof(MoveSlot));
+    double* sScratch = reinterpret_cast<double*>(smRaw + 64 + MOVE_NBUF * sizeof(MoveSlot) + MOVE_WARPSTATE);
     const uint32_t barBase = smemAddr(smRaw);
-    const uint32_t winBase = barBase + 64 + MOVE_NBUF * uint32_t(sizeof(MoveSlot)) + MOVE_SCRATCH * MOVE_BLOCK * 8;
+    const uint32_t winBase = barBase + 64 + MOVE_NBUF * uint32_t(sizeof(MoveSlot)) + MOVE_WARPSTATE + MOVE_SCRATCH * MOVE_BLOCK * 8;
     const uint32_t winBytes = uint32_t(a.stageTets) * uint32_t(sizeof(TetRec));
     const DevParams& P = *a.P;
     const unsigned FULL = 0xffffffffu;
@@ -436,6 +446,10 @@ __global__ void __launch_bounds__(MOVE_BLOCK, 1) moveKernel(const __grid_constan
 
     // warp-uniform: the entry this warp draws parcels from
     int32_t wq = 0;             // its sequence number
+    // the warp's private piece of a queue {next, end, slot} lives in shared memory (registers are for the parcels)
+    volatile int32_t* const wPiece = reinterpret_cast<volatile int32_t*>(smRaw + 64 + MOVE_NBUF * sizeof(MoveSlot)) + 4 * (threadIdx.x >> 5);
+    if (lane == 0) { wPiece[0] = 0; wPiece[1] = 0; wPiece[2] = 0; wPiece[3] = 0; }
+    __syncwarp();
     bool listDone = false;      // the end of the work list has been reached
 
     // per-lane parcel state (U and tEnd live in shared memory: they are touched once per trackToFace call)
@@ -452,13 +466,14 @@ __global__ void __launch_bounds__(MOVE_BLOCK, 1) moveKernel(const __grid_constan
     // Every lane runs through every section of the loop body and the sections are separated by __syncwarp(), so
     // the warp is converged again at each section head whatever happened in the (divergent) section before it.
     while (true) {
-        // ---- section 0: refill idle lanes from the entry the warp is drawing from ----
+        // ---- section 0: refill idle lanes.  The warp holds a private piece [wNext, wEnd) of the queue of slot wSlot and takes the next
+        // piece (one shared atomic per MOVE_BATCH parcels) when that runs out ----
         bool written = false;   // this lane's parcel left the kernel in this iteration (counted at the end of the body)
         const unsigned idle = __ballot_sync(FULL, !(st & F_ACTIVE));
         if (idle) {
-            if (listDone) {
-                if (idle == FULL) break;
-            } else {
+            int32_t wNext = wPiece[0], wEnd = wPiece[1];
+            __syncwarp();
+            if (wNext >= wEnd && !listDone) {
                 const int s = wq % MOVE_NBUF;
                 MoveSlot* const S = &sSlot[s];
                 int32_t sq;
@@ -468,35 +483,54 @@ __global__ void __launch_bounds__(MOVE_BLOCK, 1) moveKernel(const __grid_constan
                     if (S->nStaged < 0) {
                         listDone = true;
                     } else {
-                        const int nIdle = __popc(idle);
                         int32_t base = 0;
-                        if (lane == 0) base = atomicAdd(&S->head, nIdle);
+                        if (lane == 0) base = atomicAdd(&S->head, MOVE_BATCH);
                         base = __shfl_sync(FULL, base, 0);
-                        const int32_t mine = base + __popc(idle & ((1u << lane) - 1u));
-                        if (!(st & F_ACTIVE) && mine < end) {
-                            i = mine;
-                            st = F_KEEP | (uint32_t(s) << F_SLOT_SHIFT);
-                            cell = a.p.cell[i];
-                            written = true;
-                            if (cell >= 0) {
-                                tet = a.p.tet[i];
-                                pos = mk(a.p.px[i], a.p.py[i], a.p.pz[i]);
-                                myU[0] = a.p.ux[i]; myU[MOVE_BLOCK] = a.p.uy[i]; myU[2 * MOVE_BLOCK] = a.p.uz[i];
-                                const double stepFraction = (a.sfTail != nullptr && i >= a.tailStart) ? a.sfTail[i - a.tailStart] : 0.0;
-                                const double tEnd = (1.0 - stepFraction) * deltaT;
-                                myU[3 * MOVE_BLOCK] = tEnd;
-                                faceBfi = -1;
-                                hitsAndGuard = 0;
-                                if (tEnd > ROOTVSMALL) { st |= F_ACTIVE; written = false; }
-                                else if (a.cellCount) atomicAdd(&a.cellCount[cell], 1);  // nothing left to move (stepFraction == 1)
-                            }
-                        }
-                        if (base + nIdle >= end) {   // the queue is empty: this warp moves on
-                            if (lane == 0) releaseSlot(a, S, barBase + 8 * s, winBase + uint32_t(s) * winBytes, 1);
+                        wNext = base; wEnd = min(base + MOVE_BATCH, end);
+                        if (lane == 0) { wPiece[0] = wNext; wPiece[1] = wEnd; wPiece[2] = s; wPiece[3] = 0; }
+                        __syncwarp();
+                        if (base + MOVE_BATCH >= end) {   // the queue is empty after this piece: this warp moves on (its piece stays counted
+                            if (lane == 0) releaseSlot(a, S, barBase + 8 * s, winBase + uint32_t(s) * winBytes, 1);   // in `pending` through its parcels)
                             wq += 1;
                         }
                     }
+                } else {
+                    // not armed yet.  A watchdog bounds the wait: a protocol error must end as an error code, not as a hung device
+                    const int32_t c = wPiece[3] + 1;
+                    __syncwarp();
+                    if (lane == 0) wPiece[3] = c;
+                    if (c > (1 << 22)) {
+                        listDone = true;
+                        if (lane == 0) atomicAdd(&a.counters->trackingFailures, 1ULL << 32);
+                    }
                 }
+            }
+            if (wNext < wEnd) {
+                const int32_t mine = wNext + __popc(idle & ((1u << lane) - 1u));
+                const int wSlot = wPiece[2];
+                __syncwarp();
+                if (lane == 0) wPiece[0] = wNext + __popc(idle);
+                if (!(st & F_ACTIVE) && mine < wEnd) {
+                    i = mine;
+                    st = F_KEEP | (uint32_t(wSlot) << F_SLOT_SHIFT);
+                    // the whole row at once: one memory latency (a deleted parcel, cell < 0, only occurs in the unsorted tail)
+                    cell = a.p.cell[i];
+                    tet = a.p.tet[i];
+                    pos = mk(a.p.px[i], a.p.py[i], a.p.pz[i]);
+                    const V3 U = mk(a.p.ux[i], a.p.uy[i], a.p.uz[i]);
+                    const double stepFraction = (a.sfTail != nullptr && i >= a.tailStart) ? a.sfTail[i - a.tailStart] : 0.0;
+                    const double tEnd = (1.0 - stepFraction) * deltaT;
+                    myU[0] = U.x; myU[MOVE_BLOCK] = U.y; myU[2 * MOVE_BLOCK] = U.z; myU[3 * MOVE_BLOCK] = tEnd;
+                    faceBfi = -1;
+                    hitsAndGuard = 0;
+                    written = true;
+                    if (cell >= 0) {
+                        if (tEnd > ROOTVSMALL) { st |= F_ACTIVE; written = false; }
+                        else if (a.cellCount) atomicAdd(&a.cellCount[cell], 1);  // nothing left to move (stepFraction == 1)
+                    }
+                }
+            } else if (listDone && idle == FULL) {
+                break;
             }
         }
         __syncwarp();
@@ -668,8 +702,8 @@ __global__ void __launch_bounds__(MOVE_BLOCK, 1) moveKernel(const __grid_constan
     }
 }
 
-size_t moveSharedBytes(int32_t stageTets) { return 64 + MOVE_NBUF * sizeof(MoveSlot) + size_t(MOVE_SCRATCH) * MOVE_BLOCK * 8 + size_t(MOVE_NBUF) * stageTets * sizeof(TetRec); }
-int32_t moveMaxStageTets() { return int32_t((MOVE_SMEM_BUDGET - 64 - MOVE_NBUF * sizeof(MoveSlot) - size_t(MOVE_SCRATCH) * MOVE_BLOCK * 8) / (MOVE_NBUF * sizeof(TetRec))); }
+size_t moveSharedBytes(int32_t stageTets) { return 64 + MOVE_NBUF * sizeof(MoveSlot) + MOVE_WARPSTATE + size_t(MOVE_SCRATCH) * MOVE_BLOCK * 8 + size_t(MOVE_NBUF) * stageTets * sizeof(TetRec); }
+int32_t moveMaxStageTets() { return int32_t((MOVE_SMEM_BUDGET - 64 - MOVE_NBUF * sizeof(MoveSlot) - MOVE_WARPSTATE - size_t(MOVE_SCRATCH) * MOVE_BLOCK * 8) / (MOVE_NBUF * sizeof(TetRec))); }
 
 cudaError_t launchMove(const MoveArgs& a, cudaStream_t s) {
     if (a.gridBlocks <= 0) return cudaSuccess;
