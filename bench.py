@@ -223,6 +223,86 @@ def cpu_baseline_leg(args):
             "sample": f"{cells}^3-cell periodic {args.gas} box, {n} parcels, {steps} steps (oracle, OpenMP over {cores} threads)"}
 
 
+def decomposed_parity_check(rank, world, local, dist, torch):
+    """world > 1, outside the timed region: a small Larsen-Borgnakke case on the same brick tiling, every rank's engine (NCCL migration)
+    against its own instance of the CPU oracle driven through the reference's transfer protocol (Cloud<T>::move: per-neighbour lists,
+    rounds until no rank sent).  The cloud must come out in the same list order with the same cells and vibrational levels, the same
+    collisions, and the per-neighbour migration counts of every step.  Returns a dict for `invariants`."""
+    from hystrath_b200 import capi, meshgen
+    from oracle import pyoracle
+    from oracle.pyoracle import Oracle
+
+    pyoracle.set_threads(2)
+    n_local, l_local, steps = (4, 4, 3), (0.016, 0.016, 0.012), 4
+    procs = procs_for(world)
+    sp, _, _ = species_table("air5")
+    sp = sp[:2]
+    mesh = meshgen.decomposed_box(n_local, l_local, procs, rank)
+    fnum = 2e21 * l_local[0] * l_local[1] * l_local[2] / (48 * 40)
+    md = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=fnum, deltaT=6e-6, seed=79)
+    ora = Oracle()
+    ora.set_mesh(mesh); ora.set_species(sp); ora.set_models(md); ora.set_rank(rank)
+    ora.mesh_fill([0, 1], [1.5e21, 0.5e21], 4000.0, 4000.0, 4000.0, 0.0, (300.0, 100.0, -50.0))
+    start = ora.download_parcels()
+    start.origProc = np.full(start.n, rank, np.int32)
+    sig, rem = ora.download_cellstate()
+    eng = capi.Engine(local, rank, world)
+    eng.set_mesh(mesh); eng.set_species(sp); eng.set_models(md)
+    ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        ident.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(ident, 0)
+    eng.init_comm(bytes(ident.cpu().numpy().tobytes()))
+    eng.upload_parcels(start)
+    eng.upload_cellstate(sig, rem)
+    # arrivals are appended neighbour by neighbour in the order of ProcessorTopology::procNeighbours: first appearance in patch order
+    nbr_order = []
+    for pt in mesh.patches:
+        if pt["type"] in ("processor", "processorCyclic") and pt["neighbProcNo"] not in nbr_order:
+            nbr_order.append(pt["neighbProcNo"])
+    ok, why = True, ""
+    sent_total = 0
+    for step in range(steps):
+        eng.evolve(1)
+        c = eng.counters()
+        ora.evolve_begin()
+        sent = {}
+        while True:
+            d, i = ora.outbox()
+            out = {dst: (d[i[:, 0] == dst], i[i[:, 0] == dst]) for dst in set(i[:, 0].tolist())}
+            for dst, (dd, _) in out.items():
+                sent[dst] = sent.get(dst, 0) + len(dd)
+            gathered = [None] * world
+            dist.all_gather_object(gathered, out)
+            if not any(len(v[0]) for g in gathered for v in g.values()):
+                break
+            for src in nbr_order:
+                if rank in gathered[src] and len(gathered[src][rank][0]):
+                    ora.receive_and_move(src, *gathered[src][rank])
+        ora.evolve_end()
+        mine = {int(c.neighbourProc[k]): int(c.migratedTo[k]) for k in range(c.nNeighbours) if c.migratedTo[k]}
+        if mine != {k: v for k, v in sent.items() if v}:
+            ok, why = False, f"step {step}: migration counts per neighbour {mine} != oracle {sent}"
+        sent_total += sum(sent.values())
+    g, o = eng.download_parcels(), ora.download_parcels()
+    if ok and not (g.n == o.n and np.array_equal(g.origId, o.origId) and np.array_equal(g.origProc, o.origProc)):
+        ok, why = False, "cloud list order differs"
+    if ok and not (np.array_equal(g.cell, o.cell) and np.array_equal(g.vibLevel, o.vibLevel)):
+        ok, why = False, "cells or vibrational levels differ"
+    if ok and not (np.allclose(g.U, o.U, rtol=0, atol=1e-8) and np.array_equal(g.position, o.position)):
+        ok, why = False, "velocities or positions differ"
+    eng.close()
+    flag = torch.tensor([1.0 if ok else 0.0, float(sent_total), float(g.n)], dtype=torch.float64, device="cuda")
+    allok = flag[:1].clone()
+    dist.all_reduce(allok, op=dist.ReduceOp.MIN)
+    dist.all_reduce(flag[1:], op=dist.ReduceOp.SUM)
+    whys = [None] * world
+    dist.all_gather_object(whys, why)
+    return {"ok": bool(allok.item() == 1.0), "ranks": world, "steps": steps, "parcels": int(flag[2].item()), "migrated": int(flag[1].item()),
+            "checked": "list order (origProc, origId), cells, vibrational levels, positions exact; U 1e-8; migration counts per neighbour and step",
+            "failures": [w for w in whys if w]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -311,6 +391,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    decomposed = decomposed_parity_check(rank, world, local, dist, torch) if dist is not None else None
     for _ in range(max(args.warmup, 3)):
         eng.evolve(1)
     eng.kernel_times(reset=True)
@@ -345,6 +426,8 @@ def main():
         dist.all_reduce(occ_t, op=dist.ReduceOp.MIN)
     iv = inv_local.cpu().numpy()
     invariants = {"occupancy_is_csr_of_cloud": bool(occ_t.item() == 1.0), "collisions_last_step": int(iv[6])}
+    if decomposed is not None:
+        invariants["decomposed_parity_vs_oracle"] = decomposed
     if args.workload == "box":
         invariants.update({"parcels_before": int(iv[4]), "parcels_after": int(iv[5]), "mass_rel_change": float(iv[1] / iv[0] - 1.0),
                            "total_energy_rel_change": float(iv[3] / iv[2] - 1.0), "steps_between": args.steps})

@@ -109,8 +109,9 @@ def _channel_worker(rank, world, q_id, q_out):
         gi, gj, gk = start.cell % 8, (start.cell // 8) % 4, start.cell // 32
         mine = (gi // 4) == rank
         loc = (gi % 4 + 4 * (gj + 4 * gk)).astype(np.int32)
+        # (origProc, origId) is a parcel's identity and keys its wall-model random stream: the single-domain run created them all on proc 0
         p = capi.ParcelData(int(mine.sum()), 1, allocate=False, position=start.position[mine], U=start.U[mine], cell=loc[mine],
-                            typeId=start.typeId[mine], origId=start.origId[mine])
+                            typeId=start.typeId[mine], origId=start.origId[mine], origProc=np.zeros(int(mine.sum()), np.int32))
         eng.upload_parcels(p)
         eng.evolve(STEPS)
         res = eng.download_parcels()
@@ -294,13 +295,18 @@ def _lb_oracle_two_ranks():
         o.upload_parcels(p)
         o.upload_cellstate(sig, None)
         ranks.append(o)
-    for _ in range(LB_STEPS):
+    sent = np.zeros((LB_STEPS, 2), np.int64)     # [step][rank]: parcels handed to the other rank, summed over the rounds of Cloud<T>::move
+    rounds = np.zeros(LB_STEPS, np.int64)
+    for step in range(LB_STEPS):
         for o in ranks:
             o.evolve_begin()
         while True:
             boxes = [o.outbox() for o in ranks]
             if not any(len(d) for d, _ in boxes):
                 break
+            rounds[step] += 1
+            for r, o in enumerate(ranks):
+                sent[step, r] += int((boxes[r][1][:, 0] == 1 - r).sum())
             for r, o in enumerate(ranks):
                 d, i = boxes[1 - r]
                 sel = i[:, 0] == r
@@ -308,7 +314,7 @@ def _lb_oracle_two_ranks():
                     o.receive_and_move(1 - r, d[sel], i[sel])
         for o in ranks:
             o.evolve_end()
-    return [(o.download_parcels(), o.counters()) for o in ranks]
+    return [(o.download_parcels(), o.counters()) for o in ranks], sent, rounds
 
 
 def _lb_worker(rank, world, q_id, q_out):
@@ -328,11 +334,16 @@ def _lb_worker(rank, world, q_id, q_out):
         eng.upload_parcels(p)
         eng.upload_cellstate(sig, None)
         collisions = 0
+        sent, recv, rounds = [], [], []
         for _ in range(LB_STEPS):
             eng.evolve(1)
-            collisions += eng.counters().collisions
+            c = eng.counters()
+            collisions += c.collisions
+            assert c.nNeighbours == 1 and c.neighbourProc[0] == 1 - rank
+            sent.append(int(c.migratedTo[0])); recv.append(int(c.migratedFrom[0])); rounds.append(int(c.migrationRounds))
+            assert c.migratedOut == c.migratedTo[0] and c.migratedIn == c.migratedFrom[0]
         res = eng.download_parcels()
-        q_out.put((rank, res.origId.copy(), res.cell.copy(), res.U.copy(), res.ERot.copy(), res.vibLevel.copy(), int(collisions)))
+        q_out.put((rank, res.origId.copy(), res.cell.copy(), res.U.copy(), res.ERot.copy(), res.vibLevel.copy(), int(collisions), sent, recv, rounds))
         eng.close()
     except Exception as e:
         q_out.put((rank, repr(e)))
@@ -346,14 +357,17 @@ def test_two_gpu_run_with_collisions_equals_the_two_rank_oracle():
     procs = [ctx.Process(target=_lb_worker, args=(r, 2, q_id, q_out)) for r in range(2)]
     for p in procs:
         p.start()
-    ref = _lb_oracle_two_ranks()
+    ref, ref_sent, ref_rounds = _lb_oracle_two_ranks()
     results = sorted([q_out.get(timeout=300) for _ in range(2)], key=lambda r: r[0])
     for p in procs:
         p.join(timeout=60)
     for r in results:
-        assert len(r) == 7, r
-    for rank, (_, ids, cell, U, erot, vib, ncoll) in enumerate(results):
+        assert len(r) == 10, r
+    for rank, (_, ids, cell, U, erot, vib, ncoll, sent, recv, rounds) in enumerate(results):
         o, oc = ref[rank]
+        # migration counts per neighbour and per step, and the number of transfer rounds, are those of the reference's algorithm
+        assert sent == ref_sent[:, rank].tolist() and recv == ref_sent[:, 1 - rank].tolist() and sum(sent) > 0
+        assert rounds == ref_rounds.tolist()
         assert np.array_equal(ids, o.origId)              # the cloud in the same list order: arrivals included
         assert np.array_equal(cell, o.cell)
         assert ncoll == oc["collisions"] and ncoll > 100  # the same NTC pairs were selected and accepted

@@ -33,7 +33,14 @@ def test_couette_profiles_match_the_shipped_dsmcfoam_fields():
                         typeId=g["typeId"], vibLevel=g["vibLevel"], origId=g["origId"])
     eng.upload_parcels(p)
     eng.upload_cellstate(g["dsmcSigmaTcRMax"], None)
-    eng.evolve(STEPS)
+    # the run in BATCHES pieces: the scatter of the pieces gives the statistical error of the run's own averages (batch means; it
+    # contains the step-to-step correlation that 1/sqrt(N nSteps), dsmcVolFields.C:1867-1872, leaves out)
+    BATCHES = 16
+    snaps = []
+    for _ in range(BATCHES):
+        eng.evolve(STEPS // BATCHES)
+        a_, c_, n_ = eng.accumulators()
+        snaps.append((a_.copy(), c_.copy(), n_))
     assert eng.num_parcels() == 47583                      # closed box: walls re-emit, cyclic sides wrap
     wall = eng.wall_accumulators()                         # [10 wall faces][2 species][nWallQ]: upperWall first (patch-model order)
     _, _, face_centres, face_areas, _ = eng.geometry()
@@ -49,10 +56,44 @@ def test_couette_profiles_match_the_shipped_dsmcfoam_fields():
     def rows(a):
         return np.array([a[j == k].mean() for k in range(100)])
 
+    # per-batch fields -> z scores of the run's row averages against the shipped profile.  The shipped fields average 450 000 steps
+    # (endTime 5, resetAtOutputUntilTime 0.5, deltaT 1e-5: their own error is 1/sqrt(112) of this run's and is added in quadrature).
+    batch_fields = []
+    prev = (np.zeros_like(snaps[0][0]), np.zeros_like(snaps[0][1]), 0.0)
+    for a_, c_, n_ in snaps:
+        batch_fields.append(fields_ref.derive(a_ - prev[0], c_ - prev[1], n_ - prev[2], spd, [0, 1], fnum, cv, deltaT=1e-5))
+        prev = (a_, c_, n_)
+
+    def zscores(name, ref_rows, comp=None):
+        per = np.array([rows(b[name] if comp is None else b[name][:, comp]) for b in batch_fields])      # [batch][row]
+        sigma = per.std(axis=0, ddof=1) / np.sqrt(BATCHES) * np.sqrt(1.0 + STEPS / 450000.0)
+        z = (per.mean(axis=0) - ref_rows) / sigma
+        allrows = per.mean(axis=1)                                                                         # [batch]: profile average
+        zmean = (allrows.mean() - ref_rows.mean()) / (allrows.std(ddof=1) / np.sqrt(BATCHES))
+        naive = 1.0 / np.sqrt(rows(f["dsmcNMean"]) * 5 * STEPS)    # the reference's own estimate for a row of 5 cells (density error)
+        return z, zmean, sigma, naive
+
     # translational temperature: 2075 K .. 2916 K across the gap (temperature jump at both walls included)
     T, Tg = rows(f["Ttra"]), rows(g["Ttra_mixture"])
     assert Tg.min() < 2100 and Tg.max() > 2890
     assert np.abs(T / Tg - 1).max() < 0.02 and abs((T / Tg).mean() - 1) < 0.004   # measured: 0.29 % and 0.02 %
+    # ... and within the statistical error bars: north_star's 3 sigma, row by row.  100 rows: a handful beyond 3 sigma is what noise
+    # alone does (0.27 % each), a bias would push the mean square of z well above 1
+    report = []
+    for name, ref_rows, comp in (("Ttra", Tg, None), ("Trot", rows(g["Trot_mixture"]), None), ("rhoN", rows(g["rhoN_mixture"]), None),
+                                 ("UMean", rows(g["U_mixture"][:, 0]), 0)):
+        z, zmean, sigma, naive = zscores(name, ref_rows, comp)
+        report.append("%s: rms z %.2f, |z|>3 in %d rows, z of the profile mean %+.2f, sigma/ref %.2e (1/sqrt(N nSteps) %.2e)" % (
+            name, np.sqrt(np.mean(z ** 2)), int((np.abs(z) > 3).sum()), zmean, np.median(sigma / np.abs(ref_rows).clip(1e-300)), np.median(naive)))
+        if name == "UMean":
+            # the slip-velocity profile carries a +2 m/s offset against the shipped one (0.7 % of the wall speed, seen since round 1 and
+            # not explained by noise): reported, bounded, not claimed to be within 3 sigma
+            assert np.mean(z ** 2) < 25.0, report[-1]
+            continue
+        assert np.mean(z ** 2) < 3.0, report[-1]
+        assert (np.abs(z) > 3).mean() <= 0.06, report[-1]
+        assert np.abs(z).max() < 5.0, report[-1]
+    print("couette rows vs shipped, statistical error from 16 batch means:\n  " + "\n  ".join(report))
     # rotational temperature follows (Z_rot = 5)
     R, Rg = rows(f["Trot"]), rows(g["Trot_mixture"])
     assert np.abs(R / Rg - 1).max() < 0.03 and abs((R / Rg).mean() - 1) < 0.006
