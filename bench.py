@@ -164,6 +164,13 @@ def run_reference(args):
 
 
 def workload_config(args, cells_per_gpu, parcels_per_gpu):
+    if getattr(args, "workload", "box") == "wedge":
+        return {"workload": "5-species air (N2,O2,NO,N,O) Larsen-Borgnakke over a sharp 15-degree wedge at the orion107kmNR free stream "
+                            "(6053.4 m/s, 217.63 K, Mach 20; BASELINE configs[2]): %s cells, ~%d parcels per GPU, diffuse 1000 K wall, "
+                            "free-stream inflow + deletion, symmetry planes" % (args.wedge, parcels_per_gpu),
+                "cells_per_gpu": cells_per_gpu, "parcels_per_gpu": parcels_per_gpu, "parcels_per_cell": args.ppc, "gas": "air5",
+                "collision_model": "LarsenBorgnakkeVariableHardSphere", "partition": "%d slab(s) along x (decomposePar simple)" % args.gpus,
+                "l2_policy": "inputs larger than L2 (parcel state >> 126 MB), no flush needed"}
     if getattr(args, "workload", "box") == "cylinder":
         return {"workload": "2-D Mach-10 argon flow over a cylinder (BASELINE configs[1], Lofthouse): O-grid %s cells, ~%d parcels, VHS, "
                             "diffuse 500 K wall, free-stream inflow + deletion" % (args.cyl, parcels_per_gpu),
@@ -188,6 +195,20 @@ def cpu_baseline_leg(args):
     from oracle.pyoracle import Oracle
 
     cores = pyoracle.set_threads(host_cores())
+    if getattr(args, "workload", "box") == "wedge":
+        from hystrath_b200 import cases
+
+        mesh, sp, md, fill = cases.air_wedge(200, 100, 2, 25)
+        o = Oracle()
+        o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
+        o.mesh_fill(fill["type_ids"], fill["number_densities"], fill["Ttra"], fill["Trot"], fill["Tvib"], 0.0, fill["velocity"])
+        n = o.num_parcels()
+        o.evolve(1)
+        t0 = time.perf_counter()
+        o.evolve(args.cpu_steps)
+        dt = time.perf_counter() - t0
+        return {"value": n * args.cpu_steps / dt, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+                "sample": f"200x100x2-cell wedge, {n} parcels, {args.cpu_steps} steps (oracle, OpenMP over {cores} threads)"}
     if getattr(args, "workload", "box") == "cylinder":
         from hystrath_b200 import cases
 
@@ -309,8 +330,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dsmcb200", choices=["dsmcb200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("DSMCB200_BENCH_WORKLOAD", "box"), choices=["box", "cylinder"],
-                    help="box: BASELINE configs[4] weak-scaling periodic box (default, any N); cylinder: configs[1] Mach-10 argon cylinder (N=1)")
+    ap.add_argument("--workload", default=os.environ.get("DSMCB200_BENCH_WORKLOAD", "box"), choices=["box", "cylinder", "wedge"],
+                    help="box: BASELINE configs[4] weak-scaling periodic box (default, any N); cylinder: configs[1] Mach-10 argon cylinder (N=1); "
+                         "wedge: configs[2] 5-species air over a hypersonic wedge (N > 1: the same case cut into N slabs along x, strong scaling)")
+    ap.add_argument("--wedge", default="2000x1000x4", help="wedge cells nx x ny x nz")
     ap.add_argument("--cyl", default="640x1250", help="cylinder O-grid cells nr x ntheta")
     ap.add_argument("--gas", default=os.environ.get("DSMCB200_BENCH_GAS", "air5"), choices=["argon", "air5"])
     ap.add_argument("--cells", type=int, default=int(os.environ.get("DSMCB200_BENCH_CELLS", "200")), help="cells per direction per GPU")
@@ -358,6 +381,15 @@ def main():
         args.gas = "argon"
         args.ppc = 25
         mesh, sp, md, fill = cases.lofthouse_cylinder(nr, nt, args.ppc)
+        tids, dens, Tfill, vfill = fill["type_ids"], fill["number_densities"], fill["Ttra"], fill["velocity"]
+        n_cells_gpu = mesh.n_cells
+    elif args.workload == "wedge":
+        from hystrath_b200 import cases
+
+        wx, wy, wz = (int(v) for v in args.wedge.split("x"))
+        args.gas = "air5"
+        args.ppc = 25
+        mesh, sp, md, fill = cases.air_wedge(wx, wy, wz, args.ppc, procs=world, rank=rank)
         tids, dens, Tfill, vfill = fill["type_ids"], fill["number_densities"], fill["Ttra"], fill["velocity"]
         n_cells_gpu = mesh.n_cells
     else:
@@ -432,6 +464,12 @@ def main():
         invariants.update({"parcels_before": int(iv[4]), "parcels_after": int(iv[5]), "mass_rel_change": float(iv[1] / iv[0] - 1.0),
                            "total_energy_rel_change": float(iv[3] / iv[2] - 1.0), "steps_between": args.steps})
 
+    if dist is not None:
+        # dsmcDynamicLoadBalancing::update (DSMC/dynamicLoadBalancing/dsmcDynamicLoadBalancing.C:100-149): max |n_rank - n_ideal| / n_ideal
+        counts = [None] * world
+        dist.all_gather_object(counts, int(eng.num_parcels()))
+        ideal = sum(counts) / world
+        invariants["load_imbalance"] = {"parcels_per_rank": counts, "maximum_imbalance_pct": 100.0 * max(abs(c - ideal) for c in counts) / ideal}
     tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
     ntot = torch.tensor([float(n_processed)], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -520,7 +558,7 @@ def main():
         line = {
             "metric": "particle-steps/s (move+sort+NTC collide+sample)", "value": value, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if args.workload == "wedge" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, n_cells_gpu, n_local),
             "roofline": roofline, "stages": stages,
             "kernel_ms_per_step": per_step, "wall_ms_per_step": 1e3 * wall / args.steps, "setup_s": setup_s,

@@ -598,7 +598,7 @@ int stageSort(dsmcb200_ctx* c, bool histogramDone) {
     int32_t nOut = 0;
     CK(cudaMemcpyAsync(&nOut, c->dCellOffset + nCells, 4, cudaMemcpyDeviceToHost, c->stream));
     { KT t(c, "scatterIndex"); CK(launchScatterIndex(src.cell, nIn, c->dCursor, c->dPerm, c->stream)); }
-    { KT t(c, "segmentSort"); CK(launchSegmentSort(c->dCellOffset, nCells, c->dPerm, c->dCounters, c->stream)); }
+    { KT t(c, "segmentSort"); CK(launchSegmentSort(c->dCellOffset, nCells, c->dPerm, c->dCounters, c->dCursor, c->stream)); }
     CK(cudaStreamSynchronize(c->stream));  // nOut
     ParcelArrays& dst = c->buf[1 - c->cur].a;
     { KT t(c, "gather"); CK(launchGather(src, dst, c->dPerm, c->dCellCentres, c->dOctKey, nOut, c->nModes, c->internal, c->stream)); }

@@ -87,6 +87,7 @@ struct DevCounters {
     int32_t nMig[MAX_NEIGHBOURS];
     int32_t nInserted;
     int32_t bigCells;  // cells handed from collideLaneKernel to collideBigCellsKernel this step
+    int32_t bigSortCells;  // cells handed from segmentSortKernel to bigSegmentSortKernel
 };
 
 // wall accumulator quantities per (measured face, species)
@@ -184,7 +185,7 @@ cudaError_t launchMovePlan(const MovePlanArgs& m, int32_t* scanScratch, cudaStre
 cudaError_t launchExclusiveScan(const int32_t* in, int32_t* out, int32_t* out2, int32_t n, int32_t* blockSums, cudaStream_t s);
 int32_t scanScratchInts(int32_t n);
 cudaError_t launchScatterIndex(const int32_t* cell, int32_t n, int32_t* cursor, int32_t* perm, cudaStream_t s);
-cudaError_t launchSegmentSort(const int32_t* cellOffset, int32_t nCells, int32_t* perm, DevCounters* c, cudaStream_t s);
+cudaError_t launchSegmentSort(const int32_t* cellOffset, int32_t nCells, int32_t* perm, DevCounters* c, int32_t* bigList, cudaStream_t s);
 cudaError_t launchGather(const ParcelArrays& src, const ParcelArrays& dst, const int32_t* perm, const double* cellCentres,
                          uint8_t* octKey, int32_t nOut, int32_t nModes, bool hasInternal, cudaStream_t s);
 cudaError_t launchHistogram(const int32_t* cell, int32_t n, int32_t* cellCount, cudaStream_t s);

@@ -7,6 +7,8 @@
 //   -> per-cell ordering of the scattered indices (restores list order => deterministic,
 //      stable result) -> payload gather into the second buffer.
 // All integer work: results are bit-exact by construction.
+#include <algorithm>
+
 #include "engine.h"
 
 namespace dsmc {
@@ -147,7 +149,7 @@ constexpr int SEG_SMEM = 1024;  // per warp
 }
 
 __global__ void __launch_bounds__(SEG_WARPS * 32) segmentSortKernel(const int32_t* __restrict__ cellOffset, int32_t nCells,
-                                                                    int32_t* __restrict__ perm, DevCounters* counters) {
+                                                                    int32_t* __restrict__ perm, DevCounters* counters, int32_t* __restrict__ bigList) {
     __shared__ int32_t sm[SEG_WARPS][SEG_SMEM];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int32_t nWarps = gridDim.x * SEG_WARPS;
@@ -174,17 +176,46 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) segmentSortKernel(const int32_
             }
             __syncwarp();
         } else {
-            // very large cells: global-memory rank sort in chunks is O(n^2); leave the atomic order and report it
-            if (lane == 0) atomicAdd(&counters->unsortedLargeCells, 1ULL);
+            // very large cells (a heat bath in one cell: 1e5 parcels) go to bigSegmentSortKernel, one block each
+            if (lane == 0) bigList[atomicAdd(&counters->bigSortCells, 1)] = c;
         }
     }
 }
 
-cudaError_t launchSegmentSort(const int32_t* cellOffset, int32_t nCells, int32_t* perm, DevCounters* c, cudaStream_t s) {
+// The index lists of the cells segmentSortKernel left: bitonic network with ascending comparators only (flip step + half cleaners),
+// so that a length that is not a power of two needs no padding -- a partner beyond the end counts as +infinity and never swaps.
+__global__ void __launch_bounds__(1024) bigSegmentSortKernel(const int32_t* __restrict__ cellOffset, const int32_t* __restrict__ bigList,
+                                                             int32_t* __restrict__ perm, const DevCounters* counters) {
+    const int32_t nBig = counters->bigSortCells;
+    for (int32_t ib = blockIdx.x; ib < nBig; ib += gridDim.x) {
+        const int32_t c = bigList[ib];
+        int32_t* const v = perm + cellOffset[c];
+        const int32_t n = cellOffset[c + 1] - cellOffset[c];
+        for (int32_t k = 2; (k >> 1) < n; k <<= 1) {
+            for (int32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                const int32_t l = i ^ (k - 1);
+                if (l > i && l < n) { const int32_t x = v[i], y = v[l]; if (x > y) { v[i] = y; v[l] = x; } }
+            }
+            __syncthreads();
+            for (int32_t j = k >> 2; j > 0; j >>= 1) {
+                for (int32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                    const int32_t l = i ^ j;
+                    if (l > i && l < n) { const int32_t x = v[i], y = v[l]; if (x > y) { v[i] = y; v[l] = x; } }
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// bigList: nCells ints of scratch (the scatter cursors are free by now)
+cudaError_t launchSegmentSort(const int32_t* cellOffset, int32_t nCells, int32_t* perm, DevCounters* c, int32_t* bigList, cudaStream_t s) {
     int grid = (nCells + SEG_WARPS - 1) / SEG_WARPS;
     if (grid > 148 * 16) grid = 148 * 16;
     if (grid < 1) grid = 1;
-    segmentSortKernel<<<grid, SEG_WARPS * 32, 0, s>>>(cellOffset, nCells, perm, c);
+    cudaMemsetAsync(&c->bigSortCells, 0, sizeof(int32_t), s);
+    segmentSortKernel<<<grid, SEG_WARPS * 32, 0, s>>>(cellOffset, nCells, perm, c, bigList);
+    bigSegmentSortKernel<<<std::min(nCells, 296), 1024, 0, s>>>(cellOffset, bigList, perm, c);
     return cudaGetLastError();
 }
 

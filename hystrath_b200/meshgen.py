@@ -142,7 +142,8 @@ def decomposed_box(n_local, lengths_local, procs, rank, outer=("cyclic", "cyclic
     """Brick `rank` of a procs=(px,py,pz) tiling of identical bricks (weak-scaling layout).
 
     outer[d] is the treatment of the global domain boundary in direction d: "cyclic" (periodic:
-    a same-rank cyclic pair when p==1, processorCyclic otherwise) or a (type, name) spec.
+    a same-rank cyclic pair when p==1, processorCyclic otherwise), a (type, name) spec for both ends, or a pair of
+    (type, name) specs ((lo), (hi)).
     """
     px, py, pz = procs
     rx, ry, rz = rank % px, (rank // px) % py, rank // (px * py)
@@ -169,9 +170,32 @@ def decomposed_box(n_local, lengths_local, procs, rank, outer=("cyclic", "cyclic
                     # separation of the receiving patch = C_send - C_recv
                     sep[d] = -total[d] if step > 0 else total[d]
                     sides[side] = ("processorCyclic", rank_of(c), tuple(sep))
+            elif isinstance(outer[d][0], (tuple, list)):
+                sides[side] = tuple(outer[d][0 if step < 0 else 1])
             else:
                 sides[side] = tuple(outer[d])
     return box_mesh(n_local, lengths_local, origin, sides, my_proc=rank)
+
+
+def wedge_mesh(n, length, height, depth, angle_deg, procs=1, rank=0):
+    """Hypersonic wedge (BASELINE configs[2]): a sharp wedge of half-angle `angle_deg` whose surface is the lower boundary of a
+    structured n = (nx, ny, nz) hexahedral mesh, a few cells deep in z.  The grid lines x = const stay vertical; the rows are
+    stretched between the ramp y = x tan(angle) and the top y = height, so every face is planar and the cells are general
+    (non axis-aligned) hexahedra.  Patches: `wedge` (wall, lower boundary), `flow` (patch: inlet x = 0, top, outlet x = length --
+    free-stream inflow + deletion), `sides` (symmetryPlane, z = 0 and z = depth).
+    procs > 1: brick `rank` of a decomposition into `procs` slabs along x (the `simple` method of decomposePar, equal cells per
+    slab -- the shock layer makes the parcel load per slab unequal), with processor patches between the slabs."""
+    nx, ny, nz = (int(v) for v in n)
+    if nx % procs:
+        raise ValueError("nx must be a multiple of the number of slabs")
+    outer = ((("patch", "flow"), ("patch", "flow")), (("wall", "wedge"), ("patch", "flow")), ("symmetryPlane", "sides"))
+    mesh = decomposed_box((nx // procs, ny, nz), (length / procs, height, depth), (procs, 1, 1), rank, outer=outer)
+    t = np.tan(np.radians(angle_deg))
+    x, y = mesh.points[:, 0], mesh.points[:, 1]
+    yb = x * t
+    mesh.points[:, 1] = yb + (height - yb) * (y / height)
+    mesh.wedge = dict(length=length, height=height, depth=depth, tan=t)
+    return mesh
 
 
 def cylinder_ogrid(nr, ntheta, r_in, r_out, thickness=None, grading=1.0):

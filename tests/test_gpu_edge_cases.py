@@ -132,3 +132,30 @@ def test_cloud_without_tet_indices_is_located_on_the_device():
     eng.evolve(2)
     assert eng.num_parcels() == n - 2
     eng.close()
+
+
+def test_cells_with_thousands_of_parcels_keep_list_order_and_collide_like_the_oracle():
+    """Cells far beyond the in-warp ordering pass (> 1024 parcels: the heatBath tutorials put 1e5 in one cell): the block-level sort
+    restores cloud-list order, so occupancy, NTC pairs and collision counts are those of the oracle, run after run."""
+    mesh = meshgen.box_mesh((2, 1, 1), (0.02, 0.01, 0.01))
+    sp = [H.argon()]
+    fnum = 1e20 * 0.02 * 0.01 * 0.01 / 5200.0
+    md = capi.build_models("VariableHardSphere", nEquivalentParticles=fnum, deltaT=4e-6, seed=321)
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    ora.set_reorder(True)
+    start = H.same_start(eng, ora, [0], [1e20], 300.0)
+    assert start.n > 4500 and np.bincount(start.cell).min() > 2000
+    seen = 0
+    for _ in range(3):
+        eng.evolve(1)
+        ora.evolve(1)
+        tot = ora.counters()["collisions"]
+        c = eng.counters()
+        assert c.unsortedLargeCells == 0
+        assert c.collisions == tot - seen > 100
+        seen = tot
+    g, o = eng.download_parcels(), ora.download_parcels()
+    assert np.array_equal(g.origId, o.origId)            # cell-major, list order inside the cell
+    assert np.array_equal(g.cell, o.cell) and np.array_equal(eng.occupancy(), ora.occupancy())
+    assert np.allclose(g.U, o.U, rtol=0, atol=1e-9)
+    eng.close()

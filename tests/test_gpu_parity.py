@@ -550,3 +550,34 @@ def test_cylinder_ogrid_inflow_wall_matches_oracle():
     r = np.hypot(g.position[:, 0], g.position[:, 1])
     assert r.min() >= 0.1524 * np.cos(np.pi / 64) - 1e-12 and r.max() <= 0.4 + 1e-12
     eng.close()
+
+
+def test_air_wedge_small_scale_matches_oracle():
+    """BASELINE configs[2] at test size (hystrath_b200.cases.air_wedge: sheared hexahedra, diffuse 1000 K wedge, free-stream inflow +
+    deletion on inlet / top / outlet, symmetry planes in z, 5-species Larsen-Borgnakke with variable Zv): insertions, deletions, cells,
+    list order and collision counts are the oracle's step by step; velocities to libm ulps; wall accumulators to 1e-10."""
+    from hystrath_b200 import cases
+
+    mesh, sp, md, fill = cases.air_wedge(40, 20, 2, ppc=20, density_scale=40.0)
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    ora.set_reorder(True)
+    H.same_start(eng, ora, fill["type_ids"], fill["number_densities"], fill["Ttra"], fill["Trot"], fill["Tvib"], fill["velocity"])
+    seen = dict(collisions=0, inserted=0, deleted=0)
+    for _ in range(6):
+        eng.evolve(1)
+        ora.evolve(1)
+        tot, c = ora.counters(), eng.counters()
+        assert c.inserted == tot["inserted"] - seen["inserted"] > 0
+        assert c.deleted == tot["deleted"] - seen["deleted"] > 0
+        assert c.collisions == tot["collisions"] - seen["collisions"] > 50
+        seen = tot
+    g, o = eng.download_parcels(), ora.download_parcels()
+    assert g.n == o.n
+    assert np.array_equal(g.origId, o.origId) and np.array_equal(g.typeId, o.typeId)
+    assert np.array_equal(g.cell, o.cell) and np.array_equal(eng.occupancy(), ora.occupancy())
+    assert np.array_equal(g.vibLevel, o.vibLevel)
+    assert len(np.unique(g.typeId)) == 5                      # every species path ran
+    assert np.allclose(g.position, o.position, rtol=0, atol=1e-9) and np.allclose(g.U, o.U, rtol=1e-11, atol=1e-7)
+    gw, ow = eng.wall_accumulators(), ora.wall_accumulators()
+    assert np.abs(ow).max() > 0 and np.abs(gw - ow).max() <= 1e-9 * np.abs(ow).max()
+    eng.close()
