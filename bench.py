@@ -134,6 +134,8 @@ def run_reference(args):
 
     cores = pyoracle.set_threads(host_cores())   # the team size actually obtained (torchrun exports OMP_NUM_THREADS=1)
     cells = args.ref_cells
+    if getattr(args, "c1", False):
+        cells = 32
     cp = case_parameters(args.gas, cells, args.ppc)
     sp, tids, frac = species_table(args.gas)
     mesh = meshgen.box_mesh((cells,) * 3, (cp["L"],) * 3)
@@ -150,7 +152,8 @@ def run_reference(args):
     o.evolve(args.steps)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
-    sample = f"{cells}^3-cell periodic {args.gas} box, {n} parcels, {args.steps} steps after {args.warmup} warm-up (same cell size, density, dt and models as the GPU arm)"
+    sample = (f"{cells}^3-cell periodic {args.gas} box, {n} parcels, {args.steps} steps after {args.warmup} warm-up: same cell size, density, dt, models and "
+              f"cell numbering as the GPU arm's brick, a smaller brick (the oracle is a CPU port; the largest box whose run stays within a few minutes)")
     line = {
         "impl": "reference", "metric": "particle-steps/s (move+sort+NTC collide+sample)", "value": value, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
@@ -177,6 +180,11 @@ def workload_config(args, cells_per_gpu, parcels_per_gpu):
                 "cells_per_gpu": cells_per_gpu, "parcels_per_gpu": parcels_per_gpu, "parcels_per_cell": args.ppc, "gas": "argon",
                 "collision_model": "VariableHardSphere", "partition": "1 GPU",
                 "l2_policy": "inputs larger than L2 (parcel state >> 126 MB), no flush needed"}
+    if getattr(args, "c1", False):
+        return {"workload": "C1 (BASELINE configs[0]): periodic argon VHS heat-bath box, 32^3 cells, %d parcels, no walls" % parcels_per_gpu,
+                "cells_per_gpu": cells_per_gpu, "parcels_per_gpu": parcels_per_gpu, "parcels_per_cell": args.ppc, "gas": "argon",
+                "collision_model": "VariableHardSphere", "partition": "1 GPU",
+                "l2_policy": "the whole cloud (1 M parcels, 100 MB with both buffers) fits the 126 MB L2: L2-resident by nature of the case, no flush"}
     return {"workload": "weak-scaling periodic box (BASELINE configs[4]), %s, %d cells and ~%d parcels per GPU, %s" % (
         "argon VHS" if args.gas == "argon" else "5-species air (N2,O2,NO,N,O) Larsen-Borgnakke VHS", cells_per_gpu, parcels_per_gpu,
         "blockMesh cell order" if getattr(args, "numbering", "morton") == "blockMesh" else "cells renumbered along a z-order curve (renumberMesh equivalent)"),
@@ -230,11 +238,26 @@ def cpu_baseline_leg(args):
     if getattr(args, "numbering", "morton") == "morton":
         mesh, _ = meshgen.renumber_cells(mesh, meshgen.morton_order(mesh))
     model = "VariableHardSphere" if args.gas == "argon" else "LarsenBorgnakkeVariableHardSphere"
-    md = capi.build_models(model, nEquivalentParticles=cp["fnum"], deltaT=cp["dt"], seed=0xD5C00005)
+    md = capi.build_models(model, nEquivalentParticles=cp["fnum"], deltaT=cp["dt"], seed=0xD5C00001 if getattr(args, "c1", False) else 0xD5C00005)
     o = Oracle()
     o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
     o.mesh_fill(tids, [cp["n"] * f for f in frac], cp["T"], cp["T"], cp["T"])
     n = o.num_parcels()
+    if getattr(args, "c1", False):
+        # the protocol of BASELINE.md section 4: 200 steps after 20 warm-up on all host threads, and the 1-thread figure on a shorter run
+        o.evolve(20)
+        t0 = time.perf_counter()
+        o.evolve(200)
+        dt_all = time.perf_counter() - t0
+        one = pyoracle.set_threads(1)
+        t0 = time.perf_counter()
+        o.evolve(args.c1_single_thread_steps)
+        dt_one = time.perf_counter() - t0
+        pyoracle.set_threads(cores)
+        return {"value": n * 200 / dt_all, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+                "single_thread": {"value": n * args.c1_single_thread_steps / dt_one, "cores": one, "steps": args.c1_single_thread_steps},
+                "sample": f"C1 (BASELINE.md section 4): 32^3-cell periodic argon VHS box, {n} parcels, 200 steps after 20 warm-up "
+                          f"(oracle = port of the reference algorithm, OpenMP over {cores} threads; dsmcFoam+ itself cannot be built here)"}
     o.evolve(1)
     steps = args.cpu_steps
     t0 = time.perf_counter()
@@ -330,10 +353,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dsmcb200", choices=["dsmcb200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("DSMCB200_BENCH_WORKLOAD", "box"), choices=["box", "cylinder", "wedge"],
+    ap.add_argument("--workload", default=os.environ.get("DSMCB200_BENCH_WORKLOAD", "box"), choices=["box", "cylinder", "wedge", "c1"],
                     help="box: BASELINE configs[4] weak-scaling periodic box (default, any N); cylinder: configs[1] Mach-10 argon cylinder (N=1); "
                          "wedge: configs[2] 5-species air over a hypersonic wedge (N > 1: the same case cut into N slabs along x, strong scaling)")
     ap.add_argument("--wedge", default="2000x1000x4", help="wedge cells nx x ny x nz")
+    ap.add_argument("--c1-single-thread-steps", type=int, default=20, help="workload c1: steps of the 1-thread leg of BASELINE.md section 4")
     ap.add_argument("--cyl", default="640x1250", help="cylinder O-grid cells nr x ntheta")
     ap.add_argument("--gas", default=os.environ.get("DSMCB200_BENCH_GAS", "air5"), choices=["argon", "air5"])
     ap.add_argument("--cells", type=int, default=int(os.environ.get("DSMCB200_BENCH_CELLS", "200")), help="cells per direction per GPU")
@@ -343,13 +367,18 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-cells", type=int, default=32)
     ap.add_argument("--cpu-steps", type=int, default=5)
-    ap.add_argument("--ref-cells", type=int, default=48)
+    ap.add_argument("--ref-cells", type=int, default=96, help="cells per direction of the reference arm's sample: the largest box that keeps a 20-step run on 16 host threads within a few minutes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     _capture_stdout()
     if args.warmup < 3 and args.impl == "dsmcb200":
         args.warmup = max(args.warmup, 0)
+    c1 = args.workload == "c1"
+    if c1:
+        # BASELINE.md section 4 / SURVEY 8d C1: periodic argon VHS heat bath, 32^3 cells, 1 048 576 parcels expected, dt 5e-6, seed 0xD5C00001
+        args.workload, args.gas, args.cells, args.ppc, args.numbering = "box", "argon", 32, 32, "blockMesh"
+        args.c1 = True
     if args.impl == "reference":
         run_reference(args)
         return
@@ -393,6 +422,8 @@ def main():
         tids, dens, Tfill, vfill = fill["type_ids"], fill["number_densities"], fill["Ttra"], fill["velocity"]
         n_cells_gpu = mesh.n_cells
     else:
+        if getattr(args, "c1", False) and world != 1:
+            raise SystemExit("--workload c1 is a single-GPU configuration (BASELINE configs[0])")
         cp = case_parameters(args.gas, args.cells, args.ppc)
         sp, tids, frac = species_table(args.gas)
         procs = procs_for(world)
