@@ -333,7 +333,7 @@ def decomposed_parity_check(rank, world, local, dist, torch):
         ok, why = False, "cloud list order differs"
     if ok and not (np.array_equal(g.cell, o.cell) and np.array_equal(g.vibLevel, o.vibLevel)):
         ok, why = False, "cells or vibrational levels differ"
-    if ok and not (np.allclose(g.U, o.U, rtol=0, atol=1e-8) and np.array_equal(g.position, o.position)):
+    if ok and not (np.allclose(g.U, o.U, rtol=0, atol=1e-8) and np.allclose(g.position, o.position, rtol=0, atol=1e-12)):
         ok, why = False, "velocities or positions differ"
     eng.close()
     flag = torch.tensor([1.0 if ok else 0.0, float(sent_total), float(g.n)], dtype=torch.float64, device="cuda")
@@ -343,7 +343,7 @@ def decomposed_parity_check(rank, world, local, dist, torch):
     whys = [None] * world
     dist.all_gather_object(whys, why)
     return {"ok": bool(allok.item() == 1.0), "ranks": world, "steps": steps, "parcels": int(flag[2].item()), "migrated": int(flag[1].item()),
-            "checked": "list order (origProc, origId), cells, vibrational levels, positions exact; U 1e-8; migration counts per neighbour and step",
+            "checked": "list order (origProc, origId), cells, vibrational levels, migration counts per neighbour and step: exact; U to 1e-8 m/s and positions to 1e-12 m (libm vs CUDA ulps in the collision model)",
             "failures": [w for w in whys if w]}
 
 
@@ -417,7 +417,7 @@ def main():
 
         wx, wy, wz = (int(v) for v in args.wedge.split("x"))
         args.gas = "air5"
-        args.ppc = 25
+        args.ppc = 34   # per inlet-cell volume; the rows shrink towards the outlet: ~25 parcels per cell on average, ~200 M in 8 M cells
         mesh, sp, md, fill = cases.air_wedge(wx, wy, wz, args.ppc, procs=world, rank=rank)
         tids, dens, Tfill, vfill = fill["type_ids"], fill["number_densities"], fill["Ttra"], fill["velocity"]
         n_cells_gpu = mesh.n_cells
