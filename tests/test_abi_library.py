@@ -99,3 +99,25 @@ def test_decomposed_box_patch_ordering():
     assert nb[2:] == [0, 3, 0, 3]
     sep = [p.get("separation") for p in m.patches if p["type"] == "processorCyclic"]
     assert sep == [(-0.08, 0.0, 0.0), (0.0, 0.08, 0.0)]
+
+
+def test_the_openfoam_shim_only_uses_declared_entry_points_and_fields():
+    """shim/dsmcCloudB200.C cannot be compiled here (no OpenFOAM): at least every ABI function it calls is declared in the header and
+    exported by the library, and every struct member it touches exists in the ctypes mirror."""
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "shim", "dsmcCloudB200.C")).read() + open(os.path.join(root, "shim", "dsmcCloudB200.H")).read()
+    header = open(os.path.join(root, "include", "dsmcb200.h")).read()
+    lib = capi.load_library()
+    called = set(re.findall(r"\b(dsmcb200_[a-z_0-9]+)\s*\(", src))
+    assert len(called) >= 15
+    for f in called:
+        assert re.search(r"\b%s\s*\(" % f, header), f
+        assert hasattr(lib, f), f
+    for var, cls in (("models_", capi.Models), ("soa", capi.ParcelsSoA), ("pm", capi.PatchModel), ("in", capi.Inflow), ("m", capi.Mesh),
+                     ("out", capi.Patch), ("ai", capi.AccumInfo)):
+        members = {n for n, _ in cls._fields_}
+        for mem in set(re.findall(r"\b%s\.([A-Za-z_0-9]+)\b" % var, src)):
+            assert mem in members, (var, mem)
