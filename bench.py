@@ -570,11 +570,11 @@ def main():
                 gbs = n_local * sb[k] / (t * 1e-3) / 1e9
                 stages[k] = {"ms": t, "bytes_per_parcel": sb[k], "achieved_gbs": gbs, "frac": gbs / peak}
         dom = max(stage_t, key=stage_t.get)
-        # DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json: dram__bytes_read.sum +
+        # DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r02_traffic.json: dram__bytes_read.sum +
         # dram__bytes_write.sum of one launch on this workload), scaled by parcel count when the capture was taken at another size
         traffic, traffic_src = None, None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
             ent = tj.get(f"{args.workload}:{args.gas}", {}).get(dom)
             if ent:
                 traffic = ent["dram_bytes"] / ent["parcels"] * n_local
