@@ -406,7 +406,9 @@ __device__ __noinline__ void armSlot(const MoveArgs& a, MoveSlot* S, uint32_t ba
 
 // `n` units of slot S are done (parcels written back, or one warp moving on); whoever completes the entry arms the slot with the next one
 __device__ __forceinline__ void releaseSlot(const MoveArgs& a, MoveSlot* S, uint32_t bar, uint32_t win, int32_t n) {
+    __threadfence_block();   // this thread's reads of the slot and of its window are done before the count that lets the slot be re-armed
     if (atomicSub(&S->pending, n) == n) {
+        __threadfence_block();
         const int32_t c = S->copies;
         if (c > 0) {
             int32_t polls = 0;
