@@ -92,6 +92,61 @@ class Models(C.Structure):
                 ("trackFaceFluxes", C.c_int32), ("reserved0_", C.c_int32), ("sampleInterval", C.c_int32), ("reserved_", C.c_int32)]
 
 
+class Reaction(C.Structure):
+    _fields_ = [("model", C.c_int32), ("reactants", C.c_int32 * 2), ("allowSplitting", C.c_int32),
+                ("dissociationProducts", (C.c_int32 * 2) * 2), ("exchangeProducts", C.c_int32 * 2),
+                ("heatOfReactionExchange", C.c_double), ("aCoeff", C.c_double), ("bCoeff", C.c_double)]
+
+
+REACTION_MODEL_NAMES = {"dissociationQK": 1, "exchangeQK": 2, "dissociationExchangeQK": 3}
+
+
+def build_reactions(type_id_list, reactions):
+    """system/chemReactDict `reactions ( ... )` -> array of dsmcb200_reaction.  `reactions`: list of dicts with the dictionary's keys
+    (reactionModel, reactants, allowSplitting, dissociationProducts, exchangeProducts, heatOfReactionExchange, aCoeff, bCoeff);
+    species by name.  Unknown model names fail as dsmcReaction::New does (dsmcReaction.C:140-158)."""
+    ids = {n: i for i, n in enumerate(type_id_list)}
+
+    def tid(name):
+        if name not in ids:
+            raise Dsmcb200Error(f"Cannot find type id: {name}")
+        return ids[name]
+
+    arr = (Reaction * max(1, len(reactions)))()
+    for k, d in enumerate(reactions):
+        name = d["reactionModel"]
+        if name not in REACTION_MODEL_NAMES:
+            raise Dsmcb200Error(f"dsmcReaction::New(const dictionary&) : \n    unknown dsmc reaction model type {name}, constructor not in hash "
+                                f"table\n\n    Valid reaction types are :\n{sorted(REACTION_MODEL_NAMES)}")
+        r = arr[k]
+        r.model = REACTION_MODEL_NAMES[name]
+        if len(d["reactants"]) != 2:
+            raise Dsmcb200Error("There should be two reactants")
+        r.reactants[0], r.reactants[1] = tid(d["reactants"][0]), tid(d["reactants"][1])
+        r.allowSplitting = 1 if d.get("allowSplitting", True) else 0
+        for i in range(2):
+            r.dissociationProducts[i][0] = r.dissociationProducts[i][1] = -1
+        r.exchangeProducts[0] = r.exchangeProducts[1] = -1
+        if r.model != 2:
+            prods = d["dissociationProducts"]
+            if len(prods) != 2:
+                raise Dsmcb200Error(f"There should be two lists of products, instead of {len(prods)}")
+            for i, lst in enumerate(prods):
+                if len(lst) not in (0, 2):
+                    raise Dsmcb200Error(f"There should be 2 dissociation products instead of {len(lst)}")
+                for j, nm in enumerate(lst):
+                    r.dissociationProducts[i][j] = tid(nm)
+        if r.model != 1:
+            ex = d["exchangeProducts"]
+            if len(ex) != 2:
+                raise Dsmcb200Error(f"There should be two products, instead of {len(ex)}")
+            r.exchangeProducts[0], r.exchangeProducts[1] = tid(ex[0]), tid(ex[1])
+            r.heatOfReactionExchange = float(d["heatOfReactionExchange"])
+            r.aCoeff, r.bCoeff = float(d["aCoeff"]), float(d["bCoeff"])
+    arr._n = len(reactions)
+    return arr
+
+
 class ParcelsSoA(C.Structure):
     _fields_ = [("position", C.c_void_p), ("U", C.c_void_p), ("ERot", C.c_void_p), ("cell", C.c_void_p),
                 ("tetFace", C.c_void_p), ("tetPt", C.c_void_p), ("typeId", C.c_void_p), ("vibLevel", C.c_void_p),
@@ -261,6 +316,8 @@ def load_library():
         "dsmcb200_set_mesh": ([P, C.POINTER(Mesh)], C.c_int),
         "dsmcb200_set_species": ([P, C.c_int, C.POINTER(Species)], C.c_int),
         "dsmcb200_set_models": ([P, C.POINTER(Models)], C.c_int),
+        "dsmcb200_set_reactions": ([P, C.c_int, C.POINTER(Reaction)], C.c_int),
+        "dsmcb200_reaction_counts": ([P, C.c_int, C.c_void_p], C.c_int),
         "dsmcb200_reserve": ([P, C.c_int64], C.c_int),
         "dsmcb200_upload_parcels": ([P, C.c_int64, C.POINTER(ParcelsSoA)], C.c_int),
         "dsmcb200_download_parcels": ([P, C.c_int64, C.POINTER(C.c_int64), C.POINTER(ParcelsSoA)], C.c_int),
@@ -297,7 +354,8 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "dsmcb200_abi_version", "dsmcb200_create", "dsmcb200_destroy", "dsmcb200_last_error", "dsmcb200_nccl_unique_id",
-    "dsmcb200_init_comm", "dsmcb200_set_mesh", "dsmcb200_set_species", "dsmcb200_set_models", "dsmcb200_reserve",
+    "dsmcb200_init_comm", "dsmcb200_set_mesh", "dsmcb200_set_species", "dsmcb200_set_models", "dsmcb200_set_reactions",
+    "dsmcb200_reaction_counts", "dsmcb200_reserve",
     "dsmcb200_upload_parcels", "dsmcb200_download_parcels", "dsmcb200_upload_cellstate", "dsmcb200_download_cellstate",
     "dsmcb200_mesh_fill", "dsmcb200_evolve", "dsmcb200_stage", "dsmcb200_set_step", "dsmcb200_download_occupancy",
     "dsmcb200_accum_info_get", "dsmcb200_download_accumulators", "dsmcb200_upload_accumulators",
@@ -415,6 +473,18 @@ class Engine:
     def set_models(self, models: Models):
         self._models = models
         self._ck(self.lib.dsmcb200_set_models(self.h, C.byref(models)))
+
+    def set_reactions(self, reactions):
+        """reactions: the array of build_reactions()"""
+        self._reactions = reactions
+        self._ck(self.lib.dsmcb200_set_reactions(self.h, reactions._n, reactions))
+
+    def reaction_counts(self):
+        """[nReactions][3]: dissociations of reactant 0, of reactant 1, exchanges -- totals since set_reactions"""
+        n = self._reactions._n
+        out = np.zeros((max(n, 1), 3), np.int64)
+        self._ck(self.lib.dsmcb200_reaction_counts(self.h, n, _ptr(out)))
+        return out[:n]
 
     def init_comm(self, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)

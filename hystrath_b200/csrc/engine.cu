@@ -153,6 +153,15 @@ struct dsmcb200_ctx {
     double* dFaceFlux = nullptr;   // dsmcFaceTracker: [2][nSpecies][nFaces] of the current step (models.trackFaceFluxes)
     std::vector<dsmcb200_patch_model> patchModels;
     std::vector<dsmcb200_inflow> inflows;
+    // quantum-kinetic chemistry (dsmcb200_set_reactions): second products of dissociations are staged in dBorn during the collide stage
+    std::vector<dsmcb200_reaction> reactions;
+    std::vector<int64_t> reactionTotals;   // [nReactions][3] since set_reactions
+    BornRec* dBorn = nullptr;
+    unsigned long long* dBornKeys = nullptr;
+    int32_t* dBornIdx = nullptr;
+    void* dBornTemp = nullptr;
+    size_t bornTempBytes = 0;
+    int32_t bornCap = 0;
     DevParams hP{};
     DevParams* dP = nullptr;
     // device mesh
@@ -443,6 +452,93 @@ int finalize(dsmcb200_ctx* c) {
             if (in.typeIds[i] < 0 || in.typeIds[i] >= P.nSpecies) return fail(c, DSMCB200_ERR_INVALID, "inflow typeId out of range");
     }
 
+    // ---- dsmcReactions: <model>::setProperties checks and the typeId-pair addressing (dsmcReactions.C:137-165)
+    P.nReactions = int(c->reactions.size());
+    for (int i = 0; i < MAX_SPECIES; ++i) for (int j = 0; j < MAX_SPECIES; ++j) P.pairReaction[i][j] = -1;
+    if (P.nReactions > MAX_REACTIONS) return fail(c, DSMCB200_ERR_CAPACITY, "more than 32 reactions");
+    for (int k = 0; k < P.nReactions; ++k) {
+        const dsmcb200_reaction& in = c->reactions[k];
+        DevReaction& R = P.reactions[k];
+        const std::string head = "For reaction number " + std::to_string(k) + "\n";
+        if (in.model < DSMCB200_REACT_DISSOCIATION_QK || in.model > DSMCB200_REACT_DISSOCIATION_EXCHANGE_QK)
+            return fail(c, DSMCB200_ERR_UNSUPPORTED, "dsmcReaction::New(const dictionary&) : \n    unknown dsmc reaction model type " + std::to_string(in.model) +
+                        ", constructor not in hash table\n\n    Valid reaction types are :\n3(dissociationQK exchangeQK dissociationExchangeQK)");
+        R.model = in.model; R.allowSplitting = in.allowSplitting != 0; R.posMolReactant = -1;
+        int rType[2];
+        for (int r = 0; r < 2; ++r) {
+            if (in.reactants[r] < 0 || in.reactants[r] >= P.nSpecies) return fail(c, DSMCB200_ERR_INVALID, head + "Cannot find type id: " + std::to_string(in.reactants[r]));
+            R.reactants[r] = in.reactants[r];
+            rType[r] = P.sp[R.reactants[r]].type;
+            R.heatDissJ[r] = 0.0;
+            R.dissProd[r][0] = in.dissociationProducts[r][0]; R.dissProd[r][1] = in.dissociationProducts[r][1];
+        }
+        if (R.model != DSMCB200_REACT_EXCHANGE_QK) {   // dissociationQK::setProperties, dissociationQK.C:44-195
+            bool moleculeFound = false;
+            for (int r = 0; r < 2; ++r) {
+                const bool mol = rType[r] == 20 || rType[r] == 30;
+                if (mol) { moleculeFound = true; R.heatDissJ[r] = P.kB * P.sp[R.reactants[r]].thetaD; }
+            }
+            if (!moleculeFound) return fail(c, DSMCB200_ERR_INVALID, head + "None of the reactants is a molecule.");
+            for (int r = 0; r < 2; ++r) {
+                const bool mol = rType[r] == 20 || rType[r] == 30;
+                const bool hasProducts = R.dissProd[r][0] >= 0 || R.dissProd[r][1] >= 0;
+                if (!mol && hasProducts) return fail(c, DSMCB200_ERR_INVALID, head + "Reactant " + std::to_string(R.reactants[r]) + " is not a molecule \nand therefore, there should be no dissociation products");
+                if (mol && !(R.dissProd[r][0] >= 0 && R.dissProd[r][1] >= 0)) return fail(c, DSMCB200_ERR_INVALID, head + "Reactant " + std::to_string(R.reactants[r]) + " is a molecule \nand therefore, it should have dissociation products");
+                if (!mol) continue;
+                for (int q = 0; q < 2; ++q) {
+                    const int pi = R.dissProd[r][q];
+                    if (pi >= P.nSpecies) return fail(c, DSMCB200_ERR_INVALID, head + "Cannot find type id: " + std::to_string(pi));
+                    const int pt = P.sp[pi].type;
+                    if (rType[r] == 20 && pt != 10) return fail(c, DSMCB200_ERR_INVALID, head + "Dissociation product of a diatomic molecule must be an atom: " + std::to_string(pi));
+                    if (rType[r] == 30 && pt != 20 && pt != 30 && pt != 10) return fail(c, DSMCB200_ERR_INVALID, head + "Dissociation product of a polyatomic molecule must be a diatomic/polyatomic molecule instead of " + std::to_string(pi));
+                }
+            }
+        }
+        if (R.model != DSMCB200_REACT_DISSOCIATION_QK) {   // exchangeQK::setProperties, exchangeQK.C:44-176
+            bool mol = false, atom = false;
+            for (int r = 0; r < 2; ++r) {
+                if (rType[r] >= 20) { mol = true; R.posMolReactant = r; }
+                else if (rType[r] == 10 || rType[r] == 11) atom = true;
+                else return fail(c, DSMCB200_ERR_INVALID, head + "Reactant " + std::to_string(R.reactants[r]) + " is neither a molecule nor an atom");
+            }
+            if (!mol) return fail(c, DSMCB200_ERR_INVALID, head + "None of the reactants is a molecule.");
+            if (!atom) return fail(c, DSMCB200_ERR_INVALID, head + "None of the reactants is an atom.");
+            R.exchProd[0] = R.exchProd[1] = -1;
+            for (int r = 0; r < 2; ++r) {
+                const int pi = in.exchangeProducts[r];
+                if (pi < 0 || pi >= P.nSpecies) return fail(c, DSMCB200_ERR_INVALID, head + "Cannot find type id: " + std::to_string(pi));
+                const int pt = P.sp[pi].type;
+                if (pt >= 20) R.exchProd[0] = pi;
+                else if (pt == 10 || pt == 11) R.exchProd[1] = pi;
+                else return fail(c, DSMCB200_ERR_INVALID, head + "Product " + std::to_string(pi) + " is neither a molecule nor an atom");
+            }
+            if (R.exchProd[0] < 0) return fail(c, DSMCB200_ERR_INVALID, head + "None of the products is a molecule.");
+            if (R.exchProd[1] < 0) return fail(c, DSMCB200_ERR_INVALID, head + "None of the products is an atom.");
+            R.heatExchJ = in.heatOfReactionExchange * P.kB;
+            R.bCoeff = in.bCoeff;
+            const double omegaPQ = 0.5 * (P.sp[R.reactants[0]].omega + P.sp[R.reactants[1]].omega);
+            const double chiB = 2.5 - omegaPQ;
+            R.aDash = in.aCoeff * (std::pow(chiB, in.bCoeff) * std::exp(std::lgamma(chiB)) / std::exp(std::lgamma(chiB + in.bCoeff)));
+        }
+    }
+    for (int i = 0; i < P.nSpecies; ++i)
+        for (int j = i; j < P.nSpecies; ++j) {
+            int nModels = 0;
+            for (int r = 0; r < P.nReactions; ++r) {
+                const DevReaction& R = P.reactions[r];
+                const int pi = R.reactants[0] == i ? 0 : (R.reactants[1] == i ? 1 : -1);   // findIndex: the first match
+                const int qi = R.reactants[0] == j ? 0 : (R.reactants[1] == j ? 1 : -1);
+                bool yes = false;
+                if (pi != -1 && qi != -1) {
+                    if (R.model == DSMCB200_REACT_EXCHANGE_QK) yes = pi != qi;
+                    else yes = (pi == qi && R.reactants[0] == R.reactants[1]) || (pi != qi && R.reactants[0] != R.reactants[1]);
+                }
+                if (yes) { P.pairReaction[i][j] = int8_t(r); P.pairReaction[j][i] = int8_t(r); ++nModels; }
+            }
+            if (nModels > 1) return fail(c, DSMCB200_ERR_INVALID, "There is more than one reaction model specified for the typeId pair: " + std::to_string(i) + " and " + std::to_string(j));
+        }
+    c->reactionTotals.assign(size_t(3) * P.nReactions, 0);
+
     {
         // 1/Zv of dsmcCloud::postCollisionVibrationalEnergyLevel (dsmcCloud.C:1429-1504) depends on the species, the
         // partner (through omegaPQ) and the integer iMax only: tabulated on the host with the reference's expression
@@ -585,8 +681,30 @@ int ensureMigBuffers(dsmcb200_ctx* c) {
 }
 
 // ---- stage 2: dsmcCloud::buildCellOccupancy ----
+// parcels this step's dissociations may add to a cloud of n (the collide stage fails with a capacity error beyond it)
+int64_t bornHeadroom(int64_t n) { return n / 8 + 4096; }
+
+int ensureBornBuffers(dsmcb200_ctx* c) {
+    const int64_t want = bornHeadroom(c->N);
+    if (want <= c->bornCap) return 0;
+    devFree(c->dBorn); devFree(c->dBornKeys); devFree(c->dBornIdx);
+    if (c->dBornTemp) { cudaFree(c->dBornTemp); c->dBornTemp = nullptr; }
+    const int32_t cap = int32_t(std::min<int64_t>(want + want / 4, (int64_t(1) << 30)));
+    CK(devAlloc(&c->dBorn, size_t(cap)));
+    CK(devAlloc(&c->dBornKeys, size_t(cap) * 2));
+    CK(devAlloc(&c->dBornIdx, size_t(cap) * 2));
+    c->bornTempBytes = orderBornTempBytes(cap);
+    CK(cudaMalloc(&c->dBornTemp, std::max<size_t>(c->bornTempBytes, 16)));
+    c->bornCap = cap;
+    return 0;
+}
+
 int stageSort(dsmcb200_ctx* c, bool histogramDone) {
     const int32_t nCells = c->mesh.nCells;
+    if (!c->reactions.empty()) {   // room for the products of this step's dissociations: the buffers must not move after the sort
+        { int r = ensureCapacity(c, c->N + bornHeadroom(c->N)); if (r) return r; }
+        { int r = ensureBornBuffers(c); if (r) return r; }
+    }
     const int32_t nIn = int32_t(c->N);
     ParcelArrays& src = c->buf[c->cur].a;
     if (!histogramDone) {
@@ -769,16 +887,45 @@ int stageCollide(dsmcb200_ctx* c) {
     a.overallT = c->hP.invZvFormulation == 1 ? c->dOverallT : nullptr;
     a.nModes = c->internal ? c->nModes : 0;
     a.bigScratch = c->dPerm; a.bigList = c->dCursor; a.octKey = c->dOctKey; a.P = c->dP; a.counters = c->dCounters; a.step = c->step;
+    const bool chem = !c->reactions.empty();
+    if (chem) {
+        if (c->N != c->sortedN) return fail(c, DSMCB200_ERR_STATE, "collide stage with chemistry: the cloud was modified since the sort stage");
+        { int r = ensureBornBuffers(c); if (r) return r; }
+        a.born = c->dBorn;
+        a.bornCapacity = int32_t(std::min<int64_t>(c->bornCap, c->capacity - c->N));
+        CK(cudaMemsetAsync(&c->dCounters->nBorn, 0, sizeof(int32_t), c->stream));
+        CK(cudaMemsetAsync(&c->dCounters->nReact[0][0], 0, sizeof(c->dCounters->nReact), c->stream));
+    }
     CK(cudaMemsetAsync(&c->dCounters->bigCells, 0, sizeof(int32_t), c->stream));
-    KT t(c, "collide");
-    CK(launchCollide(a, c->stream));
+    {
+        KT t(c, "collide");
+        CK(launchCollide(a, c->stream));
+    }
+    if (chem) {
+        // dsmcCloud::addNewParcel: the second products join the cloud behind the sorted part, in (cell, candidate) order
+        struct { int32_t nBorn; } h{};
+        CK(cudaMemcpyAsync(&h.nBorn, &c->dCounters->nBorn, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        std::vector<unsigned long long> nReact(size_t(3) * MAX_REACTIONS);
+        CK(cudaMemcpyAsync(nReact.data(), &c->dCounters->nReact[0][0], sizeof(unsigned long long) * 3 * MAX_REACTIONS, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (size_t k = 0; k < c->reactionTotals.size(); ++k) c->reactionTotals[k] += int64_t(nReact[k]);
+        if (h.nBorn > a.bornCapacity) return fail(c, DSMCB200_ERR_CAPACITY, "more parcels created by dissociations in one step (" + std::to_string(h.nBorn) + ") than the reserve of " + std::to_string(a.bornCapacity));
+        if (h.nBorn > 0) {
+            KT t(c, "appendBorn");
+            CK(launchAppendBorn(c->buf[c->cur].a, c->dBorn, h.nBorn, int32_t(c->N), int32_t(c->nextOrigId & 0x7fffffff), c->rank, c->nModes, c->dBornKeys,
+                                c->dBornIdx, c->dBornTemp, c->bornTempBytes, c->stream));
+            c->N += h.nBorn;
+            c->nextOrigId += h.nBorn;
+            c->last.inserted += 0;
+        }
+    }
     return 0;
 }
 
 int stageSample(dsmcb200_ctx* c) {
     if (!c->occupancyValid) return fail(c, DSMCB200_ERR_STATE, "cell occupancy is stale: run the sort stage first");
     SampleArgs a{};
-    a.p = c->buf[c->cur].a; a.cellOffset = c->dCellOffset; a.nCells = c->mesh.nCells; a.acc = c->dAcc; a.nQ = c->nQ; a.nSpecies = int(c->species.size()); a.nParcels = int32_t(c->N);
+    a.p = c->buf[c->cur].a; a.cellOffset = c->dCellOffset; a.nCells = c->mesh.nCells; a.acc = c->dAcc; a.nQ = c->nQ; a.nSpecies = int(c->species.size()); a.nParcels = int32_t(c->sortedN); a.nCloud = int32_t(c->N);
     a.collCum = c->dCollCum; a.nCollsStep = c->dNColls; a.collSepStep = c->dCollSep; a.P = c->dP;
     KT t(c, "sample");
     CK(launchSample(a, c->stream));
@@ -832,6 +979,7 @@ void dsmcb200_destroy(dsmcb200_ctx* c) {
     devFree(c->dOverallT); devFree(c->dFaceFlux); devFree(c->dWallAcc); devFree(c->dSfTail); devFree(c->dInfo); devFree(c->dInfoScratch); devFree(c->dCounters); devFree(c->dBad);
     devFree(c->dZvTab); devFree(c->dMigSend); devFree(c->dMigRecv); devFree(c->dMigKey); devFree(c->dMigWork); devFree(c->dInflowScan);
     if (c->dMigTemp) cudaFree(c->dMigTemp); devFree(c->dOrdinalToPatch); devFree(c->dCountsMatrix);
+    devFree(c->dBorn); devFree(c->dBornKeys); devFree(c->dBornIdx); if (c->dBornTemp) cudaFree(c->dBornTemp);
     for (auto& p : c->dInflowAcc) devFree(p);
     for (auto& p : c->dInflowCounts) devFree(p);
     for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);
@@ -897,6 +1045,21 @@ int dsmcb200_set_models(dsmcb200_ctx* c, const dsmcb200_models* m) {
     c->inflows.assign(m->inflows, m->inflows + (m->inflows ? m->nInflows : 0));
     c->models.patchModels = nullptr; c->models.inflows = nullptr;
     c->haveModels = true;
+    return 0;
+}
+
+int dsmcb200_set_reactions(dsmcb200_ctx* c, int n, const dsmcb200_reaction* reactions) {
+    if (!c || n < 0 || (n > 0 && !reactions)) return DSMCB200_ERR_INVALID;
+    if (c->ready) return fail(c, DSMCB200_ERR_STATE, "reactions cannot change after the engine has been finalised");
+    if (n > MAX_REACTIONS) return fail(c, DSMCB200_ERR_CAPACITY, "more than 32 reactions");
+    c->reactions.assign(reactions, reactions + n);   // checked against the species in finalize (dsmcReactions::initialConfiguration)
+    return 0;
+}
+
+int dsmcb200_reaction_counts(dsmcb200_ctx* c, int n, int64_t* counts3n) {
+    if (!c || !counts3n || n < 0) return DSMCB200_ERR_INVALID;
+    if (n != int(c->reactions.size())) return fail(c, DSMCB200_ERR_INVALID, "reaction_counts: n differs from the number of reactions set");
+    for (size_t k = 0; k < size_t(3) * n; ++k) counts3n[k] = k < c->reactionTotals.size() ? c->reactionTotals[k] : 0;
     return 0;
 }
 

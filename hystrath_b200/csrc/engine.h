@@ -17,6 +17,7 @@ constexpr int MAX_PATCHES = 64;
 constexpr int MAX_NEIGHBOURS = DSMCB200_MAX_NEIGHBOURS;
 constexpr int MAX_INFLOWS = 8;
 constexpr int ZV_TABLE = 128;  // tabulated iMax range of the variable vibrational collision number
+constexpr int MAX_REACTIONS = 32;   // entries of system/chemReactDict
 
 struct DevSpecies {
     double mass, d, omega, alpha, rotDof, thetaD;
@@ -43,6 +44,21 @@ struct DevPatch {
     double Tformation, maxDepth, lengthPatch;
 };
 
+// one quantum-kinetic reaction model of system/chemReactDict (dsmcb200_reaction after dsmcReaction::setProperties)
+struct DevReaction {
+    int32_t model;              // dsmcb200_reaction_model
+    int32_t reactants[2];
+    int32_t allowSplitting;
+    int32_t dissProd[2][2];     // products of the dissociation of reactant r
+    int32_t exchProd[2];        // [0] the molecule, [1] the atom (exchangeQK.C:141-170)
+    int32_t posMolReactant;     // which reactant is the molecule of the exchange
+    int32_t pad_;
+    double heatDissJ[2];        // kB * thetaD of reactant r (dissociationQK.C:120-140)
+    double heatExchJ;           // heatOfReactionExchange * kB
+    double aDash;               // aCoeff * chiB^b * Gamma(chiB) / Gamma(chiB + b), chiB = 2.5 - omegaPQ of the reactants (exchangeQK.C:196-200)
+    double bCoeff;
+};
+
 struct DevParams {
     int32_t nSpecies, nPatches, collisionModel, invZvFormulation;
     int32_t nModes;  // max vibrational modes over species (stride of vib arrays)
@@ -60,6 +76,10 @@ struct DevParams {
     // per species pair: pi*dPQ^2, exp(lgamma(2.5-omegaPQ)), omegaPQ, reduced mass
     double vhsA[MAX_SPECIES][MAX_SPECIES], vhsG[MAX_SPECIES][MAX_SPECIES];
     double omegaPQ[MAX_SPECIES][MAX_SPECIES], mR[MAX_SPECIES][MAX_SPECIES];
+    // dsmcReactions: the reaction model of a typeId pair (-1: none), dsmcReactions.C:137-165
+    int32_t nReactions;
+    int8_t pairReaction[MAX_SPECIES][MAX_SPECIES];
+    DevReaction reactions[MAX_REACTIONS];
 };
 
 // Structure-of-arrays cloud: one array per component so every stage streams coalesced.
@@ -88,6 +108,16 @@ struct DevCounters {
     int32_t nInserted;
     int32_t bigCells;  // cells handed from collideLaneKernel to collideBigCellsKernel this step
     int32_t bigSortCells;  // cells handed from segmentSortKernel to bigSegmentSortKernel
+    int32_t nBorn;         // parcels created by dissociations this step (dsmcCloud::addNewParcel)
+    unsigned long long nReact[MAX_REACTIONS][3];   // this step: dissociations of reactant 0, of reactant 1, exchanges
+};
+
+// the second product of a dissociation (dissociationQK.C:355-370) until it joins the cloud in (cell, candidate) order
+struct BornRec {
+    unsigned long long key;     // cell << 32 | candidate index: the order in which the reference's serial loop creates them
+    double pos[3], U[3];
+    int32_t cell, tet;
+    uint8_t typeId, cls, pad_[6];
 };
 
 // wall accumulator quantities per (measured face, species)
@@ -143,6 +173,8 @@ struct CollideArgs {
     int32_t* bigScratch;          // [nParcels] sub-cell index lists of cells too large for shared memory
     int32_t* bigList;             // [nCells] ids of those cells (written by the lane kernel)
     const uint8_t* octKey;        // [nParcels] sub-cell (octant) of every sorted parcel, written by the sort's gather
+    BornRec* born;                // [bornCapacity] parcels created by reactions (nullptr without chemistry)
+    int32_t bornCapacity;
     const DevParams* P;
     DevCounters* counters;
     uint32_t step;
@@ -155,6 +187,7 @@ struct SampleArgs {
     double* acc;                  // [nCells][nSpecies][nQ]
     int32_t nQ, nSpecies;
     int32_t nParcels;             // sorted parcels (= cellOffset[nCells])
+    int32_t nCloud;               // all parcels: [nParcels, nCloud) were created by this step's reactions and are in no cell list
     double* collCum;              // [nCells][2]
     const double* nCollsStep;
     const double* collSepStep;
@@ -191,6 +224,10 @@ cudaError_t launchGather(const ParcelArrays& src, const ParcelArrays& dst, const
 cudaError_t launchHistogram(const int32_t* cell, int32_t n, int32_t* cellCount, cudaStream_t s);
 cudaError_t launchCollide(const CollideArgs& a, cudaStream_t s);
 cudaError_t launchSample(const SampleArgs& a, cudaStream_t s);
+// the parcels reactions created join the cloud at [base, base + n) in key order; work: 2 n keys + 2 n ints
+size_t orderBornTempBytes(int32_t capacity);
+cudaError_t launchAppendBorn(const ParcelArrays& p, const BornRec* born, int32_t n, int32_t base, int32_t origIdBase, int32_t origProc, int32_t nModes,
+                             unsigned long long* keyWork, int32_t* idxWork, void* temp, size_t tempBytes, cudaStream_t s);
 cudaError_t launchInfo(const ParcelArrays& p, int32_t n, const DevParams* P, double* out5, double* scratch, cudaStream_t s);
 int32_t infoScratchDoubles();
 

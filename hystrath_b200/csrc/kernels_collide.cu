@@ -16,6 +16,8 @@
 // Stage 5 follows the per-parcel accumulation of dsmcVolFields::calculateField (DSMC/macroscopicProperties/
 // derived/combined/dsmcVolFields/dsmcVolFields.C:1115-1237): parcels are cell-sorted, so each warp reduces
 // the parcels of its cell and adds one row of per-species moment sums (single writer per accumulator element).
+#include <cub/device/device_radix_sort.cuh>
+
 #include "device_models.cuh"
 #include "engine.h"
 
@@ -109,13 +111,22 @@ __device__ double postCollisionRotationalEnergy(Rng& rng, double rotationalDof, 
     return energyRatio;
 }
 
-// dsmcCloud::postCollisionVibrationalEnergyLevel (postReaction = false)
+// dsmcCloud::postCollisionVibrationalEnergyLevel; postReaction: no relaxation-number test (dsmcCloud.C:1407-1424)
 // ZV2008: inverseZvFormulation "2008" compiled in (the common formulations keep the kernel free of the temperature pointer)
 template <bool ZV2008>
 __device__ int32_t postCollisionVibrationalEnergyLevel(const DevParams& P, Rng& rng, int32_t vibLevel, int32_t iMax, double thetaV,
                                                        double thetaD, double refTempZv, double omega, double Zref, double Ec,
-                                                       const double* zvRow, const double* tMacro) {
+                                                       const double* zvRow, const double* tMacro, bool postReaction = false) {
     int32_t iDash = vibLevel;
+    if (postReaction) {
+        double func, EVib;
+        do {
+            iDash = rng.randomLabel(0, iMax);
+            EVib = iDash * P.kB * thetaV;
+            func = powNI(1.0 - EVib / Ec, 1.5 - omega);
+        } while (func < rng.sample01());
+        return iDash;
+    }
     double inverseVibrationalCollisionNumber = 1.0;
     const double fixedZv = P.Zvib;
     // invZvFormulation 0 and 2 use the quantised collision temperature; formulation 1 ("2008") the macroscopic overall
@@ -221,6 +232,8 @@ __device__ __forceinline__ double warpSumOrdered(double v) {
     return __shfl_sync(0xffffffffu, v, 0);
 }
 
+__device__ bool reactPair(const CollideArgs& a, const DevParams& P, Rng& rng, int ri, int32_t gp0, int32_t gq0, int32_t cell, int32_t cand);
+
 }  // namespace
 
 __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __grid_constant__ CollideArgs a) {
@@ -322,7 +335,7 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
         totCand += (lane == 0) ? (unsigned long long)(nCandidates > 0 ? nCandidates : 0) : 0ULL;
 
         double newMax = sigmaTcRMaxLatched;
-        double nColl = 0.0, sepSum = 0.0;
+        double nColl = 0.0, sepSum = 0.0, nReacted = 0.0;   // nReacted: accepted pairs a reaction took (counted as collisions, not measured)
 
         for (int32_t c0 = 0; c0 < nCandidates; c0 += 32) {
             const int32_t cand = c0 + lane;
@@ -365,7 +378,16 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
                         const double cR0 = mag(UP - UQ);
                         const double sTcR = sigmaTcR(P, tP, tQ, cR0);
                         if (sTcR > newMax) newMax = sTcR;
-                        if ((sTcR / sigmaTcRMaxLatched) > rng.sample01()) {
+                        bool relax = (sTcR / sigmaTcRMaxLatched) > rng.sample01();
+                        if (relax && P.nReactions > 0) {
+                            // chemical reactions (noTimeCounter.C:250-303)
+                            const int rMId = P.pairReaction[tP][tQ];
+                            if (rMId >= 0) {
+                                relax = reactPair(a, P, rng, rMId, b + cp, b + cq, c, cand);
+                                if (!relax) nReacted += 1.0;
+                            }
+                        }
+                        if (relax) {
                             double cR = -1;
                             if (LB) {
                                 // LarsenBorgnakkeVariableHardSphere::collide
@@ -406,11 +428,12 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         const double nCollTot = warpSumOrdered(nColl);
         const double sepTot = warpSumOrdered(sepSum);
+        const double nReactedTot = warpSumOrdered(nReacted);
         if (lane == 0) {
             a.sigmaTcRMax[c] = mx;
             a.nCollsStep[c] = nCollTot;
             a.collSepStep[c] = sepTot;
-            totColl += (unsigned long long)nCollTot;
+            totColl += (unsigned long long)nCollTot + (unsigned long long)nReactedTot;
         }
         if (small) {
             __syncwarp();
@@ -466,11 +489,11 @@ struct InPlace {  // accessor of the parcels of one cell where they lie in the s
     __device__ __forceinline__ void setErot(int j, double v) const { p.erot[b + j] = v; }
 };
 
-// LarsenBorgnakkeVariableHardSphere::redistribute (postReaction = false) on parcel j of the view
+// LarsenBorgnakkeVariableHardSphere::redistribute on parcel j of the view
 // NM: vibrational modes stored per parcel (P.nModes), a compile-time bound of the mode loops
 template <bool ZV2008, int NM>
 __device__ __forceinline__ void redistributeInPlace(const DevParams& P, Rng& rng, const InPlace v, int j, int tSelf, int tOther,
-                                                 double& translationalEnergy, double omegaPQ, const double* tMacro) {
+                                                 double& translationalEnergy, double omegaPQ, const double* tMacro, bool postReaction = false) {
     const DevSpecies& S = P.sp[tSelf];
     if (S.type == 0) return;  // electron
     if (P.invZelec > rng.sample01()) {
@@ -495,7 +518,8 @@ __device__ __forceinline__ void redistributeInPlace(const DevParams& P, Rng& rng
             if (iMaxP > 0) {
                 const int32_t lvl = postCollisionVibrationalEnergyLevel<ZV2008>(P, rng, lvl0[m], iMaxP, S.thetaV[m], S.thetaD, S.TrefZv[m], omegaPQ,
                                                                         S.Zref[m], EcP,
-                                                                        P.invZvTab + ((size_t(tSelf) * P.nSpecies + tOther) * MAX_MODES + m) * ZV_TABLE, tMacro);
+                                                                        P.invZvTab + ((size_t(tSelf) * P.nSpecies + tOther) * MAX_MODES + m) * ZV_TABLE, tMacro,
+                                                                        postReaction);
                 if (lvl != lvl0[m]) v.setVib(m, j, lvl);
                 translationalEnergy = EcP - lvl * P.kB * S.thetaV[m];
             }
@@ -514,10 +538,231 @@ __device__ __forceinline__ void redistributeInPlace(const DevParams& P, Rng& rng
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Quantum-kinetic chemistry inside the candidate loop (noTimeCounter.C:250-303): the reaction model of the typeId pair runs before the
+// conventional collision and says whether that still takes place (relax()).  Parcels are read and written where they lie in the cloud.
+//   dissociationQK          DSMC/reactions/derived/dissociationQK/dissociationQK.C:197-383, 481-583
+//   exchangeQK              DSMC/reactions/derived/exchangeQK/exchangeQK.C:178-362, 457-511
+//   dissociationExchangeQK  DSMC/reactions/derived/mixed/dissociationExchangeQK/dissociationExchangeQK.C:107-264
+// ------------------------------------------------------------------------------------------------
+struct PairRef {   // the two parcels of the candidate, by cloud index
+    int32_t g[2];
+};
+
+__device__ __forceinline__ double eVibTot(const DevParams& P, const ParcelArrays& p, int32_t g, const DevSpecies& S) {
+    double e = 0.0;
+#pragma unroll
+    for (int m = 0; m < MAX_MODES; ++m) if (m < S.nVib) e += p.vib[m][g] * P.kB * S.thetaV[m];
+    return e;
+}
+__device__ __forceinline__ void clearInternal(const DevParams& P, const ParcelArrays& p, int32_t g) {
+    if (p.erot) p.erot[g] = 0.0;
+#pragma unroll
+    for (int m = 0; m < MAX_MODES; ++m) if (m < P.nModes) p.vib[m][g] = 0;
+    if (p.elevel) p.elevel[g] = 0;
+}
+
+// VariableHardSphere::postReactionVelocities, VariableHardSphere.C:231-262 (UP enters as the centre-of-mass velocity)
+__device__ void postReactionVelocities(const DevParams& P, Rng& rng, int tP, int tQ, V3& UP, V3& UQ, double cR) {
+    const double mP = P.sp[tP].mass, mQ = P.sp[tQ].mass;
+    const double cosTheta = 2.0 * rng.sample01() - 1.0;
+    const double sinTheta = sqrt(1.0 - cosTheta * cosTheta);
+    const double phi = TWO_PI * rng.sample01();
+    const V3 rel = cR * mk(cosTheta, sinTheta * cos(phi), sinTheta * sin(phi));
+    UQ = UP - rel * mP / (mP + mQ);
+    UP = UP + rel * mQ / (mP + mQ);
+}
+
+// dissociationQK::testDissociation
+__device__ void testDissociation(const DevParams& P, const ParcelArrays& p, int32_t g, double translationalEnergy, int& vibModeDisso,
+                                 double& collisionEnergy, double& total, double& prob) {
+    const DevSpecies& S = P.sp[p.typeId[g]];
+    if (S.type == 20 || S.type == 30) {
+#pragma unroll
+        for (int m = 0; m < MAX_MODES; ++m) {
+            if (m >= S.nVib) break;
+            const double EVibP_m = p.vib[m][g] * P.kB * S.thetaV[m];
+            const int32_t idP = int32_t(S.thetaD / S.thetaV[m]);   // charDissQuantumLevel_m (dsmcParcelI.H:152-156)
+            collisionEnergy = translationalEnergy + EVibP_m;
+            const int32_t imaxP = int32_t(collisionEnergy / (P.kB * S.thetaV[m]));
+            if (imaxP > idP) { prob = 1.0; total += prob; vibModeDisso = m; break; }
+        }
+    }
+}
+
+// exchangeQK::testExchange
+__device__ void testExchange(const DevParams& P, const DevReaction& R, const ParcelArrays& p, int32_t g, double translationalEnergy, double omegaPQ,
+                             double& collisionEnergy, double& total, double& prob) {
+    const DevSpecies& S = P.sp[p.typeId[g]];
+    const double chiB = 2.5 - omegaPQ;
+    const double TColl = translationalEnergy / (P.kB * chiB);
+    double activationEnergy = R.aDash * powNI(TColl / 273.0, R.bCoeff) * fabs(R.heatExchJ);
+    double summation = 1.0;
+    if (R.heatExchJ < 0.0) activationEnergy -= R.heatExchJ;
+    const int nV = S.nVib;
+    if (nV == 0) { total += prob; return; }
+    int m = 0;
+    do {
+        const double kBByThetaVP = P.kB * S.thetaV[m];
+        const double EVibP_m = p.vib[m][g] * P.kB * S.thetaV[m];
+        collisionEnergy = translationalEnergy + EVibP_m;
+        if (collisionEnergy > activationEnergy) {
+            if (activationEnergy > kBByThetaVP) {
+                summation = 0.0;
+                const int32_t iaP = int32_t(collisionEnergy / kBByThetaVP);
+                for (int32_t i = 0; i <= iaP; ++i) summation += powNI(1.0 - (i * P.kB * S.thetaV[m]) / collisionEnergy, 1.5 - omegaPQ);
+            }
+            prob = powNI(1.0 - activationEnergy / collisionEnergy, 1.5 - omegaPQ) / summation;
+            m = nV;
+        }
+        m += 1;
+    } while (m < nV);
+    total += prob;
+}
+
+// dissociationQK::dissociateParticleByPartner: parcel gP splits into products[nR], gQ is the partner
+__device__ void dissociateParticleByPartner(const CollideArgs& a, const DevParams& P, Rng& rng, const DevReaction& R, int ri, int32_t gP, int32_t gQ,
+                                            int nR, int vibModeDisso, double collisionEnergy, int32_t cell, int32_t cand, bool& relax) {
+    const ParcelArrays& p = a.p;
+    const int tP = p.typeId[gP], tQ = p.typeId[gQ];
+    const int nReac = tP == tQ ? 0 : nR;
+    atomicAdd(&a.counters->nReact[ri][nReac], 1ULL);
+    if (!R.allowSplitting) return;
+    relax = false;
+    collisionEnergy -= R.heatDissJ[nR];
+    const double omegaPQ = 0.5 * (P.sp[tP].omega + P.sp[tQ].omega);
+    const double* tMacro = a.overallT ? a.overallT + cell : nullptr;
+    redistributeInPlace<true, MAX_MODES>(P, rng, InPlace{p, 0}, gQ, tQ, tP, collisionEnergy, omegaPQ, tMacro, true);
+    const double mP = P.sp[tP].mass, mQ = P.sp[tQ].mass, mR = mP * mQ / (mP + mQ);
+    const double relVelNonDissoParticle = sqrt(2.0 * collisionEnergy / mR);
+    V3 UP = mk(p.ux[gP], p.uy[gP], p.uz[gP]), UQ = mk(p.ux[gQ], p.uy[gQ], p.uz[gQ]);
+    postCollisionVelocities(P, rng, tP, tQ, UP, UQ, relVelNonDissoParticle);
+    const int typeId1 = R.dissProd[nR][0], typeId2 = R.dissProd[nR][1];
+    const double mP1 = P.sp[typeId1].mass, mP2 = P.sp[typeId2].mass, mRproducts = mP1 * mP2 / (mP1 + mP2);
+    const DevSpecies& SP = P.sp[tP];
+    const double ERotP = p.erot ? p.erot[gP] : 0.0;
+    const double EVibP_tot = eVibTot(P, p, gP, SP);
+    const double EVibP_mdisso = p.vib[vibModeDisso][gP] * P.kB * SP.thetaV[vibModeDisso];
+    const double EVibP_nondisso = EVibP_tot - EVibP_mdisso;
+    const double EEleP = SP.eElec[p.elevel ? p.elevel[gP] : 0];
+    const double translationalEnergyLeft = ERotP + EVibP_nondisso + EEleP;
+    const double cRproducts = sqrt(2.0 * translationalEnergyLeft / mRproducts);
+    V3 UP2 = mk(0.0, 0.0, 0.0);
+    postReactionVelocities(P, rng, typeId1, typeId2, UP, UP2, cRproducts);
+    p.typeId[gP] = uint8_t(typeId1);
+    clearInternal(P, p, gP);
+    p.ux[gP] = UP.x; p.uy[gP] = UP.y; p.uz[gP] = UP.z;
+    p.ux[gQ] = UQ.x; p.uy[gQ] = UQ.y; p.uz[gQ] = UQ.z;
+    // cloud_.addNewParcel(position, UP2, ..., cell, tetFace, tetPt, typeId2, -1, classification, vibLevel 0)
+    const int32_t k = atomicAdd(&a.counters->nBorn, 1);
+    if (k < a.bornCapacity) {
+        BornRec b;
+        b.key = (static_cast<unsigned long long>(uint32_t(cell)) << 32) | uint32_t(cand);
+        b.pos[0] = p.px[gP]; b.pos[1] = p.py[gP]; b.pos[2] = p.pz[gP];
+        b.U[0] = UP2.x; b.U[1] = UP2.y; b.U[2] = UP2.z;
+        b.cell = cell; b.tet = p.tet[gP];
+        b.typeId = uint8_t(typeId2); b.cls = p.cls ? p.cls[gP] : 0;
+        for (int i = 0; i < 6; ++i) b.pad_[i] = 0;
+        a.born[k] = b;
+    } else {
+        atomicAdd(&a.counters->overflow, 1ULL);
+    }
+}
+
+// exchangeQK::exchange (gP: the molecule, becomes the atom; gQ: the atom, becomes the molecule)
+__device__ void exchangeParcels(const CollideArgs& a, const DevParams& P, Rng& rng, const DevReaction& R, int ri, int32_t gP, int32_t gQ, int32_t cell,
+                                bool& relax) {
+    const ParcelArrays& p = a.p;
+    atomicAdd(&a.counters->nReact[ri][2], 1ULL);
+    if (!R.allowSplitting) return;
+    relax = false;
+    const int tP = p.typeId[gP], tQ = p.typeId[gQ];
+    const V3 UP0 = mk(p.ux[gP], p.uy[gP], p.uz[gP]), UQ0 = mk(p.ux[gQ], p.uy[gQ], p.uz[gQ]);
+    const double mP = P.sp[tP].mass, mQ = P.sp[tQ].mass, mR = mP * mQ / (mP + mQ);
+    const double cRsqr = magSqr(UP0 - UQ0);
+    double translationalEnergy = 0.5 * mR * cRsqr;
+    const V3 Ucm = (mP * UP0 + mQ * UQ0) / (mP + mQ);
+    const int typeIdMol = R.exchProd[0], typeIdAtom = R.exchProd[1];
+    const double mPExch = P.sp[typeIdAtom].mass, mQExch = P.sp[typeIdMol].mass, mRExch = mPExch * mQExch / (mPExch + mQExch);
+    const double omegaExch = 0.5 * (P.sp[typeIdAtom].omega + P.sp[typeIdAtom].omega);   // the atom twice, as in the reference (:296-301)
+    const double EVibP = eVibTot(P, p, gP, P.sp[tP]);
+    const double EEleP = P.sp[tP].eElec[p.elevel ? p.elevel[gP] : 0], EEleQ = P.sp[tQ].eElec[p.elevel ? p.elevel[gQ] : 0];
+    translationalEnergy += (p.erot ? p.erot[gP] : 0.0) + EVibP + EEleP + EEleQ + R.heatExchJ;
+    p.typeId[gP] = uint8_t(typeIdAtom); clearInternal(P, p, gP);
+    p.typeId[gQ] = uint8_t(typeIdMol); clearInternal(P, p, gQ);
+    const double* tMacro = a.overallT ? a.overallT + cell : nullptr;
+    redistributeInPlace<true, MAX_MODES>(P, rng, InPlace{p, 0}, gQ, typeIdMol, typeIdAtom, translationalEnergy, omegaExch, tMacro, true);
+    const double relVelExchMol = sqrt(2.0 * translationalEnergy / mRExch);
+    V3 UP = Ucm, UQ = UQ0;
+    postReactionVelocities(P, rng, typeIdAtom, typeIdMol, UP, UQ, relVelExchMol);
+    p.ux[gP] = UP.x; p.uy[gP] = UP.y; p.uz[gP] = UP.z;
+    p.ux[gQ] = UQ.x; p.uy[gQ] = UQ.y; p.uz[gQ] = UQ.z;
+}
+
+// <model>::reaction(p, q); returns relax().  (gp0, gq0): the candidate pair in the order noTimeCounter passes it
+__device__ __noinline__ bool reactPair(const CollideArgs& a, const DevParams& P, Rng& rng, int ri, int32_t gp0, int32_t gq0, int32_t cell, int32_t cand) {
+    const ParcelArrays& p = a.p;
+    const DevReaction& R = P.reactions[ri];
+    bool relax = true;
+    if (R.model == DSMCB200_REACT_EXCHANGE_QK) {
+        int32_t gP = gp0, gQ = gq0;   // P must be the molecule
+        { const int ty = P.sp[p.typeId[gp0]].type; if (ty == 10 || ty == 11) { gP = gq0; gQ = gp0; } }
+        const int tP = p.typeId[gP], tQ = p.typeId[gQ];
+        const double mP = P.sp[tP].mass, mQ = P.sp[tQ].mass, mR = mP * mQ / (mP + mQ);
+        const double omegaPQ = 0.5 * (P.sp[tP].omega + P.sp[tQ].omega);
+        const double translationalEnergy = 0.5 * mR * magSqr(mk(p.ux[gP], p.uy[gP], p.uz[gP]) - mk(p.ux[gQ], p.uy[gQ], p.uz[gQ]));
+        double total = 0.0, prob = 0.0, Ecoll = 0.0;
+        testExchange(P, R, p, gP, translationalEnergy, omegaPQ, Ecoll, total, prob);
+        if (total > rng.sample01()) exchangeParcels(a, P, rng, R, ri, gP, gQ, cell, relax);
+        return relax;
+    }
+    int32_t gP = gp0, gQ = gq0;
+    if (p.typeId[gp0] != R.reactants[0]) { gP = gq0; gQ = gp0; }
+    const int tP = p.typeId[gP], tQ = p.typeId[gQ];
+    const double mP = P.sp[tP].mass, mQ = P.sp[tQ].mass, mR = mP * mQ / (mP + mQ);
+    const double omegaPQ = 0.5 * (P.sp[tP].omega + P.sp[tQ].omega);
+    const double translationalEnergy = 0.5 * mR * magSqr(mk(p.ux[gP], p.uy[gP], p.uz[gP]) - mk(p.ux[gQ], p.uy[gQ], p.uz[gQ]));
+    const bool mixed = R.model == DSMCB200_REACT_DISSOCIATION_EXCHANGE_QK;
+    const int nPoss = mixed ? 3 : 2;
+    double total = 0.0, pr0 = 0.0, pr1 = 0.0, pr2 = 0.0, Ec0 = 0.0, Ec1 = 0.0, Ec2 = 0.0;
+    int vibModeDissoP = -1, vibModeDissoQ = -1;
+    testDissociation(P, p, gP, translationalEnergy, vibModeDissoP, Ec0, total, pr0);
+    if (mixed || tP != tQ) testDissociation(P, p, gQ, translationalEnergy, vibModeDissoQ, Ec1, total, pr1);
+    if (mixed) testExchange(P, R, p, R.posMolReactant == 0 ? gP : gQ, translationalEnergy, omegaPQ, Ec2, total, pr2);
+    if (total > rng.sample01()) {
+        const double n0 = pr0 / total, n1 = pr1 / total, n2 = pr2 / total;
+        // dsmcReaction::decreasing_sort_indices (dsmcReaction.C:176-205): one random number per entry breaks ties
+        const double r0 = rng.sample01(), r1 = rng.sample01(), r2 = mixed ? rng.sample01() : 0.0;
+        auto val = [&](int i) { return i == 0 ? n0 : (i == 1 ? n1 : n2); };
+        auto rnd = [&](int i) { return i == 0 ? r0 : (i == 1 ? r1 : r2); };
+        int idx0 = 0, idx1 = 1, idx2 = 2;
+        auto before = [&](int b, int a2) { return (val(b) == val(a2)) ? (rnd(b) > rnd(a2)) : (val(b) > val(a2)); };   // b sorts in front of a2
+        if (before(idx1, idx0)) { const int t = idx0; idx0 = idx1; idx1 = t; }
+        if (nPoss == 3) {
+            if (before(idx2, idx1)) { const int t = idx1; idx1 = idx2; idx2 = t; if (before(idx1, idx0)) { const int t2 = idx0; idx0 = idx1; idx1 = t2; } }
+        }
+        double cumulative = 0.0;
+        for (int k = 0; k < nPoss; ++k) {
+            const int i = k == 0 ? idx0 : (k == 1 ? idx1 : idx2);
+            const double ni = val(i);
+            if (!(ni > SMALL)) break;
+            cumulative += ni;
+            if (cumulative > rng.sample01()) {
+                if (i == 0) dissociateParticleByPartner(a, P, rng, R, ri, gP, gQ, 0, vibModeDissoP, Ec0, cell, cand, relax);
+                else if (i == 1) dissociateParticleByPartner(a, P, rng, R, ri, gQ, gP, 1, vibModeDissoQ, Ec1, cell, cand, relax);
+                else if (R.posMolReactant == 0) exchangeParcels(a, P, rng, R, ri, gP, gQ, cell, relax);
+                else exchangeParcels(a, P, rng, R, ri, gQ, gP, cell, relax);
+                break;
+            }
+        }
+    }
+    return relax;
+}
+
 __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 }  // namespace
 
-template <bool ZV2008, int NM>
+template <bool ZV2008, int NM, bool CHEM>
 __global__ void __launch_bounds__(LANE_WARPS * 32) collideLaneKernel(const __grid_constant__ CollideArgs a) {
     __shared__ LaneSmem smAll[LANE_WARPS];
     const unsigned FULL = 0xffffffffu;
@@ -634,7 +879,20 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) collideLaneKernel(const __gri
                         V3 UQ = mk(a.p.ux[gq], a.p.uy[gq], a.p.uz[gq]);
                         const double sTcR = sigmaTcR(P, tP, tQ, mag(UP - UQ));
                         if (sTcR > cellMax) cellMax = sTcR;
-                        if ((sTcR / sigmaL) > rng.sample01()) {
+                        bool relax = (sTcR / sigmaL) > rng.sample01();
+                        if constexpr (CHEM) {
+                            if (relax) {   // chemical reactions (noTimeCounter.C:250-303)
+                                const int rMId = P.pairReaction[tP][tQ];
+                                if (rMId >= 0) {
+                                    relax = reactPair(a, P, rng, rMId, gp, gq, c, k);
+                                    if (!relax) {   // later candidates of the cell see the new species
+                                        sm.typ[rel + cp] = a.p.typeId[gp]; sm.typ[rel + cq] = a.p.typeId[gq];
+                                        totColl += 1;
+                                    }
+                                }
+                            }
+                        }
+                        if (relax) {
                             double cR = -1;
                             if (LB) {
                                 const double mR = P.mR[tP][tQ];
@@ -694,11 +952,12 @@ cudaError_t launchCollide(const CollideArgs& a, cudaStream_t s) {
         if (grid > 148 * 4) grid = 148 * 4;  // persistent: 4 resident blocks per SM, grid-stride over the cell groups
         if (grid < 1) grid = 1;
         // engine.cu passes overallT only for inverseZvFormulation "2008"
-        if (a.overallT) collideLaneKernel<true, MAX_MODES><<<grid, LANE_WARPS * 32, 0, s>>>(a);
-        else if (a.nModes <= 0) collideLaneKernel<false, 0><<<grid, LANE_WARPS * 32, 0, s>>>(a);
-        else if (a.nModes == 1) collideLaneKernel<false, 1><<<grid, LANE_WARPS * 32, 0, s>>>(a);
-        else if (a.nModes == 2) collideLaneKernel<false, 2><<<grid, LANE_WARPS * 32, 0, s>>>(a);
-        else collideLaneKernel<false, MAX_MODES><<<grid, LANE_WARPS * 32, 0, s>>>(a);
+        if (a.born) collideLaneKernel<true, MAX_MODES, true><<<grid, LANE_WARPS * 32, 0, s>>>(a);   // with chemistry: the general instance
+        else if (a.overallT) collideLaneKernel<true, MAX_MODES, false><<<grid, LANE_WARPS * 32, 0, s>>>(a);
+        else if (a.nModes <= 0) collideLaneKernel<false, 0, false><<<grid, LANE_WARPS * 32, 0, s>>>(a);
+        else if (a.nModes == 1) collideLaneKernel<false, 1, false><<<grid, LANE_WARPS * 32, 0, s>>>(a);
+        else if (a.nModes == 2) collideLaneKernel<false, 2, false><<<grid, LANE_WARPS * 32, 0, s>>>(a);
+        else collideLaneKernel<false, MAX_MODES, false><<<grid, LANE_WARPS * 32, 0, s>>>(a);
     }
     int gridBig = (a.nCells + COL_WARPS - 1) / COL_WARPS;
     if (gridBig > 148 * 4) gridBig = 148 * 4;
@@ -846,6 +1105,47 @@ __global__ void __launch_bounds__(SMP_THREADS) sampleKernel(const __grid_constan
     }
 }
 
+// The parcels this step's dissociations created are part of the cloud (dsmcVolFields loops over the cloud, dsmcVolFields.C:1115) but in
+// no cell list until the next buildCellOccupancy: one thread per such parcel adds its row.
+__global__ void sampleTailKernel(const __grid_constant__ SampleArgs a) {
+    const int32_t g = a.nParcels + blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.nCloud) return;
+    const DevParams& P = *a.P;
+    const int32_t cell = a.p.cell[g];
+    if (cell < 0) return;
+    const bool internal = P.hasInternalEnergy != 0;
+    const int qFlux = 5 + (internal ? 2 + P.nModes : 0);
+    const int qClass = qFlux + (P.measureFlux ? 12 : 0);
+    const int mySp = a.p.typeId[g];
+    double* row = a.acc + (size_t(cell) * a.nSpecies + mySp) * a.nQ;
+    const double ux = a.p.ux[g], uy = a.p.uy[g], uz = a.p.uz[g];
+    const double cc = ux * ux + uy * uy + uz * uz;
+    atomicAdd(row + 0, 1.0); atomicAdd(row + 1, ux); atomicAdd(row + 2, uy); atomicAdd(row + 3, uz); atomicAdd(row + 4, cc);
+    double Eint = 0.0;
+    if (internal) {
+        const DevSpecies& Sp = P.sp[mySp];
+        const double er = a.p.erot[g];
+        atomicAdd(row + 5, er);
+        atomicAdd(row + 6, Sp.eElec[a.p.elevel[g]]);
+        Eint = er;
+#pragma unroll
+        for (int m = 0; m < MAX_MODES; ++m) {
+            if (m < P.nModes) {
+                const double ev = (m < Sp.nVib) ? a.p.vib[m][g] * P.kB * Sp.thetaV[m] : 0.0;
+                atomicAdd(row + 7 + m, ev);
+                Eint += ev;
+            }
+        }
+    }
+    if (P.measureFlux) {
+        double* f = row + qFlux;
+        atomicAdd(f + 0, ux * ux); atomicAdd(f + 1, ux * uy); atomicAdd(f + 2, ux * uz); atomicAdd(f + 3, uy * uy); atomicAdd(f + 4, uy * uz);
+        atomicAdd(f + 5, uz * uz); atomicAdd(f + 6, cc * ux); atomicAdd(f + 7, cc * uy); atomicAdd(f + 8, cc * uz);
+        atomicAdd(f + 9, Eint * ux); atomicAdd(f + 10, Eint * uy); atomicAdd(f + 11, Eint * uz);
+    }
+    if (P.measureClass) atomicAdd(row + qClass + (a.p.cls ? a.p.cls[g] : 0), 1.0);
+}
+
 cudaError_t launchSample(const SampleArgs& a, cudaStream_t s) {
     // group size: about 1000 parcels of consecutive cells, at most SMP_THREADS / nQ cells (one phase-2 thread per (cell, quantity));
     // spare threads split each cell's parcels into nSub interleaved sub-ranges (few, crowded cells)
@@ -868,6 +1168,7 @@ cudaError_t launchSample(const SampleArgs& a, cudaStream_t s) {
         const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return e;
         kernel<<<grid, SMP_THREADS, smem, s>>>(a, cpg, nSub, tile);
+        if (a.nCloud > a.nParcels) sampleTailKernel<<<(a.nCloud - a.nParcels + 127) / 128, 128, 0, s>>>(a);
         return cudaGetLastError();
     };
     switch (a.nSpecies) {
@@ -880,6 +1181,47 @@ cudaError_t launchSample(const SampleArgs& a, cudaStream_t s) {
         case 7: return go(sampleKernel<7>);
         default: return go(sampleKernel<8>);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dsmcCloud::addNewParcel for the second products of this step's dissociations: the kernels stage them in atomic order; they join the
+// cloud in the order the reference's serial candidate loop creates them (cell, then candidate), so a run is reproducible.
+// ------------------------------------------------------------------------------------------------
+__global__ void bornKeysKernel(const BornRec* born, int32_t n, unsigned long long* keys, int32_t* idx) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { keys[i] = born[i].key; idx[i] = i; }
+}
+__global__ void appendBornKernel(const __grid_constant__ ParcelArrays p, const BornRec* born, const int32_t* order, int32_t n, int32_t base,
+                                 int32_t origIdBase, int32_t origProc, int32_t nModes) {
+    const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const BornRec b = born[order[r]];
+    const int32_t g = base + r;
+    p.px[g] = b.pos[0]; p.py[g] = b.pos[1]; p.pz[g] = b.pos[2];
+    p.ux[g] = b.U[0]; p.uy[g] = b.U[1]; p.uz[g] = b.U[2];
+    if (p.erot) p.erot[g] = 0.0;
+    p.cell[g] = b.cell; p.tet[g] = b.tet;
+    p.origId[g] = int32_t((uint32_t(origIdBase) + uint32_t(r)) & 0x7fffffffu);
+    for (int m = 0; m < MAX_MODES; ++m) if (m < nModes && p.vib[m]) p.vib[m][g] = 0;
+    p.typeId[g] = b.typeId;
+    if (p.elevel) p.elevel[g] = 0;
+    if (p.cls) p.cls[g] = b.cls;
+    if (p.origProc) p.origProc[g] = uint8_t(origProc);
+}
+size_t orderBornTempBytes(int32_t capacity) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const int32_t*)nullptr,
+                                    (int32_t*)nullptr, capacity);
+    return bytes;
+}
+cudaError_t launchAppendBorn(const ParcelArrays& p, const BornRec* born, int32_t n, int32_t base, int32_t origIdBase, int32_t origProc, int32_t nModes,
+                             unsigned long long* keyWork, int32_t* idxWork, void* temp, size_t tempBytes, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    bornKeysKernel<<<(n + 255) / 256, 256, 0, s>>>(born, n, keyWork, idxWork);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, tempBytes, keyWork, keyWork + n, idxWork, idxWork + n, n, 0, 64, s);
+    if (e != cudaSuccess) return e;
+    appendBornKernel<<<(n + 255) / 256, 256, 0, s>>>(p, born, idxWork + n, n, base, origIdBase, origProc, nModes);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -189,6 +189,27 @@ typedef struct {
     int32_t reserved_;
 } dsmcb200_models;
 
+/* One entry of system/chemReactDict `reactions ( name { reactionModel M; reactants (A B); allowSplitting yes; ... } )`
+ * (DSMC/reactions/basic/dsmcReaction/dsmcReaction.C:79-120).  Quantum-kinetic models:
+ *   dissociationQK          DSMC/reactions/derived/dissociationQK/dissociationQK.C         AB + M -> A + B + M
+ *   exchangeQK              DSMC/reactions/derived/exchangeQK/exchangeQK.C                 AB + C -> A + BC
+ *   dissociationExchangeQK  DSMC/reactions/derived/mixed/dissociationExchangeQK/...C       both, competing */
+typedef enum {
+    DSMCB200_REACT_DISSOCIATION_QK = 1,
+    DSMCB200_REACT_EXCHANGE_QK = 2,
+    DSMCB200_REACT_DISSOCIATION_EXCHANGE_QK = 3
+} dsmcb200_reaction_model;
+
+typedef struct {
+    int32_t model;                       /* dsmcb200_reaction_model                                          */
+    int32_t reactants[2];                /* typeIds, in dictionary order                                     */
+    int32_t allowSplitting;              /* dsmcReaction.C:96 (default yes); no: reactions are only counted  */
+    int32_t dissociationProducts[2][2];  /* dissociationQKProperties.dissociationProducts ((a b) (c d)); -1 -1 for an empty list */
+    int32_t exchangeProducts[2];         /* exchangeQKProperties.exchangeProducts, as listed                 */
+    double heatOfReactionExchange;       /* Kelvin, > 0 exothermic (exchangeQK.C:363-367)                    */
+    double aCoeff, bCoeff;               /* activation-energy coefficients (exchangeQK.C:196-206)            */
+} dsmcb200_reaction;
+
 /* Host-side SoA view of the cloud.  Layout of vectors is OpenFOAM's
  * (x y z) interleaved.  Optional arrays may be NULL on upload (defaults:
  * ERot 0, vibLevel 0, ELevel 0, newParcel -1, classification 0, origId = i,
@@ -275,6 +296,13 @@ int dsmcb200_set_mesh(dsmcb200_ctx*, const dsmcb200_mesh*);
 int dsmcb200_set_species(dsmcb200_ctx*, int nSpecies, const dsmcb200_species*);
 /* replaces: BinaryCollisionModel::New / collisionPartnerSelection::New /
  * dsmcBoundaries ctor, DSMC/clouds/dsmcCloud.C:653-683 */
+/* replaces: dsmcReactions ctor + initialConfiguration (DSMC/reactions/basic/dsmcReactions/dsmcReactions.C:69-165): the reaction
+ * list and the typeId-pair addressing (more than one model for a pair is an error).  Call after set_species, before the first
+ * upload / evolve; n = 0 clears.  The reference's validity checks (products of a diatomic must be atoms, ...) are applied. */
+int dsmcb200_set_reactions(dsmcb200_ctx*, int n, const dsmcb200_reaction* reactions);
+/* replaces: nTotDissociationReactions_ / nTotExchangeReactions_ of the reaction models (dissociationQK.C:276-277, exchangeQK.C:278-279):
+ * counts3n[3 r + {0, 1, 2}] = dissociations of reactant 0, of reactant 1, exchanges of reaction r since set_reactions (this rank) */
+int dsmcb200_reaction_counts(dsmcb200_ctx*, int n, int64_t* counts3n);
 int dsmcb200_set_models(dsmcb200_ctx*, const dsmcb200_models*);
 /* Reserve device storage for up to maxParcels (0 -> grow on demand). */
 int dsmcb200_reserve(dsmcb200_ctx*, int64_t maxParcels);

@@ -44,6 +44,8 @@ def load():
     lib.oracle_set_reorder.argtypes = [P, C.c_int]
     lib.oracle_set_step.argtypes = [P, C.c_uint32]
     lib.oracle_set_rank.argtypes = [P, C.c_int]
+    lib.oracle_set_reactions.argtypes = [P, C.c_int, C.c_void_p]
+    lib.oracle_reaction_counts.argtypes = [P, C.c_void_p]
     lib.oracle_set_threads.argtypes = [C.c_int]
     lib.oracle_get_threads.restype = C.c_int
     lib.oracle_upload_parcels.argtypes = [P, C.c_int64, C.POINTER(capi.ParcelsSoA)]
@@ -118,6 +120,16 @@ class Oracle:
 
     def set_step(self, step):
         self.lib.oracle_set_step(self.h, step)
+
+    def set_reactions(self, reactions):
+        self._reactions = reactions
+        self._ck(self.lib.oracle_set_reactions(self.h, reactions._n, C.cast(reactions, C.c_void_p)))
+
+    def reaction_counts(self):
+        n = self._reactions._n
+        out = np.zeros((max(n, 1), 3), np.int64)
+        self.lib.oracle_reaction_counts(self.h, _ptr(out))
+        return out[:n]
 
     def set_rank(self, rank):
         """Pstream::myProcNo() of this instance: origProc of the parcels it creates."""

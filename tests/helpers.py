@@ -52,3 +52,74 @@ def vhs_equilibrium_collision_rate(n, T, sp, Tref=273.0):
     nu = 4 d^2 n sqrt(pi k Tref / m) (T/Tref)^(1-omega)  (SURVEY 8c iii), collisions/volume/time = n nu / 2."""
     nu = 4.0 * sp.diameter ** 2 * n * np.sqrt(np.pi * KB * Tref / sp.mass) * (T / Tref) ** (1.0 - sp.omega)
     return 0.5 * n * nu
+
+
+# ---- the reacting tutorial (run/hyStrath/dsmcFoam+/heatBath-5species): fixtures of tests/golden/make_golden_heatbath.py ----
+def heatbath_case():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "heatBath_5species_reactions.json")) as f:
+        return json.load(f)
+
+
+def heatbath_setup(x, scale=1.0, seed=7, reactions=True):
+    """One adiabatic cell (specular walls) of N2/O2 at 30 000 K with the tutorial's 12 QK reactions on engine / oracle `x`;
+    scale < 1 runs with fewer, heavier parcels (nEquivalentParticles = 100 / scale).  Returns (case, species dicts, fnum, cell volume)."""
+    case = heatbath_case()
+    L = case["cellSize"]
+    mesh = meshgen.box_mesh((1, 1, 1), (L,) * 3, sides={s: ("wall", "fixedWalls") for s in meshgen.SIDES})
+    fnum = case["nEquivalentParticles"] / scale
+    md = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=fnum, deltaT=case["deltaT"], seed=seed,
+                           rotationalRelaxationCollisionNumber=1.0, vibrationalRelaxationCollisionNumber=1.0,
+                           electronicRelaxationCollisionNumber=1.0, patch_models=[dict(patch=0, boundaryModel="dsmcSpecularWallPatch")])
+    sp = air5()
+    x.set_mesh(mesh); x.set_species(sp); x.set_models(md)
+    if reactions:
+        x.set_reactions(capi.build_reactions(case["typeIdList"], case["reactions"]))
+    spd = [dict(mass=s.mass, diameter=s.diameter, omega=s.omega, rotDof=s.rotationalDegreesOfFreedom,
+                thetaV=[s.thetaV[i] for i in range(s.nVibrationalModes)]) for s in sp]
+    return case, spd, fnum, L ** 3
+
+
+def heatbath_series(x, spd, fnum, vol, steps):
+    """Evolve to each step of `steps` (ascending) and return the fields of THAT step alone (the tutorial samples and resets every
+    step): dict of arrays rhoN_<species>, Ttra, Trot, Tvib, N (parcels)."""
+    from oracle import fields_ref
+    names = ["N2", "O2", "NO", "N", "O"]
+    out = {k: [] for k in ["Ttra", "Trot", "Tvib", "N"] + [f"rhoN_{n}" for n in names]}
+    done = 0
+    for s in steps:
+        if s - 1 > done:
+            x.evolve(s - 1 - done)
+        a0, _, _ = x.accumulators()
+        x.evolve(1)
+        done = s
+        a1, _, _ = x.accumulators()
+        acc = a1 - a0
+        f = fields_ref.derive(acc, None, 1.0, spd, [0, 1, 2, 3, 4], fnum, np.array([vol]))
+        out["Ttra"].append(f["Ttra"][0]); out["Trot"].append(f["Trot"][0]); out["Tvib"].append(f["Tvib"][0])
+        out["N"].append(acc[0, :, 0].sum())
+        for k, n in enumerate(names):
+            out[f"rhoN_{n}"].append(acc[0, k, 0] * fnum / vol)
+    return {k: np.array(v) for k, v in out.items()}
+
+
+def heatbath_check(series, gold, steps, fnum, vol, case):
+    """How far the run is from the shipped time series, per quantity the largest deviation over the sampled steps in units of
+    (sigma + 1 %).  Densities: sigma from the two parcel counts (a reaction converts whole parcels, so a count scatters at most like
+    a Poisson variable; the shipped run is one realisation as well); temperatures: the sqrt(2 / (3 N)) scatter of both runs.  The 1 %
+    covers the history the two realisations do not share."""
+    idx = np.searchsorted(gold["step"], steps)
+    assert np.array_equal(gold["step"][idx], steps)
+    pp_ours, pp_ref = fnum / vol, case["nEquivalentParticles"] / vol   # number density one parcel stands for
+    worst = {}
+    for n in ["N2", "O2", "NO", "N", "O"]:
+        ours, ref = series[f"rhoN_{n}"], gold[f"rhoN_{n}"][idx]
+        sigma = np.sqrt(np.maximum(ours, pp_ours) * pp_ours + np.maximum(ref, pp_ref) * pp_ref)
+        worst[n] = (np.abs(ours - ref) / (sigma + 0.01 * ref.max())).max()
+    n_ref = sum(gold[f"rhoN_{n}"][idx] for n in ["N2", "O2", "NO", "N", "O"]) / pp_ref
+    for k in ["Ttra", "Trot"]:
+        ours, ref = series[k], gold[f"{k}_mixture"][idx]
+        sigma = ref * np.sqrt(2.0 / (3.0 * series["N"]) + 2.0 / (3.0 * n_ref))
+        worst[k] = (np.abs(ours - ref) / (sigma + 0.01 * ref)).max()
+    return worst

@@ -44,7 +44,8 @@ def test_struct_sizes_agree_with_the_c_compiler(tmp_path):
 
     names = {"dsmcb200_patch": capi.Patch, "dsmcb200_species": capi.Species, "dsmcb200_patch_model": capi.PatchModel,
              "dsmcb200_inflow": capi.Inflow, "dsmcb200_models": capi.Models, "dsmcb200_parcels_soa": capi.ParcelsSoA,
-             "dsmcb200_counters": capi.Counters, "dsmcb200_accum_info": capi.AccumInfo, "dsmcb200_mesh": capi.Mesh}
+             "dsmcb200_counters": capi.Counters, "dsmcb200_accum_info": capi.AccumInfo, "dsmcb200_mesh": capi.Mesh,
+             "dsmcb200_reaction": capi.Reaction}
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "dsmcb200.h"\nint main(void) {\n' +
                    "".join(f'  printf("{n} %zu\\n", sizeof({n}));\n' for n in names) + "  return 0;\n}\n")

@@ -1,0 +1,113 @@
+"""GPU tests of the quantum-kinetic chemistry inside the NTC loop (noTimeCounter.C:250-303 with DSMC/reactions/derived/{dissociationQK,
+exchangeQK, mixed/dissociationExchangeQK}): the CUDA path through the C ABI against the CPU oracle on the same seeded input, and against
+the time series the reference ships for its reacting tutorial (tests/golden/heatBath_5species.npz)."""
+import os
+
+import numpy as np
+import pytest
+
+from hystrath_b200 import capi, meshgen
+from oracle.pyoracle import Oracle
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def reacting_box(n=(4, 4, 4), ppc=60, T=25000.0, dens=2e22, dt=2e-9):
+    case = H.heatbath_case()
+    L = 4e-5
+    mesh = meshgen.box_mesh(n, (L,) * 3)
+    fnum = dens * L ** 3 / (np.prod(n) * ppc)
+    md = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=fnum, deltaT=dt, seed=0xD5C0C4E3,
+                           rotationalRelaxationCollisionNumber=1.0, vibrationalRelaxationCollisionNumber=1.0, electronicRelaxationCollisionNumber=1.0)
+    sp = H.air5()
+    rx = capi.build_reactions(case["typeIdList"], case["reactions"])
+    return mesh, sp, md, rx, T, dens
+
+
+def test_reacting_steps_match_the_oracle_parcel_by_parcel():
+    """Five full steps of a periodic box of hot air in which every one of the 12 reactions can fire: reaction counts per reaction and
+    channel, species of every parcel, the parcels created by dissociations (identity, order in the cloud, cell) and the occupancy equal
+    the oracle's exactly; velocities and internal energies to the accuracy of pow()/exp() on the two sides."""
+    mesh, sp, md, rx, T, dens = reacting_box()
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    for x in (eng, ora):
+        x.set_reactions(rx)
+    # molecules and atoms, so that exchange reactions have partners from the first step
+    H.same_start(eng, ora, [0, 1, 2, 3, 4], [0.55 * dens, 0.15 * dens, 0.05 * dens, 0.15 * dens, 0.10 * dens], T, T, T)
+    n0 = ora.num_parcels()
+    for _ in range(5):
+        eng.evolve(1)
+        ora.evolve(1)
+        assert np.array_equal(eng.reaction_counts(), ora.reaction_counts())
+    rc = ora.reaction_counts()
+    assert rc[:, :2].sum() > 100 and rc[:, 2].sum() > 10, rc        # dissociations and exchanges took place
+    g, o = eng.download_parcels(), ora.download_parcels()
+    assert g.n == o.n == n0 + rc[:, :2].sum()                        # one new parcel per dissociation
+    assert np.array_equal(g.origId, o.origId)                        # the same cloud order, new parcels included
+    assert np.array_equal(g.typeId, o.typeId)
+    assert np.array_equal(g.cell, o.cell)
+    assert np.array_equal(g.vibLevel, o.vibLevel)
+    assert np.array_equal(eng.occupancy(), ora.occupancy())
+    assert np.allclose(g.position, o.position, rtol=0, atol=1e-15)
+    assert np.allclose(g.U, o.U, rtol=1e-9, atol=1e-6)
+    assert np.allclose(g.ERot, o.ERot, rtol=1e-9, atol=1e-30)
+    # atoms carry no internal energy, whatever they were before
+    atoms = g.typeId >= 3
+    assert np.all(g.ERot[atoms] == 0) and np.all(g.vibLevel[atoms] == 0)
+    eng.close()
+
+
+def test_reactions_conserve_mass_momentum_and_total_energy():
+    """One collide stage with chemistry: mass and momentum of every cell are unchanged, and the energy a cell loses equals the heats
+    of the reactions that took place in it (dissociation: k theta_d of the molecule; exchange: the dictionary's heat of reaction)."""
+    mesh, sp, md, rx, T, dens = reacting_box(ppc=120)
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    eng.set_reactions(rx)
+    H.same_start(eng, ora, [0, 1, 2, 3, 4], [0.55 * dens, 0.15 * dens, 0.05 * dens, 0.15 * dens, 0.10 * dens], T, T, T)
+    mass = np.array([s.mass for s in sp]); thv = np.array([s.thetaV[0] for s in sp]); thd = np.array([s.thetaD for s in sp])
+
+    def totals(p):
+        m = mass[p.typeId]
+        e = 0.5 * m * (p.U ** 2).sum(1) + p.ERot + p.vibLevel[:, 0] * H.KB * thv[p.typeId]
+        return m.sum(), (m[:, None] * p.U).sum(0), e.sum()
+
+    eng.stage(capi.STAGE_SORT)
+    a = eng.download_parcels()
+    eng.stage(capi.STAGE_COLLIDE)
+    b = eng.download_parcels()
+    rc = eng.reaction_counts()
+    assert b.n == a.n + rc[:, :2].sum() and rc.sum() > 200
+    m0, p0, e0 = totals(a)
+    m1, p1, e1 = totals(b)
+    assert abs(m1 / m0 - 1) < 1e-12
+    assert np.abs(p1 - p0).max() < 1e-10 * np.abs(mass[a.typeId][:, None] * a.U).sum()
+    case = H.heatbath_case()
+    ids = {n: i for i, n in enumerate(case["typeIdList"])}
+    heat = 0.0
+    for k, r in enumerate(case["reactions"]):
+        for ch in range(2):
+            heat += rc[k, ch] * H.KB * thd[ids[r["reactants"][ch]]]
+        if "heatOfReactionExchange" in r:
+            heat -= rc[k, 2] * H.KB * r["heatOfReactionExchange"]
+    assert abs((e0 - e1) - heat) < 1e-9 * e0, ((e0 - e1) / heat)
+    eng.close()
+
+
+def test_reacting_heat_bath_follows_the_shipped_series():
+    """The reference's heatBath-5species tutorial at its own size (one cell, 154 000 parcels, 12 reactions) on the GPU: species
+    densities and temperatures within 3 (sigma + 1 %) of the time series the reference ships, over the first 1000 steps.  The single
+    cell of 1.5e5 parcels also exercises the large-cell sort and collide paths."""
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "heatBath_5species.npz"))
+    eng = capi.Engine(0)
+    case, spd, fnum, vol = H.heatbath_setup(eng, scale=1.0)
+    eng.mesh_fill([0, 1], [case["numberDensities"]["N2"], case["numberDensities"]["O2"]], case["temperature"], case["temperature"], case["temperature"])
+    n0 = eng.num_parcels()
+    assert abs(n0 - 154118) < 2000
+    steps = np.arange(100, 1001, 100)
+    s = H.heatbath_series(eng, spd, fnum, vol, steps)
+    worst = H.heatbath_check(s, gold, steps, fnum, vol, case)
+    assert max(worst.values()) < 3.0, worst
+    rc = eng.reaction_counts()
+    assert eng.num_parcels() == n0 + rc[:, :2].sum()
+    eng.close()
