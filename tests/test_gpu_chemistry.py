@@ -13,9 +13,9 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 
 
-def reacting_box(n=(4, 4, 4), ppc=60, T=25000.0, dens=2e22, dt=2e-9):
+def reacting_box(n=(4, 4, 4), ppc=60, T=25000.0, dens=2e22, dt=2e-8):
     case = H.heatbath_case()
-    L = 4e-5
+    L = 4e-4
     mesh = meshgen.box_mesh(n, (L,) * 3)
     fnum = dens * L ** 3 / (np.prod(n) * ppc)
     md = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=fnum, deltaT=dt, seed=0xD5C0C4E3,
