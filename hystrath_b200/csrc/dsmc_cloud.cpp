@@ -114,6 +114,7 @@ dsmcCloud::dsmcCloud(const std::string& caseDir, const std::string& cloudName, i
     m.owner = owner_.data(); m.neighbour = neighbour_.data(); m.patches = patches_.data();
     check(dsmcb200_set_mesh(ctx_, &m), "dsmcb200_set_mesh");
     check(dsmcb200_set_species(ctx_, int(species_.size()), species_.data()), "dsmcb200_set_species");
+    if (!reactions_.empty()) check(dsmcb200_set_reactions(ctx_, int(reactions_.size()), reactions_.data()), "dsmcb200_set_reactions");
     models_.nPatchModels = int32_t(patchModels_.size()); models_.patchModels = patchModels_.data();
     models_.nInflows = int32_t(inflows_.size()); models_.inflows = inflows_.data();
     check(dsmcb200_set_models(ctx_, &models_), "dsmcb200_set_models");
@@ -276,10 +277,64 @@ void dsmcCloud::readProperties() {
         maxModes_ = std::max(maxModes_, int(sp.nVibrationalModes));
         species_.push_back(sp);
     }
-    if (foam::exists(caseDir_ + "/system/chemReactDict")) {
-        Dict cr = foam::readDict(caseDir_ + "/system/chemReactDict");
-        if (!cr.dictList("reactions").empty())
-            throw FoamError("chemReactDict lists reactions: QK chemistry is outside the scoped path (SURVEY 8f-2); use `reactions ();`");
+    readReactions();
+}
+
+// system/chemReactDict -> dsmcb200_reaction list (dsmcReactions ctor, dsmcReactions.C:69-118; dsmcReaction::setProperties, dsmcReaction.C:79-120;
+// the dissociationQKProperties / exchangeQKProperties sub-dictionaries of the three quantum-kinetic models)
+void dsmcCloud::readReactions() {
+    reactions_.clear(); reactionNames_.clear();
+    if (!foam::exists(caseDir_ + "/system/chemReactDict")) return;
+    Dict cr = foam::readDict(caseDir_ + "/system/chemReactDict");
+    const bool master = rank_ == 0;
+    if (master) std::printf("\nCreating dsmcReactions\n\n");
+    auto typeId = [&](const std::string& reaction, const std::string& n) {
+        for (size_t k = 0; k < typeIdList_.size(); ++k) if (typeIdList_[k] == n) return int32_t(k);
+        throw FoamError("For reaction named " + reaction + "\nCannot find type id: " + n);
+    };
+    for (auto& e : cr.dictList("reactions")) {
+        const Dict& r = *e.second;
+        const std::string name = e.first, model = r.word("reactionModel");
+        if (master) std::printf("Selecting the reaction model %s\n", model.c_str());
+        dsmcb200_reaction R{};
+        if (model == "dissociationQK") R.model = DSMCB200_REACT_DISSOCIATION_QK;
+        else if (model == "exchangeQK") R.model = DSMCB200_REACT_EXCHANGE_QK;
+        else if (model == "dissociationExchangeQK") R.model = DSMCB200_REACT_DISSOCIATION_EXCHANGE_QK;
+        else throw FoamError("dsmcReaction::New(const dictionary&) : \n    unknown dsmc reaction model type " + model +
+                             ", constructor not in hash table\n\n    Valid reaction types are :\n3(dissociationQK exchangeQK dissociationExchangeQK)");
+        const auto reactants = r.wordList("reactants");
+        if (reactants.size() != 2) throw FoamError("For reaction named " + name + "\nThere should be two reactants, instead of " + std::to_string(reactants.size()));
+        for (int k = 0; k < 2; ++k) R.reactants[k] = typeId(name, reactants[k]);
+        R.allowSplitting = r.boolOr("allowSplitting", true) ? 1 : 0;
+        for (int k = 0; k < 2; ++k) R.dissociationProducts[k][0] = R.dissociationProducts[k][1] = -1;
+        R.exchangeProducts[0] = R.exchangeProducts[1] = -1;
+        if (R.model != DSMCB200_REACT_EXCHANGE_QK) {
+            const auto& st = r.subDict("dissociationQKProperties").stream("dissociationProducts");
+            if (st.empty() || st[0].kind != foam::Node::LIST) throw FoamError("For reaction named " + name + "\ndissociationProducts must be a list of two word lists");
+            const auto& lists = st[0].list;
+            if (lists.size() != 2) throw FoamError("For reaction named " + name + "\nThere should be two lists of products, instead of " + std::to_string(lists.size()) + "\nNB: a list can be left empty");
+            for (int k = 0; k < 2; ++k) {
+                if (lists[k].kind != foam::Node::LIST) throw FoamError("For reaction named " + name + "\ndissociationProducts must be a list of two word lists");
+                const auto& prods = lists[k].list;
+                if (!prods.empty() && prods.size() != 2)
+                    throw FoamError("For reaction named " + name + "\nThere should be 2 dissociation products for molecule " + reactants[k] + " instead of " + std::to_string(prods.size()));
+                for (size_t q = 0; q < prods.size(); ++q) R.dissociationProducts[k][q] = typeId(name, prods[q].word);
+            }
+        }
+        if (R.model != DSMCB200_REACT_DISSOCIATION_QK) {
+            const Dict& x = r.subDict("exchangeQKProperties");
+            const auto prods = x.wordList("exchangeProducts");
+            if (prods.size() != 2) throw FoamError("For reaction named " + name + "\nThere should be two products, instead of " + std::to_string(prods.size()));
+            for (int k = 0; k < 2; ++k) R.exchangeProducts[k] = typeId(name, prods[k]);
+            R.heatOfReactionExchange = x.scalar("heatOfReactionExchange");
+            R.aCoeff = x.scalar("aCoeff"); R.bCoeff = x.scalar("bCoeff");
+        }
+        reactions_.push_back(R);
+        reactionNames_.push_back(name);
+    }
+    if (master) {
+        if (!reactions_.empty()) std::printf("Number of reactions created: %d\n", int(reactions_.size()));
+        else std::printf("There are no chemical reactions defined.\n");
     }
 }
 

@@ -76,6 +76,7 @@ class dsmcCloud {
     void readControl();
     void readMesh();
     void readProperties();
+    void readReactions();
     void readBoundaries();
     void readFieldProperties();
     void readCloud();
@@ -107,6 +108,8 @@ class dsmcCloud {
     // models
     std::vector<std::string> typeIdList_;
     std::vector<dsmcb200_species> species_;
+    std::vector<dsmcb200_reaction> reactions_;     // system/chemReactDict
+    std::vector<std::string> reactionNames_;
     dsmcb200_models models_{};
     std::vector<dsmcb200_patch_model> patchModels_;
     std::vector<dsmcb200_inflow> inflows_;

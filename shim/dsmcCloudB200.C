@@ -230,6 +230,113 @@ void Foam::dsmcCloud::readSpecies()
         forAll(eList, l) { s.electronicEnergyList[l] = eList[l]; s.electronicDegeneracyList[l] = gList[l]; }
     }
     ck(dsmcb200_set_species(ctx_, species_.size(), species_.begin()), "dsmcb200_set_species");
+    readReactions();
+}
+
+
+void Foam::dsmcCloud::readReactions()
+{
+    // dsmcReactions ctor (dsmcReactions.C:69-118): system/chemReactDict `reactions ( name { reactionModel M; reactants (A B); ... } )`
+    // for the three quantum-kinetic models of the engine (dissociationQK.C:44-195, exchangeQK.C:44-176)
+    IOobject header("chemReactDict", time_.system(), mesh_, IOobject::READ_IF_PRESENT, IOobject::NO_WRITE);
+    if (!header.headerOk()) return;
+    const IOdictionary chem(header);
+    if (!chem.found("reactions")) return;
+    Info<< nl << "Creating dsmcReactions" << nl << endl;
+    const PtrList<entry> reactionList(chem.lookup("reactions"));
+    HashTable<label> reactionModels;
+    reactionModels.insert("dissociationQK", DSMCB200_REACT_DISSOCIATION_QK);
+    reactionModels.insert("exchangeQK", DSMCB200_REACT_EXCHANGE_QK);
+    reactionModels.insert("dissociationExchangeQK", DSMCB200_REACT_DISSOCIATION_EXCHANGE_QK);
+    reactions_.setSize(reactionList.size());
+    forAll(reactionList, r)
+    {
+        const dictionary& dict = reactionList[r].dict();
+        const word name(reactionList[r].keyword());
+        const word model(dict.lookup("reactionModel"));
+        Info<< "Selecting the reaction model " << model << endl;
+        dsmcb200_reaction& R = reactions_[r];
+        std::memset(&R, 0, sizeof(R));
+        R.model = lookupOrFail(reactionModels, model, "dsmc reaction model");
+        const wordList reactants(dict.lookup("reactants"));
+        if (reactants.size() != 2)
+        {
+            FatalErrorIn("dsmcReaction::setProperties()") << "For reaction named " << name << nl
+                << "There should be two reactants, instead of " << reactants.size() << nl << exit(FatalError);
+        }
+        forAll(reactants, k)
+        {
+            R.reactants[k] = findIndex(typeIdList_, reactants[k]);
+            if (R.reactants[k] == -1)
+            {
+                FatalErrorIn("dsmcReaction::setProperties()") << "For reaction named " << name << nl
+                    << "Cannot find type id: " << reactants[k] << nl << exit(FatalError);
+            }
+        }
+        R.allowSplitting = Switch(dict.lookupOrDefault<Switch>("allowSplitting", true)) ? 1 : 0;
+        for (label k = 0; k < 2; ++k) { R.dissociationProducts[k][0] = R.dissociationProducts[k][1] = -1; R.exchangeProducts[k] = -1; }
+        if (R.model != DSMCB200_REACT_EXCHANGE_QK)
+        {
+            const List<wordList> products(dict.subDict("dissociationQKProperties").lookup("dissociationProducts"));
+            if (products.size() != 2)
+            {
+                FatalErrorIn("dissociationQK::setProperties()") << "For reaction named " << name << nl
+                    << "There should be two lists of products, instead of " << products.size() << nl
+                    << "NB: a list can be left empty" << nl << exit(FatalError);
+            }
+            forAll(products, k)
+            {
+                if (products[k].size() != 0 && products[k].size() != 2)
+                {
+                    FatalErrorIn("dissociationQK::setProperties()") << "For reaction named " << name << nl
+                        << "There should be 2 dissociation products for molecule " << reactants[k] << " instead of "
+                        << products[k].size() << ", that is " << products[k] << exit(FatalError);
+                }
+                forAll(products[k], q)
+                {
+                    R.dissociationProducts[k][q] = findIndex(typeIdList_, products[k][q]);
+                    if (R.dissociationProducts[k][q] == -1)
+                    {
+                        FatalErrorIn("dissociationQK::setProperties()") << "For reaction named " << name << nl
+                            << "Cannot find type id: " << products[k][q] << nl << exit(FatalError);
+                    }
+                }
+            }
+        }
+        if (R.model != DSMCB200_REACT_DISSOCIATION_QK)
+        {
+            const dictionary& x = dict.subDict("exchangeQKProperties");
+            const wordList products(x.lookup("exchangeProducts"));
+            if (products.size() != 2)
+            {
+                FatalErrorIn("exchangeQK::setProperties()") << "For reaction named " << name << nl
+                    << "There should be two products, instead of " << products.size() << nl << exit(FatalError);
+            }
+            forAll(products, k)
+            {
+                R.exchangeProducts[k] = findIndex(typeIdList_, products[k]);
+                if (R.exchangeProducts[k] == -1)
+                {
+                    FatalErrorIn("exchangeQK::setProperties()") << "For reaction named " << name << nl
+                        << "Cannot find type id: " << products[k] << nl << exit(FatalError);
+                }
+            }
+            R.heatOfReactionExchange = readScalar(x.lookup("heatOfReactionExchange"));
+            R.aCoeff = readScalar(x.lookup("aCoeff"));
+            R.bCoeff = readScalar(x.lookup("bCoeff"));
+        }
+    }
+    if (reactions_.size())
+    {
+        Info<< "Number of reactions created: " << reactions_.size() << endl;
+        // the remaining checks of <model>::setProperties (molecule / atom roles, product types) and the typeId-pair addressing of
+        // dsmcReactions::initialConfiguration are applied by the engine with the reference's messages
+        ck(dsmcb200_set_reactions(ctx_, reactions_.size(), reactions_.begin()), "dsmcb200_set_reactions");
+    }
+    else
+    {
+        Info<< "There are no chemical reactions defined." << endl;
+    }
 }
 
 
@@ -388,14 +495,6 @@ void Foam::dsmcCloud::readModels()
     lookupOrFail(partnerModels, word(particleProperties_.lookup("collisionPartnerSelectionModel")), "collisionPartnerSelection");
     lookupOrFail(coordinateSystems, particleProperties_.lookupOrDefault<word>("coordinateSystem", "dsmcCartesian"), "dsmcCoordinateSystem");
     lookupOrFail(timeStepModels, particleProperties_.lookupOrDefault<word>("timeStepModel", "constant"), "dsmcTimeStepModel");
-    if (particleProperties_.found("chemicalReactions") || IOobject("chemReactDict", time_.system(), mesh_).headerOk())
-    {
-        const IOdictionary chem(IOobject("chemReactDict", time_.system(), mesh_, IOobject::READ_IF_PRESENT, IOobject::NO_WRITE));
-        if (chem.found("reactions") && PtrList<entry>(chem.lookup("reactions")).size())
-        {
-            FatalErrorIn("dsmcCloud (dsmcb200)") << "chemReactDict lists reactions: QK chemistry is not part of this engine" << exit(FatalError);
-        }
-    }
     models_.nEquivalentParticles = readScalar(particleProperties_.lookup("nEquivalentParticles"));
     models_.seed = uint64_t(particleProperties_.lookupOrDefault<label>("seedNumber", 1));
     models_.deltaT = mesh_.time().deltaTValue();

@@ -171,3 +171,37 @@ def test_driver_parses_the_shipped_orion_dictionaries(tmp_path):
     assert "species: N2 O2" in out and "collisionModel 2 invZv 2 nEquivalentParticles 2.6708e+15" in out
     assert "patchModels 3 inflows 2 fields 3" in out
     assert "numberDensity N2 2.318e+18" in out and "velocity (6053.4 0 0)" in out
+
+
+HEATBATH = "/root/reference/run/hyStrath/dsmcFoam+/heatBath-5species"
+
+
+@pytest.mark.skipif(not os.path.isdir(HEATBATH), reason="the shipped case directory only exists next to the reference checkout")
+def test_driver_parses_the_shipped_reacting_heat_bath_dictionaries(tmp_path):
+    """The unchanged system/ and constant/ of the shipped reacting tutorial: 12 quantum-kinetic reactions in system/chemReactDict
+    (8 dissociationQK, 4 dissociationExchangeQK), five species, specular walls, per-species dsmcVolFields that reset at every write."""
+    import shutil
+
+    from hystrath_b200 import case as casew
+    from hystrath_b200 import meshgen
+
+    for sub in ("system", "constant"):
+        shutil.copytree(os.path.join(HEATBATH, sub), os.path.join(str(tmp_path), sub))
+    os.chmod(os.path.join(str(tmp_path), "constant"), 0o755)
+    os.chmod(os.path.join(str(tmp_path), "system"), 0o755)
+    casew.write_poly_mesh(str(tmp_path), meshgen.box_mesh((1, 1, 1), (1e-5,) * 3, sides={s: ("wall", "fixedWalls") for s in meshgen.SIDES}))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-initialise", "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout
+    assert "Creating dsmcReactions" in out and out.count("Selecting the reaction model dissociationQK") == 8
+    assert out.count("Selecting the reaction model dissociationExchangeQK") == 4 and "Number of reactions created: 12" in out
+    assert "species: N2 O2 NO N O" in out
+    # a reaction model the engine does not have stops like dsmcReaction::New
+    p = os.path.join(str(tmp_path), "system", "chemReactDict")
+    txt = open(p).read()
+    open(p, "w").write(txt.replace("reactionModel   dissociationQK;", "reactionModel   ionisationQK;", 1))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-initialise", "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "unknown dsmc reaction model type ionisationQK" in r.stderr and "Valid reaction types are" in r.stderr
+    open(p, "w").write(txt.replace("(O2 N2)", "(O2 Xe)", 1))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-initialise", "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "Cannot find type id: Xe" in r.stderr
