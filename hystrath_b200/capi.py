@@ -89,7 +89,7 @@ class Models(C.Structure):
                 ("deltaT", C.c_double), ("seed", C.c_uint64), ("kB", C.c_double), ("nPatchModels", C.c_int32),
                 ("nInflows", C.c_int32), ("patchModels", C.POINTER(PatchModel)), ("inflows", C.POINTER(Inflow)),
                 ("measureHeatFluxShearStress", C.c_int32), ("measureClassifications", C.c_int32),
-                ("trackFaceFluxes", C.c_int32), ("reserved0_", C.c_int32), ("sampleInterval", C.c_int32), ("reserved_", C.c_int32)]
+                ("trackFaceFluxes", C.c_int32), ("coordinateSystem", C.c_int32), ("sampleInterval", C.c_int32), ("angularCoordinate", C.c_int32)]
 
 
 class Reaction(C.Structure):
@@ -151,7 +151,7 @@ class ParcelsSoA(C.Structure):
     _fields_ = [("position", C.c_void_p), ("U", C.c_void_p), ("ERot", C.c_void_p), ("cell", C.c_void_p),
                 ("tetFace", C.c_void_p), ("tetPt", C.c_void_p), ("typeId", C.c_void_p), ("vibLevel", C.c_void_p),
                 ("ELevel", C.c_void_p), ("newParcel", C.c_void_p), ("classification", C.c_void_p), ("origId", C.c_void_p),
-                ("maxModes", C.c_int32), ("pad_", C.c_int32), ("origProc", C.c_void_p)]
+                ("maxModes", C.c_int32), ("pad_", C.c_int32), ("origProc", C.c_void_p), ("radialWeight", C.c_void_p)]
 
 
 class Counters(C.Structure):
@@ -255,7 +255,7 @@ class ParcelData:
     FIELDS = [("position", np.float64, 3), ("U", np.float64, 3), ("ERot", np.float64, 1), ("cell", np.int32, 1),
               ("tetFace", np.int32, 1), ("tetPt", np.int32, 1), ("typeId", np.int32, 1), ("vibLevel", np.int32, 0),
               ("ELevel", np.int32, 1), ("newParcel", np.int32, 1), ("classification", np.int32, 1), ("origId", np.int32, 1),
-              ("origProc", np.int32, 1)]
+              ("origProc", np.int32, 1), ("radialWeight", np.float64, 1)]
 
     def __init__(self, n=0, max_modes=1, allocate=True, **arrays):
         self.n = n
@@ -316,6 +316,8 @@ def load_library():
         "dsmcb200_set_mesh": ([P, C.POINTER(Mesh)], C.c_int),
         "dsmcb200_set_species": ([P, C.c_int, C.POINTER(Species)], C.c_int),
         "dsmcb200_set_models": ([P, C.POINTER(Models)], C.c_int),
+        "dsmcb200_set_cell_fields": ([P, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+        "dsmcb200_download_cell_fields": ([P, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
         "dsmcb200_set_reactions": ([P, C.c_int, C.POINTER(Reaction)], C.c_int),
         "dsmcb200_reaction_counts": ([P, C.c_int, C.c_void_p], C.c_int),
         "dsmcb200_reserve": ([P, C.c_int64], C.c_int),
@@ -355,7 +357,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "dsmcb200_abi_version", "dsmcb200_create", "dsmcb200_destroy", "dsmcb200_last_error", "dsmcb200_nccl_unique_id",
     "dsmcb200_init_comm", "dsmcb200_set_mesh", "dsmcb200_set_species", "dsmcb200_set_models", "dsmcb200_set_reactions",
-    "dsmcb200_reaction_counts", "dsmcb200_reserve",
+    "dsmcb200_reaction_counts", "dsmcb200_set_cell_fields", "dsmcb200_download_cell_fields", "dsmcb200_reserve",
     "dsmcb200_upload_parcels", "dsmcb200_download_parcels", "dsmcb200_upload_cellstate", "dsmcb200_download_cellstate",
     "dsmcb200_mesh_fill", "dsmcb200_evolve", "dsmcb200_stage", "dsmcb200_set_step", "dsmcb200_download_occupancy",
     "dsmcb200_accum_info_get", "dsmcb200_download_accumulators", "dsmcb200_upload_accumulators",
@@ -372,14 +374,20 @@ class Dsmcb200Error(RuntimeError):
 def build_models(collisionModel="VariableHardSphere", nEquivalentParticles=1.0, deltaT=1e-6, seed=1, Tref=273.0,
                  rotationalRelaxationCollisionNumber=5.0, vibrationalRelaxationCollisionNumber=0.0,
                  electronicRelaxationCollisionNumber=500.0, inverseZvFormulation="", kB=0.0, patch_models=(), inflows=(),
-                 measureHeatFluxShearStress=False, measureClassifications=False, sampleInterval=1, trackFaceFluxes=False):
+                 measureHeatFluxShearStress=False, measureClassifications=False, sampleInterval=1, trackFaceFluxes=False,
+                 coordinateSystem="dsmcCartesian", angularCoordinate=2):
     """POD form of constant/dsmcProperties + boundariesDict.  Unknown model names raise with the
     reference's 'Valid ... types are' message shape (BinaryCollisionModel.C:70-85)."""
     if collisionModel not in COLLISION_MODEL_NAMES:
         raise Dsmcb200Error(f"BinaryCollisionModel::New(const dictionary&, CloudType&) : \n    unknown BinaryCollisionModelType type "
                             f"{collisionModel}, constructor not in hash table\n\n    Valid BinaryCollisionModel types are :\n"
                             f"{sorted(COLLISION_MODEL_NAMES)}")
+    if coordinateSystem not in COORDINATE_SYSTEM_NAMES:
+        raise Dsmcb200Error(f"dsmcCoordinateSystem::New(const dictionary&) : \n    unknown dsmcCoordinateSystem type {coordinateSystem}, "
+                            f"constructor not in hash table\n\n    Valid coordinate system types are :\n{sorted(COORDINATE_SYSTEM_NAMES)}")
     m = Models()
+    m.coordinateSystem = COORDINATE_SYSTEM_NAMES[coordinateSystem]
+    m.angularCoordinate = int(angularCoordinate)
     m.collisionModel = COLLISION_MODEL_NAMES[collisionModel]
     m.invZvFormulation = {"pre-2008": 0, "2008": 1}.get(inverseZvFormulation, 2)
     m.Tref = Tref
@@ -431,6 +439,64 @@ def build_models(collisionModel="VariableHardSphere", nEquivalentParticles=1.0, 
     return m
 
 
+COORDINATE_SYSTEM_NAMES = {"dsmcCartesian": 0, "dsmcAxisymmetric": 1}
+
+
+def axisymmetric_axes(revolutionAxis="", polarAxis=""):
+    """(revolutionAxis, polarAxis, angularCoordinate) as component labels from the axisymmetricProperties keywords
+    (dsmcAxisymmetric::checkCoordinateSystemInputs, dsmcAxisymmetric.C:337-420; defaults x, y, z)."""
+    rev, pol, ang = 0, 1, 2
+    bad = Dsmcb200Error("Revolution and polar axes are badly defined in constant/dsmcProperties axisymmetricProperties{}")
+    if revolutionAxis == "z":
+        rev = 2
+        if polarAxis == "":
+            pol, ang = 0, 1
+        elif polarAxis == "y":
+            pol, ang = 1, 0
+        elif polarAxis == "x":
+            pol, ang = 0, 1
+        else:
+            raise bad
+    elif revolutionAxis == "y":
+        rev = 1
+        if polarAxis == "":
+            pol, ang = 2, 0
+        elif polarAxis == "x":
+            pol, ang = 0, 2
+        elif polarAxis == "z":
+            pol, ang = 2, 0
+        else:
+            raise bad
+    elif revolutionAxis == "x":
+        if polarAxis == "z":
+            pol, ang = 2, 1
+        elif polarAxis != "y":
+            raise bad
+    return rev, pol, ang
+
+
+def axisymmetric_rwf(cell_centres, face_centres, polar_axis, max_rwf):
+    """dsmcAxisymmetric::recalculateRWF, radial weighting method "cell" (dsmcAxisymmetric.C:236-275): RWF = 1 + (maxRWF - 1) r / radialExtent
+    with r = |cell centre . polar axis| and radialExtent = gMax of the face centres' polar component (:447-456)."""
+    fc = np.asarray(face_centres)[:, polar_axis]
+    radial_extent = fc.max()
+    if not radial_extent > 0:
+        radial_extent = -fc.min()
+    rwf = np.ones(len(cell_centres))
+    rwf += (max_rwf - 1.0) * np.abs(np.asarray(cell_centres)[:, polar_axis]) / radial_extent
+    return rwf, radial_extent
+
+
+def variable_time_step(cell_volumes, n_equivalent_particles, delta_t):
+    """dsmcVariableTimeStepModel (variableTimeStepModel/dsmcVariableTimeStepModel.C:48-100): the smallest cell keeps nEquivalentParticles
+    and deltaT, every other cell scales both with its volume, so that nParticles / deltaT is uniform and fluxes are conserved."""
+    V = np.asarray(cell_volumes, float)
+    ref = int(np.nonzero(np.abs(V - V.min()) < 1e-15)[0][0])
+    n = n_equivalent_particles * V / V[ref]
+    ratio = n[ref] / delta_t
+    return n, n / ratio
+
+
 class Engine:
     """One dsmcb200 context (one GPU / rank)."""
 
@@ -473,6 +539,17 @@ class Engine:
     def set_models(self, models: Models):
         self._models = models
         self._ck(self.lib.dsmcb200_set_models(self.h, C.byref(models)))
+
+    def set_cell_fields(self, nParticles=None, deltaT=None, RWF=None):
+        """per-cell nParticles (time-step model), deltaT and radial weighting factor; None = uniform"""
+        a = [None if x is None else np.ascontiguousarray(x, np.float64) for x in (nParticles, deltaT, RWF)]
+        self._ck(self.lib.dsmcb200_set_cell_fields(self.h, *[None if x is None else _ptr(x) for x in a]))
+
+    def cell_fields(self):
+        n = self.accum_info().nCells
+        out = [np.zeros(n) for _ in range(3)]
+        self._ck(self.lib.dsmcb200_download_cell_fields(self.h, *[_ptr(x) for x in out]))
+        return out
 
     def set_reactions(self, reactions):
         """reactions: the array of build_reactions()"""

@@ -105,6 +105,10 @@ __global__ void modeToStrided(const int32_t* in, int32_t* out, int32_t n, int32_
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[size_t(i) * stride + m] = in[i];
 }
+__global__ void rwfOfCell(const int32_t* cell, const double* rwfCell, double* rwf, int32_t n) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rwf[i] = (rwfCell && cell[i] >= 0) ? rwfCell[cell[i]] : 1.0;
+}
 __global__ void iotaKernel(int32_t* out, int32_t n, int32_t base) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = base + i;
@@ -162,6 +166,12 @@ struct dsmcb200_ctx {
     void* dBornTemp = nullptr;
     size_t bornTempBytes = 0;
     int32_t bornCap = 0;
+    // per-cell nParticles (time-step model), deltaT and radial weighting factor (dsmcb200_set_cell_fields); empty / nullptr = uniform
+    std::vector<double> hNPts, hDt, hRWF;
+    double *dNPts = nullptr, *dDt = nullptr, *dRWF = nullptr;
+    bool useRwf = false;           // dsmcAxisymmetric: parcels carry a radial weight
+    int32_t* dWeightCounts = nullptr; int64_t weightCountsCap = 0;
+    int64_t cloned = 0, weightDeleted = 0;
     DevParams hP{};
     DevParams* dP = nullptr;
     // device mesh
@@ -277,7 +287,9 @@ void resolveTimers(dsmcb200_ctx* c) {
     c->evUsed = 0;
 }
 
-void setArrays(ParcelBuffer& b, int64_t cap, int nModes, bool internal, bool useCls, bool useOrigProc) {
+CellFields cellFields(const dsmcb200_ctx* c) { return CellFields{c->dNPts, c->dDt, c->dRWF}; }
+
+void setArrays(ParcelBuffer& b, int64_t cap, int nModes, bool internal, bool useCls, bool useOrigProc, bool useRwf) {
     ParcelArrays& a = b.a;
     a.px = b.dslab; a.py = a.px + cap; a.pz = a.py + cap; a.ux = a.pz + cap; a.uy = a.ux + cap; a.uz = a.uy + cap;
     a.erot = internal ? a.uz + cap : nullptr;
@@ -285,14 +297,15 @@ void setArrays(ParcelBuffer& b, int64_t cap, int nModes, bool internal, bool use
     for (int m = 0; m < MAX_MODES; ++m) a.vib[m] = (internal && m < nModes) ? a.origId + cap * (1 + m) : nullptr;
     a.typeId = b.bslab; a.elevel = internal ? b.bslab + cap : nullptr; a.cls = useCls ? b.bslab + 2 * cap : nullptr;
     a.origProc = useOrigProc ? b.bslab + 3 * cap : nullptr;
+    a.rwf = useRwf ? b.dslab + 7 * cap : nullptr;
 }
 
 int allocBuffer(dsmcb200_ctx* c, ParcelBuffer& b, int64_t cap) {
     // one extra double row and one extra int row so that every buffer can stage host AoS arrays
-    CK(devAlloc(&b.dslab, size_t(cap) * 7));
+    CK(devAlloc(&b.dslab, size_t(cap) * (c->useRwf ? 8 : 7)));
     CK(devAlloc(&b.islab, size_t(cap) * (3 + MAX_MODES)));
     CK(devAlloc(&b.bslab, size_t(cap) * 4));
-    setArrays(b, cap, c->nModes, c->internal, c->useCls, c->nRanks > 1);
+    setArrays(b, cap, c->nModes, c->internal, c->useCls, c->nRanks > 1, c->useRwf);
     return 0;
 }
 
@@ -306,9 +319,9 @@ int ensureCapacity(dsmcb200_ctx* c, int64_t n) {
         const ParcelArrays& o = c->buf[c->cur].a;
         const ParcelArrays& d = nb[c->cur].a;
         const size_t nb8 = size_t(c->N) * 8, nb4 = size_t(c->N) * 4, nb1 = size_t(c->N);
-        double* const od[7] = {o.px, o.py, o.pz, o.ux, o.uy, o.uz, o.erot};
-        double* const dd[7] = {d.px, d.py, d.pz, d.ux, d.uy, d.uz, d.erot};
-        for (int k = 0; k < 7; ++k) if (od[k]) CK(cudaMemcpyAsync(dd[k], od[k], nb8, cudaMemcpyDeviceToDevice, c->stream));
+        double* const od[8] = {o.px, o.py, o.pz, o.ux, o.uy, o.uz, o.erot, o.rwf};
+        double* const dd[8] = {d.px, d.py, d.pz, d.ux, d.uy, d.uz, d.erot, d.rwf};
+        for (int k = 0; k < 8; ++k) if (od[k]) CK(cudaMemcpyAsync(dd[k], od[k], nb8, cudaMemcpyDeviceToDevice, c->stream));
         int32_t* const oi[3] = {o.cell, o.tet, o.origId};
         int32_t* const di[3] = {d.cell, d.tet, d.origId};
         for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(di[k], oi[k], nb4, cudaMemcpyDeviceToDevice, c->stream));
@@ -344,6 +357,18 @@ int ensureSfTail(dsmcb200_ctx* c, int64_t n) {
     return 0;
 }
 
+int uploadCellFields(dsmcb200_ctx* c) {
+    const size_t nC = size_t(c->mesh.nCells);
+    struct { std::vector<double>* h; double** d; } f[3] = {{&c->hNPts, &c->dNPts}, {&c->hDt, &c->dDt}, {&c->hRWF, &c->dRWF}};
+    for (auto& x : f) {
+        devFree(*x.d);
+        if (x.h->empty()) continue;
+        if (x.h->size() != nC) return fail(c, DSMCB200_ERR_INVALID, "set_cell_fields: array size differs from the number of cells");
+        CK(upload(x.d, *x.h));
+    }
+    return 0;
+}
+
 // Everything that depends on mesh + species + models: device parameter block, tet table, accumulators.
 int finalize(dsmcb200_ctx* c) {
     if (c->ready) return 0;
@@ -357,6 +382,16 @@ int finalize(dsmcb200_ctx* c) {
     if (P.nPatches > MAX_PATCHES) return fail(c, DSMCB200_ERR_CAPACITY, "more than 64 patches");
     P.collisionModel = md.collisionModel;
     P.invZvFormulation = md.invZvFormulation;
+    if (md.coordinateSystem != DSMCB200_COORD_CARTESIAN && md.coordinateSystem != DSMCB200_COORD_AXISYMMETRIC)
+        return fail(c, DSMCB200_ERR_UNSUPPORTED, "dsmcCoordinateSystem::New(const dictionary&) : \n    unknown dsmcCoordinateSystem type " + std::to_string(md.coordinateSystem) +
+                    ", constructor not in hash table\n\n    Valid coordinate system types are :\n2(dsmcCartesian dsmcAxisymmetric)");
+    P.coordinateSystem = md.coordinateSystem;
+    P.angularCoordinate = md.angularCoordinate;
+    c->useRwf = md.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC;
+    if (c->useRwf) {
+        if (md.angularCoordinate < 0 || md.angularCoordinate > 2) return fail(c, DSMCB200_ERR_INVALID, "dsmcAxisymmetric: angularCoordinate must be 0, 1 or 2");
+        if (c->nRanks > 1) return fail(c, DSMCB200_ERR_UNSUPPORTED, "dsmcAxisymmetric on a decomposed mesh: the migration record does not carry the radial weight yet");
+    }
     P.kB = md.kB > 0 ? md.kB : 1.38065e-23;  // OpenFOAM v1706 physicoChemical::k (pinned by shipped couette fields)
     P.Tref = md.Tref > 0 ? md.Tref : 273.0;
     P.nParticles = md.nEquivalentParticles;
@@ -638,6 +673,7 @@ int finalize(dsmcb200_ctx* c) {
         CK(cudaMemset(c->dFaceFlux, 0, size_t(2) * P.nSpecies * M.nFaces * 8));
     }
     CK(devAlloc(&c->dCounters, 1)); CK(cudaMemset(c->dCounters, 0, sizeof(DevCounters)));
+    { int r = uploadCellFields(c); if (r) return r; }
     CK(devAlloc(&c->dBad, 1));
     CK(devAlloc(&c->dInfo, 8)); CK(devAlloc(&c->dInfoScratch, size_t(infoScratchDoubles())));
     // inflow state
@@ -687,6 +723,7 @@ int64_t bornHeadroom(int64_t n) { return n / 8 + 4096; }
 int ensureBornBuffers(dsmcb200_ctx* c) {
     const int64_t want = bornHeadroom(c->N);
     if (want <= c->bornCap) return 0;
+    devFree(c->dNPts); devFree(c->dDt); devFree(c->dRWF); devFree(c->dWeightCounts);
     devFree(c->dBorn); devFree(c->dBornKeys); devFree(c->dBornIdx);
     if (c->dBornTemp) { cudaFree(c->dBornTemp); c->dBornTemp = nullptr; }
     const int32_t cap = int32_t(std::min<int64_t>(want + want / 4, (int64_t(1) << 30)));
@@ -738,7 +775,7 @@ int stageInflow(dsmcb200_ctx* c, int64_t tailStart) {
         a.nFaces = pi.size; a.patch = in.patch; a.patchStart = pi.start;
         a.faceOffsets = c->dFaceOffsets; a.facePoints = c->dFacePoints; a.owner = c->dOwner; a.tetBasePtIs = c->dTetBasePtIs;
         a.bfaces = c->dBFaces; a.nInternalFaces = M.nInternalFaces; a.points = c->dPoints; a.faceCentres = c->dFaceCentres; a.faceAreas = c->dFaceAreas;
-        a.origProc = c->rank;
+        a.origProc = c->rank; a.cf = cellFields(c);
         a.P = c->dP; a.nTypes = in.nTypes; a.faceFlux = c->dFaceFlux; a.nFacesAll = M.nFaces;
         for (int i = 0; i < in.nTypes; ++i) { a.typeIds[i] = in.typeIds[i]; a.numberDensities[i] = in.numberDensities[i]; }
         for (int d = 0; d < 3; ++d) a.velocity[d] = in.velocity[d];
@@ -768,7 +805,7 @@ int stageInflow(dsmcb200_ctx* c, int64_t tailStart) {
 MoveArgs moveArgs(dsmcb200_ctx* c, int32_t tailStart) {
     MoveArgs a{};
     a.p = c->buf[c->cur].a; a.plan = c->dPlan; a.planTotal = c->dPlanBase + c->nGroups + 1; a.gridBlocks = c->moveBlocks; a.stageTets = c->stageTets;
-    a.tailStart = tailStart; a.sfTail = c->dSfTail;
+    a.tailStart = tailStart; a.sfTail = c->dSfTail; a.cf = cellFields(c);
     a.tets = c->dTets; a.bfaces = c->dBFaces; a.bfaceArea = c->dBFaceArea; a.P = c->dP; a.wallAcc = c->dWallAcc; a.nWallQ = c->nWallQ;
     // boundaryMeas_ is cleaned every step (dsmcCloud.C:924) but only folded into the fields on sampled steps (dsmcVolFields.C:1081,1292)
     a.wallsDue = c->sampleCounter + 1 >= std::max(1, c->models.sampleInterval);
@@ -879,12 +916,55 @@ int stageMove(dsmcb200_ctx* c, int64_t tailStart) {
     return 0;
 }
 
+// coordSystem().evolve() (dsmcCloud.C:884) = dsmcAxisymmetric::axisymmetricWeighting + reBuildCellOccupancy (dsmcAxisymmetric.C:477-487)
+int stageWeighting(dsmcb200_ctx* c) {
+    if (!c->useRwf || !c->dRWF || c->N == 0) return 0;
+    if (!c->occupancyValid) return fail(c, DSMCB200_ERR_STATE, "radial weighting needs the cell occupancy: run the sort stage first");
+    const int32_t n = int32_t(c->N);
+    if (n + 1 > c->weightCountsCap) {
+        devFree(c->dWeightCounts);
+        c->weightCountsCap = int64_t(n) + n / 4 + 4096;
+        CK(devAlloc(&c->dWeightCounts, size_t(c->weightCountsCap) * 2 + size_t(scanScratchInts(int32_t(c->weightCountsCap))) + 8));
+    }
+    int32_t* counts = c->dWeightCounts;
+    int32_t* offsets = counts + c->weightCountsCap;
+    int32_t* scratch = offsets + c->weightCountsCap;
+    WeightArgs a{};
+    a.p = c->buf[c->cur].a; a.cf = cellFields(c); a.n = n; a.base = n; a.capacity = int32_t(c->capacity);
+    a.angularCoordinate = c->hP.angularCoordinate; a.counts = counts; a.origIdBase = int32_t(c->nextOrigId & 0x7fffffff); a.origProc = c->rank;
+    a.nModes = c->nModes; a.P = c->dP; a.counters = c->dCounters; a.step = c->step;
+    CK(cudaMemsetAsync(&c->dCounters->weightDeleted, 0, sizeof(int32_t), c->stream));
+    { KT t(c, "weighting"); CK(launchWeighting(a, 0, c->stream)); }
+    CK(launchExclusiveScan(counts, offsets, nullptr, n, scratch, c->stream));
+    int32_t total = 0, nDel = 0;
+    CK(cudaMemcpyAsync(&total, offsets + n, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&nDel, &c->dCounters->weightDeleted, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (total == 0 && nDel == 0) return 0;
+    if (total > 0) {
+        if (c->N + total > c->capacity) {
+            // the buffers move: the counts stay valid, the sorted order is kept by the copy
+            { int r = ensureCapacity(c, c->N + total); if (r) return r; }
+            a.p = c->buf[c->cur].a; a.capacity = int32_t(c->capacity);
+        }
+        a.counts = offsets;
+        KT t(c, "weighting");
+        CK(launchWeighting(a, 1, c->stream));
+        c->N += total;
+        c->nextOrigId += total;
+    }
+    c->cloned += total; c->weightDeleted += nDel;
+    c->last.deleted += nDel;
+    return stageSort(c, false);   // cloud_.reBuildCellOccupancy()
+}
+
 int stageCollide(dsmcb200_ctx* c) {
     if (!c->occupancyValid) return fail(c, DSMCB200_ERR_STATE, "cell occupancy is stale: run the sort stage first");
     CollideArgs a{};
     a.p = c->buf[c->cur].a; a.cellOffset = c->dCellOffset; a.nCells = c->mesh.nCells; a.cellCentres = c->dCellCentres;
     a.cellVolumes = c->dCellVolumes; a.sigmaTcRMax = c->dSigma; a.remainder = c->dRem; a.nCollsStep = c->dNColls; a.collSepStep = c->dCollSep;
     a.overallT = c->hP.invZvFormulation == 1 ? c->dOverallT : nullptr;
+    a.cf = cellFields(c);
     a.nModes = c->internal ? c->nModes : 0;
     a.bigScratch = c->dPerm; a.bigList = c->dCursor; a.octKey = c->dOctKey; a.P = c->dP; a.counters = c->dCounters; a.step = c->step;
     const bool chem = !c->reactions.empty();
@@ -1048,6 +1128,36 @@ int dsmcb200_set_models(dsmcb200_ctx* c, const dsmcb200_models* m) {
     return 0;
 }
 
+int dsmcb200_set_cell_fields(dsmcb200_ctx* c, const double* nParticles, const double* deltaT, const double* RWF) {
+    if (!c) return DSMCB200_ERR_INVALID;
+    if (!c->haveMesh) return fail(c, DSMCB200_ERR_STATE, "set_cell_fields: call set_mesh first");
+    const size_t nC = size_t(c->mesh.nCells);
+    auto take = [&](std::vector<double>& h, const double* src, const char* what) -> int {
+        h.clear();
+        if (!src) return 0;
+        for (size_t k = 0; k < nC; ++k) if (!(src[k] > 0)) return fail(c, DSMCB200_ERR_INVALID, std::string("set_cell_fields: ") + what + " must be positive in every cell");
+        h.assign(src, src + nC);
+        return 0;
+    };
+    { int r = take(c->hNPts, nParticles, "nParticles"); if (r) return r; }
+    { int r = take(c->hDt, deltaT, "deltaT"); if (r) return r; }
+    { int r = take(c->hRWF, RWF, "RWF"); if (r) return r; }
+    if (c->ready) { cudaSetDevice(c->device); CK(cudaStreamSynchronize(c->stream)); return uploadCellFields(c); }
+    return 0;
+}
+
+int dsmcb200_download_cell_fields(dsmcb200_ctx* c, double* nParticles, double* deltaT, double* RWF) {
+    if (!c) return DSMCB200_ERR_INVALID;
+    if (!c->haveMesh || !c->haveModels) return fail(c, DSMCB200_ERR_STATE, "download_cell_fields: call set_mesh and set_models first");
+    const size_t nC = size_t(c->mesh.nCells);
+    for (size_t k = 0; k < nC; ++k) {
+        if (nParticles) nParticles[k] = c->hNPts.empty() ? c->models.nEquivalentParticles : c->hNPts[k];
+        if (deltaT) deltaT[k] = c->hDt.empty() ? c->models.deltaT : c->hDt[k];
+        if (RWF) RWF[k] = c->hRWF.empty() ? 1.0 : c->hRWF[k];
+    }
+    return 0;
+}
+
 int dsmcb200_set_reactions(dsmcb200_ctx* c, int n, const dsmcb200_reaction* reactions) {
     if (!c || n < 0 || (n > 0 && !reactions)) return DSMCB200_ERR_INVALID;
     if (c->ready) return fail(c, DSMCB200_ERR_STATE, "reactions cannot change after the engine has been finalised");
@@ -1140,6 +1250,10 @@ int dsmcb200_upload_parcels(dsmcb200_ctx* c, int64_t n, const dsmcb200_parcels_s
         if (h->classification) { CK(cudaMemcpyAsync(sf, h->classification, size_t(n) * 4, cudaMemcpyHostToDevice, s)); i32ToU8<<<GRID(n), 0, s>>>(sf, a.cls, n32); }
         else CK(cudaMemsetAsync(a.cls, 0, size_t(n), s));
     }
+    if (a.rwf) {   // dsmcParcel::RWF_: the lagrangian field radialWeight, or the weight of the parcel's cell
+        if (h->radialWeight) CK(cudaMemcpyAsync(a.rwf, h->radialWeight, size_t(n) * 8, cudaMemcpyHostToDevice, s));
+        else rwfOfCell<<<GRID(n), 0, s>>>(a.cell, c->dRWF, a.rwf, n32);
+    }
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, c->dBad, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -1184,6 +1298,10 @@ int dsmcb200_download_parcels(dsmcb200_ctx* c, int64_t capacity, int64_t* nOut, 
         else for (int64_t i = 0; i < n; ++i) h->origProc[i] = c->rank;
     }
     if (h->newParcel) for (int64_t i = 0; i < n; ++i) h->newParcel[i] = -1;
+    if (h->radialWeight) {
+        if (a.rwf) CK(cudaMemcpyAsync(h->radialWeight, a.rwf, size_t(n) * 8, cudaMemcpyDeviceToHost, s));
+        else for (int64_t i = 0; i < n; ++i) h->radialWeight[i] = 1.0;
+    }
     if (h->vibLevel && h->maxModes > 0) {
         CK(cudaStreamSynchronize(s));
         int32_t* stv = reinterpret_cast<int32_t*>(st.dslab);  // [n][maxModes]
@@ -1231,7 +1349,7 @@ int dsmcb200_mesh_fill(dsmcb200_ctx* c, int nTypes, const int32_t* typeIds, cons
     for (int i = 0; i < nTypes; ++i) { a.typeIds[i] = typeIds[i]; a.numberDensities[i] = numberDensities[i]; }
     a.Ttra = Ttra; a.Trot = Trot; a.Tvib = Tvib; a.Telec = Telec;
     for (int d = 0; d < 3; ++d) a.velocity[d] = velocity ? velocity[d] : 0.0;
-    a.cellCount = c->dCellCount; a.origIdBase = 0; a.origProc = c->rank;
+    a.cellCount = c->dCellCount; a.origIdBase = 0; a.origProc = c->rank; a.cf = cellFields(c);
     a.p = c->buf[c->cur].a;
     CK(launchFill(a, 0, c->stream));
     CK(launchExclusiveScan(c->dCellCount, c->dCellOffset, nullptr, M.nCells, c->dScanScratch, c->stream));
@@ -1267,7 +1385,7 @@ int dsmcb200_stage(dsmcb200_ctx* c, int stage) {
     switch (stage) {
         case DSMCB200_STAGE_INFLOW: r = stageInflow(c, c->N); c->occupancyValid = false; break;  // new parcels are in no cell list; step fractions are only kept until the next stage call
         case DSMCB200_STAGE_MOVE: r = stageMove(c, c->N); c->occupancyValid = false; break;
-        case DSMCB200_STAGE_SORT: r = stageSort(c, false); break;
+        case DSMCB200_STAGE_SORT: r = stageSort(c, false); if (!r) r = stageWeighting(c); break;   // the occupancy the collide stage sees
         case DSMCB200_STAGE_COLLIDE: r = stageCollide(c); break;
         case DSMCB200_STAGE_SAMPLE: r = stageSample(c); break;
         default: return fail(c, DSMCB200_ERR_INVALID, "unknown stage");
@@ -1297,6 +1415,7 @@ int dsmcb200_evolve(dsmcb200_ctx* c, int nSteps) {
         { int r = stageMove(c, tailStart); if (r) return r; }      // Cloud<dsmcParcel>::move
         cudaEventRecord(e2, c->stream);
         { int r = stageSort(c, true); if (r) return r; }           // buildCellOccupancy()
+        { int r = stageWeighting(c); if (r) return r; }            // coordSystem().evolve()
         cudaEventRecord(e3, c->stream);
         { int r = stageCollide(c); if (r) return r; }              // collisions()
         cudaEventRecord(e4, c->stream);
@@ -1431,7 +1550,7 @@ int dsmcb200_get_counters(dsmcb200_ctx* c, dsmcb200_counters* o) {
     // dsmcCloud::info(): one pass over the cloud for the energy sums
     double e5[5] = {0, 0, 0, 0, 0};
     if (c->N > 0) {
-        CK(launchInfo(c->buf[c->cur].a, int32_t(c->N), c->dP, c->dInfo, c->dInfoScratch, c->stream));
+        CK(launchInfo(c->buf[c->cur].a, cellFields(c), int32_t(c->N), c->dP, c->dInfo, c->dInfoScratch, c->stream));
         CK(cudaMemcpyAsync(e5, c->dInfo, sizeof(e5), cudaMemcpyDeviceToHost, c->stream));
     }
     { int r = fetchCounters(c); if (r) return r; }

@@ -61,6 +61,7 @@ struct DevReaction {
 
 struct DevParams {
     int32_t nSpecies, nPatches, collisionModel, invZvFormulation;
+    int32_t coordinateSystem, angularCoordinate;   // dsmcb200_coordinate_system; dsmcAxisymmetric: the mirrored velocity component of a clone
     int32_t nModes;  // max vibrational modes over species (stride of vib arrays)
     int32_t hasInternalEnergy, measureFlux, measureClass;
     int32_t solutionD[3];
@@ -89,6 +90,16 @@ struct ParcelArrays {
     int32_t* vib[MAX_MODES];
     uint8_t *typeId, *elevel, *cls;
     uint8_t* origProc;   // particle::origProc_: with origId the unique identity of a parcel (keys its wall-model random stream)
+    double* rwf;         // dsmcParcel::RWF_ (dsmcAxisymmetric only, else nullptr): the radial weight of the cell the parcel started the step in
+};
+
+// dsmcCloud::nParticles(cell) = nPts[cell] * rwf[cell] and deltaTValue(cell) (dsmcCloudI.H:70-100); nullptr = the uniform value of DevParams
+struct CellFields {
+    const double *nPts, *dt, *rwf;
+    __host__ __device__ double nParticlesTs(const double uniform, int32_t c) const { return nPts ? nPts[c] : uniform; }
+    __host__ __device__ double nParticles(const double uniform, int32_t c) const { const double n = nPts ? nPts[c] : uniform; return rwf ? n * rwf[c] : n; }
+    __host__ __device__ double deltaT(const double uniform, int32_t c) const { return dt ? dt[c] : uniform; }
+    __host__ __device__ double RWF(int32_t c) const { return rwf ? rwf[c] : 1.0; }
 };
 
 // Packed record shipped across a processor patch (BASIC/particle/particleIO.C:121-132 +
@@ -109,13 +120,14 @@ struct DevCounters {
     int32_t bigCells;  // cells handed from collideLaneKernel to collideBigCellsKernel this step
     int32_t bigSortCells;  // cells handed from segmentSortKernel to bigSegmentSortKernel
     int32_t nBorn;         // parcels created by dissociations this step (dsmcCloud::addNewParcel)
+    int32_t weightDeleted; // parcels deleted by the radial weighting this step
     unsigned long long nReact[MAX_REACTIONS][3];   // this step: dissociations of reactant 0, of reactant 1, exchanges
 };
 
 // the second product of a dissociation (dissociationQK.C:355-370) until it joins the cloud in (cell, candidate) order
 struct BornRec {
     unsigned long long key;     // cell << 32 | candidate index: the order in which the reference's serial loop creates them
-    double pos[3], U[3];
+    double pos[3], U[3], rwf;
     int32_t cell, tet;
     uint8_t typeId, cls, pad_[6];
 };
@@ -133,6 +145,7 @@ constexpr int MOVE_NBUF = MOVE_NBUF_SZ;   // entries in flight per block (ring o
 
 struct MoveArgs {
     ParcelArrays p;
+    CellFields cf;
     // work list (launchMovePlan): plan[0 .. *planTotal) = {parcelBeg, parcelEnd, tetBeg, nTets}
     const int4* plan;
     const int32_t* planTotal;
@@ -160,6 +173,7 @@ struct MoveArgs {
 
 struct CollideArgs {
     ParcelArrays p;
+    CellFields cf;
     const int32_t* cellOffset;    // [nCells+1]
     int32_t nCells;
     const double* cellCentres;    // [nCells*3]
@@ -228,11 +242,27 @@ cudaError_t launchSample(const SampleArgs& a, cudaStream_t s);
 size_t orderBornTempBytes(int32_t capacity);
 cudaError_t launchAppendBorn(const ParcelArrays& p, const BornRec* born, int32_t n, int32_t base, int32_t origIdBase, int32_t origProc, int32_t nModes,
                              unsigned long long* keyWork, int32_t* idxWork, void* temp, size_t tempBytes, cudaStream_t s);
-cudaError_t launchInfo(const ParcelArrays& p, int32_t n, const DevParams* P, double* out5, double* scratch, cudaStream_t s);
+cudaError_t launchInfo(const ParcelArrays& p, const CellFields& cf, int32_t n, const DevParams* P, double* out5, double* scratch, cudaStream_t s);
+
+// dsmcAxisymmetric::axisymmetricWeighting (dsmcAxisymmetric.C:50-209) over the sorted cloud [0, n): pass 0 gives every parcel its cell's RWF,
+// marks the parcels to delete (cell = -1) and counts the clones of each parcel; pass 1 (counts scanned) writes the clones behind the cloud
+struct WeightArgs {
+    ParcelArrays p;
+    CellFields cf;
+    int32_t n, base, capacity;
+    int32_t angularCoordinate;
+    int32_t* counts;              // [n + 1] clones per parcel -> offsets after the scan
+    int32_t origIdBase, origProc, nModes;
+    const DevParams* P;
+    DevCounters* counters;
+    uint32_t step;
+};
+cudaError_t launchWeighting(const WeightArgs& a, int pass, cudaStream_t s);
 int32_t infoScratchDoubles();
 
 struct FillArgs {
     ParcelArrays p;
+    CellFields cf;
     int32_t nCells;
     const int32_t *cellFaceOffsets, *cellFaces, *faceOffsets, *facePoints, *owner, *tetBasePtIs, *cellTetStart;
     const double *points, *cellCentres;
@@ -270,6 +300,7 @@ cudaError_t launchLocate(const LocateArgs& a, cudaStream_t s);
 
 struct InflowArgs {
     ParcelArrays p;
+    CellFields cf;
     int32_t nFaces;               // faces of the inflow patch
     int32_t patch, patchStart;
     const int32_t *faceOffsets, *facePoints, *owner, *tetBasePtIs;

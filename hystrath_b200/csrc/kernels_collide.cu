@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
         // ---- number of candidate pairs (noTimeCounter.C:142-155)
         const double sigmaTcRMaxLatched = a.sigmaTcRMax[c];
         const double selectedPairs =
-            a.remainder[c] + 0.5 * nC * (nC - 1) * P.nParticles * sigmaTcRMaxLatched * P.deltaT / a.cellVolumes[c];
+            a.remainder[c] + 0.5 * nC * (nC - 1) * a.cf.nParticles(P.nParticles, c) * sigmaTcRMaxLatched * a.cf.deltaT(P.deltaT, c) / a.cellVolumes[c];
         const int32_t nCandidates = int32_t(selectedPairs);
         if (lane == 0) a.remainder[c] = selectedPairs - nCandidates;
         totCand += (lane == 0) ? (unsigned long long)(nCandidates > 0 ? nCandidates : 0) : 0ULL;
@@ -660,6 +660,7 @@ __device__ void dissociateParticleByPartner(const CollideArgs& a, const DevParam
         b.key = (static_cast<unsigned long long>(uint32_t(cell)) << 32) | uint32_t(cand);
         b.pos[0] = p.px[gP]; b.pos[1] = p.py[gP]; b.pos[2] = p.pz[gP];
         b.U[0] = UP2.x; b.U[1] = UP2.y; b.U[2] = UP2.z;
+        b.rwf = p.rwf ? p.rwf[gP] : 1.0;
         b.cell = cell; b.tet = p.tet[gP];
         b.typeId = uint8_t(typeId2); b.cls = p.cls ? p.cls[gP] : 0;
         for (int i = 0; i < 6; ++i) b.pad_[i] = 0;
@@ -850,7 +851,7 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) collideLaneKernel(const __gri
             int32_t nCand = 0;
             if (nMine) {
                 sigmaL = a.sigmaTcRMax[c];
-                const double selectedPairs = a.remainder[c] + 0.5 * n * (n - 1) * P.nParticles * sigmaL * P.deltaT / a.cellVolumes[c];
+                const double selectedPairs = a.remainder[c] + 0.5 * n * (n - 1) * a.cf.nParticles(P.nParticles, c) * sigmaL * a.cf.deltaT(P.deltaT, c) / a.cellVolumes[c];
                 nCand = int32_t(selectedPairs);
                 a.remainder[c] = selectedPairs - nCand;
                 if (nCand < 0) nCand = 0;
@@ -1207,6 +1208,7 @@ __global__ void appendBornKernel(const __grid_constant__ ParcelArrays p, const B
     if (p.elevel) p.elevel[g] = 0;
     if (p.cls) p.cls[g] = b.cls;
     if (p.origProc) p.origProc[g] = uint8_t(origProc);
+    if (p.rwf) p.rwf[g] = b.rwf;
 }
 size_t orderBornTempBytes(int32_t capacity) {
     size_t bytes = 0;
@@ -1230,21 +1232,25 @@ cudaError_t launchAppendBorn(const ParcelArrays& p, const BornRec* born, int32_t
 // ------------------------------------------------------------------------------------------------
 namespace { constexpr int INFO_BLOCKS = 296; constexpr int INFO_THREADS = 256; }
 
-__global__ void __launch_bounds__(INFO_THREADS) infoKernel(const __grid_constant__ ParcelArrays p, int32_t n, const DevParams* Pp, double* scratch) {
+__global__ void __launch_bounds__(INFO_THREADS) infoKernel(const __grid_constant__ ParcelArrays p, const CellFields cf, int32_t n, const DevParams* Pp, double* scratch) {
     __shared__ double red[5][INFO_THREADS / 32];
     const DevParams& P = *Pp;
     double v[5] = {0, 0, 0, 0, 0};
     for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (p.cell[i] < 0) continue;
+        const int32_t cell = p.cell[i];
+        if (cell < 0) continue;
         const DevSpecies& S = P.sp[p.typeId[i]];
         const double ux = p.ux[i], uy = p.uy[i], uz = p.uz[i];
-        v[0] += S.mass;
-        v[1] += 0.5 * S.mass * (ux * ux + uy * uy + uz * uz);
+        const double w = cf.nParticles(P.nParticles, cell);   // this->nParticles(p.cell()), dsmcCloudI.H:278
+        v[0] += S.mass * w;
+        v[1] += 0.5 * S.mass * (ux * ux + uy * uy + uz * uz) * w;
         if (P.hasInternalEnergy) {
-            v[2] += p.erot[i];
+            v[2] += p.erot[i] * w;
+            double ev = 0.0;
 #pragma unroll
-            for (int m = 0; m < MAX_MODES; ++m) if (m < S.nVib) v[3] += p.vib[m][i] * P.kB * S.thetaV[m];
-            v[4] += S.eElec[p.elevel[i]];
+            for (int m = 0; m < MAX_MODES; ++m) if (m < S.nVib) ev += p.vib[m][i] * P.kB * S.thetaV[m];
+            v[3] += ev * w;
+            v[4] += S.eElec[p.elevel[i]] * w;
         }
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1267,14 +1273,14 @@ __global__ void infoFinalKernel(const double* scratch, const DevParams* Pp, doub
     if (threadIdx.x < 5) {
         double x = 0;
         for (int b = 0; b < INFO_BLOCKS; ++b) x += scratch[b * 5 + threadIdx.x];
-        out5[threadIdx.x] = x * Pp->nParticles;
+        out5[threadIdx.x] = x;
     }
 }
 
 int32_t infoScratchDoubles() { return INFO_BLOCKS * 5; }
 
-cudaError_t launchInfo(const ParcelArrays& p, int32_t n, const DevParams* P, double* out5, double* scratch, cudaStream_t s) {
-    infoKernel<<<INFO_BLOCKS, INFO_THREADS, 0, s>>>(p, n, P, scratch);
+cudaError_t launchInfo(const ParcelArrays& p, const CellFields& cf, int32_t n, const DevParams* P, double* out5, double* scratch, cudaStream_t s) {
+    infoKernel<<<INFO_BLOCKS, INFO_THREADS, 0, s>>>(p, cf, n, P, scratch);
     infoFinalKernel<<<1, 32, 0, s>>>(scratch, P, out5);
     return cudaGetLastError();
 }

@@ -29,7 +29,7 @@ __device__ __forceinline__ void tetPointsDev(const double* points, const FaceVie
 }
 
 __device__ __forceinline__ void storeParcel(const ParcelArrays& p, const DevParams& P, int32_t slot, const V3& pos, const V3& U, double ERot,
-                                            const int32_t* vib, int elevel, int32_t cell, int32_t tet, int typeId, int32_t origId, int origProc) {
+                                            const int32_t* vib, int elevel, int32_t cell, int32_t tet, int typeId, int32_t origId, int origProc, double RWF) {
     p.px[slot] = pos.x; p.py[slot] = pos.y; p.pz[slot] = pos.z;
     p.ux[slot] = U.x; p.uy[slot] = U.y; p.uz[slot] = U.z;
     p.cell[slot] = cell; p.tet[slot] = tet; p.origId[slot] = origId;
@@ -41,6 +41,7 @@ __device__ __forceinline__ void storeParcel(const ParcelArrays& p, const DevPara
         p.elevel[slot] = uint8_t(elevel);
     }
     if (p.cls) p.cls[slot] = 0;
+    if (p.rwf) p.rwf[slot] = RWF;
 }
 
 }  // namespace
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(128) fillKernel(const __grid_constant__ FillAr
                 const DevSpecies& S = P.sp[typeId];
                 Rng rng;
                 rng.init(P.seed, uint32_t(cell), uint32_t(tetLocal * MAX_SPECIES + i), 0u, STREAM_FILL);
-                const double particlesRequired = a.numberDensities[i] * tetVolume / P.nParticles;
+                const double particlesRequired = a.numberDensities[i] * tetVolume / a.cf.nParticles(P.nParticles, cell);   // cloud_.nParticles(cellI), dsmcMeshFill.C:146
                 int32_t nParticlesToInsert = int32_t(particlesRequired);
                 if ((particlesRequired - nParticlesToInsert) > rng.sample01()) nParticlesToInsert++;
                 if (pass == 0) { count += nParticlesToInsert; continue; }
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(128) fillKernel(const __grid_constant__ FillAr
                     for (int m = 0; m < S.nVib; ++m) vib[m] = equipartitionVibrationalEnergyLevel(rng, a.Tvib, S.thetaV[m]);
                     const int elevel = equipartitionElectronicLevel(rng, P.kB, a.Telec, S);
                     U += mk(a.velocity[0], a.velocity[1], a.velocity[2]);
-                    storeParcel(a.p, P, slot, pos, U, ERot, vib, elevel, cell, tet, typeId, a.origIdBase + slot, a.origProc);
+                    storeParcel(a.p, P, slot, pos, U, ERot, vib, elevel, cell, tet, typeId, a.origIdBase + slot, a.origProc, a.cf.RWF(cell));
                     ++slot;
                 }
             }
@@ -202,9 +203,10 @@ __global__ void __launch_bounds__(128) inflowKernel(const __grid_constant__ Infl
     if (pass == 0) {
         const double sCosTheta = dot(velocity, -sF / fA) / mostProbableSpeed;
         double acc = a.accumulator[t];
-        acc += (fA * a.numberDensities[m] * P.deltaT * mostProbableSpeed *
+        const int32_t faceCell = a.owner[faceI];   // deltaTValue(faceCells()[f]), nParticles(patch, f): the cell's (dsmcFreeStreamInflowPatch.C:109-140)
+        acc += (fA * a.numberDensities[m] * a.cf.deltaT(P.deltaT, faceCell) * mostProbableSpeed *
                 (exp(-(sCosTheta * sCosTheta)) + sqrtPi * sCosTheta * (1 + erf(sCosTheta)))) /
-               (2.0 * sqrtPi * P.nParticles);
+               (2.0 * sqrtPi * a.cf.nParticles(P.nParticles, faceCell));
         int32_t nI = int32_t(acc) > 0 ? int32_t(acc) : 0;
         if ((acc - nI) > rng.sample01()) nI++;
         acc -= nI;
@@ -268,16 +270,74 @@ __global__ void __launch_bounds__(128) inflowKernel(const __grid_constant__ Infl
         for (int mo = 0; mo < S.nVib; ++mo) vib[mo] = equipartitionVibrationalEnergyLevel(rng, a.Tvib, S.thetaV[mo]);
         const int elevel = equipartitionElectronicLevel(rng, P.kB, a.Telec, S);
         const int32_t tet = a.bfaces[faceI - a.nInternalFaces].tet0 + selectedTriI - 1;
-        storeParcel(a.p, P, slot, pos, U, ERot, vib, elevel, cellI, tet, typeId, int32_t((int64_t(a.origIdBase) + (slot - a.base)) & 0x7fffffff), a.origProc);
+        storeParcel(a.p, P, slot, pos, U, ERot, vib, elevel, cellI, tet, typeId, int32_t((int64_t(a.origIdBase) + (slot - a.base)) & 0x7fffffff), a.origProc, a.cf.RWF(cellI));
         // dsmcParcel::move: a freshly inserted parcel moves a random fraction of the step (dsmcParcel.C:52-59)
         a.sfTail[slot - a.tailStart] = rng.sample01();
         if (a.faceFlux) {
             // dsmcCloud::addNewParcel with newParcel != -1 (dsmcCloud.C:429-437) -> dsmcFaceTracker::trackFaceTransition
             const double sgn = dot(U, sF) >= 0 ? 1.0 : -1.0;
-            atomicAdd(a.faceFlux + size_t(typeId) * a.nFacesAll + faceI, sgn);
-            atomicAdd(a.faceFlux + (size_t(P.nSpecies) + typeId) * a.nFacesAll + faceI, sgn * mass);
+            atomicAdd(a.faceFlux + size_t(typeId) * a.nFacesAll + faceI, sgn * a.cf.RWF(cellI));
+            atomicAdd(a.faceFlux + (size_t(P.nSpecies) + typeId) * a.nFacesAll + faceI, sgn * a.cf.RWF(cellI) * mass);
         }
     }
+}
+
+// ---- dsmcAxisymmetric::axisymmetricWeighting (DSMC/coordinateSystem/derived/axisymmetric/dsmcAxisymmetric.C:50-209) ----
+// One thread per parcel of the sorted cloud (= the occupancy loop of the reference: cell by cell, list order).  The parcel's draw comes
+// from the Philox stream (index in that order, step).  pass 0: the parcel takes its cell's RWF; with a smaller RWF than before it is
+// cloned floor(old/new - 1) times plus once more with the remaining probability, with a larger one it is deleted with probability
+// 1 - old/new.  pass 1: the clones (same state, the angular velocity component mirrored) are written behind the cloud, parent by parent.
+__global__ void __launch_bounds__(256) weightKernel(const __grid_constant__ WeightArgs a, int pass) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const DevParams& P = *a.P;
+    const ParcelArrays& p = a.p;
+    if (pass == 0) {
+        const int32_t cell = p.cell[i];
+        int32_t nClones = 0;
+        if (cell >= 0) {
+            Rng rng;
+            rng.init(P.seed, uint32_t(i), 0u, a.step, STREAM_WEIGHT);
+            const double oldRadialWeight = p.rwf[i], newRadialWeight = a.cf.RWF(cell);
+            p.rwf[i] = newRadialWeight;
+            if (oldRadialWeight > newRadialWeight) {
+                double prob = (oldRadialWeight / newRadialWeight) - 1.0;
+                while (prob > 1.0) { nClones += 1; prob -= 1.0; }
+                if (prob > rng.sample01()) nClones += 1;
+            } else if (newRadialWeight > oldRadialWeight) {
+                if ((oldRadialWeight / newRadialWeight) < rng.sample01()) {
+                    p.cell[i] = -1;   // cloud_.deleteParticle(p): dropped by the rebuild of the occupancy
+                    atomicAdd(&a.counters->weightDeleted, 1);
+                }
+            }
+        }
+        a.counts[i] = nClones;
+        return;
+    }
+    const int32_t first = a.counts[i], nClones = a.counts[i + 1] - first;
+    for (int32_t k = 0; k < nClones; ++k) {
+        const int32_t g = a.base + first + k;
+        if (g >= a.capacity) { atomicAdd(&a.counters->overflow, 1ULL); return; }
+        double U[3] = {p.ux[i], p.uy[i], p.uz[i]};
+        U[a.angularCoordinate] *= -1.0;
+        p.px[g] = p.px[i]; p.py[g] = p.py[i]; p.pz[g] = p.pz[i];
+        p.ux[g] = U[0]; p.uy[g] = U[1]; p.uz[g] = U[2];
+        p.cell[g] = p.cell[i]; p.tet[g] = p.tet[i];
+        p.origId[g] = int32_t((uint32_t(a.origIdBase) + uint32_t(first + k)) & 0x7fffffffu);
+        p.typeId[g] = p.typeId[i];
+        if (p.erot) p.erot[g] = p.erot[i];
+        for (int m = 0; m < MAX_MODES; ++m) if (m < a.nModes && p.vib[m]) p.vib[m][g] = p.vib[m][i];
+        if (p.elevel) p.elevel[g] = p.elevel[i];
+        if (p.cls) p.cls[g] = p.cls[i];
+        if (p.origProc) p.origProc[g] = uint8_t(a.origProc);
+        p.rwf[g] = p.rwf[i];
+    }
+}
+
+cudaError_t launchWeighting(const WeightArgs& a, int pass, cudaStream_t s) {
+    if (a.n <= 0) return cudaSuccess;
+    weightKernel<<<(a.n + 255) / 256, 256, 0, s>>>(a, pass);
+    return cudaGetLastError();
 }
 
 cudaError_t launchInflow(const InflowArgs& a, int pass, cudaStream_t s) {

@@ -116,6 +116,9 @@ struct WallCtx {
     double* wallAcc;
     int32_t nWallQ;
     const double* bfaceArea;
+    double parcelRWF;   // p.RWF(): the weight the parcel carries through the whole move step (dsmcCloud.C:851-862)
+    double deltaT;      // cloud_.deltaTValue(p.cell())
+    double nPts;        // coordSystem().dtModel().nParticles(patch, face) = the face cell's
 };
 
 struct Internal {  // internal energy state: read and written in place by the rare consumers (wall models, migration)
@@ -136,7 +139,7 @@ __device__ void wallMeasure(const WallCtx& w, int32_t measIndex, int32_t bfi, in
     const double m = S.mass;
     const double U_dot_nw = dot(U, nw);
     const V3 Ut = U - U_dot_nw * nw;
-    const double rwf = 1.0 / fmax(fabs(U_dot_nw) * fA * P.deltaT, SMALL);
+    const double rwf = w.parcelRWF / fmax(fabs(U_dot_nw) * fA * w.deltaT, SMALL);
     const double ev0 = S.nVib > 0 ? in.vib0 * P.kB * S.thetaV[0] : 0.0;
     const double ev1 = S.nVib > 1 ? in.vib1 * P.kB * S.thetaV[1] : 0.0;
     const double ev2 = S.nVib > 2 ? in.vib2 * P.kB * S.thetaV[2] : 0.0;
@@ -172,9 +175,9 @@ __device__ void wallMeasureDelta(const WallCtx& w, int32_t measIndex, int32_t bf
     const DevParams& P = *w.P;
     V3 Sf = mk(w.bfaceArea[3 * bfi], w.bfaceArea[3 * bfi + 1], w.bfaceArea[3 * bfi + 2]);
     const double fA = mag(Sf);
-    const double nParticle = 1.0 * P.nParticles;  // RWF * nParticles(patch, face)
-    const double deltaQ = nParticle * (preIE - postIE + (0.0 * P.kB)) / (P.deltaT * fA);
-    const V3 deltaFD = nParticle * (preIMom - postIMom) / (P.deltaT * fA);
+    const double nParticle = w.parcelRWF * w.nPts;  // p.RWF() * dtModel().nParticles(patch, face), dsmcPatchBoundary.C:456-468
+    const double deltaQ = nParticle * (preIE - postIE + (0.0 * P.kB)) / (w.deltaT * fA);
+    const V3 deltaFD = nParticle * (preIMom - postIMom) / (w.deltaT * fA);
     double* a = w.wallAcc + (size_t(measIndex) * P.nSpecies + sp) * w.nWallQ;
     atomicAdd(a + WQ_Q, deltaQ);
     atomicAdd(a + WQ_FDX, deltaFD.x);
@@ -184,7 +187,7 @@ __device__ void wallMeasureDelta(const WallCtx& w, int32_t measIndex, int32_t bf
 
 // dsmcFaceTracker::trackFaceTransition (DSMC/faceTracker/dsmcFaceTracker.C:124-198), RWF = 1.  The parcel's face() is the boundary
 // face bfi when that is >= 0, else the internal tetFace of its tet.
-__device__ __noinline__ void trackFaceTransition(const MoveArgs& a, const DevParams& P, int typeId, const V3& U, int32_t tet, int32_t bfi) {
+__device__ __noinline__ void trackFaceTransition(const MoveArgs& a, const DevParams& P, int typeId, const V3& U, int32_t tet, int32_t bfi, double RWF) {
     int32_t face, target;
     double unsignedCredit = 0.0;
     if (bfi >= 0) {
@@ -199,8 +202,8 @@ __device__ __noinline__ void trackFaceTransition(const MoveArgs& a, const DevPar
     }
     const V3 Sf = mk(a.faceAreas[3 * size_t(face)], a.faceAreas[3 * size_t(face) + 1], a.faceAreas[3 * size_t(face) + 2]);
     const double sgn = unsignedCredit != 0.0 ? 1.0 : (dot(U, Sf) >= 0 ? 1.0 : -1.0);
-    atomicAdd(a.faceFlux + size_t(typeId) * a.nFacesAll + target, sgn);
-    atomicAdd(a.faceFlux + (size_t(P.nSpecies) + typeId) * a.nFacesAll + target, sgn * P.sp[typeId].mass);
+    atomicAdd(a.faceFlux + size_t(typeId) * a.nFacesAll + target, sgn * RWF);
+    atomicAdd(a.faceFlux + (size_t(P.nSpecies) + typeId) * a.nFacesAll + target, sgn * RWF * P.sp[typeId].mass);
 }
 
 __device__ __forceinline__ void loadInternal(const MoveArgs& a, const DevParams& P, int32_t i, Internal& in) {
@@ -214,11 +217,11 @@ __device__ __forceinline__ void loadInternal(const MoveArgs& a, const DevParams&
 }
 
 // dsmcParcel::hitWallPatch / hitPatch -> dsmc{Diffuse,Specular}WallPatch::controlParticle
-__device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int sp, int patch, int32_t measIndex, int32_t bfi, V3 nw, V3 U,
+__device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int32_t cell, int sp, int patch, int32_t measIndex, int32_t bfi, V3 nw, V3 U,
                                            double depthPosition, int* wallHits) {
     const DevParams& P = *a.P;
     const DevPatch& pt = P.patch[patch];
-    WallCtx wctx{a.P, a.wallAcc, a.nWallQ, a.bfaceArea};
+    WallCtx wctx{a.P, a.wallAcc, a.nWallQ, a.bfaceArea, a.p.rwf ? a.p.rwf[i] : 1.0, a.cf.deltaT(P.deltaT, cell), a.cf.nParticlesTs(P.nParticles, cell)};
     Internal in;
     loadInternal(a, P, i, in);
     double preIE, postIE;
@@ -443,8 +446,8 @@ __global__ void __launch_bounds__(MOVE_BLOCK, 1) moveKernel(const __grid_constan
     }
     __syncthreads();
 
-    const double deltaT = P.deltaT;
-    const bool constrained = P.solutionD[0] == -1 || P.solutionD[1] == -1 || P.solutionD[2] == -1;
+    // dsmcParcel.C:76: the reduced-D corrections of position and tracking velocity apply "but not for axisymmetric cases"
+    const bool constrained = P.coordinateSystem == DSMCB200_COORD_CARTESIAN && (P.solutionD[0] == -1 || P.solutionD[1] == -1 || P.solutionD[2] == -1);
 
     // warp-uniform: the entry this warp draws parcels from
     int32_t wq = 0;             // its sequence number
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(MOVE_BLOCK, 1) moveKernel(const __grid_constan
                     pos = mk(a.p.px[i], a.p.py[i], a.p.pz[i]);
                     const V3 U = mk(a.p.ux[i], a.p.uy[i], a.p.uz[i]);
                     const double stepFraction = (a.sfTail != nullptr && i >= a.tailStart) ? a.sfTail[i - a.tailStart] : 0.0;
-                    const double tEnd = (1.0 - stepFraction) * deltaT;
+                    const double tEnd = (1.0 - stepFraction) * a.cf.deltaT(P.deltaT, cell < 0 ? 0 : cell);   // deltaTValue(orgCell), dsmcParcel.C:62-63
                     myU[0] = U.x; myU[MOVE_BLOCK] = U.y; myU[2 * MOVE_BLOCK] = U.z; myU[3 * MOVE_BLOCK] = tEnd;
                     faceBfi = -1;
                     hitsAndGuard = 0;
@@ -635,7 +638,7 @@ __global__ void __launch_bounds__(MOVE_BLOCK, 1) moveKernel(const __grid_constan
                                     st &= ~F_KEEP;  // dsmcDeletionPatch::controlParticle
                                 } else if (pt.model != DSMCB200_BND_NONE) {
                                     int wallHits = int(uint32_t(hitsAndGuard) >> 24);
-                                    const V3 U = wallInteraction(a, i, a.p.typeId[i], bf.patch, a.wallsDue ? bf.measIndex : -1, bfi, R.N0,
+                                    const V3 U = wallInteraction(a, i, cell, a.p.typeId[i], bf.patch, a.wallsDue ? bf.measIndex : -1, bfi, R.N0,
                                                                  mk(myU[0], myU[MOVE_BLOCK], myU[2 * MOVE_BLOCK]),
                                                                  pt.linearT ? comp(pos, pt.depthAxis) : 0.0, &wallHits);
                                     hitsAndGuard = (hitsAndGuard & 0xffffff) | (wallHits << 24);
@@ -661,7 +664,7 @@ __global__ void __launch_bounds__(MOVE_BLOCK, 1) moveKernel(const __grid_constan
         // ---- section 2: trackToFace returned -- back in dsmcParcel::move (DSMC/parcels/dsmcParcel.C:92-118) ----
         if (finished) {
             if constexpr (TRACK) {
-                if (st & F_FACESET) trackFaceTransition(a, P, a.p.typeId[i], mk(myU[0], myU[MOVE_BLOCK], myU[2 * MOVE_BLOCK]), tet, faceBfi);  // dsmcParcel.C:106-111
+                if (st & F_FACESET) trackFaceTransition(a, P, a.p.typeId[i], mk(myU[0], myU[MOVE_BLOCK], myU[2 * MOVE_BLOCK]), tet, faceBfi, a.p.rwf ? a.p.rwf[i] : 1.0);  // dsmcParcel.C:106-111
             }
             double tEnd = myU[3 * MOVE_BLOCK];
             if (st & F_KEEP) {
@@ -684,7 +687,7 @@ __global__ void __launch_bounds__(MOVE_BLOCK, 1) moveKernel(const __grid_constan
                     a.p.cell[i] = -1;
                     atomicAdd(&a.counters->deleted, 1ULL);
                 } else if (st & F_SWITCH) {
-                    packMigrant(a, P, i, faceBfi, tet, pos, mk(myU[0], myU[MOVE_BLOCK], myU[2 * MOVE_BLOCK]), 1.0 - tEnd / deltaT);
+                    packMigrant(a, P, i, faceBfi, tet, pos, mk(myU[0], myU[MOVE_BLOCK], myU[2 * MOVE_BLOCK]), 1.0 - tEnd / a.cf.deltaT(P.deltaT, cell));   // stepFraction = 1 - tEnd / deltaTValue(orgCell): the face cell (dsmcParcel.C:97)
                     a.p.cell[i] = -1;
                 } else {
                     a.p.px[i] = pos.x; a.p.py[i] = pos.y; a.p.pz[i] = pos.z;

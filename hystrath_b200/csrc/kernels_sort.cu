@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(256) gatherKernel(const __grid_constant__ Parc
     }
     if (src.cls) dst.cls[k] = src.cls[i];
     if (src.origProc) dst.origProc[k] = src.origProc[i];
+    if (src.rwf) dst.rwf[k] = src.rwf[i];
 }
 
 cudaError_t launchGather(const ParcelArrays& src, const ParcelArrays& dst, const int32_t* perm, const double* cellCentres,

@@ -20,7 +20,8 @@ enum PhiloxStream : uint32_t {
     STREAM_COLLIDE = 3,    // noTimeCounter candidate selection + collision model
     STREAM_WALL = 4,       // wall-model draws of a parcel
     STREAM_INFLOW = 5,     // free-stream inflow (per face)
-    STREAM_NEWPARCEL = 6   // random step fraction of freshly inserted parcels
+    STREAM_NEWPARCEL = 6,  // random step fraction of freshly inserted parcels
+    STREAM_WEIGHT = 7      // dsmcAxisymmetric::axisymmetricWeighting (per sorted parcel)
 };
 
 #if defined(__CUDACC__)

@@ -615,3 +615,70 @@ def flat_plate_mesh():
     mesh.shape = (nx, ny, 1)
     mesh.xs, mesh.ys = xs, ys
     return mesh
+
+
+def axisymmetric_cylinder_mesh(n_axial=40, n_inner=20, n_outer=40, half_depth=(0.000437, 0.00131)):
+    """The blockMesh of the reference's axisymmetric tutorial (run/hyStrath/dsmcFoam+/axisymmetricFlatnosedCylinder/system/blockMeshDict):
+    a 5-degree wedge about the x axis around a flat-nosed cylinder of radius 0.01 whose face sits at x = 0.  Three blocks -- in front of
+    the face (x in [-0.02, 0], r in [0, 0.01]; its innermost row of cells are prisms on the axis), above it (r in [0.01, 0.03]) and above
+    the cylinder (x in [0, 0.02], r in [0.01, 0.03]) -- one cell thick, cells numbered like blockMesh does (block by block, x fastest, then
+    the radial index), so cell fields written by the reference line up.  Patches: flow (patch), cylinder (wall), wedgeFront / wedgeBack
+    (symmetry), as in the dictionary."""
+    zi, zo = half_depth
+    V = {0: (-0.02, 0.01, zi), 1: (0.0, 0.01, zi), 2: (0.0, 0.01, -zi), 3: (-0.02, 0.01, -zi), 4: (-0.02, 0.0, 0.0), 5: (0.0, 0.0, 0.0),
+         6: (-0.02, 0.03, zo), 7: (0.0, 0.03, zo), 8: (-0.02, 0.03, -zo), 9: (0.0, 0.03, -zo), 10: (0.02, 0.01, zi), 11: (0.02, 0.03, zo),
+         12: (0.02, 0.01, -zi), 13: (0.02, 0.03, -zo)}
+    blocks = [((4, 5, 5, 4, 0, 1, 2, 3), (n_axial, 1, n_inner)), ((0, 1, 2, 3, 6, 7, 9, 8), (n_axial, 1, n_outer)),
+              ((1, 10, 12, 2, 7, 11, 13, 9), (n_axial, 1, n_outer))]
+    pts, index = [], {}
+    front, back = set(), set()   # points of the j = 0 / j = 1 planes of the blocks (the axis belongs to both)
+
+    def pid(x):
+        key = tuple(np.round(np.asarray(x) / 1e-12).astype(np.int64))
+        if key not in index:
+            index[key] = len(pts)
+            pts.append(tuple(float(v) for v in x))
+        return index[key]
+
+    cells = []
+    for verts, (nx, ny, nz) in blocks:
+        c = np.array([V[v] for v in verts])
+
+        def point(i, j, k):
+            a, b, g = i / nx, j / ny, k / nz
+            w = [(1 - a) * (1 - b) * (1 - g), a * (1 - b) * (1 - g), a * b * (1 - g), (1 - a) * b * (1 - g),
+                 (1 - a) * (1 - b) * g, a * (1 - b) * g, a * b * g, (1 - a) * b * g]
+            q = pid((np.array(w)[:, None] * c).sum(0))
+            (front if j == 0 else back).add(q)
+            return q
+
+        for k in range(nz):
+            for j in range(ny):
+                for i in range(nx):
+                    v = [point(i, j, k), point(i + 1, j, k), point(i + 1, j + 1, k), point(i, j + 1, k),
+                         point(i, j, k + 1), point(i + 1, j, k + 1), point(i + 1, j + 1, k + 1), point(i, j + 1, k + 1)]
+                    faces = []
+                    for f in ((0, 4, 7, 3), (1, 2, 6, 5), (0, 1, 5, 4), (3, 7, 6, 2), (0, 3, 2, 1), (4, 5, 6, 7)):
+                        lab = []
+                        for q in f:   # a collapsed edge leaves a triangle, a collapsed face nothing
+                            if v[q] not in lab:
+                                lab.append(v[q])
+                        if len(lab) >= 3:
+                            faces.append(tuple(lab))
+                    cells.append(faces)
+    points = np.array(pts)
+
+    def patch_of_face(f):
+        p = points[list(f)]
+        if all(q in front for q in f):
+            return "wedgeFront"
+        if all(q in back for q in f):
+            return "wedgeBack"
+        if np.all(np.abs(p[:, 0]) < 1e-12) and np.all(p[:, 1] <= 0.01 + 1e-12):
+            return "cylinder"   # the flat face
+        if np.all(np.abs(p[:, 1] - 0.01) < 1e-12) and np.all(p[:, 0] >= -1e-12):
+            return "cylinder"   # the side
+        return "flow"
+
+    mesh = poly_mesh_from_cells(points, cells, patch_of_face, [("flow", "patch"), ("cylinder", "wall"), ("wedgeFront", "symmetry"), ("wedgeBack", "symmetry")])
+    return mesh

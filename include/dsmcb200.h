@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DSMCB200_ABI_VERSION 2
+#define DSMCB200_ABI_VERSION 3
 #define DSMCB200_MAX_NEIGHBOURS 16
 #define DSMCB200_MAX_SPECIES 8
 #define DSMCB200_MAX_VIB_MODES 3
@@ -183,11 +183,20 @@ typedef struct {
     int32_t measureHeatFluxShearStress; /* sample the optional 2nd-moment set     */
     int32_t measureClassifications;
     int32_t trackFaceFluxes;       /* dsmcFaceTracker counters (off by default), see dsmcb200_download_face_fluxes */
-    int32_t reserved0_;
+    int32_t coordinateSystem;      /* dsmcb200_coordinate_system: dsmcProperties `coordinateSystem` (dsmcCoordinateSystem.C:81) */
     int32_t sampleInterval;        /* dsmcVolFieldsProperties.sampleInterval: stage 5 runs every n-th step (0, 1: every step;
                                       dsmcVolFields.C:1073-1081,1362)             */
-    int32_t reserved_;
+    int32_t angularCoordinate;     /* dsmcAxisymmetric: the component of U a cloned parcel gets mirrored in (0, 1, 2;
+                                      dsmcAxisymmetric.C:82, 337-420)             */
 } dsmcb200_models;
+
+/* dsmcProperties `coordinateSystem`:
+ *   dsmcCartesian      DSMC/coordinateSystem/derived/Cartesian/dsmcCartesian.C        uniform weights, 2-D tracks constrained to the mesh centre
+ *   dsmcAxisymmetric   DSMC/coordinateSystem/derived/axisymmetric/dsmcAxisymmetric.C  radial weighting factors: parcels carry the RWF of the
+ *                      cell they started the step in; after the move a parcel is cloned / deleted with the ratio of old and new RWF
+ *                      (axisymmetricWeighting, :50-209) and the occupancy is rebuilt.  The per-cell RWF comes from
+ *                      dsmcb200_set_cell_fields (the caller evaluates recalculateRWF, :236-275). */
+typedef enum { DSMCB200_COORD_CARTESIAN = 0, DSMCB200_COORD_AXISYMMETRIC = 1 } dsmcb200_coordinate_system;
 
 /* One entry of system/chemReactDict `reactions ( name { reactionModel M; reactants (A B); allowSplitting yes; ... } )`
  * (DSMC/reactions/basic/dsmcReaction/dsmcReaction.C:79-120).  Quantum-kinetic models:
@@ -231,6 +240,8 @@ typedef struct {
     int32_t pad_;
     int32_t* origProc;     /* [n] particle::origProc_ (BASIC/particle/particle.H:134): with origId the identity of a parcel; NULL on
                               upload = this rank.  Kept on the device only when nRanks > 1. */
+    double* radialWeight;  /* [n] dsmcParcel::RWF_ (the lagrangian field `radialWeight`, dsmcParcelIO.C): NULL on upload = the RWF of
+                              the parcel's cell; written on download only with dsmcAxisymmetric */
 } dsmcb200_parcels_soa;
 
 /* Counters of one evolve() (noTimeCounter.C:312-337, dsmcCloud.C:935-985,
@@ -304,6 +315,17 @@ int dsmcb200_set_reactions(dsmcb200_ctx*, int n, const dsmcb200_reaction* reacti
  * counts3n[3 r + {0, 1, 2}] = dissociations of reactant 0, of reactant 1, exchanges of reaction r since set_reactions (this rank) */
 int dsmcb200_reaction_counts(dsmcb200_ctx*, int n, int64_t* counts3n);
 int dsmcb200_set_models(dsmcb200_ctx*, const dsmcb200_models*);
+/* replaces: the volScalarFields behind dsmcCloud::nParticles(cell) and deltaTValue(cell) (DSMC/clouds/dsmcCloudI.H:70-100):
+ *   nParticles[nCells]  dsmcTimeStepModel::nParticles_ (timeStepModel/basic/dsmcTimeStepModelI.H:72-90); NULL = models.nEquivalentParticles
+ *   deltaT[nCells]      dsmcVariableTimeStepModel::deltaT_ (variableTimeStepModel/dsmcVariableTimeStepModel.C:91-100); NULL = models.deltaT
+ *   RWF[nCells]         dsmcAxisymmetric::RWF_ (axisymmetric/dsmcAxisymmetricI.H:55-73); NULL = 1
+ * A cell's parcels stand for nParticles[c] * RWF[c] molecules and advance by deltaT[c] per step: candidate pairs (noTimeCounter.C:101,148),
+ * inflow (dsmcFreeStreamInflowPatch.C:109-140), dsmcMeshFill (dsmcMeshFill.C:146), wall measurements (dsmcPatchBoundary.C:275-289,467),
+ * dsmcParcel::move (dsmcParcel.C:62-97).  The values of a boundary face are those of its cell, as the reference sets them
+ * (dsmcVariableTimeStepModel.C:83-93, dsmcAxisymmetric.C:219-230).  Call after set_mesh, at any time; the arrays are copied. */
+int dsmcb200_set_cell_fields(dsmcb200_ctx*, const double* nParticles, const double* deltaT, const double* RWF);
+/* The three fields as the engine uses them (uniform values expanded); any pointer may be NULL. */
+int dsmcb200_download_cell_fields(dsmcb200_ctx*, double* nParticles, double* deltaT, double* RWF);
 /* Reserve device storage for up to maxParcels (0 -> grow on demand). */
 int dsmcb200_reserve(dsmcb200_ctx*, int64_t maxParcels);
 

@@ -15,7 +15,8 @@ SMALL, VSMALL, GREAT = 1e-15, 1e-300, 1e15
 def derive(acc, coll, n_time_steps, species, type_ids, fnum, cell_volumes, kB=1.38065e-23, deltaT=1.0,
            mfp_tref=273.0, has_internal=True, n_modes=1):
     """acc: [nCells, nSpecies, nQ]; species: list of dicts(mass, diameter, omega, rotDof, thetaV[list]);
-    type_ids: the `typeIds` of the dsmcVolFields instance (subset of species indices)."""
+    type_ids: the `typeIds` of the dsmcVolFields instance (subset of species indices); fnum: nEquivalentParticles, or
+    cloud_.nParticles(cell) per cell for radial weighting / variable time steps (dsmcVolFields.C:1098,1128)."""
     acc = np.asarray(acc, float)
     V = np.asarray(cell_volumes, float)
     nT = float(n_time_steps)
@@ -26,7 +27,7 @@ def derive(acc, coll, n_time_steps, species, type_ids, fnum, cell_volumes, kB=1.
     dsmcNCum = Ns.sum(1)
     nCum = fnum * dsmcNCum
     mCum = fnum * (Ns * m).sum(1)
-    momentumCum = fnum * (acc[:, ids, 1:4] * m[None, :, None]).sum(1)
+    momentumCum = np.reshape(fnum, (-1, 1)) * (acc[:, ids, 1:4] * m[None, :, None]).sum(1)   # fnum: scalar or per cell (nParticles(cell))
     linearKECum = fnum * (acc[:, ids, 4] * m).sum(1)
     out = {}
     ok = dsmcNCum > 1e-3

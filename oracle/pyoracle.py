@@ -51,6 +51,8 @@ def load():
     lib.oracle_upload_parcels.argtypes = [P, C.c_int64, C.POINTER(capi.ParcelsSoA)]
     lib.oracle_download_parcels.argtypes = [P, C.POINTER(capi.ParcelsSoA)]
     lib.oracle_upload_cellstate.argtypes = [P, C.c_void_p, C.c_void_p]
+    lib.oracle_set_cell_fields.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oracle_weighting_counts.argtypes = [P, C.c_void_p, C.c_void_p]
     lib.oracle_download_cellstate.argtypes = [P, C.c_void_p, C.c_void_p]
     lib.oracle_mesh_fill.argtypes = [P, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
     lib.oracle_stage.argtypes = [P, C.c_int]
@@ -120,6 +122,16 @@ class Oracle:
 
     def set_step(self, step):
         self.lib.oracle_set_step(self.h, step)
+
+    def set_cell_fields(self, nParticles=None, deltaT=None, RWF=None):
+        a = [None if x is None else np.ascontiguousarray(x, np.float64) for x in (nParticles, deltaT, RWF)]
+        self._ck(self.lib.oracle_set_cell_fields(self.h, *[None if x is None else _ptr(x) for x in a]))
+
+    def weighting_counts(self):
+        """parcels cloned / deleted by dsmcAxisymmetric::axisymmetricWeighting since creation"""
+        a, b = C.c_int64(), C.c_int64()
+        self.lib.oracle_weighting_counts(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def set_reactions(self, reactions):
         self._reactions = reactions

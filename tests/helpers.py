@@ -123,3 +123,33 @@ def heatbath_check(series, gold, steps, fnum, vol, case):
         sigma = ref * np.sqrt(2.0 / (3.0 * series["N"]) + 2.0 / (3.0 * n_ref))
         worst[k] = (np.abs(ours - ref) / (sigma + 0.01 * ref)).max()
     return worst
+
+
+# ---- the axisymmetric tutorial (run/hyStrath/dsmcFoam+/axisymmetricFlatnosedCylinder): fixture of tests/golden/make_golden_axisym.py ----
+def axisym_gold():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "axisymmetricFlatnosedCylinder.npz"))
+
+
+def axisym_setup(x, gold, geometry, seed=11, fnum_scale=1.0):
+    """The tutorial on engine / oracle `x`: Mach-5.4 argon (1e21 m^-3, 100 K, 1000 m/s) onto a flat-nosed cylinder with a 300 K diffuse
+    wall, free-stream inflow + deletion on `flow`, symmetry planes on the wedge sides, dsmcAxisymmetric about x with radial weighting
+    method "cell" and maxRadialWeightingFactor 1000.  geometry: callable returning (cell centres, ..., face centres) after set_mesh.
+    Returns (mesh, species dicts, per-cell nParticles = F_N * RWF)."""
+    mesh = meshgen.axisymmetric_cylinder_mesh()
+    sp = [capi.make_species("Ar", float(gold["mass"]), float(gold["diameter"]), float(gold["omega"]), float(gold["alpha"]))]
+    rev, pol, ang = capi.axisymmetric_axes()
+    flow, cyl = mesh.patch_index("flow"), mesh.patch_index("cylinder")
+    fnum = float(gold["nEquivalentParticles"]) * fnum_scale
+    md = capi.build_models("VariableHardSphere", nEquivalentParticles=fnum, deltaT=float(gold["deltaT"]), seed=seed,
+                           coordinateSystem="dsmcAxisymmetric", angularCoordinate=ang,
+                           patch_models=[dict(patch=cyl, boundaryModel="dsmcDiffuseWallPatch", temperature=float(gold["wallTemperature"]), velocity=(0, 0, 0)),
+                                         dict(patch=flow, boundaryModel="dsmcDeletionPatch")],
+                           inflows=[dict(patch=flow, typeIds=[0], numberDensities=[float(gold["numberDensity"])], velocity=tuple(gold["velocity"]),
+                                         translationalTemperature=float(gold["temperature"]))])
+    x.set_mesh(mesh); x.set_species(sp); x.set_models(md)
+    cc, cv, fc, *_ = geometry()
+    rwf, _ = capi.axisymmetric_rwf(cc, fc, pol, float(gold["maxRadialWeightingFactor"]))
+    x.set_cell_fields(RWF=rwf)
+    spd = [dict(mass=sp[0].mass, diameter=sp[0].diameter, omega=sp[0].omega, rotDof=0.0, thetaV=[])]
+    return mesh, spd, fnum * rwf, cv

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/dsmcb200.h but not exported"
     assert set(capi.EXPORTED_SYMBOLS) == set(names)
-    assert lib.dsmcb200_abi_version() == 2
+    assert lib.dsmcb200_abi_version() == 3
 
 
 def test_struct_layouts_match_the_header():
@@ -33,7 +33,7 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(capi.Patch) == 64 + 8 * 4 + 24
     assert C.sizeof(capi.Species) == 64 + 5 * 8 + 8 + 9 * 8 + 8 + 8 + 16 * 8 + 16 * 4
     assert C.sizeof(capi.PatchModel) == 8 + 8 + 24 + 8 + 8 + 8   # + diffuseFraction, linearTemperature / depthAxis, formationLevelTemperature
-    assert C.sizeof(capi.ParcelsSoA) == 12 * 8 + 8 + 8
+    assert C.sizeof(capi.ParcelsSoA) == 12 * 8 + 8 + 8 + 8   # + radialWeight
     assert C.sizeof(capi.Counters) == 9 * 8 + 5 * 8 + 8 * 8 + 8 + 16 * 4 + 2 * 16 * 8
     assert C.sizeof(capi.AccumInfo) == 24
 

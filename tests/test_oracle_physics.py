@@ -462,3 +462,107 @@ def test_diffuse_wall_linear_temperature_along_the_depth_axis():
         T_expected = Tg + ((lo + 0.01) - 0.1) * (Tg - Tf) / 0.1
         assert sel.sum() > 1000
         assert abs(T_est[sel].mean() / T_expected - 1) < 0.06, (lo, T_est[sel].mean(), T_expected)
+
+
+def _weighted_box():
+    """4 x 6 x 1 box whose rows of cells carry radial weights growing with y, as an axisymmetric mesh's do"""
+    sides = {"xmin": ("cyclic",), "xmax": ("cyclic",), "ymin": ("symmetryPlane", "axis"), "ymax": ("wall", "top"),
+             "zmin": ("symmetryPlane", "front"), "zmax": ("symmetryPlane", "back")}
+    mesh = meshgen.box_mesh((4, 6, 1), (0.04, 0.06, 0.01), sides=sides)
+    rev, pol, ang = capi.axisymmetric_axes()
+    md = capi.build_models("VariableHardSphere", nEquivalentParticles=1e9, deltaT=2e-6, seed=5, coordinateSystem="dsmcAxisymmetric",
+                           angularCoordinate=ang, patch_models=[dict(patch=mesh.patch_index("top"), boundaryModel="dsmcSpecularWallPatch")])
+    return mesh, md, pol, ang
+
+
+def test_axisymmetric_axes_follow_the_dictionary_keywords():
+    """dsmcAxisymmetric::checkCoordinateSystemInputs (dsmcAxisymmetric.C:337-420)"""
+    assert capi.axisymmetric_axes() == (0, 1, 2)
+    assert capi.axisymmetric_axes("z") == (2, 0, 1) and capi.axisymmetric_axes("z", "y") == (2, 1, 0)
+    assert capi.axisymmetric_axes("y") == (1, 2, 0) and capi.axisymmetric_axes("y", "x") == (1, 0, 2)
+    assert capi.axisymmetric_axes("x", "z") == (0, 2, 1)
+    with pytest.raises(capi.Dsmcb200Error, match="badly defined"):
+        capi.axisymmetric_axes("z", "z")
+
+
+def test_radial_weighting_clones_and_deletes_with_the_weight_ratio():
+    """dsmcAxisymmetric::axisymmetricWeighting (dsmcAxisymmetric.C:50-209): a parcel that arrives in a cell with a smaller RWF is cloned
+    floor(old/new - 1) times plus once with the remaining probability (the clone mirrors the angular velocity component, keeps
+    everything else and takes the new weight); in a cell with a larger RWF it survives with probability old/new.  So the number of
+    molecules a cell's parcels stand for, sum of RWF, is conserved in expectation."""
+    mesh, md, pol, ang = _weighted_box()
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species([H.argon()]); o.set_models(md)
+    cc, cv, fc, *_ = o.geometry()
+    rwf, ext = capi.axisymmetric_rwf(cc, fc, pol, 100.0)
+    assert abs(ext - 0.06) < 1e-15 and abs(rwf[0] - (1 + 99 * 0.005 / 0.06)) < 1e-12
+    o.set_cell_fields(RWF=rwf)
+    o.mesh_fill([0], [4e18], 300.0)     # n V / (F_N RWF) parcels per cell: fewer, heavier parcels away from the axis
+    p = o.download_parcels()
+    assert np.array_equal(p.radialWeight, rwf[p.cell])
+    n_cell = np.bincount(p.cell, minlength=mesh.n_cells)
+    expect = 4e18 * cv / (1e9 * rwf)
+    assert np.abs(n_cell - expect).max() < 5 * np.sqrt(expect.max())
+    # give every parcel the weight 20: cells with RWF < 20 clone, cells with RWF > 20 delete
+    p.radialWeight[:] = 20.0
+    o.upload_parcels(p)
+    o.stage(capi.STAGE_SORT)
+    q = o.download_parcels()
+    cloned, deleted = o.weighting_counts()
+    assert q.n == p.n + cloned - deleted and cloned > 0 and deleted > 0
+    assert np.array_equal(q.radialWeight, rwf[q.cell])
+    new = q.origId >= p.n
+    assert new.sum() == cloned
+    # every clone has a parent with the same position and the mirrored angular velocity component
+    parent = {tuple(x): k for k, x in enumerate(p.position)}
+    for k in np.nonzero(new)[0][:200]:
+        j = parent[tuple(q.position[k])]
+        u = p.U[j].copy(); u[ang] *= -1.0
+        assert np.array_equal(q.U[k], u) and q.cell[k] == p.cell[j]
+    # per row of cells: sum of weights before and after agree within the binomial scatter
+    row = (np.arange(mesh.n_cells) // 4) % 6
+    for r in range(6):
+        w0 = 20.0 * np.isin(p.cell, np.nonzero(row == r)[0]).sum()
+        w1 = q.radialWeight[np.isin(q.cell, np.nonzero(row == r)[0])].sum()
+        n_r = np.isin(p.cell, np.nonzero(row == r)[0]).sum()
+        assert abs(w1 - w0) < 5 * max(rwf[row == r][0], 20.0) * np.sqrt(n_r), (r, w0, w1)
+    # ratio 20 / RWF > 2 in the first row: at least one clone per parcel there
+    first = np.nonzero(row == 0)[0]
+    assert 20.0 / rwf[first[0]] - 1 > 1.0
+    assert np.isin(q.cell, first).sum() >= 2 * np.isin(p.cell, first).sum()
+
+
+def test_variable_time_step_scales_weights_and_steps_with_the_cell_volume():
+    """dsmcVariableTimeStepModel (dsmcVariableTimeStepModel.C:48-100): nParticles and deltaT of a cell grow with its volume, their ratio is
+    uniform.  A parcel moves by U deltaT(its cell) (dsmcParcel.C:62-63) and the candidate pairs of a cell use its own weight and step
+    (noTimeCounter.C:101,148); dsmcMeshFill puts n V / nParticles(cell) parcels into a cell: the same number in every cell."""
+    sides = {s: ("cyclic",) for s in meshgen.SIDES}
+    mesh = meshgen.box_mesh((6, 2, 2), (0.06, 0.02, 0.02), sides=sides)
+    x = mesh.points[:, 0].copy()
+    mesh.points[:, 0] = 0.06 * (x / 0.06) ** 2     # cells grow along x
+    md = capi.build_models("VariableHardSphere", nEquivalentParticles=2e8, deltaT=1e-7, seed=3)
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species([H.argon()]); o.set_models(md)
+    cc, cv, *_ = o.geometry()
+    n, dt = capi.variable_time_step(cv, 2e8, 1e-7)
+    assert np.allclose(n / dt, 2e8 / 1e-7, rtol=1e-14) and np.isclose(n.min(), 2e8, rtol=1e-14) and np.isclose(n.max() / n.min(), cv.max() / cv.min())
+    o.set_cell_fields(nParticles=n, deltaT=dt)
+    o.mesh_fill([0], [1e20], 300.0)
+    p = o.download_parcels()
+    per_cell = np.bincount(p.cell, minlength=mesh.n_cells)
+    expect = 1e20 * cv.min() / 2e8
+    assert np.abs(per_cell - expect).max() < 5 * np.sqrt(expect)          # the same number of parcels in every cell
+    o.stage(capi.STAGE_MOVE)
+    q = o.download_parcels()
+    o2 = np.argsort(q.origId)
+    moved = q.position[o2] - p.position
+    moved[:, 0] -= 0.06 * np.round(moved[:, 0] / 0.06); moved[:, 1] -= 0.02 * np.round(moved[:, 1] / 0.02); moved[:, 2] -= 0.02 * np.round(moved[:, 2] / 0.02)
+    assert np.allclose(moved, p.U * dt[p.cell][:, None], rtol=1e-9, atol=1e-12)
+    # candidate pairs: 0.5 N (N - 1) nParticles sigmaTcRMax deltaT / V per cell
+    o.upload_parcels(p)
+    sig, rem = o.download_cellstate()
+    o.upload_cellstate(sig, np.zeros_like(rem))
+    o.stage(capi.STAGE_COLLIDE)
+    N = per_cell.astype(float)
+    cand = np.floor(0.5 * N * (N - 1) * n * sig * dt / cv)
+    assert o.counters()["collisionCandidates"] == int(cand.sum())
