@@ -153,3 +153,19 @@ def axisym_setup(x, gold, geometry, seed=11, fnum_scale=1.0):
     x.set_cell_fields(RWF=rwf)
     spd = [dict(mass=sp[0].mass, diameter=sp[0].diameter, omega=sp[0].omega, rotDof=0.0, thetaV=[])]
     return mesh, spd, fnum * rwf, cv
+
+
+def axisym_envelope(g):
+    """Per cell the smallest and largest value of field g over the cell and its four neighbours inside its block (the tutorial mesh is
+    three structured blocks of 40 x 20, 40 x 40 and 40 x 40 cells): what a cell may show when a steep front sits a fraction of a cell
+    away from where the shipped run has it."""
+    lo, hi = g.copy(), g.copy()
+    off = 0
+    for nx, nz in ((40, 20), (40, 40), (40, 40)):
+        b = g[off:off + nx * nz].reshape(nz, nx)
+        l, h = b.copy(), b.copy()
+        for r in (np.vstack([b[:1], b[:-1]]), np.vstack([b[1:], b[-1:]]), np.hstack([b[:, :1], b[:, :-1]]), np.hstack([b[:, 1:], b[:, -1:]])):
+            l, h = np.minimum(l, r), np.maximum(h, r)
+        lo[off:off + nx * nz], hi[off:off + nx * nz] = l.ravel(), h.ravel()
+        off += nx * nz
+    return lo, hi

@@ -106,8 +106,9 @@ def test_variable_time_step_steps_match_oracle():
 def test_axisymmetric_tutorial_follows_the_shipped_fields():
     """The reference's axisymmetricFlatnosedCylinder tutorial on the GPU at its own size (4000 cells, ~184 000 parcels): 3000 steps to
     the steady state, 3000 sampled steps, then number density, temperature, velocity and parcels per cell against the fields the
-    reference ships (averaged over 40 000 steps).  Tolerance per cell: 4.5 sigma of the sampled parcel count (sqrt(1 / (N nSteps)) with
-    a factor 3 for the correlation of successive steps) plus 3 % for the flow the coarse tutorial mesh does not resolve identically."""
+    reference ships (averaged over 40 000 steps).  Over the field: no bias (mean deviation < 0.5 %, rms < 2.5 %).  Per cell: within the
+    range the shipped field spans over the cell and its neighbours (the bow shock is a jump over two cells), widened by 4.5 sigma of
+    the sampled parcel count (sqrt(1 / (N nSteps)), a factor 3 for the correlation of successive steps) plus 3 %."""
     gold = H.axisym_gold()
     eng = capi.Engine(0)
     mesh, spd, npc, cv = H.axisym_setup(eng, gold, eng.geometry)
@@ -121,15 +122,25 @@ def test_axisymmetric_tutorial_follows_the_shipped_fields():
     f = fields_ref.derive(acc, coll, nt, spd, [0], npc, cv, has_internal=False)
     N = gold["dsmcNMean_Ar"]
     sig = 3.0 / np.sqrt(N * n_s)
-    z = np.abs(f["dsmcNMean"] / N - 1) / (4.5 * sig + 0.03)
-    assert z.max() < 1.0, ("dsmcNMean", z.max(), int(z.argmax()))
-    z = np.abs(f["rhoN"] / gold["rhoN_Ar"] - 1) / (4.5 * sig + 0.03)
-    assert z.max() < 1.0, ("rhoN", z.max(), int(z.argmax()))
-    z = np.abs(f["Ttra"] / gold["Ttra_Ar"] - 1) / (4.5 * sig + 0.03)
-    assert z.max() < 1.0, ("Ttra", z.max(), int(z.argmax()))
+    for k, g in (("dsmcNMean", N), ("rhoN", gold["rhoN_Ar"]), ("Ttra", gold["Ttra_Ar"])):
+        r = f[k] / g - 1
+        assert abs(r.mean()) < 0.005 and np.sqrt((r ** 2).mean()) < 0.025, (k, r.mean(), np.sqrt((r ** 2).mean()))   # no bias over the field
+        lo, hi = H.axisym_envelope(g)
+        tol = (4.5 * sig + 0.03) * g
+        if k == "Ttra":
+            # ahead of the shock the temperature of a cell is carried by the few fast molecules scattered back from the shock layer:
+            # a fraction (T - T_inf) / Theta of the parcels, Theta = m U_inf^2 / (3 k) = 1600 K, whose count is what scatters
+            theta = float(gold["mass"]) * 1000.0 ** 2 / (3 * H.KB)
+            tol = 4.5 * 3.0 * np.sqrt(np.maximum(g - float(gold["temperature"]), 10.0) * theta / (N * n_s)) + 0.03 * g
+        excess = np.maximum(lo - tol - f[k], f[k] - hi - tol) / tol
+        assert excess.max() < 0.0, (k, excess.max(), int(excess.argmax()))
     cbar = np.sqrt(2 * H.KB * gold["Ttra_Ar"] / float(gold["mass"]))
-    z = np.abs(f["UMean"] - gold["U_Ar"]).max(1) / (4.5 * sig * cbar + 0.03 * 1000.0)
-    assert z.max() < 1.0, ("U", z.max(), int(z.argmax()))
+    for d in range(2):
+        g = gold["U_Ar"][:, d]
+        lo, hi = H.axisym_envelope(g)
+        tol = 4.5 * sig * cbar + 0.03 * 1000.0
+        excess = np.maximum(lo - tol - f["UMean"][:, d], f["UMean"][:, d] - hi - tol) / tol
+        assert excess.max() < 0.0, ("U", d, excess.max(), int(excess.argmax()))
     # the stagnation region in front of the flat face: density rise and temperature of the shock layer
     assert 6.0 < f["rhoN"].max() / 1e21 < 1.1 * gold["rhoN_Ar"].max() / 1e21
     eng.close()
