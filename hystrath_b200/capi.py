@@ -161,7 +161,8 @@ class Counters(C.Structure):
                 ("mass", C.c_double), ("linearKineticEnergy", C.c_double), ("rotationalEnergy", C.c_double),
                 ("vibrationalEnergy", C.c_double), ("electronicEnergy", C.c_double), ("stageMs", C.c_double * 8),
                 ("nNeighbours", C.c_int32), ("migrationRounds", C.c_int32), ("neighbourProc", C.c_int32 * MAX_NEIGHBOURS),
-                ("migratedTo", C.c_int64 * MAX_NEIGHBOURS), ("migratedFrom", C.c_int64 * MAX_NEIGHBOURS)]
+                ("migratedTo", C.c_int64 * MAX_NEIGHBOURS), ("migratedFrom", C.c_int64 * MAX_NEIGHBOURS),
+                ("nMolecules", C.c_double), ("cloned", C.c_int64)]
 
 
 class AccumInfo(C.Structure):

@@ -17,7 +17,7 @@ using foam::Dict;
 using foam::FoamError;
 
 namespace {
-const double SMALL = 1e-15, VSMALL = 1e-300, GREAT = 1e15;
+const double SMALL = 1e-15, VSMALL = 1e-300, GREAT = 1e15, VGREAT = 1e300;
 
 std::string joinNames(const std::vector<std::string>& v) {
     std::ostringstream s;
@@ -67,12 +67,19 @@ void selectGeneralBoundaryModel(const std::string& name) {
 void selectFieldModel(const std::string& name) {
     if (name != "dsmcVolFields") unknownType("dsmcField::New(const dictionary&)", "dsmcField", name, {"dsmcVolFields"});
 }
-void selectCoordinateSystem(const std::string& name) {
-    if (name != "dsmcCartesian") unknownType("dsmcCoordinateSystem::New", "dsmcCoordinateSystem", name, {"dsmcCartesian"});
+int selectCoordinateSystem(const std::string& name) {
+    if (name == "dsmcCartesian") return DSMCB200_COORD_CARTESIAN;
+    if (name == "dsmcAxisymmetric") return DSMCB200_COORD_AXISYMMETRIC;
+    unknownType("dsmcCoordinateSystem::New", "dsmcCoordinateSystem", name, {"dsmcAxisymmetric", "dsmcCartesian"});
+    return 0;
 }
-void selectTimeStepModel(const std::string& name) {
-    if (name != "constant" && name != "dsmcConstantTimeStepModel")
-        unknownType("dsmcTimeStepModel::New", "dsmcTimeStepModel", name, {"constant"});
+// dsmcTimeStepModel::New builds the type name "dsmc" + Keyword + "TimeStepModel" (dsmcTimeStepModel.C:99-107)
+bool selectTimeStepModel(const std::string& name) {
+    if (name == "constant") return false;
+    if (name == "variable") return true;
+    std::string type = name.empty() ? name : "dsmc" + std::string(1, char(std::toupper(name[0]))) + name.substr(1) + "TimeStepModel";
+    unknownType("dsmcTimeStepModel::New", "dsmcTimeStepModel", type, {"dsmcConstantTimeStepModel", "dsmcVariableTimeStepModel"});
+    return false;
 }
 int patchTypeFromWord(const std::string& t) {
     if (t == "wall") return DSMCB200_PATCH_WALL;
@@ -120,12 +127,55 @@ dsmcCloud::dsmcCloud(const std::string& caseDir, const std::string& cloudName, i
     check(dsmcb200_set_models(ctx_, &models_), "dsmcb200_set_models");
     cellVolumes_.resize(nCells_); cellCentres_.resize(size_t(nCells_) * 3); faceAreas_.resize(size_t(nFaces_) * 3); faceCentres_.resize(size_t(nFaces_) * 3);
     check(dsmcb200_download_geometry(ctx_, cellCentres_.data(), cellVolumes_.data(), faceCentres_.data(), faceAreas_.data(), nullptr), "dsmcb200_download_geometry");
+    setCellFields();
     if (initialise_) { initialiseFromDict(); return; }
     readCloud();
     // counter-based RNG streams are keyed by the global time index, so a restarted run does not replay the streams of the first one
     startIndex_ = deltaT_ > 0 ? int64_t(std::llround(startTime_ / deltaT_)) : 0;
     check(dsmcb200_set_step(ctx_, uint32_t(startIndex_)), "dsmcb200_set_step");
     readResumeSampling();
+}
+
+// dsmcCloud::nParticles(cell) and deltaTValue(cell): the time-step model's nParticles_ / deltaT_ (dsmcVariableTimeStepModel.C:48-100) and the
+// radial weighting factors of dsmcAxisymmetric (radial weighting method "cell", dsmcAxisymmetric.C:236-275, 447-456)
+void dsmcCloud::setCellFields() {
+    nPtsCell_.assign(size_t(nCells_), models_.nEquivalentParticles);
+    dtCell_.assign(size_t(nCells_), deltaT_);
+    rwfCell_.assign(size_t(nCells_), 1.0);
+    if (variableTimeStep_ && nCells_ > 0) {
+        double minVolume = cellVolumes_[0];
+        for (double v : cellVolumes_) minVolume = std::min(minVolume, v);
+        if (nRanks_ > 1) {   // reduce(minVolume, minOp<scalar>()): with a sum-only reduction, through 1/V^p norms is not exact -- refuse
+            throw FoamError("timeStepModel variable on a decomposed case is not supported yet (the reference cell is the globally smallest one)");
+        }
+        int refCell = 0;
+        for (int c = 0; c < nCells_; ++c) if (std::fabs(cellVolumes_[c] - minVolume) < SMALL) { refCell = c; break; }
+        const double nParticleRef = nPtsCell_[refCell], vRef = cellVolumes_[refCell];
+        for (int c = 0; c < nCells_; ++c) nPtsCell_[c] = nParticleRef * cellVolumes_[c] / vRef;
+        const double nParticleTimeStepRatio = nPtsCell_[refCell] / dtCell_[refCell];
+        for (int c = 0; c < nCells_; ++c) dtCell_[c] = nPtsCell_[c] / nParticleTimeStepRatio;
+        if (rank_ == 0) std::printf("Variable time-step model:\n- Initial time-step [sec]\t%g\n\n", dtCell_[0]);
+    }
+    if (models_.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC) {
+        double radialExtent = -VGREAT, lowest = VGREAT;
+        for (int f = 0; f < nFaces_; ++f) { radialExtent = std::max(radialExtent, faceCentres_[3 * size_t(f) + polarAxis_]); lowest = std::min(lowest, faceCentres_[3 * size_t(f) + polarAxis_]); }
+        if (!(radialExtent > 0)) radialExtent = -lowest;
+        radialExtent_ = radialExtent;
+        for (int c = 0; c < nCells_; ++c) {
+            const double radius = std::fabs(cellCentres_[3 * size_t(c) + polarAxis_]);
+            double RWF = 1.0;
+            RWF += (maxRWF_ - 1.0) * radius / radialExtent;
+            rwfCell_[c] = RWF;
+        }
+        if (rank_ == 0)
+            std::printf("\nAxisymmetric simulation:\n- revolution axis label\t%d\n- polar axis label\t%d\n- angular coordinate label\t%d\n"
+                        "- radial weighting method\tcell-based\n- radial extent\t%g\n- maximum radial weighting factor\t%g\n\n",
+                        3 - polarAxis_ - models_.angularCoordinate, polarAxis_, models_.angularCoordinate, radialExtent, maxRWF_);
+    }
+    const bool axi = models_.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC;
+    if (variableTimeStep_ || axi)
+        check(dsmcb200_set_cell_fields(ctx_, variableTimeStep_ ? nPtsCell_.data() : nullptr, variableTimeStep_ ? dtCell_.data() : nullptr,
+                                       axi ? rwfCell_.data() : nullptr), "dsmcb200_set_cell_fields");
 }
 
 dsmcCloud::~dsmcCloud() {
@@ -218,8 +268,32 @@ void dsmcCloud::readProperties() {
     const std::string bcm = d.word("BinaryCollisionModel");
     models_.collisionModel = selectBinaryCollisionModel(bcm);
     selectCollisionPartnerSelection(d.word("collisionPartnerSelectionModel"));
-    selectCoordinateSystem(d.wordOr("coordinateSystem", "dsmcCartesian"));
-    selectTimeStepModel(d.wordOr("timeStepModel", "constant"));
+    models_.coordinateSystem = selectCoordinateSystem(d.wordOr("coordinateSystem", "dsmcCartesian"));
+    variableTimeStep_ = selectTimeStepModel(d.wordOr("timeStepModel", "constant"));
+    if (d.boolOr("nEquivalentParticlesFromFile", false))
+        throw FoamError("nEquivalentParticlesFromFile: reading the nParticles field of a previous run is not supported; the variable time-step model sets it from the cell volumes");
+    polarAxis_ = 1; models_.angularCoordinate = 2; maxRWF_ = 1.0;
+    if (models_.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC) {
+        // dsmcAxisymmetric::checkCoordinateSystemInputs (dsmcAxisymmetric.C:337-470)
+        const Dict& ax = d.subDict("axisymmetricProperties");
+        const std::string method = ax.wordOr("radialWeightingMethod", "cell");
+        if (method != "cell" && method != "particleAverage")
+            throw FoamError("The radial weighting method is badly defined. Choices in constant/dsmcProperties are \"cell\" or \"particleAverage\". Please edit the entry: radialWeightingMethod.");
+        if (method == "particleAverage")
+            throw FoamError("radialWeightingMethod particleAverage is not supported (the sampled sums are weighted per cell after the run); use \"cell\"");
+        const std::string rev = ax.wordOr("revolutionAxis", ""), pol = ax.wordOr("polarAxis", "");
+        const char* bad = "Revolution and polar axes are badly defined in constant/dsmcProperties axisymmetricProperties{}";
+        int polar = 1, ang = 2;
+        if (rev == "z") {
+            if (pol.empty()) { polar = 0; ang = 1; } else if (pol == "y") { polar = 1; ang = 0; } else if (pol == "x") { polar = 0; ang = 1; } else throw FoamError(bad);
+        } else if (rev == "y") {
+            if (pol.empty()) { polar = 2; ang = 0; } else if (pol == "x") { polar = 0; ang = 2; } else if (pol == "z") { polar = 2; ang = 0; } else throw FoamError(bad);
+        } else if (rev == "x") {
+            if (pol == "z") { polar = 2; ang = 1; } else if (pol != "y") throw FoamError(bad);
+        }
+        polarAxis_ = polar; models_.angularCoordinate = ang;
+        maxRWF_ = ax.scalar("maxRadialWeightingFactor");
+    }
     // VariableHardSphere reads Tref from VariableHardSphereCoeffs even under the LB model (VariableHardSphere.C:56-62)
     // (VariableSoftSphere.C:54-60 does the same with VariableSoftSphereCoeffs)
     const bool soft = models_.collisionModel == DSMCB200_COLL_VSS || models_.collisionModel == DSMCB200_COLL_LB_VSS;
@@ -534,6 +608,8 @@ void dsmcCloud::readCloud() {
     if (foam::exists(dir + "ELevel")) { elevel = foam::readLabelField(dir + "ELevel"); if (int64_t(elevel.size()) == n) s.ELevel = elevel.data(); }
     if (foam::exists(dir + "classification")) { cls = foam::readLabelField(dir + "classification"); if (int64_t(cls.size()) == n) s.classification = cls.data(); }
     if (foam::exists(dir + "origId")) { origId = foam::readLabelField(dir + "origId"); if (int64_t(origId.size()) == n) s.origId = origId.data(); }
+    std::vector<double> radialWeight;   // dsmcParcel::RWF_ (dsmcParcelIO.C); without the file a parcel takes its cell's weight
+    if (foam::exists(dir + "radialWeight")) { radialWeight = foam::readScalarField(dir + "radialWeight"); if (int64_t(radialWeight.size()) == n) s.radialWeight = radialWeight.data(); }
     nRead_ = n;
     // <time>/dsmcSigmaTcRMax is MUST_READ (dsmcCloud.C:625-636)
     auto sig = foam::readInternalField(root_ + "/" + timeName_ + "/dsmcSigmaTcRMax", nCells_, 1);
@@ -551,7 +627,9 @@ std::string dsmcCloud::summary() const {
     o << "  species:";
     for (auto& t : typeIdList_) o << " " << t;
     o << "\n  collisionModel " << models_.collisionModel << " invZv " << models_.invZvFormulation << " nEquivalentParticles " << models_.nEquivalentParticles
-      << " seed " << models_.seed << "\n  patchModels " << patchModels_.size() << " inflows " << inflows_.size() << " fields " << fields_.size() << "\n";
+      << " seed " << models_.seed << "\n  coordinateSystem " << (models_.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC ? "dsmcAxisymmetric" : "dsmcCartesian")
+      << " polarAxis " << polarAxis_ << " angularCoordinate " << models_.angularCoordinate << " maxRadialWeightingFactor " << maxRWF_
+      << " timeStepModel " << (variableTimeStep_ ? "variable" : "constant") << "\n  patchModels " << patchModels_.size() << " inflows " << inflows_.size() << " fields " << fields_.size() << "\n";
     for (auto& pm : patchModels_)
         if (pm.linearTemperature)
             o << "    patchModel " << boundary_[pm.patch].name << " temperature " << pm.temperature << " linearTemperature formationLevel "
@@ -610,8 +688,8 @@ void dsmcCloud::info() {
     double v[6] = {double(c.nParcels), c.mass, c.linearKineticEnergy, c.rotationalEnergy, c.vibrationalEnergy, c.electronicEnergy};
     if (nRanks_ > 1) check(dsmcb200_allreduce_sum(ctx_, v, 6), "dsmcb200_allreduce_sum");
     if (rank_ != 0) return;
-    const double nP = models_.nEquivalentParticles;
-    const double nMol = v[0] * nP;
+    const double nP = models_.nEquivalentParticles;   // nParticlesOrg (dsmcCloud.C:947)
+    const double nMol = c.nMolecules > 0 && nRanks_ == 1 ? c.nMolecules : v[0] * nP;   // infoMeasurements[6]
     // dsmcCloud.C:960-981
     std::printf("    Number of DSMC particles        = %lld\n", (long long)v[0]);
     if (v[0] > 0) {
@@ -637,7 +715,6 @@ DerivedFields dsmcCloud::calculateField(const FieldSpec& f) {
     const bool internal = ai.nModes >= 0;
     const double nT = ai.nTimeSteps > 0 ? ai.nTimeSteps : 1.0;
     const double kB = models_.kB > 0 ? models_.kB : 1.38065e-23;
-    const double FN = models_.nEquivalentParticles;
     DerivedFields o;
     auto z = [&](std::vector<double>& v, int w = 1) { v.assign(size_t(nC) * w, 0.0); };
     z(o.dsmcNMean); z(o.rhoN); z(o.rhoM); z(o.p); z(o.Ttra); z(o.Trot); z(o.Tvib); z(o.Tov); z(o.Ma); z(o.mfp); z(o.mct); z(o.mctToDt);
@@ -648,6 +725,7 @@ DerivedFields dsmcCloud::calculateField(const FieldSpec& f) {
     (void)NAvo;
     for (int c = 0; c < nC; ++c) {
         const double V = cellVolumes_[c];
+        const double FN = nPtsCell_[c] * rwfCell_[c];   // cloud_.nParticles(cell), dsmcVolFields.C:1098,1128
         double dsmcNCum = 0, mCumP = 0, ErotCum = 0, ZetaRotCum = 0, keP = 0;
         double mom[3] = {0, 0, 0};
         for (int s : f.typeIds) {
@@ -777,8 +855,8 @@ DerivedFields dsmcCloud::calculateField(const FieldSpec& f) {
             }
             if (mfp < SMALL) mfp = GREAT;
             o.mfp[c] = mfp;
-            if (mcr > SMALL) { o.mct[c] = 1.0 / mcr; o.mctToDt[c] = o.mct[c] / deltaT_; } else { o.mct[c] = GREAT; o.mctToDt[c] = GREAT; }
-            if (nCum > SMALL) o.measuredCollisionRate[c] = coll[2 * size_t(c)] * FN / (nCum * deltaT_);
+            if (mcr > SMALL) { o.mct[c] = 1.0 / mcr; o.mctToDt[c] = o.mct[c] / dtCell_[c]; } else { o.mct[c] = GREAT; o.mctToDt[c] = GREAT; }
+            if (nCum > SMALL) o.measuredCollisionRate[c] = coll[2 * size_t(c)] * FN / (nCum * dtCell_[c]);
             // mfpToDx and the separation-of-free-paths ratio (dsmcVolFields.C:1788-1836)
             if (mfp != GREAT) {
                 o.mfpToDx[c] = mfp / cellMaxDx(c);
@@ -827,7 +905,6 @@ void dsmcCloud::writeFields(const std::string& timeDir, const std::vector<double
     check(dsmcb200_accum_info_get(ctx_, &ai), "dsmcb200_accum_info_get");
     const double nT = ai.nTimeSteps > 0 ? ai.nTimeSteps : 1.0;
     const double kB = models_.kB > 0 ? models_.kB : 1.38065e-23;
-    const double FN = models_.nEquivalentParticles;
     // measured-face index of a boundary face follows the order of the patch models with a wall model
     std::vector<int> measStart(boundary_.size(), -1);
     {
@@ -861,6 +938,8 @@ void dsmcCloud::writeFields(const std::string& timeDir, const std::vector<double
                     rhoNBF += W(s, 0); rhoMBF += W(s, 3); linearKEBF += W(s, 4); ErotBF += W(s, 9); zetaRotBF += W(s, 10); qBF += W(s, 13);
                     for (int q = 0; q < 3; ++q) { momBF[q] += W(s, 6 + q); fDBF[q] += W(s, 14 + q); }
                 }
+                // the parcels' RWF is in the sums; what is left is the time-step model's nParticles of the face (dsmcVolFields.C:1905-1913)
+                const double FN = nPtsCell_[owner_[face]];
                 const double rhoNMean = rhoNBF * FN / nT, rhoMMean = rhoMBF * FN / nT, linearKEMean = linearKEBF * FN / nT;
                 w.rhoN = rhoNMean; w.rhoM = rhoMMean;
                 if (rhoMMean > VSMALL) {
@@ -1120,7 +1199,6 @@ void dsmcCloud::writeResumeSampling(const std::string& timeDir) {
         for (auto& pm : patchModels_)
             if (pm.model != DSMCB200_BND_DELETION) { measStart[pm.patch] = k; k += boundary_[pm.patch].nFaces; }
     }
-    const double FN = models_.nEquivalentParticles;
     for (auto& fs : fields_) {
         if (!fs.averagingAcrossManyRuns) continue;
         const int nT = int(fs.typeIds.size());
@@ -1158,7 +1236,12 @@ void dsmcCloud::writeResumeSampling(const std::string& timeDir) {
             }
             nColls[c] = coll[2 * size_t(c)]; collSep[c] = coll[2 * size_t(c) + 1];
         }
-        auto scaled = [&](const std::vector<double>& v) { std::vector<double> o(v); for (auto& x : o) x *= FN; return o; };
+        auto scaled = [&](const std::vector<double>& v) {   // per cell, nCmpt values each, times cloud_.nParticles(cell)
+            std::vector<double> o(v);
+            const size_t w = o.size() / size_t(std::max(nC, 1));
+            for (size_t k = 0; k < o.size(); ++k) o[k] *= nPtsCell_[k / w] * rwfCell_[k / w];
+            return o;
+        };
         const std::string name = "resumeSampling_" + fs.fieldName;
         FILE* f = std::fopen((ud + "/" + name).c_str(), "w");
         if (!f) throw FoamError("cannot write " + ud + "/" + name);
@@ -1325,6 +1408,8 @@ void dsmcCloud::write() {
     dsmcb200_parcels_soa s{};
     s.position = xyz.data(); s.U = U.data(); s.ERot = ERot.data(); s.cell = cell.data(); s.typeId = typeId.data(); s.vibLevel = vib.data();
     s.ELevel = elevel.data(); s.classification = cls.data(); s.origId = origId.data(); s.maxModes = maxModes_;
+    std::vector<double> radialWeight(static_cast<size_t>(n), 1.0);
+    s.radialWeight = radialWeight.data();
     int64_t got = 0;
     check(dsmcb200_download_parcels(ctx_, n, &got, &s), "dsmcb200_download_parcels");
     const std::string loc = timeName_ + "/lagrangian/" + cloudName_;
@@ -1342,6 +1427,7 @@ void dsmcCloud::write() {
     if (anyRot) foam::writeScalarField(cdir + "/ERot", "scalarField", loc, "ERot", ERot.data(), got);
     if (anyEl) foam::writeLabelField(cdir + "/ELevel", "labelField", loc, "ELevel", elevel.data(), got);
     foam::writeLabelListList(cdir + "/vibLevel", "labelFieldField", loc, "vibLevel", vib.data(), got, maxModes_);
+    foam::writeScalarField(cdir + "/radialWeight", "scalarField", loc, "radialWeight", radialWeight.data(), got);
     {
         const std::string ud = timeDir + "/uniform/lagrangian/" + cloudName_;
         foam::makeDirs(ud);
@@ -1362,6 +1448,20 @@ void dsmcCloud::write() {
         pv.push_back(p);
     }
     foam::writeVolField(timeDir + "/dsmcSigmaTcRMax", timeName_, "dsmcSigmaTcRMax", "[0 3 -1 0 0 0 0]", sig.data(), nCells_, 1, pv);
+    // AUTO_WRITE fields of the coordinate system / time-step model: RWF (dsmcAxisymmetric.C:316-328), nParticles and deltaT
+    // (dsmcVariableTimeStepModel.C:103-121); boundary values are the face cells'
+    auto cellField = [&](const std::string& name, const std::string& dims, const std::vector<double>& v) {
+        std::vector<foam::PatchValues> bv;
+        for (auto& b : boundary_) {
+            foam::PatchValues p;
+            p.name = b.name; p.type = b.type;
+            if (b.type == "wall" || b.type == "patch") { p.values.resize(b.nFaces); for (int k = 0; k < b.nFaces; ++k) p.values[k] = v[owner_[b.startFace + k]]; }
+            bv.push_back(p);
+        }
+        foam::writeVolField(timeDir + "/" + name, timeName_, name, dims, v.data(), nCells_, 1, bv);
+    };
+    if (models_.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC) cellField("RWF", "[0 0 0 0 0 0 0]", rwfCell_);
+    if (variableTimeStep_) { cellField("nParticles", "[0 0 0 0 0 0 0]", nPtsCell_); cellField("deltaT", "[0 0 1 0 0 0 0]", dtCell_); }
     if (initialise_) return;  // dsmcInitialise+ writes the cloud and dsmcSigmaTcRMax only
     {
         const int S = int(species_.size());

@@ -27,8 +27,8 @@ int selectCollisionPartnerSelection(const std::string& name);
 int selectPatchBoundaryModel(const std::string& name);
 void selectGeneralBoundaryModel(const std::string& name);
 void selectFieldModel(const std::string& name);
-void selectCoordinateSystem(const std::string& name);
-void selectTimeStepModel(const std::string& name);
+int selectCoordinateSystem(const std::string& name);   // dsmcb200_coordinate_system
+bool selectTimeStepModel(const std::string& name);     // true: variable
 int patchTypeFromWord(const std::string& type);
 
 struct FieldSpec {  // one dsmcVolFields entry of system/fieldPropertiesDict
@@ -76,6 +76,7 @@ class dsmcCloud {
     void readControl();
     void readMesh();
     void readProperties();
+    void setCellFields();
     void readReactions();
     void readBoundaries();
     void readFieldProperties();
@@ -109,6 +110,11 @@ class dsmcCloud {
     std::vector<std::string> typeIdList_;
     std::vector<dsmcb200_species> species_;
     std::vector<dsmcb200_reaction> reactions_;     // system/chemReactDict
+    // coordinate system / time-step model: per-cell nParticles (time-step model), deltaT and radial weighting factor
+    bool variableTimeStep_ = false;
+    int polarAxis_ = 1;
+    double maxRWF_ = 1.0, radialExtent_ = 0.0;
+    std::vector<double> nPtsCell_, dtCell_, rwfCell_;
     std::vector<std::string> reactionNames_;
     dsmcb200_models models_{};
     std::vector<dsmcb200_patch_model> patchModels_;

@@ -171,7 +171,7 @@ struct dsmcb200_ctx {
     double *dNPts = nullptr, *dDt = nullptr, *dRWF = nullptr;
     bool useRwf = false;           // dsmcAxisymmetric: parcels carry a radial weight
     int32_t* dWeightCounts = nullptr; int64_t weightCountsCap = 0;
-    int64_t cloned = 0, weightDeleted = 0;
+    int64_t cloned = 0, weightDeleted = 0, weightDeletedStep = 0;
     DevParams hP{};
     DevParams* dP = nullptr;
     // device mesh
@@ -954,7 +954,7 @@ int stageWeighting(dsmcb200_ctx* c) {
         c->nextOrigId += total;
     }
     c->cloned += total; c->weightDeleted += nDel;
-    c->last.deleted += nDel;
+    c->last.cloned = total; c->weightDeletedStep = nDel;
     return stageSort(c, false);   // cloud_.reBuildCellOccupancy()
 }
 
@@ -1402,7 +1402,7 @@ int dsmcb200_evolve(dsmcb200_ctx* c, int nSteps) {
     { int r = finalize(c); if (r) return r; }
     for (int it = 0; it < nSteps; ++it) {
         cudaEvent_t e0 = getEvent(c), e1 = getEvent(c), e2 = getEvent(c), e3 = getEvent(c), e4 = getEvent(c), e5 = getEvent(c);
-        c->last.inserted = 0; c->last.migratedIn = 0; c->last.migrationRounds = 0;
+        c->last.inserted = 0; c->last.migratedIn = 0; c->last.migrationRounds = 0; c->last.cloned = 0; c->weightDeletedStep = 0;
         c->last.nNeighbours = int32_t(c->nbrProcs.size());
         for (int k = 0; k < MAX_NEIGHBOURS; ++k) { c->last.neighbourProc[k] = k < int(c->nbrProcs.size()) ? c->nbrProcs[k] : -1; c->last.migratedTo[k] = 0; c->last.migratedFrom[k] = 0; }
         CK(cudaMemsetAsync(c->dCounters, 0, sizeof(DevCounters), c->stream));
@@ -1548,7 +1548,7 @@ int dsmcb200_get_counters(dsmcb200_ctx* c, dsmcb200_counters* o) {
     cudaSetDevice(c->device);
     { int r = finalize(c); if (r) return r; }
     // dsmcCloud::info(): one pass over the cloud for the energy sums
-    double e5[5] = {0, 0, 0, 0, 0};
+    double e5[6] = {0, 0, 0, 0, 0, 0};
     if (c->N > 0) {
         CK(launchInfo(c->buf[c->cur].a, cellFields(c), int32_t(c->N), c->dP, c->dInfo, c->dInfoScratch, c->stream));
         CK(cudaMemcpyAsync(e5, c->dInfo, sizeof(e5), cudaMemcpyDeviceToHost, c->stream));
@@ -1556,9 +1556,10 @@ int dsmcb200_get_counters(dsmcb200_ctx* c, dsmcb200_counters* o) {
     { int r = fetchCounters(c); if (r) return r; }
     dsmcb200_counters& L = c->last;
     L.nParcels = c->N; L.collisions = int64_t(c->hCounters.collisions); L.collisionCandidates = int64_t(c->hCounters.candidates);
-    L.trackingRescues = int64_t(c->hCounters.rescues); L.deleted = int64_t(c->hCounters.deleted);
+    L.trackingRescues = int64_t(c->hCounters.rescues); L.deleted = int64_t(c->hCounters.deleted) + c->weightDeletedStep;
     L.migratedOut = int64_t(c->hCounters.migratedOut); L.unsortedLargeCells = int64_t(c->hCounters.unsortedLargeCells);
     L.mass = e5[0]; L.linearKineticEnergy = e5[1]; L.rotationalEnergy = e5[2]; L.vibrationalEnergy = e5[3]; L.electronicEnergy = e5[4];
+    L.nMolecules = e5[5];
     *o = L;
     return 0;
 }

@@ -1233,15 +1233,16 @@ cudaError_t launchAppendBorn(const ParcelArrays& p, const BornRec* born, int32_t
 namespace { constexpr int INFO_BLOCKS = 296; constexpr int INFO_THREADS = 256; }
 
 __global__ void __launch_bounds__(INFO_THREADS) infoKernel(const __grid_constant__ ParcelArrays p, const CellFields cf, int32_t n, const DevParams* Pp, double* scratch) {
-    __shared__ double red[5][INFO_THREADS / 32];
+    __shared__ double red[6][INFO_THREADS / 32];
     const DevParams& P = *Pp;
-    double v[5] = {0, 0, 0, 0, 0};
+    double v[6] = {0, 0, 0, 0, 0, 0};
     for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int32_t cell = p.cell[i];
         if (cell < 0) continue;
         const DevSpecies& S = P.sp[p.typeId[i]];
         const double ux = p.ux[i], uy = p.uy[i], uz = p.uz[i];
         const double w = cf.nParticles(P.nParticles, cell);   // this->nParticles(p.cell()), dsmcCloudI.H:278
+        v[5] += w;   // infoMeasurements[6]: free molecules
         v[0] += S.mass * w;
         v[1] += 0.5 * S.mass * (ux * ux + uy * uy + uz * uz) * w;
         if (P.hasInternalEnergy) {
@@ -1255,29 +1256,29 @@ __global__ void __launch_bounds__(INFO_THREADS) infoKernel(const __grid_constant
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
+    for (int k = 0; k < 6; ++k) {
         double x = v[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
         if (lane == 0) red[k][w] = x;
     }
     __syncthreads();
-    if (threadIdx.x < 5) {
+    if (threadIdx.x < 6) {
         double x = 0;
         for (int k = 0; k < INFO_THREADS / 32; ++k) x += red[threadIdx.x][k];
-        scratch[blockIdx.x * 5 + threadIdx.x] = x;
+        scratch[blockIdx.x * 6 + threadIdx.x] = x;
     }
 }
 
 __global__ void infoFinalKernel(const double* scratch, const DevParams* Pp, double* out5) {
-    if (threadIdx.x < 5) {
+    if (threadIdx.x < 6) {
         double x = 0;
-        for (int b = 0; b < INFO_BLOCKS; ++b) x += scratch[b * 5 + threadIdx.x];
+        for (int b = 0; b < INFO_BLOCKS; ++b) x += scratch[b * 6 + threadIdx.x];
         out5[threadIdx.x] = x;
     }
 }
 
-int32_t infoScratchDoubles() { return INFO_BLOCKS * 5; }
+int32_t infoScratchDoubles() { return INFO_BLOCKS * 6; }
 
 cudaError_t launchInfo(const ParcelArrays& p, const CellFields& cf, int32_t n, const DevParams* P, double* out5, double* scratch, cudaStream_t s) {
     infoKernel<<<INFO_BLOCKS, INFO_THREADS, 0, s>>>(p, cf, n, P, scratch);

@@ -265,6 +265,9 @@ typedef struct {
     int32_t neighbourProc[DSMCB200_MAX_NEIGHBOURS];
     int64_t migratedTo[DSMCB200_MAX_NEIGHBOURS];
     int64_t migratedFrom[DSMCB200_MAX_NEIGHBOURS];
+    double nMolecules;  /* sum of nParticles(cell) over the parcels: infoMeasurements[6] (dsmcCloudI.H:268-297); the energies above carry
+                           the same per-parcel weight */
+    int64_t cloned;     /* parcels added by the radial weighting of the last step (dsmcAxisymmetric.C:64-166); its deletions are in `deleted` */
 } dsmcb200_counters;
 
 /* Sampled per-cell accumulators of stage 5: the per-species moment sums from

@@ -486,15 +486,45 @@ void Foam::dsmcCloud::readModels()
     HashTable<label> partnerModels;
     partnerModels.insert("noTimeCounter", 1);
     HashTable<label> coordinateSystems;
-    coordinateSystems.insert("dsmcCartesian", 1);
+    coordinateSystems.insert("dsmcCartesian", DSMCB200_COORD_CARTESIAN);
+    coordinateSystems.insert("dsmcAxisymmetric", DSMCB200_COORD_AXISYMMETRIC);
     HashTable<label> timeStepModels;
-    timeStepModels.insert("constant", 1);
+    timeStepModels.insert("constant", 0);
+    timeStepModels.insert("variable", 1);
 
     const word collisionModel(particleProperties_.lookup("BinaryCollisionModel"));
     models_.collisionModel = lookupOrFail(collisionModels, collisionModel, "BinaryCollisionModel");
     lookupOrFail(partnerModels, word(particleProperties_.lookup("collisionPartnerSelectionModel")), "collisionPartnerSelection");
-    lookupOrFail(coordinateSystems, particleProperties_.lookupOrDefault<word>("coordinateSystem", "dsmcCartesian"), "dsmcCoordinateSystem");
-    lookupOrFail(timeStepModels, particleProperties_.lookupOrDefault<word>("timeStepModel", "constant"), "dsmcTimeStepModel");
+    models_.coordinateSystem =
+        lookupOrFail(coordinateSystems, particleProperties_.lookupOrDefault<word>("coordinateSystem", "dsmcCartesian"), "dsmcCoordinateSystem");
+    variableTimeStep_ = lookupOrFail(timeStepModels, particleProperties_.lookupOrDefault<word>("timeStepModel", "constant"), "dsmcTimeStepModel") == 1;
+    polarAxis_ = 1; models_.angularCoordinate = 2;
+    if (models_.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC)
+    {
+        // dsmcAxisymmetric::checkCoordinateSystemInputs (dsmcAxisymmetric.C:337-420)
+        const dictionary& ax = particleProperties_.subDict("axisymmetricProperties");
+        const word rev(ax.lookupOrDefault<word>("revolutionAxis", word::null)), pol(ax.lookupOrDefault<word>("polarAxis", word::null));
+        label polarAxis = 1, angular = 2;
+        bool bad = false;
+        if (rev == "z")
+        {
+            if (pol == word::null || pol == "x") { polarAxis = 0; angular = 1; } else if (pol == "y") { polarAxis = 1; angular = 0; } else { bad = true; }
+        }
+        else if (rev == "y")
+        {
+            if (pol == word::null || pol == "z") { polarAxis = 2; angular = 0; } else if (pol == "x") { polarAxis = 0; angular = 2; } else { bad = true; }
+        }
+        else if (rev == "x")
+        {
+            if (pol == "z") { polarAxis = 2; angular = 1; } else if (pol != "y") { bad = true; }
+        }
+        if (bad)
+        {
+            FatalErrorIn("dsmcAxisymmetric::checkCoordinateSystemInputs(const bool init)")
+                << "Revolution and polar axes are badly defined in constant/dsmcProperties axisymmetricProperties{}" << exit(FatalError);
+        }
+        polarAxis_ = polarAxis; models_.angularCoordinate = angular;
+    }
     models_.nEquivalentParticles = readScalar(particleProperties_.lookup("nEquivalentParticles"));
     models_.seed = uint64_t(particleProperties_.lookupOrDefault<label>("seedNumber", 1));
     models_.deltaT = mesh_.time().deltaTValue();
@@ -523,6 +553,59 @@ void Foam::dsmcCloud::readModels()
 }
 
 
+void Foam::dsmcCloud::setCellFields()
+{
+    // the volScalarFields behind nParticles(cell) / deltaTValue(cell): dsmcVariableTimeStepModel::updatenParticles / updateTimeStep
+    // (dsmcVariableTimeStepModel.C:48-100) and dsmcAxisymmetric::checkCoordinateSystemInputs + recalculateRWF, method "cell"
+    // (dsmcAxisymmetric.C:236-275, 337-470)
+    const label nC = mesh_.nCells();
+    nParticlesCell_.setSize(nC); nParticlesCell_ = models_.nEquivalentParticles;
+    deltaTCell_.setSize(nC); deltaTCell_ = models_.deltaT;
+    RWFCell_.setSize(nC); RWFCell_ = 1.0;
+    if (variableTimeStep_)
+    {
+        const scalarField& V = mesh_.cellVolumes();
+        scalar minVolume = gMin(V);
+        label refCell = -1;
+        forAll(V, c) { if (mag(V[c] - minVolume) < SMALL) { refCell = c; break; } }
+        if (refCell == -1)
+        {
+            FatalErrorIn("dsmcCloud (dsmcb200)") << "variable time-step model: the smallest cell of the mesh is on another processor; "
+                << "the reference takes its reference cell from the local mesh (dsmcVariableTimeStepModel.C:48-68)" << exit(FatalError);
+        }
+        const scalar nParticleRef = nParticlesCell_[refCell];
+        forAll(V, c) { nParticlesCell_[c] = nParticleRef*V[c]/minVolume; }
+        const scalar nParticleTimeStepRatio = nParticlesCell_[refCell]/deltaTCell_[refCell];
+        forAll(V, c) { deltaTCell_[c] = nParticlesCell_[c]/nParticleTimeStepRatio; }
+        Info<< "Variable time-step model:" << nl << "- Initial time-step [sec]" << tab << deltaTCell_[0] << nl << endl;
+    }
+    const bool axisymmetric = models_.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC;
+    if (axisymmetric)
+    {
+        const dictionary& ax = particleProperties_.subDict("axisymmetricProperties");
+        const word method(ax.lookupOrDefault<word>("radialWeightingMethod", "cell"));
+        if (method != "cell")
+        {
+            FatalErrorIn("dsmcCloud (dsmcb200)") << "radialWeightingMethod " << method
+                << ": only the cell-based radial weighting is part of this engine" << exit(FatalError);
+        }
+        const label polarAxis = polarAxis_, angular = models_.angularCoordinate;
+        scalar radialExtent = gMax(mesh_.faceCentres().component(polarAxis));
+        if (!(radialExtent > 0)) { radialExtent = -gMin(mesh_.faceCentres().component(polarAxis)); }
+        const scalar maxRWF = readScalar(ax.lookup("maxRadialWeightingFactor"));
+        forAll(RWFCell_, c) { RWFCell_[c] = 1.0 + (maxRWF - 1.0)*mag(mesh_.cellCentres()[c].component(polarAxis))/radialExtent; }
+        Info<< nl << "Axisymmetric simulation:" << nl << "- polar axis label" << tab << polarAxis << nl << "- angular coordinate label" << tab
+            << angular << nl << "- radial weighting method" << tab << "cell-based" << nl << "- radial extent" << tab << radialExtent << nl
+            << "- maximum radial weighting factor" << tab << maxRWF << nl << endl;
+    }
+    if (variableTimeStep_ || axisymmetric)
+    {
+        ck(dsmcb200_set_cell_fields(ctx_, variableTimeStep_ ? nParticlesCell_.begin() : NULL, variableTimeStep_ ? deltaTCell_.begin() : NULL,
+                                    axisymmetric ? RWFCell_.begin() : NULL), "dsmcb200_set_cell_fields");
+    }
+}
+
+
 void Foam::dsmcCloud::readCloud()
 {
     // Cloud<dsmcParcel>::initCloud + dsmcParcel::readFields (dsmcParcelIO.C:133-335) with the stock lagrangian readers
@@ -534,6 +617,7 @@ void Foam::dsmcCloud::readCloud()
     IOField<label> ELevel(positions.fieldIOobject("ELevel", IOobject::READ_IF_PRESENT));
     IOField<label> classification(positions.fieldIOobject("classification", IOobject::READ_IF_PRESENT));
     IOField<labelField> vibLevel(positions.fieldIOobject("vibLevel", IOobject::READ_IF_PRESENT));
+    IOField<scalar> radialWeight(positions.fieldIOobject("radialWeight", IOobject::READ_IF_PRESENT));
 
     Field<vector> pos(n);
     labelList cell(n), tetFace(n), tetPt(n), origId(n), origProc(n), vib(n*maxModes_, 0);
@@ -555,6 +639,7 @@ void Foam::dsmcCloud::readCloud()
     if (ERot.size() == n) { soa.ERot = ERot.begin(); }
     if (ELevel.size() == n) { soa.ELevel = ELevel.begin(); }
     if (classification.size() == n) { soa.classification = classification.begin(); }
+    if (radialWeight.size() == n) { soa.radialWeight = radialWeight.begin(); }
     soa.vibLevel = vib.begin(); soa.maxModes = maxModes_;
     ck(dsmcb200_upload_parcels(ctx_, n, &soa), "dsmcb200_upload_parcels");
 
@@ -603,6 +688,7 @@ Foam::dsmcCloud::dsmcCloud(Time& t, const word& cloudName, const dynamicFvMesh& 
     sendMesh();
     readSpecies();
     readModels();
+    setCellFields();
     if (readFields) { readCloud(); }
 }
 
@@ -645,8 +731,8 @@ void Foam::dsmcCloud::info()
         << "    Number of DSMC particles        = " << label(nMol) << nl;
     if (nMol > VSMALL)
     {
-        const scalar nP = models_.nEquivalentParticles;
-        Info<< "    Number of molecules             = " << nMol*nP << nl
+        const scalar nP = 1.0;   // mass and energies carry nParticles(cell) per parcel (dsmcCloudI.H:268-297)
+        Info<< "    Number of molecules             = " << c.nMolecules << nl
             << "    Mass in system                  = " << v[1]*nP << nl
             << "    Average linear kinetic energy   = " << v[2]/nMol << nl
             << "    Average rotational energy       = " << v[3]/nMol << nl
@@ -679,7 +765,7 @@ void Foam::dsmcCloud::writeCloud() const
     ck(dsmcb200_download_parcels(ctx_, 0, &n64, NULL), "dsmcb200_download_parcels");
     const label n = label(n64);
     Field<vector> pos(n), U(n);
-    scalarField ERot(n, 0.0);
+    scalarField ERot(n, 0.0), radialWeight(n, 1.0);
     labelList cell(n), tetFace(n), tetPt(n), typeId(n), ELevel(n, 0), newParcel(n, -1), classification(n, 0), origId(n), origProc(n), vib(n*maxModes_, 0);
     dsmcb200_parcels_soa soa;
     std::memset(&soa, 0, sizeof(soa));
@@ -687,6 +773,7 @@ void Foam::dsmcCloud::writeCloud() const
     soa.cell = cell.begin(); soa.tetFace = tetFace.begin(); soa.tetPt = tetPt.begin(); soa.typeId = typeId.begin();
     soa.vibLevel = vib.begin(); soa.maxModes = maxModes_; soa.ELevel = ELevel.begin(); soa.newParcel = newParcel.begin();
     soa.classification = classification.begin(); soa.origId = origId.begin(); soa.origProc = origProc.begin();
+    soa.radialWeight = radialWeight.begin();
     ck(dsmcb200_download_parcels(ctx_, n, &n64, &soa), "dsmcb200_download_parcels");
 
     passiveParticleCloud outCloud(mesh_, cloudName_, IDLList<passiveParticle>());
@@ -710,7 +797,8 @@ void Foam::dsmcCloud::writeCloud() const
         fVib[i].setSize(nM);
         for (label m = 0; m < nM; ++m) { fVib[i][m] = vib[i*maxModes_ + m]; }
     }
-    fU.write(); fERot.write(); fELevel.write(); fTypeId.write(); fNewParcel.write(); fClass.write(); fVib.write();
+    IOField<scalar> fRadialWeight(outCloud.fieldIOobject("radialWeight", IOobject::NO_READ), radialWeight);
+    fU.write(); fERot.write(); fELevel.write(); fTypeId.write(); fNewParcel.write(); fClass.write(); fVib.write(); fRadialWeight.write();
 
     volScalarField sigmaTcRMax
     (
@@ -733,7 +821,7 @@ void Foam::dsmcCloud::writeFields() const
     scalarField acc(nC*nS*nQ), coll(2*nC);
     ck(dsmcb200_download_accumulators(ctx_, acc.begin(), coll.begin()), "dsmcb200_download_accumulators");
     const scalar nT = max(ai.nTimeSteps, 1.0);
-    const scalar kB = models_.kB, nP = models_.nEquivalentParticles;
+    const scalar kB = models_.kB;
     const scalarField& V = mesh_.cellVolumes();
     const bool internal = ai.nModes >= 0;
 
@@ -758,6 +846,7 @@ void Foam::dsmcCloud::writeFields() const
 
         for (label c = 0; c < nC; ++c)
         {
+            const scalar nP = nParticlesCell_[c]*RWFCell_[c];   // cloud_.nParticles(cell), dsmcVolFields.C:1098,1128
             scalar dsmcNCum = 0, mCum = 0, linearKECum = 0, ErotCum = 0, zetaRotCum = 0;
             vector momentumCum(vector::zero);
             scalar TvibSum = 0, zetaVibSum = 0, moleculesRhoN = 0;

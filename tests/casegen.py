@@ -189,3 +189,150 @@ def couette_case(path, n_steps=4, seed=5, nto=2, start_time="5"):
     casew.write_dict(os.path.join(path, "system", "boundariesDict"), "system", "boundariesDict", BOUNDARIES_DICT)
     casew.write_dict(os.path.join(path, "system", "fieldPropertiesDict"), "system", "fieldPropertiesDict", FIELD_PROPERTIES)
     return g, mesh, p
+
+
+# ---- the axisymmetric tutorial (run/hyStrath/dsmcFoam+/axisymmetricFlatnosedCylinder) as a case directory ----
+AXISYM_PROPERTIES = """
+coordinateSystem   dsmcAxisymmetric;
+
+nEquivalentParticles            2e7;
+seedNumber                      %(seed)d;
+
+axisymmetricProperties
+{
+    maxRadialWeightingFactor    1000;
+}
+
+collisionPartnerSelectionModel   		 noTimeCounter;
+BinaryCollisionModel            VariableHardSphere;
+VariableHardSphereCoeffs
+{
+    Tref        273;
+}
+
+typeIdList                      (Ar);
+
+moleculeProperties
+{
+    Ar
+    {
+        mass                                  66.3e-27;
+        diameter                              4.17e-10;
+        omega                                     0.81;
+        alpha                                      1.4;
+    }
+}
+"""
+
+AXISYM_BOUNDARIES = """
+dsmcPatchBoundaries
+(
+     boundary
+     {
+         patchBoundaryProperties
+         {
+             patchName   cylinder;
+         }
+         boundaryModel   dsmcDiffuseWallPatch;
+         dsmcDiffuseWallPatchProperties
+         {
+			      temperature 		300;
+			      velocity 			(0 0 0);
+         }
+     }
+    boundary
+    {
+        patchBoundaryProperties
+        {
+            patchName                           flow;
+        }
+        boundaryModel   dsmcDeletionPatch;
+        dsmcDeletionPatchProperties
+        {
+	          allSpecies		yes;
+        }
+    }
+);
+
+dsmcCyclicBoundaries
+(
+);
+
+dsmcGeneralBoundaries
+(
+    boundary
+    {
+        generalBoundaryProperties
+        {
+            patchName                           flow;
+        }
+        boundaryModel   dsmcFreeStreamInflowPatch;
+        dsmcFreeStreamInflowPatchProperties
+        {
+			      typeIds						(Ar);
+			      translationalTemperature           100;
+		        velocity                    (1000 0 0);
+		        numberDensities
+		        {
+		            Ar          1.0e21;
+		        }
+	      }
+    }
+);
+"""
+
+AXISYM_FIELDS = """
+dsmcFields
+(
+	  field
+    {
+       fieldModel          	dsmcVolFields;
+       timeProperties
+       {
+       	  timeOption      write;
+            resetAtOutput       on;
+          resetAtOutputUntilTime       8e-4;
+       }
+       dsmcVolFieldsProperties
+       {
+          fieldName                   Ar;
+          typeIds                     (Ar);
+          measureMeanFreePath         true;
+          averagingAcrossManyRuns     false;
+       }
+    }
+);
+"""
+
+AXISYM_INITIALISE = """
+configurations
+(
+	configuration
+  {
+      type			dsmcMeshFill;
+	    numberDensities
+	    {
+		      Ar              1.0e21;
+	    };
+	    translationalTemperature     	100;
+	    rotationalTemperature          0;
+	    vibrationalTemperature         0;
+      electronicTemperature          0;
+	    velocity        (1000 0 0);
+	}
+);
+"""
+
+
+def axisym_case(path, n_steps=40, seed=9, nto=10):
+    """The dictionaries of the shipped tutorial (keyword layout kept) on the mesh of its blockMeshDict; dsmcInitialise+ state not yet made."""
+    from hystrath_b200 import meshgen
+    mesh = meshgen.axisymmetric_cylinder_mesh()
+    casew.write_poly_mesh(path, mesh)
+    dt = 8e-8
+    casew.write_dict(os.path.join(path, "constant", "dsmcProperties"), "constant", "dsmcProperties", AXISYM_PROPERTIES % dict(seed=seed))
+    casew.write_dict(os.path.join(path, "system", "controlDict"), "system", "controlDict", CONTROL_DICT % dict(nto=nto, end=n_steps * dt, dt=dt, wi=n_steps))
+    casew.write_dict(os.path.join(path, "system", "boundariesDict"), "system", "boundariesDict", AXISYM_BOUNDARIES)
+    casew.write_dict(os.path.join(path, "system", "fieldPropertiesDict"), "system", "fieldPropertiesDict", AXISYM_FIELDS)
+    casew.write_dict(os.path.join(path, "system", "dsmcInitialiseDict"), "system", "dsmcInitialiseDict", AXISYM_INITIALISE)
+    return mesh

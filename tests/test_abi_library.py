@@ -34,7 +34,7 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(capi.Species) == 64 + 5 * 8 + 8 + 9 * 8 + 8 + 8 + 16 * 8 + 16 * 4
     assert C.sizeof(capi.PatchModel) == 8 + 8 + 24 + 8 + 8 + 8   # + diffuseFraction, linearTemperature / depthAxis, formationLevelTemperature
     assert C.sizeof(capi.ParcelsSoA) == 12 * 8 + 8 + 8 + 8   # + radialWeight
-    assert C.sizeof(capi.Counters) == 9 * 8 + 5 * 8 + 8 * 8 + 8 + 16 * 4 + 2 * 16 * 8
+    assert C.sizeof(capi.Counters) == 9 * 8 + 5 * 8 + 8 * 8 + 8 + 16 * 4 + 2 * 16 * 8 + 16
     assert C.sizeof(capi.AccumInfo) == 24
 
 

@@ -205,3 +205,40 @@ def test_driver_parses_the_shipped_reacting_heat_bath_dictionaries(tmp_path):
     open(p, "w").write(txt.replace("(O2 N2)", "(O2 Xe)", 1))
     r = subprocess.run([RUN, "-case", str(tmp_path), "-initialise", "-dryRun"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 1 and "Cannot find type id: Xe" in r.stderr
+
+
+AXISYM = "/root/reference/run/hyStrath/dsmcFoam+/axisymmetricFlatnosedCylinder"
+
+
+@pytest.mark.skipif(not os.path.isdir(AXISYM), reason="the shipped case directory only exists next to the reference checkout")
+def test_driver_parses_the_shipped_axisymmetric_dictionaries(tmp_path):
+    """The unchanged system/ and constant/ of the shipped axisymmetric tutorial (coordinateSystem dsmcAxisymmetric with
+    maxRadialWeightingFactor 1000) on the mesh its blockMeshDict describes; other coordinate systems / time-step models stop with the
+    selector's message."""
+    import shutil
+
+    from hystrath_b200 import case as casew
+    from hystrath_b200 import meshgen
+
+    for sub in ("system", "constant"):
+        shutil.copytree(os.path.join(AXISYM, sub), os.path.join(str(tmp_path), sub))
+    os.chmod(os.path.join(str(tmp_path), "constant"), 0o755)
+    casew.write_poly_mesh(str(tmp_path), meshgen.axisymmetric_cylinder_mesh())
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-initialise", "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout
+    assert "4000 cells 4 patches" in out and "patch wedgeFront symmetry 4000" in out and "patch cylinder wall 60" in out
+    assert "coordinateSystem dsmcAxisymmetric polarAxis 1 angularCoordinate 2 maxRadialWeightingFactor 1000 timeStepModel constant" in out
+    assert "nEquivalentParticles 2e+07" in out and "patchModels 2 inflows 1 fields 1" in out
+    p = os.path.join(str(tmp_path), "constant", "dsmcProperties")
+    txt = open(p).read()
+    os.chmod(p, 0o644)
+    open(p, "w").write(txt.replace("dsmcAxisymmetric;", "dsmcSpherical;"))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-initialise", "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "dsmcSpherical" in r.stderr and "dsmcAxisymmetric" in r.stderr and "dsmcCartesian" in r.stderr
+    open(p, "w").write(txt.replace("coordinateSystem   dsmcAxisymmetric;", "coordinateSystem   dsmcAxisymmetric;\ntimeStepModel adaptive;"))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-initialise", "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "dsmcAdaptiveTimeStepModel" in r.stderr and "dsmcVariableTimeStepModel" in r.stderr
+    open(p, "w").write(txt.replace("coordinateSystem   dsmcAxisymmetric;", "coordinateSystem   dsmcAxisymmetric;\ntimeStepModel variable;"))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-initialise", "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "timeStepModel variable" in r.stdout

@@ -230,3 +230,35 @@ configurations
     r2 = subprocess.run([RUN, "-case", str(tmp_path)], capture_output=True, text=True, timeout=600)
     assert r2.returncode == 0, r2.stderr + r2.stdout
     assert f"Number of DSMC particles        = {n}" in r2.stdout and "End stage 0" in r2.stdout
+
+
+def test_driver_runs_the_axisymmetric_tutorial(tmp_path):
+    """`dsmcb200_run -initialise` then the solver on the reference's axisymmetric tutorial: the written RWF field is the shipped one, the
+    start cloud holds n V / (F_N RWF) parcels per cell with their radial weights, the run clones / deletes parcels after every move and
+    writes radialWeight with the cloud; rhoN of the free stream ahead of the shock comes out as the inflow density."""
+    from tests import helpers as H
+    gold = H.axisym_gold()
+    mesh = casegen.axisym_case(str(tmp_path), n_steps=60)
+    r = subprocess.run([RUN, "-initialise", "-case", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "Axisymmetric simulation:" in r.stdout and "radial extent\t0.03" in r.stdout and "maximum radial weighting factor\t1000" in r.stdout
+    rwf = ff.read_internal_field(os.path.join(str(tmp_path), "0", "RWF"))
+    assert np.allclose(rwf, gold["RWF"], rtol=1e-9)
+    cdir = os.path.join(str(tmp_path), "0", "lagrangian", "dsmc")
+    xyz, cell = ff.read_positions(os.path.join(cdir, "positions"))
+    w = ff.read_scalar_list(os.path.join(cdir, "radialWeight"))
+    assert np.allclose(w, rwf[cell], rtol=1e-9)
+    n0 = len(cell)
+    assert abs(n0 - 130000) < 3000
+    r2 = subprocess.run([RUN, "-case", str(tmp_path)], capture_output=True, text=True, timeout=900)
+    assert r2.returncode == 0, r2.stderr + r2.stdout
+    end = [d for d in os.listdir(str(tmp_path)) if d.startswith("4.8e-06")][0]
+    rhoN = ff.read_internal_field(os.path.join(str(tmp_path), end, "rhoN_Ar"))
+    # the three columns of cells next to the inlet still see the undisturbed stream after 60 steps: rhoN = 1e21 whatever the cell's weight
+    inlet = np.concatenate([np.arange(0, 800, 40), 800 + np.arange(0, 1600, 40)])
+    assert abs(rhoN[inlet].mean() / 1e21 - 1) < 0.02 and np.abs(rhoN[inlet] / 1e21 - 1).max() < 0.25
+    cdir = os.path.join(str(tmp_path), end, "lagrangian", "dsmc")
+    xyz, cell = ff.read_positions(os.path.join(cdir, "positions"))
+    w = ff.read_scalar_list(os.path.join(cdir, "radialWeight"))
+    assert np.allclose(w, rwf[cell], rtol=1e-9) and len(cell) > n0       # every parcel carries its cell's weight after the weighting stage
+    assert os.path.exists(os.path.join(str(tmp_path), end, "RWF"))
