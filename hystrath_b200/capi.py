@@ -348,6 +348,8 @@ def load_library():
         "dsmcb200_timer_stop": ([P, C.POINTER(C.c_float)], C.c_int),
     }
     for name, (args, res) in sigs.items():
+        if os.environ.get("DSMCB200_LIB") and not hasattr(lib, name):
+            continue   # an older build selected for an A/B run: it simply lacks the newer entry points
         fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
         fn.argtypes = args
         fn.restype = res

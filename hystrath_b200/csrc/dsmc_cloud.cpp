@@ -527,12 +527,8 @@ void dsmcCloud::readFieldProperties() {
             throw FoamError("dsmcVolFields " + s.fieldName + ": sampleInterval " + std::to_string(s.sampleInterval) + " differs from field " +
                             fields_.front().fieldName + " (" + std::to_string(fields_.front().sampleInterval) +
                             "); this engine samples all fields on the same steps\nin: " + path);
-        // ... and on the reset policy of timeProperties (dsmcField.C:113-152): a field that resets at output next to one that keeps
-        // averaging cannot both be served from one accumulator set -- refused rather than silently averaged differently
-        if (!fields_.empty() && (fields_.front().resetAtOutput != s.resetAtOutput ||
-                                 fields_.front().resetAtOutputUntilTime != s.resetAtOutputUntilTime))
-            throw FoamError("dsmcVolFields " + s.fieldName + ": timeProperties (resetAtOutput / resetAtOutputUntilTime) differ from field " +
-                            fields_.front().fieldName + "; this engine resets all fields together\nin: " + path);
+        // the reset policy of timeProperties (dsmcField.C:113-152) is per field: a field that stopped resetting keeps averaging from its
+        // own baseline of the shared accumulators (write())
         models_.sampleInterval = std::max(1, s.sampleInterval);
         fields_.push_back(s);
     }
@@ -712,8 +708,12 @@ DerivedFields dsmcCloud::calculateField(const FieldSpec& f) {
     const int S = ai.nSpecies, nQ = ai.nQuantities, nC = ai.nCells;
     std::vector<double> acc(size_t(nC) * S * nQ), coll(size_t(nC) * 2);
     check(dsmcb200_download_accumulators(ctx_, acc.data(), coll.data()), "dsmcb200_download_accumulators");
+    // this field's sums since ITS last reset: the shared accumulators minus the field's baseline (dsmcField.C:113-152)
+    if (f.baseAcc.size() == acc.size()) for (size_t k = 0; k < acc.size(); ++k) acc[k] -= f.baseAcc[k];
+    if (f.baseColl.size() == coll.size()) for (size_t k = 0; k < coll.size(); ++k) coll[k] -= f.baseColl[k];
     const bool internal = ai.nModes >= 0;
-    const double nT = ai.nTimeSteps > 0 ? ai.nTimeSteps : 1.0;
+    const double nTf = ai.nTimeSteps - f.baseNT;
+    const double nT = nTf > 0 ? nTf : 1.0;
     const double kB = models_.kB > 0 ? models_.kB : 1.38065e-23;
     DerivedFields o;
     auto z = [&](std::vector<double>& v, int w = 1) { v.assign(size_t(nC) * w, 0.0); };
@@ -903,7 +903,7 @@ void dsmcCloud::writeFields(const std::string& timeDir, const std::vector<double
     if (nMeas) check(dsmcb200_download_wall_accumulators(ctx_, wall.data()), "dsmcb200_download_wall_accumulators");
     dsmcb200_accum_info ai{};
     check(dsmcb200_accum_info_get(ctx_, &ai), "dsmcb200_accum_info_get");
-    const double nT = ai.nTimeSteps > 0 ? ai.nTimeSteps : 1.0;
+    const std::vector<double> wallAll = wall;
     const double kB = models_.kB > 0 ? models_.kB : 1.38065e-23;
     // measured-face index of a boundary face follows the order of the patch models with a wall model
     std::vector<int> measStart(boundary_.size(), -1);
@@ -918,6 +918,10 @@ void dsmcCloud::writeFields(const std::string& timeDir, const std::vector<double
     bool firstField = true;
     for (auto& f : fields_) {
         DerivedFields d = calculateField(f);
+        // the wall sums of this field since its last reset
+        wall = wallAll;
+        if (f.baseWall.size() == wall.size()) for (size_t k = 0; k < wall.size(); ++k) wall[k] -= f.baseWall[k];
+        const double nT = ai.nTimeSteps - f.baseNT > 0 ? ai.nTimeSteps - f.baseNT : 1.0;
         // fields().overallT(cell) is Tov_ of fields_[0] as written here (dsmcFieldProperties.C:235-240): the "2008" Zv formulation
         // reads it in the collisions of the following steps (dsmcCloud.C:1441-1456)
         if (firstField && models_.invZvFormulation == 1 && (models_.collisionModel == DSMCB200_COLL_LB_VHS || models_.collisionModel == DSMCB200_COLL_LB_VSS))
@@ -1201,6 +1205,11 @@ void dsmcCloud::writeResumeSampling(const std::string& timeDir) {
     }
     for (auto& fs : fields_) {
         if (!fs.averagingAcrossManyRuns) continue;
+        // the sums of this field since its own last reset (dsmcCloud::write)
+        std::vector<double> accL = acc, collL = coll, wallL = wall;
+        if (fs.baseAcc.size() == accL.size()) for (size_t k = 0; k < accL.size(); ++k) accL[k] -= fs.baseAcc[k];
+        if (fs.baseColl.size() == collL.size()) for (size_t k = 0; k < collL.size(); ++k) collL[k] -= fs.baseColl[k];
+        if (fs.baseWall.size() == wallL.size()) for (size_t k = 0; k < wallL.size(); ++k) wallL[k] -= fs.baseWall[k];
         const int nT = int(fs.typeIds.size());
         auto cells = [&]() { return std::vector<double>(size_t(nC), 0.0); };
         std::vector<double> dsmcNCum = cells(), dsmcMCum = cells(), dsmcLinearKECum = cells(), dsmcErotCum = cells(), dsmcZetaRotCum = cells(),
@@ -1213,7 +1222,7 @@ void dsmcCloud::writeResumeSampling(const std::string& timeDir) {
         for (int c = 0; c < nC; ++c) {
             for (int t = 0; t < nT; ++t) {
                 const int s = fs.typeIds[t];
-                const double* r = &acc[(size_t(c) * S + s) * nQ];
+                const double* r = &accL[(size_t(c) * S + s) * nQ];
                 const double m = species_[s].mass;
                 dsmcNCum[c] += r[0]; dsmcMCum[c] += m * r[0]; dsmcLinearKECum[c] += m * r[4];
                 for (int k = 0; k < 3; ++k) dsmcMom[3 * size_t(c) + k] += m * r[1 + k];
@@ -1234,7 +1243,7 @@ void dsmcCloud::writeResumeSampling(const std::string& timeDir) {
                 }
                 if (hasClass) { cI[c] += r[qClass]; cII[c] += r[qClass + 1]; cIII[c] += r[qClass + 2]; }
             }
-            nColls[c] = coll[2 * size_t(c)]; collSep[c] = coll[2 * size_t(c) + 1];
+            nColls[c] = collL[2 * size_t(c)]; collSep[c] = collL[2 * size_t(c) + 1];
         }
         auto scaled = [&](const std::vector<double>& v) {   // per cell, nCmpt values each, times cloud_.nParticles(cell)
             std::vector<double> o(v);
@@ -1247,7 +1256,7 @@ void dsmcCloud::writeResumeSampling(const std::string& timeDir) {
         if (!f) throw FoamError("cannot write " + ud + "/" + name);
         std::fputs(foam::header("dictionary", timeName_ + "/uniform", name).c_str(), f);
         ListOut o{f, 10};
-        std::fprintf(f, "nTimeSteps      %.10g;\n\n", ai.nTimeSteps);
+        std::fprintf(f, "nTimeSteps      %.10g;\n\n", ai.nTimeSteps - fs.baseNT);
         o.entry("dsmcNCum", dsmcNCum); o.entry("dsmcMCum", dsmcMCum); o.entry("dsmcLinearKECum", dsmcLinearKECum);
         o.entryV("dsmcMomentumCum", dsmcMom); o.entry("dsmcErotCum", dsmcErotCum); o.entry("dsmcZetaRotCum", dsmcZetaRotCum);
         o.entryLL("dsmcSpeciesEelecCum", spEelec); o.entryLL("dsmcNSpeciesCum", spN); o.entryLL("dsmcMccSpeciesCum", spMcc);
@@ -1283,7 +1292,7 @@ void dsmcCloud::writeResumeSampling(const std::string& timeDir) {
                 if (measStart[j] < 0) continue;
                 for (int k = 0; k < boundary_[j].nFaces; ++k)
                     for (int s : fs.typeIds)
-                        for (int q = 0; q < nCmpt; ++q) out[j][size_t(k) * nCmpt + q] += wall[(size_t(measStart[j] + k) * S + s) * nWallQ + wq + q];
+                        for (int q = 0; q < nCmpt; ++q) out[j][size_t(k) * nCmpt + q] += wallL[(size_t(measStart[j] + k) * S + s) * nWallQ + wq + q];
             }
             return out;
         };
@@ -1293,7 +1302,7 @@ void dsmcCloud::writeResumeSampling(const std::string& timeDir) {
                 for (size_t j = 0; j < boundary_.size(); ++j) {
                     out[t][j].assign(size_t(boundary_[j].nFaces), 0.0);
                     if (measStart[j] < 0 || wq < 0) continue;
-                    for (int k = 0; k < boundary_[j].nFaces; ++k) out[t][j][k] = wall[(size_t(measStart[j] + k) * S + fs.typeIds[t]) * nWallQ + wq];
+                    for (int k = 0; k < boundary_[j].nFaces; ++k) out[t][j][k] = wallL[(size_t(measStart[j] + k) * S + fs.typeIds[t]) * nWallQ + wq];
                 }
             return out;
         };
@@ -1336,7 +1345,7 @@ void dsmcCloud::writeResumeSampling(const std::string& timeDir) {
                         for (size_t j = 0; j < boundary_.size(); ++j) {
                             std::vector<double> v(size_t(boundary_[j].nFaces), 0.0);
                             if (measStart[j] >= 0 && 17 + md < nWallQ)
-                                for (int k = 0; k < boundary_[j].nFaces; ++k) v[k] = wall[(size_t(measStart[j] + k) * S + fs.typeIds[t]) * nWallQ + 17 + md];
+                                for (int k = 0; k < boundary_[j].nFaces; ++k) v[k] = wallL[(size_t(measStart[j] + k) * S + fs.typeIds[t]) * nWallQ + 17 + md];
                             o.scalars(v.data(), int64_t(v.size())); std::fputc(' ', f);
                         }
                         std::fputs(") ", f);
@@ -1470,10 +1479,29 @@ void dsmcCloud::write() {
             if (cell[i] >= 0 && cell[i] < nCells_ && typeId[i] >= 0 && typeId[i] < S) instN[size_t(cell[i]) * S + typeId[i]] += 1.0;
         writeFields(timeDir, instN);
     }
-    // resetAtOutput (dsmcField.C:113-152): the accumulators are shared by all instances, so they reset together
+    // resetAtOutput / resetAtOutputUntilTime (dsmcField.C:113-152) are per field, the accumulators are shared: when every field resets the
+    // engine's sums are cleared; otherwise a field that resets takes the present sums as its new baseline
     bool reset = !fields_.empty();
     for (auto& f : fields_) reset = reset && f.resetAtOutput && !(time_ + deltaT_ > f.resetAtOutputUntilTime);
-    if (reset) check(dsmcb200_reset_accumulators(ctx_), "dsmcb200_reset_accumulators");
+    if (reset) {
+        check(dsmcb200_reset_accumulators(ctx_), "dsmcb200_reset_accumulators");
+        for (auto& f : fields_) { f.baseAcc.clear(); f.baseColl.clear(); f.baseWall.clear(); f.baseNT = 0; }
+    } else {
+        bool some = false;
+        for (auto& f : fields_) some = some || (f.resetAtOutput && !(time_ + deltaT_ > f.resetAtOutputUntilTime));
+        if (some) {
+            dsmcb200_accum_info ai{};
+            check(dsmcb200_accum_info_get(ctx_, &ai), "dsmcb200_accum_info_get");
+            std::vector<double> acc(size_t(ai.nCells) * ai.nSpecies * ai.nQuantities), coll(size_t(ai.nCells) * 2);
+            check(dsmcb200_download_accumulators(ctx_, acc.data(), coll.data()), "dsmcb200_download_accumulators");
+            int32_t nMeas = 0, nWallQ = 0;
+            check(dsmcb200_wall_info(ctx_, &nMeas, &nWallQ), "dsmcb200_wall_info");
+            std::vector<double> wall(size_t(std::max(nMeas, 1)) * ai.nSpecies * std::max(nWallQ, 1), 0.0);
+            if (nMeas) check(dsmcb200_download_wall_accumulators(ctx_, wall.data()), "dsmcb200_download_wall_accumulators");
+            for (auto& f : fields_)
+                if (f.resetAtOutput && !(time_ + deltaT_ > f.resetAtOutputUntilTime)) { f.baseAcc = acc; f.baseColl = coll; f.baseWall = wall; f.baseNT = ai.nTimeSteps; }
+        }
+    }
     // dsmcVolFields.C:2375-2378: only with averagingAcrossManyRuns and resetAtOutput off
     if (!reset) writeResumeSampling(timeDir);
 }

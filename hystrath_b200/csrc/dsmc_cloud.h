@@ -40,6 +40,9 @@ struct FieldSpec {  // one dsmcVolFields entry of system/fieldPropertiesDict
     double resetAtOutputUntilTime = 1e300;
     int sampleInterval = 1;
     bool averagingAcrossManyRuns = false;  // dsmcVolFields.C:1048: keep / restore uniform/resumeSampling_<fieldName>
+    // the shared accumulators as of this field's last reset (empty: zero), see dsmcCloud::write
+    std::vector<double> baseAcc, baseColl, baseWall;
+    double baseNT = 0;
 };
 
 struct DerivedFields {  // per-cell results of dsmcVolFields::calculateField for one instance

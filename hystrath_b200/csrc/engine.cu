@@ -805,7 +805,7 @@ int stageInflow(dsmcb200_ctx* c, int64_t tailStart) {
 MoveArgs moveArgs(dsmcb200_ctx* c, int32_t tailStart) {
     MoveArgs a{};
     a.p = c->buf[c->cur].a; a.plan = c->dPlan; a.planTotal = c->dPlanBase + c->nGroups + 1; a.gridBlocks = c->moveBlocks; a.stageTets = c->stageTets;
-    a.tailStart = tailStart; a.sfTail = c->dSfTail; a.cf = cellFields(c);
+    a.tailStart = tailStart; a.sfTail = c->dSfTail; a.cf = cellFields(c); a.weighted = c->useRwf ? 1 : 0;
     a.tets = c->dTets; a.bfaces = c->dBFaces; a.bfaceArea = c->dBFaceArea; a.P = c->dP; a.wallAcc = c->dWallAcc; a.nWallQ = c->nWallQ;
     // boundaryMeas_ is cleaned every step (dsmcCloud.C:924) but only folded into the fields on sampled steps (dsmcVolFields.C:1081,1292)
     a.wallsDue = c->sampleCounter + 1 >= std::max(1, c->models.sampleInterval);

@@ -146,6 +146,7 @@ constexpr int MOVE_NBUF = MOVE_NBUF_SZ;   // entries in flight per block (ring o
 struct MoveArgs {
     ParcelArrays p;
     CellFields cf;
+    int32_t weighted;             // coordinate system other than dsmcCartesian: selects the kernel instance that looks at cf / p.rwf
     // work list (launchMovePlan): plan[0 .. *planTotal) = {parcelBeg, parcelEnd, tetBeg, nTets}
     const int4* plan;
     const int32_t* planTotal;

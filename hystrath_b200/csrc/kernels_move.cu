@@ -423,7 +423,9 @@ __device__ __forceinline__ void releaseSlot(const MoveArgs& a, MoveSlot* S, uint
     }
 }
 
-template <bool TRACK>
+// TRACK: dsmcFaceTracker counters; CF: per-cell time steps / parcel weights (dsmcb200_set_cell_fields, dsmcAxisymmetric) -- the uniform
+// Cartesian instance keeps deltaT in a register and never looks at the cell fields
+template <bool TRACK, bool CF>
 __global__ void __launch_bounds__(MOVE_BLOCK, 1) moveKernel(const __grid_constant__ MoveArgs a) {
     extern __shared__ __align__(16) unsigned char smRaw[];
     // layout: [0, 8 NBUF) mbarriers | slots | per-thread scratch U.xyz, tEnd | windows
@@ -446,8 +448,9 @@ __global__ void __launch_bounds__(MOVE_BLOCK, 1) moveKernel(const __grid_constan
     }
     __syncthreads();
 
+    const double deltaT = P.deltaT;
     // dsmcParcel.C:76: the reduced-D corrections of position and tracking velocity apply "but not for axisymmetric cases"
-    const bool constrained = P.coordinateSystem == DSMCB200_COORD_CARTESIAN && (P.solutionD[0] == -1 || P.solutionD[1] == -1 || P.solutionD[2] == -1);
+    const bool constrained = (!CF || P.coordinateSystem == DSMCB200_COORD_CARTESIAN) && (P.solutionD[0] == -1 || P.solutionD[1] == -1 || P.solutionD[2] == -1);
 
     // warp-uniform: the entry this warp draws parcels from
     int32_t wq = 0;             // its sequence number
@@ -524,7 +527,9 @@ __global__ void __launch_bounds__(MOVE_BLOCK, 1) moveKernel(const __grid_constan
                     pos = mk(a.p.px[i], a.p.py[i], a.p.pz[i]);
                     const V3 U = mk(a.p.ux[i], a.p.uy[i], a.p.uz[i]);
                     const double stepFraction = (a.sfTail != nullptr && i >= a.tailStart) ? a.sfTail[i - a.tailStart] : 0.0;
-                    const double tEnd = (1.0 - stepFraction) * a.cf.deltaT(P.deltaT, cell < 0 ? 0 : cell);   // deltaTValue(orgCell), dsmcParcel.C:62-63
+                    double dtCell = deltaT;
+                    if constexpr (CF) dtCell = a.cf.deltaT(deltaT, cell < 0 ? 0 : cell);   // deltaTValue(orgCell), dsmcParcel.C:62-63
+                    const double tEnd = (1.0 - stepFraction) * dtCell;
                     myU[0] = U.x; myU[MOVE_BLOCK] = U.y; myU[2 * MOVE_BLOCK] = U.z; myU[3 * MOVE_BLOCK] = tEnd;
                     faceBfi = -1;
                     hitsAndGuard = 0;
@@ -687,7 +692,7 @@ __global__ void __launch_bounds__(MOVE_BLOCK, 1) moveKernel(const __grid_constan
                     a.p.cell[i] = -1;
                     atomicAdd(&a.counters->deleted, 1ULL);
                 } else if (st & F_SWITCH) {
-                    packMigrant(a, P, i, faceBfi, tet, pos, mk(myU[0], myU[MOVE_BLOCK], myU[2 * MOVE_BLOCK]), 1.0 - tEnd / a.cf.deltaT(P.deltaT, cell));   // stepFraction = 1 - tEnd / deltaTValue(orgCell): the face cell (dsmcParcel.C:97)
+                    packMigrant(a, P, i, faceBfi, tet, pos, mk(myU[0], myU[MOVE_BLOCK], myU[2 * MOVE_BLOCK]), 1.0 - tEnd / (CF ? a.cf.deltaT(deltaT, cell) : deltaT));   // stepFraction = 1 - tEnd / deltaTValue(orgCell): the face cell (dsmcParcel.C:97)
                     a.p.cell[i] = -1;
                 } else {
                     a.p.px[i] = pos.x; a.p.py[i] = pos.y; a.p.pz[i] = pos.z;
@@ -715,12 +720,15 @@ cudaError_t launchMove(const MoveArgs& a, cudaStream_t s) {
     const size_t smem = moveSharedBytes(a.stageTets);
     static bool attrSet = false;
     if (!attrSet) {
-        cudaFuncSetAttribute(moveKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(moveKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(moveKernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(moveKernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(moveKernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(moveKernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attrSet = true;
     }
-    if (a.faceFlux) moveKernel<true><<<a.gridBlocks, MOVE_BLOCK, smem, s>>>(a);
-    else moveKernel<false><<<a.gridBlocks, MOVE_BLOCK, smem, s>>>(a);
+    const bool cf = a.cf.nPts || a.cf.dt || a.cf.rwf || a.p.rwf || a.weighted;
+    if (a.faceFlux) { if (cf) moveKernel<true, true><<<a.gridBlocks, MOVE_BLOCK, smem, s>>>(a); else moveKernel<true, false><<<a.gridBlocks, MOVE_BLOCK, smem, s>>>(a); }
+    else { if (cf) moveKernel<false, true><<<a.gridBlocks, MOVE_BLOCK, smem, s>>>(a); else moveKernel<false, false><<<a.gridBlocks, MOVE_BLOCK, smem, s>>>(a); }
     return cudaGetLastError();
 }
 

@@ -43,18 +43,20 @@ def test_driver_rejects_unknown_models_like_the_reference(tmp_path):
     assert r.returncode == 1 and "keyword nEquivalentParticles is undefined in dictionary" in r.stderr
 
 
-def test_driver_refuses_fields_with_different_reset_policies(tmp_path):
-    """All field{} entries share one accumulator set: different timeProperties are refused, not silently merged."""
+def test_driver_accepts_fields_with_different_reset_policies(tmp_path):
+    """timeProperties are per field (dsmcField.C:113-152): one field may keep averaging while the others reset at every write (the
+    GPU driver test checks the sums); a different sampleInterval is still refused (one sampling cadence for the shared accumulators)."""
     casegen.couette_case(str(tmp_path))
     path = os.path.join(str(tmp_path), "system", "fieldPropertiesDict")
     text = open(path).read()
     assert text.count("resetAtOutput       on;") == 3
     open(path, "w").write(text.replace("resetAtOutput       on;", "resetAtOutput       off;", 1))
     r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
-    assert r.returncode == 1 and "this engine resets all fields together" in r.stderr
-    open(path, "w").write(text.replace("resetAtOutput       on;", "resetAtOutput       off;"))
-    r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
+    assert "field O2 typeIds 1 mfp 1 reset 0" in r.stdout and "field N2 typeIds 0 mfp 1 reset 1" in r.stdout
+    open(path, "w").write(text.replace("fieldName               N2;", "fieldName               N2;\n            sampleInterval 2;"))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "this engine samples all fields on the same steps" in r.stderr
 
 
 def test_driver_reads_linear_wall_temperature(tmp_path):

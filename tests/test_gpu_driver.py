@@ -262,3 +262,38 @@ def test_driver_runs_the_axisymmetric_tutorial(tmp_path):
     w = ff.read_scalar_list(os.path.join(cdir, "radialWeight"))
     assert np.allclose(w, rwf[cell], rtol=1e-9) and len(cell) > n0       # every parcel carries its cell's weight after the weighting stage
     assert os.path.exists(os.path.join(str(tmp_path), end, "RWF"))
+
+
+def test_driver_fields_with_different_reset_policies(tmp_path):
+    """timeProperties per field (dsmcField.C:113-152): O2 keeps averaging (resetAtOutput off) while N2 and mixture reset at every write.
+    Two writes of two steps each: the second O2 field averages all four steps, the second N2 field only the last two -- both from the
+    one set of accumulators the engine keeps."""
+    casegen.couette_case(str(tmp_path), n_steps=4, seed=7, nto=1)
+    fp = os.path.join(str(tmp_path), "system", "fieldPropertiesDict")
+    text = open(fp).read()
+    with open(fp, "w") as fh:
+        fh.write(text.replace("resetAtOutput       on;", "resetAtOutput       off;", 1))      # the first field{} is O2
+    cd = os.path.join(str(tmp_path), "system", "controlDict")
+    control = open(cd).read()
+    with open(cd, "w") as fh:
+        fh.write(control.replace("writeInterval   4;", "writeInterval   2;"))
+    r = subprocess.run([RUN, "-case", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    t1, t2 = os.path.join(str(tmp_path), "5.00002"), os.path.join(str(tmp_path), "5.00004")
+    o2_a, o2_b = (ff.read_internal_field(os.path.join(t, "dsmcNMean_O2")) for t in (t1, t2))
+    n2_a, n2_b = (ff.read_internal_field(os.path.join(t, "dsmcNMean_N2")) for t in (t1, t2))
+    mix_b = ff.read_internal_field(os.path.join(t2, "dsmcNMean_mixture"))
+    g = np.load(casegen.GOLD)
+    n_o2, n_n2 = int((g["typeId"] == 1).sum()), int((g["typeId"] == 0).sum())
+    # closed box: every mean sums to the species' parcel count, whatever the averaging window
+    for a, n in ((o2_a, n_o2), (o2_b, n_o2), (n2_a, n_n2), (n2_b, n_n2), (mix_b, n_o2 + n_n2)):
+        assert abs(a.sum() - n) < 1e-3 * 50
+    # the instantaneous per-cell counts of steps 3-4 differ from those of steps 1-2 ...
+    assert not np.allclose(n2_a, n2_b)
+    # ... the O2 field of the second write is the mean over all four steps: 2 x (four-step mean) - (mean of steps 1-2) = mean of steps
+    # 3-4 is non-negative and a multiple of 1/2; the N2 field (two-step window) is itself a multiple of 1/2
+    late = 2.0 * o2_b - o2_a
+    assert late.min() > -1e-6 and np.abs(late * 2 - np.round(late * 2)).max() < 1e-5
+    assert np.abs(n2_b * 2 - np.round(n2_b * 2)).max() < 1e-5
+    assert np.abs(o2_b * 4 - np.round(o2_b * 4)).max() < 1e-5 and np.abs(o2_b * 2 - np.round(o2_b * 2)).max() > 0.2   # quarter steps occur
+    assert np.allclose(mix_b - n2_b, late, atol=1e-5)      # mixture (two-step window) minus N2 = O2 over the same two steps
