@@ -174,6 +174,15 @@ def workload_config(args, cells_per_gpu, parcels_per_gpu):
                 "cells_per_gpu": cells_per_gpu, "parcels_per_gpu": parcels_per_gpu, "parcels_per_cell": args.ppc, "gas": "air5",
                 "collision_model": "LarsenBorgnakkeVariableHardSphere", "partition": "%d slab(s) along x (decomposePar simple)" % args.gpus,
                 "l2_policy": "inputs larger than L2 (parcel state >> 126 MB), no flush needed"}
+    if getattr(args, "workload", "box") == "capsule":
+        return {"workload": "3-D re-entry capsule forebody in 5-species air (N2,O2,NO,N,O) Larsen-Borgnakke at the orion107kmNR free stream "
+                            "(6053.4 m/s, 217.63 K; BASELINE configs[3]): %d^3 cells and ~%d parcels per GPU, spherical-segment heat shield "
+                            "(diffuse 1000 K wall) on the x = max plane, outflow round the shoulder, free-stream inflow + deletion on the "
+                            "other five planes" % (args.cells, parcels_per_gpu),
+                "cells_per_gpu": cells_per_gpu, "parcels_per_gpu": parcels_per_gpu, "parcels_per_cell": args.ppc, "gas": "air5",
+                "collision_model": "LarsenBorgnakkeVariableHardSphere",
+                "partition": "x".join(str(v) for v in procs_for(args.gpus)) + " bricks (decomposePar simple), NCCL migration across processor patches",
+                "l2_policy": "inputs larger than L2 (parcel state >> 126 MB per GPU), no flush needed"}
     if getattr(args, "workload", "box") == "cylinder":
         return {"workload": "2-D Mach-10 argon flow over a cylinder (BASELINE configs[1], Lofthouse): O-grid %s cells, ~%d parcels, VHS, "
                             "diffuse 500 K wall, free-stream inflow + deletion" % (args.cyl, parcels_per_gpu),
@@ -217,6 +226,20 @@ def cpu_baseline_leg(args):
         dt = time.perf_counter() - t0
         return {"value": n * args.cpu_steps / dt, "unit": "particle-steps/s", "cores": cores, "kind": "port",
                 "sample": f"200x100x2-cell wedge, {n} parcels, {args.cpu_steps} steps (oracle, OpenMP over {cores} threads)"}
+    if getattr(args, "workload", "box") == "capsule":
+        from hystrath_b200 import cases
+
+        mesh, sp, md, fill = cases.capsule_forebody((32, 32, 32), 31)
+        o = Oracle()
+        o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
+        o.mesh_fill(fill["type_ids"], fill["number_densities"], fill["Ttra"], fill["Trot"], fill["Tvib"], 0.0, fill["velocity"])
+        n = o.num_parcels()
+        o.evolve(1)
+        t0 = time.perf_counter()
+        o.evolve(args.cpu_steps)
+        dt = time.perf_counter() - t0
+        return {"value": n * args.cpu_steps / dt, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+                "sample": f"32^3-cell capsule forebody, {n} parcels, {args.cpu_steps} steps (oracle, OpenMP over {cores} threads)"}
     if getattr(args, "workload", "box") == "cylinder":
         from hystrath_b200 import cases
 
@@ -353,7 +376,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dsmcb200", choices=["dsmcb200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("DSMCB200_BENCH_WORKLOAD", "box"), choices=["box", "cylinder", "wedge", "c1"],
+    ap.add_argument("--workload", default=os.environ.get("DSMCB200_BENCH_WORKLOAD", "box"), choices=["box", "cylinder", "wedge", "c1", "capsule"],
                     help="box: BASELINE configs[4] weak-scaling periodic box (default, any N); cylinder: configs[1] Mach-10 argon cylinder (N=1); "
                          "wedge: configs[2] 5-species air over a hypersonic wedge (N > 1: the same case cut into N slabs along x, strong scaling)")
     ap.add_argument("--wedge", default="2000x1000x4", help="wedge cells nx x ny x nz")
@@ -410,6 +433,13 @@ def main():
         args.gas = "argon"
         args.ppc = 25
         mesh, sp, md, fill = cases.lofthouse_cylinder(nr, nt, args.ppc)
+        tids, dens, Tfill, vfill = fill["type_ids"], fill["number_densities"], fill["Ttra"], fill["velocity"]
+        n_cells_gpu = mesh.n_cells
+    elif args.workload == "capsule":
+        from hystrath_b200 import cases
+
+        args.gas = "air5"
+        mesh, sp, md, fill = cases.capsule_forebody((args.cells,) * 3, args.ppc, procs=procs_for(world), rank=rank)
         tids, dens, Tfill, vfill = fill["type_ids"], fill["number_densities"], fill["Ttra"], fill["velocity"]
         n_cells_gpu = mesh.n_cells
     elif args.workload == "wedge":

@@ -73,3 +73,26 @@ def air_wedge(nx=2000, ny=1000, nz=4, ppc=25, dx=0.15, angle_deg=15.0, seed=0xD5
                                rotationalRelaxationCollisionNumber=5.0, patch_models=pm, inflows=inflow)
     fill = dict(type_ids=[0, 1, 2, 3, 4], number_densities=dens, Ttra=T_inf, Trot=T_inf, Tvib=T_inf, velocity=(U_inf, 0.0, 0.0))
     return mesh, air5_species(), models, fill
+
+
+def capsule_forebody(n_local=(200, 200, 200), ppc=31, dx=0.15, seed=0xD5C00004, procs=(1, 1, 1), rank=0, density_scale=1.0):
+    """BASELINE configs[3]: 3-D re-entry capsule forebody in 5-species air at the orion107kmNR free stream (6053.4 m/s, 217.63 K;
+    run/hyStrath/dsmcFoam+/orion107kmNR/system/boundariesDict), Larsen-Borgnakke with variable Zv, diffuse 1000 K heat shield.
+    Cell size dx ~ lambda_inf / 3, dt = 0.3 dx / U_inf; procs = (px, py, pz) bricks of n_local cells each (decomposePar simple):
+    the shock layer in front of the shield makes the bricks next to the body heavier than the upstream ones."""
+    U_inf, T_inf, T_w = 6053.4, 217.63, 1000.0
+    n_N2, n_O2 = 2.318e18 * density_scale, 6.161e17 * density_scale
+    trace = 1e-3 * (n_N2 + n_O2)
+    dens = [n_N2, n_O2, trace, trace, trace]
+    mesh = meshgen.capsule_mesh(n_local, dx, procs, rank)
+    fnum = sum(dens) * dx ** 3 / ppc          # equal statistical weight everywhere, from the undistorted inlet cell
+    dt = 0.3 * dx / U_inf
+    pm = [dict(patch=mesh.patch_index("capsule"), boundaryModel="dsmcDiffuseWallPatch", temperature=T_w, velocity=(0.0, 0.0, 0.0)),
+          dict(patch=mesh.patch_index("flow"), boundaryModel="dsmcDeletionPatch"),
+          dict(patch=mesh.patch_index("outflow"), boundaryModel="dsmcDeletionPatch")]
+    inflow = [dict(patch=mesh.patch_index("flow"), typeIds=[0, 1, 2, 3, 4], numberDensities=dens, velocity=(U_inf, 0.0, 0.0),
+                   translationalTemperature=T_inf, rotationalTemperature=T_inf, vibrationalTemperature=T_inf)]
+    models = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=fnum, deltaT=dt, seed=seed,
+                               rotationalRelaxationCollisionNumber=5.0, patch_models=pm, inflows=inflow)
+    fill = dict(type_ids=[0, 1, 2, 3, 4], number_densities=dens, Ttra=T_inf, Trot=T_inf, Tvib=T_inf, velocity=(U_inf, 0.0, 0.0))
+    return mesh, air5_species(), models, fill

@@ -682,3 +682,98 @@ def axisymmetric_cylinder_mesh(n_axial=40, n_inner=20, n_outer=40, half_depth=(0
 
     mesh = poly_mesh_from_cells(points, cells, patch_of_face, [("flow", "patch"), ("cylinder", "wall"), ("wedgeFront", "symmetry"), ("wedgeBack", "symmetry")])
     return mesh
+
+
+def split_patch(mesh, name, keep, new_name, new_type):
+    """Split boundary patch `name`: the faces for which keep(face centres [n, 3]) holds stay (in their order), the others form the new
+    patch `new_name` right behind it.  Faces of one patch are contiguous, so this is a stable partition of the patch's range."""
+    k = mesh.patch_index(name)
+    p = mesh.patches[k]
+    s, n = p["start"], p["size"]
+    if not np.all(np.diff(mesh.face_offsets[s:s + n + 1]) == 4):
+        raise ValueError("split_patch expects quadrilateral faces")
+    o0 = mesh.face_offsets[s]
+    quads = mesh.face_points[o0:o0 + 4 * n].reshape(n, 4)
+    centres = mesh.points[quads].mean(1)
+    m = np.asarray(keep(centres), bool)
+    order = np.concatenate([np.nonzero(m)[0], np.nonzero(~m)[0]])
+    mesh.face_points[o0:o0 + 4 * n] = quads[order].ravel()
+    mesh.owner[s:s + n] = mesh.owner[s:s + n][order]
+    n_keep = int(m.sum())
+    p["size"] = n_keep
+    mesh.patches.insert(k + 1, {"name": new_name, "type": new_type, "start": s + n_keep, "size": n - n_keep})
+    return mesh
+
+
+def order_patches(mesh, names):
+    """Put the physical (non-processor) boundary patches into the order `names` = [(name, type), ...]; a patch the mesh does not have
+    is listed empty.  The face ranges of the patches are moved accordingly (owner, face lists)."""
+    first_proc = next((i for i, p in enumerate(mesh.patches) if p["type"].startswith("processor")), len(mesh.patches))
+    phys = {p["name"]: p for p in mesh.patches[:first_proc]}
+    if set(phys) - {n for n, _ in names}:
+        raise ValueError("order_patches: the mesh has physical patches that are not in the list")
+    b0 = mesh.n_internal
+    end_phys = mesh.patches[first_proc]["start"] if first_proc < len(mesh.patches) else mesh.n_faces
+    face_ids, ordered, cursor = [], [], b0
+    for nm, ty in names:
+        if nm in phys:
+            q = dict(phys[nm])
+            face_ids.append(np.arange(q["start"], q["start"] + q["size"]))
+            q["start"] = cursor
+            cursor += q["size"]
+            ordered.append(q)
+        else:
+            ordered.append({"name": nm, "type": ty, "start": cursor, "size": 0})
+    if cursor != end_phys:
+        raise ValueError("order_patches: physical patches do not cover the boundary range")
+    ids = np.concatenate(face_ids) if face_ids else np.zeros(0, np.int64)
+    if len(ids):
+        sizes = np.diff(mesh.face_offsets)
+        lab = [mesh.face_points[mesh.face_offsets[f]:mesh.face_offsets[f + 1]] for f in ids] if not np.all(sizes[ids] == 4) else None
+        if lab is None:
+            o0 = mesh.face_offsets[b0]
+            quads = mesh.face_points[o0:o0 + 4 * len(ids)].reshape(-1, 4)
+            mesh.face_points[o0:o0 + 4 * len(ids)] = quads[ids - b0].ravel()
+        else:
+            o0 = mesh.face_offsets[b0]
+            flat = np.concatenate(lab)
+            mesh.face_points[o0:o0 + len(flat)] = flat
+            mesh.face_offsets[b0:end_phys + 1] = o0 + np.concatenate([[0], np.cumsum(sizes[ids])])
+        mesh.owner[b0:end_phys] = mesh.owner[ids]
+    mesh.patches = ordered + mesh.patches[first_proc:]
+    return mesh
+
+
+def capsule_mesh(n_local, cell_size, procs=(1, 1, 1), rank=0, cap_radius_frac=0.3, sphere_to_cap=1.5):
+    """Re-entry capsule forebody (BASELINE configs[3]): the heat shield of a capsule -- a spherical segment of base radius R_b and sphere
+    radius sphere_to_cap * R_b -- facing a stream along +x.  The domain is a box of procs * n_local cells of size `cell_size`; its x = max
+    boundary is the body: the spherical segment (wall patch `capsule`, inside R_b of the axis through the middle of the y-z section) and,
+    around it, an open plane through which the gas that has gone round the shoulder leaves (patch `outflow`).  The grid lines are
+    compressed along x between the inlet plane and the body surface, so the cells are general hexahedra with warped faces (tracked
+    through their tet decomposition).  Inlet and the four lateral boundaries: patch `flow` (free stream in, deletion out).
+    procs = (px, py, pz): brick `rank` of the decomposition into identical bricks of n_local cells (decomposePar simple), with
+    processor patches between them; the patch list is the same on every rank (empty where a rank does not touch the boundary)."""
+    nx, ny, nz = (int(v) for v in n_local)
+    px, py, pz = procs
+    lengths = (nx * cell_size, ny * cell_size, nz * cell_size)
+    outer = ((("patch", "flow"), ("wall", "capsule")), ("patch", "flow"), ("patch", "flow"))
+    mesh = decomposed_box((nx, ny, nz), lengths, procs, rank, outer=outer)
+    Lx, Ly, Lz = px * lengths[0], py * lengths[1], pz * lengths[2]
+    Rb = cap_radius_frac * min(Ly, Lz)
+    Rs = sphere_to_cap * Rb
+    yc, zc = 0.5 * Ly, 0.5 * Lz
+
+    def bulge(y, z):
+        r2 = (y - yc) ** 2 + (z - zc) ** 2
+        return np.where(r2 < Rb * Rb, np.sqrt(np.maximum(Rs * Rs - r2, 0.0)) - np.sqrt(Rs * Rs - Rb * Rb), 0.0)
+
+    try:
+        split_patch(mesh, "capsule", lambda c: (c[:, 1] - yc) ** 2 + (c[:, 2] - zc) ** 2 < Rb * Rb, "outflow", "patch")
+    except KeyError:
+        pass   # this brick does not touch the body plane
+    # every rank lists the same physical patches, in the same order, empty where it has no faces of them (as decomposePar writes them)
+    order_patches(mesh, [("flow", "patch"), ("capsule", "wall"), ("outflow", "patch")])
+    x, y, z = mesh.points[:, 0], mesh.points[:, 1], mesh.points[:, 2]
+    mesh.points[:, 0] = x * (Lx - bulge(y, z)) / Lx
+    mesh.capsule = dict(Rb=Rb, Rs=Rs, height=Rs - np.sqrt(Rs * Rs - Rb * Rb), L=(Lx, Ly, Lz))
+    return mesh

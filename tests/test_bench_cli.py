@@ -32,3 +32,10 @@ def test_workload_description_and_stage_bytes():
     assert sum(b.STAGE_BYTES_AIR.values()) == 375.0
     cp = b.case_parameters("air5", 200, 31)
     assert abs(cp["fnum"] * 31 - 1e20 * 0.004 ** 3) < 1e-6 * 1e20 * 0.004 ** 3
+
+
+def test_capsule_workload_description():
+    b = _bench()
+    args = types.SimpleNamespace(workload="capsule", gas="air5", gpus=8, ppc=31, cells=200, numbering="morton")
+    cfg = b.workload_config(args, 8_000_000, 250_000_000)
+    assert "BASELINE configs[3]" in cfg["workload"] and cfg["partition"].startswith("2x2x2 bricks") and cfg["gas"] == "air5"

@@ -272,7 +272,8 @@ def test_driver_fields_with_different_reset_policies(tmp_path):
     fp = os.path.join(str(tmp_path), "system", "fieldPropertiesDict")
     text = open(fp).read()
     with open(fp, "w") as fh:
-        fh.write(text.replace("resetAtOutput       on;", "resetAtOutput       off;", 1))      # the first field{} is O2
+        # the first field{} is O2; the case starts at t = 5, beyond the tutorial's resetAtOutputUntilTime
+        fh.write(text.replace("resetAtOutput       on;", "resetAtOutput       off;", 1).replace("resetAtOutputUntilTime       0.5;", "resetAtOutputUntilTime       100;"))
     cd = os.path.join(str(tmp_path), "system", "controlDict")
     control = open(cd).read()
     with open(cd, "w") as fh:

@@ -581,3 +581,35 @@ def test_air_wedge_small_scale_matches_oracle():
     gw, ow = eng.wall_accumulators(), ora.wall_accumulators()
     assert np.abs(ow).max() > 0 and np.abs(gw - ow).max() <= 1e-9 * np.abs(ow).max()
     eng.close()
+
+
+def test_capsule_forebody_small_scale_matches_oracle():
+    """BASELINE configs[3] at test size (hystrath_b200.cases.capsule_forebody: hexahedra compressed towards a spherical-segment heat
+    shield, so most faces are warped and every track runs through the tet decomposition; diffuse 1000 K shield, free-stream inflow and
+    deletion on the inlet and the four lateral planes, outflow around the shoulder; 5-species Larsen-Borgnakke with variable Zv):
+    insertions, deletions, cells, list order and collision counts are the oracle's step by step; wall accumulators to 1e-9."""
+    from hystrath_b200 import cases
+
+    mesh, sp, md, fill = cases.capsule_forebody((14, 12, 12), ppc=16, density_scale=40.0)
+    assert [p["name"] for p in mesh.patches] == ["flow", "capsule", "outflow"] and mesh.patches[1]["size"] > 30
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    ora.set_reorder(True)
+    H.same_start(eng, ora, fill["type_ids"], fill["number_densities"], fill["Ttra"], fill["Trot"], fill["Tvib"], fill["velocity"])
+    seen = dict(collisions=0, inserted=0, deleted=0)
+    for _ in range(6):
+        eng.evolve(1)
+        ora.evolve(1)
+        tot, c = ora.counters(), eng.counters()
+        assert c.inserted == tot["inserted"] - seen["inserted"] > 0
+        assert c.deleted == tot["deleted"] - seen["deleted"] > 0
+        assert c.collisions == tot["collisions"] - seen["collisions"] > 50
+        seen = tot
+    g, o = eng.download_parcels(), ora.download_parcels()
+    assert g.n == o.n
+    assert np.array_equal(g.origId, o.origId) and np.array_equal(g.typeId, o.typeId)
+    assert np.array_equal(g.cell, o.cell) and np.array_equal(eng.occupancy(), ora.occupancy())
+    assert np.array_equal(g.vibLevel, o.vibLevel)
+    assert np.allclose(g.position, o.position, rtol=0, atol=1e-9) and np.allclose(g.U, o.U, rtol=1e-11, atol=1e-7)
+    gw, ow = eng.wall_accumulators(), ora.wall_accumulators()
+    assert np.abs(ow).max() > 0 and np.abs(gw - ow).max() <= 1e-9 * np.abs(ow).max()
+    eng.close()

@@ -566,3 +566,33 @@ def test_variable_time_step_scales_weights_and_steps_with_the_cell_volume():
     N = per_cell.astype(float)
     cand = np.floor(0.5 * N * (N - 1) * n * sig * dt / cv)
     assert o.counters()["collisionCandidates"] == int(cand.sum())
+
+
+def test_capsule_mesh_bricks_tile_the_single_domain_mesh():
+    """meshgen.capsule_mesh (BASELINE configs[3]): the eight bricks of a 2 x 2 x 2 decomposition have the patch list of the whole mesh
+    (empty where a brick does not touch a boundary), their cells tile the single-domain volume, the heat shield's area is the sum of
+    the bricks' shares, and processor patches pair up face by face (same centres on both sides)."""
+    whole = meshgen.capsule_mesh((12, 10, 10), 0.15)
+    o = Oracle(); o.set_mesh(whole)
+    _, cv, fc, fa, *_ = o.geometry()
+    cap = whole.patches[whole.patch_index("capsule")]
+    area = np.linalg.norm(fa[cap["start"]:cap["start"] + cap["size"]], axis=1).sum()
+    h = whole.capsule["height"]
+    # volume removed by the body = volume of the spherical segment (to the accuracy of the faceted surface)
+    seg = np.pi * h * h * (3 * whole.capsule["Rs"] - h) / 3.0
+    assert abs((1.8 * 1.5 * 1.5 - cv.sum()) / seg - 1) < 0.15
+    vol, a_sum, proc_faces = 0.0, 0.0, {}
+    for r in range(8):
+        m = meshgen.capsule_mesh((6, 5, 5), 0.15, (2, 2, 2), r)
+        assert [p["name"] for p in m.patches[:3]] == ["flow", "capsule", "outflow"]
+        b = Oracle(); b.set_mesh(m)
+        _, v, c, a, *_ = b.geometry()
+        vol += v.sum()
+        p = m.patches[1]
+        a_sum += np.linalg.norm(a[p["start"]:p["start"] + p["size"]], axis=1).sum()
+        for q in m.patches[3:]:
+            assert q["type"] == "processor"
+            proc_faces[(r, q["neighbProcNo"])] = c[q["start"]:q["start"] + q["size"]]
+    assert abs(vol / cv.sum() - 1) < 1e-12 and abs(a_sum / area - 1) < 1e-12
+    for (r, nb), c in proc_faces.items():
+        assert np.allclose(c, proc_faces[(nb, r)], atol=1e-12)      # the two sides list the shared faces in the same order
