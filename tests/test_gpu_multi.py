@@ -373,3 +373,100 @@ def test_two_gpu_run_with_collisions_equals_the_two_rank_oracle():
         assert ncoll == oc["collisions"] and ncoll > 100  # the same NTC pairs were selected and accepted
         assert np.array_equal(vib, o.vibLevel)            # variable-Zv vibrational exchange (host-tabulated 1/Zv) included
         assert np.allclose(U, o.U, rtol=0, atol=1e-8) and np.allclose(erot, o.ERot, rtol=1e-9, atol=1e-30)
+
+
+# ---- BASELINE configs[3] on two GPUs: the capsule forebody cut into two bricks along x (the upstream half and the half with the shield) ----
+CAP_N, CAP_STEPS = (7, 10, 10), 5
+
+
+def _capsule_rank(r):
+    from hystrath_b200 import cases
+    return cases.capsule_forebody(CAP_N, ppc=14, density_scale=40.0, procs=(2, 1, 1), rank=r, seed=0xD5C00004 + 7183 * r)
+
+
+def _capsule_oracle(r):
+    from oracle.pyoracle import Oracle
+    mesh, sp, md, fill = _capsule_rank(r)
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species(sp); o.set_models(md); o.set_rank(r)
+    o.mesh_fill(fill["type_ids"], fill["number_densities"], fill["Ttra"], fill["Trot"], fill["Tvib"], 0.0, fill["velocity"])
+    return o
+
+
+def _capsule_oracle_two_ranks():
+    ranks = [_capsule_oracle(r) for r in range(2)]
+    sent = np.zeros((CAP_STEPS, 2), np.int64)
+    for step in range(CAP_STEPS):
+        for o in ranks:
+            o.evolve_begin()
+        while True:
+            boxes = [o.outbox() for o in ranks]
+            if not any(len(d) for d, _ in boxes):
+                break
+            for r in range(2):
+                sent[step, r] += int((boxes[r][1][:, 0] == 1 - r).sum())
+            for r, o in enumerate(ranks):
+                d, i = boxes[1 - r]
+                sel = i[:, 0] == r
+                if sel.any():
+                    o.receive_and_move(1 - r, d[sel], i[sel])
+        for o in ranks:
+            o.evolve_end()
+    return [(o.download_parcels(), o.counters(), o.wall_accumulators()) for o in ranks], sent
+
+
+def _capsule_worker(rank, world, q_id, q_out):
+    try:
+        torch.cuda.set_device(rank)
+        mesh, sp, md, fill = _capsule_rank(rank)
+        eng = capi.Engine(rank, rank, world)
+        eng.set_mesh(mesh); eng.set_species(sp); eng.set_models(md)
+        if rank == 0:
+            ident = capi.nccl_unique_id()
+            for _ in range(world - 1):
+                q_id.put(ident)
+        else:
+            ident = q_id.get(timeout=120)
+        eng.init_comm(ident)
+        o = _capsule_oracle(rank)                      # the rank's own dsmcMeshFill, as decomposed dsmcInitialise+ does it
+        eng.upload_parcels(o.download_parcels())
+        eng.upload_cellstate(*o.download_cellstate())
+        sent, collisions, inserted, deleted = [], 0, 0, 0
+        for _ in range(CAP_STEPS):
+            eng.evolve(1)
+            c = eng.counters()
+            sent.append(int(c.migratedTo[0])); collisions += c.collisions; inserted += c.inserted; deleted += c.deleted
+        res = eng.download_parcels()
+        q_out.put((rank, res.origId.copy(), res.origProc.copy(), res.cell.copy(), res.typeId.copy(), res.vibLevel.copy(), sent, int(collisions),
+                   int(inserted), int(deleted), eng.wall_accumulators()))
+        eng.close()
+    except Exception as e:
+        q_out.put((rank, repr(e)))
+
+
+def test_two_gpu_capsule_forebody_equals_the_two_rank_oracle():
+    """The capsule forebody (BASELINE configs[3]) at test size on two GPUs: inflow, wall hits on the warped shield faces, deletion,
+    Larsen-Borgnakke collisions and NCCL migration across the processor patch; per rank the cloud (identity and order of every parcel,
+    cells, species, vibrational levels), the parcels sent per step, insertions, deletions and collision counts equal the two-rank oracle."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q_id, q_out = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_capsule_worker, args=(r, 2, q_id, q_out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ref, ref_sent = _capsule_oracle_two_ranks()
+    results = sorted([q_out.get(timeout=300) for _ in range(2)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    for r in results:
+        assert len(r) == 11, r
+    for rank, (_, ids, procs_, cell, typ, vib, sent, ncoll, nins, ndel, wall) in enumerate(results):
+        o, oc, ow = ref[rank]
+        assert sent == ref_sent[:, rank].tolist()
+        assert np.array_equal(ids, o.origId) and np.array_equal(procs_, o.origProc)
+        assert np.array_equal(cell, o.cell) and np.array_equal(typ, o.typeId) and np.array_equal(vib, o.vibLevel)
+        assert ncoll == oc["collisions"] and nins == oc["inserted"] and ndel == oc["deleted"]
+        if rank == 1:
+            assert np.abs(ow).max() > 0 and np.abs(wall - ow).max() <= 1e-9 * np.abs(ow).max()      # the shield is on rank 1
+    assert ref_sent[:, 0].sum() > 100 and ref[0][1]["inserted"] > 0 and ref[1][1]["deleted"] > 0
