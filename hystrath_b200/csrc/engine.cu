@@ -816,7 +816,7 @@ MoveArgs moveArgs(dsmcb200_ctx* c, int32_t tailStart) {
 
 // Move parcels [first, last).  useCsr: parcels [0, sortedN) are still in the order of the last sort and take the per-step work list
 // with shared-memory windows (requires first == 0); everything else is walked in plain pieces.
-int launchMoveRange(dsmcb200_ctx* c, int32_t first, int32_t last, bool useCsr, int64_t tailStart) {
+int launchMoveRange(dsmcb200_ctx* c, int32_t first, int32_t last, bool useCsr, int64_t tailStart, const char* timerName = "move") {
     if (last <= first) return 0;
     const int32_t sorted = (useCsr && first == 0 && c->csrValid && c->stageTets > 0) ? int32_t(std::min<int64_t>(c->sortedN, last)) : 0;
     const int32_t nGroups = sorted > 0 ? c->nGroups : 0;
@@ -831,7 +831,7 @@ int launchMoveRange(dsmcb200_ctx* c, int32_t first, int32_t last, bool useCsr, i
     m.nSub = c->dPlanSub; m.subBase = c->dPlanBase; m.maxTets = c->stageTets; m.plan = c->dPlan; m.planTotal = c->dPlanBase + c->nGroups + 1;
     m.tailBeg = std::max(first, sorted); m.tailEnd = last;
     { KT t(c, "movePlan"); CK(launchMovePlan(m, c->dScanScratch, c->stream)); }
-    KT t(c, "move");
+    KT t(c, timerName);
     CK(launchMove(moveArgs(c, int32_t(tailStart)), c->stream));
     return 0;
 }
@@ -861,6 +861,8 @@ int stageMove(dsmcb200_ctx* c, int64_t tailStart) {
         CK(cudaMemcpyAsync(nMig, c->dCounters->nMig, sizeof(nMig), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         std::fill(sendTo.begin(), sendTo.end(), 0);
+        {
+        KT tOrder(c, "migOrder");
         for (size_t s = 0; s < c->nbrProcs.size(); ++s) {
             if (nMig[s] > c->migCapacity) return fail(c, DSMCB200_ERR_CAPACITY, "migration buffer overflow");
             sendTo[c->nbrProcs[s]] = nMig[s];
@@ -870,12 +872,16 @@ int stageMove(dsmcb200_ctx* c, int64_t tailStart) {
             CK(orderMigrants(c->dMigSend + s * c->migCapacity, c->dMigRecv + s * c->migCapacity, c->dMigKey + s * c->migCapacity, c->dMigWork,
                              c->dMigTemp, c->migTempBytes, nMig[s], c->stream));
         }
+        }
+        cudaEvent_t evCounts0 = nullptr, evCounts1 = nullptr;
+        if (c->timeKernels) { evCounts0 = getEvent(c); evCounts1 = getEvent(c); cudaEventRecord(evCounts0, c->stream); }
         // pBufs.finishedSends(allNTrans) + reduce(transfered, orOp) -> one all-gather of the send-count rows
         int32_t* dRow = c->dCountsMatrix + size_t(R) * R;
         CK(cudaMemcpyAsync(dRow, sendTo.data(), size_t(R) * 4, cudaMemcpyHostToDevice, c->stream));
         int r = g_nccl.AllGather(dRow, c->dCountsMatrix, size_t(R), NCCL_INT32, c->comm, c->stream);
         if (r) return ncclFail(c, r, "ncclAllGather");
         CK(cudaMemcpyAsync(matrix.data(), c->dCountsMatrix, size_t(R) * R * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (c->timeKernels) { cudaEventRecord(evCounts1, c->stream); c->pending.push_back({"migCounts", {evCounts0, evCounts1}}); }
         CK(cudaStreamSynchronize(c->stream));
         bool any = false;
         for (int32_t v : matrix) if (v) { any = true; break; }
@@ -891,6 +897,8 @@ int stageMove(dsmcb200_ctx* c, int64_t tailStart) {
         }
         { int rr = ensureCapacity(c, c->N + nRecvTotal); if (rr) return rr; }
         { int rr = ensureSfTail(c, c->N + nRecvTotal - tailStart + 1); if (rr) return rr; }
+        {
+        KT tExchange(c, "migExchange");
         r = g_nccl.GroupStart();
         if (r) return ncclFail(c, r, "ncclGroupStart");
         for (size_t s = 0; s < c->nbrProcs.size(); ++s) {
@@ -899,7 +907,10 @@ int stageMove(dsmcb200_ctx* c, int64_t tailStart) {
         }
         r = g_nccl.GroupEnd();
         if (r) return ncclFail(c, r, "ncclGroupEnd");
+        }
         const int64_t firstNew = c->N;
+        {
+        KT tUnpack(c, "migUnpack");
         for (size_t s = 0; s < c->nbrProcs.size(); ++s) {
             if (!recvFrom[s]) continue;
             UnpackArgs u{};
@@ -910,8 +921,9 @@ int stageMove(dsmcb200_ctx* c, int64_t tailStart) {
             c->N += recvFrom[s];
             c->last.migratedIn += recvFrom[s];
         }
+        }
         CK(cudaMemsetAsync(c->dCounters->nMig, 0, sizeof(int32_t) * MAX_NEIGHBOURS, c->stream));
-        if (nRecvTotal) { int rr = launchMoveRange(c, int32_t(firstNew), int32_t(firstNew + nRecvTotal), false, tailStart); if (rr) return rr; }
+        if (nRecvTotal) { int rr = launchMoveRange(c, int32_t(firstNew), int32_t(firstNew + nRecvTotal), false, tailStart, "moveArrivals"); if (rr) return rr; }
     }
     return 0;
 }

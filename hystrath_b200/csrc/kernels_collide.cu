@@ -764,7 +764,7 @@ __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefet
 }  // namespace
 
 template <bool ZV2008, int NM, bool CHEM>
-__global__ void __launch_bounds__(LANE_WARPS * 32) collideLaneKernel(const __grid_constant__ CollideArgs a) {
+__global__ void __launch_bounds__(LANE_WARPS * 32, 4) collideLaneKernel(const __grid_constant__ CollideArgs a) {
     __shared__ LaneSmem smAll[LANE_WARPS];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

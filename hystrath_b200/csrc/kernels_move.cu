@@ -19,6 +19,7 @@
 // parcel takes the next one, so lanes stay busy although parcels need 1-8 visits.  A visit reads its
 // record from shared memory when the tet belongs to the run and the copy has landed, else from the
 // global table (parcels that left the run, the unsorted tail of inflow / migration arrivals).
+#define DSMC_PHILOX_LOCAL_STATE   // see philox.h: the wall path's random state stays out of the register file
 #include <cub/device/device_radix_sort.cuh>
 
 #include "device_models.cuh"
