@@ -18,7 +18,6 @@ def write_poly_mesh(case_dir, mesh):
     loc = "constant/polyMesh"
     ff.write_vector_list(os.path.join(pm, "points"), "vectorField", loc, "points", mesh.points, fmt="%.17g")
     ff.write_faces(os.path.join(pm, "faces"), loc, mesh.face_offsets, mesh.face_points)
-    ff.write_scalar_list(os.path.join(pm, "owner"), "labelList", loc, "owner", mesh.owner, fmt="%d")
     with open(os.path.join(pm, "neighbour"), "w") as f:
         f.write(ff.header("labelList", loc, "neighbour"))
         f.write(f"{len(mesh.neighbour)}\n(\n" + "\n".join(str(int(v)) for v in mesh.neighbour) + "\n)\n")

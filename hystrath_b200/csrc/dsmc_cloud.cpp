@@ -1370,7 +1370,14 @@ void dsmcCloud::readResumeSampling() {
         return;
     }
     const std::string path = root_ + "/" + timeName_ + "/uniform/resumeSampling_dsmcb200";
-    if (!foam::exists(path)) return;
+    if (!foam::exists(path)) {
+        // a case checkpointed by dsmcFoam+ itself has only the per-field dictionaries (dsmcVolFields.C:1052-1066): say that they are not read
+        for (auto& f : fields_)
+            if (f.averagingAcrossManyRuns && foam::exists(root_ + "/" + timeName_ + "/uniform/resumeSampling_" + f.fieldName))
+                std::printf("WARNING: uniform/resumeSampling_%s (written by dsmcFoam+) is not read; the averages of this run start at zero. "
+                            "Only resumeSampling_dsmcb200, written by this engine, restores the sampling.\n", f.fieldName.c_str());
+        return;
+    }
     foam::Dict d = foam::readDict(path);
     dsmcb200_accum_info ai{};
     check(dsmcb200_accum_info_get(ctx_, &ai), "dsmcb200_accum_info_get");

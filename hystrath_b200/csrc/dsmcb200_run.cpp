@@ -53,9 +53,16 @@ int main(int argc, char** argv) {
         }
         char id[128];
         const void* idPtr = nullptr;
+        std::string ncclIdPath;
         if (nRanks > 1) {
-            const std::string path = caseDir + "/.dsmcb200_nccl_id";
+            // one file per launch: a run that died before removing its file must not hand a stale id to the next one
+            std::string nonce;
+            for (const char* v : {"TORCHELASTIC_RUN_ID", "MASTER_PORT", "OMPI_MCA_orte_hnp_uri", "PMI_JOBID", "SLURM_JOB_ID"})
+                if (const char* e = std::getenv(v)) { nonce += "_"; for (const char* q = e; *q; ++q) nonce += std::isalnum(static_cast<unsigned char>(*q)) ? *q : '-'; }
+            const std::string path = caseDir + "/.dsmcb200_nccl_id" + nonce;
+            ncclIdPath = path;
             if (rank == 0) {
+                std::remove(path.c_str());
                 if (dsmcb200_nccl_unique_id(id) != 0) throw foam::FoamError("cannot create an ncclUniqueId (libnccl.so.2 missing?)");
                 FILE* f = std::fopen((path + ".tmp").c_str(), "wb");
                 if (!f) throw foam::FoamError("cannot write " + path);
@@ -74,7 +81,7 @@ int main(int argc, char** argv) {
         if (initialise) {
             // dsmcInitialise+.C:57-88
             dsmcb200::dsmcCloud dsmc(caseDir, "dsmc", rank, nRanks, device, idPtr, false, true);
-            if (nRanks > 1 && master) std::remove((caseDir + "/.dsmcb200_nccl_id").c_str());
+            if (nRanks > 1 && master) std::remove(ncclIdPath.c_str());
             if (master) std::printf("Initialising dsmc for Time = %s\n\n", dsmc.timeName().c_str());
             dsmc.write();
             if (master) std::printf("\nEnd\n\n");
@@ -82,7 +89,7 @@ int main(int argc, char** argv) {
         }
         if (master) std::printf("\nConstructing dsmcCloud \n");
         dsmcb200::dsmcCloud dsmc(caseDir, "dsmc", rank, nRanks, device, idPtr);
-        if (nRanks > 1 && master) std::remove((caseDir + "/.dsmcb200_nccl_id").c_str());
+        if (nRanks > 1 && master) std::remove(ncclIdPath.c_str());
         if (master) std::printf("\nStarting time loop\n\n");
         const auto t0 = std::chrono::steady_clock::now();
         const std::clock_t c0 = std::clock();

@@ -26,22 +26,16 @@ namespace dsmc {
 namespace {
 
 constexpr int COL_WARPS = 4;
-constexpr int COL_CAP = 128;  // parcels of a cell staged in shared memory per warp
 constexpr int BIG_CELL_THRESHOLD = 255;  // = LANE_CELL_MAX: larger cells are processed by collideBigCellsKernel
 
-struct CellView {  // the parcels of one cell, in shared memory (small cells) or in place (large cells)
+struct CellView {  // the parcels of one cell, where they lie in the sorted cloud
     double *ux, *uy, *uz, *erot;
     int32_t* vib[MAX_MODES];
     uint8_t *typ, *elev;
-    uint8_t* dirty;  // null when operating in place
     const double* tMacro;  // &overallT[cell] or null
 };
 
-struct WarpSmem {
-    double ux[COL_CAP], uy[COL_CAP], uz[COL_CAP], erot[COL_CAP];
-    int32_t vib[MAX_MODES][COL_CAP];
-    uint16_t subList[COL_CAP];
-    uint8_t typ[COL_CAP], elev[COL_CAP], oct[COL_CAP], dirty[COL_CAP];
+struct WarpSmem {   // collideBigCellsKernel works on the parcels where they lie; only the sub-cell offsets are staged
     int32_t subStart[9];
 };
 
@@ -253,34 +247,12 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
         const int32_t b = a.cellOffset[c];
         const int32_t nC = a.cellOffset[c + 1] - b;
         if (nC <= BIG_CELL_THRESHOLD || P.collisionModel == DSMCB200_COLL_NONE) continue;  // handled by collideLaneKernel
-        const bool small = false;
         const double cc[3] = {a.cellCentres[3 * c], a.cellCentres[3 * c + 1], a.cellCentres[3 * c + 2]};
         CellView v;
         v.tMacro = a.overallT ? a.overallT + c : nullptr;
-        if (small) {
-            v.ux = sm.ux; v.uy = sm.uy; v.uz = sm.uz; v.erot = sm.erot;
-            for (int m = 0; m < MAX_MODES; ++m) v.vib[m] = sm.vib[m];
-            v.typ = sm.typ; v.elev = sm.elev; v.dirty = sm.dirty;
-            for (int j = lane; j < nC; j += 32) {
-                const int32_t g = b + j;
-                sm.ux[j] = a.p.ux[g]; sm.uy[j] = a.p.uy[g]; sm.uz[j] = a.p.uz[g];
-                sm.typ[j] = a.p.typeId[g];
-                sm.dirty[j] = 0;
-                sm.oct[j] = uint8_t(octantOf(a.p.px[g], a.p.py[g], a.p.pz[g], cc));
-                if (internal) {
-                    sm.erot[j] = a.p.erot[g];
-#pragma unroll
-                    for (int m = 0; m < MAX_MODES; ++m) if (m < P.nModes) sm.vib[m][j] = a.p.vib[m][g];
-                    sm.elev[j] = a.p.elevel[g];
-                } else {
-                    sm.erot[j] = 0.0; sm.elev[j] = 0;
-                }
-            }
-        } else {
-            v.ux = a.p.ux + b; v.uy = a.p.uy + b; v.uz = a.p.uz + b; v.erot = a.p.erot ? a.p.erot + b : nullptr;
-            for (int m = 0; m < MAX_MODES; ++m) v.vib[m] = a.p.vib[m] ? a.p.vib[m] + b : nullptr;
-            v.typ = a.p.typeId + b; v.elev = a.p.elevel ? a.p.elevel + b : nullptr; v.dirty = nullptr;
-        }
+        v.ux = a.p.ux + b; v.uy = a.p.uy + b; v.uz = a.p.uz + b; v.erot = a.p.erot ? a.p.erot + b : nullptr;
+        for (int m = 0; m < MAX_MODES; ++m) v.vib[m] = a.p.vib[m] ? a.p.vib[m] + b : nullptr;
+        v.typ = a.p.typeId + b; v.elev = a.p.elevel ? a.p.elevel + b : nullptr;
         __syncwarp();
 
         // ---- the 8 Cartesian sub-cells (noTimeCounter.C:112-138): stable counting sort of parcel indices by octant
@@ -290,7 +262,7 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
         for (int j0 = 0; j0 < nC; j0 += 32) {
             const int j = j0 + lane;
             int o = -1;
-            if (j < nC) o = small ? sm.oct[j] : octantOf(a.p.px[b + j], a.p.py[b + j], a.p.pz[b + j], cc);
+            if (j < nC) o = octantOf(a.p.px[b + j], a.p.py[b + j], a.p.pz[b + j], cc);
 #pragma unroll
             for (int s = 0; s < 8; ++s) cnt[s] += __popc(__ballot_sync(0xffffffffu, o == s));
         }
@@ -311,14 +283,13 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
             for (int j0 = 0; j0 < nC; j0 += 32) {
                 const int j = j0 + lane;
                 int o = -1;
-                if (j < nC) o = small ? sm.oct[j] : octantOf(a.p.px[b + j], a.p.py[b + j], a.p.pz[b + j], cc);
+                if (j < nC) o = octantOf(a.p.px[b + j], a.p.py[b + j], a.p.pz[b + j], cc);
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
                     const unsigned m = __ballot_sync(0xffffffffu, o == s);
                     if (o == s) {
                         const int32_t posn = run[s] + __popc(m & ((1u << lane) - 1u));
-                        if (small) sm.subList[posn] = uint16_t(j);
-                        else bigScratch[b + posn] = j;
+                        bigScratch[b + posn] = j;
                     }
                     run[s] += __popc(m);
                 }
@@ -345,13 +316,13 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
             if (active) {
                 rng.init(P.seed, uint32_t(c), uint32_t(cand), a.step, STREAM_COLLIDE);
                 cp = rng.randomLabel(0, nC - 1);
-                const int sub = small ? sm.oct[cp] : octantOf(a.p.px[b + cp], a.p.py[b + cp], a.p.pz[b + cp], cc);
+                const int sub = octantOf(a.p.px[b + cp], a.p.py[b + cp], a.p.pz[b + cp], cc);
                 const int32_t s0 = sm.subStart[sub];
                 const int32_t nSC = sm.subStart[sub + 1] - s0;
                 if (nSC > 1) {
                     do {
                         const int32_t k = s0 + rng.randomLabel(0, nSC - 1);
-                        cq = small ? int32_t(sm.subList[k]) : bigScratch[b + k];
+                        cq = bigScratch[b + k];
                     } while (cp == cq);
                 } else {
                     do { cq = rng.randomLabel(0, nC - 1); } while (cp == cq);
@@ -402,7 +373,6 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
                             postCollisionVelocities(P, rng, tP, tQ, UP, UQ, cR);
                             v.ux[cp] = UP.x; v.uy[cp] = UP.y; v.uz[cp] = UP.z;
                             v.ux[cq] = UQ.x; v.uy[cq] = UQ.y; v.uz[cq] = UQ.z;
-                            if (v.dirty) { v.dirty[cp] = 1; v.dirty[cq] = 1; }
                             // cellMeasurements (VariableHardSphere.C:154-162)
                             const int32_t gp = b + cp, gq = b + cq;
                             const double dx = a.p.px[gp] - a.p.px[gq], dy = a.p.py[gp] - a.p.py[gq], dz = a.p.pz[gp] - a.p.pz[gq];
@@ -434,21 +404,6 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
             a.nCollsStep[c] = nCollTot;
             a.collSepStep[c] = sepTot;
             totColl += (unsigned long long)nCollTot + (unsigned long long)nReactedTot;
-        }
-        if (small) {
-            __syncwarp();
-            for (int j = lane; j < nC; j += 32) {
-                if (sm.dirty[j]) {
-                    const int32_t g = b + j;
-                    a.p.ux[g] = sm.ux[j]; a.p.uy[g] = sm.uy[j]; a.p.uz[g] = sm.uz[j];
-                    if (LB) {
-                        a.p.erot[g] = sm.erot[j];
-#pragma unroll
-                        for (int m = 0; m < MAX_MODES; ++m) if (m < P.nModes) a.p.vib[m][g] = sm.vib[m][j];
-                        a.p.elevel[g] = sm.elev[j];
-                    }
-                }
-            }
         }
         __syncwarp();
     }
