@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "engine.h"
@@ -244,6 +245,14 @@ namespace {
     } while (0)
 
 int fail(dsmcb200_ctx* c, int code, const std::string& msg) { c->err = msg; return code; }
+
+// host threads for the O(n) loops of upload / download (launchers such as torchrun export OMP_NUM_THREADS=1, so the team is sized here:
+// the box's cores shared among the ranks of this node, at most 16)
+int hostThreads(const dsmcb200_ctx* c) {
+    if (const char* e = std::getenv("DSMCB200_HOST_THREADS")) return std::max(1, std::atoi(e));
+    const unsigned hw = std::thread::hardware_concurrency();
+    return int(std::max(1u, std::min(16u, (hw ? hw : 1u) / unsigned(std::max(1, c->nRanks)))));
+}
 
 template <class T>
 cudaError_t devAlloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)); }
@@ -1273,7 +1282,13 @@ int dsmcb200_upload_parcels(dsmcb200_ctx* c, int64_t n, const dsmcb200_parcels_s
     if (bad) return fail(c, DSMCB200_ERR_INVALID, "upload_parcels: cell / tetFace / tetPt out of range");
     c->N = n;
     int64_t maxId = -1;
-    if (h->origId) { for (int64_t i = 0; i < n; ++i) maxId = std::max<int64_t>(maxId, h->origId[i]); } else maxId = n32 - 1;
+    if (h->origId) {   // 2.5e8 entries in the end-to-end path: reduced by the host's cores, not by one of them
+        int32_t mx = -1;
+        const int32_t* ids = h->origId;
+#pragma omp parallel for reduction(max : mx) schedule(static) num_threads(hostThreads(c))
+        for (int64_t i = 0; i < n; ++i) mx = std::max(mx, ids[i]);
+        maxId = mx;
+    } else maxId = n32 - 1;
     c->nextOrigId = maxId + 1;
     c->occupancyValid = false;
     return stageSort(c, false);  // buildCellOccupancyFromScratch (dsmcCloud.C:677)
@@ -1307,12 +1322,24 @@ int dsmcb200_download_parcels(dsmcb200_ctx* c, int64_t capacity, int64_t* nOut, 
     if (h->classification) { if (a.cls) { u8ToI32<<<GRID(n), 0, s>>>(a.cls, r4, n32); CK(cudaMemcpyAsync(h->classification, r4, size_t(n) * 4, cudaMemcpyDeviceToHost, s)); } else std::memset(h->classification, 0, size_t(n) * 4); }
     if (h->origProc) {
         if (a.origProc) { CK(cudaStreamSynchronize(s)); u8ToI32<<<GRID(n), 0, s>>>(a.origProc, r4, n32); CK(cudaMemcpyAsync(h->origProc, r4, size_t(n) * 4, cudaMemcpyDeviceToHost, s)); }
-        else for (int64_t i = 0; i < n; ++i) h->origProc[i] = c->rank;
+        else {
+            int32_t* op = h->origProc; const int32_t rk = c->rank;
+#pragma omp parallel for schedule(static) num_threads(hostThreads(c))
+            for (int64_t i = 0; i < n; ++i) op[i] = rk;
+        }
     }
-    if (h->newParcel) for (int64_t i = 0; i < n; ++i) h->newParcel[i] = -1;
+    if (h->newParcel) {
+        int32_t* np_ = h->newParcel;
+#pragma omp parallel for schedule(static) num_threads(hostThreads(c))
+        for (int64_t i = 0; i < n; ++i) np_[i] = -1;
+    }
     if (h->radialWeight) {
         if (a.rwf) CK(cudaMemcpyAsync(h->radialWeight, a.rwf, size_t(n) * 8, cudaMemcpyDeviceToHost, s));
-        else for (int64_t i = 0; i < n; ++i) h->radialWeight[i] = 1.0;
+        else {
+            double* rw = h->radialWeight;
+#pragma omp parallel for schedule(static) num_threads(hostThreads(c))
+            for (int64_t i = 0; i < n; ++i) rw[i] = 1.0;
+        }
     }
     if (h->vibLevel && h->maxModes > 0) {
         CK(cudaStreamSynchronize(s));
