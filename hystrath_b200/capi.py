@@ -478,13 +478,15 @@ def axisymmetric_axes(revolutionAxis="", polarAxis=""):
     return rev, pol, ang
 
 
-def axisymmetric_rwf(cell_centres, face_centres, polar_axis, max_rwf):
+def axisymmetric_rwf(cell_centres, face_centres, polar_axis, max_rwf, radial_extent=None):
     """dsmcAxisymmetric::recalculateRWF, radial weighting method "cell" (dsmcAxisymmetric.C:236-275): RWF = 1 + (maxRWF - 1) r / radialExtent
-    with r = |cell centre . polar axis| and radialExtent = gMax of the face centres' polar component (:447-456)."""
+    with r = |cell centre . polar axis| and radialExtent = gMax of the face centres' polar component (:447-456) -- a global maximum:
+    on a decomposed mesh pass the extent of the whole domain."""
     fc = np.asarray(face_centres)[:, polar_axis]
-    radial_extent = fc.max()
-    if not radial_extent > 0:
-        radial_extent = -fc.min()
+    if radial_extent is None:
+        radial_extent = fc.max()
+        if not radial_extent > 0:
+            radial_extent = -fc.min()
     rwf = np.ones(len(cell_centres))
     rwf += (max_rwf - 1.0) * np.abs(np.asarray(cell_centres)[:, polar_axis]) / radial_extent
     return rwf, radial_extent

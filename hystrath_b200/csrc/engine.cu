@@ -203,6 +203,7 @@ struct dsmcb200_ctx {
     int* dBad = nullptr;
     double* dZvTab = nullptr;
     MigRec *dMigSend = nullptr, *dMigRecv = nullptr;
+    double *dMigRwfSend = nullptr, *dMigRwfRecv = nullptr;   // the leavers' / arrivals' radial weights (dsmcAxisymmetric), [MAX_NEIGHBOURS][migCapacity]
     int32_t *dMigKey = nullptr, *dMigWork = nullptr;   // cloud index of each packed leaver; 3*migCapacity ints of sort workspace
     void* dMigTemp = nullptr; size_t migTempBytes = 0;
     int32_t migCapacity = 0;
@@ -399,7 +400,6 @@ int finalize(dsmcb200_ctx* c) {
     c->useRwf = md.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC;
     if (c->useRwf) {
         if (md.angularCoordinate < 0 || md.angularCoordinate > 2) return fail(c, DSMCB200_ERR_INVALID, "dsmcAxisymmetric: angularCoordinate must be 0, 1 or 2");
-        if (c->nRanks > 1) return fail(c, DSMCB200_ERR_UNSUPPORTED, "dsmcAxisymmetric on a decomposed mesh: the migration record does not carry the radial weight yet");
     }
     P.kB = md.kB > 0 ? md.kB : 1.38065e-23;  // OpenFOAM v1706 physicoChemical::k (pinned by shipped couette fields)
     P.Tref = md.Tref > 0 ? md.Tref : 273.0;
@@ -713,12 +713,13 @@ int ensureMigBuffers(dsmcb200_ctx* c) {
     if (c->nbrProcs.empty()) return 0;
     const int32_t want = int32_t(std::max<int64_t>(1 << 16, c->capacity / 8));
     if (want <= c->migCapacity) return 0;
-    devFree(c->dMigSend); devFree(c->dMigRecv); devFree(c->dMigKey); devFree(c->dMigWork);
+    devFree(c->dMigSend); devFree(c->dMigRecv); devFree(c->dMigKey); devFree(c->dMigWork); devFree(c->dMigRwfSend); devFree(c->dMigRwfRecv);
     if (c->dMigTemp) { cudaFree(c->dMigTemp); c->dMigTemp = nullptr; }
     CK(devAlloc(&c->dMigSend, size_t(want) * MAX_NEIGHBOURS));
     CK(devAlloc(&c->dMigRecv, size_t(want) * MAX_NEIGHBOURS));
     CK(devAlloc(&c->dMigKey, size_t(want) * MAX_NEIGHBOURS));
     CK(devAlloc(&c->dMigWork, size_t(want) * 3));
+    if (c->useRwf) { CK(devAlloc(&c->dMigRwfSend, size_t(want) * MAX_NEIGHBOURS)); CK(devAlloc(&c->dMigRwfRecv, size_t(want) * MAX_NEIGHBOURS)); }
     c->migTempBytes = orderMigrantsTempBytes(want);
     CK(cudaMalloc(&c->dMigTemp, std::max<size_t>(c->migTempBytes, 16)));
     c->migCapacity = want;
@@ -819,7 +820,7 @@ MoveArgs moveArgs(dsmcb200_ctx* c, int32_t tailStart) {
     // boundaryMeas_ is cleaned every step (dsmcCloud.C:924) but only folded into the fields on sampled steps (dsmcVolFields.C:1081,1292)
     a.wallsDue = c->sampleCounter + 1 >= std::max(1, c->models.sampleInterval);
     a.faceFlux = c->dFaceFlux; a.faceAreas = c->dFaceAreas; a.nFacesAll = c->mesh.nFaces;
-    a.migBuf = c->dMigSend; a.migKey = c->dMigKey; a.migCapacity = c->migCapacity; a.cellCount = c->dCellCount; a.counters = c->dCounters; a.step = c->step;
+    a.migBuf = c->dMigSend; a.migRwf = c->dMigRwfSend; a.migKey = c->dMigKey; a.migCapacity = c->migCapacity; a.cellCount = c->dCellCount; a.counters = c->dCounters; a.step = c->step;
     return a;
 }
 
@@ -879,7 +880,8 @@ int stageMove(dsmcb200_ctx* c, int64_t tailStart) {
             // particleTransferLists[neighbour] in cloud-list order (Cloud.C:283-306); the receive slab of the slot is free until the
             // exchange below and serves as scratch
             CK(orderMigrants(c->dMigSend + s * c->migCapacity, c->dMigRecv + s * c->migCapacity, c->dMigKey + s * c->migCapacity, c->dMigWork,
-                             c->dMigTemp, c->migTempBytes, nMig[s], c->stream));
+                             c->dMigTemp, c->migTempBytes, nMig[s], c->stream,
+                             c->dMigRwfSend ? c->dMigRwfSend + s * c->migCapacity : nullptr, c->dMigRwfRecv ? c->dMigRwfRecv + s * c->migCapacity : nullptr));
         }
         }
         cudaEvent_t evCounts0 = nullptr, evCounts1 = nullptr;
@@ -913,6 +915,10 @@ int stageMove(dsmcb200_ctx* c, int64_t tailStart) {
         for (size_t s = 0; s < c->nbrProcs.size(); ++s) {
             if (nMig[s]) { r = g_nccl.Send(c->dMigSend + s * c->migCapacity, size_t(nMig[s]) * sizeof(MigRec), NCCL_CHAR, c->nbrProcs[s], c->comm, c->stream); if (r) return ncclFail(c, r, "ncclSend"); }
             if (recvFrom[s]) { r = g_nccl.Recv(c->dMigRecv + s * c->migCapacity, size_t(recvFrom[s]) * sizeof(MigRec), NCCL_CHAR, c->nbrProcs[s], c->comm, c->stream); if (r) return ncclFail(c, r, "ncclRecv"); }
+            if (c->dMigRwfSend) {   // the radial weights travel next to the records
+                if (nMig[s]) { r = g_nccl.Send(c->dMigRwfSend + s * c->migCapacity, size_t(nMig[s]) * sizeof(double), NCCL_CHAR, c->nbrProcs[s], c->comm, c->stream); if (r) return ncclFail(c, r, "ncclSend"); }
+                if (recvFrom[s]) { r = g_nccl.Recv(c->dMigRwfRecv + s * c->migCapacity, size_t(recvFrom[s]) * sizeof(double), NCCL_CHAR, c->nbrProcs[s], c->comm, c->stream); if (r) return ncclFail(c, r, "ncclRecv"); }
+            }
         }
         r = g_nccl.GroupEnd();
         if (r) return ncclFail(c, r, "ncclGroupEnd");
@@ -924,6 +930,7 @@ int stageMove(dsmcb200_ctx* c, int64_t tailStart) {
             if (!recvFrom[s]) continue;
             UnpackArgs u{};
             u.p = c->buf[c->cur].a; u.recv = c->dMigRecv + s * c->migCapacity; u.nRecv = recvFrom[s]; u.base = int32_t(c->N);
+            u.recvRwf = c->dMigRwfRecv ? c->dMigRwfRecv + s * c->migCapacity : nullptr;
             u.sfTail = c->dSfTail; u.tailStart = int32_t(tailStart); u.ordinalToPatch = c->dOrdinalToPatch + s * MAX_PATCHES;
             u.bfaces = c->dBFaces; u.P = c->dP;
             CK(launchUnpack(u, c->stream));
@@ -1078,6 +1085,7 @@ void dsmcb200_destroy(dsmcb200_ctx* c) {
     devFree(c->dCellCount); devFree(c->dCellOffset); devFree(c->dCursor); devFree(c->dPerm); devFree(c->dOctKey); devFree(c->dScanScratch);
     devFree(c->dSigma); devFree(c->dRem); devFree(c->dNColls); devFree(c->dCollSep); devFree(c->dAcc); devFree(c->dCollCum);
     devFree(c->dOverallT); devFree(c->dFaceFlux); devFree(c->dWallAcc); devFree(c->dSfTail); devFree(c->dInfo); devFree(c->dInfoScratch); devFree(c->dCounters); devFree(c->dBad);
+    devFree(c->dMigRwfSend); devFree(c->dMigRwfRecv);
     devFree(c->dZvTab); devFree(c->dMigSend); devFree(c->dMigRecv); devFree(c->dMigKey); devFree(c->dMigWork); devFree(c->dInflowScan);
     if (c->dMigTemp) cudaFree(c->dMigTemp); devFree(c->dOrdinalToPatch); devFree(c->dCountsMatrix);
     devFree(c->dBorn); devFree(c->dBornKeys); devFree(c->dBornIdx); if (c->dBornTemp) cudaFree(c->dBornTemp);

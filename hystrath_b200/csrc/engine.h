@@ -165,6 +165,7 @@ struct MoveArgs {
     const double* faceAreas;      // [nFacesAll*3], read only by the face tracker
     int32_t nFacesAll;
     MigRec* migBuf;               // [MAX_NEIGHBOURS][migCapacity]
+    double* migRwf;               // [MAX_NEIGHBOURS][migCapacity] the leavers' radial weights (dsmcAxisymmetric), next to the 96-byte records; or nullptr
     int32_t* migKey;              // [MAX_NEIGHBOURS][migCapacity] cloud index of the packed parcel: the sender's list order
     int32_t migCapacity;
     int32_t* cellCount;           // histogram for the sort (stage 2), fused here
@@ -284,7 +285,7 @@ cudaError_t launchFill(const FillArgs& a, int pass, cudaStream_t s);
 // scratch: n records; work: 3*n ints; temp: orderMigrantsTempBytes(capacity) bytes.
 size_t orderMigrantsTempBytes(int32_t capacity);
 cudaError_t orderMigrants(MigRec* records, MigRec* scratch, const int32_t* keys, int32_t* work, void* temp, size_t tempBytes, int32_t n,
-                          cudaStream_t s);
+                          cudaStream_t s, double* rwf = nullptr, double* rwfScratch = nullptr);
 
 // particle::initCellFacePtOrDeleteLostParticle for a cloud that arrives without tetFace / tetPt (the `positions` file holds only
 // "(x y z) cell", particleIO.C:51-58)
@@ -332,6 +333,7 @@ cudaError_t launchInflow(const InflowArgs& a, int pass, cudaStream_t s);
 struct UnpackArgs {
     ParcelArrays p;
     const MigRec* recv;
+    const double* recvRwf;        // radial weights of the arrivals (dsmcAxisymmetric) or nullptr
     int32_t nRecv, base;
     double* sfTail;
     int32_t tailStart;

@@ -317,6 +317,7 @@ __device__ __noinline__ void packMigrant(const MoveArgs& a, const DevParams& P, 
         r.vib[0] = in.vib0; r.vib[1] = in.vib1; r.vib[2] = in.vib2;
         r.typeId = a.p.typeId[i]; r.elevel = uint8_t(in.elevel); r.cls = a.p.cls ? a.p.cls[i] : 0; r.origProc = a.p.origProc ? a.p.origProc[i] : 0;
         a.migBuf[size_t(slot) * a.migCapacity + k] = r;
+        if (a.migRwf) a.migRwf[size_t(slot) * a.migCapacity + k] = a.p.rwf ? a.p.rwf[i] : 1.0;
         a.migKey[size_t(slot) * a.migCapacity + k] = i;
     } else {
         atomicAdd(&a.counters->overflow, 1ULL);
@@ -756,8 +757,13 @@ size_t orderMigrantsTempBytes(int32_t capacity) {
     return bytes;
 }
 
+__global__ void permuteDoubles(const double* __restrict__ in, const int32_t* __restrict__ perm, double* __restrict__ out, int32_t n) {
+    const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = in[perm[k]];
+}
+
 cudaError_t orderMigrants(MigRec* records, MigRec* scratch, const int32_t* keys, int32_t* work, void* temp, size_t tempBytes, int32_t n,
-                          cudaStream_t s) {
+                          cudaStream_t s, double* rwf, double* rwfScratch) {
     if (n <= 1) return cudaSuccess;
     int32_t *keysOut = work, *idxIn = work + n, *idxOut = work + 2 * size_t(n);
     iotaI32<<<(n + 255) / 256, 256, 0, s>>>(idxIn, n);
@@ -765,6 +771,11 @@ cudaError_t orderMigrants(MigRec* records, MigRec* scratch, const int32_t* keys,
     if (e != cudaSuccess) return e;
     const int64_t threads = int64_t(n) * 6;
     permuteMigRecs<<<unsigned((threads + 255) / 256), 256, 0, s>>>(records, idxOut, scratch, n);
+    if (rwf) {
+        permuteDoubles<<<unsigned((n + 255) / 256), 256, 0, s>>>(rwf, idxOut, rwfScratch, n);
+        e = cudaMemcpyAsync(rwf, rwfScratch, size_t(n) * sizeof(double), cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return e;
+    }
     e = cudaMemcpyAsync(records, scratch, size_t(n) * sizeof(MigRec), cudaMemcpyDeviceToDevice, s);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
@@ -790,6 +801,7 @@ __global__ void unpackKernel(const __grid_constant__ UnpackArgs a) {
     a.p.tet[i] = bf.tet0 + (bf.nPts - 3) - r.tetLocal;
     a.p.origId[i] = r.origId;
     if (a.p.origProc) a.p.origProc[i] = r.origProc;
+    if (a.p.rwf) a.p.rwf[i] = a.recvRwf ? a.recvRwf[k] : 1.0;
     a.p.typeId[i] = r.typeId;
     if (P.hasInternalEnergy) {
         a.p.erot[i] = r.erot;

@@ -234,7 +234,7 @@ class Oracle:
 
     def outbox(self):
         n = self.lib.oracle_outbox_size(self.h)
-        d, i = np.zeros((n, 8)), np.zeros((n, 12), np.int32)
+        d, i = np.zeros((n, 9)), np.zeros((n, 12), np.int32)
         self._ck(self.lib.oracle_outbox_get(self.h, _ptr(d), _ptr(i)))
         return d, i
 

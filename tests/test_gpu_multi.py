@@ -470,3 +470,105 @@ def test_two_gpu_capsule_forebody_equals_the_two_rank_oracle():
         if rank == 1:
             assert np.abs(ow).max() > 0 and np.abs(wall - ow).max() <= 1e-9 * np.abs(ow).max()      # the shield is on rank 1
     assert ref_sent[:, 0].sum() > 100 and ref[0][1]["inserted"] > 0 and ref[1][1]["deleted"] > 0
+
+
+# ---- dsmcAxisymmetric on two GPUs: a weighted box cut in two along the polar axis; parcels take their radial weight across the processor patch ----
+AXI_STEPS = 5
+
+
+def _axi_rank(r):
+    outer = ("cyclic", (("symmetryPlane", "axis"), ("wall", "top")), ("symmetryPlane", "sides"))
+    mesh = meshgen.decomposed_box((4, 3, 1), (0.04, 0.03, 0.01), (1, 2, 1), r, outer=outer)
+    rev, pol, ang = capi.axisymmetric_axes()
+    md = capi.build_models("VariableHardSphere", nEquivalentParticles=1e9, deltaT=4e-6, seed=5 + 7183 * r, coordinateSystem="dsmcAxisymmetric",
+                           angularCoordinate=ang, patch_models=[dict(patch=mesh.patch_index("top"), boundaryModel="dsmcDiffuseWallPatch",
+                                                                      temperature=400.0, velocity=(0, 0, 0))] if r == 1 else [])
+    return mesh, md, pol
+
+
+def _axi_oracle(r):
+    from oracle.pyoracle import Oracle
+    mesh, md, pol = _axi_rank(r)
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species([H.argon()]); o.set_models(md); o.set_rank(r)
+    cc, cv, fc, *_ = o.geometry()
+    rwf, _ = capi.axisymmetric_rwf(cc, fc, pol, 100.0, radial_extent=0.06)
+    o.set_cell_fields(RWF=rwf)
+    o.mesh_fill([0], [4e18], 300.0)
+    return o, rwf
+
+
+def _axi_oracle_two_ranks():
+    ranks = [_axi_oracle(r)[0] for r in range(2)]
+    sent = np.zeros((AXI_STEPS, 2), np.int64)
+    for step in range(AXI_STEPS):
+        for o in ranks:
+            o.evolve_begin()
+        while True:
+            boxes = [o.outbox() for o in ranks]
+            if not any(len(d) for d, _ in boxes):
+                break
+            for r in range(2):
+                sent[step, r] += int((boxes[r][1][:, 0] == 1 - r).sum())
+            for r, o in enumerate(ranks):
+                d, i = boxes[1 - r]
+                sel = i[:, 0] == r
+                if sel.any():
+                    o.receive_and_move(1 - r, d[sel], i[sel])
+        for o in ranks:
+            o.evolve_end()
+    return [(o.download_parcels(), o.weighting_counts()) for o in ranks], sent
+
+
+def _axi_worker(rank, world, q_id, q_out):
+    try:
+        torch.cuda.set_device(rank)
+        mesh, md, pol = _axi_rank(rank)
+        eng = capi.Engine(rank, rank, world)
+        eng.set_mesh(mesh); eng.set_species([H.argon()]); eng.set_models(md)
+        if rank == 0:
+            ident = capi.nccl_unique_id()
+            for _ in range(world - 1):
+                q_id.put(ident)
+        else:
+            ident = q_id.get(timeout=120)
+        eng.init_comm(ident)
+        o, rwf = _axi_oracle(rank)
+        eng.set_cell_fields(RWF=rwf)
+        eng.upload_parcels(o.download_parcels())
+        eng.upload_cellstate(*o.download_cellstate())
+        sent = []
+        for _ in range(AXI_STEPS):
+            eng.evolve(1)
+            sent.append(int(eng.counters().migratedTo[0]))
+        res = eng.download_parcels()
+        q_out.put((rank, res.origId.copy(), res.origProc.copy(), res.cell.copy(), res.radialWeight.copy(), res.U.copy(), sent))
+        eng.close()
+    except Exception as e:
+        q_out.put((rank, repr(e)))
+
+
+def test_two_gpu_axisymmetric_run_equals_the_two_rank_oracle():
+    """Radial weighting on a decomposed mesh: a parcel that crosses the processor patch arrives with the weight of the cell it started the
+    step in (it travels next to the 96-byte record) and is cloned / deleted against the weight of the cell it ends in, on the receiving
+    rank.  Per rank the cloud (identity, order, cells, weights, velocities of the clones included) equals the two-rank oracle."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q_id, q_out = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_axi_worker, args=(r, 2, q_id, q_out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ref, ref_sent = _axi_oracle_two_ranks()
+    results = sorted([q_out.get(timeout=300) for _ in range(2)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    for r in results:
+        assert len(r) == 7, r
+    for rank, (_, ids, procs_, cell, rwf, U, sent) in enumerate(results):
+        o, (cloned, deleted) = ref[rank]
+        assert sent == ref_sent[:, rank].tolist() and sum(sent) > 20
+        assert cloned > 0 and deleted > 0
+        assert np.array_equal(ids, o.origId) and np.array_equal(procs_, o.origProc) and np.array_equal(cell, o.cell)
+        assert np.array_equal(rwf, o.radialWeight)
+        assert np.allclose(U, o.U, rtol=1e-9, atol=1e-7)
