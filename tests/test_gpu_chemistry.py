@@ -111,3 +111,40 @@ def test_reacting_heat_bath_follows_the_shipped_series():
     rc = eng.reaction_counts()
     assert eng.num_parcels() == n0 + rc[:, :2].sum()
     eng.close()
+
+
+def test_single_cell_heat_bath_relaxes_to_equilibrium_and_is_reproducible():
+    """The heatBath-5species set-up with `reactions ()`: one adiabatic cell of 154 000 parcels (block-level sort, one-warp candidate loop
+    with 1e4 candidates per step), translational energy only at the start.  With all relaxation numbers 1 the three temperatures meet at
+    the value energy conservation dictates; the total energy is conserved to rounding; two runs give the same cloud bit for bit."""
+    from oracle import fields_ref
+
+    def run():
+        eng = capi.Engine(0)
+        case, spd, fnum, vol = H.heatbath_setup(eng, scale=1.0, reactions=False)
+        eng.mesh_fill([0, 1], [case["numberDensities"]["N2"], case["numberDensities"]["O2"]], 9000.0, 0.0, 0.0)
+        e0 = eng.counters()
+        eng.evolve(300)
+        eng.reset_accumulators()
+        eng.evolve(20)
+        acc, coll, nt = eng.accumulators()
+        f = fields_ref.derive(acc, coll, nt, spd, [0, 1], fnum, np.array([vol]))
+        e1 = eng.counters()
+        p = eng.download_parcels()
+        eng.close()
+        return f, e0, e1, p
+
+    f, e0, e1, p = run()
+    tot0 = e0.linearKineticEnergy + e0.rotationalEnergy + e0.vibrationalEnergy
+    tot1 = e1.linearKineticEnergy + e1.rotationalEnergy + e1.vibrationalEnergy
+    assert e0.rotationalEnergy == 0 and e0.vibrationalEnergy == 0 and abs(tot1 / tot0 - 1) < 1e-10
+    Ttra, Trot, Tvib = f["Ttra"][0], f["Trot"][0], f["Tvib"][0]
+    assert abs(Trot / Ttra - 1) < 0.02 and abs(Tvib / Ttra - 1) < 0.03, (Ttra, Trot, Tvib)
+    # energy balance per molecule: 3/2 k T0 = (3/2 + 1) k T + <e_vib>(T) with the harmonic-oscillator mean of the two species
+    x = np.array([case_n for case_n in (1.21753030168e22, 3.23647295384e21)]); x = x / x.sum()
+    thv = np.array([3371.0, 2256.0])
+    evib = (x * thv / np.expm1(thv / Ttra)).sum()
+    assert abs((2.5 * Ttra + evib) / (1.5 * 9000.0) - 1) < 0.01
+    f2, _, _, p2 = run()
+    for k in ("origId", "cell", "typeId", "position", "U", "ERot", "vibLevel"):
+        assert np.array_equal(getattr(p, k), getattr(p2, k)), k

@@ -613,3 +613,30 @@ def test_capsule_forebody_small_scale_matches_oracle():
     gw, ow = eng.wall_accumulators(), ora.wall_accumulators()
     assert np.abs(ow).max() > 0 and np.abs(gw - ow).max() <= 1e-9 * np.abs(ow).max()
     eng.close()
+
+
+def test_one_million_parcels_track_the_oracle():
+    """BASELINE configs[0] at its own size (32^3 cells, ~1.05 M argon parcels, the C1 case of bench.py): three full steps, collision counts
+    step by step, cloud order, cells and occupancy exact, positions to rounding -- the parity statement of the small cases at the size of a
+    bench workload (work list with hundreds of windows per block, 32 768 cells through both collide kernels' bookkeeping)."""
+    mesh, sp, md = periodic_case((32, 32, 32), L=0.128, ppc=32, dens=1e20, dt=5e-6)
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    start = H.same_start(eng, ora, [0], [1e20], 300.0)
+    assert abs(start.n - 1048576) < 5000
+    seen = 0
+    for _ in range(3):
+        eng.evolve(1)
+        ora.evolve(1)
+        total = ora.counters()
+        assert eng.counters().collisions == total["collisions"] - seen > 50000
+        seen = total["collisions"]
+    g, o = eng.download_parcels(), ora.download_parcels()
+    assert g.n == o.n == start.n
+    assert np.array_equal(g.origId, o.origId) and np.array_equal(g.cell, o.cell)
+    assert np.array_equal(g.tetFace, o.tetFace) and np.array_equal(g.tetPt, o.tetPt)
+    assert np.array_equal(eng.occupancy(), ora.occupancy())
+    assert np.allclose(g.position, o.position, rtol=0, atol=1e-12) and np.allclose(g.U, o.U, rtol=1e-9, atol=1e-7)
+    ga, gc, _ = eng.accumulators()
+    oa, oc, _ = ora.accumulators()
+    assert np.array_equal(ga[:, :, 0], oa[:, :, 0]) and np.allclose(gc, oc, rtol=1e-12)
+    eng.close()
