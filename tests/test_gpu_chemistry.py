@@ -119,12 +119,12 @@ def test_single_cell_heat_bath_relaxes_to_equilibrium_and_is_reproducible():
     the value energy conservation dictates; the total energy is conserved to rounding; two runs give the same cloud bit for bit."""
     from oracle import fields_ref
 
-    def run():
+    def run(n_relax):
         eng = capi.Engine(0)
         case, spd, fnum, vol = H.heatbath_setup(eng, scale=1.0, reactions=False)
         eng.mesh_fill([0, 1], [case["numberDensities"]["N2"], case["numberDensities"]["O2"]], 9000.0, 0.0, 0.0)
         e0 = eng.counters()
-        eng.evolve(300)
+        eng.evolve(n_relax)       # ~0.011 collisions per molecule and step: 1000 steps are eleven collision times
         eng.reset_accumulators()
         eng.evolve(20)
         acc, coll, nt = eng.accumulators()
@@ -134,7 +134,7 @@ def test_single_cell_heat_bath_relaxes_to_equilibrium_and_is_reproducible():
         eng.close()
         return f, e0, e1, p
 
-    f, e0, e1, p = run()
+    f, e0, e1, p = run(1000)
     tot0 = e0.linearKineticEnergy + e0.rotationalEnergy + e0.vibrationalEnergy
     tot1 = e1.linearKineticEnergy + e1.rotationalEnergy + e1.vibrationalEnergy
     assert e0.rotationalEnergy == 0 and e0.vibrationalEnergy == 0 and abs(tot1 / tot0 - 1) < 1e-10
@@ -145,6 +145,39 @@ def test_single_cell_heat_bath_relaxes_to_equilibrium_and_is_reproducible():
     thv = np.array([3371.0, 2256.0])
     evib = (x * thv / np.expm1(thv / Ttra)).sum()
     assert abs((2.5 * Ttra + evib) / (1.5 * 9000.0) - 1) < 0.01
-    f2, _, _, p2 = run()
+    _, _, _, p = run(100)
+    _, _, _, p2 = run(100)
     for k in ("origId", "cell", "typeId", "position", "U", "ERot", "vibLevel"):
         assert np.array_equal(getattr(p, k), getattr(p2, k)), k
+
+
+def test_reaction_lists_are_checked_like_the_reference():
+    """dsmcReactions::initialConfiguration and <model>::setProperties (dsmcReactions.C:137-170, dissociationQK.C:44-195, exchangeQK.C:44-176):
+    two models for one typeId pair, molecular dissociation products of a diatomic, an exchange without an atom."""
+    names = ["N2", "O2", "NO", "N", "O"]
+
+    def engine_with(reactions):
+        eng = capi.Engine(0)
+        mesh = meshgen.box_mesh((2, 2, 2), (1e-4,) * 3)
+        eng.set_mesh(mesh); eng.set_species(H.air5())
+        eng.set_reactions(capi.build_reactions(names, reactions))
+        eng.set_models(capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=1e6, deltaT=1e-9, seed=1))
+        return eng
+
+    diss = dict(reactionModel="dissociationQK", reactants=["O2", "N2"], dissociationProducts=[["O", "O"], ["N", "N"]])
+    eng = engine_with([diss, dict(diss, reactants=["N2", "O2"], dissociationProducts=[["N", "N"], ["O", "O"]])])
+    with pytest.raises(capi.Dsmcb200Error, match="more than one reaction model specified for the typeId pair: 0 and 1"):
+        eng.mesh_fill([0, 1], [1e22, 1e22], 1000.0)
+    eng.close()
+    eng = engine_with([dict(diss, dissociationProducts=[["O", "NO"], ["N", "N"]])])
+    with pytest.raises(capi.Dsmcb200Error, match="Dissociation product of a diatomic molecule must be an atom"):
+        eng.mesh_fill([0, 1], [1e22, 1e22], 1000.0)
+    eng.close()
+    eng = engine_with([dict(reactionModel="exchangeQK", reactants=["O2", "N2"], exchangeProducts=["NO", "NO"], heatOfReactionExchange=1.0, aCoeff=0.1, bCoeff=0.1)])
+    with pytest.raises(capi.Dsmcb200Error, match="None of the reactants is an atom"):
+        eng.mesh_fill([0, 1], [1e22, 1e22], 1000.0)
+    eng.close()
+    with pytest.raises(capi.Dsmcb200Error, match="Valid reaction types are"):
+        capi.build_reactions(names, [dict(diss, reactionModel="ionisationQK")])
+    with pytest.raises(capi.Dsmcb200Error, match="Cannot find type id: Xe"):
+        capi.build_reactions(names, [dict(diss, reactants=["O2", "Xe"])])
