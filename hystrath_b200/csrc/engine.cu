@@ -180,7 +180,7 @@ struct dsmcb200_ctx {
     BFaceRec* dBFaces = nullptr;
     double *dBFaceArea = nullptr, *dPoints = nullptr, *dCellCentres = nullptr, *dCellVolumes = nullptr, *dFaceCentres = nullptr,
            *dFaceAreas = nullptr;
-    int32_t *dFaceOffsets = nullptr, *dFacePoints = nullptr, *dOwner = nullptr, *dTetBasePtIs = nullptr, *dFaceTet0 = nullptr, *dCellTetStart = nullptr, *dGroupCell = nullptr,
+    int32_t *dFaceOffsets = nullptr, *dFacePoints = nullptr, *dOwner = nullptr, *dNeighbour = nullptr, *dTetBasePtIs = nullptr, *dFaceTet0 = nullptr, *dCellTetStart = nullptr, *dGroupCell = nullptr,
             *dCellFaceOffsets = nullptr, *dCellFaces = nullptr;
     // work list of the move kernel (launchMovePlan)
     int32_t *dPlanSub = nullptr, *dPlanBase = nullptr;
@@ -657,6 +657,7 @@ int finalize(dsmcb200_ctx* c) {
         CK(upload(&c->dFaceOffsets, M.faceOffsets));
         CK(upload(&c->dFacePoints, M.facePoints));
         CK(upload(&c->dOwner, M.owner));
+        CK(upload(&c->dNeighbour, M.neighbour));
         CK(upload(&c->dTetBasePtIs, M.tetBasePtIs));
         CK(upload(&c->dFaceTet0, M.faceTet0));
         CK(upload(&c->dCellTetStart, M.cellTetStart));
@@ -1081,7 +1082,7 @@ void dsmcb200_destroy(dsmcb200_ctx* c) {
     for (int k = 0; k < 2; ++k) { devFree(c->buf[k].dslab); devFree(c->buf[k].islab); devFree(c->buf[k].bslab); }
     devFree(c->dP); devFree(c->dTets); devFree(c->dBFaces); devFree(c->dBFaceArea); devFree(c->dPoints); devFree(c->dCellCentres);
     devFree(c->dCellVolumes); devFree(c->dFaceCentres); devFree(c->dFaceAreas); devFree(c->dFaceOffsets); devFree(c->dFacePoints);
-    devFree(c->dOwner); devFree(c->dTetBasePtIs); devFree(c->dFaceTet0); devFree(c->dCellTetStart); devFree(c->dGroupCell); devFree(c->dPlanSub); devFree(c->dPlanBase); devFree(c->dPlan); devFree(c->dCellFaceOffsets); devFree(c->dCellFaces);
+    devFree(c->dOwner); devFree(c->dNeighbour); devFree(c->dTetBasePtIs); devFree(c->dFaceTet0); devFree(c->dCellTetStart); devFree(c->dGroupCell); devFree(c->dPlanSub); devFree(c->dPlanBase); devFree(c->dPlan); devFree(c->dCellFaceOffsets); devFree(c->dCellFaces);
     devFree(c->dCellCount); devFree(c->dCellOffset); devFree(c->dCursor); devFree(c->dPerm); devFree(c->dOctKey); devFree(c->dScanScratch);
     devFree(c->dSigma); devFree(c->dRem); devFree(c->dNColls); devFree(c->dCollSep); devFree(c->dAcc); devFree(c->dCollCum);
     devFree(c->dOverallT); devFree(c->dFaceFlux); devFree(c->dWallAcc); devFree(c->dSfTail); devFree(c->dInfo); devFree(c->dInfoScratch); devFree(c->dCounters); devFree(c->dBad);
@@ -1237,7 +1238,7 @@ int dsmcb200_upload_parcels(dsmcb200_ctx* c, int64_t n, const dsmcb200_parcels_s
         LocateArgs l{};
         l.px = a.px; l.py = a.py; l.pz = a.pz; l.cell = a.cell; l.tet = a.tet; l.n = n32; l.nCells = c->mesh.nCells;
         l.cellFaceOffsets = c->dCellFaceOffsets; l.cellFaces = c->dCellFaces; l.faceOffsets = c->dFaceOffsets; l.facePoints = c->dFacePoints;
-        l.owner = c->dOwner; l.tetBasePtIs = c->dTetBasePtIs; l.cellTetStart = c->dCellTetStart; l.points = c->dPoints;
+        l.owner = c->dOwner; l.neighbour = c->dNeighbour; l.nInternalFaces = c->mesh.nInternalFaces; l.tetBasePtIs = c->dTetBasePtIs; l.cellTetStart = c->dCellTetStart; l.points = c->dPoints;
         l.cellCentres = c->dCellCentres; l.lost = &c->dCounters->deleted;
         CK(cudaMemsetAsync(&c->dCounters->deleted, 0, sizeof(unsigned long long), s));
         CK(launchLocate(l, s));

@@ -295,6 +295,8 @@ struct LocateArgs {
     int32_t* tet;                 // out: tet id cellTetStart[cell] + index of (tetFace, tetPt) among the cell's tets
     int32_t n, nCells;
     const int32_t *cellFaceOffsets, *cellFaces, *faceOffsets, *facePoints, *owner, *tetBasePtIs, *cellTetStart;
+    const int32_t* neighbour;     // [nInternalFaces]: the search of polyMesh::findCellFacePt looks at the cells around the given one
+    int32_t nInternalFaces;
     const double *points, *cellCentres;
     unsigned long long* lost;     // parcels deleted (outside the inflated cell bounding box or not locatable)
 };

@@ -156,6 +156,30 @@ __global__ void __launch_bounds__(128) locateKernel(const __grid_constant__ Loca
     bool ok = false;
     if (cell >= 0 && cell < a.nCells) {
         ok = findTetFacePtDev(a, cell, p, tet);
+        if (!ok) {
+            // mesh_.findCellFacePt(position, cell, tetFace, tetPt) (particleI.H:884-890): another cell may hold the point (a position written
+            // with 10 digits next to a face, a label from a slightly different mesh).  The reference searches the whole mesh through its
+            // octree; here the cells around the given one are tried, the face neighbours and then theirs, in cells[] face order
+            int32_t found = -1;
+            for (int k = a.cellFaceOffsets[cell]; k < a.cellFaceOffsets[cell + 1] && found < 0; ++k) {
+                const int32_t f = a.cellFaces[k];
+                if (f >= a.nInternalFaces) continue;
+                const int32_t c1 = a.owner[f] == cell ? a.neighbour[f] : a.owner[f];
+                if (findTetFacePtDev(a, c1, p, tet)) found = c1;
+            }
+            for (int k = a.cellFaceOffsets[cell]; k < a.cellFaceOffsets[cell + 1] && found < 0; ++k) {
+                const int32_t f = a.cellFaces[k];
+                if (f >= a.nInternalFaces) continue;
+                const int32_t c1 = a.owner[f] == cell ? a.neighbour[f] : a.owner[f];
+                for (int k2 = a.cellFaceOffsets[c1]; k2 < a.cellFaceOffsets[c1 + 1] && found < 0; ++k2) {
+                    const int32_t f2 = a.cellFaces[k2];
+                    if (f2 >= a.nInternalFaces) continue;
+                    const int32_t c2 = a.owner[f2] == c1 ? a.neighbour[f2] : a.owner[f2];
+                    if (c2 != cell && findTetFacePtDev(a, c2, p, tet)) found = c2;
+                }
+            }
+            if (found >= 0) { ok = true; a.cell[i] = found; }
+        }
         if (!ok && pointInCellBBDev(a, cell, p, 0.1)) {
             // the parcel sits (within rounding) on the cell surface: walk towards the cell centre in trackingCorrectionTol steps
             // until a tet claims the point (particleI.H:927-976); the stored position is not changed

@@ -90,9 +90,10 @@ def test_invalid_uploads_fail_loudly():
 
 def test_cloud_without_tet_indices_is_located_on_the_device():
     """Cloud<T>::initCloud -> particle::initCellFacePtOrDeleteLostParticle (BASIC/particle/particleI.H:851-996): the `positions` file holds
-    only "(x y z) cell"; tetFace / tetPt are re-derived per parcel (first tet of the cell with tetrahedron::inside), parcels that sit on
-    the cell surface within rounding are found by walking 1e-5 steps towards the cell centre, parcels outside the 10 %-inflated cell
-    bounding box (or not locatable) are deleted."""
+    only "(x y z) cell"; tetFace / tetPt are re-derived per parcel (first tet of the cell with tetrahedron::inside); a parcel that is not in
+    the cell its label names is looked for in the cells around it (findCellFacePt) and takes that cell; a parcel just outside the mesh
+    (rounding) is found by walking 1e-5 steps towards the cell centre; parcels outside the 10 %-inflated cell bounding box that no cell
+    claims are deleted."""
     mesh, sp, md = _box()
     h = 0.004
     rng = np.random.default_rng(5)
@@ -102,10 +103,13 @@ def test_cloud_without_tet_indices_is_located_on_the_device():
     pos = (ijk + rng.random((n_in, 3))) * h
     # special points of cell 21 = (1, 1, 1): centre, a face centre, a vertex (all "inside" by the > SMALL rule)
     special = np.array([[1.5, 1.5, 1.5], [1.0, 1.5, 1.5], [1.0, 1.0, 1.0]]) * h
-    # rounding-level outside (found by the walk), 5 % outside (inside the inflated box, walk cannot reach: lost), far outside (lost)
-    outside = np.array([[1.0 - 1e-9, 1.5, 1.5], [0.95, 1.5, 1.5], [3.5, 1.5, 1.5]]) * h
-    position = np.concatenate([pos, special, outside])
-    cells = np.concatenate([cell, np.full(6, 21, np.int32)])
+    # labelled 21 but lying in other cells: across the x-min face by rounding and by 5 % (cell 20), two cells further (cell 23)
+    elsewhere = np.array([[1.0 - 1e-9, 1.5, 1.5], [0.95, 1.5, 1.5], [3.5, 1.5, 1.5]]) * h
+    # labelled 20 = (0, 1, 1) on the wall: outside the mesh by rounding (found by the walk), by 5 % (in the inflated box, no tet reachable: lost), by half a cell (lost)
+    outside = np.array([[-1e-9, 1.5, 1.5], [-0.05, 1.5, 1.5], [-0.5, 1.5, 1.5]]) * h
+    position = np.concatenate([pos, special, elsewhere, outside])
+    cells = np.concatenate([cell, np.full(6, 21, np.int32), np.full(3, 20, np.int32)])
+    expect_cell = np.concatenate([cell, [21, 21, 21, 20, 20, 23, 20]]).astype(np.int32)
     n = len(position)
     p = capi.ParcelData(n, 1, allocate=False, position=position, U=np.zeros((n, 3)), cell=cells, typeId=np.zeros(n, np.int32),
                         origId=np.arange(n, dtype=np.int32))
@@ -114,21 +118,22 @@ def test_cloud_without_tet_indices_is_located_on_the_device():
     eng.upload_parcels(p)
     assert eng.num_parcels() == n - 2                       # the two lost parcels are deleted
     g = H.by_id(eng.download_parcels())
-    assert np.array_equal(g["origId"], np.concatenate([np.arange(n_in + 4), []]).astype(np.int32))
-    assert np.array_equal(g["position"], position[: n_in + 4])   # the walk does not move the stored position
-    assert np.array_equal(g["cell"], cells[: n_in + 4])
-    # the oracle's own findTetFacePt on the parcels that are inside their cell
+    assert np.array_equal(g["origId"], np.arange(n - 2).astype(np.int32))
+    assert np.array_equal(g["position"], position[: n - 2])   # neither the search nor the walk moves the stored position
+    assert np.array_equal(g["cell"], expect_cell)
+    # the oracle's own findTetFacePt on the parcels that are inside the cell they end up with
     ora = Oracle()
     ora.set_mesh(mesh); ora.set_species(sp); ora.set_models(md)
-    q = capi.ParcelData(n_in + 3, 1, allocate=False, position=position[: n_in + 3], U=np.zeros((n_in + 3, 3)), cell=cells[: n_in + 3],
-                        typeId=np.zeros(n_in + 3, np.int32), origId=np.arange(n_in + 3, dtype=np.int32))
+    m = n_in + 6
+    q = capi.ParcelData(m, 1, allocate=False, position=position[:m], U=np.zeros((m, 3)), cell=expect_cell[:m],
+                        typeId=np.zeros(m, np.int32), origId=np.arange(m, dtype=np.int32))
     ora.upload_parcels(q)
     o = H.by_id(ora.download_parcels())
-    assert np.array_equal(g["tetFace"][: n_in + 3], o["tetFace"]) and np.array_equal(g["tetPt"][: n_in + 3], o["tetPt"])
-    # the parcel found by the walk sits in a tet of the x-min face of cell 21 and flies on normally
-    own, nb = np.asarray(mesh.owner), np.asarray(mesh.neighbour)
-    f = g["tetFace"][n_in + 3]
-    assert (own[f] == 21 and f >= mesh.n_internal) or (f < mesh.n_internal and 21 in (own[f], nb[f]))
+    assert np.array_equal(g["tetFace"][:m], o["tetFace"]) and np.array_equal(g["tetPt"][:m], o["tetPt"])
+    # the parcel found by the walk sits in a tet of the x-min wall face of cell 20 and flies on normally
+    own = np.asarray(mesh.owner)
+    f = g["tetFace"][m]
+    assert own[f] == 20 and f >= mesh.n_internal
     eng.evolve(2)
     assert eng.num_parcels() == n - 2
     eng.close()
