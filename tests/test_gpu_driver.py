@@ -298,3 +298,33 @@ def test_driver_fields_with_different_reset_policies(tmp_path):
     assert np.abs(n2_b * 2 - np.round(n2_b * 2)).max() < 1e-5
     assert np.abs(o2_b * 4 - np.round(o2_b * 4)).max() < 1e-5 and np.abs(o2_b * 2 - np.round(o2_b * 2)).max() > 0.2   # quarter steps occur
     assert np.allclose(mix_b - n2_b, late, atol=1e-5)      # mixture (two-step window) minus N2 = O2 over the same two steps
+
+
+def test_driver_variable_time_step_on_a_uniform_mesh_equals_the_constant_one(tmp_path):
+    """`timeStepModel variable` (dsmcVariableTimeStepModel.C:48-100) scales nParticles and deltaT of a cell with V / V_min.  On the couette
+    mesh every cell has the same volume, so the per-cell fields equal the uniform values and the run -- through the kernel instances that
+    read the cell fields -- must reproduce the constant-time-step run bit for bit (the written fields agree to the last printed digit);
+    the model also writes its nParticles and deltaT fields."""
+    import shutil
+
+    a, b = os.path.join(str(tmp_path), "const"), os.path.join(str(tmp_path), "var")
+    os.makedirs(a)
+    casegen.couette_case(a, n_steps=3, seed=11, nto=1)
+    shutil.copytree(a, b)
+    dp = os.path.join(b, "constant", "dsmcProperties")
+    txt = open(dp).read()
+    with open(dp, "w") as fh:
+        fh.write(txt.replace("collisionPartnerSelectionModel", "timeStepModel variable;\ncollisionPartnerSelectionModel", 1))
+    for d in (a, b):
+        r = subprocess.run([RUN, "-case", d], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr + r.stdout
+    assert "Variable time-step model:" in r.stdout
+    ta, tb = os.path.join(a, "5.00003"), os.path.join(b, "5.00003")
+    for f in ("rhoN_mixture", "Ttra_mixture", "Trot_N2", "dsmcNMean_O2", "wallHeatFlux_mixture"):
+        assert open(os.path.join(ta, f)).read() == open(os.path.join(tb, f)).read(), f
+    assert open(os.path.join(ta, "lagrangian", "dsmc", "positions")).read() == open(os.path.join(tb, "lagrangian", "dsmc", "positions")).read()
+    n = ff.read_internal_field(os.path.join(tb, "nParticles"))
+    dt = ff.read_internal_field(os.path.join(tb, "deltaT"))
+    g = np.load(casegen.GOLD)
+    assert np.allclose(n, float(g["nEquivalentParticles"]), rtol=1e-9) and np.allclose(dt, 1e-5, rtol=1e-9)
+    assert not os.path.exists(os.path.join(ta, "nParticles"))
