@@ -302,9 +302,9 @@ def test_driver_fields_with_different_reset_policies(tmp_path):
 
 def test_driver_variable_time_step_on_a_uniform_mesh_equals_the_constant_one(tmp_path):
     """`timeStepModel variable` (dsmcVariableTimeStepModel.C:48-100) scales nParticles and deltaT of a cell with V / V_min.  On the couette
-    mesh every cell has the same volume, so the per-cell fields equal the uniform values and the run -- through the kernel instances that
-    read the cell fields -- must reproduce the constant-time-step run bit for bit (the written fields agree to the last printed digit);
-    the model also writes its nParticles and deltaT fields."""
+    mesh every cell has the same volume (to a few ulp), so the per-cell fields equal the uniform values to 1e-14 and the run -- through the
+    kernel instances that read the cell fields -- reproduces the constant-time-step run: the written cloud and fields agree to the last
+    printed digit.  The model also writes its nParticles and deltaT fields."""
     import shutil
 
     a, b = os.path.join(str(tmp_path), "const"), os.path.join(str(tmp_path), "var")
