@@ -172,6 +172,8 @@ struct dsmcb200_ctx {
     double *dNPts = nullptr, *dDt = nullptr, *dRWF = nullptr;
     bool useRwf = false;           // dsmcAxisymmetric: parcels carry a radial weight
     int32_t* dWeightCounts = nullptr; int64_t weightCountsCap = 0;
+    uint32_t* dGiantBitmap = nullptr; int64_t giantWords = 0;   // scratch of giantSortKernel
+    int32_t* dGiantList = nullptr;
     int64_t cloned = 0, weightDeleted = 0, weightDeletedStep = 0;
     DevParams hP{};
     DevParams* dP = nullptr;
@@ -683,6 +685,7 @@ int finalize(dsmcb200_ctx* c) {
         CK(cudaMemset(c->dFaceFlux, 0, size_t(2) * P.nSpecies * M.nFaces * 8));
     }
     CK(devAlloc(&c->dCounters, 1)); CK(cudaMemset(c->dCounters, 0, sizeof(DevCounters)));
+    CK(devAlloc(&c->dGiantList, size_t(GIANT_LIST)));
     { int r = uploadCellFields(c); if (r) return r; }
     CK(devAlloc(&c->dBad, 1));
     CK(devAlloc(&c->dInfo, 8)); CK(devAlloc(&c->dInfoScratch, size_t(infoScratchDoubles())));
@@ -734,7 +737,6 @@ int64_t bornHeadroom(int64_t n) { return n / 8 + 4096; }
 int ensureBornBuffers(dsmcb200_ctx* c) {
     const int64_t want = bornHeadroom(c->N);
     if (want <= c->bornCap) return 0;
-    devFree(c->dNPts); devFree(c->dDt); devFree(c->dRWF); devFree(c->dWeightCounts);
     devFree(c->dBorn); devFree(c->dBornKeys); devFree(c->dBornIdx);
     if (c->dBornTemp) { cudaFree(c->dBornTemp); c->dBornTemp = nullptr; }
     const int32_t cap = int32_t(std::min<int64_t>(want + want / 4, (int64_t(1) << 30)));
@@ -764,8 +766,20 @@ int stageSort(dsmcb200_ctx* c, bool histogramDone) {
     int32_t nOut = 0;
     CK(cudaMemcpyAsync(&nOut, c->dCellOffset + nCells, 4, cudaMemcpyDeviceToHost, c->stream));
     { KT t(c, "scatterIndex"); CK(launchScatterIndex(src.cell, nIn, c->dCursor, c->dPerm, c->stream)); }
-    { KT t(c, "segmentSort"); CK(launchSegmentSort(c->dCellOffset, nCells, c->dPerm, c->dCounters, c->dCursor, c->stream)); }
-    CK(cudaStreamSynchronize(c->stream));  // nOut
+    { KT t(c, "segmentSort"); CK(launchSegmentSort(c->dCellOffset, nCells, c->dPerm, c->dCounters, c->dCursor, c->dGiantList, c->stream)); }
+    int32_t nGiant = 0;
+    CK(cudaMemcpyAsync(&nGiant, &c->dCounters->giantSortCells, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));  // nOut, nGiant
+    if (nGiant > 0) {   // cells of more than 65 536 parcels (a heat bath in one cell)
+        const int64_t words = int64_t(nIn) / 32 + 2;
+        if (words > c->giantWords) {
+            devFree(c->dGiantBitmap);
+            c->giantWords = words + words / 4;
+            CK(devAlloc(&c->dGiantBitmap, size_t(c->giantWords) * GIANT_SORT_BLOCKS));
+        }
+        KT t(c, "giantSort");
+        CK(launchGiantSort(c->dCellOffset, c->dPerm, c->dGiantList, nGiant, c->dGiantBitmap, c->giantWords, c->stream));
+    }
     ParcelArrays& dst = c->buf[1 - c->cur].a;
     { KT t(c, "gather"); CK(launchGather(src, dst, c->dPerm, c->dCellCentres, c->dOctKey, nOut, c->nModes, c->internal, c->stream)); }
     c->cur = 1 - c->cur;
@@ -1090,6 +1104,7 @@ void dsmcb200_destroy(dsmcb200_ctx* c) {
     devFree(c->dZvTab); devFree(c->dMigSend); devFree(c->dMigRecv); devFree(c->dMigKey); devFree(c->dMigWork); devFree(c->dInflowScan);
     if (c->dMigTemp) cudaFree(c->dMigTemp); devFree(c->dOrdinalToPatch); devFree(c->dCountsMatrix);
     devFree(c->dBorn); devFree(c->dBornKeys); devFree(c->dBornIdx); if (c->dBornTemp) cudaFree(c->dBornTemp);
+    devFree(c->dNPts); devFree(c->dDt); devFree(c->dRWF); devFree(c->dWeightCounts); devFree(c->dGiantBitmap); devFree(c->dGiantList);
     for (auto& p : c->dInflowAcc) devFree(p);
     for (auto& p : c->dInflowCounts) devFree(p);
     for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);

@@ -119,6 +119,7 @@ struct DevCounters {
     int32_t nInserted;
     int32_t bigCells;  // cells handed from collideLaneKernel to collideBigCellsKernel this step
     int32_t bigSortCells;  // cells handed from segmentSortKernel to bigSegmentSortKernel
+    int32_t giantSortCells;  // ... and from there to giantSortKernel (more than GIANT_SORT parcels: the one-cell heat baths)
     int32_t nBorn;         // parcels created by dissociations this step (dsmcCloud::addNewParcel)
     int32_t weightDeleted; // parcels deleted by the radial weighting this step
     unsigned long long nReact[MAX_REACTIONS][3];   // this step: dissociations of reactant 0, of reactant 1, exchanges
@@ -234,7 +235,14 @@ cudaError_t launchMovePlan(const MovePlanArgs& m, int32_t* scanScratch, cudaStre
 cudaError_t launchExclusiveScan(const int32_t* in, int32_t* out, int32_t* out2, int32_t n, int32_t* blockSums, cudaStream_t s);
 int32_t scanScratchInts(int32_t n);
 cudaError_t launchScatterIndex(const int32_t* cell, int32_t n, int32_t* cursor, int32_t* perm, cudaStream_t s);
-cudaError_t launchSegmentSort(const int32_t* cellOffset, int32_t nCells, int32_t* perm, DevCounters* c, int32_t* bigList, cudaStream_t s);
+cudaError_t launchSegmentSort(const int32_t* cellOffset, int32_t nCells, int32_t* perm, DevCounters* c, int32_t* bigList, int32_t* giantList, cudaStream_t s);
+constexpr int32_t GIANT_LIST = 32768;   // entries of giantList: 2^31 parcels / GIANT_SORT
+// cells of more than GIANT_SORT parcels (listed in giantList by the block-level sort): ordered through a bitmap of the cell's index range, one block per
+// cell at a time; bitmap: blocks * wordsPerBlock words of scratch, wordsPerBlock >= nIn / 32 + 2
+constexpr int32_t GIANT_SORT = 65536;
+constexpr int GIANT_SORT_BLOCKS = 4;
+cudaError_t launchGiantSort(const int32_t* cellOffset, int32_t* perm, const int32_t* giantList, int32_t nGiant, uint32_t* bitmap,
+                            int64_t wordsPerBlock, cudaStream_t s);
 cudaError_t launchGather(const ParcelArrays& src, const ParcelArrays& dst, const int32_t* perm, const double* cellCentres,
                          uint8_t* octKey, int32_t nOut, int32_t nModes, bool hasInternal, cudaStream_t s);
 cudaError_t launchHistogram(const int32_t* cell, int32_t n, int32_t* cellCount, cudaStream_t s);

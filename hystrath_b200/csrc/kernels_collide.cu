@@ -39,12 +39,6 @@ struct WarpSmem {   // collideBigCellsKernel works on the parcels where they lie
     int32_t subStart[9];
 };
 
-__device__ __forceinline__ int octantOf(double x, double y, double z, const double* cc) {
-    // pos(relPos.x()) + 2*pos(relPos.y()) + 4*pos(relPos.z()), pos(s) = (s >= 0) ? 1 : 0
-    const double rx = x - cc[0], ry = y - cc[1], rz = z - cc[2];
-    return (rx >= 0 ? 1 : 0) + 2 * (ry >= 0 ? 1 : 0) + 4 * (rz >= 0 ? 1 : 0);
-}
-
 __device__ __noinline__ double powNI(double a, double b) { return pow(a, b); }
 
 // VariableHardSphere::sigmaTcR
@@ -247,7 +241,6 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
         const int32_t b = a.cellOffset[c];
         const int32_t nC = a.cellOffset[c + 1] - b;
         if (nC <= BIG_CELL_THRESHOLD || P.collisionModel == DSMCB200_COLL_NONE) continue;  // handled by collideLaneKernel
-        const double cc[3] = {a.cellCentres[3 * c], a.cellCentres[3 * c + 1], a.cellCentres[3 * c + 2]};
         CellView v;
         v.tMacro = a.overallT ? a.overallT + c : nullptr;
         v.ux = a.p.ux + b; v.uy = a.p.uy + b; v.uz = a.p.uz + b; v.erot = a.p.erot ? a.p.erot + b : nullptr;
@@ -259,12 +252,16 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
         int32_t cnt[8];
 #pragma unroll
         for (int s = 0; s < 8; ++s) cnt[s] = 0;
-        for (int j0 = 0; j0 < nC; j0 += 32) {
-            const int j = j0 + lane;
-            int o = -1;
-            if (j < nC) o = octantOf(a.p.px[b + j], a.p.py[b + j], a.p.pz[b + j], cc);
+        // the sub-cell key of every sorted parcel was written by the sort's gather (the lane kernel reads the same bytes); four
+        // rows of 32 keys are in flight per iteration: a cell of 1e5 parcels is 6000 dependent round trips otherwise
+        for (int j0 = 0; j0 < nC; j0 += 128) {
+            int o[4];
 #pragma unroll
-            for (int s = 0; s < 8; ++s) cnt[s] += __popc(__ballot_sync(0xffffffffu, o == s));
+            for (int u = 0; u < 4; ++u) { const int j = j0 + 32 * u + lane; o[u] = j < nC ? int(a.octKey[b + j]) : -1; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int s = 0; s < 8; ++s) cnt[s] += __popc(__ballot_sync(0xffffffffu, o[u] == s));
         }
         int32_t start[9];
         start[0] = 0;
@@ -280,18 +277,22 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
             int32_t run[8];
 #pragma unroll
             for (int s = 0; s < 8; ++s) run[s] = start[s];
-            for (int j0 = 0; j0 < nC; j0 += 32) {
-                const int j = j0 + lane;
-                int o = -1;
-                if (j < nC) o = octantOf(a.p.px[b + j], a.p.py[b + j], a.p.pz[b + j], cc);
+            for (int j0 = 0; j0 < nC; j0 += 128) {
+                int o[4];
 #pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const unsigned m = __ballot_sync(0xffffffffu, o == s);
-                    if (o == s) {
-                        const int32_t posn = run[s] + __popc(m & ((1u << lane) - 1u));
-                        bigScratch[b + posn] = j;
+                for (int u = 0; u < 4; ++u) { const int j = j0 + 32 * u + lane; o[u] = j < nC ? int(a.octKey[b + j]) : -1; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + 32 * u + lane;
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        const unsigned m = __ballot_sync(0xffffffffu, o[u] == s);
+                        if (o[u] == s) {
+                            const int32_t posn = run[s] + __popc(m & ((1u << lane) - 1u));
+                            bigScratch[b + posn] = j;
+                        }
+                        run[s] += __popc(m);
                     }
-                    run[s] += __popc(m);
                 }
             }
         }
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
             if (active) {
                 rng.init(P.seed, uint32_t(c), uint32_t(cand), a.step, STREAM_COLLIDE);
                 cp = rng.randomLabel(0, nC - 1);
-                const int sub = octantOf(a.p.px[b + cp], a.p.py[b + cp], a.p.pz[b + cp], cc);
+                const int sub = a.octKey[b + cp];
                 const int32_t s0 = sm.subStart[sub];
                 const int32_t nSC = sm.subStart[sub + 1] - s0;
                 if (nSC > 1) {

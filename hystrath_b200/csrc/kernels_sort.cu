@@ -185,12 +185,16 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) segmentSortKernel(const int32_
 // The index lists of the cells segmentSortKernel left: bitonic network with ascending comparators only (flip step + half cleaners),
 // so that a length that is not a power of two needs no padding -- a partner beyond the end counts as +infinity and never swaps.
 __global__ void __launch_bounds__(1024) bigSegmentSortKernel(const int32_t* __restrict__ cellOffset, const int32_t* __restrict__ bigList,
-                                                             int32_t* __restrict__ perm, const DevCounters* counters) {
+                                                             int32_t* __restrict__ giantList, int32_t* __restrict__ perm, DevCounters* counters) {
     const int32_t nBig = counters->bigSortCells;
     for (int32_t ib = blockIdx.x; ib < nBig; ib += gridDim.x) {
         const int32_t c = bigList[ib];
         int32_t* const v = perm + cellOffset[c];
         const int32_t n = cellOffset[c + 1] - cellOffset[c];
+        if (n > GIANT_SORT) {   // 171 stages over global memory for 2^18 indices: left to giantSortKernel
+            if (threadIdx.x == 0) giantList[atomicAdd(&counters->giantSortCells, 1)] = c;   // at most 2^31 / GIANT_SORT entries
+            continue;
+        }
         for (int32_t k = 2; (k >> 1) < n; k <<= 1) {
             for (int32_t i = threadIdx.x; i < n; i += blockDim.x) {
                 const int32_t l = i ^ (k - 1);
@@ -208,14 +212,66 @@ __global__ void __launch_bounds__(1024) bigSegmentSortKernel(const int32_t* __re
     }
 }
 
+// A cell of more than GIANT_SORT parcels: its indices (distinct cloud positions) are marked in a bitmap over the range they span, and the
+// bitmap is read back in ascending order -- O(range / 32 + n) instead of the bitonic network's O(n log^2 n) passes over global memory.
+__global__ void __launch_bounds__(1024) giantSortKernel(const int32_t* __restrict__ cellOffset, const int32_t* __restrict__ giantList,
+                                                        int32_t* __restrict__ perm, uint32_t* __restrict__ bitmap, int64_t wordsPerBlock, int32_t nGiant) {
+    __shared__ int32_t sMin, sMax;
+    __shared__ int32_t part[1024];
+    uint32_t* const bm = bitmap + size_t(blockIdx.x) * size_t(wordsPerBlock);
+    const int tid = threadIdx.x;
+    for (int32_t g = blockIdx.x; g < nGiant; g += gridDim.x) {
+        const int32_t c = giantList[g];
+        int32_t* const v = perm + cellOffset[c];
+        const int32_t n = cellOffset[c + 1] - cellOffset[c];
+        if (tid == 0) { sMin = 0x7fffffff; sMax = -1; }
+        __syncthreads();
+        int32_t lo = 0x7fffffff, hi = -1;
+        for (int32_t k = tid; k < n; k += 1024) { const int32_t x = v[k]; lo = min(lo, x); hi = max(hi, x); }
+        atomicMin(&sMin, lo); atomicMax(&sMax, hi);
+        __syncthreads();
+        const int32_t base = sMin & ~31;
+        const int32_t W = (sMax - base) / 32 + 1;
+        for (int32_t w = tid; w < W; w += 1024) bm[w] = 0u;
+        __syncthreads();
+        for (int32_t k = tid; k < n; k += 1024) { const int32_t x = v[k] - base; atomicOr(&bm[x >> 5], 1u << (x & 31)); }
+        __syncthreads();
+        const int32_t chunk = (W + 1023) / 1024;
+        const int32_t w0 = min(W, tid * chunk), w1 = min(W, w0 + chunk);
+        int32_t cnt = 0;
+        for (int32_t w = w0; w < w1; ++w) cnt += __popc(bm[w]);
+        part[tid] = cnt;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {   // inclusive scan of the chunk counts
+            const int32_t add = tid >= o ? part[tid - o] : 0;
+            __syncthreads();
+            part[tid] += add;
+            __syncthreads();
+        }
+        int32_t off = part[tid] - cnt;
+        for (int32_t w = w0; w < w1; ++w) {
+            uint32_t word = bm[w];
+            while (word) { const int b = __ffs(word) - 1; word &= word - 1; v[off++] = base + w * 32 + b; }
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launchGiantSort(const int32_t* cellOffset, int32_t* perm, const int32_t* giantList, int32_t nGiant, uint32_t* bitmap,
+                            int64_t wordsPerBlock, cudaStream_t s) {
+    if (nGiant <= 0) return cudaSuccess;
+    giantSortKernel<<<std::min(nGiant, GIANT_SORT_BLOCKS), 1024, 0, s>>>(cellOffset, giantList, perm, bitmap, wordsPerBlock, nGiant);
+    return cudaGetLastError();
+}
+
 // bigList: nCells ints of scratch (the scatter cursors are free by now)
-cudaError_t launchSegmentSort(const int32_t* cellOffset, int32_t nCells, int32_t* perm, DevCounters* c, int32_t* bigList, cudaStream_t s) {
+cudaError_t launchSegmentSort(const int32_t* cellOffset, int32_t nCells, int32_t* perm, DevCounters* c, int32_t* bigList, int32_t* giantList, cudaStream_t s) {
     int grid = (nCells + SEG_WARPS - 1) / SEG_WARPS;
     if (grid > 148 * 16) grid = 148 * 16;
     if (grid < 1) grid = 1;
-    cudaMemsetAsync(&c->bigSortCells, 0, sizeof(int32_t), s);
+    cudaMemsetAsync(&c->bigSortCells, 0, 2 * sizeof(int32_t), s);   // bigSortCells, giantSortCells
     segmentSortKernel<<<grid, SEG_WARPS * 32, 0, s>>>(cellOffset, nCells, perm, c, bigList);
-    bigSegmentSortKernel<<<std::min(nCells, 296), 1024, 0, s>>>(cellOffset, bigList, perm, c);
+    bigSegmentSortKernel<<<std::min(nCells, 296), 1024, 0, s>>>(cellOffset, bigList, giantList, perm, c);
     return cudaGetLastError();
 }
 
