@@ -173,6 +173,7 @@ struct dsmcb200_ctx {
     bool useRwf = false;           // dsmcAxisymmetric: parcels carry a radial weight
     int32_t* dWeightCounts = nullptr; int64_t weightCountsCap = 0;
     uint32_t* dGiantBitmap = nullptr; int64_t giantWords = 0;   // scratch of giantSortKernel
+    int32_t nGiant = 0;   // cells of more than GIANT_SORT parcels found by the last sort
     int32_t* dGiantList = nullptr;
     int64_t cloned = 0, weightDeleted = 0, weightDeletedStep = 0;
     DevParams hP{};
@@ -770,6 +771,7 @@ int stageSort(dsmcb200_ctx* c, bool histogramDone) {
     int32_t nGiant = 0;
     CK(cudaMemcpyAsync(&nGiant, &c->dCounters->giantSortCells, 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));  // nOut, nGiant
+    c->nGiant = nGiant;
     if (nGiant > 0) {   // cells of more than 65 536 parcels (a heat bath in one cell)
         const int64_t words = int64_t(nIn) / 32 + 2;
         if (words > c->giantWords) {
@@ -1009,7 +1011,7 @@ int stageCollide(dsmcb200_ctx* c) {
     a.overallT = c->hP.invZvFormulation == 1 ? c->dOverallT : nullptr;
     a.cf = cellFields(c);
     a.nModes = c->internal ? c->nModes : 0;
-    a.bigScratch = c->dPerm; a.bigList = c->dCursor; a.octKey = c->dOctKey; a.P = c->dP; a.counters = c->dCounters; a.step = c->step;
+    a.bigScratch = c->dPerm; a.bigList = c->dCursor; a.octKey = c->dOctKey; a.giantList = c->dGiantList; a.nGiant = c->nGiant; a.P = c->dP; a.counters = c->dCounters; a.step = c->step;
     const bool chem = !c->reactions.empty();
     if (chem) {
         if (c->N != c->sortedN) return fail(c, DSMCB200_ERR_STATE, "collide stage with chemistry: the cloud was modified since the sort stage");

@@ -190,6 +190,8 @@ struct CollideArgs {
     int32_t* bigScratch;          // [nParcels] sub-cell index lists of cells too large for shared memory
     int32_t* bigList;             // [nCells] ids of those cells (written by the lane kernel)
     const uint8_t* octKey;        // [nParcels] sub-cell (octant) of every sorted parcel, written by the sort's gather
+    const int32_t* giantList;     // [nGiant] cells of more than GIANT_SORT parcels (written by the sort): one block each
+    int32_t nGiant;
     BornRec* born;                // [bornCapacity] parcels created by reactions (nullptr without chemistry)
     int32_t bornCapacity;
     const DevParams* P;

@@ -222,6 +222,77 @@ __device__ __forceinline__ double warpSumOrdered(double v) {
 
 __device__ bool reactPair(const CollideArgs& a, const DevParams& P, Rng& rng, int ri, int32_t gp0, int32_t gq0, int32_t cell, int32_t cand);
 
+struct CellTally {   // what the candidates of one thread add to their cell
+    double newMax, nColl, sepSum, nReacted;   // nReacted: accepted pairs a reaction took (counted as collisions, not measured)
+};
+
+// candidate `cand` of cell c picks its pair (noTimeCounter.C:160-230): P anywhere in the cell, Q from P's sub-cell when that holds another parcel
+__device__ __forceinline__ void pickPair(const CollideArgs& a, const DevParams& P, Rng& rng, const int32_t* subStart, int32_t b, int32_t nC, int32_t c,
+                                         int32_t cand, int32_t& cp, int32_t& cq) {
+    rng.init(P.seed, uint32_t(c), uint32_t(cand), a.step, STREAM_COLLIDE);
+    cp = rng.randomLabel(0, nC - 1);
+    const int sub = a.octKey[b + cp];
+    const int32_t s0 = subStart[sub];
+    const int32_t nSC = subStart[sub + 1] - s0;
+    if (nSC > 1) {
+        do {
+            const int32_t k = s0 + rng.randomLabel(0, nSC - 1);
+            cq = a.bigScratch[b + k];
+        } while (cp == cq);
+    } else {
+        do { cq = rng.randomLabel(0, nC - 1); } while (cp == cq);
+    }
+}
+
+// acceptance, reaction and collision of one candidate pair (noTimeCounter.C:232-320); the caller orders candidates that share a parcel
+__device__ __forceinline__ void collideCandidate(const CollideArgs& a, const DevParams& P, const CellView& v, bool LB, Rng& rng, int32_t b, int32_t c,
+                                                 int32_t cand, int32_t cp, int32_t cq, double sigmaTcRMaxLatched, CellTally& t) {
+    const int tP = v.typ[cp], tQ = v.typ[cq];
+    if (!(P.sp[tP].charge == -1 && P.sp[tQ].charge == -1)) {
+        V3 UP = mk(v.ux[cp], v.uy[cp], v.uz[cp]);
+        V3 UQ = mk(v.ux[cq], v.uy[cq], v.uz[cq]);
+        const double cR0 = mag(UP - UQ);
+        const double sTcR = sigmaTcR(P, tP, tQ, cR0);
+        if (sTcR > t.newMax) t.newMax = sTcR;
+        bool relax = (sTcR / sigmaTcRMaxLatched) > rng.sample01();
+        if (relax && P.nReactions > 0) {
+            // chemical reactions (noTimeCounter.C:250-303)
+            const int rMId = P.pairReaction[tP][tQ];
+            if (rMId >= 0) {
+                relax = reactPair(a, P, rng, rMId, b + cp, b + cq, c, cand);
+                if (!relax) t.nReacted += 1.0;
+            }
+        }
+        if (relax) {
+            double cR = -1;
+            if (LB) {
+                // LarsenBorgnakkeVariableHardSphere::collide
+                const double mR = P.mR[tP][tQ];
+                const double cRsqr = magSqr(UP - UQ);
+                double translationalEnergy = 0.5 * mR * cRsqr;
+                const double omegaPQ = P.omegaPQ[tP][tQ];
+                redistribute(P, rng, v, cp, tQ, translationalEnergy, omegaPQ);
+                redistribute(P, rng, v, cq, tP, translationalEnergy, omegaPQ);
+                cR = sqrt(2.0 * translationalEnergy / mR);
+            }
+            postCollisionVelocities(P, rng, tP, tQ, UP, UQ, cR);
+            v.ux[cp] = UP.x; v.uy[cp] = UP.y; v.uz[cp] = UP.z;
+            v.ux[cq] = UQ.x; v.uy[cq] = UQ.y; v.uz[cq] = UQ.z;
+            // cellMeasurements (VariableHardSphere.C:154-162)
+            const int32_t gp = b + cp, gq = b + cq;
+            const double dx = a.p.px[gp] - a.p.px[gq], dy = a.p.py[gp] - a.p.py[gq], dz = a.p.pz[gp] - a.p.pz[gq];
+            t.sepSum += sqrt(dx * dx + dy * dy + dz * dz);
+            t.nColl += 1.0;
+            // classification promotion (VariableHardSphere.C:164-187)
+            if (a.p.cls) {
+                const int clP = a.p.cls[gp], clQ = a.p.cls[gq];
+                if (clP == 0 && (clQ == 1 || clQ == 2)) a.p.cls[gp] = 2;
+                if (clQ == 0 && (clP == 1 || clP == 2)) a.p.cls[gq] = 2;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __grid_constant__ CollideArgs a) {
@@ -231,7 +302,6 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
     WarpSmem& sm = smAll[w];
     const DevParams& P = *a.P;
     const bool LB = P.collisionModel == DSMCB200_COLL_LB_VHS || P.collisionModel == DSMCB200_COLL_LB_VSS;
-    const bool internal = P.hasInternalEnergy != 0;
     const int32_t nWarps = gridDim.x * COL_WARPS;
     unsigned long long totColl = 0, totCand = 0;
 
@@ -240,7 +310,7 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
         const int32_t c = a.bigList[ib];
         const int32_t b = a.cellOffset[c];
         const int32_t nC = a.cellOffset[c + 1] - b;
-        if (nC <= BIG_CELL_THRESHOLD || P.collisionModel == DSMCB200_COLL_NONE) continue;  // handled by collideLaneKernel
+        if (nC <= BIG_CELL_THRESHOLD || nC > GIANT_SORT || P.collisionModel == DSMCB200_COLL_NONE) continue;  // collideLaneKernel / collideGiantCellsKernel
         CellView v;
         v.tMacro = a.overallT ? a.overallT + c : nullptr;
         v.ux = a.p.ux + b; v.uy = a.p.uy + b; v.uz = a.p.uz + b; v.erot = a.p.erot ? a.p.erot + b : nullptr;
@@ -306,8 +376,7 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
         if (lane == 0) a.remainder[c] = selectedPairs - nCandidates;
         totCand += (lane == 0) ? (unsigned long long)(nCandidates > 0 ? nCandidates : 0) : 0ULL;
 
-        double newMax = sigmaTcRMaxLatched;
-        double nColl = 0.0, sepSum = 0.0, nReacted = 0.0;   // nReacted: accepted pairs a reaction took (counted as collisions, not measured)
+        CellTally t{sigmaTcRMaxLatched, 0.0, 0.0, 0.0};
 
         for (int32_t c0 = 0; c0 < nCandidates; c0 += 32) {
             const int32_t cand = c0 + lane;
@@ -315,19 +384,7 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
             int32_t cp = -1, cq = -2;
             Rng rng;
             if (active) {
-                rng.init(P.seed, uint32_t(c), uint32_t(cand), a.step, STREAM_COLLIDE);
-                cp = rng.randomLabel(0, nC - 1);
-                const int sub = a.octKey[b + cp];
-                const int32_t s0 = sm.subStart[sub];
-                const int32_t nSC = sm.subStart[sub + 1] - s0;
-                if (nSC > 1) {
-                    do {
-                        const int32_t k = s0 + rng.randomLabel(0, nSC - 1);
-                        cq = bigScratch[b + k];
-                    } while (cp == cq);
-                } else {
-                    do { cq = rng.randomLabel(0, nC - 1); } while (cp == cq);
-                }
+                pickPair(a, P, rng, sm.subStart, b, nC, c, cand, cp, cq);
             }
             const unsigned activeMask = __ballot_sync(0xffffffffu, active);
             // earlier candidates of the batch that touch one of my parcels
@@ -343,50 +400,7 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
             while (done != 0xffffffffu) {
                 const bool ready = active && !((done >> lane) & 1u) && ((confl & ~done) == 0u);
                 if (ready) {
-                    const int tP = v.typ[cp], tQ = v.typ[cq];
-                    if (!(P.sp[tP].charge == -1 && P.sp[tQ].charge == -1)) {
-                        V3 UP = mk(v.ux[cp], v.uy[cp], v.uz[cp]);
-                        V3 UQ = mk(v.ux[cq], v.uy[cq], v.uz[cq]);
-                        const double cR0 = mag(UP - UQ);
-                        const double sTcR = sigmaTcR(P, tP, tQ, cR0);
-                        if (sTcR > newMax) newMax = sTcR;
-                        bool relax = (sTcR / sigmaTcRMaxLatched) > rng.sample01();
-                        if (relax && P.nReactions > 0) {
-                            // chemical reactions (noTimeCounter.C:250-303)
-                            const int rMId = P.pairReaction[tP][tQ];
-                            if (rMId >= 0) {
-                                relax = reactPair(a, P, rng, rMId, b + cp, b + cq, c, cand);
-                                if (!relax) nReacted += 1.0;
-                            }
-                        }
-                        if (relax) {
-                            double cR = -1;
-                            if (LB) {
-                                // LarsenBorgnakkeVariableHardSphere::collide
-                                const double mR = P.mR[tP][tQ];
-                                const double cRsqr = magSqr(UP - UQ);
-                                double translationalEnergy = 0.5 * mR * cRsqr;
-                                const double omegaPQ = P.omegaPQ[tP][tQ];
-                                redistribute(P, rng, v, cp, tQ, translationalEnergy, omegaPQ);
-                                redistribute(P, rng, v, cq, tP, translationalEnergy, omegaPQ);
-                                cR = sqrt(2.0 * translationalEnergy / mR);
-                            }
-                            postCollisionVelocities(P, rng, tP, tQ, UP, UQ, cR);
-                            v.ux[cp] = UP.x; v.uy[cp] = UP.y; v.uz[cp] = UP.z;
-                            v.ux[cq] = UQ.x; v.uy[cq] = UQ.y; v.uz[cq] = UQ.z;
-                            // cellMeasurements (VariableHardSphere.C:154-162)
-                            const int32_t gp = b + cp, gq = b + cq;
-                            const double dx = a.p.px[gp] - a.p.px[gq], dy = a.p.py[gp] - a.p.py[gq], dz = a.p.pz[gp] - a.p.pz[gq];
-                            sepSum += sqrt(dx * dx + dy * dy + dz * dz);
-                            nColl += 1.0;
-                            // classification promotion (VariableHardSphere.C:164-187)
-                            if (a.p.cls) {
-                                const int clP = a.p.cls[gp], clQ = a.p.cls[gq];
-                                if (clP == 0 && (clQ == 1 || clQ == 2)) a.p.cls[gp] = 2;
-                                if (clQ == 0 && (clP == 1 || clP == 2)) a.p.cls[gq] = 2;
-                            }
-                        }
-                    }
+                    collideCandidate(a, P, v, LB, rng, b, c, cand, cp, cq, sigmaTcRMaxLatched, t);
                 }
                 __syncwarp();
                 done |= __ballot_sync(0xffffffffu, ready);
@@ -394,12 +408,12 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
         }
 
         // ---- per-cell results
-        double mx = newMax;
+        double mx = t.newMax;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        const double nCollTot = warpSumOrdered(nColl);
-        const double sepTot = warpSumOrdered(sepSum);
-        const double nReactedTot = warpSumOrdered(nReacted);
+        const double nCollTot = warpSumOrdered(t.nColl);
+        const double sepTot = warpSumOrdered(t.sepSum);
+        const double nReactedTot = warpSumOrdered(t.nReacted);
         if (lane == 0) {
             a.sigmaTcRMax[c] = mx;
             a.nCollsStep[c] = nCollTot;
@@ -411,6 +425,155 @@ __global__ void __launch_bounds__(COL_WARPS * 32) collideBigCellsKernel(const __
     if (lane == 0 && (totColl | totCand)) {
         atomicAdd(&a.counters->collisions, totColl);
         atomicAdd(&a.counters->candidates, totCand);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cells of more than GIANT_SORT parcels (a heat bath in one cell: 2e5 parcels, 2e4 candidates a step): one block per cell.
+// The same algorithm as collideBigCellsKernel with batches of GIANT_THREADS candidates: a candidate runs once every EARLIER
+// candidate of its batch that shares a parcel with it has run, so the outcome is that of the reference's serial loop.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int GIANT_THREADS = 512, GIANT_WARPS = GIANT_THREADS / 32;
+}
+
+__global__ void __launch_bounds__(GIANT_THREADS) collideGiantCellsKernel(const __grid_constant__ CollideArgs a) {
+    __shared__ int32_t subStart[9];
+    __shared__ int32_t warpCnt[GIANT_WARPS][8];
+    __shared__ int32_t cpS[GIANT_THREADS], cqS[GIANT_THREADS];
+    __shared__ unsigned doneS[GIANT_WARPS];
+    __shared__ double red[GIANT_WARPS][4];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const DevParams& P = *a.P;
+    if (P.collisionModel == DSMCB200_COLL_NONE) return;
+    const bool LB = P.collisionModel == DSMCB200_COLL_LB_VHS || P.collisionModel == DSMCB200_COLL_LB_VSS;
+    const int32_t c = a.giantList[blockIdx.x];
+    const int32_t b = a.cellOffset[c];
+    const int32_t nC = a.cellOffset[c + 1] - b;
+    CellView v;
+    v.tMacro = a.overallT ? a.overallT + c : nullptr;
+    v.ux = a.p.ux + b; v.uy = a.p.uy + b; v.uz = a.p.uz + b; v.erot = a.p.erot ? a.p.erot + b : nullptr;
+    for (int m = 0; m < MAX_MODES; ++m) v.vib[m] = a.p.vib[m] ? a.p.vib[m] + b : nullptr;
+    v.typ = a.p.typeId + b; v.elev = a.p.elevel ? a.p.elevel + b : nullptr;
+
+    // ---- the 8 sub-cells: stable counting sort of the parcel indices by octant; warp w owns the w-th contiguous piece of the cell
+    const int32_t piece = ((nC + GIANT_WARPS * 128 - 1) / (GIANT_WARPS * 128)) * 128;
+    const int32_t j0w = w * piece, j1w = min(nC, j0w + piece);
+    {
+        int32_t cnt[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) cnt[s] = 0;
+        for (int j0 = j0w; j0 < j1w; j0 += 128) {
+            int o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int j = j0 + 32 * u + lane; o[u] = j < j1w ? int(a.octKey[b + j]) : -1; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int s = 0; s < 8; ++s) cnt[s] += __popc(__ballot_sync(0xffffffffu, o[u] == s));
+        }
+        if (lane < 8) {
+            int32_t val = 0;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) if (lane == s) val = cnt[s];
+            warpCnt[w][lane] = val;
+        }
+    }
+    __syncthreads();
+    {
+        int32_t run[8];
+        int32_t acc = 0;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            int32_t before = 0, total = 0;
+#pragma unroll
+            for (int ww = 0; ww < GIANT_WARPS; ++ww) { const int32_t k = warpCnt[ww][s]; total += k; if (ww < w) before += k; }
+            run[s] = acc + before;
+            if (tid == 0) subStart[s] = acc;
+            acc += total;
+        }
+        if (tid == 0) subStart[8] = acc;
+        for (int j0 = j0w; j0 < j1w; j0 += 128) {
+            int o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int j = j0 + 32 * u + lane; o[u] = j < j1w ? int(a.octKey[b + j]) : -1; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 32 * u + lane;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const unsigned m = __ballot_sync(0xffffffffu, o[u] == s);
+                    if (o[u] == s) a.bigScratch[b + run[s] + __popc(m & ((1u << lane) - 1u))] = j;
+                    run[s] += __popc(m);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- number of candidate pairs (noTimeCounter.C:142-155)
+    const double sigmaTcRMaxLatched = a.sigmaTcRMax[c];
+    const double selectedPairs =
+        a.remainder[c] + 0.5 * nC * (nC - 1) * a.cf.nParticles(P.nParticles, c) * sigmaTcRMaxLatched * a.cf.deltaT(P.deltaT, c) / a.cellVolumes[c];
+    const int32_t nCandidates = int32_t(selectedPairs);
+    __syncthreads();   // every thread has read remainder[c]
+    if (tid == 0) a.remainder[c] = selectedPairs - nCandidates;
+
+    CellTally t{sigmaTcRMaxLatched, 0.0, 0.0, 0.0};
+    for (int32_t c0 = 0; c0 < nCandidates; c0 += GIANT_THREADS) {
+        const int32_t cand = c0 + tid;
+        const bool active = cand < nCandidates;
+        int32_t cp = -1, cq = -2;
+        Rng rng;
+        if (active) pickPair(a, P, rng, subStart, b, nC, c, cand, cp, cq);
+        cpS[tid] = cp; cqS[tid] = cq;
+        __syncthreads();
+        // earlier candidates of the batch that touch one of my parcels, one word per warp of the batch
+        unsigned confl[GIANT_WARPS];
+#pragma unroll
+        for (int k = 0; k < GIANT_WARPS; ++k) {
+            confl[k] = 0;
+            if (k <= w && active) {
+                for (int jj = 0; jj < 32; ++jj) {
+                    const int j = 32 * k + jj;
+                    const int32_t pj = cpS[j], qj = cqS[j];
+                    if (j < tid && (pj == cp || pj == cq || qj == cp || qj == cq)) confl[k] |= 1u << jj;
+                }
+            }
+        }
+        const unsigned activeMask = __ballot_sync(0xffffffffu, active);
+        if (lane == 0) doneS[w] = ~activeMask;
+        __syncthreads();
+        bool mine = !active;   // this thread's candidate has run
+        for (;;) {
+            unsigned all = 0xffffffffu, pending = 0;
+#pragma unroll
+            for (int k = 0; k < GIANT_WARPS; ++k) { const unsigned d = doneS[k]; all &= d; pending |= confl[k] & ~d; }
+            if (all == 0xffffffffu) break;   // the same words for every thread: the block leaves together
+            const bool ready = !mine && pending == 0u;
+            if (ready) { collideCandidate(a, P, v, LB, rng, b, c, cand, cp, cq, sigmaTcRMaxLatched, t); mine = true; }
+            __syncthreads();   // doneS was read by everyone, the parcels written by this round are visible to the block
+            const unsigned r = __ballot_sync(0xffffffffu, ready);
+            if (lane == 0 && r) doneS[w] |= r;
+            __syncthreads();
+        }
+    }
+
+    // ---- per-cell results: fixed-shape trees, the same order on every run
+    double mx = t.newMax;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const double nCollW = warpSumOrdered(t.nColl), sepW = warpSumOrdered(t.sepSum), nReactedW = warpSumOrdered(t.nReacted);
+    if (lane == 0) { red[w][0] = mx; red[w][1] = nCollW; red[w][2] = sepW; red[w][3] = nReactedW; }
+    __syncthreads();
+    if (tid == 0) {
+        double m = red[0][0], nCollTot = red[0][1], sepTot = red[0][2], nReactedTot = red[0][3];
+        for (int k = 1; k < GIANT_WARPS; ++k) { m = fmax(m, red[k][0]); nCollTot += red[k][1]; sepTot += red[k][2]; nReactedTot += red[k][3]; }
+        a.sigmaTcRMax[c] = m;
+        a.nCollsStep[c] = nCollTot;
+        a.collSepStep[c] = sepTot;
+        atomicAdd(&a.counters->collisions, (unsigned long long)nCollTot + (unsigned long long)nReactedTot);
+        atomicAdd(&a.counters->candidates, (unsigned long long)(nCandidates > 0 ? nCandidates : 0));
     }
 }
 
@@ -920,6 +1083,7 @@ cudaError_t launchCollide(const CollideArgs& a, cudaStream_t s) {
     if (gridBig > 148 * 4) gridBig = 148 * 4;
     if (gridBig < 1) gridBig = 1;
     collideBigCellsKernel<<<gridBig, COL_WARPS * 32, 0, s>>>(a);
+    if (a.nGiant > 0) collideGiantCellsKernel<<<a.nGiant, GIANT_THREADS, 0, s>>>(a);
     return cudaGetLastError();
 }
 

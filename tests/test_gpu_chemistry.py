@@ -25,11 +25,13 @@ def reacting_box(n=(4, 4, 4), ppc=60, T=25000.0, dens=2e22, dt=2e-8):
     return mesh, sp, md, rx, T, dens
 
 
-def test_reacting_steps_match_the_oracle_parcel_by_parcel():
+@pytest.mark.parametrize("n,ppc", [((4, 4, 4), 60), ((2, 1, 1), 70000)], ids=["64-cells", "two-cells-of-70000"])
+def test_reacting_steps_match_the_oracle_parcel_by_parcel(n, ppc):
     """Five full steps of a periodic box of hot air in which every one of the 12 reactions can fire: reaction counts per reaction and
     channel, species of every parcel, the parcels created by dissociations (identity, order in the cloud, cell) and the occupancy equal
-    the oracle's exactly; velocities and internal energies to the accuracy of pow()/exp() on the two sides."""
-    mesh, sp, md, rx, T, dens = reacting_box()
+    the oracle's exactly; velocities and internal energies to the accuracy of pow()/exp() on the two sides.  The second case puts
+    70 000 parcels in each of two cells: the bitmap sort and the one-block-per-cell candidate loop (512 candidates per batch) of cells beyond 65 536 parcels."""
+    mesh, sp, md, rx, T, dens = reacting_box(n=n, ppc=ppc)
     eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
     for x in (eng, ora):
         x.set_reactions(rx)
