@@ -201,6 +201,12 @@ void dsmcCloud::readControl() {
     }
     // writePrecision (default 6 in OpenFOAM); dsmcInitialise+ forces 15 (dsmcInitialise+.C:73)
     foam::setWritePrecision(initialise_ ? 15 : int(c.labelOr("writePrecision", 6)));
+    // writeFormat ascii | binary (Time::writeFormat_): clouds and fields are written in it; what is read says its format in its header
+    {
+        const std::string wf = c.wordOr("writeFormat", "ascii");
+        if (wf != "ascii" && wf != "binary") throw FoamError("controlDict: writeFormat " + wf + " is not in enumeration: 2(ascii binary)");
+        foam::setWriteBinary(wf == "binary");
+    }
     if (initialise_) {
         // createTime.H: the start time of controlDict; a fresh case has no time directory with a cloud yet
         startTime_ = startFrom == "startTime" ? c.scalarOr("startTime", 0.0) : 0.0;
@@ -228,6 +234,17 @@ void dsmcCloud::readControl() {
     time_ = startTime_;
 }
 
+namespace {
+uint64_t fnv1a(uint64_t h, const void* data, size_t bytes) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    if (h == 0) h = 1469598103934665603ULL;
+    for (size_t i = 0; i < bytes; ++i) { h ^= p[i]; h *= 1099511628211ULL; }
+    return h;
+}
+template <class T>
+uint64_t fnv1a(uint64_t h, const std::vector<T>& v) { return fnv1a(h, v.data(), v.size() * sizeof(T)); }
+}  // namespace
+
 void dsmcCloud::readMesh() {
     const std::string pm = root_ + "/constant/polyMesh/";
     points_ = foam::readVectorField(pm + "points");
@@ -235,6 +252,7 @@ void dsmcCloud::readMesh() {
     owner_ = foam::readLabelField(pm + "owner");
     neighbour_ = foam::readLabelField(pm + "neighbour");
     boundary_ = foam::readBoundary(pm + "boundary");
+    meshHash_ = fnv1a(fnv1a(fnv1a(fnv1a(fnv1a(0, points_), faceOffsets_), facePoints_), owner_), neighbour_);
     nFaces_ = int(owner_.size());
     nInternal_ = int(neighbour_.size());
     nCells_ = 0;
@@ -607,6 +625,7 @@ void dsmcCloud::readCloud() {
     std::vector<double> radialWeight;   // dsmcParcel::RWF_ (dsmcParcelIO.C); without the file a parcel takes its cell's weight
     if (foam::exists(dir + "radialWeight")) { radialWeight = foam::readScalarField(dir + "radialWeight"); if (int64_t(radialWeight.size()) == n) s.radialWeight = radialWeight.data(); }
     nRead_ = n;
+    cloudHash_ = fnv1a(fnv1a(fnv1a(fnv1a(fnv1a(fnv1a(fnv1a(0, xyz), cell), U), typeId), ERot), vib), elevel);
     // <time>/dsmcSigmaTcRMax is MUST_READ (dsmcCloud.C:625-636)
     auto sig = foam::readInternalField(root_ + "/" + timeName_ + "/dsmcSigmaTcRMax", nCells_, 1);
     if (dryRun_) return;
@@ -636,6 +655,7 @@ std::string dsmcCloud::summary() const {
         o << " mfp " << f.measureMeanFreePath << " reset " << f.resetAtOutput << " sampleInterval " << f.sampleInterval << "\n";
     }
     o << "  parcels " << nRead_ << "\n";
+    o << "  checksum mesh " << std::hex << meshHash_ << " cloud " << cloudHash_ << std::dec << "\n";
     return o.str();
 }
 
@@ -1185,7 +1205,7 @@ void dsmcCloud::writeResumeSampling(const std::string& timeDir) {
     {
         FILE* f = std::fopen((ud + "/resumeSampling_dsmcb200").c_str(), "w");
         if (!f) throw FoamError("cannot write " + ud + "/resumeSampling_dsmcb200");
-        std::fputs(foam::header("dictionary", timeName_ + "/uniform", "resumeSampling_dsmcb200").c_str(), f);
+        std::fputs(foam::asciiHeader("dictionary", timeName_ + "/uniform", "resumeSampling_dsmcb200").c_str(), f);
         ListOut o{f, 17};
         std::fprintf(f, "nTimeSteps      %.17g;\n\nnCells          %d;\n\nnSpecies        %d;\n\nnQuantities     %d;\n\nnMeasuredFaces  %d;\n\nnWallQuantities %d;\n\n",
                      ai.nTimeSteps, nC, S, nQ, nMeas, nWallQ);
@@ -1254,7 +1274,7 @@ void dsmcCloud::writeResumeSampling(const std::string& timeDir) {
         const std::string name = "resumeSampling_" + fs.fieldName;
         FILE* f = std::fopen((ud + "/" + name).c_str(), "w");
         if (!f) throw FoamError("cannot write " + ud + "/" + name);
-        std::fputs(foam::header("dictionary", timeName_ + "/uniform", name).c_str(), f);
+        std::fputs(foam::asciiHeader("dictionary", timeName_ + "/uniform", name).c_str(), f);
         ListOut o{f, 10};
         std::fprintf(f, "nTimeSteps      %.10g;\n\n", ai.nTimeSteps - fs.baseNT);
         o.entry("dsmcNCum", dsmcNCum); o.entry("dsmcMCum", dsmcMCum); o.entry("dsmcLinearKECum", dsmcLinearKECum);
@@ -1449,7 +1469,7 @@ void dsmcCloud::write() {
         foam::makeDirs(ud);
         FILE* f = std::fopen((ud + "/cloudProperties").c_str(), "w");
         if (f) {
-            std::fputs(foam::header("dictionary", timeName_ + "/uniform/lagrangian/" + cloudName_, "cloudProperties").c_str(), f);
+            std::fputs(foam::asciiHeader("dictionary", timeName_ + "/uniform/lagrangian/" + cloudName_, "cloudProperties").c_str(), f);
             std::fprintf(f, "processor%d\n{\n    particleCount   %lld;\n}\n", rank_, (long long)got);
             std::fclose(f);
         }

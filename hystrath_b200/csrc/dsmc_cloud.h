@@ -129,6 +129,7 @@ class dsmcCloud {
     bool initialise_ = false;   // dsmcInitialise+: no cloud is read, system/dsmcInitialiseDict fills the mesh
     void initialiseFromDict();  // dsmcAllConfigurations::setInitialConfig (dsmcCloud.C:795-796)
     int64_t nRead_ = 0;
+    uint64_t meshHash_ = 0, cloudHash_ = 0;   // FNV-1a over the bytes read (printed by summary(): the same case in ASCII and binary reads the same)
 
    public:
     // -dryRun: what was parsed from the case directory (no GPU context is created)

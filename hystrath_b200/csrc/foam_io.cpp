@@ -160,21 +160,76 @@ Dict parseBody(Tokens& k, const std::string& name) {
     return d;
 }
 
-// body of a data file after the FoamFile header
-std::string dataBody(const std::string& path) {
-    std::string s = stripComments(slurp(path));
-    size_t p = s.find("FoamFile");
-    if (p != std::string::npos) {
-        size_t e = s.find('}', p);
-        if (e != std::string::npos) s = s.substr(e + 1);
+// body of a data file after the FoamFile header.  `format binary;` files (IOstream::BINARY: every contiguous list is its size followed by
+// the raw bytes in round brackets, OSstream::write(const char*, streamsize)) keep their bytes: comments are skipped by the scanner, not
+// stripped from the text.  The header's arch entry ("LSB;label=32;scalar=64") gives the label width; scalars are doubles.
+struct DataFile {
+    std::string s;
+    bool binary = false;
+    int labelBytes = 4;
+};
+DataFile openData(const std::string& path) {
+    DataFile f;
+    std::string raw = slurp(path);
+    size_t p = raw.find("FoamFile");
+    size_t e = p == std::string::npos ? std::string::npos : raw.find('}', p);
+    if (e != std::string::npos) {
+        const std::string hdr = raw.substr(p, e - p);
+        size_t q = hdr.find("format");
+        if (q != std::string::npos) {
+            q += 6;
+            while (q < hdr.size() && std::isspace(static_cast<unsigned char>(hdr[q]))) ++q;
+            f.binary = hdr.compare(q, 6, "binary") == 0;
+        }
+        if (hdr.find("label=64") != std::string::npos) f.labelBytes = 8;
+        if (f.binary && hdr.find("scalar=32") != std::string::npos) throw FoamError(path + ": binary files of a single-precision build (scalar=32) are not supported");
     }
-    return s;
+    if (f.binary) {
+        f.s = raw.substr(e + 1);
+    } else {
+        f.s = stripComments(raw);
+        p = f.s.find("FoamFile");
+        if (p != std::string::npos) {
+            e = f.s.find('}', p);
+            if (e != std::string::npos) f.s = f.s.substr(e + 1);
+        }
+    }
+    return f;
+}
+std::string dataBody(const std::string& path) {
+    return openData(path).s;
 }
 
 struct Scanner {
     const char* p;
     const char* e;
-    void ws() { while (p < e && (std::isspace(static_cast<unsigned char>(*p)))) ++p; }
+    void ws() {   // white space and, in files whose comments were not stripped, comments
+        for (;;) {
+            while (p < e && (std::isspace(static_cast<unsigned char>(*p)))) ++p;
+            if (p + 1 < e && p[0] == '/' && p[1] == '/') { while (p < e && *p != '\n') ++p; continue; }
+            if (p + 1 < e && p[0] == '/' && p[1] == '*') { p += 2; while (p + 1 < e && !(p[0] == '*' && p[1] == '/')) ++p; p += 2; continue; }
+            break;
+        }
+    }
+    // one binary block: '(' count raw bytes ')'
+    void raw(void* dst, size_t bytes) {
+        ws();
+        if (p >= e || *p != '(') throw FoamError("'(' expected in front of a binary block");
+        ++p;
+        if (size_t(e - p) < bytes + 1) throw FoamError("binary block is truncated");
+        std::memcpy(dst, p, bytes);
+        p += bytes;
+        if (*p != ')') throw FoamError("')' expected after a binary block");
+        ++p;
+    }
+    // a binary List<label>: labels of the file's width narrowed to 32 bits
+    void rawLabels(int32_t* dst, size_t n, int labelBytes) {
+        if (n == 0) return;
+        if (labelBytes == 4) { raw(dst, n * 4); return; }
+        std::vector<int64_t> w(n);
+        raw(w.data(), n * 8);
+        for (size_t i = 0; i < n; ++i) dst[i] = int32_t(w[i]);
+    }
     bool eat(char c) { ws(); if (p < e && *p == c) { ++p; return true; } return false; }
     double num() {
         ws();
@@ -194,10 +249,17 @@ struct Scanner {
     }
 };
 
+// binary lists: the size only (the block follows)
+int64_t binarySize(Scanner& sc) {
+    sc.ws();
+    while (sc.p < sc.e && !std::isdigit(static_cast<unsigned char>(*sc.p))) { ++sc.p; sc.ws(); }
+    return sc.integer();
+}
+
 // positions the scanner after "N (" and returns N; uniform form N{v} returns uniformText
 int64_t openSized(Scanner& sc, bool& uniform) {
     sc.ws();
-    while (sc.p < sc.e && !std::isdigit(static_cast<unsigned char>(*sc.p))) ++sc.p;
+    while (sc.p < sc.e && !std::isdigit(static_cast<unsigned char>(*sc.p))) { ++sc.p; sc.ws(); }
     int64_t n = sc.integer();
     sc.ws();
     uniform = false;
@@ -320,8 +382,15 @@ std::vector<std::string> listDir(const std::string& path) {
 }
 
 std::vector<double> readVectorField(const std::string& path) {
-    std::string s = dataBody(path);
+    const DataFile df = openData(path);
+    const std::string& s = df.s;
     Scanner sc{s.data(), s.data() + s.size()};
+    if (df.binary) {
+        const int64_t n = binarySize(sc);
+        std::vector<double> o(size_t(n) * 3);
+        if (n) sc.raw(o.data(), o.size() * 8);
+        return o;
+    }
     bool uni;
     int64_t n = openSized(sc, uni);
     std::vector<double> o(size_t(n) * 3);
@@ -338,9 +407,16 @@ std::vector<double> readVectorField(const std::string& path) {
     }
     return o;
 }
-std::vector<double> readScalarField(const std::string& path) {
-    std::string s = dataBody(path);
+namespace {
+std::vector<double> scalarFieldOf(const DataFile& df) {
+    const std::string& s = df.s;
     Scanner sc{s.data(), s.data() + s.size()};
+    if (df.binary) {
+        const int64_t n = binarySize(sc);
+        std::vector<double> o(static_cast<size_t>(n));
+        if (n) sc.raw(o.data(), o.size() * 8);
+        return o;
+    }
     bool uni;
     int64_t n = openSized(sc, uni);
     std::vector<double> o(static_cast<size_t>(n));
@@ -348,15 +424,36 @@ std::vector<double> readScalarField(const std::string& path) {
     for (int64_t i = 0; i < n; ++i) o[i] = sc.num();
     return o;
 }
+}  // namespace
+std::vector<double> readScalarField(const std::string& path) { return scalarFieldOf(openData(path)); }
 std::vector<int32_t> readLabelField(const std::string& path) {
-    auto v = readScalarField(path);
+    const DataFile df = openData(path);
+    if (df.binary) {
+        Scanner sc{df.s.data(), df.s.data() + df.s.size()};
+        const int64_t n = binarySize(sc);
+        std::vector<int32_t> o(static_cast<size_t>(n));
+        sc.rawLabels(o.data(), o.size(), df.labelBytes);
+        return o;
+    }
+    auto v = scalarFieldOf(df);
     std::vector<int32_t> o(v.size());
     for (size_t i = 0; i < v.size(); ++i) o[i] = int32_t(std::llround(v[i]));
     return o;
 }
 void readFaces(const std::string& path, std::vector<int32_t>& offsets, std::vector<int32_t>& labels) {
-    std::string s = dataBody(path);
+    const DataFile df = openData(path);
+    const std::string& s = df.s;
     Scanner sc{s.data(), s.data() + s.size()};
+    if (df.binary) {   // faceCompactList: the offsets (nFaces + 1) and the point labels of all faces, two contiguous lists
+        const int64_t n1 = binarySize(sc);
+        offsets.assign(size_t(n1), 0);
+        sc.rawLabels(offsets.data(), offsets.size(), df.labelBytes);
+        const int64_t m = binarySize(sc);
+        labels.assign(size_t(m), 0);
+        sc.rawLabels(labels.data(), labels.size(), df.labelBytes);
+        if (offsets.empty() || offsets.back() != int32_t(m)) throw FoamError(path + ": face offsets do not match the label list");
+        return;
+    }
     bool uni;
     int64_t n = openSized(sc, uni);
     offsets.assign(size_t(n) + 1, 0);
@@ -370,26 +467,46 @@ void readFaces(const std::string& path, std::vector<int32_t>& offsets, std::vect
     }
 }
 void readPositions(const std::string& path, std::vector<double>& xyz, std::vector<int32_t>& cell) {
-    std::string s = dataBody(path);
+    const DataFile df = openData(path);
+    const std::string& s = df.s;
     Scanner sc{s.data(), s.data() + s.size()};
     bool uni;
     int64_t n = openSized(sc, uni);
     xyz.assign(size_t(n) * 3, 0.0);
     cell.assign(size_t(n), 0);
+    if (df.binary) {
+        // particle::write(os, false) in binary (particleIO.C:121-143): position, cellI, faceI, stepFraction as one block per particle
+        const size_t bytes = 24 + 2 * size_t(df.labelBytes) + 8;
+        unsigned char rec[48];
+        for (int64_t i = 0; i < n; ++i) {
+            sc.raw(rec, bytes);
+            std::memcpy(&xyz[3 * i], rec, 24);
+            if (df.labelBytes == 4) { int32_t c; std::memcpy(&c, rec + 24, 4); cell[i] = c; }
+            else { int64_t c; std::memcpy(&c, rec + 24, 8); cell[i] = int32_t(c); }
+        }
+        return;
+    }
     for (int64_t i = 0; i < n; ++i) {
-        if (!sc.eat('(')) throw FoamError(path + ": '(' expected in positions (binary clouds are not supported)");
+        if (!sc.eat('(')) throw FoamError(path + ": '(' expected in positions");
         xyz[3 * i] = sc.num(); xyz[3 * i + 1] = sc.num(); xyz[3 * i + 2] = sc.num();
         sc.eat(')');
         cell[i] = int32_t(sc.integer());
     }
 }
 std::vector<int32_t> readLabelListList(const std::string& path, int& width) {
-    std::string s = dataBody(path);
+    const DataFile df = openData(path);
+    const std::string& s = df.s;
     Scanner sc{s.data(), s.data() + s.size()};
     bool uni;
     int64_t n = openSized(sc, uni);
     std::vector<std::vector<int32_t>> rows(static_cast<size_t>(n));
-    if (uni) {
+    if (df.binary) {   // a list of lists is not contiguous: the rows follow one another, each a size and (if not empty) a block
+        for (int64_t i = 0; i < n; ++i) {
+            const long m = sc.integer();
+            rows[i].assign(size_t(m), 0);
+            sc.rawLabels(rows[i].data(), size_t(m), df.labelBytes);
+        }
+    } else if (uni) {
         long m = sc.integer();
         sc.eat('(');
         std::vector<int32_t> r;
@@ -424,7 +541,8 @@ std::vector<int32_t> readLabelListList(const std::string& path, int& width) {
     return o;
 }
 std::vector<double> readInternalField(const std::string& path, int64_t nCells, int nCmpt) {
-    std::string s = dataBody(path);
+    const DataFile df = openData(path);
+    const std::string& s = df.s;
     size_t p = s.find("internalField");
     if (p == std::string::npos) throw FoamError(path + ": no internalField");
     Scanner sc{s.data() + p + 13, s.data() + s.size()};
@@ -441,6 +559,11 @@ std::vector<double> readInternalField(const std::string& path, int64_t nCells, i
     const char* q = std::strchr(sc.p, '>');
     if (!q) throw FoamError(path + ": malformed internalField");
     sc.p = q + 1;
+    if (df.binary) {
+        if (binarySize(sc) != nCells) throw FoamError(path + ": internalField size does not match the mesh");
+        if (nCells) sc.raw(o.data(), o.size() * 8);
+        return o;
+    }
     bool uni;
     int64_t n = openSized(sc, uni);
     if (n != nCells) throw FoamError(path + ": internalField size does not match the mesh");
@@ -453,7 +576,7 @@ std::vector<double> readInternalField(const std::string& path, int64_t nCells, i
 }
 
 std::vector<BoundaryPatch> readBoundary(const std::string& path) {
-    std::string s = dataBody(path);
+    std::string s = stripComments(dataBody(path));   // entries only, whatever the header's format says
     size_t p = 0;
     while (p < s.size() && !std::isdigit(static_cast<unsigned char>(s[p]))) ++p;
     size_t q = s.find('(', p);
@@ -484,7 +607,19 @@ std::vector<BoundaryPatch> readBoundary(const std::string& path) {
 }
 
 // ---------------------------------------------------------------------------------------------
-std::string header(const std::string& cls, const std::string& location, const std::string& object) {
+namespace {
+bool gWriteBinary = false;
+}
+void setWriteBinary(bool b) { gWriteBinary = b; }
+bool writeBinary() { return gWriteBinary; }
+
+namespace {
+std::string headerOf(const std::string& cls, const std::string& location, const std::string& object, bool binary);
+}
+std::string header(const std::string& cls, const std::string& location, const std::string& object) { return headerOf(cls, location, object, gWriteBinary); }
+std::string asciiHeader(const std::string& cls, const std::string& location, const std::string& object) { return headerOf(cls, location, object, false); }
+namespace {
+std::string headerOf(const std::string& cls, const std::string& location, const std::string& object, bool binary) {
     std::ostringstream s;
     s << "/*--------------------------------*- C++ -*----------------------------------*\\\n"
          "| =========                 |                                                 |\n"
@@ -493,11 +628,13 @@ std::string header(const std::string& cls, const std::string& location, const st
          "|   \\\\  /    A nd           | Web:      www.OpenFOAM.com                      |\n"
          "|    \\\\/     M anipulation  |                                                 |\n"
          "\\*---------------------------------------------------------------------------*/\n"
-         "FoamFile\n{\n    version     2.0;\n    format      ascii;\n    class       "
+         "FoamFile\n{\n    version     2.0;\n    format      " << (binary ? "binary" : "ascii") << ";\n"
+      << (binary ? "    arch        \"LSB;label=32;scalar=64\";\n" : "") << "    class       "
       << cls << ";\n    location    \"" << location << "\";\n    object      " << object
       << ";\n}\n// * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * //\n\n";
     return s.str();
 }
+}  // namespace
 
 namespace {
 int gWritePrecision = 10;
@@ -510,6 +647,17 @@ FILE* openw(const std::string& path) {
     FILE* f = std::fopen(path.c_str(), "w");
     if (!f) throw FoamError("cannot write " + path);
     return f;
+}
+// OSstream::write(const char*, streamsize): the bytes in round brackets
+void block(FILE* f, const void* a, size_t bytes) {
+    std::fputc('(', f);
+    if (bytes && std::fwrite(a, 1, bytes, f) != bytes) throw FoamError("short write");
+    std::fputc(')', f);
+}
+// Ostream << List<T> of a contiguous T in binary: nl, size, nl and, unless empty, the block
+void binaryList(FILE* f, const void* a, int64_t n, size_t elemBytes) {
+    std::fprintf(f, "\n%lld\n", (long long)n);
+    if (n) block(f, a, size_t(n) * elemBytes);
 }
 }  // namespace
 
@@ -533,6 +681,7 @@ void writeScalarField(const std::string& path, const std::string& cls, const std
                       const double* a, int64_t n) {
     FILE* f = openw(path);
     std::fputs(header(cls, location, object).c_str(), f);
+    if (gWriteBinary) { binaryList(f, a, n, 8); std::fputc('\n', f); std::fclose(f); return; }
     bool uni = n > 0;
     for (int64_t i = 1; i < n && uni; ++i) uni = a[i] == a[0];
     if (uni) { std::fprintf(f, "%lld{", (long long)n); fmt(f, a[0]); std::fputs("}\n", f); }
@@ -547,6 +696,7 @@ void writeLabelField(const std::string& path, const std::string& cls, const std:
                      const int32_t* a, int64_t n) {
     FILE* f = openw(path);
     std::fputs(header(cls, location, object).c_str(), f);
+    if (gWriteBinary) { binaryList(f, a, n, 4); std::fputc('\n', f); std::fclose(f); return; }
     bool uni = n > 0;
     for (int64_t i = 1; i < n && uni; ++i) uni = a[i] == a[0];
     if (uni) std::fprintf(f, "%lld{%d}\n", (long long)n, a[0]);
@@ -561,6 +711,7 @@ void writeVectorField(const std::string& path, const std::string& cls, const std
                       const double* a, int64_t n) {
     FILE* f = openw(path);
     std::fputs(header(cls, location, object).c_str(), f);
+    if (gWriteBinary) { binaryList(f, a, n, 24); std::fputc('\n', f); std::fclose(f); return; }
     std::fprintf(f, "%lld\n(\n", (long long)n);
     for (int64_t i = 0; i < n; ++i) std::fprintf(f, "(%.*g %.*g %.*g)\n", gWritePrecision, a[3 * i], gWritePrecision, a[3 * i + 1], gWritePrecision, a[3 * i + 2]);
     std::fputs(")\n", f);
@@ -570,6 +721,20 @@ void writePositions(const std::string& path, const std::string& location, const 
     FILE* f = openw(path);
     std::fputs(header("Cloud<dsmcParcel>", location, "positions").c_str(), f);
     std::fprintf(f, "%lld\n(\n", (long long)n);
+    if (gWriteBinary) {
+        // IOPosition::writeData + particle::write(os, false): position, cellI, faceI (-1 between steps), stepFraction (0) per particle
+        for (int64_t i = 0; i < n; ++i) {
+            unsigned char rec[40];
+            const int32_t face = -1;
+            const double stepFraction = 0.0;
+            std::memcpy(rec, xyz + 3 * i, 24); std::memcpy(rec + 24, cell + i, 4); std::memcpy(rec + 28, &face, 4); std::memcpy(rec + 32, &stepFraction, 8);
+            block(f, rec, 40);
+            std::fputc('\n', f);
+        }
+        std::fputs(")\n", f);
+        std::fclose(f);
+        return;
+    }
     for (int64_t i = 0; i < n; ++i) std::fprintf(f, "(%.*g %.*g %.*g) %d\n", gWritePrecision, xyz[3 * i], gWritePrecision, xyz[3 * i + 1], gWritePrecision, xyz[3 * i + 2], cell[i]);
     std::fputs(")\n", f);
     std::fclose(f);
@@ -579,6 +744,12 @@ void writeLabelListList(const std::string& path, const std::string& cls, const s
     FILE* f = openw(path);
     std::fputs(header(cls, location, object).c_str(), f);
     std::fprintf(f, "%lld\n(\n", (long long)n);
+    if (gWriteBinary) {
+        for (int64_t i = 0; i < n; ++i) binaryList(f, a + i * width, width, 4);
+        std::fputs("\n)\n", f);
+        std::fclose(f);
+        return;
+    }
     for (int64_t i = 0; i < n; ++i) {
         std::fprintf(f, "%d(", width);
         for (int k = 0; k < width; ++k) std::fprintf(f, k ? " %d" : "%d", a[i * width + k]);
@@ -597,9 +768,15 @@ void writeVolField(const std::string& path, const std::string& location, const s
         if (nCmpt == 1) fmt(f, v[0]);
         else { std::fputc('(', f); for (int d = 0; d < nCmpt; ++d) { if (d) std::fputc(' ', f); fmt(f, v[d]); } std::fputc(')', f); }
     };
-    std::fprintf(f, "internalField   nonuniform List<%s> \n%lld\n(\n", nCmpt == 1 ? "scalar" : (nCmpt == 3 ? "vector" : "tensor"), (long long)nCells);
-    for (int64_t i = 0; i < nCells; ++i) { put(internal + i * nCmpt); std::fputc('\n', f); }
-    std::fputs(")\n;\n\nboundaryField\n{\n", f);
+    if (gWriteBinary) {
+        std::fprintf(f, "internalField   nonuniform List<%s> ", nCmpt == 1 ? "scalar" : (nCmpt == 3 ? "vector" : "tensor"));
+        binaryList(f, internal, nCells, size_t(nCmpt) * 8);
+        std::fputs(";\n\nboundaryField\n{\n", f);
+    } else {
+        std::fprintf(f, "internalField   nonuniform List<%s> \n%lld\n(\n", nCmpt == 1 ? "scalar" : (nCmpt == 3 ? "vector" : "tensor"), (long long)nCells);
+        for (int64_t i = 0; i < nCells; ++i) { put(internal + i * nCmpt); std::fputc('\n', f); }
+        std::fputs(")\n;\n\nboundaryField\n{\n", f);
+    }
     for (auto& p : patches) {
         std::fprintf(f, "    %s\n    {\n", p.name.c_str());
         if (p.type == "empty" || p.type == "cyclic" || p.type == "processor" || p.type == "processorCyclic" || p.type == "symmetryPlane" ||
@@ -610,6 +787,10 @@ void writeVolField(const std::string& path, const std::string& location, const s
             const int64_t nf = int64_t(p.values.size()) / nCmpt;
             if (nf == 0) {
                 std::fputs(nCmpt == 1 ? "        value           uniform 0;\n" : (nCmpt == 3 ? "        value           uniform (0 0 0);\n" : "        value           uniform (0 0 0 0 0 0 0 0 0);\n"), f);
+            } else if (gWriteBinary) {
+                std::fprintf(f, "        value           nonuniform List<%s> ", nCmpt == 1 ? "scalar" : (nCmpt == 3 ? "vector" : "tensor"));
+                binaryList(f, p.values.data(), nf, size_t(nCmpt) * 8);
+                std::fputs(";\n", f);
             } else {
                 std::fprintf(f, "        value           nonuniform List<%s> \n%lld\n(\n", nCmpt == 1 ? "scalar" : (nCmpt == 3 ? "vector" : "tensor"), (long long)nf);
                 for (int64_t i = 0; i < nf; ++i) { put(p.values.data() + i * nCmpt); std::fputc('\n', f); }

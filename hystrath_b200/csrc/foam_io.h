@@ -1,4 +1,4 @@
-// foam_io.h -- reader/writer for the ASCII OpenFOAM files of an unchanged dsmcFoam+ case directory.
+// foam_io.h -- reader/writer for the ASCII and binary OpenFOAM files of an unchanged dsmcFoam+ case directory.
 //
 // The reference reads its configuration through OpenFOAM's IOdictionary / IOField machinery
 // (DSMC/clouds/dsmcCloud.C:597-636, DSMC/parcels/dsmcParcelIO.C:133-450,
@@ -79,7 +79,8 @@ struct BoundaryPatch {
 std::vector<BoundaryPatch> readBoundary(const std::string& path);
 
 // ---- writers ----
-std::string header(const std::string& cls, const std::string& location, const std::string& object);
+std::string header(const std::string& cls, const std::string& location, const std::string& object);       // in the write format
+std::string asciiHeader(const std::string& cls, const std::string& location, const std::string& object);  // for files this driver writes as text in any case
 void writeScalarField(const std::string& path, const std::string& cls, const std::string& location, const std::string& object,
                       const double* a, int64_t n);
 void writeLabelField(const std::string& path, const std::string& cls, const std::string& location, const std::string& object,
@@ -97,6 +98,10 @@ struct PatchValues {
 void writeVolField(const std::string& path, const std::string& location, const std::string& object, const std::string& dimensions,
                    const double* internal, int64_t nCells, int nCmpt, const std::vector<PatchValues>& patches);
 void makeDirs(const std::string& path);
+// controlDict writeFormat binary: every writer above emits `format binary;` files (contiguous lists as their size and the raw bytes in
+// round brackets, BASIC/particle/particleIO.C:121-143, BASIC/IOPosition/IOPosition.C:65-83); the readers take either format from the header
+void setWriteBinary(bool binary);
+bool writeBinary();
 // controlDict writePrecision (IOstream::defaultPrecision): significant digits of every ASCII writer above
 void setWritePrecision(int p);
 int writePrecision();

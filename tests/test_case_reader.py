@@ -244,3 +244,40 @@ def test_driver_parses_the_shipped_axisymmetric_dictionaries(tmp_path):
     open(p, "w").write(txt.replace("coordinateSystem   dsmcAxisymmetric;", "coordinateSystem   dsmcAxisymmetric;\ntimeStepModel variable;"))
     r = subprocess.run([RUN, "-case", str(tmp_path), "-initialise", "-dryRun"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "timeStepModel variable" in r.stdout
+
+
+def test_driver_reads_a_binary_case_like_the_ascii_one(tmp_path):
+    """`writeFormat binary;` cases (BASIC/particle/particleIO.C:121-143, BASIC/IOPosition/IOPosition.C:65-83: a contiguous list is its size and
+    the raw bytes in round brackets, a particle one block of position / cellI / faceI / stepFraction, faces a faceCompactList): the mesh and
+    the cloud the driver reads from the binary files are, byte for byte, those it reads from the ASCII files of the same case; the Python
+    reader agrees."""
+    casegen.couette_case(str(tmp_path))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    ascii_sum = [l for l in r.stdout.splitlines() if "checksum" in l]
+    assert len(ascii_sum) == 1 and "parcels 47583" in r.stdout
+    d = os.path.join(str(tmp_path), "5", "lagrangian", "dsmc")
+    before = {"positions": ff.read_positions(os.path.join(d, "positions")), "U": ff.read_vector_list(os.path.join(d, "U")),
+              "vibLevel": ff.read_label_list_list(os.path.join(d, "vibLevel")), "typeId": ff.read_scalar_list(os.path.join(d, "typeId"), np.int32),
+              "faces": ff.read_faces(os.path.join(str(tmp_path), "constant", "polyMesh", "faces"))}
+    ff.convert_case_to_binary(str(tmp_path), "5")
+    raw = open(os.path.join(d, "positions"), "rb").read()
+    assert b"format      binary;" in raw and len(raw) > 47583 * 43      # '(' 40 bytes ')' newline per particle
+    r2 = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r2.returncode == 0, r2.stderr
+    assert [l for l in r2.stdout.splitlines() if "checksum" in l] == ascii_sum
+    assert "1212 points 2105 faces 895 internal 500 cells 5 patches" in r2.stdout and "parcels 47583" in r2.stdout
+    after = {"positions": ff.read_positions(os.path.join(d, "positions")), "U": ff.read_vector_list(os.path.join(d, "U")),
+             "vibLevel": ff.read_label_list_list(os.path.join(d, "vibLevel")), "typeId": ff.read_scalar_list(os.path.join(d, "typeId"), np.int32),
+             "faces": ff.read_faces(os.path.join(str(tmp_path), "constant", "polyMesh", "faces"))}
+    for k in before:
+        a, b = before[k], after[k]
+        if isinstance(a, tuple):
+            assert all(np.array_equal(x, y) for x, y in zip(a, b)), k
+        else:
+            assert np.array_equal(a, b), k
+    # a truncated block is an error, not a short cloud
+    whole = open(os.path.join(d, "U"), "rb").read()
+    open(os.path.join(d, "U"), "wb").write(whole[:-5000])
+    r3 = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r3.returncode == 1 and "binary block is truncated" in r3.stderr

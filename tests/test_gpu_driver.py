@@ -330,3 +330,46 @@ def test_driver_variable_time_step_on_a_uniform_mesh_equals_the_constant_one(tmp
     g = np.load(casegen.GOLD)
     assert np.allclose(n, float(g["nEquivalentParticles"]), rtol=1e-9) and np.allclose(dt, 1e-5, rtol=1e-9)
     assert not os.path.exists(os.path.join(ta, "nParticles"))
+
+
+def test_driver_binary_case_writes_what_the_ascii_case_writes(tmp_path):
+    """`writeFormat binary;` (Time::writeFormat_; BASIC/particle/particleIO.C:121-143, BASIC/IOPosition/IOPosition.C:65-83): the couette case
+    with binary polyMesh and cloud files runs to the same cloud and volume fields as its ASCII twin written at 17 digits, bit for bit
+    (wall fields to the rounding of their atomic sums), and the driver starts again from the binary time directory it wrote."""
+    a_dir, b_dir = os.path.join(str(tmp_path), "ascii"), os.path.join(str(tmp_path), "binary")
+    for d in (a_dir, b_dir):
+        os.makedirs(d)
+        casegen.couette_case(d, n_steps=4, seed=5, nto=2)
+    for d, old, new in ((a_dir, "writePrecision  10;", "writePrecision  17;"), (b_dir, "writeFormat     ascii;", "writeFormat     binary;")):
+        cd = os.path.join(d, "system", "controlDict")
+        text = open(cd).read()
+        assert old in text
+        open(cd, "w").write(text.replace(old, new))
+    ff.convert_case_to_binary(b_dir, "5")
+    for d in (a_dir, b_dir):
+        r = subprocess.run([RUN, "-case", d], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr + r.stdout
+    ta, tb = os.path.join(a_dir, "5.00004"), os.path.join(b_dir, "5.00004")
+    ca, cb = os.path.join(ta, "lagrangian", "dsmc"), os.path.join(tb, "lagrangian", "dsmc")
+    assert b"format      binary;" in open(os.path.join(cb, "positions"), "rb").read(1200)
+    assert b"format      binary;" in open(os.path.join(tb, "rhoN_mixture"), "rb").read(1200)
+    pa, pb = ff.read_positions(os.path.join(ca, "positions")), ff.read_positions(os.path.join(cb, "positions"))
+    assert len(pa[1]) > 40000 and np.array_equal(pa[0], pb[0]) and np.array_equal(pa[1], pb[1])
+    for name in ("U",):
+        assert np.array_equal(ff.read_vector_list(os.path.join(ca, name)), ff.read_vector_list(os.path.join(cb, name))), name
+    assert np.array_equal(ff.read_scalar_list(os.path.join(ca, "ERot")), ff.read_scalar_list(os.path.join(cb, "ERot")))
+    for name in ("typeId", "origId", "classification", "newParcel"):
+        assert np.array_equal(ff.read_scalar_list(os.path.join(ca, name), np.int32), ff.read_scalar_list(os.path.join(cb, name), np.int32)), name
+    assert np.array_equal(ff.read_label_list_list(os.path.join(ca, "vibLevel")), ff.read_label_list_list(os.path.join(cb, "vibLevel")))
+    for name in ("rhoN_mixture", "Ttra_mixture", "U_mixture", "p_N2", "dsmcSigmaTcRMax"):
+        fa, fb = ff.read_internal_field(os.path.join(ta, name)), ff.read_internal_field(os.path.join(tb, name))
+        assert fa.shape == fb.shape and np.array_equal(fa, fb), name
+    for name in ("wallHeatFlux_mixture", "wallShearStress_mixture", "fD_mixture"):
+        fa, fb = ff.read_patch_field(os.path.join(ta, name), "upperWall"), ff.read_patch_field(os.path.join(tb, name), "upperWall")
+        # wall faces sum their hits with FP64 atomics: the order, and with it the last bits, differ from run to run
+        assert fa.shape == fb.shape and np.abs(fa).max() > 0 and np.allclose(fa, fb, rtol=1e-11, atol=0), name
+    # latestTime is now the binary directory: the driver reads back what it wrote
+    r = subprocess.run([RUN, "-case", b_dir, "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "startTime 5.00004" in r.stdout and f"parcels {len(pb[1])}" in r.stdout, r.stdout + r.stderr
+    ra = subprocess.run([RUN, "-case", a_dir, "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert [l for l in r.stdout.splitlines() if "checksum" in l] == [l for l in ra.stdout.splitlines() if "checksum" in l]
