@@ -121,23 +121,38 @@ cudaError_t launchHistogram(const int32_t* cell, int32_t n, int32_t* cellCount, 
 
 // Warp-aggregated: the cloud enters cell-sorted and most parcels stay in their cell, so the 32 lanes of a warp fall into a handful
 // of cells; the lanes of one cell send ONE atomic for the whole group and take consecutive slots in lane order.
-__global__ void scatterIndexKernel(const int32_t* __restrict__ cell, int32_t n, int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
-    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+namespace {
+constexpr int SCATTER_PER_THREAD = 4;   // independent elements per thread: four reads, then four atomics in flight
+}
+__global__ void __launch_bounds__(256) scatterIndexKernel(const int32_t* __restrict__ cell, int32_t n, int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
+    const int32_t i0 = blockIdx.x * (256 * SCATTER_PER_THREAD) + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const int32_t c = i < n ? cell[i] : -1;
-    const unsigned live = __ballot_sync(0xffffffffu, c >= 0);
-    if (c < 0) return;
-    const unsigned peers = __match_any_sync(live, c);
-    const int leader = __ffs(peers) - 1;
-    int32_t base = 0;
-    if (lane == leader) base = atomicAdd(&cursor[c], __popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    perm[base + __popc(peers & ((1u << lane) - 1u))] = i;
+    int32_t c[SCATTER_PER_THREAD], base[SCATTER_PER_THREAD];
+    unsigned peers[SCATTER_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < SCATTER_PER_THREAD; ++k) { const int32_t i = i0 + 256 * k; c[k] = i < n ? cell[i] : -1; }
+#pragma unroll
+    for (int k = 0; k < SCATTER_PER_THREAD; ++k) {
+        const unsigned live = __ballot_sync(0xffffffffu, c[k] >= 0);
+        peers[k] = 0u; base[k] = 0;
+        if (c[k] >= 0) {
+            peers[k] = __match_any_sync(live, c[k]);
+            if (lane == __ffs(peers[k]) - 1) base[k] = atomicAdd(&cursor[c[k]], __popc(peers[k]));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SCATTER_PER_THREAD; ++k) {
+        if (c[k] >= 0) {
+            const int32_t b = __shfl_sync(peers[k], base[k], __ffs(peers[k]) - 1);
+            perm[b + __popc(peers[k] & ((1u << lane) - 1u))] = i0 + 256 * k;
+        }
+    }
 }
 
 cudaError_t launchScatterIndex(const int32_t* cell, int32_t n, int32_t* cursor, int32_t* perm, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    scatterIndexKernel<<<(n + 255) / 256, 256, 0, s>>>(cell, n, cursor, perm);
+    const int per = 256 * SCATTER_PER_THREAD;
+    scatterIndexKernel<<<(n + per - 1) / per, 256, 0, s>>>(cell, n, cursor, perm);
     return cudaGetLastError();
 }
 
@@ -146,39 +161,59 @@ cudaError_t launchScatterIndex(const int32_t* cell, int32_t n, int32_t* cursor, 
 namespace {
 constexpr int SEG_WARPS = 8;
 constexpr int SEG_SMEM = 1024;  // per warp
+constexpr int SEG_CELLS = 4;    // cells a warp works on at a time
 }
 
 __global__ void __launch_bounds__(SEG_WARPS * 32) segmentSortKernel(const int32_t* __restrict__ cellOffset, int32_t nCells,
                                                                     int32_t* __restrict__ perm, DevCounters* counters, int32_t* __restrict__ bigList) {
-    __shared__ int32_t sm[SEG_WARPS][SEG_SMEM];
+    __shared__ __align__(16) int32_t sm[SEG_WARPS][SEG_SMEM + 32 * SEG_CELLS];   // rank-sort buffer of a medium cell | one row of 32 per small cell
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int32_t nWarps = gridDim.x * SEG_WARPS;
-    for (int32_t c = blockIdx.x * SEG_WARPS + w; c < nCells; c += nWarps) {
-        const int32_t b = cellOffset[c], n = cellOffset[c + 1] - b;
-        if (n <= 1) continue;
-        if (n <= 32) {
-            const int32_t v = lane < n ? perm[b + lane] : 0x7fffffff;
-            int rank = 0;
+    // a warp takes SEG_CELLS consecutive cells at a time: their offsets are one read and their index lists are requested together, so a
+    // cell costs a quarter of the two dependent round trips it would cost alone
+    for (int32_t c0 = (blockIdx.x * SEG_WARPS + w) * SEG_CELLS; c0 < nCells; c0 += nWarps * SEG_CELLS) {
+        const int32_t off = (lane <= SEG_CELLS && c0 + lane <= nCells) ? cellOffset[c0 + lane] : 0;
+        int32_t b[SEG_CELLS], n[SEG_CELLS], v[SEG_CELLS];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int32_t o = __shfl_sync(0xffffffffu, v, j);
-                rank += (o < v) ? 1 : 0;
-            }
-            if (lane < n) perm[b + rank] = v;
-        } else if (n <= SEG_SMEM) {
-            for (int k = lane; k < n; k += 32) sm[w][k] = perm[b + k];
-            __syncwarp();
-            for (int k = lane; k < n; k += 32) {
-                const int32_t v = sm[w][k];
-                int rank = 0;
-                for (int j = 0; j < n; ++j) rank += (sm[w][j] < v) ? 1 : 0;
-                perm[b + rank] = v;
-            }
-            __syncwarp();
-        } else {
-            // very large cells (a heat bath in one cell: 1e5 parcels) go to bigSegmentSortKernel, one block each
-            if (lane == 0) bigList[atomicAdd(&counters->bigSortCells, 1)] = c;
+        for (int k = 0; k < SEG_CELLS; ++k) {
+            b[k] = __shfl_sync(0xffffffffu, off, k);
+            const int32_t e = __shfl_sync(0xffffffffu, off, k + 1);
+            n[k] = c0 + k < nCells ? e - b[k] : 0;
         }
+#pragma unroll
+        for (int k = 0; k < SEG_CELLS; ++k) v[k] = (n[k] > 1 && n[k] <= 32 && lane < n[k]) ? perm[b[k] + lane] : 0x7fffffff;
+        // every lane compares its index with the 32 of its cell: eight broadcast 16-byte reads of shared memory instead of 32 shuffles
+#pragma unroll
+        for (int k = 0; k < SEG_CELLS; ++k) sm[w][SEG_SMEM + 32 * k + lane] = v[k];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < SEG_CELLS; ++k) {
+            if (n[k] <= 1) continue;
+            if (n[k] <= 32) {
+                int rank = 0;
+                const int4* const row = reinterpret_cast<const int4*>(&sm[w][SEG_SMEM + 32 * k]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int4 o = row[j];
+                    rank += (o.x < v[k] ? 1 : 0) + (o.y < v[k] ? 1 : 0) + (o.z < v[k] ? 1 : 0) + (o.w < v[k] ? 1 : 0);
+                }
+                if (lane < n[k]) perm[b[k] + rank] = v[k];
+            } else if (n[k] <= SEG_SMEM) {
+                for (int i = lane; i < n[k]; i += 32) sm[w][i] = perm[b[k] + i];
+                __syncwarp();
+                for (int i = lane; i < n[k]; i += 32) {
+                    const int32_t x = sm[w][i];
+                    int rank = 0;
+                    for (int j = 0; j < n[k]; ++j) rank += (sm[w][j] < x) ? 1 : 0;
+                    perm[b[k] + rank] = x;
+                }
+                __syncwarp();
+            } else {
+                // very large cells (a heat bath in one cell: 1e5 parcels) go to bigSegmentSortKernel, one block each
+                if (lane == 0) bigList[atomicAdd(&counters->bigSortCells, 1)] = c0 + k;
+            }
+        }
+        __syncwarp();   // the rows are rewritten by the next group of cells
     }
 }
 
@@ -266,7 +301,7 @@ cudaError_t launchGiantSort(const int32_t* cellOffset, int32_t* perm, const int3
 
 // bigList: nCells ints of scratch (the scatter cursors are free by now)
 cudaError_t launchSegmentSort(const int32_t* cellOffset, int32_t nCells, int32_t* perm, DevCounters* c, int32_t* bigList, int32_t* giantList, cudaStream_t s) {
-    int grid = (nCells + SEG_WARPS - 1) / SEG_WARPS;
+    int grid = (nCells + SEG_WARPS * SEG_CELLS - 1) / (SEG_WARPS * SEG_CELLS);
     if (grid > 148 * 16) grid = 148 * 16;
     if (grid < 1) grid = 1;
     cudaMemsetAsync(&c->bigSortCells, 0, 2 * sizeof(int32_t), s);   // bigSortCells, giantSortCells
