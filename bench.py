@@ -196,12 +196,14 @@ def workload_config(args, cells_per_gpu, parcels_per_gpu):
                 "l2_policy": "the whole cloud (1 M parcels, 100 MB with both buffers) fits the 126 MB L2: L2-resident by nature of the case, no flush"}
     return {"workload": "weak-scaling periodic box (BASELINE configs[4]), %s, %d cells and ~%d parcels per GPU, %s" % (
         "argon VHS" if args.gas == "argon" else "5-species air (N2,O2,NO,N,O) Larsen-Borgnakke VHS", cells_per_gpu, parcels_per_gpu,
-        "blockMesh cell order" if getattr(args, "numbering", "morton") == "blockMesh" else "cells renumbered along a z-order curve (renumberMesh equivalent)"),
+        {"blockMesh": "blockMesh cell order", "engine": "blockMesh cell order, relabelled along a z-order curve inside the library (dsmcb200_set_cell_order)"}.get(
+            getattr(args, "numbering", "morton"), "cells renumbered along a z-order curve (renumberMesh equivalent)")),
         "cells_per_gpu": cells_per_gpu, "parcels_per_gpu": parcels_per_gpu, "parcels_per_cell": args.ppc, "gas": args.gas,
         "collision_model": "VariableHardSphere" if args.gas == "argon" else "LarsenBorgnakkeVariableHardSphere",
         "partition": "x".join(str(v) for v in procs_for(args.gpus)) + " bricks",
-        "cell_numbering": "blockMesh order (x fastest)" if getattr(args, "numbering", "morton") == "blockMesh"
-                          else "cells relabelled along a z-order curve (renumberMesh equivalent)",
+        "cell_numbering": {"blockMesh": "blockMesh order (x fastest)",
+                           "engine": "blockMesh order (x fastest); the library relabels along a z-order curve (dsmcb200_set_cell_order)"}.get(
+                               getattr(args, "numbering", "morton"), "cells relabelled along a z-order curve (renumberMesh equivalent)"),
         "l2_policy": "inputs larger than L2 (parcel state >> 126 MB per GPU), no flush needed"}
 
 
@@ -385,8 +387,8 @@ def main():
     ap.add_argument("--gas", default=os.environ.get("DSMCB200_BENCH_GAS", "air5"), choices=["argon", "air5"])
     ap.add_argument("--cells", type=int, default=int(os.environ.get("DSMCB200_BENCH_CELLS", "200")), help="cells per direction per GPU")
     ap.add_argument("--ppc", type=int, default=31)
-    ap.add_argument("--numbering", default=os.environ.get("DSMCB200_BENCH_NUMBERING", "morton"), choices=["blockMesh", "morton"],
-                    help="cell labels of the box: blockMesh's x-fastest order, or relabelled along a z-order curve (meshgen.renumber_cells, a renumberMesh equivalent)")
+    ap.add_argument("--numbering", default=os.environ.get("DSMCB200_BENCH_NUMBERING", "morton"), choices=["blockMesh", "morton", "engine"],
+                    help="cell labels of the box: blockMesh's x-fastest order, or relabelled along a z-order curve (meshgen.renumber_cells, a renumberMesh equivalent), or blockMesh's order relabelled by the library itself (engine)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-cells", type=int, default=32)
     ap.add_argument("--cpu-steps", type=int, default=5)
@@ -465,6 +467,8 @@ def main():
         dens, Tfill, vfill = [cp["n"] * f for f in frac], cp["T"], (0.0, 0.0, 0.0)
         n_cells_gpu = args.cells ** 3
     eng = capi.Engine(local, rank, world)
+    if args.numbering == "engine":      # the mesh keeps blockMesh's labels, the library relabels its cells itself (dsmcb200_set_cell_order)
+        eng.set_cell_order("z-curve")
     eng.set_mesh(mesh); eng.set_species(sp); eng.set_models(md)
     if world > 1:
         ident = torch.zeros(128, dtype=torch.uint8, device="cuda")

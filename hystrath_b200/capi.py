@@ -331,6 +331,8 @@ def load_library():
         "dsmcb200_stage": ([P, C.c_int], C.c_int),
         "dsmcb200_set_step": ([P, C.c_uint32], C.c_int),
         "dsmcb200_download_occupancy": ([P, C.c_void_p], C.c_int),
+        "dsmcb200_set_cell_order": ([P, C.c_int, C.c_void_p, C.c_int32], C.c_int),
+        "dsmcb200_download_cell_order": ([P, C.c_void_p], C.c_int),
         "dsmcb200_accum_info_get": ([P, C.POINTER(AccumInfo)], C.c_int),
         "dsmcb200_download_accumulators": ([P, C.c_void_p, C.c_void_p], C.c_int),
         "dsmcb200_upload_accumulators": ([P, C.c_void_p, C.c_void_p, C.c_double], C.c_int),
@@ -363,6 +365,7 @@ EXPORTED_SYMBOLS = [
     "dsmcb200_reaction_counts", "dsmcb200_set_cell_fields", "dsmcb200_download_cell_fields", "dsmcb200_reserve",
     "dsmcb200_upload_parcels", "dsmcb200_download_parcels", "dsmcb200_upload_cellstate", "dsmcb200_download_cellstate",
     "dsmcb200_mesh_fill", "dsmcb200_evolve", "dsmcb200_stage", "dsmcb200_set_step", "dsmcb200_download_occupancy",
+    "dsmcb200_set_cell_order", "dsmcb200_download_cell_order",
     "dsmcb200_accum_info_get", "dsmcb200_download_accumulators", "dsmcb200_upload_accumulators",
     "dsmcb200_reset_accumulators", "dsmcb200_wall_info", "dsmcb200_download_wall_accumulators",
     "dsmcb200_upload_wall_accumulators", "dsmcb200_download_face_fluxes", "dsmcb200_upload_overall_temperature", "dsmcb200_get_counters",
@@ -529,6 +532,22 @@ class Engine:
     def _ck(self, rc):
         if rc != 0:
             raise Dsmcb200Error(f"dsmcb200 error {rc}: {self.lib.dsmcb200_last_error(self.h).decode()}")
+
+    CELL_ORDER = {"as-given": 0, "z-curve": 1, "given": 2}
+
+    def set_cell_order(self, mode="z-curve", new_of_old=None):
+        """Cell labels inside the engine (dsmcb200_set_cell_order; before set_mesh): "as-given", "z-curve" or "given" with a table."""
+        if new_of_old is not None:
+            t = np.ascontiguousarray(new_of_old, dtype=np.int32)
+            self._ck(self.lib.dsmcb200_set_cell_order(self.h, self.CELL_ORDER["given"], _ptr(t), len(t)))
+        else:
+            self._ck(self.lib.dsmcb200_set_cell_order(self.h, self.CELL_ORDER[mode], None, 0))
+
+    def cell_order(self):
+        """new_of_old: the engine's label of the caller's cell k."""
+        t = np.zeros(self._mesh.n_cells, np.int32)
+        self._ck(self.lib.dsmcb200_download_cell_order(self.h, _ptr(t)))
+        return t
 
     def set_mesh(self, mesh: MeshData):
         self._mesh = mesh

@@ -13,6 +13,11 @@
 
 namespace dsmcb200 {
 
+namespace {
+int gCellOrder = DSMCB200_CELL_ORDER_AS_GIVEN;
+}
+void dsmcCloud::cellOrder(int mode) { gCellOrder = mode; }
+
 using foam::Dict;
 using foam::FoamError;
 
@@ -119,6 +124,7 @@ dsmcCloud::dsmcCloud(const std::string& caseDir, const std::string& cloudName, i
     m.nPatches = int32_t(patches_.size());
     m.points = points_.data(); m.faceOffsets = faceOffsets_.data(); m.facePoints = facePoints_.data();
     m.owner = owner_.data(); m.neighbour = neighbour_.data(); m.patches = patches_.data();
+    if (gCellOrder != DSMCB200_CELL_ORDER_AS_GIVEN) check(dsmcb200_set_cell_order(ctx_, gCellOrder, nullptr, 0), "dsmcb200_set_cell_order");
     check(dsmcb200_set_mesh(ctx_, &m), "dsmcb200_set_mesh");
     check(dsmcb200_set_species(ctx_, int(species_.size()), species_.data()), "dsmcb200_set_species");
     if (!reactions_.empty()) check(dsmcb200_set_reactions(ctx_, int(reactions_.size()), reactions_.data()), "dsmcb200_set_reactions");

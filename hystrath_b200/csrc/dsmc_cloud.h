@@ -58,6 +58,8 @@ class dsmcCloud {
     dsmcCloud(const std::string& caseDir, const std::string& cloudName = "dsmc", int rank = 0, int nRanks = 1, int device = 0,
               const void* ncclId128 = nullptr, bool dryRun = false, bool initialise = false);
     ~dsmcCloud();
+    // cell labels inside the engine for clouds constructed from now on (dsmcb200_set_cell_order; the case files keep their labels)
+    static void cellOrder(int mode);
     dsmcCloud(const dsmcCloud&) = delete;
 
     void evolve();                 // dsmcCloud::evolve(): one time step

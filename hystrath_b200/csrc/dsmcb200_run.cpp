@@ -36,8 +36,9 @@ int main(int argc, char** argv) {
         else if (!std::strcmp(argv[i], "-device") && i + 1 < argc) device = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "-dryRun")) dryRun = true;
         else if (!std::strcmp(argv[i], "-initialise")) initialise = true;
+        else if (!std::strcmp(argv[i], "-renumberCells")) dsmcb200::dsmcCloud::cellOrder(DSMCB200_CELL_ORDER_Z_CURVE);   // renumberMesh in memory: the files keep their labels
         else if (!std::strcmp(argv[i], "-AMR")) { std::fprintf(stderr, "-AMR (dynamic mesh refinement) is outside the scoped path\n"); return 2; }
-        else { std::fprintf(stderr, "usage: dsmcb200_run [-initialise] -case <dir> [-parallel] [-device N]\n"); return 2; }
+        else { std::fprintf(stderr, "usage: dsmcb200_run [-initialise] -case <dir> [-parallel] [-device N] [-renumberCells]\n"); return 2; }
     }
     int rank = 0, nRanks = 1;
     if (parallel) {

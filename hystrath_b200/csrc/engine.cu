@@ -87,6 +87,13 @@ __global__ void i32ToU8(const int32_t* in, uint8_t* out, int32_t n) {
     if (i < n) out[i] = uint8_t(in[i]);
 }
 // the same with a range check: values outside [0, limit) raise *bad (typeId against typeIdList, dsmcParcelI.H constProps lookup)
+// cell labels through a table (dsmcb200_set_cell_order); labels outside the mesh stay as they are for the checks that follow
+__global__ void mapLabels(const int32_t* in, int32_t* out, const int32_t* __restrict__ table, int32_t n, int32_t nCells) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t v = in[i];
+    out[i] = (v >= 0 && v < nCells) ? table[v] : v;
+}
 __global__ void i32ToU8Checked(const int32_t* in, uint8_t* out, int32_t n, int32_t limit, int* bad) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -169,6 +176,10 @@ struct dsmcb200_ctx {
     int32_t bornCap = 0;
     // per-cell nParticles (time-step model), deltaT and radial weighting factor (dsmcb200_set_cell_fields); empty / nullptr = uniform
     std::vector<double> hNPts, hDt, hRWF;
+    // dsmcb200_set_cell_order: the engine's label of the caller's cell k is newOfOld[k] (empty: the caller's labels are used as they are)
+    int cellOrderMode = DSMCB200_CELL_ORDER_AS_GIVEN;
+    std::vector<int32_t> newOfOld, oldOfNew, userOrder;
+    int32_t *dNewOfOld = nullptr, *dOldOfNew = nullptr;
     double *dNPts = nullptr, *dDt = nullptr, *dRWF = nullptr;
     bool useRwf = false;           // dsmcAxisymmetric: parcels carry a radial weight
     int32_t* dWeightCounts = nullptr; int64_t weightCountsCap = 0;
@@ -370,6 +381,28 @@ int ensureSfTail(dsmcb200_ctx* c, int64_t n) {
     return 0;
 }
 
+// Per-cell rows between the caller's cell labels and the engine's (dsmcb200_set_cell_order).  Identity order: a plain copy.
+cudaError_t cellRowsToDevice(dsmcb200_ctx* c, void* dev, const void* user, size_t rowBytes) {
+    const size_t nC = size_t(c->mesh.nCells);
+    if (c->newOfOld.empty()) return cudaMemcpy(dev, user, nC * rowBytes, cudaMemcpyHostToDevice);
+    std::vector<char> tmp(nC * rowBytes);
+    const char* u = static_cast<const char*>(user);
+#pragma omp parallel for schedule(static) num_threads(hostThreads(c))
+    for (int64_t k = 0; k < int64_t(nC); ++k) std::memcpy(&tmp[size_t(c->newOfOld[k]) * rowBytes], u + size_t(k) * rowBytes, rowBytes);
+    return cudaMemcpy(dev, tmp.data(), nC * rowBytes, cudaMemcpyHostToDevice);
+}
+cudaError_t cellRowsToHost(dsmcb200_ctx* c, void* user, const void* dev, size_t rowBytes) {
+    const size_t nC = size_t(c->mesh.nCells);
+    if (c->newOfOld.empty()) return cudaMemcpy(user, dev, nC * rowBytes, cudaMemcpyDeviceToHost);
+    std::vector<char> tmp(nC * rowBytes);
+    cudaError_t e = cudaMemcpy(tmp.data(), dev, nC * rowBytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return e;
+    char* u = static_cast<char*>(user);
+#pragma omp parallel for schedule(static) num_threads(hostThreads(c))
+    for (int64_t k = 0; k < int64_t(nC); ++k) std::memcpy(u + size_t(k) * rowBytes, &tmp[size_t(c->newOfOld[k]) * rowBytes], rowBytes);
+    return cudaSuccess;
+}
+
 int uploadCellFields(dsmcb200_ctx* c) {
     const size_t nC = size_t(c->mesh.nCells);
     struct { std::vector<double>* h; double** d; } f[3] = {{&c->hNPts, &c->dNPts}, {&c->hDt, &c->dDt}, {&c->hRWF, &c->dRWF}};
@@ -377,7 +410,8 @@ int uploadCellFields(dsmcb200_ctx* c) {
         devFree(*x.d);
         if (x.h->empty()) continue;
         if (x.h->size() != nC) return fail(c, DSMCB200_ERR_INVALID, "set_cell_fields: array size differs from the number of cells");
-        CK(upload(x.d, *x.h));
+        if (c->newOfOld.empty()) { CK(upload(x.d, *x.h)); }
+        else { CK(devAlloc(x.d, nC)); CK(cellRowsToDevice(c, *x.d, x.h->data(), 8)); }
     }
     return 0;
 }
@@ -660,6 +694,7 @@ int finalize(dsmcb200_ctx* c) {
         CK(upload(&c->dFaceOffsets, M.faceOffsets));
         CK(upload(&c->dFacePoints, M.facePoints));
         CK(upload(&c->dOwner, M.owner));
+        if (!c->newOfOld.empty()) { CK(upload(&c->dNewOfOld, c->newOfOld)); CK(upload(&c->dOldOfNew, c->oldOfNew)); }
         CK(upload(&c->dNeighbour, M.neighbour));
         CK(upload(&c->dTetBasePtIs, M.tetBasePtIs));
         CK(upload(&c->dFaceTet0, M.faceTet0));
@@ -1107,6 +1142,7 @@ void dsmcb200_destroy(dsmcb200_ctx* c) {
     if (c->dMigTemp) cudaFree(c->dMigTemp); devFree(c->dOrdinalToPatch); devFree(c->dCountsMatrix);
     devFree(c->dBorn); devFree(c->dBornKeys); devFree(c->dBornIdx); if (c->dBornTemp) cudaFree(c->dBornTemp);
     devFree(c->dNPts); devFree(c->dDt); devFree(c->dRWF); devFree(c->dWeightCounts); devFree(c->dGiantBitmap); devFree(c->dGiantList);
+    devFree(c->dNewOfOld); devFree(c->dOldOfNew);
     for (auto& p : c->dInflowAcc) devFree(p);
     for (auto& p : c->dInflowCounts) devFree(p);
     for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);
@@ -1139,9 +1175,109 @@ int dsmcb200_init_comm(dsmcb200_ctx* c, const void* id128) {
 int dsmcb200_set_mesh(dsmcb200_ctx* c, const dsmcb200_mesh* m) {
     if (!c || !m) return DSMCB200_ERR_INVALID;
     if (c->ready) return fail(c, DSMCB200_ERR_STATE, "mesh cannot change after the engine has been finalised");
-    std::string e = c->mesh.build(*m);
+    c->newOfOld.clear(); c->oldOfNew.clear();
+    if (c->cellOrderMode == DSMCB200_CELL_ORDER_AS_GIVEN) {
+        std::string e = c->mesh.build(*m);
+        if (!e.empty()) return fail(c, DSMCB200_ERR_INVALID, e);
+        c->haveMesh = true;
+        return 0;
+    }
+    // The engine works on the same polyMesh with its cells relabelled (owner / neighbour entries only: faces, points, patches and the
+    // face lists of every cell stay as they are), so that neighbours in space are neighbours in memory; every entry point that takes
+    // or returns cell labels or per-cell rows translates (what renumberMesh would do to the case files, without touching them).
+    const int32_t nC = m->nCells;
+    if (nC < 0 || m->nFaces < 0 || (m->nFaces && (!m->owner || !m->faceOffsets || !m->facePoints || !m->points)))
+        return fail(c, DSMCB200_ERR_INVALID, "set_mesh: incomplete mesh");
+    std::vector<int32_t> newOfOld(size_t(nC), 0);
+    if (c->cellOrderMode == DSMCB200_CELL_ORDER_GIVEN) {
+        if (c->userOrder.size() != size_t(nC)) return fail(c, DSMCB200_ERR_INVALID, "set_cell_order: the permutation has not the mesh's number of cells");
+        newOfOld = c->userOrder;
+    } else {
+        // z-order curve through the cell centres (the caller's, or the mean of the face-point means of the cell's faces), 2^10 per direction
+        std::vector<double> cc(size_t(nC) * 3, 0.0);
+        if (m->cellCentres) cc.assign(m->cellCentres, m->cellCentres + size_t(nC) * 3);
+        else {
+            std::vector<double> cnt(size_t(nC), 0.0);
+            for (int32_t f = 0; f < m->nFaces; ++f) {
+                double fc[3] = {0, 0, 0};
+                const int32_t b = m->faceOffsets[f], e = m->faceOffsets[f + 1];
+                for (int32_t k = b; k < e; ++k) for (int d = 0; d < 3; ++d) fc[d] += m->points[3 * size_t(m->facePoints[k]) + d];
+                for (int d = 0; d < 3; ++d) fc[d] /= double(std::max(1, e - b));
+                const int32_t o = m->owner[f], nb = f < m->nInternalFaces ? m->neighbour[f] : -1;
+                if (o < 0 || o >= nC || nb >= nC) return fail(c, DSMCB200_ERR_INVALID, "set_mesh: owner / neighbour out of range");
+                for (int d = 0; d < 3; ++d) cc[3 * size_t(o) + d] += fc[d];
+                cnt[o] += 1.0;
+                if (nb >= 0) { for (int d = 0; d < 3; ++d) cc[3 * size_t(nb) + d] += fc[d]; cnt[nb] += 1.0; }
+            }
+            for (int32_t k = 0; k < nC; ++k) for (int d = 0; d < 3; ++d) cc[3 * size_t(k) + d] /= std::max(1.0, cnt[k]);
+        }
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int32_t k = 0; k < nC; ++k) for (int d = 0; d < 3; ++d) { lo[d] = std::min(lo[d], cc[3 * size_t(k) + d]); hi[d] = std::max(hi[d], cc[3 * size_t(k) + d]); }
+        double span = 0.0;
+        for (int d = 0; d < 3; ++d) span = std::max(span, hi[d] - lo[d]);
+        const double scale = span > 0 ? 1023.0 / span : 0.0;   // one scale for the three directions: the curve's bricks are cubes
+        std::vector<std::pair<uint32_t, int32_t>> key(static_cast<size_t>(nC));
+        for (int32_t k = 0; k < nC; ++k) {
+            uint32_t q[3], z = 0;
+            for (int d = 0; d < 3; ++d) q[d] = uint32_t(std::min(1023.0, std::max(0.0, std::floor((cc[3 * size_t(k) + d] - lo[d]) * scale))));
+            for (int b = 0; b < 10; ++b) for (int d = 0; d < 3; ++d) z |= ((q[d] >> b) & 1u) << (3 * b + d);
+            key[k] = {z, k};
+        }
+        std::sort(key.begin(), key.end());   // ties keep the caller's order (the label is the second key)
+        for (int32_t r = 0; r < nC; ++r) newOfOld[key[r].second] = r;
+    }
+    std::vector<int32_t> oldOfNew(size_t(nC), -1);
+    for (int32_t k = 0; k < nC; ++k) {
+        const int32_t r = newOfOld[k];
+        if (r < 0 || r >= nC || oldOfNew[r] >= 0) return fail(c, DSMCB200_ERR_INVALID, "set_cell_order: not a permutation of the cell labels");
+        oldOfNew[r] = k;
+    }
+    dsmcb200_mesh mm = *m;
+    std::vector<int32_t> owner(static_cast<size_t>(m->nFaces)), neighbour(static_cast<size_t>(m->nInternalFaces));
+    for (int32_t f = 0; f < m->nFaces; ++f) {
+        if (m->owner[f] < 0 || m->owner[f] >= nC) return fail(c, DSMCB200_ERR_INVALID, "set_mesh: owner out of range");
+        owner[f] = newOfOld[m->owner[f]];
+    }
+    for (int32_t f = 0; f < m->nInternalFaces; ++f) {
+        if (m->neighbour[f] < 0 || m->neighbour[f] >= nC) return fail(c, DSMCB200_ERR_INVALID, "set_mesh: neighbour out of range");
+        neighbour[f] = newOfOld[m->neighbour[f]];
+    }
+    mm.owner = owner.data(); mm.neighbour = neighbour.data();
+    std::vector<double> centres, volumes;
+    if (m->cellCentres) {
+        centres.resize(size_t(nC) * 3);
+        for (int32_t k = 0; k < nC; ++k) for (int d = 0; d < 3; ++d) centres[3 * size_t(newOfOld[k]) + d] = m->cellCentres[3 * size_t(k) + d];
+        mm.cellCentres = centres.data();
+    }
+    if (m->cellVolumes) {
+        volumes.resize(static_cast<size_t>(nC));
+        for (int32_t k = 0; k < nC; ++k) volumes[newOfOld[k]] = m->cellVolumes[k];
+        mm.cellVolumes = volumes.data();
+    }
+    std::string e = c->mesh.build(mm);
     if (!e.empty()) return fail(c, DSMCB200_ERR_INVALID, e);
+    c->newOfOld.swap(newOfOld); c->oldOfNew.swap(oldOfNew);
     c->haveMesh = true;
+    return 0;
+}
+
+int dsmcb200_set_cell_order(dsmcb200_ctx* c, int mode, const int32_t* newOfOld, int32_t nCells) {
+    if (!c) return DSMCB200_ERR_INVALID;
+    if (c->haveMesh) return fail(c, DSMCB200_ERR_STATE, "set_cell_order: call it before set_mesh");
+    if (mode != DSMCB200_CELL_ORDER_AS_GIVEN && mode != DSMCB200_CELL_ORDER_Z_CURVE && mode != DSMCB200_CELL_ORDER_GIVEN)
+        return fail(c, DSMCB200_ERR_INVALID, "set_cell_order: unknown mode");
+    if (mode == DSMCB200_CELL_ORDER_GIVEN) {
+        if (!newOfOld || nCells < 0) return fail(c, DSMCB200_ERR_INVALID, "set_cell_order: a permutation is required");
+        c->userOrder.assign(newOfOld, newOfOld + nCells);
+    } else c->userOrder.clear();
+    c->cellOrderMode = mode;
+    return 0;
+}
+
+int dsmcb200_download_cell_order(dsmcb200_ctx* c, int32_t* newOfOld) {
+    if (!c || !newOfOld) return DSMCB200_ERR_INVALID;
+    if (!c->haveMesh) return fail(c, DSMCB200_ERR_STATE, "download_cell_order: call set_mesh first");
+    for (int32_t k = 0; k < c->mesh.nCells; ++k) newOfOld[k] = c->newOfOld.empty() ? k : c->newOfOld[k];
     return 0;
 }
 
@@ -1246,6 +1382,7 @@ int dsmcb200_upload_parcels(dsmcb200_ctx* c, int64_t n, const dsmcb200_parcels_s
     CK(cudaMemcpyAsync(st.dslab, h->U, size_t(n) * 24, cudaMemcpyHostToDevice, s));
     deinterleave3<<<GRID(n), 0, s>>>(st.dslab, a.ux, a.uy, a.uz, n32);
     CK(cudaMemcpyAsync(a.cell, h->cell, size_t(n) * 4, cudaMemcpyHostToDevice, s));
+    if (c->dNewOfOld) mapLabels<<<GRID(n), 0, s>>>(a.cell, a.cell, c->dNewOfOld, n32, c->mesh.nCells);   // the caller's cell labels -> the engine's
     int32_t* sf = st.islab;                 // staging rows
     int32_t* sp2 = st.islab + c->capacity;
     CK(cudaMemsetAsync(c->dBad, 0, 4, s));
@@ -1334,8 +1471,11 @@ int dsmcb200_download_parcels(dsmcb200_ctx* c, int64_t capacity, int64_t* nOut, 
     cudaStream_t s = c->stream;
     if (h->position) { interleave3<<<GRID(n), 0, s>>>(a.px, a.py, a.pz, st.dslab, n32); CK(cudaMemcpyAsync(h->position, st.dslab, size_t(n) * 24, cudaMemcpyDeviceToHost, s)); }
     if (h->U) { interleave3<<<GRID(n), 0, s>>>(a.ux, a.uy, a.uz, st.dslab + 3 * c->capacity, n32); CK(cudaMemcpyAsync(h->U, st.dslab + 3 * c->capacity, size_t(n) * 24, cudaMemcpyDeviceToHost, s)); }
-    if (h->cell) CK(cudaMemcpyAsync(h->cell, a.cell, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
     int32_t* r0 = st.islab; int32_t* r1 = st.islab + c->capacity; int32_t* r2 = r1 + c->capacity; int32_t* r3 = r2 + c->capacity; int32_t* r4 = r3 + c->capacity;
+    if (h->cell) {
+        if (c->dOldOfNew) { mapLabels<<<GRID(n), 0, s>>>(a.cell, r0, c->dOldOfNew, n32, c->mesh.nCells); CK(cudaMemcpyAsync(h->cell, r0, size_t(n) * 4, cudaMemcpyDeviceToHost, s)); }
+        else CK(cudaMemcpyAsync(h->cell, a.cell, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+    }
     if (h->tetFace || h->tetPt) {
         fromTetId<<<GRID(n), 0, s>>>(a.tet, c->dTets, r0, r1, n32);
         if (h->tetFace) CK(cudaMemcpyAsync(h->tetFace, r0, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
@@ -1383,8 +1523,9 @@ int dsmcb200_upload_cellstate(dsmcb200_ctx* c, const double* sigma, const double
     cudaSetDevice(c->device);
     { int r = finalize(c); if (r) return r; }
     const size_t nC = size_t(c->mesh.nCells);
-    if (sigma) CK(cudaMemcpy(c->dSigma, sigma, nC * 8, cudaMemcpyHostToDevice));
-    if (rem) CK(cudaMemcpy(c->dRem, rem, nC * 8, cudaMemcpyHostToDevice));
+    (void)nC;
+    if (sigma) CK(cellRowsToDevice(c, c->dSigma, sigma, 8));
+    if (rem) CK(cellRowsToDevice(c, c->dRem, rem, 8));
     return 0;
 }
 
@@ -1394,8 +1535,9 @@ int dsmcb200_download_cellstate(dsmcb200_ctx* c, double* sigma, double* rem) {
     { int r = finalize(c); if (r) return r; }
     const size_t nC = size_t(c->mesh.nCells);
     CK(cudaStreamSynchronize(c->stream));
-    if (sigma) CK(cudaMemcpy(sigma, c->dSigma, nC * 8, cudaMemcpyDeviceToHost));
-    if (rem) CK(cudaMemcpy(rem, c->dRem, nC * 8, cudaMemcpyDeviceToHost));
+    (void)nC;
+    if (sigma) CK(cellRowsToHost(c, sigma, c->dSigma, 8));
+    if (rem) CK(cellRowsToHost(c, rem, c->dRem, 8));
     return 0;
 }
 
@@ -1511,6 +1653,15 @@ int dsmcb200_download_occupancy(dsmcb200_ctx* c, int32_t* cellOffsets) {
     { int r = finalize(c); if (r) return r; }
     if (!c->occupancyValid) return fail(c, DSMCB200_ERR_STATE, "cell occupancy is stale: run the sort stage first");
     CK(cudaStreamSynchronize(c->stream));
+    if (!c->newOfOld.empty()) {
+        // the cloud is cell-major in the engine's labels; in the caller's labels the offsets are those of the same cloud ordered by
+        // the caller's cells (a stable sort of the downloaded cloud by `cell` has this occupancy)
+        std::vector<int32_t> off(size_t(c->mesh.nCells) + 1);
+        CK(cudaMemcpy(off.data(), c->dCellOffset, off.size() * 4, cudaMemcpyDeviceToHost));
+        cellOffsets[0] = 0;
+        for (int32_t k = 0; k < c->mesh.nCells; ++k) { const int32_t r = c->newOfOld[k]; cellOffsets[k + 1] = cellOffsets[k] + (off[r + 1] - off[r]); }
+        return 0;
+    }
     CK(cudaMemcpy(cellOffsets, c->dCellOffset, size_t(c->mesh.nCells + 1) * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -1530,8 +1681,9 @@ int dsmcb200_download_accumulators(dsmcb200_ctx* c, double* acc, double* coll) {
     { int r = finalize(c); if (r) return r; }
     CK(cudaStreamSynchronize(c->stream));
     const size_t nC = size_t(c->mesh.nCells);
-    if (acc) CK(cudaMemcpy(acc, c->dAcc, nC * c->hP.nSpecies * c->nQ * 8, cudaMemcpyDeviceToHost));
-    if (coll) CK(cudaMemcpy(coll, c->dCollCum, nC * 16, cudaMemcpyDeviceToHost));
+    (void)nC;
+    if (acc) CK(cellRowsToHost(c, acc, c->dAcc, size_t(c->hP.nSpecies) * c->nQ * 8));
+    if (coll) CK(cellRowsToHost(c, coll, c->dCollCum, 16));
     return 0;
 }
 
@@ -1540,8 +1692,9 @@ int dsmcb200_upload_accumulators(dsmcb200_ctx* c, const double* acc, const doubl
     cudaSetDevice(c->device);
     { int r = finalize(c); if (r) return r; }
     const size_t nC = size_t(c->mesh.nCells);
-    if (acc) CK(cudaMemcpy(c->dAcc, acc, nC * c->hP.nSpecies * c->nQ * 8, cudaMemcpyHostToDevice));
-    if (coll) CK(cudaMemcpy(c->dCollCum, coll, nC * 16, cudaMemcpyHostToDevice));
+    (void)nC;
+    if (acc) CK(cellRowsToDevice(c, c->dAcc, acc, size_t(c->hP.nSpecies) * c->nQ * 8));
+    if (coll) CK(cellRowsToDevice(c, c->dCollCum, coll, 16));
     c->nTimeSteps = nTimeSteps;
     return 0;
 }
@@ -1582,8 +1735,8 @@ int dsmcb200_upload_overall_temperature(dsmcb200_ctx* c, const double* Tov) {
     { int r = finalize(c); if (r) return r; }
     const size_t nC = size_t(c->mesh.nCells);
     if (!c->dOverallT) CK(devAlloc(&c->dOverallT, nC));
-    CK(cudaMemcpyAsync(c->dOverallT, Tov, nC * 8, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    CK(cellRowsToDevice(c, c->dOverallT, Tov, 8));
     return 0;
 }
 
@@ -1679,9 +1832,10 @@ int dsmcb200_download_geometry(dsmcb200_ctx* c, double* cellCentres, double* cel
                                int32_t* tetBasePtIs) {
     if (!c || !c->haveMesh) return DSMCB200_ERR_STATE;
     const HostMesh& M = c->mesh;
-    for (int i = 0; i < M.nCells; ++i) {
-        if (cellCentres) { cellCentres[3 * i] = M.cellCentres[i].x; cellCentres[3 * i + 1] = M.cellCentres[i].y; cellCentres[3 * i + 2] = M.cellCentres[i].z; }
-        if (cellVolumes) cellVolumes[i] = M.cellVolumes[i];
+    for (int k = 0; k < M.nCells; ++k) {
+        const int i = c->newOfOld.empty() ? k : c->newOfOld[k];   // the caller's cell k
+        if (cellCentres) { cellCentres[3 * k] = M.cellCentres[i].x; cellCentres[3 * k + 1] = M.cellCentres[i].y; cellCentres[3 * k + 2] = M.cellCentres[i].z; }
+        if (cellVolumes) cellVolumes[k] = M.cellVolumes[i];
     }
     for (int f = 0; f < M.nFaces; ++f) {
         if (faceCentres) { faceCentres[3 * f] = M.faceCentres[f].x; faceCentres[3 * f + 1] = M.faceCentres[f].y; faceCentres[3 * f + 2] = M.faceCentres[f].z; }

@@ -335,6 +335,19 @@ def renumber_cells(mesh, new_of_old):
     return out, new_of_old
 
 
+def relabel_cells(mesh, new_of_old):
+    """The polyMesh with cell `c` called `new_of_old[c]` and nothing else changed: owner / neighbour entries only, no face is flipped or
+    moved (so an owner label may exceed its neighbour's).  This is the mesh the engine works on after dsmcb200_set_cell_order."""
+    new_of_old = np.asarray(new_of_old, dtype=np.int32)
+    out = MeshData(mesh.points, mesh.face_offsets, mesh.face_points, new_of_old[mesh.owner].astype(np.int32),
+                   new_of_old[mesh.neighbour].astype(np.int32), [dict(p) for p in mesh.patches])
+    for a in ("shape", "lengths", "origin", "r", "thickness"):
+        if hasattr(mesh, a):
+            setattr(out, a, getattr(mesh, a))
+    out.cell_numbering = "relabelled"
+    return out
+
+
 def poly_mesh_from_cells(points, cells, patch_of_face, patch_specs):
     """A polyMesh from an explicit cell list -- the general (non-hex) path of the tracker's tests.
 

@@ -306,6 +306,20 @@ int dsmcb200_init_comm(dsmcb200_ctx*, const void* id128);
 /* replaces: polyMesh addressing + tetBasePtIs used by particle::trackToFace,
  * BASIC/particle/particleTemplates.C:741-743,830-861 */
 int dsmcb200_set_mesh(dsmcb200_ctx*, const dsmcb200_mesh*);
+/* Cell labels inside the engine (what OpenFOAM's renumberMesh does to the case files, done in memory instead): the engine works on the
+ * same polyMesh with its cells relabelled so that neighbours in space are neighbours in the sorted cloud and in the tet table, and every
+ * entry point that takes or returns cell labels or per-cell rows (parcels, cell state, cell fields, accumulators, geometry, occupancy,
+ * overall temperature) translates.  Only owner / neighbour entries change: faces, points, patches and the face list of every cell stay as
+ * they are, so a run equals, label for label, the run on the mesh relabelled with the same table.  Call before set_mesh.
+ * mode AS_GIVEN: the caller's labels (default); Z_CURVE: along a z-order curve through the cell centres; GIVEN: newOfOld[nCells]. */
+typedef enum {
+    DSMCB200_CELL_ORDER_AS_GIVEN = 0,
+    DSMCB200_CELL_ORDER_Z_CURVE = 1,
+    DSMCB200_CELL_ORDER_GIVEN = 2
+} dsmcb200_cell_order;
+int dsmcb200_set_cell_order(dsmcb200_ctx*, int mode, const int32_t* newOfOldOrNull, int32_t nCells);
+/* the table in use after set_mesh: the engine's label of the caller's cell k (identity for AS_GIVEN) */
+int dsmcb200_download_cell_order(dsmcb200_ctx*, int32_t* newOfOld);
 /* replaces: dsmcCloud::buildConstProps, DSMC/clouds/dsmcCloud.C:40-59 */
 int dsmcb200_set_species(dsmcb200_ctx*, int nSpecies, const dsmcb200_species*);
 /* replaces: BinaryCollisionModel::New / collisionPartnerSelection::New /

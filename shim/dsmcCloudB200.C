@@ -162,6 +162,14 @@ void Foam::dsmcCloud::sendMesh()
     m.faceCentres = reinterpret_cast<const double*>(mesh.faceCentres().begin());
     m.faceAreas = reinterpret_cast<const double*>(mesh.faceAreas().begin());
     m.tetBasePtIs = mesh.tetBasePtIs().begin();
+    // optional, constant/dsmcProperties: `dsmcb200CellOrder zCurve;` relabels the cells inside the library (renumberMesh in memory; the
+    // fields and the cloud this class writes keep the mesh's labels)
+    const word order(particleProperties_.lookupOrDefault<word>("dsmcb200CellOrder", "asGiven"));
+    if (order == "zCurve") { ck(dsmcb200_set_cell_order(ctx_, DSMCB200_CELL_ORDER_Z_CURVE, NULL, 0), "dsmcb200_set_cell_order"); }
+    else if (order != "asGiven")
+    {
+        FatalErrorIn("dsmcCloud::sendMesh()") << "dsmcb200CellOrder " << order << " is not in enumeration: 2(asGiven zCurve)" << exit(FatalError);
+    }
     ck(dsmcb200_set_mesh(ctx_, &m), "dsmcb200_set_mesh");
 }
 

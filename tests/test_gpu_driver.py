@@ -373,3 +373,35 @@ def test_driver_binary_case_writes_what_the_ascii_case_writes(tmp_path):
     assert r.returncode == 0 and "startTime 5.00004" in r.stdout and f"parcels {len(pb[1])}" in r.stdout, r.stdout + r.stderr
     ra = subprocess.run([RUN, "-case", a_dir, "-dryRun"], capture_output=True, text=True, timeout=120)
     assert [l for l in r.stdout.splitlines() if "checksum" in l] == [l for l in ra.stdout.splitlines() if "checksum" in l]
+
+
+def test_driver_renumber_cells_keeps_the_case_labels(tmp_path):
+    """`dsmcb200_run -renumberCells` (dsmcb200_set_cell_order: renumberMesh in memory): the engine works on relabelled cells, the files keep
+    the case's labels -- every written parcel lies in the cell its `positions` entry names, and the sampled fields are those of the
+    plain run up to the collisions' different random streams (keyed by the engine's labels)."""
+    a_dir, b_dir = os.path.join(str(tmp_path), "plain"), os.path.join(str(tmp_path), "renumbered")
+    out = {}
+    for d, extra in ((a_dir, []), (b_dir, ["-renumberCells"])):
+        os.makedirs(d)
+        g, mesh, p = casegen.couette_case(d, n_steps=4, seed=5, nto=2)
+        r = subprocess.run([RUN, "-case", d] + extra, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr + r.stdout
+        t = os.path.join(d, "5.00004")
+        xyz, cell = ff.read_positions(os.path.join(t, "lagrangian", "dsmc", "positions"))
+        out[d] = dict(xyz=xyz, cell=cell, ids=ff.read_scalar_list(os.path.join(t, "lagrangian", "dsmc", "origId"), np.int32),
+                      rhoN=ff.read_internal_field(os.path.join(t, "rhoN_mixture")), sig=ff.read_internal_field(os.path.join(t, "dsmcSigmaTcRMax")))
+    a, b = out[a_dir], out[b_dir]
+    assert len(a["cell"]) == len(b["cell"]) == 47583
+    o = Oracle()
+    o.set_mesh(mesh)
+    cc, *_ = o.geometry()
+    box = np.abs(cc[1:] - cc[:-1]).max(axis=0)                   # spacing of the structured mesh per direction
+    for run in (a, b):
+        d = np.abs(run["xyz"] - cc[run["cell"]])
+        assert np.all(d <= 0.5 * box * (1 + 1e-9) + 1e-15), "a parcel is not in the cell its label names"
+    # the plain run is cell-major in the case's labels, the renumbered one in the engine's: a different order of the same kind of cloud
+    assert np.all(np.diff(a["cell"]) >= 0) and not np.all(np.diff(b["cell"]) >= 0)
+    assert sorted(a["ids"].tolist()) == sorted(b["ids"].tolist())
+    # ~95 parcels per cell: the two runs are independent samples of the same flow after the first collisions
+    assert np.abs(a["rhoN"] - b["rhoN"]).mean() < 0.1 * a["rhoN"].mean() and abs(a["rhoN"].sum() / b["rhoN"].sum() - 1) < 1e-3
+    assert np.allclose(a["sig"], b["sig"], rtol=0.5)
