@@ -185,6 +185,7 @@ struct dsmcb200_ctx {
     int32_t* dWeightCounts = nullptr; int64_t weightCountsCap = 0;
     uint32_t* dGiantBitmap = nullptr; int64_t giantWords = 0;   // scratch of giantSortKernel
     int32_t nGiant = 0;   // cells of more than GIANT_SORT parcels found by the last sort
+    double cellRadius2Max = 0.0;   // square of the largest cell-centre-to-vertex distance (mesh-wide parcel search)
     int32_t* dGiantList = nullptr;
     int64_t cloned = 0, weightDeleted = 0, weightDeletedStep = 0;
     DevParams hP{};
@@ -694,6 +695,17 @@ int finalize(dsmcb200_ctx* c) {
         CK(upload(&c->dFaceOffsets, M.faceOffsets));
         CK(upload(&c->dFacePoints, M.facePoints));
         CK(upload(&c->dOwner, M.owner));
+        {
+            double r2 = 0.0;
+            for (int32_t f = 0; f < M.nFaces; ++f)
+                for (int32_t k = M.faceOffsets[f]; k < M.faceOffsets[f + 1]; ++k) {
+                    const V3 pt = M.points[M.facePoints[k]];
+                    const V3 d0 = pt - M.cellCentres[M.owner[f]];
+                    r2 = std::max(r2, dot(d0, d0));
+                    if (f < M.nInternalFaces) { const V3 d1 = pt - M.cellCentres[M.neighbour[f]]; r2 = std::max(r2, dot(d1, d1)); }
+                }
+            c->cellRadius2Max = r2 * (1.0 + 1e-9);
+        }
         if (!c->newOfOld.empty()) { CK(upload(&c->dNewOfOld, c->newOfOld)); CK(upload(&c->dOldOfNew, c->oldOfNew)); }
         CK(upload(&c->dNeighbour, M.neighbour));
         CK(upload(&c->dTetBasePtIs, M.tetBasePtIs));
@@ -1394,8 +1406,17 @@ int dsmcb200_upload_parcels(dsmcb200_ctx* c, int64_t n, const dsmcb200_parcels_s
         l.cellFaceOffsets = c->dCellFaceOffsets; l.cellFaces = c->dCellFaces; l.faceOffsets = c->dFaceOffsets; l.facePoints = c->dFacePoints;
         l.owner = c->dOwner; l.neighbour = c->dNeighbour; l.nInternalFaces = c->mesh.nInternalFaces; l.tetBasePtIs = c->dTetBasePtIs; l.cellTetStart = c->dCellTetStart; l.points = c->dPoints;
         l.cellCentres = c->dCellCentres; l.lost = &c->dCounters->deleted;
+        l.pending = st.islab; l.nPending = &c->dCounters->nPendingLocate; l.searchRadius2 = c->cellRadius2Max;
         CK(cudaMemsetAsync(&c->dCounters->deleted, 0, sizeof(unsigned long long), s));
+        CK(cudaMemsetAsync(&c->dCounters->nPendingLocate, 0, sizeof(int32_t), s));
         CK(launchLocate(l, s));
+        int32_t nPending = 0;
+        CK(cudaMemcpyAsync(&nPending, &c->dCounters->nPendingLocate, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (nPending > LOCATE_GLOBAL_MAX)
+            return fail(c, DSMCB200_ERR_INVALID, "upload_parcels: " + std::to_string(nPending) + " parcels are neither in nor next to the cell their label names "
+                        "(the mesh-wide search of polyMesh::findCellFacePt is limited to " + std::to_string(LOCATE_GLOBAL_MAX) + " parcels per upload): wrong mesh or cell labels?");
+        CK(launchLocateGlobal(l, nPending, s));
         unsigned long long lost = 0;
         CK(cudaMemcpyAsync(&lost, &c->dCounters->deleted, sizeof(lost), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));

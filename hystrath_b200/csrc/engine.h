@@ -122,6 +122,8 @@ struct DevCounters {
     int32_t giantSortCells;  // ... and from there to giantSortKernel (more than GIANT_SORT parcels: the one-cell heat baths)
     int32_t nBorn;         // parcels created by dissociations this step (dsmcCloud::addNewParcel)
     int32_t weightDeleted; // parcels deleted by the radial weighting this step
+    int32_t nPendingLocate; // parcels an upload without tet indices sends on to the mesh-wide search
+    int32_t pad_;
     unsigned long long nReact[MAX_REACTIONS][3];   // this step: dissociations of reactant 0, of reactant 1, exchanges
 };
 
@@ -300,17 +302,22 @@ cudaError_t orderMigrants(MigRec* records, MigRec* scratch, const int32_t* keys,
 // particle::initCellFacePtOrDeleteLostParticle for a cloud that arrives without tetFace / tetPt (the `positions` file holds only
 // "(x y z) cell", particleIO.C:51-58)
 struct LocateArgs {
-    const double *px, *py, *pz;
+    double *px, *py, *pz;         // in; a parcel found by the walk towards its cell centre gets the new position (particleI.H:976)
     int32_t* cell;                // in: host cell label; out: -1 for a lost parcel
     int32_t* tet;                 // out: tet id cellTetStart[cell] + index of (tetFace, tetPt) among the cell's tets
     int32_t n, nCells;
     const int32_t *cellFaceOffsets, *cellFaces, *faceOffsets, *facePoints, *owner, *tetBasePtIs, *cellTetStart;
     const int32_t* neighbour;     // [nInternalFaces]: the search of polyMesh::findCellFacePt looks at the cells around the given one
+    int32_t* pending;             // [n] parcels that go on to the mesh-wide search (nullptr: no such search)
+    int32_t* nPending;
+    double searchRadius2;         // square of the mesh's largest cell-centre-to-vertex distance
     int32_t nInternalFaces;
     const double *points, *cellCentres;
     unsigned long long* lost;     // parcels deleted (outside the inflated cell bounding box or not locatable)
 };
 cudaError_t launchLocate(const LocateArgs& a, cudaStream_t s);
+cudaError_t launchLocateGlobal(const LocateArgs& a, int32_t nPending, cudaStream_t s);   // the parcels launchLocate listed in a.pending
+constexpr int32_t LOCATE_GLOBAL_MAX = 65536;   // parcels one upload may send through the mesh-wide search
 
 struct InflowArgs {
     ParcelArrays p;

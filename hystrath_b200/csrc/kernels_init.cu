@@ -145,6 +145,36 @@ __device__ bool pointInCellBBDev(const LocateArgs& a, int32_t cell, const V3& p,
     return p.x >= mn.x && p.x <= mx.x && p.y >= mn.y && p.y <= mx.y && p.z >= mn.z && p.z <= mx.z;
 }
 
+// The position is in the (slightly extended) bound-box of the cell but in none of its tets (written with too few digits next to a
+// boundary face, another base-point decision): particleI.H:927-976 moves it towards the cell centre in steps of
+// trackingCorrectionTol*(cC - position), at most 1/tol + 1 of them, until a tet of the cell claims it, and keeps the new position.  The
+// first 256 steps are taken one by one as the reference takes them; the tets of a cell all have the cell centre as a vertex, so once the
+// segment is inside it stays inside, and the first claiming step beyond 256 is found by bisection.
+__device__ bool walkToCellCentre(const LocateArgs& a, int32_t i, int32_t cell, const V3& p, int32_t& tet) {
+    if (!pointInCellBBDev(a, cell, p, 0.1)) return false;
+    const V3 cc = mk(a.cellCentres[3 * cell], a.cellCentres[3 * cell + 1], a.cellCentres[3 * cell + 2]);
+    const V3 step = 1.0e-5 * (cc - p);
+    const int trap = 100001;
+    V3 q = p;
+    int it = 0;
+    bool ok = false;
+    while (!ok && it < 256) { q += step; ++it; ok = findTetFacePtDev(a, cell, q, tet); }
+    if (!ok) {
+        int32_t tHi = 0;
+        if (findTetFacePtDev(a, cell, p + double(trap) * step, tHi)) {
+            int lo = it, hi = trap;   // not inside at lo, inside at hi
+            while (hi - lo > 1) {
+                const int mid = lo + (hi - lo) / 2;
+                int32_t tm = 0;
+                if (findTetFacePtDev(a, cell, p + double(mid) * step, tm)) { hi = mid; tHi = tm; } else lo = mid;
+            }
+            q = p + double(hi) * step; tet = tHi; ok = true;
+        }
+    }
+    if (ok) { a.px[i] = q.x; a.py[i] = q.y; a.pz[i] = q.z; }   // position_ = newPosition
+    return ok;
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(128) locateKernel(const __grid_constant__ LocateArgs a) {
@@ -180,16 +210,13 @@ __global__ void __launch_bounds__(128) locateKernel(const __grid_constant__ Loca
             }
             if (found >= 0) { ok = true; a.cell[i] = found; }
         }
-        if (!ok && pointInCellBBDev(a, cell, p, 0.1)) {
-            // the parcel sits (within rounding) on the cell surface: walk towards the cell centre in trackingCorrectionTol steps
-            // until a tet claims the point (particleI.H:927-976); the stored position is not changed
-            const V3 cc = mk(a.cellCentres[3 * cell], a.cellCentres[3 * cell + 1], a.cellCentres[3 * cell + 2]);
-            V3 q = p;
-            for (int it = 0; it < 200 && !ok; ++it) {
-                q += 1.0e-5 * (cc - q);
-                ok = findTetFacePtDev(a, cell, q, tet);
-            }
+        if (!ok && a.pending) {
+            // mesh-wide search (locateGlobalKernel), then the walk: in the order of particleI.H:884-976
+            a.pending[atomicAdd(a.nPending, 1)] = i;
+            a.tet[i] = 0;
+            return;
         }
+        if (!ok) ok = walkToCellCentre(a, i, cell, p, tet);
     }
     if (!ok) {   // lost: deleted by the sort (cell -1), hyStrath's change at particleI.H:892-902
         a.cell[i] = -1;
@@ -197,6 +224,39 @@ __global__ void __launch_bounds__(128) locateKernel(const __grid_constant__ Loca
         atomicAdd(a.lost, 1ULL);
     }
     a.tet[i] = tet;
+}
+
+// polyMesh::findCellFacePt for the parcels the cells around their label did not hold: the reference asks its cell octree for a cell that
+// contains the point; here a block looks through all cells whose centre is within the mesh's largest centre-to-vertex distance and takes
+// the lowest label whose tets claim the point.  No cell: back to the cell of the label for the bound-box test and the walk, else lost.
+__global__ void __launch_bounds__(256) locateGlobalKernel(const __grid_constant__ LocateArgs a, int32_t nPending) {
+    __shared__ int32_t sBest;
+    const int32_t i = a.pending[blockIdx.x];
+    const int32_t cell0 = a.cell[i];
+    const V3 p = mk(a.px[i], a.py[i], a.pz[i]);
+    if (threadIdx.x == 0) sBest = 0x7fffffff;
+    __syncthreads();
+    for (int32_t c = threadIdx.x; c < a.nCells; c += blockDim.x) {
+        if (c == cell0) continue;
+        const V3 d = p - mk(a.cellCentres[3 * c], a.cellCentres[3 * c + 1], a.cellCentres[3 * c + 2]);
+        if (dot(d, d) > a.searchRadius2) continue;
+        int32_t t;
+        if (findTetFacePtDev(a, c, p, t)) atomicMin(&sBest, c);
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    int32_t tet = 0;
+    bool ok = false;
+    if (sBest != 0x7fffffff) { ok = findTetFacePtDev(a, sBest, p, tet); if (ok) a.cell[i] = sBest; }
+    if (!ok) ok = walkToCellCentre(a, i, cell0, p, tet);
+    if (!ok) { a.cell[i] = -1; tet = 0; atomicAdd(a.lost, 1ULL); }
+    a.tet[i] = tet;
+}
+
+cudaError_t launchLocateGlobal(const LocateArgs& a, int32_t nPending, cudaStream_t s) {
+    if (nPending <= 0) return cudaSuccess;
+    locateGlobalKernel<<<nPending, 256, 0, s>>>(a, nPending);
+    return cudaGetLastError();
 }
 
 cudaError_t launchLocate(const LocateArgs& a, cudaStream_t s) {

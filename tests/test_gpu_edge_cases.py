@@ -91,9 +91,9 @@ def test_invalid_uploads_fail_loudly():
 def test_cloud_without_tet_indices_is_located_on_the_device():
     """Cloud<T>::initCloud -> particle::initCellFacePtOrDeleteLostParticle (BASIC/particle/particleI.H:851-996): the `positions` file holds
     only "(x y z) cell"; tetFace / tetPt are re-derived per parcel (first tet of the cell with tetrahedron::inside); a parcel that is not in
-    the cell its label names is looked for in the cells around it (findCellFacePt) and takes that cell; a parcel just outside the mesh
-    (rounding) is found by walking 1e-5 steps towards the cell centre; parcels outside the 10 %-inflated cell bounding box that no cell
-    claims are deleted."""
+    the cell its label names is looked for in the cells around it and then in the whole mesh (findCellFacePt) and takes that cell; a parcel just outside the mesh
+    (rounding, or by 5 % of a cell) is moved towards the cell centre in steps of 1e-5 of the distance until a tet of the cell claims it, and
+    keeps that position (particleI.H:927-976); parcels outside the 10 %-inflated cell bounding box that no cell claims are deleted."""
     mesh, sp, md = _box()
     h = 0.004
     rng = np.random.default_rng(5)
@@ -103,28 +103,37 @@ def test_cloud_without_tet_indices_is_located_on_the_device():
     pos = (ijk + rng.random((n_in, 3))) * h
     # special points of cell 21 = (1, 1, 1): centre, a face centre, a vertex (all "inside" by the > SMALL rule)
     special = np.array([[1.5, 1.5, 1.5], [1.0, 1.5, 1.5], [1.0, 1.0, 1.0]]) * h
-    # labelled 21 but lying in other cells: across the x-min face by rounding and by 5 % (cell 20), two cells further (cell 23)
-    elsewhere = np.array([[1.0 - 1e-9, 1.5, 1.5], [0.95, 1.5, 1.5], [3.5, 1.5, 1.5]]) * h
-    # labelled 20 = (0, 1, 1) on the wall: outside the mesh by rounding (found by the walk), by 5 % (in the inflated box, no tet reachable: lost), by half a cell (lost)
+    # labelled 21 but lying in other cells: across the x-min face by rounding and by 5 % (cell 20), two cells further (cell 23: the rings
+    # around the label), at the other end of the mesh (cell 63: the mesh-wide search)
+    elsewhere = np.array([[1.0 - 1e-9, 1.5, 1.5], [0.95, 1.5, 1.5], [3.5, 1.5, 1.5], [3.25, 3.5, 3.75]]) * h
+    # labelled 20 = (0, 1, 1) on the wall: outside the mesh by rounding and by 5 % (in the inflated box: both found by the walk), by half a cell (lost)
     outside = np.array([[-1e-9, 1.5, 1.5], [-0.05, 1.5, 1.5], [-0.5, 1.5, 1.5]]) * h
     position = np.concatenate([pos, special, elsewhere, outside])
-    cells = np.concatenate([cell, np.full(6, 21, np.int32), np.full(3, 20, np.int32)])
-    expect_cell = np.concatenate([cell, [21, 21, 21, 20, 20, 23, 20]]).astype(np.int32)
+    cells = np.concatenate([cell, np.full(7, 21, np.int32), np.full(3, 20, np.int32)])
+    expect_cell = np.concatenate([cell, [21, 21, 21, 20, 20, 23, 63, 20, 20]]).astype(np.int32)
     n = len(position)
     p = capi.ParcelData(n, 1, allocate=False, position=position, U=np.zeros((n, 3)), cell=cells, typeId=np.zeros(n, np.int32),
                         origId=np.arange(n, dtype=np.int32))
     eng = capi.Engine(0)
     eng.set_mesh(mesh); eng.set_species(sp); eng.set_models(md)
     eng.upload_parcels(p)
-    assert eng.num_parcels() == n - 2                       # the two lost parcels are deleted
+    assert eng.num_parcels() == n - 1                       # the lost parcel is deleted
     g = H.by_id(eng.download_parcels())
-    assert np.array_equal(g["origId"], np.arange(n - 2).astype(np.int32))
-    assert np.array_equal(g["position"], position[: n - 2])   # neither the search nor the walk moves the stored position
+    assert np.array_equal(g["origId"], np.arange(n - 1).astype(np.int32))
+    assert np.array_equal(g["position"][: n - 3], position[: n - 3])   # the search for another cell does not move a parcel ...
     assert np.array_equal(g["cell"], expect_cell)
+    # ... the walk does: the first multiple of 1e-5 (cC - position) that lies in the cell, one step for the rounding case, the
+    # ~9100th for the parcel 5 % of a cell outside (0.05 h of the 0.55 h to the centre)
+    cC = np.array([0.5, 1.5, 1.5]) * h
+    for j, (kmin, kmax) in ((n - 3, (1, 1)), (n - 2, (9000, 9200))):
+        k = (g["position"][j] - position[j])[0] / (1e-5 * (cC - position[j])[0])
+        assert kmin - 1e-6 <= k <= kmax + 1e-6 and abs(k - round(k)) < 1e-6, k
+        assert np.allclose(g["position"][j], position[j] + round(k) * 1e-5 * (cC - position[j]), rtol=0, atol=1e-16)
+        assert 0 <= g["position"][j][0] < 1e-3 * h
     # the oracle's own findTetFacePt on the parcels that are inside the cell they end up with
     ora = Oracle()
     ora.set_mesh(mesh); ora.set_species(sp); ora.set_models(md)
-    m = n_in + 6
+    m = n_in + 7
     q = capi.ParcelData(m, 1, allocate=False, position=position[:m], U=np.zeros((m, 3)), cell=expect_cell[:m],
                         typeId=np.zeros(m, np.int32), origId=np.arange(m, dtype=np.int32))
     ora.upload_parcels(q)
@@ -135,7 +144,7 @@ def test_cloud_without_tet_indices_is_located_on_the_device():
     f = g["tetFace"][m]
     assert own[f] == 20 and f >= mesh.n_internal
     eng.evolve(2)
-    assert eng.num_parcels() == n - 2
+    assert eng.num_parcels() == n - 1
     eng.close()
 
 
