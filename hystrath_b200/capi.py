@@ -346,6 +346,7 @@ def load_library():
         "dsmcb200_kernel_times": ([P, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
         "dsmcb200_download_geometry": ([P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
         "dsmcb200_allreduce_sum": ([P, C.c_void_p, C.c_int], C.c_int),
+        "dsmcb200_allreduce_min": ([P, C.c_void_p, C.c_int], C.c_int),
         "dsmcb200_timer_start": ([P], C.c_int),
         "dsmcb200_timer_stop": ([P, C.POINTER(C.c_float)], C.c_int),
     }
@@ -369,7 +370,7 @@ EXPORTED_SYMBOLS = [
     "dsmcb200_accum_info_get", "dsmcb200_download_accumulators", "dsmcb200_upload_accumulators",
     "dsmcb200_reset_accumulators", "dsmcb200_wall_info", "dsmcb200_download_wall_accumulators",
     "dsmcb200_upload_wall_accumulators", "dsmcb200_download_face_fluxes", "dsmcb200_upload_overall_temperature", "dsmcb200_get_counters",
-    "dsmcb200_kernel_times", "dsmcb200_download_geometry", "dsmcb200_timer_start", "dsmcb200_timer_stop", "dsmcb200_allreduce_sum",
+    "dsmcb200_kernel_times", "dsmcb200_download_geometry", "dsmcb200_timer_start", "dsmcb200_timer_stop", "dsmcb200_allreduce_sum", "dsmcb200_allreduce_min",
 ]
 
 

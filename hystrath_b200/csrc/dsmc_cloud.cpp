@@ -151,14 +151,17 @@ void dsmcCloud::setCellFields() {
     if (variableTimeStep_ && nCells_ > 0) {
         double minVolume = cellVolumes_[0];
         for (double v : cellVolumes_) minVolume = std::min(minVolume, v);
-        if (nRanks_ > 1) {   // reduce(minVolume, minOp<scalar>()): with a sum-only reduction, through 1/V^p norms is not exact -- refuse
-            throw FoamError("timeStepModel variable on a decomposed case is not supported yet (the reference cell is the globally smallest one)");
+        // findRefCell (dsmcVariableTimeStepModel.C:50-72): the reference cell is the smallest of the whole mesh.  On the ranks that do not
+        // own it the reference indexes cell -1; what it means there is what the owning rank computes -- nParticles and deltaT start uniform,
+        // so nParticleRef and the nParticle / time-step ratio are the same numbers on every rank and only the volume has to travel
+        double vRef = minVolume;
+        if (nRanks_ > 1) { check(dsmcb200_allreduce_min(ctx_, &vRef, 1), "dsmcb200_allreduce_min"); }
+        else {   // the first cell within SMALL of the minimum, and ITS volume (updatenParticles reads volumeCells[refCell_])
+            for (int c = 0; c < nCells_; ++c) if (std::fabs(cellVolumes_[c] - minVolume) < SMALL) { vRef = cellVolumes_[c]; break; }
         }
-        int refCell = 0;
-        for (int c = 0; c < nCells_; ++c) if (std::fabs(cellVolumes_[c] - minVolume) < SMALL) { refCell = c; break; }
-        const double nParticleRef = nPtsCell_[refCell], vRef = cellVolumes_[refCell];
+        const double nParticleRef = models_.nEquivalentParticles;
         for (int c = 0; c < nCells_; ++c) nPtsCell_[c] = nParticleRef * cellVolumes_[c] / vRef;
-        const double nParticleTimeStepRatio = nPtsCell_[refCell] / dtCell_[refCell];
+        const double nParticleTimeStepRatio = nParticleRef / deltaT_;
         for (int c = 0; c < nCells_; ++c) dtCell_[c] = nPtsCell_[c] / nParticleTimeStepRatio;
         if (rank_ == 0) std::printf("Variable time-step model:\n- Initial time-step [sec]\t%g\n\n", dtCell_[0]);
     }

@@ -1818,19 +1818,21 @@ int dsmcb200_kernel_times(dsmcb200_ctx* c, int capacity, int* n, char* names, fl
     return 0;
 }
 
-int dsmcb200_allreduce_sum(dsmcb200_ctx* c, double* vals, int n) {
+static int allreduceDoubles(dsmcb200_ctx* c, double* vals, int n, int op) {
     if (!c || !vals || n < 0 || n > 8) return DSMCB200_ERR_INVALID;
     if (c->nRanks <= 1 || !c->comm || n == 0) return 0;
     cudaSetDevice(c->device);
     { int r = finalize(c); if (r) return r; }
     CK(cudaMemcpyAsync(c->dInfo, vals, size_t(n) * 8, cudaMemcpyHostToDevice, c->stream));
-    const int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
-    int r = g_nccl.AllReduce(c->dInfo, c->dInfo, size_t(n), NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
+    const int NCCL_FLOAT64 = 8;
+    int r = g_nccl.AllReduce(c->dInfo, c->dInfo, size_t(n), NCCL_FLOAT64, op, c->comm, c->stream);
     if (r) return ncclFail(c, r, "ncclAllReduce");
     CK(cudaMemcpyAsync(vals, c->dInfo, size_t(n) * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
+int dsmcb200_allreduce_sum(dsmcb200_ctx* c, double* vals, int n) { return allreduceDoubles(c, vals, n, /* ncclSum */ 0); }
+int dsmcb200_allreduce_min(dsmcb200_ctx* c, double* vals, int n) { return allreduceDoubles(c, vals, n, /* ncclMin */ 3); }
 
 int dsmcb200_timer_start(dsmcb200_ctx* c) {
     if (!c) return DSMCB200_ERR_INVALID;

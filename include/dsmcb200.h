@@ -419,6 +419,8 @@ int dsmcb200_kernel_times(dsmcb200_ctx*, int capacity, int* n, char* names, floa
 /* Sum of vals[0..n) over all ranks (replaces the reduce(..., sumOp) calls of dsmcCloud::info and
  * noTimeCounter::collide, DSMC/clouds/dsmcCloud.C:938-958); a no-op on one rank. */
 int dsmcb200_allreduce_sum(dsmcb200_ctx*, double* vals, int n);
+/* reduce(x, minOp<scalar>()) over the ranks, e.g. gMin(mesh.V()) of dsmcVariableTimeStepModel::findRefCell (n <= 8) */
+int dsmcb200_allreduce_min(dsmcb200_ctx*, double* vals, int n);
 /* CUDA-event stopwatch on the context's launching stream (bench.py times the K steps with it). */
 int dsmcb200_timer_start(dsmcb200_ctx*);
 int dsmcb200_timer_stop(dsmcb200_ctx*, float* ms);

@@ -156,8 +156,11 @@ def test_two_gpu_channel_with_diffuse_walls_matches_single_domain_oracle():
     assert np.abs(wsum - wr).max() / np.abs(wr).max() < 1e-9 and np.abs(wr).max() > 0
 
 
-def test_two_gpu_driver_runs_decomposed_case(tmp_path):
-    """dsmcb200_run -parallel on a decomposePar-style case: processor0/ and processor1/ each hold their brick (polyMesh with processor and
+@pytest.mark.parametrize("time_step_model", ["constant", "variable"])
+def test_two_gpu_driver_runs_decomposed_case(tmp_path, time_step_model):
+    """With timeStepModel variable the reference cell is the smallest of the WHOLE mesh (dsmcVariableTimeStepModel::findRefCell reduces the
+    minimum volume over the ranks: dsmcb200_allreduce_min); on this uniform mesh every cell then keeps nEquivalentParticles and deltaT.
+    dsmcb200_run -parallel on a decomposePar-style case: processor0/ and processor1/ each hold their brick (polyMesh with processor and
     processorCyclic patches, start-time cloud), the dictionaries sit at the case root; one process per GPU, ncclUniqueId handed over through
     the case directory.  A closed channel keeps its parcels; both ranks write their time directories; the log carries the global counts."""
     import subprocess
@@ -187,6 +190,7 @@ def test_two_gpu_driver_runs_decomposed_case(tmp_path):
     casew.write_dict(os.path.join(case, "constant", "dsmcProperties"), "constant", "dsmcProperties", """
 nEquivalentParticles            %.10g;
 seedNumber                      11;
+timeStepModel                   TIME_STEP_MODEL;
 BinaryCollisionModel            VariableHardSphere;
 collisionPartnerSelectionModel  noTimeCounter;
 typeIdList                      (Ar);
@@ -194,7 +198,7 @@ moleculeProperties
 {
     Ar { mass 66.3e-27; diameter 4.17e-10; omega 0.81; alpha 1.0; }
 }
-""" % fnum)
+""".replace("TIME_STEP_MODEL", time_step_model) % fnum)
     casew.write_dict(os.path.join(case, "system", "controlDict"), "system", "controlDict", """
 application dsmcFoam+; nTerminalOutputs 5; startFrom latestTime; startTime 0; stopAt endTime; endTime 6e-5; deltaT 6e-6;
 writeControl timeStep; writeInterval 10; writeFormat ascii; writePrecision 10; timeFormat general; timePrecision 10;
@@ -232,6 +236,7 @@ dsmcFields
         assert p.returncode == 0, se + so
     log = outs[0][0]
     assert f"Number of DSMC particles        = {total}" in log and "End stage 0" in log
+    assert ("Variable time-step model:" in log) == (time_step_model == "variable")
     n_end = 0
     for rank in range(2):
         tdir = os.path.join(case, f"processor{rank}", "6e-05")
@@ -240,6 +245,12 @@ dsmcFields
         n_end += len(cell)
         assert os.path.exists(os.path.join(tdir, "rhoN_Ar")) and os.path.exists(os.path.join(tdir, "dsmcSigmaTcRMax"))
     assert n_end == total                                      # diffuse walls re-emit, processor / processorCyclic patches hand over
+    if time_step_model == "variable":                          # the model's fields: uniform on a uniform mesh, the same on both ranks
+        from hystrath_b200 import foamfile as ff
+        for rank in range(2):
+            tdir = os.path.join(case, f"processor{rank}", "6e-05")
+            assert np.allclose(ff.read_internal_field(os.path.join(tdir, "nParticles")), fnum, rtol=1e-9)
+            assert np.allclose(ff.read_internal_field(os.path.join(tdir, "deltaT")), 6e-6, rtol=1e-9)
 
 
 def ff_read_positions(path):
