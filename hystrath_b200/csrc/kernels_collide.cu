@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(GIANT_THREADS) collideGiantCellsKernel(const _
     __shared__ int32_t subStart[9];
     __shared__ int32_t warpCnt[GIANT_WARPS][8];
     __shared__ int32_t cpS[GIANT_THREADS], cqS[GIANT_THREADS];
-    __shared__ unsigned doneS[GIANT_WARPS];
+    __shared__ __align__(16) unsigned doneS[GIANT_WARPS];   // own 16-byte granules: the words are read with vector loads
     __shared__ double red[GIANT_WARPS][4];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const DevParams& P = *a.P;
