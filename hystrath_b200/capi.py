@@ -334,6 +334,8 @@ def load_library():
         "dsmcb200_set_cell_order": ([P, C.c_int, C.c_void_p, C.c_int32], C.c_int),
         "dsmcb200_download_cell_order": ([P, C.c_void_p], C.c_int),
         "dsmcb200_accum_info_get": ([P, C.POINTER(AccumInfo)], C.c_int),
+        "dsmcb200_set_sample_sets": ([P, C.c_int, C.c_void_p], C.c_int),
+        "dsmcb200_select_sample_set": ([P, C.c_int], C.c_int),
         "dsmcb200_download_accumulators": ([P, C.c_void_p, C.c_void_p], C.c_int),
         "dsmcb200_upload_accumulators": ([P, C.c_void_p, C.c_void_p, C.c_double], C.c_int),
         "dsmcb200_reset_accumulators": ([P], C.c_int),
@@ -366,7 +368,7 @@ EXPORTED_SYMBOLS = [
     "dsmcb200_reaction_counts", "dsmcb200_set_cell_fields", "dsmcb200_download_cell_fields", "dsmcb200_reserve",
     "dsmcb200_upload_parcels", "dsmcb200_download_parcels", "dsmcb200_upload_cellstate", "dsmcb200_download_cellstate",
     "dsmcb200_mesh_fill", "dsmcb200_evolve", "dsmcb200_stage", "dsmcb200_set_step", "dsmcb200_download_occupancy",
-    "dsmcb200_set_cell_order", "dsmcb200_download_cell_order",
+    "dsmcb200_set_cell_order", "dsmcb200_download_cell_order", "dsmcb200_set_sample_sets", "dsmcb200_select_sample_set",
     "dsmcb200_accum_info_get", "dsmcb200_download_accumulators", "dsmcb200_upload_accumulators",
     "dsmcb200_reset_accumulators", "dsmcb200_wall_info", "dsmcb200_download_wall_accumulators",
     "dsmcb200_upload_wall_accumulators", "dsmcb200_download_face_fluxes", "dsmcb200_upload_overall_temperature", "dsmcb200_get_counters",
@@ -543,6 +545,15 @@ class Engine:
             self._ck(self.lib.dsmcb200_set_cell_order(self.h, self.CELL_ORDER["given"], _ptr(t), len(t)))
         else:
             self._ck(self.lib.dsmcb200_set_cell_order(self.h, self.CELL_ORDER[mode], None, 0))
+
+    def set_sample_sets(self, intervals):
+        """One set of sums per distinct sampleInterval of the case's field{} entries (dsmcb200_set_sample_sets; before the engine is finalised)."""
+        t = np.ascontiguousarray(intervals, dtype=np.int32)
+        self._ck(self.lib.dsmcb200_set_sample_sets(self.h, len(t), _ptr(t)))
+
+    def select_sample_set(self, k):
+        """The set accumulators() / wall_accumulators() / reset_accumulators() / upload_accumulators() act on."""
+        self._ck(self.lib.dsmcb200_select_sample_set(self.h, int(k)))
 
     def cell_order(self):
         """new_of_old: the engine's label of the caller's cell k."""

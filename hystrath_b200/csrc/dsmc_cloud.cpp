@@ -127,6 +127,7 @@ dsmcCloud::dsmcCloud(const std::string& caseDir, const std::string& cloudName, i
     if (gCellOrder != DSMCB200_CELL_ORDER_AS_GIVEN) check(dsmcb200_set_cell_order(ctx_, gCellOrder, nullptr, 0), "dsmcb200_set_cell_order");
     check(dsmcb200_set_mesh(ctx_, &m), "dsmcb200_set_mesh");
     check(dsmcb200_set_species(ctx_, int(species_.size()), species_.data()), "dsmcb200_set_species");
+    if (sampleSets_.size() > 1) check(dsmcb200_set_sample_sets(ctx_, int(sampleSets_.size()), sampleSets_.data()), "dsmcb200_set_sample_sets");
     if (!reactions_.empty()) check(dsmcb200_set_reactions(ctx_, int(reactions_.size()), reactions_.data()), "dsmcb200_set_reactions");
     models_.nPatchModels = int32_t(patchModels_.size()); models_.patchModels = patchModels_.data();
     models_.nInflows = int32_t(inflows_.size()); models_.inflows = inflows_.data();
@@ -548,15 +549,21 @@ void dsmcCloud::readFieldProperties() {
         }
         if (s.measureHeatFluxShearStress) models_.measureHeatFluxShearStress = 1;
         if (s.measureClassifications) models_.measureClassifications = 1;
-        // every field{} shares the engine's one set of per-species accumulators, so they must agree on sampleInterval
-        // (dsmcVolFields.C:1073-1081,1362: calculateField samples when sampleInterval_ <= ++sampleCounter_)
-        if (!fields_.empty() && fields_.front().sampleInterval != s.sampleInterval)
-            throw FoamError("dsmcVolFields " + s.fieldName + ": sampleInterval " + std::to_string(s.sampleInterval) + " differs from field " +
-                            fields_.front().fieldName + " (" + std::to_string(fields_.front().sampleInterval) +
-                            "); this engine samples all fields on the same steps\nin: " + path);
+        // every field{} samples on its own cadence (dsmcVolFields.C:1073-1081,1362: calculateField samples when sampleInterval_ <=
+        // ++sampleCounter_): fields with the same sampleInterval share one set of the engine's sums (dsmcb200_set_sample_sets)
+        {
+            const int32_t iv = std::max(1, s.sampleInterval);
+            size_t k = 0;
+            while (k < sampleSets_.size() && sampleSets_[k] != iv) ++k;
+            if (k == sampleSets_.size()) {
+                if (sampleSets_.size() == 8) throw FoamError("dsmcVolFields " + s.fieldName + ": more than 8 different sampleIntervals\nin: " + path);
+                sampleSets_.push_back(iv);
+            }
+            s.set = int(k);
+        }
         // the reset policy of timeProperties (dsmcField.C:113-152) is per field: a field that stopped resetting keeps averaging from its
         // own baseline of the shared accumulators (write())
-        models_.sampleInterval = std::max(1, s.sampleInterval);
+        models_.sampleInterval = sampleSets_[0];
         fields_.push_back(s);
     }
 }
@@ -729,9 +736,14 @@ void dsmcCloud::info() {
     std::fflush(stdout);
 }
 
+void dsmcCloud::selectSet(int set) {
+    if (sampleSets_.size() > 1) check(dsmcb200_select_sample_set(ctx_, set), "dsmcb200_select_sample_set");
+}
+
 // dsmcVolFields::calculateField reductions (dsmcVolFields.C:1242-1290, 1401-1508, 1663-1790) from the per-species
 // moment sums accumulated on the device.
 DerivedFields dsmcCloud::calculateField(const FieldSpec& f) {
+    selectSet(f.set);
     dsmcb200_accum_info ai{};
     check(dsmcb200_accum_info_get(ctx_, &ai), "dsmcb200_accum_info_get");
     const int S = ai.nSpecies, nQ = ai.nQuantities, nC = ai.nCells;
@@ -923,6 +935,7 @@ double dsmcCloud::cellMaxDx(int c) const {
 }
 
 void dsmcCloud::writeFields(const std::string& timeDir, const std::vector<double>& instN) {
+    selectSet(0);
     // Boundary values (dsmcVolFields.C:1878-2206): faces of `wall` patches get every field from the wall accumulators
     // (the *BF_ arrays of boundaryMeasurements), every other non-empty, non-cyclic patch the adjacent cell value.
     int32_t nMeas = 0, nWallQ = 0;
@@ -949,6 +962,10 @@ void dsmcCloud::writeFields(const std::string& timeDir, const std::vector<double
         DerivedFields d = calculateField(f);
         // the wall sums of this field since its last reset
         wall = wallAll;
+        if (sampleSets_.size() > 1) {   // ... of this field's sample set (selected by calculateField)
+            if (nMeas) check(dsmcb200_download_wall_accumulators(ctx_, wall.data()), "dsmcb200_download_wall_accumulators");
+            check(dsmcb200_accum_info_get(ctx_, &ai), "dsmcb200_accum_info_get");
+        }
         if (f.baseWall.size() == wall.size()) for (size_t k = 0; k < wall.size(); ++k) wall[k] -= f.baseWall[k];
         const double nT = ai.nTimeSteps - f.baseNT > 0 ? ai.nTimeSteps - f.baseNT : 1.0;
         // fields().overallT(cell) is Tov_ of fields_[0] as written here (dsmcFieldProperties.C:235-240): the "2008" Zv formulation
@@ -1188,9 +1205,17 @@ struct ListOut {
 }  // namespace
 
 void dsmcCloud::writeResumeSampling(const std::string& timeDir) {
+    for (size_t set = 0; set < std::max<size_t>(1, sampleSets_.size()); ++set) writeResumeSamplingOf(timeDir, int(set));
+    selectSet(0);
+}
+
+// the fields of one sample set: uniform/resumeSampling_dsmcb200 (set 0), resumeSampling_dsmcb200_set<k> (the others)
+void dsmcCloud::writeResumeSamplingOf(const std::string& timeDir, int set) {
     bool any = false;
-    for (auto& f : fields_) any = any || f.averagingAcrossManyRuns;
+    for (auto& f : fields_) any = any || (f.set == set && f.averagingAcrossManyRuns);
     if (!any) return;
+    selectSet(set);
+    const std::string own = set == 0 ? std::string("resumeSampling_dsmcb200") : "resumeSampling_dsmcb200_set" + std::to_string(set);
     dsmcb200_accum_info ai{};
     check(dsmcb200_accum_info_get(ctx_, &ai), "dsmcb200_accum_info_get");
     const int S = ai.nSpecies, nQ = ai.nQuantities, nC = ai.nCells;
@@ -1212,9 +1237,9 @@ void dsmcCloud::writeResumeSampling(const std::string& timeDir) {
 
     // ---- the engine's own state: per-species rows, lossless
     {
-        FILE* f = std::fopen((ud + "/resumeSampling_dsmcb200").c_str(), "w");
-        if (!f) throw FoamError("cannot write " + ud + "/resumeSampling_dsmcb200");
-        std::fputs(foam::asciiHeader("dictionary", timeName_ + "/uniform", "resumeSampling_dsmcb200").c_str(), f);
+        FILE* f = std::fopen((ud + "/" + own).c_str(), "w");
+        if (!f) throw FoamError("cannot write " + ud + "/" + own);
+        std::fputs(foam::asciiHeader("dictionary", timeName_ + "/uniform", own).c_str(), f);
         ListOut o{f, 17};
         std::fprintf(f, "nTimeSteps      %.17g;\n\nnCells          %d;\n\nnSpecies        %d;\n\nnQuantities     %d;\n\nnMeasuredFaces  %d;\n\nnWallQuantities %d;\n\n",
                      ai.nTimeSteps, nC, S, nQ, nMeas, nWallQ);
@@ -1233,7 +1258,7 @@ void dsmcCloud::writeResumeSampling(const std::string& timeDir) {
             if (pm.model != DSMCB200_BND_DELETION) { measStart[pm.patch] = k; k += boundary_[pm.patch].nFaces; }
     }
     for (auto& fs : fields_) {
-        if (!fs.averagingAcrossManyRuns) continue;
+        if (!fs.averagingAcrossManyRuns || fs.set != set) continue;
         // the sums of this field since its own last reset (dsmcCloud::write)
         std::vector<double> accL = acc, collL = coll, wallL = wall;
         if (fs.baseAcc.size() == accL.size()) for (size_t k = 0; k < accL.size(); ++k) accL[k] -= fs.baseAcc[k];
@@ -1390,19 +1415,31 @@ void dsmcCloud::writeResumeSampling(const std::string& timeDir) {
 }
 
 void dsmcCloud::readResumeSampling() {
+    for (size_t set = 0; set < std::max<size_t>(1, sampleSets_.size()); ++set) readResumeSamplingOf(int(set));
+    selectSet(0);
+}
+
+void dsmcCloud::readResumeSamplingOf(int set) {
     // dsmcVolFields.C:1052-1066: read only with averagingAcrossManyRuns and resetAtOutput off
-    bool any = false, reset = !fields_.empty();
-    for (auto& f : fields_) { any = any || f.averagingAcrossManyRuns; reset = reset && f.resetAtOutput && !(time_ + deltaT_ > f.resetAtOutputUntilTime); }
+    bool any = false, reset = false, members = false;
+    for (auto& f : fields_)
+        if (f.set == set) {
+            any = any || f.averagingAcrossManyRuns;
+            const bool r = f.resetAtOutput && !(time_ + deltaT_ > f.resetAtOutputUntilTime);
+            reset = members ? (reset && r) : r;
+            members = true;
+        }
     if (!any) return;
+    selectSet(set);
     if (reset) {
         std::printf("Averaging across many runs will be enabled as soon as resetAtOutput is turned off.\n");
         return;
     }
-    const std::string path = root_ + "/" + timeName_ + "/uniform/resumeSampling_dsmcb200";
+    const std::string path = root_ + "/" + timeName_ + "/uniform/resumeSampling_dsmcb200" + (set == 0 ? std::string() : "_set" + std::to_string(set));
     if (!foam::exists(path)) {
         // a case checkpointed by dsmcFoam+ itself has only the per-field dictionaries (dsmcVolFields.C:1052-1066): say that they are not read
         for (auto& f : fields_)
-            if (f.averagingAcrossManyRuns && foam::exists(root_ + "/" + timeName_ + "/uniform/resumeSampling_" + f.fieldName))
+            if (f.set == set && f.averagingAcrossManyRuns && foam::exists(root_ + "/" + timeName_ + "/uniform/resumeSampling_" + f.fieldName))
                 std::printf("WARNING: uniform/resumeSampling_%s (written by dsmcFoam+) is not read; the averages of this run start at zero. "
                             "Only resumeSampling_dsmcb200, written by this engine, restores the sampling.\n", f.fieldName.c_str());
         return;
@@ -1518,14 +1555,17 @@ void dsmcCloud::write() {
     // resetAtOutput / resetAtOutputUntilTime (dsmcField.C:113-152) are per field, the accumulators are shared: when every field resets the
     // engine's sums are cleared; otherwise a field that resets takes the present sums as its new baseline
     bool reset = !fields_.empty();
-    for (auto& f : fields_) reset = reset && f.resetAtOutput && !(time_ + deltaT_ > f.resetAtOutputUntilTime);
-    if (reset) {
-        check(dsmcb200_reset_accumulators(ctx_), "dsmcb200_reset_accumulators");
-        for (auto& f : fields_) { f.baseAcc.clear(); f.baseColl.clear(); f.baseWall.clear(); f.baseNT = 0; }
-    } else {
-        bool some = false;
-        for (auto& f : fields_) some = some || (f.resetAtOutput && !(time_ + deltaT_ > f.resetAtOutputUntilTime));
-        if (some) {
+    for (size_t set = 0; set < std::max<size_t>(1, sampleSets_.size()); ++set) {   // the sums are shared by the fields of one sample set
+        auto resets = [&](const FieldSpec& f) { return f.resetAtOutput && !(time_ + deltaT_ > f.resetAtOutputUntilTime); };
+        bool all = true, some = false, members = false;
+        for (auto& f : fields_) if (f.set == int(set)) { members = true; all = all && resets(f); some = some || resets(f); }
+        if (!members) continue;
+        reset = reset && all;
+        selectSet(int(set));
+        if (all) {
+            check(dsmcb200_reset_accumulators(ctx_), "dsmcb200_reset_accumulators");
+            for (auto& f : fields_) if (f.set == int(set)) { f.baseAcc.clear(); f.baseColl.clear(); f.baseWall.clear(); f.baseNT = 0; }
+        } else if (some) {
             dsmcb200_accum_info ai{};
             check(dsmcb200_accum_info_get(ctx_, &ai), "dsmcb200_accum_info_get");
             std::vector<double> acc(size_t(ai.nCells) * ai.nSpecies * ai.nQuantities), coll(size_t(ai.nCells) * 2);
@@ -1535,9 +1575,10 @@ void dsmcCloud::write() {
             std::vector<double> wall(size_t(std::max(nMeas, 1)) * ai.nSpecies * std::max(nWallQ, 1), 0.0);
             if (nMeas) check(dsmcb200_download_wall_accumulators(ctx_, wall.data()), "dsmcb200_download_wall_accumulators");
             for (auto& f : fields_)
-                if (f.resetAtOutput && !(time_ + deltaT_ > f.resetAtOutputUntilTime)) { f.baseAcc = acc; f.baseColl = coll; f.baseWall = wall; f.baseNT = ai.nTimeSteps; }
+                if (f.set == int(set) && resets(f)) { f.baseAcc = acc; f.baseColl = coll; f.baseWall = wall; f.baseNT = ai.nTimeSteps; }
         }
     }
+    selectSet(0);
     // dsmcVolFields.C:2375-2378: only with averagingAcrossManyRuns and resetAtOutput off
     if (!reset) writeResumeSampling(timeDir);
 }

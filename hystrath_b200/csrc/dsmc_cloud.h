@@ -39,6 +39,7 @@ struct FieldSpec {  // one dsmcVolFields entry of system/fieldPropertiesDict
     bool resetAtOutput = true;
     double resetAtOutputUntilTime = 1e300;
     int sampleInterval = 1;
+    int set = 0;                           // the engine's sample set of this field's sampleInterval (dsmcb200_set_sample_sets)
     bool averagingAcrossManyRuns = false;  // dsmcVolFields.C:1048: keep / restore uniform/resumeSampling_<fieldName>
     // the shared accumulators as of this field's last reset (empty: zero), see dsmcCloud::write
     std::vector<double> baseAcc, baseColl, baseWall;
@@ -90,7 +91,11 @@ class dsmcCloud {
     void writeFields(const std::string& timeDir, const std::vector<double>& instN);
     double cellMaxDx(int c) const;  // largest extent of the cell's points along x, y, z (dsmcVolFields.C:1795-1821)
     void writeResumeSampling(const std::string& timeDir);  // dsmcVolFields::writeOut + the engine's own lossless checkpoint
+    void writeResumeSamplingOf(const std::string& timeDir, int set);
     void readResumeSampling();                              // dsmcVolFields::readIn
+    void readResumeSamplingOf(int set);
+    void selectSet(int set);                                // the sample set the accumulator calls act on
+    std::vector<int32_t> sampleSets_;                       // distinct sampleIntervals of the field{} entries, in order of appearance
     void check(int rc, const char* what);
 
     std::string caseDir_, root_, cloudName_, timeName_;

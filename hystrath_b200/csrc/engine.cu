@@ -87,6 +87,10 @@ __global__ void i32ToU8(const int32_t* in, uint8_t* out, int32_t n) {
     if (i < n) out[i] = uint8_t(in[i]);
 }
 // the same with a range check: values outside [0, limit) raise *bad (typeId against typeIdList, dsmcParcelI.H constProps lookup)
+__global__ void addDoubles(double* dst, const double* __restrict__ src, int32_t n) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
 // cell labels through a table (dsmcb200_set_cell_order); labels outside the mesh stay as they are for the checks that follow
 __global__ void mapLabels(const int32_t* in, int32_t* out, const int32_t* __restrict__ table, int32_t n, int32_t nCells) {
     const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -161,6 +165,13 @@ struct dsmcb200_ctx {
     std::vector<dsmcb200_species> species;
     dsmcb200_models models{};
     int sampleCounter = 0;   // steps since stage 5 last ran (sampleInterval)
+    // dsmcb200_set_sample_sets: field{} entries with their own sampleInterval (dsmcField.C:113-152) sample into their own sums.  Set 0 is
+    // dAcc / dCollCum / dWallAcc / nTimeSteps / sampleCounter with models.sampleInterval; the others live here.
+    struct SampleSet { int interval = 1, counter = 0; double *dAcc = nullptr, *dCollCum = nullptr, *dWallAcc = nullptr; double nTimeSteps = 0; };
+    std::vector<SampleSet> extraSets;
+    std::vector<int32_t> setIntervals;
+    int selectedSet = 0;
+    double* dWallStep = nullptr;   // with more than one set: the wall measurements of the step, added to every set that samples it
     double* dOverallT = nullptr;   // fields().overallT(cell) uploaded by the caller at write times (inverseZvFormulation "2008")
     double* dFaceFlux = nullptr;   // dsmcFaceTracker: [2][nSpecies][nFaces] of the current step (models.trackFaceFluxes)
     std::vector<dsmcb200_patch_model> patchModels;
@@ -403,6 +414,12 @@ cudaError_t cellRowsToHost(dsmcb200_ctx* c, void* user, const void* dev, size_t 
     for (int64_t k = 0; k < int64_t(nC); ++k) std::memcpy(u + size_t(k) * rowBytes, &tmp[size_t(c->newOfOld[k]) * rowBytes], rowBytes);
     return cudaSuccess;
 }
+
+// the sums of the sample set the accumulator entry points act on (dsmcb200_select_sample_set)
+double*& selAcc(dsmcb200_ctx* c) { return c->selectedSet == 0 ? c->dAcc : c->extraSets[c->selectedSet - 1].dAcc; }
+double*& selColl(dsmcb200_ctx* c) { return c->selectedSet == 0 ? c->dCollCum : c->extraSets[c->selectedSet - 1].dCollCum; }
+double*& selWall(dsmcb200_ctx* c) { return c->selectedSet == 0 ? c->dWallAcc : c->extraSets[c->selectedSet - 1].dWallAcc; }
+double& selSteps(dsmcb200_ctx* c) { return c->selectedSet == 0 ? c->nTimeSteps : c->extraSets[c->selectedSet - 1].nTimeSteps; }
 
 int uploadCellFields(dsmcb200_ctx* c) {
     const size_t nC = size_t(c->mesh.nCells);
@@ -728,6 +745,19 @@ int finalize(dsmcb200_ctx* c) {
     c->nWallQ = WQ_EVIBMOD0 + nModes;
     CK(devAlloc(&c->dWallAcc, size_t(c->nMeasFaces) * P.nSpecies * c->nWallQ));
     CK(cudaMemset(c->dWallAcc, 0, std::max<size_t>(1, size_t(c->nMeasFaces) * P.nSpecies * c->nWallQ) * 8));
+    if (c->setIntervals.size() > 1) {
+        const size_t nW = size_t(c->nMeasFaces) * P.nSpecies * c->nWallQ;
+        c->models.sampleInterval = c->setIntervals[0];
+        c->extraSets.assign(c->setIntervals.size() - 1, dsmcb200_ctx::SampleSet{});
+        for (size_t k = 0; k < c->extraSets.size(); ++k) {
+            auto& e = c->extraSets[k];
+            e.interval = std::max(1, int(c->setIntervals[k + 1]));
+            CK(devAlloc(&e.dAcc, nC * P.nSpecies * c->nQ)); CK(devAlloc(&e.dCollCum, nC * 2)); CK(devAlloc(&e.dWallAcc, nW));
+            CK(cudaMemset(e.dAcc, 0, nC * P.nSpecies * c->nQ * 8)); CK(cudaMemset(e.dCollCum, 0, nC * 16)); CK(cudaMemset(e.dWallAcc, 0, std::max<size_t>(1, nW) * 8));
+        }
+        CK(devAlloc(&c->dWallStep, nW));
+        CK(cudaMemset(c->dWallStep, 0, std::max<size_t>(1, nW) * 8));
+    }
     if (c->models.trackFaceFluxes) {
         CK(devAlloc(&c->dFaceFlux, size_t(2) * P.nSpecies * M.nFaces));
         CK(cudaMemset(c->dFaceFlux, 0, size_t(2) * P.nSpecies * M.nFaces * 8));
@@ -883,6 +913,10 @@ MoveArgs moveArgs(dsmcb200_ctx* c, int32_t tailStart) {
     a.tets = c->dTets; a.bfaces = c->dBFaces; a.bfaceArea = c->dBFaceArea; a.P = c->dP; a.wallAcc = c->dWallAcc; a.nWallQ = c->nWallQ;
     // boundaryMeas_ is cleaned every step (dsmcCloud.C:924) but only folded into the fields on sampled steps (dsmcVolFields.C:1081,1292)
     a.wallsDue = c->sampleCounter + 1 >= std::max(1, c->models.sampleInterval);
+    if (!c->extraSets.empty()) {   // several sample sets: the step's measurements go to dWallStep and from there to the sets that sample it
+        for (auto& e : c->extraSets) a.wallsDue = a.wallsDue || (e.counter + 1 >= e.interval);
+        a.wallAcc = c->dWallStep;
+    }
     a.faceFlux = c->dFaceFlux; a.faceAreas = c->dFaceAreas; a.nFacesAll = c->mesh.nFaces;
     a.migBuf = c->dMigSend; a.migRwf = c->dMigRwfSend; a.migKey = c->dMigKey; a.migCapacity = c->migCapacity; a.cellCount = c->dCellCount; a.counters = c->dCounters; a.step = c->step;
     return a;
@@ -1094,15 +1128,38 @@ int stageCollide(dsmcb200_ctx* c) {
     return 0;
 }
 
-int stageSample(dsmcb200_ctx* c) {
+int sampleInto(dsmcb200_ctx* c, double* acc, double* collCum, double& nTimeSteps) {
     if (!c->occupancyValid) return fail(c, DSMCB200_ERR_STATE, "cell occupancy is stale: run the sort stage first");
     SampleArgs a{};
-    a.p = c->buf[c->cur].a; a.cellOffset = c->dCellOffset; a.nCells = c->mesh.nCells; a.acc = c->dAcc; a.nQ = c->nQ; a.nSpecies = int(c->species.size()); a.nParcels = int32_t(c->sortedN); a.nCloud = int32_t(c->N);
-    a.collCum = c->dCollCum; a.nCollsStep = c->dNColls; a.collSepStep = c->dCollSep; a.P = c->dP;
+    a.p = c->buf[c->cur].a; a.cellOffset = c->dCellOffset; a.nCells = c->mesh.nCells; a.acc = acc; a.nQ = c->nQ; a.nSpecies = int(c->species.size()); a.nParcels = int32_t(c->sortedN); a.nCloud = int32_t(c->N);
+    a.collCum = collCum; a.nCollsStep = c->dNColls; a.collSepStep = c->dCollSep; a.P = c->dP;
     KT t(c, "sample");
     CK(launchSample(a, c->stream));
-    c->nTimeSteps += 1.0;
+    nTimeSteps += 1.0;
     // cellMeas_.clean() (dsmcCloud.C:925): the per-step arrays are rewritten by the next collide stage
+    return 0;
+}
+
+// the sample stage on its own (dsmcb200_stage): every set takes the sample
+int stageSample(dsmcb200_ctx* c) {
+    { int r = sampleInto(c, c->dAcc, c->dCollCum, c->nTimeSteps); if (r) return r; }
+    for (auto& e : c->extraSets) { int r = sampleInto(c, e.dAcc, e.dCollCum, e.nTimeSteps); if (r) return r; }
+    return 0;
+}
+
+// several sample sets: the wall measurements of a step are collected apart ...
+int beginWallStep(dsmcb200_ctx* c) {
+    if (c->extraSets.empty() || !c->nMeasFaces) return 0;
+    CK(cudaMemsetAsync(c->dWallStep, 0, size_t(c->nMeasFaces) * c->hP.nSpecies * c->nWallQ * 8, c->stream));
+    return 0;
+}
+// ... and added to the sets whose sampleInterval makes this step a sampled one (all of them for a move stage run on its own)
+int endWallStep(dsmcb200_ctx* c, bool everySet) {
+    if (c->extraSets.empty() || !c->nMeasFaces) return 0;
+    const int32_t n = int32_t(size_t(c->nMeasFaces) * c->hP.nSpecies * c->nWallQ);
+    if (everySet || c->sampleCounter + 1 >= std::max(1, c->models.sampleInterval)) addDoubles<<<GRID(n), 0, c->stream>>>(c->dWallAcc, c->dWallStep, n);
+    for (auto& e : c->extraSets)
+        if (everySet || e.counter + 1 >= e.interval) addDoubles<<<GRID(n), 0, c->stream>>>(e.dWallAcc, c->dWallStep, n);
     return 0;
 }
 
@@ -1154,7 +1211,8 @@ void dsmcb200_destroy(dsmcb200_ctx* c) {
     if (c->dMigTemp) cudaFree(c->dMigTemp); devFree(c->dOrdinalToPatch); devFree(c->dCountsMatrix);
     devFree(c->dBorn); devFree(c->dBornKeys); devFree(c->dBornIdx); if (c->dBornTemp) cudaFree(c->dBornTemp);
     devFree(c->dNPts); devFree(c->dDt); devFree(c->dRWF); devFree(c->dWeightCounts); devFree(c->dGiantBitmap); devFree(c->dGiantList);
-    devFree(c->dNewOfOld); devFree(c->dOldOfNew);
+    devFree(c->dNewOfOld); devFree(c->dOldOfNew); devFree(c->dWallStep);
+    for (auto& e : c->extraSets) { devFree(e.dAcc); devFree(e.dCollCum); devFree(e.dWallAcc); }
     for (auto& p : c->dInflowAcc) devFree(p);
     for (auto& p : c->dInflowCounts) devFree(p);
     for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);
@@ -1612,7 +1670,7 @@ int dsmcb200_stage(dsmcb200_ctx* c, int stage) {
     int r = 0;
     switch (stage) {
         case DSMCB200_STAGE_INFLOW: r = stageInflow(c, c->N); c->occupancyValid = false; break;  // new parcels are in no cell list; step fractions are only kept until the next stage call
-        case DSMCB200_STAGE_MOVE: r = stageMove(c, c->N); c->occupancyValid = false; break;
+        case DSMCB200_STAGE_MOVE: r = beginWallStep(c); if (!r) r = stageMove(c, c->N); if (!r) r = endWallStep(c, true); c->occupancyValid = false; break;
         case DSMCB200_STAGE_SORT: r = stageSort(c, false); if (!r) r = stageWeighting(c); break;   // the occupancy the collide stage sees
         case DSMCB200_STAGE_COLLIDE: r = stageCollide(c); break;
         case DSMCB200_STAGE_SAMPLE: r = stageSample(c); break;
@@ -1640,7 +1698,9 @@ int dsmcb200_evolve(dsmcb200_ctx* c, int nSteps) {
         cudaEventRecord(e0, c->stream);
         { int r = stageInflow(c, tailStart); if (r) return r; }    // boundaries_.controlBeforeMove()
         cudaEventRecord(e1, c->stream);
+        { int r = beginWallStep(c); if (r) return r; }
         { int r = stageMove(c, tailStart); if (r) return r; }      // Cloud<dsmcParcel>::move
+        { int r = endWallStep(c, false); if (r) return r; }
         cudaEventRecord(e2, c->stream);
         { int r = stageSort(c, true); if (r) return r; }           // buildCellOccupancy()
         { int r = stageWeighting(c); if (r) return r; }            // coordSystem().evolve()
@@ -1649,9 +1709,14 @@ int dsmcb200_evolve(dsmcb200_ctx* c, int nSteps) {
         cudaEventRecord(e4, c->stream);
         // dsmcVolFields::calculateField samples when sampleInterval_ <= ++sampleCounter_ (dsmcVolFields.C:1073-1081,1362)
         if (++c->sampleCounter >= std::max(1, c->models.sampleInterval)) {
-            { int r = stageSample(c); if (r) return r; }           // fields_.calculateFields()
+            { int r = sampleInto(c, c->dAcc, c->dCollCum, c->nTimeSteps); if (r) return r; }           // fields_.calculateFields()
             c->sampleCounter = 0;
         }
+        for (auto& e : c->extraSets)   // field{} entries with another sampleInterval
+            if (++e.counter >= e.interval) {
+                { int r = sampleInto(c, e.dAcc, e.dCollCum, e.nTimeSteps); if (r) return r; }
+                e.counter = 0;
+            }
         cudaEventRecord(e5, c->stream);
         c->step++;
         { int r = fetchCounters(c); if (r) return r; }
@@ -1687,12 +1752,29 @@ int dsmcb200_download_occupancy(dsmcb200_ctx* c, int32_t* cellOffsets) {
     return 0;
 }
 
+int dsmcb200_set_sample_sets(dsmcb200_ctx* c, int nSets, const int32_t* sampleIntervals) {
+    if (!c || nSets < 1 || nSets > 8 || !sampleIntervals) return DSMCB200_ERR_INVALID;
+    if (c->ready) return fail(c, DSMCB200_ERR_STATE, "set_sample_sets: the engine has been finalised");
+    for (int k = 0; k < nSets; ++k) if (sampleIntervals[k] < 1) return fail(c, DSMCB200_ERR_INVALID, "set_sample_sets: sampleInterval must be at least 1");
+    c->setIntervals.assign(sampleIntervals, sampleIntervals + nSets);
+    return 0;
+}
+
+int dsmcb200_select_sample_set(dsmcb200_ctx* c, int set) {
+    if (!c) return DSMCB200_ERR_INVALID;
+    cudaSetDevice(c->device);
+    { int r = finalize(c); if (r) return r; }
+    if (set < 0 || set > int(c->extraSets.size())) return fail(c, DSMCB200_ERR_INVALID, "select_sample_set: no such set");
+    c->selectedSet = set;
+    return 0;
+}
+
 int dsmcb200_accum_info_get(dsmcb200_ctx* c, dsmcb200_accum_info* o) {
     if (!c || !o) return DSMCB200_ERR_INVALID;
     cudaSetDevice(c->device);
     { int r = finalize(c); if (r) return r; }
     o->nCells = c->mesh.nCells; o->nSpecies = c->hP.nSpecies; o->nQuantities = c->nQ; o->nModes = c->internal ? c->nModes : -1;
-    o->nTimeSteps = c->nTimeSteps;
+    o->nTimeSteps = selSteps(c);
     return 0;
 }
 
@@ -1703,8 +1785,8 @@ int dsmcb200_download_accumulators(dsmcb200_ctx* c, double* acc, double* coll) {
     CK(cudaStreamSynchronize(c->stream));
     const size_t nC = size_t(c->mesh.nCells);
     (void)nC;
-    if (acc) CK(cellRowsToHost(c, acc, c->dAcc, size_t(c->hP.nSpecies) * c->nQ * 8));
-    if (coll) CK(cellRowsToHost(c, coll, c->dCollCum, 16));
+    if (acc) CK(cellRowsToHost(c, acc, selAcc(c), size_t(c->hP.nSpecies) * c->nQ * 8));
+    if (coll) CK(cellRowsToHost(c, coll, selColl(c), 16));
     return 0;
 }
 
@@ -1714,9 +1796,9 @@ int dsmcb200_upload_accumulators(dsmcb200_ctx* c, const double* acc, const doubl
     { int r = finalize(c); if (r) return r; }
     const size_t nC = size_t(c->mesh.nCells);
     (void)nC;
-    if (acc) CK(cellRowsToDevice(c, c->dAcc, acc, size_t(c->hP.nSpecies) * c->nQ * 8));
-    if (coll) CK(cellRowsToDevice(c, c->dCollCum, coll, 16));
-    c->nTimeSteps = nTimeSteps;
+    if (acc) CK(cellRowsToDevice(c, selAcc(c), acc, size_t(c->hP.nSpecies) * c->nQ * 8));
+    if (coll) CK(cellRowsToDevice(c, selColl(c), coll, 16));
+    selSteps(c) = nTimeSteps;
     return 0;
 }
 
@@ -1724,7 +1806,7 @@ int dsmcb200_upload_wall_accumulators(dsmcb200_ctx* c, const double* wall) {
     if (!c || !wall) return DSMCB200_ERR_INVALID;
     cudaSetDevice(c->device);
     { int r = finalize(c); if (r) return r; }
-    if (c->nMeasFaces) CK(cudaMemcpy(c->dWallAcc, wall, size_t(c->nMeasFaces) * c->hP.nSpecies * c->nWallQ * 8, cudaMemcpyHostToDevice));
+    if (c->nMeasFaces) CK(cudaMemcpy(selWall(c), wall, size_t(c->nMeasFaces) * c->hP.nSpecies * c->nWallQ * 8, cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -1733,11 +1815,11 @@ int dsmcb200_reset_accumulators(dsmcb200_ctx* c) {
     cudaSetDevice(c->device);
     { int r = finalize(c); if (r) return r; }
     const size_t nC = size_t(c->mesh.nCells);
-    CK(cudaMemsetAsync(c->dAcc, 0, nC * c->hP.nSpecies * c->nQ * 8, c->stream));
-    CK(cudaMemsetAsync(c->dCollCum, 0, nC * 16, c->stream));
-    if (c->nMeasFaces) CK(cudaMemsetAsync(c->dWallAcc, 0, size_t(c->nMeasFaces) * c->hP.nSpecies * c->nWallQ * 8, c->stream));
+    CK(cudaMemsetAsync(selAcc(c), 0, nC * c->hP.nSpecies * c->nQ * 8, c->stream));
+    CK(cudaMemsetAsync(selColl(c), 0, nC * 16, c->stream));
+    if (c->nMeasFaces) CK(cudaMemsetAsync(selWall(c), 0, size_t(c->nMeasFaces) * c->hP.nSpecies * c->nWallQ * 8, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    c->nTimeSteps = 0;
+    selSteps(c) = 0;
     return 0;
 }
 
@@ -1778,7 +1860,7 @@ int dsmcb200_download_wall_accumulators(dsmcb200_ctx* c, double* wall) {
     cudaSetDevice(c->device);
     { int r = finalize(c); if (r) return r; }
     CK(cudaStreamSynchronize(c->stream));
-    if (c->nMeasFaces) CK(cudaMemcpy(wall, c->dWallAcc, size_t(c->nMeasFaces) * c->hP.nSpecies * c->nWallQ * 8, cudaMemcpyDeviceToHost));
+    if (c->nMeasFaces) CK(cudaMemcpy(wall, selWall(c), size_t(c->nMeasFaces) * c->hP.nSpecies * c->nWallQ * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 

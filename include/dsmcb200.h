@@ -389,6 +389,13 @@ int dsmcb200_download_occupancy(dsmcb200_ctx*, int32_t* cellOffsets);
 /* replaces: the accumulators of dsmcVolFields (calculateField, :1115-1237) and
  * resumeSampling_<name> (writeOut/readIn, :647-835).
  * acc layout: [nCells][nSpecies][nQuantities]; coll: [nCells][2] = (nCollsCum, collisionSeparationCum). */
+/* Sample sets: every field{} of fieldPropertiesDict has its own sampleInterval (dsmcField.C:113-152, dsmcVolFields.C:1073-1081); fields
+ * that share one share a set of sums.  set_sample_sets (before the first call that finalises the engine) declares one set per distinct
+ * interval -- set 0 replaces models.sampleInterval --, each with its own cell, collision and wall accumulators and nTimeSteps;
+ * select_sample_set chooses the set accum_info_get, download / upload / reset_accumulators and download / upload_wall_accumulators act on
+ * (default 0). */
+int dsmcb200_set_sample_sets(dsmcb200_ctx*, int nSets, const int32_t* sampleIntervals);
+int dsmcb200_select_sample_set(dsmcb200_ctx*, int set);
 int dsmcb200_accum_info_get(dsmcb200_ctx*, dsmcb200_accum_info*);
 int dsmcb200_download_accumulators(dsmcb200_ctx*, double* acc, double* coll);
 int dsmcb200_upload_accumulators(dsmcb200_ctx*, const double* acc, const double* coll, double nTimeSteps);

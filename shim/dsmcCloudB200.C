@@ -470,7 +470,8 @@ void Foam::dsmcCloud::readFieldProperties()
         f.resetAtOutputUntilTime = tp.lookupOrDefault<scalar>("resetAtOutputUntilTime", VGREAT);
         const label si = p.lookupOrDefault<label>("sampleInterval", 1);
         if (i == 0) { models_.sampleInterval = si; }
-        // one accumulator set serves every instance: their sampling policy must agree
+        // this shim keeps one accumulator set for every instance, so their sampling policy must agree; the library itself offers one set per
+        // sampleInterval (dsmcb200_set_sample_sets / select_sample_set) and per-field baselines, as the standalone driver uses them
         if (si != models_.sampleInterval || f.resetAtOutput != fields_[0].resetAtOutput || f.resetAtOutputUntilTime != fields_[0].resetAtOutputUntilTime)
         {
             FatalErrorIn("dsmcCloud (dsmcb200)") << "field " << f.fieldName << ": sampleInterval / timeProperties differ from field "

@@ -45,7 +45,7 @@ def test_driver_rejects_unknown_models_like_the_reference(tmp_path):
 
 def test_driver_accepts_fields_with_different_reset_policies(tmp_path):
     """timeProperties are per field (dsmcField.C:113-152): one field may keep averaging while the others reset at every write (the
-    GPU driver test checks the sums); a different sampleInterval is still refused (one sampling cadence for the shared accumulators)."""
+    GPU driver test checks the sums), and so is sampleInterval (fields with another interval get their own set of sums)."""
     casegen.couette_case(str(tmp_path))
     path = os.path.join(str(tmp_path), "system", "fieldPropertiesDict")
     text = open(path).read()
@@ -56,7 +56,8 @@ def test_driver_accepts_fields_with_different_reset_policies(tmp_path):
     assert "field O2 typeIds 1 mfp 1 reset 0" in r.stdout and "field N2 typeIds 0 mfp 1 reset 1" in r.stdout
     open(path, "w").write(text.replace("fieldName               N2;", "fieldName               N2;\n            sampleInterval 2;"))
     r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
-    assert r.returncode == 1 and "this engine samples all fields on the same steps" in r.stderr
+    assert r.returncode == 0, r.stderr       # its own sample set (dsmcb200_set_sample_sets)
+    assert "field N2 typeIds 0 mfp 1 reset 1 sampleInterval 2" in r.stdout and "field O2 typeIds 1 mfp 1 reset 1 sampleInterval 1" in r.stdout
 
 
 def test_driver_reads_linear_wall_temperature(tmp_path):
@@ -72,7 +73,7 @@ def test_driver_reads_linear_wall_temperature(tmp_path):
 
 
 def test_driver_reads_sample_interval(tmp_path):
-    """dsmcVolFieldsProperties.sampleInterval (dsmcVolFields.C:1038) reaches the engine; fields that disagree are refused."""
+    """dsmcVolFieldsProperties.sampleInterval (dsmcVolFields.C:1038) reaches the engine; fields that disagree get sample sets of their own."""
     casegen.couette_case(str(tmp_path))
     path = os.path.join(str(tmp_path), "system", "fieldPropertiesDict")
     text = open(path).read()
@@ -83,7 +84,8 @@ def test_driver_reads_sample_interval(tmp_path):
     assert r.stdout.count(" sampleInterval 4") == 3
     open(path, "w").write(text.replace("fieldName", "sampleInterval 4;\n            fieldName", 1))
     r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
-    assert r.returncode == 1 and "this engine samples all fields on the same steps" in r.stderr
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.count(" sampleInterval 4") == 1 and r.stdout.count(" sampleInterval 1") == 2
 
 
 def test_python_reader_round_trip(tmp_path):

@@ -405,3 +405,42 @@ def test_driver_renumber_cells_keeps_the_case_labels(tmp_path):
     # ~95 parcels per cell: the two runs are independent samples of the same flow after the first collisions
     assert np.abs(a["rhoN"] - b["rhoN"]).mean() < 0.1 * a["rhoN"].mean() and abs(a["rhoN"].sum() / b["rhoN"].sum() - 1) < 1e-3
     assert np.allclose(a["sig"], b["sig"], rtol=0.5)
+
+
+def test_driver_fields_with_different_sample_intervals(tmp_path):
+    """sampleInterval is per field{} (dsmcField.C:113-152, dsmcVolFields.C:1073-1081): N2 samples every second step, the other two fields
+    every step.  Each written field equals the reduction of an oracle run made with that field's interval (the cloud does not know
+    about sampling, so the runs share their trajectory)."""
+    n_steps = 4
+    g, mesh, p = casegen.couette_case(str(tmp_path), n_steps=n_steps, seed=5, nto=2)
+    path = os.path.join(str(tmp_path), "system", "fieldPropertiesDict")
+    text = open(path).read()
+    assert "fieldName               N2;" in text
+    open(path, "w").write(text.replace("fieldName               N2;", "fieldName               N2;\n            sampleInterval 2;"))
+    r = subprocess.run([RUN, "-case", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    tdir = os.path.join(str(tmp_path), "5.00004")
+    sp = H.air5()[:2]
+    pm = [dict(patch=mesh.patch_index("upperWall"), boundaryModel="dsmcDiffuseWallPatch", temperature=3000.0, velocity=(300.0, 0, 0)),
+          dict(patch=mesh.patch_index("lowerWall"), boundaryModel="dsmcDiffuseWallPatch", temperature=2000.0, velocity=(0, 0, 0))]
+    spd = [dict(mass=s.mass, diameter=s.diameter, omega=s.omega, rotDof=2.0, thetaV=[s.thetaV[0]]) for s in sp]
+    for inst, idl, interval in (("mixture", [0, 1], 1), ("N2", [0], 2), ("O2", [1], 1)):
+        md = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=float(g["nEquivalentParticles"]), deltaT=1e-5, seed=5,
+                               patch_models=pm, inverseZvFormulation="pre-2008", rotationalRelaxationCollisionNumber=5.0,
+                               measureHeatFluxShearStress=True, sampleInterval=interval)
+        o = Oracle()
+        o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
+        o.upload_parcels(p)
+        o.upload_cellstate(g["dsmcSigmaTcRMax"], None)
+        o.set_step(500000)
+        o.evolve(n_steps)
+        acc, coll, nt = o.accumulators()
+        assert nt == n_steps // interval
+        _, cv, *_ = o.geometry()
+        f = fields_ref.derive(acc, coll, nt, spd, idl, float(g["nEquivalentParticles"]), cv, deltaT=1e-5)
+        for name in ("rhoN", "rhoM", "Ttra", "p", "Trot", "Tvib"):
+            got = ff.read_internal_field(os.path.join(tdir, f"{name}_{inst}"))
+            assert np.allclose(got, f[name], rtol=2e-9, atol=1e-300), (name, inst)
+    # the two N2 samples are not the four of the other fields
+    assert not np.allclose(ff.read_internal_field(os.path.join(tdir, "rhoN_N2")) + ff.read_internal_field(os.path.join(tdir, "rhoN_O2")),
+                           ff.read_internal_field(os.path.join(tdir, "rhoN_mixture")), rtol=1e-6)

@@ -363,6 +363,62 @@ def test_sample_interval_matches_oracle():
     eng.close()
 
 
+def test_sample_sets_with_their_own_intervals_match_oracle_runs():
+    """field{} entries with different sampleIntervals (dsmcField.C:113-152): one set of sums per interval (dsmcb200_set_sample_sets).  The
+    cloud does not know about sampling, so set k of ONE engine run equals the accumulators of an oracle run made with that interval --
+    cell sums, collision sums, wall measurements (only the steps the set samples leave any) and nTimeSteps; resetting one set leaves the
+    others alone."""
+    intervals = [1, 3, 2]
+    mesh, sp, md = wall_case()
+    eng = capi.Engine(0)
+    eng.set_sample_sets(intervals)
+    eng.set_mesh(mesh); eng.set_species(sp); eng.set_models(md)
+    oras = []
+    for iv in intervals:
+        md_k = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=md.nEquivalentParticles, deltaT=4e-6, seed=7,
+                                 patch_models=[dict(patch=mesh.patch_index("lowerWall"), boundaryModel="dsmcDiffuseWallPatch", temperature=2000.0, velocity=(0, 0, 0)),
+                                               dict(patch=mesh.patch_index("upperWall"), boundaryModel="dsmcDiffuseWallPatch", temperature=3000.0, velocity=(300.0, 0, 0))],
+                                 inverseZvFormulation="pre-2008", sampleInterval=iv)
+        o = Oracle()
+        o.set_mesh(mesh); o.set_species(sp); o.set_models(md_k)
+        oras.append(o)
+    H.same_start(eng, oras[0], [0, 1], [0.8e20, 0.2e20], 2500.0, 2500.0, 2500.0)
+    start = oras[0].download_parcels()
+    sig, rem = oras[0].download_cellstate()
+    for o in oras[1:]:
+        o.upload_parcels(start)
+        o.upload_cellstate(sig, rem)
+    eng.evolve(7)
+    for o in oras:
+        o.evolve(7)
+
+    def check(k, o):
+        eng.select_sample_set(k)
+        ga, gc, gn = eng.accumulators()
+        oa, oc, on = o.accumulators()
+        assert gn == on == 7 // intervals[k]
+        scale = np.abs(oa).max(axis=(0, 1), keepdims=True) + 1e-300
+        assert np.abs(oa).sum() > 0 and (np.abs(ga - oa) / scale).max() < 1e-9
+        assert np.allclose(gc, oc, rtol=1e-9, atol=0)
+        gw, ow = eng.wall_accumulators(), o.wall_accumulators()
+        ws = np.abs(ow).max(axis=(0, 1), keepdims=True) + 1e-300
+        assert np.abs(ow).sum() > 0 and (np.abs(gw - ow) / ws).max() < 1e-9
+        return ga, gw
+
+    sums = [check(k, o) for k, o in enumerate(oras)]
+    assert np.abs(sums[0][0]).sum() > np.abs(sums[2][0]).sum() > np.abs(sums[1][0]).sum()     # 7, 3 and 2 samples
+    eng.select_sample_set(1)
+    eng.reset_accumulators()
+    a1, _, n1 = eng.accumulators()
+    assert n1 == 0 and not a1.any() and not eng.wall_accumulators().any()
+    eng.select_sample_set(2)
+    a2, _, n2 = eng.accumulators()
+    assert n2 == 3 and np.array_equal(a2, sums[2][0]) and np.array_equal(eng.wall_accumulators(), sums[2][1])
+    with pytest.raises(capi.Dsmcb200Error, match="no such set"):
+        eng.select_sample_set(3)
+    eng.close()
+
+
 def test_diffuse_wall_with_linear_temperature_matches_oracle():
     """dsmcDiffuseWallPatch::getLocalTemperature (dsmcDiffuseWallPatch.C:141-148): groundLevelTemperature / formationLevelTemperature /
     depthAxis -- the wall temperature is a linear function of the hit position along the depth axis of the mesh bounds."""
