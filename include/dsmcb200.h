@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DSMCB200_ABI_VERSION 3
+#define DSMCB200_ABI_VERSION 4   /* 4 = 3 + set_cell_order / download_cell_order, set_sample_sets / select_sample_set, allreduce_min (no layout changed) */
 #define DSMCB200_MAX_NEIGHBOURS 16
 #define DSMCB200_MAX_SPECIES 8
 #define DSMCB200_MAX_VIB_MODES 3
