@@ -131,12 +131,12 @@ def axisym_gold():
     return np.load(os.path.join(os.path.dirname(__file__), "golden", "axisymmetricFlatnosedCylinder.npz"))
 
 
-def axisym_setup(x, gold, geometry, seed=11, fnum_scale=1.0):
+def axisym_setup(x, gold, geometry, seed=11, fnum_scale=1.0, mesh=None):
     """The tutorial on engine / oracle `x`: Mach-5.4 argon (1e21 m^-3, 100 K, 1000 m/s) onto a flat-nosed cylinder with a 300 K diffuse
     wall, free-stream inflow + deletion on `flow`, symmetry planes on the wedge sides, dsmcAxisymmetric about x with radial weighting
     method "cell" and maxRadialWeightingFactor 1000.  geometry: callable returning (cell centres, ..., face centres) after set_mesh.
     Returns (mesh, species dicts, per-cell nParticles = F_N * RWF)."""
-    mesh = meshgen.axisymmetric_cylinder_mesh()
+    mesh = mesh if mesh is not None else meshgen.axisymmetric_cylinder_mesh()
     sp = [capi.make_species("Ar", float(gold["mass"]), float(gold["diameter"]), float(gold["omega"]), float(gold["alpha"]))]
     rev, pol, ang = capi.axisymmetric_axes()
     flow, cyl = mesh.patch_index("flow"), mesh.patch_index("cylinder")

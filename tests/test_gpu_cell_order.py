@@ -119,6 +119,46 @@ def test_mesh_fill_and_uploads_without_tet_indices_follow_the_cell_order():
     eng.close()
 
 
+def test_axisymmetric_case_with_cell_fields_under_a_cell_order():
+    """Per-cell nParticles / RWF (dsmcb200_set_cell_fields) and the parcels' radial weights under the engine's own labels: three steps of the
+    axisymmetric tutorial (prisms on the axis, weighted inflow, cloning / deletion, diffuse wall) equal the oracle on the relabelled mesh."""
+    gold = H.axisym_gold()
+    base = meshgen.axisymmetric_cylinder_mesh()
+    eng = capi.Engine(0)
+    eng.set_cell_order("z-curve")
+    _, _, npc, _ = H.axisym_setup(eng, gold, eng.geometry, mesh=base)
+    t = eng.cell_order()
+    assert not np.array_equal(t, np.arange(base.n_cells))
+    ora = Oracle()
+    _, _, npc_o, _ = H.axisym_setup(ora, gold, ora.geometry, mesh=meshgen.relabel_cells(base, t))
+    assert np.allclose(npc, npc_o[t], rtol=1e-14)
+    _, _, rwf = eng.cell_fields()
+    assert np.allclose(rwf * float(gold["nEquivalentParticles"]), npc, rtol=1e-14)     # what was set comes back in the caller's labels
+    ora.mesh_fill([0], [float(gold["numberDensity"])], float(gold["temperature"]), 0, 0, 0, tuple(gold["velocity"]))
+    start = ora.download_parcels()
+    sig, rem = ora.download_cellstate()
+    inv = np.empty_like(t); inv[t] = np.arange(len(t), dtype=np.int32)
+    eng.upload_parcels(_relabelled(start, inv))
+    eng.upload_cellstate(sig[t], rem[t])
+    for _ in range(3):
+        eng.evolve(1)
+        ora.evolve(1)
+        assert eng.num_parcels() == ora.num_parcels()
+    cloned, deleted = ora.weighting_counts()
+    assert cloned > 50 and deleted > 50
+    g, o = eng.download_parcels(), ora.download_parcels()
+    assert np.array_equal(g.origId, o.origId) and np.array_equal(t[g.cell], o.cell)
+    assert np.array_equal(g.radialWeight, o.radialWeight)
+    assert np.allclose(g.position, o.position, rtol=0, atol=1e-14) and np.allclose(g.U, o.U, rtol=1e-9, atol=1e-7)
+    gw, ow = eng.wall_accumulators(), ora.wall_accumulators()
+    scale = np.abs(ow).max(axis=(0, 1), keepdims=True) + 1e-300
+    assert np.abs(ow).max() > 0 and (np.abs(gw - ow) / scale).max() < 1e-9
+    ga, _, _ = eng.accumulators()
+    oa, _, _ = ora.accumulators()
+    assert np.array_equal(ga[:, :, 0], oa[t][:, :, 0])
+    eng.close()
+
+
 def test_cell_order_is_checked():
     mesh, sp, md = _case()
     eng = capi.Engine(0)
