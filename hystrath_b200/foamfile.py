@@ -405,8 +405,9 @@ _BANNER = """/*--------------------------------*- C++ -*------------------------
 """
 
 
-def header(cls, location, obj, binary=False):
-    return (_BANNER + "FoamFile\n{\n    version     2.0;\n    format      " + ("binary;\n    arch        \"LSB;label=32;scalar=64\";\n" if binary else "ascii;\n") +
+def header(cls, location, obj, binary=False, label64=False):
+    return (_BANNER + "FoamFile\n{\n    version     2.0;\n    format      " +
+            (f"binary;\n    arch        \"LSB;label={64 if label64 else 32};scalar=64\";\n" if binary else "ascii;\n") +
             f"    class       {cls};\n    location    \"{location}\";\n    object      {obj};\n}}\n"
             "// * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * //\n\n")
 
@@ -417,11 +418,12 @@ def _binary_list(a, dtype) -> bytes:
     return f"\n{n}\n".encode() + (b"(" + a.tobytes() + b")" if n else b"")
 
 
-def write_scalar_list(path, cls, location, obj, a, fmt="%.10g", binary=False):
+def write_scalar_list(path, cls, location, obj, a, fmt="%.10g", binary=False, label64=False):
     a = np.asarray(a)
     if binary:
+        lab = np.int64 if label64 else np.int32
         with open(path, "wb") as f:
-            f.write(header(cls, location, obj, True).encode() + _binary_list(a, np.int32 if np.issubdtype(a.dtype, np.integer) else np.float64) + b"\n")
+            f.write(header(cls, location, obj, True, label64).encode() + _binary_list(a, lab if np.issubdtype(a.dtype, np.integer) else np.float64) + b"\n")
         return
     with open(path, "w") as f:
         f.write(header(cls, location, obj))
@@ -431,23 +433,24 @@ def write_scalar_list(path, cls, location, obj, a, fmt="%.10g", binary=False):
             f.write(f"{len(a)}\n(\n" + "\n".join(fmt % v for v in a) + "\n)\n")
 
 
-def write_vector_list(path, cls, location, obj, a, fmt="%.10g", binary=False):
+def write_vector_list(path, cls, location, obj, a, fmt="%.10g", binary=False, label64=False):
     if binary:
         a = np.ascontiguousarray(a, dtype=np.float64)
         with open(path, "wb") as f:
-            f.write(header(cls, location, obj, True).encode() + f"\n{len(a)}\n".encode() + (b"(" + a.tobytes() + b")" if len(a) else b"") + b"\n")
+            f.write(header(cls, location, obj, True, label64).encode() + f"\n{len(a)}\n".encode() + (b"(" + a.tobytes() + b")" if len(a) else b"") + b"\n")
         return
     with open(path, "w") as f:
         f.write(header(cls, location, obj))
         f.write(f"{len(a)}\n(\n" + "\n".join("(" + " ".join(fmt % c for c in v) + ")" for v in a) + "\n)\n")
 
 
-def write_positions(path, location, xyz, cell, fmt="%.10g", binary=False):
+def write_positions(path, location, xyz, cell, fmt="%.10g", binary=False, label64=False):
     if binary:
-        rec = np.zeros(len(cell), np.dtype([("x", np.float64, 3), ("cell", np.int32), ("face", np.int32), ("stepFraction", np.float64)]))
+        lab = np.int64 if label64 else np.int32
+        rec = np.zeros(len(cell), np.dtype([("x", np.float64, 3), ("cell", lab), ("face", lab), ("stepFraction", np.float64)]))
         rec["x"], rec["cell"], rec["face"] = xyz, cell, -1
         with open(path, "wb") as f:
-            f.write(header("Cloud<dsmcParcel>", location, "positions", True).encode() + f"{len(cell)}\n(\n".encode())
+            f.write(header("Cloud<dsmcParcel>", location, "positions", True, label64).encode() + f"{len(cell)}\n(\n".encode())
             f.write(b"".join(b"(" + r.tobytes() + b")\n" for r in rec) + b")\n")
         return
     with open(path, "w") as f:
@@ -455,21 +458,23 @@ def write_positions(path, location, xyz, cell, fmt="%.10g", binary=False):
         f.write(f"{len(cell)}\n(\n" + "\n".join("(" + " ".join(fmt % c for c in p) + f") {c}" for p, c in zip(xyz, cell)) + "\n)\n")
 
 
-def write_label_list_list(path, cls, location, obj, a, binary=False):
+def write_label_list_list(path, cls, location, obj, a, binary=False, label64=False):
     a = np.asarray(a)
     if binary:
+        lab = np.int64 if label64 else np.int32
         with open(path, "wb") as f:
-            f.write(header(cls, location, obj, True).encode() + f"{len(a)}\n(".encode() + b"".join(_binary_list(r, np.int32) for r in a) + b"\n)\n")
+            f.write(header(cls, location, obj, True, label64).encode() + f"{len(a)}\n(".encode() + b"".join(_binary_list(r, lab) for r in a) + b"\n)\n")
         return
     with open(path, "w") as f:
         f.write(header(cls, location, obj))
         f.write(f"{len(a)}\n(\n" + "\n".join(f"{len(r)}(" + " ".join(str(int(x)) for x in r) + ")" for r in a) + "\n)\n")
 
 
-def write_faces(path, location, offsets, labels, binary=False):
+def write_faces(path, location, offsets, labels, binary=False, label64=False):
     if binary:   # faceCompactIOList
+        lab = np.int64 if label64 else np.int32
         with open(path, "wb") as f:
-            f.write(header("faceCompactList", location, "faces", True).encode() + _binary_list(offsets, np.int32) + _binary_list(labels, np.int32) + b"\n")
+            f.write(header("faceCompactList", location, "faces", True, label64).encode() + _binary_list(offsets, lab) + _binary_list(labels, lab) + b"\n")
         return
     with open(path, "w") as f:
         f.write(header("faceList", location, "faces"))
@@ -478,30 +483,30 @@ def write_faces(path, location, offsets, labels, binary=False):
                                          for i in range(n)) + "\n)\n")
 
 
-def convert_case_to_binary(case_dir, time_name):
-    """Rewrite the polyMesh and the cloud of <time_name> of an ASCII case in `format binary;` (what `foamFormatConvert` does after
-    `writeFormat binary;`): the same numbers, so a reader must find the same mesh and cloud."""
+def convert_case_to_binary(case_dir, time_name, label64=False):
+    """Rewrite the polyMesh and the cloud of <time_name> of a case in `format binary;` (what `foamFormatConvert` does after
+    `writeFormat binary;`), with 32- or 64-bit labels: the same numbers, so a reader must find the same mesh and cloud."""
     import os
     pm = os.path.join(case_dir, "constant", "polyMesh")
-    write_vector_list(os.path.join(pm, "points"), "vectorField", "constant/polyMesh", "points", read_vector_list(os.path.join(pm, "points")), binary=True)
+    write_vector_list(os.path.join(pm, "points"), "vectorField", "constant/polyMesh", "points", read_vector_list(os.path.join(pm, "points")), binary=True, label64=label64)
     offs, labels = read_faces(os.path.join(pm, "faces"))
-    write_faces(os.path.join(pm, "faces"), "constant/polyMesh", offs, labels, binary=True)
+    write_faces(os.path.join(pm, "faces"), "constant/polyMesh", offs, labels, binary=True, label64=label64)
     for name in ("owner", "neighbour"):
-        write_scalar_list(os.path.join(pm, name), "labelList", "constant/polyMesh", name, read_scalar_list(os.path.join(pm, name), np.int32), binary=True)
+        write_scalar_list(os.path.join(pm, name), "labelList", "constant/polyMesh", name, read_scalar_list(os.path.join(pm, name), np.int32), binary=True, label64=label64)
     loc = f"{time_name}/lagrangian/dsmc"
     d = os.path.join(case_dir, time_name, "lagrangian", "dsmc")
     xyz, cell = read_positions(os.path.join(d, "positions"))
-    write_positions(os.path.join(d, "positions"), loc, xyz, cell, binary=True)
+    write_positions(os.path.join(d, "positions"), loc, xyz, cell, binary=True, label64=label64)
     for name in sorted(os.listdir(d)):
         path = os.path.join(d, name)
         if name == "positions" or not os.path.isfile(path):
             continue
-        cls = re.search(r"class\s+([^;]+);", open(path).read(2000)).group(1).strip()
+        cls = re.search(rb"class\s+([^;]+);", open(path, "rb").read(2000)).group(1).strip().decode()
         if cls == "vectorField":
-            write_vector_list(path, cls, loc, name, read_vector_list(path), binary=True)
+            write_vector_list(path, cls, loc, name, read_vector_list(path), binary=True, label64=label64)
         elif cls == "scalarField":
-            write_scalar_list(path, cls, loc, name, read_scalar_list(path), binary=True)
+            write_scalar_list(path, cls, loc, name, read_scalar_list(path), binary=True, label64=label64)
         elif cls == "labelField":
-            write_scalar_list(path, cls, loc, name, read_scalar_list(path, np.int32), binary=True)
+            write_scalar_list(path, cls, loc, name, read_scalar_list(path, np.int32), binary=True, label64=label64)
         elif cls in ("labelFieldField", "labelListList"):
-            write_label_list_list(path, cls, loc, name, read_label_list_list(path), binary=True)
+            write_label_list_list(path, cls, loc, name, read_label_list_list(path), binary=True, label64=label64)

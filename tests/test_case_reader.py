@@ -278,8 +278,48 @@ def test_driver_reads_a_binary_case_like_the_ascii_one(tmp_path):
             assert all(np.array_equal(x, y) for x, y in zip(a, b)), k
         else:
             assert np.array_equal(a, b), k
+    # the same case as a 64-bit-label build writes it (arch "LSB;label=64;scalar=64")
+    ff.convert_case_to_binary(str(tmp_path), "5", label64=True)
+    assert b"label=64" in open(os.path.join(d, "typeId"), "rb").read(1200)
+    r64 = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r64.returncode == 0, r64.stderr
+    assert [l for l in r64.stdout.splitlines() if "checksum" in l] == ascii_sum
     # a truncated block is an error, not a short cloud
     whole = open(os.path.join(d, "U"), "rb").read()
     open(os.path.join(d, "U"), "wb").write(whole[:-5000])
     r3 = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
     assert r3.returncode == 1 and "binary block is truncated" in r3.stderr
+
+
+def test_python_binary_round_trip(tmp_path):
+    """The Python reader / writer of `format binary;` files: every list kind of a cloud, an empty list, rows of different length, and a
+    file written by a 64-bit-label build (arch "...label=64...")."""
+    d = str(tmp_path)
+    rng = np.random.default_rng(3)
+    n = 257
+    xyz, cell = rng.random((n, 3)), rng.integers(0, 1000, n).astype(np.int32)
+    ff.write_positions(os.path.join(d, "positions"), "0/lagrangian/dsmc", xyz, cell, binary=True)
+    x2, c2 = ff.read_positions(os.path.join(d, "positions"))
+    assert np.array_equal(x2, xyz) and np.array_equal(c2, cell)
+    U = rng.standard_normal((n, 3))
+    ff.write_vector_list(os.path.join(d, "U"), "vectorField", "0/lagrangian/dsmc", "U", U, binary=True)
+    assert np.array_equal(ff.read_vector_list(os.path.join(d, "U")), U)
+    e = rng.random(n)
+    ff.write_scalar_list(os.path.join(d, "ERot"), "scalarField", "0/lagrangian/dsmc", "ERot", e, binary=True)
+    assert np.array_equal(ff.read_scalar_list(os.path.join(d, "ERot")), e)
+    ff.write_scalar_list(os.path.join(d, "typeId"), "labelField", "0/lagrangian/dsmc", "typeId", cell, binary=True)
+    assert np.array_equal(ff.read_scalar_list(os.path.join(d, "typeId"), np.int32), cell)
+    ff.write_scalar_list(os.path.join(d, "none"), "labelField", "0/lagrangian/dsmc", "none", np.zeros(0, np.int32), binary=True)
+    assert len(ff.read_scalar_list(os.path.join(d, "none"), np.int32)) == 0
+    rows = [np.array([1, 2, 3]), np.array([], int), np.array([7])]
+    ff.write_label_list_list(os.path.join(d, "vibLevel"), "labelFieldField", "0/lagrangian/dsmc", "vibLevel", np.array(rows, dtype=object), binary=True)
+    v = ff.read_label_list_list(os.path.join(d, "vibLevel"))
+    assert v.shape == (3, 3) and v.tolist() == [[1, 2, 3], [0, 0, 0], [7, 0, 0]]
+    offs, labels = np.array([0, 4, 7, 12], np.int32), rng.integers(0, 50, 12).astype(np.int32)
+    ff.write_faces(os.path.join(d, "faces"), "constant/polyMesh", offs, labels, binary=True)
+    o2, l2 = ff.read_faces(os.path.join(d, "faces"))
+    assert np.array_equal(o2, offs) and np.array_equal(l2, labels)
+    # 64-bit labels: same layout with 8-byte integers, announced in the header's arch entry
+    raw = ff.header("labelList", "constant/polyMesh", "owner", True).replace("label=32", "label=64").encode() + b"\n5\n(" + np.arange(5, dtype=np.int64).tobytes() + b")\n"
+    open(os.path.join(d, "owner"), "wb").write(raw)
+    assert ff.read_scalar_list(os.path.join(d, "owner"), np.int32).tolist() == [0, 1, 2, 3, 4]
