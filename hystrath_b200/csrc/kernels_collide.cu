@@ -1092,6 +1092,18 @@ cudaError_t launchCollide(const CollideArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 constexpr int SMP_THREADS = 256;
+#ifndef SMP_TILE_MAX
+#define SMP_TILE_MAX 512       // parcels of one chunk
+#endif
+#ifndef SMP_TILE_BYTES
+#define SMP_TILE_BYTES (40 * 1024)
+#endif
+#ifndef SMP_GROUP_PARCELS
+#define SMP_GROUP_PARCELS 1024 // parcels of the consecutive cells one block takes at a time
+#endif
+#ifndef SMP_BLOCKS_PER_SM
+#define SMP_BLOCKS_PER_SM 4    // persistent grid: blocks per SM
+#endif
 
 // sum[sp] += x with sp a run-time index and sum[] in registers: one predicated add per species
 template <int I, int S>
@@ -1272,18 +1284,18 @@ cudaError_t launchSample(const SampleArgs& a, cudaStream_t s) {
     // spare threads split each cell's parcels into nSub interleaved sub-ranges (few, crowded cells)
     const int maxCells = SMP_THREADS / a.nQ > 0 ? SMP_THREADS / a.nQ : 1;
     const double ppc = a.nCells > 0 ? double(a.nParcels) / a.nCells : 1.0;
-    int cpg = int(1024.0 / (ppc > 1.0 ? ppc : 1.0));
+    int cpg = int(double(SMP_GROUP_PARCELS) / (ppc > 1.0 ? ppc : 1.0));
     if (cpg > maxCells) cpg = maxCells;
     if (cpg < 1) cpg = 1;
     int nSub = SMP_THREADS / (cpg * a.nQ);
     if (nSub < 1) nSub = 1;
     const int stride = a.nQ | 1;
-    int tile = ((40 * 1024) / (stride * 8)) & ~31;
-    if (tile > 512) tile = 512;
+    int tile = (SMP_TILE_BYTES / (stride * 8)) & ~31;
+    if (tile > SMP_TILE_MAX) tile = SMP_TILE_MAX;
     if (tile < 32) tile = 32;
     const size_t smem = (size_t(tile) * stride + size_t(a.nSpecies) * SMP_THREADS) * sizeof(double) + size_t(cpg + 1) * 4 + tile;
     const int nGroups = (a.nCells + cpg - 1) / cpg;
-    int grid = nGroups < 148 * 4 ? nGroups : 148 * 4;
+    int grid = nGroups < 148 * SMP_BLOCKS_PER_SM ? nGroups : 148 * SMP_BLOCKS_PER_SM;
     if (grid < 1) grid = 1;
     auto go = [&](auto kernel) -> cudaError_t {
         const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
