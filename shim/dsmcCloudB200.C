@@ -455,6 +455,7 @@ void Foam::dsmcCloud::readFieldProperties()
     const PtrList<entry> fList(fieldPropertiesDict_.lookup("dsmcFields"));
     fields_.setSize(fList.size());
     models_.sampleInterval = 1;
+    sampleIntervals_.clear();
     forAll(fList, i)
     {
         const dictionary& d = fList[i].dict();
@@ -468,18 +469,36 @@ void Foam::dsmcCloud::readFieldProperties()
         const dictionary& tp = d.subDict("timeProperties");
         f.resetAtOutput = Switch(tp.lookupOrDefault<Switch>("resetAtOutput", true));
         f.resetAtOutputUntilTime = tp.lookupOrDefault<scalar>("resetAtOutputUntilTime", VGREAT);
-        const label si = p.lookupOrDefault<label>("sampleInterval", 1);
-        if (i == 0) { models_.sampleInterval = si; }
-        // this shim keeps one accumulator set for every instance, so their sampling policy must agree; the library itself offers one set per
-        // sampleInterval (dsmcb200_set_sample_sets / select_sample_set) and per-field baselines, as the standalone driver uses them
-        if (si != models_.sampleInterval || f.resetAtOutput != fields_[0].resetAtOutput || f.resetAtOutputUntilTime != fields_[0].resetAtOutputUntilTime)
+        // every field samples on its own cadence (dsmcVolFields.C:1073-1081): fields with the same sampleInterval share one set of the
+        // library's sums, resetAtOutput / resetAtOutputUntilTime stay per field through the baselines below (dsmcField.C:113-152)
+        const label si = max(label(1), p.lookupOrDefault<label>("sampleInterval", 1));
+        label set = -1;
+        forAll(sampleIntervals_, k) { if (sampleIntervals_[k] == si) { set = k; } }
+        if (set < 0)
         {
-            FatalErrorIn("dsmcCloud (dsmcb200)") << "field " << f.fieldName << ": sampleInterval / timeProperties differ from field "
-                << fields_[0].fieldName << "; the engine keeps one accumulator set" << exit(FatalError);
+            if (sampleIntervals_.size() == 8)
+            {
+                FatalErrorIn("dsmcCloud (dsmcb200)") << "field " << f.fieldName << ": more than 8 different sampleIntervals" << exit(FatalError);
+            }
+            set = sampleIntervals_.size();
+            sampleIntervals_.append(si);
         }
+        f.sampleSet = set;
+        f.baseNT = 0;
         if (Switch(p.lookupOrDefault<Switch>("measureHeatFluxShearStress", false))) { models_.measureHeatFluxShearStress = 1; }
         if (Switch(p.lookupOrDefault<Switch>("measureClassifications", false))) { models_.measureClassifications = 1; }
     }
+    if (sampleIntervals_.size()) { models_.sampleInterval = sampleIntervals_[0]; }
+    if (sampleIntervals_.size() > 1)
+    {
+        ck(dsmcb200_set_sample_sets(ctx_, sampleIntervals_.size(), sampleIntervals_.begin()), "dsmcb200_set_sample_sets");
+    }
+}
+
+
+void Foam::dsmcCloud::selectSampleSet(const label set) const
+{
+    if (sampleIntervals_.size() > 1) { ck(dsmcb200_select_sample_set(ctx_, set), "dsmcb200_select_sample_set"); }
 }
 
 
@@ -827,9 +846,9 @@ void Foam::dsmcCloud::writeFields() const
     dsmcb200_accum_info ai;
     ck(dsmcb200_accum_info_get(ctx_, &ai), "dsmcb200_accum_info_get");
     const label nC = ai.nCells, nS = ai.nSpecies, nQ = ai.nQuantities;
-    scalarField acc(nC*nS*nQ), coll(2*nC);
-    ck(dsmcb200_download_accumulators(ctx_, acc.begin(), coll.begin()), "dsmcb200_download_accumulators");
-    const scalar nT = max(ai.nTimeSteps, 1.0);
+    scalarField acc(nC*nS*nQ), coll(2*nC), accSet(nC*nS*nQ), collSet(2*nC);
+    label loadedSet = -1;
+    scalar nTSet = 0;
     const scalar kB = models_.kB;
     const scalarField& V = mesh_.cellVolumes();
     const bool internal = ai.nModes >= 0;
@@ -838,6 +857,18 @@ void Foam::dsmcCloud::writeFields() const
     {
         const fieldSpec& f = fields_[fi];
         const word& nm = f.fieldName;
+        if (f.sampleSet != loadedSet)      // the sums of this field's sample set ...
+        {
+            selectSampleSet(f.sampleSet);
+            ck(dsmcb200_accum_info_get(ctx_, &ai), "dsmcb200_accum_info_get");
+            ck(dsmcb200_download_accumulators(ctx_, accSet.begin(), collSet.begin()), "dsmcb200_download_accumulators");
+            nTSet = ai.nTimeSteps;
+            loadedSet = f.sampleSet;
+        }
+        acc = accSet; coll = collSet;      // ... since the field's own last reset
+        if (f.baseAcc.size() == acc.size()) { acc -= f.baseAcc; }
+        if (f.baseColl.size() == coll.size()) { coll -= f.baseColl; }
+        const scalar nT = max(nTSet - f.baseNT, 1.0);
         #define DSMCB200_SCALAR_FIELD(var, prefix, dims) \
             volScalarField var(IOobject(word(prefix) + "_" + nm, mesh_.time().timeName(), mesh_, IOobject::NO_READ, IOobject::NO_WRITE), \
                                mesh_, dimensionedScalar("zero", dims, 0.0), calculatedFvPatchScalarField::typeName)
@@ -930,11 +961,46 @@ void Foam::dsmcCloud::writeFields() const
         dsmcNMean.write(); rhoN.write(); rhoM.write(); p.write(); Ttra.write(); Trot.write(); Tvib.write(); Tov.write(); UMean.write();
     }
 
-    // dsmcField::updateTime (dsmcField.C:113-152): while resetAtOutput is on (and until resetAtOutputUntilTime) sampling restarts here
-    if (fields_.size() && fields_[0].resetAtOutput && time_.value() <= fields_[0].resetAtOutputUntilTime)
+    // dsmcField::updateTime (dsmcField.C:113-152): while resetAtOutput is on (and until resetAtOutputUntilTime) a field's sampling restarts
+    // here.  The sums belong to a sample set: when every field of the set resets they are cleared, otherwise a field that resets takes
+    // the present sums as its baseline.
+    forAll(sampleIntervals_, set)
     {
-        ck(dsmcb200_reset_accumulators(ctx_), "dsmcb200_reset_accumulators");
+        bool all = true, some = false;
+        forAll(fields_, fi)
+        {
+            const fieldSpec& f = fields_[fi];
+            if (f.sampleSet != set) { continue; }
+            const bool resets = f.resetAtOutput && time_.value() <= f.resetAtOutputUntilTime;
+            all = all && resets;
+            some = some || resets;
+        }
+        if (!some) { continue; }
+        selectSampleSet(set);
+        if (all)
+        {
+            ck(dsmcb200_reset_accumulators(ctx_), "dsmcb200_reset_accumulators");
+            forAll(fields_, fi)
+            {
+                const fieldSpec& f = fields_[fi];
+                if (f.sampleSet == set) { f.baseAcc.clear(); f.baseColl.clear(); f.baseNT = 0; }
+            }
+        }
+        else
+        {
+            ck(dsmcb200_accum_info_get(ctx_, &ai), "dsmcb200_accum_info_get");
+            ck(dsmcb200_download_accumulators(ctx_, accSet.begin(), collSet.begin()), "dsmcb200_download_accumulators");
+            forAll(fields_, fi)
+            {
+                const fieldSpec& f = fields_[fi];
+                if (f.sampleSet == set && f.resetAtOutput && time_.value() <= f.resetAtOutputUntilTime)
+                {
+                    f.baseAcc = accSet; f.baseColl = collSet; f.baseNT = ai.nTimeSteps;
+                }
+            }
+        }
     }
+    selectSampleSet(0);
 }
 
 
