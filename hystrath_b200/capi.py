@@ -448,7 +448,7 @@ def build_models(collisionModel="VariableHardSphere", nEquivalentParticles=1.0, 
     return m
 
 
-COORDINATE_SYSTEM_NAMES = {"dsmcCartesian": 0, "dsmcAxisymmetric": 1}
+COORDINATE_SYSTEM_NAMES = {"dsmcCartesian": 0, "dsmcAxisymmetric": 1, "dsmcSpherical": 2}
 
 
 def axisymmetric_axes(revolutionAxis="", polarAxis=""):
@@ -495,6 +495,20 @@ def axisymmetric_rwf(cell_centres, face_centres, polar_axis, max_rwf, radial_ext
             radial_extent = -fc.min()
     rwf = np.ones(len(cell_centres))
     rwf += (max_rwf - 1.0) * np.abs(np.asarray(cell_centres)[:, polar_axis]) / radial_extent
+    return rwf, radial_extent
+
+
+def spherical_rwf(cell_centres, face_centres, origin, max_rwf, radial_extent=None):
+    """dsmcSpherical::recalculateRWF, radial weighting method "cell" (dsmcSpherical.C:232-275): RWF = 1 + (maxRWF - 1) (r / radialExtent)^2
+    with r the distance of the cell centre from `origin` and radialExtent = gMax of the face centres' distances (:355-366)."""
+    o = np.asarray(origin, float)
+    d = np.asarray(face_centres) - o
+    if radial_extent is None:
+        radial_extent = np.sqrt(d[:, 0] ** 2 + d[:, 1] ** 2 + d[:, 2] ** 2).max()
+    c = np.asarray(cell_centres) - o
+    radius = np.sqrt(c[:, 0] ** 2 + c[:, 1] ** 2 + c[:, 2] ** 2)
+    rwf = np.ones(len(c))
+    rwf += (max_rwf - 1.0) * (radius / radial_extent) ** 2
     return rwf, radial_extent
 
 

@@ -75,7 +75,8 @@ void selectFieldModel(const std::string& name) {
 int selectCoordinateSystem(const std::string& name) {
     if (name == "dsmcCartesian") return DSMCB200_COORD_CARTESIAN;
     if (name == "dsmcAxisymmetric") return DSMCB200_COORD_AXISYMMETRIC;
-    unknownType("dsmcCoordinateSystem::New", "dsmcCoordinateSystem", name, {"dsmcAxisymmetric", "dsmcCartesian"});
+    if (name == "dsmcSpherical") return DSMCB200_COORD_SPHERICAL;
+    unknownType("dsmcCoordinateSystem::New", "dsmcCoordinateSystem", name, {"dsmcAxisymmetric", "dsmcCartesian", "dsmcSpherical"});
     return 0;
 }
 // dsmcTimeStepModel::New builds the type name "dsmc" + Keyword + "TimeStepModel" (dsmcTimeStepModel.C:99-107)
@@ -169,6 +170,11 @@ void dsmcCloud::setCellFields() {
     if (models_.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC) {
         double radialExtent = -VGREAT, lowest = VGREAT;
         for (int f = 0; f < nFaces_; ++f) { radialExtent = std::max(radialExtent, faceCentres_[3 * size_t(f) + polarAxis_]); lowest = std::min(lowest, faceCentres_[3 * size_t(f) + polarAxis_]); }
+        if (nRanks_ > 1) {   // gMax / gMin over the decomposed mesh (dsmcAxisymmetric.C:447-456)
+            double v[2] = {-radialExtent, lowest};
+            check(dsmcb200_allreduce_min(ctx_, v, 2), "dsmcb200_allreduce_min");
+            radialExtent = -v[0]; lowest = v[1];
+        }
         if (!(radialExtent > 0)) radialExtent = -lowest;
         radialExtent_ = radialExtent;
         for (int c = 0; c < nCells_; ++c) {
@@ -182,7 +188,26 @@ void dsmcCloud::setCellFields() {
                         "- radial weighting method\tcell-based\n- radial extent\t%g\n- maximum radial weighting factor\t%g\n\n",
                         3 - polarAxis_ - models_.angularCoordinate, polarAxis_, models_.angularCoordinate, radialExtent, maxRWF_);
     }
-    const bool axi = models_.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC;
+    if (models_.coordinateSystem == DSMCB200_COORD_SPHERICAL) {
+        // radialExtent = gMax |face centre - origin| (dsmcSpherical.C:355-368), RWF = 1 + (maxRWF - 1) (r / radialExtent)^2 (:262-274)
+        auto dist = [&](const double* x) {
+            return std::sqrt((x[0] - origin_[0]) * (x[0] - origin_[0]) + (x[1] - origin_[1]) * (x[1] - origin_[1]) + (x[2] - origin_[2]) * (x[2] - origin_[2]));
+        };
+        double radialExtent = 0.0;
+        for (int f = 0; f < nFaces_; ++f) radialExtent = std::max(radialExtent, dist(&faceCentres_[3 * size_t(f)]));
+        if (nRanks_ > 1) { double neg = -radialExtent; check(dsmcb200_allreduce_min(ctx_, &neg, 1), "dsmcb200_allreduce_min"); radialExtent = -neg; }   // gMax
+        radialExtent_ = radialExtent;
+        for (int c = 0; c < nCells_; ++c) {
+            const double radius = dist(&cellCentres_[3 * size_t(c)]);
+            double RWF = 1.0;
+            RWF += (maxRWF_ - 1.0) * (radius / radialExtent) * (radius / radialExtent);
+            rwfCell_[c] = RWF;
+        }
+        if (rank_ == 0)
+            std::printf("\nSpherical simulation:\n- coordinate system origin\t(%g %g %g)\n- radial weighting method\tcell-based\n- radial extent\t%g\n"
+                        "- maximum radial weighting factor\t%g\n\n", origin_[0], origin_[1], origin_[2], radialExtent, maxRWF_);
+    }
+    const bool axi = models_.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC || models_.coordinateSystem == DSMCB200_COORD_SPHERICAL;
     if (variableTimeStep_ || axi)
         check(dsmcb200_set_cell_fields(ctx_, variableTimeStep_ ? nPtsCell_.data() : nullptr, variableTimeStep_ ? dtCell_.data() : nullptr,
                                        axi ? rwfCell_.data() : nullptr), "dsmcb200_set_cell_fields");
@@ -321,6 +346,18 @@ void dsmcCloud::readProperties() {
         }
         polarAxis_ = polar; models_.angularCoordinate = ang;
         maxRWF_ = ax.scalar("maxRadialWeightingFactor");
+    }
+    if (models_.coordinateSystem == DSMCB200_COORD_SPHERICAL) {
+        // dsmcSpherical::checkCoordinateSystemInputs (dsmcSpherical.C:325-386)
+        const Dict& sph = d.subDict("sphericalProperties");
+        const std::string method = sph.wordOr("radialWeightingMethod", "cell");
+        if (method != "cell" && method != "particleAverage")
+            throw FoamError("The radial weighting method is badly defined. Choices in constant/dsmcProperties are \"cell\" or \"particleAverage\". Please edit the entry: radialWeightingMethod.");
+        if (method == "particleAverage")
+            throw FoamError("radialWeightingMethod particleAverage is not supported (the sampled sums are weighted per cell after the run); use \"cell\"");
+        maxRWF_ = sph.scalar("maxRadialWeightingFactor");
+        const std::vector<double> o = sph.found("origin") ? sph.vector3("origin") : std::vector<double>{0.0, 0.0, 0.0};
+        for (int k = 0; k < 3; ++k) origin_[k] = o[k];
     }
     // VariableHardSphere reads Tref from VariableHardSphereCoeffs even under the LB model (VariableHardSphere.C:56-62)
     // (VariableSoftSphere.C:54-60 does the same with VariableSoftSphereCoeffs)
@@ -658,7 +695,7 @@ std::string dsmcCloud::summary() const {
     o << "  species:";
     for (auto& t : typeIdList_) o << " " << t;
     o << "\n  collisionModel " << models_.collisionModel << " invZv " << models_.invZvFormulation << " nEquivalentParticles " << models_.nEquivalentParticles
-      << " seed " << models_.seed << "\n  coordinateSystem " << (models_.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC ? "dsmcAxisymmetric" : "dsmcCartesian")
+      << " seed " << models_.seed << "\n  coordinateSystem " << (models_.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC ? "dsmcAxisymmetric" : (models_.coordinateSystem == DSMCB200_COORD_SPHERICAL ? "dsmcSpherical" : "dsmcCartesian"))
       << " polarAxis " << polarAxis_ << " angularCoordinate " << models_.angularCoordinate << " maxRadialWeightingFactor " << maxRWF_
       << " timeStepModel " << (variableTimeStep_ ? "variable" : "constant") << "\n  patchModels " << patchModels_.size() << " inflows " << inflows_.size() << " fields " << fields_.size() << "\n";
     for (auto& pm : patchModels_)
@@ -1542,7 +1579,7 @@ void dsmcCloud::write() {
         }
         foam::writeVolField(timeDir + "/" + name, timeName_, name, dims, v.data(), nCells_, 1, bv);
     };
-    if (models_.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC) cellField("RWF", "[0 0 0 0 0 0 0]", rwfCell_);
+    if (models_.coordinateSystem != DSMCB200_COORD_CARTESIAN) cellField("RWF", "[0 0 0 0 0 0 0]", rwfCell_);
     if (variableTimeStep_) { cellField("nParticles", "[0 0 0 0 0 0 0]", nPtsCell_); cellField("deltaT", "[0 0 1 0 0 0 0]", dtCell_); }
     if (initialise_) return;  // dsmcInitialise+ writes the cloud and dsmcSigmaTcRMax only
     {

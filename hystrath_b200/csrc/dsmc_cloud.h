@@ -136,6 +136,7 @@ class dsmcCloud {
     bool initialise_ = false;   // dsmcInitialise+: no cloud is read, system/dsmcInitialiseDict fills the mesh
     void initialiseFromDict();  // dsmcAllConfigurations::setInitialConfig (dsmcCloud.C:795-796)
     int64_t nRead_ = 0;
+    double origin_[3] = {0, 0, 0};   // sphericalProperties origin (dsmcSpherical)
     uint64_t meshHash_ = 0, cloudHash_ = 0;   // FNV-1a over the bytes read (printed by summary(): the same case in ASCII and binary reads the same)
 
    public:

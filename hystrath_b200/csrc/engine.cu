@@ -447,13 +447,13 @@ int finalize(dsmcb200_ctx* c) {
     if (P.nPatches > MAX_PATCHES) return fail(c, DSMCB200_ERR_CAPACITY, "more than 64 patches");
     P.collisionModel = md.collisionModel;
     P.invZvFormulation = md.invZvFormulation;
-    if (md.coordinateSystem != DSMCB200_COORD_CARTESIAN && md.coordinateSystem != DSMCB200_COORD_AXISYMMETRIC)
+    if (md.coordinateSystem != DSMCB200_COORD_CARTESIAN && md.coordinateSystem != DSMCB200_COORD_AXISYMMETRIC && md.coordinateSystem != DSMCB200_COORD_SPHERICAL)
         return fail(c, DSMCB200_ERR_UNSUPPORTED, "dsmcCoordinateSystem::New(const dictionary&) : \n    unknown dsmcCoordinateSystem type " + std::to_string(md.coordinateSystem) +
-                    ", constructor not in hash table\n\n    Valid coordinate system types are :\n2(dsmcCartesian dsmcAxisymmetric)");
+                    ", constructor not in hash table\n\n    Valid coordinate system types are :\n3(dsmcAxisymmetric dsmcCartesian dsmcSpherical)");
     P.coordinateSystem = md.coordinateSystem;
     P.angularCoordinate = md.angularCoordinate;
-    c->useRwf = md.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC;
-    if (c->useRwf) {
+    c->useRwf = md.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC || md.coordinateSystem == DSMCB200_COORD_SPHERICAL;
+    if (md.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC) {
         if (md.angularCoordinate < 0 || md.angularCoordinate > 2) return fail(c, DSMCB200_ERR_INVALID, "dsmcAxisymmetric: angularCoordinate must be 0, 1 or 2");
     }
     P.kB = md.kB > 0 ? md.kB : 1.38065e-23;  // OpenFOAM v1706 physicoChemical::k (pinned by shipped couette fields)
@@ -1057,7 +1057,7 @@ int stageWeighting(dsmcb200_ctx* c) {
     int32_t* scratch = offsets + c->weightCountsCap;
     WeightArgs a{};
     a.p = c->buf[c->cur].a; a.cf = cellFields(c); a.n = n; a.base = n; a.capacity = int32_t(c->capacity);
-    a.angularCoordinate = c->hP.angularCoordinate; a.counts = counts; a.origIdBase = int32_t(c->nextOrigId & 0x7fffffff); a.origProc = c->rank;
+    a.angularCoordinate = c->hP.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC ? c->hP.angularCoordinate : -1; a.counts = counts; a.origIdBase = int32_t(c->nextOrigId & 0x7fffffff); a.origProc = c->rank;
     a.nModes = c->nModes; a.P = c->dP; a.counters = c->dCounters; a.step = c->step;
     CK(cudaMemsetAsync(&c->dCounters->weightDeleted, 0, sizeof(int32_t), c->stream));
     { KT t(c, "weighting"); CK(launchWeighting(a, 0, c->stream)); }

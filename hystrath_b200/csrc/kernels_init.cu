@@ -366,7 +366,8 @@ __global__ void __launch_bounds__(128) inflowKernel(const __grid_constant__ Infl
     }
 }
 
-// ---- dsmcAxisymmetric::axisymmetricWeighting (DSMC/coordinateSystem/derived/axisymmetric/dsmcAxisymmetric.C:50-209) ----
+// ---- dsmcAxisymmetric::axisymmetricWeighting (DSMC/coordinateSystem/derived/axisymmetric/dsmcAxisymmetric.C:50-209) and
+// dsmcSpherical::sphericalWeighting (.../spherical/dsmcSpherical.C:50-216: the same loop, the clone keeps the parent's velocity) ----
 // One thread per parcel of the sorted cloud (= the occupancy loop of the reference: cell by cell, list order).  The parcel's draw comes
 // from the Philox stream (index in that order, step).  pass 0: the parcel takes its cell's RWF; with a smaller RWF than before it is
 // cloned floor(old/new - 1) times plus once more with the remaining probability, with a larger one it is deleted with probability
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(256) weightKernel(const __grid_constant__ Weig
         const int32_t g = a.base + first + k;
         if (g >= a.capacity) { atomicAdd(&a.counters->overflow, 1ULL); return; }
         double U[3] = {p.ux[i], p.uy[i], p.uz[i]};
-        U[a.angularCoordinate] *= -1.0;
+        if (a.angularCoordinate >= 0) U[a.angularCoordinate] *= -1.0;   // dsmcAxisymmetric mirrors the angular component, dsmcSpherical clones as is
         p.px[g] = p.px[i]; p.py[g] = p.py[i]; p.pz[g] = p.pz[i];
         p.ux[g] = U[0]; p.uy[g] = U[1]; p.uz[g] = U[2];
         p.cell[g] = p.cell[i]; p.tet[g] = p.tet[i];

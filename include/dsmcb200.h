@@ -196,7 +196,11 @@ typedef struct {
  *                      cell they started the step in; after the move a parcel is cloned / deleted with the ratio of old and new RWF
  *                      (axisymmetricWeighting, :50-209) and the occupancy is rebuilt.  The per-cell RWF comes from
  *                      dsmcb200_set_cell_fields (the caller evaluates recalculateRWF, :236-275). */
-typedef enum { DSMCB200_COORD_CARTESIAN = 0, DSMCB200_COORD_AXISYMMETRIC = 1 } dsmcb200_coordinate_system;
+typedef enum {
+    DSMCB200_COORD_CARTESIAN = 0,
+    DSMCB200_COORD_AXISYMMETRIC = 1,
+    DSMCB200_COORD_SPHERICAL = 2    /* dsmcSpherical: the same weighting stage, clones keep their velocity (dsmcSpherical.C:50-216) */
+} dsmcb200_coordinate_system;
 
 /* One entry of system/chemReactDict `reactions ( name { reactionModel M; reactants (A B); allowSplitting yes; ... } )`
  * (DSMC/reactions/basic/dsmcReaction/dsmcReaction.C:79-120).  Quantum-kinetic models:

@@ -516,6 +516,7 @@ void Foam::dsmcCloud::readModels()
     HashTable<label> coordinateSystems;
     coordinateSystems.insert("dsmcCartesian", DSMCB200_COORD_CARTESIAN);
     coordinateSystems.insert("dsmcAxisymmetric", DSMCB200_COORD_AXISYMMETRIC);
+    coordinateSystems.insert("dsmcSpherical", DSMCB200_COORD_SPHERICAL);
     HashTable<label> timeStepModels;
     timeStepModels.insert("constant", 0);
     timeStepModels.insert("variable", 1);
@@ -626,10 +627,29 @@ void Foam::dsmcCloud::setCellFields()
             << angular << nl << "- radial weighting method" << tab << "cell-based" << nl << "- radial extent" << tab << radialExtent << nl
             << "- maximum radial weighting factor" << tab << maxRWF << nl << endl;
     }
-    if (variableTimeStep_ || axisymmetric)
+    const bool spherical = models_.coordinateSystem == DSMCB200_COORD_SPHERICAL;
+    if (spherical)
+    {
+        // dsmcSpherical::checkCoordinateSystemInputs / recalculateRWF (dsmcSpherical.C:232-275,325-386), radial weighting method "cell"
+        const dictionary& sph = particleProperties_.subDict("sphericalProperties");
+        const word method(sph.lookupOrDefault<word>("radialWeightingMethod", "cell"));
+        if (method != "cell")
+        {
+            FatalErrorIn("dsmcCloud (dsmcb200)") << "radialWeightingMethod " << method
+                << ": only the cell-based radial weighting is part of this engine" << exit(FatalError);
+        }
+        const scalar maxRWF = readScalar(sph.lookup("maxRadialWeightingFactor"));
+        const vector origin(sph.lookupOrDefault<vector>("origin", vector::zero));
+        const scalar radialExtent = gMax(mag(mesh_.faceCentres() - origin));
+        forAll(RWFCell_, c) { RWFCell_[c] = 1.0 + (maxRWF - 1.0)*sqr(mag(mesh_.cellCentres()[c] - origin)/radialExtent); }
+        Info<< nl << "Spherical simulation:" << nl << "- coordinate system origin" << tab << origin << nl << "- radial weighting method" << tab
+            << "cell-based" << nl << "- radial extent" << tab << radialExtent << nl << "- maximum radial weighting factor" << tab << maxRWF << nl << endl;
+    }
+    const bool weighted = axisymmetric || spherical;
+    if (variableTimeStep_ || weighted)
     {
         ck(dsmcb200_set_cell_fields(ctx_, variableTimeStep_ ? nParticlesCell_.begin() : NULL, variableTimeStep_ ? deltaTCell_.begin() : NULL,
-                                    axisymmetric ? RWFCell_.begin() : NULL), "dsmcb200_set_cell_fields");
+                                    weighted ? RWFCell_.begin() : NULL), "dsmcb200_set_cell_fields");
     }
 }
 

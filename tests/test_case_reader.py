@@ -237,9 +237,19 @@ def test_driver_parses_the_shipped_axisymmetric_dictionaries(tmp_path):
     p = os.path.join(str(tmp_path), "constant", "dsmcProperties")
     txt = open(p).read()
     os.chmod(p, 0o644)
+    open(p, "w").write(txt.replace("dsmcAxisymmetric;", "dsmcCylindrical;"))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-initialise", "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "dsmcCylindrical" in r.stderr and "dsmcAxisymmetric" in r.stderr and "dsmcCartesian" in r.stderr and "dsmcSpherical" in r.stderr
+    # dsmcSpherical reads sphericalProperties (dsmcSpherical.C:325-386): missing sub-dictionary -> OpenFOAM's message; with it, accepted
     open(p, "w").write(txt.replace("dsmcAxisymmetric;", "dsmcSpherical;"))
     r = subprocess.run([RUN, "-case", str(tmp_path), "-initialise", "-dryRun"], capture_output=True, text=True, timeout=120)
-    assert r.returncode == 1 and "dsmcSpherical" in r.stderr and "dsmcAxisymmetric" in r.stderr and "dsmcCartesian" in r.stderr
+    assert r.returncode == 1 and "sphericalProperties" in r.stderr
+    open(p, "w").write(txt.replace("dsmcAxisymmetric;", "dsmcSpherical;\nsphericalProperties { maxRadialWeightingFactor 50; origin (0 0 0); }"))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-initialise", "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "coordinateSystem dsmcSpherical" in r.stdout and "maxRadialWeightingFactor 50" in r.stdout, r.stderr
+    open(p, "w").write(txt.replace("dsmcAxisymmetric;", "dsmcSpherical;\nsphericalProperties { maxRadialWeightingFactor 50; radialWeightingMethod particleAverage; }"))
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-initialise", "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "particleAverage is not supported" in r.stderr
     open(p, "w").write(txt.replace("coordinateSystem   dsmcAxisymmetric;", "coordinateSystem   dsmcAxisymmetric;\ntimeStepModel adaptive;"))
     r = subprocess.run([RUN, "-case", str(tmp_path), "-initialise", "-dryRun"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 1 and "dsmcAdaptiveTimeStepModel" in r.stderr and "dsmcVariableTimeStepModel" in r.stderr

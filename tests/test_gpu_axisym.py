@@ -39,6 +39,45 @@ def test_radial_weighting_stage_matches_oracle_parcel_by_parcel():
     eng.close()
 
 
+def test_spherical_weighting_and_steps_match_oracle():
+    """dsmcSpherical (spherical/dsmcSpherical.C): the weighting stage with weights growing as r^2 about the origin -- clones with the
+    parent's velocity -- parcel by parcel, then three full steps (specular walls, VHS collisions weighted per cell, weighting after every
+    move) against the oracle."""
+    from tests.test_oracle_physics import _spherical_box
+    mesh, md = _spherical_box()
+    eng, ora = H.setup_pair(mesh, [H.argon()], md, capi.Engine, Oracle)
+    cc, cv, fc, *_ = ora.geometry()
+    rwf, _ = capi.spherical_rwf(cc, fc, (0, 0, 0), 100.0)
+    for x in (eng, ora):
+        x.set_cell_fields(RWF=rwf)
+    ora.mesh_fill([0], [4e18], 300.0)
+    p = ora.download_parcels()
+    sig, rem = ora.download_cellstate()
+    eng.upload_cellstate(sig, rem)
+    p.radialWeight[:] = 20.0
+    for x in (eng, ora):
+        x.upload_parcels(p)
+        x.stage(capi.STAGE_SORT)
+    g, o = eng.download_parcels(), ora.download_parcels()
+    cloned, deleted = ora.weighting_counts()
+    assert cloned > 50 and deleted > 50 and g.n == o.n == p.n + cloned - deleted
+    for k in ("origId", "cell", "tetFace", "tetPt", "typeId", "position", "U", "radialWeight"):
+        assert np.array_equal(getattr(g, k), getattr(o, k)), k
+    seen = 0
+    for _ in range(3):
+        eng.evolve(1)
+        ora.evolve(1)
+        assert eng.num_parcels() == ora.num_parcels()
+        tot = ora.counters()["collisions"]
+        assert eng.counters().collisions == tot - seen > 20      # cells of 9600 parcels (the centre) down to 60 (the far corner)
+        seen = tot
+    g, o = eng.download_parcels(), ora.download_parcels()
+    assert np.array_equal(g.origId, o.origId) and np.array_equal(g.cell, o.cell) and np.array_equal(g.radialWeight, o.radialWeight)
+    assert np.allclose(g.position, o.position, rtol=0, atol=1e-13) and np.allclose(g.U, o.U, rtol=1e-9, atol=1e-7)
+    assert np.array_equal(eng.occupancy(), ora.occupancy())
+    eng.close()
+
+
 def test_axisymmetric_steps_match_oracle():
     """Five full steps of the reference's axisymmetric tutorial (wedge mesh with prisms on the axis, free-stream inflow weighted by the
     face cell's RWF, deletion, diffuse wall, symmetry planes, cloning / deletion after every move): the cloud is the oracle's parcel by

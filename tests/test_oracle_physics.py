@@ -532,6 +532,46 @@ def test_radial_weighting_clones_and_deletes_with_the_weight_ratio():
     assert np.isin(q.cell, first).sum() >= 2 * np.isin(p.cell, first).sum()
 
 
+def _spherical_box():
+    """4 x 4 x 4 box around the origin of a spherical coordinate system in its corner: weights grow with the square of the radius"""
+    sides = {s: ("wall", "walls") for s in meshgen.SIDES}
+    mesh = meshgen.box_mesh((4, 4, 4), (0.04, 0.04, 0.04), sides=sides)
+    md = capi.build_models("VariableHardSphere", nEquivalentParticles=1e9, deltaT=2e-6, seed=5, coordinateSystem="dsmcSpherical",
+                           patch_models=[dict(patch=mesh.patch_index("walls"), boundaryModel="dsmcSpecularWallPatch")])
+    return mesh, md
+
+
+def test_spherical_weighting_clones_without_mirroring():
+    """dsmcSpherical (spherical/dsmcSpherical.C:50-275): RWF = 1 + (maxRWF - 1) (r / radialExtent)^2 about the origin, the same clone / delete
+    rule as the axisymmetric system, and a clone that keeps its parent's velocity."""
+    mesh, md = _spherical_box()
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species([H.argon()]); o.set_models(md)
+    cc, cv, fc, *_ = o.geometry()
+    rwf, ext = capi.spherical_rwf(cc, fc, (0, 0, 0), 100.0)
+    assert abs(ext - np.sqrt(0.04 ** 2 + 0.035 ** 2 + 0.035 ** 2)) < 1e-15    # the farthest face centre: an outer face of the corner cell
+    assert abs(rwf[0] - (1 + 99 * (3 * 0.005 ** 2) / ext ** 2)) < 1e-12 and rwf.max() < 100
+    o.set_cell_fields(RWF=rwf)
+    o.mesh_fill([0], [4e18], 300.0)
+    p = o.download_parcels()
+    assert np.array_equal(p.radialWeight, rwf[p.cell])
+    p.radialWeight[:] = 20.0
+    o.upload_parcels(p)
+    o.stage(capi.STAGE_SORT)
+    q = o.download_parcels()
+    cloned, deleted = o.weighting_counts()
+    assert q.n == p.n + cloned - deleted and cloned > 50 and deleted > 50
+    assert np.array_equal(q.radialWeight, rwf[q.cell])
+    new = np.nonzero(q.origId >= p.n)[0]
+    parent = {tuple(x): k for k, x in enumerate(p.position)}
+    for k in new[:200]:
+        j = parent[tuple(q.position[k])]
+        assert np.array_equal(q.U[k], p.U[j]) and q.cell[k] == p.cell[j]          # not mirrored
+    # the same parcels of a 2-D case are NOT pulled to the mesh centre under a non-Cartesian system (dsmcParcel.C:76)
+    o.evolve(2)
+    assert o.num_parcels() > 0
+
+
 def test_variable_time_step_scales_weights_and_steps_with_the_cell_volume():
     """dsmcVariableTimeStepModel (dsmcVariableTimeStepModel.C:48-100): nParticles and deltaT of a cell grow with its volume, their ratio is
     uniform.  A parcel moves by U deltaT(its cell) (dsmcParcel.C:62-63) and the candidate pairs of a cell use its own weight and step
