@@ -42,6 +42,7 @@ PATCH_MODEL_NAMES = {
     "dsmcSpecularWallPatch": BND_SPECULAR_WALL,
     "dsmcDeletionPatch": BND_DELETION,
     "dsmcDiffuseSpecularWallPatch": 4,
+    "dsmcCLLWallPatch": 5,
 }
 
 
@@ -72,7 +73,8 @@ class Species(C.Structure):
 class PatchModel(C.Structure):
     _fields_ = [("patch", C.c_int32), ("model", C.c_int32), ("temperature", C.c_double), ("velocity", C.c_double * 3),
                 ("diffuseFraction", C.c_double), ("linearTemperature", C.c_int32), ("depthAxis", C.c_int32),
-                ("formationLevelTemperature", C.c_double)]
+                ("formationLevelTemperature", C.c_double), ("normalAccommodationCoefficient", C.c_double),
+                ("tangentialAccommodationCoefficient", C.c_double), ("rotationalEnergyAccommodationCoefficient", C.c_double)]
 
 
 class Inflow(C.Structure):
@@ -417,6 +419,8 @@ def build_models(collisionModel="VariableHardSphere", nEquivalentParticles=1.0, 
         pm[i].model = PATCH_MODEL_NAMES[name]
         pm[i].temperature = d.get("temperature", 0.0)
         pm[i].diffuseFraction = d.get("diffuseFraction", 0.0)
+        for key in ("normalAccommodationCoefficient", "tangentialAccommodationCoefficient", "rotationalEnergyAccommodationCoefficient"):
+            setattr(pm[i], key, d.get(key, 0.0))       # dsmcCLLWallPatchProperties
         if "formationLevelTemperature" in d:   # linear T(depth), dsmcDiffuseWallPatch.C:141-148
             pm[i].linearTemperature = 1
             pm[i].formationLevelTemperature = d["formationLevelTemperature"]

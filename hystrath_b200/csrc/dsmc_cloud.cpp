@@ -61,9 +61,10 @@ int selectPatchBoundaryModel(const std::string& name) {
     if (name == "dsmcDiffuseWallPatch") return DSMCB200_BND_DIFFUSE_WALL;
     if (name == "dsmcSpecularWallPatch") return DSMCB200_BND_SPECULAR_WALL;
     if (name == "dsmcDeletionPatch") return DSMCB200_BND_DELETION;
+    if (name == "dsmcCLLWallPatch") return DSMCB200_BND_CLL_WALL;
     if (name == "dsmcDiffuseSpecularWallPatch") return DSMCB200_BND_DIFFUSE_SPECULAR_WALL;
     unknownType("dsmcPatchBoundary::New(const dictionary&)", "patch boundary", name,
-                {"dsmcDeletionPatch", "dsmcDiffuseSpecularWallPatch", "dsmcDiffuseWallPatch", "dsmcSpecularWallPatch"});
+                {"dsmcCLLWallPatch", "dsmcDeletionPatch", "dsmcDiffuseSpecularWallPatch", "dsmcDiffuseWallPatch", "dsmcSpecularWallPatch"});
 }
 void selectGeneralBoundaryModel(const std::string& name) {
     if (name != "dsmcFreeStreamInflowPatch")
@@ -515,6 +516,16 @@ void dsmcCloud::readBoundaries() {
             auto v = pr.vector3("velocity");
             for (int k = 0; k < 3; ++k) pm.velocity[k] = v[k];
         }
+        if (kind == DSMCB200_BND_CLL_WALL) {   // dsmcCLLWallPatch.C:45-75,330-334: every keyword is mandatory
+            const Dict& pr = b.subDict(model + "Properties");
+            pm.normalAccommodationCoefficient = pr.scalar("normalAccommodationCoefficient");
+            pm.tangentialAccommodationCoefficient = pr.scalar("tangentialAccommodationCoefficient");
+            pm.rotationalEnergyAccommodationCoefficient = pr.scalar("rotationalEnergyAccommodationCoefficient");
+            (void)pr.scalar("vibrationalEnergyAccommodationCoefficient");   // read by the constructor, used nowhere (the vibrational part is commented out)
+            pm.temperature = pr.scalar("temperature");
+            auto v = pr.vector3("velocity");
+            for (int k = 0; k < 3; ++k) pm.velocity[k] = v[k];
+        }
         patchModels_.push_back(pm);
     }
     if (!d.dictList("dsmcCyclicBoundaries").empty())
@@ -698,6 +709,11 @@ std::string dsmcCloud::summary() const {
       << " seed " << models_.seed << "\n  coordinateSystem " << (models_.coordinateSystem == DSMCB200_COORD_AXISYMMETRIC ? "dsmcAxisymmetric" : (models_.coordinateSystem == DSMCB200_COORD_SPHERICAL ? "dsmcSpherical" : "dsmcCartesian"))
       << " polarAxis " << polarAxis_ << " angularCoordinate " << models_.angularCoordinate << " maxRadialWeightingFactor " << maxRWF_
       << " timeStepModel " << (variableTimeStep_ ? "variable" : "constant") << "\n  patchModels " << patchModels_.size() << " inflows " << inflows_.size() << " fields " << fields_.size() << "\n";
+    for (auto& pm : patchModels_)
+        if (pm.model == DSMCB200_BND_CLL_WALL)
+            o << "    patchModel " << boundary_[pm.patch].name << " dsmcCLLWallPatch temperature " << pm.temperature << " accommodation normal "
+              << pm.normalAccommodationCoefficient << " tangential " << pm.tangentialAccommodationCoefficient << " rotational "
+              << pm.rotationalEnergyAccommodationCoefficient << "\n";
     for (auto& pm : patchModels_)
         if (pm.linearTemperature)
             o << "    patchModel " << boundary_[pm.patch].name << " temperature " << pm.temperature << " linearTemperature formationLevel "

@@ -526,9 +526,16 @@ int finalize(dsmcb200_ctx* c) {
         DevPatch& d = P.patch[pm.patch];
         if (d.type != DSMCB200_PATCH_WALL && d.type != DSMCB200_PATCH_PATCH)
             return fail(c, DSMCB200_ERR_INVALID, "Patch: " + M.patches[pm.patch].name + " must be of type wall or patch to carry a dsmcPatchBoundary model");
-        if (pm.model < DSMCB200_BND_DIFFUSE_WALL || pm.model > DSMCB200_BND_DIFFUSE_SPECULAR_WALL) return fail(c, DSMCB200_ERR_UNSUPPORTED, "unknown dsmcPatchBoundary type");
+        if (pm.model < DSMCB200_BND_DIFFUSE_WALL || pm.model > DSMCB200_BND_CLL_WALL) return fail(c, DSMCB200_ERR_UNSUPPORTED, "unknown dsmcPatchBoundary type");
         d.model = pm.model; d.T = pm.temperature; d.diffuseFraction = pm.diffuseFraction;
         d.linearT = pm.linearTemperature != 0; d.depthAxis = pm.depthAxis; d.Tformation = pm.formationLevelTemperature;
+        if (pm.model == DSMCB200_BND_CLL_WALL) {
+            const double aN = pm.normalAccommodationCoefficient, aT = pm.tangentialAccommodationCoefficient, aR = pm.rotationalEnergyAccommodationCoefficient;
+            if (!(aN >= 0 && aN <= 1) || !(aT >= 0 && aT <= 2) || !(aR >= 0 && aR <= 1))
+                return fail(c, DSMCB200_ERR_INVALID, "dsmcCLLWallPatch: accommodation coefficients out of range (normal, rotational in [0, 1], tangential in [0, 2])");
+            d.alphaN = aN; d.alphaT = aT * (2.0 - aT); d.alphaR = aR;   // dsmcCLLWallPatch.C:131-133
+            d.linearT = 0;
+        }
         if (d.linearT) {
             if (pm.depthAxis < 0 || pm.depthAxis > 2) return fail(c, DSMCB200_ERR_INVALID, "dsmcDiffuseWallPatch: depthAxis must be x, y or z");
             d.maxDepth = comp(M.boundsMax, pm.depthAxis);                       // mesh.bounds() (dsmcDiffuseWallPatch.C:181-184)

@@ -42,6 +42,7 @@ struct DevPatch {
     // dsmcDiffuseWallPatch::getLocalTemperature: T + (x[depthAxis] - maxDepth) * (T - Tformation) / lengthPatch
     int32_t linearT, depthAxis;
     double Tformation, maxDepth, lengthPatch;
+    double alphaN, alphaT, alphaR;   // dsmcCLLWallPatch: normal, tangential*(2 - tangential), rotational accommodation
 };
 
 // one quantum-kinetic reaction model of system/chemReactDict (dsmcb200_reaction after dsmcReaction::setProperties)

@@ -217,6 +217,65 @@ __device__ __forceinline__ void loadInternal(const MoveArgs& a, const DevParams&
     in.elevel = a.p.elevel[i];
 }
 
+// dsmcCLLWallPatch::controlParticle (patchBoundaries/dsmcCLLWallPatch/dsmcCLLWallPatch.C:100-300): the Cercignani-Lampis-Lord scattering
+// kernel with Lord's extension to the rotational energy; vibrational and electronic states pass unchanged (commented out in the reference)
+__device__ __noinline__ V3 cllReflection(const DevParams& P, const DevPatch& pt, Rng& rng, int sp, V3 nw, V3 U, Internal& in) {
+    const DevSpecies& S = P.sp[sp];
+    double U_dot_nw = dot(U, nw);
+    V3 Ut = U - U_dot_nw * nw;
+    while (mag(Ut) < SMALL) {
+        double r0 = rng.sample01(), r1 = rng.sample01(), r2 = rng.sample01();
+        U = mk(U.x * (0.8 + 0.2 * r0), U.y * (0.8 + 0.2 * r1), U.z * (0.8 + 0.2 * r2));
+        U_dot_nw = dot(U, nw);
+        Ut = U - U_dot_nw * nw;
+        if (magSqr(U) == 0.0) { Ut = mk(nw.y, -nw.x, 0.0); if (mag(Ut) < SMALL) Ut = mk(0.0, nw.z, -nw.y); break; }
+    }
+    const V3 tw1 = Ut / mag(Ut);
+    const V3 tw2 = cross(nw, tw1);
+    const double T = pt.T;
+    const double alphaT = pt.alphaT, alphaN = pt.alphaN, alphaR = pt.alphaR;
+    const double mostProbableVelocity = sqrt(2.0 * P.kB * T / S.mass);
+    const V3 normalisedTangentialVelocity = Ut / mostProbableVelocity;
+    const double normalisedNormalVelocity = U_dot_nw / mostProbableVelocity;
+    const double twoPi = 2.0 * PI;
+    const double thetaNormal = twoPi * rng.sample01();
+    const double rNormal = sqrt(-alphaN * log(rng.sample01()));
+    const double thetaTangential1 = twoPi * rng.sample01();
+    const double rTangential1 = sqrt(-alphaT * log(rng.sample01()));
+    const double normalisedIncidentTangentialVelocity1 = mag(normalisedTangentialVelocity);
+    const double um = sqrt(1.0 - alphaN) * normalisedNormalVelocity;
+    const double normalVelocity = sqrt((rNormal * rNormal) + (um * um) + 2.0 * rNormal * um * cos(thetaNormal));
+    const double tangentialVelocity1 = (sqrt(1.0 - alphaT) * fabs(normalisedIncidentTangentialVelocity1) + rTangential1 * cos(thetaTangential1));
+    const double tangentialVelocity2 = rTangential1 * sin(thetaTangential1);
+    U = mostProbableVelocity * (tangentialVelocity1 * tw1 + tangentialVelocity2 * tw2 - normalVelocity * nw);
+    const V3 velocity = mk(pt.vel[0], pt.vel[1], pt.vel[2]);
+    const V3 uWallNormal = dot(velocity, nw) * nw;
+    const V3 uWallTangential1 = dot(velocity, tw1) * tw1;
+    const V3 uWallTangential2 = dot(velocity, tw2) * tw2;
+    const V3 UNormal = (dot(U, nw) * nw) + uWallNormal * alphaN;
+    const V3 UTangential1 = dot(U, tw1) * tw1 + uWallTangential1 * alphaT;
+    const V3 UTangential2 = dot(U, tw2) * tw2 + uWallTangential2 * alphaT;
+    U = UNormal + UTangential1 + UTangential2;
+    if (S.rotDof == 2.0) {
+        const double om = sqrt((in.ERot * (1.0 - alphaR)) / (P.kB * T));
+        const double rRot = sqrt(-alphaR * (log(fmax(1.0 - rng.sample01(), VSMALL))));
+        const double thetaRot = twoPi * rng.sample01();
+        in.ERot = P.kB * T * ((rRot * rRot) + (om * om) + (2.0 * rRot * om * cos(thetaRot)));
+    }
+    if (S.rotDof == 3.0) {   // "polyatomic case, see Bird's DSMC2.FOR code"
+        double X = 0.0, A = 0.0;
+        do {
+            X = 4.0 * rng.sample01();
+            A = 2.7182818 * X * X * exp(-(X * X));
+        } while (A < rng.sample01());
+        const double om = sqrt((in.ERot * (1.0 - alphaR)) / (P.kB * T));
+        const double rRot = sqrt(-alphaR) * X;   // as in the reference: not a number for alphaR > 0
+        const double thetaRot = 2.0 * rng.sample01() - 1.0;
+        in.ERot = P.kB * T * ((rRot * rRot) + (om * om) + (2.0 * rRot * om * cos(thetaRot)));
+    }
+    return U;
+}
+
 // dsmcParcel::hitWallPatch / hitPatch -> dsmc{Diffuse,Specular}WallPatch::controlParticle
 __device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int32_t cell, int sp, int patch, int32_t measIndex, int32_t bfi, V3 nw, V3 U,
                                            double depthPosition, int* wallHits) {
@@ -227,6 +286,8 @@ __device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int32_t
     loadInternal(a, P, i, in);
     double preIE, postIE;
     V3 preIMom, postIMom;
+    // dsmcCLLWallPatch::initialConfiguration (dsmcCLLWallPatch.C:82-89): with both coefficients zero the wall is specular and measures nothing
+    if (pt.model == DSMCB200_BND_CLL_WALL && pt.alphaN < VSMALL && pt.alphaT < VSMALL) measIndex = -1;
     wallMeasure(wctx, measIndex, bfi, sp, U, in, preIE, preIMom);
     // the k-th hit of a parcel on a wall that draws random numbers within a step owns the Philox stream ((origProc, origId), k, step)
     Rng wallRng;
@@ -241,6 +302,9 @@ __device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int32_t
         // dsmcSpecularWallPatch::performSpecularReflection
         const double U_dot_nw = dot(U, nw);
         if (U_dot_nw > 0.0) U -= 2.0 * U_dot_nw * nw;
+    } else if (pt.model == DSMCB200_BND_CLL_WALL) {
+        U = cllReflection(P, pt, wallRng, sp, nw, U, in);
+        if (P.hasInternalEnergy) a.p.erot[i] = in.ERot;
     } else {
         // dsmcDiffuseWallPatch::performDiffuseReflection
         const DevSpecies& S = P.sp[sp];

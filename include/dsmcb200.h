@@ -32,7 +32,8 @@
 extern "C" {
 #endif
 
-#define DSMCB200_ABI_VERSION 4   /* 4 = 3 + set_cell_order / download_cell_order, set_sample_sets / select_sample_set, allreduce_min (no layout changed) */
+#define DSMCB200_ABI_VERSION 5   /* 5 = 4 + the three accommodation coefficients at the end of dsmcb200_patch_model (dsmcCLLWallPatch), COORD_SPHERICAL;
+                                    4 = 3 + set_cell_order / download_cell_order, set_sample_sets / select_sample_set, allreduce_min */
 #define DSMCB200_MAX_NEIGHBOURS 16
 #define DSMCB200_MAX_SPECIES 8
 #define DSMCB200_MAX_VIB_MODES 3
@@ -130,7 +131,8 @@ typedef enum {
     DSMCB200_BND_DIFFUSE_WALL = 1,   /* dsmcDiffuseWallPatch  */
     DSMCB200_BND_SPECULAR_WALL = 2,  /* dsmcSpecularWallPatch */
     DSMCB200_BND_DELETION = 3,       /* dsmcDeletionPatch     */
-    DSMCB200_BND_DIFFUSE_SPECULAR_WALL = 4  /* mixed/dsmcDiffuseSpecularWallPatch (Maxwell model: diffuse with probability diffuseFraction) */
+    DSMCB200_BND_DIFFUSE_SPECULAR_WALL = 4, /* mixed/dsmcDiffuseSpecularWallPatch (Maxwell model: diffuse with probability diffuseFraction) */
+    DSMCB200_BND_CLL_WALL = 5               /* dsmcCLLWallPatch (Cercignani-Lampis-Lord kernel, Lord's extension to rotation) */
 } dsmcb200_patch_model_kind;
 
 /* One entry of system/boundariesDict dsmcPatchBoundaries
@@ -148,6 +150,8 @@ typedef struct {
     int32_t linearTemperature;
     int32_t depthAxis;      /* 0 x, 1 y (default), 2 z (:169-179) */
     double formationLevelTemperature;
+    /* dsmcCLLWallPatchProperties (dsmcCLLWallPatch.C:57-62): normal / tangential / rotational-energy accommodation coefficients */
+    double normalAccommodationCoefficient, tangentialAccommodationCoefficient, rotationalEnergyAccommodationCoefficient;
 } dsmcb200_patch_model;
 
 /* One dsmcFreeStreamInflowPatch of dsmcGeneralBoundaries

@@ -356,6 +356,7 @@ void Foam::dsmcCloud::readBoundaries()
     patchModels.insert("dsmcSpecularWallPatch", DSMCB200_BND_SPECULAR_WALL);
     patchModels.insert("dsmcDiffuseSpecularWallPatch", DSMCB200_BND_DIFFUSE_SPECULAR_WALL);
     patchModels.insert("dsmcDeletionPatch", DSMCB200_BND_DELETION);
+    patchModels.insert("dsmcCLLWallPatch", DSMCB200_BND_CLL_WALL);
     HashTable<label> generalModels;
     generalModels.insert("dsmcFreeStreamInflowPatch", 1);
 
@@ -404,6 +405,18 @@ void Foam::dsmcCloud::readBoundaries()
                 pm.formationLevelTemperature = pm.temperature;
             }
             if (pm.model == DSMCB200_BND_DIFFUSE_SPECULAR_WALL) { pm.diffuseFraction = readScalar(p.lookup("diffuseFraction")); }
+        }
+        if (pm.model == DSMCB200_BND_CLL_WALL)
+        {
+            // dsmcCLLWallPatch.C:45-75,330-334
+            const dictionary& p = d.subDict(model + "Properties");
+            const vector v(p.lookup("velocity"));
+            pm.velocity[0] = v.x(); pm.velocity[1] = v.y(); pm.velocity[2] = v.z();
+            pm.temperature = readScalar(p.lookup("temperature"));
+            pm.normalAccommodationCoefficient = readScalar(p.lookup("normalAccommodationCoefficient"));
+            pm.tangentialAccommodationCoefficient = readScalar(p.lookup("tangentialAccommodationCoefficient"));
+            pm.rotationalEnergyAccommodationCoefficient = readScalar(p.lookup("rotationalEnergyAccommodationCoefficient"));
+            readScalar(p.lookup("vibrationalEnergyAccommodationCoefficient"));   // mandatory in the reference, used nowhere
         }
     }
     inflows_.setSize(gList.size());

@@ -25,14 +25,14 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/dsmcb200.h but not exported"
     assert set(capi.EXPORTED_SYMBOLS) == set(names)
-    assert lib.dsmcb200_abi_version() == 4
+    assert lib.dsmcb200_abi_version() == 5
 
 
 def test_struct_layouts_match_the_header():
     # sizes the C compiler gives the PODs (gcc x86-64); a mismatch would corrupt every call
     assert C.sizeof(capi.Patch) == 64 + 8 * 4 + 24
     assert C.sizeof(capi.Species) == 64 + 5 * 8 + 8 + 9 * 8 + 8 + 8 + 16 * 8 + 16 * 4
-    assert C.sizeof(capi.PatchModel) == 8 + 8 + 24 + 8 + 8 + 8   # + diffuseFraction, linearTemperature / depthAxis, formationLevelTemperature
+    assert C.sizeof(capi.PatchModel) == 8 + 8 + 24 + 8 + 8 + 8 + 24   # + diffuseFraction, linearTemperature / depthAxis, formationLevelTemperature, the three CLL coefficients
     assert C.sizeof(capi.ParcelsSoA) == 12 * 8 + 8 + 8 + 8   # + radialWeight
     assert C.sizeof(capi.Counters) == 9 * 8 + 5 * 8 + 8 * 8 + 8 + 16 * 4 + 2 * 16 * 8 + 16
     assert C.sizeof(capi.AccumInfo) == 24
@@ -69,7 +69,7 @@ def test_unknown_model_names_are_rejected_like_the_reference():
     with pytest.raises(capi.Dsmcb200Error, match="Valid BinaryCollisionModel types are"):
         capi.build_models("VariableSoftSphereTypo")
     with pytest.raises(capi.Dsmcb200Error, match="Valid patch boundary types are"):
-        capi.build_models("VariableHardSphere", patch_models=[dict(patch=0, boundaryModel="dsmcCLLWallPatch")])
+        capi.build_models("VariableHardSphere", patch_models=[dict(patch=0, boundaryModel="dsmcStickingWallPatch")])
     with pytest.raises(ValueError):
         capi.make_species("X", 1e-26, 1e-10, 0.7, thetaV=(1000.0,), Zref=(), TrefZv=())
 

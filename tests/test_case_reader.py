@@ -333,3 +333,22 @@ def test_python_binary_round_trip(tmp_path):
     raw = ff.header("labelList", "constant/polyMesh", "owner", True).replace("label=32", "label=64").encode() + b"\n5\n(" + np.arange(5, dtype=np.int64).tobytes() + b")\n"
     open(os.path.join(d, "owner"), "wb").write(raw)
     assert ff.read_scalar_list(os.path.join(d, "owner"), np.int32).tolist() == [0, 1, 2, 3, 4]
+
+
+def test_driver_reads_cll_wall_patch(tmp_path):
+    """boundaryModel dsmcCLLWallPatch: the four accommodation coefficients, temperature and velocity are all mandatory lookups
+    (dsmcCLLWallPatch.C:57-62,330-334), the vibrational one included although nothing uses it."""
+    from hystrath_b200 import case as casew
+    from tests.test_gpu_driver import CLL_BOUNDARIES
+
+    casegen.couette_case(str(tmp_path))
+    path = os.path.join(str(tmp_path), "system", "boundariesDict")
+    casew.write_dict(path, "system", "boundariesDict", CLL_BOUNDARIES)
+    r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "patchModel upperWall dsmcCLLWallPatch temperature 3000 accommodation normal 0.8 tangential 0.5 rotational 0.9" in r.stdout
+    assert "patchModel lowerWall dsmcCLLWallPatch temperature 2000 accommodation normal 1 tangential 1 rotational 1" in r.stdout
+    for key in ("normalAccommodationCoefficient", "vibrationalEnergyAccommodationCoefficient", "velocity"):
+        casew.write_dict(path, "system", "boundariesDict", CLL_BOUNDARIES.replace(key, key + "X", 1))
+        r = subprocess.run([RUN, "-case", str(tmp_path), "-dryRun"], capture_output=True, text=True, timeout=120)
+        assert r.returncode != 0 and f"keyword {key} is undefined in dictionary" in r.stderr + r.stdout

@@ -444,3 +444,78 @@ def test_driver_fields_with_different_sample_intervals(tmp_path):
     # the two N2 samples are not the four of the other fields
     assert not np.allclose(ff.read_internal_field(os.path.join(tdir, "rhoN_N2")) + ff.read_internal_field(os.path.join(tdir, "rhoN_O2")),
                            ff.read_internal_field(os.path.join(tdir, "rhoN_mixture")), rtol=1e-6)
+
+
+CLL_BOUNDARIES = """
+dsmcPatchBoundaries
+(
+    boundary
+    {
+        patchBoundaryProperties { patchName upperWall; }
+        boundaryModel   dsmcCLLWallPatch;
+        dsmcCLLWallPatchProperties
+        {
+            normalAccommodationCoefficient              0.8;
+            tangentialAccommodationCoefficient          0.5;
+            rotationalEnergyAccommodationCoefficient    0.9;
+            vibrationalEnergyAccommodationCoefficient   1.0;
+            temperature     3000.0;
+            velocity        (300.0 0.0 0.0);
+        }
+    }
+    boundary
+    {
+        patchBoundaryProperties { patchName lowerWall; }
+        boundaryModel   dsmcCLLWallPatch;
+        dsmcCLLWallPatchProperties
+        {
+            normalAccommodationCoefficient              1.0;
+            tangentialAccommodationCoefficient          1.0;
+            rotationalEnergyAccommodationCoefficient    1.0;
+            vibrationalEnergyAccommodationCoefficient   1.0;
+            temperature     2000.0;
+            velocity        (0.0 0.0 0.0);
+        }
+    }
+);
+dsmcCyclicBoundaries ( );
+dsmcGeneralBoundaries ( );
+"""
+
+
+def test_driver_reads_cll_wall_patches(tmp_path):
+    """system/boundariesDict with boundaryModel dsmcCLLWallPatch (dsmcCLLWallPatch.C:45-75,330-334): the driver's cloud after four steps is the
+    oracle's with the same coefficients; a dictionary without one of the mandatory keywords stops with the reference's lookup message."""
+    from hystrath_b200 import case as casew
+
+    n_steps = 4
+    g, mesh, p = casegen.couette_case(str(tmp_path), n_steps=n_steps, seed=5, nto=2)
+    casew.write_dict(os.path.join(str(tmp_path), "system", "boundariesDict"), "system", "boundariesDict", CLL_BOUNDARIES)
+    r = subprocess.run([RUN, "-case", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    sp = H.air5()[:2]
+    pm = [dict(patch=mesh.patch_index("upperWall"), boundaryModel="dsmcCLLWallPatch", temperature=3000.0, velocity=(300.0, 0, 0),
+               normalAccommodationCoefficient=0.8, tangentialAccommodationCoefficient=0.5, rotationalEnergyAccommodationCoefficient=0.9),
+          dict(patch=mesh.patch_index("lowerWall"), boundaryModel="dsmcCLLWallPatch", temperature=2000.0, velocity=(0, 0, 0),
+               normalAccommodationCoefficient=1.0, tangentialAccommodationCoefficient=1.0, rotationalEnergyAccommodationCoefficient=1.0)]
+    md = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=float(g["nEquivalentParticles"]), deltaT=1e-5,
+                           seed=5, patch_models=pm, inverseZvFormulation="pre-2008", rotationalRelaxationCollisionNumber=5.0,
+                           measureHeatFluxShearStress=True)
+    o = Oracle()
+    o.set_mesh(mesh); o.set_species(sp); o.set_models(md)
+    o.upload_parcels(p)
+    o.upload_cellstate(g["dsmcSigmaTcRMax"], None)
+    o.set_step(500000)
+    o.evolve(n_steps)
+    ref = o.download_parcels()
+    cdir = os.path.join(str(tmp_path), "5.00004", "lagrangian", "dsmc")
+    xyz, cell = ff.read_positions(os.path.join(cdir, "positions"))
+    assert np.array_equal(ff.read_scalar_list(os.path.join(cdir, "origId"), np.int32), ref.origId)
+    assert np.array_equal(cell, ref.cell) and np.allclose(xyz, ref.position, rtol=0, atol=5e-10)
+    assert np.allclose(ff.read_vector_list(os.path.join(cdir, "U")), ref.U, rtol=1e-9, atol=1e-6)
+    assert np.allclose(ff.read_scalar_list(os.path.join(cdir, "ERot"), np.float64), ref.ERot, rtol=1e-8, atol=1e-30)
+
+    casew.write_dict(os.path.join(str(tmp_path), "system", "boundariesDict"), "system", "boundariesDict",
+                     CLL_BOUNDARIES.replace("vibrationalEnergyAccommodationCoefficient   1.0;", "", 1))
+    r = subprocess.run([RUN, "-case", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "vibrationalEnergyAccommodationCoefficient" in r.stderr + r.stdout

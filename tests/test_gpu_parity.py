@@ -481,6 +481,55 @@ def test_diffuse_specular_wall_matches_oracle():
     eng.close()
 
 
+def test_cll_wall_matches_oracle():
+    """dsmcCLLWallPatch (Cercignani-Lampis-Lord kernel with Lord's rotational extension, dsmcCLLWallPatch.C:100-300): same draws in the same
+    order from the hit's Philox stream on both sides; a moving wall, a diatomic and a monatomic species; vibration / electronic levels untouched.
+    The second wall has both coefficients zero: specular, and it measures nothing (dsmcCLLWallPatch.C:82-89)."""
+    sides = {"xmin": ("cyclic",), "xmax": ("cyclic",), "ymin": ("wall", "lowerWall"), "ymax": ("wall", "upperWall"),
+             "zmin": ("cyclic",), "zmax": ("cyclic",)}
+    mesh = meshgen.box_mesh((5, 12, 3), (0.05, 0.12, 0.03), sides=sides)
+    a5 = H.air5()
+    sp = [a5[0], a5[3]]   # N2, N
+    pm = [dict(patch=mesh.patch_index("lowerWall"), boundaryModel="dsmcCLLWallPatch", temperature=1200.0, velocity=(250.0, 0, -40.0),
+               normalAccommodationCoefficient=0.7, tangentialAccommodationCoefficient=0.45, rotationalEnergyAccommodationCoefficient=0.6),
+          dict(patch=mesh.patch_index("upperWall"), boundaryModel="dsmcCLLWallPatch", temperature=500.0, velocity=(0, 0, 0),
+               normalAccommodationCoefficient=0.0, tangentialAccommodationCoefficient=0.0, rotationalEnergyAccommodationCoefficient=0.0)]
+    md = capi.build_models("LarsenBorgnakkeVariableHardSphere", nEquivalentParticles=1e20 * 0.05 * 0.12 * 0.03 / (180 * 60), deltaT=6e-6, seed=19,
+                           patch_models=pm, inverseZvFormulation="pre-2008")
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    start = H.by_id(H.same_start(eng, ora, [0, 1], [0.7e20, 0.3e20], 2000.0, 2000.0, 2000.0))
+    for x in (eng, ora):
+        x.stage(capi.STAGE_MOVE)
+        x.stage(capi.STAGE_SORT)
+    g, o = H.by_id(eng.download_parcels()), H.by_id(ora.download_parcels())
+    assert np.array_equal(g["cell"], o["cell"])
+    assert np.allclose(g["U"], o["U"], rtol=1e-11, atol=1e-8) and np.allclose(g["position"], o["position"], rtol=0, atol=1e-13)
+    assert np.allclose(g["ERot"], o["ERot"], rtol=1e-10, atol=1e-30)
+    assert np.array_equal(g["vibLevel"], o["vibLevel"]) and np.array_equal(g["vibLevel"], start["vibLevel"])
+    assert np.array_equal(g["ELevel"], start["ELevel"])
+    hit = (o["U"] != start["U"]).any(1)
+    upper = hit & (o["position"][:, 1] > 0.06)
+    lower = hit & ~upper
+    assert upper.sum() > 100 and lower.sum() > 100
+    # specular limit of the kernel: speed kept
+    assert np.allclose((o["U"][upper] ** 2).sum(1), (start["U"][upper] ** 2).sum(1), rtol=1e-10)
+    # the rotational energy of a hit N2 changed on the accommodating wall, an atom's stays zero
+    n2 = o["typeId"] == 0
+    assert (o["ERot"][lower & n2] != start["ERot"][lower & n2]).mean() > 0.99 and np.all(o["ERot"][~n2] == 0)
+    gw, ow = eng.wall_accumulators(), ora.wall_accumulators()
+    scale = np.abs(ow).max(axis=(0, 1), keepdims=True) + 1e-300
+    assert (np.abs(gw - ow) / scale).max() < 1e-10
+    # faces of the zero-coefficient wall carry nothing (measurePropertiesAtWall_ = false)
+    per_face = np.abs(ow).reshape(ow.shape[0], -1).sum(1)   # measurement faces in dsmcPatchBoundaries order: 15 lower, 15 upper
+    assert per_face.shape == (30,) and np.all(per_face[:15] > 0) and np.all(per_face[15:] == 0)
+    assert np.all(np.abs(gw).reshape(30, -1).sum(1)[15:] == 0)
+    eng.evolve(3)
+    ora.evolve(3)
+    g, o = H.by_id(eng.download_parcels()), H.by_id(ora.download_parcels())
+    assert np.array_equal(g["cell"], o["cell"]) and np.allclose(g["U"], o["U"], rtol=1e-9, atol=1e-7)
+    eng.close()
+
+
 def test_inflow_deletion_specular_counts_match_oracle():
     sides = {"xmin": ("patch", "inlet"), "xmax": ("patch", "outlet"), "ymin": ("wall", "plate"), "ymax": ("symmetryPlane", "top"),
              "zmin": ("cyclic",), "zmax": ("cyclic",)}

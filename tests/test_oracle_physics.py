@@ -636,3 +636,69 @@ def test_capsule_mesh_bricks_tile_the_single_domain_mesh():
     assert abs(vol / cv.sum() - 1) < 1e-12 and abs(a_sum / area - 1) < 1e-12
     for (r, nb), c in proc_faces.items():
         assert np.allclose(c, proc_faces[(nb, r)], atol=1e-12)      # the two sides list the shared faces in the same order
+
+
+def _cll_box(aN, sigT, aR, Tw=900.0, species=None, Trot=0.0, wall_velocity=(0, 0, 0)):
+    sides = {"xmin": ("cyclic",), "xmax": ("cyclic",), "ymin": ("wall", "walls"), "ymax": ("wall", "walls"), "zmin": ("cyclic",), "zmax": ("cyclic",)}
+    sp = species or [H.argon()]
+    wall = meshgen.box_mesh((4, 4, 4), (0.016,) * 3, sides=sides).patch_index("walls")
+    pm = [dict(patch=wall, boundaryModel="dsmcCLLWallPatch", temperature=Tw, velocity=wall_velocity, normalAccommodationCoefficient=aN,
+               tangentialAccommodationCoefficient=sigT, rotationalEnergyAccommodationCoefficient=aR)]
+    mesh, md, o = box((4, 4, 4), (0.016,) * 3, sp, "NoBinaryCollision", ppc=1500, sides=sides, dt=5e-6, patch_models=pm)
+    o.mesh_fill([0], [1e20], 300.0, Trot)
+    a = H.by_id(o.download_parcels())
+    o.evolve(1)
+    b = H.by_id(o.download_parcels())
+    hit = (a["U"] != b["U"]).any(1)
+    assert hit.sum() > 4000
+    return sp, a, b, hit, o
+
+
+def test_cll_wall_with_zero_coefficients_is_specular_and_measures_nothing():
+    """dsmcCLLWallPatch.C:82-89: alphaN = alphaT = 0 reduces the kernel to a specular wall and switches the wall measurements off."""
+    sp, a, b, hit, o = _cll_box(0.0, 0.0, 0.0)
+    ua, ub = a["U"][hit], b["U"][hit]
+    assert np.allclose(ub[:, 1], -ua[:, 1], rtol=1e-12)
+    assert np.allclose(ub[:, [0, 2]], ua[:, [0, 2]], rtol=1e-10, atol=1e-9)
+    assert np.abs(o.wall_accumulators()).sum() == 0
+
+
+def test_cll_wall_moments_follow_the_accommodation_coefficients():
+    """dsmcCLLWallPatch::controlParticle (dsmcCLLWallPatch.C:100-300).  In units of the wall's most probable speed the reflected normal
+    component has <vn'^2> = alphaN + (1 - alphaN) vn^2, and the component along the incident tangential direction has
+    <vt1'> = sqrt(1 - alphaT) |vt| with alphaT = sigma (2 - sigma), i.e. (1 - sigma) |vt|: the definitions of the two coefficients."""
+    aN, sigT, Tw = 0.6, 0.35, 900.0
+    sp, a, b, hit, o = _cll_box(aN, sigT, 1.0, Tw)
+    vmp = np.sqrt(2 * H.KB * Tw / sp[0].mass)
+    ua, ub = a["U"][hit] / vmp, b["U"][hit] / vmp
+    n = hit.sum()
+    resid = ub[:, 1] ** 2 - (1 - aN) * ua[:, 1] ** 2
+    assert abs(resid.mean() - aN) < 4 * resid.std() / np.sqrt(n)
+    ta = ua[:, [0, 2]]
+    t1 = ta / np.linalg.norm(ta, axis=1, keepdims=True)
+    vt1 = (ub[:, [0, 2]] * t1).sum(1)
+    resid = vt1 - (1 - sigT) * np.linalg.norm(ta, axis=1)
+    assert abs(resid.mean()) < 4 * resid.std() / np.sqrt(n)
+    # the component normal to both has no memory of the incident one: variance alphaT / 2
+    vt2 = ub[:, 0] * t1[:, 1] - ub[:, 2] * t1[:, 0]
+    alphaT = sigT * (2 - sigT)
+    assert abs(vt2.mean()) < 4 * vt2.std() / np.sqrt(n) and abs(vt2.var() / (alphaT / 2) - 1) < 0.06
+    # reflected parcels leave the wall
+    y = b["position"][hit, 1]
+    assert np.all(np.where(y < 0.008, ub[:, 1] > 0, ub[:, 1] < 0))
+    assert np.abs(o.wall_accumulators()).sum() > 0
+
+
+def test_cll_wall_full_accommodation_is_diffuse_and_lord_rotation():
+    """alphaN = sigma_t = 1 is the diffuse wall at T_w (flux mean kinetic energy 2 k T_w, plus the wall's velocity tangentially); Lord's
+    rotational extension for a diatomic: <ERot'> = alphaR k T_w + (1 - alphaR) ERot (dsmcCLLWallPatch.C:247-253)."""
+    Tw, aR = 900.0, 0.4
+    n2 = H.air5()[:1]
+    sp, a, b, hit, o = _cll_box(1.0, 1.0, aR, Tw, species=n2, Trot=300.0, wall_velocity=(150.0, 0, 0))
+    ub = b["U"][hit] - np.array([150.0, 0, 0])
+    ek = 0.5 * sp[0].mass * (ub ** 2).sum(1)
+    assert abs(ek.mean() / (2 * H.KB * Tw) - 1) < 4 * ek.std() / ek.mean() / np.sqrt(hit.sum())
+    assert abs(ub[:, 0].mean()) < 4 * ub[:, 0].std() / np.sqrt(hit.sum())
+    resid = b["ERot"][hit] - (1 - aR) * a["ERot"][hit]
+    assert abs(resid.mean() / (aR * H.KB * Tw) - 1) < 4 * resid.std() / resid.mean() / np.sqrt(hit.sum())
+    assert np.array_equal(a["vibLevel"], b["vibLevel"]) and np.array_equal(a["ELevel"], b["ELevel"])   # untouched (commented out upstream)
