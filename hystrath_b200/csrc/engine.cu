@@ -193,6 +193,7 @@ struct dsmcb200_ctx {
     int32_t *dNewOfOld = nullptr, *dOldOfNew = nullptr;
     double *dNPts = nullptr, *dDt = nullptr, *dRWF = nullptr;
     bool useRwf = false;           // dsmcAxisymmetric: parcels carry a radial weight
+    bool cllWalls = false;         // a dsmcCLLWallPatch among the patch models (move kernel instance)
     int32_t* dWeightCounts = nullptr; int64_t weightCountsCap = 0;
     uint32_t* dGiantBitmap = nullptr; int64_t giantWords = 0;   // scratch of giantSortKernel
     int32_t nGiant = 0;   // cells of more than GIANT_SORT parcels found by the last sort
@@ -521,6 +522,7 @@ int finalize(dsmcb200_ctx* c) {
     }
     std::vector<int32_t> measIndex(M.nFaces - M.nInternalFaces, -1);
     c->nMeasFaces = 0;
+    c->cllWalls = false;
     for (const dsmcb200_patch_model& pm : c->patchModels) {
         if (pm.patch < 0 || pm.patch >= P.nPatches) return fail(c, DSMCB200_ERR_INVALID, "patch model refers to an unknown patch");
         DevPatch& d = P.patch[pm.patch];
@@ -535,6 +537,7 @@ int finalize(dsmcb200_ctx* c) {
                 return fail(c, DSMCB200_ERR_INVALID, "dsmcCLLWallPatch: accommodation coefficients out of range (normal, rotational in [0, 1], tangential in [0, 2])");
             d.alphaN = aN; d.alphaT = aT * (2.0 - aT); d.alphaR = aR;   // dsmcCLLWallPatch.C:131-133
             d.linearT = 0;
+            c->cllWalls = true;
         }
         if (d.linearT) {
             if (pm.depthAxis < 0 || pm.depthAxis > 2) return fail(c, DSMCB200_ERR_INVALID, "dsmcDiffuseWallPatch: depthAxis must be x, y or z");
@@ -926,6 +929,7 @@ MoveArgs moveArgs(dsmcb200_ctx* c, int32_t tailStart) {
     }
     a.faceFlux = c->dFaceFlux; a.faceAreas = c->dFaceAreas; a.nFacesAll = c->mesh.nFaces;
     a.migBuf = c->dMigSend; a.migRwf = c->dMigRwfSend; a.migKey = c->dMigKey; a.migCapacity = c->migCapacity; a.cellCount = c->dCellCount; a.counters = c->dCounters; a.step = c->step;
+    a.cllWalls = c->cllWalls ? 1 : 0;
     return a;
 }
 

@@ -175,6 +175,7 @@ struct MoveArgs {
     int32_t* cellCount;           // histogram for the sort (stage 2), fused here
     DevCounters* counters;
     uint32_t step;
+    int32_t cllWalls;             // some patch carries a dsmcCLLWallPatch: selects the kernel instance that contains the CLL scattering kernel
 };
 
 struct CollideArgs {

@@ -277,6 +277,10 @@ __device__ __noinline__ V3 cllReflection(const DevParams& P, const DevPatch& pt,
 }
 
 // dsmcParcel::hitWallPatch / hitPatch -> dsmc{Diffuse,Specular}WallPatch::controlParticle
+// CLL: the instance for cases with a dsmcCLLWallPatch.  The register need of this function decides what the move kernel keeps live across
+// the call (ptxas allocates the call tree as a whole): with the CLL kernel in it the kernel's main loop spills a predicate and the stage is
+// 11 % slower (40.0 -> 44.6 ms at 248 M parcels), so cases without such a patch run the instance that does not contain it
+template <bool CLL>
 __device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int32_t cell, int sp, int patch, int32_t measIndex, int32_t bfi, V3 nw, V3 U,
                                            double depthPosition, int* wallHits) {
     const DevParams& P = *a.P;
@@ -287,7 +291,7 @@ __device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int32_t
     double preIE, postIE;
     V3 preIMom, postIMom;
     // dsmcCLLWallPatch::initialConfiguration (dsmcCLLWallPatch.C:82-89): with both coefficients zero the wall is specular and measures nothing
-    if (pt.model == DSMCB200_BND_CLL_WALL && pt.alphaN < VSMALL && pt.alphaT < VSMALL) measIndex = -1;
+    if constexpr (CLL) { if (pt.model == DSMCB200_BND_CLL_WALL && pt.alphaN < VSMALL && pt.alphaT < VSMALL) measIndex = -1; }
     wallMeasure(wctx, measIndex, bfi, sp, U, in, preIE, preIMom);
     // the k-th hit of a parcel on a wall that draws random numbers within a step owns the Philox stream ((origProc, origId), k, step)
     Rng wallRng;
@@ -302,9 +306,11 @@ __device__ __noinline__ V3 wallInteraction(const MoveArgs& a, int32_t i, int32_t
         // dsmcSpecularWallPatch::performSpecularReflection
         const double U_dot_nw = dot(U, nw);
         if (U_dot_nw > 0.0) U -= 2.0 * U_dot_nw * nw;
-    } else if (pt.model == DSMCB200_BND_CLL_WALL) {
-        U = cllReflection(P, pt, wallRng, sp, nw, U, in);
-        if (P.hasInternalEnergy) a.p.erot[i] = in.ERot;
+    } else if (CLL && pt.model == DSMCB200_BND_CLL_WALL) {
+        if constexpr (CLL) {
+            U = cllReflection(P, pt, wallRng, sp, nw, U, in);
+            if (P.hasInternalEnergy) a.p.erot[i] = in.ERot;
+        }
     } else {
         // dsmcDiffuseWallPatch::performDiffuseReflection
         const DevSpecies& S = P.sp[sp];
@@ -491,7 +497,7 @@ __device__ __forceinline__ void releaseSlot(const MoveArgs& a, MoveSlot* S, uint
 
 // TRACK: dsmcFaceTracker counters; CF: per-cell time steps / parcel weights (dsmcb200_set_cell_fields, dsmcAxisymmetric) -- the uniform
 // Cartesian instance keeps deltaT in a register and never looks at the cell fields
-template <bool TRACK, bool CF>
+template <bool TRACK, bool CF, bool CLL>
 __global__ void __launch_bounds__(MOVE_BLOCK, 1) moveKernel(const __grid_constant__ MoveArgs a) {
     extern __shared__ __align__(16) unsigned char smRaw[];
     // layout: [0, 8 NBUF) mbarriers | slots | per-thread scratch U.xyz, tEnd | windows
@@ -709,7 +715,7 @@ __global__ void __launch_bounds__(MOVE_BLOCK, 1) moveKernel(const __grid_constan
                                     st &= ~F_KEEP;  // dsmcDeletionPatch::controlParticle
                                 } else if (pt.model != DSMCB200_BND_NONE) {
                                     int wallHits = int(uint32_t(hitsAndGuard) >> 24);
-                                    const V3 U = wallInteraction(a, i, cell, a.p.typeId[i], bf.patch, a.wallsDue ? bf.measIndex : -1, bfi, R.N0,
+                                    const V3 U = wallInteraction<CLL>(a, i, cell, a.p.typeId[i], bf.patch, a.wallsDue ? bf.measIndex : -1, bfi, R.N0,
                                                                  mk(myU[0], myU[MOVE_BLOCK], myU[2 * MOVE_BLOCK]),
                                                                  pt.linearT ? comp(pos, pt.depthAxis) : 0.0, &wallHits);
                                     hitsAndGuard = (hitsAndGuard & 0xffffff) | (wallHits << 24);
@@ -786,15 +792,26 @@ cudaError_t launchMove(const MoveArgs& a, cudaStream_t s) {
     const size_t smem = moveSharedBytes(a.stageTets);
     static bool attrSet = false;
     if (!attrSet) {
-        cudaFuncSetAttribute(moveKernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(moveKernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(moveKernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(moveKernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(moveKernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(moveKernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(moveKernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(moveKernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(moveKernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(moveKernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(moveKernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(moveKernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attrSet = true;
     }
     const bool cf = a.cf.nPts || a.cf.dt || a.cf.rwf || a.p.rwf || a.weighted;
-    if (a.faceFlux) { if (cf) moveKernel<true, true><<<a.gridBlocks, MOVE_BLOCK, smem, s>>>(a); else moveKernel<true, false><<<a.gridBlocks, MOVE_BLOCK, smem, s>>>(a); }
-    else { if (cf) moveKernel<false, true><<<a.gridBlocks, MOVE_BLOCK, smem, s>>>(a); else moveKernel<false, false><<<a.gridBlocks, MOVE_BLOCK, smem, s>>>(a); }
+    void (*k)(MoveArgs) = nullptr;
+    if (a.cllWalls) {   // some patch carries a dsmcCLLWallPatch (engine.cu finalize)
+        if (a.faceFlux) k = cf ? moveKernel<true, true, true> : moveKernel<true, false, true>;
+        else k = cf ? moveKernel<false, true, true> : moveKernel<false, false, true>;
+    } else {
+        if (a.faceFlux) k = cf ? moveKernel<true, true, false> : moveKernel<true, false, false>;
+        else k = cf ? moveKernel<false, true, false> : moveKernel<false, false, false>;
+    }
+    k<<<a.gridBlocks, MOVE_BLOCK, smem, s>>>(a);
     return cudaGetLastError();
 }
 
