@@ -329,6 +329,7 @@ def load_library():
         "dsmcb200_upload_cellstate": ([P, C.c_void_p, C.c_void_p], C.c_int),
         "dsmcb200_download_cellstate": ([P, C.c_void_p, C.c_void_p], C.c_int),
         "dsmcb200_mesh_fill": ([P, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p], C.c_int),
+        "dsmcb200_zone_fill": ([P, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p], C.c_int),
         "dsmcb200_evolve": ([P, C.c_int], C.c_int),
         "dsmcb200_stage": ([P, C.c_int], C.c_int),
         "dsmcb200_set_step": ([P, C.c_uint32], C.c_int),
@@ -369,7 +370,7 @@ EXPORTED_SYMBOLS = [
     "dsmcb200_init_comm", "dsmcb200_set_mesh", "dsmcb200_set_species", "dsmcb200_set_models", "dsmcb200_set_reactions",
     "dsmcb200_reaction_counts", "dsmcb200_set_cell_fields", "dsmcb200_download_cell_fields", "dsmcb200_reserve",
     "dsmcb200_upload_parcels", "dsmcb200_download_parcels", "dsmcb200_upload_cellstate", "dsmcb200_download_cellstate",
-    "dsmcb200_mesh_fill", "dsmcb200_evolve", "dsmcb200_stage", "dsmcb200_set_step", "dsmcb200_download_occupancy",
+    "dsmcb200_mesh_fill", "dsmcb200_zone_fill", "dsmcb200_evolve", "dsmcb200_stage", "dsmcb200_set_step", "dsmcb200_download_occupancy",
     "dsmcb200_set_cell_order", "dsmcb200_download_cell_order", "dsmcb200_set_sample_sets", "dsmcb200_select_sample_set",
     "dsmcb200_accum_info_get", "dsmcb200_download_accumulators", "dsmcb200_upload_accumulators",
     "dsmcb200_reset_accumulators", "dsmcb200_wall_info", "dsmcb200_download_wall_accumulators",
@@ -658,6 +659,14 @@ class Engine:
         nd = np.ascontiguousarray(number_densities, np.float64)
         v = np.ascontiguousarray(velocity, np.float64)
         self._ck(self.lib.dsmcb200_mesh_fill(self.h, len(t), _ptr(t), _ptr(nd), Ttra, Trot, Tvib, Telec, _ptr(v)))
+
+    def zone_fill(self, zone_cells, type_ids, number_densities, Ttra, Trot=0.0, Tvib=0.0, Telec=0.0, velocity=(0.0, 0.0, 0.0)):
+        """dsmcZoneFill: the mesh fill for the cells of one cellZone, appended to the cloud."""
+        z = np.ascontiguousarray(zone_cells, np.int32)
+        t = np.ascontiguousarray(type_ids, np.int32)
+        nd = np.ascontiguousarray(number_densities, np.float64)
+        v = np.ascontiguousarray(velocity, np.float64)
+        self._ck(self.lib.dsmcb200_zone_fill(self.h, C.c_int64(len(z)), _ptr(z), len(t), _ptr(t), _ptr(nd), Ttra, Trot, Tvib, Telec, _ptr(v)))
 
     def evolve(self, n_steps=1):
         self._ck(self.lib.dsmcb200_evolve(self.h, n_steps))

@@ -132,6 +132,10 @@ __global__ void fillRemainder(double* rem, int32_t nCells, uint64_t seed) {
     r.init(seed, uint32_t(c), 0u, 0u, STREAM_REMAINDER);
     rem[c] = r.sample01();  // dsmcCloud::buildCollisionSelectionRemainderFromScratch
 }
+__global__ void fillDoubleAt(double* p, const int32_t* at, int32_t n, double v) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[at[i]] = v;
+}
 __global__ void fillDouble(double* p, int64_t n, double v) {
     int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     if (i < n) p[i] = v;
@@ -193,6 +197,7 @@ struct dsmcb200_ctx {
     int32_t *dNewOfOld = nullptr, *dOldOfNew = nullptr;
     double *dNPts = nullptr, *dDt = nullptr, *dRWF = nullptr;
     bool useRwf = false;           // dsmcAxisymmetric: parcels carry a radial weight
+    int fillsDone = 0;             // fills since the cloud was emptied (stream key of dsmcb200_mesh_fill / zone_fill)
     bool cllWalls = false;         // a dsmcCLLWallPatch among the patch models (move kernel instance)
     int32_t* dWeightCounts = nullptr; int64_t weightCountsCap = 0;
     uint32_t* dGiantBitmap = nullptr; int64_t giantWords = 0;   // scratch of giantSortKernel
@@ -1455,7 +1460,8 @@ int dsmcb200_upload_parcels(dsmcb200_ctx* c, int64_t n, const dsmcb200_parcels_s
     ParcelArrays& a = c->buf[c->cur].a;
     ParcelBuffer& st = c->buf[1 - c->cur];  // staging: the double slab holds 7*cap doubles, the int slab 6*cap ints
     cudaStream_t s = c->stream;
-    if (n == 0) { c->occupancyValid = false; return stageSort(c, false); }
+    c->fillsDone = 0;
+    if (n == 0) { c->nextOrigId = 0; c->occupancyValid = false; return stageSort(c, false); }
     const int32_t *tetFace = h->tetFace, *tetPt = h->tetPt;
     const bool locate = !tetFace || !tetPt;   // the caller has no tet indices: located on the device below
     CK(cudaMemcpyAsync(st.dslab, h->position, size_t(n) * 24, cudaMemcpyHostToDevice, s));
@@ -1631,14 +1637,33 @@ int dsmcb200_download_cellstate(dsmcb200_ctx* c, double* sigma, double* rem) {
     return 0;
 }
 
-int dsmcb200_mesh_fill(dsmcb200_ctx* c, int nTypes, const int32_t* typeIds, const double* numberDensities, double Ttra, double Trot,
-                       double Tvib, double Telec, const double velocity[3]) {
+// dsmcMeshFill (zone == nullptr: the cloud is replaced) and dsmcZoneFill (the cells of one cellZone in the zone's order, appended)
+static int fillCells(dsmcb200_ctx* c, const int32_t* zone, int64_t nZone, int nTypes, const int32_t* typeIds, const double* numberDensities, double Ttra,
+                     double Trot, double Tvib, double Telec, const double velocity[3]) {
     if (!c || !typeIds || !numberDensities || nTypes < 1 || nTypes > MAX_SPECIES) return DSMCB200_ERR_INVALID;
     cudaSetDevice(c->device);
     { int r = finalize(c); if (r) return r; }
     for (int i = 0; i < nTypes; ++i)
         if (typeIds[i] < 0 || typeIds[i] >= c->hP.nSpecies) return fail(c, DSMCB200_ERR_INVALID, "mesh_fill: typeId not defined");
     const HostMesh& M = c->mesh;
+    int32_t* dZone = nullptr;
+    if (zone) {
+        if (nZone < 0 || nZone > M.nCells) return fail(c, DSMCB200_ERR_INVALID, "zone_fill: more zone cells than cells");
+        std::vector<int32_t> z(zone, zone + nZone);
+        for (int32_t& k : z) {
+            if (k < 0 || k >= M.nCells) return fail(c, DSMCB200_ERR_INVALID, "zone_fill: cell label outside the mesh");
+            if (!c->newOfOld.empty()) k = c->newOfOld[k];   // dsmcb200_set_cell_order: the caller's label -> the engine's
+        }
+        if (nZone > 0) {
+            CK(cudaMalloc(&dZone, size_t(nZone) * 4));
+            CK(cudaMemcpyAsync(dZone, z.data(), size_t(nZone) * 4, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        }
+    } else {
+        c->N = 0; c->nextOrigId = 0; c->fillsDone = 0;
+    }
+    const int32_t nFill = zone ? int32_t(nZone) : M.nCells;
+    const int64_t base = c->N;
     FillArgs a{};
     a.nCells = M.nCells; a.cellFaceOffsets = c->dCellFaceOffsets; a.cellFaces = c->dCellFaces; a.faceOffsets = c->dFaceOffsets;
     a.facePoints = c->dFacePoints; a.owner = c->dOwner; a.tetBasePtIs = c->dTetBasePtIs; a.cellTetStart = c->dCellTetStart;
@@ -1646,30 +1671,46 @@ int dsmcb200_mesh_fill(dsmcb200_ctx* c, int nTypes, const int32_t* typeIds, cons
     for (int i = 0; i < nTypes; ++i) { a.typeIds[i] = typeIds[i]; a.numberDensities[i] = numberDensities[i]; }
     a.Ttra = Ttra; a.Trot = Trot; a.Tvib = Tvib; a.Telec = Telec;
     for (int d = 0; d < 3; ++d) a.velocity[d] = velocity ? velocity[d] : 0.0;
-    a.cellCount = c->dCellCount; a.origIdBase = 0; a.origProc = c->rank; a.cf = cellFields(c);
+    a.cellCount = c->dCellCount; a.origIdBase = int32_t(c->nextOrigId & 0x7fffffff); a.origProc = c->rank; a.cf = cellFields(c);
+    a.nFill = nFill; a.cellList = dZone; a.slotBase = int32_t(base); a.fillIndex = uint32_t(c->fillsDone++);
     a.p = c->buf[c->cur].a;
-    CK(launchFill(a, 0, c->stream));
-    CK(launchExclusiveScan(c->dCellCount, c->dCellOffset, nullptr, M.nCells, c->dScanScratch, c->stream));
     int32_t total = 0;
-    CK(cudaMemcpyAsync(&total, c->dCellOffset + M.nCells, 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    c->N = 0;
-    { int r = ensureCapacity(c, std::max<int64_t>(total, 1)); if (r) return r; }
+    if (nFill > 0) {
+        CK(launchFill(a, 0, c->stream));
+        CK(launchExclusiveScan(c->dCellCount, c->dCellOffset, nullptr, nFill, c->dScanScratch, c->stream));
+        CK(cudaMemcpyAsync(&total, c->dCellOffset + nFill, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    { int r = ensureCapacity(c, std::max<int64_t>(base + total, 1)); if (r) { if (dZone) cudaFree(dZone); return r; } }
     a.p = c->buf[c->cur].a;
     a.cellCount = c->dCellOffset;
-    CK(launchFill(a, 1, c->stream));
-    c->N = total;
-    c->nextOrigId = total;
-    // sigmaTcRMax = sigmaT(most abundant) * most probable speed (dsmcMeshFill.C:224-235)
+    if (nFill > 0) CK(launchFill(a, 1, c->stream));
+    c->N = base + total;
+    c->nextOrigId += total;
+    // sigmaTcRMax = sigmaT(most abundant) * most probable speed (dsmcMeshFill.C:224-235; dsmcZoneFill.C:246-268: the zone's cells only)
     int most = 0;
     for (int i = 1; i < nTypes; ++i) if (numberDensities[i] > numberDensities[most]) most = i;
     // the reference indexes constProps by dictionary position (SURVEY 8a quirk list); the typeId is used here
     const DevSpecies& S = c->hP.sp[typeIds[most]];
     const double sig = PI * S.d * S.d * std::sqrt(2.0 * c->hP.kB * Ttra / S.mass);
-    fillDouble<<<GRID(M.nCells), 0, c->stream>>>(c->dSigma, M.nCells, sig);
+    if (!zone) fillDouble<<<GRID(M.nCells), 0, c->stream>>>(c->dSigma, M.nCells, sig);
+    else if (nFill > 0) fillDoubleAt<<<GRID(nFill), 0, c->stream>>>(c->dSigma, dZone, nFill, sig);
+    if (dZone) { CK(cudaStreamSynchronize(c->stream)); cudaFree(dZone); }
     // the fill writes the cloud in cell order; the sort leaves that order as it is and produces the occupancy arrays and sub-cell keys
     c->occupancyValid = false; c->csrValid = false;
     return stageSort(c, false);
+}
+
+int dsmcb200_mesh_fill(dsmcb200_ctx* c, int nTypes, const int32_t* typeIds, const double* numberDensities, double Ttra, double Trot,
+                       double Tvib, double Telec, const double velocity[3]) {
+    return fillCells(c, nullptr, 0, nTypes, typeIds, numberDensities, Ttra, Trot, Tvib, Telec, velocity);
+}
+
+int dsmcb200_zone_fill(dsmcb200_ctx* c, int64_t nZoneCells, const int32_t* zoneCells, int nTypes, const int32_t* typeIds, const double* numberDensities,
+                       double Ttra, double Trot, double Tvib, double Telec, const double velocity[3]) {
+    if (!zoneCells && nZoneCells > 0) return DSMCB200_ERR_INVALID;
+    static const int32_t none = 0;
+    return fillCells(c, zoneCells ? zoneCells : &none, nZoneCells, nTypes, typeIds, numberDensities, Ttra, Trot, Tvib, Telec, velocity);
 }
 
 int dsmcb200_set_step(dsmcb200_ctx* c, uint32_t step) { if (!c) return DSMCB200_ERR_INVALID; c->step = step; return 0; }

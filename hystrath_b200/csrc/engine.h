@@ -288,9 +288,13 @@ struct FillArgs {
     double numberDensities[MAX_SPECIES];
     double Ttra, Trot, Tvib, Telec;
     double velocity[3];
-    int32_t* cellCount;   // pass 0 output / pass 1 input: offsets
+    int32_t* cellCount;   // pass 0 output / pass 1 input: offsets, one per entry of the fill
     int32_t origIdBase;
     int32_t origProc;     // this rank (particle::origProc_ of the parcels it creates)
+    int32_t nFill;                // entries: nCells (dsmcMeshFill) or the size of the zone
+    const int32_t* cellList;      // dsmcZoneFill: the zone's cells in the zone's order; nullptr: entry t is cell t
+    int32_t slotBase;             // first slot of the fill in the parcel arrays (the cloud's size when a zone fill appends)
+    uint32_t fillIndex;           // the k-th fill since the cloud was emptied draws from streams of its own
 };
 cudaError_t launchFill(const FillArgs& a, int pass, cudaStream_t s);
 

@@ -48,12 +48,14 @@ __device__ __forceinline__ void storeParcel(const ParcelArrays& p, const DevPara
 
 // pass 0: cellCount[cell] = parcels to insert; pass 1: cellCount holds exclusive offsets
 __global__ void __launch_bounds__(128) fillKernel(const __grid_constant__ FillArgs a, int pass) {
-    const int32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= a.nCells) return;
+    // entry t of the fill: cell t of the mesh (dsmcMeshFill) or the t-th cell of the zone (dsmcZoneFill, cellList)
+    const int32_t entry = blockIdx.x * blockDim.x + threadIdx.x;
+    if (entry >= a.nFill) return;
+    const int32_t cell = a.cellList ? a.cellList[entry] : entry;
     const DevParams& P = *a.P;
     const V3 Cc = mk(a.cellCentres[3 * cell], a.cellCentres[3 * cell + 1], a.cellCentres[3 * cell + 2]);
     int32_t count = 0;
-    int32_t slot = pass == 1 ? a.cellCount[cell] : 0;
+    int32_t slot = pass == 1 ? a.slotBase + a.cellCount[entry] : 0;
     int tetLocal = 0;
     for (int k = a.cellFaceOffsets[cell]; k < a.cellFaceOffsets[cell + 1]; ++k) {
         const int32_t face = a.cellFaces[k];
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(128) fillKernel(const __grid_constant__ FillAr
                 const int typeId = a.typeIds[i];
                 const DevSpecies& S = P.sp[typeId];
                 Rng rng;
-                rng.init(P.seed, uint32_t(cell), uint32_t(tetLocal * MAX_SPECIES + i), 0u, STREAM_FILL);
+                rng.init(P.seed, uint32_t(cell), uint32_t(tetLocal * MAX_SPECIES + i), a.fillIndex, STREAM_FILL);
                 const double particlesRequired = a.numberDensities[i] * tetVolume / a.cf.nParticles(P.nParticles, cell);   // cloud_.nParticles(cellI), dsmcMeshFill.C:146
                 int32_t nParticlesToInsert = int32_t(particlesRequired);
                 if ((particlesRequired - nParticlesToInsert) > rng.sample01()) nParticlesToInsert++;
@@ -81,17 +83,18 @@ __global__ void __launch_bounds__(128) fillKernel(const __grid_constant__ FillAr
                     for (int m = 0; m < S.nVib; ++m) vib[m] = equipartitionVibrationalEnergyLevel(rng, a.Tvib, S.thetaV[m]);
                     const int elevel = equipartitionElectronicLevel(rng, P.kB, a.Telec, S);
                     U += mk(a.velocity[0], a.velocity[1], a.velocity[2]);
-                    storeParcel(a.p, P, slot, pos, U, ERot, vib, elevel, cell, tet, typeId, a.origIdBase + slot, a.origProc, a.cf.RWF(cell));
+                    storeParcel(a.p, P, slot, pos, U, ERot, vib, elevel, cell, tet, typeId, a.origIdBase + (slot - a.slotBase), a.origProc, a.cf.RWF(cell));
                     ++slot;
                 }
             }
         }
     }
-    if (pass == 0) a.cellCount[cell] = count;
+    if (pass == 0) a.cellCount[entry] = count;
 }
 
 cudaError_t launchFill(const FillArgs& a, int pass, cudaStream_t s) {
-    fillKernel<<<(a.nCells + 127) / 128, 128, 0, s>>>(a, pass);
+    if (a.nFill <= 0) return cudaSuccess;
+    fillKernel<<<(a.nFill + 127) / 128, 128, 0, s>>>(a, pass);
     return cudaGetLastError();
 }
 

@@ -32,7 +32,8 @@
 extern "C" {
 #endif
 
-#define DSMCB200_ABI_VERSION 5   /* 5 = 4 + the three accommodation coefficients at the end of dsmcb200_patch_model (dsmcCLLWallPatch), COORD_SPHERICAL;
+#define DSMCB200_ABI_VERSION 6   /* 6 = 5 + dsmcb200_zone_fill (dsmcZoneFill);
+                                    5 = 4 + the three accommodation coefficients at the end of dsmcb200_patch_model (dsmcCLLWallPatch), COORD_SPHERICAL;
                                     4 = 3 + set_cell_order / download_cell_order, set_sample_sets / select_sample_set, allreduce_min */
 #define DSMCB200_MAX_NEIGHBOURS 16
 #define DSMCB200_MAX_SPECIES 8
@@ -374,6 +375,14 @@ int dsmcb200_download_cellstate(dsmcb200_ctx*, double* sigmaTcRMax, double* rema
 int dsmcb200_mesh_fill(dsmcb200_ctx*, int nTypes, const int32_t* typeIds, const double* numberDensities,
                        double translationalT, double rotationalT, double vibrationalT, double electronicT,
                        const double velocity[3]);
+/* replaces: dsmcZoneFill::setInitialConfiguration,
+ * DSMC/initialiseDsmcParcels/derived/dsmcZoneFill/dsmcZoneFill.C:71-272: the insertion of dsmcMeshFill for the cells of one
+ * cellZone (zoneCells: the zone's cell labels in the zone's order), APPENDED to the cloud as dsmcAllConfigurations runs the
+ * configurations of system/dsmcInitialiseDict one after the other; sigmaTcRMax is set for the zone's cells only (:258-268).
+ * An empty cloud to start from: dsmcb200_upload_parcels with n = 0. */
+int dsmcb200_zone_fill(dsmcb200_ctx*, int64_t nZoneCells, const int32_t* zoneCells, int nTypes, const int32_t* typeIds,
+                       const double* numberDensities, double translationalT, double rotationalT, double vibrationalT,
+                       double electronicT, const double velocity[3]);
 
 /* ---- the hot path ----------------------------------------------------- */
 /* replaces: dsmcCloud::evolve(), DSMC/clouds/dsmcCloud.C:819-926 */

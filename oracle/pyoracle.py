@@ -55,6 +55,7 @@ def load():
     lib.oracle_weighting_counts.argtypes = [P, C.c_void_p, C.c_void_p]
     lib.oracle_download_cellstate.argtypes = [P, C.c_void_p, C.c_void_p]
     lib.oracle_mesh_fill.argtypes = [P, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    lib.oracle_zone_fill.argtypes = [P, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
     lib.oracle_stage.argtypes = [P, C.c_int]
     lib.oracle_evolve.argtypes = [P, C.c_int]
     lib.oracle_outbox_get.argtypes = [P, C.c_void_p, C.c_void_p]
@@ -176,6 +177,13 @@ class Oracle:
         nd = np.ascontiguousarray(number_densities, np.float64)
         v = np.ascontiguousarray(velocity, np.float64)
         self._ck(self.lib.oracle_mesh_fill(self.h, len(t), _ptr(t), _ptr(nd), Ttra, Trot, Tvib, Telec, _ptr(v)))
+
+    def zone_fill(self, zone_cells, type_ids, number_densities, Ttra, Trot=0.0, Tvib=0.0, Telec=0.0, velocity=(0.0, 0.0, 0.0)):
+        z = np.ascontiguousarray(zone_cells, np.int32)
+        t = np.ascontiguousarray(type_ids, np.int32)
+        nd = np.ascontiguousarray(number_densities, np.float64)
+        v = np.ascontiguousarray(velocity, np.float64)
+        self._ck(self.lib.oracle_zone_fill(self.h, C.c_int64(len(z)), _ptr(z), len(t), _ptr(t), _ptr(nd), Ttra, Trot, Tvib, Telec, _ptr(v)))
 
     def evolve(self, n=1):
         self._ck(self.lib.oracle_evolve(self.h, n))

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/dsmcb200.h but not exported"
     assert set(capi.EXPORTED_SYMBOLS) == set(names)
-    assert lib.dsmcb200_abi_version() == 5
+    assert lib.dsmcb200_abi_version() == 6
 
 
 def test_struct_layouts_match_the_header():

@@ -626,6 +626,45 @@ def test_mesh_fill_on_device_matches_oracle():
     eng.close()
 
 
+def test_zone_fill_on_device_matches_oracle():
+    """dsmcZoneFill (initialiseDsmcParcels/derived/dsmcZoneFill/dsmcZoneFill.C:71-272): two configurations of one dsmcInitialiseDict, a
+    driver and a driven section at different states, the second zone's cells in descending order; the cloud is the oracle's parcel for
+    parcel (identified by origId: zone order, then tet, species and insertion order), sigmaTcRMax is set zone by zone, and three steps
+    from there stay on the oracle's."""
+    sp = H.air5()[:2]
+    mesh, _, md = periodic_case((6, 4, 4), ppc=40, species=sp, model="LarsenBorgnakkeVariableHardSphere", dens=1e21)
+    eng, ora = H.setup_pair(mesh, sp, md, capi.Engine, Oracle)
+    x = np.arange(mesh.n_cells) % 6
+    left, right = np.flatnonzero(x < 2).astype(np.int32), np.flatnonzero(x >= 2)[::-1].astype(np.int32)
+    for e in (eng, ora):
+        e.upload_parcels(capi.ParcelData(0, 1))
+        e.zone_fill(left, [0, 1], [2.4e21, 0.6e21], 3000.0, 3000.0, 3000.0, velocity=(400.0, 0, 0))
+        e.zone_fill(right, [0], [0.4e21], 300.0, 300.0, 300.0)
+    g, o = H.by_id(eng.download_parcels()), H.by_id(ora.download_parcels())
+    assert len(g["cell"]) == len(o["cell"]) > 3000
+    assert np.array_equal(g["origId"], o["origId"]) and len(np.unique(g["origId"])) == len(g["origId"])
+    assert np.array_equal(g["cell"], o["cell"]) and np.array_equal(g["typeId"], o["typeId"])
+    assert np.array_equal(g["tetFace"], o["tetFace"]) and np.array_equal(g["tetPt"], o["tetPt"])
+    assert np.allclose(g["position"], o["position"], rtol=0, atol=1e-15)
+    assert np.allclose(g["U"], o["U"], rtol=1e-12, atol=1e-9) and np.allclose(g["ERot"], o["ERot"], rtol=1e-12, atol=1e-30)
+    assert np.array_equal(g["vibLevel"], o["vibLevel"])
+    in_left = np.isin(o["cell"], left)
+    assert in_left.sum() > 3 * (~in_left).sum() and np.all(o["typeId"][~in_left] == 0)
+    gs, _ = eng.download_cellstate()
+    os_, _ = ora.download_cellstate()
+    assert np.allclose(gs, os_, rtol=1e-14) and len(np.unique(np.round(os_ / os_.max(), 12))) == 2
+    seen = ora.counters()["collisions"]
+    for _ in range(3):
+        eng.evolve(1)
+        ora.evolve(1)
+        total = ora.counters()["collisions"]     # the oracle's counter runs on, the engine's is the last step's
+        assert eng.counters().collisions == total - seen > 0
+        seen = total
+    g, o = H.by_id(eng.download_parcels()), H.by_id(ora.download_parcels())
+    assert np.array_equal(g["cell"], o["cell"]) and np.allclose(g["U"], o["U"], rtol=1e-9, atol=1e-7)
+    eng.close()
+
+
 def test_cylinder_ogrid_inflow_wall_matches_oracle():
     """BASELINE configs[1] topology at test size: body-fitted O-grid (non-axis-aligned hexahedra, 2-D with empty
     patches), hypersonic free stream, diffuse cylinder wall, inflow + deletion on the outer boundary."""

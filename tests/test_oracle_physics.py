@@ -702,3 +702,40 @@ def test_cll_wall_full_accommodation_is_diffuse_and_lord_rotation():
     resid = b["ERot"][hit] - (1 - aR) * a["ERot"][hit]
     assert abs(resid.mean() / (aR * H.KB * Tw) - 1) < 4 * resid.std() / resid.mean() / np.sqrt(hit.sum())
     assert np.array_equal(a["vibLevel"], b["vibLevel"]) and np.array_equal(a["ELevel"], b["ELevel"])   # untouched (commented out upstream)
+
+
+def test_zone_fill_is_the_mesh_fill_of_the_zone_cells():
+    """dsmcZoneFill (initialiseDsmcParcels/derived/dsmcZoneFill/dsmcZoneFill.C:71-272): one zone holding every cell in ascending order gives the
+    cloud of dsmcMeshFill; two zones give each its own state, only their own cells, and sigmaTcRMax of their own most abundant species."""
+    sp = H.air5()[:2]
+    mesh, md, o = box((6, 4, 4), (0.024, 0.016, 0.016), sp, "LarsenBorgnakkeVariableHardSphere", ppc=40, inverseZvFormulation="pre-2008")
+    o.mesh_fill([0, 1], [0.8e20, 0.2e20], 500.0, 500.0, 500.0)
+    a = o.download_parcels()
+    o.upload_parcels(capi.ParcelData(0, 1))
+    o.zone_fill(np.arange(mesh.n_cells), [0, 1], [0.8e20, 0.2e20], 500.0, 500.0, 500.0)
+    b = o.download_parcels()
+    assert a.n == b.n > 3000
+    for k in ("position", "U", "ERot", "cell", "tetFace", "tetPt", "typeId", "vibLevel", "origId"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+    x = np.arange(mesh.n_cells) % 6
+    left, right = np.flatnonzero(x < 2), np.flatnonzero(x >= 2)[::-1]
+    o.upload_parcels(capi.ParcelData(0, 1))
+    o.zone_fill(left, [0, 1], [2.4e20, 0.6e20], 3000.0, 3000.0, 3000.0, velocity=(400.0, 0, 0))
+    n_left = o.num_parcels()
+    o.zone_fill(right, [1], [0.5e20], 300.0, 300.0, 300.0)
+    n_all = o.num_parcels()
+    c = H.by_id(o.download_parcels())                                     # the cloud is kept in cell order; origId is the insertion order
+    assert np.array_equal(c["origId"], np.arange(n_all))                  # appended, ids continue
+    assert np.all(np.isin(c["cell"][:n_left], left)) and np.all(np.isin(c["cell"][n_left:], right)) and np.all(c["typeId"][n_left:] == 1)
+    assert c["cell"][n_left] == right[0] == mesh.n_cells - 1              # the zone's order, not the mesh's
+    per_cell = 40 / 1e20
+    assert abs(n_left / (len(left) * 3.0e20 * per_cell) - 1) < 0.03 and abs((n_all - n_left) / (len(right) * 0.5e20 * per_cell) - 1) < 0.03
+    U = c["U"]
+    assert abs(U[:n_left, 0].mean() - 400.0) < 25.0 and abs(U[n_left:, 0].mean()) < 10.0
+    ek = lambda U, m: 0.5 * m * ((U - U.mean(0)) ** 2).sum(1).mean() / (1.5 * H.KB)
+    assert abs(ek(U[n_left:], sp[1].mass) / 300.0 - 1) < 0.05
+    s, _ = o.download_cellstate()
+    vmp = lambda T, m: np.sqrt(2 * H.KB * T / m)
+    assert np.allclose(s[left], np.pi * sp[0].diameter ** 2 * vmp(3000.0, sp[0].mass), rtol=1e-12)
+    assert np.allclose(s[right], np.pi * sp[1].diameter ** 2 * vmp(300.0, sp[1].mass), rtol=1e-12)
